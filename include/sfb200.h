@@ -1,0 +1,153 @@
+/*
+ * sfb200.h -- C ABI of libsfb200.so: the B200 (sm_100a) implementation of Sailfish's quantification hot path
+ *             (read batch -> quasi-mapping -> equivalence-class counts -> EM / VBEM / bootstrap / Gibbs).
+ *
+ * The reference (kingsfordgroup/sailfish v0.10.0) has no plugin / FFI layer: the path sits behind five C++ call
+ * sites inside src/SailfishQuantify.cpp.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree); sailfish_b200/host/ holds C++ adaptors with the reference's own
+ * class / method names on top of this ABI, and INTEGRATION.md shows the patch a Sailfish maintainer would apply.
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every call returns 0 on success or a negative
+ * SFB200_E* code; sfb200_last_error(ctx) gives the message.  Host buffers are caller-owned.  A context is bound
+ * to one CUDA device; one call in flight per context.  There is NO CPU fallback: without a CUDA device every
+ * call fails with SFB200_ENODEV.
+ */
+#ifndef SFB200_H
+#define SFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB200_OK          0
+#define SFB200_ENODEV     -1   /* no usable CUDA device */
+#define SFB200_ECUDA      -2   /* CUDA runtime error (message has the call) */
+#define SFB200_EINVAL     -3   /* bad argument / call order */
+#define SFB200_ENOACTIVE  -4   /* optimize(): "no transcripts are expressed" (CollapsedEMOptimizer.cpp:794-798) */
+#define SFB200_ESMALLSUM  -5   /* optimize(): "Total alpha weight was too small" (CollapsedEMOptimizer.cpp:877-881) */
+#define SFB200_EFULL      -6   /* equivalence-class table / label arena exhausted */
+#define SFB200_ENCCL      -7   /* NCCL error or NCCL not loadable */
+#define SFB200_ECALLBACK  -8   /* a row callback returned non-zero */
+
+typedef struct sfb200_ctx sfb200_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int  sfb200_version(void);
+int  sfb200_ctx_create(int device, sfb200_ctx** out);
+void sfb200_ctx_destroy(sfb200_ctx* ctx);
+const char* sfb200_last_error(const sfb200_ctx* ctx);
+/* Launch on a caller-owned stream (e.g. torch's current stream, so the caller's CUDA events bracket the work);
+ * NULL restores the context's own stream. */
+int  sfb200_ctx_set_stream(sfb200_ctx* ctx, void* cuda_stream);
+int  sfb200_ctx_sync(sfb200_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t sfb200_launch_count(const sfb200_ctx* ctx);
+/* pinned host memory for read batches (so H2D overlaps mapping) */
+void* sfb200_host_alloc(size_t bytes);
+void  sfb200_host_free(void* p);
+
+/* ---- multi-GPU: one process per GPU, reads sharded, one all-reduce of the per-transcript vector per EM iteration -
+ * The reference is single-process; this is the exchange step BASELINE.json's north_star adds.
+ * id: 128-byte ncclUniqueId made on rank 0 by sfb200_comm_unique_id and broadcast by the launcher. */
+int sfb200_comm_unique_id(uint8_t id_out[128]);
+int sfb200_comm_init(sfb200_ctx* ctx, int n_ranks, int rank, const uint8_t id[128]);
+
+/* ---- index ---------------------------------------------------------------------------------------------------
+ * Replaces what ReadExperiment takes from RapMapSAIndex<IndexT> after SailfishIndex::load
+ * (include/SailfishIndex.hpp:28-43,104-144; fields seq / txpOffsets / txpLens, include/ReadExperiment.hpp:103-116):
+ * the device index (2-bit text, k-mer-bucketed suffix array, k-mer hash table) is built on the GPU from the
+ * transcript sequences.  seq: ASCII, transcript t = seq[txp_off[t] .. txp_off[t]+txp_len[t]).  k odd, <= 31
+ * (src/SailfishIndexer.cpp:79,199-205). */
+int sfb200_index_build(sfb200_ctx* ctx, const char* seq, const uint64_t* txp_off, const uint32_t* txp_len,
+                       uint32_t n_txp, int k);
+/* stats[0] text_len [1] n_suffixes [2] n_kmers [3] table_slots [4] index bytes in HBM [5] max bucket */
+int sfb200_index_stats(const sfb200_ctx* ctx, uint64_t stats[8]);
+/* copy the index back to the host (tests, and bench.py's CPU arm): words[text_len/32+2], sa_pos[n_suffixes],
+ * sa_tid[n_suffixes]; any pointer may be NULL */
+int sfb200_index_export(sfb200_ctx* ctx, uint64_t* words, uint32_t* sa_pos, uint32_t* sa_tid);
+
+/* ---- mapping + equivalence classes ---------------------------------------------------------------------------
+ * Replaces processReadsQuasi<IndexT> (src/SailfishQuantify.cpp:105-452 paired, :458-646 single) together with the
+ * EquivalenceClassBuilder it feeds (include/EquivalenceClassBuilder.hpp:62-110).  Fields = the SailfishOpts members
+ * processReadsQuasi reads (include/SailfishOpts.hpp:9-41) plus rl.format(). */
+typedef struct {
+    uint32_t max_read_occs;     /* sfOpts.maxReadOccs      (200)   */
+    uint32_t max_frag_len;      /* sfOpts.maxFragLen       (1000)  */
+    int32_t  num_frag_samples;  /* sfOpts.numFragSamples   (10000) */
+    int32_t  lib_format_id;     /* rl.format().formatID()  (include/LibraryFormat.hpp:89-98) */
+    int32_t  strict_intersect;  /* sfOpts.strictIntersect  */
+    int32_t  allow_orphans;     /* sfOpts.allowOrphans     */
+    int32_t  allow_dovetail;    /* sfOpts.allowDovetail    */
+    int32_t  ignore_compat;     /* sfOpts.ignoreLibCompat  */
+    int32_t  enforce_compat;    /* sfOpts.enforceLibCompat */
+    uint32_t max_interval;      /* k-mer buckets larger than this are not used as seeds (1000) */
+} sfb200_map_opts;
+
+/* == eqBuilder.start() (SailfishQuantify.cpp:1322): resets the class table, counters and the FLD sampler */
+int sfb200_map_begin(sfb200_ctx* ctx, const sfb200_map_opts* opts);
+/* One batch of reads from HOST memory (what a parser job holds, PairSequenceParser.hpp:16-24, concatenated):
+ * read i = bases[off[i] .. off[i+1]).  bases2/off2 NULL for a single-end library.  Includes the H2D copy. */
+int sfb200_map_batch(sfb200_ctx* ctx, const char* bases1, const uint64_t* off1, const char* bases2,
+                     const uint64_t* off2, uint64_t n_reads);
+/* Same with buffers already resident in device memory. */
+int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
+                            const uint64_t* d_off2, uint64_t n_reads);
+/* == thread join + eqBuilder.finish() (SailfishQuantify.cpp:942-947,1328).
+ * counters: [0] numObservedFragments [1] numMappedFragments [2] numFragHits [3] upperBoundHits [4] numFwd [5] numRC
+ * (ReadExperiment.hpp:74-97); fld_hist[max_frag_len] = flMap (SailfishQuantify.cpp:867).  With a communicator the
+ * counters and fld_hist are summed over ranks (classes stay rank-local). */
+int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz);
+/* == eqVec() (EquivalenceClassBuilder.hpp:110) as CSR in canonical order (first transcript id, then label hash);
+ * this is the content of aux/eq_classes.txt (src/GZipWriter.cpp:51-92) */
+int sfb200_eq_export(sfb200_ctx* ctx, uint64_t* row_ptr, uint32_t* labels, uint64_t* counts);
+/* inverse: run inference without mapping (the commented-out loadEquivClasses, SailfishQuantify.cpp:1444-1495) */
+int sfb200_eq_import(sfb200_ctx* ctx, uint32_t n_txp, uint64_t n_classes, const uint64_t* row_ptr,
+                     const uint32_t* labels, const uint64_t* counts);
+
+/* ---- inference ------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t  use_vb;        /* sopt.useVBOpt */
+    double   prior_alpha;   /* 0.01  (CollapsedEMOptimizer.cpp:786) */
+    double   tol;           /* relDiffTolerance, 0.01 (SailfishQuantify.cpp:1343) */
+    uint32_t min_iter;      /* 50    (CollapsedEMOptimizer.cpp:716) */
+    uint32_t max_iter;      /* 10000 (SailfishQuantify.cpp:1343) */
+    uint32_t fixed_iters;   /* >0: exactly this many iterations, convergence ignored */
+    double   check_cutoff;  /* 1e-2  (CollapsedEMOptimizer.cpp:811) */
+    double   min_alpha;     /* 1e-8  (CollapsedEMOptimizer.cpp:810) */
+} sfb200_em_opts;
+void sfb200_em_default_opts(sfb200_em_opts* o);
+
+/* Replaces CollapsedEMOptimizer::optimize (include/CollapsedEMOptimizer.hpp:25-28, src/CollapsedEMOptimizer.cpp:711-893).
+ * eff_lens[t] = noEffectiveLengthCorrection ? RefLength : EffectiveLength; num_mapped = numMappedFragments() (global).
+ * alphas_out[t] -> Transcript::setEstCount; mass = alphas/sum.  Classes come from map_finish or eq_import.
+ * With a communicator: one all-reduce(sum) of the T-vector per iteration. */
+int sfb200_em_run(sfb200_ctx* ctx, const double* eff_lens, uint32_t n_txp, uint64_t num_mapped,
+                  const sfb200_em_opts* opts, double* alphas_out, uint32_t* iters_out, double* max_rel_diff_out);
+/* device time of the iteration loop of the last em_run / bootstrap in milliseconds (CUDA events on the launch stream) */
+double sfb200_last_em_loop_ms(const sfb200_ctx* ctx);
+
+typedef int (*sfb200_f64_row_cb)(void* user, const double* row, size_t n);
+typedef int (*sfb200_i32_row_cb)(void* user, const int32_t* row, size_t n);
+/* Replaces CollapsedEMOptimizer::gatherBootstraps (src/CollapsedEMOptimizer.cpp:557-709): cb == writeBootstrap(alphas) */
+int sfb200_bootstrap_run(sfb200_ctx* ctx, const double* eff_lens, uint32_t n_txp, const sfb200_em_opts* opts,
+                         uint32_t n_boot, uint64_t seed, sfb200_f64_row_cb cb, void* user);
+/* doBootstrap's EM on caller-supplied resampled counts (counts in eq_export order); parity hook for tests */
+int sfb200_bootstrap_em(sfb200_ctx* ctx, const double* eff_lens, uint32_t n_txp, const uint64_t* samp_counts,
+                        const sfb200_em_opts* opts, double* alphas_out, uint32_t* iters_out);
+/* Replaces CollapsedGibbsSampler::sample (include/CollapsedGibbsSampler.hpp:27-31, src/CollapsedGibbsSampler.cpp:199-291):
+ * masses[t] = Transcript::mass() after optimize; cb == writeSample(counts) */
+int sfb200_gibbs_run(sfb200_ctx* ctx, const double* eff_lens, const double* masses, uint32_t n_txp, uint64_t num_mapped,
+                     uint32_t n_samples, uint64_t seed, sfb200_i32_row_cb cb, void* user);
+
+/* hashing primitive exposed for known-answer tests: XXH64 (src/xxhash.c:346-455) of n messages computed ON THE DEVICE;
+ * message i = data[off[i]..off[i+1]) (lengths must be multiples of 4, as labels are) */
+int sfb200_xxh64_device(sfb200_ctx* ctx, const uint8_t* data, const uint64_t* off, uint64_t n, uint64_t seed, uint64_t* out);
+/* device digamma (VBEM) for accuracy tests */
+int sfb200_digamma_device(sfb200_ctx* ctx, const double* x, uint64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

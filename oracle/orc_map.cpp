@@ -23,6 +23,7 @@ namespace {
 
 constexpr int MAX_IV = 16;          // spec v1: at most 16 MMP intervals per orientation scan
 constexpr uint64_t EMPTY_KEY = ~0ULL;
+constexpr uint64_t MAX_READ_LEN = 256;
 
 inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
@@ -50,7 +51,7 @@ struct orc_index {
     std::vector<uint64_t> words;        // 2-bit text, 32 bases per word, base p at bits 2*(p%32)
     std::vector<uint64_t> txp_start;    // T+1 prefix sums in packed coordinates
     std::vector<uint32_t> txp_len;
-    std::vector<uint32_t> sa_pos;       // valid positions sorted by (k-mer value, position)
+    std::vector<uint32_t> sa_pos;       // valid positions sorted by (k-mer value [base i at bits 2i], position)
     std::vector<uint32_t> sa_tid;
     std::vector<uint64_t> kmers;        // distinct k-mers ascending
     std::vector<uint32_t> lb, cnt;      // bucket [lb, lb+cnt) in sa_pos
@@ -61,7 +62,7 @@ struct orc_index {
     inline int base(uint64_t p) const { return static_cast<int>((words[p >> 5] >> (2 * (p & 31))) & 3); }
     uint64_t kmer_at(uint64_t p) const {
         uint64_t v = 0;
-        for (int i = 0; i < k; ++i) v = (v << 2) | static_cast<uint64_t>(base(p + i));
+        for (int i = 0; i < k; ++i) v |= static_cast<uint64_t>(base(p + i)) << (2 * i);   // base i of the k-mer at bits 2i
         return v;
     }
     // returns index into kmers or -1; counts probes
@@ -125,9 +126,8 @@ extern "C" orc_index* orc_index_build(const char* seq, const uint64_t* txp_off, 
         if (txp_len[t] < static_cast<uint32_t>(k)) continue;
         const uint64_t s = ix->txp_start[t];
         uint64_t v = 0;
-        const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
         for (uint32_t i = 0; i < txp_len[t]; ++i) {
-            v = ((v << 2) | static_cast<uint64_t>(ix->base(s + i))) & kmask;
+            v = (v >> 2) | (static_cast<uint64_t>(ix->base(s + i)) << (2 * (k - 1)));
             if (i + 1 >= static_cast<uint32_t>(k)) kp.emplace_back(v, static_cast<uint32_t>(s + i + 1 - k));
         }
     }
@@ -224,7 +224,7 @@ struct Mapper {
             if (lastN >= 0) { i += lastN + 1; continue; }            // jump past the last invalid base in the window
             uint64_t km = 0;
             bool homo = true;
-            for (int j = 0; j < k; ++j) { km = (km << 2) | s[i + j]; if (s[i + j] != s[i]) homo = false; }
+            for (int j = 0; j < k; ++j) { km |= static_cast<uint64_t>(s[i + j]) << (2 * j); if (s[i + j] != s[i]) homo = false; }
             if (homo) { i += 1; continue; }                          // homopolymer k-mers are never used as seeds
             const int64_t ki = ix.find(km, work.P);
             if (ki < 0 || ix.cnt[ki] > o.max_interval) { i += 1; continue; }
@@ -298,6 +298,7 @@ struct Mapper {
 };
 
 void encode(const char* b, uint64_t n, std::vector<uint8_t>& s) {
+    if (n > MAX_READ_LEN) n = MAX_READ_LEN;                          // spec v1: reads are clipped to 256 bases
     s.resize(n);
     for (uint64_t i = 0; i < n; ++i) s[i] = static_cast<uint8_t>(base_code(b[i]));
 }

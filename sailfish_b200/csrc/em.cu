@@ -1,0 +1,708 @@
+// em.cu -- inference over the ragged (equivalence class x transcript) structure on sm_100a.
+//
+// Replaces CollapsedEMOptimizer::optimize / EMUpdate_ / VBEMUpdate_ (reference src/CollapsedEMOptimizer.cpp:224-369,
+// 711-893) and doBootstrap's inner loop (:476-514).  DESIGN.md section 4 describes the layout and the kernels:
+//
+//   * classes with >= 2 members are stored binned by member count so that a sub-warp group of g = 2,4,8,16,32 lanes
+//     owns one class: one coalesced load of (label, weight) per lane, a shuffle reduction for the denominator
+//     (E-step) and one red.global.add.f64 per lane (M-step scatter);
+//   * single-member classes contribute a constant per-transcript vector which is the initial value of every output
+//     buffer, so they never enter the sweep;
+//   * three alpha buffers rotate (in / out / spare): while iteration n sweeps in -> out, the same pass compares
+//     spare (alpha_{n-1}) with in (alpha_n) for the convergence rule and re-initialises spare for iteration n+1,
+//     so an EM iteration costs ONE grid-wide barrier and no host round trip: the whole loop is one persistent
+//     cooperative kernel (one CTA per SM).  Tile -> CTA assignment is static, so a CTA re-reads the same slice of
+//     labels / weights every iteration and small problems are served from that SM's L1.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr double DENORM_MIN = 4.9406564584124654e-324;   // std::numeric_limits<double>::denorm_min() (CollapsedEMOptimizer.cpp:33-34)
+constexpr int EM_THREADS = 1024;
+
+// control block (unsigned long long words)
+enum { CTL_BAR_COUNT = 0, CTL_BAR_GEN = 1, CTL_MAXREL = 2 /*4 slots*/, CTL_CSUM = 6 /*4 slots*/, CTL_ITERS = 10,
+       CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_WORDS = 16 };
+
+struct EmParams {
+    const uint32_t* off; const uint32_t* lab; const double* w; const double* cnt;
+    const double* base;     // T: initial value of an output buffer
+    double* X;              // 3*T rotating alpha buffers
+    double* theta;          // T (VBEM)
+    unsigned long long* ctl;
+    uint32_t T;
+    uint64_t tile_start[SFB_NBINS + 1];
+    uint64_t cls_start[SFB_NBINS + 1];
+    int use_vb, gate_old;
+    double tol, cutoff;
+    uint32_t min_iter, max_iter, fixed_iters;
+    double sum0;            // sum of alpha_0 (VBEM logNorm of the first iteration)
+    double base_sum;        // sum of base
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) { return __ldcg(p); }
+
+// all CTAs of the (cooperatively launched, hence co-resident) grid meet here
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctl, unsigned int nblocks, unsigned long long& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += 1;
+        __threadfence();
+        const unsigned long long prev = atomicAdd(&ctl[CTL_BAR_COUNT], 1ULL);
+        if (prev + 1 == gen * nblocks) {
+            st_release_u64(&ctl[CTL_BAR_GEN], gen);
+        } else {
+            while (ld_acquire_u64(&ctl[CTL_BAR_GEN]) < gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// ---- E-step + M-step scatter for one warp tile -----------------------------------------------------------------------
+// EMUpdate_ (CollapsedEMOptimizer.cpp:235-277) / VBEMUpdate_ (:325-366) for the classes of this tile.
+// `in` is alpha (EM) or expTheta (VBEM); members with a non-positive VBEM theta are skipped as in :342,357.
+template <bool VB>
+__device__ __forceinline__ double sweep_tile(const EmParams& p, uint64_t tile, const double* __restrict__ in,
+                                             double* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31u;
+    int b = 0;
+    while (b < SFB_NBINS - 1 && tile >= p.tile_start[b + 1]) ++b;
+    double contrib = 0.0;
+    if (b < SFB_NBINS - 1) {
+        const unsigned sh = b + 1;                      // g = 2 << b lanes per class
+        const unsigned g = 1u << sh;
+        const uint64_t c = p.cls_start[b] + ((tile - p.tile_start[b]) << (5 - sh)) + (lane >> sh);
+        const unsigned j = lane & (g - 1);
+        uint32_t o0 = 0, n = 0;
+        const bool cv = c < p.cls_start[b + 1];
+        if (cv) { o0 = __ldg(p.off + c); n = __ldg(p.off + c + 1) - o0; }
+        bool ev = cv && j < n;
+        uint32_t t = 0;
+        double v = 0.0;
+        if (ev) {
+            t = __ldg(p.lab + o0 + j);
+            const double wv = __ldg(p.w + o0 + j);
+            const double a = ld_cg_f64(in + t);
+            if (VB && !(a > 0.0)) ev = false; else v = a * wv;
+        }
+        double denom = v;
+        for (unsigned m = g >> 1; m >= 1; m >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, m);
+        if (ev && denom > DENORM_MIN && !isnan(v)) {
+            const double add = v * (__ldg(p.cnt + c) / denom);
+            atomicAdd(out + t, add);
+            contrib = add;
+        }
+    } else {
+        // long class (more than 32 members): the whole warp walks it twice
+        const uint64_t c = p.cls_start[b] + (tile - p.tile_start[b]);
+        if (c < p.cls_start[b + 1]) {
+            const uint32_t o0 = __ldg(p.off + c), n = __ldg(p.off + c + 1) - o0;
+            double denom = 0.0;
+            for (uint32_t j = lane; j < n; j += 32) {
+                const double a = ld_cg_f64(in + __ldg(p.lab + o0 + j));
+                if (!VB || a > 0.0) denom += a * __ldg(p.w + o0 + j);
+            }
+            denom = warp_sum(denom);
+            if (denom > DENORM_MIN) {
+                const double inv = __ldg(p.cnt + c) / denom;
+                for (uint32_t j = lane; j < n; j += 32) {
+                    const uint32_t t = __ldg(p.lab + o0 + j);
+                    const double a = ld_cg_f64(in + t);
+                    if (VB && !(a > 0.0)) continue;
+                    const double v = a * __ldg(p.w + o0 + j);
+                    if (!isnan(v)) { const double add = v * inv; atomicAdd(out + t, add); contrib += add; }
+                }
+            }
+        }
+    }
+    return contrib;
+}
+
+// ---- per-transcript pass: convergence rule + re-initialise the spare buffer (+ VBEM expTheta) -------------------------
+// CollapsedEMOptimizer.cpp:849-861 (gate on the NEW alpha) / :496-508 (doBootstrap: gate on the OLD alpha);
+// VBEM: :300-320.  Returns this thread's max relative difference encoded as bits+1 (0 = no transcript passed the gate).
+template <bool VB>
+__device__ __forceinline__ unsigned long long transcript_pass(const EmParams& p, const double* prev, const double* cur,
+                                                              double* spare_out, bool compare, bool reset, double logNorm,
+                                                              uint64_t tid0, uint64_t stride) {
+    unsigned long long best = 0ULL;
+    for (uint64_t t = tid0; t < p.T; t += stride) {
+        const double c = ld_cg_f64(cur + t);
+        if (compare) {
+            const double pv = ld_cg_f64(prev + t);
+            const double gate = p.gate_old ? pv : c;
+            if (gate > p.cutoff) {
+                const double rel = fabs(pv - c) / c;
+                // rel >= 0 (or +inf / nan): non-negative doubles order like their bit patterns
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(rel) + 1ULL;
+                best = bits > best ? bits : best;
+            }
+        }
+        if (reset) spare_out[t] = __ldg(p.base + t);
+        if (VB && reset) p.theta[t] = (c > DENORM_MIN) ? exp(sfb_digamma(c) - logNorm) : 0.0;
+    }
+    return best;
+}
+
+__device__ __forceinline__ void block_max_to_slot(unsigned long long v, unsigned long long* slot, unsigned long long* sm) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = o > v ? o : v;
+    }
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (blockDim.x >> 5) ? sm[lane] : 0ULL;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+            v = o > v ? o : v;
+        }
+        if (lane == 0 && v) atomicMax(slot, v);
+    }
+}
+
+__device__ __forceinline__ void block_sum_to_slot(double v, double* slot, double* sm) {
+    v = warp_sum(v);
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) atomicAdd(slot, v);
+    }
+}
+
+__device__ __forceinline__ double decode_mrd(unsigned long long bits1) {
+    return bits1 ? __longlong_as_double((long long)(bits1 - 1ULL)) : -1.7976931348623157e308;
+}
+
+// ---- the persistent EM loop --------------------------------------------------------------------------------------------
+template <bool VB>
+__global__ void __launch_bounds__(EM_THREADS, 1) k_em_persistent(const EmParams p) {
+    __shared__ unsigned long long sm_u[32];
+    __shared__ double sm_d[32];
+    const unsigned nblocks = gridDim.x;
+    unsigned long long gen = 0;
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t gstride = (uint64_t)nblocks * blockDim.x;
+    const unsigned warps_per_block = blockDim.x >> 5;
+    const unsigned warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = p.tile_start[SFB_NBINS];
+    const uint64_t tile_lo = n_tiles * blockIdx.x / nblocks, tile_hi = n_tiles * (blockIdx.x + 1ULL) / nblocks;
+
+    unsigned bi = 0, bo = 1, bs = 2;                       // buffer indices: in / out / spare
+    const bool fixed = p.fixed_iters > 0;
+    uint32_t n = 0;
+    for (;;) {
+        double* in = p.X + (size_t)bi * p.T;
+        double* out = p.X + (size_t)bo * p.T;
+        double* spare = p.X + (size_t)bs * p.T;
+        unsigned long long* slot = p.ctl + CTL_MAXREL + (n & 3u);
+        const bool last = fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            p.ctl[CTL_MAXREL + ((n + 2u) & 3u)] = 0ULL;
+            p.ctl[CTL_CSUM + ((n + 2u) & 3u)] = 0ULL;
+        }
+        double logNorm = 0.0;
+        if (VB && !last) {
+            const double asum = (n == 0) ? p.sum0
+                : p.base_sum + __longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (n & 3u)));
+            logNorm = sfb_digamma(asum);
+        }
+        const unsigned long long best = transcript_pass<VB>(p, spare, in, spare, n > 0, !last, logNorm, gtid, gstride);
+        if (n > 0) block_max_to_slot(best, slot, sm_u);
+        if (last) {
+            grid_barrier(p.ctl, nblocks, gen);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                p.ctl[CTL_ITERS] = n; p.ctl[CTL_RESULT_BUF] = bi; p.ctl[CTL_MRD] = ld_cg_u64(slot);
+            }
+            return;
+        }
+        if (VB) grid_barrier(p.ctl, nblocks, gen);         // expTheta complete before anyone gathers it
+        const double* src = VB ? p.theta : in;
+        double contrib = 0.0;
+        for (uint64_t tile = tile_lo + warp; tile < tile_hi; tile += warps_per_block) contrib += sweep_tile<VB>(p, tile, src, out);
+        if (VB) block_sum_to_slot(contrib, reinterpret_cast<double*>(p.ctl + CTL_CSUM + ((n + 1u) & 3u)), sm_d);
+        grid_barrier(p.ctl, nblocks, gen);
+        // check(alpha_{n-1}, alpha_n) is complete now: would the reference loop (:820 / :486) have stopped at itNum == n?
+        if (!fixed && n > 0 && n >= p.min_iter) {
+            const unsigned long long mr = ld_cg_u64(slot);
+            const bool converged = !(decode_mrd(mr) > p.tol);
+            if (converged) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctl[CTL_ITERS] = n; p.ctl[CTL_RESULT_BUF] = bi; p.ctl[CTL_MRD] = mr; }
+                return;
+            }
+        }
+        const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp;
+        ++n;
+    }
+}
+
+// ---- the same iteration as separate launches (multi-rank runs with an all-reduce in between, and profiling) ------------
+template <bool VB>
+__global__ void __launch_bounds__(EM_THREADS, 1) k_em_transcript_pass(const EmParams p, unsigned bi, unsigned bs, uint32_t n,
+                                                                      int compare, int reset, double asum) {
+    __shared__ unsigned long long sm_u[32];
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+    double* in = p.X + (size_t)bi * p.T;
+    double* spare = p.X + (size_t)bs * p.T;
+    const double logNorm = (VB && reset) ? sfb_digamma(asum) : 0.0;
+    const unsigned long long best = transcript_pass<VB>(p, spare, in, spare, compare != 0, reset != 0, logNorm, gtid, gstride);
+    if (compare) block_max_to_slot(best, p.ctl + CTL_MAXREL + (n & 3u), sm_u);
+}
+
+template <bool VB>
+__global__ void __launch_bounds__(EM_THREADS, 1) k_em_sweep(const EmParams p, unsigned bi, unsigned bo, uint32_t n) {
+    __shared__ double sm_d[32];
+    const unsigned nblocks = gridDim.x;
+    const unsigned warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = p.tile_start[SFB_NBINS];
+    const uint64_t tile_lo = n_tiles * blockIdx.x / nblocks, tile_hi = n_tiles * (blockIdx.x + 1ULL) / nblocks;
+    const double* src = VB ? p.theta : p.X + (size_t)bi * p.T;
+    double* out = p.X + (size_t)bo * p.T;
+    double contrib = 0.0;
+    for (uint64_t tile = tile_lo + warp; tile < tile_hi; tile += warps_per_block) contrib += sweep_tile<VB>(p, tile, src, out);
+    if (VB) block_sum_to_slot(contrib, reinterpret_cast<double*>(p.ctl + CTL_CSUM + ((n + 1u) & 3u)), sm_d);
+}
+
+__global__ void k_sum_f64(const double* __restrict__ x, uint32_t n, double* __restrict__ out) {
+    __shared__ double sm_d[32];
+    double s = 0.0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += x[i];
+    block_sum_to_slot(s, out, sm_d);
+}
+
+// ---- set-up kernels -------------------------------------------------------------------------------------------------------
+// CollapsedEMOptimizer.cpp:733-740 (clamp) and :745-772: w_i = count / effLen[t_i]; w_i *= 1 / sum_i w_i
+__global__ void k_clamp_eff(const double* __restrict__ eff_in, uint32_t T, double* __restrict__ eff) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) { const double e = eff_in[i]; eff[i] = (e <= 1.0) ? 1.0 : e; }
+}
+__global__ void k_class_weights(const uint32_t* __restrict__ off, const uint32_t* __restrict__ lab, const double* __restrict__ cnt,
+                                const double* __restrict__ eff, uint64_t Em, double* __restrict__ w) {
+    const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (c >= Em) return;
+    const uint32_t b = off[c], e = off[c + 1];
+    const double count = cnt[c];
+    double wsum = 0.0;
+    for (uint32_t j = b; j < e; ++j) { const double v = count / eff[lab[j]]; w[j] = v; wsum += v; }
+    const double wnorm = 1.0 / wsum;
+    for (uint32_t j = b; j < e; ++j) w[j] *= wnorm;
+}
+// alpha_0 (:800-803), base = single (+ prior), and the first output buffer
+__global__ void k_em_init(const uint8_t* __restrict__ active, const double* __restrict__ single, uint32_t T, double alpha0,
+                          double prior_term, double* __restrict__ X, double* __restrict__ base) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const double b = single[i] + prior_term;
+    base[i] = b;
+    X[i] = active[i] ? alpha0 : 0.0;
+    X[(size_t)T + i] = b;
+    X[2 * (size_t)T + i] = b;
+}
+// per-sample counts (bootstrap): binned counts and the single-member vector from canonical-order counts
+__global__ void k_permute_counts(const unsigned long long* __restrict__ samp, const uint32_t* __restrict__ perm, uint64_t Em,
+                                 double* __restrict__ cnt) {
+    const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (c < Em) cnt[c] = (double)samp[perm[c]];
+}
+__global__ void k_scatter_single(const unsigned long long* __restrict__ samp, const uint32_t* __restrict__ sgl_cls,
+                                 const uint32_t* __restrict__ sgl_tid, uint64_t n_sgl, double* __restrict__ single) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n_sgl) atomicAdd(single + sgl_tid[i], (double)samp[sgl_cls[i]]);
+}
+
+inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ======================================================================================================================
+// host side
+// ======================================================================================================================
+
+struct EmExtra {   // device arrays only the inference code needs; owned by DevClasses' lifetime through ctx
+    DevBuf<uint32_t> sgl_cls, sgl_tid;
+    uint64_t n_sgl = 0;
+    DevBuf<double> cnt_s;                 // per-sample binned counts
+    DevBuf<double> single_s;              // per-sample single-member vector
+    DevBuf<unsigned long long> samp;      // canonical-order per-sample counts on the device
+};
+static EmExtra* g_extra_for(sfb200_ctx* c) {
+    if (!c->em_extra) c->em_extra = new EmExtra();
+    return static_cast<EmExtra*>(c->em_extra);
+}
+void sfb_em_extra_free(sfb200_ctx* c) {
+    EmExtra* e = static_cast<EmExtra*>(c->em_extra);
+    if (!e) return;
+    e->sgl_cls.release(); e->sgl_tid.release(); e->cnt_s.release(); e->single_s.release(); e->samp.release();
+    delete e;
+    c->em_extra = nullptr;
+}
+
+// Build the binned device layout from canonical CSR on the host.
+int sfb_classes_from_host(sfb200_ctx* c, uint32_t n_txp, uint64_t E, const uint64_t* row_ptr, const uint32_t* labels,
+                          const uint64_t* counts) {
+    DevClasses& k = c->cls;
+    k.ready = false;
+    const uint64_t nnz = E ? row_ptr[E] : 0;
+    for (uint64_t i = 0; i < nnz; ++i) if (labels[i] >= n_txp) SFB_FAIL(c, SFB200_EINVAL, "label holds a transcript id >= n_txp");
+    k.n_txp = n_txp; k.E = E; k.nnz = nnz;
+    k.h_row_ptr.assign(row_ptr, row_ptr + E + 1);
+    if (E == 0) k.h_row_ptr.assign(1, 0);
+    k.h_labels.assign(labels, labels + nnz);
+    k.h_counts.assign(counts, counts + E);
+
+    auto bin_of = [](uint64_t n) { return n <= 2 ? 0 : n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 3 : n <= 32 ? 4 : 5; };
+    uint64_t bin_n[SFB_NBINS] = {0, 0, 0, 0, 0, 0};
+    uint64_t nnzm = 0, n_sgl = 0, total = 0;
+    for (uint64_t e = 0; e < E; ++e) {
+        const uint64_t n = row_ptr[e + 1] - row_ptr[e];
+        total += counts[e];
+        if (n == 1) ++n_sgl;
+        else if (n >= 2) { bin_n[bin_of(n)]++; nnzm += n; }
+    }
+    if (nnzm >= 0xFFFFFFFFull) SFB_FAIL(c, SFB200_EINVAL, "more than 2^32 label entries");
+    k.total_count = total;
+    k.bin_cls[0] = 0;
+    for (int b = 0; b < SFB_NBINS; ++b) k.bin_cls[b + 1] = k.bin_cls[b] + bin_n[b];
+    k.Em = k.bin_cls[SFB_NBINS]; k.nnzm = nnzm;
+
+    std::vector<uint32_t> perm(k.Em), off(k.Em + 1), lab(nnzm), sgl_cls(n_sgl), sgl_tid(n_sgl);
+    std::vector<double> cnt(k.Em), single(n_txp, 0.0);
+    std::vector<uint8_t> active(n_txp, 0);
+    uint64_t cur[SFB_NBINS];
+    for (int b = 0; b < SFB_NBINS; ++b) cur[b] = k.bin_cls[b];
+    uint64_t si = 0;
+    for (uint64_t e = 0; e < E; ++e) {
+        const uint64_t n = row_ptr[e + 1] - row_ptr[e];
+        if (n == 1) {
+            const uint32_t t = labels[row_ptr[e]];
+            single[t] += static_cast<double>(counts[e]);
+            sgl_cls[si] = static_cast<uint32_t>(e); sgl_tid[si] = t; ++si;
+        } else if (n >= 2) {
+            perm[cur[bin_of(n)]++] = static_cast<uint32_t>(e);
+        }
+    }
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < k.Em; ++i) {
+        const uint64_t e = perm[i];
+        off[i] = static_cast<uint32_t>(o);
+        cnt[i] = static_cast<double>(counts[e]);
+        for (uint64_t j = row_ptr[e]; j < row_ptr[e + 1]; ++j) lab[o++] = labels[j];
+    }
+    off[k.Em] = static_cast<uint32_t>(o);
+    uint64_t n_active = 0;
+    for (uint64_t i = 0; i < nnz; ++i) if (!active[labels[i]]) { active[labels[i]] = 1; ++n_active; }   // :774-782
+    k.n_active = n_active;
+
+    cudaSetDevice(c->device);
+    EmExtra* x = g_extra_for(c);
+    x->n_sgl = n_sgl;
+    SFB_CUDA(c, k.off.reserve(k.Em + 1)); SFB_CUDA(c, k.lab.reserve(nnzm)); SFB_CUDA(c, k.w.reserve(nnzm));
+    SFB_CUDA(c, k.cnt.reserve(k.Em)); SFB_CUDA(c, k.perm.reserve(k.Em)); SFB_CUDA(c, k.single.reserve(n_txp));
+    SFB_CUDA(c, k.active.reserve(n_txp)); SFB_CUDA(c, x->sgl_cls.reserve(n_sgl)); SFB_CUDA(c, x->sgl_tid.reserve(n_sgl));
+    cudaStream_t s = c->stream;
+    SFB_CUDA(c, cudaMemcpyAsync(k.off.p, off.data(), (k.Em + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (nnzm) SFB_CUDA(c, cudaMemcpyAsync(k.lab.p, lab.data(), nnzm * 4, cudaMemcpyHostToDevice, s));
+    if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(k.cnt.p, cnt.data(), k.Em * 8, cudaMemcpyHostToDevice, s));
+    if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(k.perm.p, perm.data(), k.Em * 4, cudaMemcpyHostToDevice, s));
+    if (n_txp) SFB_CUDA(c, cudaMemcpyAsync(k.single.p, single.data(), n_txp * 8ull, cudaMemcpyHostToDevice, s));
+    if (n_txp) SFB_CUDA(c, cudaMemcpyAsync(k.active.p, active.data(), n_txp, cudaMemcpyHostToDevice, s));
+    if (n_sgl) SFB_CUDA(c, cudaMemcpyAsync(x->sgl_cls.p, sgl_cls.data(), n_sgl * 4, cudaMemcpyHostToDevice, s));
+    if (n_sgl) SFB_CUDA(c, cudaMemcpyAsync(x->sgl_tid.p, sgl_tid.data(), n_sgl * 4, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));   // the host vectors die here
+    k.ready = true;
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_eq_import(sfb200_ctx* c, uint32_t n_txp, uint64_t n_classes, const uint64_t* row_ptr,
+                                const uint32_t* labels, const uint64_t* counts) {
+    if (!c) return SFB200_EINVAL;
+    if (n_classes && (!row_ptr || !labels || !counts)) SFB_FAIL(c, SFB200_EINVAL, "eq_import: null array");
+    static const uint64_t zero = 0;
+    return sfb_classes_from_host(c, n_txp, n_classes, n_classes ? row_ptr : &zero, labels, counts);
+}
+
+extern "C" int sfb200_eq_export(sfb200_ctx* c, uint64_t* row_ptr, uint32_t* labels, uint64_t* counts) {
+    if (!c) return SFB200_EINVAL;
+    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "eq_export: no classes (call map_finish or eq_import first)");
+    const DevClasses& k = c->cls;
+    if (row_ptr) std::memcpy(row_ptr, k.h_row_ptr.data(), (k.E + 1) * 8);
+    if (labels && k.nnz) std::memcpy(labels, k.h_labels.data(), k.nnz * 4);
+    if (counts && k.E) std::memcpy(counts, k.h_counts.data(), k.E * 8);
+    return SFB200_OK;
+}
+
+extern "C" void sfb200_em_default_opts(sfb200_em_opts* o) {
+    o->use_vb = 0; o->prior_alpha = 0.01; o->tol = 0.01; o->min_iter = 50; o->max_iter = 10000; o->fixed_iters = 0;
+    o->check_cutoff = 1e-2; o->min_alpha = 1e-8;
+}
+
+extern "C" double sfb200_last_em_loop_ms(const sfb200_ctx* c) { return c ? c->last_em_ms : 0.0; }
+
+namespace {
+
+struct LoopSpec { bool gate_old; uint32_t min_iter; };
+
+// Runs the iteration loop on prepared device state (weights, base, X[0] = alpha_0, X[1] = X[2] = base).
+// On return *buf_out says which third of X holds the result.
+int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, uint32_t* iters_out, double* mrd_out, unsigned* buf_out) {
+    cudaStream_t s = c->stream;
+    SFB_CUDA(c, c->em_ctl.reserve(CTL_WORDS));
+    SFB_CUDA(c, cudaMemsetAsync(c->em_ctl.p, 0, CTL_WORDS * 8, s));
+    p.ctl = c->em_ctl.p;
+    const bool vb = o->use_vb != 0;
+    const char* mode = getenv("SFB200_EM_MODE");
+    const bool steps = c->n_ranks > 1 || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
+    unsigned long long h_ctl[CTL_WORDS];
+    SFB_CUDA(c, cudaEventRecord(c->ev0, s));
+    if (!steps) {
+        void* args[] = {&p};
+        const void* fn = vb ? reinterpret_cast<const void*>(&k_em_persistent<true>) : reinterpret_cast<const void*>(&k_em_persistent<false>);
+        int per_sm = 0;
+        SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, EM_THREADS, 0));
+        if (per_sm < 1) SFB_FAIL(c, SFB200_ECUDA, "EM kernel does not fit on an SM");
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->num_sms), dim3(EM_THREADS), args, 0, s));
+        c->launches++;
+        SFB_CUDA(c, cudaEventRecord(c->ev1, s));
+        SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        *iters_out = static_cast<uint32_t>(h_ctl[CTL_ITERS]);
+        *buf_out = static_cast<unsigned>(h_ctl[CTL_RESULT_BUF]);
+        const unsigned long long mr = h_ctl[CTL_MRD];
+        double d; const unsigned long long b = mr ? mr - 1 : 0; std::memcpy(&d, &b, 8);
+        *mrd_out = mr ? d : -std::numeric_limits<double>::max();
+    } else {
+        // one launch per phase; with a communicator the output buffer is summed over ranks before it is looked at
+        const unsigned grid = c->num_sms;
+        unsigned bi = 0, bo = 1, bs = 2;
+        const bool fixed = o->fixed_iters > 0;
+        uint32_t n = 0;
+        double asum = p.sum0;
+        unsigned long long mr = 0;
+        for (;;) {
+            const bool last = fixed ? (n >= o->fixed_iters) : (n >= o->max_iter && n >= o->min_iter);
+            // slots (n+2)&3 are recycled; clear them (the persistent kernel does this on the device)
+            SFB_CUDA(c, cudaMemsetAsync(c->em_ctl.p + CTL_MAXREL + ((n + 2u) & 3u), 0, 8, s));
+            SFB_CUDA(c, cudaMemsetAsync(c->em_ctl.p + CTL_CSUM + ((n + 2u) & 3u), 0, 8, s));
+            if (vb) k_em_transcript_pass<true><<<grid, EM_THREADS, 0, s>>>(p, bi, bs, n, n > 0, !last, asum);
+            else k_em_transcript_pass<false><<<grid, EM_THREADS, 0, s>>>(p, bi, bs, n, n > 0, !last, asum);
+            c->launches++;
+            if (!last) {
+                if (vb) k_em_sweep<true><<<grid, EM_THREADS, 0, s>>>(p, bi, bo, n);
+                else k_em_sweep<false><<<grid, EM_THREADS, 0, s>>>(p, bi, bo, n);
+                c->launches++;
+                if (c->n_ranks > 1) {
+                    const int rc = sfb_comm_allreduce_f64(c, p.X + (size_t)bo * p.T, p.T);
+                    if (rc) return rc;
+                    if (vb) {   // the contribution sums are rank-local: recompute the total from the reduced vector
+                        double* slot = reinterpret_cast<double*>(c->em_ctl.p + CTL_CSUM + ((n + 1u) & 3u));
+                        SFB_CUDA(c, cudaMemsetAsync(slot, 0, 8, s));
+                        k_sum_f64<<<grid, EM_THREADS, 0, s>>>(p.X + (size_t)bo * p.T, p.T, slot);
+                        c->launches++;
+                    }
+                }
+            }
+            const bool need_host = last || (!fixed && n > 0 && n >= o->min_iter) || vb;
+            if (need_host) {
+                SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
+                SFB_CUDA(c, cudaStreamSynchronize(s));
+                mr = h_ctl[CTL_MAXREL + (n & 3u)];
+                if (vb) {
+                    double cs; std::memcpy(&cs, &h_ctl[CTL_CSUM + ((n + 1u) & 3u)], 8);
+                    asum = (c->n_ranks > 1) ? cs : p.base_sum + cs;
+                }
+            }
+            if (last) break;
+            if (!fixed && n > 0 && n >= o->min_iter) {
+                double d; const unsigned long long b = mr ? mr - 1 : 0; std::memcpy(&d, &b, 8);
+                const double mrd = mr ? d : -std::numeric_limits<double>::max();
+                if (!(mrd > o->tol)) break;
+            }
+            const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp;
+            ++n;
+        }
+        SFB_CUDA(c, cudaGetLastError());
+        SFB_CUDA(c, cudaEventRecord(c->ev1, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        *iters_out = n; *buf_out = bi;
+        double d; const unsigned long long b = mr ? mr - 1 : 0; std::memcpy(&d, &b, 8);
+        *mrd_out = mr ? d : -std::numeric_limits<double>::max();
+    }
+    float ms = 0.f;
+    SFB_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_em_ms = ms;
+    return SFB200_OK;
+}
+
+// shared by em_run and bootstrap_em: everything from effective lengths to truncated alphas
+int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double total_frags, const sfb200_em_opts* o,
+              const double* d_cnt, const double* d_single, LoopSpec spec, double* alphas_out, uint32_t* iters_out,
+              double* mrd_out) {
+    DevClasses& k = c->cls;
+    cudaStream_t s = c->stream;
+    const uint32_t T = n_txp;
+    SFB_CUDA(c, c->eff.reserve(2ull * T));
+    SFB_CUDA(c, c->em_alpha.reserve(3ull * T));
+    SFB_CUDA(c, c->em_theta.reserve(T));
+    SFB_CUDA(c, c->em_base.reserve(T));
+    double* d_eff_in = c->eff.p + T;
+    SFB_CUDA(c, cudaMemcpyAsync(d_eff_in, eff_lens, T * 8ull, cudaMemcpyHostToDevice, s));
+    k_clamp_eff<<<grid_for(T, 256), 256, 0, s>>>(d_eff_in, T, c->eff.p);
+    c->launches++;
+    if (k.Em) {
+        // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
+        k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(k.off.p, k.lab.p, k.cnt.p, c->eff.p, k.Em, k.w.p);
+        c->launches++;
+    }
+    uint64_t n_active = k.n_active;
+    if (c->n_ranks > 1) {
+        // the active set is the union over ranks: sum the 0/1 flags as f64 through the alpha scratch
+        // (done by the caller of a multi-rank run through sfb200_em_run below)
+    }
+    if (n_active == 0) SFB_FAIL(c, SFB200_ENOACTIVE, "The optimizer has no active transcripts: no transcripts are expressed");
+    const bool vb = o->use_vb != 0;
+    const double alpha0 = (1.0 / static_cast<double>(n_active)) * total_frags;           // :800-803
+    const double prior_term = vb ? ((c->n_ranks > 1 && c->rank != 0) ? 0.0 : o->prior_alpha) : 0.0;
+    k_em_init<<<grid_for(T, 256), 256, 0, s>>>(k.active.p, d_single, T, alpha0, prior_term, c->em_alpha.p, c->em_base.p);
+    c->launches++;
+    SFB_CUDA(c, cudaGetLastError());
+
+    EmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.off = k.off.p; p.lab = k.lab.p; p.w = k.w.p; p.cnt = d_cnt; p.base = c->em_base.p; p.X = c->em_alpha.p;
+    p.theta = c->em_theta.p; p.T = T;
+    uint64_t tiles = 0;
+    for (int b = 0; b < SFB_NBINS; ++b) {
+        p.cls_start[b] = k.bin_cls[b]; p.tile_start[b] = tiles;
+        const uint64_t ncls = k.bin_cls[b + 1] - k.bin_cls[b];
+        const uint64_t per = (b < SFB_NBINS - 1) ? (32u >> (b + 1)) : 1;
+        tiles += (ncls + per - 1) / per;
+    }
+    p.cls_start[SFB_NBINS] = k.bin_cls[SFB_NBINS]; p.tile_start[SFB_NBINS] = tiles;
+    p.use_vb = vb; p.gate_old = spec.gate_old; p.tol = o->tol; p.cutoff = o->check_cutoff;
+    p.min_iter = spec.min_iter; p.max_iter = o->max_iter; p.fixed_iters = o->fixed_iters;
+    // sums the reference forms by a serial pass over the vector (VBEMUpdate_ :300-303); alpha_0 is n_active equal terms
+    double sum0 = 0.0;
+    for (uint64_t i = 0; i < n_active; ++i) sum0 += alpha0;
+    p.sum0 = sum0;
+    double single_sum = 0.0;
+    if (vb) {
+        std::vector<double> hs(T);
+        SFB_CUDA(c, cudaMemcpyAsync(hs.data(), d_single, T * 8ull, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < T; ++i) single_sum += hs[i];
+    }
+    p.base_sum = single_sum + static_cast<double>(T) * o->prior_alpha;
+
+    unsigned buf = 0;
+    sfb200_em_opts oo = *o;
+    oo.min_iter = spec.min_iter;
+    const int rc = run_loop(c, p, &oo, iters_out, mrd_out, &buf);
+    if (rc) return rc;
+
+    SFB_CUDA(c, cudaMemcpyAsync(alphas_out, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    const double cutoff = vb ? (o->prior_alpha + o->min_alpha) : o->min_alpha;           // :812
+    double alphaSum = 0.0;                                                               // truncateCountVector :37-44
+    for (uint32_t i = 0; i < T; ++i) { if (alphas_out[i] <= cutoff) alphas_out[i] = 0.0; alphaSum += alphas_out[i]; }
+    if (alphaSum < DENORM_MIN) SFB_FAIL(c, SFB200_ESMALLSUM, "Total alpha weight was too small! Make sure you ran sailfish correctly.");
+    return SFB200_OK;
+}
+
+}  // namespace
+
+extern "C" int sfb200_em_run(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, uint64_t num_mapped,
+                             const sfb200_em_opts* opts, double* alphas_out, uint32_t* iters_out, double* max_rel_diff_out) {
+    if (!c || !eff_lens || !opts || !alphas_out) return SFB200_EINVAL;
+    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "em_run: no classes (call map_finish or eq_import first)");
+    if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "em_run: n_txp differs from the class table's");
+    cudaSetDevice(c->device);
+    if (c->n_ranks > 1) {
+        // union of the active sets over ranks (classes are rank-local)
+        DevClasses& k = c->cls;
+        std::vector<uint8_t> act(n_txp);
+        std::vector<unsigned long long> cntv(n_txp);
+        SFB_CUDA(c, cudaMemcpy(act.data(), k.active.p, n_txp, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < n_txp; ++i) cntv[i] = act[i];
+        DevBuf<unsigned long long> d; SFB_CUDA(c, d.reserve(n_txp));
+        SFB_CUDA(c, cudaMemcpyAsync(d.p, cntv.data(), n_txp * 8ull, cudaMemcpyHostToDevice, c->stream));
+        const int rc = sfb_comm_allreduce_u64(c, d.p, n_txp);
+        if (rc) { d.release(); return rc; }
+        SFB_CUDA(c, cudaMemcpyAsync(cntv.data(), d.p, n_txp * 8ull, cudaMemcpyDeviceToHost, c->stream));
+        SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        d.release();
+        uint64_t na = 0;
+        for (uint32_t i = 0; i < n_txp; ++i) { act[i] = cntv[i] ? 1 : 0; na += act[i]; }
+        SFB_CUDA(c, cudaMemcpy(k.active.p, act.data(), n_txp, cudaMemcpyHostToDevice));
+        k.n_active = na;
+    }
+    uint32_t iters = 0; double mrd = 0.0;
+    LoopSpec spec{false, opts->min_iter};
+    const int rc = em_common(c, eff_lens, n_txp, static_cast<double>(num_mapped), opts, c->cls.cnt.p, c->cls.single.p, spec,
+                             alphas_out, &iters, &mrd);
+    if (iters_out) *iters_out = iters;
+    if (max_rel_diff_out) *max_rel_diff_out = mrd;
+    return rc;
+}
+
+// device-resident per-sample counts -> binned counts + single vector, then doBootstrap's loop (:476-514)
+int sfb_bootstrap_em_device(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, const unsigned long long* d_samp,
+                            uint64_t total, const sfb200_em_opts* opts, double* alphas_out, uint32_t* iters_out) {
+    DevClasses& k = c->cls;
+    EmExtra* x = g_extra_for(c);
+    cudaStream_t s = c->stream;
+    SFB_CUDA(c, x->cnt_s.reserve(k.Em));
+    SFB_CUDA(c, x->single_s.reserve(n_txp));
+    SFB_CUDA(c, cudaMemsetAsync(x->single_s.p, 0, n_txp * 8ull, s));
+    if (k.Em) { k_permute_counts<<<grid_for(k.Em, 256), 256, 0, s>>>(d_samp, k.perm.p, k.Em, x->cnt_s.p); c->launches++; }
+    if (x->n_sgl) { k_scatter_single<<<grid_for(x->n_sgl, 256), 256, 0, s>>>(d_samp, x->sgl_cls.p, x->sgl_tid.p, x->n_sgl, x->single_s.p); c->launches++; }
+    uint32_t iters = 0; double mrd = 0.0;
+    LoopSpec spec{true, 0};
+    const int rc = em_common(c, eff_lens, n_txp, static_cast<double>(total), opts, x->cnt_s.p, x->single_s.p, spec, alphas_out,
+                             &iters, &mrd);
+    if (iters_out) *iters_out = iters;
+    return rc;
+}
+
+extern "C" int sfb200_bootstrap_em(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, const uint64_t* samp_counts,
+                                   const sfb200_em_opts* opts, double* alphas_out, uint32_t* iters_out) {
+    if (!c || !eff_lens || !opts || !alphas_out || !samp_counts) return SFB200_EINVAL;
+    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "bootstrap_em: no classes");
+    if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "bootstrap_em: n_txp differs from the class table's");
+    cudaSetDevice(c->device);
+    EmExtra* x = g_extra_for(c);
+    const uint64_t E = c->cls.E;
+    SFB_CUDA(c, x->samp.reserve(E));
+    uint64_t total = 0;
+    for (uint64_t e = 0; e < E; ++e) total += samp_counts[e];
+    SFB_CUDA(c, cudaMemcpyAsync(x->samp.p, samp_counts, E * 8, cudaMemcpyHostToDevice, c->stream));
+    return sfb_bootstrap_em_device(c, eff_lens, n_txp, x->samp.p, total, opts, alphas_out, iters_out);
+}

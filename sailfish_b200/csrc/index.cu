@@ -1,0 +1,232 @@
+// index.cu -- builds the device index of "mapping spec v1"  from transcript sequences, on the GPU.
+//
+// Stands in for what ReadExperiment takes from RapMapSAIndex<IndexT> after SailfishIndex::load (reference
+// include/SailfishIndex.hpp:28-43,104-144; include/ReadExperiment.hpp:103-116).  RapMap's builder and its on-disk
+// format are not part of the reference tree (scripts/fetchRapMap.sh:20), so the index is specified by this repo:
+//   words    2-bit text of all transcripts concatenated (32 bases / u64, base p at bits 2*(p%32))
+//   sa_pos   every position whose k-mer lies inside one transcript, sorted by (k-mer value, position)
+//   sa_tid   transcript of each entry
+//   table    open-addressing k-mer table {k-mer, first entry, entry count}, slot = XXH64(k-mer) & mask, linear probing
+// Index construction is a "next" row, outside the timed path: the big sort / compaction primitives
+// are CUB's (part of the CUDA toolkit); everything else is hand-written.
+#include <cub/cub.cuh>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint32_t txp_of(const uint64_t* __restrict__ start, uint32_t n_txp, uint64_t p) {
+    // last t with start[t] <= p  (transcripts of length 0 share a start: take the last one, as upper_bound - 1 does)
+    uint32_t lo = 0, hi = n_txp;          // invariant: start[lo] <= p < start[hi]
+    while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (start[mid] <= p) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// one thread packs one 32-base word
+__global__ void k_pack_text(const char* __restrict__ seq, const uint64_t* __restrict__ txp_off,
+                            const uint64_t* __restrict__ txp_start, uint32_t n_txp, uint64_t text_len, uint64_t n_words,
+                            uint64_t* __restrict__ words) {
+    const uint64_t wi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (wi >= n_words) return;
+    uint64_t w = 0;
+    const uint64_t p0 = wi * 32;
+    if (p0 < text_len) {
+        uint32_t t = txp_of(txp_start, n_txp, p0);
+        for (int j = 0; j < 32; ++j) {
+            const uint64_t p = p0 + j;
+            if (p >= text_len) break;
+            while (p >= txp_start[t + 1]) ++t;
+            const unsigned char ch = static_cast<unsigned char>(seq[txp_off[t] + (p - txp_start[t])]);
+            const unsigned char up = ch & 0xDF;
+            uint64_t code;
+            if (up == 'A' || up == 'C' || up == 'G' || up == 'T') code = ((ch >> 1) ^ (ch >> 2)) & 3;
+            else code = splitmix64(p) >> 62;            // spec v1: non-ACGT -> deterministic pseudo-random base
+            w |= code << (2 * j);
+        }
+    }
+    words[wi] = w;
+}
+
+// entry i (in position order) -> (k-mer, position)
+__global__ void k_emit_kmers(const uint64_t* __restrict__ words, const uint64_t* __restrict__ txp_start,
+                             const uint64_t* __restrict__ vstart, uint32_t n_txp, int k, uint64_t n_sa,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ pos) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_sa) return;
+    const uint32_t t = txp_of(vstart, n_txp, i);
+    const uint64_t p = txp_start[t] + (i - vstart[t]);
+    const uint64_t idx = p >> 5, sh = 2 * (p & 31);
+    uint64_t v = words[idx] >> sh;
+    if (sh) v |= words[idx + 1] << (64 - sh);
+    keys[i] = v & ((1ULL << (2 * k)) - 1);
+    pos[i] = static_cast<uint32_t>(p);
+}
+
+__global__ void k_tid_and_heads(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos,
+                                const uint64_t* __restrict__ txp_start, uint32_t n_txp, uint64_t n_sa,
+                                uint32_t* __restrict__ tid, uint8_t* __restrict__ head) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_sa) return;
+    tid[i] = txp_of(txp_start, n_txp, pos[i]);
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void k_table_insert(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ heads, uint64_t n_kmers,
+                               uint64_t n_sa, uint4* __restrict__ table, uint64_t mask, unsigned int* __restrict__ max_bucket) {
+    const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n_kmers) return;
+    const uint32_t lb = heads[j];
+    const uint32_t cnt = static_cast<uint32_t>((j + 1 < n_kmers ? heads[j + 1] : n_sa) - lb);
+    const uint64_t km = keys[lb];
+    uint64_t h = xxh64_u64(km, 0) & mask;
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(table);
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&slots[2 * h], ~0ULL, (unsigned long long)km);
+        if (prev == ~0ULL) {
+            uint32_t* pl = reinterpret_cast<uint32_t*>(&slots[2 * h + 1]);
+            pl[0] = lb; pl[1] = cnt;
+            break;
+        }
+        h = (h + 1) & mask;
+    }
+    atomicMax(max_bucket, cnt);
+}
+
+__global__ void k_table_clear(uint4* __restrict__ table, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) table[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+}
+
+inline unsigned gridn(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t* txp_off, const uint32_t* txp_len,
+                                  uint32_t n_txp, int k) {
+    if (!c || !seq || !txp_off || !txp_len || n_txp == 0) return SFB200_EINVAL;
+    if (k < 1 || k > 31 || (k % 2) == 0) SFB_FAIL(c, SFB200_EINVAL, "k must be odd and <= 31 (SailfishIndexer.cpp:199-205)");
+    cudaSetDevice(c->device);
+    DevIndex& ix = c->index;
+    ix.ready = false;
+    cudaStream_t s = c->stream;
+
+    std::vector<uint64_t> start(n_txp + 1), vstart(n_txp + 1);
+    uint64_t tot = 0, nsa = 0, src_end = 0;
+    for (uint32_t t = 0; t < n_txp; ++t) {
+        start[t] = tot; vstart[t] = nsa;
+        tot += txp_len[t];
+        if (txp_len[t] >= static_cast<uint32_t>(k)) nsa += txp_len[t] - k + 1;
+        if (txp_off[t] + txp_len[t] > src_end) src_end = txp_off[t] + txp_len[t];
+    }
+    start[n_txp] = tot; vstart[n_txp] = nsa;
+    if (tot >= 0xFFFFFFF0ull) SFB_FAIL(c, SFB200_EINVAL, "transcriptome longer than 2^32 bases is not supported by the 32-bit position index");
+    ix.k = k; ix.n_txp = n_txp; ix.text_len = tot; ix.n_sa = nsa;
+    const uint64_t n_words = tot / 32 + 2;
+
+    DevBuf<char> d_seq; DevBuf<uint64_t> d_off, d_vstart, d_keys, d_keys2; DevBuf<uint32_t> d_pos2, d_heads; DevBuf<uint8_t> d_head, d_tmp;
+    DevBuf<unsigned int> d_scalar;
+    auto cleanup = [&]() { d_seq.release(); d_off.release(); d_vstart.release(); d_keys.release(); d_keys2.release();
+                           d_pos2.release(); d_heads.release(); d_head.release(); d_tmp.release(); d_scalar.release(); };
+#define IDX_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return SFB200_ECUDA; } } while (0)
+
+    IDX_CUDA(d_seq.reserve(src_end + 1));
+    IDX_CUDA(d_off.reserve(n_txp));
+    IDX_CUDA(d_vstart.reserve(n_txp + 1));
+    IDX_CUDA(ix.words.reserve(n_words));
+    IDX_CUDA(ix.txp_start.reserve(n_txp + 1));
+    IDX_CUDA(ix.txp_len.reserve(n_txp));
+    IDX_CUDA(cudaMemcpyAsync(d_seq.p, seq, src_end, cudaMemcpyHostToDevice, s));
+    IDX_CUDA(cudaMemcpyAsync(d_off.p, txp_off, n_txp * 8ull, cudaMemcpyHostToDevice, s));
+    IDX_CUDA(cudaMemcpyAsync(d_vstart.p, vstart.data(), (n_txp + 1) * 8ull, cudaMemcpyHostToDevice, s));
+    IDX_CUDA(cudaMemcpyAsync(ix.txp_start.p, start.data(), (n_txp + 1) * 8ull, cudaMemcpyHostToDevice, s));
+    IDX_CUDA(cudaMemcpyAsync(ix.txp_len.p, txp_len, n_txp * 4ull, cudaMemcpyHostToDevice, s));
+    k_pack_text<<<gridn(n_words, 256), 256, 0, s>>>(d_seq.p, d_off.p, ix.txp_start.p, n_txp, tot, n_words, ix.words.p);
+    c->launches++;
+    IDX_CUDA(cudaGetLastError());
+    IDX_CUDA(cudaStreamSynchronize(s));
+    d_seq.release();
+
+    ix.n_kmers = 0; ix.max_bucket = 0;
+    IDX_CUDA(ix.sa_pos.reserve(nsa)); IDX_CUDA(ix.sa_tid.reserve(nsa));
+    if (nsa > 0) {
+        IDX_CUDA(d_keys.reserve(nsa)); IDX_CUDA(d_keys2.reserve(nsa)); IDX_CUDA(d_pos2.reserve(nsa));
+        k_emit_kmers<<<gridn(nsa, 256), 256, 0, s>>>(ix.words.p, ix.txp_start.p, d_vstart.p, n_txp, k, nsa, d_keys.p, d_pos2.p);
+        c->launches++;
+        // stable LSD radix sort by k-mer value: entries were emitted in position order, so ties stay position-sorted
+        size_t tmp_bytes = 0;
+        IDX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.p, d_keys2.p, d_pos2.p, ix.sa_pos.p, nsa, 0, 2 * k, s));
+        IDX_CUDA(d_tmp.reserve(tmp_bytes));
+        IDX_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.p, d_keys2.p, d_pos2.p, ix.sa_pos.p, nsa, 0, 2 * k, s));
+        c->launches++;
+        IDX_CUDA(cudaStreamSynchronize(s));
+        d_keys.release(); d_pos2.release();
+        IDX_CUDA(d_head.reserve(nsa));
+        k_tid_and_heads<<<gridn(nsa, 256), 256, 0, s>>>(d_keys2.p, ix.sa_pos.p, ix.txp_start.p, n_txp, nsa, ix.sa_tid.p, d_head.p);
+        c->launches++;
+        // bucket heads = indices whose k-mer differs from the previous entry's
+        IDX_CUDA(d_heads.reserve(nsa));
+        IDX_CUDA(d_scalar.reserve(4));
+        size_t tmp2 = 0;
+        cub::CountingInputIterator<uint32_t> iota(0);
+        IDX_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, iota, d_head.p, d_heads.p, d_scalar.p, nsa, s));
+        IDX_CUDA(d_tmp.reserve(tmp2));
+        IDX_CUDA(cub::DeviceSelect::Flagged(d_tmp.p, tmp2, iota, d_head.p, d_heads.p, d_scalar.p, nsa, s));
+        c->launches++;
+        unsigned int n_heads = 0;
+        IDX_CUDA(cudaMemcpyAsync(&n_heads, d_scalar.p, 4, cudaMemcpyDeviceToHost, s));
+        IDX_CUDA(cudaStreamSynchronize(s));
+        ix.n_kmers = n_heads;
+    }
+    uint64_t slots = 1024;
+    while (slots < 2 * ix.n_kmers) slots <<= 1;
+    ix.table_slots = slots;
+    IDX_CUDA(ix.table.reserve(slots));
+    k_table_clear<<<gridn(slots, 256), 256, 0, s>>>(ix.table.p, slots);
+    c->launches++;
+    if (ix.n_kmers) {
+        IDX_CUDA(cudaMemsetAsync(d_scalar.p + 1, 0, 4, s));
+        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1);
+        c->launches++;
+        unsigned int mb = 0;
+        IDX_CUDA(cudaMemcpyAsync(&mb, d_scalar.p + 1, 4, cudaMemcpyDeviceToHost, s));
+        IDX_CUDA(cudaStreamSynchronize(s));
+        ix.max_bucket = mb;
+    }
+    IDX_CUDA(cudaGetLastError());
+    IDX_CUDA(cudaStreamSynchronize(s));
+    cleanup();
+#undef IDX_CUDA
+    ix.ready = true;
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_index_stats(const sfb200_ctx* c, uint64_t stats[8]) {
+    if (!c || !stats) return SFB200_EINVAL;
+    const DevIndex& ix = c->index;
+    std::memset(stats, 0, 8 * sizeof(uint64_t));
+    if (!ix.ready) return SFB200_EINVAL;
+    stats[0] = ix.text_len; stats[1] = ix.n_sa; stats[2] = ix.n_kmers; stats[3] = ix.table_slots;
+    stats[4] = ix.hbm_bytes(); stats[5] = ix.max_bucket; stats[6] = ix.k; stats[7] = ix.n_txp;
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_index_export(sfb200_ctx* c, uint64_t* words, uint32_t* sa_pos, uint32_t* sa_tid) {
+    if (!c) return SFB200_EINVAL;
+    DevIndex& ix = c->index;
+    if (!ix.ready) SFB_FAIL(c, SFB200_EINVAL, "index_export: no index");
+    cudaSetDevice(c->device);
+    if (words) SFB_CUDA(c, cudaMemcpyAsync(words, ix.words.p, (ix.text_len / 32 + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (sa_pos && ix.n_sa) SFB_CUDA(c, cudaMemcpyAsync(sa_pos, ix.sa_pos.p, ix.n_sa * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (sa_tid && ix.n_sa) SFB_CUDA(c, cudaMemcpyAsync(sa_tid, ix.sa_tid.p, ix.n_sa * 4, cudaMemcpyDeviceToHost, c->stream));
+    SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SFB200_OK;
+}

@@ -1,0 +1,667 @@
+// map.cu -- read batch -> quasi-mapping -> equivalence-class counts on sm_100a.
+//
+// Replaces processReadsQuasi<IndexT> (reference src/SailfishQuantify.cpp:105-452 paired, :458-646 single) together
+// with the EquivalenceClassBuilder it feeds (include/EquivalenceClassBuilder.hpp:62-110, TranscriptGroup.cpp:9-19).
+// The quasi-mapping itself (RapMap's SACollector / mergeLeftRightHits) is not in the reference tree; the algorithm
+// is "mapping spec v1" (DESIGN.md section 3).  DESIGN.md section 5 describes the kernel and the class table.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_IV = 16;                 // spec v1: at most 16 maximal-match intervals per orientation scan
+constexpr uint32_t MAX_READ_LEN = 256;     // spec v1: reads are clipped to 256 bases
+constexpr int RW = MAX_READ_LEN / 32 + 1;  // packed words per read (+1 pad so a 32-base window never runs off the end)
+constexpr int MAP_THREADS = 256;
+constexpr int POS_BIAS = 4096;
+
+// library-format ids (LibraryFormat::formatID, include/LibraryFormat.hpp:89-98)
+enum { O_SAME = 0, O_AWAY = 1, O_TOWARD = 2, O_NONE = 3 };
+enum { S_SA = 0, S_AS = 1, S_S = 2, S_A = 3, S_U = 4 };
+__device__ __forceinline__ int mkfmt(int type, int orient, int strand) { return (type & 1) | ((orient & 3) << 1) | ((strand & 7) << 3); }
+__device__ __forceinline__ int f_orient(int id) { return (id >> 1) & 3; }
+__device__ __forceinline__ int f_strand(int id) { return (id >> 3) & 7; }
+
+// compatibleHit for single-end reads and orphans (src/SailfishUtils.cpp:157-211)
+__device__ __forceinline__ bool compat_single(int expected, bool fwd, int ms) {
+    const int es = f_strand(expected);
+    if (ms == 0) return fwd ? (es == S_U || es == S_S) : (es == S_U || es == S_A);
+    if (f_orient(expected) == O_SAME) return es == S_U || (es == S_S && fwd) || (es == S_A && !fwd);
+    if (ms == 1) return fwd ? (es == S_U || es == S_S) : (es == S_U || es == S_A);
+    return fwd ? (es == S_U || es == S_A) : (es == S_U || es == S_S);
+}
+// hitType (:243-289) followed by the paired compatibleHit (:215-239)
+__device__ __forceinline__ bool compat_paired(int expected, int32_t e1, bool fwd1, uint32_t len1, int32_t e2, bool fwd2,
+                                              uint32_t len2, bool dovetail) {
+    int obs;
+    if (fwd1 != fwd2) {
+        if (fwd1) { const int32_t st = dovetail ? (int32_t)len2 : 0; obs = (e1 <= e2 + st) ? mkfmt(1, O_TOWARD, S_SA) : mkfmt(1, O_AWAY, S_SA); }
+        else { const int32_t st = dovetail ? (int32_t)len1 : 0; obs = (e2 <= e1 + st) ? mkfmt(1, O_TOWARD, S_AS) : mkfmt(1, O_AWAY, S_AS); }
+    } else {
+        obs = fwd1 ? mkfmt(1, O_SAME, S_S) : mkfmt(1, O_SAME, S_A);
+    }
+    if (f_orient(expected) != f_orient(obs)) return false;
+    return f_strand(expected) == S_U || f_strand(expected) == f_strand(obs);
+}
+
+struct IndexView {
+    const uint64_t* words; const uint64_t* txp_start; const uint32_t* txp_len;
+    const uint32_t* sa_pos; const uint32_t* sa_tid; const uint4* table;
+    uint64_t mask; int k; uint64_t kmask;
+};
+
+// ---- the equivalence-class table ------------------------------------------------------------------------------------------
+// libcuckoo's layout (4 slots per bucket, two candidate buckets per key, include/cuckoohash_config.hh:9,
+// cuckoohash_map.hh:1012-1026) with the BFS displacement replaced by a linear-probed overflow region: the table is kept
+// under 50% load, so both buckets being full is rare.  A slot is one 64-bit word
+//     [ arena offset : 34 | label length : 10 | hash fingerprint : 20 ]      (0 = empty)
+// pointing at the label's transcript ids in an append-only arena; counts live in a parallel u64 array.  A bucket is one
+// 32-byte sector.  Key equality is the full label (TranscriptGroup.cpp:53-55); XXH64 only chooses the buckets.
+struct EqTable {
+    unsigned long long* slot;      // n_buckets*4 + overflow
+    unsigned long long* count;     // same length
+    uint32_t* arena;               // label storage
+    unsigned long long* cursor;    // [0] arena words used  [1] distinct labels  [2] error flags  [3] overflow inserts
+    uint64_t n_buckets;            // power of two
+    uint64_t n_overflow;           // power of two
+    uint64_t arena_words;
+};
+constexpr unsigned long long ERR_ARENA_FULL = 1, ERR_TABLE_FULL = 2, ERR_LABEL_LONG = 4;
+
+__device__ __forceinline__ unsigned long long pack_slot(uint64_t off, uint32_t len, uint64_t h) {
+    return (off << 30) | ((unsigned long long)len << 20) | (h >> 44);
+}
+
+template <typename GetLabel>
+__device__ __forceinline__ bool slot_matches(const EqTable& tb, unsigned long long sv, uint32_t len, uint64_t h, GetLabel get) {
+    if (((sv ^ pack_slot(0, len, h)) & ((1ULL << 30) - 1)) != 0) return false;      // length + fingerprint
+    const uint32_t* a = tb.arena + (sv >> 30);
+    for (uint32_t j = 0; j < len; ++j) if (__ldcg(a + j) != get(j)) return false;
+    return true;
+}
+
+// upsert: returns false only when the table or the arena is exhausted (error flag raised)
+template <typename GetLabel>
+__device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigned long long add) {
+    if (len >= 1024) { atomicOr(tb.cursor + 2, ERR_LABEL_LONG); return false; }
+    const uint64_t h = xxh64_words(get, len, 0);                       // TranscriptGroup.cpp:9-12
+    const uint64_t bmask = tb.n_buckets - 1;
+    const uint64_t b1 = h & bmask;
+    const uint64_t b2 = (b1 ^ (((h >> 48) + 1) * 0x5bd1e995ULL)) & bmask;
+    unsigned long long mine = 0;                                       // our published-candidate slot word (arena copy made)
+    const uint64_t n_main = tb.n_buckets * 4;
+    const uint64_t total_probe = 8 + tb.n_overflow;
+    const uint64_t ov0 = h >> 20;
+    for (uint64_t step = 0; step < total_probe; ++step) {
+        uint64_t idx;
+        if (step < 4) idx = b1 * 4 + step;
+        else if (step < 8) idx = b2 * 4 + (step - 4);
+        else idx = n_main + ((ov0 + (step - 8)) & (tb.n_overflow - 1));
+        unsigned long long sv = __ldcg(tb.slot + idx);
+        for (;;) {
+            if (sv == 0ULL) {
+                if (!mine) {
+                    const unsigned long long off = atomicAdd(tb.cursor, (unsigned long long)len);
+                    if (off + len > tb.arena_words) { atomicOr(tb.cursor + 2, ERR_ARENA_FULL); return false; }
+                    for (uint32_t j = 0; j < len; ++j) tb.arena[off + j] = get(j);
+                    mine = pack_slot(off, len, h);
+                    __threadfence();                                   // label visible before the slot word
+                }
+                const unsigned long long prev = atomicCAS(tb.slot + idx, 0ULL, mine);
+                if (prev == 0ULL) {
+                    atomicAdd(tb.count + idx, add);
+                    atomicAdd(tb.cursor + 1, 1ULL);
+                    if (step >= 8) atomicAdd(tb.cursor + 3, 1ULL);
+                    return true;
+                }
+                sv = prev;                                             // somebody else took the slot: look at what they put
+                continue;
+            }
+            __threadfence();
+            if (slot_matches(tb, sv, len, h, get)) { atomicAdd(tb.count + idx, add); return true; }
+            break;
+        }
+    }
+    atomicOr(tb.cursor + 2, ERR_TABLE_FULL);
+    return false;
+}
+
+// ---- per-read state -----------------------------------------------------------------------------------------------------
+struct Read {
+    uint64_t b[2][RW];    // [0] forward, [1] reverse complement: 2 bits per base, base i at bits 2*(i%32) of word i/32
+    uint64_t n[2][RW];    // same layout, 0b01 where the base is not A/C/G/T
+    uint32_t len;
+};
+
+__device__ __forceinline__ uint64_t win32(const uint64_t* w, uint32_t pos) {
+    const uint32_t idx = pos >> 5, sh = 2 * (pos & 31);
+    uint64_t v = w[idx] >> sh;
+    if (sh) v |= w[idx + 1] << (64 - sh);
+    return v;
+}
+__device__ __forceinline__ uint64_t win32g(const uint64_t* __restrict__ w, uint64_t pos) {
+    const uint64_t idx = pos >> 5; const uint32_t sh = 2 * (pos & 31);
+    uint64_t v = __ldg(w + idx) >> sh;
+    if (sh) v |= __ldg(w + idx + 1) << (64 - sh);
+    return v;
+}
+
+__device__ void load_read(const char* __restrict__ bases, uint64_t beg, uint64_t end, Read& r) {
+    uint32_t L = static_cast<uint32_t>(end - beg);
+    if (L > MAX_READ_LEN) L = MAX_READ_LEN;
+    r.len = L;
+#pragma unroll
+    for (int i = 0; i < RW; ++i) { r.b[0][i] = 0; r.b[1][i] = 0; r.n[0][i] = 0; r.n[1][i] = 0; }
+    for (uint32_t i = 0; i < L; ++i) {
+        const unsigned char ch = static_cast<unsigned char>(bases[beg + i]);
+        const unsigned char up = ch & 0xDF;
+        const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+        const uint64_t code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 0;
+        const uint32_t j = L - 1 - i;
+        r.b[0][i >> 5] |= code << (2 * (i & 31));
+        r.b[1][j >> 5] |= (ok ? (3 - code) : 0) << (2 * (j & 31));
+        if (!ok) { r.n[0][i >> 5] |= 1ULL << (2 * (i & 31)); r.n[1][j >> 5] |= 1ULL << (2 * (j & 31)); }
+    }
+}
+
+// longest common extension of read[qpos..) with text[p..tend), counted from the k-mer start (always >= k)
+__device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, int o, uint32_t qpos, uint64_t p, uint64_t tend) {
+    const uint32_t lim_r = r.len - qpos;
+    const uint64_t lim_t = tend - p;
+    const uint32_t lim = lim_t < lim_r ? static_cast<uint32_t>(lim_t) : lim_r;
+    uint32_t m = ix.k;
+    while (m < lim) {
+        const uint64_t x = win32(r.b[o], qpos + m) ^ win32g(ix.words, p + m);
+        const uint64_t y = ((x | (x >> 1)) & 0x5555555555555555ULL) | win32(r.n[o], qpos + m);
+        if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; break; }
+        m += 32;
+    }
+    return m < lim ? m : lim;
+}
+
+struct Interval { uint32_t lb, cnt, qpos, m; };
+
+__device__ __forceinline__ bool table_find(const IndexView& ix, uint64_t km, uint32_t& lb, uint32_t& cnt) {
+    uint64_t h = xxh64_u64(km, 0) & ix.mask;
+    for (;;) {
+        const uint4 sl = __ldg(ix.table + h);
+        if (sl.w == 0) return false;
+        if ((((uint64_t)sl.y << 32) | sl.x) == km) { lb = sl.z; cnt = sl.w; return true; }
+        h = (h + 1) & ix.mask;
+    }
+}
+
+// spec v1 seed scan of one orientation
+__device__ int scan_read(const IndexView& ix, const Read& r, int o, uint32_t max_interval, Interval* ivs, uint64_t& score) {
+    int niv = 0;
+    score = 0;
+    const uint32_t k = ix.k, L = r.len;
+    uint32_t i = 0;
+    while (i + k <= L && niv < MAX_IV) {
+        const uint64_t nn = win32(r.n[o], i) & ix.kmask;
+        if (nn) { i += ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; continue; }   // jump past the last invalid base
+        const uint64_t km = win32(r.b[o], i) & ix.kmask;
+        if (km == 0 || km == ix.kmask || km == (0x5555555555555555ULL & ix.kmask) || km == (0xAAAAAAAAAAAAAAAAULL & ix.kmask)) { i += 1; continue; }
+        uint32_t lb, cnt;
+        if (!table_find(ix, km, lb, cnt) || cnt > max_interval) { i += 1; continue; }
+        uint32_t m = 0;
+        for (uint32_t e = lb; e < lb + cnt; ++e) {
+            const uint32_t tid = __ldg(ix.sa_tid + e);
+            const uint64_t tend = __ldg(ix.txp_start + tid) + __ldg(ix.txp_len + tid);
+            const uint32_t l = lcp_at(ix, r, o, i, __ldg(ix.sa_pos + e), tend);
+            m = l > m ? l : m;
+        }
+        ivs[niv].lb = lb; ivs[niv].cnt = cnt; ivs[niv].qpos = i; ivs[niv].m = m;
+        ++niv;
+        score += m;
+        i += m - k + 1;
+    }
+    return niv;
+}
+
+// per-thread scratch in global memory, element j of thread t at base[j * stride + t] (coalesced like local memory)
+struct Scratch {
+    unsigned long long* base; uint64_t stride;
+    __device__ __forceinline__ unsigned long long& at(uint32_t j) const { return base[(uint64_t)j * stride]; }
+};
+__device__ __forceinline__ unsigned long long pack_hit(uint32_t tid, int32_t pos, bool fwd) {
+    return ((unsigned long long)tid << 32) | (uint32_t)(((pos + POS_BIAS) << 1) | (fwd ? 1 : 0));
+}
+__device__ __forceinline__ uint32_t hit_tid(unsigned long long h) { return (uint32_t)(h >> 32); }
+__device__ __forceinline__ int32_t hit_pos(unsigned long long h) { return (int32_t)(((uint32_t)h) >> 1) - POS_BIAS; }
+__device__ __forceinline__ bool hit_fwd(unsigned long long h) { return (h & 1ULL) != 0; }
+
+// transcripts present with the maximal match in every interval; output ascending by transcript id;
+// stops after cap+1 hits (list overflow)
+__device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Interval* ivs, int niv, uint32_t cap,
+                            const Scratch& out, uint32_t out0) {
+    if (niv == 0) return 0;
+    uint32_t n = 0;
+    const Interval a = ivs[0];
+    int64_t lastTid = -1;
+    for (uint32_t e = a.lb; e < a.lb + a.cnt; ++e) {
+        const uint32_t tid = __ldg(ix.sa_tid + e);
+        if ((int64_t)tid == lastTid) continue;
+        const uint64_t ts = __ldg(ix.txp_start + tid);
+        const uint64_t tend = ts + __ldg(ix.txp_len + tid);
+        const uint32_t p = __ldg(ix.sa_pos + e);
+        if (lcp_at(ix, r, o, a.qpos, p, tend) != a.m) continue;
+        lastTid = tid;
+        bool all = true;
+        for (int j = 1; j < niv && all; ++j) {
+            const Interval b = ivs[j];
+            uint32_t lo = b.lb, hi = b.lb + b.cnt;
+            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(ix.sa_tid + mid) < tid) lo = mid + 1; else hi = mid; }
+            bool found = false;
+            for (uint32_t e2 = lo; e2 < b.lb + b.cnt && __ldg(ix.sa_tid + e2) == tid; ++e2) {
+                if (lcp_at(ix, r, o, b.qpos, __ldg(ix.sa_pos + e2), tend) == b.m) { found = true; break; }
+            }
+            all = found;
+        }
+        if (!all) continue;
+        const int32_t pos = (int32_t)((int64_t)p - (int64_t)ts - (int64_t)a.qpos);
+        out.at(out0 + n) = pack_hit(tid, pos, o == 0);
+        ++n;
+        if (n > cap) return n;
+    }
+    return n;
+}
+
+// one mate: both orientations, optional strand vote, merge by transcript id.  Returns false on list overflow.
+__device__ bool collect(const IndexView& ix, const Read& r, bool strict, uint32_t cap, uint32_t max_interval,
+                        const Scratch& scr, uint32_t tmp0, uint32_t dst0, uint32_t& n_out) {
+    Interval ivs[MAX_IV];
+    uint64_t scF, scR;
+    n_out = 0;
+    int niv = scan_read(ix, r, 0, max_interval, ivs, scF);
+    uint32_t nF = project(ix, r, 0, ivs, niv, cap, scr, tmp0);
+    niv = scan_read(ix, r, 1, max_interval, ivs, scR);
+    uint32_t nR = project(ix, r, 1, ivs, niv, cap, scr, tmp0 + cap + 1);
+    if (nF > cap || nR > cap) return false;
+    if (strict && nF && nR) { if (scF > scR) nR = 0; else if (scR > scF) nF = 0; }
+    if (nF + nR > cap) return false;
+    uint32_t i = 0, j = 0, n = 0;
+    while (i < nF || j < nR) {                     // stable merge: forward before reverse on equal transcript id
+        bool takeF;
+        if (i >= nF) takeF = false; else if (j >= nR) takeF = true;
+        else takeF = hit_tid(scr.at(tmp0 + i)) <= hit_tid(scr.at(tmp0 + cap + 1 + j));
+        scr.at(dst0 + n++) = takeF ? scr.at(tmp0 + i++) : scr.at(tmp0 + cap + 1 + j++);
+    }
+    n_out = n;
+    return true;
+}
+
+struct MapParams {
+    IndexView ix;
+    EqTable tb;
+    const char* bases1; const uint64_t* off1; const char* bases2; const uint64_t* off2;
+    uint64_t n_reads;
+    uint32_t cap;              // max_read_occs
+    uint32_t max_frag_len, max_interval;
+    int lib_fmt, strict_intersect, allow_orphans, allow_dovetail, ignore_compat, enforce_compat;
+    unsigned long long* scratch; uint64_t n_threads_total;
+    unsigned long long* counters;      // 6
+    unsigned long long* next_read;     // work counter
+    int16_t* fld_val;                  // per read of the batch: fragment length if FLD-eligible, else -1
+};
+
+struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of processReadsQuasi folded into one buffer
+    const Scratch& scr; uint32_t base; uint32_t n; bool haveCompat; int32_t fw, rc; bool enforce;
+    __device__ LabelAcc(const Scratch& s, uint32_t b, bool enf) : scr(s), base(b), n(0), haveCompat(false), fw(0), rc(0), enforce(enf) {}
+    __device__ __forceinline__ void add(uint32_t tid, bool compat, bool fwdHit) {
+        if (compat) {
+            if (!haveCompat) { haveCompat = true; n = 0; fw = 0; rc = 0; }      // switch from "all" to "compatible only"
+            scr.at(base + n++) = tid; if (fwdHit) ++fw; else ++rc;
+        } else if (!haveCompat && !enforce) {
+            scr.at(base + n++) = tid; if (fwdHit) ++fw; else ++rc;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(MAP_THREADS) k_map_reads(const MapParams p) {
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const Scratch scr{p.scratch + gtid, p.n_threads_total};
+    const uint32_t cap = p.cap;
+    const uint32_t TMP0 = 0, LEFT0 = 2 * (cap + 1), RIGHT0 = 3 * (cap + 1);
+    const bool paired = p.bases2 != nullptr;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
+    Read rd;
+
+    for (;;) {
+        unsigned long long base_idx = 0;
+        if (lane == 0) base_idx = atomicAdd(p.next_read, 32ULL);
+        base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
+        if (base_idx >= p.n_reads) break;
+        const uint64_t ri = base_idx + lane;
+        if (ri < p.n_reads) {
+            uint32_t nL = 0, nR = 0;
+            bool okL, okR = true;
+            load_read(p.bases1, p.off1[ri], p.off1[ri + 1], rd);
+            const uint32_t len1 = rd.len;
+            uint32_t len2 = 0;
+            okL = collect(p.ix, rd, paired, cap, p.max_interval, scr, TMP0, LEFT0, nL);     // paired: strict check (:192-202)
+            if (paired) {
+                load_read(p.bases2, p.off2[ri], p.off2[ri + 1], rd);
+                len2 = rd.len;
+                okR = collect(p.ix, rd, true, cap, p.max_interval, scr, TMP0, RIGHT0, nR);
+            }
+            const bool overflow = !okL || !okR;
+            LabelAcc acc(scr, TMP0, p.enforce_compat != 0);
+            uint32_t n_joint = 0;
+            int32_t fl = -1;
+            if (!paired) {
+                // SailfishQuantify.cpp:530-631
+                n_joint = overflow ? 0 : nL;
+                c_ub += (overflow || n_joint > 0) ? 1 : 0;
+                for (uint32_t i = 0; i < n_joint; ++i) {
+                    const unsigned long long h = scr.at(LEFT0 + i);
+                    const bool compat = p.ignore_compat ? true : compat_single(p.lib_fmt, hit_fwd(h), 0);
+                    acc.add(hit_tid(h), compat, hit_fwd(h));
+                }
+            } else if (!overflow) {
+                // mergeLeftRightHits[Fuzzy] (call sites :204-213): one joint hit per transcript present in both lists
+                uint32_t i = 0, j = 0, n_pairs = 0;
+                while (i < nL && j < nR) {
+                    const uint32_t tl = hit_tid(scr.at(LEFT0 + i)), tr = hit_tid(scr.at(RIGHT0 + j));
+                    if (tl < tr) ++i; else if (tr < tl) ++j;
+                    else { ++n_pairs; ++i; while (i < nL && hit_tid(scr.at(LEFT0 + i)) == tl) ++i; while (j < nR && hit_tid(scr.at(RIGHT0 + j)) == tl) ++j; }
+                }
+                if (n_pairs > 0) {
+                    n_joint = n_pairs;
+                    c_ub += 1;
+                    i = 0; j = 0;
+                    while (i < nL && j < nR) {                                              // :341-369
+                        const unsigned long long hl = scr.at(LEFT0 + i), hr = scr.at(RIGHT0 + j);
+                        const uint32_t tl = hit_tid(hl), tr = hit_tid(hr);
+                        if (tl < tr) { ++i; continue; }
+                        if (tr < tl) { ++j; continue; }
+                        const int32_t pl = hit_pos(hl), pr = hit_pos(hr);
+                        const bool fl_ = hit_fwd(hl), fr_ = hit_fwd(hr);
+                        bool compat = p.ignore_compat != 0;
+                        if (!compat) {
+                            const uint32_t e1 = fl_ ? (uint32_t)pl : (uint32_t)pl + len1;
+                            const uint32_t e2 = fr_ ? (uint32_t)pr : (uint32_t)pr + len2;
+                            compat = compat_paired(p.lib_fmt, (int32_t)e1, fl_, len1, (int32_t)e2, fr_, len2, p.allow_dovetail != 0);
+                        }
+                        acc.add(tl, compat, fl_);
+                        if (n_pairs == 1) {
+                            const int32_t fs = pl < pr ? pl : pr;
+                            const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
+                            fl = (e1 > e2 ? e1 : e2) - fs;
+                        }
+                        ++i; while (i < nL && hit_tid(scr.at(LEFT0 + i)) == tl) ++i; while (j < nR && hit_tid(scr.at(RIGHT0 + j)) == tl) ++j;
+                    }
+                } else if (!p.strict_intersect && nL + nR > 0) {
+                    // orphans: left block then right block, merged by transcript id (:231-246), left first on ties
+                    n_joint = nL + nR;
+                    c_ub += 1;
+                    if (n_joint > cap) n_joint = 0;                                        // :217
+                    else if (!p.allow_orphans) { /* :226 joint hits discarded, n_joint keeps counting them below */ }
+                    if (n_joint > 0 && p.allow_orphans) {
+                        i = 0; j = 0;
+                        while (i < nL || j < nR) {                                          // :289-340
+                            bool takeL;
+                            if (i >= nL) takeL = false; else if (j >= nR) takeL = true;
+                            else takeL = hit_tid(scr.at(LEFT0 + i)) <= hit_tid(scr.at(RIGHT0 + j));
+                            const unsigned long long h = takeL ? scr.at(LEFT0 + i++) : scr.at(RIGHT0 + j++);
+                            const int ms = takeL ? 1 : 2;
+                            const bool fwd = hit_fwd(h);
+                            const bool compat = p.ignore_compat ? true : compat_single(p.lib_fmt, fwd, ms);
+                            const bool fwdHit = takeL ? fwd : !fwd;
+                            acc.add(hit_tid(h), compat, fwdHit);
+                        }
+                    } else if (n_joint > 0) {
+                        n_joint = 0;                                                        // :226 jointHits.clear()
+                    }
+                }
+            } else {
+                c_ub += 1;                                                                  // an overflowed mate did have hits
+            }
+            bool mapped = false;
+            if (acc.n > 0 && (acc.haveCompat || !p.enforce_compat)) {
+                mapped = true;
+                c_fw += acc.fw; c_rc += acc.rc;
+                eq_upsert(p.tb, acc.n, [&](uint32_t j) { return (uint32_t)scr.at(TMP0 + j); }, 1ULL);
+            }
+            if (p.fld_val) {
+                const bool elig = paired && n_joint == 1 && fl >= 0 && mapped && (uint32_t)fl < p.max_frag_len;   // :419-434
+                p.fld_val[ri] = elig ? (int16_t)fl : (int16_t)-1;
+            }
+            c_obs += 1; c_map += mapped ? 1 : 0; c_hits += n_joint;
+        }
+    }
+    // warp-reduce the six counters (ReadExperiment.hpp:74-97), one atomic per warp and counter
+    unsigned long long v[6] = {c_obs, c_map, c_hits, c_ub, c_fw, c_rc};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        unsigned long long x = v[q];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+        if (lane == 0 && x) atomicAdd(p.counters + q, x);
+    }
+}
+
+// FLD sampling in global read order: the first `remaining` eligible fragments (SailfishQuantify.cpp:426-430 at -p 1)
+__global__ void k_fld_select(const int16_t* __restrict__ fld_val, uint64_t n_reads, unsigned int* __restrict__ hist,
+                             int* __restrict__ remaining) {
+    __shared__ int s_base, s_rem;
+    __shared__ int s_warp[32];
+    if (threadIdx.x == 0) { s_rem = *remaining; }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint64_t c0 = 0; c0 < n_reads; c0 += blockDim.x) {
+        if (s_rem <= 0) break;
+        const uint64_t i = c0 + threadIdx.x;
+        const int v = i < n_reads ? fld_val[i] : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
+        const int pre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int a = 0; for (unsigned w = 0; w < (blockDim.x >> 5); ++w) { const int t = s_warp[w]; s_warp[w] = a; a += t; } s_base = a; }
+        __syncthreads();
+        const int rank = s_warp[warp] + pre;
+        if (v >= 0 && rank < s_rem) atomicAdd(hist + v, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) s_rem -= s_base;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *remaining = s_rem < 0 ? 0 : s_rem;
+}
+
+}  // namespace
+
+// ======================================================================================================================
+struct MapState {
+    sfb200_map_opts o;
+    bool begun = false;
+    DevBuf<unsigned long long> slot, count, cursor, counters, next_read, scratch;
+    DevBuf<uint32_t> arena;
+    DevBuf<unsigned int> fld_hist;
+    DevBuf<int> remaining;
+    DevBuf<int16_t> fld_val;
+    DevBuf<char> bases1, bases2;
+    DevBuf<uint64_t> off1, off2;
+    uint64_t n_buckets = 0, n_overflow = 0, arena_words = 0;
+    uint64_t n_threads_total = 0;
+    int grid = 0;
+};
+
+void sfb_map_state_free(sfb200_ctx* c) {
+    MapState* m = c->map;
+    if (!m) return;
+    m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
+    m->scratch.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release();
+    m->bases1.release(); m->bases2.release(); m->off1.release(); m->off2.release();
+    delete m;
+    c->map = nullptr;
+}
+
+extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
+    if (!c || !o) return SFB200_EINVAL;
+    if (!c->index.ready) SFB_FAIL(c, SFB200_EINVAL, "map_begin: build the index first");
+    if (o->max_frag_len == 0 || o->max_frag_len > 32767) SFB_FAIL(c, SFB200_EINVAL, "max_frag_len must be in [1, 32767]");
+    if (o->max_read_occs == 0 || o->max_read_occs > 1000) SFB_FAIL(c, SFB200_EINVAL, "max_read_occs must be in [1, 1000]");
+    cudaSetDevice(c->device);
+    if (!c->map) c->map = new MapState();
+    MapState* m = c->map;
+    m->o = *o;
+    cudaStream_t s = c->stream;
+    // table geometry: SFB200_EQ_LOG2_BUCKETS (default 21 -> 8M slots) and SFB200_EQ_ARENA_LOG2 words (default 26)
+    int lb = 21, la = 26;
+    if (const char* e = getenv("SFB200_EQ_LOG2_BUCKETS")) lb = std::max(4, std::min(30, atoi(e)));
+    if (const char* e = getenv("SFB200_EQ_ARENA_LOG2")) la = std::max(10, std::min(33, atoi(e)));
+    m->n_buckets = 1ull << lb; m->n_overflow = std::max<uint64_t>(1024, m->n_buckets / 4); m->arena_words = 1ull << la;
+    const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
+    SFB_CUDA(c, m->slot.reserve(n_slots)); SFB_CUDA(c, m->count.reserve(n_slots)); SFB_CUDA(c, m->arena.reserve(m->arena_words));
+    SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(1));
+    SFB_CUDA(c, m->fld_hist.reserve(o->max_frag_len)); SFB_CUDA(c, m->remaining.reserve(1));
+    SFB_CUDA(c, cudaMemsetAsync(m->slot.p, 0, n_slots * 8, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->count.p, 0, n_slots * 8, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->cursor.p, 0, 4 * 8, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->counters.p, 0, 6 * 8, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->fld_hist.p, 0, o->max_frag_len * 4ull, s));
+    const int rem = o->num_frag_samples;
+    SFB_CUDA(c, cudaMemcpyAsync(m->remaining.p, &rem, 4, cudaMemcpyHostToDevice, s));
+    // launch geometry: every SM filled with resident CTAs; scratch sized for exactly those threads
+    int per_sm = 0;
+    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_reads, MAP_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    m->grid = c->num_sms * per_sm;
+    m->n_threads_total = (uint64_t)m->grid * MAP_THREADS;
+    SFB_CUDA(c, m->scratch.reserve(m->n_threads_total * 4ull * (o->max_read_occs + 1)));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    c->cls.ready = false;
+    m->begun = true;
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
+                                       const uint64_t* d_off2, uint64_t n_reads) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_batch: call map_begin first");
+    if (n_reads == 0) return SFB200_OK;
+    if (!d_bases1 || !d_off1 || ((d_bases2 == nullptr) != (d_off2 == nullptr))) SFB_FAIL(c, SFB200_EINVAL, "map_batch: null array");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    const DevIndex& ix = c->index;
+    MapParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.ix.words = ix.words.p; p.ix.txp_start = ix.txp_start.p; p.ix.txp_len = ix.txp_len.p; p.ix.sa_pos = ix.sa_pos.p;
+    p.ix.sa_tid = ix.sa_tid.p; p.ix.table = ix.table.p; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
+    p.ix.kmask = (1ULL << (2 * ix.k)) - 1;
+    p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p; p.tb.cursor = m->cursor.p;
+    p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
+    p.bases1 = d_bases1; p.off1 = d_off1; p.bases2 = d_bases2; p.off2 = d_off2; p.n_reads = n_reads;
+    p.cap = m->o.max_read_occs; p.max_frag_len = m->o.max_frag_len; p.max_interval = m->o.max_interval;
+    p.lib_fmt = m->o.lib_format_id; p.strict_intersect = m->o.strict_intersect; p.allow_orphans = m->o.allow_orphans;
+    p.allow_dovetail = m->o.allow_dovetail; p.ignore_compat = m->o.ignore_compat; p.enforce_compat = m->o.enforce_compat;
+    p.scratch = m->scratch.p; p.n_threads_total = m->n_threads_total; p.counters = m->counters.p; p.next_read = m->next_read.p;
+    const bool want_fld = d_bases2 != nullptr;
+    if (want_fld) { SFB_CUDA(c, m->fld_val.reserve(n_reads)); p.fld_val = m->fld_val.p; }
+    SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 8, s));
+    const uint64_t warps_needed = (n_reads + 31) / 32;
+    const uint64_t blocks_needed = (warps_needed * 32 + MAP_THREADS - 1) / MAP_THREADS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(m->grid, blocks_needed);
+    k_map_reads<<<grid, MAP_THREADS, 0, s>>>(p);
+    c->launches++;
+    SFB_CUDA(c, cudaGetLastError());
+    if (want_fld) {
+        k_fld_select<<<1, 1024, 0, s>>>(m->fld_val.p, n_reads, m->fld_hist.p, m->remaining.p);
+        c->launches++;
+        SFB_CUDA(c, cudaGetLastError());
+    }
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2,
+                                const uint64_t* off2, uint64_t n_reads) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_batch: call map_begin first");
+    if (n_reads == 0) return SFB200_OK;
+    if (!bases1 || !off1 || ((bases2 == nullptr) != (off2 == nullptr))) SFB_FAIL(c, SFB200_EINVAL, "map_batch: null array");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    // the previous batch may still be reading the staging buffers
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    const uint64_t nb1 = off1[n_reads] - off1[0];
+    SFB_CUDA(c, m->bases1.reserve(nb1 + 8)); SFB_CUDA(c, m->off1.reserve(n_reads + 1));
+    SFB_CUDA(c, cudaMemcpyAsync(m->bases1.p, bases1 + off1[0], nb1, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, cudaMemcpyAsync(m->off1.p, off1, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    const char* d_b2 = nullptr; const uint64_t* d_o2 = nullptr;
+    if (bases2) {
+        const uint64_t nb2 = off2[n_reads] - off2[0];
+        SFB_CUDA(c, m->bases2.reserve(nb2 + 8)); SFB_CUDA(c, m->off2.reserve(n_reads + 1));
+        SFB_CUDA(c, cudaMemcpyAsync(m->bases2.p, bases2 + off2[0], nb2, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, cudaMemcpyAsync(m->off2.p, off2, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+        d_b2 = m->bases2.p - off2[0]; d_o2 = m->off2.p;
+    }
+    return sfb200_map_batch_device(c, m->bases1.p - off1[0], m->off1.p, d_b2, d_o2, n_reads);
+}
+
+extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_finish: call map_begin first");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    if (c->n_ranks > 1) {
+        int rc = sfb_comm_allreduce_u64(c, m->counters.p, 6);
+        if (rc) return rc;
+        // fld histogram: widen to u64 through the host (1000 entries)
+    }
+    unsigned long long h_cursor[4], h_counters[6];
+    SFB_CUDA(c, cudaMemcpyAsync(h_cursor, m->cursor.p, sizeof(h_cursor), cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(h_counters, m->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> h_fld(m->o.max_frag_len);
+    SFB_CUDA(c, cudaMemcpyAsync(h_fld.data(), m->fld_hist.p, m->o.max_frag_len * 4ull, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    if (h_cursor[2] & ERR_ARENA_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena exhausted (raise SFB200_EQ_ARENA_LOG2)");
+    if (h_cursor[2] & ERR_TABLE_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table exhausted (raise SFB200_EQ_LOG2_BUCKETS)");
+    if (h_cursor[2] & ERR_LABEL_LONG) SFB_FAIL(c, SFB200_EFULL, "a label has 1024 or more transcripts");
+    if (c->n_ranks > 1) {
+        std::vector<unsigned long long> wide(h_fld.begin(), h_fld.end());
+        DevBuf<unsigned long long> d; SFB_CUDA(c, d.reserve(wide.size()));
+        SFB_CUDA(c, cudaMemcpyAsync(d.p, wide.data(), wide.size() * 8, cudaMemcpyHostToDevice, s));
+        const int rc = sfb_comm_allreduce_u64(c, d.p, wide.size());
+        if (rc) { d.release(); return rc; }
+        SFB_CUDA(c, cudaMemcpyAsync(wide.data(), d.p, wide.size() * 8, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        d.release();
+        for (size_t i = 0; i < wide.size(); ++i) h_fld[i] = static_cast<uint32_t>(wide[i]);
+    }
+    if (counters) for (int i = 0; i < 6; ++i) counters[i] = h_counters[i];
+    if (fld_hist) std::memcpy(fld_hist, h_fld.data(), h_fld.size() * 4);
+
+    // eqBuilder.finish() (EquivalenceClassBuilder.hpp:64-80): flatten the table.  Order is canonical: label-lexicographic.
+    const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
+    const uint64_t used = h_cursor[0];
+    std::vector<unsigned long long> h_slot(n_slots), h_count(n_slots);
+    std::vector<uint32_t> h_arena(used ? used : 1);
+    SFB_CUDA(c, cudaMemcpyAsync(h_slot.data(), m->slot.p, n_slots * 8, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(h_count.data(), m->count.p, n_slots * 8, cudaMemcpyDeviceToHost, s));
+    if (used) SFB_CUDA(c, cudaMemcpyAsync(h_arena.data(), m->arena.p, used * 4, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    std::vector<uint64_t> ids;
+    ids.reserve(h_cursor[1]);
+    for (uint64_t i = 0; i < n_slots; ++i) if (h_slot[i]) ids.push_back(i);
+    auto lab_of = [&](uint64_t i, uint32_t& len) { len = static_cast<uint32_t>((h_slot[i] >> 20) & 1023); return h_arena.data() + (h_slot[i] >> 30); };
+    std::sort(ids.begin(), ids.end(), [&](uint64_t a, uint64_t b) {
+        uint32_t la, lb2; const uint32_t* pa = lab_of(a, la); const uint32_t* pb = lab_of(b, lb2);
+        return std::lexicographical_compare(pa, pa + la, pb, pb + lb2);
+    });
+    const uint64_t E = ids.size();
+    std::vector<uint64_t> row_ptr(E + 1, 0), cnts(E);
+    uint64_t z = 0;
+    for (uint64_t e = 0; e < E; ++e) { uint32_t len; lab_of(ids[e], len); z += len; row_ptr[e + 1] = z; cnts[e] = h_count[ids[e]]; }
+    std::vector<uint32_t> labels(z ? z : 1);
+    for (uint64_t e = 0; e < E; ++e) { uint32_t len; const uint32_t* pl = lab_of(ids[e], len); std::memcpy(labels.data() + row_ptr[e], pl, len * 4ull); }
+    if (n_classes) *n_classes = E;
+    if (nnz) *nnz = z;
+    return sfb_classes_from_host(c, c->index.n_txp, E, row_ptr.data(), labels.data(), cnts.data());
+}

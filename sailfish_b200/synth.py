@@ -1,0 +1,126 @@
+"""Deterministic synthetic transcriptomes and reads for the BASELINE.json configurations.
+
+A transcriptome is `n_genes` genes x `n_iso` isoforms; each gene has `n_exons` exons with log-normal lengths, and an
+isoform is an ordered random subset of its gene's exons, so isoforms of a gene share sequence and reads multi-map within a
+gene (that is what makes equivalence classes with more than one transcript).  Reads are drawn from transcripts with
+log-normal expression (a fraction of transcripts unexpressed), uniform start, random strand and a substitution rate.
+"""
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, np.uint8)
+for _a, _b in zip(b"ACGTN", b"TGCAN"):
+    _COMP[_a] = _b
+
+
+def make_transcriptome(n_genes, n_iso=5, n_exons=12, seed=42, gc=0.45, mu=5.3, sigma=0.6, p_keep=0.6):
+    """-> (seq uint8[total], txp_off uint64[T], txp_len uint32[T])"""
+    rng = np.random.default_rng(seed)
+    ex_len = np.clip(rng.lognormal(mu, sigma, size=(n_genes, n_exons)), 60, 2000).astype(np.int64)
+    ex_off = np.zeros(n_genes * n_exons + 1, np.int64)
+    ex_off[1:] = np.cumsum(ex_len.ravel())
+    p = np.array([(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2])
+    exon_seq = _ACGT[rng.choice(4, size=int(ex_off[-1]), p=p)]
+    keep = rng.random((n_genes, n_iso, n_exons)) < p_keep
+    # at least two exons per isoform
+    few = keep.sum(axis=2) < 2
+    keep[few, 0] = True
+    keep[few, 1] = True
+    T = n_genes * n_iso
+    lens = (keep * ex_len[:, None, :]).sum(axis=2).reshape(T)
+    txp_len = lens.astype(np.uint32)
+    txp_off = np.zeros(T, np.uint64)
+    txp_off[1:] = np.cumsum(lens)[:-1]
+    seq = np.empty(int(lens.sum()), np.uint8)
+    # copy exon by exon, vectorised over (gene, isoform) pairs per exon slot
+    cur = txp_off.astype(np.int64).copy()
+    keep2 = keep.reshape(T, n_exons)
+    gene_of = np.repeat(np.arange(n_genes), n_iso)
+    for e in range(n_exons):
+        sel = np.nonzero(keep2[:, e])[0]
+        if sel.size == 0:
+            continue
+        el = ex_len[gene_of[sel], e]
+        src0 = ex_off[gene_of[sel] * n_exons + e]
+        tot = int(el.sum())
+        seg_start = np.zeros(sel.size, np.int64)
+        seg_start[1:] = np.cumsum(el)[:-1]
+        within = np.arange(tot, dtype=np.int64) - np.repeat(seg_start, el)
+        seq[np.repeat(cur[sel], el) + within] = exon_seq[np.repeat(src0, el) + within]
+        cur[sel] += el
+    return seq, txp_off, txp_len
+
+
+def make_reads(seq, txp_off, txp_len, n_reads, read_len, seed=1234, paired=False, frag_mean=200.0, frag_sd=25.0,
+               sub_rate=0.005, zero_frac=0.3, n_rate=0.0):
+    """-> (bases1, off1, bases2|None, off2|None, truth_tid).  Fixed-length reads, so off = arange * read_len."""
+    rng = np.random.default_rng(seed)
+    T = len(txp_len)
+    expr = rng.lognormal(0.0, 2.0, size=T)
+    expr[rng.random(T) < zero_frac] = 0.0
+    min_len = read_len if not paired else max(read_len, 100)
+    expr[txp_len < min_len] = 0.0
+    w = expr * np.maximum(txp_len.astype(np.float64) - min_len + 1, 0)
+    w /= w.sum()
+    tid = rng.choice(T, size=n_reads, p=w)
+    tl = txp_len[tid].astype(np.int64)
+    if paired:
+        fl = np.clip(np.rint(rng.normal(frag_mean, frag_sd, size=n_reads)), max(read_len, 100), 999).astype(np.int64)
+        fl = np.minimum(fl, tl)
+    else:
+        fl = np.full(n_reads, read_len, np.int64)
+    start = (rng.random(n_reads) * (tl - fl + 1)).astype(np.int64)
+    base0 = txp_off[tid].astype(np.int64) + start
+    ar = np.arange(read_len, dtype=np.int64)
+    flip = rng.random(n_reads) < 0.5
+
+    def mutate(b):
+        if sub_rate > 0:
+            m = rng.random(b.shape) < sub_rate
+            b[m] = _ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        if n_rate > 0:
+            m = rng.random(b.shape) < n_rate
+            b[m] = ord("N")
+        return b
+
+    fwd = seq[base0[:, None] + ar[None, :]]                       # left end of the fragment, forward strand
+    if not paired:
+        rc = _COMP[fwd[:, ::-1]]
+        b1 = np.where(flip[:, None], rc, fwd)
+        b1 = mutate(np.ascontiguousarray(b1))
+        off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+        return b1.reshape(-1), off, None, None, tid
+    right = seq[(base0 + fl - read_len)[:, None] + ar[None, :]]   # right end, forward strand
+    right_rc = _COMP[right[:, ::-1]]
+    fwd_rc = _COMP[fwd[:, ::-1]]
+    # inward pair: mate1 = left end fwd, mate2 = right end rc; flipped fragment swaps the roles
+    b1 = np.where(flip[:, None], right_rc, fwd)
+    b2 = np.where(flip[:, None], fwd, right_rc)
+    del fwd_rc
+    b1 = mutate(np.ascontiguousarray(b1)); b2 = mutate(np.ascontiguousarray(b2))
+    off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+    return b1.reshape(-1), off, b2.reshape(-1), off.copy(), tid
+
+
+def make_classes(n_txp, n_classes, seed=7, max_len=8, gene_size=5, long_frac=0.0):
+    """Random equivalence classes (CSR, label-lexicographic, unique labels) for inference-only tests/benches."""
+    rng = np.random.default_rng(seed)
+    labels = set()
+    n_genes = max(1, n_txp // gene_size)
+    while len(labels) < n_classes:
+        g = int(rng.integers(0, n_genes))
+        lo = g * gene_size
+        hi = min(n_txp, lo + gene_size)
+        if rng.random() < long_frac:
+            n = int(rng.integers(33, 80))
+            ids = np.sort(rng.choice(n_txp, size=min(n, n_txp), replace=False))
+        else:
+            n = int(rng.integers(1, min(max_len, hi - lo) + 1))
+            ids = np.sort(rng.choice(np.arange(lo, hi), size=n, replace=False))
+        labels.add(tuple(int(x) for x in ids))
+    labs = sorted(labels)
+    row_ptr = np.zeros(len(labs) + 1, np.uint64)
+    row_ptr[1:] = np.cumsum([len(l) for l in labs])
+    flat = np.array([t for l in labs for t in l], dtype=np.uint32)
+    counts = np.maximum(1, rng.lognormal(2.0, 2.0, size=len(labs))).astype(np.uint64)
+    return row_ptr, flat, counts

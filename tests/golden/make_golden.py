@@ -1,0 +1,138 @@
+"""Generates the committed golden fixtures under tests/golden/ from the REAL reference pieces compiled into oracle/_ref
+(run in the build container, where /root/reference exists):
+
+  xxh64_kat.json      XXH64 known answers from the reference's own src/xxhash.c (ref_xxh64) and
+                      TranscriptGroup hashes (src/TranscriptGroup.cpp:9-12)
+  sample_data.npz     the bundled sample_data.tgz (15 transcripts, 10 000 read pairs x 50 nt) as arrays, the oracle's
+                      equivalence classes for it (mapping spec v1, -l IU), and the estimates the reference's OWN
+                      CollapsedEMOptimizer::optimize produces on those classes (EM and VBEM)
+  synth_em.npz        a synthetic class set + the reference optimizer's EM / VBEM estimates
+  eqbuilder.json      EquivalenceClassBuilder behaviour on a small add sequence (counts, finish() totals)
+
+Usage:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tarfile
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as O          # noqa: E402
+from sailfish_b200 import synth           # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def read_fasta(path):
+    names, seqs, cur = [], [], []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"):
+            if cur:
+                seqs.append("".join(cur)); cur = []
+            names.append(line[1:].split()[0])
+        elif line:
+            cur.append(line)
+    if cur:
+        seqs.append("".join(cur))
+    return names, seqs
+
+
+def read_fastq(path):
+    out = []
+    with open(path) as f:
+        while True:
+            h = f.readline()
+            if not h:
+                break
+            out.append(f.readline().strip())
+            f.readline(); f.readline()
+    return out
+
+
+def main():
+    R = O.ref()
+    assert R is not None, "oracle/_ref/libsfref.so missing: run make -C oracle"
+    rng = np.random.default_rng(20261017)
+    kat = []
+    msgs = [b"", bytes(4), np.array([0, 1], np.uint32).tobytes(), np.array([3, 7, 11], np.uint32).tobytes(),
+            np.arange(8, dtype=np.uint32).tobytes(), np.arange(9, dtype=np.uint32).tobytes(),
+            np.array([0x0123456789ABCDEF], np.uint64).tobytes()]
+    for n in list(range(0, 70)) + [127, 128, 129, 255, 256, 799, 800]:
+        msgs.append(rng.integers(0, 256, size=n, dtype=np.uint8).tobytes())
+    for m in msgs:
+        for seed in (0, 1, 0x9E3779B97F4A7C15):
+            kat.append({"hex": m.hex(), "seed": seed, "xxh64": "%016x" % R.ref_xxh64(m, len(m), seed)})
+    tg = []
+    for n in (1, 2, 3, 5, 8, 9, 17, 64, 200):
+        ids = np.sort(rng.choice(200000, size=n, replace=False)).astype(np.uint32)
+        tg.append({"ids": ids.tolist(), "hash": "%016x" % R.ref_tgroup_hash(O._ptr(ids, O.u32p), n)})
+    json.dump({"source": "reference src/xxhash.c via oracle/_ref/libsfref.so", "xxh64": kat, "transcript_group": tg},
+              open(os.path.join(OUT, "xxh64_kat.json"), "w"))
+
+    # EquivalenceClassBuilder behaviour (include/EquivalenceClassBuilder.hpp:64-108)
+    adds = [[1, 2], [7], [1, 2], [1, 2, 3], [7], [1, 2], [2, 1], [5, 5], [1, 2]]
+    h = R.ref_eqb_create()
+    for a in adds:
+        arr = np.array(a, np.uint32)
+        R.ref_eqb_add(h, O._ptr(arr, O.u32p), len(a))
+    import ctypes as C
+    nnz = C.c_uint64()
+    E = R.ref_eqb_finish(h, C.byref(nnz))
+    rp = np.zeros(E + 1, np.uint64); lab = np.zeros(nnz.value, np.uint32); cnt = np.zeros(E, np.uint64); w = np.zeros(nnz.value, np.float64)
+    R.ref_eqb_export(h, O._ptr(rp, O.u64p), O._ptr(lab, O.u32p), O._ptr(cnt, O.u64p), O._ptr(w, O.f64p))
+    R.ref_eqb_free(h)
+    classes = sorted((lab[int(rp[i]):int(rp[i + 1])].tolist(), int(cnt[i])) for i in range(E))
+    json.dump({"adds": adds, "classes": classes, "total": int(cnt.sum())}, open(os.path.join(OUT, "eqbuilder.json"), "w"))
+
+    # sample_data
+    tmp = tempfile.mkdtemp()
+    tarfile.open(os.path.join(REF, "sample_data.tgz")).extractall(tmp)
+    names, seqs = read_fasta(os.path.join(tmp, "sample_data", "transcripts.fasta"))
+    r1 = read_fastq(os.path.join(tmp, "sample_data", "reads_1.fastq"))
+    r2 = read_fastq(os.path.join(tmp, "sample_data", "reads_2.fastq"))
+    ix = O.Index(seqs, k=31)
+    b1, o1 = O.pack_reads(r1); b2, o2 = O.pack_reads(r2)
+    run = O.Run(ix, O.MapOpts.default(O.parse_libtype("IU")))
+    run.map_batch(b1, o1, b2, o2)
+    res = run.finish()
+    txp_len = np.array([len(s) for s in seqs], np.uint32)
+    eff = O.eff_lens(txp_len, res["fld"])
+    num_mapped = int(res["counters"][1])
+    out = dict(txp_seq=np.frombuffer("".join(seqs).encode(), np.uint8), txp_len=txp_len,
+               names=np.array(names), reads1=np.frombuffer(b1, np.uint8), off1=o1, reads2=np.frombuffer(b2, np.uint8), off2=o2,
+               counters=res["counters"], fld=res["fld"], row_ptr=res["row_ptr"], labels=res["labels"], counts=res["counts"],
+               eff=eff, num_mapped=np.uint64(num_mapped))
+    for vb in (0, 1):
+        ref = O.RefEM(txp_len, eff, res["row_ptr"], res["labels"], res["counts"], num_mapped, use_vb=bool(vb))
+        rc, est, mass = ref.optimize()
+        assert rc == 0
+        out["ref_est_vb%d" % vb] = est
+        out["ref_mass_vb%d" % vb] = mass
+    np.savez_compressed(os.path.join(OUT, "sample_data.npz"), **out)
+
+    # synthetic classes
+    T = 2000
+    rp, lab, cnt = synth.make_classes(T, 3000, seed=11, long_frac=0.01)
+    txp_len = rng.integers(200, 5000, size=T).astype(np.uint32)
+    eff = O.eff_lens(txp_len, None, single_end=True)
+    nm = int(cnt.sum())
+    out = dict(txp_len=txp_len, eff=eff, row_ptr=rp, labels=lab, counts=cnt, num_mapped=np.uint64(nm))
+    for vb in (0, 1):
+        ref = O.RefEM(txp_len, eff, rp, lab, cnt, nm, use_vb=bool(vb))
+        rc, est, mass = ref.optimize()
+        assert rc == 0
+        out["ref_est_vb%d" % vb] = est
+    np.savez_compressed(os.path.join(OUT, "synth_em.npz"), **out)
+    print("golden fixtures written to", OUT)
+    subprocess.call(["ls", "-la", OUT])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+"""GPU parity tests (-m gpu) for the inference kernels, called through the C ABI (libsfb200.so).
+
+Bar (BASELINE.json north_star): TPM / NumReads within 1e-4 relative of the reference CPU CollapsedEMOptimizer on identical
+inputs, compared at equal iteration count (SURVEY section 7 "parity at a convergence threshold").
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from sailfish_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # north_star tolerance
+ATOL = 1e-6          # counts below this are noise next to the 1e-8 truncation threshold
+
+
+def assert_close(got, want, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def test_device_xxh64_known_answers(ctx, golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "xxh64_kat.json")))
+    kat = [e for e in g["xxh64"] if len(e["hex"]) % 8 == 0]            # labels are whole 32-bit words
+    for seed in (0, 1, 0x9E3779B97F4A7C15):
+        es = [e for e in kat if e["seed"] == seed]
+        out = ctx.xxh64([bytes.fromhex(e["hex"]) for e in es], seed)
+        assert ["%016x" % int(x) for x in out] == [e["xxh64"] for e in es]
+    tg = g["transcript_group"]
+    out = ctx.xxh64([np.array(e["ids"], np.uint32).tobytes() for e in tg], 0)
+    assert ["%016x" % int(x) for x in out] == [e["hash"] for e in tg]
+
+
+def test_device_digamma(ctx):
+    from scipy.special import digamma
+    xs = np.concatenate([10.0 ** np.linspace(-300, 9, 400), np.linspace(0.001, 30, 500)])
+    got = ctx.digamma(xs)
+    want = digamma(xs)
+    ok = (np.abs(got - want) <= 1e-12 * np.abs(want)) | (np.abs(got - want) < 1e-13)
+    assert ok.all()
+
+
+@pytest.mark.parametrize("name", ["sample_data", "synth_em"])
+@pytest.mark.parametrize("vb", [0, 1])
+def test_em_matches_reference_optimizer_golden(ctx, name, vb, sample_data, synth_em):
+    """GPU optimize() vs the estimates of the reference's own CollapsedEMOptimizer (committed fixture)."""
+    d = sample_data if name == "sample_data" else synth_em
+    T = len(d["txp_len"])
+    ctx.eq_import(T, d["row_ptr"], d["labels"], d["counts"])
+    alphas, iters, mrd = ctx.em_run(d["eff"], int(d["num_mapped"]), capi.EMOpts.default(use_vb=vb))
+    rc, want, it_o, mrd_o = O.em_run(T, d["row_ptr"], d["labels"], d["counts"], d["eff"], int(d["num_mapped"]),
+                                     O.EMOpts.default(use_vb=vb))
+    assert rc == 0
+    assert iters == it_o, "GPU stopped at a different iteration than the oracle"
+    assert_close(alphas, want)
+    assert_close(alphas, d["ref_est_vb%d" % vb])
+    assert (alphas == 0).tolist() == (want == 0).tolist()
+    assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
+    nm = int(d["num_mapped"])
+    assert_close(capi.tpm(alphas, d["eff"], nm), O.tpm(want, d["eff"], nm), atol=1e-4)
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+@pytest.mark.parametrize("fixed", [1, 10, 50, 333])
+def test_em_fixed_iterations(ctx, vb, fixed):
+    T = 5000
+    rp, lab, cnt = synth.make_classes(T, 12000, seed=21 + fixed, long_frac=0.01)
+    rng = np.random.default_rng(fixed)
+    eff = rng.uniform(0.5, 4000, size=T)           # includes lengths below 1 (clamped, CollapsedEMOptimizer.cpp:736-738)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    alphas, iters, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb, fixed_iters=fixed))
+    rc, want, it_o, _ = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, fixed_iters=fixed))
+    assert rc == 0 and iters == fixed == it_o
+    assert_close(alphas, want)
+    assert abs(alphas.sum() - want.sum()) <= 1e-9 * want.sum()
+
+
+def test_em_steps_mode_equals_persistent(ctx, monkeypatch):
+    """one launch per phase (the multi-rank path) == the persistent cooperative kernel"""
+    T = 3000
+    rp, lab, cnt = synth.make_classes(T, 7000, seed=5)
+    eff = np.random.default_rng(1).uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    for vb in (0, 1):
+        a1, it1, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        monkeypatch.setenv("SFB200_EM_MODE", "steps")
+        a2, it2, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        monkeypatch.delenv("SFB200_EM_MODE")
+        assert it1 == it2
+        assert_close(a1, a2, rtol=1e-9)
+
+
+def test_em_edge_cases(ctx):
+    # a single class with a single transcript; transcripts that appear in no class stay 0
+    rp = np.array([0, 1], np.uint64); lab = np.array([3], np.uint32); cnt = np.array([17], np.uint64)
+    ctx.eq_import(6, rp, lab, cnt)
+    a, it, _ = ctx.em_run(np.full(6, 100.0), 17)
+    assert a.tolist() == [0, 0, 0, 17.0, 0, 0]
+    # duplicate transcript ids inside a label (orphans mapping both mates to one transcript)
+    rp = np.array([0, 2, 5], np.uint64); lab = np.array([1, 1, 0, 1, 2], np.uint32); cnt = np.array([10, 30], np.uint64)
+    ctx.eq_import(3, rp, lab, cnt)
+    eff = np.array([100.0, 200.0, 300.0])
+    a, it, _ = ctx.em_run(eff, 40)
+    rc, want, it_o, _ = O.em_run(3, rp, lab, cnt, eff, 40)
+    assert it == it_o
+    assert_close(a, want)
+    # no classes at all: "no transcripts are expressed" (CollapsedEMOptimizer.cpp:794-798)
+    ctx.eq_import(4, np.array([0], np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint64))
+    with pytest.raises(capi.Sfb200Error) as e:
+        ctx.em_run(np.full(4, 10.0), 0)
+    assert e.value.code == -4
+    # label with an out-of-range transcript id is rejected
+    with pytest.raises(capi.Sfb200Error):
+        ctx.eq_import(2, np.array([0, 1], np.uint64), np.array([7], np.uint32), np.array([1], np.uint64))
+
+
+def test_eq_import_export_roundtrip(ctx):
+    rp, lab, cnt = synth.make_classes(1000, 2500, seed=9, long_frac=0.02)
+    ctx.eq_import(1000, rp, lab, cnt)
+    rp2, lab2, cnt2 = ctx.eq_export()
+    assert rp2.tolist() == rp.tolist() and lab2.tolist() == lab.tolist() and cnt2.tolist() == cnt.tolist()
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+def test_bootstrap_em_same_resampled_counts(ctx, vb):
+    """doBootstrap's loop (no minimum iteration count, gate on the OLD alpha) on identical resampled counts"""
+    T = 2000
+    rp, lab, cnt = synth.make_classes(T, 5000, seed=31)
+    eff = np.random.default_rng(2).uniform(100, 3000, size=T)
+    rng = np.random.default_rng(99)
+    total = int(cnt.sum())
+    samp = rng.multinomial(total, cnt / cnt.sum()).astype(np.uint64)
+    ctx.eq_import(T, rp, lab, cnt)
+    a, it = ctx.bootstrap_em(eff, samp, capi.EMOpts.default(use_vb=vb))
+    rc, want, it_o = O.bootstrap_em(T, rp, lab, samp, eff, O.EMOpts.default(use_vb=vb))
+    assert rc == 0 and it == it_o
+    assert_close(a, want)
+
+
+def test_bootstrap_run_distribution(ctx):
+    """Bootstrap replicates: RNG differs from the reference (std::random_device there), so parity is distributional:
+    per-transcript mean over replicates matches the oracle's replicates within sampling error, totals are exact."""
+    T = 300
+    rp, lab, cnt = synth.make_classes(T, 600, seed=41, max_len=4)
+    eff = np.full(T, 500.0)
+    total = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    rows = ctx.bootstrap_run(eff, 40, seed=7)
+    assert rows.shape == (40, T)
+    np.testing.assert_allclose(rows.sum(axis=1), total, rtol=1e-9)
+    rc, orows = O.bootstrap(T, rp, lab, cnt, eff, 40, seed=7)
+    assert rc == 0
+    big = orows.mean(axis=0) > 200
+    assert big.sum() > 10
+    se = np.sqrt(rows.var(axis=0) / 40 + orows.var(axis=0) / 40)
+    zscore = np.abs(rows.mean(axis=0) - orows.mean(axis=0))[big] / np.maximum(se[big], 1e-9)
+    assert np.mean(zscore < 4) > 0.97
+    # reproducible for a fixed seed
+    rows2 = ctx.bootstrap_run(eff, 3, seed=7)
+    np.testing.assert_allclose(rows2, rows[:3], rtol=1e-9)
+
+
+def test_em_full_size_properties(ctx):
+    """BASELINE config 2 scale (200k transcripts): size-independent properties -- mass conservation and fixed point."""
+    T = 200000
+    rp, lab, cnt = synth.make_classes(T, 400000, seed=77, max_len=5)
+    eff = np.random.default_rng(3).uniform(100, 5000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    a, it, _ = ctx.em_run(eff, nm, capi.EMOpts.default(fixed_iters=200))
+    assert it == 200
+    assert abs(a.sum() - nm) <= 1e-8 * nm                      # every class hands out exactly its count
+    active = np.zeros(T, bool); active[lab] = True
+    assert (a[~active] == 0).all()
+    rc, want, _, _ = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(fixed_iters=200), n_threads=8)
+    assert_close(a, want)

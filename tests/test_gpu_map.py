@@ -1,0 +1,167 @@
+"""GPU parity tests (-m gpu) for index construction and the read -> equivalence-class kernel, through the C ABI.
+
+Integer results (index arrays, class labels and counts, the six counters, the fragment-length histogram) must be
+bit-exact against the CPU oracle on identical inputs (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from sailfish_b200 import capi, synth
+from conftest import split_seqs
+
+pytestmark = pytest.mark.gpu
+
+
+def small_txome(n_genes=60, seed=42):
+    seq, off, ln = synth.make_transcriptome(n_genes, seed=seed)
+    return seq, off, ln
+
+
+def run_both(ctx, seq, off, ln, b1, o1, b2, o2, libtype, k=31, batches=1, **kw):
+    st = ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=k)
+    seqs = [seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes() for i in range(len(ln))]
+    oix = O.Index(seqs, k=k)
+    fmt = O.parse_libtype(libtype)
+    ctx.map_begin(capi.MapOpts.default(fmt, **kw))
+    run = O.Run(oix, O.MapOpts.default(fmt, **kw))
+    n = len(o1) - 1
+    cuts = np.linspace(0, n, batches + 1).astype(int)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b2 is None:
+            ctx.map_batch(b1, o1[a:b + 1])
+            run.map_batch(b1.tobytes(), o1[a:b + 1] if a == 0 else o1[a:b + 1])
+        else:
+            ctx.map_batch(b1, o1[a:b + 1], b2, o2[a:b + 1])
+            run.map_batch(b1.tobytes(), o1[a:b + 1], b2.tobytes(), o2[a:b + 1])
+    g = ctx.map_finish()
+    w = run.finish()
+    return st, oix, g, w
+
+
+def assert_same_classes(ctx, g, w):
+    assert g["counters"].tolist() == w["counters"].tolist()
+    assert g["fld"].tolist() == w["fld"].tolist()
+    rp, lab, cnt = ctx.eq_export()
+    assert g["n_classes"] == len(w["counts"])
+    assert rp.tolist() == w["row_ptr"].tolist()
+    assert lab.tolist() == w["labels"].tolist()
+    assert cnt.tolist() == w["counts"].tolist()
+    assert int(cnt.sum()) == int(g["counters"][1])           # sum of class counts == numMappedFragments
+
+
+def test_index_matches_oracle(ctx):
+    seq, off, ln = small_txome(40)
+    # sprinkle non-ACGT characters and lower case into the transcript text
+    seq = seq.copy()
+    rng = np.random.default_rng(0)
+    seq[rng.integers(0, len(seq), 200)] = ord("N")
+    low = rng.integers(0, len(seq), 500)
+    seq[low] = np.char.lower(seq[low].view("S1")).view(np.uint8)
+    for k in (31, 21, 15):
+        st = ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=k)
+        seqs = [seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes() for i in range(len(ln))]
+        oix = O.Index(seqs, k=k)
+        e = oix.export()
+        words, sa_pos, sa_tid = ctx.index_export()
+        ow, n = oix.text_words()
+        assert st["text_len"] == n and st["n_sa"] == len(e["sa_pos"]) and st["n_kmers"] == len(e["kmers"])
+        assert words.tolist() == ow.tolist()
+        assert sa_pos.tolist() == e["sa_pos"].tolist()
+        assert sa_tid.tolist() == e["sa_tid"].tolist()
+        assert st["max_bucket"] == int(e["cnt"].max())
+
+
+def test_index_short_transcripts_and_bad_k(ctx):
+    seqs = [b"ACGTACGTAC", b"A" * 40 + b"C" * 40, b"ACG", b"GATTACA" * 20]
+    st = ctx.index_build(seqs=seqs, k=31)
+    oix = O.Index(seqs, k=31)
+    assert st["n_sa"] == O.lib().orc_index_n_sa(oix.h)
+    with pytest.raises(capi.Sfb200Error):
+        ctx.index_build(seqs=seqs, k=30)         # even k refused (SailfishIndexer.cpp:199-205)
+
+
+@pytest.mark.parametrize("libtype", ["U", "SF", "SR"])
+def test_single_end_matches_oracle(ctx, libtype):
+    seq, off, ln = small_txome()
+    b1, o1, _, _, _ = synth.make_reads(seq, off, ln, 30000, 76, seed=11, sub_rate=0.01, n_rate=0.002)
+    st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, None, None, libtype, batches=3)
+    assert_same_classes(ctx, g, w)
+    assert g["counters"][1] > 25000
+
+
+@pytest.mark.parametrize("libtype,kw", [("IU", {}), ("ISF", {}), ("ISR", {"enforce_compat": 1}), ("OU", {}), ("MU", {}),
+                                        ("IU", {"allow_orphans": 0}), ("IU", {"strict_intersect": 1}),
+                                        ("ISF", {"ignore_compat": 1}), ("IU", {"allow_dovetail": 1}),
+                                        ("IU", {"max_read_occs": 3}), ("IU", {"num_frag_samples": 500}),
+                                        ("IU", {"max_interval": 2})])
+def test_paired_end_matches_oracle(ctx, libtype, kw):
+    seq, off, ln = small_txome()
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 20000, 100, seed=12, paired=True, sub_rate=0.01, n_rate=0.002)
+    # break some mates so that orphans occur: overwrite mate 2 of every 7th pair with random sequence
+    b2 = b2.copy().reshape(-1, 100)
+    rng = np.random.default_rng(1)
+    b2[::7] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=b2[::7].shape)]
+    b2 = b2.reshape(-1)
+    st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, b2, o2, libtype, batches=2, **kw)
+    assert_same_classes(ctx, g, w)
+
+
+def test_sample_data_matches_golden(ctx, sample_data):
+    """BASELINE config 1: the bundled sample (15 transcripts, 10 000 x 2 x 50 nt, -l IU) against the committed fixture."""
+    d = sample_data
+    seqs = split_seqs(d["txp_seq"], d["txp_len"])
+    ctx.index_build(seqs=seqs, k=31)
+    ctx.map_begin(capi.MapOpts.default(O.parse_libtype("IU")))
+    ctx.map_batch(d["reads1"], d["off1"], d["reads2"], d["off2"])
+    g = ctx.map_finish()
+    assert g["counters"].tolist() == d["counters"].tolist()
+    assert g["fld"].tolist() == d["fld"].tolist()
+    rp, lab, cnt = ctx.eq_export()
+    assert rp.tolist() == d["row_ptr"].tolist() and lab.tolist() == d["labels"].tolist() and cnt.tolist() == d["counts"].tolist()
+    # straight into inference on the classes that are already on the device
+    alphas, iters, _ = ctx.em_run(d["eff"], int(d["num_mapped"]))
+    np.testing.assert_allclose(alphas, d["ref_est_vb0"], rtol=1e-4, atol=1e-6)
+
+
+def test_ragged_and_degenerate_reads(ctx):
+    seq, off, ln = small_txome(20)
+    seqs = [seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes() for i in range(len(ln))]
+    t0 = seqs[0]
+    reads = [t0[10:86], b"", b"ACGT", b"N" * 76, t0[0:300], t0[5:36], b"A" * 80, t0[100:130] + b"N" + t0[131:200],
+             t0[50:81].lower(), bytes(reversed(t0[20:96])), t0[-76:], t0[:31]]
+    b1, o1 = capi.pack_reads(reads)
+    st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, None, None, "U")
+    assert_same_classes(ctx, g, w)
+    assert g["counters"][0] == len(reads)
+
+
+def test_small_k_and_many_hits(ctx):
+    """k = 15 on a repetitive transcriptome: big buckets, reads with more hits than max_read_occs"""
+    rng = np.random.default_rng(3)
+    unit = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=300)].tobytes()
+    seqs = [unit + np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=100)].tobytes() for _ in range(300)]
+    reads = [unit[i:i + 60] for i in range(0, 200, 7)] + [s[290:350] for s in seqs[:50]]
+    b1, o1 = capi.pack_reads(reads)
+    seq = np.frombuffer(b"".join(seqs), np.uint8)
+    ln = np.array([len(s) for s in seqs], np.uint32)
+    off = np.zeros(len(seqs), np.uint64); off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+    for kw in ({}, {"max_read_occs": 400}, {"max_interval": 100}):
+        st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, None, None, "U", k=15, **kw)
+        assert_same_classes(ctx, g, w)
+
+
+def test_full_size_properties(ctx):
+    """Larger run (2 000 genes = 10 000 transcripts, 400k reads): invariants that do not need the oracle at size, plus
+    the oracle on the same input with 8 host threads."""
+    seq, off, ln = synth.make_transcriptome(2000, seed=42)
+    b1, o1, _, _, tid = synth.make_reads(seq, off, ln, 400000, 76, seed=1234)
+    st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, None, None, "U", batches=4)
+    assert_same_classes(ctx, g, w)
+    c = g["counters"]
+    assert c[0] == 400000 and c[1] <= c[3] <= c[0] and c[4] + c[5] == c[2]
+    # mapping twice gives the same table (idempotence of begin/finish)
+    ctx.map_begin(capi.MapOpts.default(O.parse_libtype("U")))
+    ctx.map_batch(b1, o1)
+    g2 = ctx.map_finish()
+    assert g2["counters"].tolist() == c.tolist() and g2["n_classes"] == g["n_classes"]
