@@ -67,6 +67,8 @@ int sfb200_index_stats(const sfb200_ctx* ctx, uint64_t stats[8]);
 /* copy the index back to the host (tests, and bench.py's CPU arm): words[text_len/32+2], sa_pos[n_suffixes],
  * sa_tid[n_suffixes]; any pointer may be NULL */
 int sfb200_index_export(sfb200_ctx* ctx, uint64_t* words, uint32_t* sa_pos, uint32_t* sa_tid);
+/* the k-mer table: table_slots entries of {k-mer (u64), first entry (u32), entry count (u32)}; empty = all-ones k-mer */
+int sfb200_index_export_table(sfb200_ctx* ctx, void* table16);
 
 /* ---- mapping + equivalence classes ---------------------------------------------------------------------------
  * Replaces processReadsQuasi<IndexT> (src/SailfishQuantify.cpp:105-452 paired, :458-646 single) together with the
@@ -99,7 +101,9 @@ int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_
  * (ReadExperiment.hpp:74-97); fld_hist[max_frag_len] = flMap (SailfishQuantify.cpp:867).  With a communicator the
  * counters and fld_hist are summed over ranks (classes stay rank-local). */
 int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz);
-/* == eqVec() (EquivalenceClassBuilder.hpp:110) as CSR in canonical order (first transcript id, then label hash);
+/* device time of all mapping-kernel launches between map_begin and map_finish, in milliseconds (CUDA events) */
+double sfb200_last_map_kernel_ms(const sfb200_ctx* ctx);
+/* == eqVec() (EquivalenceClassBuilder.hpp:110) as CSR in canonical order (label-lexicographic);
  * this is the content of aux/eq_classes.txt (src/GZipWriter.cpp:51-92) */
 int sfb200_eq_export(sfb200_ctx* ctx, uint64_t* row_ptr, uint32_t* labels, uint64_t* counts);
 /* inverse: run inference without mapping (the commented-out loadEquivClasses, SailfishQuantify.cpp:1444-1495) */

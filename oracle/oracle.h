@@ -54,6 +54,11 @@ orc_index* orc_index_build(const char* seq, const uint64_t* txp_off, const uint3
 /* wrap an existing packed text + suffix order (positions sorted by (k-mer value, position)); used by bench.py's CPU arm */
 orc_index* orc_index_from_arrays(const uint64_t* words, uint64_t text_len, const uint32_t* txp_len,
                                  uint32_t n_txp, int k, const uint32_t* sa_pos, uint64_t n_sa);
+/* same with transcript ids and the k-mer table supplied as well: table16 = n_slots x {k-mer u64, first entry u32, count u32},
+ * empty = all-ones k-mer, slot = XXH64(k-mer) & (n_slots-1), linear probing */
+orc_index* orc_index_from_table(const uint64_t* words, uint64_t text_len, const uint32_t* txp_len, uint32_t n_txp, int k,
+                                const uint32_t* sa_pos, const uint32_t* sa_tid, uint64_t n_sa, const uint64_t* table16,
+                                uint64_t n_slots);
 void orc_index_free(orc_index*);
 uint64_t orc_index_n_sa(const orc_index*);       /* number of valid suffix positions */
 uint64_t orc_index_n_kmers(const orc_index*);    /* number of distinct k-mers */

@@ -65,14 +65,26 @@ struct orc_index {
         for (int i = 0; i < k; ++i) v |= static_cast<uint64_t>(base(p + i)) << (2 * i);   // base i of the k-mer at bits 2i
         return v;
     }
-    // returns index into kmers or -1; counts probes
-    int64_t find(uint64_t km, uint64_t& probes) const {
+    // optional externally built table (same scheme: XXH64(k-mer) & mask, linear probing): {k-mer, lb | cnt << 32},
+    // empty = all-ones k-mer.  Used by bench.py's CPU arm at full size (orc_index_from_table).
+    std::vector<uint64_t> ext;
+    // looks the k-mer up, counts probes; fills the bucket [lb, lb+cnt)
+    bool find(uint64_t km, uint64_t& probes, uint32_t& olb, uint32_t& ocnt) const {
         uint64_t h = orc_xxh64(&km, 8, 0) & mask;
+        if (!ext.empty()) {
+            for (;;) {
+                ++probes;
+                const uint64_t key = ext[2 * h];
+                if (key == ~0ULL) return false;
+                if (key == km) { olb = static_cast<uint32_t>(ext[2 * h + 1]); ocnt = static_cast<uint32_t>(ext[2 * h + 1] >> 32); return true; }
+                h = (h + 1) & mask;
+            }
+        }
         for (;;) {
             ++probes;
             const uint32_t s = slot[h];
-            if (s == 0xFFFFFFFFu) return -1;
-            if (kmers[s] == km) return s;
+            if (s == 0xFFFFFFFFu) return false;
+            if (kmers[s] == km) { olb = lb[s]; ocnt = cnt[s]; return true; }
             h = (h + 1) & mask;
         }
     }
@@ -157,6 +169,26 @@ extern "C" orc_index* orc_index_from_arrays(const uint64_t* words, uint64_t text
     return ix;
 }
 
+// Same, with the suffix order's transcript ids and the k-mer table supplied too (nothing is rebuilt): table16 holds
+// n_slots entries of {k-mer u64, first entry u32, entry count u32}, n_slots a power of two.
+extern "C" orc_index* orc_index_from_table(const uint64_t* words, uint64_t text_len, const uint32_t* txp_len, uint32_t n_txp,
+                                           int k, const uint32_t* sa_pos, const uint32_t* sa_tid, uint64_t n_sa,
+                                           const uint64_t* table16, uint64_t n_slots) {
+    orc_index* ix = new orc_index();
+    ix->k = k; ix->T = n_txp; ix->text_len = text_len;
+    ix->words.assign(words, words + text_len / 32 + 2);
+    ix->txp_len.assign(txp_len, txp_len + n_txp);
+    ix->txp_start.resize(n_txp + 1);
+    uint64_t tot = 0;
+    for (uint32_t t = 0; t < n_txp; ++t) { ix->txp_start[t] = tot; tot += txp_len[t]; }
+    ix->txp_start[n_txp] = tot;
+    ix->sa_pos.assign(sa_pos, sa_pos + n_sa);
+    ix->sa_tid.assign(sa_tid, sa_tid + n_sa);
+    ix->ext.assign(table16, table16 + 2 * n_slots);
+    ix->mask = n_slots - 1;
+    return ix;
+}
+
 extern "C" void orc_index_free(orc_index* ix) { delete ix; }
 extern "C" uint64_t orc_index_n_sa(const orc_index* ix) { return ix->sa_pos.size(); }
 extern "C" uint64_t orc_index_n_kmers(const orc_index* ix) { return ix->kmers.size(); }
@@ -226,9 +258,8 @@ struct Mapper {
             bool homo = true;
             for (int j = 0; j < k; ++j) { km |= static_cast<uint64_t>(s[i + j]) << (2 * j); if (s[i + j] != s[i]) homo = false; }
             if (homo) { i += 1; continue; }                          // homopolymer k-mers are never used as seeds
-            const int64_t ki = ix.find(km, work.P);
-            if (ki < 0 || ix.cnt[ki] > o.max_interval) { i += 1; continue; }
-            const uint32_t lb = ix.lb[ki], cnt = ix.cnt[ki];
+            uint32_t lb = 0, cnt = 0;
+            if (!ix.find(km, work.P, lb, cnt) || cnt > o.max_interval) { i += 1; continue; }
             uint32_t m = 0;
             for (uint32_t e = lb; e < lb + cnt; ++e) { ++work.S; m = std::max(m, lcp_at(s, i, e)); }
             ivs.push_back({lb, cnt, i, m});

@@ -80,6 +80,8 @@ def lib():
         L.orc_index_build.argtypes = [C.c_char_p, u64p, u32p, C.c_uint32, C.c_int, C.c_int]
         L.orc_index_from_arrays.restype = C.c_void_p
         L.orc_index_from_arrays.argtypes = [u64p, C.c_uint64, u32p, C.c_uint32, C.c_int, u32p, C.c_uint64]
+        L.orc_index_from_table.restype = C.c_void_p
+        L.orc_index_from_table.argtypes = [u64p, C.c_uint64, u32p, C.c_uint32, C.c_int, u32p, u32p, C.c_uint64, u64p, C.c_uint64]
         L.orc_index_free.argtypes = [C.c_void_p]
         for f in ("orc_index_n_sa", "orc_index_n_kmers", "orc_index_text_len"):
             getattr(L, f).restype = C.c_uint64
@@ -152,6 +154,18 @@ class Index:
         sa_pos = np.ascontiguousarray(sa_pos, dtype=np.uint32)
         h = L.orc_index_from_arrays(_ptr(words, u64p), int(text_len), _ptr(txp_len, u32p), len(txp_len), k,
                                     _ptr(sa_pos, u32p), len(sa_pos))
+        return cls(k=k, handle=h, txp_len=txp_len)
+
+    @classmethod
+    def from_table(cls, words, text_len, txp_len, k, sa_pos, sa_tid, table):
+        """index built elsewhere (the GPU): packed text, suffix order with transcript ids and the k-mer table"""
+        L = lib()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        txp_len = np.ascontiguousarray(txp_len, dtype=np.uint32)
+        sa_pos = np.ascontiguousarray(sa_pos, dtype=np.uint32); sa_tid = np.ascontiguousarray(sa_tid, dtype=np.uint32)
+        table = np.ascontiguousarray(table, dtype=np.uint64)
+        h = L.orc_index_from_table(_ptr(words, u64p), int(text_len), _ptr(txp_len, u32p), len(txp_len), k, _ptr(sa_pos, u32p),
+                                   _ptr(sa_tid, u32p), len(sa_pos), _ptr(table, u64p), table.size // 2)
         return cls(k=k, handle=h, txp_len=txp_len)
 
     def export(self):

@@ -75,6 +75,8 @@ SIGNATURES = {
     "sfb200_index_build": (C.c_int, [C.c_void_p, C.c_void_p, u64p, u32p, C.c_uint32, C.c_int]),
     "sfb200_index_stats": (C.c_int, [C.c_void_p, u64p]),
     "sfb200_index_export": (C.c_int, [C.c_void_p, u64p, u32p, u32p]),
+    "sfb200_index_export_table": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sfb200_last_map_kernel_ms": (C.c_double, [C.c_void_p]),
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
     "sfb200_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint64]),
     "sfb200_map_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -214,6 +216,15 @@ class Context:
         sa_tid = np.zeros(max(st["n_sa"], 1), np.uint32)
         self._chk(self.L.sfb200_index_export(self.h, _ptr(words, u64p), _ptr(sa_pos, u32p), _ptr(sa_tid, u32p)))
         return words, sa_pos[:st["n_sa"]], sa_tid[:st["n_sa"]]
+
+    def index_export_table(self):
+        st = self.index_stats()
+        tab = np.zeros((st["table_slots"], 2), np.uint64)
+        self._chk(self.L.sfb200_index_export_table(self.h, tab.ctypes.data_as(C.c_void_p)))
+        return tab
+
+    def last_map_kernel_ms(self):
+        return float(self.L.sfb200_last_map_kernel_ms(self.h))
 
     # ---- mapping
     def map_begin(self, opts):

@@ -230,3 +230,13 @@ extern "C" int sfb200_index_export(sfb200_ctx* c, uint64_t* words, uint32_t* sa_
     SFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SFB200_OK;
 }
+
+extern "C" int sfb200_index_export_table(sfb200_ctx* c, void* table16) {
+    if (!c || !table16) return SFB200_EINVAL;
+    DevIndex& ix = c->index;
+    if (!ix.ready) SFB_FAIL(c, SFB200_EINVAL, "index_export_table: no index");
+    cudaSetDevice(c->device);
+    SFB_CUDA(c, cudaMemcpyAsync(table16, ix.table.p, ix.table_slots * 16, cudaMemcpyDeviceToHost, c->stream));
+    SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SFB200_OK;
+}

@@ -488,6 +488,9 @@ struct MapState {
     uint64_t n_buckets = 0, n_overflow = 0, arena_words = 0;
     uint64_t n_threads_total = 0;
     int grid = 0;
+    std::vector<cudaEvent_t> ev;       // start/stop pairs around every k_map_reads launch since map_begin
+    size_t ev_used = 0;
+    double kernel_ms = 0.0;
 };
 
 void sfb_map_state_free(sfb200_ctx* c) {
@@ -496,6 +499,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
     m->scratch.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release();
     m->bases1.release(); m->bases2.release(); m->off1.release(); m->off2.release();
+    for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
     delete m;
     c->map = nullptr;
 }
@@ -536,6 +540,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     SFB_CUDA(c, cudaStreamSynchronize(s));
     c->cls.ready = false;
     m->begun = true;
+    m->ev_used = 0; m->kernel_ms = 0.0;
     return SFB200_OK;
 }
 
@@ -567,9 +572,13 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     const uint64_t warps_needed = (n_reads + 31) / 32;
     const uint64_t blocks_needed = (warps_needed * 32 + MAP_THREADS - 1) / MAP_THREADS;
     const unsigned grid = (unsigned)std::min<uint64_t>(m->grid, blocks_needed);
+    if (m->ev.size() < m->ev_used + 2) { cudaEvent_t a, b; SFB_CUDA(c, cudaEventCreate(&a)); SFB_CUDA(c, cudaEventCreate(&b)); m->ev.push_back(a); m->ev.push_back(b); }
+    SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used], s));
     k_map_reads<<<grid, MAP_THREADS, 0, s>>>(p);
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
+    SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));
+    m->ev_used += 2;
     if (want_fld) {
         k_fld_select<<<1, 1024, 0, s>>>(m->fld_val.p, n_reads, m->fld_hist.p, m->remaining.p);
         c->launches++;
@@ -604,6 +613,8 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
     return sfb200_map_batch_device(c, m->bases1.p - off1[0], m->off1.p, d_b2, d_o2, n_reads);
 }
 
+extern "C" double sfb200_last_map_kernel_ms(const sfb200_ctx* c) { return (c && c->map) ? c->map->kernel_ms : 0.0; }
+
 extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz) {
     if (!c) return SFB200_EINVAL;
     MapState* m = c->map;
@@ -621,6 +632,8 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
     std::vector<uint32_t> h_fld(m->o.max_frag_len);
     SFB_CUDA(c, cudaMemcpyAsync(h_fld.data(), m->fld_hist.p, m->o.max_frag_len * 4ull, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    m->kernel_ms = 0.0;
+    for (size_t i = 0; i + 1 < m->ev_used; i += 2) { float ms = 0.f; if (cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]) == cudaSuccess) m->kernel_ms += ms; }
     if (h_cursor[2] & ERR_ARENA_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena exhausted (raise SFB200_EQ_ARENA_LOG2)");
     if (h_cursor[2] & ERR_TABLE_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table exhausted (raise SFB200_EQ_LOG2_BUCKETS)");
     if (h_cursor[2] & ERR_LABEL_LONG) SFB_FAIL(c, SFB200_EFULL, "a label has 1024 or more transcripts");

@@ -52,12 +52,15 @@ def make_transcriptome(n_genes, n_iso=5, n_exons=12, seed=42, gc=0.45, mu=5.3, s
 
 
 def make_reads(seq, txp_off, txp_len, n_reads, read_len, seed=1234, paired=False, frag_mean=200.0, frag_sd=25.0,
-               sub_rate=0.005, zero_frac=0.3, n_rate=0.0):
-    """-> (bases1, off1, bases2|None, off2|None, truth_tid).  Fixed-length reads, so off = arange * read_len."""
-    rng = np.random.default_rng(seed)
+               sub_rate=0.005, zero_frac=0.3, n_rate=0.0, expr_seed=None, stream=0):
+    """-> (bases1, off1, bases2|None, off2|None, truth_tid).  Fixed-length reads, so off = arange * read_len.
+    Expression comes from `expr_seed` (default: seed); the reads themselves from (seed, stream), so a large read set can be
+    produced chunk by chunk (stream = chunk number) or shard by shard over one expression profile."""
+    erng = np.random.default_rng(seed if expr_seed is None else expr_seed)
+    rng = np.random.default_rng([seed, stream])
     T = len(txp_len)
-    expr = rng.lognormal(0.0, 2.0, size=T)
-    expr[rng.random(T) < zero_frac] = 0.0
+    expr = erng.lognormal(0.0, 2.0, size=T)
+    expr[erng.random(T) < zero_frac] = 0.0
     min_len = read_len if not paired else max(read_len, 100)
     expr[txp_len < min_len] = 0.0
     w = expr * np.maximum(txp_len.astype(np.float64) - min_len + 1, 0)

@@ -181,3 +181,18 @@ def test_eff_lens_modes():
     sm = O.eff_lens(txp_len, fld)
     assert abs(sm[3] - (5000 - 196.0 + 1)) < 1e-9                       # :822-835
     assert sm[0] == 50 - 0.0 + 1 or sm[0] >= 1
+
+
+def test_product_efflen_helper_matches_oracle():
+    """sailfish_b200/efflen.py (host side of row A9) against the oracle's restatement of SailfishQuantify.cpp:648-838"""
+    from sailfish_b200 import efflen
+    rng = np.random.default_rng(4)
+    txp_len = np.concatenate([rng.integers(20, 6000, size=500), [1, 31, 999, 1000, 1001]]).astype(np.uint32)
+    fld = np.zeros(1000, np.uint32)
+    fld[100:400] = rng.integers(0, 200, size=300)
+    assert fld.sum() >= 10000
+    for kw in (dict(fld_hist=fld), dict(fld_hist=None, single_end=True), dict(fld_hist=fld // 100), dict(fld_hist=fld, no_correction=True)):
+        mine = efflen.effective_lengths(txp_len, **kw)
+        okw = dict(single_end=kw.get("single_end", False), mode=1 if kw.get("no_correction") else 0)
+        want = O.eff_lens(txp_len, kw.get("fld_hist"), **okw)
+        np.testing.assert_allclose(mine, want, rtol=1e-12, atol=0)
