@@ -254,16 +254,24 @@ def main():
     cuts = list(range(0, n, args.batch)) + [n]
     num_mapped_global = [0]
 
+    phase = {"begin": 0.0, "batches": 0.0, "finish": 0.0, "em": 0.0}
+
     def step(host):
+        t_a = time.perf_counter()
         ctx.map_begin(map_opts)
+        t_b = time.perf_counter()
         for a, b in zip(cuts[:-1], cuts[1:]):
             if host:
                 ctx.map_batch_ptr(h_bases.data_ptr(), h_off.data_ptr() + 8 * a, 0, 0, b - a, device=False)
             else:
                 ctx.map_batch_ptr(d_bases.data_ptr(), d_off.data_ptr() + 8 * a, 0, 0, b - a, device=True)
+        t_c = time.perf_counter()
         g = ctx.map_finish()
+        t_d = time.perf_counter()
         nm = int(g["counters"][1])               # summed over ranks by map_finish when a communicator is set
         alphas, iters, _ = ctx.em_run(h_eff, nm, em_opts)
+        t_e = time.perf_counter()
+        phase["begin"] += t_b - t_a; phase["batches"] += t_c - t_b; phase["finish"] += t_d - t_c; phase["em"] += t_e - t_d
         return g, alphas, iters
 
     def timed(host, steps):
@@ -294,7 +302,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for kk in phase:
+        phase[kk] = 0.0
     ms, launches, map_ms, em_ms, g, alphas, iters = timed(False, args.steps)
+    host_phase_ms = {kk: round(v * 1e3 / args.steps, 3) for kk, v in phase.items()}
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(1):
         step(True)
@@ -327,7 +338,7 @@ def main():
             "gpu_launches": launches,
             "detail": {"map_kernel_ms_per_step": map_ms / args.steps, "em_loop_ms_per_step": em_ms / args.steps,
                        "map_kernel_reads_per_s": n / (map_ms / args.steps / 1e3), "em_iters_per_s": args.em_iters / (em_ms / args.steps / 1e3),
-                       "n_classes": E, "nnz": nnz, "mapped": int(g["counters"][1]), "observed": int(g["counters"][0])}}
+                       "host_wall_ms_per_step": host_phase_ms, "n_classes": E, "nnz": nnz, "mapped": int(g["counters"][1]), "observed": int(g["counters"][0])}}
     # EM roofline: B_em = 12 nnz + 12 E + 32 T bytes per iteration
     b_em = 12.0 * nnz + 12.0 * E + 32.0 * T
     em_gbs = b_em * args.em_iters / (em_ms / args.steps / 1e3) / 1e9

@@ -75,18 +75,27 @@ struct DevClasses {
     uint64_t bin_cls[SFB_NBINS + 1] = {0, 0, 0, 0, 0, 0, 0};   // class index range of each bin
     uint64_t n_active = 0;
     uint64_t total_count = 0;
-    DevBuf<uint32_t> off;               // Em+1 offsets into lab/w
+    DevBuf<uint32_t> start;             // Em: first entry of the class in lab/w
+    DevBuf<uint32_t> len;               // Em: member count
     DevBuf<uint32_t> lab;               // nnzm transcript ids
     DevBuf<double>   w;                 // nnzm weights (computed per run from eff_lens)
     DevBuf<double>   cnt;               // Em counts as f64 (exact below 2^53)
+    // "canonical index" of a class = its position in the order bootstrap count vectors are indexed by:
+    // import path: the caller's order; device-finish path: multi-member classes in binned order, then the singles.
     DevBuf<uint32_t> perm;              // Em: binned position -> canonical class index
+    DevBuf<uint32_t> sgl_cls, sgl_tid;  // single-member classes: canonical index and transcript
+    uint64_t n_sgl = 0;
+    DevBuf<unsigned long long> cnt_all; // E counts in canonical order (device-finish path)
     DevBuf<double>   single;            // n_txp: count of the class {t}
-    DevBuf<uint32_t> single_cls;        // n_txp: canonical class index of {t}, or ~0u
     DevBuf<uint8_t>  active;            // n_txp
-    // canonical host copy (eq_export; bootstrap count permutation)
+    // host copy in EXPORT order (label-lexicographic for the device-finish path, caller's order for eq_import);
+    // materialised lazily by sfb_classes_host() because only eq_export / bootstrap need it
+    bool host_valid = false;
+    bool from_device = false;
     std::vector<uint64_t> h_row_ptr;
     std::vector<uint32_t> h_labels;
     std::vector<uint64_t> h_counts;
+    std::vector<uint64_t> export_to_canon;   // empty = identity
     bool ready = false;
 };
 
@@ -123,6 +132,7 @@ void sfb_map_state_free(sfb200_ctx* ctx);
 void sfb_em_extra_free(sfb200_ctx* ctx);
 int sfb_classes_from_host(sfb200_ctx* ctx, uint32_t n_txp, uint64_t E, const uint64_t* row_ptr, const uint32_t* labels,
                           const uint64_t* counts);
+int sfb_classes_host(sfb200_ctx* ctx);   // make cls.h_* valid (downloads + sorts after a device-side finish)
 
 // ---- device helpers ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -13,6 +13,7 @@
 //     so an EM iteration costs ONE grid-wide barrier and no host round trip: the whole loop is one persistent
 //     cooperative kernel (one CTA per SM).  Tile -> CTA assignment is static, so a CTA re-reads the same slice of
 //     labels / weights every iteration and small problems are served from that SM's L1.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -30,7 +31,7 @@ enum { CTL_BAR_COUNT = 0, CTL_BAR_GEN = 1, CTL_MAXREL = 2 /*4 slots*/, CTL_CSUM 
        CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_WORDS = 16 };
 
 struct EmParams {
-    const uint32_t* off; const uint32_t* lab; const double* w; const double* cnt;
+    const uint32_t* start; const uint32_t* len; const uint32_t* lab; const double* w; const double* cnt;
     const double* base;     // T: initial value of an output buffer
     double* X;              // 3*T rotating alpha buffers
     double* theta;          // T (VBEM)
@@ -95,7 +96,7 @@ __device__ __forceinline__ double sweep_tile(const EmParams& p, uint64_t tile, c
         const unsigned j = lane & (g - 1);
         uint32_t o0 = 0, n = 0;
         const bool cv = c < p.cls_start[b + 1];
-        if (cv) { o0 = __ldg(p.off + c); n = __ldg(p.off + c + 1) - o0; }
+        if (cv) { o0 = __ldg(p.start + c); n = __ldg(p.len + c); }
         bool ev = cv && j < n;
         uint32_t t = 0;
         double v = 0.0;
@@ -116,7 +117,7 @@ __device__ __forceinline__ double sweep_tile(const EmParams& p, uint64_t tile, c
         // long class (more than 32 members): the whole warp walks it twice
         const uint64_t c = p.cls_start[b] + (tile - p.tile_start[b]);
         if (c < p.cls_start[b + 1]) {
-            const uint32_t o0 = __ldg(p.off + c), n = __ldg(p.off + c + 1) - o0;
+            const uint32_t o0 = __ldg(p.start + c), n = __ldg(p.len + c);
             double denom = 0.0;
             for (uint32_t j = lane; j < n; j += 32) {
                 const double a = ld_cg_f64(in + __ldg(p.lab + o0 + j));
@@ -305,11 +306,11 @@ __global__ void k_clamp_eff(const double* __restrict__ eff_in, uint32_t T, doubl
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < T) { const double e = eff_in[i]; eff[i] = (e <= 1.0) ? 1.0 : e; }
 }
-__global__ void k_class_weights(const uint32_t* __restrict__ off, const uint32_t* __restrict__ lab, const double* __restrict__ cnt,
-                                const double* __restrict__ eff, uint64_t Em, double* __restrict__ w) {
+__global__ void k_class_weights(const uint32_t* __restrict__ start, const uint32_t* __restrict__ len, const uint32_t* __restrict__ lab,
+                                const double* __restrict__ cnt, const double* __restrict__ eff, uint64_t Em, double* __restrict__ w) {
     const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (c >= Em) return;
-    const uint32_t b = off[c], e = off[c + 1];
+    const uint32_t b = start[c], e = b + len[c];
     const double count = cnt[c];
     double wsum = 0.0;
     for (uint32_t j = b; j < e; ++j) { const double v = count / eff[lab[j]]; w[j] = v; wsum += v; }
@@ -331,7 +332,7 @@ __global__ void k_em_init(const uint8_t* __restrict__ active, const double* __re
 __global__ void k_permute_counts(const unsigned long long* __restrict__ samp, const uint32_t* __restrict__ perm, uint64_t Em,
                                  double* __restrict__ cnt) {
     const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (c < Em) cnt[c] = (double)samp[perm[c]];
+    if (c < Em) cnt[c] = (double)samp[perm ? perm[c] : c];
 }
 __global__ void k_scatter_single(const unsigned long long* __restrict__ samp, const uint32_t* __restrict__ sgl_cls,
                                  const uint32_t* __restrict__ sgl_tid, uint64_t n_sgl, double* __restrict__ single) {
@@ -347,9 +348,7 @@ inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned)((n + 
 // host side
 // ======================================================================================================================
 
-struct EmExtra {   // device arrays only the inference code needs; owned by DevClasses' lifetime through ctx
-    DevBuf<uint32_t> sgl_cls, sgl_tid;
-    uint64_t n_sgl = 0;
+struct EmExtra {   // per-sample device arrays of the bootstrap path
     DevBuf<double> cnt_s;                 // per-sample binned counts
     DevBuf<double> single_s;              // per-sample single-member vector
     DevBuf<unsigned long long> samp;      // canonical-order per-sample counts on the device
@@ -361,7 +360,7 @@ static EmExtra* g_extra_for(sfb200_ctx* c) {
 void sfb_em_extra_free(sfb200_ctx* c) {
     EmExtra* e = static_cast<EmExtra*>(c->em_extra);
     if (!e) return;
-    e->sgl_cls.release(); e->sgl_tid.release(); e->cnt_s.release(); e->single_s.release(); e->samp.release();
+    e->cnt_s.release(); e->single_s.release(); e->samp.release();
     delete e;
     c->em_extra = nullptr;
 }
@@ -378,6 +377,8 @@ int sfb_classes_from_host(sfb200_ctx* c, uint32_t n_txp, uint64_t E, const uint6
     if (E == 0) k.h_row_ptr.assign(1, 0);
     k.h_labels.assign(labels, labels + nnz);
     k.h_counts.assign(counts, counts + E);
+    k.export_to_canon.clear();
+    k.host_valid = true; k.from_device = false;
 
     auto bin_of = [](uint64_t n) { return n <= 2 ? 0 : n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 3 : n <= 32 ? 4 : 5; };
     uint64_t bin_n[SFB_NBINS] = {0, 0, 0, 0, 0, 0};
@@ -394,7 +395,7 @@ int sfb_classes_from_host(sfb200_ctx* c, uint32_t n_txp, uint64_t E, const uint6
     for (int b = 0; b < SFB_NBINS; ++b) k.bin_cls[b + 1] = k.bin_cls[b] + bin_n[b];
     k.Em = k.bin_cls[SFB_NBINS]; k.nnzm = nnzm;
 
-    std::vector<uint32_t> perm(k.Em), off(k.Em + 1), lab(nnzm), sgl_cls(n_sgl), sgl_tid(n_sgl);
+    std::vector<uint32_t> perm(k.Em), start(k.Em), len(k.Em), lab(nnzm), sgl_cls(n_sgl), sgl_tid(n_sgl);
     std::vector<double> cnt(k.Em), single(n_txp, 0.0);
     std::vector<uint8_t> active(n_txp, 0);
     uint64_t cur[SFB_NBINS];
@@ -413,32 +414,70 @@ int sfb_classes_from_host(sfb200_ctx* c, uint32_t n_txp, uint64_t E, const uint6
     uint64_t o = 0;
     for (uint64_t i = 0; i < k.Em; ++i) {
         const uint64_t e = perm[i];
-        off[i] = static_cast<uint32_t>(o);
+        start[i] = static_cast<uint32_t>(o);
+        len[i] = static_cast<uint32_t>(row_ptr[e + 1] - row_ptr[e]);
         cnt[i] = static_cast<double>(counts[e]);
         for (uint64_t j = row_ptr[e]; j < row_ptr[e + 1]; ++j) lab[o++] = labels[j];
     }
-    off[k.Em] = static_cast<uint32_t>(o);
     uint64_t n_active = 0;
     for (uint64_t i = 0; i < nnz; ++i) if (!active[labels[i]]) { active[labels[i]] = 1; ++n_active; }   // :774-782
     k.n_active = n_active;
 
     cudaSetDevice(c->device);
-    EmExtra* x = g_extra_for(c);
-    x->n_sgl = n_sgl;
-    SFB_CUDA(c, k.off.reserve(k.Em + 1)); SFB_CUDA(c, k.lab.reserve(nnzm)); SFB_CUDA(c, k.w.reserve(nnzm));
+    k.n_sgl = n_sgl;
+    SFB_CUDA(c, k.start.reserve(k.Em)); SFB_CUDA(c, k.len.reserve(k.Em)); SFB_CUDA(c, k.lab.reserve(nnzm)); SFB_CUDA(c, k.w.reserve(nnzm));
     SFB_CUDA(c, k.cnt.reserve(k.Em)); SFB_CUDA(c, k.perm.reserve(k.Em)); SFB_CUDA(c, k.single.reserve(n_txp));
-    SFB_CUDA(c, k.active.reserve(n_txp)); SFB_CUDA(c, x->sgl_cls.reserve(n_sgl)); SFB_CUDA(c, x->sgl_tid.reserve(n_sgl));
+    SFB_CUDA(c, k.active.reserve(n_txp)); SFB_CUDA(c, k.sgl_cls.reserve(n_sgl)); SFB_CUDA(c, k.sgl_tid.reserve(n_sgl));
     cudaStream_t s = c->stream;
-    SFB_CUDA(c, cudaMemcpyAsync(k.off.p, off.data(), (k.Em + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(k.start.p, start.data(), k.Em * 4, cudaMemcpyHostToDevice, s));
+    if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(k.len.p, len.data(), k.Em * 4, cudaMemcpyHostToDevice, s));
     if (nnzm) SFB_CUDA(c, cudaMemcpyAsync(k.lab.p, lab.data(), nnzm * 4, cudaMemcpyHostToDevice, s));
     if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(k.cnt.p, cnt.data(), k.Em * 8, cudaMemcpyHostToDevice, s));
     if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(k.perm.p, perm.data(), k.Em * 4, cudaMemcpyHostToDevice, s));
     if (n_txp) SFB_CUDA(c, cudaMemcpyAsync(k.single.p, single.data(), n_txp * 8ull, cudaMemcpyHostToDevice, s));
     if (n_txp) SFB_CUDA(c, cudaMemcpyAsync(k.active.p, active.data(), n_txp, cudaMemcpyHostToDevice, s));
-    if (n_sgl) SFB_CUDA(c, cudaMemcpyAsync(x->sgl_cls.p, sgl_cls.data(), n_sgl * 4, cudaMemcpyHostToDevice, s));
-    if (n_sgl) SFB_CUDA(c, cudaMemcpyAsync(x->sgl_tid.p, sgl_tid.data(), n_sgl * 4, cudaMemcpyHostToDevice, s));
+    if (n_sgl) SFB_CUDA(c, cudaMemcpyAsync(k.sgl_cls.p, sgl_cls.data(), n_sgl * 4, cudaMemcpyHostToDevice, s));
+    if (n_sgl) SFB_CUDA(c, cudaMemcpyAsync(k.sgl_tid.p, sgl_tid.data(), n_sgl * 4, cudaMemcpyHostToDevice, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));   // the host vectors die here
     k.ready = true;
+    return SFB200_OK;
+}
+
+// Host copy of the classes in export order.  After a device-side finish the classes exist only on the device, in binned
+// order; eq_export (aux/eq_classes.txt, tests) wants them label-lexicographic, so download and sort here, on demand.
+int sfb_classes_host(sfb200_ctx* c) {
+    DevClasses& k = c->cls;
+    if (k.host_valid) return SFB200_OK;
+    if (!k.from_device) SFB_FAIL(c, SFB200_EINVAL, "classes have no host copy");
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> start(k.Em), len(k.Em), lab(k.nnzm ? k.nnzm : 1), sgl_tid(k.n_sgl);
+    std::vector<uint64_t> cnt_all(k.E);
+    cudaStream_t s = c->stream;
+    if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(start.data(), k.start.p, k.Em * 4, cudaMemcpyDeviceToHost, s));
+    if (k.Em) SFB_CUDA(c, cudaMemcpyAsync(len.data(), k.len.p, k.Em * 4, cudaMemcpyDeviceToHost, s));
+    if (k.nnzm) SFB_CUDA(c, cudaMemcpyAsync(lab.data(), k.lab.p, k.nnzm * 4, cudaMemcpyDeviceToHost, s));
+    if (k.n_sgl) SFB_CUDA(c, cudaMemcpyAsync(sgl_tid.data(), k.sgl_tid.p, k.n_sgl * 4, cudaMemcpyDeviceToHost, s));
+    if (k.E) SFB_CUDA(c, cudaMemcpyAsync(cnt_all.data(), k.cnt_all.p, k.E * 8, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    auto lab_of = [&](uint64_t ci, uint32_t& n) -> const uint32_t* {
+        if (ci < k.Em) { n = len[ci]; return lab.data() + start[ci]; }
+        n = 1; return sgl_tid.data() + (ci - k.Em);
+    };
+    std::vector<uint64_t> order(k.E);
+    for (uint64_t i = 0; i < k.E; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+        uint32_t na, nb; const uint32_t* pa = lab_of(a, na); const uint32_t* pb = lab_of(b, nb);
+        return std::lexicographical_compare(pa, pa + na, pb, pb + nb);
+    });
+    k.h_row_ptr.assign(k.E + 1, 0); k.h_counts.resize(k.E); k.h_labels.resize(k.nnz);
+    uint64_t z = 0;
+    for (uint64_t e = 0; e < k.E; ++e) {
+        uint32_t n; const uint32_t* pl = lab_of(order[e], n);
+        std::memcpy(k.h_labels.data() + z, pl, n * 4ull);
+        z += n; k.h_row_ptr[e + 1] = z; k.h_counts[e] = cnt_all[order[e]];
+    }
+    k.export_to_canon = order;
+    k.host_valid = true;
     return SFB200_OK;
 }
 
@@ -453,6 +492,7 @@ extern "C" int sfb200_eq_import(sfb200_ctx* c, uint32_t n_txp, uint64_t n_classe
 extern "C" int sfb200_eq_export(sfb200_ctx* c, uint64_t* row_ptr, uint32_t* labels, uint64_t* counts) {
     if (!c) return SFB200_EINVAL;
     if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "eq_export: no classes (call map_finish or eq_import first)");
+    { const int rc = sfb_classes_host(c); if (rc) return rc; }
     const DevClasses& k = c->cls;
     if (row_ptr) std::memcpy(row_ptr, k.h_row_ptr.data(), (k.E + 1) * 8);
     if (labels && k.nnz) std::memcpy(labels, k.h_labels.data(), k.nnz * 4);
@@ -579,7 +619,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     c->launches++;
     if (k.Em) {
         // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
-        k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(k.off.p, k.lab.p, k.cnt.p, c->eff.p, k.Em, k.w.p);
+        k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(k.start.p, k.len.p, k.lab.p, k.cnt.p, c->eff.p, k.Em, k.w.p);
         c->launches++;
     }
     uint64_t n_active = k.n_active;
@@ -597,7 +637,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
 
     EmParams p;
     std::memset(&p, 0, sizeof(p));
-    p.off = k.off.p; p.lab = k.lab.p; p.w = k.w.p; p.cnt = d_cnt; p.base = c->em_base.p; p.X = c->em_alpha.p;
+    p.start = k.start.p; p.len = k.len.p; p.lab = k.lab.p; p.w = k.w.p; p.cnt = d_cnt; p.base = c->em_base.p; p.X = c->em_alpha.p;
     p.theta = c->em_theta.p; p.T = T;
     uint64_t tiles = 0;
     for (int b = 0; b < SFB_NBINS; ++b) {
@@ -682,8 +722,8 @@ int sfb_bootstrap_em_device(sfb200_ctx* c, const double* eff_lens, uint32_t n_tx
     SFB_CUDA(c, x->cnt_s.reserve(k.Em));
     SFB_CUDA(c, x->single_s.reserve(n_txp));
     SFB_CUDA(c, cudaMemsetAsync(x->single_s.p, 0, n_txp * 8ull, s));
-    if (k.Em) { k_permute_counts<<<grid_for(k.Em, 256), 256, 0, s>>>(d_samp, k.perm.p, k.Em, x->cnt_s.p); c->launches++; }
-    if (x->n_sgl) { k_scatter_single<<<grid_for(x->n_sgl, 256), 256, 0, s>>>(d_samp, x->sgl_cls.p, x->sgl_tid.p, x->n_sgl, x->single_s.p); c->launches++; }
+    if (k.Em) { k_permute_counts<<<grid_for(k.Em, 256), 256, 0, s>>>(d_samp, k.from_device ? nullptr : k.perm.p, k.Em, x->cnt_s.p); c->launches++; }
+    if (k.n_sgl) { k_scatter_single<<<grid_for(k.n_sgl, 256), 256, 0, s>>>(d_samp, k.sgl_cls.p, k.sgl_tid.p, k.n_sgl, x->single_s.p); c->launches++; }
     uint32_t iters = 0; double mrd = 0.0;
     LoopSpec spec{true, 0};
     const int rc = em_common(c, eff_lens, n_txp, static_cast<double>(total), opts, x->cnt_s.p, x->single_s.p, spec, alphas_out,
@@ -703,6 +743,15 @@ extern "C" int sfb200_bootstrap_em(sfb200_ctx* c, const double* eff_lens, uint32
     SFB_CUDA(c, x->samp.reserve(E));
     uint64_t total = 0;
     for (uint64_t e = 0; e < E; ++e) total += samp_counts[e];
-    SFB_CUDA(c, cudaMemcpyAsync(x->samp.p, samp_counts, E * 8, cudaMemcpyHostToDevice, c->stream));
+    { const int rc = sfb_classes_host(c); if (rc) return rc; }      // samp_counts come in eq_export order
+    std::vector<uint64_t> canon;
+    const uint64_t* src = samp_counts;
+    if (!c->cls.export_to_canon.empty()) {
+        canon.resize(E);
+        for (uint64_t e = 0; e < E; ++e) canon[c->cls.export_to_canon[e]] = samp_counts[e];
+        src = canon.data();
+    }
+    SFB_CUDA(c, cudaMemcpyAsync(x->samp.p, src, E * 8, cudaMemcpyHostToDevice, c->stream));
+    SFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return sfb_bootstrap_em_device(c, eff_lens, n_txp, x->samp.p, total, opts, alphas_out, iters_out);
 }

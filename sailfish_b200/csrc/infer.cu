@@ -80,10 +80,17 @@ extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint3
     // denominator is positive (see oracle note); all classes are valid.
     const uint64_t totalCount = k.total_count;                                     // :662-674
     const double floatCount = static_cast<double>(totalCount);
+    // class counts in the order the per-sample count vectors are indexed by (canonical order)
+    std::vector<uint64_t> canon_counts(E);
+    if (k.from_device) {
+        SFB_CUDA(c, cudaMemcpy(canon_counts.data(), k.cnt_all.p, E * 8, cudaMemcpyDeviceToHost));
+    } else {
+        canon_counts = k.h_counts;
+    }
     std::vector<double> z(E + 1);
     double sum = 0.0;
     z[0] = 0.0;
-    for (uint64_t e = 0; e < E; ++e) { sum += static_cast<double>(k.h_counts[e]) / floatCount; z[e + 1] = sum; }   // :676-680, MultinomialSampler.hpp:30-34
+    for (uint64_t e = 0; e < E; ++e) { sum += static_cast<double>(canon_counts[e]) / floatCount; z[e + 1] = sum; }   // :676-680, MultinomialSampler.hpp:30-34
     cudaStream_t s = c->stream;
     DevBuf<double> d_z; DevBuf<unsigned long long> d_samp;
     SFB_CUDA(c, d_z.reserve(E + 1)); SFB_CUDA(c, d_samp.reserve(E));

@@ -472,13 +472,85 @@ __global__ void k_fld_select(const int16_t* __restrict__ fld_val, uint64_t n_rea
     if (threadIdx.x == 0) *remaining = s_rem < 0 ? 0 : s_rem;
 }
 
+// ---- eqBuilder.finish() on the device ---------------------------------------------------------------------------------------
+// bin of a class by member count: 0..5 as in DevClasses (g = 2,4,8,16,32 lanes, then "long"), 6 = single-member
+enum { FIN_CLS = 0, FIN_NNZ = 8, FIN_CUR_CLS = 16, FIN_CUR_NNZ = 24, FIN_ACTIVE = 32, FIN_TOTAL = 33, FIN_WORDS = 40 };
+__device__ __forceinline__ int fin_bin(uint32_t n) { return n == 1 ? SFB_NBINS : n <= 2 ? 0 : n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 3 : n <= 32 ? 4 : 5; }
+
+__global__ void k_eq_count(const unsigned long long* __restrict__ slot, uint64_t n_slots, unsigned long long* __restrict__ fin) {
+    __shared__ unsigned long long s_cls[SFB_NBINS + 1], s_nnz[SFB_NBINS + 1];
+    if (threadIdx.x <= SFB_NBINS) { s_cls[threadIdx.x] = 0; s_nnz[threadIdx.x] = 0; }
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long sv = slot[i];
+        if (sv) {
+            const uint32_t n = (uint32_t)((sv >> 20) & 1023);
+            const int b = fin_bin(n);
+            atomicAdd(&s_cls[b], 1ULL); atomicAdd(&s_nnz[b], (unsigned long long)n);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x <= SFB_NBINS && s_cls[threadIdx.x]) {
+        atomicAdd(fin + FIN_CLS + threadIdx.x, s_cls[threadIdx.x]);
+        atomicAdd(fin + FIN_NNZ + threadIdx.x, s_nnz[threadIdx.x]);
+    }
+}
+
+struct FinParams {
+    uint64_t cls_start[SFB_NBINS + 1], nnz_start[SFB_NBINS + 1];
+    uint64_t Em;
+    const unsigned long long* slot; const unsigned long long* count; const uint32_t* arena; uint64_t n_slots;
+    unsigned long long* fin;
+    uint32_t* start; uint32_t* len; uint32_t* lab; double* cnt; unsigned long long* cnt_all; double* single; uint8_t* active;
+    uint32_t* sgl_cls; uint32_t* sgl_tid;
+};
+
+// Every occupied slot claims a class position (and label space) inside its bin with an atomic cursor, then copies itself.
+// The order inside a bin is whatever the atomics produce; the E-step/M-step sums are order-free (atomic adds) anyway.
+__global__ void k_eq_fill(const FinParams p) {
+    unsigned long long total = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long sv = p.slot[i];
+        if (!sv) continue;
+        const uint32_t n = (uint32_t)((sv >> 20) & 1023);
+        const uint32_t* a = p.arena + (sv >> 30);
+        const unsigned long long cn = p.count[i];
+        total += cn;
+        const int b = fin_bin(n);
+        const uint64_t pos = atomicAdd(p.fin + FIN_CUR_CLS + b, 1ULL);
+        if (b == SFB_NBINS) {
+            const uint32_t t = a[0];
+            p.sgl_tid[pos] = t; p.sgl_cls[pos] = (uint32_t)(p.Em + pos);
+            p.cnt_all[p.Em + pos] = cn;
+            atomicAdd(p.single + t, (double)cn);
+            p.active[t] = 1;
+        } else {
+            const uint64_t c = p.cls_start[b] + pos;
+            const uint64_t o = p.nnz_start[b] + atomicAdd(p.fin + FIN_CUR_NNZ + b, (unsigned long long)n);
+            p.start[c] = (uint32_t)o; p.len[c] = n; p.cnt[c] = (double)cn; p.cnt_all[c] = cn;
+            for (uint32_t j = 0; j < n; ++j) { const uint32_t t = a[j]; p.lab[o + j] = t; p.active[t] = 1; }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+    if ((threadIdx.x & 31u) == 0 && total) atomicAdd(p.fin + FIN_TOTAL, total);
+}
+
+__global__ void k_count_active(const uint8_t* __restrict__ active, uint32_t T, unsigned long long* __restrict__ out) {
+    unsigned long long n = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) n += active[i];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) n += __shfl_xor_sync(0xffffffffu, n, m);
+    if ((threadIdx.x & 31u) == 0 && n) atomicAdd(out, n);
+}
+
 }  // namespace
 
 // ======================================================================================================================
 struct MapState {
     sfb200_map_opts o;
     bool begun = false;
-    DevBuf<unsigned long long> slot, count, cursor, counters, next_read, scratch;
+    DevBuf<unsigned long long> slot, count, cursor, counters, next_read, scratch, fin;
     DevBuf<uint32_t> arena;
     DevBuf<unsigned int> fld_hist;
     DevBuf<int> remaining;
@@ -497,7 +569,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     MapState* m = c->map;
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
-    m->scratch.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release();
+    m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release();
     m->bases1.release(); m->bases2.release(); m->off1.release(); m->off2.release();
     for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
     delete m;
@@ -651,30 +723,52 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
     if (counters) for (int i = 0; i < 6; ++i) counters[i] = h_counters[i];
     if (fld_hist) std::memcpy(fld_hist, h_fld.data(), h_fld.size() * 4);
 
-    // eqBuilder.finish() (EquivalenceClassBuilder.hpp:64-80): flatten the table.  Order is canonical: label-lexicographic.
+    // eqBuilder.finish() (EquivalenceClassBuilder.hpp:64-80): flatten the table -- on the device, straight into the binned
+    // layout the inference kernels read; nothing but 16 counters crosses PCIe.
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
-    const uint64_t used = h_cursor[0];
-    std::vector<unsigned long long> h_slot(n_slots), h_count(n_slots);
-    std::vector<uint32_t> h_arena(used ? used : 1);
-    SFB_CUDA(c, cudaMemcpyAsync(h_slot.data(), m->slot.p, n_slots * 8, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaMemcpyAsync(h_count.data(), m->count.p, n_slots * 8, cudaMemcpyDeviceToHost, s));
-    if (used) SFB_CUDA(c, cudaMemcpyAsync(h_arena.data(), m->arena.p, used * 4, cudaMemcpyDeviceToHost, s));
+    DevClasses& k = c->cls;
+    k.ready = false; k.host_valid = false; k.from_device = true; k.export_to_canon.clear();
+    k.h_row_ptr.clear(); k.h_labels.clear(); k.h_counts.clear();
+    const uint32_t T = c->index.n_txp;
+    SFB_CUDA(c, m->fin.reserve(FIN_WORDS));
+    SFB_CUDA(c, cudaMemsetAsync(m->fin.p, 0, FIN_WORDS * 8, s));
+    const unsigned fgrid = (unsigned)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)c->num_sms * 16);
+    k_eq_count<<<fgrid, 256, 0, s>>>(m->slot.p, n_slots, m->fin.p);
+    c->launches++;
+    unsigned long long h_fin[FIN_WORDS];
+    SFB_CUDA(c, cudaMemcpyAsync(h_fin, m->fin.p, sizeof(h_fin), cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
-    std::vector<uint64_t> ids;
-    ids.reserve(h_cursor[1]);
-    for (uint64_t i = 0; i < n_slots; ++i) if (h_slot[i]) ids.push_back(i);
-    auto lab_of = [&](uint64_t i, uint32_t& len) { len = static_cast<uint32_t>((h_slot[i] >> 20) & 1023); return h_arena.data() + (h_slot[i] >> 30); };
-    std::sort(ids.begin(), ids.end(), [&](uint64_t a, uint64_t b) {
-        uint32_t la, lb2; const uint32_t* pa = lab_of(a, la); const uint32_t* pb = lab_of(b, lb2);
-        return std::lexicographical_compare(pa, pa + la, pb, pb + lb2);
-    });
-    const uint64_t E = ids.size();
-    std::vector<uint64_t> row_ptr(E + 1, 0), cnts(E);
-    uint64_t z = 0;
-    for (uint64_t e = 0; e < E; ++e) { uint32_t len; lab_of(ids[e], len); z += len; row_ptr[e + 1] = z; cnts[e] = h_count[ids[e]]; }
-    std::vector<uint32_t> labels(z ? z : 1);
-    for (uint64_t e = 0; e < E; ++e) { uint32_t len; const uint32_t* pl = lab_of(ids[e], len); std::memcpy(labels.data() + row_ptr[e], pl, len * 4ull); }
+    uint64_t cls_start[SFB_NBINS + 2], nnz_start[SFB_NBINS + 2];
+    cls_start[0] = 0; nnz_start[0] = 0;
+    for (int b = 0; b <= SFB_NBINS; ++b) { cls_start[b + 1] = cls_start[b] + h_fin[FIN_CLS + b]; nnz_start[b + 1] = nnz_start[b] + h_fin[FIN_NNZ + b]; }
+    const uint64_t Em = cls_start[SFB_NBINS], nnzm = nnz_start[SFB_NBINS];
+    const uint64_t n_sgl = h_fin[FIN_CLS + SFB_NBINS];
+    const uint64_t E = Em + n_sgl, z = nnzm + n_sgl;
+    if (nnzm >= 0xFFFFFFFFull) SFB_FAIL(c, SFB200_EINVAL, "more than 2^32 label entries");
+    k.n_txp = T; k.E = E; k.nnz = z; k.Em = Em; k.nnzm = nnzm; k.n_sgl = n_sgl;
+    for (int b = 0; b <= SFB_NBINS; ++b) k.bin_cls[b] = cls_start[b];
+    SFB_CUDA(c, k.start.reserve(Em)); SFB_CUDA(c, k.len.reserve(Em)); SFB_CUDA(c, k.lab.reserve(nnzm)); SFB_CUDA(c, k.w.reserve(nnzm));
+    SFB_CUDA(c, k.cnt.reserve(Em)); SFB_CUDA(c, k.cnt_all.reserve(E)); SFB_CUDA(c, k.single.reserve(T)); SFB_CUDA(c, k.active.reserve(T));
+    SFB_CUDA(c, k.sgl_cls.reserve(n_sgl)); SFB_CUDA(c, k.sgl_tid.reserve(n_sgl));
+    SFB_CUDA(c, cudaMemsetAsync(k.single.p, 0, T * 8ull, s));
+    SFB_CUDA(c, cudaMemsetAsync(k.active.p, 0, T, s));
+    FinParams fp;
+    for (int b = 0; b <= SFB_NBINS; ++b) { fp.cls_start[b] = cls_start[b]; fp.nnz_start[b] = nnz_start[b]; }
+    fp.Em = Em;
+    fp.slot = m->slot.p; fp.count = m->count.p; fp.arena = m->arena.p; fp.n_slots = n_slots; fp.fin = m->fin.p;
+    fp.start = k.start.p; fp.len = k.len.p; fp.lab = k.lab.p; fp.cnt = k.cnt.p; fp.cnt_all = k.cnt_all.p; fp.single = k.single.p;
+    fp.active = k.active.p; fp.sgl_cls = k.sgl_cls.p; fp.sgl_tid = k.sgl_tid.p;
+    k_eq_fill<<<fgrid, 256, 0, s>>>(fp);
+    c->launches++;
+    k_count_active<<<(unsigned)std::min<uint64_t>((T + 255) / 256, 1024), 256, 0, s>>>(k.active.p, T, m->fin.p + FIN_ACTIVE);
+    c->launches++;
+    SFB_CUDA(c, cudaGetLastError());
+    SFB_CUDA(c, cudaMemcpyAsync(h_fin, m->fin.p, sizeof(h_fin), cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    k.n_active = h_fin[FIN_ACTIVE];
+    k.total_count = h_fin[FIN_TOTAL];
     if (n_classes) *n_classes = E;
     if (nnz) *nnz = z;
-    return sfb_classes_from_host(c, c->index.n_txp, E, row_ptr.data(), labels.data(), cnts.data());
+    k.ready = true;
+    return SFB200_OK;
 }
