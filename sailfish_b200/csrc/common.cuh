@@ -54,12 +54,16 @@ struct DevIndex {
     DevBuf<uint64_t> words;      // 2-bit text, 32 bases per word, base p at bits 2*(p%32)
     DevBuf<uint64_t> txp_start;  // n_txp+1
     DevBuf<uint32_t> txp_len;    // n_txp
-    DevBuf<uint32_t> sa_pos;     // n_sa, sorted by (k-mer value, position)
-    DevBuf<uint32_t> sa_tid;     // n_sa
+    DevBuf<uint64_t> txp_end;    // n_txp: txp_start[t] + txp_len[t]
+    DevBuf<uint2> sa;            // n_sa entries {position, transcript}, sorted by (k-mer value, position)
     DevBuf<uint4> table;         // {key lo, key hi, lb, cnt}; empty = cnt 0
+    // presence filter over the distinct k-mers (blocked Bloom filter, one 32-byte block per k-mer, 3 bits): answers
+    // "certainly absent" for most k-mers of the wrong read orientation without touching the table; sized to stay in L2
+    DevBuf<uint32_t> bloom;
+    uint64_t bloom_blocks = 0;   // power of two; block = 8 x u32
     bool ready = false;
     size_t hbm_bytes() const {
-        return words.bytes() + txp_start.bytes() + txp_len.bytes() + sa_pos.bytes() + sa_tid.bytes() + table.bytes();
+        return words.bytes() + txp_start.bytes() + txp_len.bytes() + txp_end.bytes() + sa.bytes() + table.bytes() + bloom.bytes();
     }
 };
 
@@ -199,6 +203,14 @@ __host__ __device__ __forceinline__ uint64_t xxh64_words(F get, uint32_t n, uint
 }
 
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
+
+// presence filter addressing shared by the index builder and the mapper: block from the high hash bits, three bit
+// positions inside the 256-bit block from disjoint hash fields (the table slot uses the low bits of the same hash)
+__device__ __forceinline__ uint64_t bloom_block(uint64_t h, uint64_t n_blocks) { return (h >> 34) & (n_blocks - 1); }
+__device__ __forceinline__ void bloom_bits(uint64_t h, uint32_t& w0, uint32_t& m0, uint32_t& w1, uint32_t& m1, uint32_t& w2, uint32_t& m2) {
+    const uint32_t a = (uint32_t)(h >> 10) & 255u, b = (uint32_t)(h >> 18) & 255u, c = (uint32_t)(h >> 26) & 255u;
+    w0 = a >> 5; m0 = 1u << (a & 31); w1 = b >> 5; m1 = 1u << (b & 31); w2 = c >> 5; m2 = 1u << (c & 31);
+}
 
 // digamma for x > 0: recurrence up to x >= 12, then the asymptotic series (same expansion as the oracle's
 // stand-in for boost::math::digamma; checked against scipy in tests/)

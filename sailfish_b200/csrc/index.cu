@@ -11,6 +11,8 @@
 // are CUB's (part of the CUDA toolkit); everything else is hand-written.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -73,21 +75,36 @@ __global__ void k_emit_kmers(const uint64_t* __restrict__ words, const uint64_t*
 
 __global__ void k_tid_and_heads(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos,
                                 const uint64_t* __restrict__ txp_start, uint32_t n_txp, uint64_t n_sa,
-                                uint32_t* __restrict__ tid, uint8_t* __restrict__ head) {
+                                uint2* __restrict__ sa, uint8_t* __restrict__ head) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n_sa) return;
-    tid[i] = txp_of(txp_start, n_txp, pos[i]);
+    const uint32_t p = pos[i];
+    sa[i] = make_uint2(p, txp_of(txp_start, n_txp, p));
     head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
+__global__ void k_txp_end(const uint64_t* __restrict__ txp_start, const uint32_t* __restrict__ txp_len, uint32_t n_txp,
+                          uint64_t* __restrict__ txp_end) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_txp) txp_end[t] = txp_start[t] + txp_len[t];
+}
+
 __global__ void k_table_insert(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ heads, uint64_t n_kmers,
-                               uint64_t n_sa, uint4* __restrict__ table, uint64_t mask, unsigned int* __restrict__ max_bucket) {
+                               uint64_t n_sa, uint4* __restrict__ table, uint64_t mask, unsigned int* __restrict__ max_bucket,
+                               uint32_t* __restrict__ bloom, uint64_t bloom_blocks) {
     const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n_kmers) return;
     const uint32_t lb = heads[j];
     const uint32_t cnt = static_cast<uint32_t>((j + 1 < n_kmers ? heads[j + 1] : n_sa) - lb);
     const uint64_t km = keys[lb];
-    uint64_t h = xxh64_u64(km, 0) & mask;
+    const uint64_t hh = xxh64_u64(km, 0);
+    {
+        uint32_t w0, m0, w1, m1, w2, m2;
+        bloom_bits(hh, w0, m0, w1, m1, w2, m2);
+        uint32_t* blk = bloom + bloom_block(hh, bloom_blocks) * 8;
+        atomicOr(blk + w0, m0); atomicOr(blk + w1, m1); atomicOr(blk + w2, m2);
+    }
+    uint64_t h = hh & mask;
     unsigned long long* slots = reinterpret_cast<unsigned long long*>(table);
     for (;;) {
         const unsigned long long prev = atomicCAS(&slots[2 * h], ~0ULL, (unsigned long long)km);
@@ -132,10 +149,10 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
     ix.k = k; ix.n_txp = n_txp; ix.text_len = tot; ix.n_sa = nsa;
     const uint64_t n_words = tot / 32 + 2;
 
-    DevBuf<char> d_seq; DevBuf<uint64_t> d_off, d_vstart, d_keys, d_keys2; DevBuf<uint32_t> d_pos2, d_heads; DevBuf<uint8_t> d_head, d_tmp;
+    DevBuf<char> d_seq; DevBuf<uint64_t> d_off, d_vstart, d_keys, d_keys2; DevBuf<uint32_t> d_pos2, d_heads, d_pos_sorted; DevBuf<uint8_t> d_head, d_tmp;
     DevBuf<unsigned int> d_scalar;
     auto cleanup = [&]() { d_seq.release(); d_off.release(); d_vstart.release(); d_keys.release(); d_keys2.release();
-                           d_pos2.release(); d_heads.release(); d_head.release(); d_tmp.release(); d_scalar.release(); };
+                           d_pos2.release(); d_heads.release(); d_head.release(); d_tmp.release(); d_scalar.release(); d_pos_sorted.release(); };
 #define IDX_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return SFB200_ECUDA; } } while (0)
 
     IDX_CUDA(d_seq.reserve(src_end + 1));
@@ -156,21 +173,25 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
     d_seq.release();
 
     ix.n_kmers = 0; ix.max_bucket = 0;
-    IDX_CUDA(ix.sa_pos.reserve(nsa)); IDX_CUDA(ix.sa_tid.reserve(nsa));
+    IDX_CUDA(ix.sa.reserve(nsa));
+    IDX_CUDA(ix.txp_end.reserve(n_txp));
+    k_txp_end<<<gridn(n_txp, 256), 256, 0, s>>>(ix.txp_start.p, ix.txp_len.p, n_txp, ix.txp_end.p);
+    c->launches++;
     if (nsa > 0) {
+        IDX_CUDA(d_pos_sorted.reserve(nsa));
         IDX_CUDA(d_keys.reserve(nsa)); IDX_CUDA(d_keys2.reserve(nsa)); IDX_CUDA(d_pos2.reserve(nsa));
         k_emit_kmers<<<gridn(nsa, 256), 256, 0, s>>>(ix.words.p, ix.txp_start.p, d_vstart.p, n_txp, k, nsa, d_keys.p, d_pos2.p);
         c->launches++;
         // stable LSD radix sort by k-mer value: entries were emitted in position order, so ties stay position-sorted
         size_t tmp_bytes = 0;
-        IDX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.p, d_keys2.p, d_pos2.p, ix.sa_pos.p, nsa, 0, 2 * k, s));
+        IDX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.p, d_keys2.p, d_pos2.p, d_pos_sorted.p, nsa, 0, 2 * k, s));
         IDX_CUDA(d_tmp.reserve(tmp_bytes));
-        IDX_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.p, d_keys2.p, d_pos2.p, ix.sa_pos.p, nsa, 0, 2 * k, s));
+        IDX_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.p, d_keys2.p, d_pos2.p, d_pos_sorted.p, nsa, 0, 2 * k, s));
         c->launches++;
         IDX_CUDA(cudaStreamSynchronize(s));
         d_keys.release(); d_pos2.release();
         IDX_CUDA(d_head.reserve(nsa));
-        k_tid_and_heads<<<gridn(nsa, 256), 256, 0, s>>>(d_keys2.p, ix.sa_pos.p, ix.txp_start.p, n_txp, nsa, ix.sa_tid.p, d_head.p);
+        k_tid_and_heads<<<gridn(nsa, 256), 256, 0, s>>>(d_keys2.p, d_pos_sorted.p, ix.txp_start.p, n_txp, nsa, ix.sa.p, d_head.p);
         c->launches++;
         // bucket heads = indices whose k-mer differs from the previous entry's
         IDX_CUDA(d_heads.reserve(nsa));
@@ -190,11 +211,18 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
     while (slots < 2 * ix.n_kmers) slots <<= 1;
     ix.table_slots = slots;
     IDX_CUDA(ix.table.reserve(slots));
+    // presence filter: >= 8 bits per k-mer, capped at 64 MB (2^21 blocks of 256 bits) so that it stays L2-resident
+    uint64_t bblocks = 64;
+    while (bblocks * 256 < 8 * ix.n_kmers && bblocks < (1ull << 21)) bblocks <<= 1;
+    if (const char* e = getenv("SFB200_BLOOM_LOG2_BLOCKS")) bblocks = 1ull << std::max(6, std::min(26, atoi(e)));
+    ix.bloom_blocks = bblocks;
+    IDX_CUDA(ix.bloom.reserve(bblocks * 8));
+    IDX_CUDA(cudaMemsetAsync(ix.bloom.p, 0, bblocks * 32, s));
     k_table_clear<<<gridn(slots, 256), 256, 0, s>>>(ix.table.p, slots);
     c->launches++;
     if (ix.n_kmers) {
         IDX_CUDA(cudaMemsetAsync(d_scalar.p + 1, 0, 4, s));
-        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1);
+        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1, ix.bloom.p, bblocks);
         c->launches++;
         unsigned int mb = 0;
         IDX_CUDA(cudaMemcpyAsync(&mb, d_scalar.p + 1, 4, cudaMemcpyDeviceToHost, s));
@@ -225,8 +253,8 @@ extern "C" int sfb200_index_export(sfb200_ctx* c, uint64_t* words, uint32_t* sa_
     if (!ix.ready) SFB_FAIL(c, SFB200_EINVAL, "index_export: no index");
     cudaSetDevice(c->device);
     if (words) SFB_CUDA(c, cudaMemcpyAsync(words, ix.words.p, (ix.text_len / 32 + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (sa_pos && ix.n_sa) SFB_CUDA(c, cudaMemcpyAsync(sa_pos, ix.sa_pos.p, ix.n_sa * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (sa_tid && ix.n_sa) SFB_CUDA(c, cudaMemcpyAsync(sa_tid, ix.sa_tid.p, ix.n_sa * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (sa_pos && ix.n_sa) SFB_CUDA(c, cudaMemcpy2DAsync(sa_pos, 4, &ix.sa.p->x, 8, 4, ix.n_sa, cudaMemcpyDeviceToHost, c->stream));
+    if (sa_tid && ix.n_sa) SFB_CUDA(c, cudaMemcpy2DAsync(sa_tid, 4, &ix.sa.p->y, 8, 4, ix.n_sa, cudaMemcpyDeviceToHost, c->stream));
     SFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SFB200_OK;
 }

@@ -48,9 +48,9 @@ __device__ __forceinline__ bool compat_paired(int expected, int32_t e1, bool fwd
 }
 
 struct IndexView {
-    const uint64_t* words; const uint64_t* txp_start; const uint32_t* txp_len;
-    const uint32_t* sa_pos; const uint32_t* sa_tid; const uint4* table;
-    uint64_t mask; int k; uint64_t kmask;
+    const uint64_t* words; const uint64_t* txp_start; const uint64_t* txp_end;
+    const uint2* sa; const uint4* table; const uint32_t* bloom;
+    uint64_t mask, bloom_blocks; int k; uint64_t kmask;
 };
 
 // ---- the equivalence-class table ------------------------------------------------------------------------------------------
@@ -184,42 +184,101 @@ __device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, i
 
 struct Interval { uint32_t lb, cnt, qpos, m; };
 
-__device__ __forceinline__ bool table_find(const IndexView& ix, uint64_t km, uint32_t& lb, uint32_t& cnt) {
-    uint64_t h = xxh64_u64(km, 0) & ix.mask;
+// continue a table lookup whose first slot (already loaded) held another k-mer: linear probing from the next slot
+__device__ __forceinline__ bool table_find_from(const IndexView& ix, uint64_t km, uint64_t h, uint32_t& lb, uint32_t& cnt) {
     for (;;) {
+        h = (h + 1) & ix.mask;
         const uint4 sl = __ldg(ix.table + h);
         if (sl.w == 0) return false;
         if ((((uint64_t)sl.y << 32) | sl.x) == km) { lb = sl.z; cnt = sl.w; return true; }
-        h = (h + 1) & ix.mask;
     }
 }
 
-// spec v1 seed scan of one orientation
-__device__ int scan_read(const IndexView& ix, const Read& r, int o, uint32_t max_interval, Interval* ivs, uint64_t& score) {
-    int niv = 0;
-    score = 0;
-    const uint32_t k = ix.k, L = r.len;
+// Spec v1 seed scans of ALL orientations of ALL mates of one fragment, as ONE loop: scan s = 2*mate + orientation.
+// A fragment has one cheap scan per mate (the orientation that matches: a hit, an extension, done) and one expensive one
+// (the other strand: a k-mer lookup that misses at every position); folding them into a single loop keeps the lanes of a
+// warp in the same code whichever of their scans is the long one.  Positions are looked up SPEC at a time: k-mers,
+// hashes, presence-filter words and first table slots of the next SPEC positions are fetched together (independent
+// loads in flight), then consumed strictly in order, so the result is exactly the one-position-at-a-time scan's.
+constexpr int SPEC = 4;
+__device__ void scan_all(const IndexView& ix, const Read* rds, int n_mates, uint32_t max_interval,
+                         Interval (*ivs)[MAX_IV], int* niv, uint64_t* score) {
+    const uint32_t k = ix.k;
+    const int ns = 2 * n_mates;
+    int s = 0, n = 0;
     uint32_t i = 0;
-    while (i + k <= L && niv < MAX_IV) {
+    uint64_t sc = 0;
+    while (s < ns) {
+        const Read& r = rds[s >> 1];
+        const int o = s & 1;
+        const uint32_t L = r.len;
+        if (!(i + k <= L && n < MAX_IV)) { niv[s] = n; score[s] = sc; ++s; i = 0; n = 0; sc = 0; continue; }
         const uint64_t nn = win32(r.n[o], i) & ix.kmask;
         if (nn) { i += ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; continue; }   // jump past the last invalid base
-        const uint64_t km = win32(r.b[o], i) & ix.kmask;
-        if (km == 0 || km == ix.kmask || km == (0x5555555555555555ULL & ix.kmask) || km == (0xAAAAAAAAAAAAAAAAULL & ix.kmask)) { i += 1; continue; }
-        uint32_t lb, cnt;
-        if (!table_find(ix, km, lb, cnt) || cnt > max_interval) { i += 1; continue; }
-        uint32_t m = 0;
-        for (uint32_t e = lb; e < lb + cnt; ++e) {
-            const uint32_t tid = __ldg(ix.sa_tid + e);
-            const uint64_t tend = __ldg(ix.txp_start + tid) + __ldg(ix.txp_len + tid);
-            const uint32_t l = lcp_at(ix, r, o, i, __ldg(ix.sa_pos + e), tend);
-            m = l > m ? l : m;
+        // candidates i .. i+nc-1: windows inside the read and free of invalid bases
+        uint64_t km[SPEC], hh[SPEC];
+        bool probe[SPEC];
+        int nc = 1;
+#pragma unroll
+        for (int j = 1; j < SPEC; ++j) {
+            if (nc == j && i + j + k <= L && (win32(r.n[o], i + j) & ix.kmask) == 0) nc = j + 1;
         }
-        ivs[niv].lb = lb; ivs[niv].cnt = cnt; ivs[niv].qpos = i; ivs[niv].m = m;
-        ++niv;
-        score += m;
-        i += m - k + 1;
+#pragma unroll
+        for (int j = 0; j < SPEC; ++j) {
+            probe[j] = false;
+            if (j < nc) {
+                km[j] = win32(r.b[o], i + j) & ix.kmask;
+                const bool homo = km[j] == 0 || km[j] == ix.kmask || km[j] == (0x5555555555555555ULL & ix.kmask) ||
+                                  km[j] == (0xAAAAAAAAAAAAAAAAULL & ix.kmask);       // homopolymer k-mers are never seeds
+                if (!homo) { hh[j] = xxh64_u64(km[j], 0); probe[j] = true; }
+            }
+        }
+        uint32_t b0[SPEC], b1[SPEC], b2[SPEC], m0[SPEC], m1[SPEC], m2[SPEC];
+#pragma unroll
+        for (int j = 0; j < SPEC; ++j) {
+            if (probe[j]) {
+                uint32_t w0, w1, w2;
+                bloom_bits(hh[j], w0, m0[j], w1, m1[j], w2, m2[j]);
+                const uint32_t* blk = ix.bloom + bloom_block(hh[j], ix.bloom_blocks) * 8;
+                b0[j] = __ldg(blk + w0); b1[j] = __ldg(blk + w1); b2[j] = __ldg(blk + w2);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SPEC; ++j) {
+            if (probe[j]) probe[j] = (b0[j] & m0[j]) && (b1[j] & m1[j]) && (b2[j] & m2[j]);   // false => certainly absent
+        }
+        uint4 sl[SPEC];
+#pragma unroll
+        for (int j = 0; j < SPEC; ++j) if (probe[j]) sl[j] = __ldg(ix.table + (hh[j] & ix.mask));
+        // consume in order
+        bool advanced = false;
+#pragma unroll
+        for (int j = 0; j < SPEC; ++j) {
+            if (advanced || j >= nc) continue;
+            bool hit = false;
+            uint32_t lb = 0, cnt = 0;
+            if (probe[j]) {
+                if (sl[j].w != 0) {
+                    if ((((uint64_t)sl[j].y << 32) | sl[j].x) == km[j]) { hit = true; lb = sl[j].z; cnt = sl[j].w; }
+                    else hit = table_find_from(ix, km[j], hh[j] & ix.mask, lb, cnt);
+                }
+            }
+            if (!hit || cnt > max_interval) continue;                                  // position i+j is not a seed
+            const uint32_t q = i + j;
+            uint32_t m = 0;
+            for (uint32_t e = lb; e < lb + cnt; ++e) {
+                const uint2 en = __ldg(ix.sa + e);
+                const uint32_t l = lcp_at(ix, r, o, q, en.x, __ldg(ix.txp_end + en.y));
+                m = l > m ? l : m;
+            }
+            ivs[s][n].lb = lb; ivs[s][n].cnt = cnt; ivs[s][n].qpos = q; ivs[s][n].m = m;
+            ++n;
+            sc += m;
+            i = q + m - k + 1;                                                         // next k-mer ends one base past the match
+            advanced = true;
+        }
+        if (!advanced) i += nc;
     }
-    return niv;
 }
 
 // per-thread scratch in global memory, element j of thread t at base[j * stride + t] (coalesced like local memory)
@@ -243,26 +302,28 @@ __device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Int
     const Interval a = ivs[0];
     int64_t lastTid = -1;
     for (uint32_t e = a.lb; e < a.lb + a.cnt; ++e) {
-        const uint32_t tid = __ldg(ix.sa_tid + e);
+        const uint2 en = __ldg(ix.sa + e);
+        const uint32_t tid = en.y;
         if ((int64_t)tid == lastTid) continue;
-        const uint64_t ts = __ldg(ix.txp_start + tid);
-        const uint64_t tend = ts + __ldg(ix.txp_len + tid);
-        const uint32_t p = __ldg(ix.sa_pos + e);
+        const uint64_t tend = __ldg(ix.txp_end + tid);
+        const uint32_t p = en.x;
         if (lcp_at(ix, r, o, a.qpos, p, tend) != a.m) continue;
         lastTid = tid;
         bool all = true;
         for (int j = 1; j < niv && all; ++j) {
             const Interval b = ivs[j];
             uint32_t lo = b.lb, hi = b.lb + b.cnt;
-            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(ix.sa_tid + mid) < tid) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(&ix.sa[mid].y) < tid) lo = mid + 1; else hi = mid; }
             bool found = false;
-            for (uint32_t e2 = lo; e2 < b.lb + b.cnt && __ldg(ix.sa_tid + e2) == tid; ++e2) {
-                if (lcp_at(ix, r, o, b.qpos, __ldg(ix.sa_pos + e2), tend) == b.m) { found = true; break; }
+            for (uint32_t e2 = lo; e2 < b.lb + b.cnt; ++e2) {
+                const uint2 en2 = __ldg(ix.sa + e2);
+                if (en2.y != tid) break;
+                if (lcp_at(ix, r, o, b.qpos, en2.x, tend) == b.m) { found = true; break; }
             }
             all = found;
         }
         if (!all) continue;
-        const int32_t pos = (int32_t)((int64_t)p - (int64_t)ts - (int64_t)a.qpos);
+        const int32_t pos = (int32_t)((int64_t)p - (int64_t)__ldg(ix.txp_start + tid) - (int64_t)a.qpos);
         out.at(out0 + n) = pack_hit(tid, pos, o == 0);
         ++n;
         if (n > cap) return n;
@@ -271,15 +332,12 @@ __device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Int
 }
 
 // one mate: both orientations, optional strand vote, merge by transcript id.  Returns false on list overflow.
-__device__ bool collect(const IndexView& ix, const Read& r, bool strict, uint32_t cap, uint32_t max_interval,
-                        const Scratch& scr, uint32_t tmp0, uint32_t dst0, uint32_t& n_out) {
-    Interval ivs[MAX_IV];
-    uint64_t scF, scR;
+__device__ bool collect(const IndexView& ix, const Read& r, bool strict, uint32_t cap, const Interval* ivF, int nivF,
+                        uint64_t scF, const Interval* ivR, int nivR, uint64_t scR, const Scratch& scr, uint32_t tmp0,
+                        uint32_t dst0, uint32_t& n_out) {
     n_out = 0;
-    int niv = scan_read(ix, r, 0, max_interval, ivs, scF);
-    uint32_t nF = project(ix, r, 0, ivs, niv, cap, scr, tmp0);
-    niv = scan_read(ix, r, 1, max_interval, ivs, scR);
-    uint32_t nR = project(ix, r, 1, ivs, niv, cap, scr, tmp0 + cap + 1);
+    uint32_t nF = project(ix, r, 0, ivF, nivF, cap, scr, tmp0);
+    uint32_t nR = project(ix, r, 1, ivR, nivR, cap, scr, tmp0 + cap + 1);
     if (nF > cap || nR > cap) return false;
     if (strict && nF && nR) { if (scF > scR) nR = 0; else if (scR > scF) nF = 0; }
     if (nF + nR > cap) return false;
@@ -329,7 +387,10 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_reads(const MapParams p) {
     const bool paired = p.bases2 != nullptr;
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
-    Read rd;
+    Read rds[2];
+    Interval ivs[4][MAX_IV];
+    int niv[4];
+    uint64_t score[4];
 
     for (;;) {
         unsigned long long base_idx = 0;
@@ -340,15 +401,13 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_reads(const MapParams p) {
         if (ri < p.n_reads) {
             uint32_t nL = 0, nR = 0;
             bool okL, okR = true;
-            load_read(p.bases1, p.off1[ri], p.off1[ri + 1], rd);
-            const uint32_t len1 = rd.len;
+            load_read(p.bases1, p.off1[ri], p.off1[ri + 1], rds[0]);
+            const uint32_t len1 = rds[0].len;
             uint32_t len2 = 0;
-            okL = collect(p.ix, rd, paired, cap, p.max_interval, scr, TMP0, LEFT0, nL);     // paired: strict check (:192-202)
-            if (paired) {
-                load_read(p.bases2, p.off2[ri], p.off2[ri + 1], rd);
-                len2 = rd.len;
-                okR = collect(p.ix, rd, true, cap, p.max_interval, scr, TMP0, RIGHT0, nR);
-            }
+            if (paired) { load_read(p.bases2, p.off2[ri], p.off2[ri + 1], rds[1]); len2 = rds[1].len; }
+            scan_all(p.ix, rds, paired ? 2 : 1, p.max_interval, ivs, niv, score);
+            okL = collect(p.ix, rds[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, TMP0, LEFT0, nL);   // paired: strict check (:192-202)
+            if (paired) okR = collect(p.ix, rds[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, TMP0, RIGHT0, nR);
             const bool overflow = !okL || !okR;
             LabelAcc acc(scr, TMP0, p.enforce_compat != 0);
             uint32_t n_joint = 0;
@@ -517,7 +576,10 @@ __global__ void k_eq_fill(const FinParams p) {
         const unsigned long long cn = p.count[i];
         total += cn;
         const int b = fin_bin(n);
-        const uint64_t pos = atomicAdd(p.fin + FIN_CUR_CLS + b, 1ULL);
+        // one 64-bit atomic hands out the class position (high half) and the label space (low half) together, so
+        // class order and label order agree and a CTA's slice of classes owns one contiguous slice of labels
+        const unsigned long long tk = atomicAdd(p.fin + FIN_CUR_CLS + b, (1ULL << 32) | (unsigned long long)n);
+        const uint64_t pos = tk >> 32;
         if (b == SFB_NBINS) {
             const uint32_t t = a[0];
             p.sgl_tid[pos] = t; p.sgl_cls[pos] = (uint32_t)(p.Em + pos);
@@ -526,7 +588,7 @@ __global__ void k_eq_fill(const FinParams p) {
             p.active[t] = 1;
         } else {
             const uint64_t c = p.cls_start[b] + pos;
-            const uint64_t o = p.nnz_start[b] + atomicAdd(p.fin + FIN_CUR_NNZ + b, (unsigned long long)n);
+            const uint64_t o = p.nnz_start[b] + (tk & 0xFFFFFFFFULL);
             p.start[c] = (uint32_t)o; p.len[c] = n; p.cnt[c] = (double)cn; p.cnt_all[c] = cn;
             for (uint32_t j = 0; j < n; ++j) { const uint32_t t = a[j]; p.lab[o + j] = t; p.active[t] = 1; }
         }
@@ -610,6 +672,23 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->n_threads_total = (uint64_t)m->grid * MAP_THREADS;
     SFB_CUDA(c, m->scratch.reserve(m->n_threads_total * 4ull * (o->max_read_occs + 1)));
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    // keep the presence filter resident in L2 while the table / suffix entries / text stream through it
+    if (!getenv("SFB200_NO_L2_PERSIST")) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t want = std::min<size_t>(c->index.bloom_blocks * 32, (size_t)prop.persistingL2CacheMaxSize);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue av;
+            std::memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = c->index.bloom.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(c->index.bloom_blocks * 32, (size_t)prop.accessPolicyMaxWindowSize);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaGetLastError();   // best effort
+        }
+    }
     c->cls.ready = false;
     m->begun = true;
     m->ev_used = 0; m->kernel_ms = 0.0;
@@ -628,8 +707,8 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     const DevIndex& ix = c->index;
     MapParams p;
     std::memset(&p, 0, sizeof(p));
-    p.ix.words = ix.words.p; p.ix.txp_start = ix.txp_start.p; p.ix.txp_len = ix.txp_len.p; p.ix.sa_pos = ix.sa_pos.p;
-    p.ix.sa_tid = ix.sa_tid.p; p.ix.table = ix.table.p; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
+    p.ix.words = ix.words.p; p.ix.txp_start = ix.txp_start.p; p.ix.txp_end = ix.txp_end.p; p.ix.sa = ix.sa.p;
+    p.ix.table = ix.table.p; p.ix.bloom = ix.bloom.p; p.ix.bloom_blocks = ix.bloom_blocks; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
     p.ix.kmask = (1ULL << (2 * ix.k)) - 1;
     p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p; p.tb.cursor = m->cursor.p;
     p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
