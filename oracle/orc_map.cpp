@@ -65,13 +65,17 @@ struct orc_index {
         for (int i = 0; i < k; ++i) v |= static_cast<uint64_t>(base(p + i)) << (2 * i);   // base i of the k-mer at bits 2i
         return v;
     }
-    // optional externally built table (same scheme: XXH64(k-mer) & mask, linear probing): {k-mer, lb | cnt << 32},
+    // optional externally built table (mix(k-mer) & mask, linear probing): {k-mer, lb | cnt << 32},
     // empty = all-ones k-mer.  Used by bench.py's CPU arm at full size (orc_index_from_table).
     std::vector<uint64_t> ext;
     // looks the k-mer up, counts probes; fills the bucket [lb, lb+cnt)
     bool find(uint64_t km, uint64_t& probes, uint32_t& olb, uint32_t& ocnt) const {
         uint64_t h = orc_xxh64(&km, 8, 0) & mask;
         if (!ext.empty()) {
+            // the externally built table is slotted with a two-multiply mixer (sailfish_b200/csrc/common.cuh: sfb_kmer_mix)
+            uint64_t x = km;
+            x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 29;
+            h = x & mask;
             for (;;) {
                 ++probes;
                 const uint64_t key = ext[2 * h];

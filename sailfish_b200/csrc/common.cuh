@@ -57,10 +57,10 @@ struct DevIndex {
     DevBuf<uint64_t> txp_end;    // n_txp: txp_start[t] + txp_len[t]
     DevBuf<uint2> sa;            // n_sa entries {position, transcript}, sorted by (k-mer value, position)
     DevBuf<uint4> table;         // {key lo, key hi, lb, cnt}; empty = cnt 0
-    // presence filter over the distinct k-mers (blocked Bloom filter, one 32-byte block per k-mer, 3 bits): answers
+    // presence filter over the distinct k-mers (blocked Bloom filter, one 64-bit block per k-mer, 3 bits): answers
     // "certainly absent" for most k-mers of the wrong read orientation without touching the table; sized to stay in L2
-    DevBuf<uint32_t> bloom;
-    uint64_t bloom_blocks = 0;   // power of two; block = 8 x u32
+    DevBuf<uint64_t> bloom;
+    uint64_t bloom_words = 0;    // power of two
     bool ready = false;
     size_t hbm_bytes() const {
         return words.bytes() + txp_start.bytes() + txp_len.bytes() + txp_end.bytes() + sa.bytes() + table.bytes() + bloom.bytes();
@@ -204,12 +204,21 @@ __host__ __device__ __forceinline__ uint64_t xxh64_words(F get, uint32_t n, uint
 
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
 
-// presence filter addressing shared by the index builder and the mapper: block from the high hash bits, three bit
-// positions inside the 256-bit block from disjoint hash fields (the table slot uses the low bits of the same hash)
-__device__ __forceinline__ uint64_t bloom_block(uint64_t h, uint64_t n_blocks) { return (h >> 34) & (n_blocks - 1); }
-__device__ __forceinline__ void bloom_bits(uint64_t h, uint32_t& w0, uint32_t& m0, uint32_t& w1, uint32_t& m1, uint32_t& w2, uint32_t& m2) {
-    const uint32_t a = (uint32_t)(h >> 10) & 255u, b = (uint32_t)(h >> 18) & 255u, c = (uint32_t)(h >> 26) & 255u;
-    w0 = a >> 5; m0 = 1u << (a & 31); w1 = b >> 5; m1 = 1u << (b & 31); w2 = c >> 5; m2 = 1u << (c & 31);
+// ---- k-mer table hashing -----------------------------------------------------------------------------------------------
+// The k-mer table and the presence filter are this repo's own structures (RapMap's index is not in the reference
+// tree), so their hash is free to choose.  XXH64 of the 8-byte k-mer costs five 64-bit multiplies per lookup -- measured
+// at ~40% of the mapping kernel's instructions -- so lookups use a two-multiply mixer; XXH64 stays where the reference
+// fixes it: the equivalence-class label hash (TranscriptGroup.cpp:9-12).
+__host__ __device__ __forceinline__ uint64_t sfb_kmer_mix(uint64_t x) {
+    x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 29;
+    return x;
+}
+// presence filter: blocked Bloom filter with one 64-bit block per k-mer and three bits inside it; the table slot uses the
+// low bits of the same mix, the filter word its high bits
+__host__ __device__ __forceinline__ uint64_t sfb_bloom_word(uint64_t h, uint64_t n_words) { return (h >> 36) & (n_words - 1); }
+__host__ __device__ __forceinline__ uint64_t sfb_bloom_mask(uint64_t h) {
+    return (1ULL << ((h >> 8) & 63)) | (1ULL << ((h >> 14) & 63)) | (1ULL << ((h >> 20) & 63));
 }
 
 // digamma for x > 0: recurrence up to x >= 12, then the asymptotic series (same expansion as the oracle's

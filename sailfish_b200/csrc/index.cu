@@ -6,7 +6,8 @@
 //   words    2-bit text of all transcripts concatenated (32 bases / u64, base p at bits 2*(p%32))
 //   sa_pos   every position whose k-mer lies inside one transcript, sorted by (k-mer value, position)
 //   sa_tid   transcript of each entry
-//   table    open-addressing k-mer table {k-mer, first entry, entry count}, slot = XXH64(k-mer) & mask, linear probing
+//   table    open-addressing k-mer table {k-mer, first entry, entry count}, slot = mix(k-mer) & mask, linear probing
+//   bloom    presence filter over the distinct k-mers (one 64-bit block per k-mer)
 // Index construction is a "next" row, outside the timed path: the big sort / compaction primitives
 // are CUB's (part of the CUDA toolkit); everything else is hand-written.
 #include <cub/cub.cuh>
@@ -91,19 +92,14 @@ __global__ void k_txp_end(const uint64_t* __restrict__ txp_start, const uint32_t
 
 __global__ void k_table_insert(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ heads, uint64_t n_kmers,
                                uint64_t n_sa, uint4* __restrict__ table, uint64_t mask, unsigned int* __restrict__ max_bucket,
-                               uint32_t* __restrict__ bloom, uint64_t bloom_blocks) {
+                               unsigned long long* __restrict__ bloom, uint64_t bloom_words) {
     const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n_kmers) return;
     const uint32_t lb = heads[j];
     const uint32_t cnt = static_cast<uint32_t>((j + 1 < n_kmers ? heads[j + 1] : n_sa) - lb);
     const uint64_t km = keys[lb];
-    const uint64_t hh = xxh64_u64(km, 0);
-    {
-        uint32_t w0, m0, w1, m1, w2, m2;
-        bloom_bits(hh, w0, m0, w1, m1, w2, m2);
-        uint32_t* blk = bloom + bloom_block(hh, bloom_blocks) * 8;
-        atomicOr(blk + w0, m0); atomicOr(blk + w1, m1); atomicOr(blk + w2, m2);
-    }
+    const uint64_t hh = sfb_kmer_mix(km);
+    atomicOr(bloom + sfb_bloom_word(hh, bloom_words), (unsigned long long)sfb_bloom_mask(hh));
     uint64_t h = hh & mask;
     unsigned long long* slots = reinterpret_cast<unsigned long long*>(table);
     for (;;) {
@@ -211,18 +207,18 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
     while (slots < 2 * ix.n_kmers) slots <<= 1;
     ix.table_slots = slots;
     IDX_CUDA(ix.table.reserve(slots));
-    // presence filter: >= 8 bits per k-mer, capped at 64 MB (2^21 blocks of 256 bits) so that it stays L2-resident
-    uint64_t bblocks = 64;
-    while (bblocks * 256 < 8 * ix.n_kmers && bblocks < (1ull << 21)) bblocks <<= 1;
-    if (const char* e = getenv("SFB200_BLOOM_LOG2_BLOCKS")) bblocks = 1ull << std::max(6, std::min(26, atoi(e)));
-    ix.bloom_blocks = bblocks;
-    IDX_CUDA(ix.bloom.reserve(bblocks * 8));
-    IDX_CUDA(cudaMemsetAsync(ix.bloom.p, 0, bblocks * 32, s));
+    // presence filter: >= 8 bits per k-mer, capped at 64 MB (2^23 words) so that it stays L2-resident
+    uint64_t bwords = 64;
+    while (bwords * 64 < 8 * ix.n_kmers && bwords < (1ull << 23)) bwords <<= 1;
+    if (const char* e = getenv("SFB200_BLOOM_LOG2_WORDS")) bwords = 1ull << std::max(6, std::min(28, atoi(e)));
+    ix.bloom_words = bwords;
+    IDX_CUDA(ix.bloom.reserve(bwords));
+    IDX_CUDA(cudaMemsetAsync(ix.bloom.p, 0, bwords * 8, s));
     k_table_clear<<<gridn(slots, 256), 256, 0, s>>>(ix.table.p, slots);
     c->launches++;
     if (ix.n_kmers) {
         IDX_CUDA(cudaMemsetAsync(d_scalar.p + 1, 0, 4, s));
-        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1, ix.bloom.p, bblocks);
+        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1, reinterpret_cast<unsigned long long*>(ix.bloom.p), bwords);
         c->launches++;
         unsigned int mb = 0;
         IDX_CUDA(cudaMemcpyAsync(&mb, d_scalar.p + 1, 4, cudaMemcpyDeviceToHost, s));

@@ -49,8 +49,8 @@ __device__ __forceinline__ bool compat_paired(int expected, int32_t e1, bool fwd
 
 struct IndexView {
     const uint64_t* words; const uint64_t* txp_start; const uint64_t* txp_end;
-    const uint2* sa; const uint4* table; const uint32_t* bloom;
-    uint64_t mask, bloom_blocks; int k; uint64_t kmask;
+    const uint2* sa; const uint4* table; const uint64_t* bloom;
+    uint64_t mask, bloom_words; int k; uint64_t kmask;
 };
 
 // ---- the equivalence-class table ------------------------------------------------------------------------------------------
@@ -130,16 +130,29 @@ __device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigne
 }
 
 // ---- per-read state -----------------------------------------------------------------------------------------------------
+// One mate.  The packed bases live in SHARED memory, lane-interleaved (word w of orientation o of this lane at
+// sb[(o*RW + w) * 32]): every k-mer window and every extension compare reads them with a dynamic index, which in local
+// memory would go out to L2 (a CTA's reads do not fit L1).  2 bits per base, base i at bits 2*(i%32) of word i/32;
+// orientation 0 = as sequenced, 1 = reverse complement.  The invalid-base masks (same layout, 0b01 where the base is not
+// A/C/G/T) are rare and stay in local memory, touched only when has_n.
 struct Read {
-    uint64_t b[2][RW];    // [0] forward, [1] reverse complement: 2 bits per base, base i at bits 2*(i%32) of word i/32
-    uint64_t n[2][RW];    // same layout, 0b01 where the base is not A/C/G/T
+    uint64_t* sb;
+    uint64_t nm[2][RW];
     uint32_t len;
+    bool has_n;
+    __device__ __forceinline__ uint64_t word(int o, uint32_t w) const { return sb[(o * RW + w) * 32]; }
 };
 
-__device__ __forceinline__ uint64_t win32(const uint64_t* w, uint32_t pos) {
+__device__ __forceinline__ uint64_t win32(const Read& r, int o, uint32_t pos) {
     const uint32_t idx = pos >> 5, sh = 2 * (pos & 31);
-    uint64_t v = w[idx] >> sh;
-    if (sh) v |= w[idx + 1] << (64 - sh);
+    uint64_t v = r.word(o, idx) >> sh;
+    if (sh) v |= r.word(o, idx + 1) << (64 - sh);
+    return v;
+}
+__device__ __forceinline__ uint64_t win32n(const Read& r, int o, uint32_t pos) {
+    const uint32_t idx = pos >> 5, sh = 2 * (pos & 31);
+    uint64_t v = r.nm[o][idx] >> sh;
+    if (sh) v |= r.nm[o][idx + 1] << (64 - sh);
     return v;
 }
 __device__ __forceinline__ uint64_t win32g(const uint64_t* __restrict__ w, uint64_t pos) {
@@ -148,22 +161,65 @@ __device__ __forceinline__ uint64_t win32g(const uint64_t* __restrict__ w, uint6
     if (sh) v |= __ldg(w + idx + 1) << (64 - sh);
     return v;
 }
+// reverse complement of one 32-base word: complement every 2-bit code, reverse the order of the codes
+__device__ __forceinline__ uint64_t revcomp32(uint64_t w) {
+    uint64_t x = __brevll(~w);
+    return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
 
 __device__ void load_read(const char* __restrict__ bases, uint64_t beg, uint64_t end, Read& r) {
     uint32_t L = static_cast<uint32_t>(end - beg);
     if (L > MAX_READ_LEN) L = MAX_READ_LEN;
     r.len = L;
-#pragma unroll
-    for (int i = 0; i < RW; ++i) { r.b[0][i] = 0; r.b[1][i] = 0; r.n[0][i] = 0; r.n[1][i] = 0; }
-    for (uint32_t i = 0; i < L; ++i) {
-        const unsigned char ch = static_cast<unsigned char>(bases[beg + i]);
-        const unsigned char up = ch & 0xDF;
-        const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
-        const uint64_t code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 0;
-        const uint32_t j = L - 1 - i;
-        r.b[0][i >> 5] |= code << (2 * (i & 31));
-        r.b[1][j >> 5] |= (ok ? (3 - code) : 0) << (2 * (j & 31));
-        if (!ok) { r.n[0][i >> 5] |= 1ULL << (2 * (i & 31)); r.n[1][j >> 5] |= 1ULL << (2 * (j & 31)); }
+    r.has_n = false;
+    const uint32_t nw = (L + 31) >> 5;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(bases) + beg;
+    for (uint32_t w = 0; w < RW; ++w) {
+        uint64_t word = 0, bad = 0;
+        if (w < nw) {
+            const uint32_t i0 = w * 32, n = (L - i0) < 32 ? (L - i0) : 32;
+            for (uint32_t j = 0; j < n; ++j) {
+                const unsigned char ch = src[i0 + j];
+                const unsigned char up = ch & 0xDF;
+                const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+                word |= (ok ? (uint64_t)(((ch >> 1) ^ (ch >> 2)) & 3) : 0ULL) << (2 * j);
+                bad |= (ok ? 0ULL : 1ULL) << (2 * j);
+            }
+        }
+        r.sb[w * 32] = word;
+        if (bad && !r.has_n) {                       // first invalid base: bring the mask arrays to a defined state
+            r.has_n = true;
+            for (int q = 0; q < RW; ++q) { r.nm[0][q] = 0; r.nm[1][q] = 0; }
+        }
+        if (bad) r.nm[0][w] = bad;
+    }
+    // reverse complement: reversed words in reverse order, then shifted down by the padding of the last word
+    const uint32_t pad = nw * 32 - L;
+    for (uint32_t w = 0; w < RW; ++w) {
+        uint64_t v = 0;
+        if (w < nw) {
+            // rc base j = comp(fw base L-1-j); in "reversed padded" coordinates that is position j + pad
+            const uint32_t pos = w * 32 + pad, idx = pos >> 5, sh = 2 * (pos & 31);
+            const uint64_t lo = idx < nw ? revcomp32(r.sb[(nw - 1 - idx) * 32]) : 0ULL;
+            const uint64_t hi = (idx + 1) < nw ? revcomp32(r.sb[(nw - 2 - idx) * 32]) : 0ULL;
+            v = lo >> sh;
+            if (sh) v |= hi << (64 - sh);
+            const uint32_t rem = L - w * 32;                            // bases of this word that exist
+            if (rem < 32) v &= (1ULL << (2 * rem)) - 1;
+        }
+        r.sb[(RW + w) * 32] = v;
+    }
+    if (r.has_n) {
+        // masks of the reverse orientation: plain reversal of the 2-bit groups (no complement)
+        for (uint32_t w = 0; w < nw; ++w) {
+            const uint32_t pos = w * 32 + pad, idx = pos >> 5, sh = 2 * (pos & 31);
+            auto rev = [](uint64_t x) { x = __brevll(x); return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1); };
+            const uint64_t lo = idx < nw ? rev(r.nm[0][nw - 1 - idx]) : 0ULL;
+            const uint64_t hi = (idx + 1) < nw ? rev(r.nm[0][nw - 2 - idx]) : 0ULL;
+            uint64_t v = lo >> sh;
+            if (sh) v |= hi << (64 - sh);
+            r.nm[1][w] = v;
+        }
     }
 }
 
@@ -174,8 +230,9 @@ __device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, i
     const uint32_t lim = lim_t < lim_r ? static_cast<uint32_t>(lim_t) : lim_r;
     uint32_t m = ix.k;
     while (m < lim) {
-        const uint64_t x = win32(r.b[o], qpos + m) ^ win32g(ix.words, p + m);
-        const uint64_t y = ((x | (x >> 1)) & 0x5555555555555555ULL) | win32(r.n[o], qpos + m);
+        const uint64_t x = win32(r, o, qpos + m) ^ win32g(ix.words, p + m);
+        uint64_t y = (x | (x >> 1)) & 0x5555555555555555ULL;
+        if (r.has_n) y |= win32n(r, o, qpos + m);
         if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; break; }
         m += 32;
     }
@@ -213,39 +270,36 @@ __device__ void scan_all(const IndexView& ix, const Read* rds, int n_mates, uint
         const int o = s & 1;
         const uint32_t L = r.len;
         if (!(i + k <= L && n < MAX_IV)) { niv[s] = n; score[s] = sc; ++s; i = 0; n = 0; sc = 0; continue; }
-        const uint64_t nn = win32(r.n[o], i) & ix.kmask;
-        if (nn) { i += ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; continue; }   // jump past the last invalid base
+        if (r.has_n) {
+            const uint64_t nn = win32n(r, o, i) & ix.kmask;
+            if (nn) { i += ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; continue; }   // jump past the last invalid base
+        }
         // candidates i .. i+nc-1: windows inside the read and free of invalid bases
         uint64_t km[SPEC], hh[SPEC];
         bool probe[SPEC];
         int nc = 1;
 #pragma unroll
         for (int j = 1; j < SPEC; ++j) {
-            if (nc == j && i + j + k <= L && (win32(r.n[o], i + j) & ix.kmask) == 0) nc = j + 1;
+            if (nc == j && i + j + k <= L && (!r.has_n || (win32n(r, o, i + j) & ix.kmask) == 0)) nc = j + 1;
         }
+        uint64_t bw[SPEC];
 #pragma unroll
         for (int j = 0; j < SPEC; ++j) {
             probe[j] = false;
             if (j < nc) {
-                km[j] = win32(r.b[o], i + j) & ix.kmask;
+                km[j] = win32(r, o, i + j) & ix.kmask;
                 const bool homo = km[j] == 0 || km[j] == ix.kmask || km[j] == (0x5555555555555555ULL & ix.kmask) ||
                                   km[j] == (0xAAAAAAAAAAAAAAAAULL & ix.kmask);       // homopolymer k-mers are never seeds
-                if (!homo) { hh[j] = xxh64_u64(km[j], 0); probe[j] = true; }
-            }
-        }
-        uint32_t b0[SPEC], b1[SPEC], b2[SPEC], m0[SPEC], m1[SPEC], m2[SPEC];
-#pragma unroll
-        for (int j = 0; j < SPEC; ++j) {
-            if (probe[j]) {
-                uint32_t w0, w1, w2;
-                bloom_bits(hh[j], w0, m0[j], w1, m1[j], w2, m2[j]);
-                const uint32_t* blk = ix.bloom + bloom_block(hh[j], ix.bloom_blocks) * 8;
-                b0[j] = __ldg(blk + w0); b1[j] = __ldg(blk + w1); b2[j] = __ldg(blk + w2);
+                if (!homo) {
+                    hh[j] = sfb_kmer_mix(km[j]);
+                    bw[j] = __ldg(ix.bloom + sfb_bloom_word(hh[j], ix.bloom_words));
+                    probe[j] = true;
+                }
             }
         }
 #pragma unroll
         for (int j = 0; j < SPEC; ++j) {
-            if (probe[j]) probe[j] = (b0[j] & m0[j]) && (b1[j] & m1[j]) && (b2[j] & m2[j]);   // false => certainly absent
+            if (probe[j]) { const uint64_t need = sfb_bloom_mask(hh[j]); probe[j] = (bw[j] & need) == need; }   // false => certainly absent
         }
         uint4 sl[SPEC];
 #pragma unroll
@@ -379,7 +433,8 @@ struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of 
     }
 };
 
-__global__ void __launch_bounds__(MAP_THREADS) k_map_reads(const MapParams p) {
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_map_reads(const MapParams p) {
+    extern __shared__ uint64_t smem_reads[];       // [warp][mate][orientation][word][lane]
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const Scratch scr{p.scratch + gtid, p.n_threads_total};
     const uint32_t cap = p.cap;
@@ -388,6 +443,12 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_reads(const MapParams p) {
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
     Read rds[2];
+    {
+        const int n_mates = p.bases2 != nullptr ? 2 : 1;
+        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * n_mates * 2 * RW * 32 + (threadIdx.x & 31u);
+        rds[0].sb = wbase;
+        rds[1].sb = wbase + (n_mates - 1) * 2 * RW * 32;
+    }
     Interval ivs[4][MAX_IV];
     int niv[4];
     uint64_t score[4];
@@ -666,7 +727,10 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     SFB_CUDA(c, cudaMemcpyAsync(m->remaining.p, &rem, 4, cudaMemcpyHostToDevice, s));
     // launch geometry: every SM filled with resident CTAs; scratch sized for exactly those threads
     int per_sm = 0;
-    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_reads, MAP_THREADS, 0));
+    // the occupancy that matters is the paired-end one (two mates of packed reads in shared memory per lane)
+    const size_t smem_pe = (size_t)MAP_THREADS * 2 * 2 * RW * 8;
+    SFB_CUDA(c, cudaFuncSetAttribute(k_map_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe));
+    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_reads, MAP_THREADS, smem_pe / 2));
     if (per_sm < 1) per_sm = 1;
     m->grid = c->num_sms * per_sm;
     m->n_threads_total = (uint64_t)m->grid * MAP_THREADS;
@@ -674,14 +738,16 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     SFB_CUDA(c, cudaStreamSynchronize(s));
     // keep the presence filter resident in L2 while the table / suffix entries / text stream through it
     if (!getenv("SFB200_NO_L2_PERSIST")) {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-            const size_t want = std::min<size_t>(c->index.bloom_blocks * 32, (size_t)prop.persistingL2CacheMaxSize);
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        if (max_persist > 0 && max_window > 0) {
+            const size_t want = std::min<size_t>(c->index.bloom_words * 8, (size_t)max_persist);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
             cudaStreamAttrValue av;
             std::memset(&av, 0, sizeof(av));
             av.accessPolicyWindow.base_ptr = c->index.bloom.p;
-            av.accessPolicyWindow.num_bytes = std::min<size_t>(c->index.bloom_blocks * 32, (size_t)prop.accessPolicyMaxWindowSize);
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(c->index.bloom_words * 8, (size_t)max_window);
             av.accessPolicyWindow.hitRatio = 1.0f;
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -708,7 +774,7 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     MapParams p;
     std::memset(&p, 0, sizeof(p));
     p.ix.words = ix.words.p; p.ix.txp_start = ix.txp_start.p; p.ix.txp_end = ix.txp_end.p; p.ix.sa = ix.sa.p;
-    p.ix.table = ix.table.p; p.ix.bloom = ix.bloom.p; p.ix.bloom_blocks = ix.bloom_blocks; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
+    p.ix.table = ix.table.p; p.ix.bloom = ix.bloom.p; p.ix.bloom_words = ix.bloom_words; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
     p.ix.kmask = (1ULL << (2 * ix.k)) - 1;
     p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p; p.tb.cursor = m->cursor.p;
     p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
@@ -725,7 +791,8 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     const unsigned grid = (unsigned)std::min<uint64_t>(m->grid, blocks_needed);
     if (m->ev.size() < m->ev_used + 2) { cudaEvent_t a, b; SFB_CUDA(c, cudaEventCreate(&a)); SFB_CUDA(c, cudaEventCreate(&b)); m->ev.push_back(a); m->ev.push_back(b); }
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used], s));
-    k_map_reads<<<grid, MAP_THREADS, 0, s>>>(p);
+    const size_t smem = (size_t)MAP_THREADS * (d_bases2 ? 2 : 1) * 2 * RW * 8;
+    k_map_reads<<<grid, MAP_THREADS, smem, s>>>(p);
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));

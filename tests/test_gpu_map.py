@@ -165,3 +165,25 @@ def test_full_size_properties(ctx):
     ctx.map_batch(b1, o1)
     g2 = ctx.map_finish()
     assert g2["counters"].tolist() == c.tolist() and g2["n_classes"] == g["n_classes"]
+
+
+def test_oracle_on_device_built_index(ctx):
+    """bench.py's CPU arm runs the oracle on the index the GPU built (arrays + k-mer table): same answers as the oracle's
+    own index, so the CPU baseline at full size measures the same algorithm on the same data."""
+    seq, off, ln = small_txome(50, seed=7)
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 5000, 100, seed=3, paired=True, sub_rate=0.01)
+    st = ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=31)
+    words, sa_pos, sa_tid = ctx.index_export()
+    table = ctx.index_export_table()
+    assert int((table[:, 0] != np.uint64(0xFFFFFFFFFFFFFFFF)).sum()) == st["n_kmers"]
+    o_dev = O.Index.from_table(words, st["text_len"], ln, 31, sa_pos, sa_tid, table)
+    seqs = [seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes() for i in range(len(ln))]
+    o_own = O.Index(seqs, k=31)
+    fmt = O.parse_libtype("IU")
+    res = []
+    for ix in (o_dev, o_own):
+        run = O.Run(ix, O.MapOpts.default(fmt))
+        run.map_batch(b1.tobytes(), o1, b2.tobytes(), o2, n_threads=4)
+        res.append(run.finish())
+    for key in ("counters", "fld", "row_ptr", "labels", "counts"):
+        assert res[0][key].tolist() == res[1][key].tolist()
