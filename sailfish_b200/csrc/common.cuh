@@ -34,7 +34,8 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T));
+        // 16 elements of slack: bulk (TMA) copies of 16-byte-aligned supersets may read past the logical end
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), (n + 16) * sizeof(T));
         if (e == cudaSuccess) cap = n ? n : 1;
         return e;
     }

@@ -44,6 +44,7 @@ struct EmParams {
     uint32_t min_iter, max_iter, fixed_iters;
     double sum0;            // sum of alpha_0 (VBEM logNorm of the first iteration)
     double base_sum;        // sum of base
+    uint32_t smem_bytes;    // dynamic shared memory given to the persistent kernel for its class slice
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -79,64 +80,150 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// ---- E-step + M-step scatter for one warp tile -----------------------------------------------------------------------
-// EMUpdate_ (CollapsedEMOptimizer.cpp:235-277) / VBEMUpdate_ (:325-366) for the classes of this tile.
-// `in` is alpha (EM) or expTheta (VBEM); members with a non-positive VBEM theta are skipped as in :342,357.
-template <bool VB>
-__device__ __forceinline__ double sweep_tile(const EmParams& p, uint64_t tile, const double* __restrict__ in,
-                                             double* __restrict__ out) {
-    const unsigned lane = threadIdx.x & 31u;
+// ---- the CTA's slice of the class structure --------------------------------------------------------------------------
+// Tile -> CTA assignment is static, so a CTA reads the same classes every iteration.  When the slice fits in shared
+// memory (it does for BASELINE configs 1-4: ~120 KB of the 227 KB per SM) it is staged there ONCE, at kernel start, with
+// TMA bulk copies (cp.async.bulk + mbarrier), and a 1000-iteration run then touches global memory only for the alpha
+// gathers and the red.add scatters.  Otherwise the same code reads the slice through the read-only path.
+struct Slice {
+    const uint32_t* start; const uint32_t* len; const double* cnt; const uint32_t* lab; const double* w;
+    uint64_t c0;      // class index that start/len/cnt[0] correspond to
+    uint64_t e0;      // entry index that lab/w[0] correspond to
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// first class of a tile (tiles of bin b hold 32 >> (b+1) classes, the long bin one)
+__device__ __forceinline__ uint64_t tile_first_class(const EmParams& p, uint64_t tile) {
     int b = 0;
     while (b < SFB_NBINS - 1 && tile >= p.tile_start[b + 1]) ++b;
+    if (tile >= p.tile_start[SFB_NBINS]) return p.cls_start[SFB_NBINS];
+    return p.cls_start[b] + ((tile - p.tile_start[b]) << (b < SFB_NBINS - 1 ? 4 - b : 0));
+}
+
+constexpr int EM_ILP = 4;     // warp tiles in flight per warp: the alpha gathers of EM_ILP tiles are issued back to back
+
+// ---- E-step + M-step scatter for the tiles of this CTA ---------------------------------------------------------------------
+// EMUpdate_ (CollapsedEMOptimizer.cpp:235-277) / VBEMUpdate_ (:325-366).  `in` is alpha (EM) or expTheta (VBEM); members with a
+// non-positive VBEM theta are skipped as in :342,357.  Returns this thread's sum of contributions (VBEM's alpha sum).
+template <bool VB>
+__device__ __forceinline__ double sweep_block(const EmParams& p, const Slice& sl, uint64_t tile_lo, uint64_t tile_hi,
+                                              const double* __restrict__ in, double* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     double contrib = 0.0;
-    if (b < SFB_NBINS - 1) {
-        const unsigned sh = b + 1;                      // g = 2 << b lanes per class
-        const unsigned g = 1u << sh;
-        const uint64_t c = p.cls_start[b] + ((tile - p.tile_start[b]) << (5 - sh)) + (lane >> sh);
-        const unsigned j = lane & (g - 1);
-        uint32_t o0 = 0, n = 0;
-        const bool cv = c < p.cls_start[b + 1];
-        if (cv) { o0 = __ldg(p.start + c); n = __ldg(p.len + c); }
-        bool ev = cv && j < n;
-        uint32_t t = 0;
-        double v = 0.0;
-        if (ev) {
-            t = __ldg(p.lab + o0 + j);
-            const double wv = __ldg(p.w + o0 + j);
-            const double a = ld_cg_f64(in + t);
-            if (VB && !(a > 0.0)) ev = false; else v = a * wv;
-        }
-        double denom = v;
-        for (unsigned m = g >> 1; m >= 1; m >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, m);
-        if (ev && denom > DENORM_MIN && !isnan(v)) {
-            const double add = v * (__ldg(p.cnt + c) / denom);
-            atomicAdd(out + t, add);
-            contrib = add;
-        }
-    } else {
-        // long class (more than 32 members): the whole warp walks it twice
-        const uint64_t c = p.cls_start[b] + (tile - p.tile_start[b]);
-        if (c < p.cls_start[b + 1]) {
-            const uint32_t o0 = __ldg(p.start + c), n = __ldg(p.len + c);
-            double denom = 0.0;
-            for (uint32_t j = lane; j < n; j += 32) {
-                const double a = ld_cg_f64(in + __ldg(p.lab + o0 + j));
-                if (!VB || a > 0.0) denom += a * __ldg(p.w + o0 + j);
-            }
-            denom = warp_sum(denom);
-            if (denom > DENORM_MIN) {
-                const double inv = __ldg(p.cnt + c) / denom;
-                for (uint32_t j = lane; j < n; j += 32) {
-                    const uint32_t t = __ldg(p.lab + o0 + j);
-                    const double a = ld_cg_f64(in + t);
-                    if (VB && !(a > 0.0)) continue;
-                    const double v = a * __ldg(p.w + o0 + j);
-                    if (!isnan(v)) { const double add = v * inv; atomicAdd(out + t, add); contrib += add; }
+    const uint64_t short_hi = tile_hi < p.tile_start[SFB_NBINS - 1] ? tile_hi : p.tile_start[SFB_NBINS - 1];
+    for (uint64_t t0 = tile_lo + warp; t0 < short_hi; t0 += (uint64_t)EM_ILP * W) {
+        uint32_t tid[EM_ILP], sh[EM_ILP];
+        uint64_t cls[EM_ILP];
+        double wv[EM_ILP], a[EM_ILP];
+        bool ev[EM_ILP];
+#pragma unroll
+        for (int u = 0; u < EM_ILP; ++u) {
+            const uint64_t tile = t0 + (uint64_t)u * W;
+            ev[u] = false; a[u] = 0.0; wv[u] = 0.0; tid[u] = 0; sh[u] = 1; cls[u] = 0;
+            if (tile < short_hi) {
+                int b = 0;
+                while (b < SFB_NBINS - 2 && tile >= p.tile_start[b + 1]) ++b;
+                sh[u] = b + 1;                                           // g = 1 << sh lanes per class
+                const uint64_t c = p.cls_start[b] + ((tile - p.tile_start[b]) << (5 - sh[u])) + (lane >> sh[u]);
+                const unsigned j = lane & ((1u << sh[u]) - 1);
+                cls[u] = c;
+                if (c < p.cls_start[b + 1]) {
+                    const uint32_t o0 = sl.start[c - sl.c0], n = sl.len[c - sl.c0];
+                    if (j < n) {
+                        tid[u] = sl.lab[o0 + j - sl.e0];
+                        wv[u] = sl.w[o0 + j - sl.e0];
+                        a[u] = ld_cg_f64(in + tid[u]);
+                        ev[u] = true;
+                    }
                 }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EM_ILP; ++u) {
+            double v = 0.0;
+            bool e = ev[u];
+            if (e) { if (VB && !(a[u] > 0.0)) e = false; else v = a[u] * wv[u]; }
+            double denom = v;
+            for (unsigned m = (1u << sh[u]) >> 1; m >= 1; m >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, m);
+            if (e && denom > DENORM_MIN && !isnan(v)) {
+                const double add = v * (sl.cnt[cls[u] - sl.c0] / denom);
+                atomicAdd(out + tid[u], add);
+                contrib += add;
+            }
+        }
+    }
+    // long classes (more than 32 members): the whole warp walks the class twice
+    const uint64_t long_lo = tile_lo > p.tile_start[SFB_NBINS - 1] ? tile_lo : p.tile_start[SFB_NBINS - 1];
+    for (uint64_t tile = long_lo + warp; tile < tile_hi; tile += W) {
+        const uint64_t c = p.cls_start[SFB_NBINS - 1] + (tile - p.tile_start[SFB_NBINS - 1]);
+        if (c >= p.cls_start[SFB_NBINS]) continue;
+        const uint32_t o0 = sl.start[c - sl.c0] - (uint32_t)sl.e0, n = sl.len[c - sl.c0];
+        double denom = 0.0;
+        for (uint32_t j = lane; j < n; j += 32) {
+            const double al = ld_cg_f64(in + sl.lab[o0 + j]);
+            if (!VB || al > 0.0) denom += al * sl.w[o0 + j];
+        }
+        denom = warp_sum(denom);
+        if (denom > DENORM_MIN) {
+            const double inv = sl.cnt[c - sl.c0] / denom;
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint32_t t = sl.lab[o0 + j];
+                const double al = ld_cg_f64(in + t);
+                if (VB && !(al > 0.0)) continue;
+                const double v = al * sl.w[o0 + j];
+                if (!isnan(v)) { const double add = v * inv; atomicAdd(out + t, add); contrib += add; }
             }
         }
     }
     return contrib;
+}
+
+// Stage the CTA's slice in shared memory (dynamic smem, 16-byte aligned) with TMA bulk copies.  Source ranges are widened
+// to 16-byte boundaries (the arrays are allocated with slack), which shifts c0 / e0 down accordingly.
+// Returns false (and leaves `sl` pointing at global memory) if the slice does not fit in `smem_bytes`.
+__device__ bool stage_slice(const EmParams& p, uint64_t tile_lo, uint64_t tile_hi, unsigned char* smem, uint32_t smem_bytes,
+                            uint64_t* bar, Slice& sl) {
+    sl.start = p.start; sl.len = p.len; sl.cnt = p.cnt; sl.lab = p.lab; sl.w = p.w; sl.c0 = 0; sl.e0 = 0;
+    const uint64_t Em = p.cls_start[SFB_NBINS];
+    uint64_t c_lo = tile_first_class(p, tile_lo), c_hi = tile_first_class(p, tile_hi);
+    if (c_hi > Em) c_hi = Em;
+    if (c_lo >= c_hi) return true;                                  // nothing to do for this CTA
+    uint64_t e_lo = __ldg(p.start + c_lo);
+    uint64_t e_hi = (uint64_t)__ldg(p.start + c_hi - 1) + __ldg(p.len + c_hi - 1);
+    c_lo &= ~3ULL; e_lo &= ~3ULL;                                    // 16-byte aligned u32 ranges (and 32-byte f64 ranges)
+    const uint64_t nc = ((c_hi - c_lo) + 3) & ~3ULL, ne = ((e_hi - e_lo) + 3) & ~3ULL;
+    const uint64_t need = nc * 4 * 2 + nc * 8 + ne * 4 + ne * 8;
+    if (need > smem_bytes) return false;
+    double* s_cnt = reinterpret_cast<double*>(smem);
+    double* s_w = s_cnt + nc;
+    uint32_t* s_start = reinterpret_cast<uint32_t*>(s_w + ne);
+    uint32_t* s_len = s_start + nc;
+    uint32_t* s_lab = s_len + nc;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"((uint32_t)need) : "memory");
+        tma_load_1d(s_cnt, p.cnt + c_lo, (uint32_t)(nc * 8), bar);
+        tma_load_1d(s_w, p.w + e_lo, (uint32_t)(ne * 8), bar);
+        tma_load_1d(s_start, p.start + c_lo, (uint32_t)(nc * 4), bar);
+        tma_load_1d(s_len, p.len + c_lo, (uint32_t)(nc * 4), bar);
+        tma_load_1d(s_lab, p.lab + e_lo, (uint32_t)(ne * 4), bar);
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n selp.u32 %0, 1, 0, q;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    }
+    sl.start = s_start; sl.len = s_len; sl.cnt = s_cnt; sl.lab = s_lab; sl.w = s_w; sl.c0 = c_lo; sl.e0 = e_lo;
+    return true;
 }
 
 // ---- per-transcript pass: convergence rule + re-initialise the spare buffer (+ VBEM expTheta) -------------------------
@@ -212,10 +299,12 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_persistent(const EmParams 
     unsigned long long gen = 0;
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint64_t gstride = (uint64_t)nblocks * blockDim.x;
-    const unsigned warps_per_block = blockDim.x >> 5;
-    const unsigned warp = threadIdx.x >> 5;
     const uint64_t n_tiles = p.tile_start[SFB_NBINS];
     const uint64_t tile_lo = n_tiles * blockIdx.x / nblocks, tile_hi = n_tiles * (blockIdx.x + 1ULL) / nblocks;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ uint64_t tma_bar;
+    Slice sl;
+    stage_slice(p, tile_lo, tile_hi, dyn_smem, p.smem_bytes, &tma_bar, sl);
 
     unsigned bi = 0, bo = 1, bs = 2;                       // buffer indices: in / out / spare
     const bool fixed = p.fixed_iters > 0;
@@ -248,7 +337,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_persistent(const EmParams 
         if (VB) grid_barrier(p.ctl, nblocks, gen);         // expTheta complete before anyone gathers it
         const double* src = VB ? p.theta : in;
         double contrib = 0.0;
-        for (uint64_t tile = tile_lo + warp; tile < tile_hi; tile += warps_per_block) contrib += sweep_tile<VB>(p, tile, src, out);
+        contrib = sweep_block<VB>(p, sl, tile_lo, tile_hi, src, out);
         if (VB) block_sum_to_slot(contrib, reinterpret_cast<double*>(p.ctl + CTL_CSUM + ((n + 1u) & 3u)), sm_d);
         grid_barrier(p.ctl, nblocks, gen);
         // check(alpha_{n-1}, alpha_n) is complete now: would the reference loop (:820 / :486) have stopped at itNum == n?
@@ -283,13 +372,13 @@ template <bool VB>
 __global__ void __launch_bounds__(EM_THREADS, 1) k_em_sweep(const EmParams p, unsigned bi, unsigned bo, uint32_t n) {
     __shared__ double sm_d[32];
     const unsigned nblocks = gridDim.x;
-    const unsigned warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
     const uint64_t n_tiles = p.tile_start[SFB_NBINS];
     const uint64_t tile_lo = n_tiles * blockIdx.x / nblocks, tile_hi = n_tiles * (blockIdx.x + 1ULL) / nblocks;
     const double* src = VB ? p.theta : p.X + (size_t)bi * p.T;
     double* out = p.X + (size_t)bo * p.T;
-    double contrib = 0.0;
-    for (uint64_t tile = tile_lo + warp; tile < tile_hi; tile += warps_per_block) contrib += sweep_tile<VB>(p, tile, src, out);
+    Slice sl;
+    sl.start = p.start; sl.len = p.len; sl.cnt = p.cnt; sl.lab = p.lab; sl.w = p.w; sl.c0 = 0; sl.e0 = 0;
+    const double contrib = sweep_block<VB>(p, sl, tile_lo, tile_hi, src, out);
     if (VB) block_sum_to_slot(contrib, reinterpret_cast<double*>(p.ctl + CTL_CSUM + ((n + 1u) & 3u)), sm_d);
 }
 
@@ -526,10 +615,18 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, uint32_t* iter
     if (!steps) {
         void* args[] = {&p};
         const void* fn = vb ? reinterpret_cast<const void*>(&k_em_persistent<true>) : reinterpret_cast<const void*>(&k_em_persistent<false>);
+        // shared memory for the CTA's class slice: what the largest slice needs (+ alignment slack), capped by the opt-in maximum
+        int max_optin = 0;
+        SFB_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        // a warp tile of the densest bin holds 16 classes (16 B each) and up to 32 entries (12 B each) = 640 B
+        const uint64_t want = (p.tile_start[SFB_NBINS] / c->num_sms + 2) * 640 + 4096;
+        const size_t smem = (size_t)std::min<uint64_t>(want, (uint64_t)max_optin - 1024);
+        SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        p.smem_bytes = (uint32_t)smem;
         int per_sm = 0;
-        SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, EM_THREADS, 0));
+        SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, EM_THREADS, smem));
         if (per_sm < 1) SFB_FAIL(c, SFB200_ECUDA, "EM kernel does not fit on an SM");
-        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->num_sms), dim3(EM_THREADS), args, 0, s));
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->num_sms), dim3(EM_THREADS), args, smem, s));
         c->launches++;
         SFB_CUDA(c, cudaEventRecord(c->ev1, s));
         SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));

@@ -204,7 +204,7 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
         ix.n_kmers = n_heads;
     }
     uint64_t slots = 1024;
-    while (slots < 2 * ix.n_kmers) slots <<= 1;
+    while (slots < 4 * ix.n_kmers) slots <<= 1;      // load <= 25%: most lookups end in the first slot
     ix.table_slots = slots;
     IDX_CUDA(ix.table.reserve(slots));
     // presence filter: >= 8 bits per k-mer, capped at 64 MB (2^23 words) so that it stays L2-resident

@@ -678,8 +678,13 @@ struct MapState {
     DevBuf<unsigned int> fld_hist;
     DevBuf<int> remaining;
     DevBuf<int16_t> fld_val;
-    DevBuf<char> bases1, bases2;
-    DevBuf<uint64_t> off1, off2;
+    // two staging sets for host batches: the H2D copy of batch j (copy stream) overlaps the mapping kernel of batch j-1
+    DevBuf<char> bases1[2], bases2[2];
+    DevBuf<uint64_t> off1[2], off2[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    bool in_use[2] = {false, false};
+    unsigned parity = 0;
     uint64_t n_buckets = 0, n_overflow = 0, arena_words = 0;
     uint64_t n_threads_total = 0;
     int grid = 0;
@@ -693,7 +698,12 @@ void sfb_map_state_free(sfb200_ctx* c) {
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
     m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release();
-    m->bases1.release(); m->bases2.release(); m->off1.release(); m->off2.release();
+    for (int i = 0; i < 2; ++i) {
+        m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
+        if (m->copied[i]) cudaEventDestroy(m->copied[i]);
+        if (m->consumed[i]) cudaEventDestroy(m->consumed[i]);
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
     delete m;
     c->map = nullptr;
@@ -758,6 +768,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     c->cls.ready = false;
     m->begun = true;
     m->ev_used = 0; m->kernel_ms = 0.0;
+    m->in_use[0] = m->in_use[1] = false; m->parity = 0;
     return SFB200_OK;
 }
 
@@ -813,22 +824,39 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
     if (n_reads == 0) return SFB200_OK;
     if (!bases1 || !off1 || ((bases2 == nullptr) != (off2 == nullptr))) SFB_FAIL(c, SFB200_EINVAL, "map_batch: null array");
     cudaSetDevice(c->device);
-    cudaStream_t s = c->stream;
-    // the previous batch may still be reading the staging buffers
-    SFB_CUDA(c, cudaStreamSynchronize(s));
+    if (!m->copy_stream) {
+        SFB_CUDA(c, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SFB_CUDA(c, cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming));
+            SFB_CUDA(c, cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming));
+        }
+    }
+    const unsigned b = m->parity;
+    m->parity ^= 1u;
+    // this staging set was last read by the kernel of two batches ago
+    if (m->in_use[b]) SFB_CUDA(c, cudaEventSynchronize(m->consumed[b]));
+    cudaStream_t cs = m->copy_stream;
     const uint64_t nb1 = off1[n_reads] - off1[0];
-    SFB_CUDA(c, m->bases1.reserve(nb1 + 8)); SFB_CUDA(c, m->off1.reserve(n_reads + 1));
-    SFB_CUDA(c, cudaMemcpyAsync(m->bases1.p, bases1 + off1[0], nb1, cudaMemcpyHostToDevice, s));
-    SFB_CUDA(c, cudaMemcpyAsync(m->off1.p, off1, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, m->bases1[b].reserve(nb1 + 8)); SFB_CUDA(c, m->off1[b].reserve(n_reads + 1));
+    SFB_CUDA(c, cudaMemcpyAsync(m->bases1[b].p, bases1 + off1[0], nb1, cudaMemcpyHostToDevice, cs));
+    SFB_CUDA(c, cudaMemcpyAsync(m->off1[b].p, off1, (n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
     const char* d_b2 = nullptr; const uint64_t* d_o2 = nullptr;
     if (bases2) {
         const uint64_t nb2 = off2[n_reads] - off2[0];
-        SFB_CUDA(c, m->bases2.reserve(nb2 + 8)); SFB_CUDA(c, m->off2.reserve(n_reads + 1));
-        SFB_CUDA(c, cudaMemcpyAsync(m->bases2.p, bases2 + off2[0], nb2, cudaMemcpyHostToDevice, s));
-        SFB_CUDA(c, cudaMemcpyAsync(m->off2.p, off2, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-        d_b2 = m->bases2.p - off2[0]; d_o2 = m->off2.p;
+        SFB_CUDA(c, m->bases2[b].reserve(nb2 + 8)); SFB_CUDA(c, m->off2[b].reserve(n_reads + 1));
+        SFB_CUDA(c, cudaMemcpyAsync(m->bases2[b].p, bases2 + off2[0], nb2, cudaMemcpyHostToDevice, cs));
+        SFB_CUDA(c, cudaMemcpyAsync(m->off2[b].p, off2, (n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
+        d_b2 = m->bases2[b].p - off2[0]; d_o2 = m->off2[b].p;
     }
-    return sfb200_map_batch_device(c, m->bases1.p - off1[0], m->off1.p, d_b2, d_o2, n_reads);
+    SFB_CUDA(c, cudaEventRecord(m->copied[b], cs));
+    SFB_CUDA(c, cudaStreamWaitEvent(c->stream, m->copied[b], 0));
+    const int rc = sfb200_map_batch_device(c, m->bases1[b].p - off1[0], m->off1[b].p, d_b2, d_o2, n_reads);
+    if (rc) return rc;
+    SFB_CUDA(c, cudaEventRecord(m->consumed[b], c->stream));
+    m->in_use[b] = true;
+    // the caller may reuse its buffers as soon as we return: wait for the copy (not for the kernel)
+    SFB_CUDA(c, cudaEventSynchronize(m->copied[b]));
+    return SFB200_OK;
 }
 
 extern "C" double sfb200_last_map_kernel_ms(const sfb200_ctx* c) { return (c && c->map) ? c->map->kernel_ms : 0.0; }
