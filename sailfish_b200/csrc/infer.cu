@@ -115,8 +115,257 @@ extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint3
     return rc;
 }
 
+// ======================================================================================================================
+// Collapsed Gibbs sampler (reference src/CollapsedGibbsSampler.cpp)
+// ======================================================================================================================
+// sampleRound_ (:96-186) walks the classes one after another because consecutive classes may share transcripts (the
+// conditional of a class depends on txpCount of its members).  Classes that share NO transcript are conditionally
+// independent, so the walk is re-ordered by a greedy colouring (classes of one colour are pairwise disjoint): colours are
+// visited in sequence, the classes of a colour in parallel -- the same Markov kernel as a sequential sweep in colour order,
+// which is a valid scan order of the same sampler (the reference's own order is libcuckoo's arbitrary bucket order).
+namespace {
+
+struct Rng {                       // counter-based stream: (seed; sample, purpose, class) -> as many uniforms as asked for
+    Philox ph; uint64_t lo, hi; uint32_t buf[4]; int left;
+    __device__ Rng(uint64_t seed, uint64_t sample, uint64_t purpose, uint64_t item) : ph(seed), lo(item << 16), hi((sample << 8) | purpose), left(0) {}
+    __device__ double u01() {
+        if (left < 2) { ph(lo++, hi, buf); left = 4; }
+        left -= 2;
+        return u01_from(buf[left], buf[left + 1]);
+    }
+};
+
+__device__ __forceinline__ double stirling_tail(double k) {
+    const double t[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509, 0.0166446911898211,
+                          0.0138761288230707, 0.0118967099458917, 0.0104112652619720, 0.00925546218271273, 0.00833056343336287};
+    if (k <= 9.0) return t[(int)k];
+    const double kp1sq = (k + 1) * (k + 1);
+    return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / (k + 1);
+}
+
+// exact Binomial(n, p) draw: sequential inversion for small n*p, Hormann's BTRS transformed rejection otherwise
+__device__ uint64_t binomial_draw(Rng& g, uint64_t n, double p) {
+    if (n == 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    if (flip) p = 1.0 - p;
+    const double dn = (double)n, q = 1.0 - p;
+    uint64_t x;
+    if (dn * p < 10.0) {
+        // waiting-time inversion: sum of geometric gaps
+        double qn = exp(dn * log1p(-p));
+        const double bound = fmin(dn, dn * p + 10.0 * sqrt(dn * p * q + 1.0));
+        double px = qn, U = g.u01();
+        double X = 0.0;
+        while (U > px) {
+            X += 1.0;
+            if (X > bound) { X = 0.0; px = qn; U = g.u01(); }
+            else { U -= px; px = ((dn - X + 1.0) * p * px) / (X * q); }
+        }
+        x = (uint64_t)X;
+    } else {
+        const double stddev = sqrt(dn * p * q);
+        const double b = 1.15 + 2.53 * stddev, a = -0.0873 + 0.0248 * b + 0.01 * p, cc = dn * p + 0.5;
+        const double v_r = 0.92 - 4.2 / b, r = p / q, alpha = (2.83 + 5.1 / b) * stddev, m = floor((dn + 1.0) * p);
+        for (;;) {
+            const double u = g.u01() - 0.5;
+            double v = g.u01();
+            const double us = 0.5 - fabs(u);
+            const double k = floor((2.0 * a / us + b) * u + cc);
+            if (us >= 0.07 && v <= v_r) { x = (uint64_t)k; break; }
+            if (k < 0.0 || k > dn) continue;
+            v = log(v * alpha / (a / (us * us) + b));
+            const double ub = (m + 0.5) * log((m + 1.0) / (r * (dn - m + 1.0))) + (dn + 1.0) * log((dn - m + 1.0) / (dn - k + 1.0)) +
+                              (k + 0.5) * log(r * (dn - k + 1.0) / (k + 1.0)) + stirling_tail(m) + stirling_tail(dn - m) -
+                              stirling_tail(k) - stirling_tail(dn - k);
+            if (v <= ub) { x = (uint64_t)k; break; }
+        }
+    }
+    return flip ? n - x : x;
+}
+
+// Multinomial(n; probs[0..k)) by conditional binomials, written into out[0..k) (MultinomialSampler.hpp:13-64 draws the same
+// distribution one uniform at a time)
+__device__ void multinomial_draw(Rng& g, uint64_t n, uint32_t k, const double* probs, unsigned long long* out) {
+    double rem_p = 0.0;
+    for (uint32_t i = 0; i < k; ++i) rem_p += probs[i];
+    uint64_t rem = n;
+    for (uint32_t i = 0; i < k; ++i) {
+        uint64_t x = 0;
+        if (rem > 0) {
+            if (i + 1 == k || !(rem_p > probs[i])) x = rem;
+            else x = binomial_draw(g, rem, fmin(1.0, fmax(0.0, probs[i] / rem_p)));
+        }
+        out[i] = x;
+        rem -= x;
+        rem_p -= probs[i];
+    }
+}
+
+struct GibbsParams {
+    const unsigned long long* row_ptr; const uint32_t* labels; const unsigned long long* counts; const double* w;
+    unsigned long long* countMap; double* probMap; int* txpCount;
+    const double* mass;            // prior + mass * numMapped (:219-221)
+    double prior;
+    uint64_t seed;
+};
+
+// initCountMap_ (:35-94): every class splits its count over its members, independently of the other classes
+__global__ void k_gibbs_init(const GibbsParams p, uint64_t E) {
+    const uint64_t eq = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (eq >= E) return;
+    const uint64_t b = p.row_ptr[eq], e = p.row_ptr[eq + 1];
+    const uint32_t k = (uint32_t)(e - b);
+    const uint64_t classCount = p.counts[eq];
+    if (k > 1) {
+        double denom = 0.0;
+        for (uint64_t j = b; j < e; ++j) { denom += (p.prior + p.mass[p.labels[j]]) * p.w[j]; p.countMap[j] = 0; }
+        if (denom > DENORM_MIN) {
+            const double norm = 1.0 / denom;
+            for (uint64_t j = b; j < e; ++j) p.probMap[j] = norm * ((p.prior + p.mass[p.labels[j]]) * p.w[j]);
+            Rng g(p.seed, 0, 1, eq);
+            multinomial_draw(g, classCount, k, p.probMap + b, p.countMap + b);
+        }
+    } else if (k == 1) {
+        p.countMap[b] = classCount;
+    }
+    for (uint64_t j = b; j < e; ++j) atomicAdd(p.txpCount + p.labels[j], (int)p.countMap[j]);
+}
+
+// sampleRound_ (:96-186) for the classes of one colour
+__global__ void k_gibbs_round(const GibbsParams p, const uint32_t* __restrict__ order, uint64_t lo, uint64_t hi, uint64_t sample) {
+    const uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const uint64_t eq = order[i];
+    const uint64_t b = p.row_ptr[eq], e = p.row_ptr[eq + 1];
+    const uint32_t k = (uint32_t)(e - b);
+    Rng g(p.seed, sample + 1, 2, eq);
+    const double sampleFrac = 0.25 + 0.5 * g.u01();                      // uniform_real_distribution(0.25, 0.75) (:106,115)
+    double denom = 0.0;
+    unsigned long long numResampled = 0;
+    for (uint64_t j = b; j < e; ++j) {                                      // :124-136
+        const uint32_t tid = p.labels[j];
+        const unsigned long long curr = p.countMap[j];
+        const unsigned long long res = (unsigned long long)round(sampleFrac * (double)curr);
+        numResampled += res;
+        p.txpCount[tid] -= (int)res;
+        p.countMap[j] = curr - res;
+        p.probMap[j] = (double)res;                                       // parked: restored below if the class is skipped
+        denom += (p.prior + (double)p.txpCount[tid]) * p.w[j];
+    }
+    if (denom > DENORM_MIN) {                                               // :138-160
+        // the resample sizes are needed again only if the class is skipped; it is not, so probMap can take the probabilities
+        const double norm = 1.0 / denom;
+        for (uint64_t j = b; j < e; ++j) p.probMap[j] = norm * ((p.prior + (double)p.txpCount[p.labels[j]]) * p.w[j]);
+        // draw into a scratch row that aliases nothing: reuse countMap increments through a second pass
+        Rng g2(p.seed, sample + 1, 3, eq);
+        double rem_p = 0.0;
+        for (uint64_t j = b; j < e; ++j) rem_p += p.probMap[j];
+        unsigned long long rem = numResampled;
+        for (uint64_t j = b; j < e; ++j) {
+            unsigned long long x = 0;
+            if (rem > 0) {
+                if (j + 1 == e || !(rem_p > p.probMap[j])) x = rem;
+                else x = binomial_draw(g2, rem, fmin(1.0, fmax(0.0, p.probMap[j] / rem_p)));
+            }
+            rem -= x; rem_p -= p.probMap[j];
+            p.countMap[j] += x;                                            // :162-176
+            p.txpCount[p.labels[j]] += (int)x;
+        }
+    } else {
+        for (uint64_t j = b; j < e; ++j) {                                  // class skipped: put the removed counts back
+            const unsigned long long res = (unsigned long long)p.probMap[j];
+            p.countMap[j] += res;
+            p.txpCount[p.labels[j]] += (int)res;
+        }
+    }
+    (void)k;
+}
+
+__global__ void k_entry_weights(const unsigned long long* __restrict__ row_ptr, const uint32_t* __restrict__ labels,
+                                const unsigned long long* __restrict__ counts, const double* __restrict__ eff_in, uint64_t E,
+                                double* __restrict__ w) {
+    const uint64_t eq = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (eq >= E) return;
+    const double count = (double)counts[eq];
+    double wsum = 0.0;
+    for (uint64_t j = row_ptr[eq]; j < row_ptr[eq + 1]; ++j) {              // CollapsedEMOptimizer.cpp:745-772
+        const double e = eff_in[labels[j]];
+        const double v = count / (e <= 1.0 ? 1.0 : e);
+        w[j] = v; wsum += v;
+    }
+    const double wnorm = 1.0 / wsum;
+    for (uint64_t j = row_ptr[eq]; j < row_ptr[eq + 1]; ++j) w[j] *= wnorm;
+}
+
+}  // namespace
+
 extern "C" int sfb200_gibbs_run(sfb200_ctx* c, const double* eff_lens, const double* masses, uint32_t n_txp, uint64_t num_mapped,
                                 uint32_t n_samples, uint64_t seed, sfb200_i32_row_cb cb, void* user) {
-    if (!c) return SFB200_EINVAL;
-    SFB_FAIL(c, SFB200_EINVAL, "gibbs_run: not built yet");
+    if (!c || !eff_lens || !masses) return SFB200_EINVAL;
+    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "gibbs_run: no classes");
+    if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "gibbs_run: n_txp differs from the class table's");
+    cudaSetDevice(c->device);
+    { const int rc = sfb_classes_host(c); if (rc) return rc; }
+    const DevClasses& k = c->cls;
+    const uint64_t E = k.E, nnz = k.nnz;
+    cudaStream_t s = c->stream;
+    // greedy colouring: colour(class) = max over its members of the next free colour of that transcript
+    std::vector<uint32_t> next_free(n_txp, 0), colour(E, 0);
+    uint32_t n_colours = 0;
+    for (uint64_t e = 0; e < E; ++e) {
+        const uint64_t b = k.h_row_ptr[e], en = k.h_row_ptr[e + 1];
+        if (en - b <= 1) { colour[e] = 0xFFFFFFFFu; continue; }            // single-member classes are never resampled (:120)
+        uint32_t col = 0;
+        for (uint64_t j = b; j < en; ++j) col = std::max(col, next_free[k.h_labels[j]]);
+        for (uint64_t j = b; j < en; ++j) next_free[k.h_labels[j]] = col + 1;
+        colour[e] = col;
+        n_colours = std::max(n_colours, col + 1);
+    }
+    std::vector<uint64_t> col_start(n_colours + 1, 0);
+    for (uint64_t e = 0; e < E; ++e) if (colour[e] != 0xFFFFFFFFu) col_start[colour[e] + 1]++;
+    for (uint32_t q = 0; q < n_colours; ++q) col_start[q + 1] += col_start[q];
+    std::vector<uint32_t> order(col_start[n_colours] ? col_start[n_colours] : 1);
+    { std::vector<uint64_t> cur(col_start.begin(), col_start.end() - 1);
+      for (uint64_t e = 0; e < E; ++e) if (colour[e] != 0xFFFFFFFFu) order[cur[colour[e]]++] = (uint32_t)e; }
+
+    DevBuf<unsigned long long> d_rp, d_cnt, d_cmap; DevBuf<uint32_t> d_lab, d_order; DevBuf<double> d_w, d_prob, d_mass, d_eff; DevBuf<int> d_txp;
+    auto cleanup = [&]() { d_rp.release(); d_cnt.release(); d_cmap.release(); d_lab.release(); d_order.release(); d_w.release();
+                           d_prob.release(); d_mass.release(); d_eff.release(); d_txp.release(); };
+#define GB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return SFB200_ECUDA; } } while (0)
+    GB_CUDA(d_rp.reserve(E + 1)); GB_CUDA(d_cnt.reserve(E)); GB_CUDA(d_cmap.reserve(nnz)); GB_CUDA(d_lab.reserve(nnz));
+    GB_CUDA(d_order.reserve(order.size())); GB_CUDA(d_w.reserve(nnz)); GB_CUDA(d_prob.reserve(nnz)); GB_CUDA(d_mass.reserve(n_txp));
+    GB_CUDA(d_eff.reserve(n_txp)); GB_CUDA(d_txp.reserve(n_txp));
+    std::vector<double> mass(n_txp);
+    const double prior = 1e-8;                                              // :215
+    for (uint32_t i = 0; i < n_txp; ++i) mass[i] = prior + masses[i] * static_cast<double>(num_mapped);   // :219-221
+    GB_CUDA(cudaMemcpyAsync(d_rp.p, k.h_row_ptr.data(), (E + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (E) GB_CUDA(cudaMemcpyAsync(d_cnt.p, k.h_counts.data(), E * 8, cudaMemcpyHostToDevice, s));
+    if (nnz) GB_CUDA(cudaMemcpyAsync(d_lab.p, k.h_labels.data(), nnz * 4, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemcpyAsync(d_mass.p, mass.data(), n_txp * 8ull, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemcpyAsync(d_eff.p, eff_lens, n_txp * 8ull, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemsetAsync(d_txp.p, 0, n_txp * 4ull, s));
+    if (E) { k_entry_weights<<<gridn(E, 128), 128, 0, s>>>(d_rp.p, d_lab.p, d_cnt.p, d_eff.p, E, d_w.p); c->launches++; }
+    GibbsParams gp;
+    gp.row_ptr = d_rp.p; gp.labels = d_lab.p; gp.counts = d_cnt.p; gp.w = d_w.p; gp.countMap = d_cmap.p; gp.probMap = d_prob.p;
+    gp.txpCount = d_txp.p; gp.mass = d_mass.p; gp.prior = prior; gp.seed = seed;
+    if (E) { k_gibbs_init<<<gridn(E, 128), 128, 0, s>>>(gp, E); c->launches++; }
+    GB_CUDA(cudaGetLastError());
+    std::vector<int32_t> row(n_txp);
+    int rc = SFB200_OK;
+    for (uint32_t smp = 0; smp < n_samples && rc == SFB200_OK; ++smp) {
+        // `bool numInternalRounds = 10;` in the reference => exactly one round per sample (:248,257)
+        for (uint32_t q = 0; q < n_colours; ++q) {
+            const uint64_t lo = col_start[q], hi = col_start[q + 1];
+            if (hi > lo) { k_gibbs_round<<<gridn(hi - lo, 128), 128, 0, s>>>(gp, d_order.p, lo, hi, smp); c->launches++; }
+        }
+        GB_CUDA(cudaGetLastError());
+        GB_CUDA(cudaMemcpyAsync(row.data(), d_txp.p, n_txp * 4ull, cudaMemcpyDeviceToHost, s));
+        GB_CUDA(cudaStreamSynchronize(s));
+        if (cb && cb(user, row.data(), n_txp) != 0) { c->err = "gibbs row callback failed"; rc = SFB200_ECALLBACK; }
+    }
+#undef GB_CUDA
+    cleanup();
+    return rc;
 }

