@@ -1,0 +1,265 @@
+// sfb200_host.hpp -- C++ adaptors with the reference's own class / method names on top of the C ABI (include/sfb200.h).
+//
+// Sailfish (kingsfordgroup/sailfish v0.10.0) has no plugin layer: the quantification hot path is five ordinary C++ call
+// sites inside src/SailfishQuantify.cpp.  The classes below keep those signatures, so mainQuantify's body can
+// call them unchanged (INTEGRATION.md shows the patch):
+//
+//   sfb200::GpuQuasiMapper::processReads        <- processReadsQuasi<IndexT>            SailfishQuantify.cpp:105-113, 458-464
+//   sfb200::EquivalenceClassBuilder             <- EquivalenceClassBuilder              include/EquivalenceClassBuilder.hpp:53-117
+//   sfb200::CollapsedEMOptimizer::optimize      <- CollapsedEMOptimizer::optimize       include/CollapsedEMOptimizer.hpp:25-28
+//   sfb200::CollapsedEMOptimizer::gatherBootstraps <- ...::gatherBootstraps             include/CollapsedEMOptimizer.hpp:30-36
+//   sfb200::CollapsedGibbsSampler::sample       <- CollapsedGibbsSampler::sample        include/CollapsedGibbsSampler.hpp:27-31
+//
+// They are templates over the experiment / options types, so they compile both against the reference's ReadExperiment /
+// Transcript / SailfishOpts headers and against any type with the same members (tests/host_adaptor_test.cpp uses a mock).
+// Header-only, plain C++11, no CUDA headers: link with -lsfb200.  There is no CPU fallback: without a CUDA device the
+// constructor of Device throws.
+#ifndef SFB200_HOST_HPP
+#define SFB200_HOST_HPP
+
+#include <cstdint>
+#include <functional>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/sfb200.h"
+
+namespace sfb200 {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// one sfb200_ctx (a CUDA device with its index, class table and inference scratch)
+class Device {
+public:
+    explicit Device(int device = 0) {
+        const int rc = sfb200_ctx_create(device, &ctx_);
+        if (rc != SFB200_OK) throw Error(rc, "sfb200: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Device() { sfb200_ctx_destroy(ctx_); }
+    Device(const Device&) = delete;
+    Device& operator=(const Device&) = delete;
+    sfb200_ctx* get() const { return ctx_; }
+    void check(int rc) const { if (rc != SFB200_OK) throw Error(rc, sfb200_last_error(ctx_)); }
+
+    // what ReadExperiment takes from the quasi index (include/ReadExperiment.hpp:103-116): concatenated transcript
+    // sequences, their offsets and lengths
+    void buildIndex(const std::string& seq, const std::vector<uint64_t>& txpOffsets, const std::vector<uint32_t>& txpLens, int k) {
+        check(sfb200_index_build(ctx_, seq.data(), txpOffsets.data(), txpLens.data(), static_cast<uint32_t>(txpLens.size()), k));
+        nTxp_ = static_cast<uint32_t>(txpLens.size());
+    }
+    uint32_t numTranscripts() const { return nTxp_; }
+    void setNumTranscripts(uint32_t n) { nTxp_ = n; }
+
+private:
+    sfb200_ctx* ctx_ = nullptr;
+    uint32_t nTxp_ = 0;
+};
+
+// ---- equivalence classes -----------------------------------------------------------------------------------------------------
+// TranscriptGroup / TGValue as the rest of Sailfish sees them through eqVec() (EquivalenceClassBuilder.hpp:18-51,110)
+struct TranscriptGroup { std::vector<uint32_t> txps; };
+struct TGValue { std::vector<double> weights; uint64_t count; };
+
+class EquivalenceClassBuilder {
+public:
+    explicit EquivalenceClassBuilder(Device& d) : dev_(d) {}
+    // == start() (EquivalenceClassBuilder.hpp:62): resets the class table, the counters and the FLD sampler
+    void start(const sfb200_map_opts& opts) { opts_ = opts; dev_.check(sfb200_map_begin(dev_.get(), &opts)); active_ = true; }
+    // == finish() (:64-80): flattens the table; the classes stay on the device for optimize()
+    bool finish() {
+        fld_.assign(opts_.max_frag_len, 0);
+        dev_.check(sfb200_map_finish(dev_.get(), counters_, fld_.data(), &nClasses_, &nnz_));
+        active_ = false;
+        haveVec_ = false;
+        return true;
+    }
+    // == eqVec() (:110): materialised on demand (aux/eq_classes.txt, --dumpEq); weights are 1/n as normalizeAux leaves them
+    std::vector<std::pair<const TranscriptGroup, TGValue>>& eqVec() {
+        if (!haveVec_) {
+            std::vector<uint64_t> rowPtr(nClasses_ + 1), counts(nClasses_ ? nClasses_ : 1);
+            std::vector<uint32_t> labels(nnz_ ? nnz_ : 1);
+            dev_.check(sfb200_eq_export(dev_.get(), rowPtr.data(), labels.data(), counts.data()));
+            countVec_.clear();
+            countVec_.reserve(nClasses_);
+            for (uint64_t e = 0; e < nClasses_; ++e) {
+                TranscriptGroup tg;
+                tg.txps.assign(labels.begin() + rowPtr[e], labels.begin() + rowPtr[e + 1]);
+                TGValue v;
+                v.count = counts[e];
+                v.weights.assign(tg.txps.size(), 1.0 / static_cast<double>(tg.txps.size()));
+                countVec_.emplace_back(std::move(tg), std::move(v));
+            }
+            haveVec_ = true;
+        }
+        return countVec_;
+    }
+    // the inverse (the commented-out loadEquivClasses, SailfishQuantify.cpp:1444-1495): classes from aux/eq_classes.txt
+    void import(uint32_t nTxp, const std::vector<uint64_t>& rowPtr, const std::vector<uint32_t>& labels, const std::vector<uint64_t>& counts) {
+        dev_.check(sfb200_eq_import(dev_.get(), nTxp, counts.size(), rowPtr.data(), labels.data(), counts.data()));
+        dev_.setNumTranscripts(nTxp);
+        nClasses_ = counts.size(); nnz_ = labels.size(); haveVec_ = false;
+    }
+    // ReadExperiment's atomics after the mapping threads joined (ReadExperiment.hpp:74-97)
+    uint64_t numObservedFragments() const { return counters_[0]; }
+    uint64_t numMappedFragments() const { return counters_[1]; }
+    uint64_t numFragHits() const { return counters_[2]; }
+    uint64_t upperBoundHits() const { return counters_[3]; }
+    uint64_t numFwd() const { return counters_[4]; }
+    uint64_t numRC() const { return counters_[5]; }
+    const std::vector<uint32_t>& fragLengthCounts() const { return fld_; }      // flMap (SailfishQuantify.cpp:867)
+    uint64_t numClasses() const { return nClasses_; }
+
+private:
+    Device& dev_;
+    sfb200_map_opts opts_{};
+    bool active_ = false, haveVec_ = false;
+    uint64_t counters_[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> fld_;
+    uint64_t nClasses_ = 0, nnz_ = 0;
+    std::vector<std::pair<const TranscriptGroup, TGValue>> countVec_;
+};
+
+// ---- mapping -------------------------------------------------------------------------------------------------------------------
+// processReadsQuasi (SailfishQuantify.cpp:105-452 paired, :458-646 single) for one parser job.  A job is whatever the parser
+// hands a worker thread (paired_parser::job / single_parser::job, :175-180,510-515): `n` reads, read i = seq(i) or
+// (seq1(i), seq2(i)).  Host worker threads may call this concurrently: batches are serialised on the device context.
+class GpuQuasiMapper {
+public:
+    explicit GpuQuasiMapper(Device& d) : dev_(d) {}
+    template <typename SeqOf>
+    void processReads(size_t n, SeqOf seq) {                                   // single-end
+        pack(n, seq, b1_, o1_);
+        std::lock_guard<std::mutex> lk(mu_);
+        dev_.check(sfb200_map_batch(dev_.get(), b1_.data(), o1_.data(), nullptr, nullptr, n));
+    }
+    template <typename SeqOf1, typename SeqOf2>
+    void processReads(size_t n, SeqOf1 seq1, SeqOf2 seq2) {                     // paired-end
+        pack(n, seq1, b1_, o1_);
+        pack(n, seq2, b2_, o2_);
+        std::lock_guard<std::mutex> lk(mu_);
+        dev_.check(sfb200_map_batch(dev_.get(), b1_.data(), o1_.data(), b2_.data(), o2_.data(), n));
+    }
+
+private:
+    template <typename SeqOf>
+    static void pack(size_t n, SeqOf seq, std::string& bases, std::vector<uint64_t>& off) {
+        bases.clear();
+        off.assign(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) { const std::string& s = seq(i); bases.append(s); off[i + 1] = bases.size(); }
+        bases.push_back('\0');
+    }
+    Device& dev_;
+    std::mutex mu_;
+    std::string b1_, b2_;
+    std::vector<uint64_t> o1_, o2_;
+};
+
+// ---- inference -----------------------------------------------------------------------------------------------------------------
+namespace detail {
+template <typename ExpT, typename OptsT>
+std::vector<double> effLens(ExpT& readExp, OptsT& sopt) {                        // CollapsedEMOptimizer.cpp:733-740
+    auto& transcripts = readExp.transcripts();
+    std::vector<double> e(transcripts.size());
+    for (size_t i = 0; i < transcripts.size(); ++i)
+        e[i] = sopt.noEffectiveLengthCorrection ? static_cast<double>(transcripts[i].RefLength) : transcripts[i].EffectiveLength;
+    return e;
+}
+inline sfb200_em_opts emOpts(bool useVB, double tol, uint32_t maxIter) {
+    sfb200_em_opts o;
+    sfb200_em_default_opts(&o);
+    o.use_vb = useVB ? 1 : 0; o.tol = tol; o.max_iter = maxIter;
+    return o;
+}
+}  // namespace detail
+
+class CollapsedEMOptimizer {
+public:
+    explicit CollapsedEMOptimizer(Device& d) : dev_(d) {}
+
+    // bool CollapsedEMOptimizer::optimize(ReadExperiment&, SailfishOpts&, double relDiffTolerance, uint32_t maxIter)
+    template <typename ExpT, typename OptsT>
+    bool optimize(ExpT& readExp, OptsT& sopt, double relDiffTolerance = 0.01, uint32_t maxIter = 10000) {
+        auto& transcripts = readExp.transcripts();
+        const std::vector<double> eff = detail::effLens(readExp, sopt);
+        std::vector<double> alphas(transcripts.size());
+        const sfb200_em_opts o = detail::emOpts(sopt.useVBOpt, relDiffTolerance, maxIter);
+        uint32_t iters = 0; double mrd = 0.0;
+        const int rc = sfb200_em_run(dev_.get(), eff.data(), static_cast<uint32_t>(eff.size()), readExp.numMappedFragments(), &o,
+                                     alphas.data(), &iters, &mrd);
+        lastIters_ = iters;
+        if (rc == SFB200_ENOACTIVE || rc == SFB200_ESMALLSUM) { lastError_ = sfb200_last_error(dev_.get()); return false; }   // :794-798, :877-881
+        dev_.check(rc);
+        double alphaSum = 0.0;
+        for (double a : alphas) alphaSum += a;
+        for (size_t i = 0; i < transcripts.size(); ++i) {                       // :883-890
+            transcripts[i].setEstCount(alphas[i]);
+            transcripts[i].setMass(alphas[i] / alphaSum);
+        }
+        return true;
+    }
+
+    // bool gatherBootstraps(ReadExperiment&, SailfishOpts&, std::function<bool(const std::vector<double>&)>&, double, uint32_t)
+    template <typename ExpT, typename OptsT>
+    bool gatherBootstraps(ExpT& readExp, OptsT& sopt, std::function<bool(const std::vector<double>&)>& writeBootstrap,
+                          double relDiffTolerance = 0.01, uint32_t maxIter = 10000, uint64_t seed = 0x5f3759dfULL) {
+        const std::vector<double> eff = detail::effLens(readExp, sopt);
+        const sfb200_em_opts o = detail::emOpts(sopt.useVBOpt, relDiffTolerance, maxIter);
+        struct Ctx { std::function<bool(const std::vector<double>&)>* f; std::vector<double> row; } cx{&writeBootstrap, {}};
+        auto tramp = [](void* u, const double* row, size_t n) -> int {
+            Ctx* c = static_cast<Ctx*>(u);
+            c->row.assign(row, row + n);
+            return (*c->f)(c->row) ? 0 : 1;
+        };
+        const int rc = sfb200_bootstrap_run(dev_.get(), eff.data(), static_cast<uint32_t>(eff.size()), &o, sopt.numBootstraps, seed,
+                                            tramp, &cx);
+        if (rc == SFB200_ENOACTIVE || rc == SFB200_ESMALLSUM || rc == SFB200_ECALLBACK) { lastError_ = sfb200_last_error(dev_.get()); return false; }
+        dev_.check(rc);
+        return true;
+    }
+    uint32_t lastIterations() const { return lastIters_; }
+    const std::string& lastError() const { return lastError_; }
+
+private:
+    Device& dev_;
+    uint32_t lastIters_ = 0;
+    std::string lastError_;
+};
+
+class CollapsedGibbsSampler {
+public:
+    explicit CollapsedGibbsSampler(Device& d) : dev_(d) {}
+    // template <typename ExpT> bool sample(ExpT&, SailfishOpts&, std::function<bool(const std::vector<int>&)>&, uint32_t)
+    template <typename ExpT, typename OptsT>
+    bool sample(ExpT& readExp, OptsT& sopt, std::function<bool(const std::vector<int>&)>& writeSample, uint32_t numSamples = 500,
+                uint64_t seed = 0x2545F491ULL) {
+        auto& transcripts = readExp.transcripts();
+        const std::vector<double> eff = detail::effLens(readExp, sopt);
+        std::vector<double> masses(transcripts.size());
+        const double numMapped = static_cast<double>(readExp.numMappedFragments());
+        for (size_t i = 0; i < transcripts.size(); ++i) masses[i] = transcripts[i].mass();
+        struct Ctx { std::function<bool(const std::vector<int>&)>* f; std::vector<int> row; } cx{&writeSample, {}};
+        auto tramp = [](void* u, const int32_t* row, size_t n) -> int {
+            Ctx* c = static_cast<Ctx*>(u);
+            c->row.assign(row, row + n);
+            return (*c->f)(c->row) ? 0 : 1;
+        };
+        dev_.check(sfb200_gibbs_run(dev_.get(), eff.data(), masses.data(), static_cast<uint32_t>(eff.size()),
+                                    readExp.numMappedFragments(), numSamples, seed, tramp, &cx));
+        // the reference overwrites Transcript::mass_ with prior + mass * numMapped and never restores it
+        // (CollapsedGibbsSampler.cpp:219-221): keep that observable side effect
+        for (size_t i = 0; i < transcripts.size(); ++i) transcripts[i].setMass(1e-8 + masses[i] * numMapped);
+        return true;
+    }
+
+private:
+    Device& dev_;
+};
+
+}  // namespace sfb200
+#endif
