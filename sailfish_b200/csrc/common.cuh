@@ -73,7 +73,23 @@ struct DevIndex {
 // g/2 < n <= g for g = 2,4,8,16,32 (b = 0..4) and n > 32 (b = 5), so a sub-warp group of g lanes owns one class.
 // Classes with one member never enter the sweep: their counts form the per-transcript vector `single`.
 constexpr int SFB_NBINS = 6;
+// CTA-partitioned copy of the multi-member classes (em_part.cuh): local classes grouped by (CTA, bin), then the pool by bin
+struct DevPartition {
+    bool valid = false;      // built for the current classes
+    bool usable = false;     // every CTA's slice fits in shared memory
+    uint32_t n_cta = 0;
+    uint64_t pool_cls[SFB_NBINS + 1] = {0, 0, 0, 0, 0, 0, 0};
+    uint64_t n_pool = 0;
+    uint64_t max_cta_bytes = 0;
+    DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
+    DevBuf<double> cnt, w, cnt_s;
+    DevBuf<unsigned long long> tbl, grp;
+    DevBuf<uint8_t> dirty;
+    void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); dirty.release(); }
+};
 struct DevClasses {
+    DevPartition part;
     uint32_t n_txp = 0;
     uint64_t E = 0, nnz = 0;            // as imported (all classes)
     uint64_t Em = 0, nnzm = 0;          // multi-member classes only

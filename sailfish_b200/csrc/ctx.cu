@@ -38,7 +38,7 @@ extern "C" void sfb200_ctx_destroy(sfb200_ctx* c) {
     c->index.txp_end.release(); c->index.sa.release(); c->index.table.release(); c->index.bloom.release();
     c->cls.start.release(); c->cls.len.release(); c->cls.lab.release(); c->cls.w.release(); c->cls.cnt.release();
     c->cls.perm.release(); c->cls.sgl_cls.release(); c->cls.sgl_tid.release(); c->cls.cnt_all.release();
-    c->cls.single.release(); c->cls.active.release();
+    c->cls.single.release(); c->cls.active.release(); c->cls.part.release();
     c->em_alpha.release(); c->em_theta.release(); c->em_base.release(); c->em_ctl.release(); c->eff.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -98,7 +98,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 // first class of a tile (tiles of bin b hold 32 >> (b+1) classes, the long bin one)
-__device__ __forceinline__ uint64_t tile_first_class(const EmParams& p, uint64_t tile) {
+template <typename P>
+__device__ __forceinline__ uint64_t tile_first_class(const P& p, uint64_t tile) {
     int b = 0;
     while (b < SFB_NBINS - 1 && tile >= p.tile_start[b + 1]) ++b;
     if (tile >= p.tile_start[SFB_NBINS]) return p.cls_start[SFB_NBINS];
@@ -110,9 +111,28 @@ constexpr int EM_ILP = 4;     // warp tiles in flight per warp: the alpha gather
 // ---- E-step + M-step scatter for the tiles of this CTA ---------------------------------------------------------------------
 // EMUpdate_ (CollapsedEMOptimizer.cpp:235-277) / VBEMUpdate_ (:325-366).  `in` is alpha (EM) or expTheta (VBEM); members with a
 // non-positive VBEM theta are skipped as in :342,357.  Returns this thread's sum of contributions (VBEM's alpha sum).
-template <bool VB>
-__device__ __forceinline__ double sweep_block(const EmParams& p, const Slice& sl, uint64_t tile_lo, uint64_t tile_hi,
-                                              const double* __restrict__ in, double* __restrict__ out) {
+struct Bins { uint64_t cls_start[SFB_NBINS + 1], tile_start[SFB_NBINS + 1]; };
+__device__ __forceinline__ void bins_set_tiles(Bins& b) {
+    uint64_t t = 0;
+    for (int i = 0; i < SFB_NBINS; ++i) {
+        b.tile_start[i] = t;
+        const uint64_t n = b.cls_start[i + 1] - b.cls_start[i];
+        const uint64_t per = i < SFB_NBINS - 1 ? (32u >> (i + 1)) : 1u;
+        t += (n + per - 1) / per;
+    }
+    b.tile_start[SFB_NBINS] = t;
+}
+
+__device__ __forceinline__ Bins em_bins(const EmParams& p) {
+    Bins b;
+    for (int i = 0; i <= SFB_NBINS; ++i) { b.cls_start[i] = p.cls_start[i]; b.tile_start[i] = p.tile_start[i]; }
+    return b;
+}
+
+// SMA: alpha vectors live in shared memory, indexed by (transcript - toff) (the CTA-local partition, see em_part.cuh)
+template <bool VB, bool SMA>
+__device__ __forceinline__ double sweep_block(const Bins& p, const Slice& sl, uint64_t tile_lo, uint64_t tile_hi,
+                                              const double* __restrict__ in, double* __restrict__ out, uint32_t toff) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     double contrib = 0.0;
     const uint64_t short_hi = tile_hi < p.tile_start[SFB_NBINS - 1] ? tile_hi : p.tile_start[SFB_NBINS - 1];
@@ -135,9 +155,9 @@ __device__ __forceinline__ double sweep_block(const EmParams& p, const Slice& sl
                 if (c < p.cls_start[b + 1]) {
                     const uint32_t o0 = sl.start[c - sl.c0], n = sl.len[c - sl.c0];
                     if (j < n) {
-                        tid[u] = sl.lab[o0 + j - sl.e0];
+                        tid[u] = sl.lab[o0 + j - sl.e0] - toff;
                         wv[u] = sl.w[o0 + j - sl.e0];
-                        a[u] = ld_cg_f64(in + tid[u]);
+                        a[u] = SMA ? in[tid[u]] : ld_cg_f64(in + tid[u]);
                         ev[u] = true;
                     }
                 }
@@ -165,15 +185,15 @@ __device__ __forceinline__ double sweep_block(const EmParams& p, const Slice& sl
         const uint32_t o0 = sl.start[c - sl.c0] - (uint32_t)sl.e0, n = sl.len[c - sl.c0];
         double denom = 0.0;
         for (uint32_t j = lane; j < n; j += 32) {
-            const double al = ld_cg_f64(in + sl.lab[o0 + j]);
+            const double al = SMA ? in[sl.lab[o0 + j] - toff] : ld_cg_f64(in + sl.lab[o0 + j]);
             if (!VB || al > 0.0) denom += al * sl.w[o0 + j];
         }
         denom = warp_sum(denom);
         if (denom > DENORM_MIN) {
             const double inv = sl.cnt[c - sl.c0] / denom;
             for (uint32_t j = lane; j < n; j += 32) {
-                const uint32_t t = sl.lab[o0 + j];
-                const double al = ld_cg_f64(in + t);
+                const uint32_t t = sl.lab[o0 + j] - toff;
+                const double al = SMA ? in[t] : ld_cg_f64(in + t);
                 if (VB && !(al > 0.0)) continue;
                 const double v = al * sl.w[o0 + j];
                 if (!isnan(v)) { const double add = v * inv; atomicAdd(out + t, add); contrib += add; }
@@ -337,7 +357,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_persistent(const EmParams 
         if (VB) grid_barrier(p.ctl, nblocks, gen);         // expTheta complete before anyone gathers it
         const double* src = VB ? p.theta : in;
         double contrib = 0.0;
-        contrib = sweep_block<VB>(p, sl, tile_lo, tile_hi, src, out);
+        contrib = sweep_block<VB, false>(em_bins(p), sl, tile_lo, tile_hi, src, out, 0u);
         if (VB) block_sum_to_slot(contrib, reinterpret_cast<double*>(p.ctl + CTL_CSUM + ((n + 1u) & 3u)), sm_d);
         grid_barrier(p.ctl, nblocks, gen);
         // check(alpha_{n-1}, alpha_n) is complete now: would the reference loop (:820 / :486) have stopped at itNum == n?
@@ -378,9 +398,11 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_sweep(const EmParams p, un
     double* out = p.X + (size_t)bo * p.T;
     Slice sl;
     sl.start = p.start; sl.len = p.len; sl.cnt = p.cnt; sl.lab = p.lab; sl.w = p.w; sl.c0 = 0; sl.e0 = 0;
-    const double contrib = sweep_block<VB>(p, sl, tile_lo, tile_hi, src, out);
+    const double contrib = sweep_block<VB, false>(em_bins(p), sl, tile_lo, tile_hi, src, out, 0u);
     if (VB) block_sum_to_slot(contrib, reinterpret_cast<double*>(p.ctl + CTL_CSUM + ((n + 1u) & 3u)), sm_d);
 }
+
+#include "em_part.cuh"
 
 __global__ void k_sum_f64(const double* __restrict__ x, uint32_t n, double* __restrict__ out) {
     __shared__ double sm_d[32];
@@ -459,6 +481,7 @@ int sfb_classes_from_host(sfb200_ctx* c, uint32_t n_txp, uint64_t E, const uint6
                           const uint64_t* counts) {
     DevClasses& k = c->cls;
     k.ready = false;
+    k.part.valid = false;
     const uint64_t nnz = E ? row_ptr[E] : 0;
     for (uint64_t i = 0; i < nnz; ++i) if (labels[i] >= n_txp) SFB_FAIL(c, SFB200_EINVAL, "label holds a transcript id >= n_txp");
     k.n_txp = n_txp; k.E = E; k.nnz = nnz;
@@ -598,11 +621,98 @@ extern "C" double sfb200_last_em_loop_ms(const sfb200_ctx* c) { return c ? c->la
 
 namespace {
 
+
+// Build the CTA partition of the current classes (em_part.cuh).  Device kernels do the per-class work; the host only scans
+// a T-long load histogram and the (n_cta+1) x 6 group table.
+int build_partition(sfb200_ctx* c) {
+    DevClasses& k = c->cls;
+    DevPartition& P = k.part;
+    P.valid = true; P.usable = false;
+    if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
+    const uint32_t T = k.n_txp, n_cta = (uint32_t)c->num_sms;
+    const uint64_t Em = k.Em, nnzm = k.nnzm;
+    if (Em == 0 || T == 0) return SFB200_OK;
+    cudaStream_t s = c->stream;
+    P.n_cta = n_cta;
+    SFB_CUDA(c, P.load.reserve(T)); SFB_CUDA(c, P.bounds.reserve(n_cta + 1)); SFB_CUDA(c, P.owner.reserve(Em)); SFB_CUDA(c, P.dirty.reserve(T));
+    SFB_CUDA(c, P.grp.reserve(3 * (size_t)(n_cta + 1) * SFB_NBINS + 4));
+    SFB_CUDA(c, P.start.reserve(Em)); SFB_CUDA(c, P.len.reserve(Em)); SFB_CUDA(c, P.lab.reserve(nnzm)); SFB_CUDA(c, P.src.reserve(Em));
+    SFB_CUDA(c, P.cnt.reserve(Em)); SFB_CUDA(c, P.w.reserve(nnzm)); SFB_CUDA(c, P.tbl.reserve((size_t)n_cta * PT_WORDS));
+    // 1. ranges balanced by work: every transcript costs its alpha slots, every label entry its 12 bytes
+    SFB_CUDA(c, cudaMemsetAsync(P.load.p, 0, T * 4ull, s));
+    k_part_load<<<grid_for(nnzm, 256), 256, 0, s>>>(k.lab.p, nnzm, P.load.p);
+    c->launches++;
+    std::vector<uint32_t> load(T), bounds(n_cta + 1);
+    SFB_CUDA(c, cudaMemcpyAsync(load.data(), P.load.p, T * 4ull, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < T; ++t) total += 3ull + load[t];
+    { uint64_t acc = 0; uint32_t i = 1; bounds[0] = 0;
+      for (uint32_t t = 0; t < T && i < n_cta; ++t) {
+          acc += 3ull + load[t];
+          while (i < n_cta && acc >= total * i / n_cta) bounds[i++] = t + 1;
+      }
+      while (i <= n_cta) bounds[i++] = T;
+      bounds[n_cta] = T; }
+    SFB_CUDA(c, cudaMemcpyAsync(P.bounds.p, bounds.data(), (n_cta + 1) * 4ull, cudaMemcpyHostToDevice, s));
+    // 2. closure of "crosses a range or touches a dirty transcript"
+    SFB_CUDA(c, cudaMemsetAsync(P.dirty.p, 0, T, s));
+    unsigned int* d_changed = reinterpret_cast<unsigned int*>(P.grp.p + 3 * (size_t)(n_cta + 1) * SFB_NBINS);
+    for (int round = 0; round < 256; ++round) {
+        SFB_CUDA(c, cudaMemsetAsync(d_changed, 0, 4, s));
+        k_part_owner<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, P.bounds.p, n_cta, P.dirty.p, P.owner.p, d_changed);
+        c->launches++;
+        unsigned int ch = 0;
+        SFB_CUDA(c, cudaMemcpyAsync(&ch, d_changed, 4, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        if (!ch) break;
+    }
+    // 3. group sizes -> offsets
+    const size_t G = (size_t)(n_cta + 1) * SFB_NBINS;
+    unsigned long long* d_grp = P.grp.p; unsigned long long* d_cls_off = P.grp.p + G; unsigned long long* d_nnz_off = P.grp.p + 2 * G;
+    SFB_CUDA(c, cudaMemsetAsync(d_grp, 0, G * 8, s));
+    k_part_count<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.len.p, Em, n_cta, d_grp);
+    c->launches++;
+    std::vector<unsigned long long> grp(G), cls_off(G + 1), nnz_off(G + 1);
+    SFB_CUDA(c, cudaMemcpyAsync(grp.data(), d_grp, G * 8, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    cls_off[0] = 0; nnz_off[0] = 0;
+    for (size_t g = 0; g < G; ++g) { cls_off[g + 1] = cls_off[g] + (grp[g] >> 32); nnz_off[g + 1] = nnz_off[g] + (grp[g] & 0xFFFFFFFFULL); }
+    SFB_CUDA(c, cudaMemcpyAsync(d_cls_off, cls_off.data(), G * 8, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, cudaMemcpyAsync(d_nnz_off, nnz_off.data(), G * 8, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, cudaMemsetAsync(d_grp, 0, G * 8, s));                  // reused as the fill cursors
+    k_part_fill<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.start.p, k.len.p, k.lab.p, k.cnt.p, Em, n_cta, d_cls_off, d_nnz_off, d_grp,
+                                                   P.start.p, P.len.p, P.lab.p, P.cnt.p, P.src.p);
+    c->launches++;
+    // 4. per-CTA table and the shared-memory budget
+    std::vector<unsigned long long> tbl((size_t)n_cta * PT_WORDS, 0);
+    uint64_t max_bytes = 0;
+    for (uint32_t i = 0; i < n_cta; ++i) {
+        unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
+        for (int b = 0; b <= SFB_NBINS; ++b) row[PT_CLS + b] = cls_off[(size_t)i * SFB_NBINS + b];
+        row[PT_ENT0] = nnz_off[(size_t)i * SFB_NBINS]; row[PT_ENT1] = nnz_off[(size_t)(i + 1) * SFB_NBINS];
+        row[PT_TXP0] = bounds[i]; row[PT_TXP1] = bounds[i + 1];
+        const uint64_t nc = row[PT_CLS + SFB_NBINS] - (row[PT_CLS] & ~3ULL) + 4, ne = row[PT_ENT1] - (row[PT_ENT0] & ~3ULL) + 4;
+        const uint64_t nt = bounds[i + 1] - bounds[i] + 4;
+        max_bytes = std::max<uint64_t>(max_bytes, nc * 16 + ne * 12 + nt * (8 * 4 + 1) + 256);
+    }
+    SFB_CUDA(c, cudaMemcpyAsync(P.tbl.p, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, s));
+    for (int b = 0; b <= SFB_NBINS; ++b) P.pool_cls[b] = cls_off[(size_t)n_cta * SFB_NBINS + std::min(b, SFB_NBINS)];
+    P.pool_cls[SFB_NBINS] = Em;
+    P.n_pool = Em - P.pool_cls[0];
+    P.max_cta_bytes = max_bytes;
+    int max_optin = 0;
+    SFB_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    P.usable = max_bytes + 2048 <= (uint64_t)max_optin;
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    return SFB200_OK;
+}
+
 struct LoopSpec { bool gate_old; uint32_t min_iter; };
 
 // Runs the iteration loop on prepared device state (weights, base, X[0] = alpha_0, X[1] = X[2] = base).
 // On return *buf_out says which third of X holds the result.
-int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, uint32_t* iters_out, double* mrd_out, unsigned* buf_out) {
+int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part, uint32_t* iters_out, double* mrd_out, unsigned* buf_out) {
     cudaStream_t s = c->stream;
     SFB_CUDA(c, c->em_ctl.reserve(CTL_WORDS));
     SFB_CUDA(c, cudaMemsetAsync(c->em_ctl.p, 0, CTL_WORDS * 8, s));
@@ -612,7 +722,26 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, uint32_t* iter
     const bool steps = c->n_ranks > 1 || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
     unsigned long long h_ctl[CTL_WORDS];
     SFB_CUDA(c, cudaEventRecord(c->ev0, s));
-    if (!steps) {
+    if (!steps && use_part) {
+        const DevPartition& P = c->cls.part;
+        PartParams q;
+        q.tbl = P.tbl.p; q.dirty = P.dirty.p; q.has_pool = P.n_pool > 0 ? 1 : 0;
+        const size_t smem = (size_t)P.max_cta_bytes + 1024;
+        q.smem_bytes = (uint32_t)smem;
+        void* args[] = {&p, &q};
+        const void* fn = vb ? reinterpret_cast<const void*>(&k_em_part<true>) : reinterpret_cast<const void*>(&k_em_part<false>);
+        SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->num_sms), dim3(EM_THREADS), args, smem, s));
+        c->launches++;
+        SFB_CUDA(c, cudaEventRecord(c->ev1, s));
+        SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        *iters_out = static_cast<uint32_t>(h_ctl[CTL_ITERS]);
+        *buf_out = static_cast<unsigned>(h_ctl[CTL_RESULT_BUF]);
+        const unsigned long long mr = h_ctl[CTL_MRD];
+        double d; const unsigned long long b = mr ? mr - 1 : 0; std::memcpy(&d, &b, 8);
+        *mrd_out = mr ? d : -std::numeric_limits<double>::max();
+    } else if (!steps) {
         void* args[] = {&p};
         const void* fn = vb ? reinterpret_cast<const void*>(&k_em_persistent<true>) : reinterpret_cast<const void*>(&k_em_persistent<false>);
         // shared memory for the CTA's class slice: what the largest slice needs (+ alignment slack), capped by the opt-in maximum
@@ -714,10 +843,34 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     SFB_CUDA(c, cudaMemcpyAsync(d_eff_in, eff_lens, T * 8ull, cudaMemcpyHostToDevice, s));
     k_clamp_eff<<<grid_for(T, 256), 256, 0, s>>>(d_eff_in, T, c->eff.p);
     c->launches++;
+    // which layout runs: the CTA-partitioned one (em_part.cuh) when a single rank drives a cooperative launch and every
+    // CTA's slice fits in shared memory; otherwise the binned layout
+    const char* mode_env = getenv("SFB200_EM_MODE");
+    const bool steps_mode = c->n_ranks > 1 || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
+    bool use_part = false;
+    if (!steps_mode && k.Em) {
+        if (!k.part.valid) { const int rc = build_partition(c); if (rc) return rc; }
+        use_part = k.part.usable;
+    }
+    DevPartition& P = k.part;
+    const uint32_t* a_start = use_part ? P.start.p : k.start.p;
+    const uint32_t* a_len = use_part ? P.len.p : k.len.p;
+    const uint32_t* a_lab = use_part ? P.lab.p : k.lab.p;
+    double* a_w = use_part ? P.w.p : k.w.p;
     if (k.Em) {
         // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
-        k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(k.start.p, k.len.p, k.lab.p, k.cnt.p, c->eff.p, k.Em, k.w.p);
+        k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
         c->launches++;
+    }
+    const double* a_cnt = d_cnt;
+    if (use_part) {
+        if (d_cnt == k.cnt.p) a_cnt = P.cnt.p;
+        else {                                                   // per-sample counts (bootstrap) into partition order
+            SFB_CUDA(c, P.cnt_s.reserve(k.Em));
+            k_part_gather_counts<<<grid_for(k.Em, 256), 256, 0, s>>>(d_cnt, P.src.p, k.Em, P.cnt_s.p);
+            c->launches++;
+            a_cnt = P.cnt_s.p;
+        }
     }
     uint64_t n_active = k.n_active;
     if (c->n_ranks > 1) {
@@ -734,16 +887,17 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
 
     EmParams p;
     std::memset(&p, 0, sizeof(p));
-    p.start = k.start.p; p.len = k.len.p; p.lab = k.lab.p; p.w = k.w.p; p.cnt = d_cnt; p.base = c->em_base.p; p.X = c->em_alpha.p;
+    p.start = a_start; p.len = a_len; p.lab = a_lab; p.w = a_w; p.cnt = a_cnt; p.base = c->em_base.p; p.X = c->em_alpha.p;
     p.theta = c->em_theta.p; p.T = T;
+    const uint64_t* bin_cls = use_part ? P.pool_cls : k.bin_cls;        // partitioned: the global-memory path sweeps only the pool
     uint64_t tiles = 0;
     for (int b = 0; b < SFB_NBINS; ++b) {
-        p.cls_start[b] = k.bin_cls[b]; p.tile_start[b] = tiles;
-        const uint64_t ncls = k.bin_cls[b + 1] - k.bin_cls[b];
+        p.cls_start[b] = bin_cls[b]; p.tile_start[b] = tiles;
+        const uint64_t ncls = bin_cls[b + 1] - bin_cls[b];
         const uint64_t per = (b < SFB_NBINS - 1) ? (32u >> (b + 1)) : 1;
         tiles += (ncls + per - 1) / per;
     }
-    p.cls_start[SFB_NBINS] = k.bin_cls[SFB_NBINS]; p.tile_start[SFB_NBINS] = tiles;
+    p.cls_start[SFB_NBINS] = bin_cls[SFB_NBINS]; p.tile_start[SFB_NBINS] = tiles;
     p.use_vb = vb; p.gate_old = spec.gate_old; p.tol = o->tol; p.cutoff = o->check_cutoff;
     p.min_iter = spec.min_iter; p.max_iter = o->max_iter; p.fixed_iters = o->fixed_iters;
     // sums the reference forms by a serial pass over the vector (VBEMUpdate_ :300-303); alpha_0 is n_active equal terms
@@ -762,7 +916,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     unsigned buf = 0;
     sfb200_em_opts oo = *o;
     oo.min_iter = spec.min_iter;
-    const int rc = run_loop(c, p, &oo, iters_out, mrd_out, &buf);
+    const int rc = run_loop(c, p, &oo, use_part, iters_out, mrd_out, &buf);
     if (rc) return rc;
 
     SFB_CUDA(c, cudaMemcpyAsync(alphas_out, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));

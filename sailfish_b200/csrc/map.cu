@@ -901,7 +901,7 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
     // layout the inference kernels read; nothing but 16 counters crosses PCIe.
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
     DevClasses& k = c->cls;
-    k.ready = false; k.host_valid = false; k.from_device = true; k.export_to_canon.clear();
+    k.ready = false; k.host_valid = false; k.from_device = true; k.export_to_canon.clear(); k.part.valid = false;
     k.h_row_ptr.clear(); k.h_labels.clear(); k.h_counts.clear();
     const uint32_t T = c->index.n_txp;
     SFB_CUDA(c, m->fin.reserve(FIN_WORDS));

@@ -87,12 +87,39 @@ def test_em_steps_mode_equals_persistent(ctx, monkeypatch):
     nm = int(cnt.sum())
     ctx.eq_import(T, rp, lab, cnt)
     for vb in (0, 1):
-        a1, it1, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        a1, it1, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))          # CTA-partitioned loop (em_part.cuh)
         monkeypatch.setenv("SFB200_EM_MODE", "steps")
         a2, it2, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
         monkeypatch.delenv("SFB200_EM_MODE")
         assert it1 == it2
         assert_close(a1, a2, rtol=1e-9)
+    # the binned-layout persistent kernel (what runs when a CTA's slice does not fit in shared memory)
+    monkeypatch.setenv("SFB200_NO_PARTITION", "1")
+    ctx.eq_import(T, rp, lab, cnt)
+    for vb in (0, 1):
+        a3, it3, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        rc, want, it_o, _ = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb))
+        assert it3 == it_o
+        assert_close(a3, want)
+    monkeypatch.delenv("SFB200_NO_PARTITION")
+    ctx.eq_import(T, rp, lab, cnt)
+
+
+def test_em_partition_with_pool(ctx):
+    """classes that cross CTA ranges (and everything they touch) go through the global-memory pool; the rest stays in
+    shared memory: both halves together must reproduce the oracle"""
+    T = 20000
+    rp, lab, cnt = synth.make_classes(T, 30000, seed=77, max_len=5, long_frac=0.002)
+    eff = np.random.default_rng(8).uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    for vb in (0, 1):
+        for kw in (dict(), dict(fixed_iters=77)):
+            a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb, **kw))
+            rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, **kw), n_threads=4)
+            assert rc == 0 and it == it_o
+            assert_close(a, want)
+            assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
 
 
 def test_em_edge_cases(ctx):
