@@ -642,9 +642,18 @@ int build_partition(sfb200_ctx* c) {
     SFB_CUDA(c, cudaMemsetAsync(P.load.p, 0, T * 4ull, s));
     k_part_load<<<grid_for(nnzm, 256), 256, 0, s>>>(k.lab.p, nnzm, P.load.p);
     c->launches++;
+    // crossing profile (reuses the owner buffer as int[T+1] scratch)
+    SFB_CUDA(c, P.owner.reserve(std::max<uint64_t>(Em, (uint64_t)T + 1)));
+    int* d_diff = reinterpret_cast<int*>(P.owner.p);
+    SFB_CUDA(c, cudaMemsetAsync(d_diff, 0, (T + 1) * 4ull, s));
+    k_part_span<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, d_diff);
+    c->launches++;
     std::vector<uint32_t> load(T), bounds(n_cta + 1);
+    std::vector<int> cross(T + 1);
     SFB_CUDA(c, cudaMemcpyAsync(load.data(), P.load.p, T * 4ull, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(cross.data(), d_diff, (T + 1) * 4ull, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    for (uint32_t t = 1; t <= T; ++t) cross[t] += cross[t - 1];
     uint64_t total = 0;
     for (uint32_t t = 0; t < T; ++t) total += 3ull + load[t];
     { uint64_t acc = 0; uint32_t i = 1; bounds[0] = 0;
@@ -654,6 +663,17 @@ int build_partition(sfb200_ctx* c) {
       }
       while (i <= n_cta) bounds[i++] = T;
       bounds[n_cta] = T; }
+    // move every boundary to the nearest position no class crosses (if there is one within half a range): fewer pool classes
+    { const uint32_t win = std::max<uint32_t>(8, T / n_cta / 2);
+      for (uint32_t i = 1; i < n_cta; ++i) {
+          const uint32_t t = bounds[i];
+          uint32_t best = t;
+          for (uint32_t d = 0; d <= win; ++d) {
+              if (t >= d && t - d > bounds[i - 1] && cross[t - d] == 0) { best = t - d; break; }
+              if (t + d < T && cross[t + d] == 0) { best = t + d; break; }
+          }
+          bounds[i] = std::max(best, bounds[i - 1]);
+      } }
     SFB_CUDA(c, cudaMemcpyAsync(P.bounds.p, bounds.data(), (n_cta + 1) * 4ull, cudaMemcpyHostToDevice, s));
     // 2. closure of "crosses a range or touches a dirty transcript"
     SFB_CUDA(c, cudaMemsetAsync(P.dirty.p, 0, T, s));
@@ -705,6 +725,10 @@ int build_partition(sfb200_ctx* c) {
     SFB_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     P.usable = max_bytes + 2048 <= (uint64_t)max_optin;
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    if (getenv("SFB200_VERBOSE"))
+        fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool), largest CTA slice %llu bytes (limit %d) -> %s\n",
+                n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, (unsigned long long)max_bytes, max_optin,
+                P.usable ? "shared-memory loop" : "binned global loop");
     return SFB200_OK;
 }
 
