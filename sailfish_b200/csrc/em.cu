@@ -130,36 +130,32 @@ __device__ __forceinline__ Bins em_bins(const EmParams& p) {
 }
 
 // SMA: alpha vectors live in shared memory, indexed by (transcript - toff) (the CTA-local partition, see em_part.cuh)
-template <bool VB, bool SMA>
-__device__ __forceinline__ double sweep_block(const Bins& p, const Slice& sl, uint64_t tile_lo, uint64_t tile_hi,
-                                              const double* __restrict__ in, double* __restrict__ out, uint32_t toff) {
+// one bin: SH = log2(lanes per class); classes [cb, ce) and tiles [tb, te) are relative to the bin's first class / tile
+template <bool VB, bool SMA, int SH>
+__device__ __forceinline__ double sweep_bin(const Slice& sl, uint32_t bin_c0 /* bin's first class, slice-relative */, uint32_t bin_nc,
+                                            uint32_t tb, uint32_t te, const double* __restrict__ in, double* __restrict__ out,
+                                            uint32_t toff) {
+    constexpr uint32_t G = 1u << SH, PER = 32u >> SH;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t e0 = (uint32_t)sl.e0;
+    const uint32_t j = lane & (G - 1), sub = lane >> SH;
     double contrib = 0.0;
-    const uint64_t short_hi = tile_hi < p.tile_start[SFB_NBINS - 1] ? tile_hi : p.tile_start[SFB_NBINS - 1];
-    for (uint64_t t0 = tile_lo + warp; t0 < short_hi; t0 += (uint64_t)EM_ILP * W) {
-        uint32_t tid[EM_ILP], sh[EM_ILP];
-        uint64_t cls[EM_ILP];
+    for (uint32_t t0 = tb + warp; t0 < te; t0 += EM_ILP * W) {
+        uint32_t tid[EM_ILP], ci[EM_ILP];
         double wv[EM_ILP], a[EM_ILP];
         bool ev[EM_ILP];
 #pragma unroll
         for (int u = 0; u < EM_ILP; ++u) {
-            const uint64_t tile = t0 + (uint64_t)u * W;
-            ev[u] = false; a[u] = 0.0; wv[u] = 0.0; tid[u] = 0; sh[u] = 1; cls[u] = 0;
-            if (tile < short_hi) {
-                int b = 0;
-                while (b < SFB_NBINS - 2 && tile >= p.tile_start[b + 1]) ++b;
-                sh[u] = b + 1;                                           // g = 1 << sh lanes per class
-                const uint64_t c = p.cls_start[b] + ((tile - p.tile_start[b]) << (5 - sh[u])) + (lane >> sh[u]);
-                const unsigned j = lane & ((1u << sh[u]) - 1);
-                cls[u] = c;
-                if (c < p.cls_start[b + 1]) {
-                    const uint32_t o0 = sl.start[c - sl.c0], n = sl.len[c - sl.c0];
-                    if (j < n) {
-                        tid[u] = sl.lab[o0 + j - sl.e0] - toff;
-                        wv[u] = sl.w[o0 + j - sl.e0];
-                        a[u] = SMA ? in[tid[u]] : ld_cg_f64(in + tid[u]);
-                        ev[u] = true;
-                    }
+            const uint32_t tile = t0 + u * W;
+            const uint32_t cl = tile * PER + sub;                       // class index inside the bin
+            ev[u] = false; a[u] = 0.0; wv[u] = 0.0; tid[u] = 0; ci[u] = bin_c0 + cl;
+            if (tile < te && cl < bin_nc) {
+                const uint32_t o0 = sl.start[ci[u]] - e0, n = sl.len[ci[u]];
+                if (j < n) {
+                    tid[u] = sl.lab[o0 + j] - toff;
+                    wv[u] = sl.w[o0 + j];
+                    a[u] = SMA ? in[tid[u]] : ld_cg_f64(in + tid[u]);
+                    ev[u] = true;
                 }
             }
         }
@@ -169,14 +165,35 @@ __device__ __forceinline__ double sweep_block(const Bins& p, const Slice& sl, ui
             bool e = ev[u];
             if (e) { if (VB && !(a[u] > 0.0)) e = false; else v = a[u] * wv[u]; }
             double denom = v;
-            for (unsigned m = (1u << sh[u]) >> 1; m >= 1; m >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, m);
+#pragma unroll
+            for (uint32_t m = G >> 1; m >= 1; m >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, m);
             if (e && denom > DENORM_MIN && !isnan(v)) {
-                const double add = v * (sl.cnt[cls[u] - sl.c0] / denom);
+                // count / denom through the correctly rounded reciprocal (<= 1 ulp from the quotient; tolerance is 1e-4)
+                const double add = v * (sl.cnt[ci[u]] * __drcp_rn(denom));
                 atomicAdd(out + tid[u], add);
                 contrib += add;
             }
         }
     }
+    return contrib;
+}
+
+template <bool VB, bool SMA>
+__device__ __forceinline__ double sweep_block(const Bins& p, const Slice& sl, uint64_t tile_lo, uint64_t tile_hi,
+                                              const double* __restrict__ in, double* __restrict__ out, uint32_t toff) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    double contrib = 0.0;
+    // bins 0..4: intersect the CTA's tile range with the bin's tiles
+#define SFB_SWEEP_BIN(B)                                                                                                        \
+    {                                                                                                                           \
+        const uint64_t lo = tile_lo > p.tile_start[B] ? tile_lo : p.tile_start[B];                                              \
+        const uint64_t hi = tile_hi < p.tile_start[B + 1] ? tile_hi : p.tile_start[B + 1];                                      \
+        if (lo < hi)                                                                                                            \
+            contrib += sweep_bin<VB, SMA, B + 1>(sl, (uint32_t)(p.cls_start[B] - sl.c0), (uint32_t)(p.cls_start[B + 1] - p.cls_start[B]), \
+                                                 (uint32_t)(lo - p.tile_start[B]), (uint32_t)(hi - p.tile_start[B]), in, out, toff); \
+    }
+    SFB_SWEEP_BIN(0) SFB_SWEEP_BIN(1) SFB_SWEEP_BIN(2) SFB_SWEEP_BIN(3) SFB_SWEEP_BIN(4)
+#undef SFB_SWEEP_BIN
     // long classes (more than 32 members): the whole warp walks the class twice
     const uint64_t long_lo = tile_lo > p.tile_start[SFB_NBINS - 1] ? tile_lo : p.tile_start[SFB_NBINS - 1];
     for (uint64_t tile = long_lo + warp; tile < tile_hi; tile += W) {
@@ -190,7 +207,7 @@ __device__ __forceinline__ double sweep_block(const Bins& p, const Slice& sl, ui
         }
         denom = warp_sum(denom);
         if (denom > DENORM_MIN) {
-            const double inv = sl.cnt[c - sl.c0] / denom;
+            const double inv = sl.cnt[c - sl.c0] * __drcp_rn(denom);
             for (uint32_t j = lane; j < n; j += 32) {
                 const uint32_t t = sl.lab[o0 + j] - toff;
                 const double al = SMA ? in[t] : ld_cg_f64(in + t);
