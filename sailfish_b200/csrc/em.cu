@@ -130,6 +130,12 @@ __device__ __forceinline__ Bins em_bins(const EmParams& p) {
 }
 
 // SMA: alpha vectors live in shared memory, indexed by (transcript - toff) (the CTA-local partition, see em_part.cuh)
+// count / denom: through the correctly rounded reciprocal (<= 1 ulp from the quotient; the tolerance is 1e-4) unless the
+// denominator is so small that its reciprocal would overflow (a resampled count of 0 must still give 0, not 0 * inf)
+__device__ __forceinline__ double sfb_div_count(double cnt, double denom) {
+    return denom > 1e-290 ? cnt * __drcp_rn(denom) : cnt / denom;
+}
+
 // one bin: SH = log2(lanes per class); classes [cb, ce) and tiles [tb, te) are relative to the bin's first class / tile
 template <bool VB, bool SMA, int SH>
 __device__ __forceinline__ double sweep_bin(const Slice& sl, uint32_t bin_c0 /* bin's first class, slice-relative */, uint32_t bin_nc,
@@ -169,7 +175,7 @@ __device__ __forceinline__ double sweep_bin(const Slice& sl, uint32_t bin_c0 /* 
             for (uint32_t m = G >> 1; m >= 1; m >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, m);
             if (e && denom > DENORM_MIN && !isnan(v)) {
                 // count / denom through the correctly rounded reciprocal (<= 1 ulp from the quotient; tolerance is 1e-4)
-                const double add = v * (sl.cnt[ci[u]] * __drcp_rn(denom));
+                const double add = v * sfb_div_count(sl.cnt[ci[u]], denom);
                 atomicAdd(out + tid[u], add);
                 contrib += add;
             }
@@ -207,7 +213,7 @@ __device__ __forceinline__ double sweep_block(const Bins& p, const Slice& sl, ui
         }
         denom = warp_sum(denom);
         if (denom > DENORM_MIN) {
-            const double inv = sl.cnt[c - sl.c0] * __drcp_rn(denom);
+            const double inv = sfb_div_count(sl.cnt[c - sl.c0], denom);
             for (uint32_t j = lane; j < n; j += 32) {
                 const uint32_t t = sl.lab[o0 + j] - toff;
                 const double al = SMA ? in[t] : ld_cg_f64(in + t);
