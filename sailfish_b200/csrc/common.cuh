@@ -113,6 +113,7 @@ struct DevClasses {
     // materialised lazily by sfb_classes_host() because only eq_export / bootstrap need it
     bool host_valid = false;
     bool from_device = false;
+    bool merged = false;                // multi-rank: the classes of all ranks were merged (every rank holds the global set)
     std::vector<uint64_t> h_row_ptr;
     std::vector<uint32_t> h_labels;
     std::vector<uint64_t> h_counts;
@@ -149,6 +150,7 @@ struct sfb200_ctx {
 
 int sfb_comm_allreduce_f64(sfb200_ctx* ctx, double* d_buf, size_t n);
 int sfb_comm_allreduce_u64(sfb200_ctx* ctx, unsigned long long* d_buf, size_t n);
+int sfb_comm_allgather(sfb200_ctx* ctx, const void* send, void* recv, size_t bytes);
 void sfb_map_state_free(sfb200_ctx* ctx);
 void sfb_em_extra_free(sfb200_ctx* ctx);
 int sfb_classes_from_host(sfb200_ctx* ctx, uint32_t n_txp, uint64_t E, const uint64_t* row_ptr, const uint32_t* labels,

@@ -77,6 +77,7 @@ struct Nccl {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -93,6 +94,7 @@ bool nccl_load() {
     g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(g_nccl.h, "ncclGetUniqueId"));
     g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(g_nccl.h, "ncclCommInitRank"));
     g_nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(g_nccl.h, "ncclAllReduce"));
+    g_nccl.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(g_nccl.h, "ncclAllGather"));
     g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(g_nccl.h, "ncclCommDestroy"));
     g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(g_nccl.h, "ncclGetErrorString"));
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce;
@@ -127,6 +129,14 @@ int sfb_comm_allreduce_f64(sfb200_ctx* c, double* d, size_t n) {
     if (c->n_ranks <= 1) return SFB200_OK;
     const int rc = g_nccl.AllReduce(d, d, n, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
     if (rc != 0) SFB_FAIL(c, SFB200_ENCCL, "ncclAllReduce(f64) failed");
+    return SFB200_OK;
+}
+// every rank contributes `bytes` bytes; recv holds n_ranks * bytes
+int sfb_comm_allgather(sfb200_ctx* c, const void* send, void* recv, size_t bytes) {
+    if (c->n_ranks <= 1) return SFB200_OK;
+    if (!g_nccl.AllGather) SFB_FAIL(c, SFB200_ENCCL, "ncclAllGather not found");
+    const int rc = g_nccl.AllGather(send, recv, bytes, /*ncclUint8*/ 1, c->comm, c->stream);
+    if (rc != 0) SFB_FAIL(c, SFB200_ENCCL, "ncclAllGather failed");
     return SFB200_OK;
 }
 int sfb_comm_allreduce_u64(sfb200_ctx* c, unsigned long long* d, size_t n) {

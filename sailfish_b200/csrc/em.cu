@@ -513,7 +513,7 @@ int sfb_classes_from_host(sfb200_ctx* c, uint32_t n_txp, uint64_t E, const uint6
     k.h_labels.assign(labels, labels + nnz);
     k.h_counts.assign(counts, counts + E);
     k.export_to_canon.clear();
-    k.host_valid = true; k.from_device = false;
+    k.host_valid = true; k.from_device = false; k.merged = false;
 
     auto bin_of = [](uint64_t n) { return n <= 2 ? 0 : n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 3 : n <= 32 ? 4 : 5; };
     uint64_t bin_n[SFB_NBINS] = {0, 0, 0, 0, 0, 0};
@@ -766,7 +766,8 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
     p.ctl = c->em_ctl.p;
     const bool vb = o->use_vb != 0;
     const char* mode = getenv("SFB200_EM_MODE");
-    const bool steps = c->n_ranks > 1 || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
+    const bool sharded = c->n_ranks > 1 && !c->cls.merged;
+    const bool steps = sharded || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
     unsigned long long h_ctl[CTL_WORDS];
     SFB_CUDA(c, cudaEventRecord(c->ev0, s));
     if (!steps && use_part) {
@@ -832,7 +833,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
                 if (vb) k_em_sweep<true><<<grid, EM_THREADS, 0, s>>>(p, bi, bo, n);
                 else k_em_sweep<false><<<grid, EM_THREADS, 0, s>>>(p, bi, bo, n);
                 c->launches++;
-                if (c->n_ranks > 1) {
+                if (sharded) {
                     const int rc = sfb_comm_allreduce_f64(c, p.X + (size_t)bo * p.T, p.T);
                     if (rc) return rc;
                     if (vb) {   // the contribution sums are rank-local: recompute the total from the reduced vector
@@ -850,7 +851,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
                 mr = h_ctl[CTL_MAXREL + (n & 3u)];
                 if (vb) {
                     double cs; std::memcpy(&cs, &h_ctl[CTL_CSUM + ((n + 1u) & 3u)], 8);
-                    asum = (c->n_ranks > 1) ? cs : p.base_sum + cs;
+                    asum = sharded ? cs : p.base_sum + cs;
                 }
             }
             if (last) break;
@@ -893,7 +894,8 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     // which layout runs: the CTA-partitioned one (em_part.cuh) when a single rank drives a cooperative launch and every
     // CTA's slice fits in shared memory; otherwise the binned layout
     const char* mode_env = getenv("SFB200_EM_MODE");
-    const bool steps_mode = c->n_ranks > 1 || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
+    const bool sharded = c->n_ranks > 1 && !k.merged;      // rank-local classes: one all-reduce per iteration
+    const bool steps_mode = sharded || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
     bool use_part = false;
     if (!steps_mode && k.Em) {
         if (!k.part.valid) { const int rc = build_partition(c); if (rc) return rc; }
@@ -927,7 +929,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     if (n_active == 0) SFB_FAIL(c, SFB200_ENOACTIVE, "The optimizer has no active transcripts: no transcripts are expressed");
     const bool vb = o->use_vb != 0;
     const double alpha0 = (1.0 / static_cast<double>(n_active)) * total_frags;           // :800-803
-    const double prior_term = vb ? ((c->n_ranks > 1 && c->rank != 0) ? 0.0 : o->prior_alpha) : 0.0;
+    const double prior_term = vb ? ((sharded && c->rank != 0) ? 0.0 : o->prior_alpha) : 0.0;
     k_em_init<<<grid_for(T, 256), 256, 0, s>>>(k.active.p, d_single, T, alpha0, prior_term, c->em_alpha.p, c->em_base.p);
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
@@ -983,7 +985,7 @@ extern "C" int sfb200_em_run(sfb200_ctx* c, const double* eff_lens, uint32_t n_t
     if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "em_run: no classes (call map_finish or eq_import first)");
     if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "em_run: n_txp differs from the class table's");
     cudaSetDevice(c->device);
-    if (c->n_ranks > 1) {
+    if (c->n_ranks > 1 && !c->cls.merged) {
         // union of the active sets over ranks (classes are rank-local)
         DevClasses& k = c->cls;
         std::vector<uint8_t> act(n_txp);

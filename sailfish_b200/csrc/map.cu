@@ -861,44 +861,10 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
 
 extern "C" double sfb200_last_map_kernel_ms(const sfb200_ctx* c) { return (c && c->map) ? c->map->kernel_ms : 0.0; }
 
-extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz) {
-    if (!c) return SFB200_EINVAL;
-    MapState* m = c->map;
-    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_finish: call map_begin first");
-    cudaSetDevice(c->device);
+// eqBuilder.finish() (EquivalenceClassBuilder.hpp:64-80): flatten the table -- on the device, straight into the binned
+// layout the inference kernels read; nothing but a few counters crosses PCIe.
+static int flatten_classes(sfb200_ctx* c, MapState* m, uint64_t* n_classes, uint64_t* nnz) {
     cudaStream_t s = c->stream;
-    if (c->n_ranks > 1) {
-        int rc = sfb_comm_allreduce_u64(c, m->counters.p, 6);
-        if (rc) return rc;
-        // fld histogram: widen to u64 through the host (1000 entries)
-    }
-    unsigned long long h_cursor[4], h_counters[6];
-    SFB_CUDA(c, cudaMemcpyAsync(h_cursor, m->cursor.p, sizeof(h_cursor), cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaMemcpyAsync(h_counters, m->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
-    std::vector<uint32_t> h_fld(m->o.max_frag_len);
-    SFB_CUDA(c, cudaMemcpyAsync(h_fld.data(), m->fld_hist.p, m->o.max_frag_len * 4ull, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    m->kernel_ms = 0.0;
-    for (size_t i = 0; i + 1 < m->ev_used; i += 2) { float ms = 0.f; if (cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]) == cudaSuccess) m->kernel_ms += ms; }
-    if (h_cursor[2] & ERR_ARENA_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena exhausted (raise SFB200_EQ_ARENA_LOG2)");
-    if (h_cursor[2] & ERR_TABLE_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table exhausted (raise SFB200_EQ_LOG2_BUCKETS)");
-    if (h_cursor[2] & ERR_LABEL_LONG) SFB_FAIL(c, SFB200_EFULL, "a label has 1024 or more transcripts");
-    if (c->n_ranks > 1) {
-        std::vector<unsigned long long> wide(h_fld.begin(), h_fld.end());
-        DevBuf<unsigned long long> d; SFB_CUDA(c, d.reserve(wide.size()));
-        SFB_CUDA(c, cudaMemcpyAsync(d.p, wide.data(), wide.size() * 8, cudaMemcpyHostToDevice, s));
-        const int rc = sfb_comm_allreduce_u64(c, d.p, wide.size());
-        if (rc) { d.release(); return rc; }
-        SFB_CUDA(c, cudaMemcpyAsync(wide.data(), d.p, wide.size() * 8, cudaMemcpyDeviceToHost, s));
-        SFB_CUDA(c, cudaStreamSynchronize(s));
-        d.release();
-        for (size_t i = 0; i < wide.size(); ++i) h_fld[i] = static_cast<uint32_t>(wide[i]);
-    }
-    if (counters) for (int i = 0; i < 6; ++i) counters[i] = h_counters[i];
-    if (fld_hist) std::memcpy(fld_hist, h_fld.data(), h_fld.size() * 4);
-
-    // eqBuilder.finish() (EquivalenceClassBuilder.hpp:64-80): flatten the table -- on the device, straight into the binned
-    // layout the inference kernels read; nothing but 16 counters crosses PCIe.
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
     DevClasses& k = c->cls;
     k.ready = false; k.host_valid = false; k.from_device = true; k.export_to_canon.clear(); k.part.valid = false;
@@ -944,5 +910,133 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
     if (n_classes) *n_classes = E;
     if (nnz) *nnz = z;
     k.ready = true;
+    return SFB200_OK;
+}
+
+namespace {
+// singles appended behind the multi-member classes so that one (start, len, count, label) quadruple describes every class
+__global__ void k_merge_pack_singles(const uint32_t* __restrict__ sgl_tid, uint64_t n_sgl, uint64_t Em, uint64_t nnzm,
+                                     uint32_t* __restrict__ start_all, uint32_t* __restrict__ len_all, uint32_t* __restrict__ lab_all) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_sgl) return;
+    start_all[Em + i] = (uint32_t)(nnzm + i); len_all[Em + i] = 1; lab_all[nnzm + i] = sgl_tid[i];
+}
+__global__ void k_merge_upsert(const EqTable tb, const uint32_t* __restrict__ start_g, const uint32_t* __restrict__ len_g,
+                               const unsigned long long* __restrict__ cnt_g, const uint32_t* __restrict__ lab_g,
+                               const unsigned long long* __restrict__ sizes /* per rank: E, nnz */, uint64_t maxE, uint64_t maxZ,
+                               int my_rank) {
+    const int r = blockIdx.y;
+    if (r == my_rank) return;
+    const uint64_t E = sizes[2 * r];
+    const uint32_t* st = start_g + (size_t)r * maxE; const uint32_t* ln = len_g + (size_t)r * maxE;
+    const unsigned long long* cn = cnt_g + (size_t)r * maxE; const uint32_t* lb = lab_g + (size_t)r * maxZ;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t* a = lb + st[i];
+        eq_upsert(tb, ln[i], [&](uint32_t j) { return a[j]; }, cn[i]);
+    }
+}
+}  // namespace
+
+static int merge_classes_over_ranks(sfb200_ctx* c, MapState* m) {
+    cudaStream_t s = c->stream;
+    DevClasses& k = c->cls;
+    const int R = c->n_ranks;
+    const uint64_t E = k.E, Z = k.nnz, Em = k.Em, nnzm = k.nnzm;
+    DevBuf<unsigned long long> d_sizes, d_cnt_g; DevBuf<uint32_t> d_start, d_len, d_lab, d_start_g, d_len_g, d_lab_g;
+    auto cleanup = [&]() { d_sizes.release(); d_cnt_g.release(); d_start.release(); d_len.release(); d_lab.release();
+                           d_start_g.release(); d_len_g.release(); d_lab_g.release(); };
+#define MG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return SFB200_ECUDA; } } while (0)
+#define MGRC(call) do { const int r__ = (call); if (r__) { cleanup(); return r__; } } while (0)
+    MG(d_sizes.reserve(2 * (size_t)R + 2));
+    unsigned long long mine[2] = {E, Z};
+    MG(cudaMemcpyAsync(d_sizes.p + 2 * (size_t)R, mine, 16, cudaMemcpyHostToDevice, s));
+    MGRC(sfb_comm_allgather(c, d_sizes.p + 2 * (size_t)R, d_sizes.p, 16));
+    std::vector<unsigned long long> sizes(2 * (size_t)R);
+    MG(cudaMemcpyAsync(sizes.data(), d_sizes.p, sizes.size() * 8, cudaMemcpyDeviceToHost, s));
+    MG(cudaStreamSynchronize(s));
+    uint64_t maxE = 1, maxZ = 1;
+    for (int r = 0; r < R; ++r) { maxE = std::max<uint64_t>(maxE, sizes[2 * r]); maxZ = std::max<uint64_t>(maxZ, sizes[2 * r + 1]); }
+    maxE = (maxE + 3) & ~3ull; maxZ = (maxZ + 3) & ~3ull;
+    MG(d_start.reserve(maxE)); MG(d_len.reserve(maxE)); MG(d_lab.reserve(maxZ));
+    MG(d_start_g.reserve(maxE * R)); MG(d_len_g.reserve(maxE * R)); MG(d_lab_g.reserve(maxZ * R)); MG(d_cnt_g.reserve(maxE * R));
+    if (Em) { MG(cudaMemcpyAsync(d_start.p, k.start.p, Em * 4, cudaMemcpyDeviceToDevice, s)); MG(cudaMemcpyAsync(d_len.p, k.len.p, Em * 4, cudaMemcpyDeviceToDevice, s)); }
+    if (nnzm) MG(cudaMemcpyAsync(d_lab.p, k.lab.p, nnzm * 4, cudaMemcpyDeviceToDevice, s));
+    if (k.n_sgl) { k_merge_pack_singles<<<(unsigned)((k.n_sgl + 255) / 256), 256, 0, s>>>(k.sgl_tid.p, k.n_sgl, Em, nnzm, d_start.p, d_len.p, d_lab.p); c->launches++; }
+    // cnt_all is exactly E long; gather through a padded copy
+    DevBuf<unsigned long long> d_cnt; MG(d_cnt.reserve(maxE));
+    if (E) MG(cudaMemcpyAsync(d_cnt.p, k.cnt_all.p, E * 8, cudaMemcpyDeviceToDevice, s));
+    int rc = sfb_comm_allgather(c, d_start.p, d_start_g.p, maxE * 4);
+    if (!rc) rc = sfb_comm_allgather(c, d_len.p, d_len_g.p, maxE * 4);
+    if (!rc) rc = sfb_comm_allgather(c, d_cnt.p, d_cnt_g.p, maxE * 8);
+    if (!rc) rc = sfb_comm_allgather(c, d_lab.p, d_lab_g.p, maxZ * 4);
+    if (rc) { d_cnt.release(); cleanup(); return rc; }
+    EqTable tb;
+    tb.slot = m->slot.p; tb.count = m->count.p; tb.arena = m->arena.p; tb.cursor = m->cursor.p;
+    tb.n_buckets = m->n_buckets; tb.n_overflow = m->n_overflow; tb.arena_words = m->arena_words;
+    k_merge_upsert<<<dim3((unsigned)std::min<uint64_t>((maxE + 255) / 256, 4096), R), 256, 0, s>>>(tb, d_start_g.p, d_len_g.p, d_cnt_g.p, d_lab_g.p,
+                                                                                                 d_sizes.p, maxE, maxZ, c->rank);
+    c->launches++;
+    MG(cudaGetLastError());
+    unsigned long long h_cursor[4];
+    MG(cudaMemcpyAsync(h_cursor, m->cursor.p, sizeof(h_cursor), cudaMemcpyDeviceToHost, s));
+    MG(cudaStreamSynchronize(s));
+    d_cnt.release();
+    cleanup();
+#undef MG
+#undef MGRC
+    if (h_cursor[2] & ERR_ARENA_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena exhausted while merging ranks");
+    if (h_cursor[2] & ERR_TABLE_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table exhausted while merging ranks");
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_finish: call map_begin first");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    if (c->n_ranks > 1) {
+        int rc = sfb_comm_allreduce_u64(c, m->counters.p, 6);
+        if (rc) return rc;
+        // fld histogram: widen to u64 through the host (1000 entries)
+    }
+    unsigned long long h_cursor[4], h_counters[6];
+    SFB_CUDA(c, cudaMemcpyAsync(h_cursor, m->cursor.p, sizeof(h_cursor), cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(h_counters, m->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> h_fld(m->o.max_frag_len);
+    SFB_CUDA(c, cudaMemcpyAsync(h_fld.data(), m->fld_hist.p, m->o.max_frag_len * 4ull, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    m->kernel_ms = 0.0;
+    for (size_t i = 0; i + 1 < m->ev_used; i += 2) { float ms = 0.f; if (cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]) == cudaSuccess) m->kernel_ms += ms; }
+    if (h_cursor[2] & ERR_ARENA_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena exhausted (raise SFB200_EQ_ARENA_LOG2)");
+    if (h_cursor[2] & ERR_TABLE_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table exhausted (raise SFB200_EQ_LOG2_BUCKETS)");
+    if (h_cursor[2] & ERR_LABEL_LONG) SFB_FAIL(c, SFB200_EFULL, "a label has 1024 or more transcripts");
+    if (c->n_ranks > 1) {
+        std::vector<unsigned long long> wide(h_fld.begin(), h_fld.end());
+        DevBuf<unsigned long long> d; SFB_CUDA(c, d.reserve(wide.size()));
+        SFB_CUDA(c, cudaMemcpyAsync(d.p, wide.data(), wide.size() * 8, cudaMemcpyHostToDevice, s));
+        const int rc = sfb_comm_allreduce_u64(c, d.p, wide.size());
+        if (rc) { d.release(); return rc; }
+        SFB_CUDA(c, cudaMemcpyAsync(wide.data(), d.p, wide.size() * 8, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        d.release();
+        for (size_t i = 0; i < wide.size(); ++i) h_fld[i] = static_cast<uint32_t>(wide[i]);
+    }
+    if (counters) for (int i = 0; i < 6; ++i) counters[i] = h_counters[i];
+    if (fld_hist) std::memcpy(fld_hist, h_fld.data(), h_fld.size() * 4);
+
+    { const int rc = flatten_classes(c, m, n_classes, nnz); if (rc) return rc; }
+    c->cls.merged = false;
+    if (c->n_ranks > 1 && !getenv("SFB200_MULTI_EM_ALLREDUCE")) {
+        // One exchange instead of one per EM iteration: all-gather every rank's (label, count) list, add the other ranks'
+        // classes to the local table (same upsert as the mapper's) and flatten again.  Every rank then holds the merged
+        // class set and runs the whole EM locally -- an EM iteration (~8 us) is shorter than an all-reduce of the
+        // per-transcript vector (~25-40 us), see DESIGN.md section 7.
+        const int rc = merge_classes_over_ranks(c, m);
+        if (rc) return rc;
+        const int rc2 = flatten_classes(c, m, n_classes, nnz);
+        if (rc2) return rc2;
+        c->cls.merged = true;
+    }
     return SFB200_OK;
 }
