@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_map_reads(const MapParams p)
 
 // FLD sampling in global read order: the first `remaining` eligible fragments (SailfishQuantify.cpp:426-430 at -p 1)
 __global__ void k_fld_select(const int16_t* __restrict__ fld_val, uint64_t n_reads, unsigned int* __restrict__ hist,
-                             int* __restrict__ remaining) {
+                             int* __restrict__ remaining, int16_t* __restrict__ samples, int total) {
     __shared__ int s_base, s_rem;
     __shared__ int s_warp[32];
     if (threadIdx.x == 0) { s_rem = *remaining; }
@@ -584,7 +584,7 @@ __global__ void k_fld_select(const int16_t* __restrict__ fld_val, uint64_t n_rea
         if (threadIdx.x == 0) { int a = 0; for (unsigned w = 0; w < (blockDim.x >> 5); ++w) { const int t = s_warp[w]; s_warp[w] = a; a += t; } s_base = a; }
         __syncthreads();
         const int rank = s_warp[warp] + pre;
-        if (v >= 0 && rank < s_rem) atomicAdd(hist + v, 1u);
+        if (v >= 0 && rank < s_rem) { atomicAdd(hist + v, 1u); samples[total - s_rem + rank] = (int16_t)v; }   // kept in read order
         __syncthreads();
         if (threadIdx.x == 0) s_rem -= s_base;
         __syncthreads();
@@ -677,7 +677,7 @@ struct MapState {
     DevBuf<uint32_t> arena;
     DevBuf<unsigned int> fld_hist;
     DevBuf<int> remaining;
-    DevBuf<int16_t> fld_val;
+    DevBuf<int16_t> fld_val, fld_samples;
     // two staging sets for host batches: the H2D copy of batch j (copy stream) overlaps the mapping kernel of batch j-1
     DevBuf<char> bases1[2], bases2[2];
     DevBuf<uint64_t> off1[2], off2[2];
@@ -697,7 +697,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     MapState* m = c->map;
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
-    m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release();
+    m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
         if (m->copied[i]) cudaEventDestroy(m->copied[i]);
@@ -728,6 +728,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     SFB_CUDA(c, m->slot.reserve(n_slots)); SFB_CUDA(c, m->count.reserve(n_slots)); SFB_CUDA(c, m->arena.reserve(m->arena_words));
     SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(1));
     SFB_CUDA(c, m->fld_hist.reserve(o->max_frag_len)); SFB_CUDA(c, m->remaining.reserve(1));
+    SFB_CUDA(c, m->fld_samples.reserve((size_t)std::max(1, o->num_frag_samples)));
     SFB_CUDA(c, cudaMemsetAsync(m->slot.p, 0, n_slots * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->count.p, 0, n_slots * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->cursor.p, 0, 4 * 8, s));
@@ -809,7 +810,7 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));
     m->ev_used += 2;
     if (want_fld) {
-        k_fld_select<<<1, 1024, 0, s>>>(m->fld_val.p, n_reads, m->fld_hist.p, m->remaining.p);
+        k_fld_select<<<1, 1024, 0, s>>>(m->fld_val.p, n_reads, m->fld_hist.p, m->remaining.p, m->fld_samples.p, m->o.num_frag_samples);
         c->launches++;
         SFB_CUDA(c, cudaGetLastError());
     }
@@ -1011,16 +1012,32 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
     if (h_cursor[2] & ERR_ARENA_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena exhausted (raise SFB200_EQ_ARENA_LOG2)");
     if (h_cursor[2] & ERR_TABLE_FULL) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table exhausted (raise SFB200_EQ_LOG2_BUCKETS)");
     if (h_cursor[2] & ERR_LABEL_LONG) SFB_FAIL(c, SFB200_EFULL, "a label has 1024 or more transcripts");
-    if (c->n_ranks > 1) {
-        std::vector<unsigned long long> wide(h_fld.begin(), h_fld.end());
-        DevBuf<unsigned long long> d; SFB_CUDA(c, d.reserve(wide.size()));
-        SFB_CUDA(c, cudaMemcpyAsync(d.p, wide.data(), wide.size() * 8, cudaMemcpyHostToDevice, s));
-        const int rc = sfb_comm_allreduce_u64(c, d.p, wide.size());
-        if (rc) { d.release(); return rc; }
-        SFB_CUDA(c, cudaMemcpyAsync(wide.data(), d.p, wide.size() * 8, cudaMemcpyDeviceToHost, s));
+    if (c->n_ranks > 1 && m->o.num_frag_samples > 0) {
+        // "the first num_frag_samples eligible fragments in global read order" with reads sharded by contiguous ranges:
+        // rank 0's samples come first, then rank 1's, ... -- gather the ordered samples and cut at the budget
+        const int total = m->o.num_frag_samples;
+        const size_t row = ((size_t)total * 2 + 8 + 15) & ~(size_t)15;          // samples + taken count, per rank
+        DevBuf<unsigned char> d_send, d_recv;
+        SFB_CUDA(c, d_send.reserve(row)); SFB_CUDA(c, d_recv.reserve(row * c->n_ranks));
+        int rem = 0;
+        SFB_CUDA(c, cudaMemcpyAsync(&rem, m->remaining.p, 4, cudaMemcpyDeviceToHost, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
-        d.release();
-        for (size_t i = 0; i < wide.size(); ++i) h_fld[i] = static_cast<uint32_t>(wide[i]);
+        const long long taken = total - rem;
+        SFB_CUDA(c, cudaMemcpyAsync(d_send.p, m->fld_samples.p, (size_t)total * 2, cudaMemcpyDeviceToDevice, s));
+        SFB_CUDA(c, cudaMemcpyAsync(d_send.p + (size_t)total * 2, &taken, 8, cudaMemcpyHostToDevice, s));
+        const int rc = sfb_comm_allgather(c, d_send.p, d_recv.p, row);
+        if (rc) { d_send.release(); d_recv.release(); return rc; }
+        std::vector<unsigned char> all(row * c->n_ranks);
+        SFB_CUDA(c, cudaMemcpyAsync(all.data(), d_recv.p, all.size(), cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        d_send.release(); d_recv.release();
+        std::fill(h_fld.begin(), h_fld.end(), 0u);
+        long long budget = total;
+        for (int r = 0; r < c->n_ranks && budget > 0; ++r) {
+            const int16_t* smp = reinterpret_cast<const int16_t*>(all.data() + row * r);
+            long long n_r; std::memcpy(&n_r, all.data() + row * r + (size_t)total * 2, 8);
+            for (long long i = 0; i < n_r && budget > 0; ++i, --budget) h_fld[smp[i]]++;
+        }
     }
     if (counters) for (int i = 0; i < 6; ++i) counters[i] = h_counters[i];
     if (fld_hist) std::memcpy(fld_hist, h_fld.data(), h_fld.size() * 4);

@@ -52,6 +52,7 @@ if rank == 0:
     for mode in ("merged", "allreduce"):
         a, it, counters, fld, ncls = res[(mode, 0)]
         assert counters.tolist() == w["counters"].tolist(), (mode, counters, w["counters"])
+        assert fld.tolist() == w["fld"].tolist(), "fragment-length sample differs from the single-process one"
         if mode == "merged":
             assert ncls == len(w["counts"]), (ncls, len(w["counts"]))
         for vb in (0, 1):
