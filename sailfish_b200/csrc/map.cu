@@ -167,32 +167,64 @@ __device__ __forceinline__ uint64_t revcomp32(uint64_t w) {
     return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
 }
 
-__device__ void load_read(const char* __restrict__ bases, uint64_t beg, uint64_t end, Read& r) {
-    uint32_t L = static_cast<uint32_t>(end - beg);
-    if (L > MAX_READ_LEN) L = MAX_READ_LEN;
-    r.len = L;
-    r.has_n = false;
-    const uint32_t nw = (L + 31) >> 5;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(bases) + beg;
-    for (uint32_t w = 0; w < RW; ++w) {
-        uint64_t word = 0, bad = 0;
-        if (w < nw) {
-            const uint32_t i0 = w * 32, n = (L - i0) < 32 ? (L - i0) : 32;
-            for (uint32_t j = 0; j < n; ++j) {
-                const unsigned char ch = src[i0 + j];
-                const unsigned char up = ch & 0xDF;
-                const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
-                word |= (ok ? (uint64_t)(((ch >> 1) ^ (ch >> 2)) & 3) : 0ULL) << (2 * j);
-                bad |= (ok ? 0ULL : 1ULL) << (2 * j);
-            }
+// ---- read packing ------------------------------------------------------------------------------------------------------------
+// k_pack_reads turns the ASCII batch into 2-bit words once (coalesced, one thread per 32-base word); the mapping kernels then
+// fetch a read as a few 8-byte words.  pk / pkn: RWP words per (fragment, mate); meta: length | has_invalid_base << 16.
+__global__ void k_pack_reads(const char* __restrict__ bases1, const uint64_t* __restrict__ off1, const char* __restrict__ bases2,
+                             const uint64_t* __restrict__ off2, uint64_t n_frags, int n_mates, uint32_t rwp,
+                             uint64_t* __restrict__ pk, uint64_t* __restrict__ pkn, uint32_t* __restrict__ meta) {
+    const uint64_t gid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t total = n_frags * n_mates * rwp;
+    if (gid >= total) return;
+    const uint32_t w = (uint32_t)(gid % rwp);
+    const uint64_t fm = gid / rwp;
+    const uint64_t frag = fm / n_mates; const int mate = (int)(fm % n_mates);
+    const char* bases = mate ? bases2 : bases1; const uint64_t* off = mate ? off2 : off1;
+    const uint64_t beg = off[frag];
+    uint64_t len64 = off[frag + 1] - beg;
+    const uint32_t L = len64 > MAX_READ_LEN ? MAX_READ_LEN : (uint32_t)len64;
+    uint64_t word = 0, bad = 0;
+    const uint32_t i0 = w * 32;
+    if (i0 < L) {
+        const uint32_t n = (L - i0) < 32 ? (L - i0) : 32;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(bases) + beg + i0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const unsigned char ch = src[j];
+            const unsigned char up = ch & 0xDF;
+            const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+            word |= (ok ? (uint64_t)(((ch >> 1) ^ (ch >> 2)) & 3) : 0ULL) << (2 * j);
+            bad |= (ok ? 0ULL : 1ULL) << (2 * j);
         }
-        r.sb[w * 32] = word;
-        if (bad && !r.has_n) {                       // first invalid base: bring the mask arrays to a defined state
-            r.has_n = true;
-            for (int q = 0; q < RW; ++q) { r.nm[0][q] = 0; r.nm[1][q] = 0; }
-        }
-        if (bad) r.nm[0][w] = bad;
     }
+    pk[gid] = word; pkn[gid] = bad;
+    if (w == 0) atomicOr(meta + fm, L);                 // meta is zeroed before the launch; other words may add the flag
+    if (bad) atomicOr(meta + fm, 1u << 16);
+}
+
+__global__ void k_max_read_len(const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2, uint64_t n_frags,
+                               unsigned int* __restrict__ out) {
+    unsigned int mx = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_frags; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t l = off1[i + 1] - off1[i];
+        if (off2) { const uint64_t l2 = off2[i + 1] - off2[i]; l = l2 > l ? l2 : l; }
+        if (l > MAX_READ_LEN) l = MAX_READ_LEN;
+        mx = (unsigned int)l > mx ? (unsigned int)l : mx;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { const unsigned int o = __shfl_xor_sync(0xffffffffu, mx, m); mx = o > mx ? o : mx; }
+    if ((threadIdx.x & 31u) == 0 && mx) atomicMax(out, mx);
+}
+
+// packed read -> this lane's shared-memory column (both orientations) + the invalid-base masks when there are any
+__device__ void load_packed(const uint64_t* __restrict__ pk, const uint64_t* __restrict__ pkn, const uint32_t* __restrict__ meta,
+                            uint64_t fm, uint32_t rwp, Read& r) {
+    const uint32_t me = meta[fm];
+    const uint32_t L = me & 0xFFFFu;
+    r.len = L;
+    r.has_n = (me >> 16) & 1u;
+    const uint32_t nw = (L + 31) >> 5;
+    const uint64_t* src = pk + fm * rwp;
+    for (uint32_t w = 0; w < RW; ++w) r.sb[w * 32] = w < nw ? __ldg(src + w) : 0ULL;
     // reverse complement: reversed words in reverse order, then shifted down by the padding of the last word
     const uint32_t pad = nw * 32 - L;
     for (uint32_t w = 0; w < RW; ++w) {
@@ -210,6 +242,8 @@ __device__ void load_read(const char* __restrict__ bases, uint64_t beg, uint64_t
         r.sb[(RW + w) * 32] = v;
     }
     if (r.has_n) {
+        const uint64_t* srcn = pkn + fm * rwp;
+        for (uint32_t w = 0; w < RW; ++w) { r.nm[0][w] = w < nw ? __ldg(srcn + w) : 0ULL; r.nm[1][w] = 0ULL; }
         // masks of the reverse orientation: plain reversal of the 2-bit groups (no complement)
         for (uint32_t w = 0; w < nw; ++w) {
             const uint32_t pos = w * 32 + pad, idx = pos >> 5, sh = 2 * (pos & 31);
@@ -251,88 +285,94 @@ __device__ __forceinline__ bool table_find_from(const IndexView& ix, uint64_t km
     }
 }
 
-// Spec v1 seed scans of ALL orientations of ALL mates of one fragment, as ONE loop: scan s = 2*mate + orientation.
-// A fragment has one cheap scan per mate (the orientation that matches: a hit, an extension, done) and one expensive one
-// (the other strand: a k-mer lookup that misses at every position); folding them into a single loop keeps the lanes of a
-// warp in the same code whichever of their scans is the long one.  Positions are looked up SPEC at a time: k-mers,
-// hashes, presence-filter words and first table slots of the next SPEC positions are fetched together (independent
-// loads in flight), then consumed strictly in order, so the result is exactly the one-position-at-a-time scan's.
+// intervals travel between the scan and the finalize kernel as one u64: lb | cnt << 32 | qpos << 46 | m << 55
+__device__ __forceinline__ unsigned long long pack_iv(uint32_t lb, uint32_t cnt, uint32_t qpos, uint32_t m) {
+    return (unsigned long long)lb | ((unsigned long long)cnt << 32) | ((unsigned long long)qpos << 46) | ((unsigned long long)m << 55);
+}
+__device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
+    Interval r; r.lb = (uint32_t)v; r.cnt = (uint32_t)(v >> 32) & 0x3FFFu; r.qpos = (uint32_t)(v >> 46) & 0x1FFu; r.m = (uint32_t)(v >> 55);
+    return r;
+}
+
+// Spec v1 seed scans of ALL orientations of ALL mates of one fragment form ONE sequence of steps: scan s = 2*mate +
+// orientation, position i, n intervals found so far.  A fragment has one cheap scan per mate (the orientation that matches:
+// a hit, an extension, done) and one expensive one (the other strand: a k-mer look-up that misses at every position).
+// One step looks SPEC positions up at once: k-mers, hashes, presence-filter words and first table slots of the next SPEC
+// positions are fetched together (independent loads in flight), then consumed strictly in order, so the result is exactly the
+// one-position-at-a-time scan's.  Returns true when the fragment's last scan has ended.
 constexpr int SPEC = 4;
-__device__ void scan_all(const IndexView& ix, const Read* rds, int n_mates, uint32_t max_interval,
-                         Interval (*ivs)[MAX_IV], int* niv, uint64_t* score) {
+struct ScanState { int s, n; uint32_t i; };
+__device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, int ns, uint32_t max_interval, ScanState& st,
+                                          unsigned long long* __restrict__ iv_out /* [ns][MAX_IV] of this fragment */,
+                                          uint8_t* __restrict__ niv_out /* [ns] */) {
     const uint32_t k = ix.k;
-    const int ns = 2 * n_mates;
-    int s = 0, n = 0;
-    uint32_t i = 0;
-    uint64_t sc = 0;
-    while (s < ns) {
-        const Read& r = rds[s >> 1];
-        const int o = s & 1;
-        const uint32_t L = r.len;
-        if (!(i + k <= L && n < MAX_IV)) { niv[s] = n; score[s] = sc; ++s; i = 0; n = 0; sc = 0; continue; }
-        if (r.has_n) {
-            const uint64_t nn = win32n(r, o, i) & ix.kmask;
-            if (nn) { i += ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; continue; }   // jump past the last invalid base
-        }
-        // candidates i .. i+nc-1: windows inside the read and free of invalid bases
-        uint64_t km[SPEC], hh[SPEC];
-        bool probe[SPEC];
-        int nc = 1;
-#pragma unroll
-        for (int j = 1; j < SPEC; ++j) {
-            if (nc == j && i + j + k <= L && (!r.has_n || (win32n(r, o, i + j) & ix.kmask) == 0)) nc = j + 1;
-        }
-        uint64_t bw[SPEC];
-#pragma unroll
-        for (int j = 0; j < SPEC; ++j) {
-            probe[j] = false;
-            if (j < nc) {
-                km[j] = win32(r, o, i + j) & ix.kmask;
-                const bool homo = km[j] == 0 || km[j] == ix.kmask || km[j] == (0x5555555555555555ULL & ix.kmask) ||
-                                  km[j] == (0xAAAAAAAAAAAAAAAAULL & ix.kmask);       // homopolymer k-mers are never seeds
-                if (!homo) {
-                    hh[j] = sfb_kmer_mix(km[j]);
-                    bw[j] = __ldg(ix.bloom + sfb_bloom_word(hh[j], ix.bloom_words));
-                    probe[j] = true;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < SPEC; ++j) {
-            if (probe[j]) { const uint64_t need = sfb_bloom_mask(hh[j]); probe[j] = (bw[j] & need) == need; }   // false => certainly absent
-        }
-        uint4 sl[SPEC];
-#pragma unroll
-        for (int j = 0; j < SPEC; ++j) if (probe[j]) sl[j] = __ldg(ix.table + (hh[j] & ix.mask));
-        // consume in order
-        bool advanced = false;
-#pragma unroll
-        for (int j = 0; j < SPEC; ++j) {
-            if (advanced || j >= nc) continue;
-            bool hit = false;
-            uint32_t lb = 0, cnt = 0;
-            if (probe[j]) {
-                if (sl[j].w != 0) {
-                    if ((((uint64_t)sl[j].y << 32) | sl[j].x) == km[j]) { hit = true; lb = sl[j].z; cnt = sl[j].w; }
-                    else hit = table_find_from(ix, km[j], hh[j] & ix.mask, lb, cnt);
-                }
-            }
-            if (!hit || cnt > max_interval) continue;                                  // position i+j is not a seed
-            const uint32_t q = i + j;
-            uint32_t m = 0;
-            for (uint32_t e = lb; e < lb + cnt; ++e) {
-                const uint2 en = __ldg(ix.sa + e);
-                const uint32_t l = lcp_at(ix, r, o, q, en.x, __ldg(ix.txp_end + en.y));
-                m = l > m ? l : m;
-            }
-            ivs[s][n].lb = lb; ivs[s][n].cnt = cnt; ivs[s][n].qpos = q; ivs[s][n].m = m;
-            ++n;
-            sc += m;
-            i = q + m - k + 1;                                                         // next k-mer ends one base past the match
-            advanced = true;
-        }
-        if (!advanced) i += nc;
+    const Read& r = rds[st.s >> 1];
+    const int o = st.s & 1;
+    const uint32_t L = r.len;
+    uint32_t i = st.i;
+    if (!(i + k <= L && st.n < MAX_IV)) { niv_out[st.s] = (uint8_t)st.n; ++st.s; st.i = 0; st.n = 0; return st.s >= ns; }
+    if (r.has_n) {
+        const uint64_t nn = win32n(r, o, i) & ix.kmask;
+        if (nn) { st.i = i + ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; return false; }   // jump past the last invalid base
     }
+    // candidates i .. i+nc-1: windows inside the read and free of invalid bases
+    uint64_t km[SPEC], hh[SPEC], bw[SPEC];
+    bool probe[SPEC];
+    int nc = 1;
+#pragma unroll
+    for (int j = 1; j < SPEC; ++j) {
+        if (nc == j && i + j + k <= L && (!r.has_n || (win32n(r, o, i + j) & ix.kmask) == 0)) nc = j + 1;
+    }
+#pragma unroll
+    for (int j = 0; j < SPEC; ++j) {
+        probe[j] = false;
+        if (j < nc) {
+            km[j] = win32(r, o, i + j) & ix.kmask;
+            const bool homo = km[j] == 0 || km[j] == ix.kmask || km[j] == (0x5555555555555555ULL & ix.kmask) ||
+                              km[j] == (0xAAAAAAAAAAAAAAAAULL & ix.kmask);           // homopolymer k-mers are never seeds
+            if (!homo) {
+                hh[j] = sfb_kmer_mix(km[j]);
+                bw[j] = __ldg(ix.bloom + sfb_bloom_word(hh[j], ix.bloom_words));
+                probe[j] = true;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SPEC; ++j) {
+        if (probe[j]) { const uint64_t need = sfb_bloom_mask(hh[j]); probe[j] = (bw[j] & need) == need; }   // false => certainly absent
+    }
+    uint4 sl[SPEC];
+#pragma unroll
+    for (int j = 0; j < SPEC; ++j) if (probe[j]) sl[j] = __ldg(ix.table + (hh[j] & ix.mask));
+    // consume in order
+    bool advanced = false;
+#pragma unroll
+    for (int j = 0; j < SPEC; ++j) {
+        if (advanced || j >= nc) continue;
+        bool hit = false;
+        uint32_t lb = 0, cnt = 0;
+        if (probe[j]) {
+            if (sl[j].w != 0) {
+                if ((((uint64_t)sl[j].y << 32) | sl[j].x) == km[j]) { hit = true; lb = sl[j].z; cnt = sl[j].w; }
+                else hit = table_find_from(ix, km[j], hh[j] & ix.mask, lb, cnt);
+            }
+        }
+        if (!hit || cnt > max_interval) continue;                                      // position i+j is not a seed
+        const uint32_t q = i + j;
+        uint32_t m = 0;
+        for (uint32_t e = lb; e < lb + cnt; ++e) {
+            const uint2 en = __ldg(ix.sa + e);
+            const uint32_t l = lcp_at(ix, r, o, q, en.x, __ldg(ix.txp_end + en.y));
+            m = l > m ? l : m;
+        }
+        iv_out[st.s * MAX_IV + st.n] = pack_iv(lb, cnt, q, m);
+        ++st.n;
+        i = q + m - k + 1;                                                             // next k-mer ends one base past the match
+        advanced = true;
+    }
+    if (!advanced) i += nc;
+    st.i = i;
+    return false;
 }
 
 // per-thread scratch in global memory, element j of thread t at base[j * stride + t] (coalesced like local memory)
@@ -416,8 +456,11 @@ struct MapParams {
     int lib_fmt, strict_intersect, allow_orphans, allow_dovetail, ignore_compat, enforce_compat;
     unsigned long long* scratch; uint64_t n_threads_total;
     unsigned long long* counters;      // 6
-    unsigned long long* next_read;     // work counter
+    unsigned long long* next_read;     // work counters: [0] scan kernel, [1] finalize kernel
     int16_t* fld_val;                  // per read of the batch: fragment length if FLD-eligible, else -1
+    // packed batch and the scan -> finalize hand-over
+    const uint64_t* pk; const uint64_t* pkn; const uint32_t* meta; uint32_t rwp; int n_mates;
+    unsigned long long* iv; uint8_t* niv;
 };
 
 struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of processReadsQuasi folded into one buffer
@@ -433,21 +476,74 @@ struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of 
     }
 };
 
-__global__ void __launch_bounds__(MAP_THREADS, 3) k_map_reads(const MapParams p) {
+// ---- scan kernel: lanes pull fragments independently ------------------------------------------------------------------------
+// The work per fragment varies (a read with a sequencing error scans ~30 more positions on the matching strand), so a
+// warp that processes 32 fragments in lock step idles most of its lanes while the slowest finishes (measured: 13 of 32
+// lanes busy).  Here a lane that has finished its fragment takes the next one from its warp's reservation (64 fragments per
+// global atomic) and the seed intervals go to global memory for the finalize kernel.
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_scan_reads(const MapParams p) {
     extern __shared__ uint64_t smem_reads[];       // [warp][mate][orientation][word][lane]
+    const unsigned lane = threadIdx.x & 31u;
+    const int n_mates = p.n_mates, ns = 2 * n_mates;
+    Read rds[2];
+    {
+        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * n_mates * 2 * RW * 32 + lane;
+        rds[0].sb = wbase;
+        rds[1].sb = wbase + (n_mates - 1) * 2 * RW * 32;
+    }
+    bool have = false, done = false;
+    uint64_t frag = 0;
+    ScanState st; st.s = 0; st.n = 0; st.i = 0;
+    unsigned long long res_next = 0, res_end = 0;          // this warp's reservation [res_next, res_end), warp-uniform
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have && !done);
+        const unsigned busy = __ballot_sync(0xffffffffu, have);
+        if (need && (busy == 0 || __popc(need) >= 8)) {     // refill several lanes at once: the refill code runs divergent
+            if (res_next == res_end) {
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(p.next_read, 64ULL);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                res_next = b < p.n_reads ? b : p.n_reads;
+                res_end = b + 64 < p.n_reads ? b + 64 : p.n_reads;
+            }
+            const unsigned long long avail = res_end - res_next;       // 0 only when the global queue is exhausted
+            if (!have && !done) {
+                const unsigned my = __popc(need & ((1u << lane) - 1));
+                if (my < avail) {
+                    frag = res_next + my;
+                    for (int mt = 0; mt < n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, frag * n_mates + mt, p.rwp, rds[mt]);
+                    st.s = 0; st.n = 0; st.i = 0;
+                    have = true;
+                } else if (avail == 0) {
+                    done = true;
+                }
+            }
+            const unsigned want = __popc(need);
+            res_next += want < avail ? want : avail;
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0 && __ballot_sync(0xffffffffu, !done) == 0) break;
+        if (have) {
+            if (scan_step(p.ix, rds, ns, p.max_interval, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.niv + frag * ns)) have = false;
+        }
+    }
+}
+
+// ---- finalize kernel: projection, mate merge, compatibility filter, label, class upsert -----------------------------------------
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapParams p) {
+    extern __shared__ uint64_t smem_reads[];
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const Scratch scr{p.scratch + gtid, p.n_threads_total};
     const uint32_t cap = p.cap;
     const uint32_t TMP0 = 0, LEFT0 = 2 * (cap + 1), RIGHT0 = 3 * (cap + 1);
-    const bool paired = p.bases2 != nullptr;
+    const bool paired = p.n_mates == 2;
+    const int ns = 2 * p.n_mates;
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
     Read rds[2];
     {
-        const int n_mates = p.bases2 != nullptr ? 2 : 1;
-        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * n_mates * 2 * RW * 32 + (threadIdx.x & 31u);
+        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * p.n_mates * 2 * RW * 32 + lane;
         rds[0].sb = wbase;
-        rds[1].sb = wbase + (n_mates - 1) * 2 * RW * 32;
+        rds[1].sb = wbase + (p.n_mates - 1) * 2 * RW * 32;
     }
     Interval ivs[4][MAX_IV];
     int niv[4];
@@ -455,18 +551,22 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_map_reads(const MapParams p)
 
     for (;;) {
         unsigned long long base_idx = 0;
-        if (lane == 0) base_idx = atomicAdd(p.next_read, 32ULL);
+        if (lane == 0) base_idx = atomicAdd(p.next_read + 1, 32ULL);
         base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
         if (base_idx >= p.n_reads) break;
         const uint64_t ri = base_idx + lane;
         if (ri < p.n_reads) {
             uint32_t nL = 0, nR = 0;
             bool okL, okR = true;
-            load_read(p.bases1, p.off1[ri], p.off1[ri + 1], rds[0]);
+            for (int mt = 0; mt < p.n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, ri * p.n_mates + mt, p.rwp, rds[mt]);
             const uint32_t len1 = rds[0].len;
-            uint32_t len2 = 0;
-            if (paired) { load_read(p.bases2, p.off2[ri], p.off2[ri + 1], rds[1]); len2 = rds[1].len; }
-            scan_all(p.ix, rds, paired ? 2 : 1, p.max_interval, ivs, niv, score);
+            const uint32_t len2 = paired ? rds[1].len : 0;
+            for (int q = 0; q < ns; ++q) {
+                niv[q] = p.niv[ri * ns + q];
+                uint64_t sc = 0;
+                for (int e = 0; e < niv[q]; ++e) { ivs[q][e] = unpack_iv(p.iv[(ri * ns + q) * MAX_IV + e]); sc += ivs[q][e].m; }
+                score[q] = sc;
+            }
             okL = collect(p.ix, rds[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, TMP0, LEFT0, nL);   // paired: strict check (:192-202)
             if (paired) okR = collect(p.ix, rds[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, TMP0, RIGHT0, nR);
             const bool overflow = !okL || !okR;
@@ -678,6 +778,12 @@ struct MapState {
     DevBuf<unsigned int> fld_hist;
     DevBuf<int> remaining;
     DevBuf<int16_t> fld_val, fld_samples;
+    DevBuf<uint64_t> pk, pkn;          // packed batch
+    DevBuf<uint32_t> meta;
+    DevBuf<unsigned long long> iv;     // seed intervals, scan -> finalize
+    DevBuf<uint8_t> niv;
+    DevBuf<unsigned int> maxlen;
+    int grid_scan = 0;
     // two staging sets for host batches: the H2D copy of batch j (copy stream) overlaps the mapping kernel of batch j-1
     DevBuf<char> bases1[2], bases2[2];
     DevBuf<uint64_t> off1[2], off2[2];
@@ -698,6 +804,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
     m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
+    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->maxlen.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
         if (m->copied[i]) cudaEventDestroy(m->copied[i]);
@@ -714,6 +821,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     if (!c->index.ready) SFB_FAIL(c, SFB200_EINVAL, "map_begin: build the index first");
     if (o->max_frag_len == 0 || o->max_frag_len > 32767) SFB_FAIL(c, SFB200_EINVAL, "max_frag_len must be in [1, 32767]");
     if (o->max_read_occs == 0 || o->max_read_occs > 1000) SFB_FAIL(c, SFB200_EINVAL, "max_read_occs must be in [1, 1000]");
+    if (o->max_interval > 16383) SFB_FAIL(c, SFB200_EINVAL, "max_interval must be <= 16383");
     cudaSetDevice(c->device);
     if (!c->map) c->map = new MapState();
     MapState* m = c->map;
@@ -726,7 +834,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->n_buckets = 1ull << lb; m->n_overflow = std::max<uint64_t>(1024, m->n_buckets / 4); m->arena_words = 1ull << la;
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
     SFB_CUDA(c, m->slot.reserve(n_slots)); SFB_CUDA(c, m->count.reserve(n_slots)); SFB_CUDA(c, m->arena.reserve(m->arena_words));
-    SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(1));
+    SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(2)); SFB_CUDA(c, m->maxlen.reserve(1));
     SFB_CUDA(c, m->fld_hist.reserve(o->max_frag_len)); SFB_CUDA(c, m->remaining.reserve(1));
     SFB_CUDA(c, m->fld_samples.reserve((size_t)std::max(1, o->num_frag_samples)));
     SFB_CUDA(c, cudaMemsetAsync(m->slot.p, 0, n_slots * 8, s));
@@ -740,8 +848,11 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     int per_sm = 0;
     // the occupancy that matters is the paired-end one (two mates of packed reads in shared memory per lane)
     const size_t smem_pe = (size_t)MAP_THREADS * 2 * 2 * RW * 8;
-    SFB_CUDA(c, cudaFuncSetAttribute(k_map_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe));
-    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_reads, MAP_THREADS, smem_pe / 2));
+    SFB_CUDA(c, cudaFuncSetAttribute(k_scan_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe));
+    SFB_CUDA(c, cudaFuncSetAttribute(k_finalize_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe));
+    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_reads, MAP_THREADS, smem_pe / 2));
+    m->grid_scan = c->num_sms * std::max(per_sm, 1);
+    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finalize_reads, MAP_THREADS, smem_pe / 2));
     if (per_sm < 1) per_sm = 1;
     m->grid = c->num_sms * per_sm;
     m->n_threads_total = (uint64_t)m->grid * MAP_THREADS;
@@ -797,14 +908,32 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     p.scratch = m->scratch.p; p.n_threads_total = m->n_threads_total; p.counters = m->counters.p; p.next_read = m->next_read.p;
     const bool want_fld = d_bases2 != nullptr;
     if (want_fld) { SFB_CUDA(c, m->fld_val.reserve(n_reads)); p.fld_val = m->fld_val.p; }
-    SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 8, s));
-    const uint64_t warps_needed = (n_reads + 31) / 32;
-    const uint64_t blocks_needed = (warps_needed * 32 + MAP_THREADS - 1) / MAP_THREADS;
-    const unsigned grid = (unsigned)std::min<uint64_t>(m->grid, blocks_needed);
+    SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 16, s));
+    const int n_mates = d_bases2 ? 2 : 1;
     if (m->ev.size() < m->ev_used + 2) { cudaEvent_t a, b; SFB_CUDA(c, cudaEventCreate(&a)); SFB_CUDA(c, cudaEventCreate(&b)); m->ev.push_back(a); m->ev.push_back(b); }
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used], s));
-    const size_t smem = (size_t)MAP_THREADS * (d_bases2 ? 2 : 1) * 2 * RW * 8;
-    k_map_reads<<<grid, MAP_THREADS, smem, s>>>(p);
+    // 1. longest read of the batch -> words per packed read
+    SFB_CUDA(c, cudaMemsetAsync(m->maxlen.p, 0, 4, s));
+    k_max_read_len<<<(unsigned)std::min<uint64_t>((n_reads + 255) / 256, 1024), 256, 0, s>>>(d_off1, d_off2, n_reads, m->maxlen.p);
+    c->launches++;
+    unsigned int maxlen = 0;
+    SFB_CUDA(c, cudaMemcpyAsync(&maxlen, m->maxlen.p, 4, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    const uint32_t rwp = std::max<uint32_t>(1, (maxlen + 31) / 32);
+    // 2. pack
+    const uint64_t n_fm = n_reads * n_mates;
+    SFB_CUDA(c, m->pk.reserve(n_fm * rwp)); SFB_CUDA(c, m->pkn.reserve(n_fm * rwp)); SFB_CUDA(c, m->meta.reserve(n_fm));
+    SFB_CUDA(c, m->iv.reserve(n_reads * (uint64_t)(2 * n_mates) * MAX_IV)); SFB_CUDA(c, m->niv.reserve(n_reads * (uint64_t)(2 * n_mates)));
+    SFB_CUDA(c, cudaMemsetAsync(m->meta.p, 0, n_fm * 4, s));
+    k_pack_reads<<<(unsigned)((n_fm * rwp + 255) / 256), 256, 0, s>>>(d_bases1, d_off1, d_bases2, d_off2, n_reads, n_mates, rwp, m->pk.p, m->pkn.p, m->meta.p);
+    c->launches++;
+    p.pk = m->pk.p; p.pkn = m->pkn.p; p.meta = m->meta.p; p.rwp = rwp; p.n_mates = n_mates; p.iv = m->iv.p; p.niv = m->niv.p;
+    // 3. seed scan (lanes pull fragments), 4. finalize (projection .. class upsert)
+    const size_t smem = (size_t)MAP_THREADS * n_mates * 2 * RW * 8;
+    const uint64_t blocks_needed = (n_reads + MAP_THREADS - 1) / MAP_THREADS;
+    k_scan_reads<<<(unsigned)std::min<uint64_t>(m->grid_scan, blocks_needed), MAP_THREADS, smem, s>>>(p);
+    c->launches++;
+    k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, smem, s>>>(p);
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));
