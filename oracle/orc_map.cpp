@@ -75,7 +75,7 @@ struct orc_index {
             // the externally built table is slotted with a two-multiply mixer (sailfish_b200/csrc/common.cuh: sfb_kmer_mix)
             uint64_t x = km;
             x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 29;
-            h = x & mask;
+            h = (x & (mask >> 1)) << 1;                                  // probing starts on an even slot
             for (;;) {
                 ++probes;
                 const uint64_t key = ext[2 * h];

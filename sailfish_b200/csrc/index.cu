@@ -100,7 +100,7 @@ __global__ void k_table_insert(const uint64_t* __restrict__ keys, const uint32_t
     const uint64_t km = keys[lb];
     const uint64_t hh = sfb_kmer_mix(km);
     atomicOr(bloom + sfb_bloom_word(hh, bloom_words), (unsigned long long)sfb_bloom_mask(hh));
-    uint64_t h = hh & mask;
+    uint64_t h = (hh & (mask >> 1)) << 1;            // probing starts on an even slot: slots h, h+1 share a 32-byte sector
     unsigned long long* slots = reinterpret_cast<unsigned long long*>(table);
     for (;;) {
         const unsigned long long prev = atomicCAS(&slots[2 * h], ~0ULL, (unsigned long long)km);

@@ -273,7 +273,7 @@ __device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, i
     return m < lim ? m : lim;
 }
 
-struct Interval { uint32_t lb, cnt, qpos, m; };
+struct Interval { uint32_t lb, cnt, qpos, m, mask; };   // mask: which of the first 32 bucket entries reach the maximal match m
 
 // continue a table lookup whose first slot (already loaded) held another k-mer: linear probing from the next slot
 __device__ __forceinline__ bool table_find_from(const IndexView& ix, uint64_t km, uint64_t h, uint32_t& lb, uint32_t& cnt) {
@@ -290,7 +290,7 @@ __device__ __forceinline__ unsigned long long pack_iv(uint32_t lb, uint32_t cnt,
     return (unsigned long long)lb | ((unsigned long long)cnt << 32) | ((unsigned long long)qpos << 46) | ((unsigned long long)m << 55);
 }
 __device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
-    Interval r; r.lb = (uint32_t)v; r.cnt = (uint32_t)(v >> 32) & 0x3FFFu; r.qpos = (uint32_t)(v >> 46) & 0x1FFu; r.m = (uint32_t)(v >> 55);
+    Interval r; r.mask = 0; r.lb = (uint32_t)v; r.cnt = (uint32_t)(v >> 32) & 0x3FFFu; r.qpos = (uint32_t)(v >> 46) & 0x1FFu; r.m = (uint32_t)(v >> 55);
     return r;
 }
 
@@ -301,7 +301,7 @@ __device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
 // positions are fetched together (independent loads in flight), then consumed strictly in order, so the result is exactly the
 // one-position-at-a-time scan's.  Returns true when the fragment's last scan has ended.
 constexpr int SPEC = 4;
-struct ScanState { int s, n; uint32_t i; };
+struct ScanState { int s, n; uint32_t i; uint32_t pend_lb, pend_cnt; };   // pend_cnt != 0: a seed waits for its extension
 __device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, int ns, uint32_t max_interval, ScanState& st,
                                           unsigned long long* __restrict__ iv_out /* [ns][MAX_IV] of this fragment */,
                                           uint8_t* __restrict__ niv_out /* [ns] */) {
@@ -341,38 +341,57 @@ __device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, 
     for (int j = 0; j < SPEC; ++j) {
         if (probe[j]) { const uint64_t need = sfb_bloom_mask(hh[j]); probe[j] = (bw[j] & need) == need; }   // false => certainly absent
     }
-    uint4 sl[SPEC];
-#pragma unroll
-    for (int j = 0; j < SPEC; ++j) if (probe[j]) sl[j] = __ldg(ix.table + (hh[j] & ix.mask));
-    // consume in order
-    bool advanced = false;
+    uint4 sl[SPEC], sl2[SPEC];
 #pragma unroll
     for (int j = 0; j < SPEC; ++j) {
-        if (advanced || j >= nc) continue;
+        if (probe[j]) {
+            const uint64_t h0 = (hh[j] & (ix.mask >> 1)) << 1;           // even slot: h0 and h0+1 share a 32-byte sector
+            sl[j] = __ldg(ix.table + h0); sl2[j] = __ldg(ix.table + h0 + 1);
+        }
+    }
+    // consume in order
+#pragma unroll
+    for (int j = 0; j < SPEC; ++j) {
+        if (j >= nc) continue;
         bool hit = false;
         uint32_t lb = 0, cnt = 0;
         if (probe[j]) {
             if (sl[j].w != 0) {
                 if ((((uint64_t)sl[j].y << 32) | sl[j].x) == km[j]) { hit = true; lb = sl[j].z; cnt = sl[j].w; }
-                else hit = table_find_from(ix, km[j], hh[j] & ix.mask, lb, cnt);
+                else if (sl2[j].w != 0) {
+                    if ((((uint64_t)sl2[j].y << 32) | sl2[j].x) == km[j]) { hit = true; lb = sl2[j].z; cnt = sl2[j].w; }
+                    else hit = table_find_from(ix, km[j], ((hh[j] & (ix.mask >> 1)) << 1) + 1, lb, cnt);
+                }
             }
         }
         if (!hit || cnt > max_interval) continue;                                      // position i+j is not a seed
-        const uint32_t q = i + j;
-        uint32_t m = 0;
-        for (uint32_t e = lb; e < lb + cnt; ++e) {
-            const uint2 en = __ldg(ix.sa + e);
-            const uint32_t l = lcp_at(ix, r, o, q, en.x, __ldg(ix.txp_end + en.y));
-            m = l > m ? l : m;
-        }
-        iv_out[st.s * MAX_IV + st.n] = pack_iv(lb, cnt, q, m);
-        ++st.n;
-        i = q + m - k + 1;                                                             // next k-mer ends one base past the match
-        advanced = true;
+        // a seed: the extension over its bucket is done later, together with other lanes' (see k_scan_reads)
+        st.i = i + j;
+        st.pend_lb = lb; st.pend_cnt = cnt;
+        return false;
     }
-    if (!advanced) i += nc;
-    st.i = i;
+    st.i = i + nc;
     return false;
+}
+
+// match extension of a pending seed: m = longest match over the bucket, mask = which of its first 32 entries reach it
+__device__ __forceinline__ void extend_seed(const IndexView& ix, const Read* rds, ScanState& st, unsigned long long* __restrict__ iv_out,
+                                            uint32_t* __restrict__ ivmask_out) {
+    const Read& r = rds[st.s >> 1];
+    const int o = st.s & 1;
+    const uint32_t q = st.i, lb = st.pend_lb, cnt = st.pend_cnt;
+    uint32_t m = 0, mask = 0;
+    for (uint32_t e = 0; e < cnt; ++e) {
+        const uint2 en = __ldg(ix.sa + lb + e);
+        const uint32_t l = lcp_at(ix, r, o, q, en.x, __ldg(ix.txp_end + en.y));
+        if (l > m) { m = l; mask = e < 32 ? (1u << e) : 0u; }
+        else if (l == m && e < 32) mask |= 1u << e;
+    }
+    iv_out[st.s * MAX_IV + st.n] = pack_iv(lb, cnt, q, m);
+    ivmask_out[st.s * MAX_IV + st.n] = mask;
+    ++st.n;
+    st.i = q + m - ix.k + 1;                                                           // next k-mer ends one base past the match
+    st.pend_cnt = 0;
 }
 
 // per-thread scratch in global memory, element j of thread t at base[j * stride + t] (coalesced like local memory)
@@ -401,7 +420,8 @@ __device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Int
         if ((int64_t)tid == lastTid) continue;
         const uint64_t tend = __ldg(ix.txp_end + tid);
         const uint32_t p = en.x;
-        if (lcp_at(ix, r, o, a.qpos, p, tend) != a.m) continue;
+        const uint32_t e_rel = e - a.lb;
+        if (e_rel < 32 ? !((a.mask >> e_rel) & 1u) : (lcp_at(ix, r, o, a.qpos, p, tend) != a.m)) continue;
         lastTid = tid;
         bool all = true;
         for (int j = 1; j < niv && all; ++j) {
@@ -412,7 +432,8 @@ __device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Int
             for (uint32_t e2 = lo; e2 < b.lb + b.cnt; ++e2) {
                 const uint2 en2 = __ldg(ix.sa + e2);
                 if (en2.y != tid) break;
-                if (lcp_at(ix, r, o, b.qpos, en2.x, tend) == b.m) { found = true; break; }
+                const uint32_t e2_rel = e2 - b.lb;
+                if (e2_rel < 32 ? ((b.mask >> e2_rel) & 1u) != 0 : (lcp_at(ix, r, o, b.qpos, en2.x, tend) == b.m)) { found = true; break; }
             }
             all = found;
         }
@@ -460,7 +481,7 @@ struct MapParams {
     int16_t* fld_val;                  // per read of the batch: fragment length if FLD-eligible, else -1
     // packed batch and the scan -> finalize hand-over
     const uint64_t* pk; const uint64_t* pkn; const uint32_t* meta; uint32_t rwp; int n_mates;
-    unsigned long long* iv; uint8_t* niv;
+    unsigned long long* iv; uint8_t* niv; uint32_t* ivmask;
 };
 
 struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of processReadsQuasi folded into one buffer
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_scan_reads(const MapParams p
     }
     bool have = false, done = false;
     uint64_t frag = 0;
-    ScanState st; st.s = 0; st.n = 0; st.i = 0;
+    ScanState st; st.s = 0; st.n = 0; st.i = 0; st.pend_lb = 0; st.pend_cnt = 0;
     unsigned long long res_next = 0, res_end = 0;          // this warp's reservation [res_next, res_end), warp-uniform
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !have && !done);
@@ -512,7 +533,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_scan_reads(const MapParams p
                 if (my < avail) {
                     frag = res_next + my;
                     for (int mt = 0; mt < n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, frag * n_mates + mt, p.rwp, rds[mt]);
-                    st.s = 0; st.n = 0; st.i = 0;
+                    st.s = 0; st.n = 0; st.i = 0; st.pend_cnt = 0;
                     have = true;
                 } else if (avail == 0) {
                     done = true;
@@ -522,7 +543,14 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_scan_reads(const MapParams p
             res_next += want < avail ? want : avail;
         }
         if (__ballot_sync(0xffffffffu, have) == 0 && __ballot_sync(0xffffffffu, !done) == 0) break;
-        if (have) {
+        // extensions are batched: lanes with a pending seed wait until 8 of them do (or nobody else can advance), so the
+        // divergent extension code runs with several lanes and their dependent loads overlap
+        const bool pend = have && st.pend_cnt != 0;
+        const unsigned pend_m = __ballot_sync(0xffffffffu, pend);
+        const unsigned adv_m = __ballot_sync(0xffffffffu, have && !pend);
+        if (pend && (__popc(pend_m) >= 8 || adv_m == 0))
+            extend_seed(p.ix, rds, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.ivmask + frag * (uint64_t)(ns * MAX_IV));
+        if (have && !pend) {
             if (scan_step(p.ix, rds, ns, p.max_interval, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.niv + frag * ns)) have = false;
         }
     }
@@ -564,7 +592,11 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapPara
             for (int q = 0; q < ns; ++q) {
                 niv[q] = p.niv[ri * ns + q];
                 uint64_t sc = 0;
-                for (int e = 0; e < niv[q]; ++e) { ivs[q][e] = unpack_iv(p.iv[(ri * ns + q) * MAX_IV + e]); sc += ivs[q][e].m; }
+                for (int e = 0; e < niv[q]; ++e) {
+                    ivs[q][e] = unpack_iv(p.iv[(ri * ns + q) * MAX_IV + e]);
+                    ivs[q][e].mask = p.ivmask[(ri * ns + q) * MAX_IV + e];
+                    sc += ivs[q][e].m;
+                }
                 score[q] = sc;
             }
             okL = collect(p.ix, rds[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, TMP0, LEFT0, nL);   // paired: strict check (:192-202)
@@ -782,6 +814,7 @@ struct MapState {
     DevBuf<uint32_t> meta;
     DevBuf<unsigned long long> iv;     // seed intervals, scan -> finalize
     DevBuf<uint8_t> niv;
+    DevBuf<uint32_t> ivmask;
     DevBuf<unsigned int> maxlen;
     int grid_scan = 0;
     // two staging sets for host batches: the H2D copy of batch j (copy stream) overlaps the mapping kernel of batch j-1
@@ -804,7 +837,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
     m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
-    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->maxlen.release();
+    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
         if (m->copied[i]) cudaEventDestroy(m->copied[i]);
@@ -924,10 +957,11 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
     const uint64_t n_fm = n_reads * n_mates;
     SFB_CUDA(c, m->pk.reserve(n_fm * rwp)); SFB_CUDA(c, m->pkn.reserve(n_fm * rwp)); SFB_CUDA(c, m->meta.reserve(n_fm));
     SFB_CUDA(c, m->iv.reserve(n_reads * (uint64_t)(2 * n_mates) * MAX_IV)); SFB_CUDA(c, m->niv.reserve(n_reads * (uint64_t)(2 * n_mates)));
+    SFB_CUDA(c, m->ivmask.reserve(n_reads * (uint64_t)(2 * n_mates) * MAX_IV));
     SFB_CUDA(c, cudaMemsetAsync(m->meta.p, 0, n_fm * 4, s));
     k_pack_reads<<<(unsigned)((n_fm * rwp + 255) / 256), 256, 0, s>>>(d_bases1, d_off1, d_bases2, d_off2, n_reads, n_mates, rwp, m->pk.p, m->pkn.p, m->meta.p);
     c->launches++;
-    p.pk = m->pk.p; p.pkn = m->pkn.p; p.meta = m->meta.p; p.rwp = rwp; p.n_mates = n_mates; p.iv = m->iv.p; p.niv = m->niv.p;
+    p.pk = m->pk.p; p.pkn = m->pkn.p; p.meta = m->meta.p; p.rwp = rwp; p.n_mates = n_mates; p.iv = m->iv.p; p.niv = m->niv.p; p.ivmask = m->ivmask.p;
     // 3. seed scan (lanes pull fragments), 4. finalize (projection .. class upsert)
     const size_t smem = (size_t)MAP_THREADS * n_mates * 2 * RW * 8;
     const uint64_t blocks_needed = (n_reads + MAP_THREADS - 1) / MAP_THREADS;
