@@ -300,7 +300,18 @@ __device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
 // One step looks SPEC positions up at once: k-mers, hashes, presence-filter words and first table slots of the next SPEC
 // positions are fetched together (independent loads in flight), then consumed strictly in order, so the result is exactly the
 // one-position-at-a-time scan's.  Returns true when the fragment's last scan has ended.
-constexpr int SPEC = 4;
+// Swept on B200 (scripts/variant_bench.sh): SPEC 2 with 4 CTAs/SM (64 registers, no spills) is the fastest; wider speculation
+// costs registers, and any spill of this kernel's state is ruinous (SPEC 4 x 3 CTAs: 23.7 ms, SPEC 2 x 4: 17.9 ms, SPEC 8: 47 ms)
+#ifndef SFB_SPEC
+#define SFB_SPEC 2
+#endif
+#ifndef SFB_EXT_BATCH
+#define SFB_EXT_BATCH 1      // seed extensions run as soon as they are found (batching them idled the waiting lanes: measured slower)
+#endif
+#ifndef SFB_SCAN_BLOCKS
+#define SFB_SCAN_BLOCKS 4
+#endif
+constexpr int SPEC = SFB_SPEC;
 struct ScanState { int s, n; uint32_t i; uint32_t pend_lb, pend_cnt; };   // pend_cnt != 0: a seed waits for its extension
 __device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, int ns, uint32_t max_interval, ScanState& st,
                                           unsigned long long* __restrict__ iv_out /* [ns][MAX_IV] of this fragment */,
@@ -502,7 +513,7 @@ struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of 
 // warp that processes 32 fragments in lock step idles most of its lanes while the slowest finishes (measured: 13 of 32
 // lanes busy).  Here a lane that has finished its fragment takes the next one from its warp's reservation (64 fragments per
 // global atomic) and the seed intervals go to global memory for the finalize kernel.
-__global__ void __launch_bounds__(MAP_THREADS, 3) k_scan_reads(const MapParams p) {
+__global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(const MapParams p) {
     extern __shared__ uint64_t smem_reads[];       // [warp][mate][orientation][word][lane]
     const unsigned lane = threadIdx.x & 31u;
     const int n_mates = p.n_mates, ns = 2 * n_mates;
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_scan_reads(const MapParams p
         const bool pend = have && st.pend_cnt != 0;
         const unsigned pend_m = __ballot_sync(0xffffffffu, pend);
         const unsigned adv_m = __ballot_sync(0xffffffffu, have && !pend);
-        if (pend && (__popc(pend_m) >= 8 || adv_m == 0))
+        if (pend && (__popc(pend_m) >= SFB_EXT_BATCH || adv_m == 0))
             extend_seed(p.ix, rds, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.ivmask + frag * (uint64_t)(ns * MAX_IV));
         if (have && !pend) {
             if (scan_step(p.ix, rds, ns, p.max_interval, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.niv + frag * ns)) have = false;
