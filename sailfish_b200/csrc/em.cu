@@ -661,15 +661,13 @@ int build_partition(sfb200_ctx* c) {
     SFB_CUDA(c, P.grp.reserve(3 * (size_t)(n_cta + 1) * SFB_NBINS + 4));
     SFB_CUDA(c, P.start.reserve(Em)); SFB_CUDA(c, P.len.reserve(Em)); SFB_CUDA(c, P.lab.reserve(nnzm)); SFB_CUDA(c, P.src.reserve(Em));
     SFB_CUDA(c, P.cnt.reserve(Em)); SFB_CUDA(c, P.w.reserve(nnzm)); SFB_CUDA(c, P.tbl.reserve((size_t)n_cta * PT_WORDS));
-    // 1. ranges balanced by work: every transcript costs its alpha slots, every label entry its 12 bytes
+    // 1. ranges balanced by sweep cost (lanes occupied by the classes whose smallest member falls in the range)
     SFB_CUDA(c, cudaMemsetAsync(P.load.p, 0, T * 4ull, s));
-    k_part_load<<<grid_for(nnzm, 256), 256, 0, s>>>(k.lab.p, nnzm, P.load.p);
-    c->launches++;
     // crossing profile (reuses the owner buffer as int[T+1] scratch)
     SFB_CUDA(c, P.owner.reserve(std::max<uint64_t>(Em, (uint64_t)T + 1)));
     int* d_diff = reinterpret_cast<int*>(P.owner.p);
     SFB_CUDA(c, cudaMemsetAsync(d_diff, 0, (T + 1) * 4ull, s));
-    k_part_span<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, d_diff);
+    k_part_span<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, d_diff, P.load.p);
     c->launches++;
     std::vector<uint32_t> load(T), bounds(n_cta + 1);
     std::vector<int> cross(T + 1);
@@ -678,10 +676,10 @@ int build_partition(sfb200_ctx* c) {
     SFB_CUDA(c, cudaStreamSynchronize(s));
     for (uint32_t t = 1; t <= T; ++t) cross[t] += cross[t - 1];
     uint64_t total = 0;
-    for (uint32_t t = 0; t < T; ++t) total += 3ull + load[t];
+    for (uint32_t t = 0; t < T; ++t) total += 1ull + load[t];
     { uint64_t acc = 0; uint32_t i = 1; bounds[0] = 0;
       for (uint32_t t = 0; t < T && i < n_cta; ++t) {
-          acc += 3ull + load[t];
+          acc += 1ull + load[t];
           while (i < n_cta && acc >= total * i / n_cta) bounds[i++] = t + 1;
       }
       while (i <= n_cta) bounds[i++] = T;

@@ -34,14 +34,18 @@ __global__ void k_part_load(const uint32_t* __restrict__ lab, uint64_t nnzm, uin
 
 // crossing profile: diff[t] accumulates +1 at (min member)+1 and -1 at (max member)+1 of every class, so that the prefix sum
 // cross[t] is the number of classes with min < t <= max, i.e. the classes a range boundary placed at t would cut
+// The same pass charges the class's sweep cost (the lanes its sub-warp group occupies) to its smallest member: ranges are
+// balanced by that, since the sweep is instruction-bound and a warp tile costs the same whatever its classes hold.
 __global__ void k_part_span(const uint32_t* __restrict__ start, const uint32_t* __restrict__ len, const uint32_t* __restrict__ lab,
-                            uint64_t Em, int* __restrict__ diff) {
+                            uint64_t Em, int* __restrict__ diff, uint32_t* __restrict__ load) {
     const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (c >= Em) return;
     const uint32_t b = start[c], n = len[c];
     uint32_t mn = lab[b], mx = mn;
     for (uint32_t j = 1; j < n; ++j) { const uint32_t t = lab[b + j]; mn = t < mn ? t : mn; mx = t > mx ? t : mx; }
     if (mn < mx) { atomicAdd(diff + mn + 1, 1); atomicSub(diff + mx + 1, 1); }
+    const uint32_t g = n <= 2 ? 2u : n <= 4 ? 4u : n <= 8 ? 8u : n <= 16 ? 16u : n <= 32 ? 32u : 2u * n;
+    atomicAdd(load + mn, g);
 }
 
 // one closure round: classes that span ranges or touch a dirty transcript go to the pool and dirty all their members
