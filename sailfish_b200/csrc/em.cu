@@ -652,7 +652,10 @@ int build_partition(sfb200_ctx* c) {
     DevPartition& P = k.part;
     P.valid = true; P.usable = false;
     if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
-    const uint32_t T = k.n_txp, n_cta = (uint32_t)c->num_sms;
+    // CTAs per SM for the partitioned loop: two half-size CTAs fill each other's __syncthreads bubbles
+    int per_sm = 2;
+    if (const char* e = getenv("SFB200_EM_CTAS_PER_SM")) per_sm = std::max(1, std::min(4, atoi(e)));
+    const uint32_t T = k.n_txp, n_cta = (uint32_t)(c->num_sms * per_sm);
     const uint64_t Em = k.Em, nnzm = k.nnzm;
     if (Em == 0 || T == 0) return SFB200_OK;
     cudaStream_t s = c->stream;
@@ -744,7 +747,7 @@ int build_partition(sfb200_ctx* c) {
     P.max_cta_bytes = max_bytes;
     int max_optin = 0;
     SFB_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    P.usable = max_bytes + 2048 <= (uint64_t)max_optin;
+    P.usable = (max_bytes + 2048) * per_sm <= (uint64_t)max_optin + 1024 * (uint64_t)(per_sm - 1);
     SFB_CUDA(c, cudaStreamSynchronize(s));
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool), largest CTA slice %llu bytes (limit %d) -> %s\n",
@@ -777,7 +780,8 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
         void* args[] = {&p, &q};
         const void* fn = vb ? reinterpret_cast<const void*>(&k_em_part<true>) : reinterpret_cast<const void*>(&k_em_part<false>);
         SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->num_sms), dim3(EM_THREADS), args, smem, s));
+        const unsigned per_sm_ctas = P.n_cta / (unsigned)c->num_sms;
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(EM_THREADS / per_sm_ctas), args, smem, s));
         c->launches++;
         SFB_CUDA(c, cudaEventRecord(c->ev1, s));
         SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
