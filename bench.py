@@ -139,7 +139,25 @@ def cpu_sample(oidx, bases, n_total, em_iters_full, threads, target_s, want_work
     return run, S
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries (NCCL prints its version banner) write to fd 1 behind Python's
+    back: point fd 1 at stderr for the duration of the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -212,7 +230,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "detail": {"map_reads_per_s": S / r["t_map"], "em_iters_per_s": r["iters"] / r["t_em"]}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -392,7 +410,7 @@ def main():
         else:
             line["roofline"] = dict(line["em_roofline"], traffic=None, kernel="k_em_part", peak_source=peak_src)
     line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

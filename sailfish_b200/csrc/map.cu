@@ -828,6 +828,10 @@ struct MapState {
     DevBuf<uint32_t> ivmask;
     DevBuf<unsigned int> maxlen;
     int grid_scan = 0;
+    // multi-rank class merge / FLD gather buffers (grow-only: cudaMalloc / cudaFree per step cost more than the exchange)
+    DevBuf<unsigned long long> mg_sizes, mg_cnt, mg_cnt_g;
+    DevBuf<uint32_t> mg_start, mg_len, mg_lab, mg_start_g, mg_len_g, mg_lab_g;
+    DevBuf<unsigned char> fld_send, fld_recv;
     // two staging sets for host batches: the H2D copy of batch j (copy stream) overlaps the mapping kernel of batch j-1
     DevBuf<char> bases1[2], bases2[2];
     DevBuf<uint64_t> off1[2], off2[2];
@@ -848,6 +852,8 @@ void sfb_map_state_free(sfb200_ctx* c) {
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
     m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
+    m->mg_sizes.release(); m->mg_cnt.release(); m->mg_cnt_g.release(); m->mg_start.release(); m->mg_len.release(); m->mg_lab.release();
+    m->mg_start_g.release(); m->mg_len_g.release(); m->mg_lab_g.release(); m->fld_send.release(); m->fld_recv.release();
     m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
@@ -1117,9 +1123,10 @@ static int merge_classes_over_ranks(sfb200_ctx* c, MapState* m) {
     DevClasses& k = c->cls;
     const int R = c->n_ranks;
     const uint64_t E = k.E, Z = k.nnz, Em = k.Em, nnzm = k.nnzm;
-    DevBuf<unsigned long long> d_sizes, d_cnt_g; DevBuf<uint32_t> d_start, d_len, d_lab, d_start_g, d_len_g, d_lab_g;
-    auto cleanup = [&]() { d_sizes.release(); d_cnt_g.release(); d_start.release(); d_len.release(); d_lab.release();
-                           d_start_g.release(); d_len_g.release(); d_lab_g.release(); };
+    DevBuf<unsigned long long>& d_sizes = m->mg_sizes; DevBuf<unsigned long long>& d_cnt_g = m->mg_cnt_g; DevBuf<unsigned long long>& d_cnt = m->mg_cnt;
+    DevBuf<uint32_t>& d_start = m->mg_start; DevBuf<uint32_t>& d_len = m->mg_len; DevBuf<uint32_t>& d_lab = m->mg_lab;
+    DevBuf<uint32_t>& d_start_g = m->mg_start_g; DevBuf<uint32_t>& d_len_g = m->mg_len_g; DevBuf<uint32_t>& d_lab_g = m->mg_lab_g;
+    auto cleanup = [&]() {};
 #define MG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return SFB200_ECUDA; } } while (0)
 #define MGRC(call) do { const int r__ = (call); if (r__) { cleanup(); return r__; } } while (0)
     MG(d_sizes.reserve(2 * (size_t)R + 2));
@@ -1138,13 +1145,13 @@ static int merge_classes_over_ranks(sfb200_ctx* c, MapState* m) {
     if (nnzm) MG(cudaMemcpyAsync(d_lab.p, k.lab.p, nnzm * 4, cudaMemcpyDeviceToDevice, s));
     if (k.n_sgl) { k_merge_pack_singles<<<(unsigned)((k.n_sgl + 255) / 256), 256, 0, s>>>(k.sgl_tid.p, k.n_sgl, Em, nnzm, d_start.p, d_len.p, d_lab.p); c->launches++; }
     // cnt_all is exactly E long; gather through a padded copy
-    DevBuf<unsigned long long> d_cnt; MG(d_cnt.reserve(maxE));
+    MG(d_cnt.reserve(maxE));
     if (E) MG(cudaMemcpyAsync(d_cnt.p, k.cnt_all.p, E * 8, cudaMemcpyDeviceToDevice, s));
     int rc = sfb_comm_allgather(c, d_start.p, d_start_g.p, maxE * 4);
     if (!rc) rc = sfb_comm_allgather(c, d_len.p, d_len_g.p, maxE * 4);
     if (!rc) rc = sfb_comm_allgather(c, d_cnt.p, d_cnt_g.p, maxE * 8);
     if (!rc) rc = sfb_comm_allgather(c, d_lab.p, d_lab_g.p, maxZ * 4);
-    if (rc) { d_cnt.release(); cleanup(); return rc; }
+    if (rc) return rc;
     EqTable tb;
     tb.slot = m->slot.p; tb.count = m->count.p; tb.arena = m->arena.p; tb.cursor = m->cursor.p;
     tb.n_buckets = m->n_buckets; tb.n_overflow = m->n_overflow; tb.arena_words = m->arena_words;
@@ -1155,7 +1162,6 @@ static int merge_classes_over_ranks(sfb200_ctx* c, MapState* m) {
     unsigned long long h_cursor[4];
     MG(cudaMemcpyAsync(h_cursor, m->cursor.p, sizeof(h_cursor), cudaMemcpyDeviceToHost, s));
     MG(cudaStreamSynchronize(s));
-    d_cnt.release();
     cleanup();
 #undef MG
 #undef MGRC
@@ -1191,7 +1197,7 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
         // rank 0's samples come first, then rank 1's, ... -- gather the ordered samples and cut at the budget
         const int total = m->o.num_frag_samples;
         const size_t row = ((size_t)total * 2 + 8 + 15) & ~(size_t)15;          // samples + taken count, per rank
-        DevBuf<unsigned char> d_send, d_recv;
+        DevBuf<unsigned char>& d_send = m->fld_send; DevBuf<unsigned char>& d_recv = m->fld_recv;
         SFB_CUDA(c, d_send.reserve(row)); SFB_CUDA(c, d_recv.reserve(row * c->n_ranks));
         int rem = 0;
         SFB_CUDA(c, cudaMemcpyAsync(&rem, m->remaining.p, 4, cudaMemcpyDeviceToHost, s));
@@ -1200,11 +1206,10 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
         SFB_CUDA(c, cudaMemcpyAsync(d_send.p, m->fld_samples.p, (size_t)total * 2, cudaMemcpyDeviceToDevice, s));
         SFB_CUDA(c, cudaMemcpyAsync(d_send.p + (size_t)total * 2, &taken, 8, cudaMemcpyHostToDevice, s));
         const int rc = sfb_comm_allgather(c, d_send.p, d_recv.p, row);
-        if (rc) { d_send.release(); d_recv.release(); return rc; }
+        if (rc) return rc;
         std::vector<unsigned char> all(row * c->n_ranks);
         SFB_CUDA(c, cudaMemcpyAsync(all.data(), d_recv.p, all.size(), cudaMemcpyDeviceToHost, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
-        d_send.release(); d_recv.release();
         std::fill(h_fld.begin(), h_fld.end(), 0u);
         long long budget = total;
         for (int r = 0; r < c->n_ranks && budget > 0; ++r) {
