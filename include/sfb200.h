@@ -57,8 +57,8 @@ int sfb200_comm_init(sfb200_ctx* ctx, int n_ranks, int rank, const uint8_t id[12
 /* ---- index ---------------------------------------------------------------------------------------------------
  * Replaces what ReadExperiment takes from RapMapSAIndex<IndexT> after SailfishIndex::load
  * (include/SailfishIndex.hpp:28-43,104-144; fields seq / txpOffsets / txpLens, include/ReadExperiment.hpp:103-116):
- * the device index (2-bit text, k-mer-bucketed suffix array, k-mer hash table) is built on the GPU from the
- * transcript sequences.  seq: ASCII, transcript t = seq[txp_off[t] .. txp_off[t]+txp_len[t]).  k odd, <= 31
+ * the device index (2-bit text, k-mer-bucketed suffix array, k-mer hash table, presence filter) is built on the GPU
+ * from the transcript sequences.  seq: ASCII, transcript t = seq[txp_off[t] .. txp_off[t]+txp_len[t]).  k odd, <= 31
  * (src/SailfishIndexer.cpp:79,199-205). */
 int sfb200_index_build(sfb200_ctx* ctx, const char* seq, const uint64_t* txp_off, const uint32_t* txp_len,
                        uint32_t n_txp, int k);
@@ -67,7 +67,8 @@ int sfb200_index_stats(const sfb200_ctx* ctx, uint64_t stats[8]);
 /* copy the index back to the host (tests, and bench.py's CPU arm): words[text_len/32+2], sa_pos[n_suffixes],
  * sa_tid[n_suffixes]; any pointer may be NULL */
 int sfb200_index_export(sfb200_ctx* ctx, uint64_t* words, uint32_t* sa_pos, uint32_t* sa_tid);
-/* the k-mer table: table_slots entries of {k-mer (u64), first entry (u32), entry count (u32)}; empty = all-ones k-mer */
+/* the k-mer table: table_slots entries of {k-mer (u64), first entry (u32), entry count (u32)}; empty = all-ones k-mer;
+ * slot = 2 * (mix(k-mer) & (table_slots/2 - 1)), linear probing (mix = sfb_kmer_mix, sailfish_b200/csrc/common.cuh) */
 int sfb200_index_export_table(sfb200_ctx* ctx, void* table16);
 
 /* ---- mapping + equivalence classes ---------------------------------------------------------------------------
@@ -99,7 +100,9 @@ int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_
 /* == thread join + eqBuilder.finish() (SailfishQuantify.cpp:942-947,1328).
  * counters: [0] numObservedFragments [1] numMappedFragments [2] numFragHits [3] upperBoundHits [4] numFwd [5] numRC
  * (ReadExperiment.hpp:74-97); fld_hist[max_frag_len] = flMap (SailfishQuantify.cpp:867).  With a communicator the
- * counters and fld_hist are summed over ranks (classes stay rank-local). */
+ * counters are summed over ranks, fld_hist holds the first num_frag_samples eligible fragments in global read order, and
+ * the classes of all ranks are merged (every rank then holds the global class set; set SFB200_MULTI_EM_ALLREDUCE=1 to keep
+ * them rank-local and all-reduce the per-transcript vector every EM iteration instead). */
 int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz);
 /* device time of all mapping-kernel launches between map_begin and map_finish, in milliseconds (CUDA events) */
 double sfb200_last_map_kernel_ms(const sfb200_ctx* ctx);
@@ -126,7 +129,7 @@ void sfb200_em_default_opts(sfb200_em_opts* o);
 /* Replaces CollapsedEMOptimizer::optimize (include/CollapsedEMOptimizer.hpp:25-28, src/CollapsedEMOptimizer.cpp:711-893).
  * eff_lens[t] = noEffectiveLengthCorrection ? RefLength : EffectiveLength; num_mapped = numMappedFragments() (global).
  * alphas_out[t] -> Transcript::setEstCount; mass = alphas/sum.  Classes come from map_finish or eq_import.
- * With a communicator: one all-reduce(sum) of the T-vector per iteration. */
+ * With a communicator and rank-local classes: one all-reduce(sum) of the T-vector per iteration. */
 int sfb200_em_run(sfb200_ctx* ctx, const double* eff_lens, uint32_t n_txp, uint64_t num_mapped,
                   const sfb200_em_opts* opts, double* alphas_out, uint32_t* iters_out, double* max_rel_diff_out);
 /* device time of the iteration loop of the last em_run / bootstrap in milliseconds (CUDA events on the launch stream) */

@@ -159,8 +159,6 @@ int sfb_classes_host(sfb200_ctx* ctx);   // make cls.h_* valid (downloads + sort
 
 // ---- device helpers ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-__device__ __forceinline__ uint64_t sfb_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
-
 // XXH64 (reference: src/xxhash.c:346-455) -- written from the published algorithm description:
 // 4 accumulator lanes over 32-byte stripes, merge, then 8/4/1-byte tail, then avalanche.
 constexpr uint64_t XXP1 = 11400714785074694791ULL;

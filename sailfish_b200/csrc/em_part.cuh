@@ -27,11 +27,6 @@ __device__ __forceinline__ uint32_t part_range_of(const uint32_t* __restrict__ b
     return lo;
 }
 
-__global__ void k_part_load(const uint32_t* __restrict__ lab, uint64_t nnzm, uint32_t* __restrict__ load) {
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < nnzm) atomicAdd(load + lab[i], 1u);
-}
-
 // crossing profile: diff[t] accumulates +1 at (min member)+1 and -1 at (max member)+1 of every class, so that the prefix sum
 // cross[t] is the number of classes with min < t <= max, i.e. the classes a range boundary placed at t would cut
 // The same pass charges the class's sweep cost (the lanes its sub-warp group occupies) to its smallest member: ranges are

@@ -737,7 +737,7 @@ __global__ void k_fld_select(const int16_t* __restrict__ fld_val, uint64_t n_rea
 
 // ---- eqBuilder.finish() on the device ---------------------------------------------------------------------------------------
 // bin of a class by member count: 0..5 as in DevClasses (g = 2,4,8,16,32 lanes, then "long"), 6 = single-member
-enum { FIN_CLS = 0, FIN_NNZ = 8, FIN_CUR_CLS = 16, FIN_CUR_NNZ = 24, FIN_ACTIVE = 32, FIN_TOTAL = 33, FIN_WORDS = 40 };
+enum { FIN_CLS = 0, FIN_NNZ = 8, FIN_CUR_CLS = 16, FIN_ACTIVE = 32, FIN_TOTAL = 33, FIN_WORDS = 40 };
 __device__ __forceinline__ int fin_bin(uint32_t n) { return n == 1 ? SFB_NBINS : n <= 2 ? 0 : n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 3 : n <= 32 ? 4 : 5; }
 
 __global__ void k_eq_count(const unsigned long long* __restrict__ slot, uint64_t n_slots, unsigned long long* __restrict__ fin) {
@@ -842,7 +842,7 @@ struct MapState {
     uint64_t n_buckets = 0, n_overflow = 0, arena_words = 0;
     uint64_t n_threads_total = 0;
     int grid = 0;
-    std::vector<cudaEvent_t> ev;       // start/stop pairs around every k_map_reads launch since map_begin
+    std::vector<cudaEvent_t> ev;       // start/stop pairs around the mapping kernels of every batch since map_begin
     size_t ev_used = 0;
     double kernel_ms = 0.0;
 };
