@@ -1,0 +1,205 @@
+"""`sailfish quant`-shaped driver on top of the C ABI: transcripts + reads -> quant.sf (and aux/).
+
+This is the plumbing around the hot path, kept deliberately thin: FASTA/FASTQ parsing in Python,
+everything between "a batch of reads" and "per-transcript counts" on the GPU through libsfb200.  Output formats follow the
+reference writers:
+
+  quant.sf              Name, Length, EffectiveLength, TPM, NumReads; doubles printed like cppformat's `{}` == printf("%g")
+                        (reference src/GZipWriter.cpp:194-248)
+  aux/eq_classes.txt    T, E, T names, then per class `n \\t tid_1 .. tid_n \\t count` (src/GZipWriter.cpp:51-92), with --dumpEq
+  aux/bootstrap/bootstraps.gz   raw little-endian f64 rows (bootstraps) or i32 rows (Gibbs) (src/GZipWriter.cpp:250-284)
+  aux/meta_info.json    the counters of src/GZipWriter.cpp:163-190 that exist on this path
+
+    python -m sailfish_b200.quant -t transcripts.fasta -l IU -1 reads_1.fastq -2 reads_2.fastq -o out_dir
+"""
+import argparse
+import gzip
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import capi, efflen
+
+# LibraryFormat ids (reference include/LibraryFormat.hpp:7-9,89-98): type | orientation << 1 | strandedness << 3
+_SE, _PE = 0, 1
+_SAME, _AWAY, _TOWARD, _NONE = 0, 1, 2, 3
+_SA, _AS, _S, _A, _U = 0, 1, 2, 3, 4
+
+
+def parse_library_format(s):
+    """parseLibraryFormatString of the CLI (reference src/SailfishUtils.cpp:63-97) -> LibraryFormat::formatID()"""
+    table = {"IU": (_PE, _TOWARD, _U), "ISF": (_PE, _TOWARD, _SA), "ISR": (_PE, _TOWARD, _AS),
+             "OU": (_PE, _AWAY, _U), "OSF": (_PE, _AWAY, _SA), "OSR": (_PE, _AWAY, _AS),
+             "MU": (_PE, _SAME, _U), "MSF": (_PE, _SAME, _S), "MSR": (_PE, _SAME, _A),
+             "U": (_SE, _NONE, _U), "SF": (_SE, _NONE, _S), "SR": (_SE, _NONE, _A)}
+    key = s.upper()
+    if key not in table:
+        raise ValueError("unknown library type %r" % s)
+    t, o, st = table[key]
+    return (t & 1) | ((o & 3) << 1) | ((st & 7) << 3)
+
+
+def _open(path):
+    return gzip.open(path, "rt") if path.endswith(".gz") else open(path, "rt")
+
+
+def read_fasta(path):
+    names, seqs, cur = [], [], []
+    with _open(path) as f:
+        for line in f:
+            line = line.strip()
+            if line.startswith(">"):
+                if cur or names:
+                    seqs.append("".join(cur)); cur = []
+                names.append(line[1:].split()[0])
+            elif line:
+                cur.append(line)
+    if names:
+        seqs.append("".join(cur))
+    return names, seqs
+
+
+def read_fastx_batches(path, batch):
+    """yields lists of sequences (FASTQ or FASTA reads), `batch` at a time"""
+    out = []
+    with _open(path) as f:
+        first = f.readline()
+        if not first:
+            return
+        fastq = first.startswith("@")
+        if fastq:
+            while first:
+                out.append(f.readline().strip())
+                f.readline(); f.readline()
+                if len(out) == batch:
+                    yield out; out = []
+                first = f.readline()
+        else:
+            cur = []
+            for line in f:
+                line = line.strip()
+                if line.startswith(">"):
+                    out.append("".join(cur)); cur = []
+                    if len(out) == batch:
+                        yield out; out = []
+                elif line:
+                    cur.append(line)
+            out.append("".join(cur))
+    if out:
+        yield out
+
+
+def fmt_g(x):
+    return "%g" % x
+
+
+def write_quant_sf(path, names, lengths, eff, alphas, num_mapped):
+    """GZipWriter::writeAbundances (reference src/GZipWriter.cpp:194-248)"""
+    tpm = capi.tpm(alphas, eff, num_mapped) if num_mapped > 0 and np.sum(alphas) > 0 else np.zeros(len(alphas))
+    with open(path, "w") as f:
+        f.write("Name\tLength\tEffectiveLength\tTPM\tNumReads\n")
+        for i, n in enumerate(names):
+            f.write("%s\t%d\t%s\t%s\t%s\n" % (n, lengths[i], fmt_g(eff[i]), fmt_g(tpm[i]), fmt_g(alphas[i])))
+    return tpm
+
+
+def write_eq_classes(path, names, row_ptr, labels, counts):
+    """GZipWriter::writeEquivCounts (reference src/GZipWriter.cpp:51-92)"""
+    with open(path, "w") as f:
+        f.write("%d\n%d\n" % (len(names), len(counts)))
+        for n in names:
+            f.write(n + "\n")
+        for e in range(len(counts)):
+            ids = labels[int(row_ptr[e]):int(row_ptr[e + 1])]
+            f.write("%d\t%s\t%d\n" % (len(ids), "\t".join(str(int(t)) for t in ids), int(counts[e])))
+
+
+def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_quant", k=31, use_vb=False, n_boot=0, n_gibbs=0,
+             dump_eq=False, batch=1_000_000, device=0, no_eff_len_correction=False, map_kw=None):
+    t_start = time.time()
+    names, seqs = read_fasta(transcripts)
+    lengths = np.array([len(s) for s in seqs], np.uint32)
+    paired = reads2 is not None
+    fmt = parse_library_format(libtype or ("IU" if paired else "U"))
+    if paired != bool(fmt & 1):
+        raise ValueError("library type %s does not match the number of read files" % libtype)
+    ctx = capi.Context(device)
+    ctx.index_build(seqs=seqs, k=k)
+    ctx.map_begin(capi.MapOpts.default(fmt, **(map_kw or {})))
+    it2 = read_fastx_batches(reads2, batch) if paired else None
+    for r1 in read_fastx_batches(reads1, batch):
+        b1, o1 = capi.pack_reads(r1)
+        if paired:
+            r2 = next(it2)
+            if len(r2) != len(r1):
+                raise ValueError("mate files have different numbers of reads")
+            b2, o2 = capi.pack_reads(r2)
+            ctx.map_batch(b1, o1, b2, o2)
+        else:
+            ctx.map_batch(b1, o1)
+    g = ctx.map_finish()
+    counters = g["counters"]
+    num_mapped = int(counters[1])
+    eff = efflen.effective_lengths(lengths, g["fld"], max_frag_len=ctx.map_opts.max_frag_len,
+                                   num_frag_samples=ctx.map_opts.num_frag_samples, single_end=not paired,
+                                   no_correction=no_eff_len_correction)
+    os.makedirs(os.path.join(out_dir, "aux"), exist_ok=True)
+    if dump_eq:
+        rp, lab, cnt = ctx.eq_export()
+        write_eq_classes(os.path.join(out_dir, "aux", "eq_classes.txt"), names, rp, lab, cnt)
+    alphas, iters, mrd = ctx.em_run(eff, num_mapped, capi.EMOpts.default(use_vb=int(use_vb)))
+    write_quant_sf(os.path.join(out_dir, "quant.sf"), names, lengths, eff, alphas, num_mapped)
+    samp_type = "none"
+    if n_boot or n_gibbs:
+        os.makedirs(os.path.join(out_dir, "aux", "bootstrap"), exist_ok=True)
+        with gzip.open(os.path.join(out_dir, "aux", "bootstrap", "names.tsv.gz"), "wt") as f:
+            f.write("\t".join(names) + "\n")
+        if n_boot:
+            rows = ctx.bootstrap_run(eff, n_boot, opts=capi.EMOpts.default(use_vb=int(use_vb)))
+            samp_type = "bootstrap"
+        else:
+            rows = ctx.gibbs_run(eff, alphas / max(alphas.sum(), 1e-300), num_mapped, n_gibbs)
+            samp_type = "gibbs"
+        with gzip.open(os.path.join(out_dir, "aux", "bootstrap", "bootstraps.gz"), "wb") as f:
+            f.write(np.ascontiguousarray(rows).tobytes())
+    meta = {"sf_version": "0.10.0-b200", "samp_type": samp_type, "frag_dist_length": int(ctx.map_opts.max_frag_len),
+            "bias_correct": False, "num_targets": len(names), "num_bootstraps": int(n_boot or n_gibbs),
+            "num_processed": int(counters[0]), "num_mapped": num_mapped,
+            "percent_mapped": 100.0 * num_mapped / max(int(counters[0]), 1), "call": "quant",
+            "em_iterations": int(iters), "elapsed_s": time.time() - t_start}
+    with open(os.path.join(out_dir, "aux", "meta_info.json"), "w") as f:
+        json.dump(meta, f, indent=4)
+    ctx.close()
+    return dict(names=names, lengths=lengths, eff=eff, alphas=alphas, counters=counters, iters=iters, meta=meta)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="sailfish_b200.quant", description="transcript quantification on B200 (sailfish quant)")
+    ap.add_argument("-t", "--transcripts", required=True, help="transcript FASTA (the index is built on the GPU from it)")
+    ap.add_argument("-l", "--libType", default=None)
+    ap.add_argument("-r", "--unmatedReads")
+    ap.add_argument("-1", "--mates1")
+    ap.add_argument("-2", "--mates2")
+    ap.add_argument("-o", "--output", required=True)
+    ap.add_argument("-k", "--kmerLen", type=int, default=31)
+    ap.add_argument("--useVBOpt", action="store_true")
+    ap.add_argument("--numBootstraps", type=int, default=0)
+    ap.add_argument("--numGibbsSamples", type=int, default=0)
+    ap.add_argument("--dumpEq", action="store_true")
+    ap.add_argument("--noEffectiveLengthCorrection", action="store_true")
+    a = ap.parse_args(argv)
+    if a.numBootstraps and a.numGibbsSamples:
+        sys.exit("--numBootstraps and --numGibbsSamples are mutually exclusive (SailfishQuantify.cpp:1281-1287)")
+    r1 = a.mates1 or a.unmatedReads
+    if not r1:
+        sys.exit("no reads given")
+    res = quantify(a.transcripts, r1, a.mates2, a.libType, a.output, a.kmerLen, a.useVBOpt, a.numBootstraps, a.numGibbsSamples,
+                   a.dumpEq, no_eff_len_correction=a.noEffectiveLengthCorrection)
+    print(json.dumps(res["meta"]))
+
+
+if __name__ == "__main__":
+    main()
