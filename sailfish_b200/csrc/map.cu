@@ -934,8 +934,26 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     return SFB200_OK;
 }
 
+static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
+                            const uint64_t* d_off2, uint64_t n_reads);
+
+// Batches of any size: the per-fragment hand-over buffers (packed reads, seed intervals) are sized for at most
+// MAX_CHUNK fragments, larger batches are walked chunk by chunk (offsets are absolute, so a chunk is a pointer shift).
 extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
                                        const uint64_t* d_off2, uint64_t n_reads) {
+    if (!c) return SFB200_EINVAL;
+    uint64_t MAX_CHUNK = 4u << 20;
+    if (const char* e = getenv("SFB200_MAX_CHUNK")) MAX_CHUNK = std::max<long long>(32, atoll(e));
+    for (uint64_t a = 0; a < n_reads || a == 0; a += MAX_CHUNK) {
+        const uint64_t n = std::min<uint64_t>(MAX_CHUNK, n_reads - a);
+        const int rc = map_chunk_device(c, d_bases1, d_off1 ? d_off1 + a : nullptr, d_bases2, d_off2 ? d_off2 + a : nullptr, n);
+        if (rc || n_reads == 0) return rc;
+    }
+    return SFB200_OK;
+}
+
+static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
+                            const uint64_t* d_off2, uint64_t n_reads) {
     if (!c) return SFB200_EINVAL;
     MapState* m = c->map;
     if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_batch: call map_begin first");

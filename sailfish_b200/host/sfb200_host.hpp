@@ -131,30 +131,45 @@ private:
 // (seq1(i), seq2(i)).  Host worker threads may call this concurrently: batches are serialised on the device context.
 class GpuQuasiMapper {
 public:
-    explicit GpuQuasiMapper(Device& d) : dev_(d) {}
+    // Parser jobs are small (1000 reads, SailfishQuantify.cpp:73); a kernel launch wants far more.  Jobs are appended to a
+    // staging batch under a mutex and the batch goes to the device when it holds `flushAt` fragments; call flush() after the
+    // worker threads joined (before EquivalenceClassBuilder::finish()).
+    explicit GpuQuasiMapper(Device& d, size_t flushAt = 1u << 20) : dev_(d), flushAt_(flushAt) { o1_.push_back(0); o2_.push_back(0); }
     template <typename SeqOf>
     void processReads(size_t n, SeqOf seq) {                                   // single-end
-        pack(n, seq, b1_, o1_);
         std::lock_guard<std::mutex> lk(mu_);
-        dev_.check(sfb200_map_batch(dev_.get(), b1_.data(), o1_.data(), nullptr, nullptr, n));
+        paired_ = false;
+        for (size_t i = 0; i < n; ++i) { b1_.append(seq(i)); o1_.push_back(b1_.size()); }
+        if (o1_.size() - 1 >= flushAt_) flushLocked();
     }
     template <typename SeqOf1, typename SeqOf2>
     void processReads(size_t n, SeqOf1 seq1, SeqOf2 seq2) {                     // paired-end
-        pack(n, seq1, b1_, o1_);
-        pack(n, seq2, b2_, o2_);
         std::lock_guard<std::mutex> lk(mu_);
-        dev_.check(sfb200_map_batch(dev_.get(), b1_.data(), o1_.data(), b2_.data(), o2_.data(), n));
+        paired_ = true;
+        for (size_t i = 0; i < n; ++i) {
+            b1_.append(seq1(i)); o1_.push_back(b1_.size());
+            b2_.append(seq2(i)); o2_.push_back(b2_.size());
+        }
+        if (o1_.size() - 1 >= flushAt_) flushLocked();
     }
+    void flush() { std::lock_guard<std::mutex> lk(mu_); flushLocked(); }
 
 private:
-    template <typename SeqOf>
-    static void pack(size_t n, SeqOf seq, std::string& bases, std::vector<uint64_t>& off) {
-        bases.clear();
-        off.assign(n + 1, 0);
-        for (size_t i = 0; i < n; ++i) { const std::string& s = seq(i); bases.append(s); off[i + 1] = bases.size(); }
-        bases.push_back('\0');
+    void flushLocked() {
+        const size_t n = o1_.size() - 1;
+        if (n == 0) return;
+        b1_.push_back('\0');
+        if (paired_) {
+            b2_.push_back('\0');
+            dev_.check(sfb200_map_batch(dev_.get(), b1_.data(), o1_.data(), b2_.data(), o2_.data(), n));
+        } else {
+            dev_.check(sfb200_map_batch(dev_.get(), b1_.data(), o1_.data(), nullptr, nullptr, n));
+        }
+        b1_.clear(); b2_.clear(); o1_.assign(1, 0); o2_.assign(1, 0);
     }
     Device& dev_;
+    size_t flushAt_;
+    bool paired_ = false;
     std::mutex mu_;
     std::string b1_, b2_;
     std::vector<uint64_t> o1_, o2_;

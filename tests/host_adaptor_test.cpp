@@ -3,6 +3,7 @@
 // members as the reference's (include/ReadExperiment.hpp, Transcript.hpp, SailfishOpts.hpp).
 // Input  (argv[1]): text file: T, then T lines "len seq"; n reads then n lines "r1 r2"
 // Output (stdout):  counters, class count, then T lines "estCount mass", then bootstrap / gibbs row sums.
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -50,10 +51,12 @@ int main(int argc, char** argv) {
         sfb200::EquivalenceClassBuilder eqb(dev);
         sfb200_map_opts mo = {200, 1000, 10000, /*IU*/ 1 | (2 << 1) | (4 << 3), 0, 1, 0, 0, 0, 1000};
         eqb.start(mo);
-        sfb200::GpuQuasiMapper mapper(dev);
-        const size_t half = n / 2;                                      // two parser jobs
-        mapper.processReads(half, [&](size_t i) -> const std::string& { return r1[i]; }, [&](size_t i) -> const std::string& { return r2[i]; });
-        mapper.processReads(n - half, [&](size_t i) -> const std::string& { return r1[half + i]; }, [&](size_t i) -> const std::string& { return r2[half + i]; });
+        sfb200::GpuQuasiMapper mapper(dev, 3000);                       // small flush threshold: exercises several device batches
+        for (size_t j0 = 0; j0 < n; j0 += 1000) {                       // parser jobs of 1000 reads (SailfishQuantify.cpp:73)
+            const size_t m = std::min<size_t>(1000, n - j0);
+            mapper.processReads(m, [&](size_t i) -> const std::string& { return r1[j0 + i]; }, [&](size_t i) -> const std::string& { return r2[j0 + i]; });
+        }
+        mapper.flush();
         eqb.finish();
         exp.mapped = eqb.numMappedFragments();
         std::printf("%llu %llu %llu %llu %llu %llu\n", (unsigned long long)eqb.numObservedFragments(), (unsigned long long)eqb.numMappedFragments(),

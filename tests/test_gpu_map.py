@@ -187,3 +187,12 @@ def test_oracle_on_device_built_index(ctx):
         res.append(run.finish())
     for key in ("counters", "fld", "row_ptr", "labels", "counts"):
         assert res[0][key].tolist() == res[1][key].tolist()
+
+
+def test_large_batches_are_chunked(ctx, monkeypatch):
+    """a batch larger than the per-launch hand-over buffers is walked in chunks: same classes, counters, FLD sample"""
+    seq, off, ln = small_txome(30, seed=5)
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 20000, 100, seed=21, paired=True, sub_rate=0.01)
+    monkeypatch.setenv("SFB200_MAX_CHUNK", "3000")
+    st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, b2, o2, "IU", batches=2)
+    assert_same_classes(ctx, g, w)
