@@ -80,7 +80,8 @@ struct DevPartition {
     uint32_t n_cta = 0;
     uint64_t pool_cls[SFB_NBINS + 1] = {0, 0, 0, 0, 0, 0, 0};
     uint64_t n_pool = 0;
-    uint64_t max_cta_bytes = 0;
+    uint64_t max_cta_bytes = 0, max_cta_bytes_vb = 0, smem_limit = 0;
+    int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
     DevBuf<double> cnt, w, cnt_s;
     DevBuf<unsigned long long> tbl, grp;

@@ -730,7 +730,7 @@ int build_partition(sfb200_ctx* c) {
     c->launches++;
     // 4. per-CTA table and the shared-memory budget
     std::vector<unsigned long long> tbl((size_t)n_cta * PT_WORDS, 0);
-    uint64_t max_bytes = 0;
+    uint64_t max_bytes = 0, max_bytes_vb = 0;
     for (uint32_t i = 0; i < n_cta; ++i) {
         unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
         for (int b = 0; b <= SFB_NBINS; ++b) row[PT_CLS + b] = cls_off[(size_t)i * SFB_NBINS + b];
@@ -738,15 +738,17 @@ int build_partition(sfb200_ctx* c) {
         row[PT_TXP0] = bounds[i]; row[PT_TXP1] = bounds[i + 1];
         const uint64_t nc = row[PT_CLS + SFB_NBINS] - (row[PT_CLS] & ~3ULL) + 4, ne = row[PT_ENT1] - (row[PT_ENT0] & ~3ULL) + 4;
         const uint64_t nt = bounds[i + 1] - bounds[i] + 4;
-        max_bytes = std::max<uint64_t>(max_bytes, nc * 16 + ne * 12 + nt * (8 * 4 + 1) + 256);
+        max_bytes = std::max<uint64_t>(max_bytes, nc * 16 + ne * 12 + nt * (8 * 2 + 1) + 256);
+        max_bytes_vb = std::max<uint64_t>(max_bytes_vb, nc * 16 + ne * 12 + nt * (8 * 3 + 1) + 256);
     }
     SFB_CUDA(c, cudaMemcpyAsync(P.tbl.p, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, s));
     for (int b = 0; b <= SFB_NBINS; ++b) P.pool_cls[b] = cls_off[(size_t)n_cta * SFB_NBINS + std::min(b, SFB_NBINS)];
     P.pool_cls[SFB_NBINS] = Em;
     P.n_pool = Em - P.pool_cls[0];
-    P.max_cta_bytes = max_bytes;
+    P.max_cta_bytes = max_bytes; P.max_cta_bytes_vb = max_bytes_vb; P.per_sm = per_sm;
     int max_optin = 0;
     SFB_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    P.smem_limit = (uint64_t)max_optin;
     P.usable = (max_bytes + 2048) * per_sm <= (uint64_t)max_optin + 1024 * (uint64_t)(per_sm - 1);
     SFB_CUDA(c, cudaStreamSynchronize(s));
     if (getenv("SFB200_VERBOSE"))
@@ -775,7 +777,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
         const DevPartition& P = c->cls.part;
         PartParams q;
         q.tbl = P.tbl.p; q.dirty = P.dirty.p; q.has_pool = P.n_pool > 0 ? 1 : 0;
-        const size_t smem = (size_t)P.max_cta_bytes + 1024;
+        const size_t smem = (size_t)(vb ? P.max_cta_bytes_vb : P.max_cta_bytes) + 1024;
         q.smem_bytes = (uint32_t)smem;
         void* args[] = {&p, &q};
         const void* fn = vb ? reinterpret_cast<const void*>(&k_em_part<true>) : reinterpret_cast<const void*>(&k_em_part<false>);
@@ -902,6 +904,8 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     if (!steps_mode && k.Em) {
         if (!k.part.valid) { const int rc = build_partition(c); if (rc) return rc; }
         use_part = k.part.usable;
+        if (use_part && o->use_vb)                                  // VBEM keeps expTheta in shared memory as well
+            use_part = (k.part.max_cta_bytes_vb + 2048) * k.part.per_sm <= k.part.smem_limit + 1024 * (uint64_t)(k.part.per_sm - 1);
     }
     DevPartition& P = k.part;
     const uint32_t* a_start = use_part ? P.start.p : k.start.p;

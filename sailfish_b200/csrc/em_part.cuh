@@ -129,8 +129,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_part(const EmParams p, con
     double* s_w = s_cnt + nc;
     double* s_a = s_w + ne;
     double* s_b = s_a + ntp;
-    double* s_base = s_b + ntp;
-    double* s_theta = s_base + ntp;                                   // VBEM only (space reserved only then)
+    double* s_theta = s_b + ntp;                                      // VBEM only (space reserved only then)
     uint32_t* s_start = reinterpret_cast<uint32_t*>(s_theta + (VB ? ntp : 0));
     uint32_t* s_len = s_start + nc;
     uint32_t* s_lab = s_len + nc;
@@ -152,11 +151,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_part(const EmParams p, con
     }
     for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) {
         const uint8_t d = q.dirty[t0 + i];
-        const double bs = d ? 0.0 : p.base[t0 + i];
         s_dirty[i] = d;
         s_a[i] = d ? 0.0 : p.X[t0 + i];                               // alpha_0 (buffer 0)
-        s_base[i] = bs;
-        s_b[i] = bs;
+        s_b[i] = d ? 0.0 : p.base[t0 + i];
     }
     if (have_cls) {
         uint32_t done = 0;
@@ -211,7 +208,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_part(const EmParams p, con
                 }
             }
             if (!last) {
-                s_prev[i] = s_base[i];
+                s_prev[i] = s_dirty[i] ? 0.0 : __ldg(p.base + t0 + i);     // base stays in global memory (coalesced, L2-resident)
                 if (VB) s_theta[i] = (cur > DENORM_MIN) ? exp(sfb_digamma(cur) - logNorm) : 0.0;
             }
         }
