@@ -188,7 +188,30 @@ __global__ void k_pack_reads(const char* __restrict__ bases1, const uint64_t* __
     if (i0 < L) {
         const uint32_t n = (L - i0) < 32 ? (L - i0) : 32;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(bases) + beg + i0;
-        for (uint32_t j = 0; j < n; ++j) {
+        uint32_t j = 0;
+        if ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+            // four bases per 32-bit load, converted with byte-parallel arithmetic
+            for (; j + 4 <= n; j += 4) {
+                const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(src + j));
+                const uint32_t up = x & 0xDFDFDFDFu;
+                uint32_t okm = 0;                                    // 0x80 in every byte that is A, C, G or T
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t K = q == 0 ? 0x41414141u : q == 1 ? 0x43434343u : q == 2 ? 0x47474747u : 0x54545454u;
+                    const uint32_t z = up ^ K;
+                    okm |= ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);     // exact zero-byte detector
+                }
+                uint32_t code = ((x >> 1) ^ (x >> 2)) & 0x03030303u;                 // A 0, C 1, G 2, T 3 in every byte
+                const uint32_t okb = okm >> 7;                                       // 1 per valid byte
+                code &= okb * 3u;                                                    // invalid bases carry code 0
+                const uint32_t c8 = (code | (code >> 6) | (code >> 12) | (code >> 18)) & 0xFFu;
+                const uint32_t nb = (~okb) & 0x01010101u;
+                const uint32_t b8 = (nb | (nb >> 6) | (nb >> 12) | (nb >> 18)) & 0x55u;
+                word |= (uint64_t)c8 << (2 * j);
+                bad |= (uint64_t)b8 << (2 * j);
+            }
+        }
+        for (; j < n; ++j) {
             const unsigned char ch = src[j];
             const unsigned char up = ch & 0xDF;
             const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
