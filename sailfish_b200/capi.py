@@ -86,6 +86,7 @@ SIGNATURES = {
     "sfb200_em_default_opts": (None, [C.POINTER(EMOpts)]),
     "sfb200_em_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.c_uint64, C.POINTER(EMOpts), f64p, u32p, f64p]),
     "sfb200_last_em_loop_ms": (C.c_double, [C.c_void_p]),
+    "sfb200_last_em_kernel": (C.c_int, [C.c_void_p]),
     "sfb200_bootstrap_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.POINTER(EMOpts), C.c_uint32, C.c_uint64, F64_ROW_CB, C.c_void_p]),
     "sfb200_bootstrap_em": (C.c_int, [C.c_void_p, f64p, C.c_uint32, u64p, C.POINTER(EMOpts), f64p, u32p]),
     "sfb200_gibbs_run": (C.c_int, [C.c_void_p, f64p, f64p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, I32_ROW_CB, C.c_void_p]),
@@ -287,6 +288,10 @@ class Context:
 
     def last_em_loop_ms(self):
         return float(self.L.sfb200_last_em_loop_ms(self.h))
+
+    def last_em_kernel(self):
+        """0 k_em_persistent, 1 k_em_part, 2 k_em_gather, 3 one launch per phase"""
+        return int(self.L.sfb200_last_em_kernel(self.h))
 
     def bootstrap_em(self, eff_lens, samp_counts, opts=None):
         opts = opts or EMOpts.default()

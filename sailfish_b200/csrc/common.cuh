@@ -86,8 +86,13 @@ struct DevPartition {
     DevBuf<double> cnt, w, cnt_s;
     DevBuf<unsigned long long> tbl, grp;
     DevBuf<uint8_t> dirty;
+    // gather layout of the atomic-free loop (em_gather.cuh): one region per CTA, geometry kept as opaque words
+    bool gather_ok = false;
+    uint32_t gth_geom[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t gather_smem = 0;           // dynamic shared memory the largest CTA needs
+    DevBuf<uint32_t> gth;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); dirty.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); dirty.release(); gth.release(); }
 };
 struct DevClasses {
     DevPartition part;
@@ -133,6 +138,7 @@ struct sfb200_ctx {
     std::string err;
     uint64_t launches = 0;
     double last_em_ms = 0.0;
+    int last_em_kernel = 0;             // see sfb200_last_em_kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevIndex index;
     DevClasses cls;

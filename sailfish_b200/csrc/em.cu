@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_sweep(const EmParams p, un
 }
 
 #include "em_part.cuh"
+#include "em_gather.cuh"
 
 __global__ void k_sum_f64(const double* __restrict__ x, uint32_t n, double* __restrict__ out) {
     __shared__ double sm_d[32];
@@ -641,16 +642,19 @@ extern "C" void sfb200_em_default_opts(sfb200_em_opts* o) {
 }
 
 extern "C" double sfb200_last_em_loop_ms(const sfb200_ctx* c) { return c ? c->last_em_ms : 0.0; }
+extern "C" int sfb200_last_em_kernel(const sfb200_ctx* c) { return c ? c->last_em_kernel : 0; }
 
 namespace {
 
 
 // Build the CTA partition of the current classes (em_part.cuh).  Device kernels do the per-class work; the host only scans
 // a T-long load histogram and the (n_cta+1) x 6 group table.
+int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
+
 int build_partition(sfb200_ctx* c) {
     DevClasses& k = c->cls;
     DevPartition& P = k.part;
-    P.valid = true; P.usable = false;
+    P.valid = true; P.usable = false; P.gather_ok = false;
     if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
     // CTAs per SM for the partitioned loop: two half-size CTAs fill each other's __syncthreads bubbles
     int per_sm = 2;
@@ -751,6 +755,7 @@ int build_partition(sfb200_ctx* c) {
     P.smem_limit = (uint64_t)max_optin;
     P.usable = (max_bytes + 2048) * per_sm <= (uint64_t)max_optin + 1024 * (uint64_t)(per_sm - 1);
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    { const int rc = build_gather(c, tbl); if (rc) return rc; }
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool), largest CTA slice %llu bytes (limit %d) -> %s\n",
                 n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, (unsigned long long)max_bytes, max_optin,
@@ -758,11 +763,62 @@ int build_partition(sfb200_ctx* c) {
     return SFB200_OK;
 }
 
+// Build the gather layout (em_gather.cuh) of the current partition: one k_gather_build CTA per partition range.
+// Leaves P.gather_ok false (and the atomic kernels in charge) when the pool is not empty, an index would not fit in
+// 16 bits, a region overflows or the largest CTA does not fit in shared memory.
+int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
+    DevPartition& P = c->cls.part;
+    P.gather_ok = false;
+    if (getenv("SFB200_EM_NO_GATHER_BUILD") || P.n_pool != 0 || P.n_cta == 0) return SFB200_OK;
+    static_assert(sizeof(GatherGeom) == sizeof(P.gth_geom), "GatherGeom is stored as 12 opaque words");
+    uint64_t max_nc = 0, max_ne = 0, max_nt = 0;
+    for (uint32_t i = 0; i < P.n_cta; ++i) {
+        const unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
+        max_nc = std::max<uint64_t>(max_nc, row[PT_CLS + SFB_NBINS] - row[PT_CLS]);
+        max_ne = std::max<uint64_t>(max_ne, row[PT_ENT1] - row[PT_ENT0]);
+        max_nt = std::max<uint64_t>(max_nt, row[PT_TXP1] - row[PT_TXP0]);
+    }
+    auto up = [](uint64_t x, uint64_t m) { return (x + m - 1) / m * m; };
+    if (up(max_nc, 32) > 65535 || up(max_nt, 32) > 65535 || max_ne > (1u << 24)) return SFB200_OK;
+    const GatherGeom g = gather_make_geom(max_nc, max_ne, max_nt);
+    cudaStream_t s = c->stream;
+    SFB_CUDA(c, P.gth.reserve((size_t)P.n_cta * g.region_words));
+    const size_t scratch = 4 * gather_scratch_words(max_nc, max_nt, g);
+    if (scratch + 1024 > P.smem_limit) return SFB200_OK;
+    SFB_CUDA(c, cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_gather_build), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+    k_gather_build<<<P.n_cta, 256, scratch, s>>>(P.start.p, P.len.p, P.lab.p, P.tbl.p, g, P.gth.p);
+    c->launches++;
+    SFB_CUDA(c, cudaGetLastError());
+    std::vector<uint32_t> hdr((size_t)P.n_cta * GH_WORDS);
+    SFB_CUDA(c, cudaMemcpy2DAsync(hdr.data(), GH_WORDS * 4, P.gth.p, (size_t)g.region_words * 4, GH_WORDS * 4, P.n_cta,
+                                  cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    bool ok = true;
+    uint64_t need = 0;
+    uint32_t max_len = 0, max_deg = 0;
+    for (uint32_t i = 0; i < P.n_cta; ++i) {
+        const uint32_t* h = hdr.data() + (size_t)i * GH_WORDS;
+        ok = ok && h[GH_OK] == 1u;
+        need = std::max<uint64_t>(need, gather_smem_need(h[GH_TILES_E], h[GH_TILES_T], h[GH_ENT_E], h[GH_ENT_T]));
+        max_len = std::max(max_len, h[GH_MAXLEN]); max_deg = std::max(max_deg, h[GH_MAXDEG]);
+    }
+    need += 256;
+    const bool fits = (need + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1);
+    std::memcpy(P.gth_geom, &g, sizeof(g));
+    P.gather_smem = need;
+    P.gather_ok = ok && fits;
+    if (getenv("SFB200_VERBOSE"))
+        fprintf(stderr, "[sfb200] EM gather layout: largest CTA %llu bytes of shared memory, largest class %u, largest degree %u -> %s\n",
+                (unsigned long long)need, max_len, max_deg, P.gather_ok ? "atomic-free loop" : (ok ? "does not fit" : "region overflow"));
+    return SFB200_OK;
+}
+
 struct LoopSpec { bool gate_old; uint32_t min_iter; };
+enum LoopKind { LOOP_BINNED = 0, LOOP_PART = 1, LOOP_GATHER = 2 };
 
 // Runs the iteration loop on prepared device state (weights, base, X[0] = alpha_0, X[1] = X[2] = base).
 // On return *buf_out says which third of X holds the result.
-int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part, uint32_t* iters_out, double* mrd_out, unsigned* buf_out) {
+int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind, uint32_t* iters_out, double* mrd_out, unsigned* buf_out) {
     cudaStream_t s = c->stream;
     SFB_CUDA(c, c->em_ctl.reserve(CTL_WORDS));
     SFB_CUDA(c, cudaMemsetAsync(c->em_ctl.p, 0, CTL_WORDS * 8, s));
@@ -773,7 +829,26 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
     const bool steps = sharded || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
     unsigned long long h_ctl[CTL_WORDS];
     SFB_CUDA(c, cudaEventRecord(c->ev0, s));
-    if (!steps && use_part) {
+    if (!steps && kind == LOOP_GATHER) {
+        const DevPartition& P = c->cls.part;
+        GatherParams q;
+        q.regions = P.gth.p; std::memcpy(&q.g, P.gth_geom, sizeof(q.g)); q.eff = c->eff.p;
+        const size_t smem = (size_t)P.gather_smem;
+        void* args[] = {&p, &q};
+        const void* fn = vb ? reinterpret_cast<const void*>(&k_em_gather<true>) : reinterpret_cast<const void*>(&k_em_gather<false>);
+        SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned per_sm_ctas = P.n_cta / (unsigned)c->num_sms;
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(EM_THREADS / per_sm_ctas), args, smem, s));
+        c->launches++;
+        SFB_CUDA(c, cudaEventRecord(c->ev1, s));
+        SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        *iters_out = static_cast<uint32_t>(h_ctl[CTL_ITERS]);
+        *buf_out = static_cast<unsigned>(h_ctl[CTL_RESULT_BUF]);
+        const unsigned long long mr = h_ctl[CTL_MRD];
+        double d; const unsigned long long b = mr ? mr - 1 : 0; std::memcpy(&d, &b, 8);
+        *mrd_out = mr ? d : -std::numeric_limits<double>::max();
+    } else if (!steps && kind == LOOP_PART) {
         const DevPartition& P = c->cls.part;
         PartParams q;
         q.tbl = P.tbl.p; q.dirty = P.dirty.p; q.has_pool = P.n_pool > 0 ? 1 : 0;
@@ -877,6 +952,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, bool use_part,
     float ms = 0.f;
     SFB_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_em_ms = ms;
+    c->last_em_kernel = steps ? 3 : (int)kind;
     return SFB200_OK;
 }
 
@@ -900,11 +976,12 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const char* mode_env = getenv("SFB200_EM_MODE");
     const bool sharded = c->n_ranks > 1 && !k.merged;      // rank-local classes: one all-reduce per iteration
     const bool steps_mode = sharded || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
-    bool use_part = false;
+    bool use_part = false, use_gather = false;
     if (!steps_mode && k.Em) {
         if (!k.part.valid) { const int rc = build_partition(c); if (rc) return rc; }
-        use_part = k.part.usable;
-        if (use_part && o->use_vb)                                  // VBEM keeps expTheta in shared memory as well
+        use_gather = k.part.gather_ok && !getenv("SFB200_EM_NO_GATHER");     // atomic-free loop (em_gather.cuh)
+        use_part = use_gather || k.part.usable;                              // both read the partition-ordered arrays
+        if (use_part && !use_gather && o->use_vb)                   // VBEM keeps expTheta in shared memory as well
             use_part = (k.part.max_cta_bytes_vb + 2048) * k.part.per_sm <= k.part.smem_limit + 1024 * (uint64_t)(k.part.per_sm - 1);
     }
     DevPartition& P = k.part;
@@ -912,7 +989,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const uint32_t* a_len = use_part ? P.len.p : k.len.p;
     const uint32_t* a_lab = use_part ? P.lab.p : k.lab.p;
     double* a_w = use_part ? P.w.p : k.w.p;
-    if (k.Em) {
+    if (k.Em && !use_gather) {
         // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
         k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
         c->launches++;
@@ -971,7 +1048,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     unsigned buf = 0;
     sfb200_em_opts oo = *o;
     oo.min_iter = spec.min_iter;
-    const int rc = run_loop(c, p, &oo, use_part, iters_out, mrd_out, &buf);
+    const int rc = run_loop(c, p, &oo, use_gather ? LOOP_GATHER : use_part ? LOOP_PART : LOOP_BINNED, iters_out, mrd_out, &buf);
     if (rc) return rc;
 
     SFB_CUDA(c, cudaMemcpyAsync(alphas_out, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,155 @@
+"""GPU parity tests (-m gpu) of the atomic-free EM loop k_em_gather (sailfish_b200/csrc/em_gather.cuh) through the C ABI.
+
+The loop runs when every multi-member class is local to one CTA's transcript range (gene-local classes: the BASELINE
+workloads); these tests assert that it is the kernel that ran (sfb200_last_em_kernel == 2) and compare it with the oracle
+(= the reference's CollapsedEMOptimizer restated) within the north_star tolerance, and with the scatter-form kernels."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from sailfish_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-6
+GATHER = 2
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+@pytest.mark.parametrize("T,E", [(5000, 12000), (60000, 150000), (300, 700)])
+def test_gather_loop_converges_like_the_oracle(ctx, vb, T, E):
+    rp, lab, cnt = synth.make_classes(T, E, seed=T + vb)                    # members stay inside a 5-transcript gene
+    eff = np.random.default_rng(T).uniform(0.5, 4000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+    assert ctx.last_em_kernel() == GATHER
+    rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb), n_threads=4)
+    assert rc == 0 and it == it_o
+    close(a, want)
+    assert (a == 0).tolist() == (want == 0).tolist()
+    assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+@pytest.mark.parametrize("fixed", [1, 2, 49, 50, 51, 400])
+def test_gather_loop_fixed_iterations(ctx, vb, fixed):
+    T = 8000
+    rp, lab, cnt = synth.make_classes(T, 20000, seed=3 + fixed)
+    eff = np.random.default_rng(fixed).uniform(50, 4000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb, fixed_iters=fixed))
+    assert ctx.last_em_kernel() == GATHER
+    rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, fixed_iters=fixed))
+    assert rc == 0 and it == fixed == it_o
+    close(a, want)
+    assert abs(a.sum() - want.sum()) <= 1e-9 * want.sum()
+    assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
+
+
+def test_gather_loop_iteration_limits(ctx):
+    """the loop rule (CollapsedEMOptimizer.cpp:820): itNum < minIter || (itNum < maxIter && !converged)"""
+    T = 2000
+    rp, lab, cnt = synth.make_classes(T, 5000, seed=12)
+    eff = np.full(T, 800.0)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    for kw in (dict(max_iter=7, min_iter=3), dict(max_iter=5, min_iter=20), dict(min_iter=0, max_iter=10000), dict(tol=1e-5)):
+        a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(**kw))
+        assert ctx.last_em_kernel() == GATHER
+        rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(**kw))
+        assert rc == 0 and it == it_o, kw
+        close(a, want)
+
+
+def test_gather_loop_equals_scatter_kernels(ctx, monkeypatch):
+    T = 30000
+    rp, lab, cnt = synth.make_classes(T, 70000, seed=5)
+    eff = np.random.default_rng(1).uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    for vb in (0, 1):
+        a1, it1, m1 = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        assert ctx.last_em_kernel() == GATHER
+        monkeypatch.setenv("SFB200_EM_NO_GATHER", "1")
+        a2, it2, m2 = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        assert ctx.last_em_kernel() == 1                                  # k_em_part
+        monkeypatch.delenv("SFB200_EM_NO_GATHER")
+        assert it1 == it2
+        close(a1, a2, rtol=1e-7)
+        assert abs(m1 - m2) <= 1e-6 * abs(m2)
+
+
+def test_gather_loop_duplicate_ids_long_classes_and_idle_transcripts(ctx):
+    """labels with a repeated transcript id (orphan pairs) and transcripts that belong to no class or only to
+    single-member classes"""
+    rng = np.random.default_rng(4)
+    T = 4000
+    labels = {}
+    for g in range(0, T - 10, 10):
+        if g % 50 == 40:
+            continue                                                       # an idle gene: its transcripts stay at 0
+        for _ in range(6):
+            n = int(rng.integers(1, 9))
+            ids = np.sort(rng.integers(g, g + 10, size=n))                 # with replacement: duplicate ids
+            labels[tuple(int(x) for x in ids)] = int(rng.integers(1, 500))
+    labs = sorted(labels)
+    rp = np.zeros(len(labs) + 1, np.uint64); rp[1:] = np.cumsum([len(l) for l in labs])
+    lab = np.array([t for l in labs for t in l], np.uint32)
+    cnt = np.array([labels[l] for l in labs], np.uint64)
+    eff = rng.uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    for vb in (0, 1):
+        a, it, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        assert ctx.last_em_kernel() == GATHER
+        rc, want, it_o, _ = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb))
+        assert rc == 0 and it == it_o
+        close(a, want)
+        idle = np.ones(T, bool); idle[lab] = False
+        assert (a[idle] == 0).all()
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+def test_gather_loop_bootstrap_counts(ctx, vb):
+    """doBootstrap's loop (gate on the OLD alpha, no minimum) on resampled counts, including classes resampled to 0"""
+    T = 6000
+    rp, lab, cnt = synth.make_classes(T, 15000, seed=31)
+    eff = np.random.default_rng(2).uniform(100, 3000, size=T)
+    total = int(cnt.sum())
+    samp = np.random.default_rng(99).multinomial(total, cnt / cnt.sum()).astype(np.uint64)
+    assert (samp == 0).any()
+    ctx.eq_import(T, rp, lab, cnt)
+    a, it = ctx.bootstrap_em(eff, samp, capi.EMOpts.default(use_vb=vb))
+    assert ctx.last_em_kernel() == GATHER
+    rc, want, it_o = O.bootstrap_em(T, rp, lab, samp, eff, O.EMOpts.default(use_vb=vb))
+    assert rc == 0 and it == it_o
+    close(a, want)
+
+
+def test_gather_loop_after_device_side_finish(ctx):
+    """mapping -> device-side class flatten -> partition -> gather layout -> EM, against the oracle on the same reads"""
+    seq, off, ln = synth.make_transcriptome(400, seed=15)
+    b1, o1, _, _, _ = synth.make_reads(seq, off, ln, 60000, 76, seed=16)
+    fmt = O.parse_libtype("U")
+    ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=31)
+    ctx.map_begin(capi.MapOpts.default(fmt))
+    ctx.map_batch(b1, o1, None, None)
+    g = ctx.map_finish()
+    rp, lab, cnt = ctx.eq_export()
+    eff = np.maximum(ln.astype(np.float64) - 75.0, 1.0)
+    nm = int(g["counters"][1])
+    for vb in (0, 1):
+        a, it, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+        assert ctx.last_em_kernel() == GATHER
+        rc, want, it_o, _ = O.em_run(len(ln), rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb))
+        assert rc == 0 and it == it_o
+        close(a, want)
+    rows = ctx.bootstrap_run(eff, 3, seed=5)
+    assert ctx.last_em_kernel() == GATHER
+    np.testing.assert_allclose(rows.sum(axis=1), int(cnt.sum()), rtol=1e-9)
