@@ -187,7 +187,16 @@ def main():
               "em_iters": args.em_iters, "batch_reads": args.batch, "l2": "inputs larger than L2 (reads %d MB, index several GB)" % (args.reads * READ_LEN >> 20)}
 
     t0 = time.time()
-    seq, off, ln = synth.make_transcriptome(args.genes, seed=42)
+    # SFB200_BENCH_CACHE=<dir>: keep the generated (deterministic) inputs between invocations of one session
+    cache = os.environ.get("SFB200_BENCH_CACHE")
+    tx_file = os.path.join(cache, "txome_%d.npz" % args.genes) if cache else None
+    if tx_file and os.path.exists(tx_file):
+        z = np.load(tx_file); seq, off, ln = z["seq"], z["off"], z["ln"]
+    else:
+        seq, off, ln = synth.make_transcriptome(args.genes, seed=42)
+        if tx_file:
+            os.makedirs(cache, exist_ok=True)
+            np.savez(tx_file, seq=seq, off=off, ln=ln)
     log("[bench] transcriptome: %d transcripts, %.1f Mnt (%.1fs)" % (len(ln), seq.size / 1e6, time.time() - t0))
     eff = efflen.effective_lengths(ln, None, single_end=True)     # SailfishQuantify.cpp:1039-1042 (single-end: Gaussian prior)
 
@@ -261,7 +270,13 @@ def main():
     n = args.reads
     t0 = time.time()
     h_bases = torch.empty(n * READ_LEN + 8, dtype=torch.uint8).pin_memory()
-    gen_reads(seq, off, ln, n, 1234 + rank, h_bases.numpy())
+    rd_file = os.path.join(cache, "reads_%d_%d_%d.npy" % (args.genes, n, 1234 + rank)) if cache else None
+    if rd_file and os.path.exists(rd_file):
+        h_bases.numpy()[:] = np.load(rd_file)
+    else:
+        gen_reads(seq, off, ln, n, 1234 + rank, h_bases.numpy())
+        if rd_file:
+            np.save(rd_file, h_bases.numpy())
     h_off = (torch.arange(n + 1, dtype=torch.int64) * READ_LEN).pin_memory()
     log("[bench] reads: %d x %d nt (%.1fs)" % (n, READ_LEN, time.time() - t0))
     d_bases = h_bases.cuda()

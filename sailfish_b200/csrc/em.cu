@@ -650,11 +650,14 @@ namespace {
 // Build the CTA partition of the current classes (em_part.cuh).  Device kernels do the per-class work; the host only scans
 // a T-long load histogram and the (n_cta+1) x 6 group table.
 int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
+// the atomic-free loop is chosen when the classes allow it; SFB200_EM_GATHER=0 / 1 overrides the default
+constexpr bool SFB_GATHER_DEFAULT = false;
+bool gather_enabled() { const char* e = getenv("SFB200_EM_GATHER"); return e ? atoi(e) != 0 : SFB_GATHER_DEFAULT; }
 
 int build_partition(sfb200_ctx* c) {
     DevClasses& k = c->cls;
     DevPartition& P = k.part;
-    P.valid = true; P.usable = false; P.gather_ok = false;
+    P.valid = true; P.usable = false; P.gather_ok = false; P.gather_tried = gather_enabled();
     if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
     // CTAs per SM for the partitioned loop: two half-size CTAs fill each other's __syncthreads bubbles
     int per_sm = 2;
@@ -697,7 +700,7 @@ int build_partition(sfb200_ctx* c) {
           const uint32_t t = bounds[i];
           uint32_t best = t;
           for (uint32_t d = 0; d <= win; ++d) {
-              if (t >= d && t - d > bounds[i - 1] && cross[t - d] == 0) { best = t - d; break; }
+              if (t >= d && t - d >= bounds[i - 1] && cross[t - d] == 0) { best = t - d; break; }   // an empty range is fine
               if (t + d < T && cross[t + d] == 0) { best = t + d; break; }
           }
           bounds[i] = std::max(best, bounds[i - 1]);
@@ -769,7 +772,8 @@ int build_partition(sfb200_ctx* c) {
 int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     DevPartition& P = c->cls.part;
     P.gather_ok = false;
-    if (getenv("SFB200_EM_NO_GATHER_BUILD") || P.n_pool != 0 || P.n_cta == 0) return SFB200_OK;
+    P.gather_tried = gather_enabled();
+    if (!gather_enabled() || P.n_pool != 0 || P.n_cta == 0) return SFB200_OK;
     static_assert(sizeof(GatherGeom) == sizeof(P.gth_geom), "GatherGeom is stored as 12 opaque words");
     uint64_t max_nc = 0, max_ne = 0, max_nt = 0;
     for (uint32_t i = 0; i < P.n_cta; ++i) {
@@ -978,8 +982,8 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const bool steps_mode = sharded || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
     bool use_part = false, use_gather = false;
     if (!steps_mode && k.Em) {
-        if (!k.part.valid) { const int rc = build_partition(c); if (rc) return rc; }
-        use_gather = k.part.gather_ok && !getenv("SFB200_EM_NO_GATHER");     // atomic-free loop (em_gather.cuh)
+        if (!k.part.valid || (gather_enabled() && !k.part.gather_tried)) { const int rc = build_partition(c); if (rc) return rc; }
+        use_gather = k.part.gather_ok && gather_enabled();                   // atomic-free loop (em_gather.cuh)
         use_part = use_gather || k.part.usable;                              // both read the partition-ordered arrays
         if (use_part && !use_gather && o->use_vb)                   // VBEM keeps expTheta in shared memory as well
             use_part = (k.part.max_cta_bytes_vb + 2048) * k.part.per_sm <= k.part.smem_limit + 1024 * (uint64_t)(k.part.per_sm - 1);

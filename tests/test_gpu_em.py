@@ -92,7 +92,7 @@ def test_em_steps_mode_equals_persistent(ctx, monkeypatch):
         a2, it2, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
         monkeypatch.delenv("SFB200_EM_MODE")
         assert it1 == it2
-        assert_close(a1, a2, rtol=1e-9)
+        assert_close(a1, a2, rtol=1e-7)      # same iterates up to rounding (the gather-form loop sums in a different order)
     # the binned-layout persistent kernel (what runs when a CTA's slice does not fit in shared memory)
     monkeypatch.setenv("SFB200_NO_PARTITION", "1")
     ctx.eq_import(T, rp, lab, cnt)

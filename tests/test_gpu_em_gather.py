@@ -15,6 +15,11 @@ RTOL, ATOL = 1e-4, 1e-6
 GATHER = 2
 
 
+@pytest.fixture(autouse=True)
+def gather_on(monkeypatch):
+    monkeypatch.setenv("SFB200_EM_GATHER", "1")
+
+
 def close(a, b, rtol=RTOL, atol=ATOL):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
 
@@ -76,10 +81,10 @@ def test_gather_loop_equals_scatter_kernels(ctx, monkeypatch):
     for vb in (0, 1):
         a1, it1, m1 = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
         assert ctx.last_em_kernel() == GATHER
-        monkeypatch.setenv("SFB200_EM_NO_GATHER", "1")
+        monkeypatch.setenv("SFB200_EM_GATHER", "0")
         a2, it2, m2 = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
         assert ctx.last_em_kernel() == 1                                  # k_em_part
-        monkeypatch.delenv("SFB200_EM_NO_GATHER")
+        monkeypatch.setenv("SFB200_EM_GATHER", "1")
         assert it1 == it2
         close(a1, a2, rtol=1e-7)
         assert abs(m1 - m2) <= 1e-6 * abs(m2)
