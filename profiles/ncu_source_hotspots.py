@@ -1,6 +1,7 @@
 import csv,subprocess,io,re,sys,collections
 rep=sys.argv[1]; cubin=sys.argv[2]; kern=sys.argv[3]; src=sys.argv[4]
-out=subprocess.run("ncu -i %s --page source --csv --kernel-name regex:%s" % (rep, kern),shell=True,capture_output=True,text=True).stdout
+ncu_kern=sys.argv[5] if len(sys.argv)>5 else kern   # demangled-name regex for ncu when `kern` is a mangled fragment
+out=subprocess.run("ncu -i %s --page source --csv --kernel-name regex:%s" % (rep, ncu_kern),shell=True,capture_output=True,text=True).stdout
 rows=list(csv.reader(io.StringIO(out)))
 hi=[i for i,r in enumerate(rows) if "Source" in r and "Address" in r][0]
 hdr=rows[hi]; si=hdr.index("Warp Stall Sampling (All Samples)"); so=hdr.index("Source"); ie=hdr.index("Instructions Executed"); te=hdr.index("Thread Instructions Executed")

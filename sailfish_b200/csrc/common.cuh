@@ -88,7 +88,7 @@ struct DevPartition {
     DevBuf<uint8_t> dirty;
     // gather layout of the atomic-free loop (em_gather.cuh): one region per CTA, geometry kept as opaque words
     bool gather_ok = false, gather_tried = false;
-    uint32_t gth_geom[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t gth_geom[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t gather_smem = 0;           // dynamic shared memory the largest CTA needs
     DevBuf<uint32_t> gth;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();

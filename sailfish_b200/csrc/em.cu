@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <limits>
 
 #include "common.cuh"
@@ -477,6 +478,14 @@ __global__ void k_scatter_single(const unsigned long long* __restrict__ samp, co
 
 inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// SFB200_TIMING=1: host wall-clock between marks of an em_run, on stderr (where does the set-up time go)
+struct HostMarks {
+    bool on; double last;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    HostMarks() : on(getenv("SFB200_TIMING") != nullptr), last(now()) {}
+    void mark(const char* what) { if (!on) return; const double t = now(); fprintf(stderr, "[sfb200-timing] %-28s %8.3f ms\n", what, t - last); last = t; }
+};
+
 }  // namespace
 
 // ======================================================================================================================
@@ -651,7 +660,7 @@ namespace {
 // a T-long load histogram and the (n_cta+1) x 6 group table.
 int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
 // the atomic-free loop is chosen when the classes allow it; SFB200_EM_GATHER=0 / 1 overrides the default
-constexpr bool SFB_GATHER_DEFAULT = false;
+constexpr bool SFB_GATHER_DEFAULT = true;
 bool gather_enabled() { const char* e = getenv("SFB200_EM_GATHER"); return e ? atoi(e) != 0 : SFB_GATHER_DEFAULT; }
 
 int build_partition(sfb200_ctx* c) {
@@ -666,6 +675,7 @@ int build_partition(sfb200_ctx* c) {
     const uint64_t Em = k.Em, nnzm = k.nnzm;
     if (Em == 0 || T == 0) return SFB200_OK;
     cudaStream_t s = c->stream;
+    HostMarks hm;
     P.n_cta = n_cta;
     SFB_CUDA(c, P.load.reserve(T)); SFB_CUDA(c, P.bounds.reserve(n_cta + 1)); SFB_CUDA(c, P.owner.reserve(Em)); SFB_CUDA(c, P.dirty.reserve(T));
     SFB_CUDA(c, P.grp.reserve(3 * (size_t)(n_cta + 1) * SFB_NBINS + 4));
@@ -684,6 +694,7 @@ int build_partition(sfb200_ctx* c) {
     SFB_CUDA(c, cudaMemcpyAsync(load.data(), P.load.p, T * 4ull, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaMemcpyAsync(cross.data(), d_diff, (T + 1) * 4ull, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    hm.mark("part: span + D2H");
     for (uint32_t t = 1; t <= T; ++t) cross[t] += cross[t - 1];
     uint64_t total = 0;
     for (uint32_t t = 0; t < T; ++t) total += 1ull + load[t];
@@ -705,6 +716,7 @@ int build_partition(sfb200_ctx* c) {
           }
           bounds[i] = std::max(best, bounds[i - 1]);
       } }
+    hm.mark("part: host bounds");
     SFB_CUDA(c, cudaMemcpyAsync(P.bounds.p, bounds.data(), (n_cta + 1) * 4ull, cudaMemcpyHostToDevice, s));
     // 2. closure of "crosses a range or touches a dirty transcript"
     SFB_CUDA(c, cudaMemsetAsync(P.dirty.p, 0, T, s));
@@ -718,6 +730,7 @@ int build_partition(sfb200_ctx* c) {
         SFB_CUDA(c, cudaStreamSynchronize(s));
         if (!ch) break;
     }
+    hm.mark("part: closure rounds");
     // 3. group sizes -> offsets
     const size_t G = (size_t)(n_cta + 1) * SFB_NBINS;
     unsigned long long* d_grp = P.grp.p; unsigned long long* d_cls_off = P.grp.p + G; unsigned long long* d_nnz_off = P.grp.p + 2 * G;
@@ -735,6 +748,7 @@ int build_partition(sfb200_ctx* c) {
     k_part_fill<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.start.p, k.len.p, k.lab.p, k.cnt.p, Em, n_cta, d_cls_off, d_nnz_off, d_grp,
                                                    P.start.p, P.len.p, P.lab.p, P.cnt.p, P.src.p);
     c->launches++;
+    hm.mark("part: counts + fill launch");
     // 4. per-CTA table and the shared-memory budget
     std::vector<unsigned long long> tbl((size_t)n_cta * PT_WORDS, 0);
     uint64_t max_bytes = 0, max_bytes_vb = 0;
@@ -758,7 +772,9 @@ int build_partition(sfb200_ctx* c) {
     P.smem_limit = (uint64_t)max_optin;
     P.usable = (max_bytes + 2048) * per_sm <= (uint64_t)max_optin + 1024 * (uint64_t)(per_sm - 1);
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    hm.mark("part: table + sync");
     { const int rc = build_gather(c, tbl); if (rc) return rc; }
+    hm.mark("part: gather layout");
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool), largest CTA slice %llu bytes (limit %d) -> %s\n",
                 n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, (unsigned long long)max_bytes, max_optin,
@@ -774,7 +790,7 @@ int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     P.gather_ok = false;
     P.gather_tried = gather_enabled();
     if (!gather_enabled() || P.n_pool != 0 || P.n_cta == 0) return SFB200_OK;
-    static_assert(sizeof(GatherGeom) == sizeof(P.gth_geom), "GatherGeom is stored as 12 opaque words");
+    static_assert(sizeof(GatherGeom) == sizeof(P.gth_geom), "GatherGeom is stored as 16 opaque words");
     uint64_t max_nc = 0, max_ne = 0, max_nt = 0;
     for (uint32_t i = 0; i < P.n_cta; ++i) {
         const unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
@@ -784,7 +800,7 @@ int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     }
     auto up = [](uint64_t x, uint64_t m) { return (x + m - 1) / m * m; };
     if (up(max_nc, 32) > 65535 || up(max_nt, 32) > 65535 || max_ne > (1u << 24)) return SFB200_OK;
-    const GatherGeom g = gather_make_geom(max_nc, max_ne, max_nt);
+    const GatherGeom g = gather_make_geom(max_nc, max_ne, max_nt, !getenv("SFB200_EM_GATHER_UNSCALED"));
     cudaStream_t s = c->stream;
     SFB_CUDA(c, P.gth.reserve((size_t)P.n_cta * g.region_words));
     const size_t scratch = 4 * gather_scratch_words(max_nc, max_nt, g);
@@ -839,7 +855,9 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         q.regions = P.gth.p; std::memcpy(&q.g, P.gth_geom, sizeof(q.g)); q.eff = c->eff.p;
         const size_t smem = (size_t)P.gather_smem;
         void* args[] = {&p, &q};
-        const void* fn = vb ? reinterpret_cast<const void*>(&k_em_gather<true>) : reinterpret_cast<const void*>(&k_em_gather<false>);
+        const void* fn = q.g.shift == 3
+            ? (vb ? reinterpret_cast<const void*>(&k_em_gather<true, 3>) : reinterpret_cast<const void*>(&k_em_gather<false, 3>))
+            : (vb ? reinterpret_cast<const void*>(&k_em_gather<true, 0>) : reinterpret_cast<const void*>(&k_em_gather<false, 0>));
         SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned per_sm_ctas = P.n_cta / (unsigned)c->num_sms;
         SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(EM_THREADS / per_sm_ctas), args, smem, s));
@@ -967,6 +985,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     DevClasses& k = c->cls;
     cudaStream_t s = c->stream;
     const uint32_t T = n_txp;
+    HostMarks hm;
     SFB_CUDA(c, c->eff.reserve(2ull * T));
     SFB_CUDA(c, c->em_alpha.reserve(3ull * T));
     SFB_CUDA(c, c->em_theta.reserve(T));
@@ -981,6 +1000,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const bool sharded = c->n_ranks > 1 && !k.merged;      // rank-local classes: one all-reduce per iteration
     const bool steps_mode = sharded || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
     bool use_part = false, use_gather = false;
+    hm.mark("em: eff H2D + clamp");
     if (!steps_mode && k.Em) {
         if (!k.part.valid || (gather_enabled() && !k.part.gather_tried)) { const int rc = build_partition(c); if (rc) return rc; }
         use_gather = k.part.gather_ok && gather_enabled();                   // atomic-free loop (em_gather.cuh)
@@ -988,6 +1008,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
         if (use_part && !use_gather && o->use_vb)                   // VBEM keeps expTheta in shared memory as well
             use_part = (k.part.max_cta_bytes_vb + 2048) * k.part.per_sm <= k.part.smem_limit + 1024 * (uint64_t)(k.part.per_sm - 1);
     }
+    hm.mark("em: partition (total)");
     DevPartition& P = k.part;
     const uint32_t* a_start = use_part ? P.start.p : k.start.p;
     const uint32_t* a_len = use_part ? P.len.p : k.len.p;
@@ -1049,17 +1070,21 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     }
     p.base_sum = single_sum + static_cast<double>(T) * o->prior_alpha;
 
+    hm.mark("em: init + sums");
     unsigned buf = 0;
     sfb200_em_opts oo = *o;
     oo.min_iter = spec.min_iter;
     const int rc = run_loop(c, p, &oo, use_gather ? LOOP_GATHER : use_part ? LOOP_PART : LOOP_BINNED, iters_out, mrd_out, &buf);
     if (rc) return rc;
+    hm.mark("em: loop (launch .. sync)");
 
     SFB_CUDA(c, cudaMemcpyAsync(alphas_out, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    hm.mark("em: alphas D2H");
     const double cutoff = vb ? (o->prior_alpha + o->min_alpha) : o->min_alpha;           // :812
     double alphaSum = 0.0;                                                               // truncateCountVector :37-44
     for (uint32_t i = 0; i < T; ++i) { if (alphas_out[i] <= cutoff) alphas_out[i] = 0.0; alphaSum += alphas_out[i]; }
+    hm.mark("em: truncate");
     if (alphaSum < DENORM_MIN) SFB_FAIL(c, SFB200_ESMALLSUM, "Total alpha weight was too small! Make sure you ran sailfish correctly.");
     return SFB200_OK;
 }

@@ -59,7 +59,70 @@ __host__ __device__ inline uint64_t gather_smem_need(uint32_t tiles_e, uint32_t 
     return f64s * 8 + u32s * 4 + u16s * 2;
 }
 
-template <bool VB>
+// sum of v[col[32 j]] for j < L.  L is uniform over the warp and small (a class has ~2-5 members, a transcript ~5-15 classes),
+// and the per-element loop overhead was measured at ~45% of the kernel's instructions: dispatch once on L to a fully unrolled
+// body (independent loads issued back to back, two accumulators), generic loop beyond 16
+// SHIFT = 3: the stored value is already the byte offset of the f64 (no index scaling per element)
+template <int SHIFT>
+__device__ __forceinline__ double col_at(const double* __restrict__ v, uint32_t stored) {
+    return SHIFT == 3 ? *reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(v) + stored) : v[stored];
+}
+template <int L, int SHIFT>
+__device__ __forceinline__ double col_sum_fixed(const uint16_t* __restrict__ col, const double* __restrict__ v) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) { const double x = col_at<SHIFT>(v, col[j << 5]); if (j & 1) s1 += x; else s0 += x; }
+    return s0 + s1;
+}
+template <int SHIFT>
+__device__ __forceinline__ double col_sum(const uint16_t* __restrict__ col, const double* __restrict__ v, uint32_t L) {
+    switch (L) {
+        case 0: return 0.0;
+        case 1: return col_sum_fixed<1, SHIFT>(col, v);
+        case 2: return col_sum_fixed<2, SHIFT>(col, v);
+        case 3: return col_sum_fixed<3, SHIFT>(col, v);
+        case 4: return col_sum_fixed<4, SHIFT>(col, v);
+        case 5: return col_sum_fixed<5, SHIFT>(col, v);
+        case 6: return col_sum_fixed<6, SHIFT>(col, v);
+        case 7: return col_sum_fixed<7, SHIFT>(col, v);
+        case 8: return col_sum_fixed<8, SHIFT>(col, v);
+        case 9: return col_sum_fixed<9, SHIFT>(col, v);
+        case 10: return col_sum_fixed<10, SHIFT>(col, v);
+        case 11: return col_sum_fixed<11, SHIFT>(col, v);
+        case 12: return col_sum_fixed<12, SHIFT>(col, v);
+        case 13: return col_sum_fixed<13, SHIFT>(col, v);
+        case 14: return col_sum_fixed<14, SHIFT>(col, v);
+        case 15: return col_sum_fixed<15, SHIFT>(col, v);
+        case 16: return col_sum_fixed<16, SHIFT>(col, v);
+        default: break;
+    }
+    double s0 = 0.0, s1 = 0.0;
+    uint32_t j = 0;
+    for (; j + 4 <= L; j += 4) {
+        const uint32_t i0 = col[j << 5], i1 = col[(j + 1) << 5], i2 = col[(j + 2) << 5], i3 = col[(j + 3) << 5];
+        const double x0 = col_at<SHIFT>(v, i0), x1 = col_at<SHIFT>(v, i1), x2 = col_at<SHIFT>(v, i2), x3 = col_at<SHIFT>(v, i3);
+        s0 += x0; s1 += x1; s0 += x2; s1 += x3;
+    }
+    for (; j < L; ++j) s0 += col_at<SHIFT>(v, col[j << 5]);
+    return s0 + s1;
+}
+
+// count / S for the E-step: hardware reciprocal seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (<= 2 ulp; the path's
+// tolerance is 1e-4) while S is comfortably normal; the exact quotient otherwise (0 for a vanishing denominator, :260)
+__device__ __forceinline__ double em_ratio(double cnt, double S) {
+    if (S > 1e-280 && S < 1e280) {
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(S));
+        double e = fma(-S, y, 1.0);
+        y = fma(y, e, y);
+        e = fma(-S, y, 1.0);
+        y = fma(y, e, y);
+        return cnt * y;
+    }
+    return (S > DENORM_MIN) ? cnt / S : 0.0;
+}
+
+template <bool VB, int SHIFT>
 __global__ void __launch_bounds__(EM_THREADS, 1) k_em_gather(const EmParams p, const GatherParams q) {
     __shared__ unsigned long long sm_u[32];
     __shared__ double sm_d[32];
@@ -135,19 +198,12 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_gather(const EmParams p, c
     for (;;) {
         if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
         // ---- E-step: r_c = count_c / sum of beta over the class's column
-        for (uint32_t k = warp; k < tiles_e; k += W) {
-            const uint32_t L = s_elen[k];
-            const uint16_t* col = s_lab_e + s_eoff[k] + lane;
-            double S = 0.0;
-            uint32_t j = 0;
-            for (; j + 4 <= L; j += 4) {
-                const uint32_t i0 = col[j << 5], i1 = col[(j + 1) << 5], i2 = col[(j + 2) << 5], i3 = col[(j + 3) << 5];
-                const double b0 = s_beta[i0], b1 = s_beta[i1], b2 = s_beta[i2], b3 = s_beta[i3];
-                S += b0; S += b1; S += b2; S += b3;
-            }
-            for (; j < L; ++j) S += s_beta[col[j << 5]];
+        for (uint32_t k0 = 0, rnd = 0; k0 < tiles_e; k0 += W, ++rnd) {
+            const uint32_t k = k0 + ((rnd & 1u) ? W - 1u - warp : warp);      // tiles are sorted by size: serpentine deal
+            if (k >= tiles_e) continue;
+            const double S = col_sum<SHIFT>(s_lab_e + s_eoff[k] + lane, s_beta, s_elen[k]);
             const uint32_t c = (k << 5) + lane;
-            s_r[c] = (S > DENORM_MIN) ? sfb_div_count(s_cnt[c], S) : 0.0;     // :260 skips classes with a vanishing denominator
+            s_r[c] = em_ratio(s_cnt[c], S);
         }
         __syncthreads();
         // ---- M-step + the convergence test of this iteration
@@ -155,17 +211,10 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_gather(const EmParams p, c
         const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
         unsigned long long best = 0ULL;
         double asum = 0.0;
-        for (uint32_t k = warp; k < tiles_t; k += W) {
-            const uint32_t L = s_tlen[k];
-            const uint16_t* col = s_cls_t + s_toff[k] + lane;
-            double acc = 0.0;
-            uint32_t j = 0;
-            for (; j + 4 <= L; j += 4) {
-                const uint32_t i0 = col[j << 5], i1 = col[(j + 1) << 5], i2 = col[(j + 2) << 5], i3 = col[(j + 3) << 5];
-                const double r0 = s_r[i0], r1 = s_r[i1], r2 = s_r[i2], r3 = s_r[i3];
-                acc += r0; acc += r1; acc += r2; acc += r3;
-            }
-            for (; j < L; ++j) acc += s_r[col[j << 5]];
+        for (uint32_t k0 = 0, rnd = 0; k0 < tiles_t; k0 += W, ++rnd) {
+            const uint32_t k = k0 + ((rnd & 1u) ? W - 1u - warp : warp);
+            if (k >= tiles_t) continue;
+            const double acc = col_sum<SHIFT>(s_cls_t + s_toff[k] + lane, s_r, s_tlen[k]);
             const uint32_t i = (k << 5) + lane;
             const double a_old = s_alpha[i];
             const double a_new = s_beta[i] * acc + s_base[i];

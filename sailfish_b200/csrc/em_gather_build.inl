@@ -29,11 +29,14 @@ struct GatherGeom {
     uint32_t o_tile_e_off, o_tile_e_len, o_tile_t_off, o_tile_t_len, o_cperm, o_tmap, o_lab_e, o_cls_t;
     uint32_t cap_tiles_e, cap_tiles_t;   // tiles per list a region has room for
     uint32_t cap_ent;                    // 16-bit entries per list a region has room for
+    uint32_t shift;                      // stored indices are (index << shift): 3 = byte offsets into an f64 array (needs
+                                         // every padded index <= 8191), 0 = plain indices
+    uint32_t pad_[3];
 };
 enum { GH_NC = 0, GH_NT, GH_TILES_E, GH_TILES_T, GH_ENT_E, GH_ENT_T, GH_OK, GH_MAXLEN, GH_MAXDEG, GH_WORDS = 16 };
 constexpr uint32_t GB_BUCKETS = 256;
 // geometry for the largest class count / entry count / transcript count of any CTA (host side)
-inline GatherGeom gather_make_geom(uint64_t max_nc, uint64_t max_ne, uint64_t max_nt) {
+inline GatherGeom gather_make_geom(uint64_t max_nc, uint64_t max_ne, uint64_t max_nt, bool allow_scaled = true) {
     auto up = [](uint64_t x, uint64_t m) { return (uint32_t)((x + m - 1) / m * m); };
     GatherGeom g;
     g.cap_tiles_e = up(max_nc / 32 + 2, 4);
@@ -49,6 +52,8 @@ inline GatherGeom gather_make_geom(uint64_t max_nc, uint64_t max_ne, uint64_t ma
     g.o_lab_e = o; o += g.cap_ent / 2;
     g.o_cls_t = o; o += g.cap_ent / 2;
     g.region_words = o;
+    g.shift = (allow_scaled && up(max_nc, 32) <= 8191 && up(max_nt, 32) <= 8191) ? 3u : 0u;
+    g.pad_[0] = g.pad_[1] = g.pad_[2] = 0;
     return g;
 }
 // scratch words gather_build_cta needs
@@ -135,7 +140,7 @@ SFB_GB_FN void gather_build_cta(const uint32_t* start, const uint32_t* len, cons
         for (uint32_t k = 0; k < tiles_t; ++k) { s_off_t[k] = acc; acc += s_len_t[k] << 5; }
         const uint32_t ent_t = acc;
         const bool ok = ent_e <= g.cap_ent && ent_t <= g.cap_ent && tiles_e <= g.cap_tiles_e && tiles_t <= g.cap_tiles_t &&
-                        nc_pad <= 65535u && nt_pad <= 65535u;
+                        (nc_pad << g.shift) <= 65535u && (nt_pad << g.shift) <= 65535u;
         s_misc[0] = ok ? 1u : 0u;
         hdr[GH_NC] = nc; hdr[GH_NT] = nt; hdr[GH_TILES_E] = tiles_e; hdr[GH_TILES_T] = tiles_t;
         hdr[GH_ENT_E] = ent_e; hdr[GH_ENT_T] = ent_t; hdr[GH_OK] = ok ? 1u : 0u;
@@ -153,14 +158,14 @@ SFB_GB_FN void gather_build_cta(const uint32_t* start, const uint32_t* len, cons
             const uint32_t base = s_off_e[k] + (pos & 31u), L = s_len_e[k];
             for (uint32_t j = 0; j < n; ++j) {
                 const uint32_t told = lab[b + j] - t0, tn = s_tnew[told];
-                lab_e[base + (j << 5)] = (uint16_t)tn;
+                lab_e[base + (j << 5)] = (uint16_t)(tn << g.shift);
                 const uint32_t slot = SFB_GB_ADD(s_tcur + told, 1u);
-                cls_t[s_off_t[tn >> 5] + (slot << 5) + (tn & 31u)] = (uint16_t)pos;
+                cls_t[s_off_t[tn >> 5] + (slot << 5) + (tn & 31u)] = (uint16_t)(pos << g.shift);
             }
-            for (uint32_t j = n; j < L; ++j) lab_e[base + (j << 5)] = (uint16_t)nt_pad;
+            for (uint32_t j = n; j < L; ++j) lab_e[base + (j << 5)] = (uint16_t)(nt_pad << g.shift);
         } else {                                      // lanes of the last tile that hold no class
             const uint32_t k = c >> 5, base = s_off_e[k] + (c & 31u), L = s_len_e[k];
-            for (uint32_t j = 0; j < L; ++j) lab_e[base + (j << 5)] = (uint16_t)nt_pad;
+            for (uint32_t j = 0; j < L; ++j) lab_e[base + (j << 5)] = (uint16_t)(nt_pad << g.shift);
         }
     }
     SFB_GB_SYNC();
@@ -169,6 +174,6 @@ SFB_GB_FN void gather_build_cta(const uint32_t* start, const uint32_t* len, cons
         uint32_t tn, d;
         if (t < nt) { tn = s_tnew[t]; d = s_deg[t]; } else { tn = t; d = 0; }   // new indices nt..nt_pad-1 hold no transcript
         const uint32_t k = tn >> 5, base = s_off_t[k] + (tn & 31u), L = s_len_t[k];
-        for (uint32_t j = d; j < L; ++j) cls_t[base + (j << 5)] = (uint16_t)nc_pad;
+        for (uint32_t j = d; j < L; ++j) cls_t[base + (j << 5)] = (uint16_t)(nc_pad << g.shift);
     }
 }

@@ -60,12 +60,14 @@ static Slice make_slice(std::mt19937_64& rng, uint32_t nc, uint32_t nt, uint32_t
     return s;
 }
 
-static int run_case(uint64_t seed, uint32_t nc, uint32_t nt, uint32_t max_len, bool dups, bool vb) {
+static int run_case(uint64_t seed, uint32_t nc, uint32_t nt, uint32_t max_len, bool dups, bool vb, bool scaled) {
     std::mt19937_64 rng(seed);
     Slice s = make_slice(rng, nc, nt, max_len, dups);
     uint64_t ne = 0;
     for (uint32_t c = 0; c < nc; ++c) ne += s.len[s.c_lo + c];
-    const GatherGeom g = gather_make_geom(nc, ne, nt);
+    const GatherGeom g = gather_make_geom(nc, ne, nt, scaled);
+    const uint32_t sh = g.shift;
+    CHECK(sh == ((scaled && ((nc + 31) / 32 * 32) <= 8191 && ((nt + 31) / 32 * 32) <= 8191) ? 3u : 0u), "shift");
     CHECK(g.region_words % 4 == 0 && g.o_lab_e % 4 == 0 && g.o_cls_t % 4 == 0 && g.o_cperm % 4 == 0 && g.o_tmap % 4 == 0, "geometry alignment");
     std::vector<uint32_t> region(g.region_words + 8, 0xDEADBEEFu), scratch(gather_scratch_words(nc, nt, g) + 8, 0xABABABABu);
     const uint32_t guard_r = 0x13572468u;
@@ -102,19 +104,22 @@ static int run_case(uint64_t seed, uint32_t nc, uint32_t nt, uint32_t max_len, b
         uint32_t n = 0, b = 0;
         if (i < nc) { n = s.len[cperm[i]]; b = s.start[cperm[i]]; CHECK(n <= elen[k], "tile L below a member count"); }
         for (uint32_t j = 0; j < elen[k]; ++j) {
-            const uint32_t v = lab_e[eoff[k] + 32 * j + lane];
+            const uint32_t raw = lab_e[eoff[k] + 32 * j + lane], v = raw >> sh;
+            CHECK((v << sh) == raw, "stored member index is not a multiple of the scale");
             if (j < n) { CHECK(v < nt && tmap[v] == s.lab[b + j], "class %u member %u", i, j); want_t[v].insert(i); }
             else CHECK(v == nt_pad, "class %u padding %u holds %u", i, j, v);
         }
     }
     // sizes are non-increasing from tile to tile (this is what bounds the padding)
-    for (uint32_t k = 1; k < tiles_e; ++k) CHECK(elen[k] <= elen[k - 1], "class tiles not sorted");
-    for (uint32_t k = 1; k < tiles_t; ++k) CHECK(tlen[k] <= tlen[k - 1], "transcript tiles not sorted");
+    // (sizes above 255 share the last bucket and stay unsorted among themselves)
+    if (h[GH_MAXLEN] < GB_BUCKETS) for (uint32_t k = 1; k < tiles_e; ++k) CHECK(elen[k] <= elen[k - 1], "class tiles not sorted");
+    if (h[GH_MAXDEG] < GB_BUCKETS) for (uint32_t k = 1; k < tiles_t; ++k) CHECK(tlen[k] <= tlen[k - 1], "transcript tiles not sorted");
     for (uint32_t i = 0; i < nt_pad; ++i) {
         const uint32_t k = i >> 5, lane = i & 31;
         std::multiset<uint32_t> got;
         for (uint32_t j = 0; j < tlen[k]; ++j) {
-            const uint32_t v = cls_t[toff[k] + 32 * j + lane];
+            const uint32_t raw = cls_t[toff[k] + 32 * j + lane], v = raw >> sh;
+            CHECK((v << sh) == raw, "stored class index is not a multiple of the scale");
             if (v == nc_pad) continue;
             CHECK(v < nc, "transcript %u holds class %u", i, v);
             got.insert(v);
@@ -177,14 +182,14 @@ static int run_case(uint64_t seed, uint32_t nc, uint32_t nt, uint32_t max_len, b
             for (uint32_t lane = 0; lane < 32; ++lane) {
                 const uint16_t* col = lab_e + eoff[k] + lane;
                 double S = 0.0;
-                for (uint32_t j = 0; j < elen[k]; ++j) S += s_beta[col[j << 5]];
+                for (uint32_t j = 0; j < elen[k]; ++j) S += s_beta[col[j << 5] >> sh];
                 s_r[(k << 5) + lane] = S > 0.0 ? s_cnt[(k << 5) + lane] / S : 0.0;
             }
         for (uint32_t k = 0; k < tiles_t; ++k)
             for (uint32_t lane = 0; lane < 32; ++lane) {
                 const uint16_t* col = cls_t + toff[k] + lane;
                 double acc = 0.0;
-                for (uint32_t j = 0; j < tlen[k]; ++j) acc += s_r[col[j << 5]];
+                for (uint32_t j = 0; j < tlen[k]; ++j) acc += s_r[col[j << 5] >> sh];
                 const uint32_t i = (k << 5) + lane;
                 s_alpha[i] = s_beta[i] * acc + s_base[i];
             }
@@ -210,9 +215,12 @@ int main() {
         {8, 0, 17, 2, false, false},        // no classes at all
         {9, 200, 5, 6, true, false},        // degrees far above the bucket cap on few transcripts
         {10, 3000, 40, 30, true, true},
+        {11, 8160, 8191, 12, false, false}, // the largest sizes the scaled (byte-offset) indices can address
+        {12, 8161, 100, 12, false, false},  // one class more: falls back to plain indices
     };
+    for (int scaled = 0; scaled < 2; ++scaled)
     for (const Case& c : cases) {
-        if (run_case(c.seed, c.nc, c.nt, c.max_len, c.dups, c.vb)) { fprintf(stderr, "case seed %llu failed\n", (unsigned long long)c.seed); return 1; }
+        if (run_case(c.seed, c.nc, c.nt, c.max_len, c.dups, c.vb, scaled != 0)) { fprintf(stderr, "case seed %llu failed\n", (unsigned long long)c.seed); return 1; }
     }
     printf("em_gather layout ok (%zu cases)\n", sizeof(cases) / sizeof(cases[0]));
     return 0;
