@@ -84,7 +84,7 @@ struct DevPartition {
     int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
     DevBuf<double> cnt, w, cnt_s;
-    DevBuf<unsigned long long> tbl, grp;
+    DevBuf<unsigned long long> tbl, grp, pre;
     DevBuf<uint8_t> dirty;
     // gather layout of the atomic-free loop (em_gather.cuh): one region per CTA, geometry kept as opaque words
     bool gather_ok = false, gather_tried = false;
@@ -92,7 +92,7 @@ struct DevPartition {
     uint64_t gather_smem = 0;           // dynamic shared memory the largest CTA needs
     DevBuf<uint32_t> gth;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); dirty.release(); gth.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); }
 };
 struct DevClasses {
     DevPartition part;

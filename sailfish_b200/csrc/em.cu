@@ -29,7 +29,7 @@ constexpr int EM_THREADS = 1024;
 
 // control block (unsigned long long words)
 enum { CTL_BAR_COUNT = 0, CTL_BAR_GEN = 1, CTL_MAXREL = 2 /*4 slots*/, CTL_CSUM = 6 /*4 slots*/, CTL_ITERS = 10,
-       CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_WORDS = 16 };
+       CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_TSUM = 13 /* sum of the truncated result */, CTL_WORDS = 16 };
 
 struct EmParams {
     const uint32_t* start; const uint32_t* len; const uint32_t* lab; const double* w; const double* cnt;
@@ -429,6 +429,18 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_sweep(const EmParams p, un
 #include "em_part.cuh"
 #include "em_gather.cuh"
 
+// truncateCountVector (CollapsedEMOptimizer.cpp:37-44): alpha <= cutoff -> 0, and the sum of what is left
+__global__ void k_truncate(double* __restrict__ x, uint32_t n, double cutoff, double* __restrict__ sum_out) {
+    __shared__ double sm_d[32];
+    double s = 0.0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v <= cutoff) { v = 0.0; x[i] = 0.0; }
+        s += v;
+    }
+    block_sum_to_slot(s, sum_out, sm_d);
+}
+
 __global__ void k_sum_f64(const double* __restrict__ x, uint32_t n, double* __restrict__ out) {
     __shared__ double sm_d[32];
     double s = 0.0;
@@ -689,35 +701,13 @@ int build_partition(sfb200_ctx* c) {
     SFB_CUDA(c, cudaMemsetAsync(d_diff, 0, (T + 1) * 4ull, s));
     k_part_span<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, d_diff, P.load.p);
     c->launches++;
-    std::vector<uint32_t> load(T), bounds(n_cta + 1);
-    std::vector<int> cross(T + 1);
-    SFB_CUDA(c, cudaMemcpyAsync(load.data(), P.load.p, T * 4ull, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaMemcpyAsync(cross.data(), d_diff, (T + 1) * 4ull, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    hm.mark("part: span + D2H");
-    for (uint32_t t = 1; t <= T; ++t) cross[t] += cross[t - 1];
-    uint64_t total = 0;
-    for (uint32_t t = 0; t < T; ++t) total += 1ull + load[t];
-    { uint64_t acc = 0; uint32_t i = 1; bounds[0] = 0;
-      for (uint32_t t = 0; t < T && i < n_cta; ++t) {
-          acc += 1ull + load[t];
-          while (i < n_cta && acc >= total * i / n_cta) bounds[i++] = t + 1;
-      }
-      while (i <= n_cta) bounds[i++] = T;
-      bounds[n_cta] = T; }
-    // move every boundary to the nearest position no class crosses (if there is one within half a range): fewer pool classes
-    { const uint32_t win = std::max<uint32_t>(8, T / n_cta / 2);
-      for (uint32_t i = 1; i < n_cta; ++i) {
-          const uint32_t t = bounds[i];
-          uint32_t best = t;
-          for (uint32_t d = 0; d <= win; ++d) {
-              if (t >= d && t - d >= bounds[i - 1] && cross[t - d] == 0) { best = t - d; break; }   // an empty range is fine
-              if (t + d < T && cross[t + d] == 0) { best = t + d; break; }
-          }
-          bounds[i] = std::max(best, bounds[i - 1]);
-      } }
-    hm.mark("part: host bounds");
-    SFB_CUDA(c, cudaMemcpyAsync(P.bounds.p, bounds.data(), (n_cta + 1) * 4ull, cudaMemcpyHostToDevice, s));
+    // boundaries: balanced by sweep cost, each moved to the nearest position no class crosses (fewer pool classes); on the device,
+    // the host reads them back together with the group sizes below
+    std::vector<uint32_t> bounds(n_cta + 1);
+    SFB_CUDA(c, P.pre.reserve(T));
+    k_part_bounds<<<1, 1024, (n_cta + 1) * sizeof(uint32_t), s>>>(P.load.p, d_diff, T, n_cta, std::max<uint32_t>(8, T / n_cta / 2), P.pre.p, P.bounds.p);
+    c->launches++;
+    hm.mark("part: span + bounds launch");
     // 2. closure of "crosses a range or touches a dirty transcript"
     SFB_CUDA(c, cudaMemsetAsync(P.dirty.p, 0, T, s));
     unsigned int* d_changed = reinterpret_cast<unsigned int*>(P.grp.p + 3 * (size_t)(n_cta + 1) * SFB_NBINS);
@@ -739,6 +729,7 @@ int build_partition(sfb200_ctx* c) {
     c->launches++;
     std::vector<unsigned long long> grp(G), cls_off(G + 1), nnz_off(G + 1);
     SFB_CUDA(c, cudaMemcpyAsync(grp.data(), d_grp, G * 8, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(bounds.data(), P.bounds.p, (n_cta + 1) * 4ull, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
     cls_off[0] = 0; nnz_off[0] = 0;
     for (size_t g = 0; g < G; ++g) { cls_off[g + 1] = cls_off[g] + (grp[g] >> 32); nnz_off[g + 1] = nnz_off[g] + (grp[g] & 0xFFFFFFFFULL); }
@@ -1059,7 +1050,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     p.min_iter = spec.min_iter; p.max_iter = o->max_iter; p.fixed_iters = o->fixed_iters;
     // sums the reference forms by a serial pass over the vector (VBEMUpdate_ :300-303); alpha_0 is n_active equal terms
     double sum0 = 0.0;
-    for (uint64_t i = 0; i < n_active; ++i) sum0 += alpha0;
+    if (vb) for (uint64_t i = 0; i < n_active; ++i) sum0 += alpha0;      // only VBEM's first logNorm reads it
     p.sum0 = sum0;
     double single_sum = 0.0;
     if (vb) {
@@ -1078,13 +1069,15 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     if (rc) return rc;
     hm.mark("em: loop (launch .. sync)");
 
-    SFB_CUDA(c, cudaMemcpyAsync(alphas_out, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    hm.mark("em: alphas D2H");
     const double cutoff = vb ? (o->prior_alpha + o->min_alpha) : o->min_alpha;           // :812
-    double alphaSum = 0.0;                                                               // truncateCountVector :37-44
-    for (uint32_t i = 0; i < T; ++i) { if (alphas_out[i] <= cutoff) alphas_out[i] = 0.0; alphaSum += alphas_out[i]; }
-    hm.mark("em: truncate");
+    double alphaSum = 0.0;                                                               // truncateCountVector :37-44, on the device
+    k_truncate<<<std::min(grid_for(T, 256), 1024u), 256, 0, s>>>(c->em_alpha.p + (size_t)buf * T, T, cutoff,
+                                                                reinterpret_cast<double*>(c->em_ctl.p + CTL_TSUM));
+    c->launches++;
+    SFB_CUDA(c, cudaMemcpyAsync(alphas_out, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(&alphaSum, c->em_ctl.p + CTL_TSUM, 8, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    hm.mark("em: truncate + alphas D2H");
     if (alphaSum < DENORM_MIN) SFB_FAIL(c, SFB200_ESMALLSUM, "Total alpha weight was too small! Make sure you ran sailfish correctly.");
     return SFB200_OK;
 }

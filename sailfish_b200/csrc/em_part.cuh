@@ -43,6 +43,61 @@ __global__ void k_part_span(const uint32_t* __restrict__ start, const uint32_t* 
     atomicAdd(load + mn, g);
 }
 
+// Range boundaries on the device (one CTA): prefix sums of the per-transcript sweep cost (1 + load) and of the crossing profile,
+// then boundary i = the first position where the cost prefix reaches i/n_cta of the total, moved to the nearest position no
+// class crosses (within `win`), then made monotone.  pre: T scratch words; diff is turned into its prefix sum in place.
+__global__ void __launch_bounds__(1024) k_part_bounds(const uint32_t* __restrict__ load, int* __restrict__ diff, uint32_t T, uint32_t n_cta,
+                                                      uint32_t win, unsigned long long* __restrict__ pre, uint32_t* __restrict__ bounds) {
+    __shared__ unsigned long long s_sum[1024];
+    __shared__ long long s_dsum[1024];
+    __shared__ unsigned long long s_total;
+    extern __shared__ uint32_t s_b[];                    // n_cta + 1
+    const uint32_t nth = blockDim.x, tid = threadIdx.x;
+    const uint32_t chunk = (T + 1 + nth - 1) / nth;      // the profile has T + 1 entries
+    const uint32_t lo = min(tid * chunk, T + 1), hi = min(lo + chunk, T + 1);
+    unsigned long long a = 0; long long d = 0;
+    for (uint32_t t = lo; t < hi; ++t) { if (t < T) a += 1ull + load[t]; d += diff[t]; }
+    s_sum[tid] = a; s_dsum[tid] = d;
+    __syncthreads();
+    if (tid == 0) {                                      // 1024 partial sums: a serial exclusive scan is a few microseconds
+        unsigned long long acc = 0; long long dacc = 0;
+        for (uint32_t j = 0; j < nth; ++j) { const unsigned long long x = s_sum[j]; s_sum[j] = acc; acc += x; const long long y = s_dsum[j]; s_dsum[j] = dacc; dacc += y; }
+        s_total = acc;
+    }
+    __syncthreads();
+    a = s_sum[tid]; d = s_dsum[tid];
+    for (uint32_t t = lo; t < hi; ++t) {
+        if (t < T) { a += 1ull + load[t]; pre[t] = a; }
+        d += diff[t]; diff[t] = (int)d;
+    }
+    __syncthreads();
+    const unsigned long long total = s_total;
+    for (uint32_t i = tid; i <= n_cta; i += nth) {
+        uint32_t b;
+        if (i == 0) b = 0;
+        else if (i == n_cta) b = T;
+        else {
+            const unsigned long long target = total * i / n_cta;
+            uint32_t l = 0, h = T;                       // first t with pre[t] >= target (T if none)
+            while (l < h) { const uint32_t mid = l + (h - l) / 2; if (pre[mid] < target) l = mid + 1; else h = mid; }
+            b = l < T ? l + 1 : T;
+            uint32_t best = b;
+            for (uint32_t dd = 0; dd <= win; ++dd) {
+                if (b >= dd && diff[b - dd] == 0) { best = b - dd; break; }
+                if (b + dd < T && diff[b + dd] == 0) { best = b + dd; break; }
+            }
+            b = best;
+        }
+        s_b[i] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t i = 1; i <= n_cta; ++i) if (s_b[i] < s_b[i - 1]) s_b[i] = s_b[i - 1];
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i <= n_cta; i += nth) bounds[i] = s_b[i];
+}
+
 // one closure round: classes that span ranges or touch a dirty transcript go to the pool and dirty all their members
 __global__ void k_part_owner(const uint32_t* __restrict__ start, const uint32_t* __restrict__ len, const uint32_t* __restrict__ lab,
                              uint64_t Em, const uint32_t* __restrict__ bounds, uint32_t n_cta, uint8_t* __restrict__ dirty,
