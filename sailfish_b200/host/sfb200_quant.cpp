@@ -1,0 +1,430 @@
+// sfb200_quant.cpp -- `sailfish quant`-shaped command line driver in C++ on top of libsfb200.
+//
+//   sfb200-quant [quant] -t transcripts.fa -l IU -1 r_1.fq[.gz] -2 r_2.fq[.gz] -o out_dir [options]
+//   sfb200-quant [quant] -t transcripts.fa -l U  -r reads.fq -o out_dir
+//
+// Option names follow the reference's `sailfish quant` (src/SailfishQuantify.cpp:1066-1150); the index is built on the GPU
+// from the transcript FASTA at start-up (-t) instead of being read from a RapMap index directory (-i), because RapMap's
+// on-disk format is not part of the reference tree.  The host side keeps the reference's structure: reader threads parse
+// FASTA/FASTQ into batches (fastx_reader.hpp), the batches go through GpuQuasiMapper / EquivalenceClassBuilder /
+// CollapsedEMOptimizer / CollapsedGibbsSampler (sfb200_host.hpp: the reference's class names over the C ABI), effective
+// lengths are computed on the host as in quasiMapReads' tail (SailfishQuantify.cpp:648-838,937-992,1034-1043) and the writers
+// reproduce GZipWriter's formats (src/GZipWriter.cpp:51-92,163-284).  There is no CPU fallback: without a CUDA device the
+// program stops with an error.
+#include <zlib.h>
+
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "fastx_reader.hpp"
+#include "sfb200_host.hpp"
+
+namespace {
+
+// ---- library format (include/LibraryFormat.hpp:7-9,89-98; parseLibraryFormatStringNew, src/SailfishUtils.cpp:63-153) ------------
+bool parse_library_format(std::string s, int32_t& id, bool& paired) {
+    for (char& ch : s) ch = (char)toupper(ch);
+    struct E { const char* n; int t, o, st; };
+    // type: 0 single 1 paired; orientation: 0 same 1 away 2 toward 3 none; strandedness: 0 SA 1 AS 2 S 3 A 4 U
+    static const E tab[] = {{"IU", 1, 2, 4}, {"ISF", 1, 2, 0}, {"ISR", 1, 2, 1}, {"OU", 1, 1, 4}, {"OSF", 1, 1, 0}, {"OSR", 1, 1, 1},
+                            {"MU", 1, 0, 4}, {"MSF", 1, 0, 2}, {"MSR", 1, 0, 3}, {"U", 0, 3, 4}, {"SF", 0, 3, 2}, {"SR", 0, 3, 3}};
+    for (const E& e : tab)
+        if (s == e.n) { id = (e.t & 1) | ((e.o & 3) << 1) | ((e.st & 7) << 3); paired = e.t == 1; return true; }
+    return false;
+}
+
+// ---- effective lengths (host, O(T + maxFragLen)) ---------------------------------------------------------------------------------
+// getNormalFragLengthDist + correction factors of a discretised normal (SailfishQuantify.cpp:648-704)
+std::vector<double> normal_correction_factors(uint32_t maxLen, double mean, double sd) {
+    std::vector<double> cf(maxLen, 0.0);
+    const double inv = 1.0 / sd;
+    double cumMass = 0.0, cumDens = 0.0;
+    for (uint32_t i = 0; i < maxLen; ++i) {
+        const double x = inv * (static_cast<double>(i) - mean);
+        const double dens = std::exp(-0.5 * x * x) * inv;
+        cumMass += static_cast<double>(i) * dens;
+        cumDens += dens;
+        if (cumDens > 0) cf[i] = cumMass / cumDens;
+    }
+    return cf;
+}
+// correctionFactorsFromCounts (SailfishQuantify.cpp:769-807): running mean of the observed fragment lengths
+std::vector<double> correction_factors_from_counts(const std::vector<uint32_t>& hist) {
+    const size_t n = hist.size();
+    std::vector<double> cf(n, 0.0);
+    double acc = 0.0;
+    uint32_t mult = n ? hist[0] : 0;
+    for (size_t i = 1; i < n; ++i) {
+        acc = static_cast<double>(static_cast<uint64_t>(hist[i]) * i) + acc;
+        mult += hist[i];
+        if (mult > 0) cf[i] = acc / static_cast<double>(mult);
+    }
+    return cf;
+}
+// computeSmoothedEffectiveLengths (:809-838) / setEffectiveLengthsDirect (:707-715) and the mode selection (:937-992, :1034-1043)
+std::vector<double> effective_lengths(const std::vector<uint32_t>& lens, const std::vector<uint32_t>& fld, uint32_t maxFragLen,
+                                      int32_t numFragSamples, bool singleEnd, bool noCorrection, double priorMean, double priorSD) {
+    std::vector<double> eff(lens.size());
+    if (noCorrection) { for (size_t i = 0; i < lens.size(); ++i) eff[i] = lens[i]; return eff; }
+    uint64_t nSamp = 0;
+    for (uint32_t c : fld) nSamp += c;
+    const bool enough = !singleEnd && nSamp >= static_cast<uint64_t>(numFragSamples);
+    const std::vector<double> cf = enough ? correction_factors_from_counts(fld) : normal_correction_factors(maxFragLen, priorMean, priorSD);
+    for (size_t i = 0; i < lens.size(); ++i) {
+        const uint32_t idx = std::min<uint32_t>(lens[i], maxFragLen - 1);
+        const double e = static_cast<double>(lens[i]) - cf[idx] + 1.0;
+        eff[i] = e < 1.0 ? static_cast<double>(lens[i]) : e;
+    }
+    return eff;
+}
+
+// ---- the experiment as the adaptors see it (Transcript / ReadExperiment members they touch) ------------------------------------
+struct Transcript {
+    std::string RefName;
+    uint32_t RefLength = 0;
+    double EffectiveLength = 0.0;
+    double estCount_ = 0.0, mass_ = 0.0;
+    void setEstCount(double v) { estCount_ = v; }
+    void setMass(double v) { mass_ = v; }
+    double mass() const { return mass_; }
+    double estCount() const { return estCount_; }
+};
+struct ReadExperiment {
+    std::vector<Transcript> txps;
+    uint64_t numMapped = 0;
+    std::vector<Transcript>& transcripts() { return txps; }
+    uint64_t numMappedFragments() const { return numMapped; }
+};
+struct SailfishOpts {
+    bool useVBOpt = false, noEffectiveLengthCorrection = false;
+    uint32_t numBootstraps = 0, numGibbsSamples = 0;
+};
+
+void make_dir(const std::string& p) { mkdir(p.c_str(), 0755); }
+
+std::string fmt_g(double x) { char b[64]; snprintf(b, sizeof b, "%g", x); return b; }   // cppformat's `{}` for doubles
+
+// GZipWriter::writeAbundances (src/GZipWriter.cpp:194-248)
+void write_quant_sf(const std::string& path, ReadExperiment& ex) {
+    const double numMapped = static_cast<double>(ex.numMapped);
+    double denom = 0.0;
+    std::vector<double> tfrac(ex.txps.size(), 0.0);
+    for (size_t i = 0; i < ex.txps.size(); ++i) {
+        const Transcript& t = ex.txps[i];
+        if (numMapped > 0 && t.EffectiveLength > 0) tfrac[i] = (t.estCount() / numMapped) / t.EffectiveLength;
+        denom += tfrac[i];
+    }
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    fprintf(f, "Name\tLength\tEffectiveLength\tTPM\tNumReads\n");
+    for (size_t i = 0; i < ex.txps.size(); ++i) {
+        const Transcript& t = ex.txps[i];
+        const double tpm = denom > 0 ? tfrac[i] / denom * 1e6 : 0.0;
+        fprintf(f, "%s\t%u\t%s\t%s\t%s\n", t.RefName.c_str(), t.RefLength, fmt_g(t.EffectiveLength).c_str(), fmt_g(tpm).c_str(),
+                fmt_g(t.estCount()).c_str());
+    }
+    fclose(f);
+}
+
+// GZipWriter::writeEquivCounts (src/GZipWriter.cpp:51-92)
+void write_eq_classes(const std::string& path, ReadExperiment& ex, sfb200::EquivalenceClassBuilder& eq) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    auto& vec = eq.eqVec();
+    fprintf(f, "%zu\n%zu\n", ex.txps.size(), vec.size());
+    for (const Transcript& t : ex.txps) fprintf(f, "%s\n", t.RefName.c_str());
+    for (auto& kv : vec) {
+        fprintf(f, "%zu\t", kv.first.txps.size());
+        for (uint32_t t : kv.first.txps) fprintf(f, "%u\t", t);
+        fprintf(f, "%llu\n", (unsigned long long)kv.second.count);
+    }
+    fclose(f);
+}
+
+struct Args {
+    std::string transcripts, libType, out, auxDir = "aux";
+    std::vector<std::string> unmated, mates1, mates2;
+    unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    int k = 31, device = 0;
+    bool dumpEq = false, parseOnly = false;
+    size_t batch = 1u << 21, blockBytes = 32u << 20;
+    SailfishOpts sopt;
+    sfb200_map_opts mopt;
+    double fldMean = 200.0, fldSD = 80.0;
+    bool discardOrphans = false;
+};
+
+[[noreturn]] void usage(const char* msg) {
+    if (msg) fprintf(stderr, "error: %s\n\n", msg);
+    fprintf(stderr,
+            "sfb200-quant [quant] -t <transcripts.fa> -l <libType> {-r <reads> | -1 <mates1> -2 <mates2>} -o <dir> [options]\n"
+            "  -t, --transcripts FILE     transcript FASTA (the index is built on the GPU from it)\n"
+            "  -l, --libType STR          IU ISF ISR OU OSF OSR MU MSF MSR U SF SR\n"
+            "  -r, --unmatedReads FILE..  single-end reads (FASTA/FASTQ, plain or .gz)\n"
+            "  -1, --mates1 FILE.. / -2, --mates2 FILE..\n"
+            "  -o, --output DIR           quant.sf and <auxDir>/ are written here\n"
+            "  -p, --threads N  -k, --kmerLen K (31)  --device N\n"
+            "  --useVBOpt  --numBootstraps N  --numGibbsSamples N  --dumpEq  --noEffectiveLengthCorrection\n"
+            "  --maxFragLen N (1000)  --numFragSamples N (10000)  --fldMean M (200)  --fldSD S (80)  -w, --maxReadOcc N (200)\n"
+            "  --strictIntersect  --ignoreLibCompat  --enforceLibCompat  --allowDovetail  --discardOrphans  --auxDir NAME\n"
+            "  --parseOnly                only parse the read files and print record / base counts (no GPU needed)\n");
+    exit(msg ? 2 : 0);
+}
+
+Args parse_args(int argc, char** argv) {
+    Args a;
+    a.mopt.max_read_occs = 200; a.mopt.max_frag_len = 1000; a.mopt.num_frag_samples = 10000; a.mopt.lib_format_id = 0;
+    a.mopt.strict_intersect = 0; a.mopt.allow_orphans = 1; a.mopt.allow_dovetail = 0; a.mopt.ignore_compat = 0;
+    a.mopt.enforce_compat = 0; a.mopt.max_interval = 1000;
+    int i = 1;
+    if (i < argc && std::string(argv[i]) == "quant") ++i;
+    auto need = [&](const std::string& o) -> std::string { if (i + 1 >= argc) usage(("missing value for " + o).c_str()); return argv[++i]; };
+    auto multi = [&](std::vector<std::string>& v) { while (i + 1 < argc && argv[i + 1][0] != '-') v.push_back(argv[++i]); };
+    for (; i < argc; ++i) {
+        const std::string o = argv[i];
+        if (o == "-h" || o == "--help") usage(nullptr);
+        else if (o == "-t" || o == "--transcripts") a.transcripts = need(o);
+        else if (o == "-l" || o == "--libType") a.libType = need(o);
+        else if (o == "-o" || o == "--output") a.out = need(o);
+        else if (o == "-r" || o == "--unmatedReads") multi(a.unmated);
+        else if (o == "-1" || o == "--mates1") multi(a.mates1);
+        else if (o == "-2" || o == "--mates2") multi(a.mates2);
+        else if (o == "-p" || o == "--threads") a.threads = (unsigned)std::max(1, atoi(need(o).c_str()));
+        else if (o == "-k" || o == "--kmerLen") a.k = atoi(need(o).c_str());
+        else if (o == "--device") a.device = atoi(need(o).c_str());
+        else if (o == "--useVBOpt") a.sopt.useVBOpt = true;
+        else if (o == "--numBootstraps") a.sopt.numBootstraps = (uint32_t)atoi(need(o).c_str());
+        else if (o == "--numGibbsSamples") a.sopt.numGibbsSamples = (uint32_t)atoi(need(o).c_str());
+        else if (o == "--dumpEq") a.dumpEq = true;
+        else if (o == "--noEffectiveLengthCorrection") a.sopt.noEffectiveLengthCorrection = true;
+        else if (o == "--maxFragLen") a.mopt.max_frag_len = (uint32_t)atoi(need(o).c_str());
+        else if (o == "--numFragSamples") a.mopt.num_frag_samples = atoi(need(o).c_str());
+        else if (o == "--fldMean") a.fldMean = atof(need(o).c_str());
+        else if (o == "--fldSD") a.fldSD = atof(need(o).c_str());
+        else if (o == "-w" || o == "--maxReadOcc") a.mopt.max_read_occs = (uint32_t)atoi(need(o).c_str());
+        else if (o == "--strictIntersect") a.mopt.strict_intersect = 1;
+        else if (o == "--ignoreLibCompat") a.mopt.ignore_compat = 1;
+        else if (o == "--enforceLibCompat") a.mopt.enforce_compat = 1;
+        else if (o == "--allowDovetail") a.mopt.allow_dovetail = 1;
+        else if (o == "--discardOrphans") a.discardOrphans = true;
+        else if (o == "--auxDir") a.auxDir = need(o);
+        else if (o == "--batchReads") a.batch = (size_t)std::max(1, atoi(need(o).c_str()));
+        else if (o == "--blockBytes") a.blockBytes = (size_t)std::max(16, atoi(need(o).c_str()));   // parser block size (tests)
+        else if (o == "--parseOnly") a.parseOnly = true;
+        else usage(("unknown option " + o).c_str());
+    }
+    if (a.discardOrphans) a.mopt.allow_orphans = 0;                       // SailfishQuantify.cpp:1204
+    return a;
+}
+
+// ---- read ingestion: a producer thread parses the next batch while the current one is copied to the device and mapped ------------
+struct PairBatch { sfb200::ReadBatch m1, m2; bool last = false; };
+
+class BatchPipe {
+public:
+    BatchPipe(const std::vector<std::string>& f1, const std::vector<std::string>& f2, size_t batch, unsigned threads, size_t block)
+        : files1_(f1), files2_(f2), batch_(batch), block_(block), threads_(threads), th_(&BatchPipe::produce, this) {}
+    ~BatchPipe() { if (th_.joinable()) th_.join(); }
+    // blocks until a batch is ready; returns nullptr after the last one
+    std::unique_ptr<PairBatch> pop() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !q_.empty() || done_; });
+        if (!err_.empty()) throw std::runtime_error(err_);
+        if (q_.empty()) return nullptr;
+        std::unique_ptr<PairBatch> b = std::move(q_.front());
+        q_.erase(q_.begin());
+        cv_.notify_all();
+        return b;
+    }
+
+private:
+    void produce() {
+        try {
+            const bool paired = !files2_.empty();
+            for (size_t fi = 0; fi < files1_.size(); ++fi) {
+                const unsigned t1 = paired ? std::max(1u, threads_ / 2) : threads_;
+                sfb200::FastxReader r1(files1_[fi], t1, block_);
+                std::unique_ptr<sfb200::FastxReader> r2;
+                if (paired) r2.reset(new sfb200::FastxReader(files2_[fi], t1, block_));
+                for (;;) {
+                    std::unique_ptr<PairBatch> b(new PairBatch());
+                    b->m1.clear(); b->m2.clear();
+                    size_t n1 = 0, n2 = 0;
+                    if (paired) {                                             // the two mates are parsed side by side
+                        std::thread other([&] { n2 = r2->next(b->m2, batch_); });
+                        n1 = r1.next(b->m1, batch_);
+                        other.join();
+                        if (n1 != n2) throw std::runtime_error("mate files " + files1_[fi] + " / " + files2_[fi] + " hold different numbers of reads");
+                    } else {
+                        n1 = r1.next(b->m1, batch_);
+                    }
+                    if (n1 == 0) break;
+                    std::unique_lock<std::mutex> lk(mu_);
+                    cv_.wait(lk, [&] { return q_.size() < 2; });
+                    q_.push_back(std::move(b));
+                    cv_.notify_all();
+                }
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu_);
+            err_ = e.what();
+        }
+        std::lock_guard<std::mutex> lk(mu_);
+        done_ = true;
+        cv_.notify_all();
+    }
+    std::vector<std::string> files1_, files2_;
+    size_t batch_, block_;
+    unsigned threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<std::unique_ptr<PairBatch>> q_;
+    bool done_ = false;
+    std::string err_;
+    std::thread th_;
+};
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        Args a = parse_args(argc, argv);
+        const bool paired_files = !a.mates1.empty() || !a.mates2.empty();
+        const std::vector<std::string>& f1 = paired_files ? a.mates1 : a.unmated;
+        if (f1.empty()) usage("no read files given");
+        if (paired_files && a.mates1.size() != a.mates2.size()) usage("--mates1 and --mates2 need the same number of files");
+        if (a.parseOnly) {
+            BatchPipe pipe(f1, a.mates2, a.batch, a.threads, a.blockBytes);
+            // FNV-1a of the mate-1 bases, the mate-2 bases and the read lengths of either mate (independent of the batching)
+            uint64_t n = 0, bases1 = 0, bases2 = 0, x[4] = {1469598103934665603ULL, 1469598103934665603ULL, 1469598103934665603ULL, 1469598103934665603ULL};
+            auto mix = [&](int k, uint64_t v) { x[k] ^= v; x[k] *= 1099511628211ULL; };
+            while (std::unique_ptr<PairBatch> b = pipe.pop()) {
+                n += b->m1.size(); bases1 += b->m1.bases.size(); bases2 += b->m2.bases.size();
+                for (char ch : b->m1.bases) mix(0, (unsigned char)ch);
+                for (char ch : b->m2.bases) mix(1, (unsigned char)ch);
+                for (size_t i = 0; i + 1 < b->m1.off.size(); ++i) mix(2, (b->m1.off[i + 1] - b->m1.off[i]) & 0xFFFF);
+                for (size_t i = 0; i + 1 < b->m2.off.size(); ++i) mix(3, (b->m2.off[i + 1] - b->m2.off[i]) & 0xFFFF);
+            }
+            printf("{\"records\": %llu, \"bases1\": %llu, \"bases2\": %llu, \"fnv1a\": [\"%016llx\", \"%016llx\", \"%016llx\", \"%016llx\"]}\n",
+                   (unsigned long long)n, (unsigned long long)bases1, (unsigned long long)bases2, (unsigned long long)x[0],
+                   (unsigned long long)x[1], (unsigned long long)x[2], (unsigned long long)x[3]);
+            return 0;
+        }
+        if (a.transcripts.empty() || a.libType.empty() || a.out.empty()) usage("-t, -l and -o are required");
+        if (a.sopt.numBootstraps && a.sopt.numGibbsSamples) usage("--numBootstraps and --numGibbsSamples are mutually exclusive (SailfishQuantify.cpp:1281-1287)");
+        bool lib_paired = false;
+        if (!parse_library_format(a.libType, a.mopt.lib_format_id, lib_paired)) usage(("unknown library type " + a.libType).c_str());
+        if (lib_paired != paired_files) usage("the library type does not match the read files given");
+
+        const double t_start = now_s();
+        // ---- transcripts + index (what SailfishIndex::load + ReadExperiment's constructor do, ReadExperiment.hpp:59-131)
+        ReadExperiment ex;
+        std::string seq; std::vector<std::string> names; std::vector<uint64_t> off; std::vector<uint32_t> lens;
+        sfb200::read_transcripts(a.transcripts, names, seq, off, lens);
+        if (names.empty()) throw std::runtime_error("no transcripts in " + a.transcripts);
+        ex.txps.resize(names.size());
+        for (size_t i = 0; i < names.size(); ++i) { ex.txps[i].RefName = names[i]; ex.txps[i].RefLength = lens[i]; }
+        sfb200::Device dev(a.device);
+        dev.buildIndex(seq, off, lens, a.k);
+        const double t_index = now_s();
+        fprintf(stderr, "[sfb200-quant] %zu transcripts, %.1f Mnt, index built in %.2f s\n", names.size(), seq.size() / 1e6, t_index - t_start);
+
+        // ---- quasi-mapping -> equivalence classes (quasiMapReads, SailfishQuantify.cpp:864-1047)
+        sfb200::EquivalenceClassBuilder eqBuilder(dev);
+        eqBuilder.start(a.mopt);
+        {
+            BatchPipe pipe(f1, a.mates2, a.batch, a.threads, a.blockBytes);
+            while (std::unique_ptr<PairBatch> b = pipe.pop()) {
+                const size_t n = b->m1.size();
+                b->m1.bases.push_back('\0');
+                if (paired_files) {
+                    b->m2.bases.push_back('\0');
+                    dev.check(sfb200_map_batch(dev.get(), b->m1.bases.data(), b->m1.off.data(), b->m2.bases.data(), b->m2.off.data(), n));
+                } else {
+                    dev.check(sfb200_map_batch(dev.get(), b->m1.bases.data(), b->m1.off.data(), nullptr, nullptr, n));
+                }
+            }
+        }
+        eqBuilder.finish();
+        ex.numMapped = eqBuilder.numMappedFragments();
+        const double t_map = now_s();
+        fprintf(stderr, "[sfb200-quant] %llu fragments, %llu mapped (%.2f%%), %llu equivalence classes, %.2f s\n",
+                (unsigned long long)eqBuilder.numObservedFragments(), (unsigned long long)ex.numMapped,
+                100.0 * ex.numMapped / std::max<uint64_t>(1, eqBuilder.numObservedFragments()), (unsigned long long)eqBuilder.numClasses(),
+                t_map - t_index);
+
+        // ---- effective lengths, inference
+        const std::vector<double> eff = effective_lengths(lens, eqBuilder.fragLengthCounts(), a.mopt.max_frag_len, a.mopt.num_frag_samples,
+                                                          !paired_files, a.sopt.noEffectiveLengthCorrection, a.fldMean, a.fldSD);
+        for (size_t i = 0; i < eff.size(); ++i) ex.txps[i].EffectiveLength = eff[i];
+        make_dir(a.out);
+        const std::string aux = a.out + "/" + a.auxDir;
+        make_dir(aux);
+        if (a.dumpEq) write_eq_classes(aux + "/eq_classes.txt", ex, eqBuilder);
+        sfb200::CollapsedEMOptimizer optimizer(dev);
+        if (!optimizer.optimize(ex, a.sopt, 0.01, 10000)) {                   // SailfishQuantify.cpp:1341-1349
+            fprintf(stderr, "[sfb200-quant] %s\n", optimizer.lastError().c_str());
+            return 1;
+        }
+        write_quant_sf(a.out + "/quant.sf", ex);
+        const char* samp_type = "none";
+        uint32_t n_samples = 0;
+        if (a.sopt.numBootstraps || a.sopt.numGibbsSamples) {                 // :1376-1410
+            make_dir(aux + "/bootstrap");
+            gzFile nf = gzopen((aux + "/bootstrap/names.tsv.gz").c_str(), "wb");
+            for (size_t i = 0; i < names.size(); ++i) { gzputs(nf, names[i].c_str()); gzputs(nf, i + 1 < names.size() ? "\t" : "\n"); }
+            gzclose(nf);
+            gzFile bf = gzopen((aux + "/bootstrap/bootstraps.gz").c_str(), "wb");
+            bool ok = true;
+            if (a.sopt.numBootstraps) {
+                samp_type = "bootstrap"; n_samples = a.sopt.numBootstraps;
+                std::function<bool(const std::vector<double>&)> w = [&](const std::vector<double>& row) {
+                    return gzwrite(bf, row.data(), (unsigned)(row.size() * sizeof(double))) > 0;             // GZipWriter.cpp:266-270
+                };
+                ok = optimizer.gatherBootstraps(ex, a.sopt, w, 0.01, 10000);
+            } else {
+                samp_type = "gibbs"; n_samples = a.sopt.numGibbsSamples;
+                sfb200::CollapsedGibbsSampler sampler(dev);
+                std::function<bool(const std::vector<int>&)> w = [&](const std::vector<int>& row) {
+                    return gzwrite(bf, row.data(), (unsigned)(row.size() * sizeof(int))) > 0;                // GZipWriter.cpp:279-283
+                };
+                ok = sampler.sample(ex, a.sopt, w, a.sopt.numGibbsSamples);
+            }
+            gzclose(bf);
+            if (!ok) { fprintf(stderr, "[sfb200-quant] posterior sampling failed: %s\n", optimizer.lastError().c_str()); return 1; }
+        }
+        // meta_info.json (GZipWriter::writeMeta, src/GZipWriter.cpp:163-190)
+        FILE* mf = fopen((aux + "/meta_info.json").c_str(), "w");
+        if (mf) {
+            fprintf(mf, "{\n    \"sf_version\": \"0.10.0-b200\",\n    \"samp_type\": \"%s\",\n    \"frag_dist_length\": %u,\n"
+                        "    \"bias_correct\": false,\n    \"num_targets\": %zu,\n    \"num_bootstraps\": %u,\n    \"num_processed\": %llu,\n"
+                        "    \"num_mapped\": %llu,\n    \"percent_mapped\": %.10g,\n    \"call\": \"quant\",\n    \"em_iterations\": %u,\n"
+                        "    \"elapsed_s\": %.3f\n}\n",
+                    samp_type, a.mopt.max_frag_len, names.size(), n_samples, (unsigned long long)eqBuilder.numObservedFragments(),
+                    (unsigned long long)ex.numMapped, 100.0 * ex.numMapped / std::max<uint64_t>(1, eqBuilder.numObservedFragments()),
+                    optimizer.lastIterations(), now_s() - t_start);
+            fclose(mf);
+        }
+        fprintf(stderr, "[sfb200-quant] EM: %u iterations; wrote %s/quant.sf (%.2f s in total)\n", optimizer.lastIterations(), a.out.c_str(),
+                now_s() - t_start);
+        return 0;
+    } catch (const sfb200::Error& e) {
+        fprintf(stderr, "[sfb200-quant] device error %d: %s\n", e.code, e.what());
+        return 3;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "[sfb200-quant] %s\n", e.what());
+        return 1;
+    }
+}

@@ -1,0 +1,144 @@
+"""The C++ host driver sfb200-quant (sailfish_b200/host/sfb200_quant.cpp + fastx_reader.hpp): the FASTA/FASTQ ingestion is
+checked on CPU against a plain Python parse (ragged reads, CRLF, no trailing newline, gzip, block and batch boundaries);
+on a GPU the whole command reproduces the reference optimizer's estimates on the bundled sample data (BASELINE config 1)."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import split_seqs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "sailfish_b200", "bin", "sfb200-quant")
+
+
+def build_exe():
+    from sailfish_b200 import capi
+    capi.lib()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "sailfish_b200", "host")])
+    return EXE
+
+
+def fnv(seqs1, seqs2):
+    M = (1 << 64) - 1
+
+    def h(vals):
+        x = 1469598103934665603
+        for v in vals:
+            x = ((x ^ v) * 1099511628211) & M
+        return "%016x" % x
+    return [h("".join(seqs1).encode()), h("".join(seqs2).encode()), h(len(s) & 0xFFFF for s in seqs1), h(len(s) & 0xFFFF for s in seqs2)]
+
+
+def rand_reads(rng, n, lo, hi):
+    return ["".join(rng.choice(list("ACGTN"), size=int(rng.integers(lo, hi + 1)))) for _ in range(n)]
+
+
+def write_fastq(path, seqs, eol="\n", final_newline=True, gz=False):
+    txt = eol.join("@r%d some description%s%s%s+%s%s" % (i, eol, s, eol, eol, "I" * len(s)) for i, s in enumerate(seqs))
+    if final_newline:
+        txt += eol
+    (gzip.open(path, "wt", newline="") if gz else open(path, "w", newline="")).write(txt)
+
+
+def parse_only(args):
+    out = subprocess.check_output([build_exe(), "--parseOnly"] + args)
+    return json.loads(out)
+
+
+@pytest.mark.parametrize("eol,final_newline,gz", [("\n", True, False), ("\r\n", True, False), ("\n", False, False), ("\n", True, True)])
+def test_fastq_ingestion_single(tmp_path, eol, final_newline, gz):
+    rng = np.random.default_rng(3)
+    seqs = rand_reads(rng, 5000, 1, 120) + ["A"] + rand_reads(rng, 10, 300, 400)
+    p = str(tmp_path / ("r.fq.gz" if gz else "r.fq"))
+    write_fastq(p, seqs, eol, final_newline, gz)
+    for block, batch in ((64, 7), (4096, 1000), (1 << 20, 1 << 20)):
+        got = parse_only(["-r", p, "--blockBytes", str(block), "--batchReads", str(batch), "-p", "3"])
+        assert got["records"] == len(seqs) and got["bases1"] == sum(len(s) for s in seqs) and got["bases2"] == 0
+        assert got["fnv1a"] == fnv(seqs, [])
+
+
+def test_fastq_ingestion_paired_and_multiple_files(tmp_path):
+    rng = np.random.default_rng(4)
+    a1, a2 = rand_reads(rng, 3000, 30, 80), rand_reads(rng, 3000, 30, 80)
+    b1, b2 = rand_reads(rng, 1234, 50, 50), rand_reads(rng, 1234, 50, 50)
+    for name, s in (("a1", a1), ("a2", a2), ("b1", b1), ("b2", b2)):
+        write_fastq(str(tmp_path / (name + ".fq")), s)
+    got = parse_only(["-1", str(tmp_path / "a1.fq"), str(tmp_path / "b1.fq"), "-2", str(tmp_path / "a2.fq"), str(tmp_path / "b2.fq"),
+                      "--blockBytes", "5000", "--batchReads", "999"])
+    assert got["records"] == 4234
+    assert got["bases1"] == sum(map(len, a1 + b1)) and got["bases2"] == sum(map(len, a2 + b2))
+    assert got["fnv1a"] == fnv(a1 + b1, a2 + b2)
+    # mate files of different length are an error, as in the reference's paired parser
+    write_fastq(str(tmp_path / "short.fq"), a2[:-1])
+    r = subprocess.run([EXE, "--parseOnly", "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "short.fq")], capture_output=True)
+    assert r.returncode != 0 and b"different numbers of reads" in r.stderr
+
+
+def test_fasta_reads_and_errors(tmp_path):
+    seqs = ["ACGTACGT", "GG", "TTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "C"]
+    p = tmp_path / "r.fa"
+    p.write_text("".join(">r%d\n%s\n" % (i, "\n".join(s[j:j + 5] for j in range(0, len(s), 5))) for i, s in enumerate(seqs)))
+    for block in (16, 64, 1 << 20):
+        got = parse_only(["-r", str(p), "--blockBytes", str(block)])
+        assert got["records"] == 4 and got["fnv1a"] == fnv(seqs, [])
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@r0\nACGT\n+\nIIII\n@r1\nAC\n")
+    r = subprocess.run([EXE, "--parseOnly", "-r", str(bad)], capture_output=True)
+    assert r.returncode != 0 and b"truncated" in r.stderr
+    r = subprocess.run([EXE, "-t", "x.fa", "-l", "XYZ", "-r", str(p), "-o", str(tmp_path / "o")], capture_output=True)
+    assert r.returncode == 2 and b"unknown library type" in r.stderr
+
+
+def test_no_cpu_fallback(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 30 + "\n")
+    fq = tmp_path / "r.fq"; fq.write_text("@r\n" + "ACGT" * 10 + "\n+\n" + "I" * 40 + "\n")
+    r = subprocess.run([build_exe(), "-t", str(fa), "-l", "U", "-r", str(fq), "-o", str(tmp_path / "o")], capture_output=True)
+    assert r.returncode == 3 and b"no usable CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_sample_data_end_to_end_cpp(sample_data, tmp_path):
+    d = sample_data
+    seqs = split_seqs(d["txp_seq"], d["txp_len"])
+    names = [str(n) for n in d["names"]]
+    fa = tmp_path / "transcripts.fasta"
+    with open(fa, "w") as f:
+        for n, s in zip(names, seqs):
+            s = s.decode()
+            f.write(">%s extra words\n%s\n" % (n, "\n".join(s[j:j + 60] for j in range(0, len(s), 60))))
+    for tag, reads, off in (("1", d["reads1"], d["off1"]), ("2", d["reads2"], d["off2"])):
+        with gzip.open(tmp_path / ("reads_%s.fastq.gz" % tag), "wt") as f:
+            for i in range(len(off) - 1):
+                s = reads[int(off[i]):int(off[i + 1])].tobytes().decode()
+                f.write("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)))
+    out = tmp_path / "q"
+    subprocess.check_call([build_exe(), "quant", "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "reads_1.fastq.gz"),
+                           "-2", str(tmp_path / "reads_2.fastq.gz"), "-o", str(out), "--dumpEq", "--numBootstraps", "3", "--batchReads", "3000"])
+    lines = open(out / "quant.sf").read().strip().split("\n")
+    assert lines[0] == "Name\tLength\tEffectiveLength\tTPM\tNumReads" and len(lines) == 1 + len(names)
+    rows = [l.split("\t") for l in lines[1:]]
+    assert [r[0] for r in rows] == names and [int(r[1]) for r in rows] == [int(x) for x in d["txp_len"]]
+    np.testing.assert_allclose([float(r[4]) for r in rows], d["ref_est_vb0"], rtol=1.2e-4, atol=1e-6)   # 1e-4 parity + %g's 6 digits
+    np.testing.assert_allclose([float(r[2]) for r in rows], d["eff"], rtol=1e-5)
+    assert abs(sum(float(r[3]) for r in rows) - 1e6) < 50
+    meta = json.load(open(out / "aux" / "meta_info.json"))
+    assert meta["num_processed"] == 10000 and meta["num_mapped"] == int(d["num_mapped"]) and meta["samp_type"] == "bootstrap"
+    eq = open(out / "aux" / "eq_classes.txt").read().split("\n")
+    assert int(eq[0]) == len(names) and int(eq[1]) == len(d["counts"])
+    boots = np.frombuffer(gzip.open(out / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.float64).reshape(3, len(names))
+    np.testing.assert_allclose(boots.sum(axis=1), float(d["num_mapped"]), rtol=1e-9)
+    # the Gibbs path and VBEM through the same command
+    out2 = tmp_path / "q2"
+    subprocess.check_call([EXE, "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "reads_1.fastq.gz"), "-2", str(tmp_path / "reads_2.fastq.gz"),
+                           "-o", str(out2), "--useVBOpt", "--numGibbsSamples", "4"])
+    rows2 = [l.split("\t") for l in open(out2 / "quant.sf").read().strip().split("\n")[1:]]
+    np.testing.assert_allclose([float(r[4]) for r in rows2], d["ref_est_vb1"], rtol=1.2e-4, atol=1e-6)
+    gib = np.frombuffer(gzip.open(out2 / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.int32).reshape(4, len(names))
+    assert (gib.sum(axis=1) == int(d["num_mapped"])).all()
