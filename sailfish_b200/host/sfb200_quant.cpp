@@ -2,10 +2,12 @@
 //
 //   sfb200-quant [quant] -t transcripts.fa -l IU -1 r_1.fq[.gz] -2 r_2.fq[.gz] -o out_dir [options]
 //   sfb200-quant [quant] -t transcripts.fa -l U  -r reads.fq -o out_dir
+//   sfb200-quant index -t transcripts.fa -o index_dir [-k 31] [-f]        then        sfb200-quant quant -i index_dir ...
 //
 // Option names follow the reference's `sailfish quant` (src/SailfishQuantify.cpp:1066-1150); the index is built on the GPU
-// from the transcript FASTA at start-up (-t) instead of being read from a RapMap index directory (-i), because RapMap's
-// on-disk format is not part of the reference tree.  The host side keeps the reference's structure: reader threads parse
+// from the transcript sequences at start-up (a fraction of a second for 200k transcripts), so the `index` command (reference
+// src/SailfishIndexer.cpp:66-237) only parses the FASTA once and stores names, lengths and sequence next to versionInfo.json
+// (include/SailfishIndexVersionInfo.hpp:22-50) and header.json; RapMap's own on-disk format is not part of the reference tree.  The host side keeps the reference's structure: reader threads parse
 // FASTA/FASTQ into batches (fastx_reader.hpp), the batches go through GpuQuasiMapper / EquivalenceClassBuilder /
 // CollapsedEMOptimizer / CollapsedGibbsSampler (sfb200_host.hpp: the reference's class names over the C ABI), effective
 // lengths are computed on the host as in quasiMapReads' tail (SailfishQuantify.cpp:648-838,937-992,1034-1043) and the writers
@@ -151,8 +153,75 @@ void write_eq_classes(const std::string& path, ReadExperiment& ex, sfb200::Equiv
     fclose(f);
 }
 
+// ---- index directory: versionInfo.json (same two fields as SailfishIndexVersionInfo), header.json, txpInfo.bin, seq.bin ---------
+constexpr uint32_t kIndexVersion = 2;                                      // sailfish::indexVersion (include/SailfishConfig.hpp:33)
+
+void write_index_dir(const std::string& dir, int k, const std::vector<std::string>& names, const std::string& seq,
+                     const std::vector<uint32_t>& lens) {
+    make_dir(dir);
+    FILE* f = fopen((dir + "/versionInfo.json").c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write into " + dir);
+    fprintf(f, "{\n    \"indexVersion\": %u,\n    \"kmerLength\": %d\n}\n", kIndexVersion, k);
+    fclose(f);
+    f = fopen((dir + "/header.json").c_str(), "w");
+    fprintf(f, "{\n    \"IndexType\": \"sfb200-text\",\n    \"IndexVersion\": \"b200-1\",\n    \"k\": %d,\n    \"NumTranscripts\": %zu,\n"
+               "    \"TextLength\": %zu,\n    \"note\": \"suffix array, k-mer table and presence filter are rebuilt on the GPU at load time\"\n}\n",
+            k, names.size(), seq.size());
+    fclose(f);
+    f = fopen((dir + "/txpInfo.bin").c_str(), "wb");
+    const uint64_t n = names.size();
+    fwrite(&n, 8, 1, f);
+    for (const std::string& s : names) { const uint32_t l = (uint32_t)s.size(); fwrite(&l, 4, 1, f); fwrite(s.data(), 1, l, f); }
+    fwrite(lens.data(), 4, lens.size(), f);
+    fclose(f);
+    f = fopen((dir + "/seq.bin").c_str(), "wb");
+    const uint64_t sl = seq.size();
+    fwrite(&sl, 8, 1, f);
+    if (fwrite(seq.data(), 1, seq.size(), f) != seq.size()) { fclose(f); throw std::runtime_error("short write to " + dir + "/seq.bin"); }
+    fclose(f);
+}
+
+int read_index_dir(const std::string& dir, std::vector<std::string>& names, std::string& seq, std::vector<uint64_t>& off,
+                   std::vector<uint32_t>& lens) {
+    FILE* f = fopen((dir + "/versionInfo.json").c_str(), "r");
+    if (!f) throw std::invalid_argument("Error: The index version file " + dir + "/versionInfo.json doesn't seem to exist.  Please try re-building the sailfish index.");
+    unsigned ver = 0; int k = 0;
+    char buf[256]; std::string txt;
+    while (fgets(buf, sizeof buf, f)) txt += buf;
+    fclose(f);
+    const size_t pv = txt.find("\"indexVersion\""), pk = txt.find("\"kmerLength\"");
+    if (pv == std::string::npos || pk == std::string::npos) throw std::runtime_error("malformed " + dir + "/versionInfo.json");
+    ver = (unsigned)atoi(txt.c_str() + txt.find(':', pv) + 1); k = atoi(txt.c_str() + txt.find(':', pk) + 1);
+    if (ver != kIndexVersion) throw std::runtime_error("index version " + std::to_string(ver) + " is not the version this program reads (" + std::to_string(kIndexVersion) + ")");
+    f = fopen((dir + "/txpInfo.bin").c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + dir + "/txpInfo.bin");
+    uint64_t n = 0;
+    if (fread(&n, 8, 1, f) != 1) { fclose(f); throw std::runtime_error("truncated txpInfo.bin"); }
+    names.resize(n); lens.resize(n); off.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t l = 0;
+        if (fread(&l, 4, 1, f) != 1) { fclose(f); throw std::runtime_error("truncated txpInfo.bin"); }
+        names[i].resize(l);
+        if (l && fread(&names[i][0], 1, l, f) != l) { fclose(f); throw std::runtime_error("truncated txpInfo.bin"); }
+    }
+    if (n && fread(lens.data(), 4, n, f) != n) { fclose(f); throw std::runtime_error("truncated txpInfo.bin"); }
+    fclose(f);
+    f = fopen((dir + "/seq.bin").c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + dir + "/seq.bin");
+    uint64_t sl = 0;
+    if (fread(&sl, 8, 1, f) != 1) { fclose(f); throw std::runtime_error("truncated seq.bin"); }
+    seq.resize(sl);
+    if (sl && fread(&seq[0], 1, sl, f) != sl) { fclose(f); throw std::runtime_error("truncated seq.bin"); }
+    fclose(f);
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < n; ++i) { off[i] = o; o += lens[i]; }
+    if (o != sl) throw std::runtime_error("index directory is inconsistent (sequence length)");
+    return k;
+}
+
 struct Args {
-    std::string transcripts, libType, out, auxDir = "aux";
+    std::string transcripts, index, libType, out, auxDir = "aux";
+    bool indexCmd = false, force = false;
     std::vector<std::string> unmated, mates1, mates2;
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int k = 31, device = 0;
@@ -168,7 +237,8 @@ struct Args {
     if (msg) fprintf(stderr, "error: %s\n\n", msg);
     fprintf(stderr,
             "sfb200-quant [quant] -t <transcripts.fa> -l <libType> {-r <reads> | -1 <mates1> -2 <mates2>} -o <dir> [options]\n"
-            "  -t, --transcripts FILE     transcript FASTA (the index is built on the GPU from it)\n"
+            "  -t, --transcripts FILE     transcript FASTA (the index is built on the GPU from it), or\n"
+            "  -i, --index DIR            a directory written by `sfb200-quant index -t FILE -o DIR [-k K] [-f]`\n"
             "  -l, --libType STR          IU ISF ISR OU OSF OSR MU MSF MSR U SF SR\n"
             "  -r, --unmatedReads FILE..  single-end reads (FASTA/FASTQ, plain or .gz)\n"
             "  -1, --mates1 FILE.. / -2, --mates2 FILE..\n"
@@ -188,12 +258,16 @@ Args parse_args(int argc, char** argv) {
     a.mopt.enforce_compat = 0; a.mopt.max_interval = 1000;
     int i = 1;
     if (i < argc && std::string(argv[i]) == "quant") ++i;
+    else if (i < argc && std::string(argv[i]) == "index") { a.indexCmd = true; ++i; }
     auto need = [&](const std::string& o) -> std::string { if (i + 1 >= argc) usage(("missing value for " + o).c_str()); return argv[++i]; };
     auto multi = [&](std::vector<std::string>& v) { while (i + 1 < argc && argv[i + 1][0] != '-') v.push_back(argv[++i]); };
     for (; i < argc; ++i) {
         const std::string o = argv[i];
         if (o == "-h" || o == "--help") usage(nullptr);
         else if (o == "-t" || o == "--transcripts") a.transcripts = need(o);
+        else if (o == "-i" || o == "--index") a.index = need(o);
+        else if (o == "-f" || o == "--force") a.force = true;
+        else if (o == "--kmerSize") a.k = atoi(need(o).c_str());
         else if (o == "-l" || o == "--libType") a.libType = need(o);
         else if (o == "-o" || o == "--output") a.out = need(o);
         else if (o == "-r" || o == "--unmatedReads") multi(a.unmated);
@@ -301,6 +375,24 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 int main(int argc, char** argv) {
     try {
         Args a = parse_args(argc, argv);
+        if (a.indexCmd) {                                                     // `sailfish index` (src/SailfishIndexer.cpp:66-237); no GPU needed
+            if (a.transcripts.empty() || a.out.empty()) usage("index needs -t <transcripts.fa> and -o <dir>");
+            if (a.k % 2 == 0 || a.k > 31 || a.k < 3) {
+                fprintf(stderr, "k-mer length should be odd to avoid a k-mer being it's own reverse complement\nplease specify an odd value of k (<= 31)\n");
+                return 1;
+            }
+            struct stat st;
+            if (!a.force && stat((a.out + "/header.json").c_str(), &st) == 0) {
+                fprintf(stderr, "All index files seem up-to-date.\nTo force a rebuild of the index, use the --force option.\n");
+                return 0;
+            }
+            std::string seq; std::vector<std::string> names; std::vector<uint64_t> off; std::vector<uint32_t> lens;
+            sfb200::read_transcripts(a.transcripts, names, seq, off, lens);
+            if (names.empty()) throw std::runtime_error("no transcripts in " + a.transcripts);
+            write_index_dir(a.out, a.k, names, seq, lens);
+            fprintf(stderr, "[sfb200-quant] index: %zu transcripts, %.1f Mnt, k = %d -> %s\n", names.size(), seq.size() / 1e6, a.k, a.out.c_str());
+            return 0;
+        }
         const bool paired_files = !a.mates1.empty() || !a.mates2.empty();
         const std::vector<std::string>& f1 = paired_files ? a.mates1 : a.unmated;
         if (f1.empty()) usage("no read files given");
@@ -322,7 +414,7 @@ int main(int argc, char** argv) {
                    (unsigned long long)x[1], (unsigned long long)x[2], (unsigned long long)x[3]);
             return 0;
         }
-        if (a.transcripts.empty() || a.libType.empty() || a.out.empty()) usage("-t, -l and -o are required");
+        if ((a.transcripts.empty() == a.index.empty()) || a.libType.empty() || a.out.empty()) usage("one of -t / -i, and -l and -o are required");
         if (a.sopt.numBootstraps && a.sopt.numGibbsSamples) usage("--numBootstraps and --numGibbsSamples are mutually exclusive (SailfishQuantify.cpp:1281-1287)");
         bool lib_paired = false;
         if (!parse_library_format(a.libType, a.mopt.lib_format_id, lib_paired)) usage(("unknown library type " + a.libType).c_str());
@@ -332,8 +424,9 @@ int main(int argc, char** argv) {
         // ---- transcripts + index (what SailfishIndex::load + ReadExperiment's constructor do, ReadExperiment.hpp:59-131)
         ReadExperiment ex;
         std::string seq; std::vector<std::string> names; std::vector<uint64_t> off; std::vector<uint32_t> lens;
-        sfb200::read_transcripts(a.transcripts, names, seq, off, lens);
-        if (names.empty()) throw std::runtime_error("no transcripts in " + a.transcripts);
+        if (!a.index.empty()) a.k = read_index_dir(a.index, names, seq, off, lens);
+        else sfb200::read_transcripts(a.transcripts, names, seq, off, lens);
+        if (names.empty()) throw std::runtime_error("no transcripts in " + (a.index.empty() ? a.transcripts : a.index));
         ex.txps.resize(names.size());
         for (size_t i = 0; i < names.size(); ++i) { ex.txps[i].RefName = names[i]; ex.txps[i].RefLength = lens[i]; }
         sfb200::Device dev(a.device);

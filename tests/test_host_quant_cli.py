@@ -93,6 +93,25 @@ def test_fasta_reads_and_errors(tmp_path):
     assert r.returncode == 2 and b"unknown library type" in r.stderr
 
 
+def test_index_command(tmp_path):
+    """`index` (reference src/SailfishIndexer.cpp:66-237): odd k, versionInfo.json with the reference's two fields, no rebuild
+    without --force; the directory holds names, lengths and sequence (the device structures are rebuilt at load time)"""
+    import struct
+    fa = tmp_path / "t.fa"; fa.write_text(">t0 gene=x\nACGTAC\nGTAC\n>t1\nNNGGCC\n")
+    idx = tmp_path / "idx"
+    r = subprocess.run([build_exe(), "index", "-t", str(fa), "-o", str(idx), "-k", "30"], capture_output=True)
+    assert r.returncode == 1 and b"should be odd" in r.stderr
+    subprocess.check_call([EXE, "index", "-t", str(fa), "-o", str(idx), "-k", "21"])
+    assert json.load(open(idx / "versionInfo.json")) == {"indexVersion": 2, "kmerLength": 21}
+    assert json.load(open(idx / "header.json"))["NumTranscripts"] == 2
+    raw = open(idx / "seq.bin", "rb").read()
+    assert struct.unpack("<Q", raw[:8])[0] == 16 and raw[8:] == b"ACGTACGTACNNGGCC"
+    info = open(idx / "txpInfo.bin", "rb").read()
+    assert info[8:14] == struct.pack("<I", 2) + b"t0" and info[-8:] == struct.pack("<II", 10, 6)
+    r = subprocess.run([EXE, "index", "-t", str(fa), "-o", str(idx)], capture_output=True)
+    assert r.returncode == 0 and b"up-to-date" in r.stderr
+
+
 def test_no_cpu_fallback(tmp_path):
     import torch
     if torch.cuda.is_available():
@@ -134,10 +153,11 @@ def test_sample_data_end_to_end_cpp(sample_data, tmp_path):
     assert int(eq[0]) == len(names) and int(eq[1]) == len(d["counts"])
     boots = np.frombuffer(gzip.open(out / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.float64).reshape(3, len(names))
     np.testing.assert_allclose(boots.sum(axis=1), float(d["num_mapped"]), rtol=1e-9)
-    # the Gibbs path and VBEM through the same command
+    # the Gibbs path and VBEM through the same command, from an index directory
     out2 = tmp_path / "q2"
-    subprocess.check_call([EXE, "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "reads_1.fastq.gz"), "-2", str(tmp_path / "reads_2.fastq.gz"),
-                           "-o", str(out2), "--useVBOpt", "--numGibbsSamples", "4"])
+    subprocess.check_call([EXE, "index", "-t", str(fa), "-o", str(tmp_path / "idx"), "-k", "31"])
+    subprocess.check_call([EXE, "quant", "-i", str(tmp_path / "idx"), "-l", "IU", "-1", str(tmp_path / "reads_1.fastq.gz"),
+                           "-2", str(tmp_path / "reads_2.fastq.gz"), "-o", str(out2), "--useVBOpt", "--numGibbsSamples", "4"])
     rows2 = [l.split("\t") for l in open(out2 / "quant.sf").read().strip().split("\n")[1:]]
     np.testing.assert_allclose([float(r[4]) for r in rows2], d["ref_est_vb1"], rtol=1.2e-4, atol=1e-6)
     gib = np.frombuffer(gzip.open(out2 / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.int32).reshape(4, len(names))
