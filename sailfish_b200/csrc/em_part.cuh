@@ -48,28 +48,45 @@ __global__ void k_part_span(const uint32_t* __restrict__ start, const uint32_t* 
 // class crosses (within `win`), then made monotone.  pre: T scratch words; diff is turned into its prefix sum in place.
 __global__ void __launch_bounds__(1024) k_part_bounds(const uint32_t* __restrict__ load, int* __restrict__ diff, uint32_t T, uint32_t n_cta,
                                                       uint32_t win, unsigned long long* __restrict__ pre, uint32_t* __restrict__ bounds) {
-    __shared__ unsigned long long s_sum[1024];
-    __shared__ long long s_dsum[1024];
+    __shared__ unsigned long long s_wa[32];
+    __shared__ long long s_wd[32];
     __shared__ unsigned long long s_total;
     extern __shared__ uint32_t s_b[];                    // n_cta + 1
-    const uint32_t nth = blockDim.x, tid = threadIdx.x;
-    const uint32_t chunk = (T + 1 + nth - 1) / nth;      // the profile has T + 1 entries
-    const uint32_t lo = min(tid * chunk, T + 1), hi = min(lo + chunk, T + 1);
-    unsigned long long a = 0; long long d = 0;
-    for (uint32_t t = lo; t < hi; ++t) { if (t < T) a += 1ull + load[t]; d += diff[t]; }
-    s_sum[tid] = a; s_dsum[tid] = d;
-    __syncthreads();
-    if (tid == 0) {                                      // 1024 partial sums: a serial exclusive scan is a few microseconds
-        unsigned long long acc = 0; long long dacc = 0;
-        for (uint32_t j = 0; j < nth; ++j) { const unsigned long long x = s_sum[j]; s_sum[j] = acc; acc += x; const long long y = s_dsum[j]; s_dsum[j] = dacc; dacc += y; }
-        s_total = acc;
+    const uint32_t nth = blockDim.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nw = nth >> 5;
+    // block-wide inclusive scans, one coalesced tile of blockDim elements at a time (the profile has T + 1 entries)
+    unsigned long long carry_a = 0; long long carry_d = 0;
+    for (uint32_t base = 0; base <= T; base += nth) {
+        const uint32_t t = base + tid;
+        unsigned long long a = t < T ? 1ull + load[t] : 0ull;
+        long long d = t <= T ? (long long)diff[t] : 0ll;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long ua = __shfl_up_sync(0xffffffffu, a, o);
+            const long long ud = __shfl_up_sync(0xffffffffu, d, o);
+            if ((int)lane >= o) { a += ua; d += ud; }
+        }
+        if (lane == 31) { s_wa[warp] = a; s_wd[warp] = d; }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long wa = lane < nw ? s_wa[lane] : 0ull;
+            long long wd = lane < nw ? s_wd[lane] : 0ll;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long ua = __shfl_up_sync(0xffffffffu, wa, o);
+                const long long ud = __shfl_up_sync(0xffffffffu, wd, o);
+                if ((int)lane >= o) { wa += ua; wd += ud; }
+            }
+            s_wa[lane] = wa; s_wd[lane] = wd;            // inclusive over the warps
+        }
+        __syncthreads();
+        a += carry_a + (warp ? s_wa[warp - 1] : 0ull);
+        d += carry_d + (warp ? s_wd[warp - 1] : 0ll);
+        if (t < T) pre[t] = a;
+        if (t <= T) diff[t] = (int)d;
+        carry_a += s_wa[nw - 1]; carry_d += s_wd[nw - 1];
+        __syncthreads();
     }
-    __syncthreads();
-    a = s_sum[tid]; d = s_dsum[tid];
-    for (uint32_t t = lo; t < hi; ++t) {
-        if (t < T) { a += 1ull + load[t]; pre[t] = a; }
-        d += diff[t]; diff[t] = (int)d;
-    }
+    if (tid == 0) s_total = carry_a;
     __syncthreads();
     const unsigned long long total = s_total;
     for (uint32_t i = tid; i <= n_cta; i += nth) {
