@@ -136,7 +136,8 @@ int sfb200_em_run(sfb200_ctx* ctx, const double* eff_lens, uint32_t n_txp, uint6
 double sfb200_last_em_loop_ms(const sfb200_ctx* ctx);
 /* which iteration loop the last em_run / bootstrap used: 0 binned layout, global-memory scatter (k_em_persistent);
  * 1 CTA-partitioned, shared-memory scatter (k_em_part); 2 CTA-partitioned, atomic-free gather form (k_em_gather);
- * 3 one launch per phase (rank-local classes with a per-iteration all-reduce, or SFB200_EM_MODE=steps) */
+ * 3 one launch per phase (rank-local classes with a per-iteration all-reduce, or SFB200_EM_MODE=steps);
+ * 4 one thread per connected component of the class structure (k_em_dense) */
 int sfb200_last_em_kernel(const sfb200_ctx* ctx);
 
 typedef int (*sfb200_f64_row_cb)(void* user, const double* row, size_t n);

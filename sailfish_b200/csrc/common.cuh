@@ -91,8 +91,14 @@ struct DevPartition {
     uint32_t gth_geom[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t gather_smem = 0;           // dynamic shared memory the largest CTA needs
     DevBuf<uint32_t> gth;
+    // dense-component layout (em_dense.cuh)
+    bool dense_ok = false, dense_tried = false;
+    uint32_t dns_geom[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t dense_smem = 0;
+    uint32_t dense_ns = 0;
+    DevBuf<uint32_t> dns;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); }
 };
 struct DevClasses {
     DevPartition part;

@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_sweep(const EmParams p, un
 
 #include "em_part.cuh"
 #include "em_gather.cuh"
+#include "em_dense.cuh"
 
 // truncateCountVector (CollapsedEMOptimizer.cpp:37-44): alpha <= cutoff -> 0, and the sum of what is left
 __global__ void k_truncate(double* __restrict__ x, uint32_t n, double cutoff, double* __restrict__ sum_out) {
@@ -674,11 +675,15 @@ int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
 // the atomic-free loop is chosen when the classes allow it; SFB200_EM_GATHER=0 / 1 overrides the default
 constexpr bool SFB_GATHER_DEFAULT = true;
 bool gather_enabled() { const char* e = getenv("SFB200_EM_GATHER"); return e ? atoi(e) != 0 : SFB_GATHER_DEFAULT; }
+// one thread per connected component (em_dense.cuh) when every component is small; SFB200_EM_DENSE=0 / 1 overrides the default
+constexpr bool SFB_DENSE_DEFAULT = false;
+bool dense_enabled() { const char* e = getenv("SFB200_EM_DENSE"); return e ? atoi(e) != 0 : SFB_DENSE_DEFAULT; }
+int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
 
 int build_partition(sfb200_ctx* c) {
     DevClasses& k = c->cls;
     DevPartition& P = k.part;
-    P.valid = true; P.usable = false; P.gather_ok = false; P.gather_tried = gather_enabled();
+    P.valid = true; P.usable = false; P.gather_ok = false; P.gather_tried = gather_enabled(); P.dense_ok = false; P.dense_tried = dense_enabled();
     if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
     // CTAs per SM for the partitioned loop: two half-size CTAs fill each other's __syncthreads bubbles
     int per_sm = 2;
@@ -766,6 +771,8 @@ int build_partition(sfb200_ctx* c) {
     hm.mark("part: table + sync");
     { const int rc = build_gather(c, tbl); if (rc) return rc; }
     hm.mark("part: gather layout");
+    { const int rc = build_dense(c, tbl); if (rc) return rc; }
+    hm.mark("part: dense layout");
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool), largest CTA slice %llu bytes (limit %d) -> %s\n",
                 n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, (unsigned long long)max_bytes, max_optin,
@@ -824,8 +831,57 @@ int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     return SFB200_OK;
 }
 
+// Build the dense-component layout (em_dense.cuh): usable when every CTA reports components of at most DN_MAX_SLOTS transcripts.
+int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
+    DevPartition& P = c->cls.part;
+    P.dense_ok = false;
+    P.dense_tried = dense_enabled();
+    if (!dense_enabled() || P.n_pool != 0 || P.n_cta == 0) return SFB200_OK;
+    static_assert(sizeof(DenseGeom) == sizeof(P.dns_geom), "DenseGeom is stored as 16 opaque words");
+    uint64_t max_nc = 0, max_nt = 0;
+    for (uint32_t i = 0; i < P.n_cta; ++i) {
+        const unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
+        max_nc = std::max<uint64_t>(max_nc, row[PT_CLS + SFB_NBINS] - row[PT_CLS]);
+        max_nt = std::max<uint64_t>(max_nt, row[PT_TXP1] - row[PT_TXP0]);
+    }
+    const DenseGeom g = dense_make_geom(max_nc, max_nt);
+    cudaStream_t s = c->stream;
+    SFB_CUDA(c, P.dns.reserve((size_t)P.n_cta * g.region_words));
+    const size_t scratch = 4 * dense_scratch_words(max_nt, g);
+    if (scratch + 1024 > P.smem_limit) return SFB200_OK;
+    SFB_CUDA(c, cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_dense_build), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+    k_dense_build<<<P.n_cta, 256, scratch, s>>>(P.start.p, P.len.p, P.lab.p, P.tbl.p, g, P.dns.p);
+    c->launches++;
+    SFB_CUDA(c, cudaGetLastError());
+    std::vector<uint32_t> hdr((size_t)P.n_cta * DH_WORDS);
+    SFB_CUDA(c, cudaMemcpy2DAsync(hdr.data(), DH_WORDS * 4, P.dns.p, (size_t)g.region_words * 4, DH_WORDS * 4, P.n_cta, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    bool ok = true;
+    uint32_t ns = 2, rounds = 0;
+    for (uint32_t i = 0; i < P.n_cta && ok; ++i) {
+        const uint32_t* h = hdr.data() + (size_t)i * DH_WORDS;
+        ok = h[DH_KIND] == 1u;
+        if (ok) { ns = std::max(ns, h[DH_NS]); rounds = std::max(rounds, h[DH_ROUNDS]); }
+    }
+    uint64_t need = 0;
+    if (ok) for (uint32_t i = 0; i < P.n_cta; ++i) {
+        const uint32_t* h = hdr.data() + (size_t)i * DH_WORDS;
+        need = std::max<uint64_t>(need, dense_smem_need(h[DH_TILES], h[DH_ENT], ns));
+    }
+    need += 256;
+    const bool fits = (need + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1);
+    std::memcpy(P.dns_geom, &g, sizeof(g));
+    P.dense_smem = need; P.dense_ns = ns;
+    P.dense_ok = ok && fits && ns <= DN_MAX_SLOTS && P.per_sm <= 2;
+    if (getenv("SFB200_VERBOSE"))
+        fprintf(stderr, "[sfb200] EM dense layout: %s (largest component %u transcripts, %u propagation rounds, %llu bytes of shared memory)\n",
+                P.dense_ok ? "one thread per component" : (ok ? "does not fit" : "components too large / not separable"), ns, rounds,
+                (unsigned long long)need);
+    return SFB200_OK;
+}
+
 struct LoopSpec { bool gate_old; uint32_t min_iter; };
-enum LoopKind { LOOP_BINNED = 0, LOOP_PART = 1, LOOP_GATHER = 2 };
+enum LoopKind { LOOP_BINNED = 0, LOOP_PART = 1, LOOP_GATHER = 2, LOOP_DENSE = 4 };
 
 // Runs the iteration loop on prepared device state (weights, base, X[0] = alpha_0, X[1] = X[2] = base).
 // On return *buf_out says which third of X holds the result.
@@ -840,7 +896,29 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
     const bool steps = sharded || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
     unsigned long long h_ctl[CTL_WORDS];
     SFB_CUDA(c, cudaEventRecord(c->ev0, s));
-    if (!steps && kind == LOOP_GATHER) {
+    if (!steps && kind == LOOP_DENSE) {
+        const DevPartition& P = c->cls.part;
+        DenseParams q;
+        q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
+        const size_t smem = (size_t)P.dense_smem;
+        void* args[] = {&p, &q};
+        const void* fn = nullptr;
+#define SFB_DENSE_CASE(N) case N: fn = vb ? reinterpret_cast<const void*>(&k_em_dense<true, N>) : reinterpret_cast<const void*>(&k_em_dense<false, N>); break;
+        switch (P.dense_ns) { SFB_DENSE_CASE(2) SFB_DENSE_CASE(3) SFB_DENSE_CASE(4) SFB_DENSE_CASE(5) SFB_DENSE_CASE(6) SFB_DENSE_CASE(7) SFB_DENSE_CASE(8)
+                              default: SFB_FAIL(c, SFB200_EINVAL, "dense EM: unexpected component size"); }
+#undef SFB_DENSE_CASE
+        SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(DENSE_THREADS), args, smem, s));
+        c->launches++;
+        SFB_CUDA(c, cudaEventRecord(c->ev1, s));
+        SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        *iters_out = static_cast<uint32_t>(h_ctl[CTL_ITERS]);
+        *buf_out = static_cast<unsigned>(h_ctl[CTL_RESULT_BUF]);
+        const unsigned long long mr = h_ctl[CTL_MRD];
+        double d; const unsigned long long b = mr ? mr - 1 : 0; std::memcpy(&d, &b, 8);
+        *mrd_out = mr ? d : -std::numeric_limits<double>::max();
+    } else if (!steps && kind == LOOP_GATHER) {
         const DevPartition& P = c->cls.part;
         GatherParams q;
         q.regions = P.gth.p; std::memcpy(&q.g, P.gth_geom, sizeof(q.g)); q.eff = c->eff.p;
@@ -990,12 +1068,13 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const char* mode_env = getenv("SFB200_EM_MODE");
     const bool sharded = c->n_ranks > 1 && !k.merged;      // rank-local classes: one all-reduce per iteration
     const bool steps_mode = sharded || !c->coop || (mode_env && std::strcmp(mode_env, "steps") == 0);
-    bool use_part = false, use_gather = false;
+    bool use_part = false, use_gather = false, use_dense = false;
     hm.mark("em: eff H2D + clamp");
     if (!steps_mode && k.Em) {
-        if (!k.part.valid || (gather_enabled() && !k.part.gather_tried)) { const int rc = build_partition(c); if (rc) return rc; }
-        use_gather = k.part.gather_ok && gather_enabled();                   // atomic-free loop (em_gather.cuh)
-        use_part = use_gather || k.part.usable;                              // both read the partition-ordered arrays
+        if (!k.part.valid || (gather_enabled() && !k.part.gather_tried) || (dense_enabled() && !k.part.dense_tried)) { const int rc = build_partition(c); if (rc) return rc; }
+        use_dense = k.part.dense_ok && dense_enabled();                      // one thread per component (em_dense.cuh)
+        use_gather = use_dense || (k.part.gather_ok && gather_enabled());    // atomic-free loop (em_gather.cuh)
+        use_part = use_gather || k.part.usable;                              // all read the partition-ordered arrays
         if (use_part && !use_gather && o->use_vb)                   // VBEM keeps expTheta in shared memory as well
             use_part = (k.part.max_cta_bytes_vb + 2048) * k.part.per_sm <= k.part.smem_limit + 1024 * (uint64_t)(k.part.per_sm - 1);
     }
@@ -1065,7 +1144,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     unsigned buf = 0;
     sfb200_em_opts oo = *o;
     oo.min_iter = spec.min_iter;
-    const int rc = run_loop(c, p, &oo, use_gather ? LOOP_GATHER : use_part ? LOOP_PART : LOOP_BINNED, iters_out, mrd_out, &buf);
+    const int rc = run_loop(c, p, &oo, use_dense ? LOOP_DENSE : use_gather ? LOOP_GATHER : use_part ? LOOP_PART : LOOP_BINNED, iters_out, mrd_out, &buf);
     if (rc) return rc;
     hm.mark("em: loop (launch .. sync)");
 

@@ -1,0 +1,208 @@
+// em_dense.cuh -- the EM loop for class structures that fall apart into small connected components (included by em.cu after
+// em_gather.cuh).
+//
+// k_em_gather was measured bound by shared-memory wavefronts: ~4000 per SM and iteration at cfg2, two thirds of them bank
+// conflicts of the f64 gathers (32 lanes read 32 unrelated transcripts / classes).  But the structure is far more local than a
+// CTA range: the isoforms of a gene and the classes over them form a connected component of a handful of transcripts.  When no
+// component has more than 8 transcripts (em_dense_build.inl checks that on the device), ONE THREAD owns a component:
+//   * its transcripts are slots 0..NS-1 and live in the thread's registers for the whole iteration (beta_j, accumulators);
+//   * a class is (count, slot mask): S_c = sum of beta over the mask, r_c = count_c / S_c, accumulate r_c into the masked slots
+//     (E-step and M-step of the component back to back, same arithmetic as k_em_gather);
+//   * everything a thread reads per class is one f64 and one byte, column-major over the 32 components of a warp tile:
+//     conflict-free, no gathers, no atomics, no shuffles and -- components being independent -- NO barrier inside an iteration.
+// CTA barriers and the grid barrier appear only where the reference needs a global quantity (the stopping rule, VBEM's
+// digamma(sum alpha)), exactly as in k_em_gather.  Transcripts outside every multi-member class ("idle") are constant after the
+// first iteration (alpha = count of their single-member class [+ prior]) and are only touched for that comparison and the result.
+
+#define SFB_GB_FN __device__ __forceinline__
+#define SFB_GB_TID threadIdx.x
+#define SFB_GB_NT blockDim.x
+#define SFB_GB_SYNC() __syncthreads()
+#define SFB_GB_ADD(p, v) atomicAdd((p), (v))
+#define SFB_GB_MAX(p, v) atomicMax((p), (v))
+#define SFB_GB_MIN(p, v) atomicMin((p), (v))
+#include "em_dense_build.inl"
+#undef SFB_GB_FN
+#undef SFB_GB_TID
+#undef SFB_GB_NT
+#undef SFB_GB_SYNC
+#undef SFB_GB_ADD
+#undef SFB_GB_MAX
+#undef SFB_GB_MIN
+
+__global__ void __launch_bounds__(256) k_dense_build(const uint32_t* __restrict__ start, const uint32_t* __restrict__ len,
+                                                     const uint32_t* __restrict__ lab, const unsigned long long* __restrict__ tbl,
+                                                     const DenseGeom g, uint32_t* __restrict__ regions) {
+    extern __shared__ __align__(16) uint32_t db_scratch[];
+    const unsigned long long* row = tbl + (size_t)blockIdx.x * PT_WORDS;
+    const uint32_t c_lo = (uint32_t)row[PT_CLS], nc = (uint32_t)(row[PT_CLS + SFB_NBINS] - row[PT_CLS]);
+    const uint32_t t0 = (uint32_t)row[PT_TXP0], nt = (uint32_t)(row[PT_TXP1] - row[PT_TXP0]);
+    dense_build_cta(start, len, lab, c_lo, nc, t0, nt, g, regions + (size_t)blockIdx.x * g.region_words, db_scratch);
+}
+
+struct DenseParams {
+    const uint32_t* regions;
+    DenseGeom g;
+    const double* eff;        // T clamped effective lengths
+};
+
+constexpr int DENSE_THREADS = 256;
+
+// shared memory a CTA of k_em_dense needs (mirrored on the host)
+__host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns) {
+    const uint64_t ncomp_pad = (uint64_t)tiles << 5;
+    return (uint64_t)((ent + 1u) & ~1u) * 8 + 4 * (uint64_t)ns * ncomp_pad * 8 + 2 * (uint64_t)((tiles + 3u) & ~3u) * 4 + (uint64_t)((ent + 15u) & ~15u);
+}
+
+template <bool VB, int NS>
+__global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p, const DenseParams q) {
+    __shared__ unsigned long long sm_u[32];
+    __shared__ double sm_d[32];
+    __shared__ uint64_t tma_bar;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const unsigned nblocks = gridDim.x;
+    unsigned long long gen = 0;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+
+    const uint32_t* region = q.regions + (size_t)blockIdx.x * q.g.region_words;
+    const uint32_t tiles = region[DH_TILES], ent = region[DH_ENT], nidle = region[DH_NIDLE];
+    const uint32_t ncomp_pad = tiles << 5;
+    double* s_cnt = reinterpret_cast<double*>(dyn_smem);                         // ent (even)
+    double* s_beta = s_cnt + ((ent + 1u) & ~1u);                                  // [NS][ncomp_pad] each
+    double* s_alpha = s_beta + (size_t)NS * ncomp_pad;
+    double* s_base = s_alpha + (size_t)NS * ncomp_pad;
+    double* s_inveff = s_base + (size_t)NS * ncomp_pad;
+    uint32_t* s_toff = reinterpret_cast<uint32_t*>(s_inveff + (size_t)NS * ncomp_pad);
+    uint32_t* s_tlen = s_toff + ((tiles + 3u) & ~3u);
+    uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_tlen + ((tiles + 3u) & ~3u));  // ent (padded to 16)
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&tma_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t b_t = ((tiles + 3u) & ~3u) * 4u, b_m = (ent + 15u) & ~15u;
+    const uint32_t tx_bytes = 2u * b_t + b_m;
+    if (tx_bytes && threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&tma_bar)), "r"(tx_bytes) : "memory");
+        if (b_t) { tma_load_1d(s_toff, region + q.g.o_tile_off, b_t, &tma_bar); tma_load_1d(s_tlen, region + q.g.o_tile_len, b_t, &tma_bar); }
+        if (b_m) tma_load_1d(s_mask, region + q.g.o_mask, b_m, &tma_bar);
+    }
+    // per-run vectors through the index maps while the bulk copies fly
+    const uint32_t* cperm = region + q.g.o_cperm;
+    const uint32_t* tmap = region + q.g.o_tmap;
+    const uint32_t* idle = region + q.g.o_idle;
+    for (uint32_t i = threadIdx.x; i < ent; i += blockDim.x) { const uint32_t c = cperm[i]; s_cnt[i] = c != DN_NONE ? p.cnt[c] : 0.0; }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) {
+        // the region stores [slot][component] for DN_MAX_SLOTS slots; a run with NS < DN_MAX_SLOTS reads the first NS rows
+        const uint32_t t = tmap[i];
+        double a = 0.0, b = 0.0, ie = 0.0;
+        if (t != DN_NONE) { a = p.X[t]; b = p.base[t]; ie = 1.0 / q.eff[t]; }
+        s_alpha[i] = a; s_base[i] = b; s_inveff[i] = ie;
+    }
+    // idle transcripts: constant from the first iteration on; their sum feeds VBEM's alpha sum
+    double idle_sum = 0.0;
+    if (VB) for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) idle_sum += p.base[idle[i]];
+    if (tx_bytes) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n selp.u32 %0, 1, 0, q;\n}"
+                         : "=r"(done) : "r"(smem_u32(&tma_bar)) : "memory");
+        }
+    }
+    __syncthreads();
+
+    const bool fixed = p.fixed_iters > 0;
+    {
+        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) {
+            const double a = s_alpha[i];
+            const double th = VB ? ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) : a;
+            s_beta[i] = th * s_inveff[i];
+        }
+    }
+    __syncthreads();
+    uint32_t n = 0;
+    unsigned long long mr_final = 0ULL;
+    for (;;) {
+        if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
+        const uint32_t m = n + 1;
+        const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
+        unsigned long long best = 0ULL;
+        double asum = 0.0;
+        // ---- one EM iteration of every component of this warp's tiles (tile -> warp is fixed, so a tile's state is only ever
+        //      touched by its own warp: no barrier)
+        for (uint32_t k = warp; k < tiles; k += W) {
+            const uint32_t qi = (k << 5) + lane;
+            double b[NS], acc[NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { b[j] = s_beta[(size_t)j * ncomp_pad + qi]; acc[j] = 0.0; }
+            const uint32_t L = s_tlen[k];
+            const double* cn = s_cnt + s_toff[k] + lane;
+            const uint8_t* mk = s_mask + s_toff[k] + lane;
+#pragma unroll 2
+            for (uint32_t e = 0; e < L; ++e) {
+                const double cnt = cn[e << 5];
+                const uint32_t msk = mk[e << 5];
+                double S = 0.0;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) S += ((msk >> j) & 1u) ? b[j] : 0.0;          // members in transcript order
+                const double r = em_ratio(cnt, S);
+#pragma unroll
+                for (int j = 0; j < NS; ++j) acc[j] += ((msk >> j) & 1u) ? r : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const size_t i = (size_t)j * ncomp_pad + qi;
+                const double a_old = s_alpha[i];
+                const double a_new = b[j] * acc[j] + s_base[i];
+                if (do_cmp) {
+                    const double gate = p.gate_old ? a_old : a_new;
+                    if (gate > p.cutoff) {
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                        best = bits > best ? bits : best;
+                    }
+                }
+                s_alpha[i] = a_new;
+                if (VB) asum += a_new; else s_beta[i] = a_new * s_inveff[i];
+            }
+        }
+        n = m;
+        if (VB || do_cmp) {
+            if (do_cmp) {                                              // idle transcripts: alpha_0 -> base at m == 1, base -> base after
+                for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) {
+                    const uint32_t t = idle[i];
+                    const double a_new = p.base[t];
+                    const double a_old = (m == 1) ? p.X[t] : a_new;
+                    const double gate = p.gate_old ? a_old : a_new;
+                    if (gate > p.cutoff) {
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                        best = bits > best ? bits : best;
+                    }
+                }
+            }
+            unsigned long long* slot = p.ctl + CTL_MAXREL + (m & 3u);
+            double* csum = reinterpret_cast<double*>(p.ctl + CTL_CSUM + (m & 3u));
+            if (do_cmp) block_max_to_slot(best, slot, sm_u);
+            if (VB) block_sum_to_slot(asum + idle_sum, csum, sm_d);
+            grid_barrier(p.ctl, nblocks, gen);
+            if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctl[CTL_MAXREL + ((m + 3u) & 3u)] = 0ULL; p.ctl[CTL_CSUM + ((m + 3u) & 3u)] = 0ULL; }
+            if (do_cmp) {
+                mr_final = ld_cg_u64(slot);
+                if (fixed) break;
+                if (!(decode_mrd(mr_final) > p.tol) || m >= p.max_iter) break;
+            }
+            if (VB) {
+                const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
+                for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) {
+                    const double a = s_alpha[i];
+                    s_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) * s_inveff[i];
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctl[CTL_ITERS] = n; p.ctl[CTL_RESULT_BUF] = 0ULL; p.ctl[CTL_MRD] = mr_final; }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) { const uint32_t t = tmap[i]; if (t != DN_NONE) p.X[t] = s_alpha[i]; }
+    if (n > 0) for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) { const uint32_t t = idle[i]; p.X[t] = p.base[t]; }
+}

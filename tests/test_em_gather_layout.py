@@ -12,3 +12,12 @@ def test_gather_layout_and_iteration(tmp_path):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "em_gather_layout_test.cpp")])
     out = subprocess.check_output([exe]).decode()
     assert "em_gather layout ok" in out
+
+
+def test_dense_layout_and_iteration(tmp_path):
+    """the dense-component layout (sailfish_b200/csrc/em_dense_build.inl): components, slots, masks, and the per-component
+    iteration of k_em_dense against the reference-shaped update -- see tests/em_dense_layout_test.cpp"""
+    exe = str(tmp_path / "em_dense_layout_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "em_dense_layout_test.cpp")])
+    out = subprocess.check_output([exe]).decode()
+    assert "em_dense layout ok" in out

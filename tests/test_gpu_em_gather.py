@@ -1,8 +1,10 @@
-"""GPU parity tests (-m gpu) of the atomic-free EM loop k_em_gather (sailfish_b200/csrc/em_gather.cuh) through the C ABI.
+"""GPU parity tests (-m gpu) of the atomic-free EM loops through the C ABI: k_em_gather (sailfish_b200/csrc/em_gather.cuh, one
+thread per class / per transcript over a transposed layout) and k_em_dense (em_dense.cuh, one thread per connected component).
 
-The loop runs when every multi-member class is local to one CTA's transcript range (gene-local classes: the BASELINE
-workloads); these tests assert that it is the kernel that ran (sfb200_last_em_kernel == 2) and compare it with the oracle
-(= the reference's CollapsedEMOptimizer restated) within the north_star tolerance, and with the scatter-form kernels."""
+They run when every multi-member class is local to one CTA's transcript range (gene-local classes: the BASELINE workloads),
+k_em_dense additionally needs components of at most 8 transcripts.  Every test runs once per loop, asserts that it is the
+kernel that ran (sfb200_last_em_kernel == 2 / 4) and compares it with the oracle (= the reference's CollapsedEMOptimizer
+restated) within the north_star tolerance, and with the scatter-form kernels."""
 import numpy as np
 import pytest
 
@@ -12,12 +14,14 @@ from sailfish_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-4, 1e-6
-GATHER = 2
+GATHER, DENSE = 2, 4
 
 
-@pytest.fixture(autouse=True)
-def gather_on(monkeypatch):
+@pytest.fixture(autouse=True, params=["gather", "dense"])
+def loop_kind(request, monkeypatch):
     monkeypatch.setenv("SFB200_EM_GATHER", "1")
+    monkeypatch.setenv("SFB200_EM_DENSE", "1" if request.param == "dense" else "0")
+    return DENSE if request.param == "dense" else GATHER
 
 
 def close(a, b, rtol=RTOL, atol=ATOL):
@@ -26,13 +30,13 @@ def close(a, b, rtol=RTOL, atol=ATOL):
 
 @pytest.mark.parametrize("vb", [0, 1])
 @pytest.mark.parametrize("T,E", [(5000, 12000), (60000, 150000), (300, 700)])
-def test_gather_loop_converges_like_the_oracle(ctx, vb, T, E):
+def test_gather_loop_converges_like_the_oracle(ctx, vb, T, E, loop_kind):
     rp, lab, cnt = synth.make_classes(T, E, seed=T + vb)                    # members stay inside a 5-transcript gene
     eff = np.random.default_rng(T).uniform(0.5, 4000, size=T)
     nm = int(cnt.sum())
     ctx.eq_import(T, rp, lab, cnt)
     a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
-    assert ctx.last_em_kernel() == GATHER
+    assert ctx.last_em_kernel() == loop_kind
     rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb), n_threads=4)
     assert rc == 0 and it == it_o
     close(a, want)
@@ -42,14 +46,14 @@ def test_gather_loop_converges_like_the_oracle(ctx, vb, T, E):
 
 @pytest.mark.parametrize("vb", [0, 1])
 @pytest.mark.parametrize("fixed", [1, 2, 49, 50, 51, 400])
-def test_gather_loop_fixed_iterations(ctx, vb, fixed):
+def test_gather_loop_fixed_iterations(ctx, vb, fixed, loop_kind):
     T = 8000
     rp, lab, cnt = synth.make_classes(T, 20000, seed=3 + fixed)
     eff = np.random.default_rng(fixed).uniform(50, 4000, size=T)
     nm = int(cnt.sum())
     ctx.eq_import(T, rp, lab, cnt)
     a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb, fixed_iters=fixed))
-    assert ctx.last_em_kernel() == GATHER
+    assert ctx.last_em_kernel() == loop_kind
     rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, fixed_iters=fixed))
     assert rc == 0 and it == fixed == it_o
     close(a, want)
@@ -57,7 +61,7 @@ def test_gather_loop_fixed_iterations(ctx, vb, fixed):
     assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
 
 
-def test_gather_loop_iteration_limits(ctx):
+def test_gather_loop_iteration_limits(ctx, loop_kind):
     """the loop rule (CollapsedEMOptimizer.cpp:820): itNum < minIter || (itNum < maxIter && !converged)"""
     T = 2000
     rp, lab, cnt = synth.make_classes(T, 5000, seed=12)
@@ -66,13 +70,13 @@ def test_gather_loop_iteration_limits(ctx):
     ctx.eq_import(T, rp, lab, cnt)
     for kw in (dict(max_iter=7, min_iter=3), dict(max_iter=5, min_iter=20), dict(min_iter=0, max_iter=10000), dict(tol=1e-5)):
         a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(**kw))
-        assert ctx.last_em_kernel() == GATHER
+        assert ctx.last_em_kernel() == loop_kind
         rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(**kw))
         assert rc == 0 and it == it_o, kw
         close(a, want)
 
 
-def test_gather_loop_equals_scatter_kernels(ctx, monkeypatch):
+def test_gather_loop_equals_scatter_kernels(ctx, monkeypatch, loop_kind):
     T = 30000
     rp, lab, cnt = synth.make_classes(T, 70000, seed=5)
     eff = np.random.default_rng(1).uniform(100, 3000, size=T)
@@ -80,19 +84,19 @@ def test_gather_loop_equals_scatter_kernels(ctx, monkeypatch):
     ctx.eq_import(T, rp, lab, cnt)
     for vb in (0, 1):
         a1, it1, m1 = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
-        assert ctx.last_em_kernel() == GATHER
-        monkeypatch.setenv("SFB200_EM_GATHER", "0")
+        assert ctx.last_em_kernel() == loop_kind
+        monkeypatch.setenv("SFB200_EM_GATHER", "0"); monkeypatch.setenv("SFB200_EM_DENSE", "0")
         a2, it2, m2 = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
         assert ctx.last_em_kernel() == 1                                  # k_em_part
-        monkeypatch.setenv("SFB200_EM_GATHER", "1")
+        monkeypatch.setenv("SFB200_EM_GATHER", "1"); monkeypatch.setenv("SFB200_EM_DENSE", "1" if loop_kind == DENSE else "0")
         assert it1 == it2
         close(a1, a2, rtol=1e-7)
         assert abs(m1 - m2) <= 1e-6 * abs(m2)
 
 
-def test_gather_loop_duplicate_ids_long_classes_and_idle_transcripts(ctx):
+def test_gather_loop_duplicate_ids_long_classes_and_idle_transcripts(ctx, loop_kind):
     """labels with a repeated transcript id (orphan pairs) and transcripts that belong to no class or only to
-    single-member classes"""
+    single-member classes; a slot mask has no multiplicity, so k_em_dense hands such class sets to k_em_gather"""
     rng = np.random.default_rng(4)
     T = 4000
     labels = {}
@@ -121,7 +125,7 @@ def test_gather_loop_duplicate_ids_long_classes_and_idle_transcripts(ctx):
 
 
 @pytest.mark.parametrize("vb", [0, 1])
-def test_gather_loop_bootstrap_counts(ctx, vb):
+def test_gather_loop_bootstrap_counts(ctx, vb, loop_kind):
     """doBootstrap's loop (gate on the OLD alpha, no minimum) on resampled counts, including classes resampled to 0"""
     T = 6000
     rp, lab, cnt = synth.make_classes(T, 15000, seed=31)
@@ -131,13 +135,13 @@ def test_gather_loop_bootstrap_counts(ctx, vb):
     assert (samp == 0).any()
     ctx.eq_import(T, rp, lab, cnt)
     a, it = ctx.bootstrap_em(eff, samp, capi.EMOpts.default(use_vb=vb))
-    assert ctx.last_em_kernel() == GATHER
+    assert ctx.last_em_kernel() == loop_kind
     rc, want, it_o = O.bootstrap_em(T, rp, lab, samp, eff, O.EMOpts.default(use_vb=vb))
     assert rc == 0 and it == it_o
     close(a, want)
 
 
-def test_gather_loop_after_device_side_finish(ctx):
+def test_gather_loop_after_device_side_finish(ctx, loop_kind):
     """mapping -> device-side class flatten -> partition -> gather layout -> EM, against the oracle on the same reads"""
     seq, off, ln = synth.make_transcriptome(400, seed=15)
     b1, o1, _, _, _ = synth.make_reads(seq, off, ln, 60000, 76, seed=16)
@@ -151,10 +155,35 @@ def test_gather_loop_after_device_side_finish(ctx):
     nm = int(g["counters"][1])
     for vb in (0, 1):
         a, it, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
-        assert ctx.last_em_kernel() == GATHER
+        assert ctx.last_em_kernel() == loop_kind
         rc, want, it_o, _ = O.em_run(len(ln), rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb))
         assert rc == 0 and it == it_o
         close(a, want)
     rows = ctx.bootstrap_run(eff, 3, seed=5)
-    assert ctx.last_em_kernel() == GATHER
+    assert ctx.last_em_kernel() == loop_kind
     np.testing.assert_allclose(rows.sum(axis=1), int(cnt.sum()), rtol=1e-9)
+
+
+def test_dense_loop_component_sizes(ctx, loop_kind):
+    """components of exactly 8 transcripts run on one thread; 9 do not (the gather loop takes over); genes of 2 and 3 too"""
+    for gene, want in ((8, loop_kind), (9, GATHER), (2, loop_kind), (3, loop_kind)):
+        T = 40 * gene * 10
+        n_cls = min(25 * T // gene, (T // gene) * (2 ** gene - 1) // 2)          # at most half of the subsets of every gene
+        rp, lab, cnt = synth.make_classes(T, n_cls, seed=gene, gene_size=gene, max_len=gene)
+        # one class spanning the whole gene, so that the component really has `gene` transcripts
+        labs = {tuple(int(x) for x in lab[int(rp[i]):int(rp[i + 1])]): int(cnt[i]) for i in range(len(cnt))}
+        for g0 in range(0, T, gene):
+            labs[tuple(range(g0, g0 + gene))] = 7
+        keys = sorted(labs)
+        rp = np.zeros(len(keys) + 1, np.uint64); rp[1:] = np.cumsum([len(k) for k in keys])
+        lab = np.array([t for k in keys for t in k], np.uint32); cnt = np.array([labs[k] for k in keys], np.uint64)
+        eff = np.random.default_rng(gene).uniform(100, 3000, size=T)
+        nm = int(cnt.sum())
+        ctx.eq_import(T, rp, lab, cnt)
+        for vb in (0, 1):
+            a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+            assert ctx.last_em_kernel() == want, (gene, ctx.last_em_kernel())
+            rc, ref, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb), n_threads=4)
+            assert rc == 0 and it == it_o
+            close(a, ref)
+            assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
