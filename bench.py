@@ -375,7 +375,7 @@ def main():
     # EM roofline: B_em = 12 nnz + 12 E + 32 T bytes per iteration
     b_em = 12.0 * nnz + 12.0 * E + 32.0 * T
     em_gbs = b_em * args.em_iters / (em_ms / args.steps / 1e3) / 1e9
-    em_kernel = ["k_em_persistent", "k_em_part", "k_em_gather", "k_em_transcript_pass+k_em_sweep"][ctx.last_em_kernel()]
+    em_kernel = ["k_em_persistent", "k_em_part", "k_em_gather", "k_em_transcript_pass+k_em_sweep", "k_em_dense"][ctx.last_em_kernel()]
     line["em_roofline"] = {"bound": "hbm", "achieved": em_gbs, "peak": peak, "unit": "GB/s", "frac": em_gbs / peak,
                            "bytes_per_iter": b_em, "kernel": em_kernel,
                            "note": "algorithmic bytes (SURVEY 8d) over time; the %.0f MB working set is staged in shared memory once, so no HBM traffic after the first iteration" % (b_em / 1e6)}

@@ -49,12 +49,15 @@ struct DenseParams {
 constexpr int DENSE_THREADS = 256;
 
 // shared memory a CTA of k_em_dense needs (mirrored on the host)
-__host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns) {
-    const uint64_t ncomp_pad = (uint64_t)tiles << 5;
+__host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns, uint32_t group) {
+    const uint64_t ncomp_pad = ((uint64_t)tiles << 5) / group;
     return (uint64_t)((ent + 1u) & ~1u) * 8 + 4 * (uint64_t)ns * ncomp_pad * 8 + 2 * (uint64_t)((tiles + 3u) & ~3u) * 4 + (uint64_t)((ent + 15u) & ~15u);
 }
 
-template <bool VB, int NS>
+// G lanes share a component: each takes every G-th class of it (all G hold the component's beta), the accumulators are summed
+// over the group with shuffles, lane 0 of the group writes the component's new state.  The longest class list of a tile sets
+// the pace of its warp, and nothing else runs on that warp: G = 4 shortens that list fourfold for 10 shuffles per slot.
+template <bool VB, int NS, int G>
 __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p, const DenseParams q) {
     __shared__ unsigned long long sm_u[32];
     __shared__ double sm_d[32];
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
 
     const uint32_t* region = q.regions + (size_t)blockIdx.x * q.g.region_words;
     const uint32_t tiles = region[DH_TILES], ent = region[DH_ENT], nidle = region[DH_NIDLE];
-    const uint32_t ncomp_pad = tiles << 5;
+    const uint32_t ncomp_pad = (tiles << 5) / G;
     double* s_cnt = reinterpret_cast<double*>(dyn_smem);                         // ent (even)
     double* s_beta = s_cnt + ((ent + 1u) & ~1u);                                  // [NS][ncomp_pad] each
     double* s_alpha = s_beta + (size_t)NS * ncomp_pad;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
         // ---- one EM iteration of every component of this warp's tiles (tile -> warp is fixed, so a tile's state is only ever
         //      touched by its own warp: no barrier)
         for (uint32_t k = warp; k < tiles; k += W) {
-            const uint32_t qi = (k << 5) + lane;
+            const uint32_t qi = k * (32u / G) + lane / G;
             double b[NS], acc[NS];
 #pragma unroll
             for (int j = 0; j < NS; ++j) { b[j] = s_beta[(size_t)j * ncomp_pad + qi]; acc[j] = 0.0; }
@@ -149,6 +152,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                 const double r = em_ratio(cnt, S);
 #pragma unroll
                 for (int j = 0; j < NS; ++j) acc[j] += ((msk >> j) & 1u) ? r : 0.0;
+            }
+            if (G > 1) {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+#pragma unroll
+                    for (int o = 1; o < G; o <<= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+                }
+                if (lane % G) continue;                                // the group's first lane owns the component's state
             }
 #pragma unroll
             for (int j = 0; j < NS; ++j) {

@@ -28,13 +28,15 @@ struct DenseGeom {
     uint32_t cap_tiles;      // component tiles a region has room for
     uint32_t cap_ent;        // class entries (padded) a region has room for
     uint32_t cap_nt;         // transcripts
-    uint32_t pad_[6];
+    uint32_t group;          // lanes per component (1, 2 or 4): a component's classes are dealt round-robin to its lanes
+    uint32_t pad_[5];
 };
-enum { DH_KIND = 0, DH_NCOMP, DH_TILES, DH_ENT, DH_NS, DH_NIDLE, DH_NT, DH_NC, DH_ROUNDS, DH_WORDS = 16 };
-inline DenseGeom dense_make_geom(uint64_t max_nc, uint64_t max_nt) {
+enum { DH_KIND = 0, DH_NCOMP, DH_TILES, DH_ENT, DH_NS, DH_NIDLE, DH_NT, DH_NC, DH_ROUNDS, DH_GROUP, DH_WORDS = 16 };
+inline DenseGeom dense_make_geom(uint64_t max_nc, uint64_t max_nt, uint32_t group = 1) {
     auto up = [](uint64_t x, uint64_t m) { return (uint32_t)((x + m - 1) / m * m); };
     DenseGeom g;
-    g.cap_tiles = up(max_nt / 2 / 32 + 2, 4);                 // a component has at least two transcripts
+    g.group = (group == 2 || group == 4) ? group : 1;
+    g.cap_tiles = up(max_nt / 2 * g.group / 32 + 2, 4);       // a component has at least two transcripts
     g.cap_ent = up(max_nc + 64 * DN_BUCKETS, 16);
     g.cap_nt = up(max_nt + 1, 4);
     uint32_t o = DH_WORDS;
@@ -45,7 +47,7 @@ inline DenseGeom dense_make_geom(uint64_t max_nc, uint64_t max_nt) {
     g.o_tmap = o; o += DN_MAX_SLOTS * 32 * g.cap_tiles;
     g.o_idle = o; o += g.cap_nt;
     g.region_words = o;
-    for (int i = 0; i < 6; ++i) g.pad_[i] = 0;
+    for (int i = 0; i < 5; ++i) g.pad_[i] = 0;
     return g;
 }
 // scratch words dense_build_cta needs
@@ -127,14 +129,15 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
     }
     SFB_GB_SYNC();
     const uint32_t ncomp = s_misc[3];
-    const uint32_t tiles = (ncomp + 31u) >> 5, ncomp_pad = tiles << 5;
+    const uint32_t G = g.group;
+    const uint32_t tiles = (ncomp * G + 31u) >> 5, ncomp_pad = (tiles << 5) / G;      // 32 / G components per warp tile
     if (tiles > g.cap_tiles) return;
     for (uint32_t t = tid; t < nt; t += nth) {
         if (s_deg[t] && s_comp[t] == t) {
             const uint32_t cc = s_ccnt[t];
             const uint32_t q = SFB_GB_ADD(s_hist + (cc < DN_BUCKETS ? cc : DN_BUCKETS - 1), 1u);
             s_q[t] = q;
-            SFB_GB_MAX(s_tlen + (q >> 5), cc);
+            SFB_GB_MAX(s_tlen + ((q * G) >> 5), (cc + G - 1) / G);       // rows of the tile: a lane takes every G-th class
         }
     }
     SFB_GB_SYNC();
@@ -172,14 +175,14 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
             if (mk & bit) s_misc[0] = 0;                                // the same transcript twice in one label
             mk |= bit;
         }
-        const uint32_t pos = s_toff[q >> 5] + (e << 5) + (q & 31u);
+        const uint32_t pos = s_toff[(q * G) >> 5] + ((e / G) << 5) + ((q * G) & 31u) + (e % G);
         cperm[pos] = c_lo + c;
         mask[pos] = (uint8_t)mk;
     }
     SFB_GB_SYNC();
     if (tid == 0) {
         hdr[DH_NCOMP] = ncomp; hdr[DH_TILES] = tiles; hdr[DH_ENT] = ent; hdr[DH_NS] = s_misc[2]; hdr[DH_NIDLE] = s_misc[4];
-        hdr[DH_NT] = nt; hdr[DH_NC] = nc; hdr[DH_ROUNDS] = rounds + 1;
+        hdr[DH_NT] = nt; hdr[DH_NC] = nc; hdr[DH_ROUNDS] = rounds + 1; hdr[DH_GROUP] = G;
         hdr[DH_KIND] = s_misc[0] ? 1u : 0u;
     }
 }

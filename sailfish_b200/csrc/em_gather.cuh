@@ -108,18 +108,22 @@ __device__ __forceinline__ double col_sum(const uint16_t* __restrict__ col, cons
 }
 
 // count / S for the E-step: hardware reciprocal seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (<= 2 ulp; the path's
-// tolerance is 1e-4) while S is comfortably normal; the exact quotient otherwise (0 for a vanishing denominator, :260)
+// tolerance is 1e-4) while S is comfortably normal.  Branch-free for the two cases that occur -- a normal S and S == 0 (padding
+// entries, classes whose members all vanished: ratio 0, :260) -- and an out-of-line exact quotient for a denormal or huge S,
+// so that a warp with some zero denominators does not walk through a division.
+__device__ __noinline__ double em_ratio_rare(double cnt, double S) { return (S > DENORM_MIN) ? cnt / S : 0.0; }
 __device__ __forceinline__ double em_ratio(double cnt, double S) {
-    if (S > 1e-280 && S < 1e280) {
-        double y;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(S));
-        double e = fma(-S, y, 1.0);
-        y = fma(y, e, y);
-        e = fma(-S, y, 1.0);
-        y = fma(y, e, y);
-        return cnt * y;
-    }
-    return (S > DENORM_MIN) ? cnt / S : 0.0;
+    const bool normal = S > 1e-280 && S < 1e280;
+    const double Ss = normal ? S : 1.0;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(Ss));
+    double e = fma(-Ss, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-Ss, y, 1.0);
+    y = fma(y, e, y);
+    double r = normal ? cnt * y : 0.0;
+    if (!normal && S != 0.0) r = em_ratio_rare(cnt, S);
+    return r;
 }
 
 template <bool VB, int SHIFT>

@@ -13,5 +13,7 @@ if [ $G -ne 0 ]; then
       -k "fixed_iterations and dense-2-0" > $OUT/${TAG}_memcheck.log 2>&1
   tail -30 $OUT/${TAG}_memcheck.log | cut -c1-300
 fi
-SFB200_EM_DENSE=1 SFB200_VERBOSE=1 SFB200_TIMING=1 timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.log
-echo "bench (dense) rc=$?  ($(( $(date +%s) - t0 )) s)"; python scripts/show_bench.py $OUT/${TAG}_bench.json; grep -E "dense|timing" $OUT/${TAG}_bench.log | tail -14
+for grp in 4 1 2; do
+  SFB200_EM_DENSE=1 SFB200_EM_DENSE_GROUP=$grp SFB200_VERBOSE=1 timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench_g$grp.json 2> $OUT/${TAG}_bench_g$grp.log
+  echo "bench (dense, $grp lanes per component) rc=$?  ($(( $(date +%s) - t0 )) s)"; python scripts/show_bench.py $OUT/${TAG}_bench_g$grp.json; grep -E "dense" $OUT/${TAG}_bench_g$grp.log | tail -1
+done

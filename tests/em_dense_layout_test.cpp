@@ -63,11 +63,12 @@ static Slice make_slice(std::mt19937_64& rng, uint32_t n_genes, uint32_t gsize, 
     return s;
 }
 
-static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cpg, bool chain, bool dup, uint32_t idle_every, bool expect_dense, bool vb) {
+static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cpg, bool chain, bool dup, uint32_t idle_every, bool expect_dense, bool vb, uint32_t G) {
     std::mt19937_64 rng(seed);
     Slice s = make_slice(rng, n_genes, gsize, cpg, chain, dup, idle_every);
     const uint32_t nc = s.nc, nt = s.nt;
-    const DenseGeom g = dense_make_geom(nc, nt);
+    const DenseGeom g = dense_make_geom(nc, nt, G);
+    CHECK(g.group == G, "group");
     CHECK(g.region_words % 4 == 0 && g.o_mask % 4 == 0 && g.o_tmap % 4 == 0 && g.o_idle % 4 == 0 && g.o_cperm % 4 == 0, "geometry alignment");
     std::vector<uint32_t> region(g.region_words + 8, 0xDEADBEEFu), scratch(dense_scratch_words(nt, g) + 8, 0xABABABABu);
     for (int i = 0; i < 8; ++i) region[g.region_words + i] = 0x13572468u;
@@ -77,9 +78,10 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
     const uint32_t* h = region.data();
     CHECK((h[DH_KIND] == 1) == expect_dense, "kind %u, expected %d", h[DH_KIND], (int)expect_dense);
     if (!expect_dense) return 0;
-    const uint32_t ncomp = h[DH_NCOMP], tiles = h[DH_TILES], ent = h[DH_ENT], NS = h[DH_NS], nidle = h[DH_NIDLE], ncomp_pad = tiles * 32;
+    const uint32_t ncomp = h[DH_NCOMP], tiles = h[DH_TILES], ent = h[DH_ENT], NS = h[DH_NS], nidle = h[DH_NIDLE], ncomp_pad = tiles * 32 / G;
+    CHECK(h[DH_GROUP] == G, "header group");
     CHECK(ncomp == 0 ? NS == 0 : (NS >= 2 && NS <= DN_MAX_SLOTS && NS <= gsize), "slots %u", NS);
-    CHECK(tiles == (ncomp + 31) / 32 && ent <= g.cap_ent, "tiles / entries");
+    CHECK(tiles == (ncomp * G + 31) / 32 && ent <= g.cap_ent, "tiles / entries");
     const uint32_t* toff = h + g.o_tile_off; const uint32_t* tlen = h + g.o_tile_len; const uint32_t* cperm = h + g.o_cperm;
     const uint8_t* mask = reinterpret_cast<const uint8_t*>(h + g.o_mask);
     const uint32_t* tmap = h + g.o_tmap; const uint32_t* idle = h + g.o_idle;
@@ -104,7 +106,7 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
     for (uint32_t k = 0; k < tiles; ++k)
         for (uint32_t e = 0; e < tlen[k]; ++e)
             for (uint32_t lane = 0; lane < 32; ++lane) {
-                const uint32_t pos = toff[k] + 32 * e + lane, c = cperm[pos], q = 32 * k + lane;
+                const uint32_t pos = toff[k] + 32 * e + lane, c = cperm[pos], q = k * (32 / G) + lane / G;
                 if (c == DN_NONE) { CHECK(mask[pos] == 0, "padding entry with a mask"); continue; }
                 CHECK(c >= s.c_lo && c < s.c_lo + nc, "cperm range"); seen_c[c - s.c_lo]++;
                 uint32_t want = 0;
@@ -158,20 +160,30 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
             if (vb) { double sum = 0.0; for (double a : s_alpha) sum += a; for (double a : idle_alpha) sum += a; ln = digamma(sum); }
             for (uint32_t i = 0; i < NS * ncomp_pad; ++i) { const double a = s_alpha[i]; s_beta[i] = (vb ? (a > 0 ? std::exp(digamma(a) - ln) : 0.0) : a) * s_inveff[i]; }
         }
-        for (uint32_t k = 0; k < tiles; ++k)
-            for (uint32_t lane = 0; lane < 32; ++lane) {
-                const uint32_t qi = 32 * k + lane;
-                double b[DN_MAX_SLOTS], acc[DN_MAX_SLOTS];
-                for (uint32_t j = 0; j < NS; ++j) { b[j] = s_beta[j * ncomp_pad + qi]; acc[j] = 0.0; }
+        for (uint32_t k = 0; k < tiles; ++k) {
+            double accs[32][DN_MAX_SLOTS], bs[32][DN_MAX_SLOTS];
+            for (uint32_t lane = 0; lane < 32; ++lane) {                // every lane: the classes of its column
+                const uint32_t qi = k * (32 / G) + lane / G;
+                for (uint32_t j = 0; j < NS; ++j) { bs[lane][j] = s_beta[j * ncomp_pad + qi]; accs[lane][j] = 0.0; }
                 for (uint32_t e = 0; e < tlen[k]; ++e) {
                     const double c = s_cnt[toff[k] + 32 * e + lane]; const uint32_t msk = mask[toff[k] + 32 * e + lane];
                     double S = 0.0;
-                    for (uint32_t j = 0; j < NS; ++j) S += ((msk >> j) & 1u) ? b[j] : 0.0;
+                    for (uint32_t j = 0; j < NS; ++j) S += ((msk >> j) & 1u) ? bs[lane][j] : 0.0;
                     const double r = S > 0.0 ? c / S : 0.0;
-                    for (uint32_t j = 0; j < NS; ++j) acc[j] += ((msk >> j) & 1u) ? r : 0.0;
+                    for (uint32_t j = 0; j < NS; ++j) accs[lane][j] += ((msk >> j) & 1u) ? r : 0.0;
                 }
-                for (uint32_t j = 0; j < NS; ++j) s_alpha[j * ncomp_pad + qi] = b[j] * acc[j] + s_base[j * ncomp_pad + qi];
             }
+            for (uint32_t j = 0; j < NS; ++j)                           // butterfly over the lanes of a group
+                for (uint32_t o = 1; o < G; o <<= 1) {
+                    double tmp[32];
+                    for (uint32_t lane = 0; lane < 32; ++lane) tmp[lane] = accs[lane][j] + accs[lane ^ o][j];
+                    for (uint32_t lane = 0; lane < 32; ++lane) accs[lane][j] = tmp[lane];
+                }
+            for (uint32_t lane = 0; lane < 32; lane += G) {             // the group's first lane owns the state
+                const uint32_t qi = k * (32 / G) + lane / G;
+                for (uint32_t j = 0; j < NS; ++j) s_alpha[j * ncomp_pad + qi] = bs[lane][j] * accs[lane][j] + s_base[j * ncomp_pad + qi];
+            }
+        }
         for (uint32_t i = 0; i < nidle; ++i) idle_alpha[i] = single[idle[i]] + prior;
         for (uint32_t i = 0; i < NS * ncomp_pad; ++i) {
             const uint32_t t = tmap[i];
@@ -196,8 +208,9 @@ int main() {
         {8, 700, 3, 300, false, false, 3, true, false},  // many components, class counts beyond one bucket width
         {9, 5, 5, 3, false, false, 1, true, false},      // no class at all (every gene silent): zero components
     };
+    for (uint32_t G : {1u, 2u, 4u})
     for (const Case& c : cases)
-        if (run_case(c.seed, c.n_genes, c.gsize, c.cpg, c.chain, c.dup, c.idle_every, c.dense, c.vb)) { fprintf(stderr, "case seed %llu failed\n", (unsigned long long)c.seed); return 1; }
+        if (run_case(c.seed, c.n_genes, c.gsize, c.cpg, c.chain, c.dup, c.idle_every, c.dense, c.vb, G)) { fprintf(stderr, "case seed %llu failed\n", (unsigned long long)c.seed); return 1; }
     printf("em_dense layout ok (%zu cases)\n", sizeof(cases) / sizeof(cases[0]));
     return 0;
 }
