@@ -844,7 +844,7 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
         max_nc = std::max<uint64_t>(max_nc, row[PT_CLS + SFB_NBINS] - row[PT_CLS]);
         max_nt = std::max<uint64_t>(max_nt, row[PT_TXP1] - row[PT_TXP0]);
     }
-    uint32_t group = 4;                                                // lanes per component (SFB200_EM_DENSE_GROUP = 1, 2, 4)
+    uint32_t group = 2;                                                // lanes per component (SFB200_EM_DENSE_GROUP = 1, 2, 4; swept on B200)
     if (const char* e = getenv("SFB200_EM_DENSE_GROUP")) group = (uint32_t)atoi(e);
     const DenseGeom g = dense_make_geom(max_nc, max_nt, group);
     cudaStream_t s = c->stream;

@@ -47,6 +47,13 @@ struct DenseParams {
 };
 
 constexpr int DENSE_THREADS = 256;
+constexpr int DENSE_ILP = 4;          // classes of one component in flight per lane
+
+template <int N>
+__device__ __forceinline__ double dense_tree_sum(const double* v) {
+    if constexpr (N == 1) return v[0];
+    else return dense_tree_sum<N / 2>(v) + dense_tree_sum<N - N / 2>(v + N / 2);
+}
 
 // shared memory a CTA of k_em_dense needs (mirrored on the host)
 __host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns, uint32_t group) {
@@ -142,16 +149,51 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             const uint32_t L = s_tlen[k];
             const double* cn = s_cnt + s_toff[k] + lane;
             const uint8_t* mk = s_mask + s_toff[k] + lane;
-#pragma unroll 2
-            for (uint32_t e = 0; e < L; ++e) {
-                const double cnt = cn[e << 5];
-                const uint32_t msk = mk[e << 5];
-                double S = 0.0;
+            // DENSE_ILP classes at a time: fp64 adds / fmas have a long dependent latency (~15 cycles measured) and this warp has
+            // nothing else to run, so the S sums (as trees), the reciprocal chains and the accumulator updates of several classes
+            // are kept independent of each other.  Denominators that are neither normal nor zero are left to a rare fix-up
+            // outside the straight-line code (a call inside it would fence the scheduler's reordering).
+            for (uint32_t e = 0; e < L; e += DENSE_ILP) {
+                double cntv[DENSE_ILP], S[DENSE_ILP], r[DENSE_ILP];
+                uint32_t msk[DENSE_ILP];
+                bool rare = false;
 #pragma unroll
-                for (int j = 0; j < NS; ++j) S += ((msk >> j) & 1u) ? b[j] : 0.0;          // members in transcript order
-                const double r = em_ratio(cnt, S);
+                for (int u = 0; u < DENSE_ILP; ++u) {
+                    const bool in = e + u < L;
+                    cntv[u] = in ? cn[(e + u) << 5] : 0.0;
+                    msk[u] = in ? (uint32_t)mk[(e + u) << 5] : 0u;
+                }
 #pragma unroll
-                for (int j = 0; j < NS; ++j) acc[j] += ((msk >> j) & 1u) ? r : 0.0;
+                for (int u = 0; u < DENSE_ILP; ++u) {
+                    double v[NS];
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) v[j] = ((msk[u] >> j) & 1u) ? b[j] : 0.0;
+                    S[u] = dense_tree_sum<NS>(v);
+                }
+#pragma unroll
+                for (int u = 0; u < DENSE_ILP; ++u) {
+                    const bool normal = S[u] > 1e-280 && S[u] < 1e280;
+                    const double Ss = normal ? S[u] : 1.0;
+                    double y;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(Ss));
+                    double t = fma(-Ss, y, 1.0);
+                    y = fma(y, t, y);
+                    t = fma(-Ss, y, 1.0);
+                    y = fma(y, t, y);
+                    r[u] = normal ? cntv[u] * y : 0.0;
+                    rare = rare || (!normal && S[u] != 0.0);
+                }
+                if (__any_sync(0xffffffffu, rare)) {
+#pragma unroll
+                    for (int u = 0; u < DENSE_ILP; ++u) r[u] = em_ratio(cntv[u], S[u]);
+                }
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    double w[DENSE_ILP];
+#pragma unroll
+                    for (int u = 0; u < DENSE_ILP; ++u) w[u] = ((msk[u] >> j) & 1u) ? r[u] : 0.0;
+                    acc[j] += dense_tree_sum<DENSE_ILP>(w);
+                }
             }
             if (G > 1) {
 #pragma unroll
