@@ -676,7 +676,7 @@ int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
 constexpr bool SFB_GATHER_DEFAULT = true;
 bool gather_enabled() { const char* e = getenv("SFB200_EM_GATHER"); return e ? atoi(e) != 0 : SFB_GATHER_DEFAULT; }
 // one thread per connected component (em_dense.cuh) when every component is small; SFB200_EM_DENSE=0 / 1 overrides the default
-constexpr bool SFB_DENSE_DEFAULT = false;
+constexpr bool SFB_DENSE_DEFAULT = true;
 bool dense_enabled() { const char* e = getenv("SFB200_EM_DENSE"); return e ? atoi(e) != 0 : SFB_DENSE_DEFAULT; }
 int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
 
