@@ -149,10 +149,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             const uint32_t L = s_tlen[k];
             const double* cn = s_cnt + s_toff[k] + lane;
             const uint8_t* mk = s_mask + s_toff[k] + lane;
-            // DENSE_ILP classes at a time: fp64 adds / fmas have a long dependent latency (~15 cycles measured) and this warp has
-            // nothing else to run, so the S sums (as trees), the reciprocal chains and the accumulator updates of several classes
-            // are kept independent of each other.  Denominators that are neither normal nor zero are left to a rare fix-up
-            // outside the straight-line code (a call inside it would fence the scheduler's reordering).
+            // DENSE_ILP classes at a time: this warp has little else to run, so the S sums (as trees), the reciprocal chains and the
+            // accumulator updates of several classes are kept independent of each other.  Denominators that are neither normal
+            // nor zero are left to a rare fix-up outside the straight-line code (a call inside it would fence the scheduler's
+            // reordering).  (Measured: no faster than one class at a time -- the loop waits for its heaviest warp, profiles/README.md.)
             for (uint32_t e = 0; e < L; e += DENSE_ILP) {
                 double cntv[DENSE_ILP], S[DENSE_ILP], r[DENSE_ILP];
                 uint32_t msk[DENSE_ILP];
