@@ -7,8 +7,9 @@ EM with exactly 1000 iterations.  One step = one whole quantification of the rea
     map_begin -> map_batch x B -> map_finish (equivalence classes) -> em_run(fixed 1000 iterations).
 `value` is reads/s with the reads already resident in HBM; `e2e` is the same metric through the C ABI with the reads in
 pinned HOST memory (H2D inside the timed region, estimates read back).  N > 1: reads are sharded over ranks (weak scaling,
-10 M per rank), counters and the fragment-length histogram are summed once, and the per-transcript vector is all-reduced
-(NCCL) every EM iteration.
+10 M per rank); counters and the fragment-length sample are combined once and the ranks' class tables are merged with one
+all-gather, after which every rank runs the EM locally (SFB200_MULTI_EM_ALLREDUCE=1 keeps the classes
+rank-local and all-reduces the per-transcript vector every iteration instead).
 
 `--impl reference` times the CPU oracle (oracle/, the restatement of the reference's algorithm; the reference binary itself
 cannot be built offline) on all host threads on a bounded proportional sample of the same workload.
