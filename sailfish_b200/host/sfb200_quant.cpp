@@ -3,6 +3,7 @@
 //   sfb200-quant [quant] -t transcripts.fa -l IU -1 r_1.fq[.gz] -2 r_2.fq[.gz] -o out_dir [options]
 //   sfb200-quant [quant] -t transcripts.fa -l U  -r reads.fq -o out_dir
 //   sfb200-quant index -t transcripts.fa -o index_dir [-k 31] [-f]        then        sfb200-quant quant -i index_dir ...
+//   sfb200-quant genes -g genes.gtf|txp2gene.tsv -q out_dir/quant.sf      (what `quant -g` does after quantification)
 //
 // Option names follow the reference's `sailfish quant` (src/SailfishQuantify.cpp:1066-1150); the index is built on the GPU
 // from the transcript sequences at start-up (a fraction of a second for 200k transcripts), so the `index` command (reference
@@ -29,6 +30,7 @@
 #include <vector>
 
 #include "fastx_reader.hpp"
+#include "gene_agg.hpp"
 #include "sfb200_host.hpp"
 
 namespace {
@@ -220,8 +222,8 @@ int read_index_dir(const std::string& dir, std::vector<std::string>& names, std:
 }
 
 struct Args {
-    std::string transcripts, index, libType, out, auxDir = "aux";
-    bool indexCmd = false, force = false;
+    std::string transcripts, index, libType, out, auxDir = "aux", geneMap, aggKey = "gene_id", quantFile;
+    bool indexCmd = false, genesCmd = false, force = false;
     std::vector<std::string> unmated, mates1, mates2;
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int k = 31, device = 0;
@@ -245,6 +247,8 @@ struct Args {
             "  -o, --output DIR           quant.sf and <auxDir>/ are written here\n"
             "  -p, --threads N  -k, --kmerLen K (31)  --device N\n"
             "  --useVBOpt  --numBootstraps N  --numGibbsSamples N  --dumpEq  --noEffectiveLengthCorrection\n"
+            "  -g, --geneMap FILE         transcript-to-gene map (.gtf, or `transcript gene` per line): also write quant.genes.sf\n"
+            "  --txpAggregationKey KEY    GTF attribute that names the gene (gene_id)\n"
             "  --maxFragLen N (1000)  --numFragSamples N (10000)  --fldMean M (200)  --fldSD S (80)  -w, --maxReadOcc N (200)\n"
             "  --strictIntersect  --ignoreLibCompat  --enforceLibCompat  --allowDovetail  --discardOrphans  --auxDir NAME\n"
             "  --parseOnly                only parse the read files and print record / base counts (no GPU needed)\n");
@@ -259,6 +263,7 @@ Args parse_args(int argc, char** argv) {
     int i = 1;
     if (i < argc && std::string(argv[i]) == "quant") ++i;
     else if (i < argc && std::string(argv[i]) == "index") { a.indexCmd = true; ++i; }
+    else if (i < argc && std::string(argv[i]) == "genes") { a.genesCmd = true; ++i; }
     auto need = [&](const std::string& o) -> std::string { if (i + 1 >= argc) usage(("missing value for " + o).c_str()); return argv[++i]; };
     auto multi = [&](std::vector<std::string>& v) { while (i + 1 < argc && argv[i + 1][0] != '-') v.push_back(argv[++i]); };
     for (; i < argc; ++i) {
@@ -267,6 +272,9 @@ Args parse_args(int argc, char** argv) {
         else if (o == "-t" || o == "--transcripts") a.transcripts = need(o);
         else if (o == "-i" || o == "--index") a.index = need(o);
         else if (o == "-f" || o == "--force") a.force = true;
+        else if (o == "-g" || o == "--geneMap") a.geneMap = need(o);
+        else if (o == "--txpAggregationKey") a.aggKey = need(o);
+        else if (o == "-q" || o == "--quantFile") a.quantFile = need(o);
         else if (o == "--kmerSize") a.k = atoi(need(o).c_str());
         else if (o == "-l" || o == "--libType") a.libType = need(o);
         else if (o == "-o" || o == "--output") a.out = need(o);
@@ -383,6 +391,19 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 int main(int argc, char** argv) {
     try {
         Args a = parse_args(argc, argv);
+        auto gene_level = [&](const std::string& quantPath) {                  // generateGeneLevelEstimates (SailfishUtils.cpp:1043-1088)
+            size_t nt = 0, ng = 0, nu = 0;
+            fprintf(stderr, "Computing gene-level abundance estimates\n");
+            const std::string outp = sfb200::generate_gene_level_estimates(a.geneMap, quantPath, a.aggKey, &nt, &ng, &nu);
+            fprintf(stderr, "There were %zu transcripts mapping to %zu genes\n", nt, ng);
+            if (nu) fprintf(stderr, "WARNING: %zu transcripts of %s are not in the map; each is reported as its own gene\n", nu, quantPath.c_str());
+            fprintf(stderr, "[sfb200-quant] wrote %s\n", outp.c_str());
+        };
+        if (a.genesCmd) {
+            if (a.geneMap.empty() || a.quantFile.empty()) usage("genes needs -g <map> and -q <quant.sf>");
+            gene_level(a.quantFile);
+            return 0;
+        }
         if (a.indexCmd) {                                                     // `sailfish index` (src/SailfishIndexer.cpp:66-237); no GPU needed
             if (a.transcripts.empty() || a.out.empty()) usage("index needs -t <transcripts.fa> and -o <dir>");
             if (a.k % 2 == 0 || a.k > 31 || a.k < 3) {
@@ -425,6 +446,13 @@ int main(int argc, char** argv) {
             return 0;
         }
         if ((a.transcripts.empty() == a.index.empty()) || a.libType.empty() || a.out.empty()) usage("one of -t / -i, and -l and -o are required");
+        if (!a.geneMap.empty()) {                                              // verified before any real work (SailfishQuantify.cpp:1208-1218)
+            struct stat gst;
+            if (stat(a.geneMap.c_str(), &gst) != 0) {
+                fprintf(stderr, "Could not find transcript <=> gene map file %s\nExiting now: please either omit the 'geneMap' option or provide a valid file\n", a.geneMap.c_str());
+                return 1;
+            }
+        }
         if (a.sopt.numBootstraps && a.sopt.numGibbsSamples) usage("--numBootstraps and --numGibbsSamples are mutually exclusive (SailfishQuantify.cpp:1281-1287)");
         bool lib_paired = false;
         if (!parse_library_format(a.libType, a.mopt.lib_format_id, lib_paired)) usage(("unknown library type " + a.libType).c_str());
@@ -521,6 +549,7 @@ int main(int argc, char** argv) {
                     optimizer.lastIterations(), now_s() - t_start);
             fclose(mf);
         }
+        if (!a.geneMap.empty()) gene_level(a.out + "/quant.sf");             // SailfishQuantify.cpp:1413-1422
         fprintf(stderr, "[sfb200-quant] EM: %u iterations; wrote %s/quant.sf (%.2f s in total)\n", optimizer.lastIterations(), a.out.c_str(),
                 now_s() - t_start);
         return 0;

@@ -112,6 +112,60 @@ def test_index_command(tmp_path):
     assert r.returncode == 0 and b"up-to-date" in r.stderr
 
 
+def gene_agg_reference(lines, t2g):
+    """aggregateEstimatesToGeneLevel restated independently (reference src/SailfishUtils.cpp:929-1041), including the running-sum
+    normaliser of :1011-1016; genes in order of first appearance"""
+    out, order, recs = [lines[0]], [], {}
+    for l in lines[1:]:
+        t = l.split()
+        g = t2g.get(t[0], t[0])
+        if g not in recs:
+            recs[g] = []; order.append(g)
+        recs[g].append((int(t[1]), float(t[2]), [float(x) for x in t[3:]]))
+    for g in order:
+        rs = recs[g]
+        vals = [0.0] * len(rs[0][2]); total = 0.0
+        for _, _, ev in rs:
+            vals = [a + b for a, b in zip(vals, ev)]
+            total += vals[0]
+        if total > 5e-324:
+            gl = sum(r[0] * (r[2][0] / total) for r in rs); ge = sum(r[1] * (r[2][0] / total) for r in rs)
+        else:
+            gl = sum(r[0] / len(rs) for r in rs); ge = sum(r[1] / len(rs) for r in rs)
+        out.append("\t".join([g, "%g" % gl, "%g" % ge] + ["%g" % v for v in vals]))
+    return out
+
+
+def test_gene_level_aggregation(tmp_path):
+    rng = np.random.default_rng(5)
+    names = ["t%03d" % i for i in range(40)]
+    lines = ["Name\tLength\tEffectiveLength\tTPM\tNumReads"]
+    for i, n in enumerate(names):
+        tpm = 0.0 if i % 7 == 0 or 8 <= i < 12 else float("%g" % rng.uniform(0, 50000))
+        lines.append("%s\t%d\t%g\t%g\t%g" % (n, rng.integers(200, 5000), rng.uniform(50, 4000), tpm, tpm * 0.37))
+    q = tmp_path / "quant.sf"; q.write_text("\n".join(lines) + "\n")
+    t2g = {n: "g%02d" % (i // 4) for i, n in enumerate(names) if i < 36}          # the last four transcripts are not in the map
+    simple = tmp_path / "t2g.tsv"; simple.write_text("".join("%s\t%s\n" % kv for kv in t2g.items()))
+    r = subprocess.run([build_exe(), "genes", "-g", str(simple), "-q", str(q)], capture_output=True)
+    assert r.returncode == 0 and b"36 transcripts mapping to 9 genes" in r.stderr and b"4 transcripts" in r.stderr
+    assert open(tmp_path / "quant.genes.sf").read().strip().split("\n") == gene_agg_reference(lines, t2g)
+    # the same map as GTF (exon lines repeat the transcript; gene_name as an alternative key)
+    gtf = tmp_path / "ann.gtf"
+    with open(gtf, "w") as f:
+        f.write("# comment\n")
+        for n, g in t2g.items():
+            for feat in ("transcript", "exon", "exon"):
+                f.write('chr1\tsrc\t%s\t1\t100\t.\t+\t.\tgene_id "%s"; transcript_id "%s"; gene_name "N%s";\n' % (feat, g, n, g))
+    os.remove(tmp_path / "quant.genes.sf")
+    subprocess.check_call([EXE, "genes", "-g", str(gtf), "-q", str(q)], stderr=subprocess.DEVNULL)
+    assert open(tmp_path / "quant.genes.sf").read().strip().split("\n") == gene_agg_reference(lines, t2g)
+    subprocess.check_call([EXE, "genes", "-g", str(gtf), "-q", str(q), "--txpAggregationKey", "gene_name"], stderr=subprocess.DEVNULL)
+    assert open(tmp_path / "quant.genes.sf").read().strip().split("\n") == gene_agg_reference(lines, {k: "N" + v for k, v in t2g.items()})
+    # a missing map stops `quant` before any work, as in the reference
+    r = subprocess.run([EXE, "quant", "-t", "x.fa", "-l", "U", "-r", "y.fq", "-o", str(tmp_path / "o"), "-g", str(tmp_path / "nope.gtf")], capture_output=True)
+    assert r.returncode == 1 and b"Could not find transcript <=> gene map file" in r.stderr
+
+
 def test_no_cpu_fallback(tmp_path):
     import torch
     if torch.cuda.is_available():
@@ -156,9 +210,13 @@ def test_sample_data_end_to_end_cpp(sample_data, tmp_path):
     # the Gibbs path and VBEM through the same command, from an index directory
     out2 = tmp_path / "q2"
     subprocess.check_call([EXE, "index", "-t", str(fa), "-o", str(tmp_path / "idx"), "-k", "31"])
+    (tmp_path / "t2g.tsv").write_text("".join("%s\tgene%d\n" % (n, i // 5) for i, n in enumerate(names)))
     subprocess.check_call([EXE, "quant", "-i", str(tmp_path / "idx"), "-l", "IU", "-1", str(tmp_path / "reads_1.fastq.gz"),
-                           "-2", str(tmp_path / "reads_2.fastq.gz"), "-o", str(out2), "--useVBOpt", "--numGibbsSamples", "4"])
+                           "-2", str(tmp_path / "reads_2.fastq.gz"), "-o", str(out2), "--useVBOpt", "--numGibbsSamples", "4", "-g", str(tmp_path / "t2g.tsv")])
     rows2 = [l.split("\t") for l in open(out2 / "quant.sf").read().strip().split("\n")[1:]]
     np.testing.assert_allclose([float(r[4]) for r in rows2], d["ref_est_vb1"], rtol=1.2e-4, atol=1e-6)
+    genes = [l.split("\t") for l in open(out2 / "quant.genes.sf").read().strip().split("\n")[1:]]
+    assert [g[0] for g in genes] == ["gene%d" % i for i in range((len(names) + 4) // 5)]
+    assert abs(sum(float(g[4]) for g in genes) - sum(float(r[4]) for r in rows2)) < 1e-3 * float(d["num_mapped"])
     gib = np.frombuffer(gzip.open(out2 / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.int32).reshape(4, len(names))
     assert (gib.sum(axis=1) == int(d["num_mapped"])).all()
