@@ -5,6 +5,7 @@
 //   effective-length helpers of SailfishQuantify.cpp and the TPM formula of GZipWriter.cpp.
 // fp64 throughout, operation order preserved, built -O3 WITHOUT -ffast-math.
 #include "oracle.h"
+#include "orc_empdist.hpp"
 #include "orc_threads.hpp"
 
 #include <algorithm>
@@ -474,29 +475,6 @@ void smoothedEffLens(const uint32_t* len, uint32_t T, const std::vector<double>&
         out[t] = effLen;
     }
 }
-// EmpiricalDistribution::buildDistribution (EmpiricalDistribution.cpp:29-94); pdf stored as float.
-struct EmpDist {
-    std::vector<float> pdfvals; float med = 0; uint32_t minVal = 0, maxVal = 0;
-    void build(const std::vector<uint32_t>& vals, const std::vector<uint32_t>& lens) {
-        const size_t n = vals.size();
-        minVal = std::numeric_limits<uint32_t>::max(); maxVal = 0;
-        double valsum = 0;
-        for (size_t i = 0; i < n; ++i) { minVal = std::min(minVal, vals[i]); maxVal = std::max(maxVal, vals[i]); valsum += lens[i]; }
-        double cumpr = 0.0; unsigned lastval = 0, maxval = 1;
-        for (; lastval < n; ++lastval) { cumpr += lens[lastval] / valsum; maxval = vals[lastval]; if (cumpr > 1.0 - 1e-6) break; }
-        pdfvals.resize(maxval);
-        valsum = 0.0;
-        for (unsigned i = 0; i < lastval; ++i) valsum += lens[i];
-        for (unsigned val = 0, i = 0; val < maxval;) {
-            if (val == vals[i]) { pdfvals[val] = static_cast<float>(lens[i] / valsum); ++val; ++i; }
-            else if (val < vals[i]) { pdfvals[val] = 0.0f; ++val; }
-        }
-        size_t i = 0, j = n - 1; unsigned u = lens[0], v = lens[n - 1];
-        while (i < j) { if (u <= v) { v -= u; u = lens[++i]; } else { u -= v; v = lens[--j]; } }
-        med = static_cast<float>(vals[i]);
-    }
-    float pdf(unsigned x) const { return x < pdfvals.size() ? pdfvals[x] : 0.0f; }
-};
 }  // namespace
 
 extern "C" int orc_eff_lens(const uint32_t* txp_len, uint32_t T, const uint32_t* fld_hist, uint32_t maxLen,

@@ -59,6 +59,43 @@ class EMOpts(C.Structure):
         return o
 
 
+class RefBias:
+    """The reference's own updateEffectiveLengths (src/SailfishUtils.cpp:611-926, compiled unmodified into oracle/_ref) on a
+    ReadExperiment built from arrays; mode 1 = --biasCorrect, 2 = --gcBiasCorrect."""
+
+    def __init__(self, mode, seqs, eff_model, read_bias, observed_gc, fld_counts, num_fwd, num_rc, gc_samp=1):
+        R = ref_em()
+        if R is None or not hasattr(R, "ref_bias_session"):
+            raise RuntimeError("oracle/_ref/libsfref_em.so was built without the bias correction")
+        self.R = R
+        self.T = len(seqs)
+        ln = np.array([len(s) for s in seqs], np.uint32)
+        eff_model = np.ascontiguousarray(eff_model, dtype=np.float64)
+        rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)
+        fc = np.ascontiguousarray(fld_counts, dtype=np.int32)
+        self.h = R.ref_bias_session(self.T, _ptr(ln, u32p), _ptr(eff_model, f64p), b"".join(seqs), int(mode), _ptr(rb, u32p), _ptr(og, u32p),
+                                    _ptr(fc, i32p), len(fc), int(num_fwd), int(num_rc), int(gc_samp), 0, None, None, None, 0, 0)
+        if not self.h:
+            raise RuntimeError("ref_bias_session failed")
+
+    def update(self, alphas, eff_in):
+        alphas = np.ascontiguousarray(alphas, dtype=np.float64); eff_in = np.ascontiguousarray(eff_in, dtype=np.float64)
+        out = np.zeros(self.T, np.float64)
+        rc = self.R.ref_bias_update(self.h, _ptr(alphas, f64p), _ptr(eff_in, f64p), _ptr(out, f64p))
+        return rc, out
+
+    def fld(self, n):
+        cdf = np.zeros(n, np.float32)
+        mx = self.R.ref_bias_fld(self.h, _ptr(cdf, f32p), n)
+        return cdf, int(mx)
+
+    def __del__(self):
+        try:
+            self.R.ref_em_free(self.h)
+        except Exception:
+            pass
+
+
 F64_ROW_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, f64p, C.c_size_t)
 I32_ROW_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, i32p, C.c_size_t)
 
@@ -99,6 +136,8 @@ def lib():
         L.orc_last_label.argtypes = [C.c_void_p, C.c_uint64, u32p, C.c_int]
         L.orc_eff_lens.argtypes = [u32p, C.c_uint32, u32p, C.c_uint32, C.c_int32, C.c_int, C.c_int, C.c_double,
                                    C.c_double, f64p]
+        L.orc_update_eff_lens.argtypes = [C.c_int, C.c_uint32, C.c_char_p, u64p, u32p, f64p, f64p, f64p, C.c_int64, C.c_int64, u32p, u32p,
+                                          u32p, C.c_uint32, C.c_uint32, f64p]
         L.orc_em_run.argtypes = [C.c_uint32, C.c_uint64, u64p, u32p, u64p, f64p, C.c_uint64, C.POINTER(EMOpts), C.c_int,
                                  f64p, u32p, f64p]
         L.orc_tpm.argtypes = [C.c_uint32, f64p, f64p, C.c_uint64, f64p]
@@ -260,6 +299,25 @@ def eff_lens(txp_len, fld_hist, max_frag_len=1000, num_frag_samples=10000, singl
     return out
 
 
+def update_eff_lens(mode, seqs, eff_model, eff_in, alphas, num_fwd, num_rc, read_bias, observed_gc, fld_counts, gc_samp=1):
+    """sailfish::utils::updateEffectiveLengths restated (oracle/orc_bias.cpp).  mode 1 = --biasCorrect, 2 = --gcBiasCorrect;
+    seqs: list of bytes (A/C/G/T).  -> (rc, eff_out)"""
+    T = len(seqs)
+    ln = np.array([len(s) for s in seqs], np.uint32)
+    off = np.zeros(T, np.uint64); off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+    cat = b"".join(seqs)
+    eff_model = np.ascontiguousarray(eff_model, dtype=np.float64); eff_in = np.ascontiguousarray(eff_in, dtype=np.float64)
+    alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+    rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)
+    fc = np.ascontiguousarray(fld_counts, dtype=np.uint32)
+    assert len(rb) == 4096 and len(og) == 101
+    out = np.zeros(T, np.float64)
+    rc = lib().orc_update_eff_lens(int(mode), T, cat, _ptr(off, u64p), _ptr(ln, u32p), _ptr(eff_model, f64p), _ptr(eff_in, f64p),
+                                   _ptr(alphas, f64p), int(num_fwd), int(num_rc), _ptr(rb, u32p), _ptr(og, u32p), _ptr(fc, u32p),
+                                   len(fc), int(gc_samp), _ptr(out, f64p))
+    return rc, out
+
+
 def _csr(row_ptr, labels, counts):
     return (np.ascontiguousarray(row_ptr, dtype=np.uint64), np.ascontiguousarray(labels, dtype=np.uint32),
             np.ascontiguousarray(counts, dtype=np.uint64))
@@ -363,6 +421,13 @@ def ref_em():
         R.ref_em_optimize.argtypes = [C.c_void_p, C.c_double, C.c_uint32, f64p, f64p]
         R.ref_em_bootstraps.argtypes = [C.c_void_p, C.c_double, C.c_uint32, f64p]
         R.ref_em_gibbs.argtypes = [C.c_void_p, C.c_uint32, i32p]
+        if hasattr(R, "ref_bias_session"):
+            R.ref_bias_session.restype = C.c_void_p
+            R.ref_bias_session.argtypes = [C.c_uint32, u32p, f64p, C.c_char_p, C.c_int, u32p, u32p, i32p, C.c_uint32, C.c_int64, C.c_int64,
+                                           C.c_uint32, C.c_uint64, u64p, u32p, u64p, C.c_uint64, C.c_int]
+            R.ref_bias_update.argtypes = [C.c_void_p, f64p, f64p, f64p]
+            R.ref_bias_fld.restype = C.c_uint32
+            R.ref_bias_fld.argtypes = [C.c_void_p, f32p, C.c_uint32]
         _ref_em = R
     return _ref_em
 

@@ -31,7 +31,20 @@ double digamma(double x) {
 }
 }}
 
-// optimize() references this template for --biasCorrect (never taken here); give the linker a body.
+// optimize() references this template for --biasCorrect / --gcBiasCorrect.  With SFREF_HAVE_BIAS the body is the reference's
+// own text (src/SailfishUtils.cpp:611-926, cut out at build time into oracle/_ref/upd_efflens.inc by oracle/Makefile);
+// otherwise a stub that must never be reached.
+#ifdef SFREF_HAVE_BIAS
+#include "ReadKmerDist.hpp"
+#include "UtilityFunctions.hpp"
+namespace sailfish { namespace utils {
+#include "upd_efflens.inc"
+template Eigen::VectorXd updateEffectiveLengths<std::vector<tbb::atomic<double>>>(
+    SailfishOpts&, ReadExperiment&, Eigen::VectorXd&, std::vector<tbb::atomic<double>>&);
+template Eigen::VectorXd updateEffectiveLengths<std::vector<double>>(
+    SailfishOpts&, ReadExperiment&, Eigen::VectorXd&, std::vector<double>&);
+}}
+#else
 namespace sailfish { namespace utils {
 template <typename AbundanceVecT>
 Eigen::VectorXd updateEffectiveLengths(SailfishOpts&, ReadExperiment&, Eigen::VectorXd& effLensIn, AbundanceVecT&) {
@@ -42,6 +55,7 @@ Eigen::VectorXd updateEffectiveLengths(SailfishOpts&, ReadExperiment&, Eigen::Ve
 template Eigen::VectorXd updateEffectiveLengths<std::vector<tbb::atomic<double>>>(
     SailfishOpts&, ReadExperiment&, Eigen::VectorXd&, std::vector<tbb::atomic<double>>&);
 }}
+#endif
 
 int rapMapSAIndex(int, char*[]) { return 1; }
 
@@ -106,6 +120,89 @@ void* ref_em_session(uint32_t n_txp, const uint32_t* txp_len, const double* eff_
     }
     s->exp->numMappedFragmentsAtomic().store(num_mapped);
     return s;
+}
+
+// Bias / GC correction.  A session as above plus what updateEffectiveLengths reads: the transcript
+// sequences (through the reference's own Transcript::setSequence / GC tables), the read-start 6-mer counts
+// (ReadExperiment::readBias()), the observed fragment GC histogram, the fragment length distribution (setFragLengthDist ->
+// EmpiricalDistribution) and the strand tallies.  mode: 1 = --biasCorrect, 2 = --gcBiasCorrect.
+void* ref_bias_session(uint32_t n_txp, const uint32_t* txp_len, const double* eff_len, const char* seq_concat, int mode,
+                       const uint32_t* read_bias_counts /* 4096 */, const uint32_t* observed_gc /* 101 */,
+                       const int32_t* fld_counts, uint32_t n_fld, int64_t num_fwd, int64_t num_rc, uint32_t gc_samp,
+                       uint64_t n_classes, const uint64_t* row_ptr, const uint32_t* labels, const uint64_t* counts, uint64_t num_mapped,
+                       int use_vb) {
+#ifndef SFREF_HAVE_BIAS
+    return nullptr;
+#else
+    auto* s = new Session();
+    char tmpl[] = "/tmp/sfref_XXXXXX";
+    if (!mkdtemp(tmpl)) { delete s; return nullptr; }
+    s->dir = tmpl;
+    { std::ofstream f(s->dir + "/versionInfo.json"); f << "{\n \"indexVersion\": 2,\n \"kmerLength\": 31\n}\n"; }
+    { std::ofstream f(s->dir + "/header.json"); cereal::JSONOutputArchive ar(f); IndexHeader h; ar(h); }
+    { std::ofstream f(s->dir + "/txpinfo.txt"); for (uint32_t t = 0; t < n_txp; ++t) f << "t" << t << " " << txp_len[t] << "\n"; }
+    { std::ofstream f(s->dir + "/seq.txt"); size_t o = 0; for (uint32_t t = 0; t < n_txp; ++t) { f.write(seq_concat + o, txp_len[t]); f << "\n"; o += txp_len[t]; } }
+    auto sink = std::make_shared<spdlog::sinks::null_sink_st>();
+    s->sopt.jointLog = std::make_shared<spdlog::logger>("refbias", sink);
+    s->sopt.numThreads = 1;
+    s->sopt.useVBOpt = use_vb != 0;
+    s->sopt.noEffectiveLengthCorrection = false;
+    s->sopt.biasCorrect = mode == 1; s->sopt.gcBiasCorrect = mode == 2; s->sopt.gcSampFactor = 1; s->sopt.pdfSampFactor = gc_samp;
+    s->sopt.numBootstraps = 0; s->sopt.numGibbsSamples = 0;
+    s->sopt.fragLenDistMax = 1000; s->sopt.fragLenDistPriorMean = 200; s->sopt.fragLenDistPriorSD = 80;
+    boost::filesystem::path p(s->dir);
+    s->exp.reset(new ReadExperiment(s->libs, p, s->sopt));
+    auto& txps = s->exp->transcripts();
+    for (uint32_t t = 0; t < n_txp; ++t) txps[t].EffectiveLength = eff_len[t];
+    for (size_t i = 0; i < 4096; ++i) s->exp->readBias().counts[i].store(read_bias_counts[i]);
+    for (size_t i = 0; i < 101; ++i) s->exp->observedGC()[i].store(observed_gc[i]);
+    s->exp->setFragLengthDist(std::vector<int32_t>(fld_counts, fld_counts + n_fld));
+    s->exp->addNumFwd(static_cast<int32_t>(num_fwd)); s->exp->addNumRC(static_cast<int32_t>(num_rc));
+    if (n_classes) {
+        auto& eqb = s->exp->equivalenceClassBuilder();
+        eqb.start();
+        for (uint64_t e = 0; e < n_classes; ++e) {
+            std::vector<uint32_t> ids(labels + row_ptr[e], labels + row_ptr[e + 1]);
+            std::vector<double> aux(ids.size(), 1.0);
+            TranscriptGroup tg(ids);
+            eqb.addGroup(std::move(tg), aux);
+        }
+        eqb.finish();
+        std::unordered_map<std::string, uint64_t> cnt;
+        for (uint64_t e = 0; e < n_classes; ++e)
+            cnt[std::string(reinterpret_cast<const char*>(labels + row_ptr[e]), 4 * (row_ptr[e + 1] - row_ptr[e]))] = counts[e];
+        for (auto& kv : eqb.eqVec()) {
+            std::string key(reinterpret_cast<const char*>(kv.first.txps.data()), 4 * kv.first.txps.size());
+            kv.second.count.store(cnt[key]);
+        }
+    }
+    s->exp->numMappedFragmentsAtomic().store(num_mapped);
+    return s;
+#endif
+}
+
+// sailfish::utils::updateEffectiveLengths (src/SailfishUtils.cpp:611-926) on (alphas, effLensIn) -> effLensOut
+int ref_bias_update(void* h, const double* alphas, const double* eff_in, double* eff_out) {
+#ifndef SFREF_HAVE_BIAS
+    return -1;
+#else
+    auto* s = static_cast<Session*>(h);
+    const size_t T = s->exp->transcripts().size();
+    std::vector<double> a(alphas, alphas + T);
+    Eigen::VectorXd in(T);
+    for (size_t i = 0; i < T; ++i) in(i) = eff_in[i];
+    Eigen::VectorXd out = sailfish::utils::updateEffectiveLengths(s->sopt, *s->exp, in, a);
+    for (size_t i = 0; i < T; ++i) eff_out[i] = out(i);
+    return 0;
+#endif
+}
+
+// the fragment length distribution as the reference's EmpiricalDistribution sees it (float cdf, maxValue)
+uint32_t ref_bias_fld(void* h, float* cdf_out, uint32_t n) {
+    auto* s = static_cast<Session*>(h);
+    EmpiricalDistribution* d = s->exp->fragLengthDist();
+    for (uint32_t i = 0; i < n; ++i) cdf_out[i] = d->cdf(i);
+    return d->maxValue();
 }
 
 void ref_em_free(void* h) {

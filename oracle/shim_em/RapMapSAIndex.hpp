@@ -1,5 +1,6 @@
 // Stand-in for RapMap's RapMapSAIndex.hpp: the four fields Sailfish reads (ReadExperiment.hpp:103-116) filled from a
-// plain text file "txpinfo.txt" (one "name length" per line).  TEST INFRASTRUCTURE ONLY.
+// plain text file "txpinfo.txt" (one "name length" per line) and, when present, "seq.txt" (one transcript sequence per line,
+// same order; without it every base is 'A').  TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <cstdint>
 #include <fstream>
@@ -14,6 +15,15 @@ class RapMapSAIndex {
         std::string name; uint32_t len; IndexT off = 0;
         while (in >> name >> len) { txpNames.push_back(name); txpLens.push_back(len); txpOffsets.push_back(off); off += len + 1; }
         seq.assign(static_cast<size_t>(off) + 1, 'A');
+        std::ifstream sq(dir + "seq.txt");
+        if (sq) {
+            std::string line;
+            for (size_t t = 0; t < txpLens.size() && std::getline(sq, line); ++t) {
+                if (line.size() != txpLens[t]) return false;
+                seq.replace(static_cast<size_t>(txpOffsets[t]), line.size(), line);
+                seq[static_cast<size_t>(txpOffsets[t]) + line.size()] = '$';
+            }
+        }
         return true;
     }
     std::vector<std::string> txpNames;

@@ -8,6 +8,8 @@
                       CollapsedEMOptimizer::optimize produces on those classes (EM and VBEM)
   synth_em.npz        a synthetic class set + the reference optimizer's EM / VBEM estimates
   eqbuilder.json      EquivalenceClassBuilder behaviour on a small add sequence (counts, finish() totals)
+  bias_efflens.npz    inputs and outputs of the reference's OWN updateEffectiveLengths (src/SailfishUtils.cpp:611-926,
+                      compiled unmodified into oracle/_ref/libsfref_em.so) for --biasCorrect and --gcBiasCorrect
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -56,7 +58,43 @@ def read_fastq(path):
     return out
 
 
+def make_bias_fixture():
+    """bias / GC effective-length correction: a small random transcriptome, read-start 6-mer counts,
+    observed fragment GC histogram, fragment length counts, strand tallies, abundances -> the reference's corrected lengths"""
+    rng = np.random.default_rng(20260117)
+    T = 48
+    lens = rng.integers(120, 2200, size=T)
+    lens[:3] = [5, 7, 150]                                                      # shorter than the 6-mer window / than the FLD
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=int(l), p=[0.3, 0.2, 0.2, 0.3]).astype(np.uint8)) for l in lens]
+    x = np.arange(1000)
+    fld = np.round(30000 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32)
+    eff_model = np.where(lens - 190.0 + 1 >= 1, lens - 190.0 + 1, lens).astype(np.float64)
+    eff_in = eff_model * rng.uniform(0.9, 1.1, size=T)                          # as after an earlier correction round
+    alphas = rng.lognormal(3, 2, size=T); alphas[rng.random(T) < 0.2] = 0.0; alphas[5] = 5e-9
+    read_bias = rng.integers(1, 3000, size=4096).astype(np.uint32)
+    observed_gc = rng.integers(1, 8000, size=101).astype(np.uint32)
+    out = dict(seq=np.frombuffer(b"".join(seqs), np.uint8), txp_len=lens.astype(np.uint32), fld=fld, eff_model=eff_model, eff_in=eff_in,
+               alphas=alphas, read_bias=read_bias, observed_gc=observed_gc, num_fwd=np.int64(61234), num_rc=np.int64(58766))
+    for mode, tag in ((1, "seq"), (2, "gc")):
+        for samp in ((1,) if mode == 1 else (1, 3)):
+            Rb = O.RefBias(mode, seqs, eff_model, read_bias, observed_gc, fld, 61234, 58766, gc_samp=samp)
+            rc, ref = Rb.update(alphas, eff_in)
+            assert rc == 0
+            out["ref_%s_samp%d" % (tag, samp)] = ref
+            # a second round on the corrected lengths, as the optimizer does at iterations 500 and 1000
+            rc, ref2 = Rb.update(alphas * 1.5, ref)
+            out["ref_%s_samp%d_round2" % (tag, samp)] = ref2
+    cdf, mx = Rb.fld(1000)
+    out["ref_fld_cdf"] = cdf; out["ref_fld_max"] = np.int64(mx)
+    np.savez_compressed(os.path.join(OUT, "bias_efflens.npz"), **out)
+    print("bias_efflens.npz: %d transcripts, %d corrected (seq), %d corrected (gc)" % (
+        T, int((out["ref_seq_samp1"] != eff_in).sum()), int((out["ref_gc_samp1"] != eff_in).sum())))
+
+
 def main():
+    if "--bias-only" in sys.argv:
+        make_bias_fixture()
+        return
     R = O.ref()
     assert R is not None, "oracle/_ref/libsfref.so missing: run make -C oracle"
     rng = np.random.default_rng(20261017)
@@ -133,6 +171,9 @@ def main():
     print("golden fixtures written to", OUT)
     subprocess.call(["ls", "-la", OUT])
 
+
+if __name__ == "__main__" and "--bias-only" not in sys.argv:
+    make_bias_fixture()
 
 if __name__ == "__main__":
     main()
