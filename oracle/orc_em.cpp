@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 #include <random>
@@ -135,8 +136,11 @@ struct LoopCfg {
     bool use_vb; double prior; double tol; uint32_t min_iter, max_iter, fixed_iters; double check_cutoff; bool gate_old;
 };
 
+// `at_top`, when given, runs at the top of every iteration with the iteration number (optimize()'s effective-length
+// recomputation at iterations 50 / 500 / 1000, :824-840; it may rewrite `w` in place).
 void em_loop(const Classes& c, const std::vector<double>& w, const uint8_t* valid, const uint64_t* counts,
-             const LoopCfg& cfg, orc::Pool& pool, std::vector<double>& alphas, uint32_t* iters_out, double* mrd_out) {
+             const LoopCfg& cfg, orc::Pool& pool, std::vector<double>& alphas, uint32_t* iters_out, double* mrd_out,
+             const std::function<void(uint32_t)>* at_top = nullptr) {
     const size_t T = c.T;
     std::vector<double> expTheta(T, 0.0);
     const bool par = pool.size() > 1;
@@ -152,6 +156,7 @@ void em_loop(const Classes& c, const std::vector<double>& w, const uint8_t* vali
         return itNum < cfg.min_iter || (itNum < cfg.max_iter && !converged);      // :820 / :486
     };
     while (keep_going()) {
+        if (at_top) (*at_top)(itNum);
         if (cfg.use_vb) {
             double alphaSum = 0.0;                                                 // :300-303 / :162-165
             for (size_t i = 0; i < T; ++i) alphaSum += alphas[i];
@@ -272,6 +277,49 @@ extern "C" int orc_em_run(uint32_t n_txp, uint64_t n_classes, const uint64_t* ro
     const double alphaSum = truncateCountVector(alphas, cutoff);                     // :875
     std::memcpy(alphas_out, alphas.data(), sizeof(double) * n_txp);
     if (alphaSum < minWeight) return -2;                                             // :877-881
+    return 0;
+}
+
+// optimize() with --biasCorrect / --gcBiasCorrect (CollapsedEMOptimizer.cpp:717,816,824-840,888): at iterations 50, 500 and 1000
+// the effective lengths are recomputed from the current alphas (orc_update_eff_lens) and the class weights rebuilt from them;
+// eff_out receives the lengths the reference stores back into Transcript::EffectiveLength.
+extern "C" int orc_update_eff_lens(int mode, uint32_t T, const char* seq, const uint64_t* off, const uint32_t* len, const double* eff_model,
+                                   const double* eff_in, const double* alphas, int64_t num_fwd, int64_t num_rc, const uint32_t* read_bias,
+                                   const uint32_t* observed_gc, const uint32_t* fld_counts, uint32_t n_fld, uint32_t gc_samp, double* eff_out);
+extern "C" int orc_em_run_bias(uint32_t n_txp, uint64_t n_classes, const uint64_t* row_ptr, const uint32_t* labels, const uint64_t* counts,
+                               const double* eff_lens, uint64_t num_mapped, const orc_em_opts* o, int n_threads, int mode, const char* seq,
+                               const uint64_t* off, const uint32_t* len, int64_t num_fwd, int64_t num_rc, const uint32_t* read_bias,
+                               const uint32_t* observed_gc, const uint32_t* fld_counts, uint32_t n_fld, uint32_t gc_samp,
+                               double* alphas_out, double* eff_out, uint32_t* iters_out, double* mrd_out) {
+    Classes c{n_txp, n_classes, row_ptr, labels, counts};
+    orc::Pool pool(n_threads);
+    std::vector<double> effLens; clamp_eff(eff_lens, n_txp, effLens);
+    std::vector<double> w; compute_weights(c, effLens, w, pool);
+    std::vector<uint8_t> active;
+    const size_t nActive = mark_active(c, active);
+    if (nActive == 0) return -1;
+    const double totalNumFrags = static_cast<double>(num_mapped);
+    const double scale = 1.0 / nActive;
+    std::vector<double> alphas(n_txp);
+    for (uint32_t i = 0; i < n_txp; ++i) alphas[i] = active[i] ? scale * totalNumFrags : 0.0;
+    int bias_rc = 0;
+    const std::function<void(uint32_t)> recompute = [&](uint32_t itNum) {               // :824-840
+        if (itNum != 50 && itNum != 500 && itNum != 1000) return;
+        std::vector<double> next(n_txp);
+        const int rc = orc_update_eff_lens(mode, n_txp, seq, off, len, eff_lens /* Transcript::EffectiveLength */, effLens.data(), alphas.data(),
+                                           num_fwd, num_rc, read_bias, observed_gc, fld_counts, n_fld, gc_samp, next.data());
+        if (rc) { bias_rc = rc; return; }
+        effLens.swap(next);
+        compute_weights(c, effLens, w, pool);                                          // updateEqClassWeights :527-556
+    };
+    LoopCfg cfg{o->use_vb != 0, o->prior_alpha, o->tol, o->min_iter, o->max_iter, o->fixed_iters, o->check_cutoff, false};
+    em_loop(c, w, nullptr, counts, cfg, pool, alphas, iters_out, mrd_out, &recompute);
+    if (bias_rc) return bias_rc;
+    const double cutoff = cfg.use_vb ? (o->prior_alpha + o->min_alpha) : o->min_alpha;
+    const double alphaSum = truncateCountVector(alphas, cutoff);
+    std::memcpy(alphas_out, alphas.data(), sizeof(double) * n_txp);
+    if (eff_out) std::memcpy(eff_out, effLens.data(), sizeof(double) * n_txp);          // :888
+    if (alphaSum < minWeight) return -2;
     return 0;
 }
 

@@ -63,7 +63,8 @@ class RefBias:
     """The reference's own updateEffectiveLengths (src/SailfishUtils.cpp:611-926, compiled unmodified into oracle/_ref) on a
     ReadExperiment built from arrays; mode 1 = --biasCorrect, 2 = --gcBiasCorrect."""
 
-    def __init__(self, mode, seqs, eff_model, read_bias, observed_gc, fld_counts, num_fwd, num_rc, gc_samp=1):
+    def __init__(self, mode, seqs, eff_model, read_bias, observed_gc, fld_counts, num_fwd, num_rc, gc_samp=1, classes=None, num_mapped=0,
+                 use_vb=False):
         R = ref_em()
         if R is None or not hasattr(R, "ref_bias_session"):
             raise RuntimeError("oracle/_ref/libsfref_em.so was built without the bias correction")
@@ -73,8 +74,14 @@ class RefBias:
         eff_model = np.ascontiguousarray(eff_model, dtype=np.float64)
         rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)
         fc = np.ascontiguousarray(fld_counts, dtype=np.int32)
-        self.h = R.ref_bias_session(self.T, _ptr(ln, u32p), _ptr(eff_model, f64p), b"".join(seqs), int(mode), _ptr(rb, u32p), _ptr(og, u32p),
-                                    _ptr(fc, i32p), len(fc), int(num_fwd), int(num_rc), int(gc_samp), 0, None, None, None, 0, 0)
+        if classes is not None:
+            rp, lab, cnt = _csr(*classes)
+            self.h = R.ref_bias_session(self.T, _ptr(ln, u32p), _ptr(eff_model, f64p), b"".join(seqs), int(mode), _ptr(rb, u32p), _ptr(og, u32p),
+                                        _ptr(fc, i32p), len(fc), int(num_fwd), int(num_rc), int(gc_samp), len(cnt), _ptr(rp, u64p),
+                                        _ptr(lab, u32p), _ptr(cnt, u64p), int(num_mapped), int(use_vb))
+        else:
+            self.h = R.ref_bias_session(self.T, _ptr(ln, u32p), _ptr(eff_model, f64p), b"".join(seqs), int(mode), _ptr(rb, u32p), _ptr(og, u32p),
+                                        _ptr(fc, i32p), len(fc), int(num_fwd), int(num_rc), int(gc_samp), 0, None, None, None, 0, 0)
         if not self.h:
             raise RuntimeError("ref_bias_session failed")
 
@@ -83,6 +90,13 @@ class RefBias:
         out = np.zeros(self.T, np.float64)
         rc = self.R.ref_bias_update(self.h, _ptr(alphas, f64p), _ptr(eff_in, f64p), _ptr(out, f64p))
         return rc, out
+
+    def optimize(self, tol=0.01, max_iter=10000):
+        """CollapsedEMOptimizer::optimize with the session's bias mode -> (rc, estCount, EffectiveLength after the run)"""
+        est = np.zeros(self.T, np.float64); mass = np.zeros(self.T, np.float64); eff = np.zeros(self.T, np.float64)
+        rc = self.R.ref_em_optimize(self.h, tol, max_iter, _ptr(est, f64p), _ptr(mass, f64p))
+        self.R.ref_txp_eff_lens(self.h, _ptr(eff, f64p))
+        return rc, est, eff
 
     def fld(self, n):
         cdf = np.zeros(n, np.float32)
@@ -138,6 +152,8 @@ def lib():
                                    C.c_double, f64p]
         L.orc_update_eff_lens.argtypes = [C.c_int, C.c_uint32, C.c_char_p, u64p, u32p, f64p, f64p, f64p, C.c_int64, C.c_int64, u32p, u32p,
                                           u32p, C.c_uint32, C.c_uint32, f64p]
+        L.orc_em_run_bias.argtypes = [C.c_uint32, C.c_uint64, u64p, u32p, u64p, f64p, C.c_uint64, C.POINTER(EMOpts), C.c_int, C.c_int,
+                                      C.c_char_p, u64p, u32p, C.c_int64, C.c_int64, u32p, u32p, u32p, C.c_uint32, C.c_uint32, f64p, f64p, u32p, f64p]
         L.orc_em_run.argtypes = [C.c_uint32, C.c_uint64, u64p, u32p, u64p, f64p, C.c_uint64, C.POINTER(EMOpts), C.c_int,
                                  f64p, u32p, f64p]
         L.orc_tpm.argtypes = [C.c_uint32, f64p, f64p, C.c_uint64, f64p]
@@ -318,6 +334,27 @@ def update_eff_lens(mode, seqs, eff_model, eff_in, alphas, num_fwd, num_rc, read
     return rc, out
 
 
+def em_run_bias(mode, seqs, row_ptr, labels, counts, eff, num_mapped, num_fwd, num_rc, read_bias, observed_gc, fld_counts, gc_samp=1,
+                opts=None, n_threads=1):
+    """optimize() with --biasCorrect (mode 1) / --gcBiasCorrect (mode 2): effective lengths recomputed at iterations 50 / 500 / 1000.
+    -> (rc, alphas, eff_out, iters, max_rel_diff)"""
+    opts = opts or EMOpts.default()
+    T = len(seqs)
+    row_ptr, labels, counts = _csr(row_ptr, labels, counts)
+    ln = np.array([len(s) for s in seqs], np.uint32)
+    off = np.zeros(T, np.uint64); off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+    eff = np.ascontiguousarray(eff, dtype=np.float64)
+    rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)
+    fc = np.ascontiguousarray(fld_counts, dtype=np.uint32)
+    alphas = np.zeros(T, np.float64); eff_out = np.zeros(T, np.float64)
+    iters = C.c_uint32(); mrd = C.c_double()
+    rc = lib().orc_em_run_bias(T, len(counts), _ptr(row_ptr, u64p), _ptr(labels, u32p), _ptr(counts, u64p), _ptr(eff, f64p), int(num_mapped),
+                               C.byref(opts), n_threads, int(mode), b"".join(seqs), _ptr(off, u64p), _ptr(ln, u32p), int(num_fwd), int(num_rc),
+                               _ptr(rb, u32p), _ptr(og, u32p), _ptr(fc, u32p), len(fc), int(gc_samp), _ptr(alphas, f64p), _ptr(eff_out, f64p),
+                               C.byref(iters), C.byref(mrd))
+    return rc, alphas, eff_out, iters.value, mrd.value
+
+
 def _csr(row_ptr, labels, counts):
     return (np.ascontiguousarray(row_ptr, dtype=np.uint64), np.ascontiguousarray(labels, dtype=np.uint32),
             np.ascontiguousarray(counts, dtype=np.uint64))
@@ -428,6 +465,7 @@ def ref_em():
             R.ref_bias_update.argtypes = [C.c_void_p, f64p, f64p, f64p]
             R.ref_bias_fld.restype = C.c_uint32
             R.ref_bias_fld.argtypes = [C.c_void_p, f32p, C.c_uint32]
+            R.ref_txp_eff_lens.argtypes = [C.c_void_p, f64p]
         _ref_em = R
     return _ref_em
 

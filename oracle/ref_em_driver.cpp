@@ -239,6 +239,13 @@ int ref_em_optimize(void* h, double tol, uint32_t max_iter, double* est_count, d
     return ok ? 0 : -1;
 }
 
+// Transcript::EffectiveLength of every transcript (optimize() stores the bias-corrected lengths there, :888)
+void ref_txp_eff_lens(void* h, double* out) {
+    auto* s = static_cast<Session*>(h);
+    auto& txps = s->exp->transcripts();
+    for (size_t t = 0; t < txps.size(); ++t) out[t] = txps[t].EffectiveLength;
+}
+
 // CollapsedEMOptimizer::gatherBootstraps (:557-709); rows appended to out[n_boot][n_txp]
 int ref_em_bootstraps(void* h, double tol, uint32_t max_iter, double* out) {
     auto* s = static_cast<Session*>(h);

@@ -86,6 +86,17 @@ def make_bias_fixture():
             out["ref_%s_samp%d_round2" % (tag, samp)] = ref2
     cdf, mx = Rb.fld(1000)
     out["ref_fld_cdf"] = cdf; out["ref_fld_max"] = np.int64(mx)
+    # the whole optimizer with the correction switched on (lengths recomputed at iterations 50 / 500 / 1000): the reference's own
+    # CollapsedEMOptimizer::optimize on classes over these transcripts, EM and VBEM
+    rp, lab, cnt = synth.make_classes(T, 150, seed=11, gene_size=4)
+    nm = int(cnt.sum())
+    out.update(row_ptr=rp, labels=lab, counts=cnt, num_mapped=np.int64(nm))
+    for mode, tag in ((1, "seq"), (2, "gc")):
+        for vb in (0, 1):
+            Ro = O.RefBias(mode, seqs, eff_model, read_bias, observed_gc, fld, 61234, 58766, classes=(rp, lab, cnt), num_mapped=nm, use_vb=bool(vb))
+            rc, est, eff_after = Ro.optimize(tol=1e-5)          # tighter than the default 0.01: the run must pass iteration 50
+            assert rc == 0
+            out["opt_%s_vb%d_est" % (tag, vb)] = est; out["opt_%s_vb%d_eff" % (tag, vb)] = eff_after
     np.savez_compressed(os.path.join(OUT, "bias_efflens.npz"), **out)
     print("bias_efflens.npz: %d transcripts, %d corrected (seq), %d corrected (gc)" % (
         T, int((out["ref_seq_samp1"] != eff_in).sum()), int((out["ref_gc_samp1"] != eff_in).sum())))

@@ -37,6 +37,25 @@ def test_oracle_matches_reference_golden(mode, tag, samp):
     np.testing.assert_allclose(out2, d["ref_%s_samp%d_round2" % (tag, samp)], rtol=1e-12)
 
 
+@pytest.mark.parametrize("mode,tag", [(1, "seq"), (2, "gc")])
+@pytest.mark.parametrize("vb", [0, 1])
+def test_optimizer_with_correction_matches_reference_golden(mode, tag, vb):
+    """optimize() with --biasCorrect / --gcBiasCorrect: lengths recomputed at iterations 50 / 500 / 1000 and the class weights
+    rebuilt (CollapsedEMOptimizer.cpp:816-840); estimates and final effective lengths of the reference's own optimizer"""
+    d = dict(np.load(GOLDEN))
+    seqs = split(d["seq"], d["txp_len"])
+    rc, a, eff, it, _ = O.em_run_bias(mode, seqs, d["row_ptr"], d["labels"], d["counts"], d["eff_model"], int(d["num_mapped"]),
+                                      int(d["num_fwd"]), int(d["num_rc"]), d["read_bias"], d["observed_gc"], d["fld"],
+                                      opts=O.EMOpts.default(use_vb=vb, tol=1e-5))
+    assert rc == 0 and it > 50
+    np.testing.assert_allclose(a, d["opt_%s_vb%d_est" % (tag, vb)], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(eff, d["opt_%s_vb%d_eff" % (tag, vb)], rtol=1e-12)
+    assert (eff != np.maximum(d["eff_model"], 1.0)).sum() > 5               # the correction did change lengths
+    # and it matters: without it the estimates differ
+    rc0, a0, _, _ = O.em_run(len(seqs), d["row_ptr"], d["labels"], d["counts"], d["eff_model"], int(d["num_mapped"]), O.EMOpts.default(use_vb=vb, tol=1e-5))
+    assert rc0 == 0 and np.max(np.abs(a0 - a)) > 1e-3
+
+
 def test_degenerate_inputs():
     d = dict(np.load(GOLDEN))
     seqs = split(d["seq"], d["txp_len"])
