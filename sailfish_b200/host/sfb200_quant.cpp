@@ -351,9 +351,11 @@ private:
                     b->m1.clear(); b->m2.clear();
                     size_t n1 = 0, n2 = 0;
                     if (paired) {                                             // the two mates are parsed side by side
-                        std::thread other([&] { n2 = r2->next(b->m2, batch_); });
-                        n1 = r1.next(b->m1, batch_);
+                        std::string err2;                                       // an exception must not leave the helper thread
+                        std::thread other([&] { try { n2 = r2->next(b->m2, batch_); } catch (const std::exception& e) { err2 = e.what(); } });
+                        try { n1 = r1.next(b->m1, batch_); } catch (...) { other.join(); throw; }
                         other.join();
+                        if (!err2.empty()) throw std::runtime_error(err2);
                         if (n1 != n2) throw std::runtime_error("mate files " + files1_[fi] + " / " + files2_[fi] + " hold different numbers of reads");
                     } else {
                         n1 = r1.next(b->m1, batch_);

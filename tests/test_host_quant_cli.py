@@ -76,6 +76,10 @@ def test_fastq_ingestion_paired_and_multiple_files(tmp_path):
     write_fastq(str(tmp_path / "short.fq"), a2[:-1])
     r = subprocess.run([EXE, "--parseOnly", "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "short.fq")], capture_output=True)
     assert r.returncode != 0 and b"different numbers of reads" in r.stderr
+    # a malformed second mate file is reported, not a crash of the helper thread
+    (tmp_path / "bad2.fq").write_text("@r0\nACGT\nIIII\n+\n" * 50)
+    r = subprocess.run([EXE, "--parseOnly", "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "bad2.fq")], capture_output=True)
+    assert r.returncode == 1 and b"malformed FASTQ record" in r.stderr
 
 
 def test_fasta_reads_and_errors(tmp_path):
