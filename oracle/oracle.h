@@ -93,6 +93,9 @@ int orc_map_batch(orc_run*, const char* bases1, const uint64_t* off1, const char
                   uint64_t n_reads, int n_threads);
 /* counters: [0] numObservedFragments [1] numMappedFragments [2] numFragHits [3] upperBoundHits [4] numFwd [5] numRC */
 int orc_map_finish(orc_run*, uint64_t counters[6], uint32_t* fld_hist /*max_frag_len*/, uint64_t* n_classes, uint64_t* nnz);
+/* --biasCorrect / --gcBiasCorrect sample collection (SailfishQuantify.cpp:255-287,372-389,555-583); call before orc_map_batch */
+void orc_run_set_bias(orc_run*, int seq_bias, int gc_bias, int32_t num_bias_samples);
+int orc_map_finish_bias(const orc_run*, uint32_t* read_bias /*4096, pseudo-count 1 included*/, uint32_t* observed_gc /*101*/);
 /* classes in canonical order (label-lexicographic): row_ptr[E+1], labels[nnz], counts[E] */
 int orc_eq_export(const orc_run*, uint64_t* row_ptr, uint32_t* labels, uint64_t* counts);
 /* mapping work counters for B_map: [0] table probes P [1] SA entries S [2] text bases compared X */

@@ -13,6 +13,7 @@
 #include "orc_threads.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -226,8 +227,54 @@ struct ThreadOut {
     uint64_t observed = 0, mapped = 0, fragHits = 0, ubHits = 0;
     int64_t numFwd = 0, numRC = 0;
     std::vector<int32_t> fld;                            // per read: fragLen if FLD-eligible else -1 (chunk order)
+    std::vector<int32_t> bias;                           // per read: 6-mer context index of its bias sample else -1 (only when collected)
+    uint32_t gc[101] = {0};                              // observed fragment GC histogram of this chunk
     Work work;
 };
+
+// ---- bias / GC sample collection (SailfishQuantify.cpp:255-287,372-389 paired; :555-583 single) ---------------------------------
+struct BiasCfg { bool seq = false, gc = false; };
+
+// ReadKmerDist<6>::update (include/ReadKmerDist.hpp:36-72) for a hit: the 6-mer context around the read start on the transcript,
+// reverse-complemented for forward hits; -1 if the window does not fit (or the start lies outside (0, RefLength))
+inline int32_t bias_context_index(const orc_index& ix, const Hit& h) {
+    constexpr int K = 6;
+    const int32_t refLen = static_cast<int32_t>(ix.txp_len[h.tid]);
+    const int32_t startPos = h.fwd ? h.pos : h.pos + static_cast<int32_t>(h.readLen);      // :276
+    if (!(startPos > 0 && startPos < refLen)) return -1;                                    // :278
+    const uint64_t t0 = ix.txp_start[h.tid];
+    uint32_t idx = 0;
+    if (h.fwd) {                                                                             // Direction::FORWARD: window starts 2 before
+        const int32_t p = startPos - 2;
+        if (!(startPos >= 2 && p + K < refLen)) return -1;
+        for (int i = K - 1; i >= 0; --i) { idx += static_cast<uint32_t>(3 - ix.base(t0 + p + i)); if (i > 0) idx <<= 2; }   // indexForKmer(.., REVERSE_COMPLEMENT)
+    } else {                                                                                 // REVERSE_COMPLEMENT: window starts 4 before
+        const int32_t p = startPos - 4;
+        if (!(startPos >= 4 && p + K < refLen)) return -1;
+        for (int i = 0; i < K; ++i) { idx += static_cast<uint32_t>(ix.base(t0 + p + i)); if (i < K - 1) idx <<= 2; }        // indexForKmer(.., FORWARD)
+    }
+    return static_cast<int32_t>(idx);
+}
+// Transcript::gcFrac(s, e) (include/Transcript.hpp:85-96): G/C bases in (s, e] over the closed interval's length
+inline int32_t gc_frac(const orc_index& ix, uint32_t tid, int32_t s, int32_t e) {
+    const uint64_t t0 = ix.txp_start[tid];
+    uint32_t n = 0;
+    for (int32_t i = s + 1; i <= e; ++i) { const int b = ix.base(t0 + i); n += (b == 1 || b == 2) ? 1u : 0u; }
+    return static_cast<int32_t>(std::lrint((100.0 * n) / (e - s + 1)));
+}
+// the per-read part of both samplers: the first hit (in jointHits order) whose context window fits gives the read's bias sample;
+// every properly paired hit inside its transcript adds one observation to the fragment GC histogram
+inline void collect_bias_samples(const orc_index& ix, const BiasCfg& bc, const std::vector<Hit>& joint, ThreadOut& t) {
+    int32_t sample = -1;
+    for (const Hit& h : joint) {
+        if (bc.seq && sample < 0) sample = bias_context_index(ix, h);
+        if (bc.gc && h.mateStatus == 3) {                                                    // :375-388
+            const int32_t start = std::min(h.pos, h.matePos), stop = start + static_cast<int32_t>(h.fragLen);
+            if (start > 0 && stop < static_cast<int32_t>(ix.txp_len[h.tid])) t.gc[gc_frac(ix, h.tid, start, stop)]++;
+        }
+    }
+    if (bc.seq) t.bias.push_back(sample);
+}
 
 struct Mapper {
     const orc_index& ix;
@@ -345,7 +392,7 @@ inline void add_class(ThreadOut& t, const std::vector<uint32_t>& label) {
 }
 
 // SailfishQuantify.cpp:215-439 (paired) for one fragment.
-void process_pair(const Mapper& mp, const orc_map_opts& o, const std::vector<uint8_t>& r1, const std::vector<uint8_t>& r2,
+void process_pair(const Mapper& mp, const orc_map_opts& o, const BiasCfg& bc, const std::vector<uint8_t>& r1, const std::vector<uint8_t>& r2,
                   ThreadOut& t, std::vector<uint32_t>* dbgLabel) {
     std::vector<Hit> left, right, joint;
     const bool okL = mp.collect(r1, 1, true, left);                   // strict check (:192-202)
@@ -390,6 +437,7 @@ void process_pair(const Mapper& mp, const orc_map_opts& o, const std::vector<uin
         int32_t fwAll = 0, fwCompat = 0, rcAll = 0, rcCompat = 0;
         bool haveCompat = false;
         std::vector<uint32_t> idsAll, idsCompat;
+        if (bc.seq || bc.gc) collect_bias_samples(mp.ix, bc, joint, t);   // inside the hit loop in the reference (:255-287,372-389)
         for (const Hit& h : joint) {
             if (!isPaired) {                                           // :289-340
                 bool compat = o.ignore_compat != 0;
@@ -419,6 +467,7 @@ void process_pair(const Mapper& mp, const orc_map_opts& o, const std::vector<uin
             mappedFrag = true; add_class(t, idsAll); t.numFwd += fwAll; t.numRC += rcAll; if (dbgLabel) *dbgLabel = idsAll;
         }
     }
+    if (bc.seq && t.bias.size() < t.fld.size() + 1) t.bias.push_back(-1);   // a fragment without hits gives no sample
     int32_t fl = -1;                                                   // :419-434 (sampling decided later, in global read order)
     if (joint.size() == 1 && joint.front().mateStatus == 3 && mappedFrag && joint.front().fragLen < o.max_frag_len)
         fl = static_cast<int32_t>(joint.front().fragLen);
@@ -429,7 +478,7 @@ void process_pair(const Mapper& mp, const orc_map_opts& o, const std::vector<uin
 }
 
 // SailfishQuantify.cpp:526-631 (single-end) for one read.
-void process_single(const Mapper& mp, const orc_map_opts& o, const std::vector<uint8_t>& r, ThreadOut& t,
+void process_single(const Mapper& mp, const orc_map_opts& o, const BiasCfg& bc, const std::vector<uint8_t>& r, ThreadOut& t,
                     std::vector<uint32_t>* dbgLabel) {
     std::vector<Hit> joint;
     const bool ok = mp.collect(r, 0, false, joint);                    // default (non-strict) check (:526-528)
@@ -440,6 +489,7 @@ void process_single(const Mapper& mp, const orc_map_opts& o, const std::vector<u
         int32_t fwAll = 0, fwCompat = 0, rcAll = 0, rcCompat = 0;
         bool haveCompat = false;
         std::vector<uint32_t> idsAll, idsCompat;
+        if (bc.seq) collect_bias_samples(mp.ix, BiasCfg{true, false}, joint, t);   // :555-583 (no fragment GC for single-end reads)
         for (const Hit& h : joint) {                                   // :547-605
             bool compat = o.ignore_compat != 0;
             if (!compat) compat = orc_compat_single(o.lib_format_id, h.pos, h.fwd, h.mateStatus) != 0;
@@ -452,6 +502,7 @@ void process_single(const Mapper& mp, const orc_map_opts& o, const std::vector<u
             mappedFrag = true; add_class(t, idsAll); t.numFwd += fwAll; t.numRC += rcAll; if (dbgLabel) *dbgLabel = idsAll;
         }
     }
+    if (bc.seq && t.bias.size() < t.fld.size() + 1) t.bias.push_back(-1);
     t.fld.push_back(-1);
     t.mapped += mappedFrag ? 1 : 0;                                    // :628-631
     t.fragHits += joint.size();
@@ -467,6 +518,9 @@ struct orc_run {
     uint64_t counters[6] = {0, 0, 0, 0, 0, 0};
     std::vector<uint32_t> fld;
     int32_t remainingFLOps;
+    BiasCfg bias;
+    int32_t remainingBiasSamples = 0;                     // sfOpts.numBiasSamples (:270,283)
+    std::vector<uint32_t> readBias, observedGC;           // with their pseudo-counts of 1 (ReadKmerDist.hpp:20-24, ReadExperiment.hpp:50)
     Work work;
     std::vector<std::vector<uint32_t>> lastLabels;        // debug: label per read of the last batch
     bool keepLabels = false;
@@ -480,6 +534,18 @@ extern "C" orc_run* orc_run_create(const orc_index* ix, const orc_map_opts* o) {
     return r;
 }
 extern "C" void orc_run_free(orc_run* r) { delete r; }
+// --biasCorrect / --gcBiasCorrect: collect the read-start 6-mer contexts (first num_bias_samples successes in read order, the
+// reference at -p 1) and the observed fragment GC histogram while mapping
+extern "C" void orc_run_set_bias(orc_run* r, int seq_bias, int gc_bias, int32_t num_bias_samples) {
+    r->bias.seq = seq_bias != 0; r->bias.gc = gc_bias != 0;
+    r->remainingBiasSamples = num_bias_samples;
+    r->readBias.assign(4096, 1u); r->observedGC.assign(101, 1u);
+}
+extern "C" int orc_map_finish_bias(const orc_run* r, uint32_t* read_bias /*4096*/, uint32_t* observed_gc /*101*/) {
+    if (r->readBias.empty()) return -1;
+    std::memcpy(read_bias, r->readBias.data(), 4096 * 4); std::memcpy(observed_gc, r->observedGC.data(), 101 * 4);
+    return 0;
+}
 extern "C" void orc_run_keep_labels(orc_run* r, int on) { r->keepLabels = on != 0; }
 
 extern "C" int orc_map_batch(orc_run* r, const char* bases1, const uint64_t* off1, const char* bases2,
@@ -502,9 +568,9 @@ extern "C" int orc_map_batch(orc_run* r, const char* bases1, const uint64_t* off
                 encode(bases1 + off1[i], off1[i + 1] - off1[i], s1);
                 if (paired) {
                     encode(bases2 + off2[i], off2[i + 1] - off2[i], s2);
-                    process_pair(mp, r->o, s1, s2, t, dbg);
+                    process_pair(mp, r->o, r->bias, s1, s2, t, dbg);
                 } else {
-                    process_single(mp, r->o, s1, t, dbg);
+                    process_single(mp, r->o, r->bias, s1, t, dbg);
                 }
             }
         }
@@ -521,6 +587,10 @@ extern "C" int orc_map_batch(orc_run* r, const char* bases1, const uint64_t* off
         for (int32_t fl : t.fld) {                                    // first num_frag_samples eligible fragments in read order
             if (fl >= 0 && r->remainingFLOps > 0) { r->fld[fl]++; r->remainingFLOps--; }
         }
+        for (int32_t idx : t.bias) {                                  // first numBiasSamples successful reads in read order
+            if (idx >= 0 && r->remainingBiasSamples > 0) { r->readBias[idx]++; r->remainingBiasSamples--; }
+        }
+        if (r->bias.gc) for (int g = 0; g < 101; ++g) r->observedGC[g] += t.gc[g];
         r->work.P += t.work.P; r->work.S += t.work.S; r->work.X += t.work.X;
     }
     return 0;

@@ -145,6 +145,8 @@ def lib():
         L.orc_run_keep_labels.argtypes = [C.c_void_p, C.c_int]
         L.orc_map_batch.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_char_p, u64p, C.c_uint64, C.c_int]
         L.orc_map_finish.argtypes = [C.c_void_p, u64p, u32p, u64p, u64p]
+        L.orc_run_set_bias.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int32]
+        L.orc_map_finish_bias.argtypes = [C.c_void_p, u32p, u32p]
         L.orc_eq_export.argtypes = [C.c_void_p, u64p, u32p, u64p]
         L.orc_map_work.argtypes = [C.c_void_p, u64p]
         L.orc_last_label.argtypes = [C.c_void_p, C.c_uint64, u32p, C.c_int]
@@ -261,6 +263,18 @@ class Run:
     def __init__(self, index, opts):
         self.index, self.opts = index, opts
         self.h = lib().orc_run_create(index.h, C.byref(opts))
+
+    def set_bias(self, seq_bias=True, gc_bias=False, num_bias_samples=1000000):
+        """--biasCorrect / --gcBiasCorrect sample collection while mapping (call before map_batch)"""
+        lib().orc_run_set_bias(self.h, int(seq_bias), int(gc_bias), int(num_bias_samples))
+
+    def finish_bias(self):
+        """-> (read_bias[4096], observed_gc[101]), pseudo-counts of 1 included"""
+        rb = np.zeros(4096, np.uint32); og = np.zeros(101, np.uint32)
+        rc = lib().orc_map_finish_bias(self.h, _ptr(rb, u32p), _ptr(og, u32p))
+        if rc:
+            raise RuntimeError("set_bias was not called")
+        return rb, og
 
     def keep_labels(self, on=True):
         lib().orc_run_keep_labels(self.h, int(on))
@@ -466,6 +480,8 @@ def ref_em():
             R.ref_bias_fld.restype = C.c_uint32
             R.ref_bias_fld.argtypes = [C.c_void_p, f32p, C.c_uint32]
             R.ref_txp_eff_lens.argtypes = [C.c_void_p, f64p]
+            R.ref_readbias_update.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+            R.ref_gc_frac.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
         _ref_em = R
     return _ref_em
 

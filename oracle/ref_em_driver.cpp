@@ -239,6 +239,26 @@ int ref_em_optimize(void* h, double tol, uint32_t max_iter, double* est_count, d
     return ok ? 0 : -1;
 }
 
+// ReadKmerDist<6>::update (include/ReadKmerDist.hpp:36-72) for a read that starts at txp[start_pos]: the bin it incremented, -1 if
+// the context window did not fit
+int ref_readbias_update(const char* txp, int len, int start_pos, int fwd) {
+#ifndef SFREF_HAVE_BIAS
+    return -2;
+#else
+    ReadKmerDist<6, uint32_t> d;
+    const bool ok = d.update(txp, txp + start_pos, txp + len, fwd ? sailfish::utils::Direction::FORWARD : sailfish::utils::Direction::REVERSE_COMPLEMENT);
+    if (!ok) return -1;
+    for (size_t i = 0; i < d.counts.size(); ++i) if (d.counts[i] == 2) return static_cast<int>(i);
+    return -1;
+#endif
+}
+// Transcript::gcFrac(s, e) (include/Transcript.hpp:85-96) through the reference's own GC tables (gcSampFactor 1)
+int ref_gc_frac(const char* seq, int len, int s, int e) {
+    Transcript t(0, "t", static_cast<uint32_t>(len));
+    t.setSequence(seq, true, 1);
+    return t.gcFrac(s, e);
+}
+
 // Transcript::EffectiveLength of every transcript (optimize() stores the bias-corrected lengths there, :888)
 void ref_txp_eff_lens(void* h, double* out) {
     auto* s = static_cast<Session*>(h);

@@ -87,3 +87,74 @@ def test_oracle_matches_reference_live():
         rc, out = O.update_eff_lens(mode, seqs, eff_model, eff_model, alphas, 1000, 3000, rb, og, fld, gc_samp=2)
         assert rc == 0 and rc_r == 0
         np.testing.assert_allclose(out, ref, rtol=1e-12)
+
+
+def _rc(b):
+    return bytes({65: 84, 67: 71, 71: 67, 84: 65}[c] for c in reversed(b))
+
+
+def test_sample_collection_matches_reference_helpers():
+    """read-start 6-mer contexts and the observed fragment GC histogram collected while mapping (SailfishQuantify.cpp:255-287,
+    372-389, 555-583): the oracle mapper against the reference's own ReadKmerDist<6>::update and Transcript::gcFrac applied to the
+    known origin of every read (single-isoform genes: every read has exactly one hit)"""
+    R = O.ref_em()
+    if R is None or not hasattr(R, "ref_readbias_update"):
+        pytest.skip("oracle/_ref/libsfref_em.so with the bias correction is not available here")
+    rng = np.random.default_rng(7)
+    T, L = 12, 60
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=int(n)).astype(np.uint8)) for n in rng.integers(300, 900, size=T)]
+    ix = O.Index(seqs, k=31)
+    # ---- single-end: forward and reverse-complement reads, including starts at the very ends of a transcript
+    reads, want = [], np.ones(4096, np.int64)
+    n_samples = 0
+    budget = 150
+    for i in range(400):
+        t = int(rng.integers(0, T)); n = len(seqs[t])
+        pos = int(rng.choice([0, 1, 2, 3, n - L, n - L - 1, n - L - 2, int(rng.integers(0, n - L + 1))]))
+        fwd = bool(rng.integers(0, 2))
+        frag = seqs[t][pos:pos + L]
+        reads.append(frag if fwd else _rc(frag))
+        start = pos if fwd else pos + L
+        idx = -1
+        if 0 < start < n:
+            idx = R.ref_readbias_update(seqs[t], n, start, int(fwd))
+        if idx >= 0 and n_samples < budget:
+            want[idx] += 1; n_samples += 1
+    b = np.frombuffer(b"".join(reads), np.uint8); off = np.arange(len(reads) + 1, dtype=np.uint64) * np.uint64(L)
+    run = O.Run(ix, O.MapOpts.default(O.parse_libtype("U")))
+    run.set_bias(True, False, budget)
+    run.map_batch(b.tobytes(), off, n_threads=3)
+    res = run.finish()
+    assert int(res["counters"][1]) == len(reads)
+    rb, og = run.finish_bias()
+    assert rb.tolist() == want.tolist() and n_samples == budget
+    assert (og == 1).all()                                                # no fragment GC from single-end reads
+    # ---- paired-end: inward pairs; the GC observation uses gcFrac(start, start + fragLen) when it lies inside the transcript
+    r1, r2, want_gc = [], [], np.ones(101, np.int64)
+    want_b = np.ones(4096, np.int64)
+    for i in range(300):
+        t = int(rng.integers(0, T)); n = len(seqs[t])
+        fl = int(rng.integers(L + 20, 260))
+        fs = int(rng.choice([0, 1, n - fl, n - fl - 1, int(rng.integers(0, n - fl + 1))]))
+        left, right = seqs[t][fs:fs + L], _rc(seqs[t][fs + fl - L:fs + fl])
+        flip = bool(rng.integers(0, 2))
+        r1.append(right if flip else left); r2.append(left if flip else right)
+        # mate 1 decides the bias sample: forward mate 1 starts at its position, a reverse-complemented one at position + length
+        pos1, fwd1 = (fs + fl - L, False) if flip else (fs, True)
+        start1 = pos1 if fwd1 else pos1 + L
+        if 0 < start1 < n:
+            idx = R.ref_readbias_update(seqs[t], n, start1, int(fwd1))
+            if idx >= 0:
+                want_b[idx] += 1
+        if fs > 0 and fs + fl < n:
+            want_gc[R.ref_gc_frac(seqs[t], n, fs, fs + fl)] += 1
+    b1 = np.frombuffer(b"".join(r1), np.uint8); b2 = np.frombuffer(b"".join(r2), np.uint8)
+    off = np.arange(len(r1) + 1, dtype=np.uint64) * np.uint64(L)
+    run = O.Run(ix, O.MapOpts.default(O.parse_libtype("IU")))
+    run.set_bias(True, True, 10 ** 6)
+    run.map_batch(b1.tobytes(), off, b2.tobytes(), off, n_threads=2)
+    res = run.finish()
+    assert int(res["counters"][1]) == len(r1)
+    rb, og = run.finish_bias()
+    assert og.tolist() == want_gc.tolist()
+    assert rb.tolist() == want_b.tolist()
