@@ -6,14 +6,17 @@
 // sfb200_map_batch takes (a parser job's std::string per mate, concatenated).  Qualities and names are dropped, as
 // processReadsQuasi only ever touches `seq` (SailfishQuantify.cpp:192-202,526-528).
 //
-// FASTQ is parsed block-wise: a block of text is cut at a record boundary (line count multiple of 4; the previous block ended
-// on one, so no guessing), the newlines are indexed with memchr, the read offsets are a prefix sum over the sequence lines, and
-// the sequence lines are copied straight into the caller's batch.  Blocks of a few MB keep the text in cache between the index
-// and the copy (measured here: 1.5 GB/s of FASTQ per file on one core, 0.43 GB/s with 32 MB blocks and freshly allocated
-// vectors); blocks above `threads` MB are indexed and copied by several threads.  The driver parses the two mate files side by
-// side and one batch ahead of the device.  Buffers are plain malloc'ed memory that is reused from block to block and from batch to batch (no zero-filling, no
-// page faults after warm-up); plain files are read with read(2), gzip through zlib.  FASTA reads (may be multi-line) take a
-// simple serial path.  Header-only, C++11, needs -lz -pthread.
+// FASTQ is parsed block-wise: a block of text (2 MB per parser thread) is cut at a record boundary (line count multiple of 4;
+// the previous block ended on one, so no guessing); the threads of a small persistent pool each pread their slice of the
+// block (plain files; gzip goes through zlib on one thread), index the newlines of their slice with memchr, and -- after a
+// serial prefix sum over the sequence-line lengths -- copy the sequence lines of their share of the records straight into the
+// caller's batch.  Buffers are plain malloc'ed memory reused from block to block and from batch to batch (no zero-filling, no
+// page faults after warm-up).  FASTA reads (may be multi-line) take a simple serial path.  The driver parses the two mate
+// files side by side and one batch ahead of the device.
+// Measured in the build container (2.7 GB of FASTQ from tmpfs): 0.43 GB/s for the first version (32 MB blocks, std::vector
+// buffers), 1.7 GB/s on one thread, 2.4 GB/s on eight -- that container moves ~5.3 GB/s through memchr however many threads
+// ask (microbenchmark), so the scaling of the parallel phases has to be measured on the GPU host.
+// Header-only, C++11, needs -lz -pthread.
 #ifndef SFB200_FASTX_READER_HPP
 #define SFB200_FASTX_READER_HPP
 
@@ -23,9 +26,14 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -69,6 +77,70 @@ private:
     size_t n_ = 0, cap_ = 0;
 };
 
+// a few persistent threads that run `fn(task)` for task = 0..n-1 and wait: the parser's parallel phases are short (a few MB of
+// text each), so spawning threads per phase costs more than the phase
+class WorkerPool {
+public:
+    explicit WorkerPool(unsigned n_threads) {
+        for (unsigned t = 1; t < n_threads; ++t) th_.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    unsigned size() const { return (unsigned)th_.size() + 1; }
+    // fn must not throw
+    void run(unsigned n_tasks, const std::function<void(unsigned)>& fn) {
+        if (n_tasks == 0) return;
+        if (th_.empty() || n_tasks == 1) { for (unsigned i = 0; i < n_tasks; ++i) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_tasks_ = n_tasks; next_ = 0; pending_ = n_tasks; ++gen_;
+        }
+        cv_.notify_all();
+        work();                                                   // the calling thread takes tasks too
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            unsigned i;
+            const std::function<void(unsigned)>* f;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= n_tasks_) return;
+                i = next_++; f = fn_;
+            }
+            (*f)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned)>* fn_ = nullptr;
+    unsigned n_tasks_ = 0, next_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
 // a batch of reads: read i = bases[off[i] .. off[i+1])
 struct ReadBatch {
     RawBuf<char> bases;
@@ -79,8 +151,10 @@ struct ReadBatch {
 
 class FastxReader {
 public:
-    explicit FastxReader(const std::string& path, unsigned threads = 4, size_t block_bytes = 2u << 20)
-        : path_(path), threads_(threads ? threads : 1), block_(block_bytes < 16 ? 16 : block_bytes) {
+    // block_bytes = 0: 2 MB per thread (each thread's share of a block stays in its cache between the newline index and the copy)
+    explicit FastxReader(const std::string& path, unsigned threads = 4, size_t block_bytes = 0)
+        : path_(path), threads_(threads ? threads : 1), block_(block_bytes == 0 ? (size_t)(threads ? threads : 1) * (2u << 20) : (block_bytes < 16 ? 16 : block_bytes)),
+          pool_(threads ? threads : 1) {
         fd_ = ::open(path.c_str(), O_RDONLY);
         if (fd_ < 0) throw std::runtime_error("cannot open " + path);
         unsigned char magic[2] = {0, 0};
@@ -111,18 +185,45 @@ public:
         return got;
     }
     uint64_t records_read() const { return n_records_; }
+    // seconds spent in: [0] reading, [1] newline index, [2] lengths + offsets, [3] copying bases, [4] moving the tail
+    const double* phase_seconds() const { return tm_; }
 
 private:
     size_t read_some(char* dst, size_t want) {
+        if (!gz_ && threads_ > 1 && want >= (8u << 20)) {             // plain file, big block: every thread preads its slice
+            const unsigned nt = threads_;
+            std::vector<long> got(nt, 0);
+            const uint64_t pos = file_pos_;
+            pool_.run(nt, [&](unsigned t) {
+                const size_t a = want * t / nt, b = want * (t + 1) / nt;
+                size_t n = 0;
+                while (n < b - a) {
+                    const ssize_t r = ::pread(fd_, dst + a + n, b - a - n, (off_t)(pos + a + n));
+                    if (r < 0) { got[t] = -1; return; }
+                    if (r == 0) break;
+                    n += (size_t)r;
+                }
+                got[t] = (long)n;
+            });
+            size_t n = 0;
+            for (unsigned t = 0; t < nt; ++t) {
+                if (got[t] < 0) throw std::runtime_error("read error in " + path_);
+                n += (size_t)got[t];
+                if ((size_t)got[t] < want * (t + 1) / nt - want * t / nt) { eof_ = true; break; }   // a short slice: end of file
+            }
+            file_pos_ += n;
+            return n;
+        }
         size_t n = 0;
         while (n < want) {
             long r;
             if (gz_) r = gzread(gz_, dst + n, (unsigned)std::min<size_t>(want - n, 1u << 30));
-            else r = (long)::read(fd_, dst + n, std::min<size_t>(want - n, 1u << 30));
+            else r = (long)::pread(fd_, dst + n, std::min<size_t>(want - n, 1u << 30), (off_t)(file_pos_ + n));
             if (r < 0) throw std::runtime_error("read error in " + path_);
             if (r == 0) { eof_ = true; break; }
             n += (size_t)r;
         }
+        file_pos_ += n;
         return n;
     }
 
@@ -130,10 +231,12 @@ private:
     bool refill() {
         // drop what the previous block's records covered; keep the tail (an incomplete record) at the front
         if (consumed_ > 0) {
+            const double t0 = now();
             const size_t tail = buf_.size() - consumed_;
             if (tail) std::memmove(buf_.data(), buf_.data() + consumed_, tail);
             buf_.resize_uninit(tail);
             consumed_ = 0;
+            tm_[4] += now() - t0;
         }
         n_rec_ = 0; rec_pos_ = 0;
         for (;;) {
@@ -141,8 +244,10 @@ private:
             if (!eof_) {
                 const size_t old = buf_.size();
                 buf_.reserve(old + block_);
+                const double t0 = now();
                 const size_t n = read_some(buf_.data() + old, block_);
                 buf_.resize_uninit(old + n);
+                tm_[0] += now() - t0;
             }
             if (buf_.empty()) return false;
             if (fmt_ == 0) {
@@ -153,7 +258,7 @@ private:
                 else throw std::runtime_error(path_ + ": neither FASTA nor FASTQ");
                 if (i) { std::memmove(buf_.data(), buf_.data() + i, buf_.size() - i); buf_.resize_uninit(buf_.size() - i); }
             }
-            if (fmt_ == 'q') index_fastq(); else index_fasta();
+            { const double t0 = now(); if (fmt_ == 'q') index_fastq(); else index_fasta(); tm_[1] += now() - t0; }
             if (n_rec_ > 0) break;
             if (eof_) {
                 for (size_t i = 0; i < buf_.size(); ++i)
@@ -173,7 +278,7 @@ private:
         const size_t len = buf_.size();
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, len >> 20));
         if (parts_.size() < nt) parts_.resize(nt);
-        auto scan = [&](unsigned t) {
+        pool_.run(nt, [&](unsigned t) {
             std::vector<size_t>& v = parts_[t];
             v.clear();
             size_t pos = len * t / nt;
@@ -184,19 +289,14 @@ private:
                 pos = (size_t)((const char*)nl - p) + 1;
                 v.push_back(pos);                              // a line starts after every newline
             }
-        };
-        if (nt == 1) scan(0);
-        else {
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < nt; ++t) th.emplace_back(scan, t);
-            for (auto& x : th) x.join();
-        }
+        });
         size_t total = 1;
-        for (unsigned t = 0; t < nt; ++t) total += parts_[t].size();
+        std::vector<size_t> part_off(nt);
+        for (unsigned t = 0; t < nt; ++t) { part_off[t] = total; total += parts_[t].size(); }
         ls_.resize_uninit(total + 1);
-        size_t k = 0;
-        ls_[k++] = 0;
-        for (unsigned t = 0; t < nt; ++t) { if (!parts_[t].empty()) std::memcpy(ls_.data() + k, parts_[t].data(), parts_[t].size() * sizeof(size_t)); k += parts_[t].size(); }
+        ls_[0] = 0;
+        pool_.run(nt, [&](unsigned t) { if (!parts_[t].empty()) std::memcpy(ls_.data() + part_off[t], parts_[t].data(), parts_[t].size() * sizeof(size_t)); });
+        const size_t k = total;
         // the last entry is `len` if the text ended with a newline (then it starts no line); otherwise the last line is unterminated
         const bool terminated = ls_[k - 1] == len && k > 1;
         size_t n_lines;
@@ -230,20 +330,21 @@ private:
             char* dst = out.bases.data();
             for (size_t i = a; i < b; ++i) std::memcpy(dst + off[i], p + ls_[4 * (r0 + i) + 1], off[i + 1] - off[i]);
         };
-        run_parallel(nt, n, lens);
+        const double t0 = now();
+        run_parallel(pool_, nt, n, lens);
         if (bad.load() != SIZE_MAX)
             throw std::runtime_error(path_ + ": malformed FASTQ record " + std::to_string(n_records_ - n_rec_ + bad.load()) + " (multi-line FASTQ is not supported)");
         uint64_t acc = base;
         for (size_t i = 0; i < n; ++i) { const uint64_t l = off[i + 1]; off[i + 1] = acc + l; acc += l; }
         out.bases.resize_uninit(acc);
-        run_parallel(nt, n, copy);
+        const double t1 = now();
+        run_parallel(pool_, nt, n, copy);
+        tm_[2] += t1 - t0; tm_[3] += now() - t1;
     }
     template <typename F>
-    static void run_parallel(unsigned nt, size_t n, F f) {
+    static void run_parallel(WorkerPool& pool, unsigned nt, size_t n, F f) {
         if (nt <= 1) { f(0, n); return; }
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(f, n * t / nt, n * (t + 1) / nt);
-        for (auto& x : th) x.join();
+        pool.run(nt, [&](unsigned t) { f(n * t / nt, n * (t + 1) / nt); });
     }
 
     // ---- FASTA: '>' header line, then sequence lines up to the next header; a record is complete when the next header (or
@@ -283,8 +384,12 @@ private:
     std::string path_;
     unsigned threads_;
     size_t block_;
+    WorkerPool pool_;
     int fd_ = -1;
     gzFile gz_ = nullptr;
+    uint64_t file_pos_ = 0;           // plain files: offset of the next unread byte
+    double tm_[5] = {0, 0, 0, 0, 0};
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
     bool eof_ = false;
     char fmt_ = 0;                 // 'q' FASTQ, 'a' FASTA
     RawBuf<char> buf_;             // text: [0, consumed_) is covered by the indexed records, the rest is the next block's head

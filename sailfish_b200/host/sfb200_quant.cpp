@@ -228,7 +228,7 @@ struct Args {
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int k = 31, device = 0;
     bool dumpEq = false, parseOnly = false, noChecksum = false;
-    size_t batch = 1u << 21, blockBytes = 2u << 20;      // 2 MB text blocks stay in cache between the newline index and the copy (measured)
+    size_t batch = 1u << 21, blockBytes = 0;             // 0: 2 MB of text per parser thread and block
     SailfishOpts sopt;
     sfb200_map_opts mopt;
     double fldMean = 200.0, fldSD = 80.0;
@@ -301,7 +301,7 @@ Args parse_args(int argc, char** argv) {
         else if (o == "--discardOrphans") a.discardOrphans = true;
         else if (o == "--auxDir") a.auxDir = need(o);
         else if (o == "--batchReads") a.batch = (size_t)std::max(1, atoi(need(o).c_str()));
-        else if (o == "--blockBytes") a.blockBytes = (size_t)std::max(16, atoi(need(o).c_str()));   // parser block size (tests)
+        else if (o == "--blockBytes") a.blockBytes = (size_t)std::max(0, atoi(need(o).c_str()));    // parser block size (tests); 0 = default
         else if (o == "--parseOnly") a.parseOnly = true;
         else if (o == "--noChecksum") a.noChecksum = true;                     // with --parseOnly: count only (parser throughput)
         else usage(("unknown option " + o).c_str());
@@ -342,6 +342,8 @@ private:
             for (size_t fi = 0; fi < files1_.size(); ++fi) {
                 const unsigned t1 = paired ? std::max(1u, threads_ / 2) : threads_;
                 sfb200::FastxReader r1(files1_[fi], t1, block_);
+                struct Report { sfb200::FastxReader& r; ~Report() { if (getenv("SFB200_PARSE_TIMING")) { const double* t = r.phase_seconds();
+                    fprintf(stderr, "[sfb200-quant] parser phases (s): read %.3f  index %.3f  lengths+offsets %.3f  copy %.3f  tail %.3f\n", t[0], t[1], t[2], t[3], t[4]); } } } report{r1};
                 std::unique_ptr<sfb200::FastxReader> r2;
                 if (paired) r2.reset(new sfb200::FastxReader(files2_[fi], t1, block_));
                 for (;;) {
