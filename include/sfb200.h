@@ -140,6 +140,23 @@ double sfb200_last_em_loop_ms(const sfb200_ctx* ctx);
  * 4 one thread per connected component of the class structure (k_em_dense) */
 int sfb200_last_em_kernel(const sfb200_ctx* ctx);
 
+/* EXPERIMENTAL (written against the pinned CPU oracle, not yet run on a GPU; nothing calls it by default).
+ * Replaces sailfish::utils::updateEffectiveLengths (src/SailfishUtils.cpp:611-926): effective lengths corrected for
+ * sequence-specific (--biasCorrect) or fragment-GC (--gcBiasCorrect) bias from the current abundances.  The model is what the
+ * reference reads from ReadExperiment: readBias().counts (include/ReadKmerDist.hpp:16-24, pseudo-counts included),
+ * observedGC(), numFwd()/numRC(), and fragLengthDist() as its float cdf table (cdf(x) = 1 for x >= n_cdf) and maxValue().
+ * eff_model[t] = Transcript::EffectiveLength (the fragment-length model's value), eff_in = the optimizer's current vector. */
+typedef struct {
+    int32_t  mode;              /* 1 = --biasCorrect, 2 = --gcBiasCorrect */
+    uint32_t gc_samp;           /* sopt.pdfSampFactor (--gcSpeedSamp), 1 */
+    int64_t  num_fwd, num_rc;
+    const uint32_t* read_bias;  /* 4096 (mode 1) */
+    const uint32_t* observed_gc;/* 101  (mode 2) */
+    const float* fld_cdf; uint32_t n_cdf; uint32_t fld_max;
+} sfb200_bias_model;
+int sfb200_bias_eff_lens(sfb200_ctx* ctx, const sfb200_bias_model* model, const double* eff_model, const double* eff_in,
+                         const double* alphas, uint32_t n_txp, double* eff_out);
+
 typedef int (*sfb200_f64_row_cb)(void* user, const double* row, size_t n);
 typedef int (*sfb200_i32_row_cb)(void* user, const int32_t* row, size_t n);
 /* Replaces CollapsedEMOptimizer::gatherBootstraps (src/CollapsedEMOptimizer.cpp:557-709): cb == writeBootstrap(alphas) */

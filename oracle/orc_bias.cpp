@@ -185,3 +185,15 @@ extern "C" int orc_update_eff_lens(int mode, uint32_t T, const char* seq, const 
     }
     return 0;
 }
+
+// EmpiricalDistribution over fragment-length counts (positions 0..n-1, as ReadExperiment::setFragLengthDist builds it): the float
+// cdf table (cdf(x) = 1 beyond it) and maxValue().  Returns the table length.
+extern "C" uint32_t orc_fld_cdf(const uint32_t* fld_counts, uint32_t n_fld, float* cdf_out, uint32_t cap, uint32_t* max_value) {
+    EmpDist fld;
+    std::vector<uint32_t> pos(n_fld), cnt(fld_counts, fld_counts + n_fld);
+    for (uint32_t i = 0; i < n_fld; ++i) pos[i] = i;
+    fld.build(pos, cnt);
+    if (max_value) *max_value = fld.maxVal;
+    for (uint32_t i = 0; i < cap && i < fld.cdfvals.size(); ++i) cdf_out[i] = fld.cdfvals[i];
+    return static_cast<uint32_t>(fld.cdfvals.size());
+}

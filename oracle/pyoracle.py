@@ -154,6 +154,8 @@ def lib():
                                    C.c_double, f64p]
         L.orc_update_eff_lens.argtypes = [C.c_int, C.c_uint32, C.c_char_p, u64p, u32p, f64p, f64p, f64p, C.c_int64, C.c_int64, u32p, u32p,
                                           u32p, C.c_uint32, C.c_uint32, f64p]
+        L.orc_fld_cdf.restype = C.c_uint32
+        L.orc_fld_cdf.argtypes = [u32p, C.c_uint32, f32p, C.c_uint32, u32p]
         L.orc_em_run_bias.argtypes = [C.c_uint32, C.c_uint64, u64p, u32p, u64p, f64p, C.c_uint64, C.POINTER(EMOpts), C.c_int, C.c_int,
                                       C.c_char_p, u64p, u32p, C.c_int64, C.c_int64, u32p, u32p, u32p, C.c_uint32, C.c_uint32, f64p, f64p, u32p, f64p]
         L.orc_em_run.argtypes = [C.c_uint32, C.c_uint64, u64p, u32p, u64p, f64p, C.c_uint64, C.POINTER(EMOpts), C.c_int,
@@ -346,6 +348,15 @@ def update_eff_lens(mode, seqs, eff_model, eff_in, alphas, num_fwd, num_rc, read
                                    _ptr(alphas, f64p), int(num_fwd), int(num_rc), _ptr(rb, u32p), _ptr(og, u32p), _ptr(fc, u32p),
                                    len(fc), int(gc_samp), _ptr(out, f64p))
     return rc, out
+
+
+def fld_cdf(fld_counts):
+    """EmpiricalDistribution over fragment-length counts -> (float32 cdf table, maxValue)"""
+    fc = np.ascontiguousarray(fld_counts, dtype=np.uint32)
+    cdf = np.zeros(len(fc) + 1, np.float32)
+    mx = C.c_uint32()
+    n = lib().orc_fld_cdf(_ptr(fc, u32p), len(fc), _ptr(cdf, f32p), len(cdf), C.byref(mx))
+    return cdf[:n].copy(), int(mx.value)
 
 
 def em_run_bias(mode, seqs, row_ptr, labels, counts, eff, num_mapped, num_fwd, num_rc, read_bias, observed_gc, fld_counts, gc_samp=1,

@@ -56,6 +56,12 @@ class EMOpts(C.Structure):
         return o
 
 
+class BiasModel(C.Structure):
+    """sfb200_bias_model"""
+    _fields_ = [("mode", C.c_int32), ("gc_samp", C.c_uint32), ("num_fwd", C.c_int64), ("num_rc", C.c_int64), ("read_bias", u32p),
+                ("observed_gc", u32p), ("fld_cdf", C.POINTER(C.c_float)), ("n_cdf", C.c_uint32), ("fld_max", C.c_uint32)]
+
+
 F64_ROW_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, f64p, C.c_size_t)
 I32_ROW_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, i32p, C.c_size_t)
 
@@ -87,6 +93,7 @@ SIGNATURES = {
     "sfb200_em_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.c_uint64, C.POINTER(EMOpts), f64p, u32p, f64p]),
     "sfb200_last_em_loop_ms": (C.c_double, [C.c_void_p]),
     "sfb200_last_em_kernel": (C.c_int, [C.c_void_p]),
+    "sfb200_bias_eff_lens": (C.c_int, [C.c_void_p, C.POINTER(BiasModel), f64p, f64p, f64p, C.c_uint32, f64p]),
     "sfb200_bootstrap_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.POINTER(EMOpts), C.c_uint32, C.c_uint64, F64_ROW_CB, C.c_void_p]),
     "sfb200_bootstrap_em": (C.c_int, [C.c_void_p, f64p, C.c_uint32, u64p, C.POINTER(EMOpts), f64p, u32p]),
     "sfb200_gibbs_run": (C.c_int, [C.c_void_p, f64p, f64p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, I32_ROW_CB, C.c_void_p]),
@@ -288,6 +295,19 @@ class Context:
 
     def last_em_loop_ms(self):
         return float(self.L.sfb200_last_em_loop_ms(self.h))
+
+    def bias_eff_lens(self, mode, eff_model, eff_in, alphas, num_fwd, num_rc, read_bias, observed_gc, fld_cdf, fld_max, gc_samp=1):
+        """EXPERIMENTAL: updateEffectiveLengths on the device (sfb200_bias_eff_lens); fld_cdf = EmpiricalDistribution's float cdf table"""
+        eff_model = np.ascontiguousarray(eff_model, dtype=np.float64); eff_in = np.ascontiguousarray(eff_in, dtype=np.float64)
+        alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+        rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)
+        cdf = np.ascontiguousarray(fld_cdf, dtype=np.float32)
+        m = BiasModel(int(mode), int(gc_samp), int(num_fwd), int(num_rc), _ptr(rb, u32p), _ptr(og, u32p),
+                      cdf.ctypes.data_as(C.POINTER(C.c_float)), len(cdf), int(fld_max))
+        out = np.zeros(len(eff_in), np.float64)
+        self._chk(self.L.sfb200_bias_eff_lens(self.h, C.byref(m), _ptr(eff_model, f64p), _ptr(eff_in, f64p), _ptr(alphas, f64p), len(eff_in),
+                                              _ptr(out, f64p)))
+        return out
 
     def last_em_kernel(self):
         """0 k_em_persistent, 1 k_em_part, 2 k_em_gather, 3 one launch per phase"""

@@ -1,0 +1,257 @@
+// bias.cu -- effective lengths corrected for sequence-specific or fragment-GC bias on the device.
+//
+// Replaces sailfish::utils::updateEffectiveLengths (reference src/SailfishUtils.cpp:611-926), which optimize() calls at
+// iterations 50 / 500 / 1000 when --biasCorrect or --gcBiasCorrect is given (src/CollapsedEMOptimizer.cpp:816-840).  Two passes
+// over every position of every expressed transcript:
+//   pass 1  expected distributions: a 4096-bin histogram over the 6-mer context of every possible fragment start (both strands,
+//           weighted by alpha/effLen and the fragment-length cdf), or a 101-bin histogram over the GC percentage of every
+//           (start, fragment length) pair;
+//   pass 2  per transcript, the sum over positions of observed/expected ratios = its corrected effective length.
+// O(sum of transcript lengths x [1 | FLD window]) -- the most expensive optional stage of the reference, embarrassingly
+// parallel.  Here: persistent CTAs deal transcripts round-robin, a CTA keeps its histogram in shared memory and adds it to the
+// global one once; the 6-mer context of a position is 12 bits of the index's 2-bit text (reverse complement = bitwise not, as
+// the codes are A 0, C 1, G 2, T 3); GC counts of any interval come from a per-word prefix of G/C counts plus one popcount.
+// The text is the device index's: a base that was not A/C/G/T in the FASTA is the deterministic substitute the index stores
+// (DESIGN.md section 3), where the reference would run off its tables (indexForKmer returns UINT32_MAX for such a window).
+//
+// STATUS: written against the CPU oracle (oracle/orc_bias.cpp, which is pinned to the reference's own function body) but NOT
+// yet run on a GPU -- the round's GPU budget was spent when it was written.  Nothing calls it by default; its parity test
+// (tests/test_gpu_bias.py) runs only with SFB200_EXPERIMENTAL=1.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BK = 6;                       // ReadKmerDist<6, ...> (include/ReadExperiment.hpp:211)
+constexpr uint32_t BNK = 4096;
+constexpr int BIAS_THREADS = 256;
+
+struct BiasView {
+    const uint64_t* words; const uint64_t* txp_start; const uint32_t* txp_len; const uint32_t* gcw;   // gcw[w] = G/C bases in words [0, w)
+    const float* cdf; uint32_t n_cdf;
+    const double* eff_model; const double* eff_in; const double* alphas;
+    uint32_t T;
+    double probFwd, probRC;
+    int32_t fldLow, fldHigh, gcSamp;
+};
+
+__device__ __forceinline__ double b_cdf(const BiasView& v, int32_t x) { return (uint32_t)x < v.n_cdf ? (double)__ldg(v.cdf + x) : 1.0; }   // EmpiricalDistribution::cdf (float)
+
+// the six bases starting at text position p, base p in the two lowest bits
+__device__ __forceinline__ uint32_t b_win6(const uint64_t* __restrict__ w, uint64_t p) {
+    const uint64_t idx = p >> 5; const uint32_t sh = 2 * (uint32_t)(p & 31);
+    uint64_t x = __ldg(w + idx) >> sh;
+    if (sh > 52) x |= __ldg(w + idx + 1) << (64 - sh);
+    return (uint32_t)x & 0xFFFu;
+}
+// indexForKmer(s, 6, FORWARD) (include/UtilityFunctions.hpp:96-119): first base most significant
+__device__ __forceinline__ uint32_t b_idx_fwd(uint32_t win) {
+    return ((win & 0x003u) << 10) | ((win & 0x00Cu) << 6) | ((win & 0x030u) << 2) | ((win & 0x0C0u) >> 2) | ((win & 0x300u) >> 6) | ((win & 0xC00u) >> 10);
+}
+// indexForKmer(s, 6, REVERSE_COMPLEMENT) (:120-140): complement of the last base most significant = bitwise not of the window
+__device__ __forceinline__ uint32_t b_idx_rc(uint32_t win) { return (~win) & 0xFFFu; }
+
+// G/C bases of the text in [0, p)
+__device__ __forceinline__ uint32_t b_gc_upto(const BiasView& v, uint64_t p) {
+    const uint64_t idx = p >> 5; const uint32_t r = (uint32_t)(p & 31);
+    uint32_t n = __ldg(v.gcw + idx);
+    if (r) { const uint64_t w = __ldg(v.words + idx); const uint64_t m = (w ^ (w >> 1)) & 0x5555555555555555ULL; n += __popcll(m & ((1ULL << (2 * r)) - 1)); }
+    return n;
+}
+// Transcript::gcFrac(s, e) (include/Transcript.hpp:85-96): G/C bases in (s, e] over e - s + 1, rounded to nearest even
+__device__ __forceinline__ int32_t b_gc_frac(const BiasView& v, uint64_t t0, int32_t s, int32_t e) {
+    const uint32_t n = b_gc_upto(v, t0 + e + 1) - b_gc_upto(v, t0 + s + 1);
+    return __double2int_rn((100.0 * n) / (double)(e - s + 1));
+}
+
+__device__ __forceinline__ bool b_eligible(const BiasView& v, uint32_t t, int32_t& refLen, int32_t& unproc) {    // :712-722
+    refLen = (int32_t)__ldg(v.txp_len + t);
+    const int32_t elen = (int32_t)__ldg(v.eff_model + t);
+    unproc = max(0, refLen - elen);
+    return !(__ldg(v.alphas + t) < 1e-8 || unproc <= 0);
+}
+
+__global__ void k_bias_gc_words(const uint64_t* __restrict__ words, uint64_t n_words, uint32_t* __restrict__ cnt) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint64_t w = words[i];
+    cnt[i] = (uint32_t)__popcll((w ^ (w >> 1)) & 0x5555555555555555ULL);
+}
+
+// ---- pass 1 (:696-786): expected distributions.  MODE 1: hist has 4096 bins, MODE 2: 101
+template <int MODE>
+__global__ void __launch_bounds__(BIAS_THREADS) k_bias_expected(const BiasView v, double* __restrict__ hist) {
+    constexpr uint32_t NB = MODE == 1 ? BNK : 101u;
+    __shared__ double s_h[NB];
+    for (uint32_t i = threadIdx.x; i < NB; i += blockDim.x) s_h[i] = 0.0;
+    __syncthreads();
+    for (uint32_t t = blockIdx.x; t < v.T; t += gridDim.x) {
+        int32_t refLen, unproc;
+        if (!b_eligible(v, t, refLen, unproc)) continue;                       // uniform over the CTA
+        const double contribution = __ldg(v.alphas + t) / __ldg(v.eff_in + t);
+        const uint64_t t0 = __ldg(v.txp_start + t);
+        for (int32_t i = (int32_t)threadIdx.x; i <= refLen - BK - 1; i += blockDim.x) {
+            if (MODE == 1) {
+                const uint32_t win = b_win6(v.words, t0 + i);
+                // forward strand (:728-741): fragment starts at i + 2, can be at most refLen - i - 1 long
+                atomicAdd(&s_h[b_idx_rc(win)], v.probFwd * contribution * b_cdf(v, refLen - i - 1));
+                // reverse-complement strand (:763-781): fragment "starts" at i + 4
+                if (i + 5 < refLen) atomicAdd(&s_h[b_idx_fwd(win)], v.probRC * contribution * b_cdf(v, i + 5));
+            } else {
+                double prev = b_cdf(v, 0);                                     // :746-758
+                for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
+                    const int32_t fragEnd = i + fl - 1;
+                    if (fragEnd >= refLen) break;
+                    const double cur = b_cdf(v, fl);
+                    atomicAdd(&s_h[b_gc_frac(v, t0, i, fragEnd)], contribution * (cur - prev));
+                    prev = cur;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < NB; i += blockDim.x) if (s_h[i] != 0.0) atomicAdd(hist + i, s_h[i]);
+}
+
+// ---- pass 2 (:811-924): ratio[bin] = observed / (expected + prior); one transcript per CTA at a time, block sum
+template <int MODE>
+__global__ void __launch_bounds__(BIAS_THREADS) k_bias_efflen(const BiasView v, const double* __restrict__ ratio, double norm,
+                                                              double* __restrict__ eff_out) {
+    __shared__ double s_w[BIAS_THREADS / 32];
+    for (uint32_t t = blockIdx.x; t < v.T; t += gridDim.x) {
+        int32_t refLen, unproc;
+        const bool go = b_eligible(v, t, refLen, unproc);
+        double sum = 0.0;
+        if (go) {
+            const uint64_t t0 = __ldg(v.txp_start + t);
+            for (int32_t i = (int32_t)threadIdx.x; i <= refLen - BK - 1; i += blockDim.x) {
+                if (MODE == 1) {
+                    const uint32_t win = b_win6(v.words, t0 + i);
+                    if (i + 2 < refLen) sum += v.probFwd * __ldg(ratio + b_idx_rc(win)) * b_cdf(v, refLen - i - 1);    // :828-838
+                    if (i + 4 < refLen) sum += v.probRC * __ldg(ratio + b_idx_fwd(win)) * b_cdf(v, i + 5);              // :875-893
+                } else {
+                    double prev = b_cdf(v, 0);                                                                          // :840-860
+                    for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
+                        const int32_t fragEnd = i + fl - 1;
+                        if (fragEnd >= refLen) break;
+                        const double cur = b_cdf(v, fl);
+                        const double sampleProb = __ldg(ratio + b_gc_frac(v, t0, i, fragEnd)) * (cur - prev);
+                        prev = cur;
+                        sum += sampleProb * v.probFwd; sum += sampleProb * v.probRC;     // gcFactors[fragStart] and gcFactors[fragEnd]
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+        __syncthreads();
+        if ((threadIdx.x & 31u) == 0) s_w[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double eff = 0.0;
+            for (int w = 0; w < BIAS_THREADS / 32; ++w) eff += s_w[w];
+            eff *= norm;                                                          // txomeNormFactor / readNormFactor (:901-912)
+            const double in = __ldg(v.eff_in + t);
+            eff_out[t] = (go && unproc > 0 && eff > (double)unproc) ? eff : in;   // :916-922
+        }
+    }
+}
+
+inline unsigned b_grid(uint64_t n, unsigned th) { return (unsigned)((n + th - 1) / th); }
+
+}  // namespace
+
+extern "C" int sfb200_bias_eff_lens(sfb200_ctx* c, const sfb200_bias_model* m, const double* eff_model, const double* eff_in,
+                                    const double* alphas, uint32_t n_txp, double* eff_out) {
+    if (!c || !m || !eff_model || !eff_in || !alphas || !eff_out) return SFB200_EINVAL;
+    if (!c->index.ready) SFB_FAIL(c, SFB200_EINVAL, "bias_eff_lens: build the index first (the correction reads the transcript sequences)");
+    if (n_txp != c->index.n_txp) SFB_FAIL(c, SFB200_EINVAL, "bias_eff_lens: n_txp differs from the index's");
+    if (m->mode != 1 && m->mode != 2) SFB_FAIL(c, SFB200_EINVAL, "bias_eff_lens: mode must be 1 (sequence bias) or 2 (fragment GC bias)");
+    if (!m->fld_cdf || (m->mode == 1 && !m->read_bias) || (m->mode == 2 && !m->observed_gc)) SFB_FAIL(c, SFB200_EINVAL, "bias_eff_lens: null model array");
+    const int64_t numMappings = m->num_fwd + m->num_rc;
+    if (numMappings == 0) { std::memcpy(eff_out, eff_in, n_txp * sizeof(double)); return SFB200_OK; }      // :627-632: correction skipped
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    const DevIndex& ix = c->index;
+    const uint32_t T = n_txp;
+    const bool seq = m->mode == 1;
+    const uint32_t NB = seq ? BNK : 101u;
+    const uint64_t n_words = ix.text_len / 32 + 2;
+    DevBuf<uint32_t> d_gcw; DevBuf<unsigned char> d_tmp; DevBuf<float> d_cdf; DevBuf<double> d_vec, d_hist;
+    auto cleanup = [&]() { d_gcw.release(); d_tmp.release(); d_cdf.release(); d_vec.release(); d_hist.release(); };
+#define BIAS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return SFB200_ECUDA; } } while (0)
+    BIAS_CUDA(d_cdf.reserve(m->n_cdf ? m->n_cdf : 1));
+    BIAS_CUDA(d_vec.reserve(3ull * T + T));                       // eff_model | eff_in | alphas | eff_out
+    BIAS_CUDA(d_hist.reserve(2ull * NB));                         // expected | ratio
+    if (m->n_cdf) BIAS_CUDA(cudaMemcpyAsync(d_cdf.p, m->fld_cdf, m->n_cdf * sizeof(float), cudaMemcpyHostToDevice, s));
+    BIAS_CUDA(cudaMemcpyAsync(d_vec.p, eff_model, T * 8ull, cudaMemcpyHostToDevice, s));
+    BIAS_CUDA(cudaMemcpyAsync(d_vec.p + T, eff_in, T * 8ull, cudaMemcpyHostToDevice, s));
+    BIAS_CUDA(cudaMemcpyAsync(d_vec.p + 2ull * T, alphas, T * 8ull, cudaMemcpyHostToDevice, s));
+    BiasView v;
+    v.words = ix.words.p; v.txp_start = ix.txp_start.p; v.txp_len = ix.txp_len.p; v.gcw = nullptr;
+    v.cdf = d_cdf.p; v.n_cdf = m->n_cdf; v.eff_model = d_vec.p; v.eff_in = d_vec.p + T; v.alphas = d_vec.p + 2ull * T; v.T = T;
+    v.probFwd = static_cast<double>(m->num_fwd) / numMappings; v.probRC = static_cast<double>(m->num_rc) / numMappings;
+    v.fldLow = 0; v.fldHigh = 1; v.gcSamp = (int32_t)std::max<uint32_t>(1, m->gc_samp);
+    auto cdf = [&](uint32_t x) -> float { return x < m->n_cdf ? m->fld_cdf[x] : 1.0f; };
+    if (!seq) {                                                   // :668-687
+        bool first = false, second = false;
+        for (uint32_t i = 0; i <= m->fld_max; ++i) {
+            const float density = cdf(i);
+            if (!first && density >= 0.005) { first = true; v.fldLow = (int32_t)i; }
+            if (!second && density >= 0.995) { second = true; v.fldHigh = (int32_t)i; }
+        }
+        // per-word G/C counts -> exclusive prefix
+        BIAS_CUDA(d_gcw.reserve(n_words + 1));
+        k_bias_gc_words<<<b_grid(n_words, 256), 256, 0, s>>>(ix.words.p, n_words, d_gcw.p);
+        c->launches++;
+        size_t tmp = 0;
+        BIAS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_gcw.p, d_gcw.p, (int)n_words, s));
+        BIAS_CUDA(d_tmp.reserve(tmp));
+        BIAS_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp, d_gcw.p, d_gcw.p, (int)n_words, s));
+        c->launches++;
+        v.gcw = d_gcw.p;
+    }
+    // ---- pass 1: expected distribution, starting from 1.0 in every bin (:649-651, :669-671)
+    std::vector<double> h_hist(NB, 1.0);
+    BIAS_CUDA(cudaMemcpyAsync(d_hist.p, h_hist.data(), NB * 8ull, cudaMemcpyHostToDevice, s));
+    const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)c->num_sms * 8);
+    if (seq) k_bias_expected<1><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p); else k_bias_expected<2><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p);
+    c->launches++;
+    BIAS_CUDA(cudaGetLastError());
+    BIAS_CUDA(cudaMemcpyAsync(h_hist.data(), d_hist.p, NB * 8ull, cudaMemcpyDeviceToHost, s));
+    BIAS_CUDA(cudaStreamSynchronize(s));
+    // ---- priors, normalisers, observed / expected (:789-804)
+    double txomeNorm = 0.0, readNorm = 0.0;
+    for (uint32_t i = 0; i < NB; ++i) txomeNorm += h_hist[i];
+    std::vector<double> ratio(NB);
+    if (seq) {
+        uint32_t tc = 0;                                          // ReadKmerDist::totalCount() accumulates in CountT (uint32)
+        for (uint32_t i = 0; i < NB; ++i) tc += m->read_bias[i];
+        readNorm = static_cast<double>(tc);
+        const double pmass = static_cast<double>(BNK);
+        const double prior = ((pmass / (readNorm - pmass)) * txomeNorm) / pmass;
+        for (uint32_t i = 0; i < NB; ++i) ratio[i] = m->read_bias[i] / (h_hist[i] + prior);
+    } else {
+        for (uint32_t i = 0; i < NB; ++i) readNorm += m->observed_gc[i];
+        const double pmass = 101.0;
+        const double prior = ((pmass / (readNorm - pmass)) * txomeNorm) / 101.0;
+        for (uint32_t i = 0; i < NB; ++i) ratio[i] = m->observed_gc[i] / (prior + h_hist[i]);
+    }
+    BIAS_CUDA(cudaMemcpyAsync(d_hist.p + NB, ratio.data(), NB * 8ull, cudaMemcpyHostToDevice, s));
+    // ---- pass 2
+    double* d_out = d_vec.p + 3ull * T;
+    const double norm = txomeNorm / readNorm;
+    if (seq) k_bias_efflen<1><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p + NB, norm, d_out); else k_bias_efflen<2><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p + NB, norm, d_out);
+    c->launches++;
+    BIAS_CUDA(cudaGetLastError());
+    BIAS_CUDA(cudaMemcpyAsync(eff_out, d_out, T * 8ull, cudaMemcpyDeviceToHost, s));
+    BIAS_CUDA(cudaStreamSynchronize(s));
+#undef BIAS_CUDA
+    cleanup();
+    return SFB200_OK;
+}

@@ -89,6 +89,14 @@ def test_oracle_matches_reference_live():
         np.testing.assert_allclose(out, ref, rtol=1e-12)
 
 
+def test_fld_cdf_matches_reference_table():
+    d = dict(np.load(GOLDEN))
+    cdf, mx = O.fld_cdf(d["fld"])
+    assert mx == int(d["ref_fld_max"])
+    full = np.ones(1000, np.float32); full[:len(cdf)] = cdf
+    assert (full == d["ref_fld_cdf"]).all()                                # float table of the reference's EmpiricalDistribution, bit for bit
+
+
 def _rc(b):
     return bytes({65: 84, 67: 71, 71: 67, 84: 65}[c] for c in reversed(b))
 
