@@ -27,54 +27,17 @@
 
 namespace {
 
-constexpr int BK = 6;                       // ReadKmerDist<6, ...> (include/ReadExperiment.hpp:211)
-constexpr uint32_t BNK = 4096;
 constexpr int BIAS_THREADS = 256;
 
-struct BiasView {
-    const uint64_t* words; const uint64_t* txp_start; const uint32_t* txp_len; const uint32_t* gcw;   // gcw[w] = G/C bases in words [0, w)
-    const float* cdf; uint32_t n_cdf;
-    const double* eff_model; const double* eff_in; const double* alphas;
-    uint32_t T;
-    double probFwd, probRC;
-    int32_t fldLow, fldHigh, gcSamp;
-};
-
-__device__ __forceinline__ double b_cdf(const BiasView& v, int32_t x) { return (uint32_t)x < v.n_cdf ? (double)__ldg(v.cdf + x) : 1.0; }   // EmpiricalDistribution::cdf (float)
-
-// the six bases starting at text position p, base p in the two lowest bits
-__device__ __forceinline__ uint32_t b_win6(const uint64_t* __restrict__ w, uint64_t p) {
-    const uint64_t idx = p >> 5; const uint32_t sh = 2 * (uint32_t)(p & 31);
-    uint64_t x = __ldg(w + idx) >> sh;
-    if (sh > 52) x |= __ldg(w + idx + 1) << (64 - sh);
-    return (uint32_t)x & 0xFFFu;
-}
-// indexForKmer(s, 6, FORWARD) (include/UtilityFunctions.hpp:96-119): first base most significant
-__device__ __forceinline__ uint32_t b_idx_fwd(uint32_t win) {
-    return ((win & 0x003u) << 10) | ((win & 0x00Cu) << 6) | ((win & 0x030u) << 2) | ((win & 0x0C0u) >> 2) | ((win & 0x300u) >> 6) | ((win & 0xC00u) >> 10);
-}
-// indexForKmer(s, 6, REVERSE_COMPLEMENT) (:120-140): complement of the last base most significant = bitwise not of the window
-__device__ __forceinline__ uint32_t b_idx_rc(uint32_t win) { return (~win) & 0xFFFu; }
-
-// G/C bases of the text in [0, p)
-__device__ __forceinline__ uint32_t b_gc_upto(const BiasView& v, uint64_t p) {
-    const uint64_t idx = p >> 5; const uint32_t r = (uint32_t)(p & 31);
-    uint32_t n = __ldg(v.gcw + idx);
-    if (r) { const uint64_t w = __ldg(v.words + idx); const uint64_t m = (w ^ (w >> 1)) & 0x5555555555555555ULL; n += __popcll(m & ((1ULL << (2 * r)) - 1)); }
-    return n;
-}
-// Transcript::gcFrac(s, e) (include/Transcript.hpp:85-96): G/C bases in (s, e] over e - s + 1, rounded to nearest even
-__device__ __forceinline__ int32_t b_gc_frac(const BiasView& v, uint64_t t0, int32_t s, int32_t e) {
-    const uint32_t n = b_gc_upto(v, t0 + e + 1) - b_gc_upto(v, t0 + s + 1);
-    return __double2int_rn((100.0 * n) / (double)(e - s + 1));
-}
-
-__device__ __forceinline__ bool b_eligible(const BiasView& v, uint32_t t, int32_t& refLen, int32_t& unproc) {    // :712-722
-    refLen = (int32_t)__ldg(v.txp_len + t);
-    const int32_t elen = (int32_t)__ldg(v.eff_model + t);
-    unproc = max(0, refLen - elen);
-    return !(__ldg(v.alphas + t) < 1e-8 || unproc <= 0);
-}
+#define SFB_BD __device__ __forceinline__
+#define SFB_LDG(p) __ldg(p)
+#define SFB_POPC64(x) __popcll(x)
+#define SFB_D2I_RN(x) __double2int_rn(x)
+#include "bias_core.inl"
+#undef SFB_BD
+#undef SFB_LDG
+#undef SFB_POPC64
+#undef SFB_D2I_RN
 
 __global__ void k_bias_gc_words(const uint64_t* __restrict__ words, uint64_t n_words, uint32_t* __restrict__ cnt) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -96,22 +59,9 @@ __global__ void __launch_bounds__(BIAS_THREADS) k_bias_expected(const BiasView v
         const double contribution = __ldg(v.alphas + t) / __ldg(v.eff_in + t);
         const uint64_t t0 = __ldg(v.txp_start + t);
         for (int32_t i = (int32_t)threadIdx.x; i <= refLen - BK - 1; i += blockDim.x) {
-            if (MODE == 1) {
-                const uint32_t win = b_win6(v.words, t0 + i);
-                // forward strand (:728-741): fragment starts at i + 2, can be at most refLen - i - 1 long
-                atomicAdd(&s_h[b_idx_rc(win)], v.probFwd * contribution * b_cdf(v, refLen - i - 1));
-                // reverse-complement strand (:763-781): fragment "starts" at i + 4
-                if (i + 5 < refLen) atomicAdd(&s_h[b_idx_fwd(win)], v.probRC * contribution * b_cdf(v, i + 5));
-            } else {
-                double prev = b_cdf(v, 0);                                     // :746-758
-                for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
-                    const int32_t fragEnd = i + fl - 1;
-                    if (fragEnd >= refLen) break;
-                    const double cur = b_cdf(v, fl);
-                    atomicAdd(&s_h[b_gc_frac(v, t0, i, fragEnd)], contribution * (cur - prev));
-                    prev = cur;
-                }
-            }
+            auto add = [&](uint32_t bin, double x) { atomicAdd(&s_h[bin], x); };
+            if (MODE == 1) b_expected_seq(v, t0, refLen, i, contribution, add);
+            else b_expected_gc(v, t0, refLen, i, contribution, add);
         }
     }
     __syncthreads();
@@ -130,21 +80,7 @@ __global__ void __launch_bounds__(BIAS_THREADS) k_bias_efflen(const BiasView v, 
         if (go) {
             const uint64_t t0 = __ldg(v.txp_start + t);
             for (int32_t i = (int32_t)threadIdx.x; i <= refLen - BK - 1; i += blockDim.x) {
-                if (MODE == 1) {
-                    const uint32_t win = b_win6(v.words, t0 + i);
-                    if (i + 2 < refLen) sum += v.probFwd * __ldg(ratio + b_idx_rc(win)) * b_cdf(v, refLen - i - 1);    // :828-838
-                    if (i + 4 < refLen) sum += v.probRC * __ldg(ratio + b_idx_fwd(win)) * b_cdf(v, i + 5);              // :875-893
-                } else {
-                    double prev = b_cdf(v, 0);                                                                          // :840-860
-                    for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
-                        const int32_t fragEnd = i + fl - 1;
-                        if (fragEnd >= refLen) break;
-                        const double cur = b_cdf(v, fl);
-                        const double sampleProb = __ldg(ratio + b_gc_frac(v, t0, i, fragEnd)) * (cur - prev);
-                        prev = cur;
-                        sum += sampleProb * v.probFwd; sum += sampleProb * v.probRC;     // gcFactors[fragStart] and gcFactors[fragEnd]
-                    }
-                }
+                sum += MODE == 1 ? b_eff_seq(v, ratio, t0, refLen, i) : b_eff_gc(v, ratio, t0, refLen, i);
             }
         }
 #pragma unroll

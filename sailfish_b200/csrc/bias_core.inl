@@ -1,0 +1,95 @@
+// bias_core.inl -- the per-position arithmetic of the bias / GC effective-length correction (bias.cu), written against four
+// macros so that the same text is CUDA device code and plain host code for the CPU check (tests/bias_core_test.cpp):
+//   SFB_BD            function qualifiers          SFB_LDG(p)      read-only load of *p
+//   SFB_POPC64(x)     population count of a u64    SFB_D2I_RN(x)   double -> int, round to nearest even
+// Text layout: the device index's 2-bit text (base p at bits 2*(p%32) of word p/32, codes A 0 C 1 G 2 T 3), transcripts
+// concatenated without separators, txp_start[t] = first position of transcript t.
+
+constexpr int BK = 6;                       // ReadKmerDist<6, ...> (include/ReadExperiment.hpp:211)
+constexpr uint32_t BNK = 4096;
+
+struct BiasView {
+    const uint64_t* words; const uint64_t* txp_start; const uint32_t* txp_len; const uint32_t* gcw;   // gcw[w] = G/C bases in words [0, w)
+    const float* cdf; uint32_t n_cdf;
+    const double* eff_model; const double* eff_in; const double* alphas;
+    uint32_t T;
+    double probFwd, probRC;
+    int32_t fldLow, fldHigh, gcSamp;
+};
+
+SFB_BD double b_cdf(const BiasView& v, int32_t x) { return (uint32_t)x < v.n_cdf ? (double)SFB_LDG(v.cdf + x) : 1.0; }   // EmpiricalDistribution::cdf (float)
+
+// the six bases starting at text position p, base p in the two lowest bits
+SFB_BD uint32_t b_win6(const uint64_t* __restrict__ w, uint64_t p) {
+    const uint64_t idx = p >> 5; const uint32_t sh = 2 * (uint32_t)(p & 31);
+    uint64_t x = SFB_LDG(w + idx) >> sh;
+    if (sh > 52) x |= SFB_LDG(w + idx + 1) << (64 - sh);
+    return (uint32_t)x & 0xFFFu;
+}
+// indexForKmer(s, 6, FORWARD) (include/UtilityFunctions.hpp:96-119): first base most significant
+SFB_BD uint32_t b_idx_fwd(uint32_t win) {
+    return ((win & 0x003u) << 10) | ((win & 0x00Cu) << 6) | ((win & 0x030u) << 2) | ((win & 0x0C0u) >> 2) | ((win & 0x300u) >> 6) | ((win & 0xC00u) >> 10);
+}
+// indexForKmer(s, 6, REVERSE_COMPLEMENT) (:120-140): complement of the last base most significant = bitwise not of the window
+SFB_BD uint32_t b_idx_rc(uint32_t win) { return (~win) & 0xFFFu; }
+
+// G/C bases of the text in [0, p)
+SFB_BD uint32_t b_gc_upto(const BiasView& v, uint64_t p) {
+    const uint64_t idx = p >> 5; const uint32_t r = (uint32_t)(p & 31);
+    uint32_t n = SFB_LDG(v.gcw + idx);
+    if (r) { const uint64_t w = SFB_LDG(v.words + idx); const uint64_t m = (w ^ (w >> 1)) & 0x5555555555555555ULL; n += SFB_POPC64(m & ((1ULL << (2 * r)) - 1)); }
+    return n;
+}
+// Transcript::gcFrac(s, e) (include/Transcript.hpp:85-96): G/C bases in (s, e] over e - s + 1, rounded to nearest even
+SFB_BD int32_t b_gc_frac(const BiasView& v, uint64_t t0, int32_t s, int32_t e) {
+    const uint32_t n = b_gc_upto(v, t0 + e + 1) - b_gc_upto(v, t0 + s + 1);
+    return SFB_D2I_RN((100.0 * n) / (double)(e - s + 1));
+}
+
+SFB_BD bool b_eligible(const BiasView& v, uint32_t t, int32_t& refLen, int32_t& unproc) {    // :712-722
+    refLen = (int32_t)SFB_LDG(v.txp_len + t);
+    const int32_t elen = (int32_t)SFB_LDG(v.eff_model + t);
+    unproc = refLen - elen > 0 ? refLen - elen : 0;
+    return !(SFB_LDG(v.alphas + t) < 1e-8 || unproc <= 0);
+}
+
+// ---- per-position bodies shared by the kernels and the CPU check ---------------------------------------------------------------
+// pass 1, sequence bias (:728-741, :763-781): both strands' contributions of position i; add(bin, value)
+template <typename Add>
+SFB_BD void b_expected_seq(const BiasView& v, uint64_t t0, int32_t refLen, int32_t i, double contribution, Add add) {
+    const uint32_t win = b_win6(v.words, t0 + i);
+    add(b_idx_rc(win), v.probFwd * contribution * b_cdf(v, refLen - i - 1));        // forward: fragment starts at i + 2, at most refLen - i - 1 long
+    if (i + 5 < refLen) add(b_idx_fwd(win), v.probRC * contribution * b_cdf(v, i + 5));   // reverse complement: "starts" at i + 4
+}
+// pass 1, fragment GC bias (:746-758)
+template <typename Add>
+SFB_BD void b_expected_gc(const BiasView& v, uint64_t t0, int32_t refLen, int32_t i, double contribution, Add add) {
+    double prev = b_cdf(v, 0);
+    for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
+        const int32_t fragEnd = i + fl - 1;
+        if (fragEnd >= refLen) break;
+        const double cur = b_cdf(v, fl);
+        add((uint32_t)b_gc_frac(v, t0, i, fragEnd), contribution * (cur - prev));
+        prev = cur;
+    }
+}
+// pass 2 (:828-838, :875-893 / :840-860): position i's share of the transcript's corrected length (before the normaliser)
+SFB_BD double b_eff_seq(const BiasView& v, const double* ratio, uint64_t t0, int32_t refLen, int32_t i) {
+    const uint32_t win = b_win6(v.words, t0 + i);
+    double s = 0.0;
+    if (i + 2 < refLen) s += v.probFwd * SFB_LDG(ratio + b_idx_rc(win)) * b_cdf(v, refLen - i - 1);
+    if (i + 4 < refLen) s += v.probRC * SFB_LDG(ratio + b_idx_fwd(win)) * b_cdf(v, i + 5);
+    return s;
+}
+SFB_BD double b_eff_gc(const BiasView& v, const double* ratio, uint64_t t0, int32_t refLen, int32_t i) {
+    double prev = b_cdf(v, 0), s = 0.0;
+    for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
+        const int32_t fragEnd = i + fl - 1;
+        if (fragEnd >= refLen) break;
+        const double cur = b_cdf(v, fl);
+        const double sampleProb = SFB_LDG(ratio + b_gc_frac(v, t0, i, fragEnd)) * (cur - prev);
+        prev = cur;
+        s += sampleProb * v.probFwd; s += sampleProb * v.probRC;                   // gcFactors[fragStart] and gcFactors[fragEnd]
+    }
+    return s;
+}

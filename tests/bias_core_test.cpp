@@ -1,0 +1,129 @@
+// CPU check of the per-position arithmetic of the device-side bias / GC correction (sailfish_b200/csrc/bias_core.inl, the text
+// bias.cu compiles for the GPU): 2-bit text windows, 6-mer context indices, GC prefix counts, the two passes.  The kernels' loop
+// structure is replayed serially here (transcripts, positions, histogram, normalisers, per-transcript sums) and the result is
+// compared with the CPU oracle (oracle/orc_bias.cpp, pinned to the reference's own updateEffectiveLengths).  Built and run by
+// tests/test_bias_core.py; links oracle/liboracle.so -- test infrastructure on both sides.
+#include <stdint.h>
+#include <stddef.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+#include <vector>
+
+#define SFB_BD static inline
+#define SFB_LDG(p) (*(p))
+#define SFB_POPC64(x) __builtin_popcountll(x)
+#define SFB_D2I_RN(x) ((int32_t)std::lrint(x))
+#include "../sailfish_b200/csrc/bias_core.inl"
+
+extern "C" int orc_update_eff_lens(int mode, uint32_t T, const char* seq, const uint64_t* off, const uint32_t* len, const double* eff_model,
+                                   const double* eff_in, const double* alphas, int64_t num_fwd, int64_t num_rc, const uint32_t* read_bias,
+                                   const uint32_t* observed_gc, const uint32_t* fld_counts, uint32_t n_fld, uint32_t gc_samp, double* eff_out);
+extern "C" uint32_t orc_fld_cdf(const uint32_t* fld_counts, uint32_t n_fld, float* cdf_out, uint32_t cap, uint32_t* max_value);
+
+#define CHECK(cond, ...) do { if (!(cond)) { fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } } while (0)
+
+static int run(int mode, uint32_t gc_samp, uint64_t seed) {
+    std::mt19937_64 rng(seed);
+    const uint32_t T = 90;
+    std::vector<uint32_t> len(T);
+    std::vector<uint64_t> off(T), tstart(T + 1);
+    std::string seq;
+    for (uint32_t t = 0; t < T; ++t) {
+        len[t] = t < 3 ? 4 + 2 * t : (t < 8 ? 60 + 20 * t : 200 + (uint32_t)(rng() % 1500));            // a few transcripts shorter than the 6-mer window
+        off[t] = seq.size(); tstart[t] = seq.size();
+        for (uint32_t i = 0; i < len[t]; ++i) seq.push_back("ACGT"[(rng() % 10) < 3 ? 0 : (rng() % 4)]);
+    }
+    tstart[T] = seq.size();
+    // the device index's text: 2 bits per base, base p at bits 2*(p%32) of word p/32, two words of slack
+    std::vector<uint64_t> words(seq.size() / 32 + 2, 0);
+    for (size_t p = 0; p < seq.size(); ++p) { const uint64_t c = seq[p] == 'A' ? 0 : seq[p] == 'C' ? 1 : seq[p] == 'G' ? 2 : 3; words[p >> 5] |= c << (2 * (p & 31)); }
+    std::vector<uint32_t> gcw(words.size() + 1, 0);
+    for (size_t w = 0; w < words.size(); ++w) gcw[w + 1] = gcw[w] + (uint32_t)__builtin_popcountll((words[w] ^ (words[w] >> 1)) & 0x5555555555555555ULL);
+    // helpers against the plain string
+    for (int k = 0; k < 2000; ++k) {
+        const uint32_t t = 3 + (uint32_t)(rng() % (T - 3));
+        const uint32_t i = (uint32_t)(rng() % (len[t] - 6));
+        const uint32_t win = b_win6(words.data(), tstart[t] + i);
+        uint32_t f = 0, r = 0;
+        for (int j = 0; j < 6; ++j) { const uint32_t c = (uint32_t)std::string("ACGT").find(seq[off[t] + i + j]); f = (f << 2) | c; }
+        for (int j = 5; j >= 0; --j) { const uint32_t c = 3 - (uint32_t)std::string("ACGT").find(seq[off[t] + i + j]); r = (r << 2) | c; }
+        CHECK(b_idx_fwd(win) == f && b_idx_rc(win) == r, "6-mer index at transcript %u position %u", t, i);
+    }
+    std::vector<uint32_t> fld(1000);
+    for (uint32_t x = 0; x < 1000; ++x) fld[x] = (uint32_t)std::lround(30000.0 * std::exp(-0.5 * std::pow((x - 190.0) / 30.0, 2)));
+    std::vector<float> cdf(1001);
+    uint32_t fld_max = 0;
+    const uint32_t n_cdf = orc_fld_cdf(fld.data(), 1000, cdf.data(), 1001, &fld_max);
+    std::vector<double> eff_model(T), eff_in(T), alphas(T), want(T), got(T);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    for (uint32_t t = 0; t < T; ++t) {
+        eff_model[t] = len[t] > 189 ? len[t] - 189.0 : len[t];
+        eff_in[t] = eff_model[t] * (0.9 + 0.2 * U(rng));
+        alphas[t] = U(rng) < 0.2 ? 0.0 : std::exp(3 + 2 * (U(rng) - 0.5) * 3);
+    }
+    std::vector<uint32_t> rb(4096), og(101);
+    for (auto& x : rb) x = 1 + (uint32_t)(rng() % 3000);
+    for (auto& x : og) x = 1 + (uint32_t)(rng() % 8000);
+    const int64_t nf = 61234, nr = 58766;
+    CHECK(orc_update_eff_lens(mode, T, seq.data(), off.data(), len.data(), eff_model.data(), eff_in.data(), alphas.data(), nf, nr, rb.data(), og.data(),
+                              fld.data(), 1000, gc_samp, want.data()) == 0, "oracle failed");
+    // ---- what sfb200_bias_eff_lens does, serially
+    BiasView v;
+    v.words = words.data(); v.txp_start = tstart.data(); v.txp_len = len.data(); v.gcw = gcw.data();
+    v.cdf = cdf.data(); v.n_cdf = n_cdf; v.eff_model = eff_model.data(); v.eff_in = eff_in.data(); v.alphas = alphas.data(); v.T = T;
+    v.probFwd = (double)nf / (nf + nr); v.probRC = (double)nr / (nf + nr);
+    v.fldLow = 0; v.fldHigh = 1; v.gcSamp = (int32_t)gc_samp;
+    if (mode == 2) {
+        bool first = false, second = false;
+        for (uint32_t i = 0; i <= fld_max; ++i) {
+            const float d = i < n_cdf ? cdf[i] : 1.0f;
+            if (!first && d >= 0.005) { first = true; v.fldLow = (int32_t)i; }
+            if (!second && d >= 0.995) { second = true; v.fldHigh = (int32_t)i; }
+        }
+    }
+    const uint32_t NB = mode == 1 ? BNK : 101u;
+    std::vector<double> hist(NB, 1.0), ratio(NB);
+    auto add = [&](uint32_t bin, double x) { hist[bin] += x; };
+    for (uint32_t t = 0; t < T; ++t) {
+        int32_t refLen, unproc;
+        if (!b_eligible(v, t, refLen, unproc)) continue;
+        const double contribution = alphas[t] / eff_in[t];
+        for (int32_t i = 0; i <= refLen - BK - 1; ++i) {
+            if (mode == 1) b_expected_seq(v, tstart[t], refLen, i, contribution, add); else b_expected_gc(v, tstart[t], refLen, i, contribution, add);
+        }
+    }
+    double txomeNorm = 0.0, readNorm = 0.0;
+    for (double h : hist) txomeNorm += h;
+    if (mode == 1) {
+        uint32_t tc = 0; for (uint32_t x : rb) tc += x; readNorm = tc;
+        const double prior = ((4096.0 / (readNorm - 4096.0)) * txomeNorm) / 4096.0;
+        for (uint32_t i = 0; i < NB; ++i) ratio[i] = rb[i] / (hist[i] + prior);
+    } else {
+        for (uint32_t x : og) readNorm += x;
+        const double prior = ((101.0 / (readNorm - 101.0)) * txomeNorm) / 101.0;
+        for (uint32_t i = 0; i < NB; ++i) ratio[i] = og[i] / (prior + hist[i]);
+    }
+    size_t changed = 0;
+    for (uint32_t t = 0; t < T; ++t) {
+        int32_t refLen, unproc;
+        const bool go = b_eligible(v, t, refLen, unproc);
+        double sum = 0.0;
+        if (go) for (int32_t i = 0; i <= refLen - BK - 1; ++i) sum += mode == 1 ? b_eff_seq(v, ratio.data(), tstart[t], refLen, i) : b_eff_gc(v, ratio.data(), tstart[t], refLen, i);
+        const double eff = sum * (txomeNorm / readNorm);
+        got[t] = (go && unproc > 0 && eff > (double)unproc) ? eff : eff_in[t];
+        CHECK(std::fabs(got[t] - want[t]) <= 1e-10 * std::fabs(want[t]), "mode %d transcript %u: %.17g vs oracle %.17g", mode, t, got[t], want[t]);
+        changed += got[t] != eff_in[t];
+    }
+    CHECK(changed > 20, "only %zu transcripts were corrected", changed);
+    return 0;
+}
+
+int main() {
+    if (run(1, 1, 1) || run(2, 1, 2) || run(2, 3, 3) || run(1, 1, 4)) return 1;
+    printf("bias core ok\n");
+    return 0;
+}
