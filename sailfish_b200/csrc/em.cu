@@ -844,7 +844,8 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
         max_nc = std::max<uint64_t>(max_nc, row[PT_CLS + SFB_NBINS] - row[PT_CLS]);
         max_nt = std::max<uint64_t>(max_nt, row[PT_TXP1] - row[PT_TXP0]);
     }
-    uint32_t group = 2;                                                // lanes per component (SFB200_EM_DENSE_GROUP = 1, 2, 4; swept on B200)
+    uint32_t group = 2;                                                // lanes per component (SFB200_EM_DENSE_GROUP = 1, 2, 4; swept on B200);
+                                                                       // 0 = balanced by class count (not yet run on a GPU: opt-in)
     if (const char* e = getenv("SFB200_EM_DENSE_GROUP")) group = (uint32_t)atoi(e);
     const DenseGeom g = dense_make_geom(max_nc, max_nt, group);
     cudaStream_t s = c->stream;
@@ -868,7 +869,7 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     uint64_t need = 0;
     if (ok) for (uint32_t i = 0; i < P.n_cta; ++i) {
         const uint32_t* h = hdr.data() + (size_t)i * DH_WORDS;
-        need = std::max<uint64_t>(need, dense_smem_need(h[DH_TILES], h[DH_ENT], ns, g.group));
+        need = std::max<uint64_t>(need, dense_smem_need(h[DH_TILES], h[DH_ENT], ns, g.group, h[DH_NCOMP]));
     }
     need += 256;
     const bool fits = (need + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1);
@@ -906,7 +907,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))
-#define SFB_DENSE_CASE(N) case N: fn = q.g.group == 4 ? SFB_DENSE_FN(N, 4) : q.g.group == 2 ? SFB_DENSE_FN(N, 2) : SFB_DENSE_FN(N, 1); break;
+#define SFB_DENSE_CASE(N) case N: fn = q.g.group == 4 ? SFB_DENSE_FN(N, 4) : q.g.group == 2 ? SFB_DENSE_FN(N, 2) : q.g.group == 0 ? SFB_DENSE_FN(N, 0) : SFB_DENSE_FN(N, 1); break;
         switch (P.dense_ns) { SFB_DENSE_CASE(2) SFB_DENSE_CASE(3) SFB_DENSE_CASE(4) SFB_DENSE_CASE(5) SFB_DENSE_CASE(6) SFB_DENSE_CASE(7) SFB_DENSE_CASE(8)
                               default: SFB_FAIL(c, SFB200_EINVAL, "dense EM: unexpected component size"); }
 #undef SFB_DENSE_CASE

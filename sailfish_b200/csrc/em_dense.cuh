@@ -56,9 +56,10 @@ __device__ __forceinline__ double dense_tree_sum(const double* v) {
 }
 
 // shared memory a CTA of k_em_dense needs (mirrored on the host)
-__host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns, uint32_t group) {
-    const uint64_t ncomp_pad = ((uint64_t)tiles << 5) / group;
-    return (uint64_t)((ent + 1u) & ~1u) * 8 + 4 * (uint64_t)ns * ncomp_pad * 8 + 2 * (uint64_t)((tiles + 3u) & ~3u) * 4 + (uint64_t)((ent + 15u) & ~15u);
+__host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns, uint32_t group, uint32_t ncomp) {
+    const uint64_t ncomp_pad = group ? ((uint64_t)tiles << 5) / group : (((uint64_t)ncomp + 31u) & ~31ull);
+    return (uint64_t)((ent + 1u) & ~1u) * 8 + 4 * (uint64_t)ns * ncomp_pad * 8 + 2 * (uint64_t)((tiles + 3u) & ~3u) * 4 + (uint64_t)((ent + 15u) & ~15u) +
+           (group ? 0 : (uint64_t)tiles * 32 * 4);
 }
 
 // G lanes share a component: each takes every G-th class of it (all G hold the component's beta), the accumulators are summed
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
 
     const uint32_t* region = q.regions + (size_t)blockIdx.x * q.g.region_words;
     const uint32_t tiles = region[DH_TILES], ent = region[DH_ENT], nidle = region[DH_NIDLE];
-    const uint32_t ncomp_pad = (tiles << 5) / G;
+    const uint32_t ncomp_pad = G ? (tiles << 5) / G : ((region[DH_NCOMP] + 31u) & ~31u);      // G == 0: balanced layout, lanes per component vary
     double* s_cnt = reinterpret_cast<double*>(dyn_smem);                         // ent (even)
     double* s_beta = s_cnt + ((ent + 1u) & ~1u);                                  // [NS][ncomp_pad] each
     double* s_alpha = s_beta + (size_t)NS * ncomp_pad;
@@ -85,17 +86,19 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     uint32_t* s_toff = reinterpret_cast<uint32_t*>(s_inveff + (size_t)NS * ncomp_pad);
     uint32_t* s_tlen = s_toff + ((tiles + 3u) & ~3u);
     uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_tlen + ((tiles + 3u) & ~3u));  // ent (padded to 16)
+    uint32_t* s_lane = reinterpret_cast<uint32_t*>(s_mask + ((ent + 15u) & ~15u));   // G == 0: 32 * tiles lane descriptors
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&tma_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t b_t = ((tiles + 3u) & ~3u) * 4u, b_m = (ent + 15u) & ~15u;
-    const uint32_t tx_bytes = 2u * b_t + b_m;
+    const uint32_t b_t = ((tiles + 3u) & ~3u) * 4u, b_m = (ent + 15u) & ~15u, b_l = G ? 0u : tiles * 128u;
+    const uint32_t tx_bytes = 2u * b_t + b_m + b_l;
     if (tx_bytes && threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&tma_bar)), "r"(tx_bytes) : "memory");
         if (b_t) { tma_load_1d(s_toff, region + q.g.o_tile_off, b_t, &tma_bar); tma_load_1d(s_tlen, region + q.g.o_tile_len, b_t, &tma_bar); }
         if (b_m) tma_load_1d(s_mask, region + q.g.o_mask, b_m, &tma_bar);
+        if (b_l) tma_load_1d(s_lane, region + q.g.o_lane, b_l, &tma_bar);
     }
     // per-run vectors through the index maps while the bulk copies fly
     const uint32_t* cperm = region + q.g.o_cperm;
@@ -142,10 +145,18 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
         // ---- one EM iteration of every component of this warp's tiles (tile -> warp is fixed, so a tile's state is only ever
         //      touched by its own warp: no barrier)
         for (uint32_t k = warp; k < tiles; k += W) {
-            const uint32_t qi = k * (32u / G) + lane / G;
+            uint32_t qi, glanes = G, grank = G ? lane % (G ? G : 1) : 0;
+            bool idle_lane = false;
+            if (G) qi = k * (32u / (G ? G : 1)) + lane / (G ? G : 1);
+            else {
+                const uint32_t info = s_lane[(k << 5) + lane];
+                idle_lane = info == DN_NONE;
+                qi = idle_lane ? 0u : (info & 0xFFFFu);
+                glanes = 1u << ((info >> 16) & 0xFu); grank = info >> 20;
+            }
             double b[NS], acc[NS];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) { b[j] = s_beta[(size_t)j * ncomp_pad + qi]; acc[j] = 0.0; }
+            for (int j = 0; j < NS; ++j) { b[j] = idle_lane ? 0.0 : s_beta[(size_t)j * ncomp_pad + qi]; acc[j] = 0.0; }
             const uint32_t L = s_tlen[k];
             const double* cn = s_cnt + s_toff[k] + lane;
             const uint8_t* mk = s_mask + s_toff[k] + lane;
@@ -201,7 +212,17 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
 #pragma unroll
                     for (int o = 1; o < G; o <<= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
                 }
-                if (lane % G) continue;                                // the group's first lane owns the component's state
+                if (grank) continue;                                   // the group's first lane owns the component's state
+            } else if (G == 0) {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+#pragma unroll
+                    for (int o = 1; o < (int)DN_MAX_GROUP; o <<= 1) {  // groups are aligned powers of two: lane ^ o stays inside for o < glanes
+                        const double other = __shfl_xor_sync(0xffffffffu, acc[j], o);
+                        if ((uint32_t)o < glanes) acc[j] += other;
+                    }
+                }
+                if (idle_lane || grank) continue;
             }
 #pragma unroll
             for (int j = 0; j < NS; ++j) {

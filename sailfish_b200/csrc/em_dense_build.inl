@@ -20,7 +20,7 @@
 
 #ifndef SFB_DENSE_GEOM_DEFINED
 #define SFB_DENSE_GEOM_DEFINED
-constexpr uint32_t DN_MAX_SLOTS = 8, DN_MAX_ROUNDS = 48, DN_BUCKETS = 256, DN_NONE = 0xFFFFFFFFu;
+constexpr uint32_t DN_MAX_SLOTS = 8, DN_MAX_ROUNDS = 48, DN_BUCKETS = 256, DN_NONE = 0xFFFFFFFFu, DN_ROWS = 4, DN_MAX_GROUP = 8;
 // identical for every CTA region; offsets in 32-bit words from the region start, all multiples of 4 (16 bytes)
 struct DenseGeom {
     uint32_t region_words;
@@ -28,15 +28,18 @@ struct DenseGeom {
     uint32_t cap_tiles;      // component tiles a region has room for
     uint32_t cap_ent;        // class entries (padded) a region has room for
     uint32_t cap_nt;         // transcripts
-    uint32_t group;          // lanes per component (1, 2 or 4): a component's classes are dealt round-robin to its lanes
-    uint32_t pad_[5];
+    uint32_t group;          // lanes per component (1, 2 or 4): a component's classes are dealt round-robin to its lanes;
+                             // 0 = as many lanes (1, 2, 4 or 8) as it takes to leave a lane at most DN_ROWS classes ("balanced")
+    uint32_t o_lane;         // group 0: per lane of every tile  component | log2(lanes of the component) << 16 | lane's rank << 20
+    uint32_t pad_[4];
 };
 enum { DH_KIND = 0, DH_NCOMP, DH_TILES, DH_ENT, DH_NS, DH_NIDLE, DH_NT, DH_NC, DH_ROUNDS, DH_GROUP, DH_WORDS = 16 };
 inline DenseGeom dense_make_geom(uint64_t max_nc, uint64_t max_nt, uint32_t group = 1) {
     auto up = [](uint64_t x, uint64_t m) { return (uint32_t)((x + m - 1) / m * m); };
     DenseGeom g;
-    g.group = (group == 2 || group == 4) ? group : 1;
-    g.cap_tiles = up(max_nt / 2 * g.group / 32 + 2, 4);       // a component has at least two transcripts
+    g.group = (group == 0 || group == 2 || group == 4) ? group : 1;
+    // a component has at least two transcripts; balanced: at most 2 (cc / DN_ROWS + 1) lanes per component
+    g.cap_tiles = g.group ? up(max_nt / 2 * g.group / 32 + 2, 4) : up((max_nc / 2 + max_nt) / 32 + 2, 4);
     g.cap_ent = up(max_nc + 64 * DN_BUCKETS, 16);
     g.cap_nt = up(max_nt + 1, 4);
     uint32_t o = DH_WORDS;
@@ -46,12 +49,13 @@ inline DenseGeom dense_make_geom(uint64_t max_nc, uint64_t max_nt, uint32_t grou
     g.o_mask = o; o += g.cap_ent / 4;
     g.o_tmap = o; o += DN_MAX_SLOTS * 32 * g.cap_tiles;
     g.o_idle = o; o += g.cap_nt;
+    g.o_lane = o; o += 32 * g.cap_tiles;
     g.region_words = o;
-    for (int i = 0; i < 5; ++i) g.pad_[i] = 0;
+    for (int i = 0; i < 4; ++i) g.pad_[i] = 0;
     return g;
 }
 // scratch words dense_build_cta needs
-inline size_t dense_scratch_words(uint64_t max_nt, const DenseGeom& g) { return 7 * (size_t)max_nt + DN_BUCKETS + 2 * (size_t)g.cap_tiles + 16; }
+inline size_t dense_scratch_words(uint64_t max_nt, const DenseGeom& g) { return 9 * (size_t)max_nt + DN_BUCKETS + 2 * (size_t)g.cap_tiles + 16; }
 #endif
 
 SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const uint32_t* lab, uint32_t c_lo, uint32_t nc,
@@ -68,6 +72,8 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
     uint32_t* s_tlen = s_hist + DN_BUCKETS;  // cap_tiles
     uint32_t* s_toff = s_tlen + g.cap_tiles; // cap_tiles
     uint32_t* s_misc = s_toff + g.cap_tiles; // [0] ok [1] changed [2] max size [3] components [4] idle [5] rounds [6] tiles [7] entries
+    uint32_t* s_gq = s_misc + 16;            // nt: balanced layout, lanes of component q
+    uint32_t* s_lb = s_gq + nt;              // nt: balanced layout, first lane of component q
     uint32_t* hdr = region;
     uint32_t* cperm = region + g.o_cperm;
     uint8_t* mask = reinterpret_cast<uint8_t*>(region + g.o_mask);
@@ -129,15 +135,35 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
     }
     SFB_GB_SYNC();
     const uint32_t ncomp = s_misc[3];
-    const uint32_t G = g.group;
-    const uint32_t tiles = (ncomp * G + 31u) >> 5, ncomp_pad = (tiles << 5) / G;      // 32 / G components per warp tile
-    if (tiles > g.cap_tiles) return;
+    const uint32_t G = g.group;                                         // 0: balanced (lanes per component from its class count)
     for (uint32_t t = tid; t < nt; t += nth) {
         if (s_deg[t] && s_comp[t] == t) {
             const uint32_t cc = s_ccnt[t];
             const uint32_t q = SFB_GB_ADD(s_hist + (cc < DN_BUCKETS ? cc : DN_BUCKETS - 1), 1u);
             s_q[t] = q;
-            SFB_GB_MAX(s_tlen + ((q * G) >> 5), (cc + G - 1) / G);       // rows of the tile: a lane takes every G-th class
+            uint32_t lanes = G;                                          // balanced: 1, 2, 4 or 8 lanes so that a lane holds <= DN_ROWS classes
+            if (G == 0) { const uint32_t need = (cc + DN_ROWS - 1) / DN_ROWS; lanes = 1; while (lanes < need && lanes < DN_MAX_GROUP) lanes <<= 1; }
+            s_gq[q] = lanes;
+        }
+    }
+    SFB_GB_SYNC();
+    // first lane of every component: components are numbered by descending class count, so their lane counts (powers of two)
+    // never increase and every group starts on a multiple of its size
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (uint32_t q = 0; q < ncomp; ++q) { s_lb[q] = acc; acc += s_gq[q]; }
+        s_misc[6] = (acc + 31u) >> 5;
+        if (ncomp > 0xFFFFu) s_misc[0] = 0;                             // the lane table keeps the component in 16 bits
+        if (G == 0) for (uint32_t q = 1; q < ncomp; ++q) if (s_gq[q] > s_gq[q - 1]) s_misc[0] = 0;   // counts >= 255 share a bucket unsorted
+    }
+    SFB_GB_SYNC();
+    const uint32_t tiles = s_misc[6];
+    const uint32_t ncomp_pad = G ? (tiles << 5) / G : ((ncomp + 31u) & ~31u);
+    if (tiles > g.cap_tiles || !s_misc[0]) return;
+    for (uint32_t t = tid; t < nt; t += nth) {
+        if (s_deg[t] && s_comp[t] == t) {
+            const uint32_t q = s_q[t], gq = s_gq[q];
+            SFB_GB_MAX(s_tlen + (s_lb[q] >> 5), (s_ccnt[t] + gq - 1) / gq);   // rows of the tile: a lane takes every gq-th class
         }
     }
     SFB_GB_SYNC();
@@ -153,6 +179,15 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
     for (uint32_t k = tid; k < tiles; k += nth) { region[g.o_tile_off + k] = s_toff[k]; region[g.o_tile_len + k] = s_tlen[k]; }
     for (uint32_t i = tid; i < DN_MAX_SLOTS * ncomp_pad; i += nth) tmap[i] = DN_NONE;
     for (uint32_t i = tid; i < ent; i += nth) { cperm[i] = DN_NONE; mask[i] = 0; }
+    if (G == 0) {
+        uint32_t* lane_tab = region + g.o_lane;
+        for (uint32_t i = tid; i < (tiles << 5); i += nth) lane_tab[i] = DN_NONE;
+        SFB_GB_SYNC();
+        for (uint32_t q = tid; q < ncomp; q += nth) {
+            const uint32_t gq = s_gq[q], lg = gq == 1 ? 0u : gq == 2 ? 1u : gq == 4 ? 2u : 3u;
+            for (uint32_t r = 0; r < gq; ++r) lane_tab[s_lb[q] + r] = q | (lg << 16) | (r << 20);
+        }
+    }
     SFB_GB_SYNC();
     // ---- slots: rank of a transcript among the members of its component, in transcript order
     for (uint32_t t = tid; t < nt; t += nth) {
@@ -175,7 +210,8 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
             if (mk & bit) s_misc[0] = 0;                                // the same transcript twice in one label
             mk |= bit;
         }
-        const uint32_t pos = s_toff[(q * G) >> 5] + ((e / G) << 5) + ((q * G) & 31u) + (e % G);
+        const uint32_t gq = s_gq[q], lb = s_lb[q];
+        const uint32_t pos = s_toff[lb >> 5] + ((e / gq) << 5) + (lb & 31u) + (e % gq);
         cperm[pos] = c_lo + c;
         mask[pos] = (uint8_t)mk;
     }

@@ -78,14 +78,31 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
     const uint32_t* h = region.data();
     CHECK((h[DH_KIND] == 1) == expect_dense, "kind %u, expected %d", h[DH_KIND], (int)expect_dense);
     if (!expect_dense) return 0;
-    const uint32_t ncomp = h[DH_NCOMP], tiles = h[DH_TILES], ent = h[DH_ENT], NS = h[DH_NS], nidle = h[DH_NIDLE], ncomp_pad = tiles * 32 / G;
+    const uint32_t ncomp = h[DH_NCOMP], tiles = h[DH_TILES], ent = h[DH_ENT], NS = h[DH_NS], nidle = h[DH_NIDLE], ncomp_pad = G ? tiles * 32 / G : (ncomp + 31) / 32 * 32;
+    const uint32_t* lane_tab = h + g.o_lane;                              // balanced layout (G == 0): component | log2(lanes) << 16 | rank << 20 per lane
+    auto comp_of = [&](uint32_t k, uint32_t lane) -> uint32_t { if (G) return k * (32 / G) + lane / G; const uint32_t i = lane_tab[32 * k + lane]; return i == DN_NONE ? DN_NONE : (i & 0xFFFFu); };
+    auto lanes_of = [&](uint32_t k, uint32_t lane) -> uint32_t { if (G) return G; const uint32_t i = lane_tab[32 * k + lane]; return i == DN_NONE ? 1u : 1u << ((i >> 16) & 0xFu); };
+    auto rank_of = [&](uint32_t k, uint32_t lane) -> uint32_t { if (G) return lane % G; const uint32_t i = lane_tab[32 * k + lane]; return i == DN_NONE ? 1u : i >> 20; };
     CHECK(h[DH_GROUP] == G, "header group");
     CHECK(ncomp == 0 ? NS == 0 : (NS >= 2 && NS <= DN_MAX_SLOTS && NS <= gsize), "slots %u", NS);
-    CHECK(tiles == (ncomp * G + 31) / 32 && ent <= g.cap_ent, "tiles / entries");
+    CHECK((G == 0 || tiles == (ncomp * G + 31) / 32) && ent <= g.cap_ent && tiles <= g.cap_tiles, "tiles / entries");
+    if (G == 0) {
+        // every component owns an aligned run of 1, 2, 4 or 8 lanes with ranks 0..lanes-1, enough for <= DN_ROWS classes per lane (up to 32 classes)
+        std::vector<uint32_t> seen_lanes(ncomp, 0);
+        for (uint32_t i = 0; i < tiles * 32; ++i) {
+            const uint32_t info = lane_tab[i];
+            if (info == DN_NONE) continue;
+            const uint32_t q = info & 0xFFFFu, gl = 1u << ((info >> 16) & 0xFu), r = info >> 20;
+            CHECK(q < ncomp && gl <= DN_MAX_GROUP && r < gl && (i - r) % gl == 0, "lane %u: component %u, %u lanes, rank %u", i, q, gl, r);
+            CHECK((lane_tab[i - r] & 0xFFFFu) == q, "lane %u is not in its component's run", i);
+            seen_lanes[q] += 1;
+        }
+        for (uint32_t q = 0; q < ncomp; ++q) CHECK(seen_lanes[q] >= 1, "component %u has no lane", q);
+    }
     const uint32_t* toff = h + g.o_tile_off; const uint32_t* tlen = h + g.o_tile_len; const uint32_t* cperm = h + g.o_cperm;
     const uint8_t* mask = reinterpret_cast<const uint8_t*>(h + g.o_mask);
     const uint32_t* tmap = h + g.o_tmap; const uint32_t* idle = h + g.o_idle;
-    { uint32_t acc = 0; for (uint32_t k = 0; k < tiles; ++k) { CHECK(toff[k] == acc, "tile offset"); acc += 32 * tlen[k]; if (k) CHECK(tlen[k] <= tlen[k - 1], "tiles not sorted"); } CHECK(acc == ent, "entries"); }
+    { uint32_t acc = 0; for (uint32_t k = 0; k < tiles; ++k) { CHECK(toff[k] == acc, "tile offset"); acc += 32 * tlen[k]; if (k && G) CHECK(tlen[k] <= tlen[k - 1], "tiles not sorted"); if (!G) CHECK(tlen[k] <= std::max<uint32_t>(DN_ROWS, 300 / DN_MAX_GROUP + 1), "balanced tile with %u rows", tlen[k]); } CHECK(acc == ent, "entries"); }
     // every transcript is either idle or in exactly one (slot, component); slots of a component ascend with the transcript id
     std::vector<int> where(nt, 0);
     for (uint32_t i = 0; i < nidle; ++i) { CHECK(idle[i] >= s.t0 && idle[i] < s.t0 + nt, "idle range"); where[idle[i] - s.t0] += 1; }
@@ -106,8 +123,9 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
     for (uint32_t k = 0; k < tiles; ++k)
         for (uint32_t e = 0; e < tlen[k]; ++e)
             for (uint32_t lane = 0; lane < 32; ++lane) {
-                const uint32_t pos = toff[k] + 32 * e + lane, c = cperm[pos], q = k * (32 / G) + lane / G;
+                const uint32_t pos = toff[k] + 32 * e + lane, c = cperm[pos], q = comp_of(k, lane);
                 if (c == DN_NONE) { CHECK(mask[pos] == 0, "padding entry with a mask"); continue; }
+                CHECK(q != DN_NONE, "class entry on an idle lane");
                 CHECK(c >= s.c_lo && c < s.c_lo + nc, "cperm range"); seen_c[c - s.c_lo]++;
                 uint32_t want = 0;
                 for (uint32_t j = 0; j < s.len[c]; ++j) { auto it = pos_of.find(s.lab[s.start[c] + j]); CHECK(it != pos_of.end() && it->second.first == q, "class %u is in the wrong column", c); want |= 1u << it->second.second; }
@@ -163,8 +181,8 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
         for (uint32_t k = 0; k < tiles; ++k) {
             double accs[32][DN_MAX_SLOTS], bs[32][DN_MAX_SLOTS];
             for (uint32_t lane = 0; lane < 32; ++lane) {                // every lane: the classes of its column
-                const uint32_t qi = k * (32 / G) + lane / G;
-                for (uint32_t j = 0; j < NS; ++j) { bs[lane][j] = s_beta[j * ncomp_pad + qi]; accs[lane][j] = 0.0; }
+                const uint32_t qi = comp_of(k, lane);
+                for (uint32_t j = 0; j < NS; ++j) { bs[lane][j] = qi == DN_NONE ? 0.0 : s_beta[j * ncomp_pad + qi]; accs[lane][j] = 0.0; }
                 for (uint32_t e = 0; e < tlen[k]; ++e) {
                     const double c = s_cnt[toff[k] + 32 * e + lane]; const uint32_t msk = mask[toff[k] + 32 * e + lane];
                     double S = 0.0;
@@ -173,14 +191,15 @@ static int run_case(uint64_t seed, uint32_t n_genes, uint32_t gsize, uint32_t cp
                     for (uint32_t j = 0; j < NS; ++j) accs[lane][j] += ((msk >> j) & 1u) ? r : 0.0;
                 }
             }
-            for (uint32_t j = 0; j < NS; ++j)                           // butterfly over the lanes of a group
-                for (uint32_t o = 1; o < G; o <<= 1) {
+            for (uint32_t j = 0; j < NS; ++j)                           // butterfly over the lanes of a group (masked by the lane's group size)
+                for (uint32_t o = 1; o < (G ? G : DN_MAX_GROUP); o <<= 1) {
                     double tmp[32];
-                    for (uint32_t lane = 0; lane < 32; ++lane) tmp[lane] = accs[lane][j] + accs[lane ^ o][j];
+                    for (uint32_t lane = 0; lane < 32; ++lane) tmp[lane] = accs[lane][j] + (o < lanes_of(k, lane) ? accs[lane ^ o][j] : 0.0);
                     for (uint32_t lane = 0; lane < 32; ++lane) accs[lane][j] = tmp[lane];
                 }
-            for (uint32_t lane = 0; lane < 32; lane += G) {             // the group's first lane owns the state
-                const uint32_t qi = k * (32 / G) + lane / G;
+            for (uint32_t lane = 0; lane < 32; ++lane) {                // the group's first lane owns the state
+                const uint32_t qi = comp_of(k, lane);
+                if (qi == DN_NONE || rank_of(k, lane) != 0) continue;
                 for (uint32_t j = 0; j < NS; ++j) s_alpha[j * ncomp_pad + qi] = bs[lane][j] * accs[lane][j] + s_base[j * ncomp_pad + qi];
             }
         }
@@ -208,7 +227,7 @@ int main() {
         {8, 700, 3, 300, false, false, 3, true, false},  // many components, class counts beyond one bucket width
         {9, 5, 5, 3, false, false, 1, true, false},      // no class at all (every gene silent): zero components
     };
-    for (uint32_t G : {1u, 2u, 4u})
+    for (uint32_t G : {1u, 2u, 4u, 0u})
     for (const Case& c : cases)
         if (run_case(c.seed, c.n_genes, c.gsize, c.cpg, c.chain, c.dup, c.idle_every, c.dense, c.vb, G)) { fprintf(stderr, "case seed %llu failed\n", (unsigned long long)c.seed); return 1; }
     printf("em_dense layout ok (%zu cases)\n", sizeof(cases) / sizeof(cases[0]));
