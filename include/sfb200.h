@@ -140,7 +140,7 @@ double sfb200_last_em_loop_ms(const sfb200_ctx* ctx);
  * 4 one thread per connected component of the class structure (k_em_dense) */
 int sfb200_last_em_kernel(const sfb200_ctx* ctx);
 
-/* EXPERIMENTAL (written against the pinned CPU oracle, not yet run on a GPU; nothing calls it by default).
+/* Not called by the quantification drivers yet (parity-tested on its own: tests/test_gpu_bias.py).
  * Replaces sailfish::utils::updateEffectiveLengths (src/SailfishUtils.cpp:611-926): effective lengths corrected for
  * sequence-specific (--biasCorrect) or fragment-GC (--gcBiasCorrect) bias from the current abundances.  The model is what the
  * reference reads from ReadExperiment: readBias().counts (include/ReadKmerDist.hpp:16-24, pseudo-counts included),

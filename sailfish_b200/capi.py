@@ -297,7 +297,7 @@ class Context:
         return float(self.L.sfb200_last_em_loop_ms(self.h))
 
     def bias_eff_lens(self, mode, eff_model, eff_in, alphas, num_fwd, num_rc, read_bias, observed_gc, fld_cdf, fld_max, gc_samp=1):
-        """EXPERIMENTAL: updateEffectiveLengths on the device (sfb200_bias_eff_lens); fld_cdf = EmpiricalDistribution's float cdf table"""
+        """updateEffectiveLengths on the device (sfb200_bias_eff_lens); fld_cdf = EmpiricalDistribution's float cdf table"""
         eff_model = np.ascontiguousarray(eff_model, dtype=np.float64); eff_in = np.ascontiguousarray(eff_in, dtype=np.float64)
         alphas = np.ascontiguousarray(alphas, dtype=np.float64)
         rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)

@@ -14,9 +14,9 @@
 // The text is the device index's: a base that was not A/C/G/T in the FASTA is the deterministic substitute the index stores
 // (DESIGN.md section 3), where the reference would run off its tables (indexForKmer returns UINT32_MAX for such a window).
 //
-// STATUS: written against the CPU oracle (oracle/orc_bias.cpp, which is pinned to the reference's own function body) but NOT
-// yet run on a GPU -- the round's GPU budget was spent when it was written.  Nothing calls it by default; its parity test
-// (tests/test_gpu_bias.py) runs only with SFB200_EXPERIMENTAL=1.
+// STATUS: parity with the CPU oracle (oracle/orc_bias.cpp, which is pinned to the reference's own function body) is green on a
+// B200 (tests/test_gpu_bias.py; profiles/r01f_experimental_gpu.txt); not timed or profiled yet, and the quantification drivers
+// do not call it yet.
 #include <cub/cub.cuh>
 
 #include <algorithm>

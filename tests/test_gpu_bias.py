@@ -1,16 +1,13 @@
-"""GPU parity test of the EXPERIMENTAL device-side bias / GC effective-length correction (sailfish_b200/csrc/bias.cu,
-sfb200_bias_eff_lens) against the CPU oracle, which is pinned to the reference's own updateEffectiveLengths
-(tests/test_oracle_bias.py).  The kernels were written after the round's GPU budget was spent and have not run on a GPU yet, so
-this test only runs with SFB200_EXPERIMENTAL=1; nothing in the product calls the entry point by default."""
-import os
-
+"""GPU parity test of the device-side bias / GC effective-length correction (sailfish_b200/csrc/bias.cu, sfb200_bias_eff_lens;
+SURVEY 8a row A18) against the CPU oracle, which is pinned to the reference's own updateEffectiveLengths
+(tests/test_oracle_bias.py).  First green run on a B200: profiles/r01f_experimental_gpu.txt.  The entry point is not called by
+the quantification pipeline yet."""
 import numpy as np
 import pytest
 
 from oracle import pyoracle as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1",
-                                                   reason="experimental kernels: set SFB200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode,gc_samp", [(1, 1), (2, 1), (2, 3)])
