@@ -156,6 +156,15 @@ typedef struct {
 } sfb200_bias_model;
 int sfb200_bias_eff_lens(sfb200_ctx* ctx, const sfb200_bias_model* model, const double* eff_model, const double* eff_in,
                          const double* alphas, uint32_t n_txp, double* eff_out);
+/* Replaces CollapsedEMOptimizer::optimize when sopt.biasCorrect or sopt.gcBiasCorrect is set (src/CollapsedEMOptimizer.cpp:820-840):
+ * as sfb200_em_run, and at the top of iterations 50, 500 and 1000 the effective lengths are recomputed from the current alphas
+ * (sfb200_bias_eff_lens) and the class weights with them (updateEqClassWeights, :527-556).  eff_lens[t] = Transcript::EffectiveLength;
+ * eff_out (optional) = the lengths the run ended with, which the reference writes to quant.sf (:888).  The index must be resident
+ * (the correction reads the transcript sequences).  Single rank, or classes merged over ranks.
+ * Parity: tests/test_gpu_bias.py (needs SFB200_EXPERIMENTAL=1 until it has had its first GPU run). */
+int sfb200_em_run_bias(sfb200_ctx* ctx, const double* eff_lens, uint32_t n_txp, uint64_t num_mapped, const sfb200_em_opts* opts,
+                       const sfb200_bias_model* model, double* alphas_out, double* eff_out, uint32_t* iters_out,
+                       double* max_rel_diff_out);
 
 typedef int (*sfb200_f64_row_cb)(void* user, const double* row, size_t n);
 typedef int (*sfb200_i32_row_cb)(void* user, const int32_t* row, size_t n);

@@ -94,6 +94,7 @@ SIGNATURES = {
     "sfb200_last_em_loop_ms": (C.c_double, [C.c_void_p]),
     "sfb200_last_em_kernel": (C.c_int, [C.c_void_p]),
     "sfb200_bias_eff_lens": (C.c_int, [C.c_void_p, C.POINTER(BiasModel), f64p, f64p, f64p, C.c_uint32, f64p]),
+    "sfb200_em_run_bias": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.c_uint64, C.POINTER(EMOpts), C.POINTER(BiasModel), f64p, f64p, u32p, f64p]),
     "sfb200_bootstrap_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.POINTER(EMOpts), C.c_uint32, C.c_uint64, F64_ROW_CB, C.c_void_p]),
     "sfb200_bootstrap_em": (C.c_int, [C.c_void_p, f64p, C.c_uint32, u64p, C.POINTER(EMOpts), f64p, u32p]),
     "sfb200_gibbs_run": (C.c_int, [C.c_void_p, f64p, f64p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, I32_ROW_CB, C.c_void_p]),
@@ -308,6 +309,26 @@ class Context:
         self._chk(self.L.sfb200_bias_eff_lens(self.h, C.byref(m), _ptr(eff_model, f64p), _ptr(eff_in, f64p), _ptr(alphas, f64p), len(eff_in),
                                               _ptr(out, f64p)))
         return out
+
+    @staticmethod
+    def _bias_model(mode, num_fwd, num_rc, read_bias, observed_gc, fld_cdf, fld_max, gc_samp):
+        rb = np.ascontiguousarray(read_bias, dtype=np.uint32); og = np.ascontiguousarray(observed_gc, dtype=np.uint32)
+        cdf = np.ascontiguousarray(fld_cdf, dtype=np.float32)
+        m = BiasModel(int(mode), int(gc_samp), int(num_fwd), int(num_rc), _ptr(rb, u32p), _ptr(og, u32p),
+                      cdf.ctypes.data_as(C.POINTER(C.c_float)), len(cdf), int(fld_max))
+        return m, (rb, og, cdf)                                    # the arrays must outlive the call
+
+    def em_run_bias(self, mode, eff_lens, num_mapped, num_fwd, num_rc, read_bias, observed_gc, fld_cdf, fld_max, gc_samp=1, opts=None):
+        """optimize() with bias (mode 1) / GC (mode 2) correction (sfb200_em_run_bias) -> (alphas, final eff lens, iters, max_rel_diff)"""
+        opts = opts or EMOpts.default()
+        eff = np.ascontiguousarray(eff_lens, dtype=np.float64)
+        m, keep = self._bias_model(mode, num_fwd, num_rc, read_bias, observed_gc, fld_cdf, fld_max, gc_samp)
+        alphas = np.zeros(len(eff), np.float64); eff_out = np.zeros(len(eff), np.float64)
+        iters = C.c_uint32(); mrd = C.c_double()
+        self._chk(self.L.sfb200_em_run_bias(self.h, _ptr(eff, f64p), len(eff), int(num_mapped), C.byref(opts), C.byref(m), _ptr(alphas, f64p),
+                                            _ptr(eff_out, f64p), C.byref(iters), C.byref(mrd)))
+        del keep
+        return alphas, eff_out, iters.value, mrd.value
 
     def last_em_kernel(self):
         """0 k_em_persistent, 1 k_em_part, 2 k_em_gather, 3 one launch per phase"""

@@ -21,6 +21,7 @@
 #include <limits>
 
 #include "common.cuh"
+#include "em_segments.hpp"
 
 namespace {
 
@@ -1052,10 +1053,18 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
     return SFB200_OK;
 }
 
+// bias / GC correction inside the optimizer (optimize() :820-840): the model, and where the final effective lengths go
+struct EmBias { const sfb200_bias_model* model; double* eff_out; };
+
+__global__ void k_em_restart(const double* __restrict__ base, uint32_t T, double* __restrict__ X) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) { const double b = base[i]; X[(size_t)T + i] = b; X[2 * (size_t)T + i] = b; }
+}
+
 // shared by em_run and bootstrap_em: everything from effective lengths to truncated alphas
 int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double total_frags, const sfb200_em_opts* o,
               const double* d_cnt, const double* d_single, LoopSpec spec, double* alphas_out, uint32_t* iters_out,
-              double* mrd_out) {
+              double* mrd_out, const EmBias* eb = nullptr) {
     DevClasses& k = c->cls;
     cudaStream_t s = c->stream;
     const uint32_t T = n_txp;
@@ -1149,8 +1158,52 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     unsigned buf = 0;
     sfb200_em_opts oo = *o;
     oo.min_iter = spec.min_iter;
-    const int rc = run_loop(c, p, &oo, use_dense ? LOOP_DENSE : use_gather ? LOOP_GATHER : use_part ? LOOP_PART : LOOP_BINNED, iters_out, mrd_out, &buf);
-    if (rc) return rc;
+    const LoopKind kind = use_dense ? LOOP_DENSE : use_gather ? LOOP_GATHER : use_part ? LOOP_PART : LOOP_BINNED;
+    if (!eb) {
+        const int rc = run_loop(c, p, &oo, kind, iters_out, mrd_out, &buf);
+        if (rc) return rc;
+    } else {
+        // one launch per stretch between the iterations at which the reference recomputes the effective lengths (em_segments.hpp);
+        // between two launches: alphas to the host, sfb200_bias_eff_lens, new lengths into c->eff (the gather / dense loops read it
+        // at launch, the scatter loops through the class weights, recomputed as updateEqClassWeights does, :527-556)
+        static const uint32_t pauses[3] = {50, 500, 1000};
+        std::vector<double> h_alpha(T), h_eff(T), h_next(T);
+        for (uint32_t i = 0; i < T; ++i) h_eff[i] = eff_lens[i] <= 1.0 ? 1.0 : eff_lens[i];      // what k_clamp_eff left in c->eff
+        float loop_ms = 0.f;
+        auto update = [&](uint32_t) -> int {
+            SFB_CUDA(c, cudaMemcpyAsync(h_alpha.data(), c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToHost, s));
+            SFB_CUDA(c, cudaStreamSynchronize(s));
+            const int rc = sfb200_bias_eff_lens(c, eb->model, eff_lens, h_eff.data(), h_alpha.data(), T, h_next.data());
+            if (rc) return rc;
+            h_eff.swap(h_next);
+            SFB_CUDA(c, cudaMemcpyAsync(c->eff.p, h_eff.data(), T * 8ull, cudaMemcpyHostToDevice, s));
+            if (k.Em && !use_gather) {
+                k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
+                c->launches++;
+            }
+            // the next launch starts from the current alphas: X[0] = alphas, X[1] = X[2] = base
+            if (buf != 0) SFB_CUDA(c, cudaMemcpyAsync(c->em_alpha.p, c->em_alpha.p + (size_t)buf * T, T * 8ull, cudaMemcpyDeviceToDevice, s));
+            k_em_restart<<<grid_for(T, 256), 256, 0, s>>>(c->em_base.p, T, c->em_alpha.p);
+            c->launches++;
+            buf = 0;
+            double sum = 0.0;
+            if (vb) for (uint32_t i = 0; i < T; ++i) sum += h_alpha[i];                          // VBEMUpdate_'s serial alpha sum (:300-303)
+            p.sum0 = sum;
+            return SFB200_OK;
+        };
+        auto run = [&](const sfb::SegLimits& lim, uint32_t, uint32_t* it, double* mrd) -> int {
+            sfb200_em_opts so = oo;
+            so.min_iter = lim.min_iter; so.max_iter = lim.max_iter; so.fixed_iters = lim.fixed_iters;
+            p.min_iter = lim.min_iter; p.max_iter = lim.max_iter; p.fixed_iters = lim.fixed_iters;
+            const int rc = run_loop(c, p, &so, kind, it, mrd, &buf);
+            loop_ms += c->last_em_ms;
+            return rc;
+        };
+        const int rc = sfb::run_segments(spec.min_iter, o->max_iter, o->fixed_iters, o->tol, pauses, 3, run, update, iters_out, mrd_out);
+        if (rc) return rc;
+        c->last_em_ms = loop_ms;
+        if (eb->eff_out) std::memcpy(eb->eff_out, h_eff.data(), T * 8ull);                        // :888 the lengths quant.sf reports
+    }
     hm.mark("em: loop (launch .. sync)");
 
     const double cutoff = vb ? (o->prior_alpha + o->min_alpha) : o->min_alpha;           // :812
@@ -1197,6 +1250,27 @@ extern "C" int sfb200_em_run(sfb200_ctx* c, const double* eff_lens, uint32_t n_t
     LoopSpec spec{false, opts->min_iter};
     const int rc = em_common(c, eff_lens, n_txp, static_cast<double>(num_mapped), opts, c->cls.cnt.p, c->cls.single.p, spec,
                              alphas_out, &iters, &mrd);
+    if (iters_out) *iters_out = iters;
+    if (max_rel_diff_out) *max_rel_diff_out = mrd;
+    return rc;
+}
+
+/* optimize() with --biasCorrect / --gcBiasCorrect: the effective lengths are recomputed from the current abundances at the top of
+ * iterations 50, 500 and 1000 (:820-840) and the final ones are returned (:888) */
+extern "C" int sfb200_em_run_bias(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, uint64_t num_mapped, const sfb200_em_opts* opts,
+                                  const sfb200_bias_model* model, double* alphas_out, double* eff_out, uint32_t* iters_out,
+                                  double* max_rel_diff_out) {
+    if (!c || !eff_lens || !opts || !alphas_out || !model) return SFB200_EINVAL;
+    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "em_run_bias: no classes (call map_finish or eq_import first)");
+    if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "em_run_bias: n_txp differs from the class table's");
+    if (c->n_ranks > 1 && !c->cls.merged) SFB_FAIL(c, SFB200_EINVAL, "em_run_bias: classes must be merged over ranks first (map_finish with the communicator attached)");
+    if (!c->index.ready || c->index.n_txp != n_txp) SFB_FAIL(c, SFB200_EINVAL, "em_run_bias: the correction reads the transcript sequences of the index; build or load it first");
+    cudaSetDevice(c->device);
+    uint32_t iters = 0; double mrd = 0.0;
+    LoopSpec spec{false, opts->min_iter};
+    EmBias eb{model, eff_out};
+    const int rc = em_common(c, eff_lens, n_txp, static_cast<double>(num_mapped), opts, c->cls.cnt.p, c->cls.single.p, spec,
+                             alphas_out, &iters, &mrd, &eb);
     if (iters_out) *iters_out = iters;
     if (max_rel_diff_out) *max_rel_diff_out = mrd;
     return rc;

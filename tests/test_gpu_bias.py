@@ -31,3 +31,53 @@ def test_bias_eff_lens_matches_oracle(ctx, mode, gc_samp):
     assert ((got != eff_in) == (want != eff_in)).all() and (want != eff_in).sum() > 50
     # no strand tallies: the correction is skipped
     assert (ctx.bias_eff_lens(mode, eff_model, eff_in, alphas, 0, 0, rb, og, cdf, mx) == eff_in).all()
+
+
+# ---- the optimizer with the correction inside (sfb200_em_run_bias): effective lengths recomputed at iterations 50 / 500 / 1000 ------------
+# Written after the round's GPU budget was spent: the launch scheduling is checked on CPU (tests/em_segments_test.cpp), the entry point
+# has not run on a GPU yet, so these cases need SFB200_EXPERIMENTAL=1.
+import os
+
+from sailfish_b200 import capi, synth
+
+_experimental = pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SFB200_EXPERIMENTAL=1")
+
+
+@_experimental
+@pytest.mark.parametrize("loops", ["default", "scatter", "steps"])
+@pytest.mark.parametrize("mode,vb,kw", [
+    (1, 0, {}), (2, 0, {}), (1, 1, {}), (2, 1, {}),                              # default limits: one recomputation, at iteration 50
+    (1, 0, {"fixed_iters": 49}), (1, 0, {"fixed_iters": 50}), (2, 0, {"fixed_iters": 51}),
+    (1, 0, {"fixed_iters": 520}), (2, 1, {"fixed_iters": 1003}),                # two and three recomputations
+    (2, 0, {"min_iter": 10, "max_iter": 30}), (1, 0, {"min_iter": 600, "max_iter": 40}),
+])
+def test_em_run_bias_matches_oracle(ctx, monkeypatch, loops, mode, vb, kw):
+    if loops == "scatter":
+        monkeypatch.setenv("SFB200_EM_GATHER", "0"); monkeypatch.setenv("SFB200_EM_DENSE", "0")
+    elif loops == "steps":
+        monkeypatch.setenv("SFB200_EM_MODE", "steps")
+    rng = np.random.default_rng(100 * mode + vb)
+    T = 400
+    lens = rng.integers(250, 3000, size=T)
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=int(n), p=[0.3, 0.2, 0.2, 0.3]).astype(np.uint8)) for n in lens]
+    ctx.index_build(seqs=seqs, k=31)
+    rp, lab, cnt = synth.make_classes(T, 1000, seed=5 + mode)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    x = np.arange(1000)
+    fld = np.round(30000 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32)
+    cdf, mx = O.fld_cdf(fld)
+    eff = np.where(lens - 189.0 >= 1, lens - 189.0, lens).astype(np.float64)
+    rb = rng.integers(1, 3000, size=4096).astype(np.uint32); og = rng.integers(1, 8000, size=101).astype(np.uint32)
+    nf, nr = 61234, 58766
+    a, eff_got, it, mrd = ctx.em_run_bias(mode, eff, nm, nf, nr, rb, og, cdf, mx, opts=capi.EMOpts.default(use_vb=vb, **kw))
+    rc, want, eff_want, it_o, mrd_o = O.em_run_bias(mode, seqs, rp, lab, cnt, eff, nm, nf, nr, rb, og, fld, opts=O.EMOpts.default(use_vb=vb, **kw))
+    assert rc == 0 and it == it_o
+    np.testing.assert_allclose(eff_got, eff_want, rtol=1e-7)
+    np.testing.assert_allclose(a, want, rtol=1e-4, atol=1e-6)
+    assert (a == 0).tolist() == (want == 0).tolist()
+    if it >= 50:
+        assert (eff_got != np.maximum(eff, 1.0)).sum() > 50                     # the correction did happen
+        assert abs(mrd - mrd_o) <= 1e-5 * max(abs(mrd_o), 1e-12)
+    else:
+        assert (eff_got == np.maximum(eff, 1.0)).all()
