@@ -97,6 +97,16 @@ int sfb200_map_batch(sfb200_ctx* ctx, const char* bases1, const uint64_t* off1, 
 /* Same with buffers already resident in device memory. */
 int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
                             const uint64_t* d_off2, uint64_t n_reads);
+/* --biasCorrect / --gcBiasCorrect: collect, while mapping, what the reference collects in processReadsQuasi
+ * (src/SailfishQuantify.cpp:255-287 and :555-583: the 6-mer context around the start of each read's first hit that has one,
+ * readBias().update, for the first num_bias_samples such reads in read order -- sfOpts.numBiasSamples, the reference at -p 1;
+ * :372-389: observedGC()[gcFrac(start, stop)]++ for every properly paired hit inside its transcript).
+ * Call after map_begin and before the first batch.  Parity: tests/test_gpu_map.py (SFB200_EXPERIMENTAL=1 until first GPU run). */
+int sfb200_map_set_bias(sfb200_ctx* ctx, int seq_bias, int gc_bias, int32_t num_bias_samples);
+/* readExp.readBias().counts (4096 bins) and readExp.observedGC() (101 bins), both with the reference's initial count of 1 per
+ * bin -- the arrays sfb200_bias_model takes.  With a communicator: summed over ranks. */
+int sfb200_map_get_bias(sfb200_ctx* ctx, uint32_t* read_bias, uint32_t* observed_gc);
+
 /* == thread join + eqBuilder.finish() (SailfishQuantify.cpp:942-947,1328).
  * counters: [0] numObservedFragments [1] numMappedFragments [2] numFragHits [3] upperBoundHits [4] numFwd [5] numRC
  * (ReadExperiment.hpp:74-97); fld_hist[max_frag_len] = flMap (SailfishQuantify.cpp:867).  With a communicator the

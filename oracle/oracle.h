@@ -60,6 +60,9 @@ orc_index* orc_index_from_table(const uint64_t* words, uint64_t text_len, const 
                                 const uint32_t* sa_pos, const uint32_t* sa_tid, uint64_t n_sa, const uint64_t* table16,
                                 uint64_t n_slots);
 void orc_index_free(orc_index*);
+/* per-hit pieces of the bias sample collection: ReadKmerDist<6>::update's bin for a hit (-1 = no sample), Transcript::gcFrac */
+int32_t orc_bias_context_index(const orc_index*, uint32_t tid, int32_t pos, int fwd, uint32_t read_len);
+int32_t orc_gc_frac(const orc_index*, uint32_t tid, int32_t s, int32_t e);
 uint64_t orc_index_n_sa(const orc_index*);       /* number of valid suffix positions */
 uint64_t orc_index_n_kmers(const orc_index*);    /* number of distinct k-mers */
 uint64_t orc_index_text_len(const orc_index*);   /* packed coordinate space length */

@@ -546,6 +546,12 @@ extern "C" int orc_map_finish_bias(const orc_run* r, uint32_t* read_bias /*4096*
     std::memcpy(read_bias, r->readBias.data(), 4096 * 4); std::memcpy(observed_gc, r->observedGC.data(), 101 * 4);
     return 0;
 }
+// the two per-hit functions on their own, for tests of the device-side helpers (tests/bias_core_test.cpp)
+extern "C" int32_t orc_bias_context_index(const orc_index* ix, uint32_t tid, int32_t pos, int fwd, uint32_t read_len) {
+    Hit h{tid, pos, fwd != 0, read_len, 0};
+    return bias_context_index(*ix, h);
+}
+extern "C" int32_t orc_gc_frac(const orc_index* ix, uint32_t tid, int32_t s, int32_t e) { return gc_frac(*ix, tid, s, e); }
 extern "C" void orc_run_keep_labels(orc_run* r, int on) { r->keepLabels = on != 0; }
 
 extern "C" int orc_map_batch(orc_run* r, const char* bases1, const uint64_t* off1, const char* bases2,

@@ -86,6 +86,8 @@ SIGNATURES = {
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
     "sfb200_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint64]),
     "sfb200_map_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "sfb200_map_set_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32]),
+    "sfb200_map_get_bias": (C.c_int, [C.c_void_p, u32p, u32p]),
     "sfb200_map_finish": (C.c_int, [C.c_void_p, u64p, u32p, u64p, u64p]),
     "sfb200_eq_export": (C.c_int, [C.c_void_p, u64p, u32p, u64p]),
     "sfb200_eq_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, u64p, u32p, u64p]),
@@ -262,6 +264,16 @@ class Context:
         else:
             self._chk(f(self.h, C.c_void_p(p_bases1), C.cast(C.c_void_p(p_off1), u64p), C.c_void_p(p_bases2) if p_bases2 else None,
                         C.cast(C.c_void_p(p_off2), u64p) if p_off2 else None, n))
+
+    def map_set_bias(self, seq_bias=True, gc_bias=False, num_bias_samples=1000000):
+        """collect the bias / GC samples while mapping (after map_begin, before the first batch)"""
+        self._chk(self.L.sfb200_map_set_bias(self.h, int(seq_bias), int(gc_bias), int(num_bias_samples)))
+
+    def map_get_bias(self):
+        """-> (read_bias[4096], observed_gc[101]) with the initial count of 1 per bin"""
+        rb = np.zeros(4096, np.uint32); og = np.zeros(101, np.uint32)
+        self._chk(self.L.sfb200_map_get_bias(self.h, _ptr(rb, u32p), _ptr(og, u32p)))
+        return rb, og
 
     def map_finish(self):
         counters = np.zeros(6, np.uint64)

@@ -93,3 +93,38 @@ SFB_BD double b_eff_gc(const BiasView& v, const double* ratio, uint64_t t0, int3
     }
     return s;
 }
+
+// ---- the mapper's side: what one hit contributes to the observed distributions (SailfishQuantify.cpp:255-287, :372-389, :555-583) ---------
+// G/C bases of the text in [a, b), straight from the 2-bit words (a fragment spans at most a few dozen words)
+SFB_BD uint32_t b_gc_range(const uint64_t* __restrict__ words, uint64_t a, uint64_t b) {
+    if (b <= a) return 0;
+    const uint64_t w0 = a >> 5, w1 = (b - 1) >> 5;
+    uint32_t n = 0;
+    for (uint64_t w = w0; w <= w1; ++w) {
+        const uint64_t x = SFB_LDG(words + w);
+        uint64_t m = (x ^ (x >> 1)) & 0x5555555555555555ULL;
+        if (w == w0) m &= ~0ULL << (2 * (uint32_t)(a & 31));
+        if (w == w1) { const uint32_t hi = 2 * (uint32_t)((b - 1) & 31) + 2; if (hi < 64) m &= (1ULL << hi) - 1; }
+        n += SFB_POPC64(m);
+    }
+    return n;
+}
+// Transcript::gcFrac(s, e) without the prefix array
+SFB_BD int32_t b_gc_frac_range(const uint64_t* __restrict__ words, uint64_t t0, int32_t s, int32_t e) {
+    return SFB_D2I_RN((100.0 * b_gc_range(words, t0 + s + 1, t0 + e + 1)) / (double)(e - s + 1));
+}
+// ReadKmerDist<6>::update (include/ReadKmerDist.hpp:36-72) for a hit at `pos` of a read of `readLen` bases: the bin of the 6-mer context
+// around the read's start on the transcript (2 bases before it for a forward hit, reverse-complemented; 4 before for a
+// reverse-complement hit), or -1 when the start lies outside (0, refLen) or the window does not fit
+SFB_BD int32_t b_read_start_index(const uint64_t* __restrict__ words, uint64_t t0, int32_t refLen, int32_t pos, bool fwd, uint32_t readLen) {
+    const int32_t startPos = fwd ? pos : pos + (int32_t)readLen;
+    if (!(startPos > 0 && startPos < refLen)) return -1;
+    if (fwd) {
+        const int32_t p = startPos - 2;
+        if (!(startPos >= 2 && p + BK < refLen)) return -1;
+        return (int32_t)b_idx_rc(b_win6(words, t0 + p));
+    }
+    const int32_t p = startPos - 4;
+    if (!(startPos >= 4 && p + BK < refLen)) return -1;
+    return (int32_t)b_idx_fwd(b_win6(words, t0 + p));
+}

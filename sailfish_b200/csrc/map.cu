@@ -53,6 +53,21 @@ struct IndexView {
     uint64_t mask, bloom_words; int k; uint64_t kmask;
 };
 
+// the per-hit arithmetic of the bias / GC sample collection, shared with bias.cu and the CPU check (tests/bias_core_test.cpp)
+#define SFB_BD __device__ __forceinline__
+#define SFB_LDG(p) __ldg(p)
+#define SFB_POPC64(x) __popcll(x)
+#define SFB_D2I_RN(x) __double2int_rn(x)
+#include "bias_core.inl"
+#undef SFB_BD
+#undef SFB_LDG
+#undef SFB_POPC64
+#undef SFB_D2I_RN
+__device__ __forceinline__ int32_t hit_read_start_index(const IndexView& ix, uint32_t tid, int32_t pos, bool fwd, uint32_t readLen) {
+    const uint64_t t0 = ix.txp_start[tid];
+    return b_read_start_index(ix.words, t0, (int32_t)(ix.txp_end[tid] - t0), pos, fwd, readLen);
+}
+
 // ---- the equivalence-class table ------------------------------------------------------------------------------------------
 // libcuckoo's layout (4 slots per bucket, two candidate buckets per key, include/cuckoohash_config.hh:9,
 // cuckoohash_map.hh:1012-1026) with the BFS displacement replaced by a linear-probed overflow region: the table is kept
@@ -516,6 +531,10 @@ struct MapParams {
     // packed batch and the scan -> finalize hand-over
     const uint64_t* pk; const uint64_t* pkn; const uint32_t* meta; uint32_t rwp; int n_mates;
     unsigned long long* iv; uint8_t* niv; uint32_t* ivmask;
+    // bias / GC sample collection (k_finalize_reads_bias only)
+    int16_t* bias_val;                 // per read of the batch: bin of its read-start context, or -1
+    unsigned int* gc_hist;             // observed fragment GC histogram (101 bins), accumulated over batches
+    int bias_seq, bias_gc;
 };
 
 struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of processReadsQuasi folded into one buffer
@@ -591,7 +610,11 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
 }
 
 // ---- finalize kernel: projection, mate merge, compatibility filter, label, class upsert -----------------------------------------
-__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapParams p) {
+// BIAS: additionally what --biasCorrect / --gcBiasCorrect collect per hit (SailfishQuantify.cpp:255-287, :372-389, :555-583): the
+// read-start context of the read's first hit that has one (p.bias_val, sampled in read order by k_bias_select) and the GC
+// percentage of every properly paired hit that lies inside its transcript (s_gc, the CTA's 101-bin histogram)
+template <bool BIAS>
+__device__ __forceinline__ void finalize_reads_body(const MapParams& p, unsigned int* s_gc) {
     extern __shared__ uint64_t smem_reads[];
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const Scratch scr{p.scratch + gtid, p.n_threads_total};
@@ -639,12 +662,14 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapPara
             LabelAcc acc(scr, TMP0, p.enforce_compat != 0);
             uint32_t n_joint = 0;
             int32_t fl = -1;
+            int32_t bsample = -1;
             if (!paired) {
                 // SailfishQuantify.cpp:530-631
                 n_joint = overflow ? 0 : nL;
                 c_ub += (overflow || n_joint > 0) ? 1 : 0;
                 for (uint32_t i = 0; i < n_joint; ++i) {
                     const unsigned long long h = scr.at(LEFT0 + i);
+                    if (BIAS) { if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, hit_tid(h), hit_pos(h), hit_fwd(h), len1); }
                     const bool compat = p.ignore_compat ? true : compat_single(p.lib_fmt, hit_fwd(h), 0);
                     acc.add(hit_tid(h), compat, hit_fwd(h));
                 }
@@ -667,6 +692,16 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapPara
                         if (tr < tl) { ++j; continue; }
                         const int32_t pl = hit_pos(hl), pr = hit_pos(hr);
                         const bool fl_ = hit_fwd(hl), fr_ = hit_fwd(hr);
+                        if (BIAS) {
+                            if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, tl, pl, fl_, len1);
+                            if (p.bias_gc) {                                                // :375-388
+                                const int32_t start = pl < pr ? pl : pr;
+                                const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
+                                const int32_t stop = e1 > e2 ? e1 : e2;                      // start + fragLen
+                                const uint64_t t0 = p.ix.txp_start[tl];
+                                if (start > 0 && stop < (int32_t)(p.ix.txp_end[tl] - t0)) atomicAdd(s_gc + b_gc_frac_range(p.ix.words, t0, start, stop), 1u);
+                            }
+                        }
                         bool compat = p.ignore_compat != 0;
                         if (!compat) {
                             const uint32_t e1 = fl_ ? (uint32_t)pl : (uint32_t)pl + len1;
@@ -696,6 +731,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapPara
                             const unsigned long long h = takeL ? scr.at(LEFT0 + i++) : scr.at(RIGHT0 + j++);
                             const int ms = takeL ? 1 : 2;
                             const bool fwd = hit_fwd(h);
+                            if (BIAS) { if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, hit_tid(h), hit_pos(h), fwd, ms == 1 ? len1 : len2); }
                             const bool compat = p.ignore_compat ? true : compat_single(p.lib_fmt, fwd, ms);
                             const bool fwdHit = takeL ? fwd : !fwd;
                             acc.add(hit_tid(h), compat, fwdHit);
@@ -717,6 +753,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapPara
                 const bool elig = paired && n_joint == 1 && fl >= 0 && mapped && (uint32_t)fl < p.max_frag_len;   // :419-434
                 p.fld_val[ri] = elig ? (int16_t)fl : (int16_t)-1;
             }
+            if (BIAS) { if (p.bias_val) p.bias_val[ri] = (int16_t)bsample; }
             c_obs += 1; c_map += mapped ? 1 : 0; c_hits += n_joint;
         }
     }
@@ -729,6 +766,42 @@ __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapPara
         for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
         if (lane == 0 && x) atomicAdd(p.counters + q, x);
     }
+}
+
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapParams p) { finalize_reads_body<false>(p, nullptr); }
+
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads_bias(const MapParams p) {
+    __shared__ unsigned int s_gc[101];
+    for (unsigned i = threadIdx.x; i < 101; i += blockDim.x) s_gc[i] = 0;
+    __syncthreads();
+    finalize_reads_body<true>(p, s_gc);
+    __syncthreads();
+    if (p.bias_gc) for (unsigned i = threadIdx.x; i < 101; i += blockDim.x) if (s_gc[i]) atomicAdd(p.gc_hist + i, s_gc[i]);
+}
+
+// read-start contexts in global read order: the first `remaining` reads that have one (sfOpts.numBiasSamples, :270-285 at -p 1)
+__global__ void k_bias_select(const int16_t* __restrict__ bias_val, uint64_t n_reads, unsigned int* __restrict__ hist, int* __restrict__ remaining) {
+    __shared__ int s_base, s_rem;
+    __shared__ int s_warp[32];
+    if (threadIdx.x == 0) { s_rem = *remaining; }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint64_t c0 = 0; c0 < n_reads; c0 += blockDim.x) {
+        if (s_rem <= 0) break;
+        const uint64_t i = c0 + threadIdx.x;
+        const int v = i < n_reads ? bias_val[i] : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
+        const int pre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int a = 0; for (unsigned w = 0; w < (blockDim.x >> 5); ++w) { const int t = s_warp[w]; s_warp[w] = a; a += t; } s_base = a; }
+        __syncthreads();
+        if (v >= 0 && s_warp[warp] + pre < s_rem) atomicAdd(hist + v, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) s_rem -= s_base;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *remaining = s_rem < 0 ? 0 : s_rem;
 }
 
 // FLD sampling in global read order: the first `remaining` eligible fragments (SailfishQuantify.cpp:426-430 at -p 1)
@@ -862,6 +935,11 @@ struct MapState {
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     bool in_use[2] = {false, false};
     bool primed = false;               // a host batch has been mapped since map_begin (see sfb200_map_batch)
+    // --biasCorrect / --gcBiasCorrect sample collection (sfb200_map_set_bias)
+    bool bias_seq = false, bias_gc = false;
+    DevBuf<int16_t> bias_val;
+    DevBuf<unsigned int> bias_hist;    // [0, 4096) read-start contexts, [4096, 4197) fragment GC percentages; without pseudo-counts
+    DevBuf<int> bias_remaining;
     unsigned parity = 0;
     uint64_t n_buckets = 0, n_overflow = 0, arena_words = 0;
     uint64_t n_threads_total = 0;
@@ -879,6 +957,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     m->mg_sizes.release(); m->mg_cnt.release(); m->mg_cnt_g.release(); m->mg_start.release(); m->mg_len.release(); m->mg_lab.release();
     m->mg_start_g.release(); m->mg_len_g.release(); m->mg_lab_g.release(); m->fld_send.release(); m->fld_recv.release();
     m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release();
+    m->bias_val.release(); m->bias_hist.release(); m->bias_remaining.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
         if (m->copied[i]) cudaEventDestroy(m->copied[i]);
@@ -955,6 +1034,56 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->begun = true;
     m->ev_used = 0; m->kernel_ms = 0.0;
     m->in_use[0] = m->in_use[1] = false; m->parity = 0; m->primed = false;
+    m->bias_seq = m->bias_gc = false;
+    return SFB200_OK;
+}
+
+constexpr uint32_t BIAS_HIST_WORDS = BNK + 101;
+
+extern "C" int sfb200_map_set_bias(sfb200_ctx* c, int seq_bias, int gc_bias, int32_t num_bias_samples) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_set_bias: call map_begin first");
+    if (m->ev_used) SFB_FAIL(c, SFB200_EINVAL, "map_set_bias: call it before the first batch");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    m->bias_seq = seq_bias != 0; m->bias_gc = gc_bias != 0;
+    SFB_CUDA(c, m->bias_hist.reserve(BIAS_HIST_WORDS)); SFB_CUDA(c, m->bias_remaining.reserve(1));
+    SFB_CUDA(c, cudaMemsetAsync(m->bias_hist.p, 0, BIAS_HIST_WORDS * 4ull, s));
+    const int rem = num_bias_samples < 0 ? 0 : num_bias_samples;
+    SFB_CUDA(c, cudaMemcpyAsync(m->bias_remaining.p, &rem, 4, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, cudaFuncSetAttribute(k_finalize_reads_bias, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MAP_THREADS * 2 * 2 * RW * 8)));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_map_get_bias(sfb200_ctx* c, uint32_t* read_bias, uint32_t* observed_gc) {
+    if (!c || !read_bias || !observed_gc) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun || !m->bias_hist.p) SFB_FAIL(c, SFB200_EINVAL, "map_get_bias: map_set_bias was not called");
+    cudaSetDevice(c->device);
+    std::vector<unsigned int> h(BIAS_HIST_WORDS);
+    if (c->n_ranks > 1) {
+        // every rank collected from its own reads: the model is the sum (the sampling limit then applies per rank)
+        std::vector<unsigned long long> w(BIAS_HIST_WORDS);
+        SFB_CUDA(c, cudaMemcpyAsync(h.data(), m->bias_hist.p, BIAS_HIST_WORDS * 4ull, cudaMemcpyDeviceToHost, c->stream));
+        SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (uint32_t i = 0; i < BIAS_HIST_WORDS; ++i) w[i] = h[i];
+        DevBuf<unsigned long long> d; SFB_CUDA(c, d.reserve(BIAS_HIST_WORDS));
+        SFB_CUDA(c, cudaMemcpyAsync(d.p, w.data(), BIAS_HIST_WORDS * 8ull, cudaMemcpyHostToDevice, c->stream));
+        const int rc = sfb_comm_allreduce_u64(c, d.p, BIAS_HIST_WORDS);
+        if (rc) { d.release(); return rc; }
+        SFB_CUDA(c, cudaMemcpyAsync(w.data(), d.p, BIAS_HIST_WORDS * 8ull, cudaMemcpyDeviceToHost, c->stream));
+        SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        d.release();
+        for (uint32_t i = 0; i < BIAS_HIST_WORDS; ++i) h[i] = (unsigned int)w[i];
+    } else {
+        SFB_CUDA(c, cudaMemcpyAsync(h.data(), m->bias_hist.p, BIAS_HIST_WORDS * 4ull, cudaMemcpyDeviceToHost, c->stream));
+        SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    // both distributions start from a count of one per bin (ReadKmerDist.hpp:20-24, ReadExperiment.hpp:50)
+    for (uint32_t i = 0; i < BNK; ++i) read_bias[i] = h[i] + 1u;
+    for (uint32_t i = 0; i < 101; ++i) observed_gc[i] = h[BNK + i] + 1u;
     return SFB200_OK;
 }
 
@@ -1026,13 +1155,25 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     const uint64_t blocks_needed = (n_reads + MAP_THREADS - 1) / MAP_THREADS;
     k_scan_reads<<<(unsigned)std::min<uint64_t>(m->grid_scan, blocks_needed), MAP_THREADS, smem, s>>>(p);
     c->launches++;
-    k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, smem, s>>>(p);
+    const bool bias = m->bias_seq || m->bias_gc;
+    if (!bias) {
+        k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, smem, s>>>(p);
+    } else {
+        if (m->bias_seq) { SFB_CUDA(c, m->bias_val.reserve(n_reads)); p.bias_val = m->bias_val.p; }
+        p.gc_hist = m->bias_hist.p + BNK; p.bias_seq = m->bias_seq ? 1 : 0; p.bias_gc = (m->bias_gc && n_mates == 2) ? 1 : 0;
+        k_finalize_reads_bias<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, smem, s>>>(p);
+    }
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));
     m->ev_used += 2;
     if (want_fld) {
         k_fld_select<<<1, 1024, 0, s>>>(m->fld_val.p, n_reads, m->fld_hist.p, m->remaining.p, m->fld_samples.p, m->o.num_frag_samples);
+        c->launches++;
+        SFB_CUDA(c, cudaGetLastError());
+    }
+    if (m->bias_seq) {
+        k_bias_select<<<1, 1024, 0, s>>>(m->bias_val.p, n_reads, m->bias_hist.p, m->bias_remaining.p);
         c->launches++;
         SFB_CUDA(c, cudaGetLastError());
     }

@@ -22,6 +22,11 @@
 extern "C" int orc_update_eff_lens(int mode, uint32_t T, const char* seq, const uint64_t* off, const uint32_t* len, const double* eff_model,
                                    const double* eff_in, const double* alphas, int64_t num_fwd, int64_t num_rc, const uint32_t* read_bias,
                                    const uint32_t* observed_gc, const uint32_t* fld_counts, uint32_t n_fld, uint32_t gc_samp, double* eff_out);
+struct orc_index;
+extern "C" orc_index* orc_index_build(const char* seq, const uint64_t* txp_off, const uint32_t* txp_len, uint32_t n_txp, int k, int n_threads);
+extern "C" void orc_index_free(orc_index*);
+extern "C" int32_t orc_bias_context_index(const orc_index*, uint32_t tid, int32_t pos, int fwd, uint32_t read_len);
+extern "C" int32_t orc_gc_frac(const orc_index*, uint32_t tid, int32_t s, int32_t e);
 extern "C" uint32_t orc_fld_cdf(const uint32_t* fld_counts, uint32_t n_fld, float* cdf_out, uint32_t cap, uint32_t* max_value);
 
 #define CHECK(cond, ...) do { if (!(cond)) { fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } } while (0)
@@ -52,6 +57,33 @@ static int run(int mode, uint32_t gc_samp, uint64_t seed) {
         for (int j = 0; j < 6; ++j) { const uint32_t c = (uint32_t)std::string("ACGT").find(seq[off[t] + i + j]); f = (f << 2) | c; }
         for (int j = 5; j >= 0; --j) { const uint32_t c = 3 - (uint32_t)std::string("ACGT").find(seq[off[t] + i + j]); r = (r << 2) | c; }
         CHECK(b_idx_fwd(win) == f && b_idx_rc(win) == r, "6-mer index at transcript %u position %u", t, i);
+    }
+    // the mapper-side helpers against the oracle's per-hit functions (positions on, off and around both transcript ends)
+    {
+        orc_index* oix = orc_index_build(seq.data(), off.data(), len.data(), T, 31, 1);
+        CHECK(oix != nullptr, "oracle index");
+        size_t n_valid = 0, n_gc = 0;
+        for (int k = 0; k < 40000; ++k) {
+            const uint32_t t = (uint32_t)(rng() % T);
+            const uint32_t rl = 20 + (uint32_t)(rng() % 130);
+            const int L = (int)len[t];
+            const int32_t pos = (k & 3) == 0 ? (int32_t)(rng() % 12) - 6 : (k & 3) == 1 ? L - (int32_t)(rng() % (rl + 12)) : (int32_t)(rng() % (uint32_t)(L + 40)) - 20;
+            const bool fwd = (rng() & 1) != 0;
+            const int32_t got_i = b_read_start_index(words.data(), tstart[t], L, pos, fwd, rl);
+            const int32_t want_i = orc_bias_context_index(oix, t, pos, fwd ? 1 : 0, rl);
+            CHECK(got_i == want_i, "read-start context: transcript %u (len %d) pos %d fwd %d readLen %u: %d vs %d", t, L, pos, (int)fwd, rl, got_i, want_i);
+            n_valid += got_i >= 0;
+            if (L > 3) {
+                const int32_t s0 = 1 + (int32_t)(rng() % (uint32_t)(L - 2)), e0 = s0 + (int32_t)(rng() % (uint32_t)(L - s0 - 1 + 1));
+                if (s0 > 0 && e0 < L && e0 >= s0) {
+                    CHECK(b_gc_frac_range(words.data(), tstart[t], s0, e0) == orc_gc_frac(oix, t, s0, e0), "gcFrac transcript %u (%d, %d]", t, s0, e0);
+                    CHECK(b_gc_frac_range(words.data(), tstart[t], s0, e0) == b_gc_frac(BiasView{words.data(), tstart.data(), len.data(), gcw.data()}, tstart[t], s0, e0), "gcFrac (prefix form) transcript %u", t);
+                    ++n_gc;
+                }
+            }
+        }
+        orc_index_free(oix);
+        CHECK(n_valid > 5000 && n_gc > 5000, "too few helper cases: %zu contexts, %zu intervals", n_valid, n_gc);
     }
     std::vector<uint32_t> fld(1000);
     for (uint32_t x = 0; x < 1000; ++x) fld[x] = (uint32_t)std::lround(30000.0 * std::exp(-0.5 * std::pow((x - 190.0) / 30.0, 2)));
