@@ -70,11 +70,18 @@ class EquivalenceClassBuilder {
 public:
     explicit EquivalenceClassBuilder(Device& d) : dev_(d) {}
     // == start() (EquivalenceClassBuilder.hpp:62): resets the class table, the counters and the FLD sampler
-    void start(const sfb200_map_opts& opts) { opts_ = opts; dev_.check(sfb200_map_begin(dev_.get(), &opts)); active_ = true; }
+    void start(const sfb200_map_opts& opts) { opts_ = opts; dev_.check(sfb200_map_begin(dev_.get(), &opts)); active_ = true; bias_ = false; }
+    // sopt.biasCorrect / sopt.gcBiasCorrect: collect readExp.readBias() and readExp.observedGC() while mapping
+    // (SailfishQuantify.cpp:255-287, :372-389, :555-583); call between start() and the first batch
+    void collectBias(bool seqBias, bool gcBias, int32_t numBiasSamples) {
+        dev_.check(sfb200_map_set_bias(dev_.get(), seqBias ? 1 : 0, gcBias ? 1 : 0, numBiasSamples));
+        bias_ = true;
+    }
     // == finish() (:64-80): flattens the table; the classes stay on the device for optimize()
     bool finish() {
         fld_.assign(opts_.max_frag_len, 0);
         dev_.check(sfb200_map_finish(dev_.get(), counters_, fld_.data(), &nClasses_, &nnz_));
+        if (bias_) { readBias_.assign(4096, 0); observedGC_.assign(101, 0); dev_.check(sfb200_map_get_bias(dev_.get(), readBias_.data(), observedGC_.data())); }
         active_ = false;
         haveVec_ = false;
         return true;
@@ -113,14 +120,16 @@ public:
     uint64_t numFwd() const { return counters_[4]; }
     uint64_t numRC() const { return counters_[5]; }
     const std::vector<uint32_t>& fragLengthCounts() const { return fld_; }      // flMap (SailfishQuantify.cpp:867)
+    const std::vector<uint32_t>& readBiasCounts() const { return readBias_; }   // readExp.readBias().counts, after collectBias()
+    const std::vector<uint32_t>& observedGC() const { return observedGC_; }     // readExp.observedGC()
     uint64_t numClasses() const { return nClasses_; }
 
 private:
     Device& dev_;
     sfb200_map_opts opts_{};
-    bool active_ = false, haveVec_ = false;
+    bool active_ = false, haveVec_ = false, bias_ = false;
     uint64_t counters_[6] = {0, 0, 0, 0, 0, 0};
-    std::vector<uint32_t> fld_;
+    std::vector<uint32_t> fld_, readBias_, observedGC_;
     uint64_t nClasses_ = 0, nnz_ = 0;
     std::vector<std::pair<const TranscriptGroup, TGValue>> countVec_;
 };
@@ -193,6 +202,47 @@ inline sfb200_em_opts emOpts(bool useVB, double tol, uint32_t maxIter) {
 }
 }  // namespace detail
 
+// What updateEffectiveLengths reads from the experiment (src/SailfishUtils.cpp:611-690): the two observed distributions, the strand
+// tallies and readExp.fragLengthDist().  fragLengthCounts = what setFragLengthDist received (ReadExperiment.hpp:160-167: the
+// observed histogram, or getNormalFragLengthCounts when too few fragments were sampled); its cdf table is built as
+// EmpiricalDistribution does (src/EmpiricalDistribution.cpp:29-90: float pdf / cdf, truncated where the cumulative mass passes
+// 1 - 1e-6; maxValue() is the largest position, whatever its count).
+class BiasModel {
+public:
+    BiasModel(bool gcBias, const std::vector<uint32_t>& readBias, const std::vector<uint32_t>& observedGC, uint64_t numFwd, uint64_t numRC,
+              const std::vector<uint32_t>& fragLengthCounts, uint32_t pdfSampFactor = 1)
+        : readBias_(readBias), observedGC_(observedGC) {
+        const size_t n = fragLengthCounts.size();
+        double total = 0.0;
+        for (uint32_t c : fragLengthCounts) total += c;
+        size_t last = 0, maxval = 1;
+        double cum = 0.0;
+        for (; last < n; ++last) { cum += fragLengthCounts[last] / total; maxval = last; if (cum > 1.0 - 1e-6) break; }
+        double kept = 0.0;
+        for (size_t i = 0; i < last && i < n; ++i) kept += fragLengthCounts[i];
+        cdf_.resize(n ? maxval : 0);
+        float run = 0.0f;
+        for (size_t v = 0; v < cdf_.size(); ++v) {
+            const float pdf = static_cast<float>(fragLengthCounts[v] / kept);
+            run = v ? run + pdf : pdf;
+            cdf_[v] = run;
+        }
+        m_.mode = gcBias ? 2 : 1; m_.gc_samp = pdfSampFactor ? pdfSampFactor : 1;
+        m_.num_fwd = static_cast<int64_t>(numFwd); m_.num_rc = static_cast<int64_t>(numRC);
+        m_.read_bias = readBias_.data(); m_.observed_gc = observedGC_.data();
+        m_.fld_cdf = cdf_.data(); m_.n_cdf = static_cast<uint32_t>(cdf_.size()); m_.fld_max = n ? static_cast<uint32_t>(n - 1) : 0;
+    }
+    BiasModel(const BiasModel&) = delete;
+    BiasModel& operator=(const BiasModel&) = delete;
+    const sfb200_bias_model* get() const { return &m_; }
+    const std::vector<float>& cdf() const { return cdf_; }
+
+private:
+    std::vector<uint32_t> readBias_, observedGC_;
+    std::vector<float> cdf_;
+    sfb200_bias_model m_;
+};
+
 class CollapsedEMOptimizer {
 public:
     explicit CollapsedEMOptimizer(Device& d) : dev_(d) {}
@@ -213,6 +263,30 @@ public:
         double alphaSum = 0.0;
         for (double a : alphas) alphaSum += a;
         for (size_t i = 0; i < transcripts.size(); ++i) {                       // :883-890
+            transcripts[i].setEstCount(alphas[i]);
+            transcripts[i].setMass(alphas[i] / alphaSum);
+        }
+        return true;
+    }
+
+    // optimize() when sopt.biasCorrect or sopt.gcBiasCorrect is set (CollapsedEMOptimizer.cpp:820-840, :888): the effective lengths are
+    // recomputed on the device at iterations 50 / 500 / 1000 and the transcripts leave with the corrected EffectiveLength
+    template <typename ExpT, typename OptsT>
+    bool optimizeWithBias(ExpT& readExp, OptsT& sopt, const BiasModel& model, double relDiffTolerance = 0.01, uint32_t maxIter = 10000) {
+        auto& transcripts = readExp.transcripts();
+        const std::vector<double> eff = detail::effLens(readExp, sopt);
+        std::vector<double> alphas(transcripts.size()), effOut(transcripts.size());
+        const sfb200_em_opts o = detail::emOpts(sopt.useVBOpt, relDiffTolerance, maxIter);
+        uint32_t iters = 0; double mrd = 0.0;
+        const int rc = sfb200_em_run_bias(dev_.get(), eff.data(), static_cast<uint32_t>(eff.size()), readExp.numMappedFragments(), &o, model.get(),
+                                          alphas.data(), effOut.data(), &iters, &mrd);
+        lastIters_ = iters;
+        if (rc == SFB200_ENOACTIVE || rc == SFB200_ESMALLSUM) { lastError_ = sfb200_last_error(dev_.get()); return false; }
+        dev_.check(rc);
+        double alphaSum = 0.0;
+        for (double a : alphas) alphaSum += a;
+        for (size_t i = 0; i < transcripts.size(); ++i) {                       // :883-890
+            transcripts[i].EffectiveLength = effOut[i];
             transcripts[i].setEstCount(alphas[i]);
             transcripts[i].setMass(alphas[i] / alphaSum);
         }

@@ -62,6 +62,17 @@ std::vector<double> normal_correction_factors(uint32_t maxLen, double mean, doub
     }
     return cf;
 }
+// getNormalFragLengthCounts (SailfishQuantify.cpp:675-704): the prior normal as rounded counts, what setFragLengthDist receives when
+// too few fragment lengths were observed
+std::vector<uint32_t> normal_frag_length_counts(uint32_t maxLen, int32_t totalCount, double mean, double sd) {
+    std::vector<uint32_t> dist(maxLen, 0);
+    const double inv = 1.0 / sd;
+    auto kernel = [&](double p) { const double x = inv * (p - mean); return std::exp(-0.5 * x * x) * inv; };
+    double totalMass = 0.0;
+    for (uint32_t i = 0; i < maxLen; ++i) totalMass += kernel(static_cast<double>(i));
+    if (totalMass > 0) for (uint32_t i = 0; i < maxLen; ++i) dist[i] = static_cast<uint32_t>(static_cast<int>(std::round(kernel(static_cast<double>(i)) * totalCount / totalMass)));
+    return dist;
+}
 // correctionFactorsFromCounts (SailfishQuantify.cpp:769-807): running mean of the observed fragment lengths
 std::vector<double> correction_factors_from_counts(const std::vector<uint32_t>& hist) {
     const size_t n = hist.size();
@@ -112,6 +123,9 @@ struct ReadExperiment {
 struct SailfishOpts {
     bool useVBOpt = false, noEffectiveLengthCorrection = false;
     uint32_t numBootstraps = 0, numGibbsSamples = 0;
+    bool biasCorrect = false, gcBiasCorrect = false;                          // SailfishQuantify.cpp:1089-1090
+    int32_t numBiasSamples = 1000000;                                         // :1131
+    uint32_t pdfSampFactor = 1;                                               // --gcSpeedSamp (:1103)
 };
 
 void make_dir(const std::string& p) { mkdir(p.c_str(), 0755); }
@@ -247,6 +261,7 @@ struct Args {
             "  -o, --output DIR           quant.sf and <auxDir>/ are written here\n"
             "  -p, --threads N  -k, --kmerLen K (31)  --device N\n"
             "  --useVBOpt  --numBootstraps N  --numGibbsSamples N  --dumpEq  --noEffectiveLengthCorrection\n"
+            "  --biasCorrect | --gcBiasCorrect  [--numBiasSamples N (1000000)]  [--gcSpeedSamp N (1)]\n"
             "  -g, --geneMap FILE         transcript-to-gene map (.gtf, or `transcript gene` per line): also write quant.genes.sf\n"
             "  --txpAggregationKey KEY    GTF attribute that names the gene (gene_id)\n"
             "  --maxFragLen N (1000)  --numFragSamples N (10000)  --fldMean M (200)  --fldSD S (80)  -w, --maxReadOcc N (200)\n"
@@ -289,6 +304,10 @@ Args parse_args(int argc, char** argv) {
         else if (o == "--numGibbsSamples") a.sopt.numGibbsSamples = (uint32_t)atoi(need(o).c_str());
         else if (o == "--dumpEq") a.dumpEq = true;
         else if (o == "--noEffectiveLengthCorrection") a.sopt.noEffectiveLengthCorrection = true;
+        else if (o == "--biasCorrect") a.sopt.biasCorrect = true;
+        else if (o == "--gcBiasCorrect") a.sopt.gcBiasCorrect = true;
+        else if (o == "--numBiasSamples") a.sopt.numBiasSamples = atoi(need(o).c_str());
+        else if (o == "--gcSpeedSamp") a.sopt.pdfSampFactor = (uint32_t)std::max(1, atoi(need(o).c_str()));
         else if (o == "--maxFragLen") a.mopt.max_frag_len = (uint32_t)atoi(need(o).c_str());
         else if (o == "--numFragSamples") a.mopt.num_frag_samples = atoi(need(o).c_str());
         else if (o == "--fldMean") a.fldMean = atof(need(o).c_str());
@@ -457,6 +476,16 @@ int main(int argc, char** argv) {
                 return 1;
             }
         }
+        if (a.sopt.biasCorrect && a.sopt.gcBiasCorrect) {                     // SailfishQuantify.cpp:1293-1297
+            fprintf(stderr, "Enabling both sequence-specific and fragment GC bias correction simultaneously is not yet supported. Please disable one of these options.\n");
+            return 1;
+        }
+        if (a.sopt.gcBiasCorrect && !paired_files) {                          // :1298-1309
+            fprintf(stderr, "[sfb200-quant] Fragment GC bias correction is currently only implemented for paired-end libraries. It is being disabled\n");
+            a.sopt.gcBiasCorrect = false;
+        }
+        const bool doBias = a.sopt.biasCorrect || a.sopt.gcBiasCorrect;
+        if (doBias && a.sopt.noEffectiveLengthCorrection) usage("--biasCorrect / --gcBiasCorrect need the effective length correction (the reference has no fragment length distribution without it)");
         if (a.sopt.numBootstraps && a.sopt.numGibbsSamples) usage("--numBootstraps and --numGibbsSamples are mutually exclusive (SailfishQuantify.cpp:1281-1287)");
         bool lib_paired = false;
         if (!parse_library_format(a.libType, a.mopt.lib_format_id, lib_paired)) usage(("unknown library type " + a.libType).c_str());
@@ -479,6 +508,7 @@ int main(int argc, char** argv) {
         // ---- quasi-mapping -> equivalence classes (quasiMapReads, SailfishQuantify.cpp:864-1047)
         sfb200::EquivalenceClassBuilder eqBuilder(dev);
         eqBuilder.start(a.mopt);
+        if (doBias) eqBuilder.collectBias(a.sopt.biasCorrect, a.sopt.gcBiasCorrect, a.sopt.numBiasSamples);
         {
             BatchPipe pipe(f1, a.mates2, a.batch, a.threads, a.blockBytes);
             while (std::unique_ptr<PairBatch> b = pipe.pop()) {
@@ -510,7 +540,21 @@ int main(int argc, char** argv) {
         make_dir(aux);
         if (a.dumpEq) write_eq_classes(aux + "/eq_classes.txt", ex, eqBuilder);
         sfb200::CollapsedEMOptimizer optimizer(dev);
-        if (!optimizer.optimize(ex, a.sopt, 0.01, 10000)) {                   // SailfishQuantify.cpp:1341-1349
+        bool opt_ok;
+        if (doBias) {
+            // readExp.setFragLengthDist (:966-984, :1039): the observed histogram when enough fragments were sampled, else the rounded normal
+            uint64_t nSamp = 0;
+            for (uint32_t c : eqBuilder.fragLengthCounts()) nSamp += c;
+            const bool enough = paired_files && nSamp >= static_cast<uint64_t>(a.mopt.num_frag_samples);
+            const std::vector<uint32_t> fldCounts = enough ? eqBuilder.fragLengthCounts()
+                                                           : normal_frag_length_counts(a.mopt.max_frag_len, a.mopt.num_frag_samples, a.fldMean, a.fldSD);
+            sfb200::BiasModel model(a.sopt.gcBiasCorrect, eqBuilder.readBiasCounts(), eqBuilder.observedGC(), eqBuilder.numFwd(), eqBuilder.numRC(),
+                                    fldCounts, a.sopt.pdfSampFactor);
+            opt_ok = optimizer.optimizeWithBias(ex, a.sopt, model, 0.01, 10000);
+        } else {
+            opt_ok = optimizer.optimize(ex, a.sopt, 0.01, 10000);             // SailfishQuantify.cpp:1341-1349
+        }
+        if (!opt_ok) {
             fprintf(stderr, "[sfb200-quant] %s\n", optimizer.lastError().c_str());
             return 1;
         }
@@ -545,10 +589,10 @@ int main(int argc, char** argv) {
         FILE* mf = fopen((aux + "/meta_info.json").c_str(), "w");
         if (mf) {
             fprintf(mf, "{\n    \"sf_version\": \"0.10.0-b200\",\n    \"samp_type\": \"%s\",\n    \"frag_dist_length\": %u,\n"
-                        "    \"bias_correct\": false,\n    \"num_targets\": %zu,\n    \"num_bootstraps\": %u,\n    \"num_processed\": %llu,\n"
+                        "    \"bias_correct\": %s,\n    \"num_targets\": %zu,\n    \"num_bootstraps\": %u,\n    \"num_processed\": %llu,\n"
                         "    \"num_mapped\": %llu,\n    \"percent_mapped\": %.10g,\n    \"call\": \"quant\",\n    \"em_iterations\": %u,\n"
                         "    \"elapsed_s\": %.3f\n}\n",
-                    samp_type, a.mopt.max_frag_len, names.size(), n_samples, (unsigned long long)eqBuilder.numObservedFragments(),
+                    samp_type, a.mopt.max_frag_len, doBias ? "true" : "false", names.size(), n_samples, (unsigned long long)eqBuilder.numObservedFragments(),
                     (unsigned long long)ex.numMapped, 100.0 * ex.numMapped / std::max<uint64_t>(1, eqBuilder.numObservedFragments()),
                     optimizer.lastIterations(), now_s() - t_start);
             fclose(mf);

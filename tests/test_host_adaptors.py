@@ -33,6 +33,17 @@ def test_adaptors_compile_with_plain_gxx():
         assert rc == 3
 
 
+def test_bias_model_cdf_equals_empirical_distribution(tmp_path):
+    from oracle import pyoracle as O
+    from sailfish_b200 import capi
+    O.lib(); capi.lib()
+    exe = str(tmp_path / "bias_model_test")
+    odir, ldir = os.path.join(ROOT, "oracle"), os.path.join(ROOT, "sailfish_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "bias_model_test.cpp"),
+                           "-L" + odir, "-loracle", "-Wl,-rpath," + odir, "-L" + ldir, "-lsfb200", "-Wl,-rpath," + ldir, "-pthread"])
+    assert "bias model ok" in subprocess.check_output([exe]).decode()
+
+
 @pytest.mark.gpu
 def test_adaptors_reproduce_oracle(sample_data, tmp_path):
     from oracle import pyoracle as O

@@ -170,6 +170,19 @@ def test_gene_level_aggregation(tmp_path):
     assert r.returncode == 1 and b"Could not find transcript <=> gene map file" in r.stderr
 
 
+def test_bias_option_checks(tmp_path):
+    """SailfishQuantify.cpp:1293-1309: the two corrections exclude each other; GC correction is switched off for single-end libraries"""
+    fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 30 + "\n")
+    fq = tmp_path / "r.fq"; fq.write_text("@r\n" + "ACGT" * 10 + "\n+\n" + "I" * 40 + "\n")
+    base = [build_exe(), "quant", "-t", str(fa), "-l", "U", "-r", str(fq), "-o", str(tmp_path / "o")]
+    r = subprocess.run(base + ["--biasCorrect", "--gcBiasCorrect"], capture_output=True)
+    assert r.returncode == 1 and b"simultaneously is not yet supported" in r.stderr
+    r = subprocess.run(base + ["--gcBiasCorrect"], capture_output=True)
+    assert b"only implemented for paired-end libraries" in r.stderr
+    r = subprocess.run(base + ["--biasCorrect", "--noEffectiveLengthCorrection"], capture_output=True)
+    assert r.returncode == 2 or b"need the effective length correction" in r.stderr + r.stdout
+
+
 def test_no_cpu_fallback(tmp_path):
     import torch
     if torch.cuda.is_available():
@@ -224,3 +237,50 @@ def test_sample_data_end_to_end_cpp(sample_data, tmp_path):
     assert abs(sum(float(g[4]) for g in genes) - sum(float(r[4]) for r in rows2)) < 1e-3 * float(d["num_mapped"])
     gib = np.frombuffer(gzip.open(out2 / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.int32).reshape(4, len(names))
     assert (gib.sum(axis=1) == int(d["num_mapped"])).all()
+
+
+_experimental = pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SFB200_EXPERIMENTAL=1")
+
+
+@_experimental
+@pytest.mark.gpu
+@pytest.mark.parametrize("flag,mode", [("--biasCorrect", 1), ("--gcBiasCorrect", 2)])
+def test_sample_data_bias_correction_cpp(sample_data, tmp_path, flag, mode):
+    """`sfb200-quant quant --biasCorrect / --gcBiasCorrect` against the oracle's pipeline: samples collected while mapping, effective
+    lengths recomputed inside the optimizer, corrected lengths in quant.sf"""
+    from oracle import pyoracle as O
+    d = sample_data
+    seqs = split_seqs(d["txp_seq"], d["txp_len"])
+    names = [str(n) for n in d["names"]]
+    fa = tmp_path / "transcripts.fasta"
+    with open(fa, "w") as f:
+        for n, s in zip(names, seqs):
+            f.write(">%s\n%s\n" % (n, s.decode()))
+    for tag, reads, off in (("1", d["reads1"], d["off1"]), ("2", d["reads2"], d["off2"])):
+        with open(tmp_path / ("reads_%s.fastq" % tag), "w") as f:
+            for i in range(len(off) - 1):
+                s = reads[int(off[i]):int(off[i + 1])].tobytes().decode()
+                f.write("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)))
+    out = tmp_path / "q"
+    subprocess.check_call([build_exe(), "quant", "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "reads_1.fastq"), "-2", str(tmp_path / "reads_2.fastq"),
+                           "-o", str(out), flag, "--fldMean", "200", "--fldSD", "80", "--batchReads", "3000"])
+    rows = [l.split("\t") for l in open(out / "quant.sf").read().strip().split("\n")[1:]]
+    # the oracle's run of the same pipeline
+    oix = O.Index(seqs, k=31)
+    fmt = O.parse_libtype("IU")
+    run = O.Run(oix, O.MapOpts.default(fmt))
+    run.set_bias(mode == 1, mode == 2, 1000000)
+    run.map_batch(d["reads1"].tobytes(), d["off1"], d["reads2"].tobytes(), d["off2"], n_threads=4)
+    w = run.finish()
+    rb, og = run.finish_bias()
+    assert int(w["fld"].sum()) < 10000                               # too few sampled fragments: the prior normal is the FLD (:966-976)
+    x = np.arange(1000, dtype=np.float64)
+    dens = np.exp(-0.5 * ((x - 200.0) / 80.0) ** 2) / 80.0
+    fld = np.floor(dens * 10000 / dens.sum() + 0.5).astype(np.uint32)
+    rc, want, eff_want, it_o, _ = O.em_run_bias(mode, seqs, w["row_ptr"], w["labels"], w["counts"], d["eff"], int(w["counters"][1]),
+                                                int(w["counters"][4]), int(w["counters"][5]), rb, og, fld)
+    assert rc == 0 and it_o >= 50
+    np.testing.assert_allclose([float(r[4]) for r in rows], want, rtol=1.2e-4, atol=1e-6)
+    np.testing.assert_allclose([float(r[2]) for r in rows], eff_want, rtol=1e-5)
+    assert (np.abs(eff_want - np.maximum(d["eff"], 1.0)) > 1e-6).sum() > 10
+    assert json.load(open(out / "aux" / "meta_info.json"))["bias_correct"] is True
