@@ -98,6 +98,85 @@ __global__ void __launch_bounds__(BIAS_THREADS) k_bias_efflen(const BiasView v, 
     }
 }
 
+// ---- the fragment GC passes in sliding form (bias_core.inl, b_gc_slide): a thread owns one sampled fragment length and walks the
+// transcript, so its G/C count changes by one base per step.  SLIDE_THREADS fragment lengths per tile.
+constexpr int SLIDE_THREADS = 128;
+constexpr int SLIDE_STRIDE = SLIDE_THREADS + 1;             // counts laid out [bin][fragment length]: conflict-free both ways
+
+// pass 1: per (fragment length, bin) integer counts in shared memory (a private column per thread: plain read-modify-write),
+// folded into the CTA's 101 doubles once per transcript and tile by one thread per bin; w[k] = cdf(fl_k) - cdf(fl_{k-1})
+__global__ void __launch_bounds__(SLIDE_THREADS) k_bias_expected_gc_slide(const BiasView v, const double* __restrict__ w, int n_fl,
+                                                                          double* __restrict__ hist) {
+    extern __shared__ uint32_t s_cnt[];                      // 101 x SLIDE_STRIDE
+    __shared__ double s_h[101];
+    for (uint32_t i = threadIdx.x; i < 101u * SLIDE_STRIDE; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x < 101) s_h[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (uint32_t t = blockIdx.x; t < v.T; t += gridDim.x) {
+        int32_t refLen, unproc;
+        if (!b_eligible(v, t, refLen, unproc)) continue;                           // uniform over the CTA
+        const double contribution = __ldg(v.alphas + t) / __ldg(v.eff_in + t);
+        const uint64_t t0 = __ldg(v.txp_start + t);
+        for (int tile = 0; tile < n_fl; tile += SLIDE_THREADS) {
+            const int k = tile + (int)threadIdx.x;
+            if (k < n_fl) {
+                int32_t last = -1; uint32_t run = 0;                               // consecutive starts mostly fall into the same bin
+                b_gc_slide(v.words, t0, refLen, v.fldLow + k * v.gcSamp, [&](int32_t bin) {
+                    if (bin == last) { ++run; return; }
+                    if (run) s_cnt[last * SLIDE_STRIDE + threadIdx.x] += run;
+                    last = bin; run = 1;
+                });
+                if (run) s_cnt[last * SLIDE_STRIDE + threadIdx.x] += run;
+            }
+            __syncthreads();
+            if (threadIdx.x < 101) {
+                const int nf = n_fl - tile < SLIDE_THREADS ? n_fl - tile : SLIDE_THREADS;
+                uint32_t* row = s_cnt + threadIdx.x * SLIDE_STRIDE;
+                double acc = 0.0;
+                for (int f = 0; f < nf; ++f) { const uint32_t c = row[f]; if (c) { acc += __ldg(w + tile + f) * (double)c; row[f] = 0; } }
+                s_h[threadIdx.x] += contribution * acc;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x < 101 && s_h[threadIdx.x] != 0.0) atomicAdd(hist + threadIdx.x, s_h[threadIdx.x]);
+}
+
+// pass 2: wf[k] = w[k] probFwd + w[k] probRC; a transcript's length = norm * sum_k wf[k] * sum_starts ratio[bin(start, fl_k)]
+__global__ void __launch_bounds__(SLIDE_THREADS) k_bias_efflen_gc_slide(const BiasView v, const double* __restrict__ ratio,
+                                                                        const double* __restrict__ wf, int n_fl, double norm,
+                                                                        double* __restrict__ eff_out) {
+    __shared__ double s_ratio[101];
+    __shared__ double s_w[SLIDE_THREADS / 32];
+    if (threadIdx.x < 101) s_ratio[threadIdx.x] = ratio[threadIdx.x];
+    __syncthreads();
+    for (uint32_t t = blockIdx.x; t < v.T; t += gridDim.x) {
+        int32_t refLen, unproc;
+        const bool go = b_eligible(v, t, refLen, unproc);
+        double sum = 0.0;
+        if (go) {
+            const uint64_t t0 = __ldg(v.txp_start + t);
+            for (int k = (int)threadIdx.x; k < n_fl; k += SLIDE_THREADS) {
+                double acc = 0.0;
+                b_gc_slide(v.words, t0, refLen, v.fldLow + k * v.gcSamp, [&](int32_t bin) { acc += s_ratio[bin]; });
+                sum += __ldg(wf + k) * acc;
+            }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+        __syncthreads();
+        if ((threadIdx.x & 31u) == 0) s_w[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double eff = 0.0;
+            for (int q = 0; q < SLIDE_THREADS / 32; ++q) eff += s_w[q];
+            eff *= norm;
+            const double in = __ldg(v.eff_in + t);
+            eff_out[t] = (go && unproc > 0 && eff > (double)unproc) ? eff : in;
+        }
+    }
+}
+
 inline unsigned b_grid(uint64_t n, unsigned th) { return (unsigned)((n + th - 1) / th); }
 
 }  // namespace
@@ -118,8 +197,8 @@ extern "C" int sfb200_bias_eff_lens(sfb200_ctx* c, const sfb200_bias_model* m, c
     const bool seq = m->mode == 1;
     const uint32_t NB = seq ? BNK : 101u;
     const uint64_t n_words = ix.text_len / 32 + 2;
-    DevBuf<uint32_t> d_gcw; DevBuf<unsigned char> d_tmp; DevBuf<float> d_cdf; DevBuf<double> d_vec, d_hist;
-    auto cleanup = [&]() { d_gcw.release(); d_tmp.release(); d_cdf.release(); d_vec.release(); d_hist.release(); };
+    DevBuf<uint32_t> d_gcw; DevBuf<unsigned char> d_tmp; DevBuf<float> d_cdf; DevBuf<double> d_vec, d_hist, d_w;
+    auto cleanup = [&]() { d_gcw.release(); d_tmp.release(); d_cdf.release(); d_vec.release(); d_hist.release(); d_w.release(); };
 #define BIAS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return SFB200_ECUDA; } } while (0)
     BIAS_CUDA(d_cdf.reserve(m->n_cdf ? m->n_cdf : 1));
     BIAS_CUDA(d_vec.reserve(3ull * T + T));                       // eff_model | eff_in | alphas | eff_out
@@ -141,6 +220,25 @@ extern "C" int sfb200_bias_eff_lens(sfb200_ctx* c, const sfb200_bias_model* m, c
             if (!first && density >= 0.005) { first = true; v.fldLow = (int32_t)i; }
             if (!second && density >= 0.995) { second = true; v.fldHigh = (int32_t)i; }
         }
+    }
+    // the GC passes in sliding form: opt-in (SFB200_BIAS_GC_SLIDE=1) until they have had their first GPU run
+    const char* slide_env = getenv("SFB200_BIAS_GC_SLIDE");
+    const bool slide = !seq && slide_env && atoi(slide_env) != 0 && v.fldLow >= 1 && v.fldHigh >= v.fldLow;
+    int n_fl = 0;
+    if (slide) {
+        std::vector<double> w2;
+        double prev = static_cast<double>(cdf(0));
+        for (int32_t fl = v.fldLow; fl <= v.fldHigh; fl += v.gcSamp) {
+            const double cur = static_cast<double>(cdf((uint32_t)fl));
+            w2.push_back(cur - prev);
+            prev = cur;
+        }
+        n_fl = (int)w2.size();
+        for (int k = 0; k < n_fl; ++k) w2.push_back(w2[k] * v.probFwd + w2[k] * v.probRC);
+        BIAS_CUDA(d_w.reserve(w2.size()));
+        BIAS_CUDA(cudaMemcpyAsync(d_w.p, w2.data(), w2.size() * 8ull, cudaMemcpyHostToDevice, s));
+        BIAS_CUDA(cudaStreamSynchronize(s));                  // w2 is a local
+    } else if (!seq) {
         // per-word G/C counts -> exclusive prefix
         BIAS_CUDA(d_gcw.reserve(n_words + 1));
         k_bias_gc_words<<<b_grid(n_words, 256), 256, 0, s>>>(ix.words.p, n_words, d_gcw.p);
@@ -156,7 +254,12 @@ extern "C" int sfb200_bias_eff_lens(sfb200_ctx* c, const sfb200_bias_model* m, c
     std::vector<double> h_hist(NB, 1.0);
     BIAS_CUDA(cudaMemcpyAsync(d_hist.p, h_hist.data(), NB * 8ull, cudaMemcpyHostToDevice, s));
     const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)c->num_sms * 8);
-    if (seq) k_bias_expected<1><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p); else k_bias_expected<2><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p);
+    const size_t slide_smem = 101ull * SLIDE_STRIDE * sizeof(uint32_t);
+    if (slide) {
+        BIAS_CUDA(cudaFuncSetAttribute(k_bias_expected_gc_slide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slide_smem));
+        k_bias_expected_gc_slide<<<grid, SLIDE_THREADS, slide_smem, s>>>(v, d_w.p, n_fl, d_hist.p);
+    } else if (seq) k_bias_expected<1><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p);
+    else k_bias_expected<2><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p);
     c->launches++;
     BIAS_CUDA(cudaGetLastError());
     BIAS_CUDA(cudaMemcpyAsync(h_hist.data(), d_hist.p, NB * 8ull, cudaMemcpyDeviceToHost, s));
@@ -182,7 +285,9 @@ extern "C" int sfb200_bias_eff_lens(sfb200_ctx* c, const sfb200_bias_model* m, c
     // ---- pass 2
     double* d_out = d_vec.p + 3ull * T;
     const double norm = txomeNorm / readNorm;
-    if (seq) k_bias_efflen<1><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p + NB, norm, d_out); else k_bias_efflen<2><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p + NB, norm, d_out);
+    if (slide) k_bias_efflen_gc_slide<<<grid, SLIDE_THREADS, 0, s>>>(v, d_hist.p + NB, d_w.p + n_fl, n_fl, norm, d_out);
+    else if (seq) k_bias_efflen<1><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p + NB, norm, d_out);
+    else k_bias_efflen<2><<<grid, BIAS_THREADS, 0, s>>>(v, d_hist.p + NB, norm, d_out);
     c->launches++;
     BIAS_CUDA(cudaGetLastError());
     BIAS_CUDA(cudaMemcpyAsync(eff_out, d_out, T * 8ull, cudaMemcpyDeviceToHost, s));

@@ -128,3 +128,37 @@ SFB_BD int32_t b_read_start_index(const uint64_t* __restrict__ words, uint64_t t
     if (!(startPos >= 4 && p + BK < refLen)) return -1;
     return (int32_t)b_idx_fwd(b_win6(words, t0 + p));
 }
+
+// ---- fragment GC passes in sliding form ------------------------------------------------------------------------------------------
+// For a fixed fragment length fl the bin of the fragment starting at i is lrint(100 n / fl), n = G/C among positions i+1 .. i+fl-1
+// (gcFrac's divisor e - s + 1 IS fl), and moving the start by one base changes n by the base entering minus the base leaving.
+// The weight of a fragment length, cdf(fl) - cdf(previous sampled fl), does not depend on the position either.  So one thread
+// can own one fragment length and walk the transcript: no prefix loads, no fp64 division, no atomics (bias.cu, k_bias_*_slide).
+//
+// lrint(100 n / fl) in integers, ties to even.  Exact: 100 n / fl is a multiple of 1 / fl, so it is either a tie or at least
+// 1 / (2 fl) >= 5e-4 away from one -- the correctly rounded double quotient rounds the same way
+SFB_BD int32_t b_gc_bin(uint32_t n, uint32_t fl) {
+    const uint32_t x = 200u * n + fl, d = 2u * fl;
+    uint32_t q = x / d;
+    if (q * d == x && (q & 1u)) --q;
+    return (int32_t)q;
+}
+SFB_BD uint32_t b_gc_bit(const uint64_t* __restrict__ words, uint64_t p) {
+    const uint64_t w = SFB_LDG(words + (p >> 5));
+    const uint32_t sh = 2 * (uint32_t)(p & 31);
+    return (uint32_t)(((w >> sh) ^ (w >> (sh + 1))) & 1ULL);
+}
+// last start of a fragment of fl bases the two passes visit on a transcript of refLen bases (i <= refLen - BK - 1 and
+// fragEnd = i + fl - 1 < refLen); negative = none
+SFB_BD int32_t b_gc_last_start(int32_t refLen, int32_t fl) { const int32_t a = refLen - BK - 1, b = refLen - fl; return a < b ? a : b; }
+// visit(bin) for every start 0 .. b_gc_last_start; fl >= 1
+template <typename Visit>
+SFB_BD void b_gc_slide(const uint64_t* __restrict__ words, uint64_t t0, int32_t refLen, int32_t fl, Visit visit) {
+    const int32_t hi = b_gc_last_start(refLen, fl);
+    if (hi < 0) return;
+    uint32_t n = b_gc_range(words, t0 + 1, t0 + (uint64_t)fl);
+    for (int32_t i = 0; i <= hi; ++i) {
+        visit(b_gc_bin(n, (uint32_t)fl));
+        n += b_gc_bit(words, t0 + (uint64_t)(i + fl)) - b_gc_bit(words, t0 + (uint64_t)(i + 1));
+    }
+}

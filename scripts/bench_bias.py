@@ -35,7 +35,9 @@ def main():
     alphas = rng.lognormal(3, 2, size=T); alphas[rng.random(T) < 0.2] = 0.0
     rb = rng.integers(1, 3000, size=4096).astype(np.uint32); og = rng.integers(1, 8000, size=101).astype(np.uint32)
     out = {"transcripts": int(T), "bases": int(ln.sum()), "index_s": round(t_index, 3)}
-    for mode, name in ((1, "seq"), (2, "gc")):
+    for mode, name in ((1, "seq"), (2, "gc"), (2, "gc_slide")):
+        if name == "gc_slide":
+            os.environ["SFB200_BIAS_GC_SLIDE"] = "1"          # read by the library at every call
         ctx.bias_eff_lens(mode, eff, eff, alphas, 600000, 590000, rb, og, cdf, mx, gc_samp=a.gc_samp)      # warm-up
         t0 = time.time()
         got = ctx.bias_eff_lens(mode, eff, eff, alphas, 600000, 590000, rb, og, cdf, mx, gc_samp=a.gc_samp)

@@ -44,6 +44,33 @@ _experimental = pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1",
 
 
 @_experimental
+@pytest.mark.parametrize("gc_samp", [1, 3, 7])
+def test_bias_eff_lens_sliding_gc_passes(ctx, monkeypatch, gc_samp):
+    """SFB200_BIAS_GC_SLIDE=1: the fragment GC passes with one thread per fragment length (k_bias_*_gc_slide; CPU check of the same text:
+    tests/bias_core_test.cpp) against the oracle and against the default kernels"""
+    rng = np.random.default_rng(29)
+    T = 300
+    lens = rng.integers(100, 3000, size=T)
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=int(n), p=[0.3, 0.2, 0.2, 0.3]).astype(np.uint8)) for n in lens]
+    ctx.index_build(seqs=seqs, k=31)
+    x = np.arange(1000)
+    fld = np.round(30000 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32)
+    cdf, mx = O.fld_cdf(fld)
+    eff_model = np.where(lens - 189.0 >= 1, lens - 189.0, lens).astype(np.float64)
+    eff_in = eff_model * rng.uniform(0.9, 1.1, size=T)
+    alphas = rng.lognormal(3, 2, size=T); alphas[rng.random(T) < 0.2] = 0.0
+    rb = rng.integers(1, 3000, size=4096).astype(np.uint32); og = rng.integers(1, 8000, size=101).astype(np.uint32)
+    plain = ctx.bias_eff_lens(2, eff_model, eff_in, alphas, 61234, 58766, rb, og, cdf, mx, gc_samp=gc_samp)
+    monkeypatch.setenv("SFB200_BIAS_GC_SLIDE", "1")
+    got = ctx.bias_eff_lens(2, eff_model, eff_in, alphas, 61234, 58766, rb, og, cdf, mx, gc_samp=gc_samp)
+    rc, want = O.update_eff_lens(2, seqs, eff_model, eff_in, alphas, 61234, 58766, rb, og, fld, gc_samp=gc_samp)
+    assert rc == 0
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    np.testing.assert_allclose(got, plain, rtol=1e-9)
+    assert ((got != eff_in) == (want != eff_in)).all() and (want != eff_in).sum() > 50
+
+
+@_experimental
 @pytest.mark.parametrize("loops", ["default", "scatter", "steps"])
 @pytest.mark.parametrize("mode,vb,kw", [
     (1, 0, {}), (2, 0, {}), (1, 1, {}), (2, 1, {}),                              # default limits: one recomputation, at iteration 50
