@@ -50,3 +50,46 @@ def effective_lengths(txp_len, fld_hist=None, max_frag_len=1000, num_frag_sample
     idx = np.minimum(txp_len.astype(np.int64), max_frag_len - 1)
     eff = txp_len.astype(np.float64) - cf[idx] + 1.0
     return np.where(eff < 1.0, txp_len.astype(np.float64), eff)
+
+
+def normal_frag_length_counts(max_len=1000, total_count=10000, mean=200.0, sd=80.0):
+    """getNormalFragLengthCounts (:675-704): the prior normal as rounded counts -- what setFragLengthDist receives when fewer than
+    numFragSamples fragment lengths were observed"""
+    i = np.arange(max_len, dtype=np.float64)
+    inv = 1.0 / sd
+    x = inv * (i - mean)
+    dens = np.exp(-0.5 * x * x) * inv
+    total = 0.0
+    for d in dens:                                   # the reference's running sum
+        total += float(d)
+    if not total > 0:
+        return np.zeros(max_len, np.uint32)
+    v = dens * total_count / total
+    return np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5)).astype(np.int64).astype(np.uint32)      # std::round
+
+
+def empirical_cdf(counts):
+    """EmpiricalDistribution(pos = 0..n-1, counts) (src/EmpiricalDistribution.cpp:29-90) -> (float32 cdf table, maxValue()).
+    The table stops where the cumulative mass passes 1 - 1e-6; pdf and cdf are float, the cdf a running float sum."""
+    counts = np.asarray(counts, dtype=np.uint32)
+    n = len(counts)
+    total = 0.0
+    for c in counts:
+        total += float(c)
+    cum, last, maxval = 0.0, 0, 1
+    while last < n:
+        cum += float(counts[last]) / total
+        maxval = last
+        if cum > 1.0 - 1e-6:
+            break
+        last += 1
+    kept = 0.0
+    for c in counts[:min(last, n)]:
+        kept += float(c)
+    cdf = np.zeros(maxval if n else 0, np.float32)
+    run = np.float32(0.0)
+    for v in range(len(cdf)):
+        pdf = np.float32(float(counts[v]) / kept)
+        run = pdf if v == 0 else np.float32(run + pdf)
+        cdf[v] = run
+    return cdf, (n - 1 if n else 0)

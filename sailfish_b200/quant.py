@@ -118,7 +118,8 @@ def write_eq_classes(path, names, row_ptr, labels, counts):
 
 
 def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_quant", k=31, use_vb=False, n_boot=0, n_gibbs=0,
-             dump_eq=False, batch=1_000_000, device=0, no_eff_len_correction=False, map_kw=None):
+             dump_eq=False, batch=1_000_000, device=0, no_eff_len_correction=False, map_kw=None, bias_correct=False,
+             gc_bias_correct=False, num_bias_samples=1000000, gc_speed_samp=1):
     t_start = time.time()
     names, seqs = read_fasta(transcripts)
     lengths = np.array([len(s) for s in seqs], np.uint32)
@@ -129,6 +130,16 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
     ctx = capi.Context(device)
     ctx.index_build(seqs=seqs, k=k)
     ctx.map_begin(capi.MapOpts.default(fmt, **(map_kw or {})))
+    if bias_correct and gc_bias_correct:                                      # SailfishQuantify.cpp:1293-1297
+        raise ValueError("Enabling both sequence-specific and fragment GC bias correction simultaneously is not yet supported.")
+    if gc_bias_correct and not paired:                                        # :1298-1309
+        print("Fragment GC bias correction is currently only implemented for paired-end libraries. It is being disabled", file=sys.stderr)
+        gc_bias_correct = False
+    do_bias = bias_correct or gc_bias_correct
+    if do_bias and no_eff_len_correction:
+        raise ValueError("bias correction needs the effective length correction")
+    if do_bias:
+        ctx.map_set_bias(bias_correct, gc_bias_correct, num_bias_samples)
     it2 = read_fastx_batches(reads2, batch) if paired else None
     for r1 in read_fastx_batches(reads1, batch):
         b1, o1 = capi.pack_reads(r1)
@@ -150,7 +161,17 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
     if dump_eq:
         rp, lab, cnt = ctx.eq_export()
         write_eq_classes(os.path.join(out_dir, "aux", "eq_classes.txt"), names, rp, lab, cnt)
-    alphas, iters, mrd = ctx.em_run(eff, num_mapped, capi.EMOpts.default(use_vb=int(use_vb)))
+    if do_bias:
+        # readExp.setFragLengthDist (:966-984, :1039) -> EmpiricalDistribution's cdf table; the optimizer recomputes the effective
+        # lengths at iterations 50 / 500 / 1000 and quant.sf reports the corrected ones (CollapsedEMOptimizer.cpp:820-840, :888)
+        enough = paired and int(np.asarray(g["fld"], np.uint64).sum()) >= ctx.map_opts.num_frag_samples
+        fld_counts = g["fld"] if enough else efflen.normal_frag_length_counts(ctx.map_opts.max_frag_len, ctx.map_opts.num_frag_samples)
+        cdf, fld_max = efflen.empirical_cdf(fld_counts)
+        rb, og = ctx.map_get_bias()
+        alphas, eff, iters, mrd = ctx.em_run_bias(2 if gc_bias_correct else 1, eff, num_mapped, int(counters[4]), int(counters[5]), rb, og,
+                                                  cdf, fld_max, gc_samp=gc_speed_samp, opts=capi.EMOpts.default(use_vb=int(use_vb)))
+    else:
+        alphas, iters, mrd = ctx.em_run(eff, num_mapped, capi.EMOpts.default(use_vb=int(use_vb)))
     write_quant_sf(os.path.join(out_dir, "quant.sf"), names, lengths, eff, alphas, num_mapped)
     samp_type = "none"
     if n_boot or n_gibbs:
@@ -166,7 +187,7 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
         with gzip.open(os.path.join(out_dir, "aux", "bootstrap", "bootstraps.gz"), "wb") as f:
             f.write(np.ascontiguousarray(rows).tobytes())
     meta = {"sf_version": "0.10.0-b200", "samp_type": samp_type, "frag_dist_length": int(ctx.map_opts.max_frag_len),
-            "bias_correct": False, "num_targets": len(names), "num_bootstraps": int(n_boot or n_gibbs),
+            "bias_correct": bool(do_bias), "num_targets": len(names), "num_bootstraps": int(n_boot or n_gibbs),
             "num_processed": int(counters[0]), "num_mapped": num_mapped,
             "percent_mapped": 100.0 * num_mapped / max(int(counters[0]), 1), "call": "quant",
             "em_iterations": int(iters), "elapsed_s": time.time() - t_start}
@@ -190,6 +211,10 @@ def main(argv=None):
     ap.add_argument("--numGibbsSamples", type=int, default=0)
     ap.add_argument("--dumpEq", action="store_true")
     ap.add_argument("--noEffectiveLengthCorrection", action="store_true")
+    ap.add_argument("--biasCorrect", action="store_true")
+    ap.add_argument("--gcBiasCorrect", action="store_true")
+    ap.add_argument("--numBiasSamples", type=int, default=1000000)
+    ap.add_argument("--gcSpeedSamp", type=int, default=1)
     a = ap.parse_args(argv)
     if a.numBootstraps and a.numGibbsSamples:
         sys.exit("--numBootstraps and --numGibbsSamples are mutually exclusive (SailfishQuantify.cpp:1281-1287)")
@@ -197,7 +222,8 @@ def main(argv=None):
     if not r1:
         sys.exit("no reads given")
     res = quantify(a.transcripts, r1, a.mates2, a.libType, a.output, a.kmerLen, a.useVBOpt, a.numBootstraps, a.numGibbsSamples,
-                   a.dumpEq, no_eff_len_correction=a.noEffectiveLengthCorrection)
+                   a.dumpEq, no_eff_len_correction=a.noEffectiveLengthCorrection, bias_correct=a.biasCorrect,
+                   gc_bias_correct=a.gcBiasCorrect, num_bias_samples=a.numBiasSamples, gc_speed_samp=a.gcSpeedSamp)
     print(json.dumps(res["meta"]))
 
 

@@ -25,6 +25,26 @@ def test_percent_g_formatting():
     assert quant.fmt_g(100.0) == "100" and quant.fmt_g(33.3333333) == "33.3333"
 
 
+def test_fragment_length_tables_for_the_bias_model():
+    """efflen.empirical_cdf == EmpiricalDistribution's float cdf table (the oracle's restatement, pinned to the reference's class in
+    tests/test_oracle_bias.py), bit for bit; efflen.normal_frag_length_counts == getNormalFragLengthCounts"""
+    from oracle import pyoracle as O
+    from sailfish_b200 import efflen
+    rng = np.random.default_rng(1)
+    x = np.arange(1000)
+    sparse = np.zeros(1000, np.uint32); sparse[rng.integers(0, 1000, 40)] = rng.integers(1, 50, 40)
+    cases = [np.round(30000 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32), efflen.normal_frag_length_counts(),
+             rng.integers(0, 1000, size=1000).astype(np.uint32), np.full(300, 7, np.uint32), sparse, np.array([5], np.uint32)]
+    for c in cases:
+        got, mx = efflen.empirical_cdf(c)
+        want, mx_o = O.fld_cdf(c)
+        assert mx == mx_o and got.tobytes() == np.asarray(want, np.float32).tobytes()
+    nc = efflen.normal_frag_length_counts(1000, 10000, 200.0, 80.0)
+    assert nc.dtype == np.uint32 and len(nc) == 1000 and int(nc[200]) == int(nc.max()) and abs(int(nc.sum()) - 10000) < 20
+    dens = np.exp(-0.5 * ((x - 200.0) / 80.0) ** 2) / 80.0
+    assert nc.tolist() == np.floor(dens * 10000 / dens.sum() + 0.5).astype(np.uint32).tolist()
+
+
 def test_fastx_readers(tmp_path):
     fa = tmp_path / "t.fa"; fa.write_text(">a desc\nACGT\nAC\n>b\nGG\n")
     assert quant.read_fasta(str(fa)) == (["a", "b"], ["ACGTAC", "GG"])
