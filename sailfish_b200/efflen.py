@@ -39,13 +39,58 @@ def correction_factors_from_counts(hist):
     return cf
 
 
+def empirical_effective_lengths(txp_len, fld_hist):
+    """computeEmpiricalEffectiveLengths (--unsmoothedFLD, :717-767): sum_l pdf(l) * (RefLength - l + 1) with EmpiricalDistribution's
+    float pdf over jointMap (every length 0 .. maxFragLen-1, :944-947); transcripts not longer than the median keep RefLength"""
+    txp_len = np.asarray(txp_len, dtype=np.uint32)
+    counts = np.asarray(fld_hist, dtype=np.uint32)
+    n = len(counts)
+    total = 0.0
+    for c in counts:
+        total += float(c)
+    cum, last, maxval = 0.0, 0, 1
+    while last < n:
+        cum += float(counts[last]) / total
+        maxval = last
+        if cum > 1.0 - 1e-6:
+            break
+        last += 1
+    kept = 0.0
+    for c in counts[:min(last, n)]:
+        kept += float(c)
+    pdf = np.zeros(n, np.float32)                                   # pdf(l) = 0 beyond the table
+    pdf[:maxval] = (counts[:maxval].astype(np.float64) / kept).astype(np.float32)
+    i, j = 0, n - 1                                                 # the median by walking in from both ends (EmpiricalDistribution.cpp:83-93)
+    u, v = int(counts[0]), int(counts[n - 1])
+    while i < j:
+        if u <= v:
+            v -= u; i += 1; u = int(counts[i])
+        else:
+            u -= v; j -= 1; v = int(counts[j])
+    median = float(np.float32(i))
+    max_val = n - 1
+    eff = np.zeros(len(txp_len), np.float64)
+    pd = pdf.astype(np.float64)
+    for t, L in enumerate(txp_len.tolist()):
+        if L <= median or not max_val > 0:
+            eff[t] = L
+            continue
+        e = 0.0
+        for l in range(0, min(L, max_val) + 1):                     # the reference's running sum
+            e += pd[l] * (L - l + 1.0)
+        eff[t] = e
+    return eff
+
+
 def effective_lengths(txp_len, fld_hist=None, max_frag_len=1000, num_frag_samples=10000, single_end=False,
-                      no_correction=False, prior_mean=200.0, prior_sd=80.0):
-    """-> float64[T]: Transcript::EffectiveLength for the default (smoothed) mode and --noEffectiveLengthCorrection."""
+                      no_correction=False, prior_mean=200.0, prior_sd=80.0, unsmoothed=False):
+    """-> float64[T]: Transcript::EffectiveLength for the default (smoothed) mode, --unsmoothedFLD and --noEffectiveLengthCorrection."""
     txp_len = np.asarray(txp_len, dtype=np.uint32)
     if no_correction:
         return txp_len.astype(np.float64)
     enough = (not single_end) and fld_hist is not None and int(np.asarray(fld_hist, np.uint64).sum()) >= num_frag_samples
+    if enough and unsmoothed:
+        return empirical_effective_lengths(txp_len, fld_hist)
     cf = correction_factors_from_counts(fld_hist) if enough else normal_correction_factors(max_frag_len, prior_mean, prior_sd)
     idx = np.minimum(txp_len.astype(np.int64), max_frag_len - 1)
     eff = txp_len.astype(np.float64) - cf[idx] + 1.0

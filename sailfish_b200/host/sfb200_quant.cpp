@@ -87,13 +87,45 @@ std::vector<double> correction_factors_from_counts(const std::vector<uint32_t>& 
     return cf;
 }
 // computeSmoothedEffectiveLengths (:809-838) / setEffectiveLengthsDirect (:707-715) and the mode selection (:937-992, :1034-1043)
+// computeEmpiricalEffectiveLengths (--unsmoothedFLD, :717-767): sum over fragment lengths of pdf(l) * (RefLength - l + 1), with the
+// pdf EmpiricalDistribution builds from jointMap (every length 0 .. maxFragLen-1 with its count, :944-947): float, truncated where
+// the cumulative mass passes 1 - 1e-6 (src/EmpiricalDistribution.cpp:29-94); transcripts not longer than the median keep RefLength
+std::vector<double> empirical_effective_lengths(const std::vector<uint32_t>& lens, const std::vector<uint32_t>& fld) {
+    const size_t n = fld.size();
+    std::vector<double> eff(lens.size());
+    double total = 0.0;
+    for (uint32_t c : fld) total += c;
+    size_t last = 0, maxval = 1;
+    double cum = 0.0;
+    for (; last < n; ++last) { cum += fld[last] / total; maxval = last; if (cum > 1.0 - 1e-6) break; }
+    double kept = 0.0;
+    for (size_t i = 0; i < last && i < n; ++i) kept += fld[i];
+    std::vector<float> pdf(n ? maxval : 0);
+    for (size_t v = 0; v < pdf.size(); ++v) pdf[v] = static_cast<float>(fld[v] / kept);
+    size_t i = 0, j = n ? n - 1 : 0;                                          // the median by walking in from both ends (:83-93)
+    unsigned u = n ? fld[0] : 0, v = n ? fld[n - 1] : 0;
+    while (i < j) { if (u <= v) { v -= u; u = fld[++i]; } else { u -= v; v = fld[--j]; } }
+    const float median = static_cast<float>(i);
+    const uint32_t minVal = 0, maxVal = n ? static_cast<uint32_t>(n - 1) : 0;
+    for (size_t t = 0; t < lens.size(); ++t) {
+        const double refLen = lens[t];
+        if (refLen <= median || !(maxVal > minVal)) { eff[t] = refLen; continue; }
+        double e = 0.0;
+        for (size_t l = minVal; l <= std::min(lens[t], maxVal); ++l) e += (l < pdf.size() ? pdf[l] : 0.0f) * (lens[t] - l + 1.0);
+        eff[t] = e;
+    }
+    return eff;
+}
+
 std::vector<double> effective_lengths(const std::vector<uint32_t>& lens, const std::vector<uint32_t>& fld, uint32_t maxFragLen,
-                                      int32_t numFragSamples, bool singleEnd, bool noCorrection, double priorMean, double priorSD) {
+                                      int32_t numFragSamples, bool singleEnd, bool noCorrection, double priorMean, double priorSD,
+                                      bool unsmoothed = false) {
     std::vector<double> eff(lens.size());
     if (noCorrection) { for (size_t i = 0; i < lens.size(); ++i) eff[i] = lens[i]; return eff; }
     uint64_t nSamp = 0;
     for (uint32_t c : fld) nSamp += c;
     const bool enough = !singleEnd && nSamp >= static_cast<uint64_t>(numFragSamples);
+    if (enough && unsmoothed) return empirical_effective_lengths(lens, fld);  // :985-986
     const std::vector<double> cf = enough ? correction_factors_from_counts(fld) : normal_correction_factors(maxFragLen, priorMean, priorSD);
     for (size_t i = 0; i < lens.size(); ++i) {
         const uint32_t idx = std::min<uint32_t>(lens[i], maxFragLen - 1);
@@ -123,6 +155,7 @@ struct ReadExperiment {
 struct SailfishOpts {
     bool useVBOpt = false, noEffectiveLengthCorrection = false;
     uint32_t numBootstraps = 0, numGibbsSamples = 0;
+    bool useUnsmoothedFLD = false;                                            // --unsmoothedFLD (SailfishQuantify.cpp:1109)
     bool biasCorrect = false, gcBiasCorrect = false;                          // SailfishQuantify.cpp:1089-1090
     int32_t numBiasSamples = 1000000;                                         // :1131
     uint32_t pdfSampFactor = 1;                                               // --gcSpeedSamp (:1103)
@@ -237,7 +270,8 @@ int read_index_dir(const std::string& dir, std::vector<std::string>& names, std:
 
 struct Args {
     std::string transcripts, index, libType, out, auxDir = "aux", geneMap, aggKey = "gene_id", quantFile;
-    bool indexCmd = false, genesCmd = false, force = false;
+    bool indexCmd = false, genesCmd = false, efflensCmd = false, efflensSingle = false, force = false;
+    std::string lensFile, fldFile;
     std::vector<std::string> unmated, mates1, mates2;
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int k = 31, device = 0;
@@ -261,6 +295,7 @@ struct Args {
             "  -o, --output DIR           quant.sf and <auxDir>/ are written here\n"
             "  -p, --threads N  -k, --kmerLen K (31)  --device N\n"
             "  --useVBOpt  --numBootstraps N  --numGibbsSamples N  --dumpEq  --noEffectiveLengthCorrection\n"
+            "  --unsmoothedFLD            effective lengths from the observed fragment length distribution itself\n"
             "  --biasCorrect | --gcBiasCorrect  [--numBiasSamples N (1000000)]  [--gcSpeedSamp N (1)]\n"
             "  -g, --geneMap FILE         transcript-to-gene map (.gtf, or `transcript gene` per line): also write quant.genes.sf\n"
             "  --txpAggregationKey KEY    GTF attribute that names the gene (gene_id)\n"
@@ -279,6 +314,7 @@ Args parse_args(int argc, char** argv) {
     if (i < argc && std::string(argv[i]) == "quant") ++i;
     else if (i < argc && std::string(argv[i]) == "index") { a.indexCmd = true; ++i; }
     else if (i < argc && std::string(argv[i]) == "genes") { a.genesCmd = true; ++i; }
+    else if (i < argc && std::string(argv[i]) == "efflens") { a.efflensCmd = true; ++i; }
     auto need = [&](const std::string& o) -> std::string { if (i + 1 >= argc) usage(("missing value for " + o).c_str()); return argv[++i]; };
     auto multi = [&](std::vector<std::string>& v) { while (i + 1 < argc && argv[i + 1][0] != '-') v.push_back(argv[++i]); };
     for (; i < argc; ++i) {
@@ -304,6 +340,10 @@ Args parse_args(int argc, char** argv) {
         else if (o == "--numGibbsSamples") a.sopt.numGibbsSamples = (uint32_t)atoi(need(o).c_str());
         else if (o == "--dumpEq") a.dumpEq = true;
         else if (o == "--noEffectiveLengthCorrection") a.sopt.noEffectiveLengthCorrection = true;
+        else if (o == "--unsmoothedFLD") a.sopt.useUnsmoothedFLD = true;
+        else if (o == "--lensFile") a.lensFile = need(o);                      // `efflens` only
+        else if (o == "--fldFile") a.fldFile = need(o);
+        else if (o == "--singleEnd") a.efflensSingle = true;
         else if (o == "--biasCorrect") a.sopt.biasCorrect = true;
         else if (o == "--gcBiasCorrect") a.sopt.gcBiasCorrect = true;
         else if (o == "--numBiasSamples") a.sopt.numBiasSamples = atoi(need(o).c_str());
@@ -422,6 +462,19 @@ int main(int argc, char** argv) {
             if (nu) fprintf(stderr, "WARNING: %zu transcripts of %s are not in the map; each is reported as its own gene\n", nu, quantPath.c_str());
             fprintf(stderr, "[sfb200-quant] wrote %s\n", outp.c_str());
         };
+        if (a.efflensCmd) {
+            // test hook, no GPU: the effective lengths `quant` would compute for transcript lengths (--lensFile, one per line) and a
+            // fragment length histogram (--fldFile, counts for 0 .. maxFragLen-1), printed with 17 significant digits
+            if (a.lensFile.empty() || a.fldFile.empty()) usage("efflens needs --lensFile and --fldFile");
+            std::vector<uint32_t> lens, fld;
+            { std::ifstream f(a.lensFile); for (uint64_t x; f >> x;) lens.push_back((uint32_t)x); }
+            { std::ifstream f(a.fldFile); for (uint64_t x; f >> x;) fld.push_back((uint32_t)x); }
+            if (fld.size() != a.mopt.max_frag_len) usage("--fldFile must hold --maxFragLen counts");
+            const std::vector<double> eff = effective_lengths(lens, fld, a.mopt.max_frag_len, a.mopt.num_frag_samples, a.efflensSingle,
+                                                              a.sopt.noEffectiveLengthCorrection, a.fldMean, a.fldSD, a.sopt.useUnsmoothedFLD);
+            for (double e : eff) printf("%.17g\n", e);
+            return 0;
+        }
         if (a.genesCmd) {
             if (a.geneMap.empty() || a.quantFile.empty()) usage("genes needs -g <map> and -q <quant.sf>");
             gene_level(a.quantFile);
@@ -533,7 +586,7 @@ int main(int argc, char** argv) {
 
         // ---- effective lengths, inference
         const std::vector<double> eff = effective_lengths(lens, eqBuilder.fragLengthCounts(), a.mopt.max_frag_len, a.mopt.num_frag_samples,
-                                                          !paired_files, a.sopt.noEffectiveLengthCorrection, a.fldMean, a.fldSD);
+                                                          !paired_files, a.sopt.noEffectiveLengthCorrection, a.fldMean, a.fldSD, a.sopt.useUnsmoothedFLD);
         for (size_t i = 0; i < eff.size(); ++i) ex.txps[i].EffectiveLength = eff[i];
         make_dir(a.out);
         const std::string aux = a.out + "/" + a.auxDir;

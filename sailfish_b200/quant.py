@@ -119,7 +119,7 @@ def write_eq_classes(path, names, row_ptr, labels, counts):
 
 def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_quant", k=31, use_vb=False, n_boot=0, n_gibbs=0,
              dump_eq=False, batch=1_000_000, device=0, no_eff_len_correction=False, map_kw=None, bias_correct=False,
-             gc_bias_correct=False, num_bias_samples=1000000, gc_speed_samp=1):
+             gc_bias_correct=False, num_bias_samples=1000000, gc_speed_samp=1, unsmoothed_fld=False):
     t_start = time.time()
     names, seqs = read_fasta(transcripts)
     lengths = np.array([len(s) for s in seqs], np.uint32)
@@ -156,7 +156,7 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
     num_mapped = int(counters[1])
     eff = efflen.effective_lengths(lengths, g["fld"], max_frag_len=ctx.map_opts.max_frag_len,
                                    num_frag_samples=ctx.map_opts.num_frag_samples, single_end=not paired,
-                                   no_correction=no_eff_len_correction)
+                                   no_correction=no_eff_len_correction, unsmoothed=unsmoothed_fld)
     os.makedirs(os.path.join(out_dir, "aux"), exist_ok=True)
     if dump_eq:
         rp, lab, cnt = ctx.eq_export()
@@ -211,6 +211,7 @@ def main(argv=None):
     ap.add_argument("--numGibbsSamples", type=int, default=0)
     ap.add_argument("--dumpEq", action="store_true")
     ap.add_argument("--noEffectiveLengthCorrection", action="store_true")
+    ap.add_argument("--unsmoothedFLD", action="store_true")
     ap.add_argument("--biasCorrect", action="store_true")
     ap.add_argument("--gcBiasCorrect", action="store_true")
     ap.add_argument("--numBiasSamples", type=int, default=1000000)
@@ -223,7 +224,8 @@ def main(argv=None):
         sys.exit("no reads given")
     res = quantify(a.transcripts, r1, a.mates2, a.libType, a.output, a.kmerLen, a.useVBOpt, a.numBootstraps, a.numGibbsSamples,
                    a.dumpEq, no_eff_len_correction=a.noEffectiveLengthCorrection, bias_correct=a.biasCorrect,
-                   gc_bias_correct=a.gcBiasCorrect, num_bias_samples=a.numBiasSamples, gc_speed_samp=a.gcSpeedSamp)
+                   gc_bias_correct=a.gcBiasCorrect, num_bias_samples=a.numBiasSamples, gc_speed_samp=a.gcSpeedSamp,
+                   unsmoothed_fld=a.unsmoothedFLD)
     print(json.dumps(res["meta"]))
 
 

@@ -170,6 +170,31 @@ def test_gene_level_aggregation(tmp_path):
     assert r.returncode == 1 and b"Could not find transcript <=> gene map file" in r.stderr
 
 
+@pytest.mark.parametrize("mode,flags,kw", [(0, [], {}), (2, ["--unsmoothedFLD"], {"unsmoothed": True}),
+                                           (1, ["--noEffectiveLengthCorrection"], {"no_correction": True})])
+def test_effective_lengths_equal_oracle(tmp_path, mode, flags, kw):
+    """SURVEY 8a row A9 on the host: `sfb200-quant efflens` (the function `quant` calls) and sailfish_b200/efflen.py against the
+    oracle's restatement of the quasiMapReads tail -- smoothed, --unsmoothedFLD (EmpiricalDistribution's float pdf) and direct"""
+    from oracle import pyoracle as O
+    from sailfish_b200 import efflen
+    rng = np.random.default_rng(4)
+    x = np.arange(1000)
+    lens = np.concatenate([rng.integers(20, 5000, size=400), [1, 5, 150, 189, 190, 191, 250, 999, 1000, 1001]]).astype(np.uint32)
+    sparse = np.zeros(1000, np.uint32); sparse[rng.integers(100, 400, 60)] += rng.integers(100, 500, 60).astype(np.uint32)
+    cases = [np.round(30000 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32), rng.integers(0, 100, size=1000).astype(np.uint32), sparse,
+             np.round(30 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32)]           # the last: too few samples -> prior normal
+    np.savetxt(tmp_path / "lens.txt", lens, fmt="%d")
+    for fld in cases:
+        np.savetxt(tmp_path / "fld.txt", fld, fmt="%d")
+        for single in (False, True):
+            want = O.eff_lens(lens, fld, mode=mode, single_end=single)
+            got_py = efflen.effective_lengths(lens, fld, single_end=single, **kw)
+            out = subprocess.check_output([build_exe(), "efflens", "--lensFile", str(tmp_path / "lens.txt"), "--fldFile", str(tmp_path / "fld.txt")]
+                                          + flags + (["--singleEnd"] if single else [])).decode().split()
+            assert got_py.tolist() == want.tolist()
+            assert [float(v) for v in out] == want.tolist()
+
+
 def test_bias_option_checks(tmp_path):
     """SailfishQuantify.cpp:1293-1309: the two corrections exclude each other; GC correction is switched off for single-end libraries"""
     fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 30 + "\n")
