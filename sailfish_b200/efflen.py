@@ -48,6 +48,8 @@ def empirical_effective_lengths(txp_len, fld_hist):
     total = 0.0
     for c in counts:
         total += float(c)
+    if not total > 0:                                               # nothing observed: no distribution to correct with
+        return txp_len.astype(np.float64)
     cum, last, maxval = 0.0, 0, 1
     while last < n:
         cum += float(counts[last]) / total
@@ -121,6 +123,8 @@ def empirical_cdf(counts):
     total = 0.0
     for c in counts:
         total += float(c)
+    if not total > 0:                                # nothing observed (the reference would divide by zero): an empty table
+        return np.zeros(0, np.float32), (n - 1 if n else 0)
     cum, last, maxval = 0.0, 0, 1
     while last < n:
         cum += float(counts[last]) / total

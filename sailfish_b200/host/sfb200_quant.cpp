@@ -23,8 +23,10 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -90,9 +92,8 @@ std::vector<double> correction_factors_from_counts(const std::vector<uint32_t>& 
 // computeEmpiricalEffectiveLengths (--unsmoothedFLD, :717-767): sum over fragment lengths of pdf(l) * (RefLength - l + 1), with the
 // pdf EmpiricalDistribution builds from jointMap (every length 0 .. maxFragLen-1 with its count, :944-947): float, truncated where
 // the cumulative mass passes 1 - 1e-6 (src/EmpiricalDistribution.cpp:29-94); transcripts not longer than the median keep RefLength
-std::vector<double> empirical_effective_lengths(const std::vector<uint32_t>& lens, const std::vector<uint32_t>& fld) {
+std::vector<float> empirical_pdf(const std::vector<uint32_t>& fld) {
     const size_t n = fld.size();
-    std::vector<double> eff(lens.size());
     double total = 0.0;
     for (uint32_t c : fld) total += c;
     size_t last = 0, maxval = 1;
@@ -102,6 +103,15 @@ std::vector<double> empirical_effective_lengths(const std::vector<uint32_t>& len
     for (size_t i = 0; i < last && i < n; ++i) kept += fld[i];
     std::vector<float> pdf(n ? maxval : 0);
     for (size_t v = 0; v < pdf.size(); ++v) pdf[v] = static_cast<float>(fld[v] / kept);
+    return pdf;
+}
+std::vector<double> empirical_effective_lengths(const std::vector<uint32_t>& lens, const std::vector<uint32_t>& fld) {
+    const size_t n = fld.size();
+    std::vector<double> eff(lens.size());
+    uint64_t observed = 0;
+    for (uint32_t c : fld) observed += c;
+    if (observed == 0) { for (size_t t = 0; t < lens.size(); ++t) eff[t] = lens[t]; return eff; }   // nothing observed: no distribution to correct with
+    const std::vector<float> pdf = empirical_pdf(fld);
     size_t i = 0, j = n ? n - 1 : 0;                                          // the median by walking in from both ends (:83-93)
     unsigned u = n ? fld[0] : 0, v = n ? fld[n - 1] : 0;
     while (i < j) { if (u <= v) { v -= u; u = fld[++i]; } else { u -= v; v = fld[--j]; } }
@@ -162,6 +172,31 @@ struct SailfishOpts {
 };
 
 void make_dir(const std::string& p) { mkdir(p.c_str(), 0755); }
+
+// writeVectorToFile (src/GZipWriter.cpp:23-43): the raw elements, gzip level 6
+template <typename T>
+bool write_vector_gz(const std::string& path, const std::vector<T>& v) {
+    gzFile f = gzopen(path.c_str(), "wb6");
+    if (!f) return false;
+    const bool ok = v.empty() || gzwrite(f, v.data(), (unsigned)(v.size() * sizeof(T))) > 0;
+    gzclose(f);
+    return ok;
+}
+// EmpiricalDistribution::realize (src/EmpiricalDistribution.cpp:127-144): 10000 draws from the pdf, as counts per length 0 .. maxValue.
+// The reference seeds from std::random_device (aux/fld.gz differs from run to run); here the seed is fixed.
+std::vector<int32_t> realize_fld(const std::vector<uint32_t>& fldCounts, uint32_t numSamp = 10000) {
+    const std::vector<float> pdf = empirical_pdf(fldCounts);
+    std::vector<double> padded(fldCounts.size(), 0.0);
+    for (size_t i = 0; i < padded.size() && i < pdf.size(); ++i) padded[i] = pdf[i];
+    std::vector<int32_t> samples(padded.size(), 0);
+    double mass = 0.0;
+    for (double x : padded) mass += x;
+    if (padded.empty() || !(mass > 0.0)) return samples;                      // no observations at all (also catches NaN)
+    std::mt19937 gen(0x5f3759df);
+    std::discrete_distribution<int32_t> d(padded.begin(), padded.end());
+    for (uint32_t i = 0; i < numSamp; ++i) ++samples[d(gen)];
+    return samples;
+}
 
 std::string fmt_g(double x) { char b[64]; snprintf(b, sizeof b, "%g", x); return b; }   // cppformat's `{}` for doubles
 
@@ -473,6 +508,13 @@ int main(int argc, char** argv) {
             const std::vector<double> eff = effective_lengths(lens, fld, a.mopt.max_frag_len, a.mopt.num_frag_samples, a.efflensSingle,
                                                               a.sopt.noEffectiveLengthCorrection, a.fldMean, a.fldSD, a.sopt.useUnsmoothedFLD);
             for (double e : eff) printf("%.17g\n", e);
+            if (!a.out.empty()) {                                              // and aux/fld.gz as `quant` would write it
+                uint64_t nSamp = 0;
+                for (uint32_t c : fld) nSamp += c;
+                const bool enough = !a.efflensSingle && nSamp >= static_cast<uint64_t>(a.mopt.num_frag_samples);
+                make_dir(a.out);
+                if (!write_vector_gz(a.out + "/fld.gz", realize_fld(enough ? fld : normal_frag_length_counts(a.mopt.max_frag_len, a.mopt.num_frag_samples, a.fldMean, a.fldSD)))) return 1;
+            }
             return 0;
         }
         if (a.genesCmd) {
@@ -545,6 +587,8 @@ int main(int argc, char** argv) {
         if (lib_paired != paired_files) usage("the library type does not match the read files given");
 
         const double t_start = now_s();
+        std::string run_start;                                                // SailfishQuantify.cpp:1204-1206
+        { const std::time_t now = std::time(nullptr); run_start = std::asctime(std::localtime(&now)); if (!run_start.empty()) run_start.pop_back(); }
         // ---- transcripts + index (what SailfishIndex::load + ReadExperiment's constructor do, ReadExperiment.hpp:59-131)
         ReadExperiment ex;
         std::string seq; std::vector<std::string> names; std::vector<uint64_t> off; std::vector<uint32_t> lens;
@@ -593,14 +637,14 @@ int main(int argc, char** argv) {
         make_dir(aux);
         if (a.dumpEq) write_eq_classes(aux + "/eq_classes.txt", ex, eqBuilder);
         sfb200::CollapsedEMOptimizer optimizer(dev);
+        // readExp.setFragLengthDist (:966-984, :1039): the observed histogram when enough fragments were sampled, else the rounded normal
+        uint64_t nSamp = 0;
+        for (uint32_t c : eqBuilder.fragLengthCounts()) nSamp += c;
+        const bool enough = paired_files && nSamp >= static_cast<uint64_t>(a.mopt.num_frag_samples);
+        const std::vector<uint32_t> fldCounts = enough ? eqBuilder.fragLengthCounts()
+                                                       : normal_frag_length_counts(a.mopt.max_frag_len, a.mopt.num_frag_samples, a.fldMean, a.fldSD);
         bool opt_ok;
         if (doBias) {
-            // readExp.setFragLengthDist (:966-984, :1039): the observed histogram when enough fragments were sampled, else the rounded normal
-            uint64_t nSamp = 0;
-            for (uint32_t c : eqBuilder.fragLengthCounts()) nSamp += c;
-            const bool enough = paired_files && nSamp >= static_cast<uint64_t>(a.mopt.num_frag_samples);
-            const std::vector<uint32_t> fldCounts = enough ? eqBuilder.fragLengthCounts()
-                                                           : normal_frag_length_counts(a.mopt.max_frag_len, a.mopt.num_frag_samples, a.fldMean, a.fldSD);
             sfb200::BiasModel model(a.sopt.gcBiasCorrect, eqBuilder.readBiasCounts(), eqBuilder.observedGC(), eqBuilder.numFwd(), eqBuilder.numRC(),
                                     fldCounts, a.sopt.pdfSampFactor);
             opt_ok = optimizer.optimizeWithBias(ex, a.sopt, model, 0.01, 10000);
@@ -638,16 +682,30 @@ int main(int argc, char** argv) {
             gzclose(bf);
             if (!ok) { fprintf(stderr, "[sfb200-quant] posterior sampling failed: %s\n", optimizer.lastError().c_str()); return 1; }
         }
+        // the binary vectors of GZipWriter::writeMeta (src/GZipWriter.cpp:139-161).  The reference never fills the two "expected" vectors
+        // (nothing calls setExpectedSeqBias / setExpectedGCBias), so they are what ReadExperiment's constructor leaves: all ones.
+        if (!a.sopt.noEffectiveLengthCorrection) write_vector_gz(aux + "/fld.gz", realize_fld(fldCounts));   // fragLengthDist() is unset otherwise
+        {
+            std::vector<int32_t> obsBias(4096, 1), obsGC(101, 1);              // the initial count of one per bin
+            if (doBias) {
+                for (size_t i = 0; i < obsBias.size(); ++i) obsBias[i] = static_cast<int32_t>(eqBuilder.readBiasCounts()[i]);
+                for (size_t i = 0; i < obsGC.size(); ++i) obsGC[i] = static_cast<int32_t>(eqBuilder.observedGC()[i]);
+            }
+            write_vector_gz(aux + "/expected_bias.gz", std::vector<double>(4096, 1.0));
+            write_vector_gz(aux + "/observed_bias.gz", obsBias);
+            write_vector_gz(aux + "/expected_gc.gz", std::vector<double>(101, 1.0));
+            write_vector_gz(aux + "/observed_gc.gz", obsGC);
+        }
         // meta_info.json (GZipWriter::writeMeta, src/GZipWriter.cpp:163-190)
         FILE* mf = fopen((aux + "/meta_info.json").c_str(), "w");
         if (mf) {
             fprintf(mf, "{\n    \"sf_version\": \"0.10.0-b200\",\n    \"samp_type\": \"%s\",\n    \"frag_dist_length\": %u,\n"
-                        "    \"bias_correct\": %s,\n    \"num_targets\": %zu,\n    \"num_bootstraps\": %u,\n    \"num_processed\": %llu,\n"
-                        "    \"num_mapped\": %llu,\n    \"percent_mapped\": %.10g,\n    \"call\": \"quant\",\n    \"em_iterations\": %u,\n"
-                        "    \"elapsed_s\": %.3f\n}\n",
-                    samp_type, a.mopt.max_frag_len, doBias ? "true" : "false", names.size(), n_samples, (unsigned long long)eqBuilder.numObservedFragments(),
+                        "    \"bias_correct\": %s,\n    \"num_bias_bins\": 4096,\n    \"num_targets\": %zu,\n    \"num_bootstraps\": %u,\n    \"num_processed\": %llu,\n"
+                        "    \"num_mapped\": %llu,\n    \"percent_mapped\": %.10g,\n    \"call\": \"quant\",\n    \"start_time\": \"%s\",\n"
+                        "    \"em_iterations\": %u,\n    \"elapsed_s\": %.3f\n}\n",
+                    samp_type, a.mopt.max_frag_len - 1 /* fragLengthDist()->maxValue() */, a.sopt.biasCorrect ? "true" : "false", names.size(), n_samples, (unsigned long long)eqBuilder.numObservedFragments(),
                     (unsigned long long)ex.numMapped, 100.0 * ex.numMapped / std::max<uint64_t>(1, eqBuilder.numObservedFragments()),
-                    optimizer.lastIterations(), now_s() - t_start);
+                    run_start.c_str(), optimizer.lastIterations(), now_s() - t_start);
             fclose(mf);
         }
         if (!a.geneMap.empty()) gene_level(a.out + "/quant.sf");             // SailfishQuantify.cpp:1413-1422

@@ -117,6 +117,27 @@ def write_eq_classes(path, names, row_ptr, labels, counts):
             f.write("%d\t%s\t%d\n" % (len(ids), "\t".join(str(int(t)) for t in ids), int(counts[e])))
 
 
+def write_aux_vectors(aux, fld_counts, obs_bias, obs_gc):
+    """the binary vectors of GZipWriter::writeMeta (src/GZipWriter.cpp:139-161): raw little-endian elements, gzip.  fld.gz is a
+    realisation of 10000 draws from the fragment length pdf (random in the reference, fixed seed here; skipped when there is no
+    distribution); the two "expected" vectors are never filled by the reference and stay all ones"""
+    if fld_counts is not None:
+        pdf = np.zeros(len(fld_counts), np.float64)
+        cdf, _ = efflen.empirical_cdf(fld_counts)
+        pdf[:len(cdf)] = np.diff(np.concatenate([[0.0], cdf.astype(np.float64)]))
+        pdf = np.where(np.isfinite(pdf) & (pdf > 0), pdf, 0.0)
+        samples = np.zeros(len(pdf), np.int32)
+        if pdf.sum() > 0:
+            draws = np.random.default_rng(0x5f3759df).choice(len(pdf), size=10000, p=pdf / pdf.sum())
+            samples = np.bincount(draws, minlength=len(pdf)).astype(np.int32)
+        with gzip.open(os.path.join(aux, "fld.gz"), "wb") as f:
+            f.write(samples.tobytes())
+    for fn, arr in (("expected_bias.gz", np.ones(4096, np.float64)), ("observed_bias.gz", np.asarray(obs_bias).astype(np.int32)),
+                    ("expected_gc.gz", np.ones(101, np.float64)), ("observed_gc.gz", np.asarray(obs_gc).astype(np.int32))):
+        with gzip.open(os.path.join(aux, fn), "wb") as f:
+            f.write(np.ascontiguousarray(arr).tobytes())
+
+
 def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_quant", k=31, use_vb=False, n_boot=0, n_gibbs=0,
              dump_eq=False, batch=1_000_000, device=0, no_eff_len_correction=False, map_kw=None, bias_correct=False,
              gc_bias_correct=False, num_bias_samples=1000000, gc_speed_samp=1, unsmoothed_fld=False):
@@ -173,6 +194,12 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
     else:
         alphas, iters, mrd = ctx.em_run(eff, num_mapped, capi.EMOpts.default(use_vb=int(use_vb)))
     write_quant_sf(os.path.join(out_dir, "quant.sf"), names, lengths, eff, alphas, num_mapped)
+    counts = None
+    if not no_eff_len_correction:
+        enough = paired and int(np.asarray(g["fld"], np.uint64).sum()) >= ctx.map_opts.num_frag_samples
+        counts = g["fld"] if enough else efflen.normal_frag_length_counts(ctx.map_opts.max_frag_len, ctx.map_opts.num_frag_samples)
+    obs_bias, obs_gc = (ctx.map_get_bias() if do_bias else (np.ones(4096, np.uint32), np.ones(101, np.uint32)))
+    write_aux_vectors(os.path.join(out_dir, "aux"), counts, obs_bias, obs_gc)
     samp_type = "none"
     if n_boot or n_gibbs:
         os.makedirs(os.path.join(out_dir, "aux", "bootstrap"), exist_ok=True)
@@ -186,10 +213,10 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
             samp_type = "gibbs"
         with gzip.open(os.path.join(out_dir, "aux", "bootstrap", "bootstraps.gz"), "wb") as f:
             f.write(np.ascontiguousarray(rows).tobytes())
-    meta = {"sf_version": "0.10.0-b200", "samp_type": samp_type, "frag_dist_length": int(ctx.map_opts.max_frag_len),
-            "bias_correct": bool(do_bias), "num_targets": len(names), "num_bootstraps": int(n_boot or n_gibbs),
+    meta = {"sf_version": "0.10.0-b200", "samp_type": samp_type, "frag_dist_length": int(ctx.map_opts.max_frag_len) - 1,
+            "bias_correct": bool(bias_correct), "num_bias_bins": 4096, "num_targets": len(names), "num_bootstraps": int(n_boot or n_gibbs),
             "num_processed": int(counters[0]), "num_mapped": num_mapped,
-            "percent_mapped": 100.0 * num_mapped / max(int(counters[0]), 1), "call": "quant",
+            "percent_mapped": 100.0 * num_mapped / max(int(counters[0]), 1), "call": "quant", "start_time": time.asctime(time.localtime(t_start)),
             "em_iterations": int(iters), "elapsed_s": time.time() - t_start}
     with open(os.path.join(out_dir, "aux", "meta_info.json"), "w") as f:
         json.dump(meta, f, indent=4)

@@ -193,6 +193,72 @@ def test_effective_lengths_equal_oracle(tmp_path, mode, flags, kw):
                                           + flags + (["--singleEnd"] if single else [])).decode().split()
             assert got_py.tolist() == want.tolist()
             assert [float(v) for v in out] == want.tolist()
+    # aux/fld.gz as `quant` writes it: 10000 draws from the fragment length pdf as int32 counts per length
+    subprocess.check_call([build_exe(), "efflens", "--lensFile", str(tmp_path / "lens.txt"), "--fldFile", str(tmp_path / "fld.txt"), "-o", str(tmp_path / "aux")],
+                          stdout=subprocess.DEVNULL)
+    fld_real = np.frombuffer(gzip.open(tmp_path / "aux" / "fld.gz").read(), dtype=np.int32)
+    assert len(fld_real) == 1000 and int(fld_real.sum()) == 10000 and abs(float((fld_real * np.arange(1000)).sum()) / 10000 - 200.0) < 5     # prior N(200, 80)
+    np.savetxt(tmp_path / "fld.txt", np.zeros(1000, np.uint32), fmt="%d")
+    subprocess.check_call([build_exe(), "efflens", "--lensFile", str(tmp_path / "lens.txt"), "--fldFile", str(tmp_path / "fld.txt"), "-o", str(tmp_path / "aux0"),
+                           "--numFragSamples", "0"], stdout=subprocess.DEVNULL)
+    assert not np.frombuffer(gzip.open(tmp_path / "aux0" / "fld.gz").read(), dtype=np.int32).any()       # no observations: nothing to draw from
+
+
+def test_driver_host_flow_with_stub_device(tmp_path):
+    """sfb200_quant.cpp linked against tests/stub_sfb200.cpp (a test double of the C ABI: canned device results, call log): the
+    driver's HOST flow -- effective lengths, FLD hand-over to the bias model, corrected lengths in quant.sf, every aux file --
+    without a GPU.  The real thing runs in the gpu tests below."""
+    exe = str(tmp_path / "sfb200-quant-stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-Wall", "-pthread", "-o", exe, os.path.join(ROOT, "sailfish_b200", "host", "sfb200_quant.cpp"),
+                           os.path.join(ROOT, "tests", "stub_sfb200.cpp"), "-lz"])
+    fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 100 + "\n>t1\n" + "GGCA" * 150 + "\n>t2\n" + "TTGA" * 60 + "\n")
+    for tag in "12":
+        (tmp_path / ("r%s.fq" % tag)).write_text("".join("@r%d\n%s\n+\n%s\n" % (i, "ACGT" * 10, "I" * 40) for i in range(4)))
+    base = [exe, "quant", "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "r1.fq"), "-2", str(tmp_path / "r2.fq")]
+    log = tmp_path / "log.txt"
+    env = dict(os.environ, SFB200_STUB_LOG=str(log))
+
+    def run(args, out):
+        if log.exists():
+            log.unlink()
+        subprocess.check_call(base + ["-o", str(tmp_path / out)] + args, env=env, stderr=subprocess.DEVNULL)
+        rows = [l.split("\t") for l in open(tmp_path / out / "quant.sf").read().strip().split("\n")[1:]]
+        return log.read_text().strip().split("\n"), rows, json.load(open(tmp_path / out / "aux" / "meta_info.json"))
+
+    def vec(out, name, dt):
+        return np.frombuffer(gzip.open(tmp_path / out / "aux" / name).read(), dtype=dt)
+
+    # plain run: smoothed effective lengths from the observed FLD (12000 samples on 180..219), no bias calls, every aux file
+    calls, rows, meta = run(["--dumpEq", "--numBootstraps", "2"], "o1")
+    assert [c.split()[0] for c in calls] == ["index_build", "map_begin", "map_batch", "em_run"]
+    assert calls[3] == "em_run 3 vb=0 eff0=201.500000 eff1=401.500000"
+    assert [r[0] for r in rows] == ["t0", "t1", "t2"] and [r[2] for r in rows] == ["201.5", "401.5", "41.5"] and [r[4] for r in rows] == ["2", "1", "0"]
+    assert meta["frag_dist_length"] == 999 and meta["bias_correct"] is False and meta["num_bias_bins"] == 4096 and meta["samp_type"] == "bootstrap"
+    assert meta["num_processed"] == 4 and meta["num_mapped"] == 3 and meta["em_iterations"] == 51 and "start_time" in meta
+    real = vec("o1", "fld.gz", np.int32)
+    assert len(real) == 1000 and real.sum() == 10000 and real[:180].sum() == 0 and real[219:].sum() == 0      # bin 219 is cut by the 1 - 1e-6 rule
+    assert (vec("o1", "observed_bias.gz", np.int32) == 1).all() and len(vec("o1", "observed_gc.gz", np.int32)) == 101
+    assert (vec("o1", "expected_bias.gz", np.float64) == 1.0).all() and len(vec("o1", "expected_gc.gz", np.float64)) == 101
+    boots = np.frombuffer(gzip.open(tmp_path / "o1" / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.float64)
+    assert boots.tolist() == [1.0] * 3 + [2.0] * 3
+    # --unsmoothedFLD
+    calls, rows, meta = run(["--unsmoothedFLD", "--useVBOpt"], "o2")
+    assert calls[3].startswith("em_run 3 vb=1 eff0=202.0000")                                                  # mean of 180..218, float pdf
+    # --gcBiasCorrect: samples requested before the first batch; the model carries the FLD table, the strand tallies, both observed arrays
+    calls, rows, meta = run(["--gcBiasCorrect", "--gcSpeedSamp", "3", "--numBiasSamples", "1234"], "o3")
+    assert [c.split()[0] for c in calls] == ["index_build", "map_begin", "map_set_bias", "map_batch", "em_run_bias"]
+    assert calls[2] == "map_set_bias 0 1 1234"
+    assert calls[4].startswith("em_run_bias 3 mode=2 gc_samp=3 fwd=2 rc=1 n_cdf=219 fld_max=999 rb7=8 og100=101 cdf_last=1.0000")
+    assert [r[2] for r in rows] == ["100.75", "200.75", "20.75"]                                               # the corrected lengths (stub: half)
+    assert meta["bias_correct"] is False                                                                       # opts.biasCorrect only (GZipWriter.cpp:178)
+    assert vec("o3", "observed_gc.gz", np.int32).tolist() == list(range(1, 102)) and vec("o3", "observed_bias.gz", np.int32)[:3].tolist() == [1, 2, 3]
+    # --biasCorrect with too few sampled fragment lengths (--numFragSamples above what was seen): the prior normal is the FLD
+    calls, rows, meta = run(["--biasCorrect", "--numFragSamples", "20000"], "o4")
+    assert calls[2] == "map_set_bias 1 0 1000000" and " mode=1 gc_samp=1 " in calls[4] and meta["bias_correct"] is True
+    n_cdf = int(calls[4].split("n_cdf=")[1].split()[0])
+    assert 400 < n_cdf < 700                                                                                   # N(200, 80) truncated at 1 - 1e-6
+    real = vec("o4", "fld.gz", np.int32)
+    assert real.sum() == 10000 and abs(float((real * np.arange(1000)).sum()) / 10000 - 200) < 5
 
 
 def test_bias_option_checks(tmp_path):
@@ -308,4 +374,7 @@ def test_sample_data_bias_correction_cpp(sample_data, tmp_path, flag, mode):
     np.testing.assert_allclose([float(r[4]) for r in rows], want, rtol=1.2e-4, atol=1e-6)
     np.testing.assert_allclose([float(r[2]) for r in rows], eff_want, rtol=1e-5)
     assert (np.abs(eff_want - np.maximum(d["eff"], 1.0)) > 1e-6).sum() > 10
-    assert json.load(open(out / "aux" / "meta_info.json"))["bias_correct"] is True
+    assert json.load(open(out / "aux" / "meta_info.json"))["bias_correct"] is (flag == "--biasCorrect")     # opts.biasCorrect (GZipWriter.cpp:178)
+    og_file = np.frombuffer(gzip.open(out / "aux" / "observed_gc.gz").read(), dtype=np.int32)
+    rb_file = np.frombuffer(gzip.open(out / "aux" / "observed_bias.gz").read(), dtype=np.int32)
+    assert og_file.tolist() == og.tolist() and rb_file.tolist() == rb.tolist()
