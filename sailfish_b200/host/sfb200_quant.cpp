@@ -18,6 +18,7 @@
 
 #include <sys/stat.h>
 
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -172,6 +173,42 @@ struct SailfishOpts {
 };
 
 void make_dir(const std::string& p) { mkdir(p.c_str(), 0755); }
+
+std::string json_escape(const std::string& v) {
+    std::string o;
+    for (char ch : v) { if (ch == '"' || ch == '\\') o.push_back('\\'); if ((unsigned char)ch >= 0x20) o.push_back(ch); }
+    return o;
+}
+// cmd_info.json (SailfishQuantify.cpp:1262-1276): sf_version, then every option as given, under its long name; one value is a
+// string, several (or none, for a switch) an array
+void write_cmd_info(const std::string& path, int argc, char** argv) {
+    static const char* const shortNames[][2] = {{"-t", "transcripts"}, {"-i", "index"}, {"-l", "libType"}, {"-o", "output"}, {"-r", "unmatedReads"},
+                                                {"-1", "mates1"}, {"-2", "mates2"}, {"-p", "threads"}, {"-g", "geneMap"}, {"-k", "kmerLen"},
+                                                {"-w", "maxReadOcc"}, {"-f", "force"}, {"-q", "quantFile"}};
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return;
+    fprintf(f, "{\n    \"sf_version\": \"0.10.0-b200\"");
+    for (int i = 1; i < argc; ++i) {
+        const std::string o = argv[i];
+        if (o.size() < 2 || o[0] != '-') continue;                             // the sub-command word
+        std::string key = o.compare(0, 2, "--") == 0 ? o.substr(2) : o;
+        for (const auto& sn : shortNames) if (o == sn[0]) key = sn[1];
+        std::vector<std::string> vals;
+        auto is_option = [](const char* t) {                                   // "-1" / "-2" are options, other "-<digit>..." tokens are numbers
+            return t[0] == '-' && t[1] != '\0' && (!std::isdigit((unsigned char)t[1]) || ((t[1] == '1' || t[1] == '2') && t[2] == '\0'));
+        };
+        while (i + 1 < argc && !is_option(argv[i + 1])) vals.push_back(argv[++i]);
+        fprintf(f, ",\n    \"%s\": ", json_escape(key).c_str());
+        if (vals.size() == 1) fprintf(f, "\"%s\"", json_escape(vals[0]).c_str());
+        else {
+            fprintf(f, "[");
+            for (size_t v = 0; v < vals.size(); ++v) fprintf(f, "%s\"%s\"", v ? ", " : "", json_escape(vals[v]).c_str());
+            fprintf(f, "]");
+        }
+    }
+    fprintf(f, "\n}\n");
+    fclose(f);
+}
 
 // writeVectorToFile (src/GZipWriter.cpp:23-43): the raw elements, gzip level 6
 template <typename T>
@@ -633,6 +670,7 @@ int main(int argc, char** argv) {
                                                           !paired_files, a.sopt.noEffectiveLengthCorrection, a.fldMean, a.fldSD, a.sopt.useUnsmoothedFLD);
         for (size_t i = 0; i < eff.size(); ++i) ex.txps[i].EffectiveLength = eff[i];
         make_dir(a.out);
+        write_cmd_info(a.out + "/cmd_info.json", argc, argv);
         const std::string aux = a.out + "/" + a.auxDir;
         make_dir(aux);
         if (a.dumpEq) write_eq_classes(aux + "/eq_classes.txt", ex, eqBuilder);

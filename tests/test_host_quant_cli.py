@@ -241,6 +241,9 @@ def test_driver_host_flow_with_stub_device(tmp_path):
     assert (vec("o1", "expected_bias.gz", np.float64) == 1.0).all() and len(vec("o1", "expected_gc.gz", np.float64)) == 101
     boots = np.frombuffer(gzip.open(tmp_path / "o1" / "aux" / "bootstrap" / "bootstraps.gz").read(), dtype=np.float64)
     assert boots.tolist() == [1.0] * 3 + [2.0] * 3
+    cmd = json.load(open(tmp_path / "o1" / "cmd_info.json"))                                                     # SailfishQuantify.cpp:1262-1276
+    assert cmd["transcripts"] == str(fa) and cmd["libType"] == "IU" and cmd["mates1"] == str(tmp_path / "r1.fq") and cmd["output"] == str(tmp_path / "o1")
+    assert cmd["dumpEq"] == [] and cmd["numBootstraps"] == "2" and list(cmd)[0] == "sf_version"
     # --unsmoothedFLD
     calls, rows, meta = run(["--unsmoothedFLD", "--useVBOpt"], "o2")
     assert calls[3].startswith("em_run 3 vb=1 eff0=202.0000")                                                  # mean of 180..218, float pdf
