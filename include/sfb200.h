@@ -97,6 +97,16 @@ int sfb200_map_batch(sfb200_ctx* ctx, const char* bases1, const uint64_t* off1, 
 /* Same with buffers already resident in device memory. */
 int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
                             const uint64_t* d_off2, uint64_t n_reads);
+/* Read ingestion on the device (replaces the parser threads of quasiMapReads, src/SailfishQuantify.cpp:882-898,
+ * 996-1005, include/PairSequenceParser.hpp:28-191, for plain four-line FASTQ).  text1 (and text2 for a paired library) = a block of
+ * FASTQ TEXT in HOST memory that starts at a record boundary; its complete records -- at most max_records (0 = no limit), the same
+ * number from both mates -- are extracted on the GPU and mapped as by sfb200_map_batch.  *n_records = how many, *consumed1/2 = the
+ * bytes of text they cover: the caller keeps text[consumed ..) and puts it in front of what it reads next.  A final record
+ * without a trailing newline needs one appended.  Gzipped input is inflated by the caller first.
+ * Not yet run on a GPU (parity test: tests/test_gpu_map.py with SFB200_EXPERIMENTAL=1; CPU check of the arithmetic:
+ * tests/fastq_core_test.cpp). */
+int sfb200_map_fastq(sfb200_ctx* ctx, const char* text1, uint64_t n1, const char* text2, uint64_t n2, uint64_t max_records,
+                     uint64_t* n_records, uint64_t* consumed1, uint64_t* consumed2);
 /* --biasCorrect / --gcBiasCorrect: collect, while mapping, what the reference collects in processReadsQuasi
  * (src/SailfishQuantify.cpp:255-287 and :555-583: the 6-mer context around the start of each read's first hit that has one,
  * readBias().update, for the first num_bias_samples such reads in read order -- sfOpts.numBiasSamples, the reference at -p 1;

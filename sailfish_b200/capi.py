@@ -86,6 +86,7 @@ SIGNATURES = {
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
     "sfb200_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint64]),
     "sfb200_map_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "sfb200_map_fastq": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, u64p, u64p, u64p]),
     "sfb200_map_set_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32]),
     "sfb200_map_get_bias": (C.c_int, [C.c_void_p, u32p, u32p]),
     "sfb200_map_finish": (C.c_int, [C.c_void_p, u64p, u32p, u64p, u64p]),
@@ -264,6 +265,13 @@ class Context:
         else:
             self._chk(f(self.h, C.c_void_p(p_bases1), C.cast(C.c_void_p(p_off1), u64p), C.c_void_p(p_bases2) if p_bases2 else None,
                         C.cast(C.c_void_p(p_off2), u64p) if p_off2 else None, n))
+
+    def map_fastq(self, text1, text2=None, max_records=0):
+        """FASTQ TEXT (bytes, starting at a record boundary) -> extracted and mapped on the device; -> (records, consumed1, consumed2)"""
+        n = C.c_uint64(); c1 = C.c_uint64(); c2 = C.c_uint64()
+        self._chk(self.L.sfb200_map_fastq(self.h, text1, len(text1), text2, len(text2) if text2 is not None else 0, int(max_records),
+                                          C.byref(n), C.byref(c1), C.byref(c2) if text2 is not None else None))
+        return n.value, c1.value, c2.value
 
     def map_set_bias(self, seq_bias=True, gc_bias=False, num_bias_samples=1000000):
         """collect the bias / GC samples while mapping (after map_begin, before the first batch)"""

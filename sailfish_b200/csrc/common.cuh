@@ -159,6 +159,7 @@ struct sfb200_ctx {
     DevBuf<double> em_base;             // n_txp (initial value of every output buffer: single counts (+ prior))
     DevBuf<unsigned long long> em_ctl;  // control block of the persistent kernel
     DevBuf<double> eff;                 // n_txp clamped effective lengths
+    void* fastq = nullptr;              // fastq.cu: staging buffers of the device-side FASTQ extraction
 };
 
 int sfb_comm_allreduce_f64(sfb200_ctx* ctx, double* d_buf, size_t n);
@@ -166,6 +167,7 @@ int sfb_comm_allreduce_u64(sfb200_ctx* ctx, unsigned long long* d_buf, size_t n)
 int sfb_comm_allgather(sfb200_ctx* ctx, const void* send, void* recv, size_t bytes);
 void sfb_map_state_free(sfb200_ctx* ctx);
 void sfb_em_extra_free(sfb200_ctx* ctx);
+void sfb_fastq_free(sfb200_ctx* ctx);
 int sfb_classes_from_host(sfb200_ctx* ctx, uint32_t n_txp, uint64_t E, const uint64_t* row_ptr, const uint32_t* labels,
                           const uint64_t* counts);
 int sfb_classes_host(sfb200_ctx* ctx);   // make cls.h_* valid (downloads + sorts after a device-side finish)

@@ -347,7 +347,7 @@ struct Args {
     std::vector<std::string> unmated, mates1, mates2;
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int k = 31, device = 0;
-    bool dumpEq = false, parseOnly = false, noChecksum = false;
+    bool dumpEq = false, parseOnly = false, noChecksum = false, deviceParse = false;
     size_t batch = 1u << 21, blockBytes = 0;             // 0: 2 MB of text per parser thread and block
     SailfishOpts sopt;
     sfb200_map_opts mopt;
@@ -373,6 +373,7 @@ struct Args {
             "  --txpAggregationKey KEY    GTF attribute that names the gene (gene_id)\n"
             "  --maxFragLen N (1000)  --numFragSamples N (10000)  --fldMean M (200)  --fldSD S (80)  -w, --maxReadOcc N (200)\n"
             "  --strictIntersect  --ignoreLibCompat  --enforceLibCompat  --allowDovetail  --discardOrphans  --auxDir NAME\n"
+            "  --deviceParse              send the FASTQ text to the GPU as it is and find the reads there (plain four-line FASTQ only)\n"
             "  --parseOnly                only parse the read files and print record / base counts (no GPU needed)\n");
     exit(msg ? 2 : 0);
 }
@@ -434,11 +435,86 @@ Args parse_args(int argc, char** argv) {
         else if (o == "--batchReads") a.batch = (size_t)std::max(1, atoi(need(o).c_str()));
         else if (o == "--blockBytes") a.blockBytes = (size_t)std::max(0, atoi(need(o).c_str()));    // parser block size (tests); 0 = default
         else if (o == "--parseOnly") a.parseOnly = true;
+        else if (o == "--deviceParse") a.deviceParse = true;                   // FASTQ text is parsed on the GPU (sfb200_map_fastq)
         else if (o == "--noChecksum") a.noChecksum = true;                     // with --parseOnly: count only (parser throughput)
         else usage(("unknown option " + o).c_str());
     }
     if (a.discardOrphans) a.mopt.allow_orphans = 0;                       // SailfishQuantify.cpp:1204
     return a;
+}
+
+// ---- read ingestion on the device (--deviceParse): the host only reads the files; sfb200_map_fastq finds the records -----------------
+// One mate's text: the files one after another (records do not span files; a file whose last line lacks its newline gets one),
+// read block-wise behind whatever the previous call left unconsumed.
+class RawTextStream {
+public:
+    explicit RawTextStream(const std::vector<std::string>& files) : files_(files) {}
+    ~RawTextStream() { if (fd_ >= 0) ::close(fd_); }
+    // top the buffer up to about `want` bytes; false when nothing is left at all
+    bool fill(size_t want) {
+        while (buf_.size() < want && !done_) {
+            if (fd_ < 0) {
+                if (next_ >= files_.size()) { done_ = true; break; }
+                fd_ = ::open(files_[next_].c_str(), O_RDONLY);
+                if (fd_ < 0) throw std::runtime_error("cannot open " + files_[next_]);
+                unsigned char magic[2] = {0, 0};
+                if (::pread(fd_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
+                    throw std::runtime_error(files_[next_] + ": --deviceParse reads plain FASTQ text; inflate gzipped files first (or drop the option)");
+                pos_ = 0;
+            }
+            const size_t old = buf_.size(), room = want - old;
+            buf_.resize(old + room);
+            const ssize_t r = ::pread(fd_, &buf_[old], room, (off_t)pos_);
+            if (r < 0) throw std::runtime_error("read error in " + files_[next_]);
+            buf_.resize(old + (size_t)r);
+            pos_ += (uint64_t)r;
+            if (r == 0) {                                                      // end of this file
+                if (!buf_.empty() && buf_.back() != '\n') buf_.push_back('\n');
+                ::close(fd_); fd_ = -1; ++next_;
+            }
+        }
+        return !buf_.empty();
+    }
+    const char* data() const { return buf_.data(); }
+    size_t size() const { return buf_.size(); }
+    bool exhausted() const { return done_; }
+    void consume(size_t n) { buf_.erase(0, n); }
+    bool only_whitespace() const { for (char ch : buf_) if (ch != '\n' && ch != '\r' && ch != ' ') return false; return true; }
+
+private:
+    std::vector<std::string> files_;
+    size_t next_ = 0;
+    int fd_ = -1;
+    uint64_t pos_ = 0;
+    bool done_ = false;
+    std::string buf_;
+};
+
+// all reads of a library through sfb200_map_fastq; returns the number of fragments
+uint64_t map_fastq_files(sfb200::Device& dev, const std::vector<std::string>& f1, const std::vector<std::string>& f2, size_t blockBytes) {
+    const bool paired = !f2.empty();
+    RawTextStream s1(f1), s2(f2);
+    size_t want = blockBytes ? blockBytes : (size_t)256 << 20;
+    uint64_t total = 0;
+    for (;;) {
+        const bool have1 = s1.fill(want), have2 = paired ? s2.fill(want) : false;
+        if (!have1 && !have2) break;
+        uint64_t n = 0, c1 = 0, c2 = 0;
+        dev.check(sfb200_map_fastq(dev.get(), s1.data(), s1.size(), paired ? s2.data() : nullptr, paired ? s2.size() : 0, 0, &n, &c1, paired ? &c2 : nullptr));
+        if (n == 0) {
+            if (s1.exhausted() && (!paired || s2.exhausted())) {               // no complete record is left
+                if (!s1.only_whitespace() || (paired && !s2.only_whitespace()))
+                    throw std::runtime_error(paired && s1.only_whitespace() != s2.only_whitespace() ? "mate files hold different numbers of reads" : "truncated record at end of file");
+                break;
+            }
+            want *= 2;                                                         // a record longer than the block (or one mate far behind)
+            continue;
+        }
+        total += n;
+        s1.consume((size_t)c1);
+        if (paired) s2.consume((size_t)c2);
+    }
+    return total;
 }
 
 // ---- read ingestion: a producer thread parses the next batch while the current one is copied to the device and mapped ------------
@@ -643,7 +719,9 @@ int main(int argc, char** argv) {
         sfb200::EquivalenceClassBuilder eqBuilder(dev);
         eqBuilder.start(a.mopt);
         if (doBias) eqBuilder.collectBias(a.sopt.biasCorrect, a.sopt.gcBiasCorrect, a.sopt.numBiasSamples);
-        {
+        if (a.deviceParse) {
+            map_fastq_files(dev, f1, a.mates2, a.blockBytes);
+        } else {
             BatchPipe pipe(f1, a.mates2, a.batch, a.threads, a.blockBytes);
             while (std::unique_ptr<PairBatch> b = pipe.pop()) {
                 const size_t n = b->m1.size();

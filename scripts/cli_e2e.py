@@ -20,6 +20,7 @@ ap.add_argument("--genes", type=int, default=40000)
 ap.add_argument("--reads", type=int, default=4_000_000)
 ap.add_argument("--dir", default="/dev/shm/sfb200_cli")
 ap.add_argument("--threads", type=int, default=0)
+ap.add_argument("--device-parse", action="store_true", help="pass --deviceParse: FASTQ text parsed on the GPU (sfb200_map_fastq)")
 a = ap.parse_args()
 os.makedirs(a.dir, exist_ok=True)
 seq, off, ln = synth.make_transcriptome(a.genes, seed=42)
@@ -52,6 +53,8 @@ exe = os.path.join(ROOT, "sailfish_b200", "bin", "sfb200-quant")
 cmd = [exe, "quant", "-t", fa, "-l", "U", "-r", fq, "-o", os.path.join(a.dir, "out")]
 if a.threads:
     cmd += ["-p", str(a.threads)]
+if a.device_parse:
+    cmd += ["--deviceParse"]
 t0 = time.time()
 r = subprocess.run(cmd, capture_output=True, text=True)
 dt = time.time() - t0
@@ -59,7 +62,7 @@ log = r.stderr
 m_idx = re.search(r"index built in ([0-9.]+) s", log)
 m_map = re.search(r"equivalence classes, ([0-9.]+) s", log)
 m_tot = re.search(r"\(([0-9.]+) s in total\)", log)
-out = {"rc": r.returncode, "reads": a.reads, "transcripts": int(len(ln)), "fastq_bytes": os.path.getsize(fq), "wall_s": dt,
+out = {"rc": r.returncode, "device_parse": bool(a.device_parse), "reads": a.reads, "transcripts": int(len(ln)), "fastq_bytes": os.path.getsize(fq), "wall_s": dt,
        "transcripts_and_index_s": float(m_idx.group(1)) if m_idx else None, "ingest_and_map_s": float(m_map.group(1)) if m_map else None,
        "total_s": float(m_tot.group(1)) if m_tot else None}
 if m_map:

@@ -13,5 +13,9 @@ for f in tests/test_gpu_bias.py tests/test_gpu_map.py tests/test_gpu_em_gather.p
 done
 timeout 600 python scripts/bench_bias.py > $OUT/${TAG}_bench_bias.json 2> $OUT/${TAG}_bench_bias.log
 echo "bench_bias rc=$?  ($(( $(date +%s) - t0 )) s)"; cat $OUT/${TAG}_bench_bias.json
+timeout 600 python scripts/cli_e2e.py --reads 4000000 > $OUT/${TAG}_cli_e2e_host_parse.json 2> $OUT/${TAG}_cli_e2e_host_parse.log
+echo "cli e2e (host parser) rc=$?  ($(( $(date +%s) - t0 )) s)"; cat $OUT/${TAG}_cli_e2e_host_parse.json
+timeout 600 python scripts/cli_e2e.py --reads 4000000 --device-parse > $OUT/${TAG}_cli_e2e_device_parse.json 2> $OUT/${TAG}_cli_e2e_device_parse.log
+echo "cli e2e (--deviceParse) rc=$?  ($(( $(date +%s) - t0 )) s)"; cat $OUT/${TAG}_cli_e2e_device_parse.json
 SFB200_EM_DENSE_GROUP=0 timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench_dense0.json 2> $OUT/${TAG}_bench_dense0.log
 echo "bench (balanced dense) rc=$?  ($(( $(date +%s) - t0 )) s)"; python scripts/show_bench.py $OUT/${TAG}_bench_dense0.json

@@ -29,6 +29,23 @@ int sfb200_index_build(sfb200_ctx* c, const char*, const uint64_t*, const uint32
 int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) { c->max_frag_len = o->max_frag_len; c->reads = 0; logf("map_begin %d", o->lib_format_id); return SFB200_OK; }
 int sfb200_map_set_bias(sfb200_ctx*, int s, int g, int32_t n) { logf("map_set_bias %d %d %d", s, g, n); return SFB200_OK; }
 int sfb200_map_batch(sfb200_ctx* c, const char*, const uint64_t*, const char* b2, const uint64_t*, uint64_t n) { c->reads += n; logf("map_batch %llu %d", (unsigned long long)n, b2 ? 1 : 0); return SFB200_OK; }
+// records = complete four-line groups; *consumed = the bytes the first n of them cover
+static uint64_t stub_records(const char* t, uint64_t n) { uint64_t nl = 0; for (uint64_t i = 0; i < n; ++i) nl += t[i] == '\n'; return nl / 4; }
+static uint64_t stub_consumed(const char* t, uint64_t n, uint64_t recs) { uint64_t nl = 0; for (uint64_t i = 0; i < n; ++i) if (t[i] == '\n' && ++nl == 4 * recs) return i + 1; return 0; }
+int sfb200_map_fastq(sfb200_ctx* c, const char* t1, uint64_t n1, const char* t2, uint64_t n2, uint64_t max_records, uint64_t* n_records, uint64_t* c1, uint64_t* c2) {
+    uint64_t n = stub_records(t1, n1);
+    if (t2) { const uint64_t m = stub_records(t2, n2); if (m < n) n = m; }
+    if (max_records && n > max_records) n = max_records;
+    *n_records = n; *c1 = stub_consumed(t1, n1, n);
+    if (t2) *c2 = stub_consumed(t2, n2, n);
+    for (uint64_t i = 0, line = 0; n && i < *c1; ++i) {                       // the driver must hand over text that starts at a record boundary
+        if (line % 4 == 0 && (i == 0 || t1[i - 1] == '\n') && t1[i] != '@') { logf("map_fastq BAD_START at %llu", (unsigned long long)i); return SFB200_EINVAL; }
+        if (t1[i] == '\n') ++line;
+    }
+    c->reads += n;
+    logf("map_fastq %llu %llu %llu paired=%d", (unsigned long long)n, (unsigned long long)*c1, (unsigned long long)(t2 ? *c2 : 0), t2 ? 1 : 0);
+    return SFB200_OK;
+}
 int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* fld, uint64_t* E, uint64_t* nnz) {
     const uint64_t v[6] = {c->reads, 3, 5, 4, 2, 1};
     std::memcpy(counters, v, sizeof v);

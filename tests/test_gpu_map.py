@@ -249,3 +249,61 @@ def test_bias_samples_match_oracle(ctx, paired, libtype, seq_bias, gc_bias, n_sa
         assert int(og.sum()) - 101 > 5000
     else:
         assert int(og.sum()) == 101
+
+
+@_experimental
+@pytest.mark.parametrize("paired,eol,block", [(True, "\n", 0), (True, "\r\n", 300000), (False, "\n", 70000), (True, "\n", 9000)])
+def test_map_fastq_equals_map_batch(ctx, paired, eol, block):
+    """sfb200_map_fastq (FASTQ text parsed on the device, fastq.cu) gives the classes, counters and FLD of sfb200_map_batch on the same
+    reads -- whole text at once and block-wise with the unconsumed tail carried over (mate 2 has longer headers, so its blocks hold
+    fewer records)"""
+    seq, off, ln = small_txome()
+    n, L = 12000, 100 if paired else 76
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, n, L, seed=31, paired=paired, sub_rate=0.01, n_rate=0.002)
+
+    def text(bases, offs, long_names):
+        recs = []
+        for i in range(n):
+            s_ = bases[int(offs[i]):int(offs[i + 1])].tobytes().decode()
+            recs.append("@r%d%s%s%s%s+%s%s%s" % (i, " description of the read" * 2 if long_names else "", eol, s_, eol, eol, "@" * len(s_), eol))
+        return "".join(recs).encode()
+
+    t1 = text(b1, o1, False)
+    t2 = text(b2, o2, True) if paired else None
+    ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=31)
+    oix = O.Index(split_seqs(seq, ln), k=31)
+    fmt = O.parse_libtype("IU" if paired else "U")
+    run = O.Run(oix, O.MapOpts.default(fmt))
+    if paired:
+        run.map_batch(b1.tobytes(), o1, b2.tobytes(), o2, n_threads=4)
+    else:
+        run.map_batch(b1.tobytes(), o1, n_threads=4)
+    w = run.finish()
+    ctx.map_begin(capi.MapOpts.default(fmt))
+    if block == 0:
+        got, c1, c2 = ctx.map_fastq(t1, t2)
+        assert got == n and c1 == len(t1) and (not paired or c2 == len(t2))
+    else:
+        p1 = p2 = 0
+        buf1 = buf2 = b""
+        total = calls = 0
+        while True:
+            take1 = max(0, block - len(buf1)); buf1 += t1[p1:p1 + take1]; p1 += take1
+            if paired:
+                take2 = max(0, block - len(buf2)); buf2 += t2[p2:p2 + take2]; p2 += take2
+            if not buf1 and not buf2:
+                break
+            got, c1, c2 = ctx.map_fastq(buf1, buf2 if paired else None)
+            assert got > 0
+            total += got; calls += 1
+            buf1 = buf1[c1:]
+            if paired:
+                buf2 = buf2[c2:]
+        assert total == n and calls > 3
+    g = ctx.map_finish()
+    assert_same_classes(ctx, g, w)
+    # malformed text is refused
+    ctx.map_begin(capi.MapOpts.default(fmt))
+    with pytest.raises(capi.Sfb200Error):
+        ctx.map_fastq(b">a\nACGT\n>b\nGGCC\n", b">a\nACGT\n>b\nGGCC\n" if paired else None)
+    ctx.map_finish()

@@ -264,6 +264,59 @@ def test_driver_host_flow_with_stub_device(tmp_path):
     assert real.sum() == 10000 and abs(float((real * np.arange(1000)).sum()) / 10000 - 200) < 5
 
 
+def test_device_parse_feeding_with_stub_device(tmp_path):
+    """--deviceParse: the driver reads raw FASTQ text block-wise and carries what sfb200_map_fastq did not consume over to the next
+    block.  With the stub (tests/stub_sfb200.cpp: counts complete four-line records and checks that every block starts with '@'):
+    several files per mate, a last line without its newline, CRLF, tiny blocks, mates whose records differ in size."""
+    exe = str(tmp_path / "sfb200-quant-stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-Wall", "-pthread", "-o", exe, os.path.join(ROOT, "sailfish_b200", "host", "sfb200_quant.cpp"),
+                           os.path.join(ROOT, "tests", "stub_sfb200.cpp"), "-lz"])
+    fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 100 + "\n")
+    rng = np.random.default_rng(8)
+
+    def fastq(path, n, first, eol="\n", final_newline=True, long_names=False):
+        recs = []
+        for i in range(n):
+            L = int(rng.integers(30, 120))
+            name = "@read%d%s" % (first + i, " a much longer description of this read" * 3 if long_names else "")
+            recs.append(name + eol + "ACGT" * (L // 4) + eol + "+" + eol + "@" * (L // 4 * 4) + eol)
+        text = "".join(recs)
+        path.write_text(text if final_newline else text[:-len(eol)], newline="")
+
+    fastq(tmp_path / "a1.fq", 700, 0); fastq(tmp_path / "a2.fq", 700, 0, long_names=True)              # mate 2 records are 4x larger
+    fastq(tmp_path / "b1.fq", 300, 700, final_newline=False); fastq(tmp_path / "b2.fq", 300, 700, eol="\r\n")
+    log = tmp_path / "log.txt"
+    env = dict(os.environ, SFB200_STUB_LOG=str(log))
+    for block in ("0", "4096", "700"):
+        if log.exists():
+            log.unlink()
+        subprocess.check_call([exe, "quant", "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "a1.fq"), str(tmp_path / "b1.fq"), "-2", str(tmp_path / "a2.fq"),
+                               str(tmp_path / "b2.fq"), "-o", str(tmp_path / ("o" + block)), "--deviceParse", "--blockBytes", block], env=env, stderr=subprocess.DEVNULL)
+        calls = [l for l in log.read_text().strip().split("\n") if l.startswith("map_fastq")]
+        assert not any("BAD_START" in c for c in calls)
+        assert sum(int(c.split()[1]) for c in calls) == 1000 and all(c.endswith("paired=1") for c in calls)
+        assert sum(int(c.split()[2]) for c in calls) == (tmp_path / "a1.fq").stat().st_size + (tmp_path / "b1.fq").stat().st_size + 1     # + the appended newline
+        assert json.load(open(tmp_path / ("o" + block) / "aux" / "meta_info.json"))["num_processed"] == 1000
+        if block != "0":
+            assert len(calls) > 10
+    # single-end; a truncated file and mates of different length are errors
+    log.unlink()
+    subprocess.check_call([exe, "quant", "-t", str(fa), "-l", "U", "-r", str(tmp_path / "a1.fq"), "-o", str(tmp_path / "os"), "--deviceParse", "--blockBytes", "5000"],
+                          env=env, stderr=subprocess.DEVNULL)
+    assert sum(int(l.split()[1]) for l in log.read_text().strip().split("\n") if l.startswith("map_fastq")) == 700
+    whole = (tmp_path / "a1.fq").read_text()
+    (tmp_path / "trunc.fq").write_text(whole[:whole.rindex("@read") + 20])                      # the last record stops inside its sequence line
+    r = subprocess.run([exe, "quant", "-t", str(fa), "-l", "U", "-r", str(tmp_path / "trunc.fq"), "-o", str(tmp_path / "ot"), "--deviceParse"], env=env, capture_output=True)
+    assert r.returncode == 1 and b"truncated record" in r.stderr
+    r = subprocess.run([exe, "quant", "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "b2.fq"), "-o", str(tmp_path / "om"), "--deviceParse"],
+                       env=env, capture_output=True)
+    assert r.returncode == 1 and b"different numbers of reads" in r.stderr
+    with gzip.open(tmp_path / "z.fq.gz", "wt") as f:
+        f.write((tmp_path / "a1.fq").read_text())
+    r = subprocess.run([exe, "quant", "-t", str(fa), "-l", "U", "-r", str(tmp_path / "z.fq.gz"), "-o", str(tmp_path / "oz"), "--deviceParse"], env=env, capture_output=True)
+    assert r.returncode == 1 and b"inflate gzipped files first" in r.stderr
+
+
 def test_bias_option_checks(tmp_path):
     """SailfishQuantify.cpp:1293-1309: the two corrections exclude each other; GC correction is switched off for single-end libraries"""
     fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 30 + "\n")

@@ -32,3 +32,13 @@ def test_parser_matches_python(tmp_path_factory, seqs, crlf, final_nl, fasta, bl
     got = json.loads(out)
     assert got["records"] == len(seqs) and got["bases1"] == sum(map(len, seqs))
     assert got["fnv1a"] == fnv(seqs, [])
+
+
+def test_device_fastq_extraction_arithmetic(tmp_path):
+    """sailfish_b200/csrc/fastq_core.inl (the per-chunk bodies of k_fq_count / k_fq_mark / k_fq_copy) compiled as host code and
+    replayed over random FASTQ text -- see tests/fastq_core_test.cpp"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fastq_core_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(root, "tests", "fastq_core_test.cpp")])
+    assert "fastq core ok" in subprocess.check_output([exe]).decode()
