@@ -448,11 +448,14 @@ Args parse_args(int argc, char** argv) {
 // read block-wise behind whatever the previous call left unconsumed.
 class RawTextStream {
 public:
-    explicit RawTextStream(const std::vector<std::string>& files) : files_(files) {}
-    ~RawTextStream() { if (fd_ >= 0) ::close(fd_); }
+    RawTextStream(const std::vector<std::string>& files, unsigned threads) : files_(files), threads_(threads ? threads : 1) {}
+    ~RawTextStream() { if (fd_ >= 0) ::close(fd_); if (buf_) sfb200_host_free(buf_); }
+    RawTextStream(const RawTextStream&) = delete;
+    RawTextStream& operator=(const RawTextStream&) = delete;
     // top the buffer up to about `want` bytes; false when nothing is left at all
     bool fill(size_t want) {
-        while (buf_.size() < want && !done_) {
+        reserve(want + 1);
+        while (size_ < want && !done_) {
             if (fd_ < 0) {
                 if (next_ >= files_.size()) { done_ = true; break; }
                 fd_ = ::open(files_[next_].c_str(), O_RDONLY);
@@ -460,40 +463,69 @@ public:
                 unsigned char magic[2] = {0, 0};
                 if (::pread(fd_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
                     throw std::runtime_error(files_[next_] + ": --deviceParse reads plain FASTQ text; inflate gzipped files first (or drop the option)");
-                pos_ = 0;
+                struct stat st;
+                if (fstat(fd_, &st) != 0 || !S_ISREG(st.st_mode)) throw std::runtime_error(files_[next_] + ": --deviceParse needs a regular file");
+                file_size_ = (uint64_t)st.st_size; pos_ = 0;
             }
-            const size_t old = buf_.size(), room = want - old;
-            buf_.resize(old + room);
-            const ssize_t r = ::pread(fd_, &buf_[old], room, (off_t)pos_);
-            if (r < 0) throw std::runtime_error("read error in " + files_[next_]);
-            buf_.resize(old + (size_t)r);
-            pos_ += (uint64_t)r;
-            if (r == 0) {                                                      // end of this file
-                if (!buf_.empty() && buf_.back() != '\n') buf_.push_back('\n');
+            const size_t room = (size_t)std::min<uint64_t>(want - size_, file_size_ - pos_);
+            read_exact(buf_ + size_, room, pos_);
+            size_ += room; pos_ += room;
+            if (pos_ == file_size_) {                                          // end of this file
+                if (size_ > 0 && buf_[size_ - 1] != '\n') buf_[size_++] = '\n';   // reserve() keeps one byte of room for this
                 ::close(fd_); fd_ = -1; ++next_;
             }
         }
-        return !buf_.empty();
+        return size_ > 0;
     }
-    const char* data() const { return buf_.data(); }
-    size_t size() const { return buf_.size(); }
+    const char* data() const { return buf_; }
+    size_t size() const { return size_; }
     bool exhausted() const { return done_; }
-    void consume(size_t n) { buf_.erase(0, n); }
-    bool only_whitespace() const { for (char ch : buf_) if (ch != '\n' && ch != '\r' && ch != ' ') return false; return true; }
+    void consume(size_t n) { if (n < size_) std::memmove(buf_, buf_ + n, size_ - n); size_ -= n; }
+    bool only_whitespace() const { for (size_t i = 0; i < size_; ++i) if (buf_[i] != '\n' && buf_[i] != '\r' && buf_[i] != ' ') return false; return true; }
 
 private:
+    // page-locked memory: the H2D copy of a block runs at the PCIe rate instead of being staged through the driver's bounce buffers
+    void reserve(size_t n) {
+        n += files_.size() + 1;                                                // a newline may be appended per file
+        if (n <= cap_) return;
+        char* nb = static_cast<char*>(sfb200_host_alloc(n));
+        if (!nb) throw std::runtime_error("cannot allocate page-locked host memory for the FASTQ text");
+        if (size_) std::memcpy(nb, buf_, size_);
+        if (buf_) sfb200_host_free(buf_);
+        buf_ = nb; cap_ = n;
+    }
+    // large reads are split over a few threads (one pread stream does not saturate a page cache, let alone an NVMe array)
+    void read_exact(char* dst, size_t n, uint64_t pos) {
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, n >> 24));      // at least 16 MB per thread
+        std::vector<std::thread> th;
+        std::vector<int> bad(nt, 0);
+        auto part = [&](unsigned t) {
+            size_t a = n * t / nt; const size_t b = n * (t + 1) / nt;
+            while (a < b) {
+                const ssize_t r = ::pread(fd_, dst + a, b - a, (off_t)(pos + a));
+                if (r <= 0) { bad[t] = 1; return; }
+                a += (size_t)r;
+            }
+        };
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(part, t);
+        part(0);
+        for (std::thread& x : th) x.join();
+        for (int b : bad) if (b) throw std::runtime_error("read error in " + files_[next_]);
+    }
     std::vector<std::string> files_;
+    unsigned threads_;
     size_t next_ = 0;
     int fd_ = -1;
-    uint64_t pos_ = 0;
+    uint64_t pos_ = 0, file_size_ = 0;
     bool done_ = false;
-    std::string buf_;
+    char* buf_ = nullptr;
+    size_t cap_ = 0, size_ = 0;
 };
 
 // all reads of a library through sfb200_map_fastq; returns the number of fragments
-uint64_t map_fastq_files(sfb200::Device& dev, const std::vector<std::string>& f1, const std::vector<std::string>& f2, size_t blockBytes) {
+uint64_t map_fastq_files(sfb200::Device& dev, const std::vector<std::string>& f1, const std::vector<std::string>& f2, size_t blockBytes, unsigned threads) {
     const bool paired = !f2.empty();
-    RawTextStream s1(f1), s2(f2);
+    RawTextStream s1(f1, threads), s2(f2, threads);
     size_t want = blockBytes ? blockBytes : (size_t)256 << 20;
     uint64_t total = 0;
     for (;;) {
@@ -720,7 +752,7 @@ int main(int argc, char** argv) {
         eqBuilder.start(a.mopt);
         if (doBias) eqBuilder.collectBias(a.sopt.biasCorrect, a.sopt.gcBiasCorrect, a.sopt.numBiasSamples);
         if (a.deviceParse) {
-            map_fastq_files(dev, f1, a.mates2, a.blockBytes);
+            map_fastq_files(dev, f1, a.mates2, a.blockBytes, a.threads);
         } else {
             BatchPipe pipe(f1, a.mates2, a.batch, a.threads, a.blockBytes);
             while (std::unique_ptr<PairBatch> b = pipe.pop()) {
