@@ -444,65 +444,140 @@ Args parse_args(int argc, char** argv) {
 }
 
 // ---- read ingestion on the device (--deviceParse): the host only reads the files; sfb200_map_fastq finds the records -----------------
-// One mate's text: the files one after another (records do not span files; a file whose last line lacks its newline gets one),
-// read block-wise behind whatever the previous call left unconsumed.
+// One mate's text, the files one after another (records do not span files; a file whose last line lacks its newline gets one).
+// A reader thread fills page-locked blocks ahead of the device (H2D from page-locked memory runs at the PCIe rate, and the next
+// block is read while the current one is extracted and mapped).  Every block has `head` free bytes in front of its data: the
+// part of the previous block that sfb200_map_fastq did not consume (an incomplete record, or records the other mate had no
+// partner for yet) is copied there, so the device always sees one contiguous text that starts at a record boundary.
 class RawTextStream {
 public:
-    RawTextStream(const std::vector<std::string>& files, unsigned threads) : files_(files), threads_(threads ? threads : 1) {}
-    ~RawTextStream() { if (fd_ >= 0) ::close(fd_); if (buf_) sfb200_host_free(buf_); }
+    struct Block { char* mem = nullptr; size_t cap = 0, head = 0, len = 0; };
+    RawTextStream(const std::vector<std::string>& files, size_t block, unsigned threads)
+        : files_(files), block_(block), threads_(threads ? threads : 1), th_(&RawTextStream::produce, this) {}
+    ~RawTextStream() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        if (th_.joinable()) th_.join();
+        for (Block* b : all_) { if (b->mem) sfb200_host_free(b->mem); delete b; }
+    }
     RawTextStream(const RawTextStream&) = delete;
     RawTextStream& operator=(const RawTextStream&) = delete;
-    // top the buffer up to about `want` bytes; false when nothing is left at all
-    bool fill(size_t want) {
-        reserve(want + 1);
-        while (size_ < want && !done_) {
-            if (fd_ < 0) {
-                if (next_ >= files_.size()) { done_ = true; break; }
-                fd_ = ::open(files_[next_].c_str(), O_RDONLY);
-                if (fd_ < 0) throw std::runtime_error("cannot open " + files_[next_]);
-                unsigned char magic[2] = {0, 0};
-                if (::pread(fd_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
-                    throw std::runtime_error(files_[next_] + ": --deviceParse reads plain FASTQ text; inflate gzipped files first (or drop the option)");
-                struct stat st;
-                if (fstat(fd_, &st) != 0 || !S_ISREG(st.st_mode)) throw std::runtime_error(files_[next_] + ": --deviceParse needs a regular file");
-                file_size_ = (uint64_t)st.st_size; pos_ = 0;
-            }
-            const size_t room = (size_t)std::min<uint64_t>(want - size_, file_size_ - pos_);
-            read_exact(buf_ + size_, room, pos_);
-            size_ += room; pos_ += room;
-            if (pos_ == file_size_) {                                          // end of this file
-                if (size_ > 0 && buf_[size_ - 1] != '\n') buf_[size_++] = '\n';   // reserve() keeps one byte of room for this
-                ::close(fd_); fd_ = -1; ++next_;
-            }
+
+    const char* data() const { return cur_ ? cur_->mem + start_ : nullptr; }
+    size_t size() const { return len_; }
+    bool exhausted() const { return drained_; }
+    void consume(size_t n) { start_ += n; len_ -= n; }
+    bool only_whitespace() const { for (size_t i = 0; i < len_; ++i) { const char ch = data()[i]; if (ch != '\n' && ch != '\r' && ch != ' ') return false; } return true; }
+    // make more text available behind what is left: at least `min_len` bytes unless the files end first; false = nothing at all is left
+    bool fill(size_t min_len) {
+        while (len_ < min_len && !drained_) {
+            Block* nb = pop();
+            if (!nb) { drained_ = true; break; }
+            if (len_ > nb->head) nb = grow(nb, len_);                          // the carried text does not fit in front: rare, a bigger block
+            if (len_) std::memcpy(nb->mem + nb->head - len_, cur_->mem + start_, len_);
+            if (cur_) recycle(cur_);
+            cur_ = nb; start_ = nb->head - len_; len_ += nb->len;
         }
-        return size_ > 0;
+        return len_ > 0;
     }
-    const char* data() const { return buf_; }
-    size_t size() const { return size_; }
-    bool exhausted() const { return done_; }
-    void consume(size_t n) { if (n < size_) std::memmove(buf_, buf_ + n, size_ - n); size_ -= n; }
-    bool only_whitespace() const { for (size_t i = 0; i < size_; ++i) if (buf_[i] != '\n' && buf_[i] != '\r' && buf_[i] != ' ') return false; return true; }
 
 private:
-    // page-locked memory: the H2D copy of a block runs at the PCIe rate instead of being staged through the driver's bounce buffers
-    void reserve(size_t n) {
-        n += files_.size() + 1;                                                // a newline may be appended per file
-        if (n <= cap_) return;
-        char* nb = static_cast<char*>(sfb200_host_alloc(n));
-        if (!nb) throw std::runtime_error("cannot allocate page-locked host memory for the FASTQ text");
-        if (size_) std::memcpy(nb, buf_, size_);
-        if (buf_) sfb200_host_free(buf_);
-        buf_ = nb; cap_ = n;
+    Block* make(size_t head, size_t data_cap) {
+        Block* b = new Block();
+        b->cap = head + data_cap + files_.size() + 2;                          // a newline may be appended per file
+        b->mem = static_cast<char*>(sfb200_host_alloc(b->cap));
+        if (!b->mem) { delete b; throw std::runtime_error("cannot allocate page-locked host memory for the FASTQ text"); }
+        b->head = head; b->len = 0;
+        std::lock_guard<std::mutex> lk(mu_);
+        all_.push_back(b);
+        return b;
+    }
+    Block* grow(Block* nb, size_t need_head) {
+        Block* g = make(need_head, nb->len);
+        std::memcpy(g->mem + g->head, nb->mem + nb->head, nb->len);
+        g->len = nb->len;
+        recycle(nb);
+        return g;
+    }
+    Block* pop() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !ready_.empty() || eof_ || !err_.empty(); });
+        if (!err_.empty()) throw std::runtime_error(err_);
+        if (ready_.empty()) return nullptr;
+        Block* b = ready_.front();
+        ready_.erase(ready_.begin());
+        cv_.notify_all();
+        return b;
+    }
+    void recycle(Block* b) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (b->head == block_ && free_.size() < 3) free_.push_back(b);         // odd-sized (grown) blocks are simply kept until the end
+        cv_.notify_all();
+    }
+    void produce() {
+        try {
+            if (files_.empty()) { std::lock_guard<std::mutex> lk(mu_); eof_ = true; cv_.notify_all(); return; }
+            int fd = -1;
+            size_t next = 0;
+            uint64_t pos = 0, fsize = 0;
+            char last_char = '\n';
+            for (;;) {
+                Block* b = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    cv_.wait(lk, [&] { return stop_ || ready_.size() < 2; });
+                    if (stop_) break;
+                    if (!free_.empty()) { b = free_.back(); free_.pop_back(); }
+                }
+                if (!b) b = make(block_, block_);
+                b->len = 0;
+                bool more = true;
+                while (b->len < block_) {
+                    if (fd < 0) {
+                        if (next >= files_.size()) { more = false; break; }
+                        fd = ::open(files_[next].c_str(), O_RDONLY);
+                        if (fd < 0) throw std::runtime_error("cannot open " + files_[next]);
+                        unsigned char magic[2] = {0, 0};
+                        if (::pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b)
+                            throw std::runtime_error(files_[next] + ": --deviceParse reads plain FASTQ text; inflate gzipped files first (or drop the option)");
+                        struct stat st;
+                        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) throw std::runtime_error(files_[next] + ": --deviceParse needs a regular file");
+                        fsize = (uint64_t)st.st_size; pos = 0;
+                    }
+                    const size_t room = (size_t)std::min<uint64_t>(block_ - b->len, fsize - pos);
+                    char* dst = b->mem + b->head + b->len;
+                    read_exact(fd, dst, room, pos, files_[next]);
+                    if (room) last_char = dst[room - 1];
+                    b->len += room; pos += room;
+                    if (pos == fsize) {                                        // end of this file
+                        if (fsize > 0 && last_char != '\n') { b->mem[b->head + b->len++] = '\n'; last_char = '\n'; }
+                        ::close(fd); fd = -1; ++next;
+                    }
+                }
+                {
+                    std::lock_guard<std::mutex> lk(mu_);
+                    if (b->len) ready_.push_back(b); else free_.push_back(b);
+                    if (!more) eof_ = true;
+                }
+                cv_.notify_all();
+                if (!more) break;
+            }
+            if (fd >= 0) ::close(fd);
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu_);
+            err_ = e.what(); eof_ = true;
+            cv_.notify_all();
+        }
     }
     // large reads are split over a few threads (one pread stream does not saturate a page cache, let alone an NVMe array)
-    void read_exact(char* dst, size_t n, uint64_t pos) {
+    void read_exact(int fd, char* dst, size_t n, uint64_t pos, const std::string& name) {
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, n >> 24));      // at least 16 MB per thread
         std::vector<std::thread> th;
         std::vector<int> bad(nt, 0);
         auto part = [&](unsigned t) {
             size_t a = n * t / nt; const size_t b = n * (t + 1) / nt;
             while (a < b) {
-                const ssize_t r = ::pread(fd_, dst + a, b - a, (off_t)(pos + a));
+                const ssize_t r = ::pread(fd, dst + a, b - a, (off_t)(pos + a));
                 if (r <= 0) { bad[t] = 1; return; }
                 a += (size_t)r;
             }
@@ -510,38 +585,50 @@ private:
         for (unsigned t = 1; t < nt; ++t) th.emplace_back(part, t);
         part(0);
         for (std::thread& x : th) x.join();
-        for (int b : bad) if (b) throw std::runtime_error("read error in " + files_[next_]);
+        for (int b : bad) if (b) throw std::runtime_error("read error in " + name);
     }
+
     std::vector<std::string> files_;
+    size_t block_;
     unsigned threads_;
-    size_t next_ = 0;
-    int fd_ = -1;
-    uint64_t pos_ = 0, file_size_ = 0;
-    bool done_ = false;
-    char* buf_ = nullptr;
-    size_t cap_ = 0, size_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<Block*> ready_, free_, all_;
+    bool eof_ = false, stop_ = false;
+    std::string err_;
+    // consumer side
+    Block* cur_ = nullptr;
+    size_t start_ = 0, len_ = 0;
+    bool drained_ = false;
+    std::thread th_;                                                           // last member: starts when everything else exists
 };
 
 // all reads of a library through sfb200_map_fastq; returns the number of fragments
 uint64_t map_fastq_files(sfb200::Device& dev, const std::vector<std::string>& f1, const std::vector<std::string>& f2, size_t blockBytes, unsigned threads) {
     const bool paired = !f2.empty();
-    RawTextStream s1(f1, threads), s2(f2, threads);
-    size_t want = blockBytes ? blockBytes : (size_t)256 << 20;
+    const size_t block = blockBytes ? blockBytes : (size_t)64 << 20;          // x 2 (room in front) x up to 4 blocks per mate, page-locked
+    RawTextStream s1(f1, block, threads), s2(f2, block, threads);
+    size_t want = block;                                                       // a mate that is ahead (text left over) takes no new block
     uint64_t total = 0;
     for (;;) {
         const bool have1 = s1.fill(want), have2 = paired ? s2.fill(want) : false;
         if (!have1 && !have2) break;
         uint64_t n = 0, c1 = 0, c2 = 0;
-        dev.check(sfb200_map_fastq(dev.get(), s1.data(), s1.size(), paired ? s2.data() : nullptr, paired ? s2.size() : 0, 0, &n, &c1, paired ? &c2 : nullptr));
+        if (have1 && (!paired || have2))
+            dev.check(sfb200_map_fastq(dev.get(), s1.data(), s1.size(), paired ? s2.data() : nullptr, paired ? s2.size() : 0, 0, &n, &c1, paired ? &c2 : nullptr));
         if (n == 0) {
+            if (paired && ((s1.exhausted() && s1.only_whitespace()) != (s2.exhausted() && s2.only_whitespace())) &&
+                (s1.exhausted() || s2.exhausted()) && (s1.only_whitespace() != s2.only_whitespace()))
+                throw std::runtime_error("mate files hold different numbers of reads");
             if (s1.exhausted() && (!paired || s2.exhausted())) {               // no complete record is left
                 if (!s1.only_whitespace() || (paired && !s2.only_whitespace()))
                     throw std::runtime_error(paired && s1.only_whitespace() != s2.only_whitespace() ? "mate files hold different numbers of reads" : "truncated record at end of file");
                 break;
             }
-            want *= 2;                                                         // a record longer than the block (or one mate far behind)
+            want += block;                                                     // a record longer than the block (or one mate far behind)
             continue;
         }
+        want = block;
         total += n;
         s1.consume((size_t)c1);
         if (paired) s2.consume((size_t)c2);
