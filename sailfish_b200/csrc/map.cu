@@ -610,171 +610,21 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
 }
 
 // ---- finalize kernel: projection, mate merge, compatibility filter, label, class upsert -----------------------------------------
-// BIAS: additionally what --biasCorrect / --gcBiasCorrect collect per hit (SailfishQuantify.cpp:255-287, :372-389, :555-583): the
-// read-start context of the read's first hit that has one (p.bias_val, sampled in read order by k_bias_select) and the GC
-// percentage of every properly paired hit that lies inside its transcript (s_gc, the CTA's 101-bin histogram)
-template <bool BIAS>
-__device__ __forceinline__ void finalize_reads_body(const MapParams& p, unsigned int* s_gc) {
-    extern __shared__ uint64_t smem_reads[];
-    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const Scratch scr{p.scratch + gtid, p.n_threads_total};
-    const uint32_t cap = p.cap;
-    const uint32_t TMP0 = 0, LEFT0 = 2 * (cap + 1), RIGHT0 = 3 * (cap + 1);
-    const bool paired = p.n_mates == 2;
-    const int ns = 2 * p.n_mates;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
-    Read rds[2];
-    {
-        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * p.n_mates * 2 * RW * 32 + lane;
-        rds[0].sb = wbase;
-        rds[1].sb = wbase + (p.n_mates - 1) * 2 * RW * 32;
-    }
-    Interval ivs[4][MAX_IV];
-    int niv[4];
-    uint64_t score[4];
-
-    for (;;) {
-        unsigned long long base_idx = 0;
-        if (lane == 0) base_idx = atomicAdd(p.next_read + 1, 32ULL);
-        base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
-        if (base_idx >= p.n_reads) break;
-        const uint64_t ri = base_idx + lane;
-        if (ri < p.n_reads) {
-            uint32_t nL = 0, nR = 0;
-            bool okL, okR = true;
-            for (int mt = 0; mt < p.n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, ri * p.n_mates + mt, p.rwp, rds[mt]);
-            const uint32_t len1 = rds[0].len;
-            const uint32_t len2 = paired ? rds[1].len : 0;
-            for (int q = 0; q < ns; ++q) {
-                niv[q] = p.niv[ri * ns + q];
-                uint64_t sc = 0;
-                for (int e = 0; e < niv[q]; ++e) {
-                    ivs[q][e] = unpack_iv(p.iv[(ri * ns + q) * MAX_IV + e]);
-                    ivs[q][e].mask = p.ivmask[(ri * ns + q) * MAX_IV + e];
-                    sc += ivs[q][e].m;
-                }
-                score[q] = sc;
-            }
-            okL = collect(p.ix, rds[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, TMP0, LEFT0, nL);   // paired: strict check (:192-202)
-            if (paired) okR = collect(p.ix, rds[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, TMP0, RIGHT0, nR);
-            const bool overflow = !okL || !okR;
-            LabelAcc acc(scr, TMP0, p.enforce_compat != 0);
-            uint32_t n_joint = 0;
-            int32_t fl = -1;
-            int32_t bsample = -1;
-            if (!paired) {
-                // SailfishQuantify.cpp:530-631
-                n_joint = overflow ? 0 : nL;
-                c_ub += (overflow || n_joint > 0) ? 1 : 0;
-                for (uint32_t i = 0; i < n_joint; ++i) {
-                    const unsigned long long h = scr.at(LEFT0 + i);
-                    if (BIAS) { if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, hit_tid(h), hit_pos(h), hit_fwd(h), len1); }
-                    const bool compat = p.ignore_compat ? true : compat_single(p.lib_fmt, hit_fwd(h), 0);
-                    acc.add(hit_tid(h), compat, hit_fwd(h));
-                }
-            } else if (!overflow) {
-                // mergeLeftRightHits[Fuzzy] (call sites :204-213): one joint hit per transcript present in both lists
-                uint32_t i = 0, j = 0, n_pairs = 0;
-                while (i < nL && j < nR) {
-                    const uint32_t tl = hit_tid(scr.at(LEFT0 + i)), tr = hit_tid(scr.at(RIGHT0 + j));
-                    if (tl < tr) ++i; else if (tr < tl) ++j;
-                    else { ++n_pairs; ++i; while (i < nL && hit_tid(scr.at(LEFT0 + i)) == tl) ++i; while (j < nR && hit_tid(scr.at(RIGHT0 + j)) == tl) ++j; }
-                }
-                if (n_pairs > 0) {
-                    n_joint = n_pairs;
-                    c_ub += 1;
-                    i = 0; j = 0;
-                    while (i < nL && j < nR) {                                              // :341-369
-                        const unsigned long long hl = scr.at(LEFT0 + i), hr = scr.at(RIGHT0 + j);
-                        const uint32_t tl = hit_tid(hl), tr = hit_tid(hr);
-                        if (tl < tr) { ++i; continue; }
-                        if (tr < tl) { ++j; continue; }
-                        const int32_t pl = hit_pos(hl), pr = hit_pos(hr);
-                        const bool fl_ = hit_fwd(hl), fr_ = hit_fwd(hr);
-                        if (BIAS) {
-                            if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, tl, pl, fl_, len1);
-                            if (p.bias_gc) {                                                // :375-388
-                                const int32_t start = pl < pr ? pl : pr;
-                                const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
-                                const int32_t stop = e1 > e2 ? e1 : e2;                      // start + fragLen
-                                const uint64_t t0 = p.ix.txp_start[tl];
-                                if (start > 0 && stop < (int32_t)(p.ix.txp_end[tl] - t0)) atomicAdd(s_gc + b_gc_frac_range(p.ix.words, t0, start, stop), 1u);
-                            }
-                        }
-                        bool compat = p.ignore_compat != 0;
-                        if (!compat) {
-                            const uint32_t e1 = fl_ ? (uint32_t)pl : (uint32_t)pl + len1;
-                            const uint32_t e2 = fr_ ? (uint32_t)pr : (uint32_t)pr + len2;
-                            compat = compat_paired(p.lib_fmt, (int32_t)e1, fl_, len1, (int32_t)e2, fr_, len2, p.allow_dovetail != 0);
-                        }
-                        acc.add(tl, compat, fl_);
-                        if (n_pairs == 1) {
-                            const int32_t fs = pl < pr ? pl : pr;
-                            const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
-                            fl = (e1 > e2 ? e1 : e2) - fs;
-                        }
-                        ++i; while (i < nL && hit_tid(scr.at(LEFT0 + i)) == tl) ++i; while (j < nR && hit_tid(scr.at(RIGHT0 + j)) == tl) ++j;
-                    }
-                } else if (!p.strict_intersect && nL + nR > 0) {
-                    // orphans: left block then right block, merged by transcript id (:231-246), left first on ties
-                    n_joint = nL + nR;
-                    c_ub += 1;
-                    if (n_joint > cap) n_joint = 0;                                        // :217
-                    else if (!p.allow_orphans) { /* :226 joint hits discarded, n_joint keeps counting them below */ }
-                    if (n_joint > 0 && p.allow_orphans) {
-                        i = 0; j = 0;
-                        while (i < nL || j < nR) {                                          // :289-340
-                            bool takeL;
-                            if (i >= nL) takeL = false; else if (j >= nR) takeL = true;
-                            else takeL = hit_tid(scr.at(LEFT0 + i)) <= hit_tid(scr.at(RIGHT0 + j));
-                            const unsigned long long h = takeL ? scr.at(LEFT0 + i++) : scr.at(RIGHT0 + j++);
-                            const int ms = takeL ? 1 : 2;
-                            const bool fwd = hit_fwd(h);
-                            if (BIAS) { if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, hit_tid(h), hit_pos(h), fwd, ms == 1 ? len1 : len2); }
-                            const bool compat = p.ignore_compat ? true : compat_single(p.lib_fmt, fwd, ms);
-                            const bool fwdHit = takeL ? fwd : !fwd;
-                            acc.add(hit_tid(h), compat, fwdHit);
-                        }
-                    } else if (n_joint > 0) {
-                        n_joint = 0;                                                        // :226 jointHits.clear()
-                    }
-                }
-            } else {
-                c_ub += 1;                                                                  // an overflowed mate did have hits
-            }
-            bool mapped = false;
-            if (acc.n > 0 && (acc.haveCompat || !p.enforce_compat)) {
-                mapped = true;
-                c_fw += acc.fw; c_rc += acc.rc;
-                eq_upsert(p.tb, acc.n, [&](uint32_t j) { return (uint32_t)scr.at(TMP0 + j); }, 1ULL);
-            }
-            if (p.fld_val) {
-                const bool elig = paired && n_joint == 1 && fl >= 0 && mapped && (uint32_t)fl < p.max_frag_len;   // :419-434
-                p.fld_val[ri] = elig ? (int16_t)fl : (int16_t)-1;
-            }
-            if (BIAS) { if (p.bias_val) p.bias_val[ri] = (int16_t)bsample; }
-            c_obs += 1; c_map += mapped ? 1 : 0; c_hits += n_joint;
-        }
-    }
-    // warp-reduce the six counters (ReadExperiment.hpp:74-97), one atomic per warp and counter
-    unsigned long long v[6] = {c_obs, c_map, c_hits, c_ub, c_fw, c_rc};
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        unsigned long long x = v[q];
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-        if (lane == 0 && x) atomicAdd(p.counters + q, x);
-    }
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapParams p) {
+#define SFB_FIN_BIAS 0
+#include "map_finalize_body.inl"
+#undef SFB_FIN_BIAS
 }
-
-__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapParams p) { finalize_reads_body<false>(p, nullptr); }
 
 __global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads_bias(const MapParams p) {
     __shared__ unsigned int s_gc[101];
     for (unsigned i = threadIdx.x; i < 101; i += blockDim.x) s_gc[i] = 0;
     __syncthreads();
-    finalize_reads_body<true>(p, s_gc);
+    {
+#define SFB_FIN_BIAS 1
+#include "map_finalize_body.inl"
+#undef SFB_FIN_BIAS
+    }
     __syncthreads();
     if (p.bias_gc) for (unsigned i = threadIdx.x; i < 101; i += blockDim.x) if (s_gc[i]) atomicAdd(p.gc_hist + i, s_gc[i]);
 }
