@@ -1,7 +1,7 @@
-"""Times the device-side bias / GC effective-length correction (sfb200_bias_eff_lens) and the optimizer with the correction inside
-(sfb200_em_run_bias) at a BASELINE-config-2-like size, and -- on a sample -- the CPU oracle beside it.
-usage (GPU box): python scripts/bench_bias.py [--genes 40000] [--cpu-transcripts 400]
-Prints one JSON line.  Not part of bench.py: bias correction is off by default in the reference."""
+"""Times the device-side bias / GC effective-length correction (sfb200_bias_eff_lens; default kernels and the sliding GC form) at a
+BASELINE-config-2-like size.  usage (GPU box): python scripts/bench_bias.py [--genes 40000] [--gc-samp 1]
+Prints one JSON line.  Not part of bench.py: bias correction is off by default in the reference.  Product code
+only (nothing under oracle/ is used): parity is the tests' business (tests/test_gpu_bias.py)."""
 import argparse
 import json
 import os
@@ -11,13 +11,12 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from sailfish_b200 import capi, synth          # noqa: E402
+from sailfish_b200 import capi, efflen, synth          # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--genes", type=int, default=40000)
-    ap.add_argument("--cpu-transcripts", type=int, default=400)
     ap.add_argument("--gc-samp", type=int, default=1)
     a = ap.parse_args()
     seq, off, ln = synth.make_transcriptome(a.genes, seed=1)
@@ -29,8 +28,7 @@ def main():
     rng = np.random.default_rng(3)
     x = np.arange(1000)
     fld = np.round(30000 * np.exp(-0.5 * ((x - 190) / 30.0) ** 2)).astype(np.uint32)
-    from oracle import pyoracle as O          # the FLD table restatement and the CPU leg (checker / baseline only)
-    cdf, mx = O.fld_cdf(fld)
+    cdf, mx = efflen.empirical_cdf(fld)
     eff = np.where(ln - 189.0 >= 1, ln - 189.0, ln).astype(np.float64)
     alphas = rng.lognormal(3, 2, size=T); alphas[rng.random(T) < 0.2] = 0.0
     rb = rng.integers(1, 3000, size=4096).astype(np.uint32); og = rng.integers(1, 8000, size=101).astype(np.uint32)
@@ -44,13 +42,6 @@ def main():
         dt = time.time() - t0
         out[name + "_gpu_s"] = round(dt, 4)
         out[name + "_gpu_Mpos_per_s"] = round(float(ln.sum()) / dt / 1e6, 1)
-        # CPU oracle on the first few transcripts, scaled by positions
-        n = min(a.cpu_transcripts, T)
-        seqs = [seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes() for i in range(n)]
-        t0 = time.time()
-        rc, want = O.update_eff_lens(mode, seqs, eff[:n], eff[:n], alphas[:n], 600000, 590000, rb, og, fld, gc_samp=a.gc_samp)
-        dt_cpu = time.time() - t0
-        out[name + "_cpu_Mpos_per_s_1thread"] = round(float(ln[:n].sum()) / dt_cpu / 1e6, 3)
         out[name + "_changed"] = int((got != eff).sum())
     print(json.dumps(out))
 
