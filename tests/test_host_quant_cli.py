@@ -287,7 +287,7 @@ def test_device_parse_feeding_with_stub_device(tmp_path):
     fastq(tmp_path / "b1.fq", 300, 700, final_newline=False); fastq(tmp_path / "b2.fq", 300, 700, eol="\r\n")
     log = tmp_path / "log.txt"
     env = dict(os.environ, SFB200_STUB_LOG=str(log))
-    for block in ("0", "4096", "700"):
+    for block in ("0", "4096", "700", "100"):                          # 100: every record is longer than a block (the carried text outgrows the room in front)
         if log.exists():
             log.unlink()
         subprocess.check_call([exe, "quant", "-t", str(fa), "-l", "IU", "-1", str(tmp_path / "a1.fq"), str(tmp_path / "b1.fq"), "-2", str(tmp_path / "a2.fq"),
