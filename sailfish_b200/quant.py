@@ -117,6 +117,63 @@ def write_eq_classes(path, names, row_ptr, labels, counts):
             f.write("%d\t%s\t%d\n" % (len(ids), "\t".join(str(int(t)) for t in ids), int(counts[e])))
 
 
+def map_fastq_files(ctx, files1, files2=None, block=64 << 20):
+    """--deviceParse: FASTQ text goes to the GPU as it is (capi.Context.map_fastq); what a call did not consume -- an incomplete
+    record, or records the other mate had no partner for yet -- is put in front of the next block.  Plain four-line FASTQ only."""
+    def stream(files):
+        for path in files:
+            with open(path, "rb") as f:
+                if f.read(2) == b"\x1f\x8b":
+                    raise ValueError("%s: --deviceParse reads plain FASTQ text; inflate gzipped files first (or drop the option)" % path)
+                f.seek(0)
+                last = b"\n"
+                while True:
+                    chunk = f.read(block)
+                    if not chunk:
+                        break
+                    last = chunk[-1:]
+                    yield chunk
+                if last != b"\n":
+                    yield b"\n"                                   # a file whose last line lacks its newline gets one
+    paired = files2 is not None
+    s1, s2 = stream(files1), stream(files2) if paired else iter(())
+    buf1 = buf2 = b""
+    done1 = done2 = False
+    want, total = block, 0
+    while True:
+        while len(buf1) < want and not done1:
+            nxt = next(s1, None)
+            done1 = nxt is None
+            buf1 += nxt or b""
+        while paired and len(buf2) < want and not done2:
+            nxt = next(s2, None)
+            done2 = nxt is None
+            buf2 += nxt or b""
+        if not buf1 and not buf2:
+            break
+        n = c1 = c2 = 0
+        if buf1 and (not paired or buf2):
+            n, c1, c2 = ctx.map_fastq(buf1, buf2 if paired else None)
+        if n == 0:
+            if done1 and (not paired or done2):
+                if buf1.strip() or (paired and buf2.strip()):
+                    raise ValueError("mate files hold different numbers of reads" if paired and bool(buf1.strip()) != bool(buf2.strip())
+                                     else "truncated record at end of file")
+                break
+            if paired:
+                out1, out2 = done1 and not buf1.strip(), done2 and not buf2.strip()      # a mate with nothing left at all
+                if out1 != out2 and (buf2.strip() if out1 else buf1.strip()):
+                    raise ValueError("mate files hold different numbers of reads")
+            want += block
+            continue
+        want = block
+        total += n
+        buf1 = buf1[c1:]
+        if paired:
+            buf2 = buf2[c2:]
+    return total
+
+
 def write_aux_vectors(aux, fld_counts, obs_bias, obs_gc):
     """the binary vectors of GZipWriter::writeMeta (src/GZipWriter.cpp:139-161): raw little-endian elements, gzip.  fld.gz is a
     realisation of 10000 draws from the fragment length pdf (random in the reference, fixed seed here; skipped when there is no
@@ -140,7 +197,8 @@ def write_aux_vectors(aux, fld_counts, obs_bias, obs_gc):
 
 def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_quant", k=31, use_vb=False, n_boot=0, n_gibbs=0,
              dump_eq=False, batch=1_000_000, device=0, no_eff_len_correction=False, map_kw=None, bias_correct=False,
-             gc_bias_correct=False, num_bias_samples=1000000, gc_speed_samp=1, unsmoothed_fld=False):
+             gc_bias_correct=False, num_bias_samples=1000000, gc_speed_samp=1, unsmoothed_fld=False, device_parse=False,
+             block_bytes=64 << 20):
     t_start = time.time()
     names, seqs = read_fasta(transcripts)
     lengths = np.array([len(s) for s in seqs], np.uint32)
@@ -161,8 +219,10 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
         raise ValueError("bias correction needs the effective length correction")
     if do_bias:
         ctx.map_set_bias(bias_correct, gc_bias_correct, num_bias_samples)
-    it2 = read_fastx_batches(reads2, batch) if paired else None
-    for r1 in read_fastx_batches(reads1, batch):
+    it2 = read_fastx_batches(reads2, batch) if paired and not device_parse else None
+    if device_parse:
+        map_fastq_files(ctx, [reads1], [reads2] if paired else None, block_bytes)
+    for r1 in (() if device_parse else read_fastx_batches(reads1, batch)):
         b1, o1 = capi.pack_reads(r1)
         if paired:
             r2 = next(it2)
@@ -239,6 +299,8 @@ def main(argv=None):
     ap.add_argument("--dumpEq", action="store_true")
     ap.add_argument("--noEffectiveLengthCorrection", action="store_true")
     ap.add_argument("--unsmoothedFLD", action="store_true")
+    ap.add_argument("--deviceParse", action="store_true", help="FASTQ text parsed on the GPU (plain four-line FASTQ)")
+    ap.add_argument("--blockBytes", type=int, default=64 << 20)
     ap.add_argument("--biasCorrect", action="store_true")
     ap.add_argument("--gcBiasCorrect", action="store_true")
     ap.add_argument("--numBiasSamples", type=int, default=1000000)
@@ -252,7 +314,7 @@ def main(argv=None):
     res = quantify(a.transcripts, r1, a.mates2, a.libType, a.output, a.kmerLen, a.useVBOpt, a.numBootstraps, a.numGibbsSamples,
                    a.dumpEq, no_eff_len_correction=a.noEffectiveLengthCorrection, bias_correct=a.biasCorrect,
                    gc_bias_correct=a.gcBiasCorrect, num_bias_samples=a.numBiasSamples, gc_speed_samp=a.gcSpeedSamp,
-                   unsmoothed_fld=a.unsmoothedFLD)
+                   unsmoothed_fld=a.unsmoothedFLD, device_parse=a.deviceParse, block_bytes=a.blockBytes)
     print(json.dumps(res["meta"]))
 
 

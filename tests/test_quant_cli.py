@@ -88,6 +88,20 @@ class _StubContext:
     def map_batch(self, b1, o1, b2=None, o2=None):
         self._rec("map_batch", len(o1) - 1, b2 is not None)
 
+    def map_fastq(self, t1, t2=None, max_records=0):
+        def recs(t):
+            return t.count(b"\n") // 4
+
+        def consumed(t, n):
+            pos = -1
+            for _ in range(4 * n):
+                pos = t.index(b"\n", pos + 1)
+            return pos + 1
+        n = min(recs(t1), recs(t2)) if t2 is not None else recs(t1)
+        assert n == 0 or t1[:1] == b"@"                      # every block must start at a record boundary
+        self._rec("map_fastq", n, t2 is not None)
+        return n, consumed(t1, n), consumed(t2, n) if t2 is not None else 0
+
     def map_finish(self):
         fld = np.zeros(self.map_opts.max_frag_len, np.uint32); fld[180:220] = 300          # 12000 sampled fragment lengths
         return dict(counters=np.array([4, 3, 5, 4, 2, 1], np.uint64), fld=fld, n_classes=2, nnz=3)
@@ -155,6 +169,17 @@ def test_driver_host_flow_with_stub_device(tmp_path, monkeypatch):
     np.testing.assert_allclose([float(r[2]) for r in rows], [0.5 * (400 - 199.5 + 1), 0.5 * (600 - 199.5 + 1), 0.5 * (240 - 199.5 + 1)], rtol=1e-5)
     assert json.load(open(out / "aux" / "meta_info.json"))["bias_correct"] is False                          # opts.biasCorrect only
     assert np.frombuffer(gzip.open(out / "aux" / "observed_gc.gz").read(), dtype=np.int32).tolist() == list(range(1, 102))
+    # --deviceParse: raw text block-wise, the unconsumed tail carried over; mate 2 has longer records and no final newline
+    (tmp_path / "d1.fq").write_text("".join("@r%d\n%s\n+\n%s\n" % (i, "ACGT" * 10, "I" * 40) for i in range(50)))
+    (tmp_path / "d2.fq").write_text("".join("@r%d with a long description\n%s\n+\n%s\n" % (i, "ACGT" * 20, "@" * 80) for i in range(50))[:-1])
+    for blk in ("100000", "1000", "150"):
+        quant.main(["-t", str(fa), "-l", "IU", "-1", str(tmp_path / "d1.fq"), "-2", str(tmp_path / "d2.fq"), "-o", str(tmp_path / ("od" + blk)),
+                    "--deviceParse", "--blockBytes", blk])
+        calls = [c for c in _StubContext.calls if c[0] == "map_fastq"]
+        assert sum(c[1][0] for c in calls) == 50 and all(c[1][1] for c in calls) and "map_batch" not in [c[0] for c in _StubContext.calls]
+        assert blk == "100000" or len(calls) > 5
+    with pytest.raises(ValueError):
+        quant.main(["-t", str(fa), "-l", "IU", "-1", str(tmp_path / "d1.fq"), "-2", str(tmp_path / "r2.fq"), "-o", str(tmp_path / "odx"), "--deviceParse"])
     # option checks (SailfishQuantify.cpp:1293-1309)
     with pytest.raises(ValueError):
         quant.main(base + ["-o", str(tmp_path / "o4"), "--biasCorrect", "--gcBiasCorrect"])
