@@ -98,8 +98,8 @@ int sfb200_map_batch(sfb200_ctx* ctx, const char* bases1, const uint64_t* off1, 
 int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
                             const uint64_t* d_off2, uint64_t n_reads);
 /* Read ingestion on the device (replaces the parser threads of quasiMapReads, src/SailfishQuantify.cpp:882-898,
- * 996-1005, include/PairSequenceParser.hpp:28-191, for plain four-line FASTQ).  text1 (and text2 for a paired library) = a block of
- * FASTQ TEXT in HOST memory that starts at a record boundary; its complete records -- at most max_records (0 = no limit), the same
+ * 996-1005, include/PairSequenceParser.hpp:28-191, for plain four-line FASTQ and two-line FASTA reads -- the first character of
+ * text1 says which).  text1 (and text2 for a paired library) = a block of FASTQ TEXT in HOST memory that starts at a record boundary; its complete records -- at most max_records (0 = no limit), the same
  * number from both mates -- are extracted on the GPU and mapped as by sfb200_map_batch.  *n_records = how many, *consumed1/2 = the
  * bytes of text they cover: the caller keeps text[consumed ..) and puts it in front of what it reads next.  A final record
  * without a trailing newline needs one appended.  Gzipped input is inflated by the caller first.

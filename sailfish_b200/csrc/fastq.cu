@@ -49,9 +49,10 @@ __global__ void k_fq_count(const char* __restrict__ text, uint64_t n, uint64_t n
     if (c < n_chunks) cnt[c] = fq_count_newlines(text, n, c);
 }
 __global__ void k_fq_mark(const char* __restrict__ text, uint64_t n, uint64_t n_chunks, const uint32_t* __restrict__ nl_base, uint64_t n_rec,
-                          uint64_t* __restrict__ seq_start, uint32_t* __restrict__ seq_len, uint64_t* __restrict__ rec_end, uint32_t* __restrict__ err) {
+                          uint32_t lines_per_rec, uint64_t* __restrict__ seq_start, uint32_t* __restrict__ seq_len, uint64_t* __restrict__ rec_end,
+                          uint32_t* __restrict__ err) {
     const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (c < n_chunks) fq_mark_chunk(text, n, c, nl_base[c], n_rec, seq_start, seq_len, rec_end, err);
+    if (c < n_chunks) fq_mark_chunk(text, n, c, nl_base[c], n_rec, lines_per_rec, seq_start, seq_len, rec_end, err);
 }
 __global__ void k_fq_len_to_u64(const uint32_t* __restrict__ len, uint64_t n, uint64_t* __restrict__ out) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -89,10 +90,10 @@ int fq_stage(sfb200_ctx* c, FqState* st, FqMate& x, const char* text, uint64_t n
 }
 
 // records [0, n_rec) of a staged mate -> bases / off; *consumed = bytes of text they cover
-int fq_extract(sfb200_ctx* c, FqState* st, FqMate& x, uint64_t n_rec, uint64_t* consumed) {
+int fq_extract(sfb200_ctx* c, FqState* st, FqMate& x, uint64_t n_rec, uint32_t lines_per_rec, uint64_t* consumed) {
     cudaStream_t s = c->stream;
     SFB_CUDA(c, x.seq_start.reserve(n_rec)); SFB_CUDA(c, x.len.reserve(n_rec)); SFB_CUDA(c, x.rec_end.reserve(n_rec)); SFB_CUDA(c, x.off.reserve(n_rec + 1));
-    k_fq_mark<<<fq_grid(x.n_chunks, 256), 256, 0, s>>>(x.text.p, x.n_text, x.n_chunks, x.cnt.p, n_rec, x.seq_start.p, x.len.p, x.rec_end.p, st->err.p);
+    k_fq_mark<<<fq_grid(x.n_chunks, 256), 256, 0, s>>>(x.text.p, x.n_text, x.n_chunks, x.cnt.p, n_rec, lines_per_rec, x.seq_start.p, x.len.p, x.rec_end.p, st->err.p);
     c->launches++;
     k_fq_len_to_u64<<<fq_grid(n_rec + 1, 256), 256, 0, s>>>(x.len.p, n_rec, x.off.p);
     c->launches++;
@@ -138,16 +139,18 @@ extern "C" int sfb200_map_fastq(sfb200_ctx* c, const char* text1, uint64_t n1, c
     SFB_CUDA(c, cudaMemsetAsync(st->err.p, 0, 4, s));
     { const int rc = fq_stage(c, st, st->m[0], text1, n1); if (rc) return rc; }
     if (paired) { const int rc = fq_stage(c, st, st->m[1], text2, n2); if (rc) return rc; }
-    uint64_t n_rec = st->m[0].n_newlines / 4;
-    if (paired) n_rec = std::min<uint64_t>(n_rec, st->m[1].n_newlines / 4);
+    // FASTQ ('@': four lines per record) or FASTA reads ('>': two); both mates in the same format
+    const uint32_t lpr = (n1 > 0 && text1[0] == '>') ? 2u : 4u;
+    uint64_t n_rec = st->m[0].n_newlines / lpr;
+    if (paired) n_rec = std::min<uint64_t>(n_rec, st->m[1].n_newlines / lpr);
     if (max_records) n_rec = std::min<uint64_t>(n_rec, max_records);
     if (n_rec == 0) return SFB200_OK;
-    { const int rc = fq_extract(c, st, st->m[0], n_rec, consumed1); if (rc) return rc; }
-    if (paired) { const int rc = fq_extract(c, st, st->m[1], n_rec, consumed2); if (rc) return rc; }
+    { const int rc = fq_extract(c, st, st->m[0], n_rec, lpr, consumed1); if (rc) return rc; }
+    if (paired) { const int rc = fq_extract(c, st, st->m[1], n_rec, lpr, consumed2); if (rc) return rc; }
     uint32_t err = 0;
     SFB_CUDA(c, cudaMemcpyAsync(&err, st->err.p, 4, cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
-    if (err & FQ_ERR_HEADER) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: a record does not start with '@' (four-line FASTQ records expected)");
+    if (err & FQ_ERR_HEADER) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: a record does not start with '@' / '>' (four-line FASTQ or two-line FASTA records expected, both mates alike)");
     if (err & FQ_ERR_PLUS) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: the line after a sequence does not start with '+' (four-line FASTQ records expected)");
     if (err & FQ_ERR_LONG) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: sequence line longer than 16 M bases");
     const int rc = sfb200_map_batch_device(c, st->m[0].bases.p, st->m[0].off.p, paired ? st->m[1].bases.p : nullptr, paired ? st->m[1].off.p : nullptr, n_rec);

@@ -7,7 +7,8 @@
 //   SFB_FQ_OR(p, v)   atomic OR on a uint32_t
 //
 // A block starts at a record boundary.  Newline j (0-based) of the block ends line j; record r owns lines 4r .. 4r+3 (header,
-// sequence, '+', qualities -- the form the reference's parser reads, include/PairSequenceParser.hpp, and every sequencer writes).
+// sequence, '+', qualities -- the form the reference's parser reads, include/PairSequenceParser.hpp, and every sequencer writes),
+// or, for FASTA reads, lines 2r and 2r+1 ('>' header, the sequence on ONE line; wrapped sequences are refused).
 // Only complete records are extracted: the caller carries the rest of the text over to the front of its next block.
 
 constexpr uint32_t FQ_CHUNK = 512;                    // bytes of text per thread
@@ -25,15 +26,18 @@ SFB_FQ uint32_t fq_count_newlines(const char* __restrict__ text, uint64_t n, uin
 // seq_start[r] = first base, seq_len[r] = bases (a '\r' before the newline is not one), rec_end[r] = one past the record's last newline.
 // seq_len is written by the thread that sees the END of the sequence line and needs its start: the start is at most max_line bytes
 // back, found by scanning for the previous newline (the header's) -- records do not straddle threads otherwise.
-SFB_FQ void fq_mark_chunk(const char* __restrict__ text, uint64_t n, uint64_t c, uint64_t nl_base, uint64_t n_rec, uint64_t* __restrict__ seq_start,
-                          uint32_t* __restrict__ seq_len, uint64_t* __restrict__ rec_end, uint32_t* __restrict__ err) {
+// lines_per_rec = 4 (FASTQ, header character '@') or 2 (FASTA, '>').
+SFB_FQ void fq_mark_chunk(const char* __restrict__ text, uint64_t n, uint64_t c, uint64_t nl_base, uint64_t n_rec, uint32_t lines_per_rec,
+                          uint64_t* __restrict__ seq_start, uint32_t* __restrict__ seq_len, uint64_t* __restrict__ rec_end, uint32_t* __restrict__ err) {
     const uint64_t a = c * FQ_CHUNK, b = a + FQ_CHUNK < n ? a + FQ_CHUNK : n;
+    const bool fastq = lines_per_rec == 4;
+    const char hdr = fastq ? '@' : '>';
     uint64_t j = nl_base;
-    if (c == 0 && n_rec > 0 && text[0] != '@') SFB_FQ_OR(err, FQ_ERR_HEADER);
+    if (c == 0 && n_rec > 0 && text[0] != hdr) SFB_FQ_OR(err, FQ_ERR_HEADER);
     for (uint64_t p = a; p < b; ++p) {
         if (text[p] != '\n') continue;
-        const uint64_t r = j >> 2;
-        const uint32_t k = (uint32_t)(j & 3);
+        const uint64_t r = fastq ? j >> 2 : j >> 1;
+        const uint32_t k = (uint32_t)(fastq ? j & 3 : j & 1);
         ++j;
         if (r >= n_rec) return;
         if (k == 0) {
@@ -44,7 +48,12 @@ SFB_FQ void fq_mark_chunk(const char* __restrict__ text, uint64_t n, uint64_t c,
             const uint64_t e = (p > s && text[p - 1] == '\r') ? p - 1 : p;
             if (e - s > 0xFFFFFFu) SFB_FQ_OR(err, FQ_ERR_LONG);
             seq_len[r] = (uint32_t)(e - s);
-            if (p + 1 < n && text[p + 1] != '+') SFB_FQ_OR(err, FQ_ERR_PLUS);
+            if (fastq) {
+                if (p + 1 < n && text[p + 1] != '+') SFB_FQ_OR(err, FQ_ERR_PLUS);
+            } else {
+                rec_end[r] = p + 1;
+                if (r + 1 < n_rec && text[p + 1] != '>') SFB_FQ_OR(err, FQ_ERR_HEADER);  // a wrapped sequence (or anything else) is not read as bases
+            }
         } else if (k == 3) {
             rec_end[r] = p + 1;
             if (r + 1 < n_rec && text[p + 1] != '@') SFB_FQ_OR(err, FQ_ERR_HEADER);   // the next wanted record's header

@@ -373,7 +373,7 @@ struct Args {
             "  --txpAggregationKey KEY    GTF attribute that names the gene (gene_id)\n"
             "  --maxFragLen N (1000)  --numFragSamples N (10000)  --fldMean M (200)  --fldSD S (80)  -w, --maxReadOcc N (200)\n"
             "  --strictIntersect  --ignoreLibCompat  --enforceLibCompat  --allowDovetail  --discardOrphans  --auxDir NAME\n"
-            "  --deviceParse              send the FASTQ text to the GPU as it is and find the reads there (plain four-line FASTQ only)\n"
+            "  --deviceParse              send the read files' text to the GPU as it is and find the reads there (plain four-line FASTQ or two-line FASTA)\n"
             "  --parseOnly                only parse the read files and print record / base counts (no GPU needed)\n");
     exit(msg ? 2 : 0);
 }

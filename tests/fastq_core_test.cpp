@@ -19,14 +19,14 @@
 struct Extracted { std::vector<std::string> seqs; uint64_t consumed = 0; uint32_t err = 0; uint64_t n_rec = 0; };
 
 // what fastq.cu does with one mate's block, serially
-static Extracted extract(const std::string& text, uint64_t max_records) {
+static Extracted extract(const std::string& text, uint64_t max_records, uint32_t lpr = 4) {
     Extracted out;
     const uint64_t n = text.size(), n_chunks = (n + FQ_CHUNK - 1) / FQ_CHUNK;
     std::vector<uint32_t> cnt(n_chunks + 1, 0);
     for (uint64_t c = 0; c < n_chunks; ++c) cnt[c] = fq_count_newlines(text.data(), n, c);
     uint32_t run = 0;
     for (uint64_t c = 0; c <= n_chunks; ++c) { const uint32_t v = cnt[c]; cnt[c] = run; run += v; }      // exclusive scan
-    uint64_t n_rec = cnt[n_chunks] / 4;
+    uint64_t n_rec = cnt[n_chunks] / lpr;
     if (max_records && n_rec > max_records) n_rec = max_records;
     out.n_rec = n_rec;
     if (!n_rec) return out;
@@ -36,7 +36,7 @@ static Extracted extract(const std::string& text, uint64_t max_records) {
     std::vector<uint64_t> order(n_chunks);
     for (uint64_t c = 0; c < n_chunks; ++c) order[c] = (c * 7919) % n_chunks;
     if (n_chunks % 7919 == 0) for (uint64_t c = 0; c < n_chunks; ++c) order[c] = c;
-    for (uint64_t c : order) fq_mark_chunk(text.data(), n, c, cnt[c], n_rec, seq_start.data(), len.data(), rec_end.data(), &out.err);
+    for (uint64_t c : order) fq_mark_chunk(text.data(), n, c, cnt[c], n_rec, lpr, seq_start.data(), len.data(), rec_end.data(), &out.err);
     for (uint64_t r = 0; r < n_rec; ++r) off[r + 1] = off[r] + len[r];
     std::string bases(off[n_rec], '?');
     for (uint64_t r = 0; r < n_rec; ++r) for (uint32_t lane = 0; lane < 32; ++lane) fq_copy_record(text.data(), seq_start[r], len[r], &bases[off[r]], lane, 32);
@@ -83,10 +83,34 @@ int main() {
             for (size_t r = 0; r < complete; ++r) CHECK(got.seqs[r] == want[r], "rep %d variant %d record %zu: '%s' vs '%s'", rep, variant, r, got.seqs[r].c_str(), want[r].c_str());
         }
     }
+    // FASTA reads: two lines per record
+    for (int rep = 0; rep < 100; ++rep) {
+        const std::string eol = rep % 4 == 1 ? "\r\n" : "\n";
+        const size_t n_rec = 1 + rng() % 200;
+        std::vector<std::string> want;
+        std::vector<uint64_t> ends;
+        std::string text;
+        for (size_t r = 0; r < n_rec; ++r) {
+            std::string s(rng() % 15 == 0 ? 0 : 20 + rng() % 400, 'A');
+            for (auto& ch : s) ch = alpha[rng() % 5];
+            text += ">read" + std::to_string(r) + eol + s + eol;
+            want.push_back(s); ends.push_back(text.size());
+        }
+        const std::string blk = rep % 2 ? text.substr(0, rng() % text.size()) : text;
+        size_t complete = 0;
+        while (complete < n_rec && ends[complete] <= blk.size()) ++complete;
+        const Extracted got = extract(blk, 0, 2);
+        CHECK(got.err == 0 && got.n_rec == complete && got.consumed == (complete ? ends[complete - 1] : 0), "FASTA rep %d: err %u, %llu records (expected %zu)", rep, got.err,
+              (unsigned long long)got.n_rec, complete);
+        for (size_t r = 0; r < complete; ++r) CHECK(got.seqs[r] == want[r], "FASTA rep %d record %zu", rep, r);
+    }
     // malformed input is reported, not mis-parsed silently
     {
         const std::string fasta = ">a\nACGT\n>b\nGGCC\n";
-        CHECK(extract(fasta, 0).err & FQ_ERR_HEADER, "FASTA text must raise the header flag");
+        CHECK(extract(fasta, 0).err & FQ_ERR_HEADER, "FASTA text read as FASTQ must raise the header flag");
+        const std::string wrapped = ">a\nACGT\nACGT\n>b\nGGCC\nGG\n";
+        CHECK(extract(wrapped, 0, 2).err & FQ_ERR_HEADER, "wrapped FASTA sequences are refused");
+        CHECK(extract(std::string("@a\nAC\n+\nII\n@b\nAC\n+\nII\n"), 0, 2).err & FQ_ERR_HEADER, "FASTQ text read as FASTA");
         const std::string noplus = "@a\nACGT\nACGT\nIIII\n@b\nAC\n+\nII\n";
         CHECK(extract(noplus, 0).err & FQ_ERR_PLUS, "missing '+' line");
         const std::string shifted = "@a\nACGT\n+\nIIII\n\n@b\nAC\n+\nII\n@c\nA\n+\nI\n";           // a blank line between records

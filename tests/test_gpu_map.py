@@ -252,8 +252,9 @@ def test_bias_samples_match_oracle(ctx, paired, libtype, seq_bias, gc_bias, n_sa
 
 
 @_experimental
-@pytest.mark.parametrize("paired,eol,block", [(True, "\n", 0), (True, "\r\n", 300000), (False, "\n", 70000), (True, "\n", 9000)])
-def test_map_fastq_equals_map_batch(ctx, paired, eol, block):
+@pytest.mark.parametrize("paired,eol,block,fasta", [(True, "\n", 0, False), (True, "\r\n", 300000, False), (False, "\n", 70000, False), (True, "\n", 9000, False),
+                                                    (True, "\n", 50000, True)])
+def test_map_fastq_equals_map_batch(ctx, paired, eol, block, fasta):
     """sfb200_map_fastq (FASTQ text parsed on the device, fastq.cu) gives the classes, counters and FLD of sfb200_map_batch on the same
     reads -- whole text at once and block-wise with the unconsumed tail carried over (mate 2 has longer headers, so its blocks hold
     fewer records)"""
@@ -265,7 +266,10 @@ def test_map_fastq_equals_map_batch(ctx, paired, eol, block):
         recs = []
         for i in range(n):
             s_ = bases[int(offs[i]):int(offs[i + 1])].tobytes().decode()
-            recs.append("@r%d%s%s%s%s+%s%s%s" % (i, " description of the read" * 2 if long_names else "", eol, s_, eol, eol, "@" * len(s_), eol))
+            if fasta:
+                recs.append(">r%d%s%s%s%s" % (i, " description of the read" * 2 if long_names else "", eol, s_, eol))
+            else:
+                recs.append("@r%d%s%s%s%s+%s%s%s" % (i, " description of the read" * 2 if long_names else "", eol, s_, eol, eol, "@" * len(s_), eol))
         return "".join(recs).encode()
 
     t1 = text(b1, o1, False)
@@ -305,5 +309,5 @@ def test_map_fastq_equals_map_batch(ctx, paired, eol, block):
     # malformed text is refused
     ctx.map_begin(capi.MapOpts.default(fmt))
     with pytest.raises(capi.Sfb200Error):
-        ctx.map_fastq(b">a\nACGT\n>b\nGGCC\n", b">a\nACGT\n>b\nGGCC\n" if paired else None)
+        ctx.map_fastq(b">a\nACGT\nAC\n>b\nGGCC\nGG\n", b">a\nACGT\nAC\n>b\nGGCC\nGG\n" if paired else None)     # wrapped FASTA
     ctx.map_finish()
