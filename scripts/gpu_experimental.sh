@@ -19,3 +19,10 @@ timeout 600 python scripts/cli_e2e.py --reads 4000000 --device-parse > $OUT/${TA
 echo "cli e2e (--deviceParse) rc=$?  ($(( $(date +%s) - t0 )) s)"; cat $OUT/${TAG}_cli_e2e_device_parse.json
 SFB200_EM_DENSE_GROUP=0 timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench_dense0.json 2> $OUT/${TAG}_bench_dense0.log
 echo "bench (balanced dense) rc=$?  ($(( $(date +%s) - t0 )) s)"; python scripts/show_bench.py $OUT/${TAG}_bench_dense0.json
+# ncu of the new kernels (one GPU, few launches): the bias / GC passes in both forms, and the device-side FASTQ extraction
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bias_expected|k_bias_efflen' -c 6 -f -o $OUT/${TAG}_bias \
+    python scripts/bench_bias.py --genes 8000 > $OUT/${TAG}_ncu_bias.log 2>&1
+echo "ncu bias rc=$?  ($(( $(date +%s) - t0 )) s)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fq_' -c 8 -f -o $OUT/${TAG}_fq \
+    sailfish_b200/bin/sfb200-quant quant -t /dev/shm/sfb200_cli/t.fa -l U -r /dev/shm/sfb200_cli/r.fq -o /dev/shm/sfb200_cli/out_ncu --deviceParse > $OUT/${TAG}_ncu_fq.log 2>&1
+echo "ncu fastq rc=$?  ($(( $(date +%s) - t0 )) s)"
