@@ -5,7 +5,7 @@
 // Finding newlines and copying 100-byte lines is bandwidth work the GPU does at HBM speed; what stays on the host is reading the
 // file (or inflating it) and carrying the incomplete record at the end of a block over to the next one.
 //
-//   k_fq_count    newlines per 512-byte chunk                       -> exclusive scan (CUB) -> index of every chunk's first newline
+//   k_fq_count    newlines per 512-byte chunk (8 bytes per load)     -> exclusive scan (CUB) -> index of every chunk's first newline
 //   k_fq_mark     newline j ends line j of the block; record r = lines 4r .. 4r+3: sequence start / length, record end, format checks
 //   k_fq_copy     a warp per record copies its bases to bases[off[r] ..), off = exclusive scan of the lengths
 //   then sfb200_map_batch_device on the extracted arrays (k_pack_reads -> k_scan_reads -> k_finalize_reads, map.cu)
@@ -24,9 +24,15 @@ namespace {
 
 #define SFB_FQ __device__ __forceinline__
 #define SFB_FQ_OR(p, v) atomicOr((p), (v))
+#define SFB_FQ_LD8(p) (*reinterpret_cast<const unsigned long long*>(p))
+#define SFB_FQ_POPC(x) __popcll(x)
+#define SFB_FQ_CTZ(x) (__ffsll((long long)(x)) - 1)
 #include "fastq_core.inl"
 #undef SFB_FQ
 #undef SFB_FQ_OR
+#undef SFB_FQ_LD8
+#undef SFB_FQ_POPC
+#undef SFB_FQ_CTZ
 
 struct FqMate {
     DevBuf<char> text, bases;

@@ -5,6 +5,8 @@
 // device code and plain host code for the CPU check (tests/fastq_core_test.cpp):
 //   SFB_FQ            function qualifiers
 //   SFB_FQ_OR(p, v)   atomic OR on a uint32_t
+//   SFB_FQ_LD8(p)     the 8 bytes at p as a little-endian u64 (p is 8-byte aligned on the device: chunks start at multiples of 512)
+//   SFB_FQ_POPC(x) / SFB_FQ_CTZ(x)   population count / index of the lowest set bit of a non-zero u64
 //
 // A block starts at a record boundary.  Newline j (0-based) of the block ends line j; record r owns lines 4r .. 4r+3 (header,
 // sequence, '+', qualities -- the form the reference's parser reads, include/PairSequenceParser.hpp, and every sequencer writes),
@@ -14,11 +16,20 @@
 constexpr uint32_t FQ_CHUNK = 512;                    // bytes of text per thread
 constexpr uint32_t FQ_ERR_HEADER = 1, FQ_ERR_PLUS = 2, FQ_ERR_LONG = 4;
 
+// 0x80 in every byte of v that is '\n', 0 elsewhere (exact: no carries between bytes), so the text is scanned 8 bytes at a time
+SFB_FQ uint64_t fq_newline_mask(uint64_t v) {
+    v ^= 0x0a0a0a0a0a0a0a0aULL;
+    const uint64_t t = (v & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL;
+    return ~(t | v | 0x7f7f7f7f7f7f7f7fULL);
+}
+
 // pass 1: newlines in chunk c of text[0, n)
 SFB_FQ uint32_t fq_count_newlines(const char* __restrict__ text, uint64_t n, uint64_t c) {
     const uint64_t a = c * FQ_CHUNK, b = a + FQ_CHUNK < n ? a + FQ_CHUNK : n;
     uint32_t k = 0;
-    for (uint64_t p = a; p < b; ++p) k += text[p] == '\n';
+    uint64_t p = a;
+    for (; p + 8 <= b; p += 8) k += (uint32_t)SFB_FQ_POPC(fq_newline_mask(SFB_FQ_LD8(text + p)));
+    for (; p < b; ++p) k += text[p] == '\n';
     return k;
 }
 
@@ -34,8 +45,22 @@ SFB_FQ void fq_mark_chunk(const char* __restrict__ text, uint64_t n, uint64_t c,
     const char hdr = fastq ? '@' : '>';
     uint64_t j = nl_base;
     if (c == 0 && n_rec > 0 && text[0] != hdr) SFB_FQ_OR(err, FQ_ERR_HEADER);
-    for (uint64_t p = a; p < b; ++p) {
-        if (text[p] != '\n') continue;
+    uint64_t word = 0, wbase = a;                                    // pending newline bits of the 8 bytes at wbase
+    uint64_t q = a;                                                  // next byte not yet loaded
+    for (;;) {
+        uint64_t p;
+        if (word) {
+            p = wbase + (SFB_FQ_CTZ(word) >> 3);
+            word &= word - 1;
+        } else if (q + 8 <= b) {
+            word = fq_newline_mask(SFB_FQ_LD8(text + q)); wbase = q; q += 8;
+            continue;
+        } else if (q < b) {
+            p = q++;
+            if (text[p] != '\n') continue;
+        } else {
+            return;
+        }
         const uint64_t r = fastq ? j >> 2 : j >> 1;
         const uint32_t k = (uint32_t)(fastq ? j & 3 : j & 1);
         ++j;

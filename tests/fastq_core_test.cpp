@@ -12,6 +12,10 @@
 
 #define SFB_FQ static inline
 #define SFB_FQ_OR(p, v) (*(p) |= (v))
+static inline uint64_t ld8(const char* p) { uint64_t v; __builtin_memcpy(&v, p, 8); return v; }
+#define SFB_FQ_LD8(p) ld8(p)
+#define SFB_FQ_POPC(x) __builtin_popcountll(x)
+#define SFB_FQ_CTZ(x) __builtin_ctzll(x)
 #include "../sailfish_b200/csrc/fastq_core.inl"
 
 #define CHECK(cond, ...) do { if (!(cond)) { fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } } while (0)
