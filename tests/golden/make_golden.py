@@ -8,6 +8,9 @@
                       CollapsedEMOptimizer::optimize produces on those classes (EM and VBEM)
   synth_em.npz        a synthetic class set + the reference optimizer's EM / VBEM estimates
   eqbuilder.json      EquivalenceClassBuilder behaviour on a small add sequence (counts, finish() totals)
+  ref_samplers.npz    a class set + per-transcript moments of the replicates the reference's OWN gatherBootstraps
+                      (src/CollapsedEMOptimizer.cpp:557-709, EM and VBEM) and CollapsedGibbsSampler::sample
+                      (src/CollapsedGibbsSampler.cpp:199-291) produce on it (both compiled unmodified into libsfref_em.so)
   bias_efflens.npz    inputs and outputs of the reference's OWN updateEffectiveLengths (src/SailfishUtils.cpp:611-926,
                       compiled unmodified into oracle/_ref/libsfref_em.so) for --biasCorrect and --gcBiasCorrect
 
@@ -102,10 +105,55 @@ def make_bias_fixture():
         T, int((out["ref_seq_samp1"] != eff_in).sum()), int((out["ref_gc_samp1"] != eff_in).sum())))
 
 
+def make_sampler_fixture():
+    """bootstrap / Gibbs (SURVEY 8a rows A16 / A17): the reference seeds its generators from std::random_device, so what can be
+    pinned is the DISTRIBUTION of its replicates -- per-transcript mean and variance over many replicates, plus the exact
+    invariants (every replicate conserves the fragment total)."""
+    T = 300
+    rp, lab, cnt = synth.make_classes(T, 600, seed=41, max_len=4)
+    eff = np.random.default_rng(5).uniform(200, 3000, size=T)
+    txp_len = np.maximum(eff, 1).astype(np.uint32)
+    nm = int(cnt.sum())
+    out = dict(txp_len=txp_len, eff=eff, row_ptr=rp, labels=lab, counts=cnt, num_mapped=np.int64(nm))
+    NB, NG, BURN, NCHAIN = 400, 900, 200, 64
+    for vb in (0, 1):
+        ref = O.RefEM(txp_len, eff, rp, lab, cnt, nm, use_vb=bool(vb), n_boot=NB)
+        rc, rows = ref.bootstraps()
+        assert rc == 0 and rows.shape == (NB, T)
+        if not vb:
+            assert np.allclose(rows.sum(axis=1), nm, rtol=1e-9)          # EM hands out exactly the resampled total
+        out["boot_vb%d_mean" % vb] = rows.mean(axis=0); out["boot_vb%d_var" % vb] = rows.var(axis=0)
+        out["boot_vb%d_sum" % vb] = rows.sum(axis=1)
+    out["boot_n"] = np.int64(NB)
+    # Gibbs: chains started at the EM estimate mix slowly for some transcripts (integrated autocorrelation times of 100 and more), so
+    # the pinned quantity is the mean / variance over a FIXED window of the chain (samples BURN .. NG), and its spread over
+    # NCHAIN independent runs of the reference's sampler
+    wm, wv = [], []
+    for ch in range(NCHAIN):
+        ref = O.RefEM(txp_len, eff, rp, lab, cnt, nm)
+        rc, est, mass = ref.optimize()
+        assert rc == 0
+        rc, g = ref.gibbs(NG)
+        assert rc == 0 and (g.sum(axis=1) == nm).all()
+        g = g[BURN:].astype(np.float64)
+        wm.append(g.mean(axis=0)); wv.append(g.var(axis=0))
+    wm, wv = np.array(wm), np.array(wv)
+    out["em_est"] = est
+    out["gibbs_n"] = np.int64(NG); out["gibbs_burn"] = np.int64(BURN); out["gibbs_chains"] = np.int64(NCHAIN)
+    out["gibbs_wmean_mean"] = wm.mean(axis=0); out["gibbs_wmean_sd"] = wm.std(axis=0, ddof=1)
+    out["gibbs_wvar_mean"] = wv.mean(axis=0); out["gibbs_wvar_sd"] = wv.std(axis=0, ddof=1)
+    np.savez_compressed(os.path.join(OUT, "ref_samplers.npz"), **out)
+    print("ref_samplers.npz: %d bootstraps x 2 modes, %d Gibbs chains of %d samples (burn-in %d) of the reference's own samplers" % (NB, NCHAIN, NG, BURN))
+
+
 def main():
     if "--bias-only" in sys.argv:
         make_bias_fixture()
         return
+    if "--samplers-only" in sys.argv:
+        make_sampler_fixture()
+        return
+    make_sampler_fixture()
     R = O.ref()
     assert R is not None, "oracle/_ref/libsfref.so missing: run make -C oracle"
     rng = np.random.default_rng(20261017)
@@ -183,7 +231,7 @@ def main():
     subprocess.call(["ls", "-la", OUT])
 
 
-if __name__ == "__main__" and "--bias-only" not in sys.argv:
+if __name__ == "__main__" and "--bias-only" not in sys.argv and "--samplers-only" not in sys.argv:
     make_bias_fixture()
 
 if __name__ == "__main__":

@@ -34,16 +34,13 @@ def test_bias_eff_lens_matches_oracle(ctx, mode, gc_samp):
 
 
 # ---- the optimizer with the correction inside (sfb200_em_run_bias): effective lengths recomputed at iterations 50 / 500 / 1000 ------------
-# Written after the round's GPU budget was spent: the launch scheduling is checked on CPU (tests/em_segments_test.cpp), the entry point
-# has not run on a GPU yet, so these cases need SFB200_EXPERIMENTAL=1.
+# The launch scheduling is also checked on CPU (tests/em_segments_test.cpp).  First B200 run: profiles/r02a_experimental_gpu.txt.
 import os
 
 from sailfish_b200 import capi, synth
 
-_experimental = pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SFB200_EXPERIMENTAL=1")
 
 
-@_experimental
 @pytest.mark.parametrize("gc_samp", [1, 3, 7])
 def test_bias_eff_lens_sliding_gc_passes(ctx, monkeypatch, gc_samp):
     """SFB200_BIAS_GC_SLIDE=1: the fragment GC passes with one thread per fragment length (k_bias_*_gc_slide; CPU check of the same text:
@@ -70,7 +67,6 @@ def test_bias_eff_lens_sliding_gc_passes(ctx, monkeypatch, gc_samp):
     assert ((got != eff_in) == (want != eff_in)).all() and (want != eff_in).sum() > 50
 
 
-@_experimental
 @pytest.mark.parametrize("loops", ["default", "scatter", "steps"])
 @pytest.mark.parametrize("mode,vb,kw", [
     (1, 0, {}), (2, 0, {}), (1, 1, {}), (2, 1, {}),                              # default limits: one recomputation, at iteration 50
@@ -103,7 +99,7 @@ def test_em_run_bias_matches_oracle(ctx, monkeypatch, loops, mode, vb, kw):
     np.testing.assert_allclose(eff_got, eff_want, rtol=1e-6)
     np.testing.assert_allclose(a, want, rtol=1e-4, atol=1e-6)
     assert (a == 0).tolist() == (want == 0).tolist()
-    if it >= 50:
+    if it > 50:                                                                 # the recomputation sits at the TOP of iteration 50 (:822)
         assert (eff_got != np.maximum(eff, 1.0)).sum() > 50                     # the correction did happen
         assert abs(mrd - mrd_o) <= 1e-5 * max(abs(mrd_o), 1e-12)
     else:

@@ -20,17 +20,12 @@ GATHER, DENSE = 2, 4
 import os
 
 # "dense-balanced" (lanes per component chosen from its class count, SFB200_EM_DENSE_GROUP=0) is opt-in.  Its layout and iteration
-# are checked on CPU (tests/em_dense_layout_test.cpp); on a B200 the fixed-iteration and component-size tests have been run with it
-# (profiles/r01f_experimental_gpu.txt), so those run always and the remaining ones only with SFB200_EXPERIMENTAL=1
+# are checked on CPU (tests/em_dense_layout_test.cpp) and every case below is green with it on a B200 (profiles/r02a_experimental_gpu.txt)
 _KINDS = ["gather", "dense", "dense-balanced"]
-_BALANCED_VERIFIED = ("test_gather_loop_fixed_iterations", "test_dense_loop_component_sizes")
 
 
 @pytest.fixture(autouse=True, params=_KINDS)
 def loop_kind(request, monkeypatch):
-    if (request.param == "dense-balanced" and os.environ.get("SFB200_EXPERIMENTAL") != "1"
-            and request.node.originalname not in _BALANCED_VERIFIED):
-        pytest.skip("balanced dense layout: set SFB200_EXPERIMENTAL=1 for the cases that have not run on a GPU yet")
     monkeypatch.setenv("SFB200_EM_GATHER", "1")
     monkeypatch.setenv("SFB200_EM_DENSE", "0" if request.param == "gather" else "1")
     if request.param == "dense-balanced":

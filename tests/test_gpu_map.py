@@ -199,14 +199,11 @@ def test_large_batches_are_chunked(ctx, monkeypatch):
 
 
 # ---- bias / GC sample collection while mapping (sfb200_map_set_bias / sfb200_map_get_bias) ----------------------------------------
-# Written after the round's GPU budget was spent: the per-hit arithmetic is checked on CPU (tests/bias_core_test.cpp), the kernel
-# variant (k_finalize_reads_bias) and k_bias_select have not run on a GPU yet, so these cases need SFB200_EXPERIMENTAL=1.
+# The per-hit arithmetic is also checked on CPU (tests/bias_core_test.cpp).  First B200 run: profiles/r02a_experimental_gpu.txt.
 import os
 
-_experimental = pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SFB200_EXPERIMENTAL=1")
 
 
-@_experimental
 @pytest.mark.parametrize("paired,libtype,seq_bias,gc_bias,n_samples,kw", [
     (True, "IU", 1, 1, 1000000, {}), (True, "IU", 1, 0, 3000, {}), (True, "ISF", 0, 1, 0, {}), (True, "IU", 1, 1, 1000000, {"allow_orphans": 0}),
     (True, "OU", 1, 1, 1000000, {"max_read_occs": 3}), (False, "U", 1, 0, 1000000, {}), (False, "SR", 1, 1, 2500, {}),
@@ -251,7 +248,6 @@ def test_bias_samples_match_oracle(ctx, paired, libtype, seq_bias, gc_bias, n_sa
         assert int(og.sum()) == 101
 
 
-@_experimental
 @pytest.mark.parametrize("paired,eol,block,fasta", [(True, "\n", 0, False), (True, "\r\n", 300000, False), (False, "\n", 70000, False), (True, "\n", 9000, False),
                                                     (True, "\n", 50000, True)])
 def test_map_fastq_equals_map_batch(ctx, paired, eol, block, fasta):

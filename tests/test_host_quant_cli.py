@@ -386,10 +386,8 @@ def test_sample_data_end_to_end_cpp(sample_data, tmp_path):
     assert (gib.sum(axis=1) == int(d["num_mapped"])).all()
 
 
-_experimental = pytest.mark.skipif(os.environ.get("SFB200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set SFB200_EXPERIMENTAL=1")
 
 
-@_experimental
 @pytest.mark.gpu
 @pytest.mark.parametrize("flag,mode", [("--biasCorrect", 1), ("--gcBiasCorrect", 2)])
 def test_sample_data_bias_correction_cpp(sample_data, tmp_path, flag, mode):
