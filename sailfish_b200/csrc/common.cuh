@@ -56,12 +56,16 @@ struct DevIndex {
     DevBuf<uint64_t> txp_start;  // n_txp+1
     DevBuf<uint32_t> txp_len;    // n_txp
     DevBuf<uint64_t> txp_end;    // n_txp: txp_start[t] + txp_len[t]
-    DevBuf<uint2> sa;            // n_sa entries {position, transcript}, sorted by (k-mer value, position)
+    // n_sa entries sorted by (k-mer value, position), 16 bytes each: {text position, transcript, position inside the transcript,
+    // bases left to the transcript's end}.  The last two are redundant with txp_start / txp_end, but having them in the entry removes a
+    // dependent random load from every match extension and every projected hit
+    DevBuf<uint4> sa;
     DevBuf<uint4> table;         // {key lo, key hi, lb, cnt}; empty = cnt 0
-    // presence filter over the distinct k-mers (blocked Bloom filter, one 64-bit block per k-mer, 3 bits): answers
-    // "certainly absent" for most k-mers of the wrong read orientation without touching the table; sized to stay in L2
+    // presence filter over the distinct k-mers: answers "certainly absent" for most k-mers of the wrong read orientation without
+    // touching the table.  Blocked Bloom filter whose block (one 32-byte sector = 4 words) is chosen by the k-mer's ANCHOR m-mer, so
+    // that the successive k-mers of a read mostly fall into the same sector (sfb_bloom_word below)
     DevBuf<uint64_t> bloom;
-    uint64_t bloom_words = 0;    // power of two
+    uint64_t bloom_words = 0;    // power of two, >= 64
     bool ready = false;
     size_t hbm_bytes() const {
         return words.bytes() + txp_start.bytes() + txp_len.bytes() + txp_end.bytes() + sa.bytes() + table.bytes() + bloom.bytes();
@@ -236,22 +240,7 @@ __host__ __device__ __forceinline__ uint64_t xxh64_words(F get, uint32_t n, uint
 
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
 
-// ---- k-mer table hashing -----------------------------------------------------------------------------------------------
-// The k-mer table and the presence filter are this repo's own structures (RapMap's index is not in the reference
-// tree), so their hash is free to choose.  XXH64 of the 8-byte k-mer costs five 64-bit multiplies per lookup -- measured
-// at ~40% of the mapping kernel's instructions -- so lookups use a two-multiply mixer; XXH64 stays where the reference
-// fixes it: the equivalence-class label hash (TranscriptGroup.cpp:9-12).
-__host__ __device__ __forceinline__ uint64_t sfb_kmer_mix(uint64_t x) {
-    x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 32;
-    x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 29;
-    return x;
-}
-// presence filter: blocked Bloom filter with one 64-bit block per k-mer and three bits inside it; the table slot uses the
-// low bits of the same mix, the filter word its high bits
-__host__ __device__ __forceinline__ uint64_t sfb_bloom_word(uint64_t h, uint64_t n_words) { return (h >> 36) & (n_words - 1); }
-__host__ __device__ __forceinline__ uint64_t sfb_bloom_mask(uint64_t h) {
-    return (1ULL << ((h >> 8) & 63)) | (1ULL << ((h >> 14) & 63)) | (1ULL << ((h >> 20) & 63));
-}
+#include "kmer_filter.hpp"     // k-mer table hash + the presence filter's addressing (also compiled by the CPU tests)
 
 // digamma for x > 0: recurrence up to x >= 12, then the asymptotic series (same expansion as the oracle's
 // stand-in for boost::math::digamma; checked against scipy in tests/)

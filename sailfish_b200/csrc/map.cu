@@ -49,8 +49,9 @@ __device__ __forceinline__ bool compat_paired(int expected, int32_t e1, bool fwd
 
 struct IndexView {
     const uint64_t* words; const uint64_t* txp_start; const uint64_t* txp_end;
-    const uint2* sa; const uint4* table; const uint64_t* bloom;
+    const uint4* sa; const uint4* table; const uint64_t* bloom;
     uint64_t mask, bloom_words; int k; uint64_t kmask;
+    SfbBloomGeom bg;
 };
 
 // the per-hit arithmetic of the bias / GC sample collection, shared with bias.cu and the CPU check (tests/bias_core_test.cpp)
@@ -100,9 +101,8 @@ __device__ __forceinline__ bool slot_matches(const EqTable& tb, unsigned long lo
 
 // upsert: returns false only when the table or the arena is exhausted (error flag raised)
 template <typename GetLabel>
-__device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigned long long add) {
+__device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigned long long add, uint64_t h /* XXH64 of the label */) {
     if (len >= 1024) { atomicOr(tb.cursor + 2, ERR_LABEL_LONG); return false; }
-    const uint64_t h = xxh64_words(get, len, 0);                       // TranscriptGroup.cpp:9-12
     const uint64_t bmask = tb.n_buckets - 1;
     const uint64_t b1 = h & bmask;
     const uint64_t b2 = (b1 ^ (((h >> 48) + 1) * 0x5bd1e995ULL)) & bmask;
@@ -150,12 +150,13 @@ __device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigne
 // memory would go out to L2 (a CTA's reads do not fit L1).  2 bits per base, base i at bits 2*(i%32) of word i/32;
 // orientation 0 = as sequenced, 1 = reverse complement.  The invalid-base masks (same layout, 0b01 where the base is not
 // A/C/G/T) are rare and stay in local memory, touched only when has_n.
+extern __shared__ uint64_t smem_reads[];       // scan kernel: [warp][mate][orientation][word][lane]
 struct Read {
-    uint64_t* sb;
+    uint32_t sb;                               // index of this lane's column of this mate in smem_reads
     uint64_t nm[2][RW];
     uint32_t len;
     bool has_n;
-    __device__ __forceinline__ uint64_t word(int o, uint32_t w) const { return sb[(o * RW + w) * 32]; }
+    __device__ __forceinline__ uint64_t word(int o, uint32_t w) const { return smem_reads[sb + (o * RW + w) * 32]; }
 };
 
 __device__ __forceinline__ uint64_t win32(const Read& r, int o, uint32_t pos) {
@@ -262,7 +263,7 @@ __device__ void load_packed(const uint64_t* __restrict__ pk, const uint64_t* __r
     r.has_n = (me >> 16) & 1u;
     const uint32_t nw = (L + 31) >> 5;
     const uint64_t* src = pk + fm * rwp;
-    for (uint32_t w = 0; w < RW; ++w) r.sb[w * 32] = w < nw ? __ldg(src + w) : 0ULL;
+    for (uint32_t w = 0; w < RW; ++w) smem_reads[r.sb + w * 32] = w < nw ? __ldg(src + w) : 0ULL;
     // reverse complement: reversed words in reverse order, then shifted down by the padding of the last word
     const uint32_t pad = nw * 32 - L;
     for (uint32_t w = 0; w < RW; ++w) {
@@ -270,14 +271,14 @@ __device__ void load_packed(const uint64_t* __restrict__ pk, const uint64_t* __r
         if (w < nw) {
             // rc base j = comp(fw base L-1-j); in "reversed padded" coordinates that is position j + pad
             const uint32_t pos = w * 32 + pad, idx = pos >> 5, sh = 2 * (pos & 31);
-            const uint64_t lo = idx < nw ? revcomp32(r.sb[(nw - 1 - idx) * 32]) : 0ULL;
-            const uint64_t hi = (idx + 1) < nw ? revcomp32(r.sb[(nw - 2 - idx) * 32]) : 0ULL;
+            const uint64_t lo = idx < nw ? revcomp32(smem_reads[r.sb + (nw - 1 - idx) * 32]) : 0ULL;
+            const uint64_t hi = (idx + 1) < nw ? revcomp32(smem_reads[r.sb + (nw - 2 - idx) * 32]) : 0ULL;
             v = lo >> sh;
             if (sh) v |= hi << (64 - sh);
             const uint32_t rem = L - w * 32;                            // bases of this word that exist
             if (rem < 32) v &= (1ULL << (2 * rem)) - 1;
         }
-        r.sb[(RW + w) * 32] = v;
+        smem_reads[r.sb + (RW + w) * 32] = v;
     }
     if (r.has_n) {
         const uint64_t* srcn = pkn + fm * rwp;
@@ -295,11 +296,11 @@ __device__ void load_packed(const uint64_t* __restrict__ pk, const uint64_t* __r
     }
 }
 
-// longest common extension of read[qpos..) with text[p..tend), counted from the k-mer start (always >= k)
-__device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, int o, uint32_t qpos, uint64_t p, uint64_t tend) {
+// longest common extension of read[qpos..) with text[p..p+rem), counted from the k-mer start (always >= k); rem = bases from p to the
+// end of p's transcript (carried by the suffix entry)
+__device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, int o, uint32_t qpos, uint64_t p, uint32_t rem) {
     const uint32_t lim_r = r.len - qpos;
-    const uint64_t lim_t = tend - p;
-    const uint32_t lim = lim_t < lim_r ? static_cast<uint32_t>(lim_t) : lim_r;
+    const uint32_t lim = rem < lim_r ? rem : lim_r;
     uint32_t m = ix.k;
     while (m < lim) {
         const uint64_t x = win32(r, o, qpos + m) ^ win32g(ix.words, p + m);
@@ -344,7 +345,7 @@ __device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
 #define SFB_SPEC 2
 #endif
 #ifndef SFB_EXT_BATCH
-#define SFB_EXT_BATCH 1      // seed extensions run as soon as they are found (batching them idled the waiting lanes: measured slower)
+#define SFB_EXT_BATCH 4      // pending seeds a warp collects before it extends them together (extend_coop)
 #endif
 #ifndef SFB_SCAN_BLOCKS
 #define SFB_SCAN_BLOCKS 4
@@ -352,8 +353,7 @@ __device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
 constexpr int SPEC = SFB_SPEC;
 struct ScanState { int s, n; uint32_t i; uint32_t pend_lb, pend_cnt; };   // pend_cnt != 0: a seed waits for its extension
 __device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, int ns, uint32_t max_interval, ScanState& st,
-                                          unsigned long long* __restrict__ iv_out /* [ns][MAX_IV] of this fragment */,
-                                          uint8_t* __restrict__ niv_out /* [ns] */) {
+                                          uint8_t* __restrict__ niv_out /* [ns] of this fragment */) {
     const uint32_t k = ix.k;
     const Read& r = rds[st.s >> 1];
     const int o = st.s & 1;
@@ -381,7 +381,7 @@ __device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, 
                               km[j] == (0xAAAAAAAAAAAAAAAAULL & ix.kmask);           // homopolymer k-mers are never seeds
             if (!homo) {
                 hh[j] = sfb_kmer_mix(km[j]);
-                bw[j] = __ldg(ix.bloom + sfb_bloom_word(hh[j], ix.bloom_words));
+                bw[j] = __ldg(ix.bloom + sfb_bloom_word(km[j], hh[j], ix.bg, ix.bloom_words));
                 probe[j] = true;
             }
         }
@@ -431,8 +431,8 @@ __device__ __forceinline__ void extend_seed(const IndexView& ix, const Read* rds
     const uint32_t q = st.i, lb = st.pend_lb, cnt = st.pend_cnt;
     uint32_t m = 0, mask = 0;
     for (uint32_t e = 0; e < cnt; ++e) {
-        const uint2 en = __ldg(ix.sa + lb + e);
-        const uint32_t l = lcp_at(ix, r, o, q, en.x, __ldg(ix.txp_end + en.y));
+        const uint4 en = __ldg(ix.sa + lb + e);
+        const uint32_t l = lcp_at(ix, r, o, q, en.x, en.w);
         if (l > m) { m = l; mask = e < 32 ? (1u << e) : 0u; }
         else if (l == m && e < 32) mask |= 1u << e;
     }
@@ -443,10 +443,115 @@ __device__ __forceinline__ void extend_seed(const IndexView& ix, const Read* rds
     st.pend_cnt = 0;
 }
 
-// per-thread scratch in global memory, element j of thread t at base[j * stride + t] (coalesced like local memory)
+// Match extension of the warp's pending seeds, done by the whole warp.  A seed's extension is a chain of dependent random loads
+// (suffix entry -> text words) per bucket entry; run by the lane that found the seed it keeps 1-3 lanes of the warp busy for
+// ~cnt x 3 memory round trips.  Here the warp splits into 8 groups of 4 lanes, a group takes one pending seed (its owner's packed read
+// is readable by every lane: it lives in shared memory), the group's lanes take the bucket entries round-robin, and a lane has the
+// first two text windows of its entry in flight together.  Seeds of reads with invalid bases stay with their owner (the masks are
+// in its local memory): extend_seed below.
+#ifndef SFB_EXT_GROUP
+#define SFB_EXT_GROUP 4
+#endif
+constexpr unsigned EXT_G = SFB_EXT_GROUP, EXT_NG = 32 / EXT_G;
+__device__ __forceinline__ uint32_t lcp_clean(const IndexView& ix, uint32_t sb, uint32_t len, int o, uint32_t qpos, uint64_t p, uint32_t rem) {
+    const uint32_t lim_r = len - qpos;
+    const uint32_t lim = rem < lim_r ? rem : lim_r;
+    uint32_t m = ix.k;
+    if (m >= lim) return lim;
+    // text windows [p+m, p+m+32) and [p+m+32, p+m+64): three words, loaded together
+    const uint64_t P = p + m;
+    const uint64_t idx = P >> 5; const uint32_t sh = 2 * (P & 31);
+    const uint64_t w0 = __ldg(ix.words + idx), w1 = __ldg(ix.words + idx + 1), w2 = __ldg(ix.words + idx + 2);
+    const uint64_t t0 = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+    const uint64_t t1 = sh ? ((w1 >> sh) | (w2 << (64 - sh))) : w1;
+    auto rwin = [&](uint32_t pos) {
+        const uint32_t i = pos >> 5, s2 = 2 * (pos & 31);
+        uint64_t v = smem_reads[sb + (o * RW + i) * 32] >> s2;
+        if (s2) v |= smem_reads[sb + (o * RW + i + 1) * 32] << (64 - s2);
+        return v;
+    };
+    uint64_t x = rwin(qpos + m) ^ t0;
+    uint64_t y = (x | (x >> 1)) & 0x5555555555555555ULL;
+    if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; return m < lim ? m : lim; }
+    m += 32;
+    if (m >= lim) return lim;
+    x = rwin(qpos + m) ^ t1;
+    y = (x | (x >> 1)) & 0x5555555555555555ULL;
+    if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; return m < lim ? m : lim; }
+    m += 32;
+    while (m < lim) {
+        x = rwin(qpos + m) ^ win32g(ix.words, p + m);
+        y = (x | (x >> 1)) & 0x5555555555555555ULL;
+        if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; break; }
+        m += 32;
+    }
+    return m < lim ? m : lim;
+}
+
+// all 32 lanes call this; todo = lanes whose pending seed belongs to a read without invalid bases
+__device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds, ScanState& st, unsigned todo, unsigned lane,
+                                            unsigned long long* __restrict__ iv_all, uint32_t* __restrict__ ivmask_all, uint64_t iv_base) {
+    const unsigned grp = lane / EXT_G, sub = lane % EXT_G;
+    const uint32_t my_len = rds[(st.s >> 1) & 1].len;                  // only read from lanes that own a pending seed
+    while (todo) {
+        const unsigned src = __fns(todo, 0, (int)grp + 1);             // owner lane of this group's seed, 0xFFFFFFFF if there is none
+        const bool act = src < 32u;
+        const unsigned sl = act ? src : lane;
+        const uint32_t lb = __shfl_sync(0xffffffffu, st.pend_lb, sl);
+        uint32_t cnt = __shfl_sync(0xffffffffu, st.pend_cnt, sl);
+        if (!act) cnt = 0;                                             // a group without a seed idles through this round
+        const uint32_t q = __shfl_sync(0xffffffffu, st.i, sl);
+        const int ss = __shfl_sync(0xffffffffu, st.s, sl);
+        const uint32_t len = __shfl_sync(0xffffffffu, my_len, sl);
+        // the owner's packed mate in shared memory: same warp region, its lane's column
+        const uint32_t sb = ((ss >> 1) ? rds[1].sb : rds[0].sb) + sl - lane;
+        uint32_t best = 0, mask = 0;
+        for (uint32_t e = sub; e < cnt; e += EXT_G) {
+            const uint4 en = __ldg(ix.sa + lb + e);
+            const uint32_t l = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.w);
+            if (l > best) { best = l; mask = e < 32 ? (1u << e) : 0u; }
+            else if (l == best && e < 32) mask |= 1u << e;
+        }
+#pragma unroll
+        for (unsigned d = 1; d < EXT_G; d <<= 1) {
+            const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), om = __shfl_xor_sync(0xffffffffu, mask, d);
+            if (ob > best) { best = ob; mask = om; } else if (ob == best) mask |= om;
+        }
+        // hand the result back to the owners served in this round: the first EXT_NG set bits of todo
+        const unsigned rank = __popc(todo & ((1u << lane) - 1));
+        const bool mine = ((todo >> lane) & 1u) && rank < EXT_NG;
+        const unsigned from = mine ? rank * EXT_G : lane;
+        const uint32_t m = __shfl_sync(0xffffffffu, best, from), mk = __shfl_sync(0xffffffffu, mask, from);
+        if (mine) {
+            iv_all[iv_base + st.s * MAX_IV + st.n] = pack_iv(st.pend_lb, st.pend_cnt, st.i, m);
+            ivmask_all[iv_base + st.s * MAX_IV + st.n] = mk;
+            ++st.n;
+            st.i = st.i + m - ix.k + 1;
+            st.pend_cnt = 0;
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+// Per-thread hit lists.  Five regions of max_read_occs+1 entries per thread: the two orientation projections of the mate being
+// collected (R_A, R_B), the left and right mate's merged lists, and the label under construction.  The first FIN_S entries of every
+// region live in SHARED memory (lane-interleaved, [region][entry][lane] per warp) -- a read rarely hits more than a handful of
+// transcripts -- the rest in a thread-interleaved global scratch (element j of thread t at base[j * stride + t], coalesced like local
+// memory).  Lists are written, merged, filtered, hashed and compared entry by entry, each step a dependent access: in shared memory
+// that is ~30 cycles, through L2 it was ~300 (ncu, round 1: 18% issue utilisation).
+constexpr uint32_t FIN_S = 6;
+enum { R_A = 0, R_B = 1, R_LEFT = 2, R_RIGHT = 3, R_LABEL = 4, N_REGIONS = 5 };
 struct Scratch {
-    unsigned long long* base; uint64_t stride;
-    __device__ __forceinline__ unsigned long long& at(uint32_t j) const { return base[(uint64_t)j * stride]; }
+    unsigned long long* sm;        // this lane's column of its warp's shared block
+    unsigned long long* base;      // this thread's column of the global scratch
+    uint64_t stride; uint32_t cap1;
+    __device__ __forceinline__ unsigned long long& at(uint32_t region, uint32_t j) const {
+        return j < FIN_S ? sm[(region * FIN_S + j) * 32] : base[(uint64_t)(region * cap1 + j) * stride];
+    }
+    // the same entry of another lane of this warp (delta = that lane - this lane)
+    __device__ __forceinline__ unsigned long long peer(int delta, uint32_t region, uint32_t j) const {
+        return j < FIN_S ? sm[(int)((region * FIN_S + j) * 32) + delta] : base[(int64_t)((uint64_t)(region * cap1 + j) * stride) + delta];
+    }
 };
 __device__ __forceinline__ unsigned long long pack_hit(uint32_t tid, int32_t pos, bool fwd) {
     return ((unsigned long long)tid << 32) | (uint32_t)(((pos + POS_BIAS) << 1) | (fwd ? 1 : 0));
@@ -455,22 +560,53 @@ __device__ __forceinline__ uint32_t hit_tid(unsigned long long h) { return (uint
 __device__ __forceinline__ int32_t hit_pos(unsigned long long h) { return (int32_t)(((uint32_t)h) >> 1) - POS_BIAS; }
 __device__ __forceinline__ bool hit_fwd(unsigned long long h) { return (h & 1ULL) != 0; }
 
+// The finalize kernel does not stage the packed reads: it needs read bases only for bucket entries beyond the 32 the scan's mask
+// covers (buckets of more than 32 positions).  Those few extensions read the packed mate straight from global memory.
+struct ReadG { const uint64_t* pk; const uint64_t* pkn; uint32_t len; bool has_n; };
+__device__ __forceinline__ uint64_t gwin32(const uint64_t* __restrict__ w, uint32_t pos) {
+    const uint32_t idx = pos >> 5, sh = 2 * (pos & 31);
+    uint64_t v = w[idx] >> sh;
+    if (sh) v |= w[idx + 1] << (64 - sh);
+    return v;
+}
+// 32-base window at `pos` of orientation o (1 = reverse complement; plain reversal for the invalid-base masks)
+__device__ __forceinline__ uint64_t readg_win(const uint64_t* __restrict__ w, uint32_t len, int o, uint32_t pos, bool complement) {
+    if (o == 0) return gwin32(w, pos);
+    // rc base j = comp(fw base len-1-j): the window covers fw bases [len-pos-32, len-pos), reversed
+    const int32_t s = (int32_t)len - (int32_t)pos - 32;
+    uint64_t f = gwin32(w, s >= 0 ? (uint32_t)s : 0u);
+    uint64_t x = __brevll(complement ? ~f : f);
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    return s >= 0 ? x : (x >> (2 * (uint32_t)(-s)));
+}
+__device__ __noinline__ uint32_t lcp_global(const IndexView& ix, const ReadG& r, int o, uint32_t qpos, uint64_t p, uint32_t rem) {
+    const uint32_t lim_r = r.len - qpos;
+    const uint32_t lim = rem < lim_r ? rem : lim_r;
+    uint32_t m = ix.k;
+    while (m < lim) {
+        const uint64_t x = readg_win(r.pk, r.len, o, qpos + m, true) ^ win32g(ix.words, p + m);
+        uint64_t y = (x | (x >> 1)) & 0x5555555555555555ULL;
+        if (r.has_n) y |= readg_win(r.pkn, r.len, o, qpos + m, false);
+        if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; break; }
+        m += 32;
+    }
+    return m < lim ? m : lim;
+}
+
 // transcripts present with the maximal match in every interval; output ascending by transcript id;
 // stops after cap+1 hits (list overflow)
-__device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Interval* ivs, int niv, uint32_t cap,
-                            const Scratch& out, uint32_t out0) {
+__device__ uint32_t project(const IndexView& ix, const ReadG& r, int o, const Interval* ivs, int niv, uint32_t cap,
+                            const Scratch& out, uint32_t region) {
     if (niv == 0) return 0;
     uint32_t n = 0;
     const Interval a = ivs[0];
     int64_t lastTid = -1;
     for (uint32_t e = a.lb; e < a.lb + a.cnt; ++e) {
-        const uint2 en = __ldg(ix.sa + e);
+        const uint4 en = __ldg(ix.sa + e);
         const uint32_t tid = en.y;
         if ((int64_t)tid == lastTid) continue;
-        const uint64_t tend = __ldg(ix.txp_end + tid);
-        const uint32_t p = en.x;
         const uint32_t e_rel = e - a.lb;
-        if (e_rel < 32 ? !((a.mask >> e_rel) & 1u) : (lcp_at(ix, r, o, a.qpos, p, tend) != a.m)) continue;
+        if (e_rel < 32 ? !((a.mask >> e_rel) & 1u) : (lcp_global(ix, r, o, a.qpos, en.x, en.w) != a.m)) continue;
         lastTid = tid;
         bool all = true;
         for (int j = 1; j < niv && all; ++j) {
@@ -479,38 +615,42 @@ __device__ uint32_t project(const IndexView& ix, const Read& r, int o, const Int
             while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(&ix.sa[mid].y) < tid) lo = mid + 1; else hi = mid; }
             bool found = false;
             for (uint32_t e2 = lo; e2 < b.lb + b.cnt; ++e2) {
-                const uint2 en2 = __ldg(ix.sa + e2);
+                const uint4 en2 = __ldg(ix.sa + e2);
                 if (en2.y != tid) break;
                 const uint32_t e2_rel = e2 - b.lb;
-                if (e2_rel < 32 ? ((b.mask >> e2_rel) & 1u) != 0 : (lcp_at(ix, r, o, b.qpos, en2.x, tend) == b.m)) { found = true; break; }
+                if (e2_rel < 32 ? ((b.mask >> e2_rel) & 1u) != 0 : (lcp_global(ix, r, o, b.qpos, en2.x, en2.w) == b.m)) { found = true; break; }
             }
             all = found;
         }
         if (!all) continue;
-        const int32_t pos = (int32_t)((int64_t)p - (int64_t)__ldg(ix.txp_start + tid) - (int64_t)a.qpos);
-        out.at(out0 + n) = pack_hit(tid, pos, o == 0);
+        const int32_t pos = (int32_t)en.z - (int32_t)a.qpos;
+        out.at(region, n) = pack_hit(tid, pos, o == 0);
         ++n;
         if (n > cap) return n;
     }
     return n;
 }
 
-// one mate: both orientations, optional strand vote, merge by transcript id.  Returns false on list overflow.
-__device__ bool collect(const IndexView& ix, const Read& r, bool strict, uint32_t cap, const Interval* ivF, int nivF,
-                        uint64_t scF, const Interval* ivR, int nivR, uint64_t scR, const Scratch& scr, uint32_t tmp0,
-                        uint32_t dst0, uint32_t& n_out) {
-    n_out = 0;
-    uint32_t nF = project(ix, r, 0, ivF, nivF, cap, scr, tmp0);
-    uint32_t nR = project(ix, r, 1, ivR, nivR, cap, scr, tmp0 + cap + 1);
+// one mate: both orientations, optional strand vote, merge by transcript id.  Returns false on list overflow.  The list ends up in
+// region `where` (a projection region when only one orientation hit -- the usual case -- else `dst`)
+__device__ bool collect(const IndexView& ix, const ReadG& r, bool strict, uint32_t cap, const Interval* ivF, int nivF,
+                        uint64_t scF, const Interval* ivR, int nivR, uint64_t scR, const Scratch& scr,
+                        uint32_t dst, uint32_t& n_out, uint32_t& where) {
+    n_out = 0; where = dst;
+    uint32_t nF = project(ix, r, 0, ivF, nivF, cap, scr, R_A);
+    uint32_t nR = project(ix, r, 1, ivR, nivR, cap, scr, R_B);
     if (nF > cap || nR > cap) return false;
     if (strict && nF && nR) { if (scF > scR) nR = 0; else if (scR > scF) nF = 0; }
     if (nF + nR > cap) return false;
+    if (nR == 0) { n_out = nF; where = R_A; return true; }
+    if (nF == 0) { n_out = nR; where = R_B; return true; }
     uint32_t i = 0, j = 0, n = 0;
     while (i < nF || j < nR) {                     // stable merge: forward before reverse on equal transcript id
         bool takeF;
         if (i >= nF) takeF = false; else if (j >= nR) takeF = true;
-        else takeF = hit_tid(scr.at(tmp0 + i)) <= hit_tid(scr.at(tmp0 + cap + 1 + j));
-        scr.at(dst0 + n++) = takeF ? scr.at(tmp0 + i++) : scr.at(tmp0 + cap + 1 + j++);
+        else takeF = hit_tid(scr.at(R_A, i)) <= hit_tid(scr.at(R_B, j));
+        const unsigned long long h = takeF ? scr.at(R_A, i++) : scr.at(R_B, j++);
+        scr.at(dst, n++) = h;
     }
     n_out = n;
     return true;
@@ -538,14 +678,14 @@ struct MapParams {
 };
 
 struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of processReadsQuasi folded into one buffer
-    const Scratch& scr; uint32_t base; uint32_t n; bool haveCompat; int32_t fw, rc; bool enforce;
-    __device__ LabelAcc(const Scratch& s, uint32_t b, bool enf) : scr(s), base(b), n(0), haveCompat(false), fw(0), rc(0), enforce(enf) {}
+    const Scratch& scr; uint32_t n; bool haveCompat; int32_t fw, rc; bool enforce;
+    __device__ LabelAcc(const Scratch& s, bool enf) : scr(s), n(0), haveCompat(false), fw(0), rc(0), enforce(enf) {}
     __device__ __forceinline__ void add(uint32_t tid, bool compat, bool fwdHit) {
         if (compat) {
             if (!haveCompat) { haveCompat = true; n = 0; fw = 0; rc = 0; }      // switch from "all" to "compatible only"
-            scr.at(base + n++) = tid; if (fwdHit) ++fw; else ++rc;
+            scr.at(R_LABEL, n++) = tid; if (fwdHit) ++fw; else ++rc;
         } else if (!haveCompat && !enforce) {
-            scr.at(base + n++) = tid; if (fwdHit) ++fw; else ++rc;
+            scr.at(R_LABEL, n++) = tid; if (fwdHit) ++fw; else ++rc;
         }
     }
 };
@@ -556,19 +696,19 @@ struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of 
 // lanes busy).  Here a lane that has finished its fragment takes the next one from its warp's reservation (64 fragments per
 // global atomic) and the seed intervals go to global memory for the finalize kernel.
 __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(const MapParams p) {
-    extern __shared__ uint64_t smem_reads[];       // [warp][mate][orientation][word][lane]
     const unsigned lane = threadIdx.x & 31u;
     const int n_mates = p.n_mates, ns = 2 * n_mates;
     Read rds[2];
     {
-        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * n_mates * 2 * RW * 32 + lane;
+        const uint32_t wbase = (threadIdx.x >> 5) * n_mates * 2 * RW * 32 + lane;
         rds[0].sb = wbase;
         rds[1].sb = wbase + (n_mates - 1) * 2 * RW * 32;
     }
     bool have = false, done = false;
-    uint64_t frag = 0;
+    uint32_t frag = 0;                                     // a chunk holds at most 2^22 fragments (map_chunk_device): 32-bit indices
+    const uint32_t n_reads = (uint32_t)p.n_reads;
     ScanState st; st.s = 0; st.n = 0; st.i = 0; st.pend_lb = 0; st.pend_cnt = 0;
-    unsigned long long res_next = 0, res_end = 0;          // this warp's reservation [res_next, res_end), warp-uniform
+    uint32_t res_next = 0, res_end = 0;                    // this warp's reservation [res_next, res_end), warp-uniform
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !have && !done);
         const unsigned busy = __ballot_sync(0xffffffffu, have);
@@ -577,15 +717,15 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
                 unsigned long long b = 0;
                 if (lane == 0) b = atomicAdd(p.next_read, 64ULL);
                 b = __shfl_sync(0xffffffffu, b, 0);
-                res_next = b < p.n_reads ? b : p.n_reads;
-                res_end = b + 64 < p.n_reads ? b + 64 : p.n_reads;
+                res_next = b < n_reads ? (uint32_t)b : n_reads;
+                res_end = b + 64 < n_reads ? (uint32_t)b + 64 : n_reads;
             }
-            const unsigned long long avail = res_end - res_next;       // 0 only when the global queue is exhausted
+            const uint32_t avail = res_end - res_next;                 // 0 only when the global queue is exhausted
             if (!have && !done) {
                 const unsigned my = __popc(need & ((1u << lane) - 1));
                 if (my < avail) {
                     frag = res_next + my;
-                    for (int mt = 0; mt < n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, frag * n_mates + mt, p.rwp, rds[mt]);
+                    for (int mt = 0; mt < n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, (uint64_t)frag * n_mates + mt, p.rwp, rds[mt]);
                     st.s = 0; st.n = 0; st.i = 0; st.pend_cnt = 0;
                     have = true;
                 } else if (avail == 0) {
@@ -596,15 +736,21 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
             res_next += want < avail ? want : avail;
         }
         if (__ballot_sync(0xffffffffu, have) == 0 && __ballot_sync(0xffffffffu, !done) == 0) break;
-        // extensions are batched: lanes with a pending seed wait until 8 of them do (or nobody else can advance), so the
-        // divergent extension code runs with several lanes and their dependent loads overlap
-        const bool pend = have && st.pend_cnt != 0;
+        // extensions are batched: lanes with a pending seed wait until SFB_EXT_BATCH of them do (or nobody else can advance), then the
+        // whole warp extends them together (extend_coop)
+        bool pend = have && st.pend_cnt != 0;
         const unsigned pend_m = __ballot_sync(0xffffffffu, pend);
         const unsigned adv_m = __ballot_sync(0xffffffffu, have && !pend);
-        if (pend && (__popc(pend_m) >= SFB_EXT_BATCH || adv_m == 0))
-            extend_seed(p.ix, rds, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.ivmask + frag * (uint64_t)(ns * MAX_IV));
+        if (pend_m && (__popc(pend_m) >= SFB_EXT_BATCH || adv_m == 0)) {
+            const uint64_t ivb = frag * (uint64_t)(ns * MAX_IV);
+            const bool dirty = pend && rds[st.s >> 1].has_n;
+            const unsigned clean_m = pend_m & ~__ballot_sync(0xffffffffu, dirty);
+            if (clean_m) extend_coop(p.ix, rds, st, clean_m, lane, p.iv, p.ivmask, ivb);
+            if (dirty) extend_seed(p.ix, rds, st, p.iv + ivb, p.ivmask + ivb);
+            pend = false;                                  // every pending seed of the warp has been extended
+        }
         if (have && !pend) {
-            if (scan_step(p.ix, rds, ns, p.max_interval, st, p.iv + frag * (uint64_t)(ns * MAX_IV), p.niv + frag * ns)) have = false;
+            if (scan_step(p.ix, rds, ns, p.max_interval, st, p.niv + (uint64_t)frag * ns)) have = false;
         }
     }
 }
@@ -759,6 +905,8 @@ __global__ void k_count_active(const uint8_t* __restrict__ active, uint32_t T, u
 }  // namespace
 
 // ======================================================================================================================
+constexpr size_t FIN_SMEM = (size_t)(MAP_THREADS / 32) * N_REGIONS * FIN_S * 32 * 8;      // finalize: hit lists in shared memory
+
 struct MapState {
     sfb200_map_opts o;
     bool begun = false;
@@ -849,17 +997,19 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     SFB_CUDA(c, cudaMemcpyAsync(m->remaining.p, &rem, 4, cudaMemcpyHostToDevice, s));
     // launch geometry: every SM filled with resident CTAs; scratch sized for exactly those threads
     int per_sm = 0;
-    // the occupancy that matters is the paired-end one (two mates of packed reads in shared memory per lane)
+    // scan: the packed mates of a lane's fragment live in shared memory (paired-end: two mates); the grid is sized for the
+    // single-end occupancy, a paired-end launch simply leaves some of those CTAs waiting for a slot
     const size_t smem_pe = (size_t)MAP_THREADS * 2 * 2 * RW * 8;
     SFB_CUDA(c, cudaFuncSetAttribute(k_scan_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe));
-    SFB_CUDA(c, cudaFuncSetAttribute(k_finalize_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe));
     SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_reads, MAP_THREADS, smem_pe / 2));
     m->grid_scan = c->num_sms * std::max(per_sm, 1);
-    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finalize_reads, MAP_THREADS, smem_pe / 2));
+    // finalize: the hit lists' first FIN_S entries per region in shared memory
+    SFB_CUDA(c, cudaFuncSetAttribute(k_finalize_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
+    SFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finalize_reads, MAP_THREADS, FIN_SMEM));
     if (per_sm < 1) per_sm = 1;
     m->grid = c->num_sms * per_sm;
     m->n_threads_total = (uint64_t)m->grid * MAP_THREADS;
-    SFB_CUDA(c, m->scratch.reserve(m->n_threads_total * 4ull * (o->max_read_occs + 1)));
+    SFB_CUDA(c, m->scratch.reserve(m->n_threads_total * (uint64_t)N_REGIONS * (o->max_read_occs + 1)));
     SFB_CUDA(c, cudaStreamSynchronize(s));
     // keep the presence filter resident in L2 while the table / suffix entries / text stream through it
     if (!getenv("SFB200_NO_L2_PERSIST")) {
@@ -902,7 +1052,7 @@ extern "C" int sfb200_map_set_bias(sfb200_ctx* c, int seq_bias, int gc_bias, int
     SFB_CUDA(c, cudaMemsetAsync(m->bias_hist.p, 0, BIAS_HIST_WORDS * 4ull, s));
     const int rem = num_bias_samples < 0 ? 0 : num_bias_samples;
     SFB_CUDA(c, cudaMemcpyAsync(m->bias_remaining.p, &rem, 4, cudaMemcpyHostToDevice, s));
-    SFB_CUDA(c, cudaFuncSetAttribute(k_finalize_reads_bias, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MAP_THREADS * 2 * 2 * RW * 8)));
+    SFB_CUDA(c, cudaFuncSetAttribute(k_finalize_reads_bias, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     SFB_CUDA(c, cudaStreamSynchronize(s));
     return SFB200_OK;
 }
@@ -946,7 +1096,7 @@ extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, cons
                                        const uint64_t* d_off2, uint64_t n_reads) {
     if (!c) return SFB200_EINVAL;
     uint64_t MAX_CHUNK = 4u << 20;
-    if (const char* e = getenv("SFB200_MAX_CHUNK")) MAX_CHUNK = std::max<long long>(32, atoll(e));
+    if (const char* e = getenv("SFB200_MAX_CHUNK")) MAX_CHUNK = std::min<long long>(1ll << 30, std::max<long long>(32, atoll(e)));   // the scan kernel indexes a chunk with 32 bits
     for (uint64_t a = 0; a < n_reads || a == 0; a += MAX_CHUNK) {
         const uint64_t n = std::min<uint64_t>(MAX_CHUNK, n_reads - a);
         const int rc = map_chunk_device(c, d_bases1, d_off1 ? d_off1 + a : nullptr, d_bases2, d_off2 ? d_off2 + a : nullptr, n);
@@ -970,6 +1120,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     p.ix.words = ix.words.p; p.ix.txp_start = ix.txp_start.p; p.ix.txp_end = ix.txp_end.p; p.ix.sa = ix.sa.p;
     p.ix.table = ix.table.p; p.ix.bloom = ix.bloom.p; p.ix.bloom_words = ix.bloom_words; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
     p.ix.kmask = (1ULL << (2 * ix.k)) - 1;
+    p.ix.bg = sfb_bloom_geom(ix.k, ix.bloom_words);
     p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p; p.tb.cursor = m->cursor.p;
     p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
     p.bases1 = d_bases1; p.off1 = d_off1; p.bases2 = d_bases2; p.off2 = d_off2; p.n_reads = n_reads;
@@ -1007,11 +1158,11 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     c->launches++;
     const bool bias = m->bias_seq || m->bias_gc;
     if (!bias) {
-        k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, smem, s>>>(p);
+        k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, FIN_SMEM, s>>>(p);
     } else {
         if (m->bias_seq) { SFB_CUDA(c, m->bias_val.reserve(n_reads)); p.bias_val = m->bias_val.p; }
         p.gc_hist = m->bias_hist.p + BNK; p.bias_seq = m->bias_seq ? 1 : 0; p.bias_gc = (m->bias_gc && n_mates == 2) ? 1 : 0;
-        k_finalize_reads_bias<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, smem, s>>>(p);
+        k_finalize_reads_bias<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, FIN_SMEM, s>>>(p);
     }
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
@@ -1166,7 +1317,8 @@ __global__ void k_merge_upsert(const EqTable tb, const uint32_t* __restrict__ st
     const unsigned long long* cn = cnt_g + (size_t)r * maxE; const uint32_t* lb = lab_g + (size_t)r * maxZ;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t* a = lb + st[i];
-        eq_upsert(tb, ln[i], [&](uint32_t j) { return a[j]; }, cn[i]);
+        auto get = [&](uint32_t j) { return a[j]; };
+        eq_upsert(tb, ln[i], get, cn[i], xxh64_words(get, ln[i], 0));
     }
 }
 }  // namespace

@@ -1,24 +1,21 @@
 // map_finalize_body.inl -- the body of k_finalize_reads, included once per kernel entry point (map.cu) with SFB_FIN_BIAS 0 or 1.
-// Plain textual inclusion (no device-function wrapper): the default kernel is then token for token the kernel that was profiled
-// and parity-tested, and compiles to the same SASS.  SFB_FIN_BIAS 1 adds what --biasCorrect / --gcBiasCorrect collect per hit
+// Plain textual inclusion (no device-function wrapper).  SFB_FIN_BIAS 1 adds what --biasCorrect / --gcBiasCorrect collect per hit
 // (SailfishQuantify.cpp:255-287, :372-389, :555-583): the read-start context of the read's first hit that has one (p.bias_val,
 // sampled in read order by k_bias_select) and the GC percentage of every properly paired hit that lies inside its transcript
 // (s_gc, the CTA's 101-bin histogram, declared by the including kernel).
-    extern __shared__ uint64_t smem_reads[];
+//
+// A lane owns one read per round; its hit lists live in shared memory (Scratch, map.cu).  The class upsert at the end of a round is
+// warp-aggregated: lanes whose labels are equal (same XXH64, verified member by member) elect a leader that adds the group's count
+// with ONE table probe and ONE atomic (EquivalenceClassBuilder::addGroup, include/EquivalenceClassBuilder.hpp:90-108, called once
+// per read by the reference).
+    extern __shared__ unsigned long long smem_hits[];      // [warp][region][entry][lane]
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const Scratch scr{p.scratch + gtid, p.n_threads_total};
+    const unsigned lane = threadIdx.x & 31u;
     const uint32_t cap = p.cap;
-    const uint32_t TMP0 = 0, LEFT0 = 2 * (cap + 1), RIGHT0 = 3 * (cap + 1);
+    const Scratch scr{smem_hits + (size_t)(threadIdx.x >> 5) * (N_REGIONS * FIN_S * 32) + lane, p.scratch + gtid, p.n_threads_total, cap + 1};
     const bool paired = p.n_mates == 2;
     const int ns = 2 * p.n_mates;
-    const unsigned lane = threadIdx.x & 31u;
     unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
-    Read rds[2];
-    {
-        uint64_t* wbase = smem_reads + (size_t)(threadIdx.x >> 5) * p.n_mates * 2 * RW * 32 + lane;
-        rds[0].sb = wbase;
-        rds[1].sb = wbase + (p.n_mates - 1) * 2 * RW * 32;
-    }
     Interval ivs[4][MAX_IV];
     int niv[4];
     uint64_t score[4];
@@ -29,12 +26,19 @@
         base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
         if (base_idx >= p.n_reads) break;
         const uint64_t ri = base_idx + lane;
+        bool mapped = false;
+        uint32_t lab_n = 0;
         if (ri < p.n_reads) {
-            uint32_t nL = 0, nR = 0;
+            uint32_t nL = 0, nR = 0, wL = R_LEFT, wR = R_RIGHT;
             bool okL, okR = true;
-            for (int mt = 0; mt < p.n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, ri * p.n_mates + mt, p.rwp, rds[mt]);
-            const uint32_t len1 = rds[0].len;
-            const uint32_t len2 = paired ? rds[1].len : 0;
+            ReadG rg[2];
+            for (int mt = 0; mt < p.n_mates; ++mt) {
+                const uint64_t fm = ri * p.n_mates + mt;
+                const uint32_t me = p.meta[fm];
+                rg[mt].pk = p.pk + fm * p.rwp; rg[mt].pkn = p.pkn + fm * p.rwp; rg[mt].len = me & 0xFFFFu; rg[mt].has_n = (me >> 16) & 1u;
+            }
+            const uint32_t len1 = rg[0].len;
+            const uint32_t len2 = paired ? rg[1].len : 0;
             for (int q = 0; q < ns; ++q) {
                 niv[q] = p.niv[ri * ns + q];
                 uint64_t sc = 0;
@@ -45,10 +49,16 @@
                 }
                 score[q] = sc;
             }
-            okL = collect(p.ix, rds[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, TMP0, LEFT0, nL);   // paired: strict check (:192-202)
-            if (paired) okR = collect(p.ix, rds[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, TMP0, RIGHT0, nR);
+            okL = collect(p.ix, rg[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, R_LEFT, nL, wL);   // paired: strict check (:192-202)
+            if (paired) {
+                if (okL && wL != R_LEFT) {            // the projection regions are about to be reused by the right mate
+                    for (uint32_t i = 0; i < nL; ++i) { const unsigned long long h = scr.at(wL, i); scr.at(R_LEFT, i) = h; }
+                    wL = R_LEFT;
+                }
+                okR = collect(p.ix, rg[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, R_RIGHT, nR, wR);
+            }
             const bool overflow = !okL || !okR;
-            LabelAcc acc(scr, TMP0, p.enforce_compat != 0);
+            LabelAcc acc(scr, p.enforce_compat != 0);
             uint32_t n_joint = 0;
             int32_t fl = -1;
 #if SFB_FIN_BIAS
@@ -59,7 +69,7 @@
                 n_joint = overflow ? 0 : nL;
                 c_ub += (overflow || n_joint > 0) ? 1 : 0;
                 for (uint32_t i = 0; i < n_joint; ++i) {
-                    const unsigned long long h = scr.at(LEFT0 + i);
+                    const unsigned long long h = scr.at(wL, i);
 #if SFB_FIN_BIAS
                     if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, hit_tid(h), hit_pos(h), hit_fwd(h), len1);
 #endif
@@ -70,16 +80,16 @@
                 // mergeLeftRightHits[Fuzzy] (call sites :204-213): one joint hit per transcript present in both lists
                 uint32_t i = 0, j = 0, n_pairs = 0;
                 while (i < nL && j < nR) {
-                    const uint32_t tl = hit_tid(scr.at(LEFT0 + i)), tr = hit_tid(scr.at(RIGHT0 + j));
+                    const uint32_t tl = hit_tid(scr.at(wL, i)), tr = hit_tid(scr.at(wR, j));
                     if (tl < tr) ++i; else if (tr < tl) ++j;
-                    else { ++n_pairs; ++i; while (i < nL && hit_tid(scr.at(LEFT0 + i)) == tl) ++i; while (j < nR && hit_tid(scr.at(RIGHT0 + j)) == tl) ++j; }
+                    else { ++n_pairs; ++i; while (i < nL && hit_tid(scr.at(wL, i)) == tl) ++i; while (j < nR && hit_tid(scr.at(wR, j)) == tl) ++j; }
                 }
                 if (n_pairs > 0) {
                     n_joint = n_pairs;
                     c_ub += 1;
                     i = 0; j = 0;
                     while (i < nL && j < nR) {                                              // :341-369
-                        const unsigned long long hl = scr.at(LEFT0 + i), hr = scr.at(RIGHT0 + j);
+                        const unsigned long long hl = scr.at(wL, i), hr = scr.at(wR, j);
                         const uint32_t tl = hit_tid(hl), tr = hit_tid(hr);
                         if (tl < tr) { ++i; continue; }
                         if (tr < tl) { ++j; continue; }
@@ -107,7 +117,7 @@
                             const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
                             fl = (e1 > e2 ? e1 : e2) - fs;
                         }
-                        ++i; while (i < nL && hit_tid(scr.at(LEFT0 + i)) == tl) ++i; while (j < nR && hit_tid(scr.at(RIGHT0 + j)) == tl) ++j;
+                        ++i; while (i < nL && hit_tid(scr.at(wL, i)) == tl) ++i; while (j < nR && hit_tid(scr.at(wR, j)) == tl) ++j;
                     }
                 } else if (!p.strict_intersect && nL + nR > 0) {
                     // orphans: left block then right block, merged by transcript id (:231-246), left first on ties
@@ -120,8 +130,8 @@
                         while (i < nL || j < nR) {                                          // :289-340
                             bool takeL;
                             if (i >= nL) takeL = false; else if (j >= nR) takeL = true;
-                            else takeL = hit_tid(scr.at(LEFT0 + i)) <= hit_tid(scr.at(RIGHT0 + j));
-                            const unsigned long long h = takeL ? scr.at(LEFT0 + i++) : scr.at(RIGHT0 + j++);
+                            else takeL = hit_tid(scr.at(wL, i)) <= hit_tid(scr.at(wR, j));
+                            const unsigned long long h = takeL ? scr.at(wL, i++) : scr.at(wR, j++);
                             const int ms = takeL ? 1 : 2;
                             const bool fwd = hit_fwd(h);
 #if SFB_FIN_BIAS
@@ -138,11 +148,10 @@
             } else {
                 c_ub += 1;                                                                  // an overflowed mate did have hits
             }
-            bool mapped = false;
             if (acc.n > 0 && (acc.haveCompat || !p.enforce_compat)) {
                 mapped = true;
+                lab_n = acc.n;
                 c_fw += acc.fw; c_rc += acc.rc;
-                eq_upsert(p.tb, acc.n, [&](uint32_t j) { return (uint32_t)scr.at(TMP0 + j); }, 1ULL);
             }
             if (p.fld_val) {
                 const bool elig = paired && n_joint == 1 && fl >= 0 && mapped && (uint32_t)fl < p.max_frag_len;   // :419-434
@@ -153,6 +162,24 @@
 #endif
             c_obs += 1; c_map += mapped ? 1 : 0; c_hits += n_joint;
         }
+        // ---- warp-aggregated class upsert (the warp is convergent here) ----
+        const unsigned map_m = __ballot_sync(0xffffffffu, mapped);
+        if (mapped) {
+            auto get = [&](uint32_t j) { return (uint32_t)scr.at(R_LABEL, j); };
+            const uint64_t h = xxh64_words(get, lab_n, 0);                                 // TranscriptGroup.cpp:9-12
+            const unsigned grp = __match_any_sync(map_m, h);
+            const int leader = __ffs(grp) - 1;
+            const uint32_t lead_n = __shfl_sync(grp, lab_n, leader);
+            bool same = lead_n == lab_n;
+            if (same && (int)lane != leader) {                                               // equal hashes are not yet equal labels
+                const int d = leader - (int)lane;
+                for (uint32_t j = 0; j < lab_n && same; ++j) same = (uint32_t)scr.peer(d, R_LABEL, j) == get(j);
+            }
+            const unsigned agree = __ballot_sync(map_m, same) & grp;
+            if ((int)lane == leader) eq_upsert(p.tb, lab_n, get, (unsigned long long)__popc(agree), h);
+            else if (!same) eq_upsert(p.tb, lab_n, get, 1ULL, h);
+        }
+        __syncwarp();                                      // the next round overwrites the label region other lanes may still be comparing
     }
     // warp-reduce the six counters (ReadExperiment.hpp:74-97), one atomic per warp and counter
     unsigned long long v[6] = {c_obs, c_map, c_hits, c_ub, c_fw, c_rc};
