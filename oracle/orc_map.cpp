@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -93,33 +94,55 @@ struct orc_index {
             h = (h + 1) & mask;
         }
     }
-    void finish_from_sa() {
+    // everything derived from the suffix order: transcript of every entry, the distinct k-mers with their buckets, the k-mer table.
+    // n_threads > 1: entries are cut into per-thread ranges (bucket heads found independently, lists concatenated in range order --
+    // the result does not depend on the thread count) and the table is filled with compare-and-swap (slot order may differ between
+    // runs; look-ups do not depend on it).
+    void finish_from_sa(int n_threads = 1) {
         const uint64_t n = sa_pos.size();
         sa_tid.resize(n);
         kmers.clear(); lb.clear(); cnt.clear();
-        uint64_t prev = EMPTY_KEY;
-        for (uint64_t i = 0; i < n; ++i) {
-            const uint64_t p = sa_pos[i];
-            const uint32_t t = static_cast<uint32_t>(std::upper_bound(txp_start.begin(), txp_start.end(), p) - txp_start.begin() - 1);
-            sa_tid[i] = t;
-            const uint64_t km = kmer_at(p);
-            if (km != prev) { kmers.push_back(km); lb.push_back(static_cast<uint32_t>(i)); cnt.push_back(0); prev = km; }
-            cnt.back()++;
-        }
+        orc::Pool pool(n_threads);
+        const int W = pool.size();
+        std::vector<std::vector<uint64_t>> t_km(W);
+        std::vector<std::vector<uint32_t>> t_lb(W);
+        std::vector<uint64_t> t_b(W, 0), t_e(W, 0);
+        pool.run_each([&](size_t w) {
+            const uint64_t per = (n + W - 1) / W;
+            const uint64_t b = std::min<uint64_t>(n, per * w), e = std::min<uint64_t>(n, b + per);
+            t_b[w] = b; t_e[w] = e;
+            uint64_t prev = b ? kmer_at(sa_pos[b - 1]) : EMPTY_KEY;
+            for (uint64_t i = b; i < e; ++i) {
+                const uint64_t p = sa_pos[i];
+                sa_tid[i] = static_cast<uint32_t>(std::upper_bound(txp_start.begin(), txp_start.end(), p) - txp_start.begin() - 1);
+                const uint64_t km = kmer_at(p);
+                if (km != prev) { t_km[w].push_back(km); t_lb[w].push_back(static_cast<uint32_t>(i)); prev = km; }
+            }
+        });
+        size_t total = 0;
+        for (int w = 0; w < W; ++w) total += t_km[w].size();
+        kmers.reserve(total); lb.reserve(total);
+        for (int w = 0; w < W; ++w) { kmers.insert(kmers.end(), t_km[w].begin(), t_km[w].end()); lb.insert(lb.end(), t_lb[w].begin(), t_lb[w].end()); }
+        cnt.resize(total);
+        for (size_t i = 0; i < total; ++i) cnt[i] = static_cast<uint32_t>((i + 1 < total ? lb[i + 1] : n) - lb[i]);
         uint64_t cap = 16;
         while (cap < 2 * kmers.size()) cap <<= 1;
         mask = cap - 1;
         slot.assign(cap, 0xFFFFFFFFu);
-        for (uint64_t i = 0; i < kmers.size(); ++i) {
-            uint64_t h = orc_xxh64(&kmers[i], 8, 0) & mask;
-            while (slot[h] != 0xFFFFFFFFu) h = (h + 1) & mask;
-            slot[h] = static_cast<uint32_t>(i);
-        }
+        pool.parallel_for(kmers.size(), [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+                uint64_t h = orc_xxh64(&kmers[i], 8, 0) & mask;
+                for (;;) {
+                    if (slot[h] == 0xFFFFFFFFu && __sync_bool_compare_and_swap(&slot[h], 0xFFFFFFFFu, static_cast<uint32_t>(i))) break;
+                    h = (h + 1) & mask;
+                }
+            }
+        });
     }
 };
 
 extern "C" orc_index* orc_index_build(const char* seq, const uint64_t* txp_off, const uint32_t* txp_len,
-                                      uint32_t n_txp, int k, int /*n_threads*/) {
+                                      uint32_t n_txp, int k, int n_threads) {
     if (k < 1 || k > 31) return nullptr;
     orc_index* ix = new orc_index();
     ix->k = k; ix->T = n_txp;
@@ -138,21 +161,49 @@ extern "C" orc_index* orc_index_build(const char* seq, const uint64_t* txp_off, 
             ix->words[p >> 5] |= static_cast<uint64_t>(c) << (2 * (p & 31));
         }
     }
-    std::vector<std::pair<uint64_t, uint32_t>> kp;
-    for (uint32_t t = 0; t < n_txp; ++t) {
-        if (txp_len[t] < static_cast<uint32_t>(k)) continue;
-        const uint64_t s = ix->txp_start[t];
-        uint64_t v = 0;
-        for (uint32_t i = 0; i < txp_len[t]; ++i) {
-            v = (v >> 2) | (static_cast<uint64_t>(ix->base(s + i)) << (2 * (k - 1)));
-            if (i + 1 >= static_cast<uint32_t>(k)) kp.emplace_back(v, static_cast<uint32_t>(s + i + 1 - k));
+    // (k-mer, position) pairs sorted by k-mer then position.  Large inputs (bench.py's CPU arm: 3.4e8 positions): the pairs are
+    // binned by the k-mer's top 12 bits, every thread emits the pairs of a contiguous transcript range into per-(thread, bin) runs laid
+    // out in thread order -- so a bin holds its pairs in position order before it is sorted -- and the bins are sorted in parallel.
+    orc::Pool pool(n_threads);
+    const int W = pool.size();
+    const int NB = 4096, bshift = 2 * k > 12 ? 2 * k - 12 : 0;
+    std::vector<uint64_t> tb(W + 1, 0);
+    for (int w = 0; w <= W; ++w) tb[w] = static_cast<uint64_t>(n_txp) * w / W;
+    std::vector<uint64_t> counts(static_cast<size_t>(W) * NB, 0);
+    auto each_kmer = [&](uint32_t t0, uint32_t t1, const std::function<void(uint64_t, uint32_t)>& fn) {
+        for (uint32_t t = t0; t < t1; ++t) {
+            if (txp_len[t] < static_cast<uint32_t>(k)) continue;
+            const uint64_t s = ix->txp_start[t];
+            uint64_t v = 0;
+            for (uint32_t i = 0; i < txp_len[t]; ++i) {
+                v = (v >> 2) | (static_cast<uint64_t>(ix->base(s + i)) << (2 * (k - 1)));
+                if (i + 1 >= static_cast<uint32_t>(k)) fn(v, static_cast<uint32_t>(s + i + 1 - k));
+            }
         }
+    };
+    pool.run_each([&](size_t w) {
+        uint64_t* c = counts.data() + w * NB;
+        each_kmer(static_cast<uint32_t>(tb[w]), static_cast<uint32_t>(tb[w + 1]), [&](uint64_t v, uint32_t) { ++c[(v >> bshift) & (NB - 1)]; });
+    });
+    std::vector<uint64_t> start(static_cast<size_t>(W) * NB, 0), bin_start(NB + 1, 0);
+    uint64_t acc = 0;
+    for (int b = 0; b < NB; ++b) {
+        bin_start[b] = acc;
+        for (int w = 0; w < W; ++w) { start[static_cast<size_t>(w) * NB + b] = acc; acc += counts[static_cast<size_t>(w) * NB + b]; }
     }
-    std::sort(kp.begin(), kp.end());
+    bin_start[NB] = acc;
+    std::vector<std::pair<uint64_t, uint32_t>> kp(acc);
+    pool.run_each([&](size_t w) {
+        uint64_t* c = start.data() + w * NB;
+        each_kmer(static_cast<uint32_t>(tb[w]), static_cast<uint32_t>(tb[w + 1]), [&](uint64_t v, uint32_t p) { kp[c[(v >> bshift) & (NB - 1)]++] = {v, p}; });
+    });
+    pool.parallel_for(NB, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) std::sort(kp.begin() + bin_start[i], kp.begin() + bin_start[i + 1]);
+    });
     ix->sa_pos.resize(kp.size());
-    for (size_t i = 0; i < kp.size(); ++i) ix->sa_pos[i] = kp[i].second;
+    pool.parallel_for(kp.size(), [&](size_t b, size_t e) { for (size_t i = b; i < e; ++i) ix->sa_pos[i] = kp[i].second; });
     std::vector<std::pair<uint64_t, uint32_t>>().swap(kp);
-    ix->finish_from_sa();
+    ix->finish_from_sa(n_threads);
     return ix;
 }
 

@@ -206,6 +206,16 @@ class Index:
             raise RuntimeError("orc_index_build failed")
 
     @classmethod
+    def from_text(cls, seq, txp_off, txp_len, k=31, n_threads=1):
+        """index over transcripts given as one uint8 text + offsets + lengths (no per-transcript Python objects), built on n_threads"""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        offs = np.ascontiguousarray(txp_off, dtype=np.uint64); lens = np.ascontiguousarray(txp_len, dtype=np.uint32)
+        h = lib().orc_index_build(seq.ctypes.data_as(C.c_char_p), _ptr(offs, u64p), _ptr(lens, u32p), len(lens), k, int(n_threads))
+        if not h:
+            raise RuntimeError("orc_index_build failed")
+        return cls(k=k, handle=h, txp_len=lens)
+
+    @classmethod
     def from_arrays(cls, words, text_len, txp_len, k, sa_pos):
         L = lib()
         words = np.ascontiguousarray(words, dtype=np.uint64)

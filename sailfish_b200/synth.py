@@ -13,10 +13,45 @@ for _a, _b in zip(b"ACGTN", b"TGCAN"):
     _COMP[_a] = _b
 
 
-def make_transcriptome(n_genes, n_iso=5, n_exons=12, seed=42, gc=0.45, mu=5.3, sigma=0.6, p_keep=0.6):
-    """-> (seq uint8[total], txp_off uint64[T], txp_len uint32[T])"""
+def make_transcriptome(n_genes, n_iso=5, n_exons=12, seed=42, gc=0.45, mu=5.3, sigma=0.6, p_keep=0.6,
+                       family_frac=0.0, family_genes=(10, 400), family_share=0.5, repeat_frac=0.0, repeat_len=300):
+    """-> (seq uint8[total], txp_off uint64[T], txp_len uint32[T])
+
+    family_frac > 0 gives the class structure of a real annotation (paralog families, repeats) instead of genes that share nothing:
+    that fraction of the genes is grouped into families of family_genes[0]..family_genes[1] genes (log-uniform sizes, members
+    scattered over the gene order as paralogs are over a genome); every member takes each exon slot from the family's founder
+    with probability family_share, so reads from those exons map to 50..2000 transcripts of many genes, equivalence classes cross
+    gene boundaries and the (class x transcript) graph gets large connected components.  repeat_frac > 0 additionally replaces one
+    exon of that fraction of ALL genes by one of 8 repeat elements of repeat_len bases (k-mer buckets of thousands of positions)."""
     rng = np.random.default_rng(seed)
     ex_len = np.clip(rng.lognormal(mu, sigma, size=(n_genes, n_exons)), 60, 2000).astype(np.int64)
+    ex_src = np.arange(n_genes * n_exons, dtype=np.int64)        # exon slot -> the slot whose sequence it carries
+    if family_frac > 0 or repeat_frac > 0:
+        frng = np.random.default_rng([seed, 77])
+        if family_frac > 0:
+            pool = frng.permutation(n_genes)[:int(n_genes * family_frac)]
+            at = 0
+            while at < len(pool):
+                lo, hi = family_genes
+                size = int(np.exp(frng.uniform(np.log(lo), np.log(hi))))
+                mem = pool[at:at + size]
+                at += size
+                if len(mem) < 2:
+                    break
+                founder = mem[0]
+                share = frng.random((len(mem) - 1, n_exons)) < family_share
+                for e in range(n_exons):
+                    g = mem[1:][share[:, e]]
+                    ex_src[g * n_exons + e] = founder * n_exons + e
+                    ex_len[g, e] = ex_len[founder, e]
+        if repeat_frac > 0:
+            hosts = frng.permutation(n_genes)[:int(n_genes * repeat_frac)]
+            donors = hosts[:8]
+            ex_len[donors, 0] = repeat_len
+            slot = frng.integers(0, n_exons, size=len(hosts))
+            which = donors[frng.integers(0, len(donors), size=len(hosts))]
+            ex_src[hosts[8:] * n_exons + slot[8:]] = which[8:] * n_exons
+            ex_len[hosts[8:], slot[8:]] = repeat_len
     ex_off = np.zeros(n_genes * n_exons + 1, np.int64)
     ex_off[1:] = np.cumsum(ex_len.ravel())
     p = np.array([(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2])
@@ -41,7 +76,7 @@ def make_transcriptome(n_genes, n_iso=5, n_exons=12, seed=42, gc=0.45, mu=5.3, s
         if sel.size == 0:
             continue
         el = ex_len[gene_of[sel], e]
-        src0 = ex_off[gene_of[sel] * n_exons + e]
+        src0 = ex_off[ex_src[gene_of[sel] * n_exons + e]]
         tot = int(el.sum())
         seg_start = np.zeros(sel.size, np.int64)
         seg_start[1:] = np.cumsum(el)[:-1]
@@ -127,3 +162,74 @@ def make_classes(n_txp, n_classes, seed=7, max_len=8, gene_size=5, long_frac=0.0
     flat = np.array([t for l in labs for t in l], dtype=np.uint32)
     counts = np.maximum(1, rng.lognormal(2.0, 2.0, size=len(labs))).astype(np.uint64)
     return row_ptr, flat, counts
+
+
+def expression_weights(txp_len, read_len, paired, expr_seed, zero_frac=0.3):
+    """the per-transcript sampling weights make_reads / make_reads_device draw fragments with (expression x effective length)"""
+    erng = np.random.default_rng(expr_seed)
+    T = len(txp_len)
+    expr = erng.lognormal(0.0, 2.0, size=T)
+    expr[erng.random(T) < zero_frac] = 0.0
+    min_len = read_len if not paired else max(read_len, 100)
+    expr[txp_len < min_len] = 0.0
+    w = expr * np.maximum(txp_len.astype(np.float64) - min_len + 1, 0)
+    return w / w.sum()
+
+
+def make_reads_device(seq_d, txp_off, txp_len, n_reads, read_len, seed=1234, paired=False, frag_mean=200.0, frag_sd=25.0,
+                      sub_rate=0.005, expr_seed=1234, chunk=4_000_000, out1=None, out2=None):
+    """make_reads on the GPU with torch (plumbing for the 100 M-pair configurations, which numpy would take minutes to draw).
+    seq_d: the transcriptome as a uint8 CUDA tensor.  Same model as make_reads (same expression profile for the same expr_seed),
+    different random stream.  Fills / returns uint8 CUDA tensors of n_reads*read_len ASCII bases per mate and the true transcript
+    of every fragment (int32)."""
+    import torch
+    dev = seq_d.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    w = expression_weights(txp_len, read_len, paired, expr_seed)
+    cdf = torch.from_numpy(np.cumsum(w)).to(dev)
+    off_d = torch.from_numpy(txp_off.astype(np.int64)).to(dev)
+    len_d = torch.from_numpy(txp_len.astype(np.int64)).to(dev)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    comp = torch.zeros(256, dtype=torch.uint8, device=dev)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    b1 = out1 if out1 is not None else torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    b2 = None
+    if paired:
+        b2 = out2 if out2 is not None else torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    truth = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    ar = torch.arange(read_len, device=dev, dtype=torch.int64)
+    min_fl = max(read_len, 100)
+    for a0 in range(0, n_reads, chunk):
+        n = min(chunk, n_reads - a0)
+        u = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+        tid = torch.searchsorted(cdf, u).clamp_(max=len(txp_len) - 1)
+        truth[a0:a0 + n] = tid.to(torch.int32)
+        tl = len_d[tid]
+        if paired:
+            fl = torch.round(torch.randn(n, generator=g, device=dev) * frag_sd + frag_mean).to(torch.int64).clamp_(min_fl, 999)
+            fl = torch.minimum(fl, tl)
+        else:
+            fl = torch.full((n,), read_len, dtype=torch.int64, device=dev)
+        start = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (tl - fl + 1).to(torch.float64)).to(torch.int64)
+        base0 = off_d[tid] + start
+        flip = torch.rand(n, generator=g, device=dev) < 0.5
+
+        def mutate(x):
+            if sub_rate > 0:
+                m = torch.rand(x.shape, generator=g, device=dev) < sub_rate
+                r = acgt[torch.randint(0, 4, x.shape, generator=g, device=dev)]
+                x = torch.where(m, r, x)
+            return x
+
+        fwd = seq_d[base0[:, None] + ar[None, :]]
+        if not paired:
+            rc = comp[fwd.flip(1).to(torch.int64)]
+            b1[a0 * read_len:(a0 + n) * read_len] = mutate(torch.where(flip[:, None], rc, fwd)).reshape(-1)
+            continue
+        right = seq_d[(base0 + fl - read_len)[:, None] + ar[None, :]]
+        right_rc = comp[right.flip(1).to(torch.int64)]
+        b1[a0 * read_len:(a0 + n) * read_len] = mutate(torch.where(flip[:, None], right_rc, fwd)).reshape(-1)
+        b2[a0 * read_len:(a0 + n) * read_len] = mutate(torch.where(flip[:, None], fwd, right_rc)).reshape(-1)
+    return b1, b2, truth
