@@ -56,19 +56,17 @@ struct DevIndex {
     DevBuf<uint64_t> txp_start;  // n_txp+1
     DevBuf<uint32_t> txp_len;    // n_txp
     DevBuf<uint64_t> txp_end;    // n_txp: txp_start[t] + txp_len[t]
-    // n_sa entries sorted by (k-mer value, position), 16 bytes each: {text position, transcript, position inside the transcript,
-    // bases left to the transcript's end}.  The last two are redundant with txp_start / txp_end, but having them in the entry removes a
-    // dependent random load from every match extension and every projected hit
+    // n_sa entries sorted by (k-mer value, position), 16 bytes each: {transcript, position inside it, text position, bases left to the
+    // transcript's end}.  Positions inside / bases left are redundant with txp_start / txp_end, but having them in the entry removes a
+    // dependent random load from every match extension and every projected hit, and each kernel reads only its 8-byte half
     DevBuf<uint4> sa;
     DevBuf<uint4> table;         // {key lo, key hi, lb, cnt}; empty = cnt 0
-    // presence filter over the distinct k-mers: answers "certainly absent" for most k-mers of the wrong read orientation without
-    // touching the table.  Blocked Bloom filter whose block (one 32-byte sector = 4 words) is chosen by the k-mer's ANCHOR m-mer, so
-    // that the successive k-mers of a read mostly fall into the same sector (sfb_bloom_word below)
-    DevBuf<uint64_t> bloom;
-    uint64_t bloom_words = 0;    // power of two, >= 64
+    // presence filter: bitmap over the m-mers of the text (kmer_filter.hpp); one bit decides k-m+1 read positions
+    DevBuf<uint32_t> mfilter;
+    int mf_m = 0;
     bool ready = false;
     size_t hbm_bytes() const {
-        return words.bytes() + txp_start.bytes() + txp_len.bytes() + txp_end.bytes() + sa.bytes() + table.bytes() + bloom.bytes();
+        return words.bytes() + txp_start.bytes() + txp_len.bytes() + txp_end.bytes() + sa.bytes() + table.bytes() + mfilter.bytes();
     }
 };
 

@@ -36,7 +36,7 @@ extern "C" void sfb200_ctx_destroy(sfb200_ctx* c) {
     sfb_em_extra_free(c);
     sfb_fastq_free(c);
     c->index.words.release(); c->index.txp_start.release(); c->index.txp_len.release();
-    c->index.txp_end.release(); c->index.sa.release(); c->index.table.release(); c->index.bloom.release();
+    c->index.txp_end.release(); c->index.sa.release(); c->index.table.release(); c->index.mfilter.release();
     c->cls.start.release(); c->cls.len.release(); c->cls.lab.release(); c->cls.w.release(); c->cls.cnt.release();
     c->cls.perm.release(); c->cls.sgl_cls.release(); c->cls.sgl_tid.release(); c->cls.cnt_all.release();
     c->cls.single.release(); c->cls.active.release(); c->cls.part.release();

@@ -4,10 +4,10 @@
 // include/SailfishIndex.hpp:28-43,104-144; include/ReadExperiment.hpp:103-116).  RapMap's builder and its on-disk
 // format are not part of the reference tree (scripts/fetchRapMap.sh:20), so the index is specified by this repo:
 //   words    2-bit text of all transcripts concatenated (32 bases / u64, base p at bits 2*(p%32))
-//   sa       every position whose k-mer lies inside one transcript, sorted by (k-mer value, position): {position, transcript,
-//            position inside the transcript, bases left to its end}
+//   sa       every position whose k-mer lies inside one transcript, sorted by (k-mer value, position): {transcript, position
+//            inside it, text position, bases left to the transcript's end}
 //   table    open-addressing k-mer table {k-mer, first entry, entry count}, slot = mix(k-mer) & mask, linear probing
-//   bloom    presence filter over the distinct k-mers (sector chosen by the k-mer's anchor, common.cuh)
+//   mfilter  presence filter: bitmap over the m-mers of the text (kmer_filter.hpp)
 // Index construction is a "next" row, outside the timed path: the big sort / compaction primitives
 // are CUB's (part of the CUDA toolkit); everything else is hand-written.
 #include <cub/cub.cuh>
@@ -81,7 +81,7 @@ __global__ void k_tid_and_heads(const uint64_t* __restrict__ keys, const uint32_
     if (i >= n_sa) return;
     const uint32_t p = pos[i];
     const uint32_t t = txp_of(txp_start, n_txp, p);
-    sa[i] = make_uint4(p, t, (uint32_t)(p - txp_start[t]), (uint32_t)(txp_start[t + 1] - p));
+    sa[i] = make_uint4(t, (uint32_t)(p - txp_start[t]), p, (uint32_t)(txp_start[t + 1] - p));
     head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
@@ -92,15 +92,13 @@ __global__ void k_txp_end(const uint64_t* __restrict__ txp_start, const uint32_t
 }
 
 __global__ void k_table_insert(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ heads, uint64_t n_kmers,
-                               uint64_t n_sa, uint4* __restrict__ table, uint64_t mask, unsigned int* __restrict__ max_bucket,
-                               unsigned long long* __restrict__ bloom, uint64_t bloom_words, SfbBloomGeom geom) {
+                               uint64_t n_sa, uint4* __restrict__ table, uint64_t mask, unsigned int* __restrict__ max_bucket) {
     const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n_kmers) return;
     const uint32_t lb = heads[j];
     const uint32_t cnt = static_cast<uint32_t>((j + 1 < n_kmers ? heads[j + 1] : n_sa) - lb);
     const uint64_t km = keys[lb];
     const uint64_t hh = sfb_kmer_mix(km);
-    atomicOr(bloom + sfb_bloom_word(km, hh, geom, bloom_words), (unsigned long long)sfb_bloom_mask(hh));
     uint64_t h = (hh & (mask >> 1)) << 1;            // probing starts on an even slot: slots h, h+1 share a 32-byte sector
     unsigned long long* slots = reinterpret_cast<unsigned long long*>(table);
     for (;;) {
@@ -113,6 +111,19 @@ __global__ void k_table_insert(const uint64_t* __restrict__ keys, const uint32_t
         h = (h + 1) & mask;
     }
     atomicMax(max_bucket, cnt);
+}
+
+// one thread per text position: the m-mer that starts there
+__global__ void k_mfilter_build(const uint64_t* __restrict__ words, uint64_t n_pos, int m, uint32_t* __restrict__ bits) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_pos) return;
+    const uint64_t idx = p >> 5, sh = 2 * (p & 31);
+    uint64_t v = words[idx] >> sh;
+    if (sh) v |= words[idx + 1] << (64 - sh);
+    v &= (1ULL << (2 * m)) - 1;
+    const uint32_t bit = 1u << (v & 31);
+    uint32_t* w = bits + (v >> 5);
+    if (!(*w & bit)) atomicOr(w, bit);
 }
 
 __global__ void k_table_clear(uint4* __restrict__ table, uint64_t n) {
@@ -208,19 +219,20 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
     while (slots < 4 * ix.n_kmers) slots <<= 1;      // load <= 25%: most lookups end in the first slot
     ix.table_slots = slots;
     IDX_CUDA(ix.table.reserve(slots));
-    // presence filter: >= 16 bits per k-mer (three of them set), at most 4 GB.  It need not fit L2: a read touches a handful of its
-    // sectors, not one per position (common.cuh)
-    uint64_t bwords = 64;
-    while (bwords * 64 < 16 * ix.n_kmers && bwords < (1ull << 29)) bwords <<= 1;
-    if (const char* e = getenv("SFB200_BLOOM_LOG2_WORDS")) bwords = 1ull << std::max(6, std::min(29, atoi(e)));
-    ix.bloom_words = bwords;
-    IDX_CUDA(ix.bloom.reserve(bwords));
-    IDX_CUDA(cudaMemsetAsync(ix.bloom.p, 0, bwords * 8, s));
+    // presence filter: every m-mer window of the packed text (windows that span two transcripts set a few spare bits: harmless)
+    ix.mf_m = sfb_mfilter_m(k, tot);
+    const uint64_t mf_words = sfb_mfilter_words(ix.mf_m);
+    IDX_CUDA(ix.mfilter.reserve(mf_words));
+    IDX_CUDA(cudaMemsetAsync(ix.mfilter.p, 0, mf_words * 4, s));
+    if (tot >= (uint64_t)ix.mf_m) {
+        k_mfilter_build<<<gridn(tot - ix.mf_m + 1, 256), 256, 0, s>>>(ix.words.p, tot - ix.mf_m + 1, ix.mf_m, ix.mfilter.p);
+        c->launches++;
+    }
     k_table_clear<<<gridn(slots, 256), 256, 0, s>>>(ix.table.p, slots);
     c->launches++;
     if (ix.n_kmers) {
         IDX_CUDA(cudaMemsetAsync(d_scalar.p + 1, 0, 4, s));
-        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1, reinterpret_cast<unsigned long long*>(ix.bloom.p), bwords, sfb_bloom_geom(k, bwords));
+        k_table_insert<<<gridn(ix.n_kmers, 256), 256, 0, s>>>(d_keys2.p, d_heads.p, ix.n_kmers, nsa, ix.table.p, slots - 1, d_scalar.p + 1);
         c->launches++;
         unsigned int mb = 0;
         IDX_CUDA(cudaMemcpyAsync(&mb, d_scalar.p + 1, 4, cudaMemcpyDeviceToHost, s));
@@ -251,8 +263,8 @@ extern "C" int sfb200_index_export(sfb200_ctx* c, uint64_t* words, uint32_t* sa_
     if (!ix.ready) SFB_FAIL(c, SFB200_EINVAL, "index_export: no index");
     cudaSetDevice(c->device);
     if (words) SFB_CUDA(c, cudaMemcpyAsync(words, ix.words.p, (ix.text_len / 32 + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (sa_pos && ix.n_sa) SFB_CUDA(c, cudaMemcpy2DAsync(sa_pos, 4, &ix.sa.p->x, 16, 4, ix.n_sa, cudaMemcpyDeviceToHost, c->stream));
-    if (sa_tid && ix.n_sa) SFB_CUDA(c, cudaMemcpy2DAsync(sa_tid, 4, &ix.sa.p->y, 16, 4, ix.n_sa, cudaMemcpyDeviceToHost, c->stream));
+    if (sa_pos && ix.n_sa) SFB_CUDA(c, cudaMemcpy2DAsync(sa_pos, 4, &ix.sa.p->z, 16, 4, ix.n_sa, cudaMemcpyDeviceToHost, c->stream));
+    if (sa_tid && ix.n_sa) SFB_CUDA(c, cudaMemcpy2DAsync(sa_tid, 4, &ix.sa.p->x, 16, 4, ix.n_sa, cudaMemcpyDeviceToHost, c->stream));
     SFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SFB200_OK;
 }

@@ -18,38 +18,16 @@ SFB_HD uint64_t sfb_kmer_mix(uint64_t x) {
     x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 29;
     return x;
 }
-// Presence filter with locality.  A read is scanned k-mer by k-mer, and on the strand that does not match every one of its ~L-k
-// k-mers is looked up and found absent: with a hashed filter word per k-mer that is one random 32-byte sector per position.  Here the
-// SECTOR (4 words) is chosen by an anchor the neighbouring k-mers share: the first position i < k-14 of the k-mer where
-// base[i] == base[i+1] and base[i+2] is A or C (one position in eight; if there is none, the first doubled base; if none, 0), and the
-// 15-mer that starts there.  While the scan moves on by one base the anchor stays where it is until it leaves the window, so the
-// k-mers of a read touch ~L/8 sectors instead of L-k.  The word inside the sector and the three bits come from the k-mer's own mix.
-// k < 19 has no room for a window: the low bases of the k-mer choose the sector.
-struct SfbBloomGeom { uint64_t wmask; int shift; };      // wmask: bit 2i set for anchor positions i; shift = 64 - log2(sectors)
-SFB_HD SfbBloomGeom sfb_bloom_geom(int k, uint64_t n_words) {
-    SfbBloomGeom g;
-    const int w = k >= 19 ? k - 14 : 0;
-    g.wmask = w ? (0x5555555555555555ULL & ((1ULL << (2 * w)) - 1)) : 0ULL;
-    int lg = 0;
-    while ((4ULL << lg) < n_words) ++lg;
-    g.shift = 64 - (lg ? lg : 1);                // bloom_words >= 64, so lg >= 4
-    return g;
+// ---- presence filter: a direct-addressed bitmap over m-mers ---------------------------------------------------------------------------
+// A read is scanned k-mer by k-mer, and on the strand that does not match every one of its L-k+1 k-mers is absent from the index.
+// A k-mer can only be present if every m-mer inside it occurs in the transcriptome, and the LAST m-mer of the k-mer at read position i
+// (bases i+k-m .. i+k-1) lies inside the k-mers of positions i .. i+k-m as well: if that one m-mer is absent, k-m+1 positions are
+// decided by one bit.  The bitmap has 4^m bits, addressed by the m-mer's 2m bits directly (no hashing): m = 15 -> 128 MB, which a
+// transcriptome of a few hundred Mnt fills to ~25%; larger texts take m = 16 (512 MB).  k <= m: m = k (the bitmap is then exact).
+SFB_HD int sfb_mfilter_m(int k, uint64_t text_len) {
+    const int m = text_len > 600000000ULL ? 16 : 15;
+    return m < k ? m : k;
 }
-SFB_HD uint64_t sfb_bloom_word(uint64_t km, uint64_t h, const SfbBloomGeom& g, uint64_t n_words) {
-    const uint64_t e = km ^ (km >> 2);
-    const uint64_t q = ~(e | (e >> 1)) & g.wmask;
-    const uint64_t a1 = q & ~(km >> 5);
-    const uint64_t a = a1 ? a1 : q;
-#ifdef __CUDA_ARCH__
-    const int sh = a ? (__ffsll((long long)a) - 1) : 0;
-#else
-    const int sh = a ? __builtin_ctzll(a) : 0;
-#endif
-    const uint64_t mm = (km >> sh) & 0x3FFFFFFFULL;
-    const uint64_t sector = (mm * 0x9E3779B97F4A7C15ULL) >> g.shift;
-    return ((sector << 2) | ((h >> 6) & 3)) & (n_words - 1);
-}
-SFB_HD uint64_t sfb_bloom_mask(uint64_t h) {
-    return (1ULL << ((h >> 8) & 63)) | (1ULL << ((h >> 14) & 63)) | (1ULL << ((h >> 20) & 63));
-}
-
+SFB_HD uint64_t sfb_mfilter_words(int m) { return ((1ULL << (2 * m)) + 31) / 32; }      // 32-bit words
+// m-mer that starts at base `off` of the k-mer km (base i at bits 2i)
+SFB_HD uint64_t sfb_mfilter_key(uint64_t km, int off, int m) { return (km >> (2 * off)) & ((1ULL << (2 * m)) - 1); }

@@ -49,10 +49,14 @@ __device__ __forceinline__ bool compat_paired(int expected, int32_t e1, bool fwd
 
 struct IndexView {
     const uint64_t* words; const uint64_t* txp_start; const uint64_t* txp_end;
-    const uint4* sa; const uint4* table; const uint64_t* bloom;
-    uint64_t mask, bloom_words; int k; uint64_t kmask;
-    SfbBloomGeom bg;
+    const uint4* sa; const uint4* table; const uint32_t* mfilter;
+    uint64_t mask; int k; uint64_t kmask;
+    int mf_m;                     // m of the m-mer presence bitmap (kmer_filter.hpp)
 };
+// a suffix entry is {transcript, position inside it, text position, bases left to the transcript's end}: the finalize kernel reads the
+// first half, the scan kernel's match extension the second
+__device__ __forceinline__ uint2 sa_tid_rel(const IndexView& ix, uint64_t e) { return __ldg(reinterpret_cast<const uint2*>(ix.sa + e)); }
+__device__ __forceinline__ uint2 sa_pos_rem(const IndexView& ix, uint64_t e) { return __ldg(reinterpret_cast<const uint2*>(ix.sa + e) + 1); }
 
 // the per-hit arithmetic of the bias / GC sample collection, shared with bias.cu and the CPU check (tests/bias_core_test.cpp)
 #define SFB_BD __device__ __forceinline__
@@ -135,7 +139,8 @@ __device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigne
                 sv = prev;                                             // somebody else took the slot: look at what they put
                 continue;
             }
-            __threadfence();
+            // no fence on this side: the slot word and the label are read from L2 (ld.cg), the label's address depends on the slot
+            // word, and the writer published the label with a fence before its CAS (a fence here costs an L1 flush per probe)
             if (slot_matches(tb, sv, len, h, get)) { atomicAdd(tb.count + idx, add); return true; }
             break;
         }
@@ -151,13 +156,13 @@ __device__ bool eq_upsert(const EqTable& tb, uint32_t len, GetLabel get, unsigne
 // orientation 0 = as sequenced, 1 = reverse complement.  The invalid-base masks (same layout, 0b01 where the base is not
 // A/C/G/T) are rare and stay in local memory, touched only when has_n.
 extern __shared__ uint64_t smem_reads[];       // scan kernel: [warp][mate][orientation][word][lane]
-struct Read {
+struct Read {                                  // scalars only: selected by mate with ?: they stay in registers
     uint32_t sb;                               // index of this lane's column of this mate in smem_reads
-    uint64_t nm[2][RW];
     uint32_t len;
     bool has_n;
     __device__ __forceinline__ uint64_t word(int o, uint32_t w) const { return smem_reads[sb + (o * RW + w) * 32]; }
 };
+struct ReadN { uint64_t nm[2][RW]; };          // invalid-base masks of one mate: local memory, touched only when has_n
 
 __device__ __forceinline__ uint64_t win32(const Read& r, int o, uint32_t pos) {
     const uint32_t idx = pos >> 5, sh = 2 * (pos & 31);
@@ -165,7 +170,7 @@ __device__ __forceinline__ uint64_t win32(const Read& r, int o, uint32_t pos) {
     if (sh) v |= r.word(o, idx + 1) << (64 - sh);
     return v;
 }
-__device__ __forceinline__ uint64_t win32n(const Read& r, int o, uint32_t pos) {
+__device__ __forceinline__ uint64_t win32n(const ReadN& r, int o, uint32_t pos) {
     const uint32_t idx = pos >> 5, sh = 2 * (pos & 31);
     uint64_t v = r.nm[o][idx] >> sh;
     if (sh) v |= r.nm[o][idx + 1] << (64 - sh);
@@ -256,7 +261,7 @@ __global__ void k_max_read_len(const uint64_t* __restrict__ off1, const uint64_t
 
 // packed read -> this lane's shared-memory column (both orientations) + the invalid-base masks when there are any
 __device__ void load_packed(const uint64_t* __restrict__ pk, const uint64_t* __restrict__ pkn, const uint32_t* __restrict__ meta,
-                            uint64_t fm, uint32_t rwp, Read& r) {
+                            uint64_t fm, uint32_t rwp, Read& r, ReadN& rn) {
     const uint32_t me = meta[fm];
     const uint32_t L = me & 0xFFFFu;
     r.len = L;
@@ -282,30 +287,30 @@ __device__ void load_packed(const uint64_t* __restrict__ pk, const uint64_t* __r
     }
     if (r.has_n) {
         const uint64_t* srcn = pkn + fm * rwp;
-        for (uint32_t w = 0; w < RW; ++w) { r.nm[0][w] = w < nw ? __ldg(srcn + w) : 0ULL; r.nm[1][w] = 0ULL; }
+        for (uint32_t w = 0; w < RW; ++w) { rn.nm[0][w] = w < nw ? __ldg(srcn + w) : 0ULL; rn.nm[1][w] = 0ULL; }
         // masks of the reverse orientation: plain reversal of the 2-bit groups (no complement)
         for (uint32_t w = 0; w < nw; ++w) {
             const uint32_t pos = w * 32 + pad, idx = pos >> 5, sh = 2 * (pos & 31);
             auto rev = [](uint64_t x) { x = __brevll(x); return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1); };
-            const uint64_t lo = idx < nw ? rev(r.nm[0][nw - 1 - idx]) : 0ULL;
-            const uint64_t hi = (idx + 1) < nw ? rev(r.nm[0][nw - 2 - idx]) : 0ULL;
+            const uint64_t lo = idx < nw ? rev(rn.nm[0][nw - 1 - idx]) : 0ULL;
+            const uint64_t hi = (idx + 1) < nw ? rev(rn.nm[0][nw - 2 - idx]) : 0ULL;
             uint64_t v = lo >> sh;
             if (sh) v |= hi << (64 - sh);
-            r.nm[1][w] = v;
+            rn.nm[1][w] = v;
         }
     }
 }
 
 // longest common extension of read[qpos..) with text[p..p+rem), counted from the k-mer start (always >= k); rem = bases from p to the
 // end of p's transcript (carried by the suffix entry)
-__device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, int o, uint32_t qpos, uint64_t p, uint32_t rem) {
+__device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, const ReadN& rn, int o, uint32_t qpos, uint64_t p, uint32_t rem) {
     const uint32_t lim_r = r.len - qpos;
     const uint32_t lim = rem < lim_r ? rem : lim_r;
     uint32_t m = ix.k;
     while (m < lim) {
         const uint64_t x = win32(r, o, qpos + m) ^ win32g(ix.words, p + m);
         uint64_t y = (x | (x >> 1)) & 0x5555555555555555ULL;
-        if (r.has_n) y |= win32n(r, o, qpos + m);
+        if (r.has_n) y |= win32n(rn, o, qpos + m);
         if (y) { m += static_cast<uint32_t>(__ffsll(static_cast<long long>(y)) - 1) >> 1; break; }
         m += 32;
     }
@@ -335,104 +340,89 @@ __device__ __forceinline__ Interval unpack_iv(unsigned long long v) {
 
 // Spec v1 seed scans of ALL orientations of ALL mates of one fragment form ONE sequence of steps: scan s = 2*mate +
 // orientation, position i, n intervals found so far.  A fragment has one cheap scan per mate (the orientation that matches:
-// a hit, an extension, done) and one expensive one (the other strand: a k-mer look-up that misses at every position).
-// One step looks SPEC positions up at once: k-mers, hashes, presence-filter words and first table slots of the next SPEC
-// positions are fetched together (independent loads in flight), then consumed strictly in order, so the result is exactly the
-// one-position-at-a-time scan's.  Returns true when the fragment's last scan has ended.
-// Swept on B200 (scripts/variant_bench.sh): SPEC 2 with 4 CTAs/SM (64 registers, no spills) is the fastest; wider speculation
-// costs registers, and any spill of this kernel's state is ruinous (SPEC 4 x 3 CTAs: 23.7 ms, SPEC 2 x 4: 17.9 ms, SPEC 8: 47 ms)
-#ifndef SFB_SPEC
-#define SFB_SPEC 2
-#endif
+// a hit, an extension, done) and one expensive one (the other strand: every k-mer absent).  One step decides as many positions as
+// one round of loads allows, with the m-mer bitmap (kmer_filter.hpp): the LAST m-mer of the k-mer at i lies inside the k-mers of
+// i .. i+J-1 (J = k-m+1), so if it is absent all J positions are decided -- and then the same test at i+J, whose load is already in
+// flight, may decide J more; the m-mer in the MIDDLE of the k-mer decides J/2+1 positions when the last one is present.  Only a
+// position that passes all of them is looked up in the k-mer table.  Skipped positions are exactly positions whose k-mer is
+// absent (or whose window holds an invalid base -- never a seed either), so the result equals the one-position-at-a-time scan's.
+// Returns true when the fragment's last scan has ended.
 #ifndef SFB_EXT_BATCH
 #define SFB_EXT_BATCH 4      // pending seeds a warp collects before it extends them together (extend_coop)
 #endif
 #ifndef SFB_SCAN_BLOCKS
 #define SFB_SCAN_BLOCKS 4
 #endif
-constexpr int SPEC = SFB_SPEC;
 struct ScanState { int s, n; uint32_t i; uint32_t pend_lb, pend_cnt; };   // pend_cnt != 0: a seed waits for its extension
-__device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, int ns, uint32_t max_interval, ScanState& st,
+__device__ __forceinline__ bool mf_test(const IndexView& ix, uint64_t key) {
+    return (__ldg(ix.mfilter + (key >> 5)) >> (key & 31)) & 1u;
+}
+__device__ __forceinline__ bool scan_step(const IndexView& ix, const Read* rds, const ReadN* rns, int ns, uint32_t max_interval, ScanState& st,
                                           uint8_t* __restrict__ niv_out /* [ns] of this fragment */) {
     const uint32_t k = ix.k;
-    const Read& r = rds[st.s >> 1];
+    const bool m1 = (st.s >> 1) != 0;
+    Read r; r.sb = m1 ? rds[1].sb : rds[0].sb; r.len = m1 ? rds[1].len : rds[0].len; r.has_n = m1 ? rds[1].has_n : rds[0].has_n;
     const int o = st.s & 1;
     const uint32_t L = r.len;
-    uint32_t i = st.i;
+    const uint32_t i = st.i;
     if (!(i + k <= L && st.n < MAX_IV)) { niv_out[st.s] = (uint8_t)st.n; ++st.s; st.i = 0; st.n = 0; return st.s >= ns; }
     if (r.has_n) {
-        const uint64_t nn = win32n(r, o, i) & ix.kmask;
+        const uint64_t nn = win32n(rns[st.s >> 1], o, i) & ix.kmask;
         if (nn) { st.i = i + ((63 - __clzll(static_cast<long long>(nn))) >> 1) + 1; return false; }   // jump past the last invalid base
     }
-    // candidates i .. i+nc-1: windows inside the read and free of invalid bases
-    uint64_t km[SPEC], hh[SPEC], bw[SPEC];
-    bool probe[SPEC];
-    int nc = 1;
-#pragma unroll
-    for (int j = 1; j < SPEC; ++j) {
-        if (nc == j && i + j + k <= L && (!r.has_n || (win32n(r, o, i + j) & ix.kmask) == 0)) nc = j + 1;
+    const int m = ix.mf_m;
+    const uint32_t J = k - m + 1;
+    const uint64_t km = win32(r, o, i) & ix.kmask;
+    // the look-ahead position i+J: only when its window lies inside the read and (reads with invalid bases) is clean
+    bool ahead = i + J + k <= L;
+    uint64_t km2 = 0;
+    if (ahead) {
+        km2 = win32(r, o, i + J) & ix.kmask;
+        if (r.has_n && (win32n(rns[st.s >> 1], o, i + J) & ix.kmask) != 0) ahead = false;
     }
-#pragma unroll
-    for (int j = 0; j < SPEC; ++j) {
-        probe[j] = false;
-        if (j < nc) {
-            km[j] = win32(r, o, i + j) & ix.kmask;
-            const bool homo = km[j] == 0 || km[j] == ix.kmask || km[j] == (0x5555555555555555ULL & ix.kmask) ||
-                              km[j] == (0xAAAAAAAAAAAAAAAAULL & ix.kmask);           // homopolymer k-mers are never seeds
-            if (!homo) {
-                hh[j] = sfb_kmer_mix(km[j]);
-                bw[j] = __ldg(ix.bloom + sfb_bloom_word(km[j], hh[j], ix.bg, ix.bloom_words));
-                probe[j] = true;
+    const uint32_t half = (J - 1) >> 1;
+    const bool b_last = mf_test(ix, sfb_mfilter_key(km, k - m, m));
+    const bool b_next = ahead ? mf_test(ix, sfb_mfilter_key(km2, k - m, m)) : true;
+    const bool b_mid = half ? mf_test(ix, sfb_mfilter_key(km, half, m)) : true;
+    if (!b_last) { st.i = i + ((ahead && !b_next) ? 2 * J : J); return false; }
+    if (!b_mid) { st.i = i + half + 1; return false; }                 // the m-mer at `half` lies inside the k-mers of i .. i+half
+    // homopolymer k-mers are never seeds: a k-mer equals itself shifted by one base
+    const bool homo = ((km ^ (km >> 2)) & (ix.kmask >> 2)) == 0;
+    bool hit = false;
+    uint32_t lb = 0, cnt = 0;
+    if (!homo) {
+        const uint64_t hh = sfb_kmer_mix(km);
+        const uint64_t h0 = (hh & (ix.mask >> 1)) << 1;               // even slot: h0 and h0+1 share a 32-byte sector
+        const uint4 sl = __ldg(ix.table + h0), sl2 = __ldg(ix.table + h0 + 1);
+        if (sl.w != 0) {
+            if ((((uint64_t)sl.y << 32) | sl.x) == km) { hit = true; lb = sl.z; cnt = sl.w; }
+            else if (sl2.w != 0) {
+                if ((((uint64_t)sl2.y << 32) | sl2.x) == km) { hit = true; lb = sl2.z; cnt = sl2.w; }
+                else hit = table_find_from(ix, km, h0 + 1, lb, cnt);
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < SPEC; ++j) {
-        if (probe[j]) { const uint64_t need = sfb_bloom_mask(hh[j]); probe[j] = (bw[j] & need) == need; }   // false => certainly absent
-    }
-    uint4 sl[SPEC], sl2[SPEC];
-#pragma unroll
-    for (int j = 0; j < SPEC; ++j) {
-        if (probe[j]) {
-            const uint64_t h0 = (hh[j] & (ix.mask >> 1)) << 1;           // even slot: h0 and h0+1 share a 32-byte sector
-            sl[j] = __ldg(ix.table + h0); sl2[j] = __ldg(ix.table + h0 + 1);
-        }
-    }
-    // consume in order
-#pragma unroll
-    for (int j = 0; j < SPEC; ++j) {
-        if (j >= nc) continue;
-        bool hit = false;
-        uint32_t lb = 0, cnt = 0;
-        if (probe[j]) {
-            if (sl[j].w != 0) {
-                if ((((uint64_t)sl[j].y << 32) | sl[j].x) == km[j]) { hit = true; lb = sl[j].z; cnt = sl[j].w; }
-                else if (sl2[j].w != 0) {
-                    if ((((uint64_t)sl2[j].y << 32) | sl2[j].x) == km[j]) { hit = true; lb = sl2[j].z; cnt = sl2[j].w; }
-                    else hit = table_find_from(ix, km[j], ((hh[j] & (ix.mask >> 1)) << 1) + 1, lb, cnt);
-                }
-            }
-        }
-        if (!hit || cnt > max_interval) continue;                                      // position i+j is not a seed
+    if (hit && cnt <= max_interval) {
         // a seed: the extension over its bucket is done later, together with other lanes' (see k_scan_reads)
-        st.i = i + j;
         st.pend_lb = lb; st.pend_cnt = cnt;
         return false;
     }
-    st.i = i + nc;
+    st.i = i + 1;
     return false;
 }
 
 // match extension of a pending seed: m = longest match over the bucket, mask = which of its first 32 entries reach it
-__device__ __forceinline__ void extend_seed(const IndexView& ix, const Read* rds, ScanState& st, unsigned long long* __restrict__ iv_out,
-                                            uint32_t* __restrict__ ivmask_out) {
-    const Read& r = rds[st.s >> 1];
+__device__ __forceinline__ void extend_seed(const IndexView& ix, const Read* rds, const ReadN* rns, ScanState& st,
+                                            unsigned long long* __restrict__ iv_out, uint32_t* __restrict__ ivmask_out) {
+    const bool m1 = (st.s >> 1) != 0;
+    Read r; r.sb = m1 ? rds[1].sb : rds[0].sb; r.len = m1 ? rds[1].len : rds[0].len; r.has_n = m1 ? rds[1].has_n : rds[0].has_n;
+    const ReadN& rn = rns[st.s >> 1];
     const int o = st.s & 1;
     const uint32_t q = st.i, lb = st.pend_lb, cnt = st.pend_cnt;
     uint32_t m = 0, mask = 0;
     for (uint32_t e = 0; e < cnt; ++e) {
-        const uint4 en = __ldg(ix.sa + lb + e);
-        const uint32_t l = lcp_at(ix, r, o, q, en.x, en.w);
+        const uint2 en = sa_pos_rem(ix, lb + e);
+        const uint32_t l = lcp_at(ix, r, rn, o, q, en.x, en.y);
         if (l > m) { m = l; mask = e < 32 ? (1u << e) : 0u; }
         else if (l == m && e < 32) mask |= 1u << e;
     }
@@ -492,7 +482,7 @@ __device__ __forceinline__ uint32_t lcp_clean(const IndexView& ix, uint32_t sb, 
 __device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds, ScanState& st, unsigned todo, unsigned lane,
                                             unsigned long long* __restrict__ iv_all, uint32_t* __restrict__ ivmask_all, uint64_t iv_base) {
     const unsigned grp = lane / EXT_G, sub = lane % EXT_G;
-    const uint32_t my_len = rds[(st.s >> 1) & 1].len;                  // only read from lanes that own a pending seed
+    const uint32_t my_len = (st.s >> 1) ? rds[1].len : rds[0].len;     // only read from lanes that own a pending seed
     while (todo) {
         const unsigned src = __fns(todo, 0, (int)grp + 1);             // owner lane of this group's seed, 0xFFFFFFFF if there is none
         const bool act = src < 32u;
@@ -507,8 +497,8 @@ __device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds
         const uint32_t sb = ((ss >> 1) ? rds[1].sb : rds[0].sb) + sl - lane;
         uint32_t best = 0, mask = 0;
         for (uint32_t e = sub; e < cnt; e += EXT_G) {
-            const uint4 en = __ldg(ix.sa + lb + e);
-            const uint32_t l = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.w);
+            const uint2 en = sa_pos_rem(ix, lb + e);
+            const uint32_t l = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.y);
             if (l > best) { best = l; mask = e < 32 ? (1u << e) : 0u; }
             else if (l == best && e < 32) mask |= 1u << e;
         }
@@ -541,16 +531,23 @@ __device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds
 // that is ~30 cycles, through L2 it was ~300 (ncu, round 1: 18% issue utilisation).
 constexpr uint32_t FIN_S = 6;
 enum { R_A = 0, R_B = 1, R_LEFT = 2, R_RIGHT = 3, R_LABEL = 4, N_REGIONS = 5 };
+extern __shared__ unsigned long long smem_hits[];      // finalize kernel: [warp][region][entry][lane]
 struct Scratch {
-    unsigned long long* sm;        // this lane's column of its warp's shared block
+    uint32_t so;                   // index of this lane's column of its warp's block in smem_hits
     unsigned long long* base;      // this thread's column of the global scratch
     uint64_t stride; uint32_t cap1;
-    __device__ __forceinline__ unsigned long long& at(uint32_t region, uint32_t j) const {
-        return j < FIN_S ? sm[(region * FIN_S + j) * 32] : base[(uint64_t)(region * cap1 + j) * stride];
+    __device__ __forceinline__ unsigned long long get(uint32_t region, uint32_t j) const {
+        if (j < FIN_S) return smem_hits[so + (region * FIN_S + j) * 32];
+        return base[(uint64_t)(region * cap1 + j) * stride];
+    }
+    __device__ __forceinline__ void set(uint32_t region, uint32_t j, unsigned long long v) const {
+        if (j < FIN_S) smem_hits[so + (region * FIN_S + j) * 32] = v;
+        else base[(uint64_t)(region * cap1 + j) * stride] = v;
     }
     // the same entry of another lane of this warp (delta = that lane - this lane)
     __device__ __forceinline__ unsigned long long peer(int delta, uint32_t region, uint32_t j) const {
-        return j < FIN_S ? sm[(int)((region * FIN_S + j) * 32) + delta] : base[(int64_t)((uint64_t)(region * cap1 + j) * stride) + delta];
+        if (j < FIN_S) return smem_hits[(int)(so + (region * FIN_S + j) * 32) + delta];
+        return base[(int64_t)((uint64_t)(region * cap1 + j) * stride) + delta];
     }
 };
 __device__ __forceinline__ unsigned long long pack_hit(uint32_t tid, int32_t pos, bool fwd) {
@@ -594,37 +591,45 @@ __device__ __noinline__ uint32_t lcp_global(const IndexView& ix, const ReadG& r,
 }
 
 // transcripts present with the maximal match in every interval; output ascending by transcript id;
-// stops after cap+1 hits (list overflow)
+// stops after cap+1 hits (list overflow).  The first four suffix entries of the first interval's bucket are loaded together (most
+// buckets are no larger), so the walk over the bucket is one memory round trip instead of one per entry.
 __device__ uint32_t project(const IndexView& ix, const ReadG& r, int o, const Interval* ivs, int niv, uint32_t cap,
                             const Scratch& out, uint32_t region) {
     if (niv == 0) return 0;
     uint32_t n = 0;
     const Interval a = ivs[0];
-    int64_t lastTid = -1;
-    for (uint32_t e = a.lb; e < a.lb + a.cnt; ++e) {
-        const uint4 en = __ldg(ix.sa + e);
-        const uint32_t tid = en.y;
-        if ((int64_t)tid == lastTid) continue;
-        const uint32_t e_rel = e - a.lb;
-        if (e_rel < 32 ? !((a.mask >> e_rel) & 1u) : (lcp_global(ix, r, o, a.qpos, en.x, en.w) != a.m)) continue;
+    uint32_t lastTid = 0xFFFFFFFFu;                 // transcript ids are < 2^32 - 1
+    uint2 pre0 = make_uint2(0, 0), pre1 = pre0, pre2 = pre0, pre3 = pre0;
+    pre0 = sa_tid_rel(ix, a.lb);
+    if (a.cnt > 1) pre1 = sa_tid_rel(ix, a.lb + 1);
+    if (a.cnt > 2) pre2 = sa_tid_rel(ix, a.lb + 2);
+    if (a.cnt > 3) pre3 = sa_tid_rel(ix, a.lb + 3);
+    for (uint32_t e_rel = 0; e_rel < a.cnt; ++e_rel) {
+        uint2 en;
+        if (e_rel < 4) en = e_rel == 0 ? pre0 : e_rel == 1 ? pre1 : e_rel == 2 ? pre2 : pre3;
+        else en = sa_tid_rel(ix, a.lb + e_rel);
+        const uint32_t tid = en.x;
+        if (tid == lastTid) continue;
+        if (e_rel < 32) { if (!((a.mask >> e_rel) & 1u)) continue; }
+        else { const uint2 pr = sa_pos_rem(ix, a.lb + e_rel); if (lcp_global(ix, r, o, a.qpos, pr.x, pr.y) != a.m) continue; }
         lastTid = tid;
         bool all = true;
         for (int j = 1; j < niv && all; ++j) {
             const Interval b = ivs[j];
             uint32_t lo = b.lb, hi = b.lb + b.cnt;
-            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(&ix.sa[mid].y) < tid) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(&ix.sa[mid].x) < tid) lo = mid + 1; else hi = mid; }
             bool found = false;
             for (uint32_t e2 = lo; e2 < b.lb + b.cnt; ++e2) {
-                const uint4 en2 = __ldg(ix.sa + e2);
-                if (en2.y != tid) break;
+                if (__ldg(&ix.sa[e2].x) != tid) break;
                 const uint32_t e2_rel = e2 - b.lb;
-                if (e2_rel < 32 ? ((b.mask >> e2_rel) & 1u) != 0 : (lcp_global(ix, r, o, b.qpos, en2.x, en2.w) == b.m)) { found = true; break; }
+                if (e2_rel < 32) { if ((b.mask >> e2_rel) & 1u) { found = true; break; } }
+                else { const uint2 pr = sa_pos_rem(ix, e2); if (lcp_global(ix, r, o, b.qpos, pr.x, pr.y) == b.m) { found = true; break; } }
             }
             all = found;
         }
         if (!all) continue;
-        const int32_t pos = (int32_t)en.z - (int32_t)a.qpos;
-        out.at(region, n) = pack_hit(tid, pos, o == 0);
+        const int32_t pos = (int32_t)en.y - (int32_t)a.qpos;
+        out.set(region, n, pack_hit(tid, pos, o == 0));
         ++n;
         if (n > cap) return n;
     }
@@ -648,9 +653,9 @@ __device__ bool collect(const IndexView& ix, const ReadG& r, bool strict, uint32
     while (i < nF || j < nR) {                     // stable merge: forward before reverse on equal transcript id
         bool takeF;
         if (i >= nF) takeF = false; else if (j >= nR) takeF = true;
-        else takeF = hit_tid(scr.at(R_A, i)) <= hit_tid(scr.at(R_B, j));
-        const unsigned long long h = takeF ? scr.at(R_A, i++) : scr.at(R_B, j++);
-        scr.at(dst, n++) = h;
+        else takeF = hit_tid(scr.get(R_A, i)) <= hit_tid(scr.get(R_B, j));
+        const unsigned long long h = takeF ? scr.get(R_A, i++) : scr.get(R_B, j++);
+        scr.set(dst, n++, h);
     }
     n_out = n;
     return true;
@@ -683,9 +688,9 @@ struct LabelAcc {                       // the txpIDsAll / txpIDsCompat pair of 
     __device__ __forceinline__ void add(uint32_t tid, bool compat, bool fwdHit) {
         if (compat) {
             if (!haveCompat) { haveCompat = true; n = 0; fw = 0; rc = 0; }      // switch from "all" to "compatible only"
-            scr.at(R_LABEL, n++) = tid; if (fwdHit) ++fw; else ++rc;
+            scr.set(R_LABEL, n++, tid); if (fwdHit) ++fw; else ++rc;
         } else if (!haveCompat && !enforce) {
-            scr.at(R_LABEL, n++) = tid; if (fwdHit) ++fw; else ++rc;
+            scr.set(R_LABEL, n++, tid); if (fwdHit) ++fw; else ++rc;
         }
     }
 };
@@ -699,6 +704,8 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
     const unsigned lane = threadIdx.x & 31u;
     const int n_mates = p.n_mates, ns = 2 * n_mates;
     Read rds[2];
+    ReadN rns[2];
+    rds[0].len = rds[1].len = 0; rds[0].has_n = rds[1].has_n = false;
     {
         const uint32_t wbase = (threadIdx.x >> 5) * n_mates * 2 * RW * 32 + lane;
         rds[0].sb = wbase;
@@ -725,7 +732,8 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
                 const unsigned my = __popc(need & ((1u << lane) - 1));
                 if (my < avail) {
                     frag = res_next + my;
-                    for (int mt = 0; mt < n_mates; ++mt) load_packed(p.pk, p.pkn, p.meta, (uint64_t)frag * n_mates + mt, p.rwp, rds[mt]);
+                    load_packed(p.pk, p.pkn, p.meta, (uint64_t)frag * n_mates, p.rwp, rds[0], rns[0]);
+                    if (n_mates == 2) load_packed(p.pk, p.pkn, p.meta, (uint64_t)frag * n_mates + 1, p.rwp, rds[1], rns[1]);
                     st.s = 0; st.n = 0; st.i = 0; st.pend_cnt = 0;
                     have = true;
                 } else if (avail == 0) {
@@ -743,26 +751,29 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
         const unsigned adv_m = __ballot_sync(0xffffffffu, have && !pend);
         if (pend_m && (__popc(pend_m) >= SFB_EXT_BATCH || adv_m == 0)) {
             const uint64_t ivb = frag * (uint64_t)(ns * MAX_IV);
-            const bool dirty = pend && rds[st.s >> 1].has_n;
+            const bool dirty = pend && ((st.s >> 1) ? rds[1].has_n : rds[0].has_n);
             const unsigned clean_m = pend_m & ~__ballot_sync(0xffffffffu, dirty);
             if (clean_m) extend_coop(p.ix, rds, st, clean_m, lane, p.iv, p.ivmask, ivb);
-            if (dirty) extend_seed(p.ix, rds, st, p.iv + ivb, p.ivmask + ivb);
+            if (dirty) extend_seed(p.ix, rds, rns, st, p.iv + ivb, p.ivmask + ivb);
             pend = false;                                  // every pending seed of the warp has been extended
         }
         if (have && !pend) {
-            if (scan_step(p.ix, rds, ns, p.max_interval, st, p.niv + (uint64_t)frag * ns)) have = false;
+            if (scan_step(p.ix, rds, rns, ns, p.max_interval, st, p.niv + (uint64_t)frag * ns)) have = false;
         }
     }
 }
 
 // ---- finalize kernel: projection, mate merge, compatibility filter, label, class upsert -----------------------------------------
-__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads(const MapParams p) {
+#ifndef SFB_FIN_BLOCKS
+#define SFB_FIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(MAP_THREADS, SFB_FIN_BLOCKS) k_finalize_reads(const MapParams p) {
 #define SFB_FIN_BIAS 0
 #include "map_finalize_body.inl"
 #undef SFB_FIN_BIAS
 }
 
-__global__ void __launch_bounds__(MAP_THREADS, 3) k_finalize_reads_bias(const MapParams p) {
+__global__ void __launch_bounds__(MAP_THREADS, SFB_FIN_BLOCKS) k_finalize_reads_bias(const MapParams p) {
     __shared__ unsigned int s_gc[101];
     for (unsigned i = threadIdx.x; i < 101; i += blockDim.x) s_gc[i] = 0;
     __syncthreads();
@@ -1011,19 +1022,20 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->n_threads_total = (uint64_t)m->grid * MAP_THREADS;
     SFB_CUDA(c, m->scratch.reserve(m->n_threads_total * (uint64_t)N_REGIONS * (o->max_read_occs + 1)));
     SFB_CUDA(c, cudaStreamSynchronize(s));
-    // keep the presence filter resident in L2 while the table / suffix entries / text stream through it
+    // keep (as much as the device allows of) the m-mer bitmap resident in L2 while the table / suffix entries / text stream through it
     if (!getenv("SFB200_NO_L2_PERSIST")) {
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
         if (max_persist > 0 && max_window > 0) {
-            const size_t want = std::min<size_t>(c->index.bloom_words * 8, (size_t)max_persist);
+            const size_t bytes = c->index.mfilter.bytes();
+            const size_t want = std::min<size_t>(bytes, (size_t)max_persist);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
             cudaStreamAttrValue av;
             std::memset(&av, 0, sizeof(av));
-            av.accessPolicyWindow.base_ptr = c->index.bloom.p;
-            av.accessPolicyWindow.num_bytes = std::min<size_t>(c->index.bloom_words * 8, (size_t)max_window);
-            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.base_ptr = c->index.mfilter.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
@@ -1118,9 +1130,8 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     MapParams p;
     std::memset(&p, 0, sizeof(p));
     p.ix.words = ix.words.p; p.ix.txp_start = ix.txp_start.p; p.ix.txp_end = ix.txp_end.p; p.ix.sa = ix.sa.p;
-    p.ix.table = ix.table.p; p.ix.bloom = ix.bloom.p; p.ix.bloom_words = ix.bloom_words; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
+    p.ix.table = ix.table.p; p.ix.mfilter = ix.mfilter.p; p.ix.mf_m = ix.mf_m; p.ix.mask = ix.table_slots - 1; p.ix.k = ix.k;
     p.ix.kmask = (1ULL << (2 * ix.k)) - 1;
-    p.ix.bg = sfb_bloom_geom(ix.k, ix.bloom_words);
     p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p; p.tb.cursor = m->cursor.p;
     p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
     p.bases1 = d_bases1; p.off1 = d_off1; p.bases2 = d_bases2; p.off2 = d_off2; p.n_reads = n_reads;

@@ -8,14 +8,13 @@
 // warp-aggregated: lanes whose labels are equal (same XXH64, verified member by member) elect a leader that adds the group's count
 // with ONE table probe and ONE atomic (EquivalenceClassBuilder::addGroup, include/EquivalenceClassBuilder.hpp:90-108, called once
 // per read by the reference).
-    extern __shared__ unsigned long long smem_hits[];      // [warp][region][entry][lane]
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t cap = p.cap;
-    const Scratch scr{smem_hits + (size_t)(threadIdx.x >> 5) * (N_REGIONS * FIN_S * 32) + lane, p.scratch + gtid, p.n_threads_total, cap + 1};
+    const Scratch scr{(threadIdx.x >> 5) * (N_REGIONS * FIN_S * 32) + lane, p.scratch + gtid, p.n_threads_total, cap + 1};
     const bool paired = p.n_mates == 2;
     const int ns = 2 * p.n_mates;
-    unsigned long long c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;
+    uint32_t c_obs = 0, c_map = 0, c_hits = 0, c_ub = 0, c_fw = 0, c_rc = 0;     // per thread and chunk (<= 2^22 fragments x 200 hits / 10^5 threads)
     Interval ivs[4][MAX_IV];
     int niv[4];
     uint64_t score[4];
@@ -39,10 +38,21 @@
             }
             const uint32_t len1 = rg[0].len;
             const uint32_t len2 = paired ? rg[1].len : 0;
-            for (int q = 0; q < ns; ++q) {
-                niv[q] = p.niv[ri * ns + q];
+            // the interval counts of all scans in one load, and the first interval of every scan loaded before the counts are known
+            // (the hand-over arrays are allocated for MAX_IV intervals per scan, so the load is always in bounds)
+            const uint32_t nv = paired ? *reinterpret_cast<const uint32_t*>(p.niv + ri * 4) : *reinterpret_cast<const uint16_t*>(p.niv + ri * 2);
+            unsigned long long iv0[4]; uint32_t mk0[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < ns) { iv0[q] = p.iv[(ri * ns + q) * MAX_IV]; mk0[q] = p.ivmask[(ri * ns + q) * MAX_IV]; }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q >= ns) continue;
+                niv[q] = (nv >> (8 * q)) & 0xFFu;
                 uint64_t sc = 0;
-                for (int e = 0; e < niv[q]; ++e) {
+                if (niv[q] > 0) { ivs[q][0] = unpack_iv(iv0[q]); ivs[q][0].mask = mk0[q]; sc = ivs[q][0].m; }
+                for (int e = 1; e < niv[q]; ++e) {
                     ivs[q][e] = unpack_iv(p.iv[(ri * ns + q) * MAX_IV + e]);
                     ivs[q][e].mask = p.ivmask[(ri * ns + q) * MAX_IV + e];
                     sc += ivs[q][e].m;
@@ -52,7 +62,7 @@
             okL = collect(p.ix, rg[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, R_LEFT, nL, wL);   // paired: strict check (:192-202)
             if (paired) {
                 if (okL && wL != R_LEFT) {            // the projection regions are about to be reused by the right mate
-                    for (uint32_t i = 0; i < nL; ++i) { const unsigned long long h = scr.at(wL, i); scr.at(R_LEFT, i) = h; }
+                    for (uint32_t i = 0; i < nL; ++i) scr.set(R_LEFT, i, scr.get(wL, i));
                     wL = R_LEFT;
                 }
                 okR = collect(p.ix, rg[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, R_RIGHT, nR, wR);
@@ -69,7 +79,7 @@
                 n_joint = overflow ? 0 : nL;
                 c_ub += (overflow || n_joint > 0) ? 1 : 0;
                 for (uint32_t i = 0; i < n_joint; ++i) {
-                    const unsigned long long h = scr.at(wL, i);
+                    const unsigned long long h = scr.get(wL, i);
 #if SFB_FIN_BIAS
                     if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, hit_tid(h), hit_pos(h), hit_fwd(h), len1);
 #endif
@@ -80,16 +90,16 @@
                 // mergeLeftRightHits[Fuzzy] (call sites :204-213): one joint hit per transcript present in both lists
                 uint32_t i = 0, j = 0, n_pairs = 0;
                 while (i < nL && j < nR) {
-                    const uint32_t tl = hit_tid(scr.at(wL, i)), tr = hit_tid(scr.at(wR, j));
+                    const uint32_t tl = hit_tid(scr.get(wL, i)), tr = hit_tid(scr.get(wR, j));
                     if (tl < tr) ++i; else if (tr < tl) ++j;
-                    else { ++n_pairs; ++i; while (i < nL && hit_tid(scr.at(wL, i)) == tl) ++i; while (j < nR && hit_tid(scr.at(wR, j)) == tl) ++j; }
+                    else { ++n_pairs; ++i; while (i < nL && hit_tid(scr.get(wL, i)) == tl) ++i; while (j < nR && hit_tid(scr.get(wR, j)) == tl) ++j; }
                 }
                 if (n_pairs > 0) {
                     n_joint = n_pairs;
                     c_ub += 1;
                     i = 0; j = 0;
                     while (i < nL && j < nR) {                                              // :341-369
-                        const unsigned long long hl = scr.at(wL, i), hr = scr.at(wR, j);
+                        const unsigned long long hl = scr.get(wL, i), hr = scr.get(wR, j);
                         const uint32_t tl = hit_tid(hl), tr = hit_tid(hr);
                         if (tl < tr) { ++i; continue; }
                         if (tr < tl) { ++j; continue; }
@@ -117,7 +127,7 @@
                             const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
                             fl = (e1 > e2 ? e1 : e2) - fs;
                         }
-                        ++i; while (i < nL && hit_tid(scr.at(wL, i)) == tl) ++i; while (j < nR && hit_tid(scr.at(wR, j)) == tl) ++j;
+                        ++i; while (i < nL && hit_tid(scr.get(wL, i)) == tl) ++i; while (j < nR && hit_tid(scr.get(wR, j)) == tl) ++j;
                     }
                 } else if (!p.strict_intersect && nL + nR > 0) {
                     // orphans: left block then right block, merged by transcript id (:231-246), left first on ties
@@ -130,8 +140,8 @@
                         while (i < nL || j < nR) {                                          // :289-340
                             bool takeL;
                             if (i >= nL) takeL = false; else if (j >= nR) takeL = true;
-                            else takeL = hit_tid(scr.at(wL, i)) <= hit_tid(scr.at(wR, j));
-                            const unsigned long long h = takeL ? scr.at(wL, i++) : scr.at(wR, j++);
+                            else takeL = hit_tid(scr.get(wL, i)) <= hit_tid(scr.get(wR, j));
+                            const unsigned long long h = takeL ? scr.get(wL, i++) : scr.get(wR, j++);
                             const int ms = takeL ? 1 : 2;
                             const bool fwd = hit_fwd(h);
 #if SFB_FIN_BIAS
@@ -165,7 +175,7 @@
         // ---- warp-aggregated class upsert (the warp is convergent here) ----
         const unsigned map_m = __ballot_sync(0xffffffffu, mapped);
         if (mapped) {
-            auto get = [&](uint32_t j) { return (uint32_t)scr.at(R_LABEL, j); };
+            auto get = [&](uint32_t j) { return (uint32_t)scr.get(R_LABEL, j); };
             const uint64_t h = xxh64_words(get, lab_n, 0);                                 // TranscriptGroup.cpp:9-12
             const unsigned grp = __match_any_sync(map_m, h);
             const int leader = __ffs(grp) - 1;
@@ -182,7 +192,7 @@
         __syncwarp();                                      // the next round overwrites the label region other lanes may still be comparing
     }
     // warp-reduce the six counters (ReadExperiment.hpp:74-97), one atomic per warp and counter
-    unsigned long long v[6] = {c_obs, c_map, c_hits, c_ub, c_fw, c_rc};
+    const unsigned long long v[6] = {c_obs, c_map, c_hits, c_ub, c_fw, c_rc};
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         unsigned long long x = v[q];

@@ -1,6 +1,7 @@
-// CPU check of the presence filter's addressing (sailfish_b200/csrc/kmer_filter.hpp): no false negatives, the false-positive
-// rate at the size index.cu chooses, and the locality the scan kernel relies on (distinct 32-byte sectors touched by the successive
-// k-mers of a read).  Prints "ok <fpr> <sectors per 46 k-mers>"; exit code 1 on failure.
+// CPU check of the m-mer presence bitmap (sailfish_b200/csrc/kmer_filter.hpp) and of the skipping rule the scan kernel builds on it
+// (map.cu: scan_step): with the bitmap of a text, "the last m-mer of the k-mer at i is absent => positions i .. i+k-m hold no indexed
+// k-mer", "the m-mer at offset h is absent => positions i .. i+h hold none".  The skipping scan must report exactly the positions a
+// one-position-at-a-time scan reports.  Prints "ok <positions probed per read position>"; exit code 1 on failure.
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -16,46 +17,44 @@ static uint64_t kmer_at(const std::vector<uint8_t>& t, size_t p, int k) {
 }
 
 int main(int argc, char** argv) {
-    const int k = argc > 1 ? atoi(argv[1]) : 31;
-    const size_t N = 2000000;
-    std::mt19937_64 rng(12345);
-    std::vector<uint8_t> text(N + k);
+    const int k = argc > 1 ? atoi(argv[1]) : 11, m = argc > 2 ? atoi(argv[2]) : 6;
+    const size_t N = argc > 3 ? atol(argv[3]) : 3000;
+    if (sfb_mfilter_m(31, 300000000ULL) != 15 || sfb_mfilter_m(31, 1700000000ULL) != 16 || sfb_mfilter_m(15, 1000) != 15 ||
+        sfb_mfilter_m(11, 1000) != 11 || sfb_mfilter_words(15) != (1ULL << 30) / 32) { printf("geometry\n"); return 1; }
+    std::mt19937_64 rng(99 + k * 131 + m);
+    std::vector<uint8_t> text(N);
     for (auto& b : text) b = rng() & 3;
-    // the filter as index.cu sizes it: >= 16 bits per k-mer
-    uint64_t words = 64;
-    while (words * 64 < 16 * N) words <<= 1;
-    const SfbBloomGeom g = sfb_bloom_geom(k, words);
-    std::vector<uint64_t> bloom(words, 0);
-    for (size_t p = 0; p < N; ++p) {
-        const uint64_t km = kmer_at(text, p, k), h = sfb_kmer_mix(km);
-        bloom[sfb_bloom_word(km, h, g, words)] |= sfb_bloom_mask(h);
-    }
-    // no false negatives
-    for (size_t p = 0; p < N; p += 7) {
-        const uint64_t km = kmer_at(text, p, k), h = sfb_kmer_mix(km);
-        const uint64_t need = sfb_bloom_mask(h);
-        if ((bloom[sfb_bloom_word(km, h, g, words)] & need) != need) { printf("false negative at %zu\n", p); return 1; }
-    }
-    // false positives: k-mers of an unrelated random text (absent with overwhelming probability for k >= 19)
-    std::vector<uint8_t> other(400000 + k);
-    for (auto& b : other) b = rng() & 3;
-    size_t fp = 0, probes = 0;
-    double sectors = 0; size_t windows = 0;
-    for (size_t r = 0; r + 76 <= other.size(); r += 76) {        // "reads" of 76 bases: 46 k-mers each for k = 31
-        std::set<uint64_t> sec;
-        for (size_t i = 0; i + k <= 76; ++i) {
-            const uint64_t km = kmer_at(other, r + i, k), h = sfb_kmer_mix(km);
-            const uint64_t w = sfb_bloom_word(km, h, g, words), need = sfb_bloom_mask(h);
-            if (w >= words) { printf("word out of range\n"); return 1; }
-            sec.insert(w >> 2);
+    std::vector<uint32_t> bits(sfb_mfilter_words(m), 0);
+    std::set<uint64_t> kmers;
+    for (size_t p = 0; p + m <= N; ++p) { const uint64_t v = kmer_at(text, p, m); bits[v >> 5] |= 1u << (v & 31); }
+    for (size_t p = 0; p + k <= N; ++p) kmers.insert(kmer_at(text, p, k));
+    auto test = [&](uint64_t key) { return (bits[key >> 5] >> (key & 31)) & 1u; };
+    const uint32_t J = k - m + 1, half = (J - 1) >> 1;
+    size_t probes = 0, positions = 0;
+    for (int trial = 0; trial < 400; ++trial) {
+        // a "read": partly a copy of the text (with a substitution), partly random
+        const size_t L = 60 + rng() % 60;
+        std::vector<uint8_t> r(L);
+        for (auto& b : r) b = rng() & 3;
+        if (trial & 1) { const size_t s = rng() % (N - L); for (size_t i = 0; i < L; ++i) r[i] = text[s + i]; r[rng() % L] ^= 1; }
+        std::vector<size_t> want, got;
+        for (size_t i = 0; i + k <= L; ++i) if (kmers.count(kmer_at(r, i, k))) want.push_back(i);
+        size_t i = 0;
+        while (i + k <= L) {
+            const uint64_t km = kmer_at(r, i, k);
+            const bool ahead = i + J + k <= L;
+            const bool b_last = test(sfb_mfilter_key(km, k - m, m));
+            const bool b_next = ahead ? test(sfb_mfilter_key(kmer_at(r, i + J, k), k - m, m)) : true;
+            const bool b_mid = half ? test(sfb_mfilter_key(km, half, m)) : true;
             ++probes;
-            if ((bloom[w] & need) == need) ++fp;
+            if (!b_last) { i += (ahead && !b_next) ? 2 * J : J; continue; }
+            if (!b_mid) { i += half + 1; continue; }
+            if (kmers.count(km)) got.push_back(i);                 // the table look-up
+            i += 1;
         }
-        sectors += sec.size(); ++windows;
+        positions += L - k + 1;
+        if (got != want) { printf("trial %d: skipping scan differs (%zu vs %zu present positions)\n", trial, got.size(), want.size()); return 1; }
     }
-    const double fpr = (double)fp / probes, per_read = sectors / windows;
-    printf("ok %.5f %.2f\n", fpr, per_read);
-    if (k >= 19 && fpr > 0.02) return 1;
-    if (k == 31 && per_read > 12.0) return 1;
+    printf("ok %.3f\n", (double)probes / positions);
     return 0;
 }
