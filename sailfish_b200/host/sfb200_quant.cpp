@@ -19,6 +19,10 @@
 #include <sys/stat.h>
 
 #include <cctype>
+#include <cerrno>
+#include <cstring>
+#include <stdexcept>
+#include <unistd.h>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -172,7 +176,19 @@ struct SailfishOpts {
     uint32_t pdfSampFactor = 1;                                               // --gcSpeedSamp (:1103)
 };
 
-void make_dir(const std::string& p) { mkdir(p.c_str(), 0755); }
+// mkdir -p; throws when a component cannot be created or is not a directory (the reference creates the output directory up front,
+// SailfishQuantify.cpp:1320-1335, so an unwritable -o fails before any work is done)
+void make_dir(const std::string& p) {
+    if (p.empty()) return;
+    for (size_t at = 1; at <= p.size(); ++at) {
+        if (at != p.size() && p[at] != '/') continue;
+        const std::string part = p.substr(0, at);
+        if (mkdir(part.c_str(), 0755) != 0 && errno != EEXIST) throw std::runtime_error("cannot create directory " + part + ": " + strerror(errno));
+    }
+    struct stat st;
+    if (stat(p.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) throw std::runtime_error(p + " is not a directory");
+    if (access(p.c_str(), W_OK) != 0) throw std::runtime_error("directory " + p + " is not writable");
+}
 
 std::string json_escape(const std::string& v) {
     std::string o;
@@ -643,7 +659,12 @@ class BatchPipe {
 public:
     BatchPipe(const std::vector<std::string>& f1, const std::vector<std::string>& f2, size_t batch, unsigned threads, size_t block)
         : files1_(f1), files2_(f2), batch_(batch), block_(block), threads_(threads), th_(&BatchPipe::produce, this) {}
-    ~BatchPipe() { if (th_.joinable()) th_.join(); }
+    // a consumer that stops early (device error while mapping) must not leave the producer waiting for room in the queue
+    ~BatchPipe() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        if (th_.joinable()) th_.join();
+    }
     // blocks until a batch is ready; returns nullptr after the last one
     std::unique_ptr<PairBatch> pop() {
         std::unique_lock<std::mutex> lk(mu_);
@@ -690,7 +711,8 @@ private:
                     }
                     if (n1 == 0) break;
                     std::unique_lock<std::mutex> lk(mu_);
-                    cv_.wait(lk, [&] { return q_.size() < 2; });
+                    cv_.wait(lk, [&] { return stop_ || q_.size() < 2; });
+                    if (stop_) return;
                     q_.push_back(std::move(b));
                     cv_.notify_all();
                 }
@@ -709,7 +731,7 @@ private:
     std::mutex mu_;
     std::condition_variable cv_;
     std::vector<std::unique_ptr<PairBatch>> q_, free_;
-    bool done_ = false;
+    bool done_ = false, stop_ = false;
     std::string err_;
     std::thread th_;
 };
@@ -776,6 +798,7 @@ int main(int argc, char** argv) {
         const std::vector<std::string>& f1 = paired_files ? a.mates1 : a.unmated;
         if (f1.empty()) usage("no read files given");
         if (paired_files && a.mates1.size() != a.mates2.size()) usage("--mates1 and --mates2 need the same number of files");
+        if (!a.parseOnly && !a.out.empty()) { make_dir(a.out); make_dir(a.out + "/" + a.auxDir); }   // fail fast, before the index is built
         if (a.parseOnly) {
             BatchPipe pipe(f1, a.mates2, a.batch, a.threads, a.blockBytes);
             // FNV-1a of the mate-1 bases, the mate-2 bases and the read lengths of either mate (independent of the batching)
@@ -896,9 +919,11 @@ int main(int argc, char** argv) {
         if (a.sopt.numBootstraps || a.sopt.numGibbsSamples) {                 // :1376-1410
             make_dir(aux + "/bootstrap");
             gzFile nf = gzopen((aux + "/bootstrap/names.tsv.gz").c_str(), "wb");
+            if (!nf) throw std::runtime_error("cannot open " + aux + "/bootstrap/names.tsv.gz for writing");
             for (size_t i = 0; i < names.size(); ++i) { gzputs(nf, names[i].c_str()); gzputs(nf, i + 1 < names.size() ? "\t" : "\n"); }
             gzclose(nf);
             gzFile bf = gzopen((aux + "/bootstrap/bootstraps.gz").c_str(), "wb");
+            if (!bf) throw std::runtime_error("cannot open " + aux + "/bootstrap/bootstraps.gz for writing");
             bool ok = true;
             if (a.sopt.numBootstraps) {
                 samp_type = "bootstrap"; n_samples = a.sopt.numBootstraps;

@@ -204,6 +204,31 @@ def test_effective_lengths_equal_oracle(tmp_path, mode, flags, kw):
     assert not np.frombuffer(gzip.open(tmp_path / "aux0" / "fld.gz").read(), dtype=np.int32).any()       # no observations: nothing to draw from
 
 
+def test_driver_error_paths_with_stub_device(tmp_path):
+    """a device error while mapping must end the run (the producer thread used to wait for queue room for ever), and an
+    output directory that cannot be created must fail before any work is done; nested output directories are created."""
+    exe = str(tmp_path / "sfb200-quant-stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-Wall", "-pthread", "-o", exe, os.path.join(ROOT, "sailfish_b200", "host", "sfb200_quant.cpp"),
+                           os.path.join(ROOT, "tests", "stub_sfb200.cpp"), "-lz"])
+    fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 100 + "\n>t1\n" + "GGCA" * 150 + "\n")
+    fq = tmp_path / "r.fq"; fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, "ACGT" * 10, "I" * 40) for i in range(400)))
+    log = tmp_path / "log.txt"
+    base = [exe, "quant", "-t", str(fa), "-l", "U", "-r", str(fq), "--batchReads", "10"]
+    # 40 batches queued behind a failing device call: the process must exit (non-zero), not hang
+    r = subprocess.run(base + ["-o", str(tmp_path / "o_fail")], env=dict(os.environ, SFB200_STUB_LOG=str(log), SFB200_STUB_FAIL_MAP="1"),
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "map_batch FAILS" in log.read_text()
+    # an output path below a regular file: refused before the index is built
+    log.unlink()
+    r = subprocess.run(base + ["-o", str(fq) + "/sub/out"], env=dict(os.environ, SFB200_STUB_LOG=str(log)), capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "cannot create directory" in (r.stderr + r.stdout)
+    assert not log.exists() or "index_build" not in log.read_text()
+    # nested output directories are created
+    r = subprocess.run(base + ["-o", str(tmp_path / "a" / "b" / "c")], env=dict(os.environ, SFB200_STUB_LOG=str(log)), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "a" / "b" / "c" / "quant.sf").exists() and (tmp_path / "a" / "b" / "c" / "aux" / "meta_info.json").exists()
+
+
 def test_driver_host_flow_with_stub_device(tmp_path):
     """sfb200_quant.cpp linked against tests/stub_sfb200.cpp (a test double of the C ABI: canned device results, call log): the
     driver's HOST flow -- effective lengths, FLD hand-over to the bias model, corrected lengths in quant.sf, every aux file --
