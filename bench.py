@@ -49,7 +49,7 @@ CONFIGS = {
     4: dict(genes=40_000, reads=50_000_000, read_len=100, paired=True, infer="em", fixed_iters=0, n_boot=0, n_gibbs=0, batch=4_000_000),
     5: dict(genes=200_000, reads=50_000_000, read_len=150, paired=True, infer="em", fixed_iters=0, n_boot=0, n_gibbs=0, batch=4_000_000),
 }
-EM_KERNELS = ["k_em_persistent", "k_em_part", "k_em_gather", "k_em_transcript_pass+k_em_sweep", "k_em_dense"]
+EM_KERNELS = ["k_em_persistent", "k_em_part", "k_em_gather", "k_em_transcript_pass+k_em_sweep", "k_em_dense", "k_em_dense (components + pool loop)"]
 
 
 def log(*a):
@@ -560,7 +560,7 @@ def main():
     # working set in shared memory (no HBM traffic after the first iteration): their bound is on-chip, the HBM figure is an equivalent
     b_em = 12.0 * nnz + 12.0 * E + 32.0 * T
     em_gbs = b_em * m["iters"] / (m["em_ms"] / 1e3) / 1e9
-    on_chip = m["em_kernel"] in ("k_em_dense", "k_em_gather", "k_em_part")
+    on_chip = m["em_kernel"].startswith(("k_em_dense", "k_em_gather", "k_em_part"))
     em_traffic = None
     try:
         em_traffic = json.load(open(os.path.join(ROOT, "profiles", "em_kernel_traffic.json"))).get(m["em_kernel"])

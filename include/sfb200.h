@@ -157,7 +157,9 @@ double sfb200_last_em_loop_ms(const sfb200_ctx* ctx);
 /* which iteration loop the last em_run / bootstrap used: 0 binned layout, global-memory scatter (k_em_persistent);
  * 1 CTA-partitioned, shared-memory scatter (k_em_part); 2 CTA-partitioned, atomic-free gather form (k_em_gather);
  * 3 one launch per phase (rank-local classes with a per-iteration all-reduce, or SFB200_EM_MODE=steps);
- * 4 one thread per connected component of the class structure (k_em_dense) */
+ * 4 one thread per connected component of the class structure (k_em_dense);
+ * 5 k_em_dense with a pool loop: small components on component threads, the rest (large components, classes that cross CTA ranges)
+ *   as an independent sub-problem on CTAs of their own */
 int sfb200_last_em_kernel(const sfb200_ctx* ctx);
 
 /* Not called by the quantification drivers yet (parity-tested on its own: tests/test_gpu_bias.py).

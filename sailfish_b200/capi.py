@@ -351,7 +351,7 @@ class Context:
         return alphas, eff_out, iters.value, mrd.value
 
     def last_em_kernel(self):
-        """0 k_em_persistent, 1 k_em_part, 2 k_em_gather, 3 one launch per phase"""
+        """0 k_em_persistent, 1 k_em_part, 2 k_em_gather, 3 one launch per phase, 4 k_em_dense, 5 k_em_dense with a pool loop (hybrid)"""
         return int(self.L.sfb200_last_em_kernel(self.h))
 
     def bootstrap_em(self, eff_lens, samp_counts, opts=None):

@@ -81,7 +81,10 @@ struct DevPartition {
     bool usable = false;     // every CTA's slice fits in shared memory
     uint32_t n_cta = 0;
     uint64_t pool_cls[SFB_NBINS + 1] = {0, 0, 0, 0, 0, 0, 0};
-    uint64_t n_pool = 0;
+    uint64_t n_pool = 0, pool_nnz = 0;
+    uint32_t n_pool_cta = 0;            // hybrid runs (em_dense.cuh): CTAs that run the pool loop, launched after the n_cta component CTAs
+    uint32_t n_dirty = 0;               // pool transcripts
+    DevBuf<uint32_t> dlist;             // their ids
     uint64_t max_cta_bytes = 0, max_cta_bytes_vb = 0, smem_limit = 0;
     int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
@@ -100,7 +103,7 @@ struct DevPartition {
     uint32_t dense_ns = 0;
     DevBuf<uint32_t> dns;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); }
 };
 struct DevClasses {
     DevPartition part;

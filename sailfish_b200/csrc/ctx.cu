@@ -4,6 +4,8 @@
 
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 extern "C" int sfb200_version(void) { return 100; }
@@ -22,6 +24,9 @@ extern "C" int sfb200_ctx_create(int device, sfb200_ctx** out) {
     c->coop = prop.cooperativeLaunch;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SFB200_ECUDA; }
     c->stream = c->own_stream;
+    // the mapping kernels read random 32-byte sectors (table slots, suffix entries, bitmap words): SFB200_L2_FETCH=32|64|128 sets the
+    // granularity L2 fetches from HBM with (a device-wide hint; default: the driver's)
+    if (const char* e = getenv("SFB200_L2_FETCH")) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)); cudaGetLastError(); }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     *out = c;

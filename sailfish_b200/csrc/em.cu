@@ -30,7 +30,8 @@ constexpr int EM_THREADS = 1024;
 
 // control block (unsigned long long words)
 enum { CTL_BAR_COUNT = 0, CTL_BAR_GEN = 1, CTL_MAXREL = 2 /*4 slots*/, CTL_CSUM = 6 /*4 slots*/, CTL_ITERS = 10,
-       CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_TSUM = 13 /* sum of the truncated result */, CTL_WORDS = 16 };
+       CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_TSUM = 13 /* sum of the truncated result */,
+       CTL_PBAR_COUNT = 14, CTL_PBAR_GEN = 15 /* barrier among the pool CTAs of a hybrid run (em_dense.cuh) */, CTL_WORDS = 16 };
 
 struct EmParams {
     const uint32_t* start; const uint32_t* len; const uint32_t* lab; const double* w; const double* cnt;
@@ -679,19 +680,22 @@ bool gather_enabled() { const char* e = getenv("SFB200_EM_GATHER"); return e ? a
 // one thread per connected component (em_dense.cuh) when every component is small; SFB200_EM_DENSE=0 / 1 overrides the default
 constexpr bool SFB_DENSE_DEFAULT = true;
 bool dense_enabled() { const char* e = getenv("SFB200_EM_DENSE"); return e ? atoi(e) != 0 : SFB_DENSE_DEFAULT; }
-int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl);
+int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl, bool mark_large, bool* marked);
 
-int build_partition(sfb200_ctx* c) {
+// hybrid runs (em_dense.cuh): small components on the component CTAs, everything else in the pool loop; SFB200_EM_HYBRID=0 switches it off
+bool hybrid_enabled() { const char* e = getenv("SFB200_EM_HYBRID"); return e ? atoi(e) != 0 : true; }
+
+__global__ void k_dirty_list(const uint8_t* __restrict__ dirty, uint32_t T, uint32_t* __restrict__ list, unsigned int* __restrict__ n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T && dirty[t]) list[atomicAdd(n, 1u)] = t;
+}
+
+// the partition for n_cta ranges; *marked_again is set when the dense builder sent large components to the pool and wants another pass
+int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
     DevClasses& k = c->cls;
     DevPartition& P = k.part;
-    P.valid = true; P.usable = false; P.gather_ok = false; P.gather_tried = gather_enabled(); P.dense_ok = false; P.dense_tried = dense_enabled();
-    if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
-    // CTAs per SM for the partitioned loop: two half-size CTAs fill each other's __syncthreads bubbles
-    int per_sm = 2;
-    if (const char* e = getenv("SFB200_EM_CTAS_PER_SM")) per_sm = std::max(1, std::min(4, atoi(e)));
-    const uint32_t T = k.n_txp, n_cta = (uint32_t)(c->num_sms * per_sm);
+    const uint32_t T = k.n_txp;
     const uint64_t Em = k.Em, nnzm = k.nnzm;
-    if (Em == 0 || T == 0) return SFB200_OK;
     cudaStream_t s = c->stream;
     HostMarks hm;
     P.n_cta = n_cta;
@@ -714,70 +718,115 @@ int build_partition(sfb200_ctx* c) {
     k_part_bounds<<<1, 1024, (n_cta + 1) * sizeof(uint32_t), s>>>(P.load.p, d_diff, T, n_cta, std::max<uint32_t>(8, T / n_cta / 2), P.pre.p, P.bounds.p);
     c->launches++;
     hm.mark("part: span + bounds launch");
-    // 2. closure of "crosses a range or touches a dirty transcript"
     SFB_CUDA(c, cudaMemsetAsync(P.dirty.p, 0, T, s));
     unsigned int* d_changed = reinterpret_cast<unsigned int*>(P.grp.p + 3 * (size_t)(n_cta + 1) * SFB_NBINS);
-    for (int round = 0; round < 256; ++round) {
-        SFB_CUDA(c, cudaMemsetAsync(d_changed, 0, 4, s));
-        k_part_owner<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, P.bounds.p, n_cta, P.dirty.p, P.owner.p, d_changed);
-        c->launches++;
-        unsigned int ch = 0;
-        SFB_CUDA(c, cudaMemcpyAsync(&ch, d_changed, 4, cudaMemcpyDeviceToHost, s));
-        SFB_CUDA(c, cudaStreamSynchronize(s));
-        if (!ch) break;
-    }
-    hm.mark("part: closure rounds");
-    // 3. group sizes -> offsets
-    const size_t G = (size_t)(n_cta + 1) * SFB_NBINS;
-    unsigned long long* d_grp = P.grp.p; unsigned long long* d_cls_off = P.grp.p + G; unsigned long long* d_nnz_off = P.grp.p + 2 * G;
-    SFB_CUDA(c, cudaMemsetAsync(d_grp, 0, G * 8, s));
-    k_part_count<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.len.p, Em, n_cta, d_grp);
-    c->launches++;
-    std::vector<unsigned long long> grp(G), cls_off(G + 1), nnz_off(G + 1);
-    SFB_CUDA(c, cudaMemcpyAsync(grp.data(), d_grp, G * 8, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaMemcpyAsync(bounds.data(), P.bounds.p, (n_cta + 1) * 4ull, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    cls_off[0] = 0; nnz_off[0] = 0;
-    for (size_t g = 0; g < G; ++g) { cls_off[g + 1] = cls_off[g] + (grp[g] >> 32); nnz_off[g + 1] = nnz_off[g] + (grp[g] & 0xFFFFFFFFULL); }
-    SFB_CUDA(c, cudaMemcpyAsync(d_cls_off, cls_off.data(), G * 8, cudaMemcpyHostToDevice, s));
-    SFB_CUDA(c, cudaMemcpyAsync(d_nnz_off, nnz_off.data(), G * 8, cudaMemcpyHostToDevice, s));
-    SFB_CUDA(c, cudaMemsetAsync(d_grp, 0, G * 8, s));                  // reused as the fill cursors
-    k_part_fill<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.start.p, k.len.p, k.lab.p, k.cnt.p, Em, n_cta, d_cls_off, d_nnz_off, d_grp,
-                                                   P.start.p, P.len.p, P.lab.p, P.cnt.p, P.src.p);
-    c->launches++;
-    hm.mark("part: counts + fill launch");
-    // 4. per-CTA table and the shared-memory budget
     std::vector<unsigned long long> tbl((size_t)n_cta * PT_WORDS, 0);
-    uint64_t max_bytes = 0, max_bytes_vb = 0;
-    for (uint32_t i = 0; i < n_cta; ++i) {
-        unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
-        for (int b = 0; b <= SFB_NBINS; ++b) row[PT_CLS + b] = cls_off[(size_t)i * SFB_NBINS + b];
-        row[PT_ENT0] = nnz_off[(size_t)i * SFB_NBINS]; row[PT_ENT1] = nnz_off[(size_t)(i + 1) * SFB_NBINS];
-        row[PT_TXP0] = bounds[i]; row[PT_TXP1] = bounds[i + 1];
-        const uint64_t nc = row[PT_CLS + SFB_NBINS] - (row[PT_CLS] & ~3ULL) + 4, ne = row[PT_ENT1] - (row[PT_ENT0] & ~3ULL) + 4;
-        const uint64_t nt = bounds[i + 1] - bounds[i] + 4;
-        max_bytes = std::max<uint64_t>(max_bytes, nc * 16 + ne * 12 + nt * (8 * 2 + 1) + 256);
-        max_bytes_vb = std::max<uint64_t>(max_bytes_vb, nc * 16 + ne * 12 + nt * (8 * 3 + 1) + 256);
-    }
-    SFB_CUDA(c, cudaMemcpyAsync(P.tbl.p, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, s));
-    for (int b = 0; b <= SFB_NBINS; ++b) P.pool_cls[b] = cls_off[(size_t)n_cta * SFB_NBINS + std::min(b, SFB_NBINS)];
-    P.pool_cls[SFB_NBINS] = Em;
-    P.n_pool = Em - P.pool_cls[0];
-    P.max_cta_bytes = max_bytes; P.max_cta_bytes_vb = max_bytes_vb; P.per_sm = per_sm;
     int max_optin = 0;
     SFB_CUDA(c, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     P.smem_limit = (uint64_t)max_optin;
-    P.usable = (max_bytes + 2048) * per_sm <= (uint64_t)max_optin + 1024 * (uint64_t)(per_sm - 1);
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    hm.mark("part: table + sync");
-    { const int rc = build_gather(c, tbl); if (rc) return rc; }
-    hm.mark("part: gather layout");
-    { const int rc = build_dense(c, tbl); if (rc) return rc; }
-    hm.mark("part: dense layout");
+    for (int pass = 0; pass < 3; ++pass) {
+        // 2. closure of "crosses a range or touches a dirty transcript" (pass > 0: the dense builder marked large components dirty)
+        for (int round = 0; round < 256; ++round) {
+            SFB_CUDA(c, cudaMemsetAsync(d_changed, 0, 4, s));
+            k_part_owner<<<grid_for(Em, 256), 256, 0, s>>>(k.start.p, k.len.p, k.lab.p, Em, P.bounds.p, n_cta, P.dirty.p, P.owner.p, d_changed);
+            c->launches++;
+            unsigned int ch = 0;
+            SFB_CUDA(c, cudaMemcpyAsync(&ch, d_changed, 4, cudaMemcpyDeviceToHost, s));
+            SFB_CUDA(c, cudaStreamSynchronize(s));
+            if (!ch) break;
+        }
+        hm.mark("part: closure rounds");
+        // 3. group sizes -> offsets
+        const size_t G = (size_t)(n_cta + 1) * SFB_NBINS;
+        unsigned long long* d_grp = P.grp.p; unsigned long long* d_cls_off = P.grp.p + G; unsigned long long* d_nnz_off = P.grp.p + 2 * G;
+        SFB_CUDA(c, cudaMemsetAsync(d_grp, 0, G * 8, s));
+        k_part_count<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.len.p, Em, n_cta, d_grp);
+        c->launches++;
+        std::vector<unsigned long long> grp(G), cls_off(G + 1), nnz_off(G + 1);
+        SFB_CUDA(c, cudaMemcpyAsync(grp.data(), d_grp, G * 8, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaMemcpyAsync(bounds.data(), P.bounds.p, (n_cta + 1) * 4ull, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        cls_off[0] = 0; nnz_off[0] = 0;
+        for (size_t g = 0; g < G; ++g) { cls_off[g + 1] = cls_off[g] + (grp[g] >> 32); nnz_off[g + 1] = nnz_off[g] + (grp[g] & 0xFFFFFFFFULL); }
+        SFB_CUDA(c, cudaMemcpyAsync(d_cls_off, cls_off.data(), G * 8, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, cudaMemcpyAsync(d_nnz_off, nnz_off.data(), G * 8, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, cudaMemsetAsync(d_grp, 0, G * 8, s));                  // reused as the fill cursors
+        k_part_fill<<<grid_for(Em, 256), 256, 0, s>>>(P.owner.p, k.start.p, k.len.p, k.lab.p, k.cnt.p, Em, n_cta, d_cls_off, d_nnz_off, d_grp,
+                                                       P.start.p, P.len.p, P.lab.p, P.cnt.p, P.src.p);
+        c->launches++;
+        hm.mark("part: counts + fill launch");
+        // 4. per-CTA table and the shared-memory budget
+        uint64_t max_bytes = 0, max_bytes_vb = 0;
+        for (uint32_t i = 0; i < n_cta; ++i) {
+            unsigned long long* row = tbl.data() + (size_t)i * PT_WORDS;
+            for (int b = 0; b <= SFB_NBINS; ++b) row[PT_CLS + b] = cls_off[(size_t)i * SFB_NBINS + b];
+            row[PT_ENT0] = nnz_off[(size_t)i * SFB_NBINS]; row[PT_ENT1] = nnz_off[(size_t)(i + 1) * SFB_NBINS];
+            row[PT_TXP0] = bounds[i]; row[PT_TXP1] = bounds[i + 1];
+            const uint64_t nc = row[PT_CLS + SFB_NBINS] - (row[PT_CLS] & ~3ULL) + 4, ne = row[PT_ENT1] - (row[PT_ENT0] & ~3ULL) + 4;
+            const uint64_t nt = bounds[i + 1] - bounds[i] + 4;
+            max_bytes = std::max<uint64_t>(max_bytes, nc * 16 + ne * 12 + nt * (8 * 2 + 1) + 256);
+            max_bytes_vb = std::max<uint64_t>(max_bytes_vb, nc * 16 + ne * 12 + nt * (8 * 3 + 1) + 256);
+        }
+        SFB_CUDA(c, cudaMemcpyAsync(P.tbl.p, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, s));
+        for (int b = 0; b <= SFB_NBINS; ++b) P.pool_cls[b] = cls_off[(size_t)n_cta * SFB_NBINS + std::min(b, SFB_NBINS)];
+        P.pool_cls[SFB_NBINS] = Em;
+        P.n_pool = Em - P.pool_cls[0];
+        P.pool_nnz = nnz_off[G] - nnz_off[(size_t)n_cta * SFB_NBINS];
+        P.max_cta_bytes = max_bytes; P.max_cta_bytes_vb = max_bytes_vb; P.per_sm = per_sm;
+        P.usable = (max_bytes + 2048) * per_sm <= (uint64_t)max_optin + 1024 * (uint64_t)(per_sm - 1);
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        hm.mark("part: table + sync");
+        { const int rc = build_gather(c, tbl); if (rc) return rc; }
+        hm.mark("part: gather layout");
+        bool marked = false;
+        // components too large for a thread go to the pool only when there is a pool anyway (classes that cross ranges): a class
+        // set that is local everywhere stays with the on-chip gather loop
+        { const int rc = build_dense(c, tbl, pass < 2 && P.n_pool > 0, &marked); if (rc) return rc; }
+        hm.mark("part: dense layout");
+        if (!marked) break;
+    }
+    // the pool's transcripts as a list (hybrid runs walk it instead of all T)
+    P.n_dirty = 0;
+    if (P.n_pool) {
+        SFB_CUDA(c, P.dlist.reserve(T));
+        SFB_CUDA(c, cudaMemsetAsync(d_changed, 0, 4, s));
+        k_dirty_list<<<grid_for(T, 256), 256, 0, s>>>(P.dirty.p, T, P.dlist.p, d_changed);
+        c->launches++;
+        unsigned int nd = 0;
+        SFB_CUDA(c, cudaMemcpyAsync(&nd, d_changed, 4, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        P.n_dirty = nd;
+    }
     if (getenv("SFB200_VERBOSE"))
-        fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool), largest CTA slice %llu bytes (limit %d) -> %s\n",
-                n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, (unsigned long long)max_bytes, max_optin,
-                P.usable ? "shared-memory loop" : "binned global loop");
+        fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool, %u pool transcripts), largest CTA slice %llu bytes (limit %d) -> %s\n",
+                n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, P.n_dirty, (unsigned long long)P.max_cta_bytes, max_optin,
+                P.dense_ok ? (P.n_pool ? "component threads + pool loop" : "component threads") : P.usable ? "shared-memory loop" : "binned global loop");
+    return SFB200_OK;
+}
+
+int build_partition(sfb200_ctx* c) {
+    DevClasses& k = c->cls;
+    DevPartition& P = k.part;
+    P.valid = true; P.usable = false; P.gather_ok = false; P.gather_tried = gather_enabled(); P.dense_ok = false; P.dense_tried = dense_enabled();
+    P.n_pool_cta = 0;
+    if (getenv("SFB200_NO_PARTITION")) return SFB200_OK;
+    // CTAs per SM for the partitioned loop: two half-size CTAs fill each other's __syncthreads bubbles
+    int per_sm = 2;
+    if (const char* e = getenv("SFB200_EM_CTAS_PER_SM")) per_sm = std::max(1, std::min(4, atoi(e)));
+    const uint32_t n_full = (uint32_t)(c->num_sms * per_sm);
+    if (k.Em == 0 || k.n_txp == 0) return SFB200_OK;
+    { const int rc = build_partition_n(c, n_full, per_sm); if (rc) return rc; }
+    if (P.dense_ok && P.n_pool > 0) {
+        // hybrid: some of the CTAs run the pool loop instead of owning a range -- as many as the pool's share of the label entries
+        // suggests (x 1.5: its sweep goes through L2), at least 8, at most two thirds; the ranges are rebuilt for the rest
+        const double share = (double)P.pool_nnz / (double)std::max<uint64_t>(1, k.nnzm);
+        uint32_t np = (uint32_t)std::ceil(1.5 * share * n_full);
+        if (const char* e = getenv("SFB200_EM_POOL_CTAS")) np = (uint32_t)atoi(e);
+        np = std::max<uint32_t>(8, std::min<uint32_t>(np, n_full * 2 / 3));
+        { const int rc = build_partition_n(c, n_full - np, per_sm); if (rc) return rc; }
+        if (P.dense_ok) P.n_pool_cta = P.n_pool ? np : 0;
+        else { const int rc = build_partition_n(c, n_full, per_sm); if (rc) return rc; P.dense_ok = false; }   // keep the other loops' geometry
+    }
     return SFB200_OK;
 }
 
@@ -833,11 +882,13 @@ int build_gather(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
 }
 
 // Build the dense-component layout (em_dense.cuh): usable when every CTA reports components of at most DN_MAX_SLOTS transcripts.
-int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
+int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl, bool mark_large, bool* marked) {
     DevPartition& P = c->cls.part;
     P.dense_ok = false;
     P.dense_tried = dense_enabled();
-    if (!dense_enabled() || P.n_pool != 0 || P.n_cta == 0) return SFB200_OK;
+    *marked = false;
+    const bool hybrid = hybrid_enabled() && c->coop;
+    if (!dense_enabled() || (P.n_pool != 0 && !hybrid) || P.n_cta == 0) return SFB200_OK;
     static_assert(sizeof(DenseGeom) == sizeof(P.dns_geom), "DenseGeom is stored as 16 opaque words");
     uint64_t max_nc = 0, max_nt = 0;
     for (uint32_t i = 0; i < P.n_cta; ++i) {
@@ -854,7 +905,7 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     const size_t scratch = 4 * dense_scratch_words(max_nt, g);
     if (scratch + 1024 > P.smem_limit) return SFB200_OK;
     SFB_CUDA(c, cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_dense_build), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
-    k_dense_build<<<P.n_cta, 256, scratch, s>>>(P.start.p, P.len.p, P.lab.p, P.tbl.p, g, P.dns.p);
+    k_dense_build<<<P.n_cta, 256, scratch, s>>>(P.start.p, P.len.p, P.lab.p, P.tbl.p, g, P.dns.p, P.dirty.p, (hybrid && mark_large) ? 1 : 0);
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
     std::vector<uint32_t> hdr((size_t)P.n_cta * DH_WORDS);
@@ -862,6 +913,8 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl) {
     SFB_CUDA(c, cudaStreamSynchronize(s));
     bool ok = true;
     uint32_t ns = 2, rounds = 0;
+    for (uint32_t i = 0; i < P.n_cta; ++i) if (hdr[(size_t)i * DH_WORDS + DH_KIND] == 2u) *marked = true;
+    if (*marked) return SFB200_OK;                                     // large components were sent to the pool: the caller builds again
     for (uint32_t i = 0; i < P.n_cta && ok; ++i) {
         const uint32_t* h = hdr.data() + (size_t)i * DH_WORDS;
         ok = h[DH_KIND] == 1u;
@@ -904,6 +957,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         const DevPartition& P = c->cls.part;
         DenseParams q;
         q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
+        q.n_dense = P.n_cta; q.dlist = P.dlist.p; q.n_dirty = P.n_dirty;
         const size_t smem = (size_t)P.dense_smem;
         void* args[] = {&p, &q};
         const void* fn = nullptr;
@@ -914,7 +968,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
 #undef SFB_DENSE_CASE
 #undef SFB_DENSE_FN
         SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(DENSE_THREADS), args, smem, s));
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta + P.n_pool_cta), dim3(DENSE_THREADS), args, smem, s));
         c->launches++;
         SFB_CUDA(c, cudaEventRecord(c->ev1, s));
         SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
@@ -1049,7 +1103,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
     float ms = 0.f;
     SFB_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_em_ms = ms;
-    c->last_em_kernel = steps ? 3 : (int)kind;
+    c->last_em_kernel = steps ? 3 : (kind == LOOP_DENSE && c->cls.part.n_pool_cta) ? 5 : (int)kind;
     return SFB200_OK;
 }
 
@@ -1098,7 +1152,8 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const uint32_t* a_len = use_part ? P.len.p : k.len.p;
     const uint32_t* a_lab = use_part ? P.lab.p : k.lab.p;
     double* a_w = use_part ? P.w.p : k.w.p;
-    if (k.Em && !use_gather) {
+    const bool hybrid_pool = use_dense && P.n_pool > 0;                 // the pool loop of a hybrid run sweeps in the weighted scatter form
+    if (k.Em && (!use_gather || hybrid_pool)) {
         // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
         k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
         c->launches++;
@@ -1177,7 +1232,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
             if (rc) return rc;
             h_eff.swap(h_next);
             SFB_CUDA(c, cudaMemcpyAsync(c->eff.p, h_eff.data(), T * 8ull, cudaMemcpyHostToDevice, s));
-            if (k.Em && !use_gather) {
+            if (k.Em && (!use_gather || hybrid_pool)) {
                 k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
                 c->launches++;
             }

@@ -32,19 +32,127 @@
 
 __global__ void __launch_bounds__(256) k_dense_build(const uint32_t* __restrict__ start, const uint32_t* __restrict__ len,
                                                      const uint32_t* __restrict__ lab, const unsigned long long* __restrict__ tbl,
-                                                     const DenseGeom g, uint32_t* __restrict__ regions) {
+                                                     const DenseGeom g, uint32_t* __restrict__ regions, uint8_t* dirty, int mark_large) {
     extern __shared__ __align__(16) uint32_t db_scratch[];
     const unsigned long long* row = tbl + (size_t)blockIdx.x * PT_WORDS;
     const uint32_t c_lo = (uint32_t)row[PT_CLS], nc = (uint32_t)(row[PT_CLS + SFB_NBINS] - row[PT_CLS]);
     const uint32_t t0 = (uint32_t)row[PT_TXP0], nt = (uint32_t)(row[PT_TXP1] - row[PT_TXP0]);
-    dense_build_cta(start, len, lab, c_lo, nc, t0, nt, g, regions + (size_t)blockIdx.x * g.region_words, db_scratch);
+    dense_build_cta(start, len, lab, c_lo, nc, t0, nt, g, regions + (size_t)blockIdx.x * g.region_words, db_scratch, dirty, mark_large ? dirty : nullptr);
 }
 
 struct DenseParams {
     const uint32_t* regions;
     DenseGeom g;
     const double* eff;        // T clamped effective lengths
+    // hybrid runs: CTAs [0, n_dense) own the small components, CTAs [n_dense, gridDim.x) run the pool loop over the classes of
+    // everything else (components too large for a thread, classes that cross CTA ranges) -- an independent sub-problem
+    uint32_t n_dense;
+    const uint32_t* dlist;    // transcripts of the pool ("dirty"), n_dirty of them
+    uint32_t n_dirty;
 };
+
+// barrier among the pool CTAs only (same protocol as grid_barrier, its own counter words)
+__device__ __forceinline__ void pool_barrier(unsigned long long* ctl, unsigned int n_cta, unsigned long long& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += 1;
+        __threadfence();
+        const unsigned long long prev = atomicAdd(&ctl[CTL_PBAR_COUNT], 1ULL);
+        if (prev + 1 == gen * n_cta) st_release_u64(&ctl[CTL_PBAR_GEN], gen);
+        else while (ld_acquire_u64(&ctl[CTL_PBAR_GEN]) < gen) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// The pool loop of a hybrid run: EMUpdate_ / VBEMUpdate_ over the pool classes in the scatter form of k_em_persistent (binned layout,
+// gathers and red.add through L2 -- the pool's alpha vector is a few hundred KB), restricted to the pool's transcripts, on the pool
+// CTAs only.  The pool shares no transcript with the components the other CTAs own, so the two groups meet only where the reference
+// needs a global quantity: the stopping rule and VBEM's digamma(sum alpha) -- at the same iterations, through the same grid barrier,
+// as k_em_dense's own loop below (the break logic is a copy of it).  An EM iteration costs the pool ONE barrier among its own CTAs.
+template <bool VB>
+__device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParams& q) {
+    __shared__ unsigned long long pl_u[32];
+    __shared__ double pl_d[32];
+    const unsigned nblocks = gridDim.x, NP = nblocks - q.n_dense, pi = blockIdx.x - q.n_dense;
+    unsigned long long gen = 0, gen_p = 0;
+    Slice sl; sl.start = p.start; sl.len = p.len; sl.cnt = p.cnt; sl.lab = p.lab; sl.w = p.w; sl.c0 = 0; sl.e0 = 0;
+    const Bins pb = em_bins(p);
+    const uint64_t pool_tiles = p.tile_start[SFB_NBINS];
+    const uint64_t tile_lo = pool_tiles * pi / NP, tile_hi = pool_tiles * (pi + 1ULL) / NP;
+    const uint32_t d_lo = (uint32_t)((uint64_t)q.n_dirty * pi / NP), d_hi = (uint32_t)((uint64_t)q.n_dirty * (pi + 1ULL) / NP);
+    const bool fixed = p.fixed_iters > 0;
+    unsigned bi = 0, bo = 1, bs = 2;
+    uint32_t n = 0;
+    if (VB) {
+        const double logNorm = sfb_digamma(p.sum0);
+        for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
+            const uint32_t t = q.dlist[i];
+            const double a = p.X[t];
+            p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+        }
+        pool_barrier(p.ctl, NP, gen_p);
+    }
+    for (;;) {
+        if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
+        const uint32_t m = n + 1;
+        const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
+        const double* in = p.X + (size_t)bi * p.T;
+        double* out = p.X + (size_t)bo * p.T;
+        double* spare = p.X + (size_t)bs * p.T;
+        // the spare buffer (the input of the previous iteration) becomes an output buffer again: back to its initial value, for this
+        // CTA's share of the pool transcripts (every CTA keeps the same share, and nobody gathers from that buffer any more)
+        if (n > 0) for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; spare[t] = __ldg(p.base + t); }
+        sweep_block<VB, false>(pb, sl, tile_lo, tile_hi, VB ? p.theta : in, out, 0u);
+        pool_barrier(p.ctl, NP, gen_p);
+        unsigned long long best = 0ULL;
+        double asum = 0.0;
+        if (VB || do_cmp) {
+            for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
+                const uint32_t t = q.dlist[i];
+                const double a_new = ld_cg_f64(out + t);
+                if (do_cmp) {
+                    const double a_old = ld_cg_f64(in + t);
+                    const double gate = p.gate_old ? a_old : a_new;
+                    if (gate > p.cutoff) {
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                        best = bits > best ? bits : best;
+                    }
+                }
+                asum += a_new;
+            }
+        }
+        n = m;
+        { const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp; }       // bi now names the newest alphas
+        if (VB || do_cmp) {
+            unsigned long long* slot = p.ctl + CTL_MAXREL + (m & 3u);
+            double* csum = reinterpret_cast<double*>(p.ctl + CTL_CSUM + (m & 3u));
+            if (do_cmp) block_max_to_slot(best, slot, pl_u);
+            if (VB) block_sum_to_slot(asum, csum, pl_d);
+            grid_barrier(p.ctl, nblocks, gen);                        // block 0 (a component CTA) recycles the slots afterwards
+            if (do_cmp) {
+                const unsigned long long mr = ld_cg_u64(slot);
+                if (fixed) break;
+                if (!(decode_mrd(mr) > p.tol) || m >= p.max_iter) break;
+            }
+            if (VB) {
+                const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
+                const double* cur = p.X + (size_t)bi * p.T;
+                for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
+                    const uint32_t t = q.dlist[i];
+                    const double a = ld_cg_f64(cur + t);
+                    p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+                }
+                pool_barrier(p.ctl, NP, gen_p);
+            }
+        }
+    }
+    // the component CTAs leave their result in the first third of X: so does the pool
+    if (bi != 0) {
+        const double* cur = p.X + (size_t)bi * p.T;
+        for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; p.X[t] = ld_cg_f64(cur + t); }
+    }
+}
 
 constexpr int DENSE_THREADS = 256;
 constexpr int DENSE_ILP = 4;          // classes of one component in flight per lane
@@ -72,6 +180,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     __shared__ uint64_t tma_bar;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     const unsigned nblocks = gridDim.x;
+    if (blockIdx.x >= q.n_dense) { dense_pool_loop<VB>(p, q); return; }
     unsigned long long gen = 0;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
 

@@ -58,8 +58,12 @@ inline DenseGeom dense_make_geom(uint64_t max_nc, uint64_t max_nt, uint32_t grou
 inline size_t dense_scratch_words(uint64_t max_nt, const DenseGeom& g) { return 9 * (size_t)max_nt + DN_BUCKETS + 2 * (size_t)g.cap_tiles + 16; }
 #endif
 
+// dirty_in (may be null): transcripts whose classes were all sent to the pool -- they belong to the pool loop, not to the idle list.
+// dirty_out (may be null): instead of just giving up on a component that is too large for one thread (or on a propagation that does
+// not settle), mark its transcripts there and report DH_KIND = 2: the caller sends their classes to the pool and builds again.
 SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const uint32_t* lab, uint32_t c_lo, uint32_t nc,
-                               uint32_t t0, uint32_t nt, const DenseGeom g, uint32_t* region, uint32_t* scratch) {
+                               uint32_t t0, uint32_t nt, const DenseGeom g, uint32_t* region, uint32_t* scratch,
+                               const uint8_t* dirty_in = nullptr, uint8_t* dirty_out = nullptr) {
     const uint32_t tid = SFB_GB_TID, nth = SFB_GB_NT;
     uint32_t* s_comp = scratch;              // nt: component label (smallest local index of the component)
     uint32_t* s_deg = s_comp + nt;           // nt: number of local classes the transcript belongs to
@@ -111,7 +115,13 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
         if (rounds + 1 >= DN_MAX_ROUNDS) { if (tid == 0) s_misc[0] = 0; break; }
     }
     SFB_GB_SYNC();
-    if (!s_misc[0]) return;
+    if (!s_misc[0]) {
+        if (dirty_out) {                                               // not settled: everything with a local class goes to the pool
+            for (uint32_t t = tid; t < nt; t += nth) if (s_deg[t]) dirty_out[t0 + t] = 1;
+            if (tid == 0) hdr[DH_KIND] = 2u;
+        }
+        return;
+    }
     // labels are not yet roots everywhere if a label moved after a class last looked at it: they are, because the loop only
     // ends after a full round in which no class saw two different labels among its members, and a label is always the index of
     // a transcript that carries it (the minimum never leaves its own transcript)
@@ -119,7 +129,7 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
     for (uint32_t c = tid; c < nc; c += nth) SFB_GB_ADD(s_ccnt + s_comp[lab[start[c_lo + c]] - t0], 1u);
     SFB_GB_SYNC();
     for (uint32_t t = tid; t < nt; t += nth) {
-        if (!s_deg[t]) { const uint32_t p = SFB_GB_ADD(s_misc + 4, 1u); idle[p] = t0 + t; }
+        if (!s_deg[t]) { if (!(dirty_in && dirty_in[t0 + t])) { const uint32_t p = SFB_GB_ADD(s_misc + 4, 1u); idle[p] = t0 + t; } }
         else if (s_comp[t] == t) {
             SFB_GB_MAX(s_misc + 2, s_size[t]);
             const uint32_t cc = s_ccnt[t];
@@ -127,7 +137,13 @@ SFB_GB_FN void dense_build_cta(const uint32_t* start, const uint32_t* len, const
         }
     }
     SFB_GB_SYNC();
-    if (s_misc[2] > DN_MAX_SLOTS) return;                              // a component too large for one thread
+    if (s_misc[2] > DN_MAX_SLOTS) {                                    // a component too large for one thread
+        if (dirty_out) {
+            for (uint32_t t = tid; t < nt; t += nth) if (s_deg[t] && s_size[s_comp[t]] > DN_MAX_SLOTS) dirty_out[t0 + t] = 1;
+            if (tid == 0) hdr[DH_KIND] = 2u;
+        }
+        return;
+    }
     if (tid == 0) {
         uint32_t acc = 0;
         for (int b = (int)DN_BUCKETS - 1; b >= 0; --b) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }

@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
 
 // ---- finalize kernel: projection, mate merge, compatibility filter, label, class upsert -----------------------------------------
 #ifndef SFB_FIN_BLOCKS
-#define SFB_FIN_BLOCKS 3
+#define SFB_FIN_BLOCKS 2      // 106 registers without spills; 3 CTAs (80 registers, spills) measured 5% slower (profiles/r02c_variants.txt)
 #endif
 __global__ void __launch_bounds__(MAP_THREADS, SFB_FIN_BLOCKS) k_finalize_reads(const MapParams p) {
 #define SFB_FIN_BIAS 0

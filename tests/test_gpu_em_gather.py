@@ -198,3 +198,64 @@ def test_dense_loop_component_sizes(ctx, loop_kind):
             assert rc == 0 and it == it_o
             close(a, ref)
             assert abs(mrd - mrd_o) <= 1e-6 * max(abs(mrd_o), 1e-12)
+
+
+def paralog_classes(T, seed, n_fam=6, fam_genes=(8, 60), gene=5):
+    """gene-local classes plus families whose members are scattered over the transcript order: classes that cross genes (and CTA
+    ranges), connected components of hundreds of transcripts, labels of up to ~100 members"""
+    rng = np.random.default_rng(seed)
+    labs = {}
+    n_genes = T // gene
+    for g in range(n_genes):
+        for _ in range(4):
+            n = int(rng.integers(1, gene + 1))
+            ids = tuple(sorted(int(x) for x in rng.choice(np.arange(g * gene, (g + 1) * gene), size=n, replace=False)))
+            labs[ids] = int(max(1, rng.lognormal(2.0, 2.0)))
+    for f in range(n_fam):
+        genes = rng.choice(n_genes, size=int(rng.integers(*fam_genes)), replace=False)
+        members = np.concatenate([np.arange(g * gene, (g + 1) * gene) for g in genes])
+        for _ in range(12 * len(genes)):
+            n = int(rng.integers(2, min(100, len(members)) + 1)) if rng.random() < 0.2 else int(rng.integers(2, 7))
+            ids = tuple(sorted(int(x) for x in rng.choice(members, size=n, replace=False)))
+            labs[ids] = int(max(1, rng.lognormal(2.0, 2.0)))
+    keys = sorted(labs)
+    rp = np.zeros(len(keys) + 1, np.uint64); rp[1:] = np.cumsum([len(k) for k in keys])
+    return rp, np.array([t for k in keys for t in k], np.uint32), np.array([labs[k] for k in keys], np.uint64)
+
+
+@pytest.mark.parametrize("T,seed", [(6000, 1), (40000, 2)])
+def test_hybrid_components_and_pool_loop(ctx, monkeypatch, loop_kind, T, seed):
+    """class sets with paralog families: the small components run on component threads, everything else -- large components,
+    classes that cross CTA ranges -- in the pool loop on CTAs of its own (sfb200_last_em_kernel == 5); EM and VBEM, converging and
+    fixed-iteration runs, and a bootstrap-style run against the oracle = the reference's optimizer"""
+    if loop_kind != DENSE:
+        pytest.skip("the pool loop belongs to the dense kernel")
+    rp, lab, cnt = paralog_classes(T, seed)
+    eff = np.random.default_rng(seed).uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    for vb in (0, 1):
+        for kw in ({}, {"fixed_iters": 37}, {"min_iter": 5, "max_iter": 60}):
+            a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb, **kw))
+            assert ctx.last_em_kernel() == 5, ctx.last_em_kernel()
+            rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, **kw), n_threads=4)
+            assert rc == 0 and it == it_o, (vb, kw, it, it_o)
+            close(a, want)
+            assert (a == 0).tolist() == (want == 0).tolist()
+            if not kw.get("fixed_iters"):
+                assert abs(mrd - mrd_o) <= 1e-5 * max(abs(mrd_o), 1e-12)
+    # the same classes with the hybrid switched off: the partitioned scatter loop; both agree
+    a1, it1, _ = ctx.em_run(eff, nm, capi.EMOpts.default(fixed_iters=50))
+    monkeypatch.setenv("SFB200_EM_HYBRID", "0")
+    ctx.eq_import(T, rp, lab, cnt)
+    a2, it2, _ = ctx.em_run(eff, nm, capi.EMOpts.default(fixed_iters=50))
+    assert ctx.last_em_kernel() in (0, 1)
+    close(a1, a2, rtol=1e-7)
+    monkeypatch.delenv("SFB200_EM_HYBRID")
+    ctx.eq_import(T, rp, lab, cnt)
+    # resampled counts (bootstrap): doBootstrap's loop rule on the same layout
+    samp = np.random.default_rng(9).multinomial(nm, cnt / cnt.sum()).astype(np.uint64)
+    a, it = ctx.bootstrap_em(eff, samp, capi.EMOpts.default())
+    rc, want, it_o = O.bootstrap_em(T, rp, lab, samp, eff, O.EMOpts.default())
+    assert rc == 0 and it == it_o
+    close(a, want)
