@@ -103,15 +103,15 @@ int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_
  * number from both mates -- are extracted on the GPU and mapped as by sfb200_map_batch.  *n_records = how many, *consumed1/2 = the
  * bytes of text they cover: the caller keeps text[consumed ..) and puts it in front of what it reads next.  A final record
  * without a trailing newline needs one appended.  Gzipped input is inflated by the caller first.
- * Not yet run on a GPU (parity test: tests/test_gpu_map.py with SFB200_EXPERIMENTAL=1; CPU check of the arithmetic:
- * tests/fastq_core_test.cpp). */
+ * Parity: tests/test_gpu_map.py::test_map_fastq_equals_map_batch (green on a B200, profiles/r02a_experimental_gpu.txt); CPU check of the
+ * arithmetic: tests/fastq_core_test.cpp. */
 int sfb200_map_fastq(sfb200_ctx* ctx, const char* text1, uint64_t n1, const char* text2, uint64_t n2, uint64_t max_records,
                      uint64_t* n_records, uint64_t* consumed1, uint64_t* consumed2);
 /* --biasCorrect / --gcBiasCorrect: collect, while mapping, what the reference collects in processReadsQuasi
  * (src/SailfishQuantify.cpp:255-287 and :555-583: the 6-mer context around the start of each read's first hit that has one,
  * readBias().update, for the first num_bias_samples such reads in read order -- sfOpts.numBiasSamples, the reference at -p 1;
  * :372-389: observedGC()[gcFrac(start, stop)]++ for every properly paired hit inside its transcript).
- * Call after map_begin and before the first batch.  Parity: tests/test_gpu_map.py (SFB200_EXPERIMENTAL=1 until first GPU run). */
+ * Call after map_begin and before the first batch.  Parity: tests/test_gpu_map.py. */
 int sfb200_map_set_bias(sfb200_ctx* ctx, int seq_bias, int gc_bias, int32_t num_bias_samples);
 /* readExp.readBias().counts (4096 bins) and readExp.observedGC() (101 bins), both with the reference's initial count of 1 per
  * bin -- the arrays sfb200_bias_model takes.  With a communicator: summed over ranks. */
@@ -126,6 +126,9 @@ int sfb200_map_get_bias(sfb200_ctx* ctx, uint32_t* read_bias, uint32_t* observed
 int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz);
 /* device time of all mapping-kernel launches between map_begin and map_finish, in milliseconds (CUDA events) */
 double sfb200_last_map_kernel_ms(const sfb200_ctx* ctx);
+/* Mates longer than 256 bases are mapped by their first 256 (mapping spec v1; the reference maps the whole read,
+ * SailfishQuantify.cpp:192-213): how many mates were cut since map_begin.  The drivers print a warning when it is not zero. */
+uint64_t sfb200_map_clipped(sfb200_ctx* ctx);
 /* == eqVec() (EquivalenceClassBuilder.hpp:110) as CSR in canonical order (label-lexicographic);
  * this is the content of aux/eq_classes.txt (src/GZipWriter.cpp:51-92) */
 int sfb200_eq_export(sfb200_ctx* ctx, uint64_t* row_ptr, uint32_t* labels, uint64_t* counts);

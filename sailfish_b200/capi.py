@@ -83,6 +83,7 @@ SIGNATURES = {
     "sfb200_index_export": (C.c_int, [C.c_void_p, u64p, u32p, u32p]),
     "sfb200_index_export_table": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sfb200_last_map_kernel_ms": (C.c_double, [C.c_void_p]),
+    "sfb200_map_clipped": (C.c_uint64, [C.c_void_p]),
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
     "sfb200_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint64]),
     "sfb200_map_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -239,6 +240,10 @@ class Context:
         return float(self.L.sfb200_last_map_kernel_ms(self.h))
 
     # ---- mapping
+    def map_clipped(self):
+        """mates longer than 256 bases (mapped by their first 256) since map_begin"""
+        return int(self.L.sfb200_map_clipped(self.h))
+
     def map_begin(self, opts):
         self.map_opts = opts
         self._chk(self.L.sfb200_map_begin(self.h, C.byref(opts)))

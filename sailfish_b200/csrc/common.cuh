@@ -84,7 +84,9 @@ struct DevPartition {
     uint64_t n_pool = 0, pool_nnz = 0;
     uint32_t n_pool_cta = 0;            // hybrid runs (em_dense.cuh): CTAs that run the pool loop, launched after the n_cta component CTAs
     uint32_t n_dirty = 0;               // pool transcripts
-    DevBuf<uint32_t> dlist;             // their ids
+    DevBuf<uint32_t> dlist;             // the pool as its own problem: class CSR over pool-local ids, its transpose, local id -> transcript
+    DevBuf<double> pool_f64;            // r of the pool classes, beta of the pool transcripts
+    uint64_t pool_nz = 0;               // label entries of the pool classes
     uint64_t max_cta_bytes = 0, max_cta_bytes_vb = 0, smem_limit = 0;
     int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
@@ -103,7 +105,7 @@ struct DevPartition {
     uint32_t dense_ns = 0;
     DevBuf<uint32_t> dns;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); pool_f64.release(); }
 };
 struct DevClasses {
     DevPartition part;

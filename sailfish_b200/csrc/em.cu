@@ -685,11 +685,6 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl, bool 
 // hybrid runs (em_dense.cuh): small components on the component CTAs, everything else in the pool loop; SFB200_EM_HYBRID=0 switches it off
 bool hybrid_enabled() { const char* e = getenv("SFB200_EM_HYBRID"); return e ? atoi(e) != 0 : true; }
 
-__global__ void k_dirty_list(const uint8_t* __restrict__ dirty, uint32_t T, uint32_t* __restrict__ list, unsigned int* __restrict__ n) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < T && dirty[t]) list[atomicAdd(n, 1u)] = t;
-}
-
 // the partition for n_cta ranges; *marked_again is set when the dense builder sent large components to the pool and wants another pass
 int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
     DevClasses& k = c->cls;
@@ -785,17 +780,42 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         hm.mark("part: dense layout");
         if (!marked) break;
     }
-    // the pool's transcripts as a list (hybrid runs walk it instead of all T)
+    // the pool as its own small problem (hybrid runs, em_dense.cuh): pool-local transcript ids, the classes as CSR over them and the
+    // transpose.  The pool classes are the last group of the partition order, their label entries the tail of P.lab.
     P.n_dirty = 0;
-    if (P.n_pool) {
-        SFB_CUDA(c, P.dlist.reserve(T));
-        SFB_CUDA(c, cudaMemsetAsync(d_changed, 0, 4, s));
-        k_dirty_list<<<grid_for(T, 256), 256, 0, s>>>(P.dirty.p, T, P.dlist.p, d_changed);
-        c->launches++;
-        unsigned int nd = 0;
-        SFB_CUDA(c, cudaMemcpyAsync(&nd, d_changed, 4, cudaMemcpyDeviceToHost, s));
+    if (P.n_pool && P.dense_ok) {
+        const uint64_t c0 = P.pool_cls[0], n_pc = P.n_pool, e1 = nnzm;
+        std::vector<uint32_t> h_start(n_pc), h_lab;
+        SFB_CUDA(c, cudaMemcpyAsync(h_start.data(), P.start.p + c0, n_pc * 4, cudaMemcpyDeviceToHost, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
-        P.n_dirty = nd;
+        const uint64_t e0 = h_start[0], nz = e1 - e0;
+        h_lab.resize(nz);
+        SFB_CUDA(c, cudaMemcpyAsync(h_lab.data(), P.lab.p + e0, nz * 4, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        std::vector<uint32_t> ids(h_lab);
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        const uint32_t nd = (uint32_t)ids.size();
+        // one upload: pc_start[n_pc + 1] | pc_lid[nz] | pt_start[nd + 1] | pt_cls[nz] | dlist[nd]
+        std::vector<uint32_t> buf((size_t)n_pc + 1 + nz + nd + 1 + nz + nd);
+        uint32_t* pc_start = buf.data(); uint32_t* pc_lid = pc_start + n_pc + 1; uint32_t* pt_start = pc_lid + nz; uint32_t* pt_cls = pt_start + nd + 1;
+        uint32_t* dl = pt_cls + nz;
+        for (uint64_t q = 0; q < n_pc; ++q) pc_start[q] = (uint32_t)(h_start[q] - e0);
+        pc_start[n_pc] = (uint32_t)nz;
+        std::fill(pt_start, pt_start + nd + 1, 0u);
+        for (uint64_t j = 0; j < nz; ++j) {
+            const uint32_t i = (uint32_t)(std::lower_bound(ids.begin(), ids.end(), h_lab[j]) - ids.begin());
+            pc_lid[j] = i; pt_start[i + 1]++;
+        }
+        for (uint32_t i = 0; i < nd; ++i) pt_start[i + 1] += pt_start[i];
+        { std::vector<uint32_t> cur(pt_start, pt_start + nd);
+          for (uint64_t q = 0; q < n_pc; ++q) for (uint32_t j = pc_start[q]; j < pc_start[q + 1]; ++j) pt_cls[cur[pc_lid[j]]++] = (uint32_t)q; }
+        std::copy(ids.begin(), ids.end(), dl);
+        SFB_CUDA(c, P.dlist.reserve(buf.size()));
+        SFB_CUDA(c, cudaMemcpyAsync(P.dlist.p, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, P.pool_f64.reserve(n_pc + nd));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        P.n_dirty = nd; P.pool_nz = nz;
     }
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool, %u pool transcripts), largest CTA slice %llu bytes (limit %d) -> %s\n",
@@ -957,8 +977,14 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         const DevPartition& P = c->cls.part;
         DenseParams q;
         q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
-        q.n_dense = P.n_cta; q.dlist = P.dlist.p; q.n_dirty = P.n_dirty;
-        const size_t smem = (size_t)P.dense_smem;
+        q.n_dense = P.n_cta; q.n_dirty = P.n_dirty; q.n_pc = (uint32_t)P.n_pool; q.pool_c0 = (uint32_t)P.pool_cls[0];
+        q.pc_start = P.dlist.p; q.pc_lid = q.pc_start + P.n_pool + 1; q.pt_start = q.pc_lid + P.pool_nz; q.pt_cls = q.pt_start + P.n_dirty + 1;
+        q.dlist = q.pt_cls + P.pool_nz; q.pool_r = P.pool_f64.p; q.pool_beta = P.pool_f64.p + P.n_pool;
+        // the pool CTAs keep the pool's beta vector in shared memory when that does not cost the component CTAs their second CTA per SM
+        const size_t pool_smem = P.n_pool_cta ? (size_t)P.n_dirty * 8 + 256 : 0;
+        const size_t smem_2 = (size_t)(P.smem_limit + 1024) / 2 - 2048;
+        q.beta_in_smem = (P.n_pool_cta && pool_smem <= std::max<size_t>(smem_2, (size_t)P.dense_smem)) ? 1u : 0u;
+        const size_t smem = q.beta_in_smem ? std::max<size_t>((size_t)P.dense_smem, pool_smem) : (size_t)P.dense_smem;
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))
@@ -1152,8 +1178,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const uint32_t* a_len = use_part ? P.len.p : k.len.p;
     const uint32_t* a_lab = use_part ? P.lab.p : k.lab.p;
     double* a_w = use_part ? P.w.p : k.w.p;
-    const bool hybrid_pool = use_dense && P.n_pool > 0;                 // the pool loop of a hybrid run sweeps in the weighted scatter form
-    if (k.Em && (!use_gather || hybrid_pool)) {
+    if (k.Em && !use_gather) {
         // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
         k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
         c->launches++;
@@ -1232,7 +1257,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
             if (rc) return rc;
             h_eff.swap(h_next);
             SFB_CUDA(c, cudaMemcpyAsync(c->eff.p, h_eff.data(), T * 8ull, cudaMemcpyHostToDevice, s));
-            if (k.Em && (!use_gather || hybrid_pool)) {
+            if (k.Em && !use_gather) {
                 k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
                 c->launches++;
             }

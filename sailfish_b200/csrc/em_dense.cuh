@@ -47,8 +47,15 @@ struct DenseParams {
     // hybrid runs: CTAs [0, n_dense) own the small components, CTAs [n_dense, gridDim.x) run the pool loop over the classes of
     // everything else (components too large for a thread, classes that cross CTA ranges) -- an independent sub-problem
     uint32_t n_dense;
-    const uint32_t* dlist;    // transcripts of the pool ("dirty"), n_dirty of them
-    uint32_t n_dirty;
+    uint32_t n_dirty;         // pool transcripts
+    uint32_t n_pc;            // pool classes
+    uint32_t pool_c0;         // position of the first pool class in the partition-ordered arrays (p.cnt)
+    uint32_t beta_in_smem;    // the pool's beta vector fits in the CTA's shared memory
+    const uint32_t* pc_start; const uint32_t* pc_lid;     // pool classes x pool-local transcript ids (CSR)
+    const uint32_t* pt_start; const uint32_t* pt_cls;     // the transpose: pool transcripts x pool-local class ids
+    const uint32_t* dlist;    // pool-local id -> transcript
+    double* pool_r;           // n_pc: count / S of the current iteration
+    double* pool_beta;        // n_dirty: beta of the current iteration
 };
 
 // barrier among the pool CTAs only (same protocol as grid_barrier, its own counter words)
@@ -65,65 +72,90 @@ __device__ __forceinline__ void pool_barrier(unsigned long long* ctl, unsigned i
     __syncthreads();
 }
 
-// The pool loop of a hybrid run: EMUpdate_ / VBEMUpdate_ over the pool classes in the scatter form of k_em_persistent (binned layout,
-// gathers and red.add through L2 -- the pool's alpha vector is a few hundred KB), restricted to the pool's transcripts, on the pool
-// CTAs only.  The pool shares no transcript with the components the other CTAs own, so the two groups meet only where the reference
-// needs a global quantity: the stopping rule and VBEM's digamma(sum alpha) -- at the same iterations, through the same grid barrier,
-// as k_em_dense's own loop below (the break logic is a copy of it).  An EM iteration costs the pool ONE barrier among its own CTAs.
+// first row whose first entry is at or beyond `target` (rows cut by entries, so that long rows do not pile up on one CTA)
+__device__ __forceinline__ uint32_t pool_row_at(const uint32_t* __restrict__ start, uint32_t n_rows, uint64_t target) {
+    uint32_t lo = 0, hi = n_rows;
+    while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(start + mid) < target) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// The pool loop of a hybrid run: EMUpdate_ / VBEMUpdate_ over the pool classes in the GATHER form of k_em_gather (em_gather.cuh:
+// beta_i = theta_i / effLen_i, S_c = sum of beta over the class, r_c = count_c / S_c, alpha'_i = base_i + beta_i * sum of r over the
+// classes of i -- no atomics: a repeat family's transcripts sit in thousands of classes, and scattered adds to one address serialise),
+// one WARP per row in both steps (rows are as long as 200 entries for classes, thousands for transcripts), on the pool CTAs only.
+// Every pool CTA keeps the whole beta vector of the pool in shared memory when it fits.  The pool shares no transcript with the
+// components the other CTAs own, so the two groups meet only where the reference needs a global quantity: the stopping rule and VBEM's
+// digamma(sum alpha) -- at the same iterations, through the same grid barrier, as k_em_dense's own loop below (the break logic is a
+// copy of it).  An EM iteration costs the pool two barriers among its own CTAs (r complete, beta complete).
 template <bool VB>
-__device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParams& q) {
+__device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParams& q, double* s_beta) {
     __shared__ unsigned long long pl_u[32];
     __shared__ double pl_d[32];
     const unsigned nblocks = gridDim.x, NP = nblocks - q.n_dense, pi = blockIdx.x - q.n_dense;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     unsigned long long gen = 0, gen_p = 0;
-    Slice sl; sl.start = p.start; sl.len = p.len; sl.cnt = p.cnt; sl.lab = p.lab; sl.w = p.w; sl.c0 = 0; sl.e0 = 0;
-    const Bins pb = em_bins(p);
-    const uint64_t pool_tiles = p.tile_start[SFB_NBINS];
-    const uint64_t tile_lo = pool_tiles * pi / NP, tile_hi = pool_tiles * (pi + 1ULL) / NP;
-    const uint32_t d_lo = (uint32_t)((uint64_t)q.n_dirty * pi / NP), d_hi = (uint32_t)((uint64_t)q.n_dirty * (pi + 1ULL) / NP);
+    const uint32_t nd = q.n_dirty, npc = q.n_pc;
+    const uint64_t nnz = __ldg(q.pc_start + npc);
+    const uint32_t c_lo = pool_row_at(q.pc_start, npc, nnz * pi / NP), c_hi = pi + 1 == NP ? npc : pool_row_at(q.pc_start, npc, nnz * (pi + 1ULL) / NP);
+    const uint32_t t_lo = pool_row_at(q.pt_start, nd, nnz * pi / NP), t_hi = pi + 1 == NP ? nd : pool_row_at(q.pt_start, nd, nnz * (pi + 1ULL) / NP);
     const bool fixed = p.fixed_iters > 0;
-    unsigned bi = 0, bo = 1, bs = 2;
-    uint32_t n = 0;
-    if (VB) {
-        const double logNorm = sfb_digamma(p.sum0);
-        for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
-            const uint32_t t = q.dlist[i];
+    const double* cnt = p.cnt + q.pool_c0;
+    const bool in_smem = q.beta_in_smem != 0;
+    // beta_0 of the whole pool, computed by every CTA for itself
+    {
+        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
+        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
+            const uint32_t t = __ldg(q.dlist + i);
             const double a = p.X[t];
-            p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+            const double th = VB ? ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) : a;
+            const double b = th / __ldg(q.eff + t);
+            if (in_smem) s_beta[i] = b;
+            else if (i >= t_lo && i < t_hi) q.pool_beta[i] = b;        // the global copy: every CTA writes its own rows
         }
-        pool_barrier(p.ctl, NP, gen_p);
+        if (!in_smem) pool_barrier(p.ctl, NP, gen_p); else __syncthreads();
     }
+    uint32_t n = 0;
     for (;;) {
         if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
         const uint32_t m = n + 1;
         const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
-        const double* in = p.X + (size_t)bi * p.T;
-        double* out = p.X + (size_t)bo * p.T;
-        double* spare = p.X + (size_t)bs * p.T;
-        // the spare buffer (the input of the previous iteration) becomes an output buffer again: back to its initial value, for this
-        // CTA's share of the pool transcripts (every CTA keeps the same share, and nobody gathers from that buffer any more)
-        if (n > 0) for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; spare[t] = __ldg(p.base + t); }
-        sweep_block<VB, false>(pb, sl, tile_lo, tile_hi, VB ? p.theta : in, out, 0u);
+        // ---- E-step: r_c of this CTA's classes
+        for (uint32_t c = c_lo + warp; c < c_hi; c += W) {
+            const uint32_t b = __ldg(q.pc_start + c), e = __ldg(q.pc_start + c + 1);
+            double S = 0.0;
+            for (uint32_t j = b + lane; j < e; j += 32) {
+                const uint32_t i = __ldg(q.pc_lid + j);
+                S += in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
+            }
+            S = warp_sum(S);
+            if (lane == 0) q.pool_r[c] = em_ratio(cnt[c], S);
+        }
         pool_barrier(p.ctl, NP, gen_p);
+        // ---- M-step of this CTA's transcripts + the convergence test
         unsigned long long best = 0ULL;
         double asum = 0.0;
-        if (VB || do_cmp) {
-            for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
-                const uint32_t t = q.dlist[i];
-                const double a_new = ld_cg_f64(out + t);
+        for (uint32_t i = t_lo + warp; i < t_hi; i += W) {
+            const uint32_t b = __ldg(q.pt_start + i), e = __ldg(q.pt_start + i + 1);
+            double acc = 0.0;
+            for (uint32_t j = b + lane; j < e; j += 32) acc += ld_cg_f64(q.pool_r + __ldg(q.pt_cls + j));
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const uint32_t t = __ldg(q.dlist + i);
+                const double beta = in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
+                const double a_old = p.X[t];
+                const double a_new = beta * acc + __ldg(p.base + t);
                 if (do_cmp) {
-                    const double a_old = ld_cg_f64(in + t);
                     const double gate = p.gate_old ? a_old : a_new;
                     if (gate > p.cutoff) {
                         const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
                         best = bits > best ? bits : best;
                     }
                 }
-                asum += a_new;
+                p.X[t] = a_new;
+                if (VB) asum += a_new; else q.pool_beta[i] = a_new / __ldg(q.eff + t);
             }
         }
         n = m;
-        { const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp; }       // bi now names the newest alphas
         if (VB || do_cmp) {
             unsigned long long* slot = p.ctl + CTL_MAXREL + (m & 3u);
             double* csum = reinterpret_cast<double*>(p.ctl + CTL_CSUM + (m & 3u));
@@ -137,20 +169,18 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
             }
             if (VB) {
                 const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
-                const double* cur = p.X + (size_t)bi * p.T;
-                for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
-                    const uint32_t t = q.dlist[i];
-                    const double a = ld_cg_f64(cur + t);
-                    p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+                for (uint32_t i = t_lo + threadIdx.x; i < t_hi; i += blockDim.x) {
+                    const uint32_t t = __ldg(q.dlist + i);
+                    const double a = p.X[t];                            // written by this CTA above
+                    q.pool_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) / __ldg(q.eff + t);
                 }
-                pool_barrier(p.ctl, NP, gen_p);
             }
         }
-    }
-    // the component CTAs leave their result in the first third of X: so does the pool
-    if (bi != 0) {
-        const double* cur = p.X + (size_t)bi * p.T;
-        for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; p.X[t] = ld_cg_f64(cur + t); }
+        pool_barrier(p.ctl, NP, gen_p);                                // beta of every pool transcript is in place
+        if (in_smem) {
+            for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) s_beta[i] = ld_cg_f64(q.pool_beta + i);
+            __syncthreads();
+        }
     }
 }
 
@@ -180,7 +210,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     __shared__ uint64_t tma_bar;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     const unsigned nblocks = gridDim.x;
-    if (blockIdx.x >= q.n_dense) { dense_pool_loop<VB>(p, q); return; }
+    if (blockIdx.x >= q.n_dense) { dense_pool_loop<VB>(p, q, reinterpret_cast<double*>(dyn_smem)); return; }
     unsigned long long gen = 0;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
 

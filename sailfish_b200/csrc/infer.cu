@@ -39,81 +39,9 @@ __host__ __device__ inline double u01_from(uint32_t hi, uint32_t lo) {       // 
     return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// MultinomialSampler::operator() for k > 100 (:48-63): lower_bound over z[0..k), step back if z[it] > u.
-// z has k+1 entries, z[0] = 0, z[i] = p_0 + ... + p_{i-1} accumulated left to right as the reference's table is.
-__device__ __forceinline__ uint32_t pick_class(const double* __restrict__ z, uint32_t k, double u) {
-    uint32_t lo = 0, hi = k;                           // search [0, k): first i with z[i] >= u, k if none
-    while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(z + mid) < u) lo = mid + 1; else hi = mid; }
-    uint32_t off = lo;
-    if (__ldg(z + off) > u && off > 0) off -= 1;
-    return off < k ? off : k - 1;
-}
-
-// one draw per thread (two per Philox call); N = total fragments, k = number of classes
-__global__ void k_multinomial_draws(const double* __restrict__ z, uint32_t k, uint64_t n_draws, uint64_t seed,
-                                    unsigned long long* __restrict__ samp) {
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint64_t d0 = 2 * i;
-    if (d0 >= n_draws) return;
-    uint32_t r[4];
-    Philox ph(seed);
-    ph(i, 0x6d756c74ULL /* "mult" */, r);
-    atomicAdd(samp + pick_class(z, k, u01_from(r[0], r[1])), 1ULL);
-    if (d0 + 1 < n_draws) atomicAdd(samp + pick_class(z, k, u01_from(r[2], r[3])), 1ULL);
-}
-
 inline unsigned gridn(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
-
-extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, const sfb200_em_opts* opts,
-                                    uint32_t n_boot, uint64_t seed, sfb200_f64_row_cb cb, void* user) {
-    if (!c || !eff_lens || !opts) return SFB200_EINVAL;
-    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "bootstrap_run: no classes");
-    if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "bootstrap_run: n_txp differs from the class table's");
-    cudaSetDevice(c->device);
-    const DevClasses& k = c->cls;
-    const uint64_t E = k.E;
-    if (E == 0 || k.n_active == 0) SFB_FAIL(c, SFB200_ENOACTIVE, "The optimizer has no active transcripts: no transcripts are expressed");
-    if (E >= 0xFFFFFFFFull) SFB_FAIL(c, SFB200_EINVAL, "too many classes");
-    // markDegenerateClasses (:372-433) never drops a class here: with uniform positive alphas over the active set every
-    // denominator is positive (see oracle note); all classes are valid.
-    const uint64_t totalCount = k.total_count;                                     // :662-674
-    const double floatCount = static_cast<double>(totalCount);
-    // class counts in the order the per-sample count vectors are indexed by (canonical order)
-    std::vector<uint64_t> canon_counts(E);
-    if (k.from_device) {
-        SFB_CUDA(c, cudaMemcpy(canon_counts.data(), k.cnt_all.p, E * 8, cudaMemcpyDeviceToHost));
-    } else {
-        canon_counts = k.h_counts;
-    }
-    std::vector<double> z(E + 1);
-    double sum = 0.0;
-    z[0] = 0.0;
-    for (uint64_t e = 0; e < E; ++e) { sum += static_cast<double>(canon_counts[e]) / floatCount; z[e + 1] = sum; }   // :676-680, MultinomialSampler.hpp:30-34
-    cudaStream_t s = c->stream;
-    DevBuf<double> d_z; DevBuf<unsigned long long> d_samp;
-    SFB_CUDA(c, d_z.reserve(E + 1)); SFB_CUDA(c, d_samp.reserve(E));
-    SFB_CUDA(c, cudaMemcpyAsync(d_z.p, z.data(), (E + 1) * 8, cudaMemcpyHostToDevice, s));
-    std::vector<double> alphas(n_txp);
-    // MultinomialSampler takes n as uint32_t (:15): the reference wraps above 2^32 fragments; we keep 64 bits
-    int rc = SFB200_OK;
-    double loop_ms = 0.0;
-    for (uint32_t b = 0; b < n_boot && rc == SFB200_OK; ++b) {
-        cudaMemsetAsync(d_samp.p, 0, E * 8, s);
-        if (totalCount) {
-            k_multinomial_draws<<<gridn((totalCount + 1) / 2, 256), 256, 0, s>>>(d_z.p, (uint32_t)E, totalCount, seed + 0x9E3779B97F4A7C15ULL * (b + 1), d_samp.p);
-            c->launches++;
-        }
-        uint32_t iters = 0;
-        rc = sfb_bootstrap_em_device(c, eff_lens, n_txp, d_samp.p, totalCount, opts, alphas.data(), &iters);
-        loop_ms += c->last_em_ms;
-        if (rc == SFB200_OK && cb && cb(user, alphas.data(), n_txp) != 0) { c->err = "bootstrap row callback failed"; rc = SFB200_ECALLBACK; }
-    }
-    c->last_em_ms = loop_ms;
-    d_z.release(); d_samp.release();
-    return rc;
-}
 
 // ======================================================================================================================
 // Collapsed Gibbs sampler (reference src/CollapsedGibbsSampler.cpp)
@@ -369,3 +297,112 @@ extern "C" int sfb200_gibbs_run(sfb200_ctx* c, const double* eff_lens, const dou
     cleanup();
     return rc;
 }
+
+// ---- bootstrap resampling -----------------------------------------------------------------------------------------------------
+// gatherBootstraps draws, per replicate, numMappedFragments class indices from the multinomial over the class counts
+// (MultinomialSampler.hpp:13-64: one uniform and one binary search over the cumulative table per fragment).  The count vector it
+// ends up with is Multinomial(N; counts / N), and that is drawn here directly, by conditional binomials down a tree of fan-out
+// SPLIT_FAN over the classes: a node's share is split over its children by one thread, all nodes of a level in parallel.  E binomial
+// draws instead of N uniform draws with N binary searches and N atomics (E = 4e5, N = 1e7 at cfg2) -- the same distribution, a
+// different stream of random numbers (the reference's own is seeded from std::random_device: parity is distributional either way).
+namespace {
+constexpr uint32_t SPLIT_FAN = 48;
+
+template <typename W>
+__global__ void k_level_sums(const W* __restrict__ lower, uint64_t n_lower, uint64_t n_upper, double* __restrict__ upper) {
+    const uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (q >= n_upper) return;
+    const uint64_t b = q * SPLIT_FAN, e = b + SPLIT_FAN < n_lower ? b + SPLIT_FAN : n_lower;
+    double s = 0.0;
+    for (uint64_t i = b; i < e; ++i) s += (double)lower[i];             // exact: integers below 2^53
+    upper[q] = s;
+}
+// one thread per node of the upper level: its share over its children, weights = the children's totals
+template <typename W>
+__global__ void k_level_split(const W* __restrict__ lower_w, uint64_t n_lower, const unsigned long long* __restrict__ upper_share,
+                              uint64_t n_upper, uint64_t seed, uint32_t level, unsigned long long* __restrict__ lower_share) {
+    const uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (q >= n_upper) return;
+    const uint64_t b = q * SPLIT_FAN, e = b + SPLIT_FAN < n_lower ? b + SPLIT_FAN : n_lower;
+    Rng g(seed, level, 7, q);
+    double rem_p = 0.0;
+    for (uint64_t i = b; i < e; ++i) rem_p += (double)lower_w[i];
+    unsigned long long rem = upper_share[q];
+    for (uint64_t i = b; i < e; ++i) {
+        const double pi = (double)lower_w[i];
+        unsigned long long x = 0;
+        if (rem > 0) {
+            if (i + 1 == e || !(rem_p > pi)) x = rem;
+            else x = binomial_draw(g, rem, fmin(1.0, fmax(0.0, pi / rem_p)));
+        }
+        lower_share[i] = x;
+        rem -= x; rem_p -= pi;
+    }
+}
+
+struct SplitTree {
+    std::vector<uint64_t> n;                       // nodes per level, n[0] = classes, n.back() = 1
+    std::vector<double*> sums;                     // level >= 1
+    std::vector<unsigned long long*> share;        // level >= 1 (level 0 is the caller's sample vector)
+    DevBuf<double> d_sums; DevBuf<unsigned long long> d_share;
+    void release() { d_sums.release(); d_share.release(); }
+};
+}  // namespace
+
+extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, const sfb200_em_opts* opts,
+                                    uint32_t n_boot, uint64_t seed, sfb200_f64_row_cb cb, void* user) {
+    if (!c || !eff_lens || !opts) return SFB200_EINVAL;
+    if (!c->cls.ready) SFB_FAIL(c, SFB200_EINVAL, "bootstrap_run: no classes");
+    if (n_txp != c->cls.n_txp) SFB_FAIL(c, SFB200_EINVAL, "bootstrap_run: n_txp differs from the class table's");
+    cudaSetDevice(c->device);
+    const DevClasses& k = c->cls;
+    const uint64_t E = k.E;
+    if (E == 0 || k.n_active == 0) SFB_FAIL(c, SFB200_ENOACTIVE, "The optimizer has no active transcripts: no transcripts are expressed");
+    if (E >= 0xFFFFFFFFull) SFB_FAIL(c, SFB200_EINVAL, "too many classes");
+    // markDegenerateClasses (:372-433) never drops a class here: with uniform positive alphas over the active set every
+    // denominator is positive (see oracle note); all classes are valid.
+    const uint64_t totalCount = k.total_count;                                     // :662-674
+    // class counts in the order the per-sample count vectors are indexed by (canonical order)
+    std::vector<uint64_t> canon_counts(E);
+    if (k.from_device) {
+        SFB_CUDA(c, cudaMemcpy(canon_counts.data(), k.cnt_all.p, E * 8, cudaMemcpyDeviceToHost));
+    } else {
+        canon_counts = k.h_counts;
+    }
+    cudaStream_t s = c->stream;
+    DevBuf<unsigned long long> d_samp, d_cnt;
+    SplitTree tr;
+    tr.n.push_back(E);
+    while (tr.n.back() > 1) tr.n.push_back((tr.n.back() + SPLIT_FAN - 1) / SPLIT_FAN);
+    if (tr.n.size() == 1) tr.n.push_back(1);                                          // a single class still has a root above it
+    uint64_t upper_total = 0;
+    for (size_t l = 1; l < tr.n.size(); ++l) upper_total += tr.n[l];
+    SFB_CUDA(c, d_samp.reserve(E)); SFB_CUDA(c, d_cnt.reserve(E)); SFB_CUDA(c, tr.d_sums.reserve(upper_total)); SFB_CUDA(c, tr.d_share.reserve(upper_total));
+    tr.sums.assign(tr.n.size(), nullptr); tr.share.assign(tr.n.size(), nullptr);
+    { uint64_t at = 0; for (size_t l = 1; l < tr.n.size(); ++l) { tr.sums[l] = tr.d_sums.p + at; tr.share[l] = tr.d_share.p + at; at += tr.n[l]; } }
+    SFB_CUDA(c, cudaMemcpyAsync(d_cnt.p, canon_counts.data(), E * 8, cudaMemcpyHostToDevice, s));
+    k_level_sums<unsigned long long><<<gridn(tr.n[1], 128), 128, 0, s>>>(d_cnt.p, E, tr.n[1], tr.sums[1]);
+    for (size_t l = 2; l < tr.n.size(); ++l) k_level_sums<double><<<gridn(tr.n[l], 128), 128, 0, s>>>(tr.sums[l - 1], tr.n[l - 1], tr.n[l], tr.sums[l]);
+    c->launches += tr.n.size() - 1;
+    const unsigned long long h_total = totalCount;
+    SFB_CUDA(c, cudaMemcpyAsync(tr.share.back(), &h_total, 8, cudaMemcpyHostToDevice, s));    // the root's share is N, for every replicate
+    std::vector<double> alphas(n_txp);
+    // MultinomialSampler takes n as uint32_t (:15): the reference wraps above 2^32 fragments; we keep 64 bits
+    int rc = SFB200_OK;
+    double loop_ms = 0.0;
+    for (uint32_t b = 0; b < n_boot && rc == SFB200_OK; ++b) {
+        const uint64_t sd = seed + 0x9E3779B97F4A7C15ULL * (b + 1);
+        for (size_t l = tr.n.size() - 1; l >= 2; --l)
+            k_level_split<double><<<gridn(tr.n[l], 64), 64, 0, s>>>(tr.sums[l - 1], tr.n[l - 1], tr.share[l], tr.n[l], sd, (uint32_t)l, tr.share[l - 1]);
+        k_level_split<unsigned long long><<<gridn(tr.n[1], 64), 64, 0, s>>>(d_cnt.p, E, tr.share[1], tr.n[1], sd, 1u, d_samp.p);
+        c->launches += tr.n.size() - 1;
+        uint32_t iters = 0;
+        rc = sfb_bootstrap_em_device(c, eff_lens, n_txp, d_samp.p, totalCount, opts, alphas.data(), &iters);
+        loop_ms += c->last_em_ms;
+        if (rc == SFB200_OK && cb && cb(user, alphas.data(), n_txp) != 0) { c->err = "bootstrap row callback failed"; rc = SFB200_ECALLBACK; }
+    }
+    c->last_em_ms = loop_ms;
+    tr.release(); d_samp.release(); d_cnt.release();
+    return rc;
+}
+

@@ -246,17 +246,19 @@ __global__ void k_pack_reads(const char* __restrict__ bases1, const uint64_t* __
 }
 
 __global__ void k_max_read_len(const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2, uint64_t n_frags,
-                               unsigned int* __restrict__ out) {
-    unsigned int mx = 0;
+                               unsigned int* __restrict__ out, unsigned long long* __restrict__ clipped) {
+    unsigned int mx = 0, nclip = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_frags; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t l = off1[i + 1] - off1[i];
-        if (off2) { const uint64_t l2 = off2[i + 1] - off2[i]; l = l2 > l ? l2 : l; }
+        nclip += l > MAX_READ_LEN;
+        if (off2) { const uint64_t l2 = off2[i + 1] - off2[i]; nclip += l2 > MAX_READ_LEN; l = l2 > l ? l2 : l; }
         if (l > MAX_READ_LEN) l = MAX_READ_LEN;
         mx = (unsigned int)l > mx ? (unsigned int)l : mx;
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) { const unsigned int o = __shfl_xor_sync(0xffffffffu, mx, m); mx = o > mx ? o : mx; }
     if ((threadIdx.x & 31u) == 0 && mx) atomicMax(out, mx);
+    if (nclip) atomicAdd(clipped, (unsigned long long)nclip);          // rare: no reduction
 }
 
 // packed read -> this lane's shared-memory column (both orientations) + the invalid-base masks when there are any
@@ -932,6 +934,7 @@ struct MapState {
     DevBuf<uint8_t> niv;
     DevBuf<uint32_t> ivmask;
     DevBuf<unsigned int> maxlen;
+    DevBuf<unsigned long long> clipped;   // mates cut to MAX_READ_LEN since map_begin
     int grid_scan = 0;
     // multi-rank class merge / FLD gather buffers (grow-only: cudaMalloc / cudaFree per step cost more than the exchange)
     DevBuf<unsigned long long> mg_sizes, mg_cnt, mg_cnt_g;
@@ -965,7 +968,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
     m->mg_sizes.release(); m->mg_cnt.release(); m->mg_cnt_g.release(); m->mg_start.release(); m->mg_len.release(); m->mg_lab.release();
     m->mg_start_g.release(); m->mg_len_g.release(); m->mg_lab_g.release(); m->fld_send.release(); m->fld_recv.release();
-    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release();
+    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release(); m->clipped.release();
     m->bias_val.release(); m->bias_hist.release(); m->bias_remaining.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
@@ -996,13 +999,14 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->n_buckets = 1ull << lb; m->n_overflow = std::max<uint64_t>(1024, m->n_buckets / 4); m->arena_words = 1ull << la;
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
     SFB_CUDA(c, m->slot.reserve(n_slots)); SFB_CUDA(c, m->count.reserve(n_slots)); SFB_CUDA(c, m->arena.reserve(m->arena_words));
-    SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(2)); SFB_CUDA(c, m->maxlen.reserve(1));
+    SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(2)); SFB_CUDA(c, m->maxlen.reserve(1)); SFB_CUDA(c, m->clipped.reserve(1));
     SFB_CUDA(c, m->fld_hist.reserve(o->max_frag_len)); SFB_CUDA(c, m->remaining.reserve(1));
     SFB_CUDA(c, m->fld_samples.reserve((size_t)std::max(1, o->num_frag_samples)));
     SFB_CUDA(c, cudaMemsetAsync(m->slot.p, 0, n_slots * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->count.p, 0, n_slots * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->cursor.p, 0, 4 * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->counters.p, 0, 6 * 8, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->clipped.p, 0, 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->fld_hist.p, 0, o->max_frag_len * 4ull, s));
     const int rem = o->num_frag_samples;
     SFB_CUDA(c, cudaMemcpyAsync(m->remaining.p, &rem, 4, cudaMemcpyHostToDevice, s));
@@ -1147,7 +1151,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used], s));
     // 1. longest read of the batch -> words per packed read
     SFB_CUDA(c, cudaMemsetAsync(m->maxlen.p, 0, 4, s));
-    k_max_read_len<<<(unsigned)std::min<uint64_t>((n_reads + 255) / 256, 1024), 256, 0, s>>>(d_off1, d_off2, n_reads, m->maxlen.p);
+    k_max_read_len<<<(unsigned)std::min<uint64_t>((n_reads + 255) / 256, 1024), 256, 0, s>>>(d_off1, d_off2, n_reads, m->maxlen.p, m->clipped.p);
     c->launches++;
     unsigned int maxlen = 0;
     SFB_CUDA(c, cudaMemcpyAsync(&maxlen, m->maxlen.p, 4, cudaMemcpyDeviceToHost, s));
@@ -1256,6 +1260,15 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
 }
 
 extern "C" double sfb200_last_map_kernel_ms(const sfb200_ctx* c) { return (c && c->map) ? c->map->kernel_ms : 0.0; }
+
+extern "C" uint64_t sfb200_map_clipped(sfb200_ctx* c) {
+    if (!c || !c->map || !c->map->clipped.p) return 0;
+    cudaSetDevice(c->device);
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, c->map->clipped.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return 0;
+    cudaStreamSynchronize(c->stream);
+    return v;
+}
 
 // eqBuilder.finish() (EquivalenceClassBuilder.hpp:64-80): flatten the table -- on the device, straight into the binned
 // layout the inference kernels read; nothing but a few counters crosses PCIe.

@@ -884,6 +884,9 @@ int main(int argc, char** argv) {
                 (unsigned long long)eqBuilder.numObservedFragments(), (unsigned long long)ex.numMapped,
                 100.0 * ex.numMapped / std::max<uint64_t>(1, eqBuilder.numObservedFragments()), (unsigned long long)eqBuilder.numClasses(),
                 t_map - t_index);
+        if (const uint64_t nclip = sfb200_map_clipped(dev.get()))
+            fprintf(stderr, "[sfb200-quant] WARNING: %llu mates are longer than 256 bases and were mapped by their first 256 (the reference maps the whole read)\n",
+                    (unsigned long long)nclip);
 
         // ---- effective lengths, inference
         const std::vector<double> eff = effective_lengths(lens, eqBuilder.fragLengthCounts(), a.mopt.max_frag_len, a.mopt.num_frag_samples,

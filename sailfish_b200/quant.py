@@ -233,6 +233,10 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
         else:
             ctx.map_batch(b1, o1)
     g = ctx.map_finish()
+    n_clip = ctx.map_clipped()
+    if n_clip:
+        print("WARNING: %d mates are longer than 256 bases and were mapped by their first 256 (the reference maps the whole read)" % n_clip,
+              file=sys.stderr)
     counters = g["counters"]
     num_mapped = int(counters[1])
     eff = efflen.effective_lengths(lengths, g["fld"], max_frag_len=ctx.map_opts.max_frag_len,

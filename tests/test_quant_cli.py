@@ -102,6 +102,9 @@ class _StubContext:
         self._rec("map_fastq", n, t2 is not None)
         return n, consumed(t1, n), consumed(t2, n) if t2 is not None else 0
 
+    def map_clipped(self):
+        return 0
+
     def map_finish(self):
         fld = np.zeros(self.map_opts.max_frag_len, np.uint32); fld[180:220] = 300          # 12000 sampled fragment lengths
         return dict(counters=np.array([4, 3, 5, 4, 2, 1], np.uint64), fld=fld, n_classes=2, nnz=3)
