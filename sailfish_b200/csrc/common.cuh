@@ -87,6 +87,8 @@ struct DevPartition {
     DevBuf<uint32_t> dlist;             // the pool as its own problem: class CSR over pool-local ids, its transpose, local id -> transcript
     DevBuf<double> pool_f64;            // r of the pool classes, beta of the pool transcripts
     uint64_t pool_nz = 0;               // label entries of the pool classes
+    uint64_t pool_ch_off = 0; uint32_t n_ch = 0;   // chunks of the transpose: offset inside dlist, count
+    DevBuf<unsigned int> pool_done;
     uint64_t max_cta_bytes = 0, max_cta_bytes_vb = 0, smem_limit = 0;
     int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
@@ -105,7 +107,7 @@ struct DevPartition {
     uint32_t dense_ns = 0;
     DevBuf<uint32_t> dns;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); pool_f64.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); pool_f64.release(); pool_done.release(); }
 };
 struct DevClasses {
     DevPartition part;
@@ -166,6 +168,7 @@ struct sfb200_ctx {
     DevBuf<double> em_base;             // n_txp (initial value of every output buffer: single counts (+ prior))
     DevBuf<unsigned long long> em_ctl;  // control block of the persistent kernel
     DevBuf<double> eff;                 // n_txp clamped effective lengths
+    bool eff_resident = false;          // set by a bootstrap run after its first replicate: c->eff already holds this run's lengths
     void* fastq = nullptr;              // fastq.cu: staging buffers of the device-side FASTQ extraction
 };
 

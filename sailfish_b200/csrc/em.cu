@@ -796,7 +796,7 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         std::sort(ids.begin(), ids.end());
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
         const uint32_t nd = (uint32_t)ids.size();
-        // one upload: pc_start[n_pc + 1] | pc_lid[nz] | pt_start[nd + 1] | pt_cls[nz] | dlist[nd]
+        // one upload: pc_start[n_pc + 1] | pc_lid[nz] | pt_start[nd + 1] | pt_cls[nz] | dlist[nd] | chunks of the transpose (below)
         std::vector<uint32_t> buf((size_t)n_pc + 1 + nz + nd + 1 + nz + nd);
         uint32_t* pc_start = buf.data(); uint32_t* pc_lid = pc_start + n_pc + 1; uint32_t* pt_start = pc_lid + nz; uint32_t* pt_cls = pt_start + nd + 1;
         uint32_t* dl = pt_cls + nz;
@@ -811,9 +811,23 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         { std::vector<uint32_t> cur(pt_start, pt_start + nd);
           for (uint64_t q = 0; q < n_pc; ++q) for (uint32_t j = pc_start[q]; j < pc_start[q + 1]; ++j) pt_cls[cur[pc_lid[j]]++] = (uint32_t)q; }
         std::copy(ids.begin(), ids.end(), dl);
+        // the transpose in chunks of at most 256 entries (POOL_CHUNK, em_dense.cuh): ch_beg[n_ch + 1] | ch_row[n_ch] | ch_n[n_ch]
+        std::vector<uint32_t> ch_beg, ch_row, ch_n;
+        { const uint32_t* pts = buf.data() + n_pc + 1 + nz;
+          for (uint32_t i = 0; i < nd; ++i) {
+              const uint32_t b0 = pts[i], e0r = pts[i + 1], nchunks = std::max<uint32_t>(1, (e0r - b0 + 255) / 256);
+              for (uint32_t q = 0; q < nchunks; ++q) { ch_beg.push_back(b0 + q * 256); ch_row.push_back(i); ch_n.push_back(nchunks); }
+          } }
+        const uint32_t n_ch = (uint32_t)ch_row.size();
+        ch_beg.push_back((uint32_t)nz);
+        P.pool_ch_off = buf.size(); P.n_ch = n_ch;
+        buf.insert(buf.end(), ch_beg.begin(), ch_beg.end()); buf.insert(buf.end(), ch_row.begin(), ch_row.end()); buf.insert(buf.end(), ch_n.begin(), ch_n.end());
+        SFB_CUDA(c, P.pool_done.reserve(nd));
+        SFB_CUDA(c, cudaMemsetAsync(P.pool_done.p, 0, nd * 4ull, s));
         SFB_CUDA(c, P.dlist.reserve(buf.size()));
         SFB_CUDA(c, cudaMemcpyAsync(P.dlist.p, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, s));
-        SFB_CUDA(c, P.pool_f64.reserve(n_pc + nd));
+        SFB_CUDA(c, P.pool_f64.reserve(n_pc + 2ull * nd));
+        SFB_CUDA(c, cudaMemsetAsync(P.pool_f64.p + n_pc + nd, 0, nd * 8ull, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
         P.n_dirty = nd; P.pool_nz = nz;
     }
@@ -980,6 +994,8 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         q.n_dense = P.n_cta; q.n_dirty = P.n_dirty; q.n_pc = (uint32_t)P.n_pool; q.pool_c0 = (uint32_t)P.pool_cls[0];
         q.pc_start = P.dlist.p; q.pc_lid = q.pc_start + P.n_pool + 1; q.pt_start = q.pc_lid + P.pool_nz; q.pt_cls = q.pt_start + P.n_dirty + 1;
         q.dlist = q.pt_cls + P.pool_nz; q.pool_r = P.pool_f64.p; q.pool_beta = P.pool_f64.p + P.n_pool;
+        q.n_ch = P.n_ch; q.ch_beg = P.dlist.p + P.pool_ch_off; q.ch_row = q.ch_beg + P.n_ch + 1; q.ch_n = q.ch_row + P.n_ch;
+        q.pool_acc = P.pool_f64.p + P.n_pool + P.n_dirty; q.pool_done = P.pool_done.p;
         // the pool CTAs keep the pool's beta vector in shared memory when that does not cost the component CTAs their second CTA per SM
         const size_t pool_smem = P.n_pool_cta ? (size_t)P.n_dirty * 8 + 256 : 0;
         const size_t smem_2 = (size_t)(P.smem_limit + 1024) / 2 - 2048;
@@ -1154,9 +1170,11 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     SFB_CUDA(c, c->em_theta.reserve(T));
     SFB_CUDA(c, c->em_base.reserve(T));
     double* d_eff_in = c->eff.p + T;
-    SFB_CUDA(c, cudaMemcpyAsync(d_eff_in, eff_lens, T * 8ull, cudaMemcpyHostToDevice, s));
-    k_clamp_eff<<<grid_for(T, 256), 256, 0, s>>>(d_eff_in, T, c->eff.p);
-    c->launches++;
+    if (!c->eff_resident) {                                 // a bootstrap run uploads the lengths once, not once per replicate
+        SFB_CUDA(c, cudaMemcpyAsync(d_eff_in, eff_lens, T * 8ull, cudaMemcpyHostToDevice, s));
+        k_clamp_eff<<<grid_for(T, 256), 256, 0, s>>>(d_eff_in, T, c->eff.p);
+        c->launches++;
+    }
     // which layout runs: the CTA-partitioned one (em_part.cuh) when a single rank drives a cooperative launch and every
     // CTA's slice fits in shared memory; otherwise the binned layout
     const char* mode_env = getenv("SFB200_EM_MODE");
@@ -1226,11 +1244,14 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     if (vb) for (uint64_t i = 0; i < n_active; ++i) sum0 += alpha0;      // only VBEM's first logNorm reads it
     p.sum0 = sum0;
     double single_sum = 0.0;
-    if (vb) {
-        std::vector<double> hs(T);
-        SFB_CUDA(c, cudaMemcpyAsync(hs.data(), d_single, T * 8ull, cudaMemcpyDeviceToHost, s));
+    if (vb) {                                               // counts of the single-member classes: integers, any summation order is exact
+        SFB_CUDA(c, c->em_ctl.reserve(CTL_WORDS));
+        double* d_sum = reinterpret_cast<double*>(c->em_ctl.p + CTL_TSUM);
+        SFB_CUDA(c, cudaMemsetAsync(d_sum, 0, 8, s));
+        k_sum_f64<<<std::min(grid_for(T, 256), 1024u), 256, 0, s>>>(d_single, T, d_sum);
+        c->launches++;
+        SFB_CUDA(c, cudaMemcpyAsync(&single_sum, d_sum, 8, cudaMemcpyDeviceToHost, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
-        for (uint32_t i = 0; i < T; ++i) single_sum += hs[i];
     }
     p.base_sum = single_sum + static_cast<double>(T) * o->prior_alpha;
 

@@ -54,9 +54,16 @@ struct DenseParams {
     const uint32_t* pc_start; const uint32_t* pc_lid;     // pool classes x pool-local transcript ids (CSR)
     const uint32_t* pt_start; const uint32_t* pt_cls;     // the transpose: pool transcripts x pool-local class ids
     const uint32_t* dlist;    // pool-local id -> transcript
+    // the transpose cut into chunks of at most POOL_CHUNK entries (a transcript of a repeat family sits in thousands of classes: its
+    // row is summed by many warps): chunk k = entries [ch_beg[k], ch_beg[k+1]) of row ch_row[k], which has ch_n[k] chunks
+    uint32_t n_ch;
+    const uint32_t* ch_beg; const uint32_t* ch_row; const uint32_t* ch_n;
     double* pool_r;           // n_pc: count / S of the current iteration
     double* pool_beta;        // n_dirty: beta of the current iteration
+    double* pool_acc;         // n_dirty: partial row sums of multi-chunk rows (zero between iterations)
+    unsigned int* pool_done;  // n_dirty: chunks of the row summed so far (zero between iterations)
 };
+constexpr uint32_t POOL_CHUNK = 256;
 
 // barrier among the pool CTAs only (same protocol as grid_barrier, its own counter words)
 __device__ __forceinline__ void pool_barrier(unsigned long long* ctl, unsigned int n_cta, unsigned long long& gen) {
@@ -97,7 +104,9 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
     const uint32_t nd = q.n_dirty, npc = q.n_pc;
     const uint64_t nnz = __ldg(q.pc_start + npc);
     const uint32_t c_lo = pool_row_at(q.pc_start, npc, nnz * pi / NP), c_hi = pi + 1 == NP ? npc : pool_row_at(q.pc_start, npc, nnz * (pi + 1ULL) / NP);
-    const uint32_t t_lo = pool_row_at(q.pt_start, nd, nnz * pi / NP), t_hi = pi + 1 == NP ? nd : pool_row_at(q.pt_start, nd, nnz * (pi + 1ULL) / NP);
+    // rows by index for the per-transcript passes (initial beta, VBEM's expTheta), chunks by entries for the M-step
+    const uint32_t t_lo = (uint32_t)((uint64_t)nd * pi / NP), t_hi = (uint32_t)((uint64_t)nd * (pi + 1ULL) / NP);
+    const uint32_t k_lo = pool_row_at(q.ch_beg, q.n_ch, nnz * pi / NP), k_hi = pi + 1 == NP ? q.n_ch : pool_row_at(q.ch_beg, q.n_ch, nnz * (pi + 1ULL) / NP);
     const bool fixed = p.fixed_iters > 0;
     const double* cnt = p.cnt + q.pool_c0;
     const bool in_smem = q.beta_in_smem != 0;
@@ -123,9 +132,12 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
         for (uint32_t c = c_lo + warp; c < c_hi; c += W) {
             const uint32_t b = __ldg(q.pc_start + c), e = __ldg(q.pc_start + c + 1);
             double S = 0.0;
-            for (uint32_t j = b + lane; j < e; j += 32) {
-                const uint32_t i = __ldg(q.pc_lid + j);
-                S += in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
+            for (uint32_t j0 = b; j0 < e; j0 += 128) {
+                uint32_t li[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; li[u] = j < e ? __ldg(q.pc_lid + j) : 0xFFFFFFFFu; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (li[u] != 0xFFFFFFFFu) S += in_smem ? s_beta[li[u]] : ld_cg_f64(q.pool_beta + li[u]);
             }
             S = warp_sum(S);
             if (lane == 0) q.pool_r[c] = em_ratio(cnt[c], S);
@@ -134,25 +146,40 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
         // ---- M-step of this CTA's transcripts + the convergence test
         unsigned long long best = 0ULL;
         double asum = 0.0;
-        for (uint32_t i = t_lo + warp; i < t_hi; i += W) {
-            const uint32_t b = __ldg(q.pt_start + i), e = __ldg(q.pt_start + i + 1);
+        for (uint32_t k = k_lo + warp; k < k_hi; k += W) {
+            const uint32_t b = __ldg(q.ch_beg + k), e = __ldg(q.ch_beg + k + 1), i = __ldg(q.ch_row + k), nch = __ldg(q.ch_n + k);
             double acc = 0.0;
-            for (uint32_t j = b + lane; j < e; j += 32) acc += ld_cg_f64(q.pool_r + __ldg(q.pt_cls + j));
+            for (uint32_t j0 = b; j0 < e; j0 += 128) {                  // four independent gathers per lane in flight
+                uint32_t ci[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; ci[u] = j < e ? __ldg(q.pt_cls + j) : 0xFFFFFFFFu; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (ci[u] != 0xFFFFFFFFu) acc += ld_cg_f64(q.pool_r + ci[u]);
+            }
             acc = warp_sum(acc);
             if (lane == 0) {
-                const uint32_t t = __ldg(q.dlist + i);
-                const double beta = in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
-                const double a_old = p.X[t];
-                const double a_new = beta * acc + __ldg(p.base + t);
-                if (do_cmp) {
-                    const double gate = p.gate_old ? a_old : a_new;
-                    if (gate > p.cutoff) {
-                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
-                        best = bits > best ? bits : best;
-                    }
+                bool fin = true;
+                if (nch > 1) {                                          // the warp that adds the row's last chunk finishes the row
+                    atomicAdd(q.pool_acc + i, acc);
+                    __threadfence();
+                    fin = atomicAdd(q.pool_done + i, 1u) + 1u == nch;
+                    if (fin) { __threadfence(); acc = ld_cg_f64(q.pool_acc + i); q.pool_acc[i] = 0.0; q.pool_done[i] = 0u; }
                 }
-                p.X[t] = a_new;
-                if (VB) asum += a_new; else q.pool_beta[i] = a_new / __ldg(q.eff + t);
+                if (fin) {
+                    const uint32_t t = __ldg(q.dlist + i);
+                    const double beta = in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
+                    const double a_old = ld_cg_f64(p.X + t);            // written by whichever CTA finished the row last time
+                    const double a_new = beta * acc + __ldg(p.base + t);
+                    if (do_cmp) {
+                        const double gate = p.gate_old ? a_old : a_new;
+                        if (gate > p.cutoff) {
+                            const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                            best = bits > best ? bits : best;
+                        }
+                    }
+                    p.X[t] = a_new;
+                    if (VB) asum += a_new; else q.pool_beta[i] = a_new / __ldg(q.eff + t);
+                }
             }
         }
         n = m;
@@ -171,13 +198,14 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
                 const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
                 for (uint32_t i = t_lo + threadIdx.x; i < t_hi; i += blockDim.x) {
                     const uint32_t t = __ldg(q.dlist + i);
-                    const double a = p.X[t];                            // written by this CTA above
+                    const double a = ld_cg_f64(p.X + t);                // the grid barrier above ordered the M-step's writes
                     q.pool_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) / __ldg(q.eff + t);
                 }
             }
         }
         pool_barrier(p.ctl, NP, gen_p);                                // beta of every pool transcript is in place
         if (in_smem) {
+#pragma unroll 8
             for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) s_beta[i] = ld_cg_f64(q.pool_beta + i);
             __syncthreads();
         }

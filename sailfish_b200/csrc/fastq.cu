@@ -11,8 +11,9 @@
 //   then sfb200_map_batch_device on the extracted arrays (k_pack_reads -> k_scan_reads -> k_finalize_reads, map.cu)
 // The per-chunk bodies are in fastq_core.inl, which tests/fastq_core_test.cpp compiles as host code.
 //
-// STATUS: written after the round's GPU budget was spent; the arithmetic is checked on CPU, the kernels have NOT run on a GPU yet.
-// Nothing calls the entry point by default (sfb200-quant --deviceParse opts in); its parity test needs SFB200_EXPERIMENTAL=1.
+// The copy and the extraction of a block run on a stream of their own, into one of two staging sets, while the mapping kernels of the
+// previous block still run on the context's stream: a call returns as soon as its mapping kernels are enqueued.
+// Parity: tests/test_gpu_map.py::test_map_fastq_equals_map_batch; `sfb200-quant --deviceParse` opts in.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -41,12 +42,20 @@ struct FqMate {
     uint64_t n_text = 0, n_chunks = 0, n_newlines = 0;
 };
 struct FqState {
-    FqMate m[2];
+    FqMate sets[2][2];                           // two staging sets x two mates
+    unsigned parity = 0;
     DevBuf<unsigned char> tmp;
     DevBuf<uint32_t> err;
+    cudaStream_t xs = nullptr;                   // copy + extraction stream
+    cudaEvent_t extracted = nullptr, mapped[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
     void release() {
-        for (FqMate& x : m) { x.text.release(); x.bases.release(); x.cnt.release(); x.len.release(); x.seq_start.release(); x.rec_end.release(); x.off.release(); }
+        for (auto& st : sets) for (FqMate& x : st) { x.text.release(); x.bases.release(); x.cnt.release(); x.len.release(); x.seq_start.release(); x.rec_end.release(); x.off.release(); }
         tmp.release(); err.release();
+        if (xs) cudaStreamDestroy(xs);
+        if (extracted) cudaEventDestroy(extracted);
+        for (cudaEvent_t& e : mapped) if (e) cudaEventDestroy(e);
+        xs = nullptr; extracted = nullptr; mapped[0] = mapped[1] = nullptr;
     }
 };
 
@@ -74,10 +83,10 @@ inline unsigned fq_grid(uint64_t n, unsigned th) { return (unsigned)((n + th - 1
 
 // text -> device, newline counts, their exclusive scan; leaves the number of newlines in x.n_newlines
 int fq_stage(sfb200_ctx* c, FqState* st, FqMate& x, const char* text, uint64_t n) {
-    cudaStream_t s = c->stream;
+    cudaStream_t s = st->xs;
     x.n_text = n; x.n_chunks = (n + FQ_CHUNK - 1) / FQ_CHUNK; x.n_newlines = 0;
     if (n == 0) return SFB200_OK;
-    if (x.n_chunks >= (1ull << 31)) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: block too large (at most 1 TB of text per call)");
+    if (n >= (1ull << 31)) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: block too large (at most 2 GB of text per call: newline counts and record indices are 32-bit)");
     SFB_CUDA(c, x.text.reserve(n + 1)); SFB_CUDA(c, x.cnt.reserve(x.n_chunks + 1));
     SFB_CUDA(c, cudaMemcpyAsync(x.text.p, text, n, cudaMemcpyHostToDevice, s));
     k_fq_count<<<fq_grid(x.n_chunks, 256), 256, 0, s>>>(x.text.p, n, x.n_chunks, x.cnt.p);
@@ -97,7 +106,7 @@ int fq_stage(sfb200_ctx* c, FqState* st, FqMate& x, const char* text, uint64_t n
 
 // records [0, n_rec) of a staged mate -> bases / off; *consumed = bytes of text they cover
 int fq_extract(sfb200_ctx* c, FqState* st, FqMate& x, uint64_t n_rec, uint32_t lines_per_rec, uint64_t* consumed) {
-    cudaStream_t s = c->stream;
+    cudaStream_t s = st->xs;
     SFB_CUDA(c, x.seq_start.reserve(n_rec)); SFB_CUDA(c, x.len.reserve(n_rec)); SFB_CUDA(c, x.rec_end.reserve(n_rec)); SFB_CUDA(c, x.off.reserve(n_rec + 1));
     k_fq_mark<<<fq_grid(x.n_chunks, 256), 256, 0, s>>>(x.text.p, x.n_text, x.n_chunks, x.cnt.p, n_rec, lines_per_rec, x.seq_start.p, x.len.p, x.rec_end.p, st->err.p);
     c->launches++;
@@ -137,32 +146,46 @@ extern "C" int sfb200_map_fastq(sfb200_ctx* c, const char* text1, uint64_t n1, c
     cudaSetDevice(c->device);
     if (!c->fastq) c->fastq = new FqState();
     FqState* st = static_cast<FqState*>(c->fastq);
-    cudaStream_t s = c->stream;
+    if (!st->xs) {
+        SFB_CUDA(c, cudaStreamCreateWithFlags(&st->xs, cudaStreamNonBlocking));
+        SFB_CUDA(c, cudaEventCreateWithFlags(&st->extracted, cudaEventDisableTiming));
+        for (cudaEvent_t& e : st->mapped) SFB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t s = st->xs;
     const bool paired = text2 != nullptr;
     *n_records = 0; *consumed1 = 0;
     if (consumed2) *consumed2 = 0;
+    const unsigned set = st->parity;
+    st->parity ^= 1u;
+    FqMate* m = st->sets[set];
+    // this staging set was last read by the mapping kernels of the call before the previous one
+    if (st->used[set]) SFB_CUDA(c, cudaEventSynchronize(st->mapped[set]));
     SFB_CUDA(c, st->err.reserve(1));
     SFB_CUDA(c, cudaMemsetAsync(st->err.p, 0, 4, s));
-    { const int rc = fq_stage(c, st, st->m[0], text1, n1); if (rc) return rc; }
-    if (paired) { const int rc = fq_stage(c, st, st->m[1], text2, n2); if (rc) return rc; }
+    { const int rc = fq_stage(c, st, m[0], text1, n1); if (rc) return rc; }
+    if (paired) { const int rc = fq_stage(c, st, m[1], text2, n2); if (rc) return rc; }
     // FASTQ ('@': four lines per record) or FASTA reads ('>': two); both mates in the same format
     const uint32_t lpr = (n1 > 0 && text1[0] == '>') ? 2u : 4u;
-    uint64_t n_rec = st->m[0].n_newlines / lpr;
-    if (paired) n_rec = std::min<uint64_t>(n_rec, st->m[1].n_newlines / lpr);
+    uint64_t n_rec = m[0].n_newlines / lpr;
+    if (paired) n_rec = std::min<uint64_t>(n_rec, m[1].n_newlines / lpr);
     if (max_records) n_rec = std::min<uint64_t>(n_rec, max_records);
     if (n_rec == 0) return SFB200_OK;
-    { const int rc = fq_extract(c, st, st->m[0], n_rec, lpr, consumed1); if (rc) return rc; }
-    if (paired) { const int rc = fq_extract(c, st, st->m[1], n_rec, lpr, consumed2); if (rc) return rc; }
+    { const int rc = fq_extract(c, st, m[0], n_rec, lpr, consumed1); if (rc) return rc; }
+    if (paired) { const int rc = fq_extract(c, st, m[1], n_rec, lpr, consumed2); if (rc) return rc; }
     uint32_t err = 0;
     SFB_CUDA(c, cudaMemcpyAsync(&err, st->err.p, 4, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaEventRecord(st->extracted, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
     if (err & FQ_ERR_HEADER) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: a record does not start with '@' / '>' (four-line FASTQ or two-line FASTA records expected, both mates alike)");
     if (err & FQ_ERR_PLUS) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: the line after a sequence does not start with '+' (four-line FASTQ records expected)");
     if (err & FQ_ERR_LONG) SFB_FAIL(c, SFB200_EINVAL, "map_fastq: sequence line longer than 16 M bases");
-    const int rc = sfb200_map_batch_device(c, st->m[0].bases.p, st->m[0].off.p, paired ? st->m[1].bases.p : nullptr, paired ? st->m[1].off.p : nullptr, n_rec);
+    // the mapping kernels run on the context's stream, behind those of the previous block; the caller's text is already on the device,
+    // so the call returns without waiting for them
+    SFB_CUDA(c, cudaStreamWaitEvent(c->stream, st->extracted, 0));
+    const int rc = sfb200_map_batch_device(c, m[0].bases.p, m[0].off.p, paired ? m[1].bases.p : nullptr, paired ? m[1].off.p : nullptr, n_rec);
     if (rc) return rc;
-    // the staging buffers are reused by the next call: wait for the mapping kernels that read them
-    SFB_CUDA(c, cudaStreamSynchronize(s));
+    SFB_CUDA(c, cudaEventRecord(st->mapped[set], c->stream));
+    st->used[set] = true;
     *n_records = n_rec;
     return SFB200_OK;
 }

@@ -398,9 +398,11 @@ extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint3
         c->launches += tr.n.size() - 1;
         uint32_t iters = 0;
         rc = sfb_bootstrap_em_device(c, eff_lens, n_txp, d_samp.p, totalCount, opts, alphas.data(), &iters);
+        c->eff_resident = true;                             // the same lengths for every replicate of this run
         loop_ms += c->last_em_ms;
         if (rc == SFB200_OK && cb && cb(user, alphas.data(), n_txp) != 0) { c->err = "bootstrap row callback failed"; rc = SFB200_ECALLBACK; }
     }
+    c->eff_resident = false;
     c->last_em_ms = loop_ms;
     tr.release(); d_samp.release(); d_cnt.release();
     return rc;

@@ -21,19 +21,24 @@ ap.add_argument("--reads", type=int, default=4_000_000)
 ap.add_argument("--dir", default="/dev/shm/sfb200_cli")
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--device-parse", action="store_true", help="pass --deviceParse: FASTQ text parsed on the GPU (sfb200_map_fastq)")
+ap.add_argument("--reuse", action="store_true", help="keep the files of an earlier invocation with the same sizes")
 a = ap.parse_args()
 os.makedirs(a.dir, exist_ok=True)
-seq, off, ln = synth.make_transcriptome(a.genes, seed=42)
 fa = os.path.join(a.dir, "t.fa")
-with open(fa, "wb") as f:
-    for i in range(len(ln)):
+fq = os.path.join(a.dir, "r.fq")
+L = 76
+have = a.reuse and os.path.exists(fa) and os.path.exists(fq) and os.path.getsize(fq) == a.reads * (11 + L + 3 + L + 1)
+if have:
+    ln = np.zeros(a.genes * 5, np.uint32)
+else:
+    seq, off, ln = synth.make_transcriptome(a.genes, seed=42)
+with open(fa, "wb") if not have else open(os.devnull, "wb") as f:
+    for i in range(len(ln) if not have else 0):
         f.write(b">t%d\n" % i)
         f.write(seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes())
         f.write(b"\n")
-L = 76
-fq = os.path.join(a.dir, "r.fq")
-with open(fq, "wb") as f:
-    done = 0
+with open(fq, "wb") if not have else open(os.devnull, "wb") as f:
+    done = 0 if not have else a.reads
     c = 0
     while done < a.reads:
         n = min(1_000_000, a.reads - done)
