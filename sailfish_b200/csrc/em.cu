@@ -830,6 +830,13 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         SFB_CUDA(c, cudaMemsetAsync(P.pool_f64.p + n_pc + nd, 0, nd * 8ull, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
         P.n_dirty = nd; P.pool_nz = nz;
+        if (getenv("SFB200_VERBOSE")) {
+            uint32_t max_row = 0, max_cls = 0;
+            for (uint32_t i = 0; i < nd; ++i) max_row = std::max(max_row, pt_start[i + 1] - pt_start[i]);
+            for (uint64_t q = 0; q < n_pc; ++q) max_cls = std::max(max_cls, pc_start[q + 1] - pc_start[q]);
+            fprintf(stderr, "[sfb200] EM pool: %llu classes, %u transcripts, %llu entries, %u chunks, longest class %u, largest degree %u\n",
+                    (unsigned long long)n_pc, nd, (unsigned long long)nz, n_ch, max_cls, max_row);
+        }
     }
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool, %u pool transcripts), largest CTA slice %llu bytes (limit %d) -> %s\n",
@@ -1000,6 +1007,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         const size_t pool_smem = P.n_pool_cta ? (size_t)P.n_dirty * 8 + 256 : 0;
         const size_t smem_2 = (size_t)(P.smem_limit + 1024) / 2 - 2048;
         q.beta_in_smem = (P.n_pool_cta && pool_smem <= std::max<size_t>(smem_2, (size_t)P.dense_smem)) ? 1u : 0u;
+        if (getenv("SFB200_EM_POOL_GLOBAL")) q.beta_in_smem = 0u;
         const size_t smem = q.beta_in_smem ? std::max<size_t>((size_t)P.dense_smem, pool_smem) : (size_t)P.dense_smem;
         void* args[] = {&p, &q};
         const void* fn = nullptr;

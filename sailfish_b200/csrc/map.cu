@@ -84,7 +84,7 @@ struct EqTable {
     unsigned long long* slot;      // n_buckets*4 + overflow
     unsigned long long* count;     // same length
     uint32_t* arena;               // label storage
-    unsigned long long* cursor;    // [0] arena words used  [1] distinct labels  [2] error flags  [3] overflow inserts
+    unsigned long long* cursor;    // [0] arena words used  [1] distinct labels  [2] error flags  [3] overflow inserts  [4] reads listed for a retry
     uint64_t n_buckets;            // power of two
     uint64_t n_overflow;           // power of two
     uint64_t arena_words;
@@ -679,6 +679,8 @@ struct MapParams {
     const uint64_t* pk; const uint64_t* pkn; const uint32_t* meta; uint32_t rwp; int n_mates;
     unsigned long long* iv; uint8_t* niv; uint32_t* ivmask;
     // bias / GC sample collection (k_finalize_reads_bias only)
+    // class-table growth: reads whose upsert failed are listed (retry_out) and finalized again after the table has grown (retry_in)
+    uint32_t* retry_out; const uint32_t* retry_in; uint64_t n_retry;
     int16_t* bias_val;                 // per read of the batch: bin of its read-start context, or -1
     unsigned int* gc_hist;             // observed fragment GC histogram (101 bins), accumulated over batches
     int bias_seq, bias_gc;
@@ -915,6 +917,27 @@ __global__ void k_count_active(const uint8_t* __restrict__ active, uint32_t T, u
     if ((threadIdx.x & 31u) == 0 && n) atomicAdd(out, n);
 }
 
+// growth: every class of the old table moves into a larger one (same arena, same slot word: the label does not move)
+__global__ void k_eq_rehash(const unsigned long long* __restrict__ old_slot, const unsigned long long* __restrict__ old_count,
+                            uint64_t n_old, const EqTable nt) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_old; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long sv = old_slot[i];
+        if (!sv) continue;
+        const uint32_t len = (uint32_t)((sv >> 20) & 1023);
+        const uint32_t* a = nt.arena + (sv >> 30);
+        const uint64_t h = xxh64_words([&](uint32_t j) { return a[j]; }, len, 0);
+        const uint64_t bmask = nt.n_buckets - 1;
+        const uint64_t b1 = h & bmask, b2 = (b1 ^ (((h >> 48) + 1) * 0x5bd1e995ULL)) & bmask;
+        const uint64_t n_main = nt.n_buckets * 4, ov0 = h >> 20;
+        bool placed = false;
+        for (uint64_t step = 0; step < 8 + nt.n_overflow && !placed; ++step) {
+            const uint64_t idx = step < 4 ? b1 * 4 + step : step < 8 ? b2 * 4 + (step - 4) : n_main + ((ov0 + (step - 8)) & (nt.n_overflow - 1));
+            if (nt.slot[idx] == 0ULL && atomicCAS(nt.slot + idx, 0ULL, sv) == 0ULL) { nt.count[idx] = old_count[i]; placed = true; }
+        }
+        if (!placed) atomicOr(nt.cursor + 2, ERR_TABLE_FULL);             // cannot happen: the new table is twice the old one
+    }
+}
+
 }  // namespace
 
 // ======================================================================================================================
@@ -935,6 +958,10 @@ struct MapState {
     DevBuf<uint32_t> ivmask;
     DevBuf<unsigned int> maxlen;
     DevBuf<unsigned long long> clipped;   // mates cut to MAX_READ_LEN since map_begin
+    DevBuf<uint32_t> retry[2];            // reads of the last chunk whose class upsert found the table / arena full
+    MapParams last_p;                     // the last chunk's launch parameters (its hand-over buffers stay valid until the next pack)
+    bool have_last = false;
+    uint32_t n_grown = 0;                 // how often the class table / arena grew since map_begin
     int grid_scan = 0;
     // multi-rank class merge / FLD gather buffers (grow-only: cudaMalloc / cudaFree per step cost more than the exchange)
     DevBuf<unsigned long long> mg_sizes, mg_cnt, mg_cnt_g;
@@ -968,7 +995,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
     m->mg_sizes.release(); m->mg_cnt.release(); m->mg_cnt_g.release(); m->mg_start.release(); m->mg_len.release(); m->mg_lab.release();
     m->mg_start_g.release(); m->mg_len_g.release(); m->mg_lab_g.release(); m->fld_send.release(); m->fld_recv.release();
-    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release(); m->clipped.release();
+    m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release(); m->clipped.release(); m->retry[0].release(); m->retry[1].release();
     m->bias_val.release(); m->bias_hist.release(); m->bias_remaining.release();
     for (int i = 0; i < 2; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
@@ -999,12 +1026,12 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->n_buckets = 1ull << lb; m->n_overflow = std::max<uint64_t>(1024, m->n_buckets / 4); m->arena_words = 1ull << la;
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
     SFB_CUDA(c, m->slot.reserve(n_slots)); SFB_CUDA(c, m->count.reserve(n_slots)); SFB_CUDA(c, m->arena.reserve(m->arena_words));
-    SFB_CUDA(c, m->cursor.reserve(4)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(2)); SFB_CUDA(c, m->maxlen.reserve(1)); SFB_CUDA(c, m->clipped.reserve(1));
+    SFB_CUDA(c, m->cursor.reserve(8)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(2)); SFB_CUDA(c, m->maxlen.reserve(1)); SFB_CUDA(c, m->clipped.reserve(1));
     SFB_CUDA(c, m->fld_hist.reserve(o->max_frag_len)); SFB_CUDA(c, m->remaining.reserve(1));
     SFB_CUDA(c, m->fld_samples.reserve((size_t)std::max(1, o->num_frag_samples)));
     SFB_CUDA(c, cudaMemsetAsync(m->slot.p, 0, n_slots * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->count.p, 0, n_slots * 8, s));
-    SFB_CUDA(c, cudaMemsetAsync(m->cursor.p, 0, 4 * 8, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->cursor.p, 0, 8 * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->counters.p, 0, 6 * 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->clipped.p, 0, 8, s));
     SFB_CUDA(c, cudaMemsetAsync(m->fld_hist.p, 0, o->max_frag_len * 4ull, s));
@@ -1051,6 +1078,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->ev_used = 0; m->kernel_ms = 0.0;
     m->in_use[0] = m->in_use[1] = false; m->parity = 0; m->primed = false;
     m->bias_seq = m->bias_gc = false;
+    m->have_last = false; m->n_grown = 0;
     return SFB200_OK;
 }
 
@@ -1106,6 +1134,76 @@ extern "C" int sfb200_map_get_bias(sfb200_ctx* c, uint32_t* read_bias, uint32_t*
 static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
                             const uint64_t* d_off2, uint64_t n_reads);
 
+// ---- a class table that grows (libcuckoo grows too: include/cuckoohash_map.hh, cuckoo_expand_simple) --------------------------------
+// The table starts at the geometry of map_begin.  When an upsert finds both buckets and the overflow region full, or the label arena
+// exhausted, the read is put on a retry list instead of being lost; before the next chunk is packed (and in map_finish) the host looks
+// at the error flags -- it synchronises there anyway -- doubles what was full (classes re-inserted by k_eq_rehash; labels stay where
+// they are, the arena is copied) and finalizes the listed reads again, upsert only.
+static int eq_resize(sfb200_ctx* c, MapState* m, uint64_t new_buckets, uint64_t new_arena_words) {
+    cudaStream_t s = c->stream;
+    if (new_arena_words > m->arena_words) {
+        if (new_arena_words > (1ull << 34)) SFB_FAIL(c, SFB200_EFULL, "equivalence-class label arena cannot grow beyond 2^34 words");
+        unsigned long long used = 0;
+        SFB_CUDA(c, cudaMemcpyAsync(&used, m->cursor.p, 8, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        used = std::min<unsigned long long>(used, m->arena_words);       // reservations beyond the end were refused
+        DevBuf<uint32_t> na;
+        SFB_CUDA(c, na.reserve(new_arena_words));
+        SFB_CUDA(c, cudaMemcpyAsync(na.p, m->arena.p, used * 4, cudaMemcpyDeviceToDevice, s));
+        SFB_CUDA(c, cudaMemcpyAsync(m->cursor.p, &used, 8, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        m->arena.release(); m->arena = na; m->arena_words = new_arena_words;
+    }
+    if (new_buckets > m->n_buckets) {
+        const uint64_t n_old = m->n_buckets * 4 + m->n_overflow;
+        const uint64_t n_over = std::max<uint64_t>(1024, new_buckets / 4), n_new = new_buckets * 4 + n_over;
+        DevBuf<unsigned long long> ns, nc;
+        SFB_CUDA(c, ns.reserve(n_new)); SFB_CUDA(c, nc.reserve(n_new));
+        SFB_CUDA(c, cudaMemsetAsync(ns.p, 0, n_new * 8, s)); SFB_CUDA(c, cudaMemsetAsync(nc.p, 0, n_new * 8, s));
+        EqTable nt;
+        nt.slot = ns.p; nt.count = nc.p; nt.arena = m->arena.p; nt.cursor = m->cursor.p;
+        nt.n_buckets = new_buckets; nt.n_overflow = n_over; nt.arena_words = m->arena_words;
+        k_eq_rehash<<<(unsigned)std::min<uint64_t>((n_old + 255) / 256, (uint64_t)c->num_sms * 16), 256, 0, s>>>(m->slot.p, m->count.p, n_old, nt);
+        c->launches++;
+        SFB_CUDA(c, cudaGetLastError());
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        m->slot.release(); m->count.release();
+        m->slot = ns; m->count = nc; m->n_buckets = new_buckets; m->n_overflow = n_over;
+    }
+    m->n_grown++;
+    return SFB200_OK;
+}
+
+// called with the stream idle: grows what the last chunk found full and finalizes its listed reads again
+static int eq_grow_and_retry(sfb200_ctx* c, MapState* m) {
+    cudaStream_t s = c->stream;
+    for (int round = 0; round < 48; ++round) {
+        unsigned long long cur[8];
+        SFB_CUDA(c, cudaMemcpyAsync(cur, m->cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        const unsigned long long flags = cur[2] & (ERR_ARENA_FULL | ERR_TABLE_FULL), n_retry = cur[4];
+        if (!flags && !n_retry) return SFB200_OK;
+        if (!m->have_last) SFB_FAIL(c, SFB200_EFULL, "equivalence-class table full with nothing to replay");
+        { const int rc = eq_resize(c, m, (flags & ERR_TABLE_FULL) ? m->n_buckets * 2 : m->n_buckets,
+                                   (flags & ERR_ARENA_FULL) ? m->arena_words * 2 : m->arena_words); if (rc) return rc; }
+        const unsigned long long keep = cur[2] & ~(ERR_ARENA_FULL | ERR_TABLE_FULL), zero = 0;
+        SFB_CUDA(c, cudaMemcpyAsync(m->cursor.p + 2, &keep, 8, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, cudaMemcpyAsync(m->cursor.p + 4, &zero, 8, cudaMemcpyHostToDevice, s));
+        SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 16, s));
+        MapParams p = m->last_p;
+        p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p;
+        p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
+        p.retry_in = m->retry[round & 1].p; p.retry_out = m->retry[(round & 1) ^ 1].p; p.n_retry = n_retry;
+        p.fld_val = nullptr; p.bias_val = nullptr; p.bias_seq = 0; p.bias_gc = 0;
+        if (n_retry) {
+            k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, (n_retry + MAP_THREADS - 1) / MAP_THREADS), MAP_THREADS, FIN_SMEM, s>>>(p);
+            c->launches++;
+            SFB_CUDA(c, cudaGetLastError());
+        }
+    }
+    SFB_FAIL(c, SFB200_EFULL, "equivalence-class table still full after 48 doublings");
+}
+
 // Batches of any size: the per-fragment hand-over buffers (packed reads, seed intervals) are sized for at most
 // MAX_CHUNK fragments, larger batches are walked chunk by chunk (offsets are absolute, so a chunk is a pointer shift).
 extern "C" int sfb200_map_batch_device(sfb200_ctx* c, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
@@ -1154,8 +1252,21 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     k_max_read_len<<<(unsigned)std::min<uint64_t>((n_reads + 255) / 256, 1024), 256, 0, s>>>(d_off1, d_off2, n_reads, m->maxlen.p, m->clipped.p);
     c->launches++;
     unsigned int maxlen = 0;
+    unsigned long long h_cur[8];
     SFB_CUDA(c, cudaMemcpyAsync(&maxlen, m->maxlen.p, 4, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaMemcpyAsync(h_cur, m->cursor.p, sizeof(h_cur), cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaStreamSynchronize(s));
+    // the previous chunk is finished: if its upserts found the table or the arena full, grow and replay them while its hand-over
+    // buffers are still intact (the pack below overwrites them)
+    if ((h_cur[2] & (ERR_ARENA_FULL | ERR_TABLE_FULL)) || h_cur[4]) {
+        const int rc = eq_grow_and_retry(c, m);
+        if (rc) return rc;
+        SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 16, s));
+        p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p;
+        p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
+    }
+    SFB_CUDA(c, m->retry[0].reserve(n_reads)); SFB_CUDA(c, m->retry[1].reserve(n_reads));
+    p.retry_out = m->retry[0].p; p.retry_in = nullptr; p.n_retry = 0;
     const uint32_t rwp = std::max<uint32_t>(1, (maxlen + 31) / 32);
     // 2. pack
     const uint64_t n_fm = n_reads * n_mates;
@@ -1181,6 +1292,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     }
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
+    m->last_p = p; m->have_last = true;
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));
     m->ev_used += 2;
     if (want_fld) {
@@ -1381,6 +1493,18 @@ static int merge_classes_over_ranks(sfb200_ctx* c, MapState* m) {
     if (!rc) rc = sfb_comm_allgather(c, d_cnt.p, d_cnt_g.p, maxE * 8);
     if (!rc) rc = sfb_comm_allgather(c, d_lab.p, d_lab_g.p, maxZ * 4);
     if (rc) return rc;
+    // room for every rank's classes before they are added (an upsert that fails here has no chunk to replay)
+    {
+        uint64_t all_E = 0, other_Z = 0;
+        for (int r = 0; r < R; ++r) { all_E += sizes[2 * r]; if (r != c->rank) other_Z += sizes[2 * r + 1]; }
+        uint64_t nb = m->n_buckets, na = m->arena_words;
+        while (nb * 4 < 2 * all_E) nb *= 2;
+        unsigned long long used = 0;
+        MG(cudaMemcpyAsync(&used, m->cursor.p, 8, cudaMemcpyDeviceToHost, s));
+        MG(cudaStreamSynchronize(s));
+        while (na < used + other_Z + 64) na *= 2;
+        if (nb != m->n_buckets || na != m->arena_words) { const int rg = eq_resize(c, m, nb, na); if (rg) return rg; }
+    }
     EqTable tb;
     tb.slot = m->slot.p; tb.count = m->count.p; tb.arena = m->arena.p; tb.cursor = m->cursor.p;
     tb.n_buckets = m->n_buckets; tb.n_overflow = m->n_overflow; tb.arena_words = m->arena_words;
@@ -1410,6 +1534,7 @@ extern "C" int sfb200_map_finish(sfb200_ctx* c, uint64_t counters[6], uint32_t* 
         if (rc) return rc;
         // fld histogram: widen to u64 through the host (1000 entries)
     }
+    { const int rc = eq_grow_and_retry(c, m); if (rc) return rc; }      // the last chunk may have found the table / arena full
     unsigned long long h_cursor[4], h_counters[6];
     SFB_CUDA(c, cudaMemcpyAsync(h_cursor, m->cursor.p, sizeof(h_cursor), cudaMemcpyDeviceToHost, s));
     SFB_CUDA(c, cudaMemcpyAsync(h_counters, m->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, s));

@@ -19,15 +19,20 @@
     int niv[4];
     uint64_t score[4];
 
+    // retry pass (p.retry_in != nullptr): the class table or the label arena was full when these reads were finalized; the table has
+    // grown since (sfb_eq_grow, map.cu) and only their class upsert is repeated -- they were counted the first time
+    const bool retry = p.retry_in != nullptr;
+    const uint64_t n_work = retry ? p.n_retry : p.n_reads;
     for (;;) {
         unsigned long long base_idx = 0;
         if (lane == 0) base_idx = atomicAdd(p.next_read + 1, 32ULL);
         base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
-        if (base_idx >= p.n_reads) break;
-        const uint64_t ri = base_idx + lane;
+        if (base_idx >= n_work) break;
+        const bool have_read = base_idx + lane < n_work;
+        const uint64_t ri = have_read ? (retry ? (uint64_t)p.retry_in[base_idx + lane] : base_idx + lane) : 0;
         bool mapped = false;
         uint32_t lab_n = 0;
-        if (ri < p.n_reads) {
+        if (have_read) {
             uint32_t nL = 0, nR = 0, wL = R_LEFT, wR = R_RIGHT;
             bool okL, okR = true;
             ReadG rg[2];
@@ -107,7 +112,7 @@
                         const bool fl_ = hit_fwd(hl), fr_ = hit_fwd(hr);
 #if SFB_FIN_BIAS
                         if (p.bias_seq && bsample < 0) bsample = hit_read_start_index(p.ix, tl, pl, fl_, len1);
-                        if (p.bias_gc) {                                                // :375-388
+                        if (p.bias_gc && !retry) {                                      // :375-388
                             const int32_t start = pl < pr ? pl : pr;
                             const int32_t e1 = pl + (int32_t)len1, e2 = pr + (int32_t)len2;
                             const int32_t stop = e1 > e2 ? e1 : e2;                      // start + fragLen
@@ -163,15 +168,16 @@
                 lab_n = acc.n;
                 c_fw += acc.fw; c_rc += acc.rc;
             }
-            if (p.fld_val) {
+            if (p.fld_val && !retry) {
                 const bool elig = paired && n_joint == 1 && fl >= 0 && mapped && (uint32_t)fl < p.max_frag_len;   // :419-434
                 p.fld_val[ri] = elig ? (int16_t)fl : (int16_t)-1;
             }
 #if SFB_FIN_BIAS
-            if (p.bias_val) p.bias_val[ri] = (int16_t)bsample;
+            if (p.bias_val && !retry) p.bias_val[ri] = (int16_t)bsample;
 #endif
             c_obs += 1; c_map += mapped ? 1 : 0; c_hits += n_joint;
         }
+        bool failed = false;                               // the upsert this lane's read took part in found the table or the arena full
         // ---- warp-aggregated class upsert (the warp is convergent here) ----
         const unsigned map_m = __ballot_sync(0xffffffffu, mapped);
         if (mapped) {
@@ -186,8 +192,12 @@
                 for (uint32_t j = 0; j < lab_n && same; ++j) same = (uint32_t)scr.peer(d, R_LABEL, j) == get(j);
             }
             const unsigned agree = __ballot_sync(map_m, same) & grp;
-            if ((int)lane == leader) eq_upsert(p.tb, lab_n, get, (unsigned long long)__popc(agree), h);
-            else if (!same) eq_upsert(p.tb, lab_n, get, 1ULL, h);
+            bool ok = true;
+            if ((int)lane == leader) ok = eq_upsert(p.tb, lab_n, get, (unsigned long long)__popc(agree), h);
+            else if (!same) ok = eq_upsert(p.tb, lab_n, get, 1ULL, h);
+            const bool lead_ok = __shfl_sync(grp, (int)ok, leader) != 0;   // the members of a group share their leader's fate
+            failed = same ? !lead_ok : !ok;
+            if (failed && p.retry_out) p.retry_out[atomicAdd(p.tb.cursor + 4, 1ULL)] = (uint32_t)ri;
         }
         __syncwarp();                                      // the next round overwrites the label region other lanes may still be comparing
     }
@@ -198,5 +208,5 @@
         unsigned long long x = v[q];
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-        if (lane == 0 && x) atomicAdd(p.counters + q, x);
+        if (lane == 0 && x && !retry) atomicAdd(p.counters + q, x);
     }

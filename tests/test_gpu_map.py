@@ -307,3 +307,21 @@ def test_map_fastq_equals_map_batch(ctx, paired, eol, block, fasta):
     with pytest.raises(capi.Sfb200Error):
         ctx.map_fastq(b">a\nACGT\nAC\n>b\nGGCC\nGG\n", b">a\nACGT\nAC\n>b\nGGCC\nGG\n" if paired else None)     # wrapped FASTA
     ctx.map_finish()
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_class_table_and_arena_grow(ctx, monkeypatch, paired):
+    """a class table of 16 buckets and a label arena of 1024 words: both fill up many times over; the reads whose upsert failed are
+    replayed after every doubling (libcuckoo grows too, include/cuckoohash_map.hh) -- classes, counters and FLD equal the oracle's"""
+    monkeypatch.setenv("SFB200_EQ_LOG2_BUCKETS", "4")
+    monkeypatch.setenv("SFB200_EQ_ARENA_LOG2", "10")
+    monkeypatch.setenv("SFB200_MAX_CHUNK", "7000")
+    seq, off, ln = synth.make_transcriptome(600, seed=11)
+    if paired:
+        b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 60000, 100, seed=5, paired=True, sub_rate=0.01)
+        st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, b2, o2, "IU", batches=3)
+    else:
+        b1, o1, _, _, _ = synth.make_reads(seq, off, ln, 60000, 76, seed=5)
+        st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, None, None, "U", batches=3)
+    assert g["n_classes"] > 1500                                         # far more classes than the 64 + 1024 slots it started with
+    assert_same_classes(ctx, g, w)
