@@ -811,6 +811,9 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         { std::vector<uint32_t> cur(pt_start, pt_start + nd);
           for (uint64_t q = 0; q < n_pc; ++q) for (uint32_t j = pc_start[q]; j < pc_start[q + 1]; ++j) pt_cls[cur[pc_lid[j]]++] = (uint32_t)q; }
         std::copy(ids.begin(), ids.end(), dl);
+        uint32_t max_row = 0, max_cls = 0;
+        for (uint32_t i = 0; i < nd; ++i) max_row = std::max(max_row, pt_start[i + 1] - pt_start[i]);
+        for (uint64_t q = 0; q < n_pc; ++q) max_cls = std::max(max_cls, pc_start[q + 1] - pc_start[q]);
         // the transpose in chunks of at most 256 entries (POOL_CHUNK, em_dense.cuh): ch_beg[n_ch + 1] | ch_row[n_ch] | ch_n[n_ch]
         std::vector<uint32_t> ch_beg, ch_row, ch_n;
         { const uint32_t* pts = buf.data() + n_pc + 1 + nz;
@@ -830,13 +833,10 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         SFB_CUDA(c, cudaMemsetAsync(P.pool_f64.p + n_pc + nd, 0, nd * 8ull, s));
         SFB_CUDA(c, cudaStreamSynchronize(s));
         P.n_dirty = nd; P.pool_nz = nz;
-        if (getenv("SFB200_VERBOSE")) {
-            uint32_t max_row = 0, max_cls = 0;
-            for (uint32_t i = 0; i < nd; ++i) max_row = std::max(max_row, pt_start[i + 1] - pt_start[i]);
-            for (uint64_t q = 0; q < n_pc; ++q) max_cls = std::max(max_cls, pc_start[q + 1] - pc_start[q]);
+        if (getenv("SFB200_VERBOSE"))
             fprintf(stderr, "[sfb200] EM pool: %llu classes, %u transcripts, %llu entries, %u chunks, longest class %u, largest degree %u\n",
                     (unsigned long long)n_pc, nd, (unsigned long long)nz, n_ch, max_cls, max_row);
-        }
+    }
     }
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool, %u pool transcripts), largest CTA slice %llu bytes (limit %d) -> %s\n",

@@ -63,7 +63,7 @@ struct DenseParams {
     double* pool_acc;         // n_dirty: partial row sums of multi-chunk rows (zero between iterations)
     unsigned int* pool_done;  // n_dirty: chunks of the row summed so far (zero between iterations)
 };
-constexpr uint32_t POOL_CHUNK = 256;
+constexpr uint32_t POOL_CHUNK = 256, POOL_SHORT = 16;
 
 // barrier among the pool CTAs only (same protocol as grid_barrier, its own counter words)
 __device__ __forceinline__ void pool_barrier(unsigned long long* ctl, unsigned int n_cta, unsigned long long& gen) {
@@ -128,58 +128,107 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
         if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
         const uint32_t m = n + 1;
         const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
+        // Rows are short (a handful of entries) with few long ones.  A row is a chain of dependent L2 round trips (start -> index ->
+        // value -> result), so a CTA wants one row per THREAD in flight, not one per warp: a thread sums a row of up to POOL_SHORT
+        // entries by itself (four gathers in flight); longer rows of the same batch are then summed by the whole warp, one after another.
         // ---- E-step: r_c of this CTA's classes
-        for (uint32_t c = c_lo + warp; c < c_hi; c += W) {
-            const uint32_t b = __ldg(q.pc_start + c), e = __ldg(q.pc_start + c + 1);
-            double S = 0.0;
-            for (uint32_t j0 = b; j0 < e; j0 += 128) {
-                uint32_t li[4];
+        for (uint32_t base = c_lo; base < c_hi; base += blockDim.x) {
+            const uint32_t c = base + threadIdx.x;
+            const bool valid = c < c_hi;
+            uint32_t b = 0, e = 0;
+            if (valid) { b = __ldg(q.pc_start + c); e = __ldg(q.pc_start + c + 1); }
+            const bool is_long = valid && e - b > POOL_SHORT;
+            if (valid && !is_long) {
+                double S = 0.0;
+                for (uint32_t j0 = b; j0 < e; j0 += 4) {
+                    uint32_t li[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; li[u] = j < e ? __ldg(q.pc_lid + j) : 0xFFFFFFFFu; }
+                    for (int u = 0; u < 4; ++u) li[u] = j0 + u < e ? __ldg(q.pc_lid + j0 + u) : 0xFFFFFFFFu;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) if (li[u] != 0xFFFFFFFFu) S += in_smem ? s_beta[li[u]] : ld_cg_f64(q.pool_beta + li[u]);
+                    for (int u = 0; u < 4; ++u) if (li[u] != 0xFFFFFFFFu) S += in_smem ? s_beta[li[u]] : ld_cg_f64(q.pool_beta + li[u]);
+                }
+                q.pool_r[c] = em_ratio(cnt[c], S);
             }
-            S = warp_sum(S);
-            if (lane == 0) q.pool_r[c] = em_ratio(cnt[c], S);
+            unsigned longm = __ballot_sync(0xffffffffu, is_long);
+            while (longm) {
+                const int src = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const uint32_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
+                double S = 0.0;
+                for (uint32_t j0 = bb; j0 < ee; j0 += 128) {
+                    uint32_t li[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; li[u] = j < ee ? __ldg(q.pc_lid + j) : 0xFFFFFFFFu; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (li[u] != 0xFFFFFFFFu) S += in_smem ? s_beta[li[u]] : ld_cg_f64(q.pool_beta + li[u]);
+                }
+                S = warp_sum(S);
+                if ((int)lane == src) q.pool_r[c] = em_ratio(cnt[c], S);
+            }
         }
         pool_barrier(p.ctl, NP, gen_p);
         // ---- M-step of this CTA's transcripts + the convergence test
         unsigned long long best = 0ULL;
         double asum = 0.0;
-        for (uint32_t k = k_lo + warp; k < k_hi; k += W) {
-            const uint32_t b = __ldg(q.ch_beg + k), e = __ldg(q.ch_beg + k + 1), i = __ldg(q.ch_row + k), nch = __ldg(q.ch_n + k);
-            double acc = 0.0;
-            for (uint32_t j0 = b; j0 < e; j0 += 128) {                  // four independent gathers per lane in flight
-                uint32_t ci[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; ci[u] = j < e ? __ldg(q.pt_cls + j) : 0xFFFFFFFFu; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (ci[u] != 0xFFFFFFFFu) acc += ld_cg_f64(q.pool_r + ci[u]);
+        // a row's sum is complete: new alpha, the convergence test, new beta
+        auto finish_row = [&](uint32_t i, double acc) {
+            const uint32_t t = __ldg(q.dlist + i);
+            const double beta = in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
+            const double a_old = ld_cg_f64(p.X + t);                    // written by whichever CTA finished the row last time
+            const double a_new = beta * acc + __ldg(p.base + t);
+            if (do_cmp) {
+                const double gate = p.gate_old ? a_old : a_new;
+                if (gate > p.cutoff) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                    best = bits > best ? bits : best;
+                }
             }
-            acc = warp_sum(acc);
-            if (lane == 0) {
-                bool fin = true;
-                if (nch > 1) {                                          // the warp that adds the row's last chunk finishes the row
-                    atomicAdd(q.pool_acc + i, acc);
-                    __threadfence();
-                    fin = atomicAdd(q.pool_done + i, 1u) + 1u == nch;
-                    if (fin) { __threadfence(); acc = ld_cg_f64(q.pool_acc + i); q.pool_acc[i] = 0.0; q.pool_done[i] = 0u; }
+            p.X[t] = a_new;
+            if (VB) asum += a_new; else q.pool_beta[i] = a_new / __ldg(q.eff + t);
+        };
+        // a chunk's partial sum: rows of one chunk finish at once, the warp / thread that adds a row's last chunk finishes the row
+        auto add_chunk = [&](uint32_t i, uint32_t nch, double acc) {
+            if (nch > 1) {
+                atomicAdd(q.pool_acc + i, acc);
+                __threadfence();
+                if (atomicAdd(q.pool_done + i, 1u) + 1u != nch) return;
+                __threadfence();
+                acc = ld_cg_f64(q.pool_acc + i); q.pool_acc[i] = 0.0; q.pool_done[i] = 0u;
+            }
+            finish_row(i, acc);
+        };
+        for (uint32_t base = k_lo; base < k_hi; base += blockDim.x) {
+            const uint32_t k = base + threadIdx.x;
+            const bool valid = k < k_hi;
+            uint32_t b = 0, e = 0, i = 0, nch = 1;
+            if (valid) { b = __ldg(q.ch_beg + k); e = __ldg(q.ch_beg + k + 1); i = __ldg(q.ch_row + k); nch = __ldg(q.ch_n + k); }
+            const bool is_long = valid && e - b > POOL_SHORT;
+            if (valid && !is_long) {
+                double acc = 0.0;
+                for (uint32_t j0 = b; j0 < e; j0 += 4) {
+                    uint32_t ci[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ci[u] = j0 + u < e ? __ldg(q.pt_cls + j0 + u) : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (ci[u] != 0xFFFFFFFFu) acc += ld_cg_f64(q.pool_r + ci[u]);
                 }
-                if (fin) {
-                    const uint32_t t = __ldg(q.dlist + i);
-                    const double beta = in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
-                    const double a_old = ld_cg_f64(p.X + t);            // written by whichever CTA finished the row last time
-                    const double a_new = beta * acc + __ldg(p.base + t);
-                    if (do_cmp) {
-                        const double gate = p.gate_old ? a_old : a_new;
-                        if (gate > p.cutoff) {
-                            const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
-                            best = bits > best ? bits : best;
-                        }
-                    }
-                    p.X[t] = a_new;
-                    if (VB) asum += a_new; else q.pool_beta[i] = a_new / __ldg(q.eff + t);
+                add_chunk(i, nch, acc);
+            }
+            unsigned longm = __ballot_sync(0xffffffffu, is_long);
+            while (longm) {
+                const int src = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const uint32_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
+                double acc = 0.0;
+                for (uint32_t j0 = bb; j0 < ee; j0 += 128) {
+                    uint32_t ci[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; ci[u] = j < ee ? __ldg(q.pt_cls + j) : 0xFFFFFFFFu; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (ci[u] != 0xFFFFFFFFu) acc += ld_cg_f64(q.pool_r + ci[u]);
                 }
+                acc = warp_sum(acc);
+                if ((int)lane == src) add_chunk(i, nch, acc);
             }
         }
         n = m;

@@ -5,8 +5,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 export SFB200_BENCH_CACHE=/dev/shm/sfb200_cache
 t0=$(date +%s)
-timeout 600 python -m pytest tests/test_gpu_map.py -m gpu -x -q --tb=short -p no:cacheprovider > $OUT/${TAG}_t_map.log 2>&1
-echo "map tests rc=$?  ($(( $(date +%s) - t0 )) s)"; tail -4 $OUT/${TAG}_t_map.log | cut -c1-300; grep -E "^E " $OUT/${TAG}_t_map.log | head -10 | cut -c1-300
+timeout 600 python -m pytest tests/test_gpu_em_gather.py -m gpu -x -q -k "hybrid or dense" --tb=short -p no:cacheprovider > $OUT/${TAG}_t_em.log 2>&1
+echo "map tests rc=$?  ($(( $(date +%s) - t0 )) s)"; tail -4 $OUT/${TAG}_t_em.log | cut -c1-300; grep -E "^E " $OUT/${TAG}_t_em.log | head -10 | cut -c1-300
 run() { # label, env...
   local label=$1; shift
   env "$@" SFB200_VERBOSE=1 timeout 300 python bench.py --steps 1 --no-cpu-baseline --structure paralog --reads 4000000 --no-realistic 2> $OUT/${TAG}_probe.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$label:', d['detail']['em_kernel'], round(d['detail']['em_loop_ms_per_step'],2), 'ms per 1000 iterations')"
