@@ -837,7 +837,6 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
             fprintf(stderr, "[sfb200] EM pool: %llu classes, %u transcripts, %llu entries, %u chunks, longest class %u, largest degree %u\n",
                     (unsigned long long)n_pc, nd, (unsigned long long)nz, n_ch, max_cls, max_row);
     }
-    }
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool, %u pool transcripts), largest CTA slice %llu bytes (limit %d) -> %s\n",
                 n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, P.n_dirty, (unsigned long long)P.max_cta_bytes, max_optin,

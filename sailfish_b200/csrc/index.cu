@@ -217,6 +217,7 @@ extern "C" int sfb200_index_build(sfb200_ctx* c, const char* seq, const uint64_t
     }
     uint64_t slots = 1024;
     while (slots < 4 * ix.n_kmers) slots <<= 1;      // load <= 25%: most lookups end in the first slot
+    if (slots * 16 > (32ull << 30) && (slots >> 1) * 2 >= 5 * ix.n_kmers) slots >>= 1;   // metatranscriptome scale: up to 40% rather than 64+ GB
     ix.table_slots = slots;
     IDX_CUDA(ix.table.reserve(slots));
     // presence filter: every m-mer window of the packed text (windows that span two transcripts set a few spare bits: harmless)
