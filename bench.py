@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -390,11 +390,13 @@ class GpuRun:
         t_e = time.perf_counter()
         nm = int(g["counters"][1])               # summed over ranks by map_finish when a communicator is set
         alphas, iters, _ = ctx.em_run(eff, nm, self.em_opts)
+        self.last_em_ms = ctx.last_em_loop_ms()          # of the optimizer run itself (bootstrap_run adds its replicates' loops)
         t_f = time.perf_counter()
         extra = {}
         if wl.n_boot:
             rows = ctx.bootstrap_run(eff, wl.n_boot, seed=7, opts=self.em_opts)
             extra["boot_mean_total"] = float(rows.sum(axis=1).mean())
+            extra["boot_loop_ms"] = ctx.last_em_loop_ms()
         t_g = time.perf_counter()
         if wl.n_gibbs:
             rows = ctx.gibbs_run(eff, alphas / alphas.sum(), nm, wl.n_gibbs, seed=7)
@@ -416,7 +418,7 @@ class GpuRun:
             e0.record(self.stream)
             for _ in range(steps):
                 out = self.step(host)
-                map_ms += ctx.last_map_kernel_ms(); em_ms += ctx.last_em_loop_ms()
+                map_ms += ctx.last_map_kernel_ms(); em_ms += self.last_em_ms
             e1.record(self.stream)
         torch.cuda.synchronize()
         if dist is not None:
@@ -485,7 +487,7 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
