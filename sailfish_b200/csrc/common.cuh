@@ -105,9 +105,12 @@ struct DevPartition {
     uint32_t dns_geom[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t dense_smem = 0;
     uint32_t dense_ns = 0;
+    bool dense_stream = false;          // counts / base / 1/effLen streamed from a per-CTA global block (em_dense.cuh)
+    uint32_t stream_ent = 0, stream_state = 0;
+    DevBuf<double> dns_f64;
     DevBuf<uint32_t> dns;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); pool_f64.release(); pool_done.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); pool_f64.release(); pool_done.release(); dns_f64.release(); }
 };
 struct DevClasses {
     DevPartition part;

@@ -966,13 +966,31 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl, bool 
         need = std::max<uint64_t>(need, dense_smem_need(h[DH_TILES], h[DH_ENT], ns, g.group, h[DH_NCOMP]));
     }
     need += 256;
-    const bool fits = (need + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1);
+    bool fits = (need + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1);
     std::memcpy(P.dns_geom, &g, sizeof(g));
+    P.dense_stream = false;
+    if (getenv("SFB200_EM_FORCE_STREAM")) fits = false;                 // tests: the streaming variant on class sets that would fit
+    if (ok && !fits && g.group == 2 && ns <= DN_MAX_SLOTS && !getenv("SFB200_EM_NO_STREAM")) {
+        // the slice of a CTA does not fit: keep only beta and alpha in shared memory, stream counts / base / 1/effLen from a global block
+        uint64_t need_s = 0, max_ent = 0, max_state = 0;
+        for (uint32_t i = 0; i < P.n_cta; ++i) {
+            const uint32_t* h = hdr.data() + (size_t)i * DH_WORDS;
+            need_s = std::max<uint64_t>(need_s, dense_smem_need_stream(h[DH_TILES], ns, g.group));
+            max_ent = std::max<uint64_t>(max_ent, (h[DH_ENT] + 1u) & ~1u);
+            max_state = std::max<uint64_t>(max_state, (uint64_t)ns * (((uint64_t)h[DH_TILES] << 5) / g.group));
+        }
+        need_s += 256;
+        if ((need_s + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1)) {
+            P.stream_ent = (uint32_t)max_ent; P.stream_state = (uint32_t)max_state;
+            SFB_CUDA(c, P.dns_f64.reserve((size_t)P.n_cta * (max_ent + 2 * max_state)));
+            P.dense_stream = true; fits = true; need = need_s;
+        }
+    }
     P.dense_smem = need; P.dense_ns = ns;
     P.dense_ok = ok && fits && ns <= DN_MAX_SLOTS && P.per_sm <= 2;
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM dense layout: %s (largest component %u transcripts, %u propagation rounds, %llu bytes of shared memory)\n",
-                P.dense_ok ? "one thread per component" : (ok ? "does not fit" : "components too large / not separable"), ns, rounds,
+                P.dense_ok ? (P.dense_stream ? "one thread per component, counts streamed from global memory" : "one thread per component") : (ok ? "does not fit" : "components too large / not separable"), ns, rounds,
                 (unsigned long long)need);
     return SFB200_OK;
 }
@@ -997,6 +1015,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         const DevPartition& P = c->cls.part;
         DenseParams q;
         q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
+        q.stream_buf = P.dns_f64.p; q.stream_ent = P.stream_ent; q.stream_state = P.stream_state; q.stream_stride = P.stream_ent + 2 * P.stream_state;
         q.n_dense = P.n_cta; q.n_dirty = P.n_dirty; q.n_pc = (uint32_t)P.n_pool; q.pool_c0 = (uint32_t)P.pool_cls[0];
         q.pc_start = P.dlist.p; q.pc_lid = q.pc_start + P.n_pool + 1; q.pt_start = q.pc_lid + P.pool_nz; q.pt_cls = q.pt_start + P.n_dirty + 1;
         q.dlist = q.pt_cls + P.pool_nz; q.pool_r = P.pool_f64.p; q.pool_beta = P.pool_f64.p + P.n_pool;
@@ -1011,11 +1030,13 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))
-#define SFB_DENSE_CASE(N) case N: fn = q.g.group == 4 ? SFB_DENSE_FN(N, 4) : q.g.group == 2 ? SFB_DENSE_FN(N, 2) : q.g.group == 0 ? SFB_DENSE_FN(N, 0) : SFB_DENSE_FN(N, 1); break;
+#define SFB_DENSE_FN_S(N) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, 2, true>) : reinterpret_cast<const void*>(&k_em_dense<false, N, 2, true>))
+#define SFB_DENSE_CASE(N) case N: fn = P.dense_stream ? SFB_DENSE_FN_S(N) : q.g.group == 4 ? SFB_DENSE_FN(N, 4) : q.g.group == 2 ? SFB_DENSE_FN(N, 2) : q.g.group == 0 ? SFB_DENSE_FN(N, 0) : SFB_DENSE_FN(N, 1); break;
         switch (P.dense_ns) { SFB_DENSE_CASE(2) SFB_DENSE_CASE(3) SFB_DENSE_CASE(4) SFB_DENSE_CASE(5) SFB_DENSE_CASE(6) SFB_DENSE_CASE(7) SFB_DENSE_CASE(8)
                               default: SFB_FAIL(c, SFB200_EINVAL, "dense EM: unexpected component size"); }
 #undef SFB_DENSE_CASE
 #undef SFB_DENSE_FN
+#undef SFB_DENSE_FN_S
         SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta + P.n_pool_cta), dim3(DENSE_THREADS), args, smem, s));
         c->launches++;

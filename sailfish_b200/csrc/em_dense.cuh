@@ -44,6 +44,10 @@ struct DenseParams {
     const uint32_t* regions;
     DenseGeom g;
     const double* eff;        // T clamped effective lengths
+    // streaming runs (the per-CTA working set does not fit in shared memory: metatranscriptome scale): class counts, base and 1/effLen
+    // live in a per-CTA global block (stream_buf + blockIdx.x * stream_stride: [cnt: stream_ent][base: stream_state][1/eff: stream_state])
+    // and the masks are read from the region; only beta and alpha stay in shared memory
+    double* stream_buf; uint32_t stream_stride, stream_ent, stream_state;
     // hybrid runs: CTAs [0, n_dense) own the small components, CTAs [n_dense, gridDim.x) run the pool loop over the classes of
     // everything else (components too large for a thread, classes that cross CTA ranges) -- an independent sub-problem
     uint32_t n_dense;
@@ -271,6 +275,10 @@ __device__ __forceinline__ double dense_tree_sum(const double* v) {
 }
 
 // shared memory a CTA of k_em_dense needs (mirrored on the host)
+__host__ __device__ inline uint64_t dense_smem_need_stream(uint32_t tiles, uint32_t ns, uint32_t group) {
+    const uint64_t ncomp_pad = ((uint64_t)tiles << 5) / (group ? group : 1);
+    return 2 * (uint64_t)ns * ncomp_pad * 8 + 2 * (uint64_t)((tiles + 3u) & ~3u) * 4;
+}
 __host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent, uint32_t ns, uint32_t group, uint32_t ncomp) {
     const uint64_t ncomp_pad = group ? ((uint64_t)tiles << 5) / group : (((uint64_t)ncomp + 31u) & ~31ull);
     return (uint64_t)((ent + 1u) & ~1u) * 8 + 4 * (uint64_t)ns * ncomp_pad * 8 + 2 * (uint64_t)((tiles + 3u) & ~3u) * 4 + (uint64_t)((ent + 15u) & ~15u) +
@@ -280,7 +288,9 @@ __host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent
 // G lanes share a component: each takes every G-th class of it (all G hold the component's beta), the accumulators are summed
 // over the group with shuffles, lane 0 of the group writes the component's new state.  The longest class list of a tile sets
 // the pace of its warp, and nothing else runs on that warp: G = 4 shortens that list fourfold for 10 shuffles per slot.
-template <bool VB, int NS, int G>
+// STREAM: the class counts, base and 1/effLen of the CTA are read from global memory every iteration (coalesced 256-byte rows; the whole
+// run's stream is a few tens of MB and stays in L2) instead of shared memory -- for class sets whose per-CTA slice does not fit.
+template <bool VB, int NS, int G, bool STREAM = false>
 __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p, const DenseParams q) {
     __shared__ unsigned long long sm_u[32];
     __shared__ double sm_d[32];
@@ -294,21 +304,23 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     const uint32_t* region = q.regions + (size_t)blockIdx.x * q.g.region_words;
     const uint32_t tiles = region[DH_TILES], ent = region[DH_ENT], nidle = region[DH_NIDLE];
     const uint32_t ncomp_pad = G ? (tiles << 5) / G : ((region[DH_NCOMP] + 31u) & ~31u);      // G == 0: balanced layout, lanes per component vary
-    double* s_cnt = reinterpret_cast<double*>(dyn_smem);                         // ent (even)
-    double* s_beta = s_cnt + ((ent + 1u) & ~1u);                                  // [NS][ncomp_pad] each
+    double* gbuf = STREAM ? q.stream_buf + (size_t)blockIdx.x * q.stream_stride : nullptr;
+    double* s_cnt = STREAM ? gbuf : reinterpret_cast<double*>(dyn_smem);         // ent (even)
+    double* s_beta = STREAM ? reinterpret_cast<double*>(dyn_smem) : s_cnt + ((ent + 1u) & ~1u);   // [NS][ncomp_pad] each
     double* s_alpha = s_beta + (size_t)NS * ncomp_pad;
-    double* s_base = s_alpha + (size_t)NS * ncomp_pad;
-    double* s_inveff = s_base + (size_t)NS * ncomp_pad;
-    uint32_t* s_toff = reinterpret_cast<uint32_t*>(s_inveff + (size_t)NS * ncomp_pad);
+    double* s_base = STREAM ? gbuf + q.stream_ent : s_alpha + (size_t)NS * ncomp_pad;
+    double* s_inveff = STREAM ? s_base + q.stream_state : s_base + (size_t)NS * ncomp_pad;
+    uint32_t* s_toff = reinterpret_cast<uint32_t*>(STREAM ? s_alpha + (size_t)NS * ncomp_pad : s_inveff + (size_t)NS * ncomp_pad);
     uint32_t* s_tlen = s_toff + ((tiles + 3u) & ~3u);
-    uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_tlen + ((tiles + 3u) & ~3u));  // ent (padded to 16)
-    uint32_t* s_lane = reinterpret_cast<uint32_t*>(s_mask + ((ent + 15u) & ~15u));   // G == 0: 32 * tiles lane descriptors
+    uint8_t* s_mask = STREAM ? const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(region + q.g.o_mask))
+                             : reinterpret_cast<uint8_t*>(s_tlen + ((tiles + 3u) & ~3u));          // ent (padded to 16)
+    uint32_t* s_lane = reinterpret_cast<uint32_t*>(s_mask + ((ent + 15u) & ~15u));   // G == 0: 32 * tiles lane descriptors (never with STREAM)
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&tma_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t b_t = ((tiles + 3u) & ~3u) * 4u, b_m = (ent + 15u) & ~15u, b_l = G ? 0u : tiles * 128u;
+    const uint32_t b_t = ((tiles + 3u) & ~3u) * 4u, b_m = STREAM ? 0u : ((ent + 15u) & ~15u), b_l = G ? 0u : tiles * 128u;
     const uint32_t tx_bytes = 2u * b_t + b_m + b_l;
     if (tx_bytes && threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&tma_bar)), "r"(tx_bytes) : "memory");

@@ -260,3 +260,28 @@ def test_hybrid_components_and_pool_loop(ctx, monkeypatch, loop_kind, T, seed):
     rc, want, it_o = O.bootstrap_em(T, rp, lab, samp, eff, O.EMOpts.default())
     assert rc == 0 and it == it_o
     close(a, want)
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+def test_dense_loop_streaming_variant(ctx, monkeypatch, loop_kind, vb):
+    """k_em_dense with the class counts, base and 1/effLen streamed from global memory (what runs when a CTA's slice does not fit in
+    shared memory: 1 M transcripts) reproduces the oracle and the shared-memory variant"""
+    if loop_kind != DENSE or os.environ.get("SFB200_EM_DENSE_GROUP") == "0":
+        pytest.skip("the streaming variant belongs to the dense kernel with two lanes per component")
+    T = 30000
+    rp, lab, cnt = synth.make_classes(T, 70000, seed=15)
+    eff = np.random.default_rng(2).uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    ctx.eq_import(T, rp, lab, cnt)
+    a0, it0, _ = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb))
+    assert ctx.last_em_kernel() == DENSE
+    monkeypatch.setenv("SFB200_EM_FORCE_STREAM", "1")
+    ctx.eq_import(T, rp, lab, cnt)                                        # the layout is rebuilt for the new setting
+    for kw in ({}, {"fixed_iters": 23}):
+        a, it, mrd = ctx.em_run(eff, nm, capi.EMOpts.default(use_vb=vb, **kw))
+        assert ctx.last_em_kernel() == DENSE
+        rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, **kw), n_threads=4)
+        assert rc == 0 and it == it_o
+        close(a, want)
+        if not kw:
+            close(a, a0, rtol=1e-9)
