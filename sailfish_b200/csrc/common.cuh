@@ -85,10 +85,9 @@ struct DevPartition {
     uint32_t n_pool_cta = 0;            // hybrid runs (em_dense.cuh): CTAs that run the pool loop, launched after the n_cta component CTAs
     uint32_t n_dirty = 0;               // pool transcripts
     DevBuf<uint32_t> dlist;             // the pool as its own problem: class CSR over pool-local ids, its transpose, local id -> transcript
-    DevBuf<double> pool_f64;            // r of the pool classes, beta of the pool transcripts
     uint64_t pool_nz = 0;               // label entries of the pool classes
-    uint64_t pool_ch_off = 0; uint32_t n_ch = 0;   // chunks of the transpose: offset inside dlist, count
-    DevBuf<unsigned int> pool_done;
+    uint32_t pool_ncomp = 0, pool_np = 0;
+    uint64_t pool_smem = 0, pool_o[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // shared memory of the largest pool CTA; offsets of the pool arrays inside dlist
     uint64_t max_cta_bytes = 0, max_cta_bytes_vb = 0, smem_limit = 0;
     int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;
@@ -110,7 +109,7 @@ struct DevPartition {
     DevBuf<double> dns_f64;
     DevBuf<uint32_t> dns;
     void release() { start.release(); len.release(); lab.release(); src.release(); bounds.release(); owner.release(); load.release();
-                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); pool_f64.release(); pool_done.release(); dns_f64.release(); }
+                     cnt.release(); w.release(); cnt_s.release(); tbl.release(); grp.release(); pre.release(); dirty.release(); gth.release(); dns.release(); dlist.release(); dns_f64.release(); }
 };
 struct DevClasses {
     DevPartition part;

@@ -780,67 +780,124 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
         hm.mark("part: dense layout");
         if (!marked) break;
     }
-    // the pool as its own small problem (hybrid runs, em_dense.cuh): pool-local transcript ids, the classes as CSR over them and the
-    // transpose.  The pool classes are the last group of the partition order, their label entries the tail of P.lab.
-    P.n_dirty = 0;
-    if (P.n_pool && P.dense_ok) {
-        const uint64_t c0 = P.pool_cls[0], n_pc = P.n_pool, e1 = nnzm;
-        std::vector<uint32_t> h_start(n_pc), h_lab;
-        SFB_CUDA(c, cudaMemcpyAsync(h_start.data(), P.start.p + c0, n_pc * 4, cudaMemcpyDeviceToHost, s));
-        SFB_CUDA(c, cudaStreamSynchronize(s));
-        const uint64_t e0 = h_start[0], nz = e1 - e0;
-        h_lab.resize(nz);
-        SFB_CUDA(c, cudaMemcpyAsync(h_lab.data(), P.lab.p + e0, nz * 4, cudaMemcpyDeviceToHost, s));
-        SFB_CUDA(c, cudaStreamSynchronize(s));
-        std::vector<uint32_t> ids(h_lab);
-        std::sort(ids.begin(), ids.end());
-        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-        const uint32_t nd = (uint32_t)ids.size();
-        // one upload: pc_start[n_pc + 1] | pc_lid[nz] | pt_start[nd + 1] | pt_cls[nz] | dlist[nd] | chunks of the transpose (below)
-        std::vector<uint32_t> buf((size_t)n_pc + 1 + nz + nd + 1 + nz + nd);
-        uint32_t* pc_start = buf.data(); uint32_t* pc_lid = pc_start + n_pc + 1; uint32_t* pt_start = pc_lid + nz; uint32_t* pt_cls = pt_start + nd + 1;
-        uint32_t* dl = pt_cls + nz;
-        for (uint64_t q = 0; q < n_pc; ++q) pc_start[q] = (uint32_t)(h_start[q] - e0);
-        pc_start[n_pc] = (uint32_t)nz;
-        std::fill(pt_start, pt_start + nd + 1, 0u);
-        for (uint64_t j = 0; j < nz; ++j) {
-            const uint32_t i = (uint32_t)(std::lower_bound(ids.begin(), ids.end(), h_lab[j]) - ids.begin());
-            pc_lid[j] = i; pt_start[i + 1]++;
-        }
-        for (uint32_t i = 0; i < nd; ++i) pt_start[i + 1] += pt_start[i];
-        { std::vector<uint32_t> cur(pt_start, pt_start + nd);
-          for (uint64_t q = 0; q < n_pc; ++q) for (uint32_t j = pc_start[q]; j < pc_start[q + 1]; ++j) pt_cls[cur[pc_lid[j]]++] = (uint32_t)q; }
-        std::copy(ids.begin(), ids.end(), dl);
-        uint32_t max_row = 0, max_cls = 0;
-        for (uint32_t i = 0; i < nd; ++i) max_row = std::max(max_row, pt_start[i + 1] - pt_start[i]);
-        for (uint64_t q = 0; q < n_pc; ++q) max_cls = std::max(max_cls, pc_start[q + 1] - pc_start[q]);
-        // the transpose in chunks of at most 256 entries (POOL_CHUNK, em_dense.cuh): ch_beg[n_ch + 1] | ch_row[n_ch] | ch_n[n_ch]
-        std::vector<uint32_t> ch_beg, ch_row, ch_n;
-        { const uint32_t* pts = buf.data() + n_pc + 1 + nz;
-          for (uint32_t i = 0; i < nd; ++i) {
-              const uint32_t b0 = pts[i], e0r = pts[i + 1], nchunks = std::max<uint32_t>(1, (e0r - b0 + 255) / 256);
-              for (uint32_t q = 0; q < nchunks; ++q) { ch_beg.push_back(b0 + q * 256); ch_row.push_back(i); ch_n.push_back(nchunks); }
-          } }
-        const uint32_t n_ch = (uint32_t)ch_row.size();
-        ch_beg.push_back((uint32_t)nz);
-        P.pool_ch_off = buf.size(); P.n_ch = n_ch;
-        buf.insert(buf.end(), ch_beg.begin(), ch_beg.end()); buf.insert(buf.end(), ch_row.begin(), ch_row.end()); buf.insert(buf.end(), ch_n.begin(), ch_n.end());
-        SFB_CUDA(c, P.pool_done.reserve(nd));
-        SFB_CUDA(c, cudaMemsetAsync(P.pool_done.p, 0, nd * 4ull, s));
-        SFB_CUDA(c, P.dlist.reserve(buf.size()));
-        SFB_CUDA(c, cudaMemcpyAsync(P.dlist.p, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, s));
-        SFB_CUDA(c, P.pool_f64.reserve(n_pc + 2ull * nd));
-        SFB_CUDA(c, cudaMemsetAsync(P.pool_f64.p + n_pc + nd, 0, nd * 8ull, s));
-        SFB_CUDA(c, cudaStreamSynchronize(s));
-        P.n_dirty = nd; P.pool_nz = nz;
-        if (getenv("SFB200_VERBOSE"))
-            fprintf(stderr, "[sfb200] EM pool: %llu classes, %u transcripts, %llu entries, %u chunks, longest class %u, largest degree %u\n",
-                    (unsigned long long)n_pc, nd, (unsigned long long)nz, n_ch, max_cls, max_row);
-    }
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM partition: %u CTAs, %llu classes (%llu in the pool, %u pool transcripts), largest CTA slice %llu bytes (limit %d) -> %s\n",
                 n_cta, (unsigned long long)Em, (unsigned long long)P.n_pool, P.n_dirty, (unsigned long long)P.max_cta_bytes, max_optin,
                 P.dense_ok ? (P.n_pool ? "component threads + pool loop" : "component threads") : P.usable ? "shared-memory loop" : "binned global loop");
+    return SFB200_OK;
+}
+
+// The pool of a hybrid run as work for CTAs of its own (em_dense.cuh: dense_pool_loop).  The pool classes are the last group of the
+// partition order, their label entries the tail of P.lab.  They fall apart into connected components; whole components are packed onto
+// `np` CTAs (largest first, onto the least loaded CTA), and every CTA gets its classes as CSR over CTA-local transcript ids plus the
+// transpose.  *ok = false (the caller keeps k_em_part) when a CTA's beta / alpha / r would not fit beside the component CTAs' shared memory.
+int build_pool(sfb200_ctx* c, uint32_t np, bool* ok, bool count_only = false) {
+    DevClasses& k = c->cls;
+    DevPartition& P = k.part;
+    cudaStream_t s = c->stream;
+    *ok = false;
+    const uint64_t c0 = P.pool_cls[0], n_pc = P.n_pool, e1 = k.nnzm;
+    if (!n_pc || !np) return SFB200_OK;
+    std::vector<uint32_t> h_start(n_pc), h_lab;
+    SFB_CUDA(c, cudaMemcpyAsync(h_start.data(), P.start.p + c0, n_pc * 4, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    const uint64_t e0 = h_start[0], nz = e1 - e0;
+    h_lab.resize(nz);
+    SFB_CUDA(c, cudaMemcpyAsync(h_lab.data(), P.lab.p + e0, nz * 4, cudaMemcpyDeviceToHost, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    auto row_b = [&](uint64_t q) { return (uint64_t)h_start[q] - e0; };
+    auto row_e = [&](uint64_t q) { return q + 1 < n_pc ? (uint64_t)h_start[q + 1] - e0 : nz; };
+    std::vector<uint32_t> ids(h_lab);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    const uint32_t nd = (uint32_t)ids.size();
+    std::vector<uint32_t> lid(nz);
+    for (uint64_t j = 0; j < nz; ++j) lid[j] = (uint32_t)(std::lower_bound(ids.begin(), ids.end(), h_lab[j]) - ids.begin());
+    // connected components (union-find over the pool's transcripts)
+    std::vector<uint32_t> parent(nd);
+    for (uint32_t i = 0; i < nd; ++i) parent[i] = i;
+    auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (uint64_t q = 0; q < n_pc; ++q) {
+        const uint32_t r0 = find(lid[row_b(q)]);
+        for (uint64_t j = row_b(q) + 1; j < row_e(q); ++j) { const uint32_t r = find(lid[j]); if (r != r0) parent[r] = r0; }
+    }
+    std::vector<uint32_t> comp_of(nd), comp_root;                      // dense component numbers
+    { std::vector<uint32_t> num(nd, 0xFFFFFFFFu);
+      for (uint32_t i = 0; i < nd; ++i) { const uint32_t r = find(i); if (num[r] == 0xFFFFFFFFu) { num[r] = (uint32_t)comp_root.size(); comp_root.push_back(r); } comp_of[i] = num[r]; } }
+    const uint32_t ncomp = (uint32_t)comp_root.size();
+    P.pool_ncomp = ncomp;
+    np = std::min(np, std::max<uint32_t>(1, ncomp));
+    P.pool_np = np;
+    if (count_only) return SFB200_OK;
+    std::vector<uint64_t> comp_ent(ncomp, 0), comp_nt(ncomp, 0), comp_nc(ncomp, 0);
+    for (uint32_t i = 0; i < nd; ++i) comp_nt[comp_of[i]]++;
+    for (uint64_t q = 0; q < n_pc; ++q) { const uint32_t cc = comp_of[lid[row_b(q)]]; comp_nc[cc]++; comp_ent[cc] += row_e(q) - row_b(q); }
+    // pack: largest component first onto the CTA with the fewest entries so far
+    std::vector<uint32_t> order(ncomp), cta_of(ncomp);
+    for (uint32_t i = 0; i < ncomp; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return comp_ent[a] != comp_ent[b] ? comp_ent[a] > comp_ent[b] : a < b; });
+    std::vector<uint64_t> load(np, 0), cta_nt(np, 0), cta_nc(np, 0);
+    for (uint32_t oi = 0; oi < ncomp; ++oi) {
+        const uint32_t cc = order[oi];
+        uint32_t best = 0;
+        for (uint32_t b = 1; b < np; ++b) if (load[b] < load[best]) best = b;
+        cta_of[cc] = best; load[best] += comp_ent[cc] + 1; cta_nt[best] += comp_nt[cc]; cta_nc[best] += comp_nc[cc];
+    }
+    uint64_t max_smem = 0, max_ent = 0;
+    for (uint32_t b = 0; b < np; ++b) { max_smem = std::max<uint64_t>(max_smem, (2 * cta_nt[b] + cta_nc[b]) * 8); max_ent = std::max<uint64_t>(max_ent, load[b]); }
+    max_smem += 256;
+    const uint64_t smem_2 = (P.smem_limit + 1024) / 2 - 2048;           // what a CTA may use with two CTAs per SM
+    if (getenv("SFB200_VERBOSE"))
+        fprintf(stderr, "[sfb200] EM pool: %llu classes, %u transcripts, %llu entries in %u components on %u CTAs (largest CTA: %llu entries, %llu bytes of shared memory)\n",
+                (unsigned long long)n_pc, nd, (unsigned long long)nz, ncomp, np, (unsigned long long)max_ent, (unsigned long long)max_smem);
+    if (max_smem > smem_2) return SFB200_OK;                            // a component too large for one CTA: not for this loop
+    // per-CTA numbering
+    std::vector<uint64_t> t_off(np + 1, 0), c_off(np + 1, 0), e_off(np + 1, 0);
+    for (uint32_t b = 0; b < np; ++b) { t_off[b + 1] = t_off[b] + cta_nt[b]; c_off[b + 1] = c_off[b] + cta_nc[b]; e_off[b + 1] = e_off[b] + (load[b] - 0); }
+    // load[] counted one extra per component; recompute the entry offsets from the rows themselves
+    std::vector<uint64_t> cta_ne(np, 0);
+    for (uint64_t q = 0; q < n_pc; ++q) cta_ne[cta_of[comp_of[lid[row_b(q)]]]] += row_e(q) - row_b(q);
+    for (uint32_t b = 0; b < np; ++b) e_off[b + 1] = e_off[b] + cta_ne[b];
+    std::vector<uint32_t> tloc(nd), tcur(np, 0), ccur(np, 0);
+    const uint64_t n_tbl = 8ull * np, sz_cs = n_pc + np, sz_ts = (uint64_t)nd + np;
+    std::vector<uint32_t> buf(n_tbl + nd + n_pc + sz_cs + nz + sz_ts + nz, 0);
+    uint32_t* tbl = buf.data(); uint32_t* tglob = tbl + n_tbl; uint32_t* cpart = tglob + nd; uint32_t* cs = cpart + n_pc; uint32_t* ce = cs + sz_cs;
+    uint32_t* ts = ce + nz; uint32_t* te = ts + sz_ts;
+    for (uint32_t i = 0; i < nd; ++i) { const uint32_t b = cta_of[comp_of[i]]; tloc[i] = tcur[b]; tglob[t_off[b] + tcur[b]++] = ids[i]; }
+    // classes in CTA order; their rows; degree counts for the transpose
+    std::vector<uint32_t> cloc(n_pc);
+    std::vector<uint64_t> ecur(np, 0);
+    for (uint64_t q = 0; q < n_pc; ++q) {
+        const uint32_t b = cta_of[comp_of[lid[row_b(q)]]];
+        const uint32_t lc = ccur[b]++;
+        cloc[q] = lc;
+        cpart[c_off[b] + lc] = (uint32_t)(c0 + q);
+        cs[c_off[b] + b + lc] = (uint32_t)ecur[b];
+        for (uint64_t j = row_b(q); j < row_e(q); ++j) { ce[e_off[b] + ecur[b]++] = tloc[lid[j]]; ts[t_off[b] + b + tloc[lid[j]] + 1]++; }
+        cs[c_off[b] + b + lc + 1] = (uint32_t)ecur[b];
+    }
+    for (uint32_t b = 0; b < np; ++b) {                                 // degree counts -> starts (relative to the CTA's first entry)
+        uint32_t* st = ts + t_off[b] + b;
+        st[0] = 0;
+        for (uint64_t i = 0; i < cta_nt[b]; ++i) st[i + 1] += st[i];
+    }
+    { std::vector<uint32_t> cur(sz_ts);
+      for (uint32_t b = 0; b < np; ++b) for (uint64_t i = 0; i <= cta_nt[b]; ++i) cur[t_off[b] + b + i] = ts[t_off[b] + b + i];
+      for (uint64_t q = 0; q < n_pc; ++q) {
+          const uint32_t b = cta_of[comp_of[lid[row_b(q)]]];
+          for (uint64_t j = row_b(q); j < row_e(q); ++j) te[e_off[b] + cur[t_off[b] + b + tloc[lid[j]]]++] = cloc[q];
+      } }
+    for (uint32_t b = 0; b < np; ++b) {
+        uint32_t* r = tbl + 8ull * b;
+        r[0] = (uint32_t)t_off[b]; r[1] = (uint32_t)cta_nt[b]; r[2] = (uint32_t)c_off[b]; r[3] = (uint32_t)cta_nc[b]; r[4] = (uint32_t)e_off[b]; r[5] = (uint32_t)cta_ne[b];
+    }
+    SFB_CUDA(c, P.dlist.reserve(buf.size()));
+    SFB_CUDA(c, cudaMemcpyAsync(P.dlist.p, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, s));
+    SFB_CUDA(c, cudaStreamSynchronize(s));
+    P.n_dirty = nd; P.pool_nz = nz; P.pool_smem = max_smem;
+    P.pool_o[0] = 0; P.pool_o[1] = n_tbl; P.pool_o[2] = n_tbl + nd; P.pool_o[3] = n_tbl + nd + n_pc; P.pool_o[4] = P.pool_o[3] + sz_cs;
+    P.pool_o[5] = P.pool_o[4] + nz; P.pool_o[6] = P.pool_o[5] + sz_ts;
+    *ok = true;
     return SFB200_OK;
 }
 
@@ -862,9 +919,13 @@ int build_partition(sfb200_ctx* c) {
         const double share = (double)P.pool_nnz / (double)std::max<uint64_t>(1, k.nnzm);
         uint32_t np = (uint32_t)std::ceil(1.5 * share * n_full);
         if (const char* e = getenv("SFB200_EM_POOL_CTAS")) np = (uint32_t)atoi(e);
-        np = std::max<uint32_t>(8, std::min<uint32_t>(np, n_full * 2 / 3));
+        np = std::max<uint32_t>(4, std::min<uint32_t>(np, n_full * 2 / 3));
+        { bool dummy; const int rc = build_pool(c, np, &dummy, true); if (rc) return rc; }       // how many components are there to hand out
+        np = std::min(np, std::max<uint32_t>(1, P.pool_ncomp));
         { const int rc = build_partition_n(c, n_full - np, per_sm); if (rc) return rc; }
-        if (P.dense_ok) P.n_pool_cta = P.n_pool ? np : 0;
+        bool pool_ok = P.dense_ok && P.n_pool == 0;
+        if (P.dense_ok && P.n_pool) { const int rc = build_pool(c, np, &pool_ok); if (rc) return rc; }
+        if (pool_ok) P.n_pool_cta = P.n_pool ? P.pool_np : 0;
         else { const int rc = build_partition_n(c, n_full, per_sm); if (rc) return rc; P.dense_ok = false; }   // keep the other loops' geometry
     }
     return SFB200_OK;
@@ -1016,17 +1077,11 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         DenseParams q;
         q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
         q.stream_buf = P.dns_f64.p; q.stream_ent = P.stream_ent; q.stream_state = P.stream_state; q.stream_stride = P.stream_ent + 2 * P.stream_state;
-        q.n_dense = P.n_cta; q.n_dirty = P.n_dirty; q.n_pc = (uint32_t)P.n_pool; q.pool_c0 = (uint32_t)P.pool_cls[0];
-        q.pc_start = P.dlist.p; q.pc_lid = q.pc_start + P.n_pool + 1; q.pt_start = q.pc_lid + P.pool_nz; q.pt_cls = q.pt_start + P.n_dirty + 1;
-        q.dlist = q.pt_cls + P.pool_nz; q.pool_r = P.pool_f64.p; q.pool_beta = P.pool_f64.p + P.n_pool;
-        q.n_ch = P.n_ch; q.ch_beg = P.dlist.p + P.pool_ch_off; q.ch_row = q.ch_beg + P.n_ch + 1; q.ch_n = q.ch_row + P.n_ch;
-        q.pool_acc = P.pool_f64.p + P.n_pool + P.n_dirty; q.pool_done = P.pool_done.p;
-        // the pool CTAs keep the pool's beta vector in shared memory when that does not cost the component CTAs their second CTA per SM
-        const size_t pool_smem = P.n_pool_cta ? (size_t)P.n_dirty * 8 + 256 : 0;
-        const size_t smem_2 = (size_t)(P.smem_limit + 1024) / 2 - 2048;
-        q.beta_in_smem = (P.n_pool_cta && pool_smem <= std::max<size_t>(smem_2, (size_t)P.dense_smem)) ? 1u : 0u;
-        if (getenv("SFB200_EM_POOL_GLOBAL")) q.beta_in_smem = 0u;
-        const size_t smem = q.beta_in_smem ? std::max<size_t>((size_t)P.dense_smem, pool_smem) : (size_t)P.dense_smem;
+        q.n_dense = P.n_cta;
+        q.pool_tbl = P.dlist.p + P.pool_o[0]; q.pool_tglob = P.dlist.p + P.pool_o[1]; q.pool_cpart = P.dlist.p + P.pool_o[2];
+        q.pool_cs = P.dlist.p + P.pool_o[3]; q.pool_ce = P.dlist.p + P.pool_o[4]; q.pool_ts = P.dlist.p + P.pool_o[5]; q.pool_te = P.dlist.p + P.pool_o[6];
+        // every CTA of the launch gets the same amount of shared memory: what the component CTAs or the pool CTAs need, whichever is more
+        const size_t smem = P.n_pool_cta ? std::max<size_t>((size_t)P.dense_smem, (size_t)P.pool_smem) : (size_t)P.dense_smem;
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))

@@ -48,138 +48,106 @@ struct DenseParams {
     // live in a per-CTA global block (stream_buf + blockIdx.x * stream_stride: [cnt: stream_ent][base: stream_state][1/eff: stream_state])
     // and the masks are read from the region; only beta and alpha stay in shared memory
     double* stream_buf; uint32_t stream_stride, stream_ent, stream_state;
-    // hybrid runs: CTAs [0, n_dense) own the small components, CTAs [n_dense, gridDim.x) run the pool loop over the classes of
-    // everything else (components too large for a thread, classes that cross CTA ranges) -- an independent sub-problem
+    // hybrid runs: CTAs [0, n_dense) own the small components, CTAs [n_dense, gridDim.x) the connected components of everything else
+    // (components too large for a thread, classes that cross CTA ranges), whole components per CTA
     uint32_t n_dense;
-    uint32_t n_dirty;         // pool transcripts
-    uint32_t n_pc;            // pool classes
-    uint32_t pool_c0;         // position of the first pool class in the partition-ordered arrays (p.cnt)
-    uint32_t beta_in_smem;    // the pool's beta vector fits in the CTA's shared memory
-    const uint32_t* pc_start; const uint32_t* pc_lid;     // pool classes x pool-local transcript ids (CSR)
-    const uint32_t* pt_start; const uint32_t* pt_cls;     // the transpose: pool transcripts x pool-local class ids
-    const uint32_t* dlist;    // pool-local id -> transcript
-    // the transpose cut into chunks of at most POOL_CHUNK entries (a transcript of a repeat family sits in thousands of classes: its
-    // row is summed by many warps): chunk k = entries [ch_beg[k], ch_beg[k+1]) of row ch_row[k], which has ch_n[k] chunks
-    uint32_t n_ch;
-    const uint32_t* ch_beg; const uint32_t* ch_row; const uint32_t* ch_n;
-    double* pool_r;           // n_pc: count / S of the current iteration
-    double* pool_beta;        // n_dirty: beta of the current iteration
-    double* pool_acc;         // n_dirty: partial row sums of multi-chunk rows (zero between iterations)
-    unsigned int* pool_done;  // n_dirty: chunks of the row summed so far (zero between iterations)
+    const uint32_t* pool_tbl;     // per pool CTA: {first transcript, transcripts, first class, classes, first entry, entries, -, -}
+    const uint32_t* pool_tglob;   // pool transcript (in CTA order) -> transcript id
+    const uint32_t* pool_cpart;   // pool class (in CTA order) -> position in the partition-ordered arrays (p.cnt)
+    const uint32_t* pool_cs; const uint32_t* pool_ce;     // per CTA: class rows (n_c + 1 starts, relative to the CTA's first entry) x CTA-local transcript ids
+    const uint32_t* pool_ts; const uint32_t* pool_te;     // per CTA: the transpose (n_t + 1 starts) x CTA-local class ids
 };
-constexpr uint32_t POOL_CHUNK = 256, POOL_SHORT = 16;
+constexpr uint32_t POOL_SHORT = 16;
 
-// barrier among the pool CTAs only (same protocol as grid_barrier, its own counter words)
-__device__ __forceinline__ void pool_barrier(unsigned long long* ctl, unsigned int n_cta, unsigned long long& gen) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        gen += 1;
-        __threadfence();
-        const unsigned long long prev = atomicAdd(&ctl[CTL_PBAR_COUNT], 1ULL);
-        if (prev + 1 == gen * n_cta) st_release_u64(&ctl[CTL_PBAR_GEN], gen);
-        else while (ld_acquire_u64(&ctl[CTL_PBAR_GEN]) < gen) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-// first row whose first entry is at or beyond `target` (rows cut by entries, so that long rows do not pile up on one CTA)
-__device__ __forceinline__ uint32_t pool_row_at(const uint32_t* __restrict__ start, uint32_t n_rows, uint64_t target) {
-    uint32_t lo = 0, hi = n_rows;
-    while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(start + mid) < target) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-
-// The pool loop of a hybrid run: EMUpdate_ / VBEMUpdate_ over the pool classes in the GATHER form of k_em_gather (em_gather.cuh:
-// beta_i = theta_i / effLen_i, S_c = sum of beta over the class, r_c = count_c / S_c, alpha'_i = base_i + beta_i * sum of r over the
-// classes of i -- no atomics: a repeat family's transcripts sit in thousands of classes, and scattered adds to one address serialise),
-// one WARP per row in both steps (rows are as long as 200 entries for classes, thousands for transcripts), on the pool CTAs only.
-// Every pool CTA keeps the whole beta vector of the pool in shared memory when it fits.  The pool shares no transcript with the
-// components the other CTAs own, so the two groups meet only where the reference needs a global quantity: the stopping rule and VBEM's
-// digamma(sum alpha) -- at the same iterations, through the same grid barrier, as k_em_dense's own loop below (the break logic is a
-// copy of it).  An EM iteration costs the pool two barriers among its own CTAs (r complete, beta complete).
+// The pool CTAs of a hybrid run.  The pool -- large components, classes that cross CTA ranges -- shares no transcript with the
+// components the other CTAs own, and it falls apart into connected components itself (a paralog family, the hosts of a repeat
+// element): the host packs WHOLE components onto CTAs (em.cu: build_pool), so a pool CTA, like a component CTA, iterates without any
+// other CTA: beta, alpha and r of its components live in its shared memory, the two steps are separated by __syncthreads only, and
+// the row indices come from global memory through L1 (nothing invalidates it: no fences inside an iteration).  EMUpdate_ /
+// VBEMUpdate_ in the gather form of em_gather.cuh (no atomics); a thread per row for rows of up to POOL_SHORT entries, the warp for
+// longer ones.  The grid barrier appears where k_em_dense's own loop has it (the break logic is a copy of that loop's).
 template <bool VB>
-__device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParams& q, double* s_beta) {
+__device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParams& q, double* smem) {
     __shared__ unsigned long long pl_u[32];
     __shared__ double pl_d[32];
-    const unsigned nblocks = gridDim.x, NP = nblocks - q.n_dense, pi = blockIdx.x - q.n_dense;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    unsigned long long gen = 0, gen_p = 0;
-    const uint32_t nd = q.n_dirty, npc = q.n_pc;
-    const uint64_t nnz = __ldg(q.pc_start + npc);
-    const uint32_t c_lo = pool_row_at(q.pc_start, npc, nnz * pi / NP), c_hi = pi + 1 == NP ? npc : pool_row_at(q.pc_start, npc, nnz * (pi + 1ULL) / NP);
-    // rows by index for the per-transcript passes (initial beta, VBEM's expTheta), chunks by entries for the M-step
-    const uint32_t t_lo = (uint32_t)((uint64_t)nd * pi / NP), t_hi = (uint32_t)((uint64_t)nd * (pi + 1ULL) / NP);
-    const uint32_t k_lo = pool_row_at(q.ch_beg, q.n_ch, nnz * pi / NP), k_hi = pi + 1 == NP ? q.n_ch : pool_row_at(q.ch_beg, q.n_ch, nnz * (pi + 1ULL) / NP);
+    const unsigned nblocks = gridDim.x, pi = blockIdx.x - q.n_dense;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long gen = 0;
+    const uint32_t* tb = q.pool_tbl + 8u * pi;
+    const uint32_t t_off = tb[0], n_t = tb[1], c_off = tb[2], n_c = tb[3], e_off = tb[4];
+    const uint32_t* tglob = q.pool_tglob + t_off;
+    const uint32_t* cpart = q.pool_cpart + c_off;
+    const uint32_t* cs = q.pool_cs + c_off + pi;
+    const uint32_t* ce = q.pool_ce + e_off;
+    const uint32_t* ts = q.pool_ts + t_off + pi;
+    const uint32_t* te = q.pool_te + e_off;
+    double* s_beta = smem;
+    double* s_alpha = s_beta + n_t;
+    double* s_r = s_alpha + n_t;
     const bool fixed = p.fixed_iters > 0;
-    const double* cnt = p.cnt + q.pool_c0;
-    const bool in_smem = q.beta_in_smem != 0;
-    // beta_0 of the whole pool, computed by every CTA for itself
     {
         const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
-        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-            const uint32_t t = __ldg(q.dlist + i);
+        for (uint32_t i = threadIdx.x; i < n_t; i += blockDim.x) {
+            const uint32_t t = __ldg(tglob + i);
             const double a = p.X[t];
             const double th = VB ? ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) : a;
-            const double b = th / __ldg(q.eff + t);
-            if (in_smem) s_beta[i] = b;
-            else if (i >= t_lo && i < t_hi) q.pool_beta[i] = b;        // the global copy: every CTA writes its own rows
+            s_alpha[i] = a; s_beta[i] = th / __ldg(q.eff + t);
         }
-        if (!in_smem) pool_barrier(p.ctl, NP, gen_p); else __syncthreads();
+        __syncthreads();
     }
+    // sum of vals[idx[j]] over the row [b, e): by this thread (short rows) ...
+    auto row_sum_thread = [&](const uint32_t* idx, const double* vals, uint32_t b, uint32_t e) {
+        double s = 0.0;
+        for (uint32_t j0 = b; j0 < e; j0 += 4) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = j0 + u < e ? __ldg(idx + j0 + u) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (v[u] != 0xFFFFFFFFu) s += vals[v[u]];
+        }
+        return s;
+    };
+    // ... or by the whole warp
+    auto row_sum_warp = [&](const uint32_t* idx, const double* vals, uint32_t b, uint32_t e) {
+        double s = 0.0;
+        for (uint32_t j0 = b; j0 < e; j0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; v[u] = j < e ? __ldg(idx + j) : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (v[u] != 0xFFFFFFFFu) s += vals[v[u]];
+        }
+        return warp_sum(s);
+    };
     uint32_t n = 0;
     for (;;) {
         if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
         const uint32_t m = n + 1;
         const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
-        // Rows are short (a handful of entries) with few long ones.  A row is a chain of dependent L2 round trips (start -> index ->
-        // value -> result), so a CTA wants one row per THREAD in flight, not one per warp: a thread sums a row of up to POOL_SHORT
-        // entries by itself (four gathers in flight); longer rows of the same batch are then summed by the whole warp, one after another.
-        // ---- E-step: r_c of this CTA's classes
-        for (uint32_t base = c_lo; base < c_hi; base += blockDim.x) {
+        // ---- E-step: r_c = count_c / sum of beta over the class
+        for (uint32_t base = 0; base < n_c; base += blockDim.x) {
             const uint32_t c = base + threadIdx.x;
-            const bool valid = c < c_hi;
+            const bool valid = c < n_c;
             uint32_t b = 0, e = 0;
-            if (valid) { b = __ldg(q.pc_start + c); e = __ldg(q.pc_start + c + 1); }
+            if (valid) { b = __ldg(cs + c); e = __ldg(cs + c + 1); }
             const bool is_long = valid && e - b > POOL_SHORT;
-            if (valid && !is_long) {
-                double S = 0.0;
-                for (uint32_t j0 = b; j0 < e; j0 += 4) {
-                    uint32_t li[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) li[u] = j0 + u < e ? __ldg(q.pc_lid + j0 + u) : 0xFFFFFFFFu;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (li[u] != 0xFFFFFFFFu) S += in_smem ? s_beta[li[u]] : ld_cg_f64(q.pool_beta + li[u]);
-                }
-                q.pool_r[c] = em_ratio(cnt[c], S);
-            }
+            if (valid && !is_long) s_r[c] = em_ratio(p.cnt[__ldg(cpart + c)], row_sum_thread(ce, s_beta, b, e));
             unsigned longm = __ballot_sync(0xffffffffu, is_long);
             while (longm) {
                 const int src = __ffs(longm) - 1;
                 longm &= longm - 1;
-                const uint32_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
-                double S = 0.0;
-                for (uint32_t j0 = bb; j0 < ee; j0 += 128) {
-                    uint32_t li[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; li[u] = j < ee ? __ldg(q.pc_lid + j) : 0xFFFFFFFFu; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (li[u] != 0xFFFFFFFFu) S += in_smem ? s_beta[li[u]] : ld_cg_f64(q.pool_beta + li[u]);
-                }
-                S = warp_sum(S);
-                if ((int)lane == src) q.pool_r[c] = em_ratio(cnt[c], S);
+                const double S = row_sum_warp(ce, s_beta, __shfl_sync(0xffffffffu, b, src), __shfl_sync(0xffffffffu, e, src));
+                if ((int)lane == src) s_r[c] = em_ratio(p.cnt[__ldg(cpart + c)], S);
             }
         }
-        pool_barrier(p.ctl, NP, gen_p);
-        // ---- M-step of this CTA's transcripts + the convergence test
+        __syncthreads();
+        // ---- M-step: alpha'_i = base_i + beta_i * sum of r over the classes of i; the convergence test; the next beta
         unsigned long long best = 0ULL;
         double asum = 0.0;
-        // a row's sum is complete: new alpha, the convergence test, new beta
         auto finish_row = [&](uint32_t i, double acc) {
-            const uint32_t t = __ldg(q.dlist + i);
-            const double beta = in_smem ? s_beta[i] : ld_cg_f64(q.pool_beta + i);
-            const double a_old = ld_cg_f64(p.X + t);                    // written by whichever CTA finished the row last time
-            const double a_new = beta * acc + __ldg(p.base + t);
+            const uint32_t t = __ldg(tglob + i);
+            const double a_old = s_alpha[i];
+            const double a_new = s_beta[i] * acc + __ldg(p.base + t);
             if (do_cmp) {
                 const double gate = p.gate_old ? a_old : a_new;
                 if (gate > p.cutoff) {
@@ -187,54 +155,25 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
                     best = bits > best ? bits : best;
                 }
             }
-            p.X[t] = a_new;
-            if (VB) asum += a_new; else q.pool_beta[i] = a_new / __ldg(q.eff + t);
+            s_alpha[i] = a_new;
+            if (VB) asum += a_new; else s_beta[i] = a_new / __ldg(q.eff + t);
         };
-        // a chunk's partial sum: rows of one chunk finish at once, the warp / thread that adds a row's last chunk finishes the row
-        auto add_chunk = [&](uint32_t i, uint32_t nch, double acc) {
-            if (nch > 1) {
-                atomicAdd(q.pool_acc + i, acc);
-                __threadfence();
-                if (atomicAdd(q.pool_done + i, 1u) + 1u != nch) return;
-                __threadfence();
-                acc = ld_cg_f64(q.pool_acc + i); q.pool_acc[i] = 0.0; q.pool_done[i] = 0u;
-            }
-            finish_row(i, acc);
-        };
-        for (uint32_t base = k_lo; base < k_hi; base += blockDim.x) {
-            const uint32_t k = base + threadIdx.x;
-            const bool valid = k < k_hi;
-            uint32_t b = 0, e = 0, i = 0, nch = 1;
-            if (valid) { b = __ldg(q.ch_beg + k); e = __ldg(q.ch_beg + k + 1); i = __ldg(q.ch_row + k); nch = __ldg(q.ch_n + k); }
+        for (uint32_t base = 0; base < n_t; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            const bool valid = i < n_t;
+            uint32_t b = 0, e = 0;
+            if (valid) { b = __ldg(ts + i); e = __ldg(ts + i + 1); }
             const bool is_long = valid && e - b > POOL_SHORT;
-            if (valid && !is_long) {
-                double acc = 0.0;
-                for (uint32_t j0 = b; j0 < e; j0 += 4) {
-                    uint32_t ci[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) ci[u] = j0 + u < e ? __ldg(q.pt_cls + j0 + u) : 0xFFFFFFFFu;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (ci[u] != 0xFFFFFFFFu) acc += ld_cg_f64(q.pool_r + ci[u]);
-                }
-                add_chunk(i, nch, acc);
-            }
+            if (valid && !is_long) finish_row(i, row_sum_thread(te, s_r, b, e));
             unsigned longm = __ballot_sync(0xffffffffu, is_long);
             while (longm) {
                 const int src = __ffs(longm) - 1;
                 longm &= longm - 1;
-                const uint32_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
-                double acc = 0.0;
-                for (uint32_t j0 = bb; j0 < ee; j0 += 128) {
-                    uint32_t ci[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; ci[u] = j < ee ? __ldg(q.pt_cls + j) : 0xFFFFFFFFu; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (ci[u] != 0xFFFFFFFFu) acc += ld_cg_f64(q.pool_r + ci[u]);
-                }
-                acc = warp_sum(acc);
-                if ((int)lane == src) add_chunk(i, nch, acc);
+                const double acc = row_sum_warp(te, s_r, __shfl_sync(0xffffffffu, b, src), __shfl_sync(0xffffffffu, e, src));
+                if ((int)lane == src) finish_row(i, acc);
             }
         }
+        __syncthreads();
         n = m;
         if (VB || do_cmp) {
             unsigned long long* slot = p.ctl + CTL_MAXREL + (m & 3u);
@@ -249,20 +188,16 @@ __device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParam
             }
             if (VB) {
                 const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
-                for (uint32_t i = t_lo + threadIdx.x; i < t_hi; i += blockDim.x) {
-                    const uint32_t t = __ldg(q.dlist + i);
-                    const double a = ld_cg_f64(p.X + t);                // the grid barrier above ordered the M-step's writes
-                    q.pool_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) / __ldg(q.eff + t);
+                for (uint32_t i = threadIdx.x; i < n_t; i += blockDim.x) {
+                    const double a = s_alpha[i];
+                    s_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) / __ldg(q.eff + __ldg(tglob + i));
                 }
+                __syncthreads();
             }
         }
-        pool_barrier(p.ctl, NP, gen_p);                                // beta of every pool transcript is in place
-        if (in_smem) {
-#pragma unroll 8
-            for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) s_beta[i] = ld_cg_f64(q.pool_beta + i);
-            __syncthreads();
-        }
     }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_t; i += blockDim.x) p.X[__ldg(tglob + i)] = s_alpha[i];
 }
 
 constexpr int DENSE_THREADS = 256;

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <ctime>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -390,17 +392,23 @@ extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint3
     // MultinomialSampler takes n as uint32_t (:15): the reference wraps above 2^32 fragments; we keep 64 bits
     int rc = SFB200_OK;
     double loop_ms = 0.0;
+    const bool timing = getenv("SFB200_TIMING") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t_mark = now_ms();
     for (uint32_t b = 0; b < n_boot && rc == SFB200_OK; ++b) {
         const uint64_t sd = seed + 0x9E3779B97F4A7C15ULL * (b + 1);
         for (size_t l = tr.n.size() - 1; l >= 2; --l)
             k_level_split<double><<<gridn(tr.n[l], 64), 64, 0, s>>>(tr.sums[l - 1], tr.n[l - 1], tr.share[l], tr.n[l], sd, (uint32_t)l, tr.share[l - 1]);
         k_level_split<unsigned long long><<<gridn(tr.n[1], 64), 64, 0, s>>>(d_cnt.p, E, tr.share[1], tr.n[1], sd, 1u, d_samp.p);
         c->launches += tr.n.size() - 1;
+        if (timing) { cudaStreamSynchronize(s); const double t1 = now_ms(); fprintf(stderr, "[sfb200-timing] bootstrap %u: resampling %.3f ms\n", b, t1 - t_mark); t_mark = t1; }
         uint32_t iters = 0;
         rc = sfb_bootstrap_em_device(c, eff_lens, n_txp, d_samp.p, totalCount, opts, alphas.data(), &iters);
+        if (timing) { const double t1 = now_ms(); fprintf(stderr, "[sfb200-timing] bootstrap %u: em %.3f ms (loop %.3f ms, %u iterations)\n", b, t1 - t_mark, c->last_em_ms, iters); t_mark = t1; }
         c->eff_resident = true;                             // the same lengths for every replicate of this run
         loop_ms += c->last_em_ms;
         if (rc == SFB200_OK && cb && cb(user, alphas.data(), n_txp) != 0) { c->err = "bootstrap row callback failed"; rc = SFB200_ECALLBACK; }
+        if (timing) { const double t1 = now_ms(); fprintf(stderr, "[sfb200-timing] bootstrap %u: callback %.3f ms\n", b, t1 - t_mark); t_mark = t1; }
     }
     c->eff_resident = false;
     c->last_em_ms = loop_ms;
