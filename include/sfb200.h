@@ -70,6 +70,13 @@ int sfb200_index_export(sfb200_ctx* ctx, uint64_t* words, uint32_t* sa_pos, uint
 /* the k-mer table: table_slots entries of {k-mer (u64), first entry (u32), entry count (u32)}; empty = all-ones k-mer;
  * slot = 2 * (mix(k-mer) & (table_slots/2 - 1)), linear probing (mix = sfb_kmer_mix, sailfish_b200/csrc/common.cuh) */
 int sfb200_index_export_table(sfb200_ctx* ctx, void* table16);
+/* The device index as ONE file (what SailfishIndex::load reads from the index directory, include/SailfishIndex.hpp:80-144: the
+ * RapMap structures ready to use): a header (magic, format version, k, sizes) followed by the arrays as they lie in HBM -- packed
+ * text, transcript starts / lengths, suffix entries, k-mer table, m-mer bitmap.  save streams HBM -> file in 64 MB pieces, load file
+ * -> HBM; a file written for another format version or a truncated one is refused (SFB200_EINVAL).  Building the index from the
+ * sequences takes 0.1 - 0.6 s on a B200 (200 k - 1 M transcripts), so the drivers rebuild by default and use the file on request. */
+int sfb200_index_save(sfb200_ctx* ctx, const char* path);
+int sfb200_index_load(sfb200_ctx* ctx, const char* path);
 
 /* ---- mapping + equivalence classes ---------------------------------------------------------------------------
  * Replaces processReadsQuasi<IndexT> (src/SailfishQuantify.cpp:105-452 paired, :458-646 single) together with the

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sfb200_index_stats": (C.c_int, [C.c_void_p, u64p]),
     "sfb200_index_export": (C.c_int, [C.c_void_p, u64p, u32p, u32p]),
     "sfb200_index_export_table": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sfb200_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "sfb200_index_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sfb200_last_map_kernel_ms": (C.c_double, [C.c_void_p]),
     "sfb200_map_clipped": (C.c_uint64, [C.c_void_p]),
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
@@ -214,6 +216,13 @@ class Context:
                                             len(txp_len), k))
         self.n_txp = len(txp_len)
         self.txp_len = txp_len
+        return self.index_stats()
+
+    def index_save(self, path):
+        self._chk(self.L.sfb200_index_save(self.h, os.fsencode(path)))
+
+    def index_load(self, path):
+        self._chk(self.L.sfb200_index_load(self.h, os.fsencode(path)))
         return self.index_stats()
 
     def index_stats(self):

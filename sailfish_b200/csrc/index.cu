@@ -279,3 +279,91 @@ extern "C" int sfb200_index_export_table(sfb200_ctx* c, void* table16) {
     SFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SFB200_OK;
 }
+
+// ---- the index as a file ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct IndexFileHeader {
+    char magic[8];                 // "SFB200IX"
+    uint32_t version, k;
+    uint32_t n_txp, mf_m, max_bucket, pad_;
+    uint64_t text_len, n_sa, n_kmers, table_slots;
+    uint64_t bytes[7];             // words, txp_start, txp_len, txp_end, sa, table, mfilter
+};
+constexpr uint32_t INDEX_FILE_VERSION = 2;       // 2: 16-byte suffix entries, m-mer bitmap
+constexpr size_t IO_PIECE = 64u << 20;
+
+int stream_out(sfb200_ctx* c, FILE* f, const void* d_ptr, uint64_t bytes, std::vector<char>& buf) {
+    for (uint64_t at = 0; at < bytes; at += IO_PIECE) {
+        const size_t n = (size_t)std::min<uint64_t>(IO_PIECE, bytes - at);
+        SFB_CUDA(c, cudaMemcpyAsync(buf.data(), static_cast<const char*>(d_ptr) + at, n, cudaMemcpyDeviceToHost, c->stream));
+        SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (fwrite(buf.data(), 1, n, f) != n) SFB_FAIL(c, SFB200_EINVAL, "index_save: write failed");
+    }
+    return SFB200_OK;
+}
+int stream_in(sfb200_ctx* c, FILE* f, void* d_ptr, uint64_t bytes, std::vector<char>& buf) {
+    for (uint64_t at = 0; at < bytes; at += IO_PIECE) {
+        const size_t n = (size_t)std::min<uint64_t>(IO_PIECE, bytes - at);
+        if (fread(buf.data(), 1, n, f) != n) SFB_FAIL(c, SFB200_EINVAL, "index_load: the file is truncated");
+        SFB_CUDA(c, cudaMemcpyAsync(static_cast<char*>(d_ptr) + at, buf.data(), n, cudaMemcpyHostToDevice, c->stream));
+        SFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return SFB200_OK;
+}
+}  // namespace
+
+extern "C" int sfb200_index_save(sfb200_ctx* c, const char* path) {
+    if (!c || !path) return SFB200_EINVAL;
+    DevIndex& ix = c->index;
+    if (!ix.ready) SFB_FAIL(c, SFB200_EINVAL, "index_save: no index");
+    cudaSetDevice(c->device);
+    IndexFileHeader h;
+    std::memset(&h, 0, sizeof(h));
+    std::memcpy(h.magic, "SFB200IX", 8);
+    h.version = INDEX_FILE_VERSION; h.k = (uint32_t)ix.k; h.n_txp = ix.n_txp; h.mf_m = (uint32_t)ix.mf_m; h.max_bucket = ix.max_bucket;
+    h.text_len = ix.text_len; h.n_sa = ix.n_sa; h.n_kmers = ix.n_kmers; h.table_slots = ix.table_slots;
+    const void* ptr[7] = {ix.words.p, ix.txp_start.p, ix.txp_len.p, ix.txp_end.p, ix.sa.p, ix.table.p, ix.mfilter.p};
+    h.bytes[0] = (ix.text_len / 32 + 2) * 8; h.bytes[1] = (ix.n_txp + 1ull) * 8; h.bytes[2] = ix.n_txp * 4ull; h.bytes[3] = ix.n_txp * 8ull;
+    h.bytes[4] = ix.n_sa * 16; h.bytes[5] = ix.table_slots * 16; h.bytes[6] = sfb_mfilter_words(ix.mf_m) * 4;
+    FILE* f = fopen(path, "wb");
+    if (!f) SFB_FAIL(c, SFB200_EINVAL, std::string("index_save: cannot open ") + path);
+    std::vector<char> buf(IO_PIECE);
+    int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? SFB200_OK : SFB200_EINVAL;
+    for (int i = 0; i < 7 && rc == SFB200_OK; ++i) rc = stream_out(c, f, ptr[i], h.bytes[i], buf);
+    if (fclose(f) != 0 && rc == SFB200_OK) { c->err = "index_save: close failed"; rc = SFB200_EINVAL; }
+    return rc;
+}
+
+extern "C" int sfb200_index_load(sfb200_ctx* c, const char* path) {
+    if (!c || !path) return SFB200_EINVAL;
+    cudaSetDevice(c->device);
+    DevIndex& ix = c->index;
+    ix.ready = false;
+    FILE* f = fopen(path, "rb");
+    if (!f) SFB_FAIL(c, SFB200_EINVAL, std::string("index_load: cannot open ") + path);
+    IndexFileHeader h;
+    auto fail = [&](const char* msg) { fclose(f); c->err = msg; return SFB200_EINVAL; };
+    if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "SFB200IX", 8) != 0) return fail("index_load: not an sfb200 index file");
+    if (h.version != INDEX_FILE_VERSION) return fail("index_load: the file was written by another format version (rebuild the index)");
+    if (h.k < 1 || h.k > 31 || h.n_txp == 0 || h.bytes[0] != (h.text_len / 32 + 2) * 8 || h.bytes[4] != h.n_sa * 16 ||
+        h.bytes[5] != h.table_slots * 16 || (h.table_slots & (h.table_slots - 1)) != 0 || h.bytes[6] != sfb_mfilter_words((int)h.mf_m) * 4)
+        return fail("index_load: inconsistent header");
+    ix.k = (int)h.k; ix.n_txp = h.n_txp; ix.mf_m = (int)h.mf_m; ix.max_bucket = h.max_bucket;
+    ix.text_len = h.text_len; ix.n_sa = h.n_sa; ix.n_kmers = h.n_kmers; ix.table_slots = h.table_slots;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = ix.words.reserve(h.bytes[0] / 8);
+    if (e == cudaSuccess) e = ix.txp_start.reserve(h.n_txp + 1ull);
+    if (e == cudaSuccess) e = ix.txp_len.reserve(h.n_txp);
+    if (e == cudaSuccess) e = ix.txp_end.reserve(h.n_txp);
+    if (e == cudaSuccess) e = ix.sa.reserve(std::max<uint64_t>(1, h.n_sa));
+    if (e == cudaSuccess) e = ix.table.reserve(h.table_slots);
+    if (e == cudaSuccess) e = ix.mfilter.reserve(h.bytes[6] / 4);
+    if (e != cudaSuccess) { fclose(f); c->err = std::string("index_load: ") + cudaGetErrorString(e); return SFB200_ECUDA; }
+    void* ptr[7] = {ix.words.p, ix.txp_start.p, ix.txp_len.p, ix.txp_end.p, ix.sa.p, ix.table.p, ix.mfilter.p};
+    std::vector<char> buf(IO_PIECE);
+    int rc = SFB200_OK;
+    for (int i = 0; i < 7 && rc == SFB200_OK; ++i) rc = stream_in(c, f, ptr[i], h.bytes[i], buf);
+    fclose(f);
+    if (rc == SFB200_OK) ix.ready = true;
+    return rc;
+}

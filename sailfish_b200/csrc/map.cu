@@ -485,6 +485,37 @@ __device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds
                                             unsigned long long* __restrict__ iv_all, uint32_t* __restrict__ ivmask_all, uint64_t iv_base) {
     const unsigned grp = lane / EXT_G, sub = lane % EXT_G;
     const uint32_t my_len = (st.s >> 1) ? rds[1].len : rds[0].len;     // only read from lanes that own a pending seed
+    // seeds with large buckets first (paralog families, repeats: hundreds of positions): the whole warp takes one seed, a bucket entry per
+    // lane per round -- in a 4-lane group such a seed would keep the other 28 lanes waiting for cnt / 4 rounds of dependent loads
+    unsigned big = todo & __ballot_sync(0xffffffffu, st.pend_cnt > 4u * EXT_G);
+    todo &= ~big;
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t lb = __shfl_sync(0xffffffffu, st.pend_lb, src), cnt = __shfl_sync(0xffffffffu, st.pend_cnt, src);
+        const uint32_t q = __shfl_sync(0xffffffffu, st.i, src), len = __shfl_sync(0xffffffffu, my_len, src);
+        const int ss = __shfl_sync(0xffffffffu, st.s, src);
+        const uint32_t sb = ((ss >> 1) ? rds[1].sb : rds[0].sb) + (unsigned)src - lane;
+        uint32_t best = 0, mask = 0;
+        for (uint32_t e = lane; e < cnt; e += 32) {
+            const uint2 en = sa_pos_rem(ix, lb + e);
+            const uint32_t l = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.y);
+            if (l > best) { best = l; mask = e < 32 ? (1u << e) : 0u; }
+            else if (l == best && e < 32) mask |= 1u << e;
+        }
+#pragma unroll
+        for (unsigned d = 1; d < 32; d <<= 1) {
+            const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), om = __shfl_xor_sync(0xffffffffu, mask, d);
+            if (ob > best) { best = ob; mask = om; } else if (ob == best) mask |= om;
+        }
+        if ((int)lane == src) {
+            iv_all[iv_base + st.s * MAX_IV + st.n] = pack_iv(st.pend_lb, st.pend_cnt, st.i, best);
+            ivmask_all[iv_base + st.s * MAX_IV + st.n] = mask;
+            ++st.n;
+            st.i = st.i + best - ix.k + 1;
+            st.pend_cnt = 0;
+        }
+    }
     while (todo) {
         const unsigned src = __fns(todo, 0, (int)grp + 1);             // owner lane of this group's seed, 0xFFFFFFFF if there is none
         const bool act = src < 32u;

@@ -53,6 +53,9 @@ public:
         check(sfb200_index_build(ctx_, seq.data(), txpOffsets.data(), txpLens.data(), static_cast<uint32_t>(txpLens.size()), k));
         nTxp_ = static_cast<uint32_t>(txpLens.size());
     }
+    // the built index as one file and back (what SailfishIndex::load takes from the index directory, include/SailfishIndex.hpp:80-144)
+    void saveIndex(const std::string& path) const { check(sfb200_index_save(ctx_, path.c_str())); }
+    void loadIndex(const std::string& path, uint32_t nTxp) { check(sfb200_index_load(ctx_, path.c_str())); nTxp_ = nTxp; }
     uint32_t numTranscripts() const { return nTxp_; }
     void setNumTranscripts(uint32_t n) { nTxp_ = n; }
 

@@ -358,7 +358,7 @@ int read_index_dir(const std::string& dir, std::vector<std::string>& names, std:
 
 struct Args {
     std::string transcripts, index, libType, out, auxDir = "aux", geneMap, aggKey = "gene_id", quantFile;
-    bool indexCmd = false, genesCmd = false, efflensCmd = false, efflensSingle = false, force = false;
+    bool indexCmd = false, genesCmd = false, efflensCmd = false, efflensSingle = false, force = false, saveDeviceIndex = false;
     std::string lensFile, fldFile;
     std::vector<std::string> unmated, mates1, mates2;
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
@@ -412,6 +412,7 @@ Args parse_args(int argc, char** argv) {
         else if (o == "-t" || o == "--transcripts") a.transcripts = need(o);
         else if (o == "-i" || o == "--index") a.index = need(o);
         else if (o == "-f" || o == "--force") a.force = true;
+        else if (o == "--saveDeviceIndex") a.saveDeviceIndex = true;
         else if (o == "-g" || o == "--geneMap") a.geneMap = need(o);
         else if (o == "--txpAggregationKey") a.aggKey = need(o);
         else if (o == "-q" || o == "--quantFile") a.quantFile = need(o);
@@ -792,6 +793,15 @@ int main(int argc, char** argv) {
             if (names.empty()) throw std::runtime_error("no transcripts in " + a.transcripts);
             write_index_dir(a.out, a.k, names, seq, lens);
             fprintf(stderr, "[sfb200-quant] index: %zu transcripts, %.1f Mnt, k = %d -> %s\n", names.size(), seq.size() / 1e6, a.k, a.out.c_str());
+            if (a.saveDeviceIndex) {                                           // the device structures as well (needs the GPU): quant -i loads them
+                std::vector<uint64_t> off(lens.size());
+                uint64_t at = 0;
+                for (size_t i = 0; i < lens.size(); ++i) { off[i] = at; at += lens[i]; }
+                sfb200::Device dev(a.device);
+                dev.buildIndex(seq, off, lens, a.k);
+                dev.saveIndex(a.out + "/device_index.bin");
+                fprintf(stderr, "[sfb200-quant] index: device structures written to %s/device_index.bin\n", a.out.c_str());
+            }
             return 0;
         }
         const bool paired_files = !a.mates1.empty() || !a.mates2.empty();
@@ -853,7 +863,9 @@ int main(int argc, char** argv) {
         ex.txps.resize(names.size());
         for (size_t i = 0; i < names.size(); ++i) { ex.txps[i].RefName = names[i]; ex.txps[i].RefLength = lens[i]; }
         sfb200::Device dev(a.device);
-        dev.buildIndex(seq, off, lens, a.k);
+        struct stat ist;
+        if (!a.index.empty() && stat((a.index + "/device_index.bin").c_str(), &ist) == 0) dev.loadIndex(a.index + "/device_index.bin", (uint32_t)lens.size());
+        else dev.buildIndex(seq, off, lens, a.k);
         const double t_index = now_s();
         fprintf(stderr, "[sfb200-quant] %zu transcripts, %.1f Mnt, index built in %.2f s\n", names.size(), seq.size() / 1e6, t_index - t_start);
 

@@ -5,6 +5,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 export SFB200_BENCH_CACHE=/dev/shm/sfb200_cache
 t0=$(date +%s)
+timeout 900 python -m pytest tests/test_gpu_map.py -m gpu -x -q --tb=short -p no:cacheprovider > $OUT/${TAG}_t_map.log 2>&1
+echo "map tests rc=$?  ($(( $(date +%s) - t0 )) s)"; tail -4 $OUT/${TAG}_t_map.log | cut -c1-300; grep -E "^E " $OUT/${TAG}_t_map.log | head -8 | cut -c1-300
 timeout 900 python -m pytest tests/test_gpu_em_gather.py -m gpu -x -q --tb=short -p no:cacheprovider -k "hybrid or streaming or dense_loop" > $OUT/${TAG}_t_em.log 2>&1
 G=$?
 echo "em tests rc=$G  ($(( $(date +%s) - t0 )) s)"; tail -5 $OUT/${TAG}_t_em.log | cut -c1-300

@@ -29,6 +29,8 @@ void sfb200_host_free(void* p) { std::free(p); }
 const char* sfb200_last_error(const sfb200_ctx*) { return "stub"; }
 int sfb200_index_build(sfb200_ctx* c, const char*, const uint64_t*, const uint32_t*, uint32_t n, int k) { c->T = n; logf("index_build %u %d", n, k); return SFB200_OK; }
 int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) { c->max_frag_len = o->max_frag_len; c->reads = 0; logf("map_begin %d", o->lib_format_id); return SFB200_OK; }
+int sfb200_index_save(sfb200_ctx*, const char* p) { logf("index_save %s", p); FILE* f = fopen(p, "wb"); if (f) fclose(f); return SFB200_OK; }
+int sfb200_index_load(sfb200_ctx*, const char* p) { logf("index_load %s", p); return SFB200_OK; }
 uint64_t sfb200_map_clipped(sfb200_ctx*) { return getenv("SFB200_STUB_CLIPPED") ? 7 : 0; }
 int sfb200_map_set_bias(sfb200_ctx*, int s, int g, int32_t n) { logf("map_set_bias %d %d %d", s, g, n); return SFB200_OK; }
 int sfb200_map_batch(sfb200_ctx* c, const char*, const uint64_t*, const char* b2, const uint64_t*, uint64_t n) {

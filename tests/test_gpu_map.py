@@ -325,3 +325,33 @@ def test_class_table_and_arena_grow(ctx, monkeypatch, paired):
         st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, None, None, "U", batches=3)
     assert g["n_classes"] > 1500                                         # far more classes than the 64 + 1024 slots it started with
     assert_same_classes(ctx, g, w)
+
+
+def test_index_file_round_trip(ctx, tmp_path):
+    """sfb200_index_save / sfb200_index_load (what SailfishIndex::load reads from the index directory, SailfishIndex.hpp:80-144): a
+    fresh context that loads the file maps reads to the same classes as the context that built the index; damaged files are refused"""
+    seq, off, ln = small_txome(40, seed=9)
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 8000, 100, seed=4, paired=True, sub_rate=0.01)
+    st = ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=31)
+    path = str(tmp_path / "index.bin")
+    ctx.index_save(path)
+    fmt = O.parse_libtype("IU")
+    ctx.map_begin(capi.MapOpts.default(fmt)); ctx.map_batch(b1, o1, b2, o2); g = ctx.map_finish()
+    want = (g["counters"].tolist(), g["fld"].tolist(), [a.tolist() for a in ctx.eq_export()])
+    other = capi.Context(0)
+    try:
+        st2 = other.index_load(path)
+        assert {k: st2[k] for k in ("text_len", "n_sa", "n_kmers", "max_bucket")} == {k: st[k] for k in ("text_len", "n_sa", "n_kmers", "max_bucket")}
+        w1, p1, t1 = ctx.index_export(); w2, p2, t2 = other.index_export()
+        assert w1.tolist() == w2.tolist() and p1.tolist() == p2.tolist() and t1.tolist() == t2.tolist()
+        other.map_begin(capi.MapOpts.default(fmt)); other.map_batch(b1, o1, b2, o2); g2 = other.map_finish()
+        assert (g2["counters"].tolist(), g2["fld"].tolist(), [a.tolist() for a in other.eq_export()]) == want
+        blob = open(path, "rb").read()
+        open(path, "wb").write(blob[:len(blob) // 2])
+        with pytest.raises(capi.Sfb200Error):
+            other.index_load(path)                                    # truncated
+        open(path, "wb").write(b"XXXXXXXX" + blob[8:])
+        with pytest.raises(capi.Sfb200Error):
+            other.index_load(path)                                    # not an index file
+    finally:
+        other.close()

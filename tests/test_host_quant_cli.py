@@ -229,6 +229,29 @@ def test_driver_error_paths_with_stub_device(tmp_path):
     assert (tmp_path / "a" / "b" / "c" / "quant.sf").exists() and (tmp_path / "a" / "b" / "c" / "aux" / "meta_info.json").exists()
 
 
+def test_driver_device_index_file_with_stub_device(tmp_path):
+    """`index --saveDeviceIndex` writes the device structures next to the sequence; `quant -i <dir>` then loads them instead of building"""
+    exe = str(tmp_path / "sfb200-quant-stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-Wall", "-pthread", "-o", exe, os.path.join(ROOT, "sailfish_b200", "host", "sfb200_quant.cpp"),
+                           os.path.join(ROOT, "tests", "stub_sfb200.cpp"), "-lz"])
+    fa = tmp_path / "t.fa"; fa.write_text(">t0\n" + "ACGT" * 100 + "\n>t1\n" + "GGCA" * 150 + "\n")
+    fq = tmp_path / "r.fq"; fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, "ACGT" * 10, "I" * 40) for i in range(8)))
+    log = tmp_path / "log.txt"
+    env = dict(os.environ, SFB200_STUB_LOG=str(log))
+    idx = tmp_path / "idx"
+    subprocess.check_call([exe, "index", "-t", str(fa), "-o", str(idx), "-k", "31", "--saveDeviceIndex"], env=env, stderr=subprocess.DEVNULL)
+    calls = [c.split()[0] for c in log.read_text().strip().split("\n")]
+    assert calls == ["index_build", "index_save"] and (idx / "device_index.bin").exists() and (idx / "versionInfo.json").exists()
+    log.unlink()
+    subprocess.check_call([exe, "quant", "-i", str(idx), "-l", "U", "-r", str(fq), "-o", str(tmp_path / "o")], env=env, stderr=subprocess.DEVNULL)
+    calls = [c.split()[0] for c in log.read_text().strip().split("\n")]
+    assert calls[0] == "index_load" and "index_build" not in calls and (tmp_path / "o" / "quant.sf").exists()
+    # without the file the index is rebuilt from the stored sequence
+    (idx / "device_index.bin").unlink(); log.unlink()
+    subprocess.check_call([exe, "quant", "-i", str(idx), "-l", "U", "-r", str(fq), "-o", str(tmp_path / "o2")], env=env, stderr=subprocess.DEVNULL)
+    assert log.read_text().split()[0] == "index_build"
+
+
 def test_driver_host_flow_with_stub_device(tmp_path):
     """sfb200_quant.cpp linked against tests/stub_sfb200.cpp (a test double of the C ABI: canned device results, call log): the
     driver's HOST flow -- effective lengths, FLD hand-over to the bias model, corrected lengths in quant.sf, every aux file --
