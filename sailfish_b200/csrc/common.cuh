@@ -84,10 +84,8 @@ struct DevPartition {
     uint64_t n_pool = 0, pool_nnz = 0;
     uint32_t n_pool_cta = 0;            // hybrid runs (em_dense.cuh): CTAs that run the pool loop, launched after the n_cta component CTAs
     uint32_t n_dirty = 0;               // pool transcripts
-    DevBuf<uint32_t> dlist;             // the pool as its own problem: class CSR over pool-local ids, its transpose, local id -> transcript
+    DevBuf<uint32_t> dlist;             // hybrid runs: the pool's transcripts
     uint64_t pool_nz = 0;               // label entries of the pool classes
-    uint32_t pool_ncomp = 0, pool_np = 0;
-    uint64_t pool_smem = 0, pool_o[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // shared memory of the largest pool CTA; offsets of the pool arrays inside dlist
     uint64_t max_cta_bytes = 0, max_cta_bytes_vb = 0, smem_limit = 0;
     int per_sm = 1;
     DevBuf<uint32_t> start, len, lab, src, bounds, owner, load;

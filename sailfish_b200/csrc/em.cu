@@ -787,118 +787,9 @@ int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {
     return SFB200_OK;
 }
 
-// The pool of a hybrid run as work for CTAs of its own (em_dense.cuh: dense_pool_loop).  The pool classes are the last group of the
-// partition order, their label entries the tail of P.lab.  They fall apart into connected components; whole components are packed onto
-// `np` CTAs (largest first, onto the least loaded CTA), and every CTA gets its classes as CSR over CTA-local transcript ids plus the
-// transpose.  *ok = false (the caller keeps k_em_part) when a CTA's beta / alpha / r would not fit beside the component CTAs' shared memory.
-int build_pool(sfb200_ctx* c, uint32_t np, bool* ok, bool count_only = false) {
-    DevClasses& k = c->cls;
-    DevPartition& P = k.part;
-    cudaStream_t s = c->stream;
-    *ok = false;
-    const uint64_t c0 = P.pool_cls[0], n_pc = P.n_pool, e1 = k.nnzm;
-    if (!n_pc || !np) return SFB200_OK;
-    std::vector<uint32_t> h_start(n_pc), h_lab;
-    SFB_CUDA(c, cudaMemcpyAsync(h_start.data(), P.start.p + c0, n_pc * 4, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    const uint64_t e0 = h_start[0], nz = e1 - e0;
-    h_lab.resize(nz);
-    SFB_CUDA(c, cudaMemcpyAsync(h_lab.data(), P.lab.p + e0, nz * 4, cudaMemcpyDeviceToHost, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    auto row_b = [&](uint64_t q) { return (uint64_t)h_start[q] - e0; };
-    auto row_e = [&](uint64_t q) { return q + 1 < n_pc ? (uint64_t)h_start[q + 1] - e0 : nz; };
-    std::vector<uint32_t> ids(h_lab);
-    std::sort(ids.begin(), ids.end());
-    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-    const uint32_t nd = (uint32_t)ids.size();
-    std::vector<uint32_t> lid(nz);
-    for (uint64_t j = 0; j < nz; ++j) lid[j] = (uint32_t)(std::lower_bound(ids.begin(), ids.end(), h_lab[j]) - ids.begin());
-    // connected components (union-find over the pool's transcripts)
-    std::vector<uint32_t> parent(nd);
-    for (uint32_t i = 0; i < nd; ++i) parent[i] = i;
-    auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    for (uint64_t q = 0; q < n_pc; ++q) {
-        const uint32_t r0 = find(lid[row_b(q)]);
-        for (uint64_t j = row_b(q) + 1; j < row_e(q); ++j) { const uint32_t r = find(lid[j]); if (r != r0) parent[r] = r0; }
-    }
-    std::vector<uint32_t> comp_of(nd), comp_root;                      // dense component numbers
-    { std::vector<uint32_t> num(nd, 0xFFFFFFFFu);
-      for (uint32_t i = 0; i < nd; ++i) { const uint32_t r = find(i); if (num[r] == 0xFFFFFFFFu) { num[r] = (uint32_t)comp_root.size(); comp_root.push_back(r); } comp_of[i] = num[r]; } }
-    const uint32_t ncomp = (uint32_t)comp_root.size();
-    P.pool_ncomp = ncomp;
-    np = std::min(np, std::max<uint32_t>(1, ncomp));
-    P.pool_np = np;
-    if (count_only) return SFB200_OK;
-    std::vector<uint64_t> comp_ent(ncomp, 0), comp_nt(ncomp, 0), comp_nc(ncomp, 0);
-    for (uint32_t i = 0; i < nd; ++i) comp_nt[comp_of[i]]++;
-    for (uint64_t q = 0; q < n_pc; ++q) { const uint32_t cc = comp_of[lid[row_b(q)]]; comp_nc[cc]++; comp_ent[cc] += row_e(q) - row_b(q); }
-    // pack: largest component first onto the CTA with the fewest entries so far
-    std::vector<uint32_t> order(ncomp), cta_of(ncomp);
-    for (uint32_t i = 0; i < ncomp; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return comp_ent[a] != comp_ent[b] ? comp_ent[a] > comp_ent[b] : a < b; });
-    std::vector<uint64_t> load(np, 0), cta_nt(np, 0), cta_nc(np, 0);
-    for (uint32_t oi = 0; oi < ncomp; ++oi) {
-        const uint32_t cc = order[oi];
-        uint32_t best = 0;
-        for (uint32_t b = 1; b < np; ++b) if (load[b] < load[best]) best = b;
-        cta_of[cc] = best; load[best] += comp_ent[cc] + 1; cta_nt[best] += comp_nt[cc]; cta_nc[best] += comp_nc[cc];
-    }
-    uint64_t max_smem = 0, max_ent = 0;
-    for (uint32_t b = 0; b < np; ++b) { max_smem = std::max<uint64_t>(max_smem, (2 * cta_nt[b] + cta_nc[b]) * 8); max_ent = std::max<uint64_t>(max_ent, load[b]); }
-    max_smem += 256;
-    const uint64_t smem_2 = (P.smem_limit + 1024) / 2 - 2048;           // what a CTA may use with two CTAs per SM
-    if (getenv("SFB200_VERBOSE"))
-        fprintf(stderr, "[sfb200] EM pool: %llu classes, %u transcripts, %llu entries in %u components on %u CTAs (largest CTA: %llu entries, %llu bytes of shared memory)\n",
-                (unsigned long long)n_pc, nd, (unsigned long long)nz, ncomp, np, (unsigned long long)max_ent, (unsigned long long)max_smem);
-    if (max_smem > smem_2) return SFB200_OK;                            // a component too large for one CTA: not for this loop
-    // per-CTA numbering
-    std::vector<uint64_t> t_off(np + 1, 0), c_off(np + 1, 0), e_off(np + 1, 0);
-    for (uint32_t b = 0; b < np; ++b) { t_off[b + 1] = t_off[b] + cta_nt[b]; c_off[b + 1] = c_off[b] + cta_nc[b]; e_off[b + 1] = e_off[b] + (load[b] - 0); }
-    // load[] counted one extra per component; recompute the entry offsets from the rows themselves
-    std::vector<uint64_t> cta_ne(np, 0);
-    for (uint64_t q = 0; q < n_pc; ++q) cta_ne[cta_of[comp_of[lid[row_b(q)]]]] += row_e(q) - row_b(q);
-    for (uint32_t b = 0; b < np; ++b) e_off[b + 1] = e_off[b] + cta_ne[b];
-    std::vector<uint32_t> tloc(nd), tcur(np, 0), ccur(np, 0);
-    const uint64_t n_tbl = 8ull * np, sz_cs = n_pc + np, sz_ts = (uint64_t)nd + np;
-    std::vector<uint32_t> buf(n_tbl + nd + n_pc + sz_cs + nz + sz_ts + nz, 0);
-    uint32_t* tbl = buf.data(); uint32_t* tglob = tbl + n_tbl; uint32_t* cpart = tglob + nd; uint32_t* cs = cpart + n_pc; uint32_t* ce = cs + sz_cs;
-    uint32_t* ts = ce + nz; uint32_t* te = ts + sz_ts;
-    for (uint32_t i = 0; i < nd; ++i) { const uint32_t b = cta_of[comp_of[i]]; tloc[i] = tcur[b]; tglob[t_off[b] + tcur[b]++] = ids[i]; }
-    // classes in CTA order; their rows; degree counts for the transpose
-    std::vector<uint32_t> cloc(n_pc);
-    std::vector<uint64_t> ecur(np, 0);
-    for (uint64_t q = 0; q < n_pc; ++q) {
-        const uint32_t b = cta_of[comp_of[lid[row_b(q)]]];
-        const uint32_t lc = ccur[b]++;
-        cloc[q] = lc;
-        cpart[c_off[b] + lc] = (uint32_t)(c0 + q);
-        cs[c_off[b] + b + lc] = (uint32_t)ecur[b];
-        for (uint64_t j = row_b(q); j < row_e(q); ++j) { ce[e_off[b] + ecur[b]++] = tloc[lid[j]]; ts[t_off[b] + b + tloc[lid[j]] + 1]++; }
-        cs[c_off[b] + b + lc + 1] = (uint32_t)ecur[b];
-    }
-    for (uint32_t b = 0; b < np; ++b) {                                 // degree counts -> starts (relative to the CTA's first entry)
-        uint32_t* st = ts + t_off[b] + b;
-        st[0] = 0;
-        for (uint64_t i = 0; i < cta_nt[b]; ++i) st[i + 1] += st[i];
-    }
-    { std::vector<uint32_t> cur(sz_ts);
-      for (uint32_t b = 0; b < np; ++b) for (uint64_t i = 0; i <= cta_nt[b]; ++i) cur[t_off[b] + b + i] = ts[t_off[b] + b + i];
-      for (uint64_t q = 0; q < n_pc; ++q) {
-          const uint32_t b = cta_of[comp_of[lid[row_b(q)]]];
-          for (uint64_t j = row_b(q); j < row_e(q); ++j) te[e_off[b] + cur[t_off[b] + b + tloc[lid[j]]]++] = cloc[q];
-      } }
-    for (uint32_t b = 0; b < np; ++b) {
-        uint32_t* r = tbl + 8ull * b;
-        r[0] = (uint32_t)t_off[b]; r[1] = (uint32_t)cta_nt[b]; r[2] = (uint32_t)c_off[b]; r[3] = (uint32_t)cta_nc[b]; r[4] = (uint32_t)e_off[b]; r[5] = (uint32_t)cta_ne[b];
-    }
-    SFB_CUDA(c, P.dlist.reserve(buf.size()));
-    SFB_CUDA(c, cudaMemcpyAsync(P.dlist.p, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, s));
-    SFB_CUDA(c, cudaStreamSynchronize(s));
-    P.n_dirty = nd; P.pool_nz = nz; P.pool_smem = max_smem;
-    P.pool_o[0] = 0; P.pool_o[1] = n_tbl; P.pool_o[2] = n_tbl + nd; P.pool_o[3] = n_tbl + nd + n_pc; P.pool_o[4] = P.pool_o[3] + sz_cs;
-    P.pool_o[5] = P.pool_o[4] + nz; P.pool_o[6] = P.pool_o[5] + sz_ts;
-    *ok = true;
-    return SFB200_OK;
+__global__ void k_dirty_list(const uint8_t* __restrict__ dirty, uint32_t T, uint32_t* __restrict__ list, unsigned int* __restrict__ n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T && dirty[t]) list[atomicAdd(n, 1u)] = t;
 }
 
 int build_partition(sfb200_ctx* c) {
@@ -913,20 +804,20 @@ int build_partition(sfb200_ctx* c) {
     const uint32_t n_full = (uint32_t)(c->num_sms * per_sm);
     if (k.Em == 0 || k.n_txp == 0) return SFB200_OK;
     { const int rc = build_partition_n(c, n_full, per_sm); if (rc) return rc; }
+    P.n_dirty = 0;
     if (P.dense_ok && P.n_pool > 0) {
-        // hybrid: some of the CTAs run the pool loop instead of owning a range -- as many as the pool's share of the label entries
-        // suggests (x 1.5: its sweep goes through L2), at least 8, at most two thirds; the ranges are rebuilt for the rest
-        const double share = (double)P.pool_nnz / (double)std::max<uint64_t>(1, k.nnzm);
-        uint32_t np = (uint32_t)std::ceil(1.5 * share * n_full);
-        if (const char* e = getenv("SFB200_EM_POOL_CTAS")) np = (uint32_t)atoi(e);
-        np = std::max<uint32_t>(4, std::min<uint32_t>(np, n_full * 2 / 3));
-        { bool dummy; const int rc = build_pool(c, np, &dummy, true); if (rc) return rc; }       // how many components are there to hand out
-        np = std::min(np, std::max<uint32_t>(1, P.pool_ncomp));
-        { const int rc = build_partition_n(c, n_full - np, per_sm); if (rc) return rc; }
-        bool pool_ok = P.dense_ok && P.n_pool == 0;
-        if (P.dense_ok && P.n_pool) { const int rc = build_pool(c, np, &pool_ok); if (rc) return rc; }
-        if (pool_ok) P.n_pool_cta = P.n_pool ? P.pool_np : 0;
-        else { const int rc = build_partition_n(c, n_full, per_sm); if (rc) return rc; P.dense_ok = false; }   // keep the other loops' geometry
+        // hybrid: the pool's transcripts as a list (every CTA looks after a share of them, em_dense.cuh)
+        cudaStream_t s = c->stream;
+        unsigned int* d_n = reinterpret_cast<unsigned int*>(P.grp.p);
+        SFB_CUDA(c, P.dlist.reserve(k.n_txp));
+        SFB_CUDA(c, cudaMemsetAsync(d_n, 0, 4, s));
+        k_dirty_list<<<grid_for(k.n_txp, 256), 256, 0, s>>>(P.dirty.p, k.n_txp, P.dlist.p, d_n);
+        c->launches++;
+        unsigned int nd = 0;
+        SFB_CUDA(c, cudaMemcpyAsync(&nd, d_n, 4, cudaMemcpyDeviceToHost, s));
+        SFB_CUDA(c, cudaStreamSynchronize(s));
+        P.n_dirty = nd;
+        if (getenv("SFB200_VERBOSE")) fprintf(stderr, "[sfb200] EM hybrid: %llu pool classes over %u transcripts swept by all CTAs\n", (unsigned long long)P.n_pool, nd);
     }
     return SFB200_OK;
 }
@@ -1077,11 +968,8 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         DenseParams q;
         q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
         q.stream_buf = P.dns_f64.p; q.stream_ent = P.stream_ent; q.stream_state = P.stream_state; q.stream_stride = P.stream_ent + 2 * P.stream_state;
-        q.n_dense = P.n_cta;
-        q.pool_tbl = P.dlist.p + P.pool_o[0]; q.pool_tglob = P.dlist.p + P.pool_o[1]; q.pool_cpart = P.dlist.p + P.pool_o[2];
-        q.pool_cs = P.dlist.p + P.pool_o[3]; q.pool_ce = P.dlist.p + P.pool_o[4]; q.pool_ts = P.dlist.p + P.pool_o[5]; q.pool_te = P.dlist.p + P.pool_o[6];
-        // every CTA of the launch gets the same amount of shared memory: what the component CTAs or the pool CTAs need, whichever is more
-        const size_t smem = P.n_pool_cta ? std::max<size_t>((size_t)P.dense_smem, (size_t)P.pool_smem) : (size_t)P.dense_smem;
+        q.dlist = P.dlist.p; q.n_dirty = P.n_pool ? P.n_dirty : 0;
+        const size_t smem = (size_t)P.dense_smem;
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))
@@ -1093,7 +981,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
 #undef SFB_DENSE_FN
 #undef SFB_DENSE_FN_S
         SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta + P.n_pool_cta), dim3(DENSE_THREADS), args, smem, s));
+        SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(DENSE_THREADS), args, smem, s));
         c->launches++;
         SFB_CUDA(c, cudaEventRecord(c->ev1, s));
         SFB_CUDA(c, cudaMemcpyAsync(h_ctl, c->em_ctl.p, sizeof(h_ctl), cudaMemcpyDeviceToHost, s));
@@ -1228,7 +1116,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
     float ms = 0.f;
     SFB_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_em_ms = ms;
-    c->last_em_kernel = steps ? 3 : (kind == LOOP_DENSE && c->cls.part.n_pool_cta) ? 5 : (int)kind;
+    c->last_em_kernel = steps ? 3 : (kind == LOOP_DENSE && c->cls.part.n_pool) ? 5 : (int)kind;
     return SFB200_OK;
 }
 
@@ -1279,7 +1167,8 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
     const uint32_t* a_len = use_part ? P.len.p : k.len.p;
     const uint32_t* a_lab = use_part ? P.lab.p : k.lab.p;
     double* a_w = use_part ? P.w.p : k.w.p;
-    if (k.Em && !use_gather) {
+    const bool hybrid_pool = use_dense && P.n_pool > 0;                 // the pool of a hybrid run is swept in the weighted scatter form
+    if (k.Em && (!use_gather || hybrid_pool)) {
         // weights always come from the ORIGINAL counts (the reference computes them once in optimize(), :745-772)
         k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
         c->launches++;
@@ -1361,7 +1250,7 @@ int em_common(sfb200_ctx* c, const double* eff_lens, uint32_t n_txp, double tota
             if (rc) return rc;
             h_eff.swap(h_next);
             SFB_CUDA(c, cudaMemcpyAsync(c->eff.p, h_eff.data(), T * 8ull, cudaMemcpyHostToDevice, s));
-            if (k.Em && !use_gather) {
+            if (k.Em && (!use_gather || hybrid_pool)) {
                 k_class_weights<<<grid_for(k.Em, 128), 128, 0, s>>>(a_start, a_len, a_lab, use_part ? P.cnt.p : k.cnt.p, c->eff.p, k.Em, a_w);
                 c->launches++;
             }

@@ -48,157 +48,11 @@ struct DenseParams {
     // live in a per-CTA global block (stream_buf + blockIdx.x * stream_stride: [cnt: stream_ent][base: stream_state][1/eff: stream_state])
     // and the masks are read from the region; only beta and alpha stay in shared memory
     double* stream_buf; uint32_t stream_stride, stream_ent, stream_state;
-    // hybrid runs: CTAs [0, n_dense) own the small components, CTAs [n_dense, gridDim.x) the connected components of everything else
-    // (components too large for a thread, classes that cross CTA ranges), whole components per CTA
-    uint32_t n_dense;
-    const uint32_t* pool_tbl;     // per pool CTA: {first transcript, transcripts, first class, classes, first entry, entries, -, -}
-    const uint32_t* pool_tglob;   // pool transcript (in CTA order) -> transcript id
-    const uint32_t* pool_cpart;   // pool class (in CTA order) -> position in the partition-ordered arrays (p.cnt)
-    const uint32_t* pool_cs; const uint32_t* pool_ce;     // per CTA: class rows (n_c + 1 starts, relative to the CTA's first entry) x CTA-local transcript ids
-    const uint32_t* pool_ts; const uint32_t* pool_te;     // per CTA: the transpose (n_t + 1 starts) x CTA-local class ids
+    // hybrid runs: the classes the components do not cover -- components too large for a thread, classes that cross CTA ranges: the
+    // "pool", p.start/len/lab/w/cnt binned as k_em_part's pool -- are swept by ALL CTAs in the scatter form every iteration
+    const uint32_t* dlist;    // the pool's transcripts
+    uint32_t n_dirty;         // 0: no pool
 };
-constexpr uint32_t POOL_SHORT = 16;
-
-// The pool CTAs of a hybrid run.  The pool -- large components, classes that cross CTA ranges -- shares no transcript with the
-// components the other CTAs own, and it falls apart into connected components itself (a paralog family, the hosts of a repeat
-// element): the host packs WHOLE components onto CTAs (em.cu: build_pool), so a pool CTA, like a component CTA, iterates without any
-// other CTA: beta, alpha and r of its components live in its shared memory, the two steps are separated by __syncthreads only, and
-// the row indices come from global memory through L1 (nothing invalidates it: no fences inside an iteration).  EMUpdate_ /
-// VBEMUpdate_ in the gather form of em_gather.cuh (no atomics); a thread per row for rows of up to POOL_SHORT entries, the warp for
-// longer ones.  The grid barrier appears where k_em_dense's own loop has it (the break logic is a copy of that loop's).
-template <bool VB>
-__device__ __noinline__ void dense_pool_loop(const EmParams& p, const DenseParams& q, double* smem) {
-    __shared__ unsigned long long pl_u[32];
-    __shared__ double pl_d[32];
-    const unsigned nblocks = gridDim.x, pi = blockIdx.x - q.n_dense;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long gen = 0;
-    const uint32_t* tb = q.pool_tbl + 8u * pi;
-    const uint32_t t_off = tb[0], n_t = tb[1], c_off = tb[2], n_c = tb[3], e_off = tb[4];
-    const uint32_t* tglob = q.pool_tglob + t_off;
-    const uint32_t* cpart = q.pool_cpart + c_off;
-    const uint32_t* cs = q.pool_cs + c_off + pi;
-    const uint32_t* ce = q.pool_ce + e_off;
-    const uint32_t* ts = q.pool_ts + t_off + pi;
-    const uint32_t* te = q.pool_te + e_off;
-    double* s_beta = smem;
-    double* s_alpha = s_beta + n_t;
-    double* s_r = s_alpha + n_t;
-    const bool fixed = p.fixed_iters > 0;
-    {
-        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
-        for (uint32_t i = threadIdx.x; i < n_t; i += blockDim.x) {
-            const uint32_t t = __ldg(tglob + i);
-            const double a = p.X[t];
-            const double th = VB ? ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) : a;
-            s_alpha[i] = a; s_beta[i] = th / __ldg(q.eff + t);
-        }
-        __syncthreads();
-    }
-    // sum of vals[idx[j]] over the row [b, e): by this thread (short rows) ...
-    auto row_sum_thread = [&](const uint32_t* idx, const double* vals, uint32_t b, uint32_t e) {
-        double s = 0.0;
-        for (uint32_t j0 = b; j0 < e; j0 += 4) {
-            uint32_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = j0 + u < e ? __ldg(idx + j0 + u) : 0xFFFFFFFFu;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (v[u] != 0xFFFFFFFFu) s += vals[v[u]];
-        }
-        return s;
-    };
-    // ... or by the whole warp
-    auto row_sum_warp = [&](const uint32_t* idx, const double* vals, uint32_t b, uint32_t e) {
-        double s = 0.0;
-        for (uint32_t j0 = b; j0 < e; j0 += 128) {
-            uint32_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + lane + 32u * u; v[u] = j < e ? __ldg(idx + j) : 0xFFFFFFFFu; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (v[u] != 0xFFFFFFFFu) s += vals[v[u]];
-        }
-        return warp_sum(s);
-    };
-    uint32_t n = 0;
-    for (;;) {
-        if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
-        const uint32_t m = n + 1;
-        const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
-        // ---- E-step: r_c = count_c / sum of beta over the class
-        for (uint32_t base = 0; base < n_c; base += blockDim.x) {
-            const uint32_t c = base + threadIdx.x;
-            const bool valid = c < n_c;
-            uint32_t b = 0, e = 0;
-            if (valid) { b = __ldg(cs + c); e = __ldg(cs + c + 1); }
-            const bool is_long = valid && e - b > POOL_SHORT;
-            if (valid && !is_long) s_r[c] = em_ratio(p.cnt[__ldg(cpart + c)], row_sum_thread(ce, s_beta, b, e));
-            unsigned longm = __ballot_sync(0xffffffffu, is_long);
-            while (longm) {
-                const int src = __ffs(longm) - 1;
-                longm &= longm - 1;
-                const double S = row_sum_warp(ce, s_beta, __shfl_sync(0xffffffffu, b, src), __shfl_sync(0xffffffffu, e, src));
-                if ((int)lane == src) s_r[c] = em_ratio(p.cnt[__ldg(cpart + c)], S);
-            }
-        }
-        __syncthreads();
-        // ---- M-step: alpha'_i = base_i + beta_i * sum of r over the classes of i; the convergence test; the next beta
-        unsigned long long best = 0ULL;
-        double asum = 0.0;
-        auto finish_row = [&](uint32_t i, double acc) {
-            const uint32_t t = __ldg(tglob + i);
-            const double a_old = s_alpha[i];
-            const double a_new = s_beta[i] * acc + __ldg(p.base + t);
-            if (do_cmp) {
-                const double gate = p.gate_old ? a_old : a_new;
-                if (gate > p.cutoff) {
-                    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
-                    best = bits > best ? bits : best;
-                }
-            }
-            s_alpha[i] = a_new;
-            if (VB) asum += a_new; else s_beta[i] = a_new / __ldg(q.eff + t);
-        };
-        for (uint32_t base = 0; base < n_t; base += blockDim.x) {
-            const uint32_t i = base + threadIdx.x;
-            const bool valid = i < n_t;
-            uint32_t b = 0, e = 0;
-            if (valid) { b = __ldg(ts + i); e = __ldg(ts + i + 1); }
-            const bool is_long = valid && e - b > POOL_SHORT;
-            if (valid && !is_long) finish_row(i, row_sum_thread(te, s_r, b, e));
-            unsigned longm = __ballot_sync(0xffffffffu, is_long);
-            while (longm) {
-                const int src = __ffs(longm) - 1;
-                longm &= longm - 1;
-                const double acc = row_sum_warp(te, s_r, __shfl_sync(0xffffffffu, b, src), __shfl_sync(0xffffffffu, e, src));
-                if ((int)lane == src) finish_row(i, acc);
-            }
-        }
-        __syncthreads();
-        n = m;
-        if (VB || do_cmp) {
-            unsigned long long* slot = p.ctl + CTL_MAXREL + (m & 3u);
-            double* csum = reinterpret_cast<double*>(p.ctl + CTL_CSUM + (m & 3u));
-            if (do_cmp) block_max_to_slot(best, slot, pl_u);
-            if (VB) block_sum_to_slot(asum, csum, pl_d);
-            grid_barrier(p.ctl, nblocks, gen);                        // block 0 (a component CTA) recycles the slots afterwards
-            if (do_cmp) {
-                const unsigned long long mr = ld_cg_u64(slot);
-                if (fixed) break;
-                if (!(decode_mrd(mr) > p.tol) || m >= p.max_iter) break;
-            }
-            if (VB) {
-                const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
-                for (uint32_t i = threadIdx.x; i < n_t; i += blockDim.x) {
-                    const double a = s_alpha[i];
-                    s_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) / __ldg(q.eff + __ldg(tglob + i));
-                }
-                __syncthreads();
-            }
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_t; i += blockDim.x) p.X[__ldg(tglob + i)] = s_alpha[i];
-}
 
 constexpr int DENSE_THREADS = 256;
 constexpr int DENSE_ILP = 4;          // classes of one component in flight per lane
@@ -232,7 +86,6 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     __shared__ uint64_t tma_bar;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     const unsigned nblocks = gridDim.x;
-    if (blockIdx.x >= q.n_dense) { dense_pool_loop<VB>(p, q, reinterpret_cast<double*>(dyn_smem)); return; }
     unsigned long long gen = 0;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
 
@@ -288,6 +141,25 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     __syncthreads();
 
     const bool fixed = p.fixed_iters > 0;
+    // ---- the pool (hybrid runs): its transcripts keep their alphas in the three rotating global buffers of k_em_persistent (in / out /
+    // spare), every CTA sweeps its share of the pool's tiles with gathers and red.add through L2 and looks after its share of the pool's
+    // transcripts; the pool costs one grid barrier per iteration (sweep complete) -- the price of classes that tie CTAs together
+    const bool has_pool = q.n_dirty > 0;
+    const Bins pb = em_bins(p);
+    const uint64_t pool_tiles = p.tile_start[SFB_NBINS];
+    const uint64_t ptile_lo = pool_tiles * blockIdx.x / nblocks, ptile_hi = pool_tiles * (blockIdx.x + 1ULL) / nblocks;
+    const uint32_t d_lo = (uint32_t)((uint64_t)q.n_dirty * blockIdx.x / nblocks), d_hi = (uint32_t)((uint64_t)q.n_dirty * (blockIdx.x + 1ULL) / nblocks);
+    Slice sl_pool; sl_pool.start = p.start; sl_pool.len = p.len; sl_pool.cnt = p.cnt; sl_pool.lab = p.lab; sl_pool.w = p.w; sl_pool.c0 = 0; sl_pool.e0 = 0;
+    unsigned bi = 0, bo = 1, bs = 2;
+    if (VB && has_pool) {
+        const double logNorm = sfb_digamma(p.sum0);
+        for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
+            const uint32_t t = q.dlist[i];
+            const double a = p.X[t];
+            p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+        }
+        grid_barrier(p.ctl, nblocks, gen);
+    }
     {
         const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
         for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) {
@@ -403,6 +275,32 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                 if (VB) asum += a_new; else s_beta[i] = a_new * s_inveff[i];
             }
         }
+        if (has_pool) {
+            const double* in = p.X + (size_t)bi * p.T;
+            double* out = p.X + (size_t)bo * p.T;
+            double* spare = p.X + (size_t)bs * p.T;
+            // the spare buffer (the input of the previous iteration) becomes an output buffer again: back to its initial value for this
+            // CTA's share of the pool's transcripts (every CTA keeps its share, and nobody gathers from that buffer any more)
+            if (n > 0) for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; spare[t] = __ldg(p.base + t); }
+            sweep_block<VB, false>(pb, sl_pool, ptile_lo, ptile_hi, VB ? p.theta : in, out, 0u);
+            grid_barrier(p.ctl, nblocks, gen);
+            if (VB || do_cmp) {
+                for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
+                    const uint32_t t = q.dlist[i];
+                    const double a_new = ld_cg_f64(out + t);
+                    if (do_cmp) {
+                        const double a_old = ld_cg_f64(in + t);
+                        const double gate = p.gate_old ? a_old : a_new;
+                        if (gate > p.cutoff) {
+                            const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                            best = bits > best ? bits : best;
+                        }
+                    }
+                    asum += a_new;
+                }
+            }
+            { const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp; }   // bi now names the pool's newest alphas
+        }
         n = m;
         if (VB || do_cmp) {
             if (do_cmp) {                                              // idle transcripts: alpha_0 -> base at m == 1, base -> base after
@@ -435,10 +333,24 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                     s_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) * s_inveff[i];
                 }
                 __syncthreads();
+                if (has_pool) {                                        // the pool's expTheta, complete before anyone's next sweep gathers it
+                    const double* cur = p.X + (size_t)bi * p.T;
+                    for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
+                        const uint32_t t = q.dlist[i];
+                        const double a = ld_cg_f64(cur + t);
+                        p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+                    }
+                    grid_barrier(p.ctl, nblocks, gen);
+                }
             }
         }
     }
     __syncthreads();
+    // the components leave their result in the first third of X: so does the pool
+    if (has_pool && bi != 0) {
+        const double* cur = p.X + (size_t)bi * p.T;
+        for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; p.X[t] = ld_cg_f64(cur + t); }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctl[CTL_ITERS] = n; p.ctl[CTL_RESULT_BUF] = 0ULL; p.ctl[CTL_MRD] = mr_final; }
     for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) { const uint32_t t = tmap[i]; if (t != DN_NONE) p.X[t] = s_alpha[i]; }
     if (n > 0) for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) { const uint32_t t = idle[i]; p.X[t] = p.base[t]; }
