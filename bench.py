@@ -326,7 +326,14 @@ class GpuRun:
         self.st = self.ctx.index_build(seq=self.seq, txp_off=self.off, txp_len=self.ln, k=31)
         log("[bench] index: %d positions, %d k-mers, %.2f GB in HBM, max bucket %d (%.1fs)" % (
             self.st["n_sa"], self.st["n_kmers"], self.st["hbm_bytes"] / 1e9, self.st["max_bucket"], time.time() - t0))
-        self.make_reads()
+        # the page-locked read buffers are allocated on the GPU's NUMA node (sfb200_bind_host_near_device: what the host program does
+        # for its parser threads); the CPU set is restored afterwards so that the CPU leg keeps every host core
+        cpus = os.sched_getaffinity(0)
+        self.numa_cpus = capi.bind_host_near_device(local_rank)
+        try:
+            self.make_reads()
+        finally:
+            os.sched_setaffinity(0, cpus)
         self.map_opts = capi.MapOpts.default(wl.lib)
         if wl.fixed_iters:
             self.em_opts = capi.EMOpts.default(fixed_iters=wl.fixed_iters, use_vb=wl.use_vb)
@@ -557,7 +564,8 @@ def main():
             "detail": {"map_kernel_ms_per_step": m["map_ms"], "em_loop_ms_per_step": m["em_ms"], "em_iters": m["iters"], "em_kernel": m["em_kernel"],
                        "map_kernel_reads_per_s": n / (m["map_ms"] / 1e3), "em_iters_per_s": m["iters"] / (m["em_ms"] / 1e3),
                        "host_wall_ms_per_step": m["host_phase_ms"], "n_classes": E, "nnz": nnz, "mapped": int(g["counters"][1]),
-                       "observed": int(g["counters"][0]), "index_hbm_gb": round(run.st["hbm_bytes"] / 1e9, 2), **m["extra"]}}
+                       "observed": int(g["counters"][0]), "index_hbm_gb": round(run.st["hbm_bytes"] / 1e9, 2),
+                       "host_cpus_on_gpu_node": run.numa_cpus, **m["extra"]}}
     # EM roofline: B_em = 12 nnz + 12 E + 32 T algorithmic bytes per iteration.  The dense / gather / part loops keep their
     # working set in shared memory (no HBM traffic after the first iteration): their bound is on-chip, the HBM figure is an equivalent
     b_em = 12.0 * nnz + 12.0 * E + 32.0 * T

@@ -75,6 +75,7 @@ SIGNATURES = {
     "sfb200_ctx_sync": (C.c_int, [C.c_void_p]),
     "sfb200_launch_count": (C.c_uint64, [C.c_void_p]),
     "sfb200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "sfb200_bind_host_near_device": (C.c_int, [C.c_int]),
     "sfb200_host_free": (None, [C.c_void_p]),
     "sfb200_comm_unique_id": (C.c_int, [u8p]),
     "sfb200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u8p]),
@@ -132,6 +133,15 @@ def lib():
             f.argtypes = args
         _lib = L
     return _lib
+
+
+def bind_host_near_device(device=0):
+    """Keep this process (and the threads it starts from now on) on the CPUs of the GPU's NUMA node, so that page-locked buffers
+    allocated afterwards are node-local.  -> number of CPUs bound, 0 if nothing changed (include/sfb200.h)."""
+    rc = lib().sfb200_bind_host_near_device(int(device))
+    if rc < 0:
+        raise Sfb200Error(rc, "sfb200_bind_host_near_device(%d)" % device)
+    return rc
 
 
 def _ptr(a, t):

@@ -6,6 +6,12 @@
 
 #include <cstdlib>
 
+#include <cctype>
+#include <cstdio>
+#include <string>
+
+#include <sched.h>
+
 #include "common.cuh"
 
 extern "C" int sfb200_version(void) { return 100; }
@@ -31,6 +37,57 @@ extern "C" int sfb200_ctx_create(int device, sfb200_ctx** out) {
     cudaEventCreate(&c->ev1);
     *out = c;
     return SFB200_OK;
+}
+
+// "0-13,56-69" -> CPU set; false when the text holds anything else
+static bool parse_cpulist(const std::string& txt, cpu_set_t* set) {
+    CPU_ZERO(set);
+    size_t i = 0;
+    int n = 0;
+    while (i < txt.size()) {
+        if (isspace((unsigned char)txt[i]) || txt[i] == ',') { ++i; continue; }
+        if (!isdigit((unsigned char)txt[i])) return false;
+        long a = 0, b;
+        while (i < txt.size() && isdigit((unsigned char)txt[i])) a = a * 10 + (txt[i++] - '0');
+        b = a;
+        if (i < txt.size() && txt[i] == '-') {
+            ++i; b = 0;
+            if (i >= txt.size() || !isdigit((unsigned char)txt[i])) return false;
+            while (i < txt.size() && isdigit((unsigned char)txt[i])) b = b * 10 + (txt[i++] - '0');
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+    }
+    return n > 0;
+}
+
+static bool slurp(const std::string& path, std::string* out) {
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char buf[4096];
+    const size_t n = fread(buf, 1, sizeof(buf) - 1, f);
+    fclose(f);
+    out->assign(buf, n);
+    return n > 0;
+}
+
+extern "C" int sfb200_bind_host_near_device(int device) {
+    if (const char* e = getenv("SFB200_NO_BIND")) if (atoi(e) != 0) return 0;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return SFB200_ENODEV; }
+    for (char* p = bus; *p; ++p) *p = (char)tolower((unsigned char)*p);                 // sysfs spells the address in lower case
+    std::string txt;
+    if (!slurp(std::string("/sys/bus/pci/devices/") + bus + "/numa_node", &txt)) return 0;
+    const int node = atoi(txt.c_str());
+    if (node < 0) return 0;                                                             // the platform does not say
+    if (!slurp("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist", &txt)) return 0;
+    cpu_set_t want, have, both;
+    if (!parse_cpulist(txt, &want)) return 0;
+    if (sched_getaffinity(0, sizeof(have), &have) != 0) return SFB200_EINVAL;
+    CPU_AND(&both, &want, &have);                                                       // never widen what the launcher allowed
+    const int n = CPU_COUNT(&both);
+    if (n == 0 || n == CPU_COUNT(&have)) return 0;
+    if (sched_setaffinity(0, sizeof(both), &both) != 0) return SFB200_EINVAL;
+    return n;
 }
 
 extern "C" void sfb200_ctx_destroy(sfb200_ctx* c) {

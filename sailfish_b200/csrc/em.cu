@@ -683,7 +683,7 @@ bool dense_enabled() { const char* e = getenv("SFB200_EM_DENSE"); return e ? ato
 int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl, bool mark_large, bool* marked);
 
 // hybrid runs (em_dense.cuh): small components on the component CTAs, everything else in the pool loop; SFB200_EM_HYBRID=0 switches it off
-bool hybrid_enabled() { const char* e = getenv("SFB200_EM_HYBRID"); return e ? atoi(e) != 0 : true; }
+bool hybrid_enabled() { const char* e = getenv("SFB200_EM_HYBRID"); return e ? atoi(e) != 0 : false; }   // opt-in: 16.9 vs 17.5 us per iteration on the paralog set, not worth a default
 
 // the partition for n_cta ranges; *marked_again is set when the dense builder sent large components to the pool and wants another pass
 int build_partition_n(sfb200_ctx* c, uint32_t n_cta, int per_sm) {

@@ -37,7 +37,10 @@ struct Error : std::runtime_error {
 // one sfb200_ctx (a CUDA device with its index, class table and inference scratch)
 class Device {
 public:
-    explicit Device(int device = 0) {
+    // bindHost: keep the calling thread (and the parser / reader threads it starts later) on the GPU's NUMA node -- page-locked
+    // batches are then node-local, which is what lets eight ranks of one host copy at the PCIe rate each (sfb200.h)
+    explicit Device(int device = 0, bool bindHost = false) {
+        if (bindHost) sfb200_bind_host_near_device(device);
         const int rc = sfb200_ctx_create(device, &ctx_);
         if (rc != SFB200_OK) throw Error(rc, "sfb200: no usable CUDA device (there is no CPU fallback)");
     }

@@ -862,7 +862,7 @@ int main(int argc, char** argv) {
         if (names.empty()) throw std::runtime_error("no transcripts in " + (a.index.empty() ? a.transcripts : a.index));
         ex.txps.resize(names.size());
         for (size_t i = 0; i < names.size(); ++i) { ex.txps[i].RefName = names[i]; ex.txps[i].RefLength = lens[i]; }
-        sfb200::Device dev(a.device);
+        sfb200::Device dev(a.device, /*bindHost=*/true);         // parser / reader threads start later and inherit the CPU set
         struct stat ist;
         if (!a.index.empty() && stat((a.index + "/device_index.bin").c_str(), &ist) == 0) dev.loadIndex(a.index + "/device_index.bin", (uint32_t)lens.size());
         else dev.buildIndex(seq, off, lens, a.k);

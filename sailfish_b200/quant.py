@@ -206,6 +206,7 @@ def quantify(transcripts, reads1, reads2=None, libtype=None, out_dir="sailfish_q
     fmt = parse_library_format(libtype or ("IU" if paired else "U"))
     if paired != bool(fmt & 1):
         raise ValueError("library type %s does not match the number of read files" % libtype)
+    capi.bind_host_near_device(device)          # reader buffers on the GPU's NUMA node (one process per GPU)
     ctx = capi.Context(device)
     ctx.index_build(seqs=seqs, k=k)
     ctx.map_begin(capi.MapOpts.default(fmt, **(map_kw or {})))

@@ -26,6 +26,7 @@ int sfb200_ctx_create(int, sfb200_ctx** out) { *out = new sfb200_ctx{0, 1000, 0}
 void sfb200_ctx_destroy(sfb200_ctx* c) { delete c; }
 void* sfb200_host_alloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
 void sfb200_host_free(void* p) { std::free(p); }
+int sfb200_bind_host_near_device(int) { return 0; }
 const char* sfb200_last_error(const sfb200_ctx*) { return "stub"; }
 int sfb200_index_build(sfb200_ctx* c, const char*, const uint64_t*, const uint32_t*, uint32_t n, int k) { c->T = n; logf("index_build %u %d", n, k); return SFB200_OK; }
 int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) { c->max_frag_len = o->max_frag_len; c->reads = 0; logf("map_begin %d", o->lib_format_id); return SFB200_OK; }
