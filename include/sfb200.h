@@ -50,7 +50,7 @@ void  sfb200_host_free(void* p);
 /* One process per GPU on a multi-socket host: restrict the CALLING thread (and the threads it creates afterwards) to the CPUs of the
  * NUMA node the device hangs off, so that page-locked read buffers allocated afterwards are node-local and the H2D copies of several
  * ranks do not cross the socket interconnect.  Returns the number of CPUs in the new affinity mask, 0 when nothing was changed
- * (single node, node unknown, or SFB200_NO_BIND=1), < 0 on error.  Call before sfb200_host_alloc / before starting parser threads.
+ * (single node, node or device unknown, or SFB200_NO_BIND=1), < 0 on error.  Call before sfb200_host_alloc / before starting parser threads.
  * (The reference has no counterpart: its parser and mapper threads share one address space, src/SailfishQuantify.cpp:445-520.) */
 int  sfb200_bind_host_near_device(int device);
 

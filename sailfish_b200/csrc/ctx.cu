@@ -73,7 +73,7 @@ static bool slurp(const std::string& path, std::string* out) {
 extern "C" int sfb200_bind_host_near_device(int device) {
     if (const char* e = getenv("SFB200_NO_BIND")) if (atoi(e) != 0) return 0;
     char bus[32] = {0};
-    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return SFB200_ENODEV; }
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return 0; }   // no such device: sfb200_ctx_create says so
     for (char* p = bus; *p; ++p) *p = (char)tolower((unsigned char)*p);                 // sysfs spells the address in lower case
     std::string txt;
     if (!slurp(std::string("/sys/bus/pci/devices/") + bus + "/numa_node", &txt)) return 0;

@@ -319,7 +319,11 @@ __device__ __forceinline__ uint32_t lcp_at(const IndexView& ix, const Read& r, c
     return m < lim ? m : lim;
 }
 
-struct Interval { uint32_t lb, cnt, qpos, m, mask; };   // mask: which of the first 32 bucket entries reach the maximal match m
+// mask: buckets of at most 32 positions -- which entries reach the maximal match m; larger buckets -- offset of the bucket's words in
+// the chunk's IvPool (one word per 32 entries, see extend_coop), or IV_NO_EXT
+struct Interval { uint32_t lb, cnt, qpos, m, mask; };
+constexpr uint32_t IV_NO_EXT = 0xFFFFFFFFu;
+struct IvPool { unsigned long long* words; unsigned long long* cursor; unsigned long long cap; };
 
 // continue a table lookup whose first slot (already loaded) held another k-mer: linear probing from the next slot
 __device__ __forceinline__ bool table_find_from(const IndexView& ix, uint64_t km, uint64_t h, uint32_t& lb, uint32_t& cnt) {
@@ -429,7 +433,7 @@ __device__ __forceinline__ void extend_seed(const IndexView& ix, const Read* rds
         else if (l == m && e < 32) mask |= 1u << e;
     }
     iv_out[st.s * MAX_IV + st.n] = pack_iv(lb, cnt, q, m);
-    ivmask_out[st.s * MAX_IV + st.n] = mask;
+    ivmask_out[st.s * MAX_IV + st.n] = cnt <= 32u ? mask : IV_NO_EXT;                  // big bucket: the finalize kernel extends again
     ++st.n;
     st.i = q + m - ix.k + 1;                                                           // next k-mer ends one base past the match
     st.pend_cnt = 0;
@@ -482,7 +486,8 @@ __device__ __forceinline__ uint32_t lcp_clean(const IndexView& ix, uint32_t sb, 
 
 // all 32 lanes call this; todo = lanes whose pending seed belongs to a read without invalid bases
 __device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds, ScanState& st, unsigned todo, unsigned lane,
-                                            unsigned long long* __restrict__ iv_all, uint32_t* __restrict__ ivmask_all, uint64_t iv_base) {
+                                            unsigned long long* __restrict__ iv_all, uint32_t* __restrict__ ivmask_all, uint64_t iv_base,
+                                            const IvPool pool) {
     const unsigned grp = lane / EXT_G, sub = lane % EXT_G;
     const uint32_t my_len = (st.s >> 1) ? rds[1].len : rds[0].len;     // only read from lanes that own a pending seed
     // seeds with large buckets first (paralog families, repeats: hundreds of positions): the whole warp takes one seed, a bucket entry per
@@ -497,16 +502,36 @@ __device__ __forceinline__ void extend_coop(const IndexView& ix, const Read* rds
         const int ss = __shfl_sync(0xffffffffu, st.s, src);
         const uint32_t sb = ((ss >> 1) ? rds[1].sb : rds[0].sb) + (unsigned)src - lane;
         uint32_t best = 0, mask = 0;
-        for (uint32_t e = lane; e < cnt; e += 32) {
-            const uint2 en = sa_pos_rem(ix, lb + e);
-            const uint32_t l = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.y);
-            if (l > best) { best = l; mask = e < 32 ? (1u << e) : 0u; }
-            else if (l == best && e < 32) mask |= 1u << e;
-        }
+        if (cnt <= 32u) {
+            if (lane < cnt) {
+                const uint2 en = sa_pos_rem(ix, lb + lane);
+                best = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.y);
+                mask = 1u << lane;
+            }
 #pragma unroll
-        for (unsigned d = 1; d < 32; d <<= 1) {
-            const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), om = __shfl_xor_sync(0xffffffffu, mask, d);
-            if (ob > best) { best = ob; mask = om; } else if (ob == best) mask |= om;
+            for (unsigned d = 1; d < 32; d <<= 1) {
+                const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), om = __shfl_xor_sync(0xffffffffu, mask, d);
+                if (ob > best) { best = ob; mask = om; } else if (ob == best) mask |= om;
+            }
+        } else {
+            // more than 32 positions: one word per round of 32 entries goes to the chunk's pool -- the round's longest match in the high
+            // half, which of its entries reach it in the low half; an entry reaches the seed's maximal match iff its round's maximum
+            // IS that match and its bit is set.  The interval's mask word carries the pool offset (IV_NO_EXT: pool exhausted, the
+            // finalize kernel then extends the entries itself)
+            const uint32_t rounds = (cnt + 31u) >> 5;
+            unsigned long long po = 0;
+            if (lane == 0) po = atomicAdd(pool.cursor, (unsigned long long)rounds);
+            po = __shfl_sync(0xffffffffu, po, 0);
+            mask = po + rounds <= pool.cap ? (uint32_t)po : IV_NO_EXT;
+            for (uint32_t r = 0; r < rounds; ++r) {
+                const uint32_t e = r * 32u + lane;
+                uint32_t l = 0;
+                if (e < cnt) { const uint2 en = sa_pos_rem(ix, lb + e); l = lcp_clean(ix, sb, len, ss & 1, q, en.x, en.y); }
+                const uint32_t mr = __reduce_max_sync(0xffffffffu, l);
+                const unsigned bits = __ballot_sync(0xffffffffu, e < cnt && l == mr);
+                if (lane == 0 && mask != IV_NO_EXT) pool.words[mask + r] = ((unsigned long long)mr << 32) | bits;
+                best = mr > best ? mr : best;
+            }
         }
         if ((int)lane == src) {
             iv_all[iv_base + st.s * MAX_IV + st.n] = pack_iv(st.pend_lb, st.pend_cnt, st.i, best);
@@ -623,11 +648,37 @@ __device__ __noinline__ uint32_t lcp_global(const IndexView& ix, const ReadG& r,
     return m < lim ? m : lim;
 }
 
+// which of the bucket entries [base, base + 32) of interval a reach its maximal match
+__device__ __forceinline__ uint32_t reach_bits(const IndexView& ix, const ReadG& r, int o, const Interval& a, uint32_t base, const IvPool& pool) {
+    if (a.cnt <= 32u) return a.mask;
+    if (a.mask != IV_NO_EXT) {
+        const unsigned long long w = __ldg(pool.words + a.mask + (base >> 5));
+        return (uint32_t)(w >> 32) == a.m ? (uint32_t)w : 0u;
+    }
+    uint32_t bits = 0;                                   // no pool words (pool exhausted, or a read with invalid bases): extend here
+    const uint32_t end = a.cnt - base < 32u ? a.cnt - base : 32u;
+    for (uint32_t j = 0; j < end; ++j) {
+        const uint2 pr = sa_pos_rem(ix, a.lb + base + j);
+        if (lcp_global(ix, r, o, a.qpos, pr.x, pr.y) == a.m) bits |= 1u << j;
+    }
+    return bits;
+}
+__device__ __forceinline__ bool reach_one(const IndexView& ix, const ReadG& r, int o, const Interval& b, uint32_t e_rel, const IvPool& pool) {
+    if (b.cnt <= 32u) return (b.mask >> e_rel) & 1u;
+    if (b.mask != IV_NO_EXT) {
+        const unsigned long long w = __ldg(pool.words + b.mask + (e_rel >> 5));
+        return (uint32_t)(w >> 32) == b.m && ((w >> (e_rel & 31u)) & 1ULL);
+    }
+    const uint2 pr = sa_pos_rem(ix, b.lb + e_rel);
+    return lcp_global(ix, r, o, b.qpos, pr.x, pr.y) == b.m;
+}
+
 // transcripts present with the maximal match in every interval; output ascending by transcript id;
 // stops after cap+1 hits (list overflow).  The first four suffix entries of the first interval's bucket are loaded together (most
-// buckets are no larger), so the walk over the bucket is one memory round trip instead of one per entry.
+// buckets are no larger), so the walk over the bucket is one memory round trip instead of one per entry; only entries that reach
+// the maximal match are visited (their bits: the scan's mask, or its pool words for buckets of more than 32 positions).
 __device__ uint32_t project(const IndexView& ix, const ReadG& r, int o, const Interval* ivs, int niv, uint32_t cap,
-                            const Scratch& out, uint32_t region) {
+                            const Scratch& out, uint32_t region, const IvPool& pool) {
     if (niv == 0) return 0;
     uint32_t n = 0;
     const Interval a = ivs[0];
@@ -637,34 +688,35 @@ __device__ uint32_t project(const IndexView& ix, const ReadG& r, int o, const In
     if (a.cnt > 1) pre1 = sa_tid_rel(ix, a.lb + 1);
     if (a.cnt > 2) pre2 = sa_tid_rel(ix, a.lb + 2);
     if (a.cnt > 3) pre3 = sa_tid_rel(ix, a.lb + 3);
-    for (uint32_t e_rel = 0; e_rel < a.cnt; ++e_rel) {
-        uint2 en;
-        if (e_rel < 4) en = e_rel == 0 ? pre0 : e_rel == 1 ? pre1 : e_rel == 2 ? pre2 : pre3;
-        else en = sa_tid_rel(ix, a.lb + e_rel);
-        const uint32_t tid = en.x;
-        if (tid == lastTid) continue;
-        if (e_rel < 32) { if (!((a.mask >> e_rel) & 1u)) continue; }
-        else { const uint2 pr = sa_pos_rem(ix, a.lb + e_rel); if (lcp_global(ix, r, o, a.qpos, pr.x, pr.y) != a.m) continue; }
-        lastTid = tid;
-        bool all = true;
-        for (int j = 1; j < niv && all; ++j) {
-            const Interval b = ivs[j];
-            uint32_t lo = b.lb, hi = b.lb + b.cnt;
-            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(&ix.sa[mid].x) < tid) lo = mid + 1; else hi = mid; }
-            bool found = false;
-            for (uint32_t e2 = lo; e2 < b.lb + b.cnt; ++e2) {
-                if (__ldg(&ix.sa[e2].x) != tid) break;
-                const uint32_t e2_rel = e2 - b.lb;
-                if (e2_rel < 32) { if ((b.mask >> e2_rel) & 1u) { found = true; break; } }
-                else { const uint2 pr = sa_pos_rem(ix, e2); if (lcp_global(ix, r, o, b.qpos, pr.x, pr.y) == b.m) { found = true; break; } }
+    for (uint32_t base = 0; base < a.cnt; base += 32u) {
+        uint32_t bits = reach_bits(ix, r, o, a, base, pool);
+        while (bits) {
+            const uint32_t e_rel = base + (uint32_t)__ffs((int)bits) - 1u;
+            bits &= bits - 1u;
+            uint2 en;
+            if (e_rel < 4) en = e_rel == 0 ? pre0 : e_rel == 1 ? pre1 : e_rel == 2 ? pre2 : pre3;
+            else en = sa_tid_rel(ix, a.lb + e_rel);
+            const uint32_t tid = en.x;
+            if (tid == lastTid) continue;
+            lastTid = tid;
+            bool all = true;
+            for (int j = 1; j < niv && all; ++j) {
+                const Interval b = ivs[j];
+                uint32_t lo = b.lb, hi = b.lb + b.cnt;
+                while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (__ldg(&ix.sa[mid].x) < tid) lo = mid + 1; else hi = mid; }
+                bool found = false;
+                for (uint32_t e2 = lo; e2 < b.lb + b.cnt; ++e2) {
+                    if (__ldg(&ix.sa[e2].x) != tid) break;
+                    if (reach_one(ix, r, o, b, e2 - b.lb, pool)) { found = true; break; }
+                }
+                all = found;
             }
-            all = found;
+            if (!all) continue;
+            const int32_t pos = (int32_t)en.y - (int32_t)a.qpos;
+            out.set(region, n, pack_hit(tid, pos, o == 0));
+            ++n;
+            if (n > cap) return n;
         }
-        if (!all) continue;
-        const int32_t pos = (int32_t)en.y - (int32_t)a.qpos;
-        out.set(region, n, pack_hit(tid, pos, o == 0));
-        ++n;
-        if (n > cap) return n;
     }
     return n;
 }
@@ -673,10 +725,10 @@ __device__ uint32_t project(const IndexView& ix, const ReadG& r, int o, const In
 // region `where` (a projection region when only one orientation hit -- the usual case -- else `dst`)
 __device__ bool collect(const IndexView& ix, const ReadG& r, bool strict, uint32_t cap, const Interval* ivF, int nivF,
                         uint64_t scF, const Interval* ivR, int nivR, uint64_t scR, const Scratch& scr,
-                        uint32_t dst, uint32_t& n_out, uint32_t& where) {
+                        uint32_t dst, uint32_t& n_out, uint32_t& where, const IvPool& pool) {
     n_out = 0; where = dst;
-    uint32_t nF = project(ix, r, 0, ivF, nivF, cap, scr, R_A);
-    uint32_t nR = project(ix, r, 1, ivR, nivR, cap, scr, R_B);
+    uint32_t nF = project(ix, r, 0, ivF, nivF, cap, scr, R_A, pool);
+    uint32_t nR = project(ix, r, 1, ivR, nivR, cap, scr, R_B, pool);
     if (nF > cap || nR > cap) return false;
     if (strict && nF && nR) { if (scF > scR) nR = 0; else if (scR > scF) nF = 0; }
     if (nF + nR > cap) return false;
@@ -708,10 +760,13 @@ struct MapParams {
     int16_t* fld_val;                  // per read of the batch: fragment length if FLD-eligible, else -1
     // packed batch and the scan -> finalize hand-over
     const uint64_t* pk; const uint64_t* pkn; const uint32_t* meta; uint32_t rwp; int n_mates;
-    unsigned long long* iv; uint8_t* niv; uint32_t* ivmask;
+    unsigned long long* iv; uint8_t* niv; uint32_t* ivmask; IvPool pool;
     // bias / GC sample collection (k_finalize_reads_bias only)
     // class-table growth: reads whose upsert failed are listed (retry_out) and finalized again after the table has grown (retry_in)
     uint32_t* retry_out; const uint32_t* retry_in; uint64_t n_retry;
+    // reads with a big seed bucket are set aside by the main finalize pass (heavy_out, counted in tb.cursor[5]) and finalized by a
+    // second launch (heavy_in): map_finalize_body.inl
+    uint32_t* heavy_out; const uint32_t* heavy_in;
     int16_t* bias_val;                 // per read of the batch: bin of its read-start context, or -1
     unsigned int* gc_hist;             // observed fragment GC histogram (101 bins), accumulated over batches
     int bias_seq, bias_gc;
@@ -788,7 +843,7 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
             const uint64_t ivb = frag * (uint64_t)(ns * MAX_IV);
             const bool dirty = pend && ((st.s >> 1) ? rds[1].has_n : rds[0].has_n);
             const unsigned clean_m = pend_m & ~__ballot_sync(0xffffffffu, dirty);
-            if (clean_m) extend_coop(p.ix, rds, st, clean_m, lane, p.iv, p.ivmask, ivb);
+            if (clean_m) extend_coop(p.ix, rds, st, clean_m, lane, p.iv, p.ivmask, ivb, p.pool);
             if (dirty) extend_seed(p.ix, rds, rns, st, p.iv + ivb, p.ivmask + ivb);
             pend = false;                                  // every pending seed of the warp has been extended
         }
@@ -801,6 +856,9 @@ __global__ void __launch_bounds__(MAP_THREADS, SFB_SCAN_BLOCKS) k_scan_reads(con
 // ---- finalize kernel: projection, mate merge, compatibility filter, label, class upsert -----------------------------------------
 #ifndef SFB_FIN_BLOCKS
 #define SFB_FIN_BLOCKS 2      // 106 registers without spills; 3 CTAs (80 registers, spills) measured 5% slower (profiles/r02c_variants.txt)
+#endif
+#ifndef SFB_HEAVY_CNT
+#define SFB_HEAVY_CNT 32u      // a read with a seed bucket larger than this is finalized in the heavy pass
 #endif
 __global__ void __launch_bounds__(MAP_THREADS, SFB_FIN_BLOCKS) k_finalize_reads(const MapParams p) {
 #define SFB_FIN_BIAS 0
@@ -978,6 +1036,9 @@ struct MapState {
     sfb200_map_opts o;
     bool begun = false;
     DevBuf<unsigned long long> slot, count, cursor, counters, next_read, scratch, fin;
+    DevBuf<uint32_t> heavy;            // reads set aside by the main finalize pass
+    DevBuf<unsigned long long> ivpool; // extension words of big seed buckets (IvPool)
+    bool defer_heavy = true;           // SFB200_NO_HEAVY_PASS=1: one pass (A/B)
     DevBuf<uint32_t> arena;
     DevBuf<unsigned int> fld_hist;
     DevBuf<int> remaining;
@@ -1023,7 +1084,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     MapState* m = c->map;
     if (!m) return;
     m->slot.release(); m->count.release(); m->cursor.release(); m->counters.release(); m->next_read.release();
-    m->scratch.release(); m->fin.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
+    m->scratch.release(); m->fin.release(); m->heavy.release(); m->ivpool.release(); m->arena.release(); m->fld_hist.release(); m->remaining.release(); m->fld_val.release(); m->fld_samples.release();
     m->mg_sizes.release(); m->mg_cnt.release(); m->mg_cnt_g.release(); m->mg_start.release(); m->mg_len.release(); m->mg_lab.release();
     m->mg_start_g.release(); m->mg_len_g.release(); m->mg_lab_g.release(); m->fld_send.release(); m->fld_recv.release();
     m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release(); m->clipped.release(); m->retry[0].release(); m->retry[1].release();
@@ -1051,6 +1112,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->o = *o;
     cudaStream_t s = c->stream;
     // table geometry: SFB200_EQ_LOG2_BUCKETS (default 21 -> 8M slots) and SFB200_EQ_ARENA_LOG2 words (default 26)
+    { const char* e = getenv("SFB200_NO_HEAVY_PASS"); m->defer_heavy = !(e && atoi(e) != 0); }
     int lb = 21, la = 26;
     if (const char* e = getenv("SFB200_EQ_LOG2_BUCKETS")) lb = std::max(4, std::min(30, atoi(e)));
     if (const char* e = getenv("SFB200_EQ_ARENA_LOG2")) la = std::max(10, std::min(33, atoi(e)));
@@ -1225,6 +1287,7 @@ static int eq_grow_and_retry(sfb200_ctx* c, MapState* m) {
         p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p;
         p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
         p.retry_in = m->retry[round & 1].p; p.retry_out = m->retry[(round & 1) ^ 1].p; p.n_retry = n_retry;
+        p.heavy_out = nullptr; p.heavy_in = nullptr;
         p.fld_val = nullptr; p.bias_val = nullptr; p.bias_seq = 0; p.bias_gc = 0;
         if (n_retry) {
             k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, (n_retry + MAP_THREADS - 1) / MAP_THREADS), MAP_THREADS, FIN_SMEM, s>>>(p);
@@ -1308,21 +1371,41 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     k_pack_reads<<<(unsigned)((n_fm * rwp + 255) / 256), 256, 0, s>>>(d_bases1, d_off1, d_bases2, d_off2, n_reads, n_mates, rwp, m->pk.p, m->pkn.p, m->meta.p);
     c->launches++;
     p.pk = m->pk.p; p.pkn = m->pkn.p; p.meta = m->meta.p; p.rwp = rwp; p.n_mates = n_mates; p.iv = m->iv.p; p.niv = m->niv.p; p.ivmask = m->ivmask.p;
+    // per chunk: the number of reads set aside for the heavy finalize pass (cursor[5]) and the pool of per-round extension words of
+    // big seed buckets (cursor[6]; 32 bytes per read -- a bucket of 1000 positions takes 32 words; when the pool runs out the
+    // finalize kernel extends those entries itself)
+    uint64_t pool_cap = std::max<uint64_t>(1u << 16, 4 * n_reads);
+    if (const char* e = getenv("SFB200_IVPOOL_WORDS")) pool_cap = (uint64_t)std::max<long long>(1, atoll(e));     // tests: a pool that runs out
+    SFB_CUDA(c, m->ivpool.reserve(pool_cap));
+    SFB_CUDA(c, cudaMemsetAsync(m->cursor.p + 5, 0, 16, s));
+    p.pool.words = m->ivpool.p; p.pool.cursor = m->cursor.p + 6; p.pool.cap = pool_cap;
     // 3. seed scan (lanes pull fragments), 4. finalize (projection .. class upsert)
     const size_t smem = (size_t)MAP_THREADS * n_mates * 2 * RW * 8;
     const uint64_t blocks_needed = (n_reads + MAP_THREADS - 1) / MAP_THREADS;
     k_scan_reads<<<(unsigned)std::min<uint64_t>(m->grid_scan, blocks_needed), MAP_THREADS, smem, s>>>(p);
     c->launches++;
     const bool bias = m->bias_seq || m->bias_gc;
-    if (!bias) {
-        k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, FIN_SMEM, s>>>(p);
-    } else {
+    if (bias) {
         if (m->bias_seq) { SFB_CUDA(c, m->bias_val.reserve(n_reads)); p.bias_val = m->bias_val.p; }
         p.gc_hist = m->bias_hist.p + BNK; p.bias_seq = m->bias_seq ? 1 : 0; p.bias_gc = (m->bias_gc && n_mates == 2) ? 1 : 0;
-        k_finalize_reads_bias<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, FIN_SMEM, s>>>(p);
     }
-    c->launches++;
-    SFB_CUDA(c, cudaGetLastError());
+    // main pass, then the reads it set aside (big seed buckets); the second launch reads their number on the device
+    const bool defer = m->defer_heavy;
+    if (defer) {
+        SFB_CUDA(c, m->heavy.reserve(n_reads));
+        p.heavy_out = m->heavy.p;
+    }
+    for (int pass = 0; pass < (defer ? 2 : 1); ++pass) {
+        if (pass == 1) {
+            SFB_CUDA(c, cudaMemsetAsync(m->next_read.p + 1, 0, 8, s));
+            p.heavy_out = nullptr; p.heavy_in = m->heavy.p;
+        }
+        if (!bias) k_finalize_reads<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, FIN_SMEM, s>>>(p);
+        else k_finalize_reads_bias<<<(unsigned)std::min<uint64_t>(m->grid, blocks_needed), MAP_THREADS, FIN_SMEM, s>>>(p);
+        c->launches++;
+        SFB_CUDA(c, cudaGetLastError());
+    }
+    p.heavy_out = nullptr; p.heavy_in = nullptr;                       // a replay after table growth (eq_grow_and_retry) lists its reads itself
     m->last_p = p; m->have_last = true;
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used + 1], s));
     m->ev_used += 2;

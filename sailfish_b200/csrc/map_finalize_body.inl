@@ -20,29 +20,34 @@
     uint64_t score[4];
 
     // retry pass (p.retry_in != nullptr): the class table or the label arena was full when these reads were finalized; the table has
-    // grown since (sfb_eq_grow, map.cu) and only their class upsert is repeated -- they were counted the first time
+    // grown since (sfb_eq_grow, map.cu) and only their class upsert is repeated -- they were counted the first time.
+    // heavy pass (p.heavy_in != nullptr): the reads the main pass set aside because one of their seeds has a bucket of more than
+    // SFB_HEAVY_CNT positions (repeats, paralog families).  Walking such a bucket is hundreds of dependent loads by ONE lane; in the
+    // main pass the other 31 lanes of the warp waited for it (ncu on the paralog set: 2 of 32 lanes active, 7.2 ms per 2 M reads
+    // against 0.6 ms without such reads).  Set aside and finalized together, every lane of a warp has such a read.
     const bool retry = p.retry_in != nullptr;
-    const uint64_t n_work = retry ? p.n_retry : p.n_reads;
+    const bool heavy_pass = p.heavy_in != nullptr;
+    const uint32_t* __restrict__ list_in = retry ? p.retry_in : p.heavy_in;
+    const uint64_t n_work = retry ? p.n_retry : heavy_pass ? (uint64_t)__ldcg(p.tb.cursor + 5) : p.n_reads;
     for (;;) {
         unsigned long long base_idx = 0;
         if (lane == 0) base_idx = atomicAdd(p.next_read + 1, 32ULL);
         base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
         if (base_idx >= n_work) break;
-        const bool have_read = base_idx + lane < n_work;
-        const uint64_t ri = have_read ? (retry ? (uint64_t)p.retry_in[base_idx + lane] : base_idx + lane) : 0;
+        bool have_read = base_idx + lane < n_work;
+        const uint64_t ri = have_read ? (list_in ? (uint64_t)list_in[base_idx + lane] : base_idx + lane) : 0;
         bool mapped = false;
         uint32_t lab_n = 0;
+        uint32_t len1 = 0, len2 = 0;
+        ReadG rg[2];
         if (have_read) {
-            uint32_t nL = 0, nR = 0, wL = R_LEFT, wR = R_RIGHT;
-            bool okL, okR = true;
-            ReadG rg[2];
             for (int mt = 0; mt < p.n_mates; ++mt) {
                 const uint64_t fm = ri * p.n_mates + mt;
                 const uint32_t me = p.meta[fm];
                 rg[mt].pk = p.pk + fm * p.rwp; rg[mt].pkn = p.pkn + fm * p.rwp; rg[mt].len = me & 0xFFFFu; rg[mt].has_n = (me >> 16) & 1u;
             }
-            const uint32_t len1 = rg[0].len;
-            const uint32_t len2 = paired ? rg[1].len : 0;
+            len1 = rg[0].len;
+            len2 = paired ? rg[1].len : 0;
             // the interval counts of all scans in one load, and the first interval of every scan loaded before the counts are known
             // (the hand-over arrays are allocated for MAX_IV intervals per scan, so the load is always in bounds)
             const uint32_t nv = paired ? *reinterpret_cast<const uint32_t*>(p.niv + ri * 4) : *reinterpret_cast<const uint16_t*>(p.niv + ri * 2);
@@ -51,26 +56,36 @@
             for (int q = 0; q < 4; ++q) {
                 if (q < ns) { iv0[q] = p.iv[(ri * ns + q) * MAX_IV]; mk0[q] = p.ivmask[(ri * ns + q) * MAX_IV]; }
             }
+            uint32_t big = 0;                                   // largest bucket among this read's seeds
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (q >= ns) continue;
                 niv[q] = (nv >> (8 * q)) & 0xFFu;
                 uint64_t sc = 0;
-                if (niv[q] > 0) { ivs[q][0] = unpack_iv(iv0[q]); ivs[q][0].mask = mk0[q]; sc = ivs[q][0].m; }
+                if (niv[q] > 0) { ivs[q][0] = unpack_iv(iv0[q]); ivs[q][0].mask = mk0[q]; sc = ivs[q][0].m; big = ivs[q][0].cnt > big ? ivs[q][0].cnt : big; }
                 for (int e = 1; e < niv[q]; ++e) {
                     ivs[q][e] = unpack_iv(p.iv[(ri * ns + q) * MAX_IV + e]);
                     ivs[q][e].mask = p.ivmask[(ri * ns + q) * MAX_IV + e];
                     sc += ivs[q][e].m;
+                    big = ivs[q][e].cnt > big ? ivs[q][e].cnt : big;
                 }
                 score[q] = sc;
             }
-            okL = collect(p.ix, rg[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, R_LEFT, nL, wL);   // paired: strict check (:192-202)
+            if (p.heavy_out && big > SFB_HEAVY_CNT) {          // main pass: not now
+                p.heavy_out[atomicAdd(p.tb.cursor + 5, 1ULL)] = (uint32_t)ri;
+                have_read = false;
+            }
+        }
+        if (have_read) {
+            uint32_t nL = 0, nR = 0, wL = R_LEFT, wR = R_RIGHT;
+            bool okL, okR = true;
+            okL = collect(p.ix, rg[0], paired, cap, ivs[0], niv[0], score[0], ivs[1], niv[1], score[1], scr, R_LEFT, nL, wL, p.pool);   // paired: strict check (:192-202)
             if (paired) {
                 if (okL && wL != R_LEFT) {            // the projection regions are about to be reused by the right mate
                     for (uint32_t i = 0; i < nL; ++i) scr.set(R_LEFT, i, scr.get(wL, i));
                     wL = R_LEFT;
                 }
-                okR = collect(p.ix, rg[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, R_RIGHT, nR, wR);
+                okR = collect(p.ix, rg[1], true, cap, ivs[2], niv[2], score[2], ivs[3], niv[3], score[3], scr, R_RIGHT, nR, wR, p.pool);
             }
             const bool overflow = !okL || !okR;
             LabelAcc acc(scr, p.enforce_compat != 0);

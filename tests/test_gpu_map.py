@@ -151,6 +151,32 @@ def test_small_k_and_many_hits(ctx):
         assert_same_classes(ctx, g, w)
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_repeats_and_families_match_oracle(ctx, paired, monkeypatch):
+    """Paralog families and repeat elements (synth.make_transcriptome): seed buckets of hundreds of positions next to ordinary reads.
+    The finalize kernel sets the reads with a bucket of more than 32 positions aside and runs them in a second pass, with the scan's
+    per-round extension words instead of its 32-bit mask; the classes must not change -- with the pool (default), with a pool too
+    small for most buckets (SFB200_IVPOOL_WORDS: the finalize kernel extends the entries itself) and in one pass (SFB200_NO_HEAVY_PASS)."""
+    seq, off, ln = synth.make_transcriptome(1500, seed=5, family_frac=0.2, family_genes=(10, 120), repeat_frac=0.5, repeat_len=200)
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 40000, 76, seed=9, paired=paired, sub_rate=0.01, n_rate=0.002)
+    lib = "IU" if paired else "U"
+    st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, b2, o2, lib, batches=2)
+    assert st["max_bucket"] > 200                              # the case is what it says
+    assert_same_classes(ctx, g, w)
+    for env in ({"SFB200_IVPOOL_WORDS": "64"}, {"SFB200_NO_HEAVY_PASS": "1"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        ctx.map_begin(capi.MapOpts.default(O.parse_libtype(lib)))
+        if paired:
+            ctx.map_batch(b1, o1, b2, o2)
+        else:
+            ctx.map_batch(b1, o1)
+        g2 = ctx.map_finish()
+        assert_same_classes(ctx, g2, w)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+
+
 def test_full_size_properties(ctx):
     """Larger run (2 000 genes = 10 000 transcripts, 400k reads): invariants that do not need the oracle at size, plus
     the oracle on the same input with 8 host threads."""
