@@ -3,6 +3,10 @@ rep=sys.argv[1]; cubin=sys.argv[2]; kern=sys.argv[3]; src=sys.argv[4]
 ncu_kern=sys.argv[5] if len(sys.argv)>5 else kern   # demangled-name regex for ncu when `kern` is a mangled fragment
 out=subprocess.run("ncu -i %s --page source --csv --kernel-name regex:%s" % (rep, ncu_kern),shell=True,capture_output=True,text=True).stdout
 rows=list(csv.reader(io.StringIO(out)))
+# one block of rows per captured launch of the kernel ("Kernel Name" line, header line, SASS rows); argv[6] = which block (default 0)
+starts=[i for i,r in enumerate(rows) if r and r[0]=="Kernel Name"]+[len(rows)]
+blk=int(sys.argv[6]) if len(sys.argv)>6 else 0
+rows=rows[starts[blk]:starts[blk+1]] if len(starts)>1 else rows
 hi=[i for i,r in enumerate(rows) if "Source" in r and "Address" in r][0]
 hdr=rows[hi]; si=hdr.index("Warp Stall Sampling (All Samples)"); so=hdr.index("Source"); ie=hdr.index("Instructions Executed"); te=hdr.index("Thread Instructions Executed")
 body=[r for r in rows[hi+1:] if len(r)>si]
