@@ -222,6 +222,8 @@ int sfb200_gibbs_run(sfb200_ctx* ctx, const double* eff_lens, const double* mass
 int sfb200_xxh64_device(sfb200_ctx* ctx, const uint8_t* data, const uint64_t* off, uint64_t n, uint64_t seed, uint64_t* out);
 /* device digamma (VBEM) for accuracy tests */
 int sfb200_digamma_device(sfb200_ctx* ctx, const double* x, uint64_t n, double* out);
+/* exp(digamma(x)) as the VBEM kernels evaluate it (series without the logarithm, csrc/vb_math.hpp) */
+int sfb200_exp_digamma_device(sfb200_ctx* ctx, const double* x, uint64_t n, double* out);
 
 #ifdef __cplusplus
 }

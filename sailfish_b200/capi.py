@@ -107,6 +107,7 @@ SIGNATURES = {
     "sfb200_gibbs_run": (C.c_int, [C.c_void_p, f64p, f64p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, I32_ROW_CB, C.c_void_p]),
     "sfb200_xxh64_device": (C.c_int, [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, u64p]),
     "sfb200_digamma_device": (C.c_int, [C.c_void_p, f64p, C.c_uint64, f64p]),
+    "sfb200_exp_digamma_device": (C.c_int, [C.c_void_p, f64p, C.c_uint64, f64p]),
 }
 
 
@@ -419,6 +420,12 @@ class Context:
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros(len(x), np.float64)
         self._chk(self.L.sfb200_digamma_device(self.h, _ptr(x, f64p), len(x), _ptr(out, f64p)))
+        return out
+
+    def exp_digamma(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(len(x), np.float64)
+        self._chk(self.L.sfb200_exp_digamma_device(self.h, _ptr(x, f64p), len(x), _ptr(out, f64p)))
         return out
 
 

@@ -248,22 +248,5 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p);
 
 #include "kmer_filter.hpp"     // k-mer table hash + the presence filter's addressing (also compiled by the CPU tests)
 
-// digamma for x > 0: recurrence up to x >= 12, then the asymptotic series (same expansion as the oracle's
-// stand-in for boost::math::digamma; checked against scipy in tests/).  The recurrence psi(x) = psi(x + n) - sum 1/(x + k) is the
-// expensive part of a VBEM iteration (up to twelve fp64 divisions per transcript): the sum of reciprocals is P'/P of the polynomial
-// P = prod (x + k), built with two multiplies and an FMA per factor and ONE division -- after a first term taken by itself
-// when x < 1, so that P stays far from the denormal range for the tiny alphas VBEM produces.
-__host__ __device__ inline double sfb_digamma(double x) {
-    double acc = 0.0;
-    if (x < 1.0) { acc = -1.0 / x; x += 1.0; }
-    if (x < 12.0) {
-        double P = 1.0, Q = 0.0;                     // P = prod (x + k), Q = dP/dx
-        while (x < 12.0) { Q = fma(Q, x, P); P *= x; x += 1.0; }
-        acc -= Q / P;
-    }
-    const double inv = 1.0 / x, inv2 = inv * inv;
-    const double series = inv2 * (1.0 / 12.0 - inv2 * (1.0 / 120.0 - inv2 * (1.0 / 252.0 - inv2 * (1.0 / 240.0 -
-                          inv2 * (1.0 / 132.0 - inv2 * (691.0 / 32760.0 - inv2 * (1.0 / 12.0)))))));
-    return acc + log(x) - 0.5 * inv - series;
-}
+#include "vb_math.hpp"         // sfb_digamma, sfb_exp_digamma (also compiled by the CPU tests)
 #endif

@@ -240,12 +240,16 @@ extern "C" int sfb200_xxh64_device(sfb200_ctx* c, const uint8_t* data, const uin
     return SFB200_OK;
 }
 
-__global__ void k_digamma(const double* __restrict__ x, uint64_t n, double* __restrict__ out) {
+__global__ void k_digamma(const double* __restrict__ x, uint64_t n, double* __restrict__ out, int exp_form) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = sfb_digamma(x[i]);
+    if (i < n) out[i] = exp_form ? sfb_exp_digamma(x[i]) : sfb_digamma(x[i]);
 }
 
-extern "C" int sfb200_digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* out) {
+static int digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* out, int exp_form);
+extern "C" int sfb200_digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* out) { return digamma_device(c, x, n, out, 0); }
+extern "C" int sfb200_exp_digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* out) { return digamma_device(c, x, n, out, 1); }
+
+static int digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* out, int exp_form) {
     if (!c || !x || !out) return SFB200_EINVAL;
     if (n == 0) return SFB200_OK;
     cudaSetDevice(c->device);
@@ -253,7 +257,7 @@ extern "C" int sfb200_digamma_device(sfb200_ctx* c, const double* x, uint64_t n,
     SFB_CUDA(c, d_x.reserve(n));
     SFB_CUDA(c, d_o.reserve(n));
     SFB_CUDA(c, cudaMemcpyAsync(d_x.p, x, n * 8, cudaMemcpyHostToDevice, c->stream));
-    k_digamma<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_x.p, n, d_o.p);
+    k_digamma<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_x.p, n, d_o.p, exp_form);
     c->launches++;
     SFB_CUDA(c, cudaGetLastError());
     SFB_CUDA(c, cudaMemcpyAsync(out, d_o.p, n * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -280,6 +280,7 @@ __device__ __forceinline__ unsigned long long transcript_pass(const EmParams& p,
                                                               double* spare_out, bool compare, bool reset, double logNorm,
                                                               uint64_t tid0, uint64_t stride) {
     unsigned long long best = 0ULL;
+    const double thetaScale = (VB && reset) ? exp(-logNorm) : 0.0;
     for (uint64_t t = tid0; t < p.T; t += stride) {
         const double c = ld_cg_f64(cur + t);
         if (compare) {
@@ -293,7 +294,7 @@ __device__ __forceinline__ unsigned long long transcript_pass(const EmParams& p,
             }
         }
         if (reset) spare_out[t] = __ldg(p.base + t);
-        if (VB && reset) p.theta[t] = (c > DENORM_MIN) ? exp(sfb_digamma(c) - logNorm) : 0.0;
+        if (VB && reset) p.theta[t] = (c > DENORM_MIN) ? sfb_exp_theta(c, logNorm, thetaScale) : 0.0;
     }
     return best;
 }

@@ -152,19 +152,19 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     Slice sl_pool; sl_pool.start = p.start; sl_pool.len = p.len; sl_pool.cnt = p.cnt; sl_pool.lab = p.lab; sl_pool.w = p.w; sl_pool.c0 = 0; sl_pool.e0 = 0;
     unsigned bi = 0, bo = 1, bs = 2;
     if (VB && has_pool) {
-        const double logNorm = sfb_digamma(p.sum0);
+        const double logNorm = sfb_digamma(p.sum0), thetaScale = exp(-logNorm);
         for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
             const uint32_t t = q.dlist[i];
             const double a = p.X[t];
-            p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+            p.theta[t] = (a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0;
         }
         grid_barrier(p.ctl, nblocks, gen);
     }
     {
-        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
+        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0, thetaScale = VB ? exp(-logNorm) : 0.0;
         for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) {
             const double a = s_alpha[i];
-            const double th = VB ? ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) : a;
+            const double th = VB ? ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) : a;
             s_beta[i] = th * s_inveff[i];
         }
     }
@@ -328,9 +328,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             }
             if (VB) {
                 const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
+                const double thetaScale = exp(-logNorm);
                 for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) {
                     const double a = s_alpha[i];
-                    s_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) * s_inveff[i];
+                    s_beta[i] = ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) * s_inveff[i];
                 }
                 __syncthreads();
                 if (has_pool) {                                        // the pool's expTheta, complete before anyone's next sweep gathers it
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                     for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) {
                         const uint32_t t = q.dlist[i];
                         const double a = ld_cg_f64(cur + t);
-                        p.theta[t] = (a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0;
+                        p.theta[t] = (a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0;
                     }
                     grid_barrier(p.ctl, nblocks, gen);
                 }

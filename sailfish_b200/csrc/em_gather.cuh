@@ -189,10 +189,10 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_gather(const EmParams p, c
     const bool fixed = p.fixed_iters > 0;
     // beta of alpha_0
     {
-        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0;
+        const double logNorm = VB ? sfb_digamma(p.sum0) : 0.0, thetaScale = VB ? exp(-logNorm) : 0.0;
         for (uint32_t i = threadIdx.x; i < nt_pad; i += blockDim.x) {
             const double a = s_alpha[i];
-            const double th = VB ? ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) : a;
+            const double th = VB ? ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) : a;
             s_beta[i] = th * s_inveff[i];
         }
     }
@@ -248,9 +248,10 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_gather(const EmParams p, c
             }
             if (VB) {
                 const double logNorm = sfb_digamma(__longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (m & 3u))));
+                const double thetaScale = exp(-logNorm);
                 for (uint32_t i = threadIdx.x; i < nt_pad; i += blockDim.x) {
                     const double a = s_alpha[i];
-                    s_beta[i] = ((a > DENORM_MIN) ? exp(sfb_digamma(a) - logNorm) : 0.0) * s_inveff[i];
+                    s_beta[i] = ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) * s_inveff[i];
                 }
             }
         }

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_part(const EmParams p, con
                 : p.base_sum + __longlong_as_double((long long)ld_cg_u64(p.ctl + CTL_CSUM + (n & 3u)));
             logNorm = sfb_digamma(asum);
         }
+        const double thetaScale = (VB && !last) ? exp(-logNorm) : 0.0;
         unsigned long long best = 0ULL;
         if (has_pool) best = transcript_pass<VB>(p, spare, in, spare, do_cmp, !last, logNorm, gtid, gstride);
         for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) {       // local transcript pass
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) k_em_part(const EmParams p, con
             }
             if (!last) {
                 s_prev[i] = s_dirty[i] ? 0.0 : __ldg(p.base + t0 + i);     // base stays in global memory (coalesced, L2-resident)
-                if (VB) s_theta[i] = (cur > DENORM_MIN) ? exp(sfb_digamma(cur) - logNorm) : 0.0;
+                if (VB) s_theta[i] = (cur > DENORM_MIN) ? sfb_exp_theta(cur, logNorm, thetaScale) : 0.0;
             }
         }
         if (do_cmp) block_max_to_slot(best, slot, sm_u);

@@ -1060,11 +1060,13 @@ struct MapState {
     DevBuf<uint32_t> mg_start, mg_len, mg_lab, mg_start_g, mg_len_g, mg_lab_g;
     DevBuf<unsigned char> fld_send, fld_recv;
     // two staging sets for host batches: the H2D copy of batch j (copy stream) overlaps the mapping kernel of batch j-1
-    DevBuf<char> bases1[2], bases2[2];
-    DevBuf<uint64_t> off1[2], off2[2];
+    // staging sets for host batches (N_STAGE = 3: the piece being copied, the piece whose kernels are being enqueued, the piece
+    // whose kernels run)
+    DevBuf<char> bases1[3], bases2[3];
+    DevBuf<uint64_t> off1[3], off2[3];
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
-    bool in_use[2] = {false, false};
+    cudaEvent_t copied[3] = {nullptr, nullptr, nullptr}, consumed[3] = {nullptr, nullptr, nullptr};
+    bool in_use[3] = {false, false, false};
     bool primed = false;               // a host batch has been mapped since map_begin (see sfb200_map_batch)
     // --biasCorrect / --gcBiasCorrect sample collection (sfb200_map_set_bias)
     bool bias_seq = false, bias_gc = false;
@@ -1089,7 +1091,7 @@ void sfb_map_state_free(sfb200_ctx* c) {
     m->mg_start_g.release(); m->mg_len_g.release(); m->mg_lab_g.release(); m->fld_send.release(); m->fld_recv.release();
     m->pk.release(); m->pkn.release(); m->meta.release(); m->iv.release(); m->niv.release(); m->ivmask.release(); m->maxlen.release(); m->clipped.release(); m->retry[0].release(); m->retry[1].release();
     m->bias_val.release(); m->bias_hist.release(); m->bias_remaining.release();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         m->bases1[i].release(); m->bases2[i].release(); m->off1[i].release(); m->off2[i].release();
         if (m->copied[i]) cudaEventDestroy(m->copied[i]);
         if (m->consumed[i]) cudaEventDestroy(m->consumed[i]);
@@ -1169,7 +1171,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     c->cls.ready = false;
     m->begun = true;
     m->ev_used = 0; m->kernel_ms = 0.0;
-    m->in_use[0] = m->in_use[1] = false; m->parity = 0; m->primed = false;
+    m->in_use[0] = m->in_use[1] = m->in_use[2] = false; m->parity = 0; m->primed = false;
     m->bias_seq = m->bias_gc = false;
     m->have_last = false; m->n_grown = 0;
     return SFB200_OK;
@@ -1422,42 +1424,47 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     return SFB200_OK;
 }
 
-// one host batch: H2D on the copy stream into one of two staging sets, then the mapping kernels on the compute stream
-static int map_batch_host_one(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2, const uint64_t* off2,
-                              uint64_t n_reads) {
+// Host batches travel in pieces: piece j+1 is on the copy stream while the kernels of piece j are enqueued (a host round trip: the
+// chunk's longest read comes back before the pack kernel is sized) and the kernels of piece j-1 run -- three staging sets.  The copy
+// engine never waits for the host, so a batch costs max(copy, kernels) plus the kernels of its LAST piece; pieces are therefore small
+// (SFB200_HOST_PIECE reads, default 512 k: 0.5 ms of kernels), and the first ones after map_begin smaller still (nothing to hide
+// behind yet).
+constexpr unsigned N_STAGE = 3;
+struct HostPiece { uint64_t at, n; unsigned set; };
+
+static int host_piece_copy(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2, const uint64_t* off2, HostPiece& pc) {
     MapState* m = c->map;
-    if (!m->copy_stream) {
-        SFB_CUDA(c, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            SFB_CUDA(c, cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming));
-            SFB_CUDA(c, cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming));
-        }
-    }
-    const unsigned b = m->parity;
-    m->parity ^= 1u;
-    // this staging set was last read by the kernel of two batches ago
+    const unsigned b = pc.set = m->parity;
+    m->parity = (m->parity + 1u) % N_STAGE;
+    // this staging set was last read by the kernels of three pieces ago
     if (m->in_use[b]) SFB_CUDA(c, cudaEventSynchronize(m->consumed[b]));
     cudaStream_t cs = m->copy_stream;
-    const uint64_t nb1 = off1[n_reads] - off1[0];
-    SFB_CUDA(c, m->bases1[b].reserve(nb1 + 8)); SFB_CUDA(c, m->off1[b].reserve(n_reads + 1));
-    SFB_CUDA(c, cudaMemcpyAsync(m->bases1[b].p, bases1 + off1[0], nb1, cudaMemcpyHostToDevice, cs));
-    SFB_CUDA(c, cudaMemcpyAsync(m->off1[b].p, off1, (n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
-    const char* d_b2 = nullptr; const uint64_t* d_o2 = nullptr;
+    const uint64_t* o1 = off1 + pc.at;
+    const uint64_t nb1 = o1[pc.n] - o1[0];
+    SFB_CUDA(c, m->bases1[b].reserve(nb1 + 8)); SFB_CUDA(c, m->off1[b].reserve(pc.n + 1));
+    SFB_CUDA(c, cudaMemcpyAsync(m->bases1[b].p, bases1 + o1[0], nb1, cudaMemcpyHostToDevice, cs));
+    SFB_CUDA(c, cudaMemcpyAsync(m->off1[b].p, o1, (pc.n + 1) * 8, cudaMemcpyHostToDevice, cs));
     if (bases2) {
-        const uint64_t nb2 = off2[n_reads] - off2[0];
-        SFB_CUDA(c, m->bases2[b].reserve(nb2 + 8)); SFB_CUDA(c, m->off2[b].reserve(n_reads + 1));
-        SFB_CUDA(c, cudaMemcpyAsync(m->bases2[b].p, bases2 + off2[0], nb2, cudaMemcpyHostToDevice, cs));
-        SFB_CUDA(c, cudaMemcpyAsync(m->off2[b].p, off2, (n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
-        d_b2 = m->bases2[b].p - off2[0]; d_o2 = m->off2[b].p;
+        const uint64_t* o2 = off2 + pc.at;
+        const uint64_t nb2 = o2[pc.n] - o2[0];
+        SFB_CUDA(c, m->bases2[b].reserve(nb2 + 8)); SFB_CUDA(c, m->off2[b].reserve(pc.n + 1));
+        SFB_CUDA(c, cudaMemcpyAsync(m->bases2[b].p, bases2 + o2[0], nb2, cudaMemcpyHostToDevice, cs));
+        SFB_CUDA(c, cudaMemcpyAsync(m->off2[b].p, o2, (pc.n + 1) * 8, cudaMemcpyHostToDevice, cs));
     }
     SFB_CUDA(c, cudaEventRecord(m->copied[b], cs));
+    return SFB200_OK;
+}
+
+static int host_piece_map(sfb200_ctx* c, const uint64_t* off1, const uint64_t* off2, const HostPiece& pc) {
+    MapState* m = c->map;
+    const unsigned b = pc.set;
     SFB_CUDA(c, cudaStreamWaitEvent(c->stream, m->copied[b], 0));
-    const int rc = sfb200_map_batch_device(c, m->bases1[b].p - off1[0], m->off1[b].p, d_b2, d_o2, n_reads);
+    // offsets are absolute positions in the caller's arrays: shift the base pointers instead of the offsets
+    const char* d_b2 = off2 ? m->bases2[b].p - off2[pc.at] : nullptr;
+    const int rc = sfb200_map_batch_device(c, m->bases1[b].p - off1[pc.at], m->off1[b].p, d_b2, off2 ? m->off2[b].p : nullptr, pc.n);
     if (rc) return rc;
     SFB_CUDA(c, cudaEventRecord(m->consumed[b], c->stream));
     m->in_use[b] = true;
-    // the caller may reuse its buffers as soon as we return: wait for the copy (not for the kernel)
-    SFB_CUDA(c, cudaEventSynchronize(m->copied[b]));
     return SFB200_OK;
 }
 
@@ -1469,20 +1476,46 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
     if (n_reads == 0) return SFB200_OK;
     if (!bases1 || !off1 || ((bases2 == nullptr) != (off2 == nullptr))) SFB_FAIL(c, SFB200_EINVAL, "map_batch: null array");
     cudaSetDevice(c->device);
-    // The copy of the first reads after map_begin has no kernel to hide behind: start with a small piece and double it, so
-    // that only ~10 MB of H2D are exposed; later batches overlap with the kernels of their predecessor as a whole.
-    uint64_t done = 0;
-    if (!m->primed) {
-        uint64_t piece = 128u << 10;
-        if (const char* e = getenv("SFB200_MAP_RAMP")) piece = (uint64_t)std::max<long long>(0, atoll(e));
-        while (piece && n_reads - done > 2 * piece) {
-            const int rc = map_batch_host_one(c, bases1, off1 + done, bases2, off2 ? off2 + done : nullptr, piece);
-            if (rc) return rc;
-            done += piece; piece *= 2;
+    if (!m->copy_stream) {
+        SFB_CUDA(c, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (unsigned i = 0; i < N_STAGE; ++i) {
+            SFB_CUDA(c, cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming));
+            SFB_CUDA(c, cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming));
         }
-        m->primed = true;
     }
-    return map_batch_host_one(c, bases1, off1 + done, bases2, off2 ? off2 + done : nullptr, n_reads - done);
+    uint64_t piece = 512u << 10, ramp = 128u << 10;
+    if (const char* e = getenv("SFB200_HOST_PIECE")) piece = (uint64_t)std::max<long long>(1024, atoll(e));
+    if (const char* e = getenv("SFB200_MAP_RAMP")) ramp = (uint64_t)std::max<long long>(0, atoll(e));
+    if (m->primed || ramp == 0 || ramp > piece) ramp = piece;        // the first pieces after map_begin: 128 k, 256 k, ... reads
+    m->primed = true;
+    uint64_t at = 0;
+    auto next_piece = [&](HostPiece& pc) {
+        pc.at = at;
+        pc.n = std::min<uint64_t>(ramp, n_reads - at);
+        if (n_reads - at - pc.n < pc.n / 2) pc.n = n_reads - at;        // no sliver at the end
+        at += pc.n;
+        ramp = std::min<uint64_t>(piece, ramp * 2);
+    };
+    HostPiece cur, nxt;
+    next_piece(cur);
+    { const int rc = host_piece_copy(c, bases1, off1, bases2, off2, cur); if (rc) return rc; }
+    unsigned last_set = cur.set;
+    for (;;) {
+        const bool more = at < n_reads;
+        if (more) {
+            next_piece(nxt);
+            const int rc = host_piece_copy(c, bases1, off1, bases2, off2, nxt);
+            if (rc) return rc;
+            last_set = nxt.set;
+        }
+        const int rc = host_piece_map(c, off1, off2, cur);
+        if (rc) return rc;
+        if (!more) break;
+        cur = nxt;
+    }
+    // the caller may reuse its buffers as soon as we return: wait for the last copy (not for the kernels)
+    SFB_CUDA(c, cudaEventSynchronize(m->copied[last_set]));
+    return SFB200_OK;
 }
 
 extern "C" double sfb200_last_map_kernel_ms(const sfb200_ctx* c) { return (c && c->map) ? c->map->kernel_ms : 0.0; }

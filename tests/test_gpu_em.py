@@ -43,6 +43,17 @@ def test_device_digamma(ctx):
     assert ok.all()
 
 
+def test_device_exp_digamma(ctx):
+    """exp(digamma(x)) as the VBEM kernels evaluate it (csrc/vb_math.hpp: series without the logarithm) against scipy; the host build
+    of the same header is checked against mpmath at 50 digits in tests/test_vb_math.py"""
+    from scipy.special import digamma
+    xs = np.concatenate([10.0 ** np.linspace(-2.5, 9, 600), np.linspace(0.002, 40, 800), [15.999999, 16.0, 16.000001]])
+    got = ctx.exp_digamma(xs)
+    want = np.exp(digamma(xs))
+    assert (np.abs(got - want) <= 2e-12 * want).all()
+    assert (ctx.exp_digamma(np.array([1e-3, 5e-4, 1e-9])) == 0.0).all()         # a transcript without reads: exactly 0, as exp(-1000 - logNorm)
+
+
 @pytest.mark.parametrize("name", ["sample_data", "synth_em"])
 @pytest.mark.parametrize("vb", [0, 1])
 def test_em_matches_reference_optimizer_golden(ctx, name, vb, sample_data, synth_em):

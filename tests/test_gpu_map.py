@@ -177,6 +177,31 @@ def test_repeats_and_families_match_oracle(ctx, paired, monkeypatch):
             monkeypatch.delenv(k_)
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_host_batches_in_small_pieces(ctx, paired, monkeypatch):
+    """sfb200_map_batch copies a host batch piece by piece through three staging sets (copy of piece j+1 | enqueue of j | kernels of
+    j-1).  With 1024-read pieces a 30 000-read batch rotates through the sets ten times; ragged read lengths make every piece's byte
+    range different."""
+    seq, off, ln = small_txome()
+    reads1, reads2 = [], []
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, 30000, 100, seed=21, paired=paired, sub_rate=0.01, n_rate=0.002)
+    rng = np.random.default_rng(4)
+    cut = rng.integers(40, 101, size=30000)
+    for i in range(30000):
+        reads1.append(b1[int(o1[i]):int(o1[i]) + int(cut[i])].tobytes())
+        if paired:
+            reads2.append(b2[int(o2[i]):int(o2[i]) + int(cut[(i * 7) % 30000])].tobytes())
+    b1, o1 = capi.pack_reads(reads1)
+    if paired:
+        b2, o2 = capi.pack_reads(reads2)
+    lib = "IU" if paired else "U"
+    monkeypatch.setenv("SFB200_HOST_PIECE", "1024")
+    for ramp in ("0", "128"):
+        monkeypatch.setenv("SFB200_MAP_RAMP", ramp)
+        st, oix, g, w = run_both(ctx, seq, off, ln, b1, o1, b2 if paired else None, o2 if paired else None, lib, batches=2)
+        assert_same_classes(ctx, g, w)
+
+
 def test_full_size_properties(ctx):
     """Larger run (2 000 genes = 10 000 transcripts, 400k reads): invariants that do not need the oracle at size, plus
     the oracle on the same input with 8 host threads."""
