@@ -459,6 +459,7 @@ class GpuRun:
             self.step(True)
             ms_e2e, _, _, _, _ = self.timed(True, steps)
             r["ms_e2e"] = ms_e2e
+            r["h2d_map_bytes"] = self.ctx.map_h2d_bytes()          # of the last step (the counter restarts at map_begin)
             r["e2e_value"] = total_reads * steps / (ms_e2e / 1e3)
         return r
 
@@ -536,8 +537,7 @@ def main():
     if wl.fixed_iters:
         assert m["iters"] == wl.fixed_iters
     n, L, T = wl.reads, wl.read_len, len(run.ln)
-    nmates = 2 if wl.paired else 1
-    h2d = nmates * (n * L + (n + 1) * 8) + T * 8
+    h2d = m["h2d_map_bytes"] + T * 8               # what sfb200_map_batch sent (bases; offsets unless the reads have one length) + eff. lengths
     d2h = T * 8 + 6 * 8 + 4000 + wl.n_boot * T * 8 + wl.n_gibbs * T * 4
 
     if rank != 0:

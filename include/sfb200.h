@@ -139,6 +139,10 @@ int sfb200_map_get_bias(sfb200_ctx* ctx, uint32_t* read_bias, uint32_t* observed
 int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz);
 /* device time of all mapping-kernel launches between map_begin and map_finish, in milliseconds (CUDA events) */
 double sfb200_last_map_kernel_ms(const sfb200_ctx* ctx);
+/* bytes sfb200_map_batch has sent to the device since map_begin (bench.py's h2d_bytes_per_step).  Host batches travel in pieces of
+ * SFB200_HOST_PIECE reads (512 k), the copy of a piece overlapping the kernels of the one before; the offsets of a piece whose reads
+ * all have one length are written on the device instead of copied. */
+uint64_t sfb200_map_h2d_bytes(const sfb200_ctx* ctx);
 /* Mates longer than 256 bases are mapped by their first 256 (mapping spec v1; the reference maps the whole read,
  * SailfishQuantify.cpp:192-213): how many mates were cut since map_begin.  The drivers print a warning when it is not zero. */
 uint64_t sfb200_map_clipped(sfb200_ctx* ctx);

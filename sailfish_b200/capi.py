@@ -86,6 +86,7 @@ SIGNATURES = {
     "sfb200_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sfb200_index_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sfb200_last_map_kernel_ms": (C.c_double, [C.c_void_p]),
+    "sfb200_map_h2d_bytes": (C.c_uint64, [C.c_void_p]),
     "sfb200_map_clipped": (C.c_uint64, [C.c_void_p]),
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
     "sfb200_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint64]),
@@ -258,6 +259,9 @@ class Context:
 
     def last_map_kernel_ms(self):
         return float(self.L.sfb200_last_map_kernel_ms(self.h))
+
+    def map_h2d_bytes(self):
+        return int(self.L.sfb200_map_h2d_bytes(self.h))
 
     # ---- mapping
     def map_clipped(self):

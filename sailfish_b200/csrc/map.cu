@@ -1039,6 +1039,8 @@ struct MapState {
     DevBuf<uint32_t> heavy;            // reads set aside by the main finalize pass
     DevBuf<unsigned long long> ivpool; // extension words of big seed buckets (IvPool)
     bool defer_heavy = true;           // SFB200_NO_HEAVY_PASS=1: one pass (A/B)
+    bool elide_offsets = true;         // SFB200_COPY_OFFSETS=1: always copy the offsets of host batches (A/B)
+    uint64_t h2d_bytes = 0;            // host batches since map_begin: bytes sent to the device
     DevBuf<uint32_t> arena;
     DevBuf<unsigned int> fld_hist;
     DevBuf<int> remaining;
@@ -1115,6 +1117,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     cudaStream_t s = c->stream;
     // table geometry: SFB200_EQ_LOG2_BUCKETS (default 21 -> 8M slots) and SFB200_EQ_ARENA_LOG2 words (default 26)
     { const char* e = getenv("SFB200_NO_HEAVY_PASS"); m->defer_heavy = !(e && atoi(e) != 0); }
+    { const char* e = getenv("SFB200_COPY_OFFSETS"); m->elide_offsets = !(e && atoi(e) != 0); }
     int lb = 21, la = 26;
     if (const char* e = getenv("SFB200_EQ_LOG2_BUCKETS")) lb = std::max(4, std::min(30, atoi(e)));
     if (const char* e = getenv("SFB200_EQ_ARENA_LOG2")) la = std::max(10, std::min(33, atoi(e)));
@@ -1171,7 +1174,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     c->cls.ready = false;
     m->begun = true;
     m->ev_used = 0; m->kernel_ms = 0.0;
-    m->in_use[0] = m->in_use[1] = m->in_use[2] = false; m->parity = 0; m->primed = false;
+    m->in_use[0] = m->in_use[1] = m->in_use[2] = false; m->parity = 0; m->primed = false; m->h2d_bytes = 0;
     m->bias_seq = m->bias_gc = false;
     m->have_last = false; m->n_grown = 0;
     return SFB200_OK;
@@ -1432,6 +1435,24 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
 constexpr unsigned N_STAGE = 3;
 struct HostPiece { uint64_t at, n; unsigned set; };
 
+// Reads of one length (the usual sequencer output): the piece's offsets are an arithmetic progression, written on the device instead
+// of copied -- 8 of every read's ~84 bytes on a path that is bound by the host link (bench.py e2e; with eight ranks on one host the
+// link is shared: profiles/r02o_scaling.json)
+__global__ void k_iota_offsets(uint64_t* __restrict__ out, uint64_t first, uint64_t step, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = first + i * step;
+}
+static bool uniform_offsets(const uint64_t* o, uint64_t n) {
+    const uint64_t L = o[1] - o[0];
+    for (uint64_t a = 0; a < n; a += 8192) {
+        const uint64_t e = std::min<uint64_t>(n, a + 8192);
+        uint64_t bad = 0;
+        for (uint64_t i = a; i < e; ++i) bad |= (o[i + 1] - o[i]) ^ L;
+        if (bad) return false;
+    }
+    return true;
+}
+static int copy_offsets(sfb200_ctx* c, MapState* m, uint64_t* dst, const uint64_t* o, uint64_t n, cudaStream_t cs);
+
 static int host_piece_copy(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2, const uint64_t* off2, HostPiece& pc) {
     MapState* m = c->map;
     const unsigned b = pc.set = m->parity;
@@ -1443,15 +1464,29 @@ static int host_piece_copy(sfb200_ctx* c, const char* bases1, const uint64_t* of
     const uint64_t nb1 = o1[pc.n] - o1[0];
     SFB_CUDA(c, m->bases1[b].reserve(nb1 + 8)); SFB_CUDA(c, m->off1[b].reserve(pc.n + 1));
     SFB_CUDA(c, cudaMemcpyAsync(m->bases1[b].p, bases1 + o1[0], nb1, cudaMemcpyHostToDevice, cs));
-    SFB_CUDA(c, cudaMemcpyAsync(m->off1[b].p, o1, (pc.n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    { const int rc = copy_offsets(c, m, m->off1[b].p, o1, pc.n, cs); if (rc) return rc; }
+    m->h2d_bytes += nb1;
     if (bases2) {
         const uint64_t* o2 = off2 + pc.at;
         const uint64_t nb2 = o2[pc.n] - o2[0];
         SFB_CUDA(c, m->bases2[b].reserve(nb2 + 8)); SFB_CUDA(c, m->off2[b].reserve(pc.n + 1));
         SFB_CUDA(c, cudaMemcpyAsync(m->bases2[b].p, bases2 + o2[0], nb2, cudaMemcpyHostToDevice, cs));
-        SFB_CUDA(c, cudaMemcpyAsync(m->off2[b].p, o2, (pc.n + 1) * 8, cudaMemcpyHostToDevice, cs));
+        { const int rc = copy_offsets(c, m, m->off2[b].p, o2, pc.n, cs); if (rc) return rc; }
+        m->h2d_bytes += nb2;
     }
     SFB_CUDA(c, cudaEventRecord(m->copied[b], cs));
+    return SFB200_OK;
+}
+
+static int copy_offsets(sfb200_ctx* c, MapState* m, uint64_t* dst, const uint64_t* o, uint64_t n, cudaStream_t cs) {
+    if (m->elide_offsets && n >= 1024 && uniform_offsets(o, n)) {
+        k_iota_offsets<<<(unsigned)std::min<uint64_t>((n + 256) / 256, 1024), 256, 0, cs>>>(dst, o[0], o[1] - o[0], n + 1);
+        c->launches++;
+        SFB_CUDA(c, cudaGetLastError());
+    } else {
+        SFB_CUDA(c, cudaMemcpyAsync(dst, o, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+        m->h2d_bytes += (n + 1) * 8;
+    }
     return SFB200_OK;
 }
 
@@ -1517,6 +1552,8 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
     SFB_CUDA(c, cudaEventSynchronize(m->copied[last_set]));
     return SFB200_OK;
 }
+
+extern "C" uint64_t sfb200_map_h2d_bytes(const sfb200_ctx* c) { return (c && c->map) ? c->map->h2d_bytes : 0; }
 
 extern "C" double sfb200_last_map_kernel_ms(const sfb200_ctx* c) { return (c && c->map) ? c->map->kernel_ms : 0.0; }
 
