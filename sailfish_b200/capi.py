@@ -90,6 +90,7 @@ SIGNATURES = {
     "sfb200_map_clipped": (C.c_uint64, [C.c_void_p]),
     "sfb200_map_begin": (C.c_int, [C.c_void_p, C.POINTER(MapOpts)]),
     "sfb200_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint64]),
+    "sfb200_map_batch_fixed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64]),
     "sfb200_map_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "sfb200_map_fastq": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, u64p, u64p, u64p]),
     "sfb200_map_set_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32]),
@@ -294,6 +295,21 @@ class Context:
         else:
             self._chk(f(self.h, C.c_void_p(p_bases1), C.cast(C.c_void_p(p_off1), u64p), C.c_void_p(p_bases2) if p_bases2 else None,
                         C.cast(C.c_void_p(p_off2), u64p) if p_off2 else None, n))
+
+    def map_batch_fixed(self, b1, len1, b2=None, len2=0, n=None):
+        """host arrays of reads of one length per mate, stored back to back (no offsets)"""
+        b1 = np.ascontiguousarray(b1, dtype=np.uint8)
+        if n is None:
+            n = len(b1) // int(len1) if len1 else 0
+        p2 = None
+        if b2 is not None:
+            b2 = np.ascontiguousarray(b2, dtype=np.uint8)
+            p2 = b2.ctypes.data_as(C.c_void_p)
+        self._chk(self.L.sfb200_map_batch_fixed(self.h, b1.ctypes.data_as(C.c_void_p), int(len1), p2, int(len2), int(n)))
+
+    def map_batch_fixed_ptr(self, p_bases1, len1, p_bases2, len2, n):
+        """raw pointers to (pinned) host memory"""
+        self._chk(self.L.sfb200_map_batch_fixed(self.h, C.c_void_p(p_bases1), int(len1), C.c_void_p(p_bases2) if p_bases2 else None, int(len2), int(n)))
 
     def map_fastq(self, text1, text2=None, max_records=0):
         """FASTQ TEXT (bytes, starting at a record boundary) -> extracted and mapped on the device; -> (records, consumed1, consumed2)"""

@@ -101,6 +101,7 @@ struct DevPartition {
     bool dense_ok = false, dense_tried = false;
     uint32_t dns_geom[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t dense_smem = 0;
+    uint64_t dense_smem_lag = 0;        // with the alpha ring of the lagged stopping rule (0: does not fit)
     uint32_t dense_ns = 0;
     bool dense_stream = false;          // counts / base / 1/effLen streamed from a per-CTA global block (em_dense.cuh)
     uint32_t stream_ent = 0, stream_state = 0;

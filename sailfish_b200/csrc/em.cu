@@ -31,7 +31,9 @@ constexpr int EM_THREADS = 1024;
 // control block (unsigned long long words)
 enum { CTL_BAR_COUNT = 0, CTL_BAR_GEN = 1, CTL_MAXREL = 2 /*4 slots*/, CTL_CSUM = 6 /*4 slots*/, CTL_ITERS = 10,
        CTL_RESULT_BUF = 11, CTL_MRD = 12, CTL_TSUM = 13 /* sum of the truncated result */,
-       CTL_PBAR_COUNT = 14, CTL_PBAR_GEN = 15 /* barrier among the pool CTAs of a hybrid run (em_dense.cuh) */, CTL_WORDS = 16 };
+       CTL_PBAR_COUNT = 14, CTL_PBAR_GEN = 15 /* barrier among the pool CTAs of a hybrid run (em_dense.cuh) */,
+       // k_em_dense's lagged stopping rule (em_dense.cuh): 16 slots each of max relative change, alpha sum and arrivals
+       CTL_LAG_MAX = 16, CTL_LAG_SUM = 32, CTL_LAG_ARR = 48, CTL_WORDS = 64 };
 
 struct EmParams {
     const uint32_t* start; const uint32_t* len; const uint32_t* lab; const double* w; const double* cnt;
@@ -940,6 +942,16 @@ int build_dense(sfb200_ctx* c, const std::vector<unsigned long long>& tbl, bool 
         }
     }
     P.dense_smem = need; P.dense_ns = ns;
+    // the alpha ring of the lagged stopping rule (em_dense.cuh), when it fits next to the working set
+    P.dense_smem_lag = 0;
+    if (ok && fits && !P.dense_stream) {
+        uint64_t ring = 0;
+        for (uint32_t i = 0; i < P.n_cta; ++i) {
+            const uint32_t* h = hdr.data() + (size_t)i * DH_WORDS;
+            ring = std::max<uint64_t>(ring, dense_smem_ring(h[DH_TILES], ns, g.group, h[DH_NCOMP]));
+        }
+        if ((need + ring + 2048) * P.per_sm <= P.smem_limit + 1024 * (uint64_t)(P.per_sm - 1)) P.dense_smem_lag = need + ring;
+    }
     P.dense_ok = ok && fits && ns <= DN_MAX_SLOTS && P.per_sm <= 2;
     if (getenv("SFB200_VERBOSE"))
         fprintf(stderr, "[sfb200] EM dense layout: %s (largest component %u transcripts, %u propagation rounds, %llu bytes of shared memory)\n",
@@ -970,17 +982,24 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         q.regions = P.dns.p; std::memcpy(&q.g, P.dns_geom, sizeof(q.g)); q.eff = c->eff.p;
         q.stream_buf = P.dns_f64.p; q.stream_ent = P.stream_ent; q.stream_state = P.stream_state; q.stream_stride = P.stream_ent + 2 * P.stream_state;
         q.dlist = P.dlist.p; q.n_dirty = P.n_pool ? P.n_dirty : 0;
-        const size_t smem = (size_t)P.dense_smem;
+        // the stopping rule (and VBEM's alpha sum) consumed DN_LAG iterations late instead of behind a grid barrier per iteration:
+        // whenever an iteration needs a global quantity at all (not EM with a fixed count) and the alpha ring fits
+        const char* e_lag = getenv("SFB200_EM_NO_LAG");
+        const bool no_lag = e_lag && atoi(e_lag) != 0;
+        q.lag = (!no_lag && P.dense_smem_lag && !P.dense_stream && q.g.group == 2 && q.n_dirty == 0 && (vb || o->fixed_iters == 0)) ? 1u : 0u;
+        const size_t smem = (size_t)(q.lag ? P.dense_smem_lag : P.dense_smem);
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))
+#define SFB_DENSE_FN_L(N) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, 2, false, true>) : reinterpret_cast<const void*>(&k_em_dense<false, N, 2, false, true>))
 #define SFB_DENSE_FN_S(N) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, 2, true>) : reinterpret_cast<const void*>(&k_em_dense<false, N, 2, true>))
-#define SFB_DENSE_CASE(N) case N: fn = P.dense_stream ? SFB_DENSE_FN_S(N) : q.g.group == 4 ? SFB_DENSE_FN(N, 4) : q.g.group == 2 ? SFB_DENSE_FN(N, 2) : q.g.group == 0 ? SFB_DENSE_FN(N, 0) : SFB_DENSE_FN(N, 1); break;
+#define SFB_DENSE_CASE(N) case N: fn = P.dense_stream ? SFB_DENSE_FN_S(N) : q.lag ? SFB_DENSE_FN_L(N) : q.g.group == 4 ? SFB_DENSE_FN(N, 4) : q.g.group == 2 ? SFB_DENSE_FN(N, 2) : q.g.group == 0 ? SFB_DENSE_FN(N, 0) : SFB_DENSE_FN(N, 1); break;
         switch (P.dense_ns) { SFB_DENSE_CASE(2) SFB_DENSE_CASE(3) SFB_DENSE_CASE(4) SFB_DENSE_CASE(5) SFB_DENSE_CASE(6) SFB_DENSE_CASE(7) SFB_DENSE_CASE(8)
                               default: SFB_FAIL(c, SFB200_EINVAL, "dense EM: unexpected component size"); }
 #undef SFB_DENSE_CASE
 #undef SFB_DENSE_FN
 #undef SFB_DENSE_FN_S
+#undef SFB_DENSE_FN_L
         SFB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SFB_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(P.n_cta), dim3(DENSE_THREADS), args, smem, s));
         c->launches++;

@@ -52,7 +52,26 @@ struct DenseParams {
     // "pool", p.start/len/lab/w/cnt binned as k_em_part's pool -- are swept by ALL CTAs in the scatter form every iteration
     const uint32_t* dlist;    // the pool's transcripts
     uint32_t n_dirty;         // 0: no pool
+    // lagged stopping rule (see k_em_dense): 0 = the global quantities of an iteration are known before the next one starts (a grid
+    // barrier per iteration), 1 = they are consumed DN_LAG iterations later
+    uint32_t lag;
 };
+
+// Lagged stopping rule.  The components of a CTA do not depend on other CTAs; what ties the grid together is the reference's stopping
+// rule (max relative change over ALL transcripts, every iteration from minIter on: CollapsedEMOptimizer.cpp:849-861) and VBEM's
+// digamma(sum alpha).  A grid barrier per iteration for them costs more than the iteration (measured: 10.2 us per iteration to
+// convergence against 2.6 us with a fixed count, VBEM 13 us): every CTA waits for the slowest one, then for two L2 round trips.
+// Instead a CTA publishes its part of iteration m (atomicMax / atomicAdd into slot m % 16, then an arrival count) and goes on; the
+// decision for iteration m is read DN_LAG iterations later, when every CTA has long arrived.  The alphas of the last DN_LAG + 1
+// iterations stay in a shared-memory ring, so when iteration x turns out to have met the rule, alpha_x is what the run returns:
+// same iteration count, same numbers as the synchronous loop.  VBEM's expTheta takes digamma(sum alpha) of DN_LAG iterations ago:
+// the sum is the same number up to rounding (every iteration redistributes the same counts) and scales ALL expThetas alike, which
+// cancels in every class's shares.
+// Slot reuse: CTAs are at most DN_LAG iterations apart (nobody passes m + DN_LAG before everybody has arrived at m), so the slots of
+// iterations m - 2 DN_LAG .. m + DN_LAG may be live when CTA 0 is at m; it clears the slot of m + DN_LAG + 1 (last used 16 iterations
+// earlier) before its own arrival at m.  Arrival counters only grow.
+constexpr uint32_t DN_LAG = 3, DN_RING = 4, DN_LAG_SLOTS = 16;
+static_assert(DN_RING == DN_LAG + 1 && (DN_RING & (DN_RING - 1)) == 0 && DN_LAG_SLOTS > 3 * DN_LAG + 1, "lagged stopping rule geometry");
 
 constexpr int DENSE_THREADS = 256;
 constexpr int DENSE_ILP = 4;          // classes of one component in flight per lane
@@ -74,12 +93,18 @@ __host__ __device__ inline uint64_t dense_smem_need(uint32_t tiles, uint32_t ent
            (group ? 0 : (uint64_t)tiles * 32 * 4);
 }
 
+// the alpha ring of the lagged stopping rule: DN_RING - 1 more copies of the alpha array
+__host__ __device__ inline uint64_t dense_smem_ring(uint32_t tiles, uint32_t ns, uint32_t group, uint32_t ncomp) {
+    const uint64_t ncomp_pad = group ? ((uint64_t)tiles << 5) / group : (((uint64_t)ncomp + 31u) & ~31ull);
+    return (uint64_t)(DN_RING - 1) * ns * ncomp_pad * 8 + 16;
+}
+
 // G lanes share a component: each takes every G-th class of it (all G hold the component's beta), the accumulators are summed
 // over the group with shuffles, lane 0 of the group writes the component's new state.  The longest class list of a tile sets
 // the pace of its warp, and nothing else runs on that warp: G = 4 shortens that list fourfold for 10 shuffles per slot.
 // STREAM: the class counts, base and 1/effLen of the CTA are read from global memory every iteration (coalesced 256-byte rows; the whole
 // run's stream is a few tens of MB and stays in L2) instead of shared memory -- for class sets whose per-CTA slice does not fit.
-template <bool VB, int NS, int G, bool STREAM = false>
+template <bool VB, int NS, int G, bool STREAM = false, bool LAGGED = false>
 __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p, const DenseParams q) {
     __shared__ unsigned long long sm_u[32];
     __shared__ double sm_d[32];
@@ -103,6 +128,11 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     uint8_t* s_mask = STREAM ? const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(region + q.g.o_mask))
                              : reinterpret_cast<uint8_t*>(s_tlen + ((tiles + 3u) & ~3u));          // ent (padded to 16)
     uint32_t* s_lane = reinterpret_cast<uint32_t*>(s_mask + ((ent + 15u) & ~15u));   // G == 0: 32 * tiles lane descriptors (never with STREAM)
+    constexpr bool lagged = LAGGED;                                                   // host (q.lag): never with STREAM or a pool
+    double* s_ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_lane + (G ? 0u : tiles * 32u)) + 15u) & ~(uintptr_t)15u);
+    const size_t ring_stride = (size_t)NS * ncomp_pad;
+    // alphas after iteration `it` (lagged runs): slot it % DN_RING of the ring, slot 0 being s_alpha itself
+    auto ring = [&](uint32_t it) -> double* { const uint32_t h = it & (DN_RING - 1u); return h == 0u ? s_alpha : s_ring + (size_t)(h - 1u) * ring_stride; };
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&tma_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -128,6 +158,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
         if (t != DN_NONE) { a = p.X[t]; b = p.base[t]; ie = 1.0 / q.eff[t]; }
         s_alpha[i] = a; s_base[i] = b; s_inveff[i] = ie;
     }
+    if (lagged) for (uint32_t i = threadIdx.x; i < (DN_RING - 1u) * (uint32_t)ring_stride; i += blockDim.x) s_ring[i] = 0.0;
     // idle transcripts: constant from the first iteration on; their sum feeds VBEM's alpha sum
     double idle_sum = 0.0;
     if (VB) for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) idle_sum += p.base[idle[i]];
@@ -177,6 +208,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
         const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
         unsigned long long best = 0ULL;
         double asum = 0.0;
+        const double* a_rd = lagged ? ring(n) : s_alpha;
+        double* a_wr = lagged ? ring(m) : s_alpha;
         // ---- one EM iteration of every component of this warp's tiles (tile -> warp is fixed, so a tile's state is only ever
         //      touched by its own warp: no barrier)
         for (uint32_t k = warp; k < tiles; k += W) {
@@ -262,7 +295,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
                 const size_t i = (size_t)j * ncomp_pad + qi;
-                const double a_old = s_alpha[i];
+                const double a_old = a_rd[i];
                 const double a_new = b[j] * acc[j] + s_base[i];
                 if (do_cmp) {
                     const double gate = p.gate_old ? a_old : a_new;
@@ -271,7 +304,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                         best = bits > best ? bits : best;
                     }
                 }
-                s_alpha[i] = a_new;
+                a_wr[i] = a_new;
                 if (VB) asum += a_new; else s_beta[i] = a_new * s_inveff[i];
             }
         }
@@ -302,19 +335,68 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             { const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp; }   // bi now names the pool's newest alphas
         }
         n = m;
-        if (VB || do_cmp) {
-            if (do_cmp) {                                              // idle transcripts: alpha_0 -> base at m == 1, base -> base after
-                for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) {
-                    const uint32_t t = idle[i];
-                    const double a_new = p.base[t];
-                    const double a_old = (m == 1) ? p.X[t] : a_new;
-                    const double gate = p.gate_old ? a_old : a_new;
-                    if (gate > p.cutoff) {
-                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
-                        best = bits > best ? bits : best;
-                    }
+        if (do_cmp) {                                                  // idle transcripts: alpha_0 -> base at m == 1, base -> base after
+            for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) {
+                const uint32_t t = idle[i];
+                const double a_new = p.base[t];
+                const double a_old = (m == 1) ? p.X[t] : a_new;
+                const double gate = p.gate_old ? a_old : a_new;
+                if (gate > p.cutoff) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
+                    best = bits > best ? bits : best;
                 }
             }
+        }
+        if (lagged) {
+            // publish this CTA's part of iteration m, then arrive
+            if (do_cmp) block_max_to_slot(best, p.ctl + CTL_LAG_MAX + (m & (DN_LAG_SLOTS - 1u)), sm_u);
+            if (VB) block_sum_to_slot(asum + idle_sum, reinterpret_cast<double*>(p.ctl + CTL_LAG_SUM + (m & (DN_LAG_SLOTS - 1u))), sm_d);
+            if (threadIdx.x == 0) {
+                if (blockIdx.x == 0) {
+                    const uint32_t z = (m + DN_LAG + 1u) & (DN_LAG_SLOTS - 1u);
+                    p.ctl[CTL_LAG_MAX + z] = 0ULL; p.ctl[CTL_LAG_SUM + z] = 0ULL;
+                }
+                __threadfence();
+                atomicAdd(p.ctl + CTL_LAG_ARR + (m & (DN_LAG_SLOTS - 1u)), 1ULL);
+            }
+            // the iterations whose global quantities are due: m - DN_LAG, and after the final iteration all that are left, in order
+            const bool final_it = fixed ? (m >= p.fixed_iters) : (m >= p.max_iter && m >= p.min_iter);
+            uint32_t x = m > DN_LAG ? m - DN_LAG : 0u;
+            const uint32_t x_hi = final_it ? m : x;
+            if (final_it && x == 0u) x = 1u;
+            bool stop = false;
+            unsigned long long sum_bits = 0ULL;
+            bool have_sum = false;
+            for (; x >= 1u && x <= x_hi; ++x) {
+                if (threadIdx.x == 0) {
+                    const unsigned long long want = (unsigned long long)nblocks * ((x - 1u) / DN_LAG_SLOTS + 1u);
+                    while (ld_acquire_u64(p.ctl + CTL_LAG_ARR + (x & (DN_LAG_SLOTS - 1u))) < want) { }
+                    sm_u[0] = ld_cg_u64(p.ctl + CTL_LAG_MAX + (x & (DN_LAG_SLOTS - 1u)));
+                    sm_u[1] = ld_cg_u64(p.ctl + CTL_LAG_SUM + (x & (DN_LAG_SLOTS - 1u)));
+                }
+                __syncthreads();
+                const unsigned long long mr = sm_u[0];
+                sum_bits = sm_u[1]; have_sum = true;
+                __syncthreads();                                       // sm_u is scratch of the block reductions as well
+                const bool checked = fixed ? (x >= p.fixed_iters) : (x >= p.min_iter);
+                if (checked && (fixed || x >= p.max_iter || !(decode_mrd(mr) > p.tol))) {
+                    stop = true; mr_final = mr; n = x;                 // the run ends with alpha_x: still in the ring
+                    break;
+                }
+            }
+            if (stop) break;
+            if (VB) {
+                const double logNorm = sfb_digamma(have_sum ? __longlong_as_double((long long)sum_bits) : p.sum0);
+                const double thetaScale = exp(-logNorm);
+                for (uint32_t i = threadIdx.x; i < (uint32_t)ring_stride; i += blockDim.x) {
+                    const double a = a_wr[i];
+                    s_beta[i] = ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) * s_inveff[i];
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        if (VB || do_cmp) {
             unsigned long long* slot = p.ctl + CTL_MAXREL + (m & 3u);
             double* csum = reinterpret_cast<double*>(p.ctl + CTL_CSUM + (m & 3u));
             if (do_cmp) block_max_to_slot(best, slot, sm_u);
@@ -353,6 +435,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
         for (uint32_t i = d_lo + threadIdx.x; i < d_hi; i += blockDim.x) { const uint32_t t = q.dlist[i]; p.X[t] = ld_cg_f64(cur + t); }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctl[CTL_ITERS] = n; p.ctl[CTL_RESULT_BUF] = 0ULL; p.ctl[CTL_MRD] = mr_final; }
-    for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) { const uint32_t t = tmap[i]; if (t != DN_NONE) p.X[t] = s_alpha[i]; }
+    const double* a_res = lagged ? ring(n) : s_alpha;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)NS * ncomp_pad; i += blockDim.x) { const uint32_t t = tmap[i]; if (t != DN_NONE) p.X[t] = a_res[i]; }
     if (n > 0) for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) { const uint32_t t = idle[i]; p.X[t] = p.base[t]; }
 }

@@ -1039,7 +1039,6 @@ struct MapState {
     DevBuf<uint32_t> heavy;            // reads set aside by the main finalize pass
     DevBuf<unsigned long long> ivpool; // extension words of big seed buckets (IvPool)
     bool defer_heavy = true;           // SFB200_NO_HEAVY_PASS=1: one pass (A/B)
-    bool elide_offsets = true;         // SFB200_COPY_OFFSETS=1: always copy the offsets of host batches (A/B)
     uint64_t h2d_bytes = 0;            // host batches since map_begin: bytes sent to the device
     DevBuf<uint32_t> arena;
     DevBuf<unsigned int> fld_hist;
@@ -1117,7 +1116,6 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     cudaStream_t s = c->stream;
     // table geometry: SFB200_EQ_LOG2_BUCKETS (default 21 -> 8M slots) and SFB200_EQ_ARENA_LOG2 words (default 26)
     { const char* e = getenv("SFB200_NO_HEAVY_PASS"); m->defer_heavy = !(e && atoi(e) != 0); }
-    { const char* e = getenv("SFB200_COPY_OFFSETS"); m->elide_offsets = !(e && atoi(e) != 0); }
     int lb = 21, la = 26;
     if (const char* e = getenv("SFB200_EQ_LOG2_BUCKETS")) lb = std::max(4, std::min(30, atoi(e)));
     if (const char* e = getenv("SFB200_EQ_ARENA_LOG2")) la = std::max(10, std::min(33, atoi(e)));
@@ -1430,86 +1428,78 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
 // Host batches travel in pieces: piece j+1 is on the copy stream while the kernels of piece j are enqueued (a host round trip: the
 // chunk's longest read comes back before the pack kernel is sized) and the kernels of piece j-1 run -- three staging sets.  The copy
 // engine never waits for the host, so a batch costs max(copy, kernels) plus the kernels of its LAST piece; pieces are therefore small
-// (SFB200_HOST_PIECE reads, default 512 k: 0.5 ms of kernels), and the first ones after map_begin smaller still (nothing to hide
+// (SFB200_HOST_PIECE reads, default 1 M: 0.9 ms of kernels; measured 20.5 ms per 10 M reads against 20.8 with 512 k, 22.3 with 256 k
+// and 21.1 with whole 2.5 M batches, profiles/r02q_e2e_ab.txt), and the first ones after map_begin smaller still (nothing to hide
 // behind yet).
 constexpr unsigned N_STAGE = 3;
 struct HostPiece { uint64_t at, n; unsigned set; };
+// a host batch: offsets arrays, or (o == nullptr) reads of one length L stored back to back
+struct HostBatch {
+    const char* b1; const uint64_t* o1; uint64_t L1;
+    const char* b2; const uint64_t* o2; uint64_t L2;
+    uint64_t n;
+    uint64_t at1(uint64_t i) const { return o1 ? o1[i] : i * L1; }
+    uint64_t at2(uint64_t i) const { return o2 ? o2[i] : i * L2; }
+};
 
-// Reads of one length (the usual sequencer output): the piece's offsets are an arithmetic progression, written on the device instead
-// of copied -- 8 of every read's ~84 bytes on a path that is bound by the host link (bench.py e2e; with eight ranks on one host the
-// link is shared: profiles/r02o_scaling.json)
+// Reads of one length (the usual sequencer output, sfb200_map_batch_fixed): the piece's offsets are an arithmetic progression, written
+// on the device instead of copied -- 8 of every read's ~84 bytes on a path that is bound by the host link (with eight ranks on one
+// host the link is shared: profiles/r02o_scaling.json)
 __global__ void k_iota_offsets(uint64_t* __restrict__ out, uint64_t first, uint64_t step, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = first + i * step;
 }
-static bool uniform_offsets(const uint64_t* o, uint64_t n) {
-    const uint64_t L = o[1] - o[0];
-    for (uint64_t a = 0; a < n; a += 8192) {
-        const uint64_t e = std::min<uint64_t>(n, a + 8192);
-        uint64_t bad = 0;
-        for (uint64_t i = a; i < e; ++i) bad |= (o[i + 1] - o[i]) ^ L;
-        if (bad) return false;
-    }
-    return true;
-}
-static int copy_offsets(sfb200_ctx* c, MapState* m, uint64_t* dst, const uint64_t* o, uint64_t n, cudaStream_t cs);
 
-static int host_piece_copy(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2, const uint64_t* off2, HostPiece& pc) {
+static int copy_offsets(sfb200_ctx* c, MapState* m, uint64_t* dst, const uint64_t* o, uint64_t L, uint64_t at, uint64_t n, cudaStream_t cs) {
+    if (!o) {
+        k_iota_offsets<<<(unsigned)std::min<uint64_t>((n + 256) / 256, 1024), 256, 0, cs>>>(dst, at * L, L, n + 1);
+        c->launches++;
+        SFB_CUDA(c, cudaGetLastError());
+    } else {
+        SFB_CUDA(c, cudaMemcpyAsync(dst, o + at, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+        m->h2d_bytes += (n + 1) * 8;
+    }
+    return SFB200_OK;
+}
+
+static int host_piece_copy(sfb200_ctx* c, const HostBatch& hb, HostPiece& pc) {
     MapState* m = c->map;
     const unsigned b = pc.set = m->parity;
     m->parity = (m->parity + 1u) % N_STAGE;
     // this staging set was last read by the kernels of three pieces ago
     if (m->in_use[b]) SFB_CUDA(c, cudaEventSynchronize(m->consumed[b]));
     cudaStream_t cs = m->copy_stream;
-    const uint64_t* o1 = off1 + pc.at;
-    const uint64_t nb1 = o1[pc.n] - o1[0];
+    const uint64_t f1 = hb.at1(pc.at), nb1 = hb.at1(pc.at + pc.n) - f1;
     SFB_CUDA(c, m->bases1[b].reserve(nb1 + 8)); SFB_CUDA(c, m->off1[b].reserve(pc.n + 1));
-    SFB_CUDA(c, cudaMemcpyAsync(m->bases1[b].p, bases1 + o1[0], nb1, cudaMemcpyHostToDevice, cs));
-    { const int rc = copy_offsets(c, m, m->off1[b].p, o1, pc.n, cs); if (rc) return rc; }
+    SFB_CUDA(c, cudaMemcpyAsync(m->bases1[b].p, hb.b1 + f1, nb1, cudaMemcpyHostToDevice, cs));
+    { const int rc = copy_offsets(c, m, m->off1[b].p, hb.o1, hb.L1, pc.at, pc.n, cs); if (rc) return rc; }
     m->h2d_bytes += nb1;
-    if (bases2) {
-        const uint64_t* o2 = off2 + pc.at;
-        const uint64_t nb2 = o2[pc.n] - o2[0];
+    if (hb.b2) {
+        const uint64_t f2 = hb.at2(pc.at), nb2 = hb.at2(pc.at + pc.n) - f2;
         SFB_CUDA(c, m->bases2[b].reserve(nb2 + 8)); SFB_CUDA(c, m->off2[b].reserve(pc.n + 1));
-        SFB_CUDA(c, cudaMemcpyAsync(m->bases2[b].p, bases2 + o2[0], nb2, cudaMemcpyHostToDevice, cs));
-        { const int rc = copy_offsets(c, m, m->off2[b].p, o2, pc.n, cs); if (rc) return rc; }
+        SFB_CUDA(c, cudaMemcpyAsync(m->bases2[b].p, hb.b2 + f2, nb2, cudaMemcpyHostToDevice, cs));
+        { const int rc = copy_offsets(c, m, m->off2[b].p, hb.o2, hb.L2, pc.at, pc.n, cs); if (rc) return rc; }
         m->h2d_bytes += nb2;
     }
     SFB_CUDA(c, cudaEventRecord(m->copied[b], cs));
     return SFB200_OK;
 }
 
-static int copy_offsets(sfb200_ctx* c, MapState* m, uint64_t* dst, const uint64_t* o, uint64_t n, cudaStream_t cs) {
-    if (m->elide_offsets && n >= 1024 && uniform_offsets(o, n)) {
-        k_iota_offsets<<<(unsigned)std::min<uint64_t>((n + 256) / 256, 1024), 256, 0, cs>>>(dst, o[0], o[1] - o[0], n + 1);
-        c->launches++;
-        SFB_CUDA(c, cudaGetLastError());
-    } else {
-        SFB_CUDA(c, cudaMemcpyAsync(dst, o, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
-        m->h2d_bytes += (n + 1) * 8;
-    }
-    return SFB200_OK;
-}
-
-static int host_piece_map(sfb200_ctx* c, const uint64_t* off1, const uint64_t* off2, const HostPiece& pc) {
+static int host_piece_map(sfb200_ctx* c, const HostBatch& hb, const HostPiece& pc) {
     MapState* m = c->map;
     const unsigned b = pc.set;
     SFB_CUDA(c, cudaStreamWaitEvent(c->stream, m->copied[b], 0));
     // offsets are absolute positions in the caller's arrays: shift the base pointers instead of the offsets
-    const char* d_b2 = off2 ? m->bases2[b].p - off2[pc.at] : nullptr;
-    const int rc = sfb200_map_batch_device(c, m->bases1[b].p - off1[pc.at], m->off1[b].p, d_b2, off2 ? m->off2[b].p : nullptr, pc.n);
+    const char* d_b2 = hb.b2 ? m->bases2[b].p - hb.at2(pc.at) : nullptr;
+    const int rc = sfb200_map_batch_device(c, m->bases1[b].p - hb.at1(pc.at), m->off1[b].p, d_b2, hb.b2 ? m->off2[b].p : nullptr, pc.n);
     if (rc) return rc;
     SFB_CUDA(c, cudaEventRecord(m->consumed[b], c->stream));
     m->in_use[b] = true;
     return SFB200_OK;
 }
 
-extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2,
-                                const uint64_t* off2, uint64_t n_reads) {
-    if (!c) return SFB200_EINVAL;
+static int map_host_batch(sfb200_ctx* c, const HostBatch& hb) {
     MapState* m = c->map;
-    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_batch: call map_begin first");
-    if (n_reads == 0) return SFB200_OK;
-    if (!bases1 || !off1 || ((bases2 == nullptr) != (off2 == nullptr))) SFB_FAIL(c, SFB200_EINVAL, "map_batch: null array");
+    const uint64_t n_reads = hb.n;
     cudaSetDevice(c->device);
     if (!m->copy_stream) {
         SFB_CUDA(c, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
@@ -1518,7 +1508,7 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
             SFB_CUDA(c, cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming));
         }
     }
-    uint64_t piece = 512u << 10, ramp = 128u << 10;
+    uint64_t piece = 1u << 20, ramp = 128u << 10;
     if (const char* e = getenv("SFB200_HOST_PIECE")) piece = (uint64_t)std::max<long long>(1024, atoll(e));
     if (const char* e = getenv("SFB200_MAP_RAMP")) ramp = (uint64_t)std::max<long long>(0, atoll(e));
     if (m->primed || ramp == 0 || ramp > piece) ramp = piece;        // the first pieces after map_begin: 128 k, 256 k, ... reads
@@ -1533,17 +1523,17 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
     };
     HostPiece cur, nxt;
     next_piece(cur);
-    { const int rc = host_piece_copy(c, bases1, off1, bases2, off2, cur); if (rc) return rc; }
+    { const int rc = host_piece_copy(c, hb, cur); if (rc) return rc; }
     unsigned last_set = cur.set;
     for (;;) {
         const bool more = at < n_reads;
         if (more) {
             next_piece(nxt);
-            const int rc = host_piece_copy(c, bases1, off1, bases2, off2, nxt);
+            const int rc = host_piece_copy(c, hb, nxt);
             if (rc) return rc;
             last_set = nxt.set;
         }
-        const int rc = host_piece_map(c, off1, off2, cur);
+        const int rc = host_piece_map(c, hb, cur);
         if (rc) return rc;
         if (!more) break;
         cur = nxt;
@@ -1551,6 +1541,27 @@ extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_
     // the caller may reuse its buffers as soon as we return: wait for the last copy (not for the kernels)
     SFB_CUDA(c, cudaEventSynchronize(m->copied[last_set]));
     return SFB200_OK;
+}
+
+extern "C" int sfb200_map_batch(sfb200_ctx* c, const char* bases1, const uint64_t* off1, const char* bases2,
+                                const uint64_t* off2, uint64_t n_reads) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_batch: call map_begin first");
+    if (n_reads == 0) return SFB200_OK;
+    if (!bases1 || !off1 || ((bases2 == nullptr) != (off2 == nullptr))) SFB_FAIL(c, SFB200_EINVAL, "map_batch: null array");
+    const HostBatch hb{bases1, off1, 0, bases2, off2, 0, n_reads};
+    return map_host_batch(c, hb);
+}
+
+extern "C" int sfb200_map_batch_fixed(sfb200_ctx* c, const char* bases1, uint32_t len1, const char* bases2, uint32_t len2, uint64_t n_reads) {
+    if (!c) return SFB200_EINVAL;
+    MapState* m = c->map;
+    if (!m || !m->begun) SFB_FAIL(c, SFB200_EINVAL, "map_batch_fixed: call map_begin first");
+    if (n_reads == 0) return SFB200_OK;
+    if (!bases1) SFB_FAIL(c, SFB200_EINVAL, "map_batch_fixed: null array");
+    const HostBatch hb{bases1, nullptr, len1, bases2, nullptr, bases2 ? len2 : 0, n_reads};
+    return map_host_batch(c, hb);
 }
 
 extern "C" uint64_t sfb200_map_h2d_bytes(const sfb200_ctx* c) { return (c && c->map) ? c->map->h2d_bytes : 0; }

@@ -653,6 +653,16 @@ uint64_t map_fastq_files(sfb200::Device& dev, const std::vector<std::string>& f1
     return total;
 }
 
+// do all n reads of a batch have one length?  (off[0] == 0: ReadBatch::clear)
+static bool one_length(const uint64_t* off, size_t n, uint32_t* len) {
+    if (n == 0 || off[0] != 0 || off[1] > 0xFFFFFFFFull) return false;
+    const uint64_t L = off[1];
+    uint64_t bad = 0;
+    for (size_t i = 0; i < n; ++i) bad |= (off[i + 1] - off[i]) ^ L;
+    *len = (uint32_t)L;
+    return bad == 0;
+}
+
 // ---- read ingestion: a producer thread parses the next batch while the current one is copied to the device and mapped ------------
 struct PairBatch { sfb200::ReadBatch m1, m2; bool last = false; };
 
@@ -880,11 +890,16 @@ int main(int argc, char** argv) {
             while (std::unique_ptr<PairBatch> b = pipe.pop()) {
                 const size_t n = b->m1.size();
                 b->m1.bases.push_back('\0');
+                // reads of one length (the usual case): no offsets over the host link (sfb200_map_batch_fixed)
+                uint32_t len1 = 0, len2 = 0;
+                const bool fixed = one_length(b->m1.off.data(), n, &len1) && (!paired_files || one_length(b->m2.off.data(), n, &len2));
                 if (paired_files) {
                     b->m2.bases.push_back('\0');
-                    dev.check(sfb200_map_batch(dev.get(), b->m1.bases.data(), b->m1.off.data(), b->m2.bases.data(), b->m2.off.data(), n));
+                    if (fixed) dev.check(sfb200_map_batch_fixed(dev.get(), b->m1.bases.data(), len1, b->m2.bases.data(), len2, n));
+                    else dev.check(sfb200_map_batch(dev.get(), b->m1.bases.data(), b->m1.off.data(), b->m2.bases.data(), b->m2.off.data(), n));
                 } else {
-                    dev.check(sfb200_map_batch(dev.get(), b->m1.bases.data(), b->m1.off.data(), nullptr, nullptr, n));
+                    if (fixed) dev.check(sfb200_map_batch_fixed(dev.get(), b->m1.bases.data(), len1, nullptr, 0, n));
+                    else dev.check(sfb200_map_batch(dev.get(), b->m1.bases.data(), b->m1.off.data(), nullptr, nullptr, n));
                 }
                 pipe.recycle(std::move(b));                            // sfb200_map_batch returns when the host buffers are free again
             }

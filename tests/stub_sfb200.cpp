@@ -37,6 +37,9 @@ int sfb200_map_set_bias(sfb200_ctx*, int s, int g, int32_t n) { logf("map_set_bi
 int sfb200_map_batch(sfb200_ctx* c, const char*, const uint64_t*, const char* b2, const uint64_t*, uint64_t n) {
     if (getenv("SFB200_STUB_FAIL_MAP")) { logf("map_batch FAILS"); return SFB200_EFULL; }       // a device error in the middle of the run
     c->reads += n; logf("map_batch %llu %d", (unsigned long long)n, b2 ? 1 : 0); return SFB200_OK; }
+int sfb200_map_batch_fixed(sfb200_ctx* c, const char*, uint32_t, const char* b2, uint32_t, uint64_t n) {
+    if (getenv("SFB200_STUB_FAIL_MAP")) { logf("map_batch FAILS"); return SFB200_EFULL; }
+    c->reads += n; logf("map_batch %llu %d", (unsigned long long)n, b2 ? 1 : 0); return SFB200_OK; }
 // records = complete four-line groups; *consumed = the bytes the first n of them cover
 static uint64_t stub_records(const char* t, uint64_t n) { uint64_t nl = 0; for (uint64_t i = 0; i < n; ++i) nl += t[i] == '\n'; return nl / 4; }
 static uint64_t stub_consumed(const char* t, uint64_t n, uint64_t recs) { uint64_t nl = 0; for (uint64_t i = 0; i < n; ++i) if (t[i] == '\n' && ++nl == 4 * recs) return i + 1; return 0; }

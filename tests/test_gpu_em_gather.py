@@ -285,3 +285,39 @@ def test_dense_loop_streaming_variant(ctx, monkeypatch, loop_kind, vb):
         close(a, want)
         if not kw:
             close(a, a0, rtol=1e-9)
+
+
+@pytest.mark.parametrize("vb", [0, 1])
+def test_dense_loop_lagged_stopping_rule(ctx, monkeypatch, loop_kind, vb):
+    """k_em_dense reads the global quantities of an iteration (max relative change, VBEM's alpha sum) three iterations late instead of
+    behind a grid barrier per iteration, and returns the alphas of the iteration that met the rule from a shared-memory ring
+    (em_dense.cuh): same iteration count and estimates as the oracle and as the synchronous loop (SFB200_EM_NO_LAG=1) -- to
+    convergence, at the iteration cap (cap below / at / just above the lag), with minIter above the converging iteration, with a
+    loose tolerance that is met inside the first lag window, and with a fixed count (VBEM).  (The bootstrap's form of the rule -- gate on
+    the old alphas, no minIter -- runs through the same code in the bootstrap tests.)"""
+    if loop_kind != DENSE or os.environ.get("SFB200_EM_DENSE_GROUP", "2") != "2":
+        pytest.skip("the lagged rule belongs to the dense kernel with two lanes per component")
+    T = 30000
+    rp, lab, cnt = synth.make_classes(T, 70000, seed=15)
+    eff = np.random.default_rng(2).uniform(100, 3000, size=T)
+    nm = int(cnt.sum())
+    cases = [{}, {"max_iter": 1, "min_iter": 1}, {"max_iter": 2, "min_iter": 1}, {"max_iter": 3, "min_iter": 2}, {"max_iter": 4, "min_iter": 1},
+             {"max_iter": 5, "min_iter": 1}, {"max_iter": 37}, {"max_iter": 60}, {"min_iter": 1}, {"min_iter": 400},
+             {"min_iter": 1, "tol": 0.5}]                               # stops inside the first lag window
+    if vb:
+        cases += [{"fixed_iters": 1}, {"fixed_iters": 2}, {"fixed_iters": 23}]
+    for kw in cases:
+        o = capi.EMOpts.default(use_vb=vb, **kw)
+        monkeypatch.delenv("SFB200_EM_NO_LAG", raising=False)
+        ctx.eq_import(T, rp, lab, cnt)
+        a, it, mrd = ctx.em_run(eff, nm, o)
+        assert ctx.last_em_kernel() == DENSE
+        monkeypatch.setenv("SFB200_EM_NO_LAG", "1")
+        a_s, it_s, mrd_s = ctx.em_run(eff, nm, o)
+        rc, want, it_o, mrd_o = O.em_run(T, rp, lab, cnt, eff, nm, O.EMOpts.default(use_vb=vb, **kw), n_threads=4)
+        assert rc == 0 and it == it_o == it_s, (kw, it, it_s, it_o)
+        close(a, want)
+        if vb:
+            close(a, a_s, rtol=1e-9)
+        else:
+            assert (a == a_s).all() and mrd == mrd_s                     # EM: the very same arithmetic, CTA by CTA

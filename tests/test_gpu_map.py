@@ -202,6 +202,37 @@ def test_host_batches_in_small_pieces(ctx, paired, monkeypatch):
         assert_same_classes(ctx, g, w)
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_fixed_length_host_batches(ctx, paired, monkeypatch):
+    """sfb200_map_batch_fixed: reads of one length per mate stored back to back, no offsets array (they are written on the device);
+    mates of different lengths, several calls, small pieces"""
+    seq, off, ln = small_txome()
+    n, L1, L2 = 20000, 100, 83
+    b1, o1, b2, o2, _ = synth.make_reads(seq, off, ln, n, L1, seed=23, paired=paired, sub_rate=0.01, n_rate=0.002)
+    if paired:
+        b2 = np.ascontiguousarray(b2[:n * L1].reshape(n, L1)[:, :L2]).reshape(-1)
+        o2 = np.arange(n + 1, dtype=np.uint64) * L2
+    seqs = [seq[int(off[i]):int(off[i]) + int(ln[i])].tobytes() for i in range(len(ln))]
+    ctx.index_build(seq=seq, txp_off=off, txp_len=ln, k=31)
+    fmt = O.parse_libtype("IU" if paired else "U")
+    run = O.Run(O.Index(seqs, k=31), O.MapOpts.default(fmt))
+    if paired:
+        run.map_batch(b1.tobytes(), o1, b2.tobytes(), o2)
+    else:
+        run.map_batch(b1.tobytes(), o1)
+    w = run.finish()
+    monkeypatch.setenv("SFB200_HOST_PIECE", "2048")
+    ctx.map_begin(capi.MapOpts.default(fmt))
+    for a, b in ((0, 7000), (7000, 7001), (7001, n)):
+        if paired:
+            ctx.map_batch_fixed(b1[a * L1:b * L1], L1, b2[a * L2:b * L2], L2)
+        else:
+            ctx.map_batch_fixed(b1[a * L1:b * L1], L1)
+    g = ctx.map_finish()
+    assert_same_classes(ctx, g, w)
+    assert ctx.map_h2d_bytes() == n * L1 + (n * L2 if paired else 0)      # bases only
+
+
 def test_full_size_properties(ctx):
     """Larger run (2 000 genes = 10 000 transcripts, 400k reads): invariants that do not need the oracle at size, plus
     the oracle on the same input with 8 host threads."""
