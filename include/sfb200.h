@@ -143,7 +143,7 @@ int sfb200_map_finish(sfb200_ctx* ctx, uint64_t counters[6], uint32_t* fld_hist,
 /* device time of all mapping-kernel launches between map_begin and map_finish, in milliseconds (CUDA events) */
 double sfb200_last_map_kernel_ms(const sfb200_ctx* ctx);
 /* bytes sfb200_map_batch[_fixed] has sent to the device since map_begin (bench.py's h2d_bytes_per_step).  Host batches travel in
- * pieces of SFB200_HOST_PIECE reads (1 M), the copy of a piece overlapping the kernels of the one before. */
+ * pieces of SFB200_HOST_PIECE reads (512 k), the copy of a piece overlapping the kernels of the one before. */
 uint64_t sfb200_map_h2d_bytes(const sfb200_ctx* ctx);
 /* Mates longer than 256 bases are mapped by their first 256 (mapping spec v1; the reference maps the whole read,
  * SailfishQuantify.cpp:192-213): how many mates were cut since map_begin.  The drivers print a warning when it is not zero. */

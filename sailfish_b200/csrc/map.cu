@@ -1428,8 +1428,8 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
 // Host batches travel in pieces: piece j+1 is on the copy stream while the kernels of piece j are enqueued (a host round trip: the
 // chunk's longest read comes back before the pack kernel is sized) and the kernels of piece j-1 run -- three staging sets.  The copy
 // engine never waits for the host, so a batch costs max(copy, kernels) plus the kernels of its LAST piece; pieces are therefore small
-// (SFB200_HOST_PIECE reads, default 1 M: 0.9 ms of kernels; measured 20.5 ms per 10 M reads against 20.8 with 512 k, 22.3 with 256 k
-// and 21.1 with whole 2.5 M batches, profiles/r02q_e2e_ab.txt), and the first ones after map_begin smaller still (nothing to hide
+// (SFB200_HOST_PIECE reads, default 512 k: 0.5 ms of kernels; measured with fixed-length reads 19.6 ms per 10 M reads against 20.1 with
+// 1 M pieces and 21.0 with whole 2.5 M batches, profiles/r02r_e2e_ab.txt), and the first ones after map_begin smaller still (nothing to hide
 // behind yet).
 constexpr unsigned N_STAGE = 3;
 struct HostPiece { uint64_t at, n; unsigned set; };
@@ -1508,7 +1508,7 @@ static int map_host_batch(sfb200_ctx* c, const HostBatch& hb) {
             SFB_CUDA(c, cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming));
         }
     }
-    uint64_t piece = 1u << 20, ramp = 128u << 10;
+    uint64_t piece = 512u << 10, ramp = 128u << 10;
     if (const char* e = getenv("SFB200_HOST_PIECE")) piece = (uint64_t)std::max<long long>(1024, atoll(e));
     if (const char* e = getenv("SFB200_MAP_RAMP")) ramp = (uint64_t)std::max<long long>(0, atoll(e));
     if (m->primed || ramp == 0 || ramp > piece) ramp = piece;        // the first pieces after map_begin: 128 k, 256 k, ... reads
