@@ -123,7 +123,7 @@ class Workload:
             c["reads"] = reads
         if genes:
             c["genes"] = genes
-        if em_iters is not None and cfg_id == 2:
+        if em_iters is not None:                     # a fixed iteration count (default for config 2; a diagnostic elsewhere)
             c["fixed_iters"] = em_iters
         if batch:
             c["batch"] = batch

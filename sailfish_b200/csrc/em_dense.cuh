@@ -57,19 +57,21 @@ struct DenseParams {
     uint32_t lag;
 };
 
-// Lagged stopping rule.  The components of a warp's tiles do not depend on anything else; what ties the grid together is the
-// reference's stopping rule (max relative change over ALL transcripts, every iteration from minIter on:
-// CollapsedEMOptimizer.cpp:849-861) and VBEM's digamma(sum alpha).  Barriers for them cost more than the iteration (measured: 9.3 us
-// per iteration to convergence against 2.7 us with a fixed count, VBEM 12.6 us): every iteration ends when the slowest warp of the
-// slowest CTA has finished, plus two L2 round trips.  Instead every WARP publishes its part of iteration m (atomicMax / atomicAdd
-// into slot m % 16, then an arrival count with release semantics) and goes on; what the grid found in iteration m is read DN_LAG
-// iterations later, when every warp has long arrived.  The alphas of the last DN_LAG + 1 iterations stay in a shared-memory ring, so
-// when iteration x turns out to have met the rule, alpha_x is what the run returns: same iteration count, same numbers as the
-// synchronous loop.  VBEM's expTheta takes digamma(sum alpha) of DN_LAG iterations ago: the sum is the same number up to rounding
-// (every iteration redistributes the same counts) and scales ALL expThetas alike, which cancels in every class's shares.
-// Slot reuse: warps are at most DN_LAG iterations apart (nobody passes m + DN_LAG before everybody has arrived at m), so the slots of
-// iterations m - 2 DN_LAG .. m + DN_LAG may be live when warp 0 of CTA 0 is at m; it clears the slot of m + DN_LAG + 1 (last used 16
-// iterations earlier) before its own arrival at m.  Arrival counters only grow.
+// Lagged stopping rule.  The components of a CTA do not depend on other CTAs; what ties the grid together is the reference's stopping
+// rule (max relative change over ALL transcripts, every iteration from minIter on: CollapsedEMOptimizer.cpp:849-861) and VBEM's
+// digamma(sum alpha).  A grid barrier per iteration for them costs more than the iteration (measured: 10.2 us per iteration to
+// convergence against 2.6 us with a fixed count, VBEM 13 us): every CTA waits for the slowest one, then for two L2 round trips.
+// Instead a CTA publishes its part of iteration m (atomicMax / atomicAdd into slot m % 16, then an arrival count) and goes on; the
+// decision for iteration m is read DN_LAG iterations later, when every CTA has long arrived.  The alphas of the last DN_LAG + 1
+// iterations stay in a shared-memory ring, so when iteration x turns out to have met the rule, alpha_x is what the run returns:
+// same iteration count, same numbers as the synchronous loop.  VBEM's expTheta takes digamma(sum alpha) of DN_LAG iterations ago:
+// the sum is the same number up to rounding (every iteration redistributes the same counts) and scales ALL expThetas alike, which
+// cancels in every class's shares.
+// The arrival for iteration m is sent one iteration later (its atomics are performed by then, so the fence before it is free), and
+// what is due at iteration m is loaded before m's sweep and looked at after it: neither costs a round trip on the critical path.
+// Slot reuse: CTAs are at most DN_LAG iterations apart (nobody passes m + DN_LAG before everybody has arrived at m), so the slots of
+// iterations m - 2 DN_LAG .. m + DN_LAG may be live when CTA 0 is at m; it clears the slot of m + DN_LAG + 1 (last used 16 iterations
+// earlier) before its own arrival at m.  Arrival counters only grow.
 constexpr uint32_t DN_LAG = 3, DN_RING = 4, DN_LAG_SLOTS = 16;
 static_assert(DN_RING == DN_LAG + 1 && (DN_RING & (DN_RING - 1)) == 0 && DN_LAG_SLOTS > 3 * DN_LAG + 1, "lagged stopping rule geometry");
 
@@ -202,16 +204,25 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     __syncthreads();
     uint32_t n = 0;
     unsigned long long mr_final = 0ULL;
-    // lagged runs compare the idle transcripts once (m == 1); afterwards their alpha no longer changes and all that is left of them in
-    // the stopping rule is "a transcript past the gate with relative change 0"
+    // the idle transcripts are compared once (m == 1); afterwards their alpha no longer changes and all that is left of them in the
+    // stopping rule is "a transcript past the gate with relative change 0"
     unsigned long long idle_later = 0ULL;
-    if (lagged) for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) if (p.base[idle[i]] > p.cutoff) idle_later = 1ULL;
+    for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) if (p.base[idle[i]] > p.cutoff) idle_later = 1ULL;
     for (;;) {
         if (fixed ? (n >= p.fixed_iters) : (n >= p.max_iter && n >= p.min_iter)) break;
         const uint32_t m = n + 1;
         const bool do_cmp = fixed ? (m >= p.fixed_iters) : (m >= p.min_iter);
         unsigned long long best = 0ULL;
         double asum = 0.0;
+        double bnum = -1.0, bden = 1.0;
+        // lagged runs: what the grid found DN_LAG iterations ago is loaded now and looked at after the sweep
+        unsigned long long pf_arr = 0ULL, pf_mr = 0ULL, pf_sum = 0ULL;
+        if (lagged && threadIdx.x == 0 && m > DN_LAG) {
+            const uint32_t xs = (m - DN_LAG) & (DN_LAG_SLOTS - 1u);
+            pf_arr = ld_acquire_u64(p.ctl + CTL_LAG_ARR + xs);
+            pf_mr = ld_cg_u64(p.ctl + CTL_LAG_MAX + xs);
+            pf_sum = ld_cg_u64(p.ctl + CTL_LAG_SUM + xs);
+        }
         const double* a_rd = lagged ? ring(n) : s_alpha;
         double* a_wr = lagged ? ring(m) : s_alpha;
         // ---- one EM iteration of every component of this warp's tiles (tile -> warp is fixed, so a tile's state is only ever
@@ -302,15 +313,20 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                 const double a_old = a_rd[i];
                 const double a_new = b[j] * acc[j] + s_base[i];
                 if (do_cmp) {
+                    // max of |old - new| / new without a division per slot: the largest quotient is kept as (numerator, denominator)
+                    // and compared by cross-multiplication; it is divided once per thread and iteration (rounding is monotonic, so
+                    // that IS the max of the rounded quotients, up to the rounding of the products between near-equal candidates)
                     const double gate = p.gate_old ? a_old : a_new;
-                    if (gate > p.cutoff) {
-                        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a_old - a_new) / a_new) + 1ULL;
-                        best = bits > best ? bits : best;
-                    }
+                    const double num = fabs(a_old - a_new);
+                    if (gate > p.cutoff && num * bden > bnum * a_new) { bnum = num; bden = a_new; }
                 }
                 a_wr[i] = a_new;
                 if (VB) asum += a_new; else s_beta[i] = a_new * s_inveff[i];
             }
+        }
+        if (do_cmp && bnum >= 0.0) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(bnum / bden) + 1ULL;
+            best = bits > best ? bits : best;
         }
         if (has_pool) {
             const double* in = p.X + (size_t)bi * p.T;
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             { const unsigned tmp = bs; bs = bi; bi = bo; bo = tmp; }   // bi now names the pool's newest alphas
         }
         n = m;
-        if (do_cmp && !(lagged && m > 1u)) {                           // idle transcripts: alpha_0 -> base at m == 1, base -> base after
+        if (do_cmp && m == 1u) {                                       // idle transcripts: alpha_0 -> base at m == 1, base -> base after (idle_later)
             for (uint32_t i = threadIdx.x; i < nidle; i += blockDim.x) {
                 const uint32_t t = idle[i];
                 const double a_new = p.base[t];
@@ -351,26 +367,23 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                 }
             }
         }
+        if (do_cmp && m > 1u) best = idle_later > best ? idle_later : best;
         if (lagged) {
-            // ---- per WARP: publish this warp's part of iteration m, arrive, read what is due, go on -- no CTA barrier either, so a
-            //      warp waits for nobody unless somebody is more than DN_LAG iterations behind
-            if (do_cmp && m > 1u) best = idle_later > best ? idle_later : best;     // an idle transcript past the gate: relative change 0
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
-            double asum_w = 0.0;
-            if (VB) asum_w = warp_sum(asum + idle_sum);
-            const uint32_t slot = m & (DN_LAG_SLOTS - 1u);
-            if (lane == 0) {
-                if (do_cmp && best) atomicMax(p.ctl + CTL_LAG_MAX + slot, best);
-                if (VB) atomicAdd(reinterpret_cast<double*>(p.ctl + CTL_LAG_SUM + slot), asum_w);
-                if (blockIdx.x == 0 && warp == 0) {
+            // publish this CTA's part of iteration m; the ARRIVAL for it goes out one iteration later (below), when its atomics have
+            // long been performed and the fence in front of the arrival costs nothing
+            if (threadIdx.x == 0 && m > 1u) { __threadfence(); atomicAdd(p.ctl + CTL_LAG_ARR + ((m - 1u) & (DN_LAG_SLOTS - 1u)), 1ULL); }
+            if (do_cmp) block_max_to_slot(best, p.ctl + CTL_LAG_MAX + (m & (DN_LAG_SLOTS - 1u)), sm_u);
+            if (VB) block_sum_to_slot(asum + idle_sum, reinterpret_cast<double*>(p.ctl + CTL_LAG_SUM + (m & (DN_LAG_SLOTS - 1u))), sm_d);
+            const bool final_it = fixed ? (m >= p.fixed_iters) : (m >= p.max_iter && m >= p.min_iter);
+            if (threadIdx.x == 0) {
+                if (blockIdx.x == 0) {
                     const uint32_t z = (m + DN_LAG + 1u) & (DN_LAG_SLOTS - 1u);
                     p.ctl[CTL_LAG_MAX + z] = 0ULL; p.ctl[CTL_LAG_SUM + z] = 0ULL;
                 }
-                red_release_add_u64(p.ctl + CTL_LAG_ARR + slot, 1ULL);            // after this lane's atomics and stores above
+                if (final_it) { __threadfence(); atomicAdd(p.ctl + CTL_LAG_ARR + (m & (DN_LAG_SLOTS - 1u)), 1ULL); }   // no later iteration
             }
-            // the iterations whose global quantities are due: m - DN_LAG, and after the final iteration all that are left, in order
-            const bool final_it = fixed ? (m >= p.fixed_iters) : (m >= p.max_iter && m >= p.min_iter);
+            // the iterations whose global quantities are due: m - DN_LAG (loaded by thread 0 before the sweep), and after the final
+            // iteration all that are left, in order
             uint32_t x = m > DN_LAG ? m - DN_LAG : 0u;
             const uint32_t x_hi = final_it ? m : x;
             if (final_it && x == 0u) x = 1u;
@@ -378,38 +391,35 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             unsigned long long sum_bits = 0ULL;
             bool have_sum = false;
             for (; x >= 1u && x <= x_hi; ++x) {
-                unsigned long long mr = 0ULL;
-                if (lane == 0) {
-                    const unsigned long long want = (unsigned long long)nblocks * W * ((x - 1u) / DN_LAG_SLOTS + 1u);
-                    while (ld_acquire_u64(p.ctl + CTL_LAG_ARR + (x & (DN_LAG_SLOTS - 1u))) < want) { }
-                    mr = ld_cg_u64(p.ctl + CTL_LAG_MAX + (x & (DN_LAG_SLOTS - 1u)));
-                    sum_bits = ld_cg_u64(p.ctl + CTL_LAG_SUM + (x & (DN_LAG_SLOTS - 1u)));
+                if (threadIdx.x == 0) {
+                    const unsigned long long want = (unsigned long long)nblocks * ((x - 1u) / DN_LAG_SLOTS + 1u);
+                    if (!(x + DN_LAG == m && pf_arr >= want)) {
+                        while (ld_acquire_u64(p.ctl + CTL_LAG_ARR + (x & (DN_LAG_SLOTS - 1u))) < want) { }
+                        pf_mr = ld_cg_u64(p.ctl + CTL_LAG_MAX + (x & (DN_LAG_SLOTS - 1u)));
+                        pf_sum = ld_cg_u64(p.ctl + CTL_LAG_SUM + (x & (DN_LAG_SLOTS - 1u)));
+                    }
+                    sm_u[0] = pf_mr; sm_u[1] = pf_sum;
                 }
-                mr = __shfl_sync(0xffffffffu, mr, 0);
-                sum_bits = __shfl_sync(0xffffffffu, sum_bits, 0);
-                have_sum = true;
+                __syncthreads();
+                const unsigned long long mr = sm_u[0];
+                sum_bits = sm_u[1]; have_sum = true;
                 const bool checked = fixed ? (x >= p.fixed_iters) : (x >= p.min_iter);
                 if (checked && (fixed || x >= p.max_iter || !(decode_mrd(mr) > p.tol))) {
                     stop = true; mr_final = mr; n = x;                 // the run ends with alpha_x: still in the ring
                     break;
                 }
+                if (x < x_hi) __syncthreads();                         // thread 0 writes sm_u again
             }
             if (stop) break;
             if (VB) {
-                // expTheta of this warp's components for its next sweep
                 const double logNorm = sfb_digamma(have_sum ? __longlong_as_double((long long)sum_bits) : p.sum0);
                 const double thetaScale = exp(-logNorm);
-                constexpr uint32_t CPT = 32u / (G ? G : 1);            // components per tile
-                __syncwarp();
-                for (uint32_t k = warp; k < tiles; k += W) {
-                    for (uint32_t idx = lane; idx < (uint32_t)NS * CPT; idx += 32u) {
-                        const size_t i = (size_t)(idx / CPT) * ncomp_pad + k * CPT + idx % CPT;
-                        const double a = a_wr[i];
-                        s_beta[i] = ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) * s_inveff[i];
-                    }
+                for (uint32_t i = threadIdx.x; i < (uint32_t)ring_stride; i += blockDim.x) {
+                    const double a = a_wr[i];
+                    s_beta[i] = ((a > DENORM_MIN) ? sfb_exp_theta(a, logNorm, thetaScale) : 0.0) * s_inveff[i];
                 }
+                __syncthreads();
             }
-            __syncwarp();
             continue;
         }
         if (VB || do_cmp) {

@@ -756,7 +756,7 @@ struct MapParams {
     int lib_fmt, strict_intersect, allow_orphans, allow_dovetail, ignore_compat, enforce_compat;
     unsigned long long* scratch; uint64_t n_threads_total;
     unsigned long long* counters;      // 6
-    unsigned long long* next_read;     // work counters: [0] scan kernel, [1] finalize kernel
+    unsigned long long* next_read;     // work counters: [0] scan kernel, [1] finalize kernel, [2..4] reads set aside for the heavy pass, by bin
     int16_t* fld_val;                  // per read of the batch: fragment length if FLD-eligible, else -1
     // packed batch and the scan -> finalize hand-over
     const uint64_t* pk; const uint64_t* pkn; const uint32_t* meta; uint32_t rwp; int n_mates;
@@ -764,8 +764,8 @@ struct MapParams {
     // bias / GC sample collection (k_finalize_reads_bias only)
     // class-table growth: reads whose upsert failed are listed (retry_out) and finalized again after the table has grown (retry_in)
     uint32_t* retry_out; const uint32_t* retry_in; uint64_t n_retry;
-    // reads with a big seed bucket are set aside by the main finalize pass (heavy_out, counted in tb.cursor[5]) and finalized by a
-    // second launch (heavy_in): map_finalize_body.inl
+    // reads with a big seed bucket are set aside by the main finalize pass (heavy_out: three bins of n_reads entries, counted in
+    // next_read[2..4]) and finalized by a second launch (heavy_in): map_finalize_body.inl
     uint32_t* heavy_out; const uint32_t* heavy_in;
     int16_t* bias_val;                 // per read of the batch: bin of its read-start context, or -1
     unsigned int* gc_hist;             // observed fragment GC histogram (101 bins), accumulated over batches
@@ -1122,7 +1122,7 @@ extern "C" int sfb200_map_begin(sfb200_ctx* c, const sfb200_map_opts* o) {
     m->n_buckets = 1ull << lb; m->n_overflow = std::max<uint64_t>(1024, m->n_buckets / 4); m->arena_words = 1ull << la;
     const uint64_t n_slots = m->n_buckets * 4 + m->n_overflow;
     SFB_CUDA(c, m->slot.reserve(n_slots)); SFB_CUDA(c, m->count.reserve(n_slots)); SFB_CUDA(c, m->arena.reserve(m->arena_words));
-    SFB_CUDA(c, m->cursor.reserve(8)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(2)); SFB_CUDA(c, m->maxlen.reserve(1)); SFB_CUDA(c, m->clipped.reserve(1));
+    SFB_CUDA(c, m->cursor.reserve(8)); SFB_CUDA(c, m->counters.reserve(6)); SFB_CUDA(c, m->next_read.reserve(8)); SFB_CUDA(c, m->maxlen.reserve(1)); SFB_CUDA(c, m->clipped.reserve(1));
     SFB_CUDA(c, m->fld_hist.reserve(o->max_frag_len)); SFB_CUDA(c, m->remaining.reserve(1));
     SFB_CUDA(c, m->fld_samples.reserve((size_t)std::max(1, o->num_frag_samples)));
     SFB_CUDA(c, cudaMemsetAsync(m->slot.p, 0, n_slots * 8, s));
@@ -1285,7 +1285,7 @@ static int eq_grow_and_retry(sfb200_ctx* c, MapState* m) {
         const unsigned long long keep = cur[2] & ~(ERR_ARENA_FULL | ERR_TABLE_FULL), zero = 0;
         SFB_CUDA(c, cudaMemcpyAsync(m->cursor.p + 2, &keep, 8, cudaMemcpyHostToDevice, s));
         SFB_CUDA(c, cudaMemcpyAsync(m->cursor.p + 4, &zero, 8, cudaMemcpyHostToDevice, s));
-        SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 16, s));
+        SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 64, s));
         MapParams p = m->last_p;
         p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p;
         p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
@@ -1340,7 +1340,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     p.scratch = m->scratch.p; p.n_threads_total = m->n_threads_total; p.counters = m->counters.p; p.next_read = m->next_read.p;
     const bool want_fld = d_bases2 != nullptr;
     if (want_fld) { SFB_CUDA(c, m->fld_val.reserve(n_reads)); p.fld_val = m->fld_val.p; }
-    SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 16, s));
+    SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 64, s));
     const int n_mates = d_bases2 ? 2 : 1;
     if (m->ev.size() < m->ev_used + 2) { cudaEvent_t a, b; SFB_CUDA(c, cudaEventCreate(&a)); SFB_CUDA(c, cudaEventCreate(&b)); m->ev.push_back(a); m->ev.push_back(b); }
     SFB_CUDA(c, cudaEventRecord(m->ev[m->ev_used], s));
@@ -1358,7 +1358,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     if ((h_cur[2] & (ERR_ARENA_FULL | ERR_TABLE_FULL)) || h_cur[4]) {
         const int rc = eq_grow_and_retry(c, m);
         if (rc) return rc;
-        SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 16, s));
+        SFB_CUDA(c, cudaMemsetAsync(m->next_read.p, 0, 64, s));
         p.tb.slot = m->slot.p; p.tb.count = m->count.p; p.tb.arena = m->arena.p;
         p.tb.n_buckets = m->n_buckets; p.tb.n_overflow = m->n_overflow; p.tb.arena_words = m->arena_words;
     }
@@ -1374,7 +1374,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     k_pack_reads<<<(unsigned)((n_fm * rwp + 255) / 256), 256, 0, s>>>(d_bases1, d_off1, d_bases2, d_off2, n_reads, n_mates, rwp, m->pk.p, m->pkn.p, m->meta.p);
     c->launches++;
     p.pk = m->pk.p; p.pkn = m->pkn.p; p.meta = m->meta.p; p.rwp = rwp; p.n_mates = n_mates; p.iv = m->iv.p; p.niv = m->niv.p; p.ivmask = m->ivmask.p;
-    // per chunk: the number of reads set aside for the heavy finalize pass (cursor[5]) and the pool of per-round extension words of
+    // per chunk: the pool of per-round extension words of
     // big seed buckets (cursor[6]; 32 bytes per read -- a bucket of 1000 positions takes 32 words; when the pool runs out the
     // finalize kernel extends those entries itself)
     uint64_t pool_cap = std::max<uint64_t>(1u << 16, 4 * n_reads);
@@ -1395,7 +1395,7 @@ static int map_chunk_device(sfb200_ctx* c, const char* d_bases1, const uint64_t*
     // main pass, then the reads it set aside (big seed buckets); the second launch reads their number on the device
     const bool defer = m->defer_heavy;
     if (defer) {
-        SFB_CUDA(c, m->heavy.reserve(n_reads));
+        SFB_CUDA(c, m->heavy.reserve(3 * n_reads));
         p.heavy_out = m->heavy.p;
     }
     for (int pass = 0; pass < (defer ? 2 : 1); ++pass) {

@@ -27,15 +27,24 @@
     // against 0.6 ms without such reads).  Set aside and finalized together, every lane of a warp has such a read.
     const bool retry = p.retry_in != nullptr;
     const bool heavy_pass = p.heavy_in != nullptr;
-    const uint32_t* __restrict__ list_in = retry ? p.retry_in : p.heavy_in;
-    const uint64_t n_work = retry ? p.n_retry : heavy_pass ? (uint64_t)__ldcg(p.tb.cursor + 5) : p.n_reads;
+    // the heavy list is kept in three bins by the size of the read's largest bucket (p.n_reads entries apart, counted in
+    // p.next_read[2..4]) and walked from the largest bin down, so that the reads of a warp cost about the same
+    const uint64_t hv2 = heavy_pass ? (uint64_t)__ldcg(p.next_read + 4) : 0, hv1 = heavy_pass ? (uint64_t)__ldcg(p.next_read + 3) : 0;
+    const uint64_t hv0 = heavy_pass ? (uint64_t)__ldcg(p.next_read + 2) : 0;
+    const uint64_t n_work = retry ? p.n_retry : heavy_pass ? hv0 + hv1 + hv2 : p.n_reads;
     for (;;) {
         unsigned long long base_idx = 0;
         if (lane == 0) base_idx = atomicAdd(p.next_read + 1, 32ULL);
         base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
         if (base_idx >= n_work) break;
         bool have_read = base_idx + lane < n_work;
-        const uint64_t ri = have_read ? (list_in ? (uint64_t)list_in[base_idx + lane] : base_idx + lane) : 0;
+        uint64_t ri = 0;
+        if (have_read) {
+            const uint64_t w = base_idx + lane;
+            if (retry) ri = p.retry_in[w];
+            else if (heavy_pass) ri = w < hv2 ? p.heavy_in[2 * p.n_reads + w] : w < hv2 + hv1 ? p.heavy_in[p.n_reads + (w - hv2)] : p.heavy_in[w - hv2 - hv1];
+            else ri = w;
+        }
         bool mapped = false;
         uint32_t lab_n = 0;
         uint32_t len1 = 0, len2 = 0;
@@ -72,7 +81,8 @@
                 score[q] = sc;
             }
             if (p.heavy_out && big > SFB_HEAVY_CNT) {          // main pass: not now
-                p.heavy_out[atomicAdd(p.tb.cursor + 5, 1ULL)] = (uint32_t)ri;
+                const uint32_t bin = big <= 64u ? 0u : big <= 256u ? 1u : 2u;
+                p.heavy_out[bin * p.n_reads + atomicAdd(p.next_read + 2 + bin, 1ULL)] = (uint32_t)ri;
                 have_read = false;
             }
         }
