@@ -30,6 +30,6 @@ echo "ncu map rc=$?  ($(( $(date +%s) - t0 )) s)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_em_dense|k_em_part' -c 1 -f -o $OUT/${TAG}_em \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-realistic > $OUT/${TAG}_ncu_em.log 2>&1
 echo "ncu em rc=$?  ($(( $(date +%s) - t0 )) s)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_scan_reads|k_finalize_reads|k_em_part' --launch-skip 8 -c 3 -f -o $OUT/${TAG}_paralog \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_scan_reads|k_finalize_reads' --launch-skip 12 -c 3 -f -o $OUT/${TAG}_paralog \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-realistic --structure paralog --reads 4000000 > $OUT/${TAG}_ncu_paralog.log 2>&1
 echo "ncu paralog rc=$?  ($(( $(date +%s) - t0 )) s)"
