@@ -24,7 +24,7 @@ echo "reference arm rc=$?  ($(( $(date +%s) - t0 )) s)"; cut -c1-400 $OUT/${TAG}
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-realistic > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "ncu launch list rc=$?  ($(( $(date +%s) - t0 )) s)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_scan_reads|k_finalize_reads|k_pack_reads' --launch-skip 30 -c 3 -f -o $OUT/${TAG}_map \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_scan_reads|k_finalize_reads|k_pack_reads' --launch-skip 32 -c 4 -f -o $OUT/${TAG}_map \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-realistic > $OUT/${TAG}_ncu_map.log 2>&1
 echo "ncu map rc=$?  ($(( $(date +%s) - t0 )) s)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_em_dense|k_em_part' -c 1 -f -o $OUT/${TAG}_em \

@@ -1,7 +1,8 @@
 #!/bin/bash
 # Multi-GPU session on ONE box with N GPUs: the 2-rank parity test, then the bench line at every N in the list, launched exactly as
 # the driver does (torchrun for N > 1), optionally the reference arm under torchrun and config 4 at the largest N.
-# usage: /usr/local/graft/bin/gpurun --gpus 8 --timeout 1800 -- 'bash scripts/gpu_multi.sh <tag> "1 2 4 8" [cfg4]'
+# usage: /usr/local/graft/bin/gpurun --gpus 8 --timeout 1800 -- '[SFB200_MULTI_AB=1] bash scripts/gpu_multi.sh <tag> "1 2 4 8" [cfg4]'
+# (SFB200_MULTI_AB=1 adds the reference arm under torchrun and the largest N without NUMA binding)
 TAG=${1:-r02n}
 NS=${2:-"1 2"}
 CFG4=${3:-}
@@ -23,12 +24,12 @@ for N in $NS; do
     fi
     echo "bench N=$N rc=$?  ($(( $(date +%s) - t0 )) s)"; python scripts/show_bench.py $OUT/${TAG}_bench_n$N.json 2>&1 | tail -4
 done
-if [ "$last" != "1" ]; then
+if [ "$last" != "1" ] && [ -n "$SFB200_MULTI_AB" ]; then
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $last --master-addr 127.0.0.1 --master-port 29611 \
         bench.py --impl reference --gpus $last --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference_n$last.json 2> $OUT/${TAG}_bench_reference_n$last.log
     echo "reference arm under torchrun N=$last rc=$?  ($(( $(date +%s) - t0 )) s)"; grep '^{' $OUT/${TAG}_bench_reference_n$last.json | cut -c1-300
 fi
-if [ "$last" != "1" ]; then
+if [ "$last" != "1" ] && [ -n "$SFB200_MULTI_AB" ]; then
     # the same largest N with the page-locked buffers wherever the kernel puts them (no NUMA binding): what the binding buys
     SFB200_NO_BIND=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $last --master-addr 127.0.0.1 --master-port 29622 \
         bench.py --gpus $last --no-realistic > $OUT/${TAG}_bench_n${last}_nobind.json 2> $OUT/${TAG}_bench_n${last}_nobind.log
