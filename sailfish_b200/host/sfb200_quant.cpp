@@ -568,6 +568,11 @@ private:
                     b->len += room; pos += room;
                     if (pos == fsize) {                                        // end of this file
                         if (fsize > 0 && last_char != '\n') { b->mem[b->head + b->len++] = '\n'; last_char = '\n'; }
+                        // blank lines at the end of a file (the host parser skips them) would shift every record of the next file
+                        char* m0 = b->mem + b->head;
+                        while (b->len >= 2 && m0[b->len - 1] == '\n' &&
+                               (m0[b->len - 2] == '\n' || (b->len >= 3 && m0[b->len - 2] == '\r' && m0[b->len - 3] == '\n')))
+                            b->len -= (m0[b->len - 2] == '\r') ? 2 : 1;
                         ::close(fd); fd = -1; ++next;
                     }
                 }

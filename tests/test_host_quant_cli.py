@@ -347,6 +347,14 @@ def test_device_parse_feeding_with_stub_device(tmp_path):
         assert json.load(open(tmp_path / ("o" + block) / "aux" / "meta_info.json"))["num_processed"] == 1000
         if block != "0":
             assert len(calls) > 10
+    # blank lines at the end of a file (some writers leave them; the host parser skips them) must not shift the next file's records
+    (tmp_path / "c1.fq").write_text((tmp_path / "a1.fq").read_text() + "\n\n", newline="")
+    (tmp_path / "c2.fq").write_text((tmp_path / "b2.fq").read_bytes().decode() + "\r\n", newline="")
+    log.unlink()
+    subprocess.check_call([exe, "quant", "-t", str(fa), "-l", "U", "-r", str(tmp_path / "c1.fq"), str(tmp_path / "c2.fq"), str(tmp_path / "a1.fq"),
+                           "-o", str(tmp_path / "ob"), "--deviceParse", "--blockBytes", "0"], env=env, stderr=subprocess.DEVNULL)
+    calls = [l for l in log.read_text().strip().split("\n") if l.startswith("map_fastq")]
+    assert not any("BAD_START" in c for c in calls) and sum(int(c.split()[1]) for c in calls) == 700 + 300 + 700
     # single-end; a truncated file and mates of different length are errors
     log.unlink()
     subprocess.check_call([exe, "quant", "-t", str(fa), "-l", "U", "-r", str(tmp_path / "a1.fq"), "-o", str(tmp_path / "os"), "--deviceParse", "--blockBytes", "5000"],
