@@ -307,19 +307,25 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
                 }
                 if (idle_lane || grank) continue;
             }
+            if (do_cmp) {
+                // max of |old - new| / new without a division per slot: the largest quotient is kept as (numerator, denominator) and
+                // compared by cross-multiplication; it is divided once per thread and iteration (rounding is monotonic, so that IS
+                // the max of the rounded quotients, up to the rounding of the products between near-equal candidates).  A loop of
+                // its own, so that iterations without the rule (all but the last of a fixed-count run) skip it with one branch.
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                const size_t i = (size_t)j * ncomp_pad + qi;
-                const double a_old = a_rd[i];
-                const double a_new = b[j] * acc[j] + s_base[i];
-                if (do_cmp) {
-                    // max of |old - new| / new without a division per slot: the largest quotient is kept as (numerator, denominator)
-                    // and compared by cross-multiplication; it is divided once per thread and iteration (rounding is monotonic, so
-                    // that IS the max of the rounded quotients, up to the rounding of the products between near-equal candidates)
+                for (int j = 0; j < NS; ++j) {
+                    const size_t i = (size_t)j * ncomp_pad + qi;
+                    const double a_old = a_rd[i];
+                    const double a_new = b[j] * acc[j] + s_base[i];
                     const double gate = p.gate_old ? a_old : a_new;
                     const double num = fabs(a_old - a_new);
                     if (gate > p.cutoff && num * bden > bnum * a_new) { bnum = num; bden = a_new; }
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const size_t i = (size_t)j * ncomp_pad + qi;
+                const double a_new = b[j] * acc[j] + s_base[i];
                 a_wr[i] = a_new;
                 if (VB) asum += a_new; else s_beta[i] = a_new * s_inveff[i];
             }
