@@ -106,23 +106,43 @@ __global__ void __launch_bounds__(1024) k_part_bounds(const uint32_t* __restrict
     if (tid == 0) s_total = carry_a;
     __syncthreads();
     const unsigned long long total = s_total;
-    for (uint32_t i = tid; i <= n_cta; i += nth) {
+    // a WARP per boundary: a 32-ary search for the cost target (4 rounds of one load per lane instead of 18 dependent loads) and the
+    // lanes of the warp looking at 32 window offsets at a time (a thread by itself walked the window with two dependent loads per
+    // offset: one boundary far from any uncrossed position cost win x 2 round trips, ~0.3 ms, whatever the other threads did)
+    for (uint32_t i = warp; i <= n_cta; i += nw) {
         uint32_t b;
         if (i == 0) b = 0;
         else if (i == n_cta) b = T;
         else {
             const unsigned long long target = total * i / n_cta;
-            uint32_t l = 0, h = T;                       // first t with pre[t] >= target (T if none)
-            while (l < h) { const uint32_t mid = l + (h - l) / 2; if (pre[mid] < target) l = mid + 1; else h = mid; }
+            uint32_t l = 0, h = T;                       // first t with pre[t] >= target (T if none): the answer lies in [l, h]
+            while (l < h) {
+                const uint32_t step = (h - l + 31u) / 32u;
+                const uint32_t c_lo = l + lane * step;                          // this lane's chunk [c_lo, c_hi)
+                const uint32_t c_hi = c_lo + step < h ? c_lo + step : h;
+                const bool ge = c_lo < c_hi && pre[c_hi - 1] >= target;         // the chunk's last element has reached the target
+                const unsigned m = __ballot_sync(0xffffffffu, ge);
+                if (m == 0u) { l = h; break; }                                  // nothing below h has
+                const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+                const uint32_t k_lo = l + k * step, k_hi = (k_lo + step < h ? k_lo + step : h);
+                l = k_lo; h = k_hi - 1u;                                        // pre[k_hi - 1] >= target: the answer is at most k_hi - 1
+            }
             b = l < T ? l + 1 : T;
             uint32_t best = b;
-            for (uint32_t dd = 0; dd <= win; ++dd) {
-                if (b >= dd && diff[b - dd] == 0) { best = b - dd; break; }
-                if (b + dd < T && diff[b + dd] == 0) { best = b + dd; break; }
+            for (uint32_t d0 = 0; d0 <= win; d0 += 32u) {
+                const uint32_t dd = d0 + lane;
+                const bool okm = dd <= win && b >= dd && diff[b - dd] == 0;
+                const bool okp = dd <= win && b + dd < T && diff[b + dd] == 0;
+                const unsigned mm = __ballot_sync(0xffffffffu, okm), mp = __ballot_sync(0xffffffffu, okp);
+                if (mm | mp) {                                                  // the smallest offset, the position below before the one above
+                    const uint32_t k = (uint32_t)__ffs((int)(mm | mp)) - 1u;
+                    best = ((mm >> k) & 1u) ? b - (d0 + k) : b + (d0 + k);
+                    break;
+                }
             }
             b = best;
         }
-        s_b[i] = b;
+        if (lane == 0) s_b[i] = b;
     }
     __syncthreads();
     if (tid == 0) {
