@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
                     const size_t i = (size_t)j * ncomp_pad + qi;
-                    const double a_old = a_rd[i];
+                    double a_old;
+                    if constexpr (lagged) a_old = a_rd[i]; else a_old = s_alpha[i];
                     const double a_new = b[j] * acc[j] + s_base[i];
                     const double gate = p.gate_old ? a_old : a_new;
                     const double num = fabs(a_old - a_new);
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
             for (int j = 0; j < NS; ++j) {
                 const size_t i = (size_t)j * ncomp_pad + qi;
                 const double a_new = b[j] * acc[j] + s_base[i];
-                a_wr[i] = a_new;
+                if constexpr (lagged) a_wr[i] = a_new; else s_alpha[i] = a_new;       // (the same array; a second base register costs an IMAD per slot)
                 if (VB) asum += a_new; else s_beta[i] = a_new * s_inveff[i];
             }
         }

@@ -53,54 +53,59 @@ __global__ void __launch_bounds__(1024) k_part_bounds(const uint32_t* __restrict
     __shared__ unsigned long long s_total;
     extern __shared__ uint32_t s_b[];                    // n_cta + 1
     const uint32_t nth = blockDim.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nw = nth >> 5;
-    // block-wide inclusive scans over tiles of PB_ITEMS * blockDim elements (the profile has T + 1 entries): a thread scans its
-    // PB_ITEMS consecutive elements in registers, the block scans the thread totals (one element per thread and three barriers per
-    // blockDim elements made this kernel 0.29 ms at T = 200 k: 196 tiles)
+    // block-wide inclusive scans over tiles of PB_ITEMS * blockDim elements (the profile has T + 1 entries).  A tile is PB_ITEMS
+    // sub-tiles of blockDim consecutive elements, thread tid holding element tid of each (coalesced loads and stores: with a thread's
+    // elements next to each other every load touched 32 sectors and this one-CTA kernel spent 0.3 ms waiting for them); each warp scans
+    // its 32 elements of every sub-tile, the PB_ITEMS x 32 warp totals are scanned in shared memory, three barriers per tile.
     constexpr int PB_ITEMS = 8;
+    __shared__ unsigned long long s_ta[PB_ITEMS * 32];
+    __shared__ long long s_td[PB_ITEMS * 32];
     unsigned long long carry_a = 0; long long carry_d = 0;
     for (uint32_t base = 0; base <= T; base += nth * PB_ITEMS) {
-        const uint32_t t0 = base + tid * PB_ITEMS;
         unsigned long long av[PB_ITEMS]; long long dv[PB_ITEMS];
 #pragma unroll
         for (int q = 0; q < PB_ITEMS; ++q) {
-            const uint32_t t = t0 + q;
+            const uint32_t t = base + q * nth + tid;
             av[q] = t < T ? 1ull + load[t] : 0ull;
             dv[q] = t <= T ? (long long)diff[t] : 0ll;
         }
 #pragma unroll
-        for (int q = 1; q < PB_ITEMS; ++q) { av[q] += av[q - 1]; dv[q] += dv[q - 1]; }
-        unsigned long long a = av[PB_ITEMS - 1];
-        long long d = dv[PB_ITEMS - 1];
+        for (int q = 0; q < PB_ITEMS; ++q) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long ua = __shfl_up_sync(0xffffffffu, a, o);
-            const long long ud = __shfl_up_sync(0xffffffffu, d, o);
-            if ((int)lane >= o) { a += ua; d += ud; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long ua = __shfl_up_sync(0xffffffffu, av[q], o);
+                const long long ud = __shfl_up_sync(0xffffffffu, dv[q], o);
+                if ((int)lane >= o) { av[q] += ua; dv[q] += ud; }
+            }
+            if (lane == 31) { s_ta[q * 32 + warp] = av[q]; s_td[q * 32 + warp] = dv[q]; }
         }
-        if (lane == 31) { s_wa[warp] = a; s_wd[warp] = d; }
+        if (nw < 32 && lane == 31) for (int q = 0; q < PB_ITEMS; ++q) for (uint32_t w = nw; w < 32; ++w) { s_ta[q * 32 + w] = 0; s_td[q * 32 + w] = 0; }
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long wa = lane < nw ? s_wa[lane] : 0ull;
-            long long wd = lane < nw ? s_wd[lane] : 0ll;
+        // warp q scans the 32 warp totals of sub-tile q (inclusive); s_wa / s_wd take the sub-tile totals
+        if (warp < (uint32_t)PB_ITEMS) {
+            unsigned long long wa = s_ta[warp * 32 + lane];
+            long long wd = s_td[warp * 32 + lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned long long ua = __shfl_up_sync(0xffffffffu, wa, o);
                 const long long ud = __shfl_up_sync(0xffffffffu, wd, o);
                 if ((int)lane >= o) { wa += ua; wd += ud; }
             }
-            s_wa[lane] = wa; s_wd[lane] = wd;            // inclusive over the warps
+            s_ta[warp * 32 + lane] = wa; s_td[warp * 32 + lane] = wd;
+            if (lane == 31) { s_wa[warp] = wa; s_wd[warp] = wd; }
         }
         __syncthreads();
-        // what lies in front of this thread's elements: earlier tiles, earlier warps, earlier threads of the warp
-        const unsigned long long ex_a = carry_a + (warp ? s_wa[warp - 1] : 0ull) + (a - av[PB_ITEMS - 1]);
-        const long long ex_d = carry_d + (warp ? s_wd[warp - 1] : 0ll) + (d - dv[PB_ITEMS - 1]);
+        unsigned long long run_a = carry_a; long long run_d = carry_d;              // everything in front of sub-tile q
 #pragma unroll
         for (int q = 0; q < PB_ITEMS; ++q) {
-            const uint32_t t = t0 + q;
+            const uint32_t t = base + q * nth + tid;
+            const unsigned long long ex_a = run_a + (warp ? s_ta[q * 32 + warp - 1] : 0ull);
+            const long long ex_d = run_d + (warp ? s_td[q * 32 + warp - 1] : 0ll);
             if (t < T) pre[t] = ex_a + av[q];
             if (t <= T) diff[t] = (int)(ex_d + dv[q]);
+            run_a += s_wa[q]; run_d += s_wd[q];
         }
-        carry_a += s_wa[nw - 1]; carry_d += s_wd[nw - 1];
+        carry_a = run_a; carry_d = run_d;
         __syncthreads();
     }
     if (tid == 0) s_total = carry_a;
