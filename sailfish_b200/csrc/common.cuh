@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/sfb200.h"
@@ -41,6 +42,17 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     size_t bytes() const { return cap * sizeof(T); }
+};
+
+// A function's own scratch buffers: released when the function returns, on the error paths of SFB_CUDA / SFB_FAIL as well.
+// (DevBuf itself has no destructor: the long-lived ones are members that are copied and swapped when tables grow.)
+template <typename... Bufs>
+struct DevBufScope {
+    std::tuple<Bufs&...> bufs;
+    explicit DevBufScope(Bufs&... b) : bufs(b...) {}
+    ~DevBufScope() { std::apply([](auto&... b) { (b.release(), ...); }, bufs); }
+    DevBufScope(const DevBufScope&) = delete;
+    DevBufScope& operator=(const DevBufScope&) = delete;
 };
 
 // ---- the device index (mapping spec v1) ---------------------------------------------------

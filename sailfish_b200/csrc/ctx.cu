@@ -226,6 +226,7 @@ extern "C" int sfb200_xxh64_device(sfb200_ctx* c, const uint8_t* data, const uin
     for (uint64_t i = 0; i <= n; ++i) if (off[i] % 4) SFB_FAIL(c, SFB200_EINVAL, "message offsets must be multiples of 4");
     cudaSetDevice(c->device);
     DevBuf<uint8_t> d_data; DevBuf<uint64_t> d_off, d_out;
+    DevBufScope<DevBuf<uint8_t>, DevBuf<uint64_t>, DevBuf<uint64_t>> scope(d_data, d_off, d_out);
     SFB_CUDA(c, d_data.reserve(total + 4));
     SFB_CUDA(c, d_off.reserve(n + 1));
     SFB_CUDA(c, d_out.reserve(n));
@@ -236,7 +237,6 @@ extern "C" int sfb200_xxh64_device(sfb200_ctx* c, const uint8_t* data, const uin
     SFB_CUDA(c, cudaGetLastError());
     SFB_CUDA(c, cudaMemcpyAsync(out, d_out.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     SFB_CUDA(c, cudaStreamSynchronize(c->stream));
-    d_data.release(); d_off.release(); d_out.release();
     return SFB200_OK;
 }
 
@@ -254,6 +254,7 @@ static int digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* ou
     if (n == 0) return SFB200_OK;
     cudaSetDevice(c->device);
     DevBuf<double> d_x, d_o;
+    DevBufScope<DevBuf<double>, DevBuf<double>> scope(d_x, d_o);
     SFB_CUDA(c, d_x.reserve(n));
     SFB_CUDA(c, d_o.reserve(n));
     SFB_CUDA(c, cudaMemcpyAsync(d_x.p, x, n * 8, cudaMemcpyHostToDevice, c->stream));
@@ -262,6 +263,5 @@ static int digamma_device(sfb200_ctx* c, const double* x, uint64_t n, double* ou
     SFB_CUDA(c, cudaGetLastError());
     SFB_CUDA(c, cudaMemcpyAsync(out, d_o.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     SFB_CUDA(c, cudaStreamSynchronize(c->stream));
-    d_x.release(); d_o.release();
     return SFB200_OK;
 }

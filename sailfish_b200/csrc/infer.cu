@@ -374,6 +374,7 @@ extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint3
     cudaStream_t s = c->stream;
     DevBuf<unsigned long long> d_samp, d_cnt;
     SplitTree tr;
+    DevBufScope<DevBuf<unsigned long long>, DevBuf<unsigned long long>, DevBuf<double>, DevBuf<unsigned long long>> scope(d_samp, d_cnt, tr.d_sums, tr.d_share);
     tr.n.push_back(E);
     while (tr.n.back() > 1) tr.n.push_back((tr.n.back() + SPLIT_FAN - 1) / SPLIT_FAN);
     if (tr.n.size() == 1) tr.n.push_back(1);                                          // a single class still has a root above it
@@ -412,7 +413,6 @@ extern "C" int sfb200_bootstrap_run(sfb200_ctx* c, const double* eff_lens, uint3
     }
     c->eff_resident = false;
     c->last_em_ms = loop_ms;
-    tr.release(); d_samp.release(); d_cnt.release();
-    return rc;
+    return rc;                                              // `scope` releases the replicate buffers
 }
 
