@@ -457,7 +457,7 @@ class GpuRun:
         host_phase_ms = {kk: round(v * 1e3 / steps, 3) for kk, v in self.phase.items()}
         clocks = sampler.stop() if sampler else None
         r = {"ms": ms, "launches": launches, "map_ms": map_ms / steps, "em_ms": em_ms / steps, "g": g, "alphas": alphas, "iters": iters,
-             "eff": eff, "extra": extra, "host_phase_ms": host_phase_ms, "clocks": clocks, "em_kernel": EM_KERNELS[self.ctx.last_em_kernel()]}
+             "eff": eff, "extra": extra, "host_phase_ms": host_phase_ms, "clocks": clocks, "em_kernel": EM_KERNELS[self.ctx.last_em_kernel()], "em_variant": self.ctx.last_em_variant()}
         total_reads = wl.reads * self.world
         r["value"] = total_reads * steps / (ms / 1e3)
         if with_e2e:
@@ -566,7 +566,7 @@ def main():
             "data": "synthetic", "config": wl.config(), "clocks": m["clocks"],
             "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": m["ms_e2e"] / steps},
             "gpu_launches": m["launches"],
-            "detail": {"map_kernel_ms_per_step": m["map_ms"], "em_loop_ms_per_step": m["em_ms"], "em_iters": m["iters"], "em_kernel": m["em_kernel"],
+            "detail": {"map_kernel_ms_per_step": m["map_ms"], "em_loop_ms_per_step": m["em_ms"], "em_iters": m["iters"], "em_kernel": m["em_kernel"] + (" (streaming variant)" if m["em_variant"] & 1 else "") + (" (lagged stopping rule)" if m["em_variant"] & 2 else ""),
                        "map_kernel_reads_per_s": n / (m["map_ms"] / 1e3), "em_iters_per_s": m["iters"] / (m["em_ms"] / 1e3),
                        "host_wall_ms_per_step": m["host_phase_ms"], "n_classes": E, "nnz": nnz, "mapped": int(g["counters"][1]),
                        "observed": int(g["counters"][0]), "index_hbm_gb": round(run.st["hbm_bytes"] / 1e9, 2),
@@ -575,10 +575,11 @@ def main():
     # working set in shared memory (no HBM traffic after the first iteration): their bound is on-chip, the HBM figure is an equivalent
     b_em = 12.0 * nnz + 12.0 * E + 32.0 * T
     em_gbs = b_em * m["iters"] / (m["em_ms"] / 1e3) / 1e9
-    on_chip = m["em_kernel"].startswith(("k_em_dense", "k_em_gather", "k_em_part"))
+    streamed = bool(m["em_variant"] & 1)             # k_em_dense reading counts / base / 1/effLen from a global block every iteration
+    on_chip = m["em_kernel"].startswith(("k_em_dense", "k_em_gather", "k_em_part")) and not streamed
     em_traffic = None
     try:
-        em_traffic = json.load(open(os.path.join(ROOT, "profiles", "em_kernel_traffic.json"))).get(m["em_kernel"])
+        em_traffic = None if streamed else json.load(open(os.path.join(ROOT, "profiles", "em_kernel_traffic.json"))).get(m["em_kernel"])
     except Exception:
         pass
     line["em_roofline"] = {"bound": "on-chip (shared memory / issue)" if on_chip else "hbm", "achieved": em_gbs, "peak": peak, "unit": "GB/s",

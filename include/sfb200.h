@@ -183,6 +183,9 @@ double sfb200_last_em_loop_ms(const sfb200_ctx* ctx);
  * 5 k_em_dense with a pool loop: small components on component threads, the rest (large components, classes that cross CTA ranges)
  *   as an independent sub-problem on CTAs of their own */
 int sfb200_last_em_kernel(const sfb200_ctx* ctx);
+/* how k_em_dense ran (0 for the other kernels): bit 0 = class counts / base / 1/effLen streamed from global memory (the slice of a CTA
+ * did not fit in shared memory), bit 1 = lagged stopping rule */
+int sfb200_last_em_variant(const sfb200_ctx* ctx);
 
 /* Not called by the quantification drivers yet (parity-tested on its own: tests/test_gpu_bias.py).
  * Replaces sailfish::utils::updateEffectiveLengths (src/SailfishUtils.cpp:611-926): effective lengths corrected for

@@ -102,6 +102,7 @@ SIGNATURES = {
     "sfb200_em_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.c_uint64, C.POINTER(EMOpts), f64p, u32p, f64p]),
     "sfb200_last_em_loop_ms": (C.c_double, [C.c_void_p]),
     "sfb200_last_em_kernel": (C.c_int, [C.c_void_p]),
+    "sfb200_last_em_variant": (C.c_int, [C.c_void_p]),
     "sfb200_bias_eff_lens": (C.c_int, [C.c_void_p, C.POINTER(BiasModel), f64p, f64p, f64p, C.c_uint32, f64p]),
     "sfb200_em_run_bias": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.c_uint64, C.POINTER(EMOpts), C.POINTER(BiasModel), f64p, f64p, u32p, f64p]),
     "sfb200_bootstrap_run": (C.c_int, [C.c_void_p, f64p, C.c_uint32, C.POINTER(EMOpts), C.c_uint32, C.c_uint64, F64_ROW_CB, C.c_void_p]),
@@ -394,6 +395,10 @@ class Context:
                                             _ptr(eff_out, f64p), C.byref(iters), C.byref(mrd)))
         del keep
         return alphas, eff_out, iters.value, mrd.value
+
+    def last_em_variant(self):
+        """bit 0: k_em_dense streamed its counts from global memory; bit 1: lagged stopping rule"""
+        return int(self.L.sfb200_last_em_variant(self.h))
 
     def last_em_kernel(self):
         """0 k_em_persistent, 1 k_em_part, 2 k_em_gather, 3 one launch per phase, 4 k_em_dense, 5 k_em_dense with a pool loop (hybrid)"""

@@ -167,6 +167,7 @@ struct sfb200_ctx {
     uint64_t launches = 0;
     double last_em_ms = 0.0;
     int last_em_kernel = 0;             // see sfb200_last_em_kernel
+    int last_em_variant = 0;            // see sfb200_last_em_variant
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevIndex index;
     DevClasses cls;

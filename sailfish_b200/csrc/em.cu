@@ -674,6 +674,7 @@ extern "C" void sfb200_em_default_opts(sfb200_em_opts* o) {
 
 extern "C" double sfb200_last_em_loop_ms(const sfb200_ctx* c) { return c ? c->last_em_ms : 0.0; }
 extern "C" int sfb200_last_em_kernel(const sfb200_ctx* c) { return c ? c->last_em_kernel : 0; }
+extern "C" int sfb200_last_em_variant(const sfb200_ctx* c) { return c ? c->last_em_variant : 0; }
 
 namespace {
 
@@ -978,6 +979,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
     const char* mode = getenv("SFB200_EM_MODE");
     const bool sharded = c->n_ranks > 1 && !c->cls.merged;
     const bool steps = sharded || !c->coop || (mode && std::strcmp(mode, "steps") == 0);
+    c->last_em_variant = 0;
     unsigned long long h_ctl[CTL_WORDS];
     SFB_CUDA(c, cudaEventRecord(c->ev0, s));
     if (!steps && kind == LOOP_DENSE) {
@@ -992,6 +994,7 @@ int run_loop(sfb200_ctx* c, EmParams& p, const sfb200_em_opts* o, LoopKind kind,
         const bool no_lag = e_lag && atoi(e_lag) != 0;
         q.lag = (!no_lag && P.dense_smem_lag && !P.dense_stream && q.g.group == 2 && q.n_dirty == 0 && (vb || o->fixed_iters == 0)) ? 1u : 0u;
         const size_t smem = (size_t)(q.lag ? P.dense_smem_lag : P.dense_smem);
+        c->last_em_variant = (P.dense_stream ? 1 : 0) | (q.lag ? 2 : 0);
         void* args[] = {&p, &q};
         const void* fn = nullptr;
 #define SFB_DENSE_FN(N, GG) (vb ? reinterpret_cast<const void*>(&k_em_dense<true, N, GG>) : reinterpret_cast<const void*>(&k_em_dense<false, N, GG>))
