@@ -111,10 +111,13 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
     __shared__ unsigned long long sm_u[32];
     __shared__ double sm_d[32];
     __shared__ uint64_t tma_bar;
+    __shared__ unsigned long long s_pmax[2], s_res[4];          // lagged rule: the CTA's max of iteration m (by parity), what is due
+    __shared__ double s_psum[2];                                 //              the CTA's alpha sum of iteration m (by parity)
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     const unsigned nblocks = gridDim.x;
     unsigned long long gen = 0;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    if (threadIdx.x < 2) { s_pmax[threadIdx.x] = 0ULL; s_psum[threadIdx.x] = 0.0; }
 
     const uint32_t* region = q.regions + (size_t)blockIdx.x * q.g.region_words;
     const uint32_t tiles = region[DH_TILES], ent = region[DH_ENT], nidle = region[DH_NIDLE];
@@ -376,46 +379,67 @@ __global__ void __launch_bounds__(DENSE_THREADS, 2) k_em_dense(const EmParams p,
         }
         if (do_cmp && m > 1u) best = idle_later > best ? idle_later : best;
         if (lagged) {
-            // publish this CTA's part of iteration m; the ARRIVAL for it goes out one iteration later (below), when its atomics have
-            // long been performed and the fence in front of the arrival costs nothing
-            if (threadIdx.x == 0 && m > 1u) { __threadfence(); atomicAdd(p.ctl + CTL_LAG_ARR + ((m - 1u) & (DN_LAG_SLOTS - 1u)), 1ULL); }
-            if (do_cmp) block_max_to_slot(best, p.ctl + CTL_LAG_MAX + (m & (DN_LAG_SLOTS - 1u)), sm_u);
-            if (VB) block_sum_to_slot(asum + idle_sum, reinterpret_cast<double*>(p.ctl + CTL_LAG_SUM + (m & (DN_LAG_SLOTS - 1u))), sm_d);
+            // ---- ONE CTA barrier per iteration.  Before it: the warps fold their part of iteration m into shared memory (atomics, two
+            // slots by the parity of m) and thread 0 puts what the grid found in iteration m - DN_LAG (loaded before the sweep) where
+            // everybody can read it.  After it: thread 0 sends the arrival for m - 1 (its atomics went out an iteration ago, so the
+            // fence in front of it is free), then the CTA's part of m to the global slots; everybody else is already in the next sweep.
+            const uint32_t par = m & 1u;
+            if (do_cmp) {
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
+                if (lane == 0 && best) atomicMax(&s_pmax[par], best);
+            }
+            if (VB) {
+                const double v = warp_sum(asum + idle_sum);
+                if (lane == 0) atomicAdd(&s_psum[par], v);
+            }
             const bool final_it = fixed ? (m >= p.fixed_iters) : (m >= p.max_iter && m >= p.min_iter);
+            uint32_t x = m > DN_LAG ? m - DN_LAG : 0u;
+            if (threadIdx.x == 0 && x >= 1u) {
+                const unsigned long long want = (unsigned long long)nblocks * ((x - 1u) / DN_LAG_SLOTS + 1u);
+                if (pf_arr < want) {                                   // not there yet when it was loaded before the sweep: rare
+                    while (ld_acquire_u64(p.ctl + CTL_LAG_ARR + (x & (DN_LAG_SLOTS - 1u))) < want) { }
+                    pf_mr = ld_cg_u64(p.ctl + CTL_LAG_MAX + (x & (DN_LAG_SLOTS - 1u)));
+                    pf_sum = ld_cg_u64(p.ctl + CTL_LAG_SUM + (x & (DN_LAG_SLOTS - 1u)));
+                }
+                s_res[par * 2u] = pf_mr; s_res[par * 2u + 1u] = pf_sum;
+            }
+            __syncthreads();
             if (threadIdx.x == 0) {
+                if (m > 1u) { __threadfence(); atomicAdd(p.ctl + CTL_LAG_ARR + ((m - 1u) & (DN_LAG_SLOTS - 1u)), 1ULL); }
+                const uint32_t slot = m & (DN_LAG_SLOTS - 1u);
+                if (do_cmp) { const unsigned long long v = s_pmax[par]; s_pmax[par] = 0ULL; if (v) atomicMax(p.ctl + CTL_LAG_MAX + slot, v); }
+                if (VB) { const double v = s_psum[par]; s_psum[par] = 0.0; atomicAdd(reinterpret_cast<double*>(p.ctl + CTL_LAG_SUM + slot), v); }
                 if (blockIdx.x == 0) {
                     const uint32_t z = (m + DN_LAG + 1u) & (DN_LAG_SLOTS - 1u);
                     p.ctl[CTL_LAG_MAX + z] = 0ULL; p.ctl[CTL_LAG_SUM + z] = 0ULL;
                 }
-                if (final_it) { __threadfence(); atomicAdd(p.ctl + CTL_LAG_ARR + (m & (DN_LAG_SLOTS - 1u)), 1ULL); }   // no later iteration
+                if (final_it) { __threadfence(); atomicAdd(p.ctl + CTL_LAG_ARR + slot, 1ULL); }        // no later iteration
             }
-            // the iterations whose global quantities are due: m - DN_LAG (loaded by thread 0 before the sweep), and after the final
-            // iteration all that are left, in order
-            uint32_t x = m > DN_LAG ? m - DN_LAG : 0u;
-            const uint32_t x_hi = final_it ? m : x;
-            if (final_it && x == 0u) x = 1u;
             bool stop = false;
             unsigned long long sum_bits = 0ULL;
             bool have_sum = false;
-            for (; x >= 1u && x <= x_hi; ++x) {
-                if (threadIdx.x == 0) {
-                    const unsigned long long want = (unsigned long long)nblocks * ((x - 1u) / DN_LAG_SLOTS + 1u);
-                    if (!(x + DN_LAG == m && pf_arr >= want)) {
-                        while (ld_acquire_u64(p.ctl + CTL_LAG_ARR + (x & (DN_LAG_SLOTS - 1u))) < want) { }
-                        pf_mr = ld_cg_u64(p.ctl + CTL_LAG_MAX + (x & (DN_LAG_SLOTS - 1u)));
-                        pf_sum = ld_cg_u64(p.ctl + CTL_LAG_SUM + (x & (DN_LAG_SLOTS - 1u)));
-                    }
-                    sm_u[0] = pf_mr; sm_u[1] = pf_sum;
-                }
-                __syncthreads();
-                const unsigned long long mr = sm_u[0];
-                sum_bits = sm_u[1]; have_sum = true;
+            if (x >= 1u) {
+                const unsigned long long mr = s_res[par * 2u];
+                sum_bits = s_res[par * 2u + 1u]; have_sum = true;
                 const bool checked = fixed ? (x >= p.fixed_iters) : (x >= p.min_iter);
-                if (checked && (fixed || x >= p.max_iter || !(decode_mrd(mr) > p.tol))) {
-                    stop = true; mr_final = mr; n = x;                 // the run ends with alpha_x: still in the ring
-                    break;
+                if (checked && (fixed || x >= p.max_iter || !(decode_mrd(mr) > p.tol))) { stop = true; mr_final = mr; n = x; }   // alpha_x is still in the ring
+            }
+            if (!stop && final_it) {
+                // the last iteration: what is left (m - DN_LAG + 1 .. m) is waited for and looked at in order
+                for (x = x + 1u; x <= m; ++x) {
+                    __syncthreads();                                   // everybody has read sm_u
+                    if (threadIdx.x == 0) {
+                        const unsigned long long want = (unsigned long long)nblocks * ((x - 1u) / DN_LAG_SLOTS + 1u);
+                        while (ld_acquire_u64(p.ctl + CTL_LAG_ARR + (x & (DN_LAG_SLOTS - 1u))) < want) { }
+                        sm_u[0] = ld_cg_u64(p.ctl + CTL_LAG_MAX + (x & (DN_LAG_SLOTS - 1u)));
+                        sm_u[1] = ld_cg_u64(p.ctl + CTL_LAG_SUM + (x & (DN_LAG_SLOTS - 1u)));
+                    }
+                    __syncthreads();
+                    const unsigned long long mr = sm_u[0];
+                    const bool checked = fixed ? (x >= p.fixed_iters) : (x >= p.min_iter);
+                    if (checked && (fixed || x >= p.max_iter || !(decode_mrd(mr) > p.tol))) { stop = true; mr_final = mr; n = x; break; }
                 }
-                if (x < x_hi) __syncthreads();                         // thread 0 writes sm_u again
             }
             if (stop) break;
             if (VB) {
