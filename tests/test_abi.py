@@ -35,6 +35,17 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == -1          # SFB200_ENODEV
 
 
+def test_host_binding_is_a_no_op_without_a_device():
+    """sfb200_bind_host_near_device: no such device (or no NUMA information) leaves the affinity alone and says so with 0 -- saying
+    "no usable device" loudly is sfb200_ctx_create's job"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    before = os.sched_getaffinity(0)
+    assert capi.bind_host_near_device(0) == 0 and capi.bind_host_near_device(7) == 0
+    assert os.sched_getaffinity(0) == before
+
+
 def test_product_does_not_reference_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may import, link or execute oracle/."""
     pkg = os.path.join(ROOT, "sailfish_b200")
