@@ -61,10 +61,6 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) { return __ldcg(p); }
-// fire-and-forget add that orders this thread's earlier writes and atomics before it (what a consumer's ld.acquire pairs with)
-__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
 
 // all CTAs of the (cooperatively launched, hence co-resident) grid meet here
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctl, unsigned int nblocks, unsigned long long& gen) {

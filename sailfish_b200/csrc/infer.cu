@@ -347,7 +347,6 @@ struct SplitTree {
     std::vector<double*> sums;                     // level >= 1
     std::vector<unsigned long long*> share;        // level >= 1 (level 0 is the caller's sample vector)
     DevBuf<double> d_sums; DevBuf<unsigned long long> d_share;
-    void release() { d_sums.release(); d_share.release(); }
 };
 }  // namespace
 

@@ -3,9 +3,9 @@
 #pragma once
 #include <cmath>
 #if defined(__CUDACC__)
-#define SFB_HD __host__ __device__
+#define SFB_VB_HD __host__ __device__
 #else
-#define SFB_HD
+#define SFB_VB_HD
 #endif
 
 // digamma for x > 0: recurrence up to x >= 12, then the asymptotic series (same expansion as the oracle's
@@ -13,7 +13,7 @@
 // expensive part of a VBEM iteration (up to twelve fp64 divisions per transcript): the sum of reciprocals is P'/P of the polynomial
 // P = prod (x + k), built with two multiplies and an FMA per factor and ONE division -- after a first term taken by itself
 // when x < 1, so that P stays far from the denormal range for the tiny alphas VBEM produces.
-SFB_HD inline double sfb_digamma(double x) {
+SFB_VB_HD inline double sfb_digamma(double x) {
     double acc = 0.0;
     if (x < 1.0) { acc = -1.0 / x; x += 1.0; }
     if (x < 12.0) {
@@ -35,7 +35,7 @@ SFB_HD inline double sfb_digamma(double x) {
 // shifts x up and its sum of reciprocals goes through ONE exponential.  Relative error against mpmath over [1e-3, 1e9]: 1.1e-13
 // (from exp of the -1/x term of tiny alphas), the exp(digamma - logNorm) form it replaces: 1.8e-13 (tests/test_vb_math.py runs
 // the host build of both against mpmath; tests/test_gpu_em.py the device build).
-SFB_HD inline double sfb_exp_digamma(double x) {
+SFB_VB_HD inline double sfb_exp_digamma(double x) {
     double mult = 1.0;
     if (x < 16.0) {
         double acc = 0.0;
@@ -64,6 +64,6 @@ SFB_HD inline double sfb_exp_digamma(double x) {
 // VBEM's expTheta = exp(digamma(alpha) - logNorm), logNorm = digamma(sum alpha) -- one number per iteration, and so is
 // scale = exp(-logNorm).  The product form needs scale to be an ordinary number (sum alpha >= 1 gives logNorm >= -0.58; the other
 // form stays for a degenerate sum).
-SFB_HD inline double sfb_exp_theta(double alpha, double logNorm, double scale) {
+SFB_VB_HD inline double sfb_exp_theta(double alpha, double logNorm, double scale) {
     return (logNorm > -600.0 && logNorm < 600.0) ? sfb_exp_digamma(alpha) * scale : exp(sfb_digamma(alpha) - logNorm);
 }
